@@ -1,0 +1,121 @@
+/* zygpu.h — device ABI of the B200 surface-integration backend for zyg.
+ *
+ * This is the boundary a Zig host binds with `extern fn` / @cImport: plain C,
+ * pointers and sizes only. zyg has no device API of its own; each entry point names the reference
+ * code whose role it takes over.
+ *
+ * Conventions (same as src/capi/capi.zig): every function returns 0 on success (or a non-negative
+ * id) and -1 on failure; zygpu_last_error() holds the message. One caller thread per device.
+ * Buffers are caller-owned; the library copies what it needs.
+ */
+#ifndef ZYGPU_H
+#define ZYGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- host-side scene compile ------------------------------------------------------------- */
+
+/* A compiled triangle mesh: reference-order binary BVH + the derived device layout.
+ * Replaces shape_provider.zig:847-924 (buildDescAsync/buildBVH) + triangle_tree_builder.zig:33-65. */
+typedef struct zyg_mesh zyg_mesh;
+
+/* Argument meaning follows su_triangle_mesh_create (src/capi/capi.zig:379-423): `parts` holds
+ * num_parts x {start_index, num_indices, material}; strides are in floats; indices may be NULL
+ * (then triangle i uses vertices 3i..3i+2); normals / uvs may be NULL. num_threads = 0 uses all
+ * host cores (the result never depends on it). */
+int zyg_mesh_build(uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles, const uint32_t* indices,
+                   uint32_t num_vertices, const float* positions, uint32_t positions_stride, const float* normals,
+                   uint32_t normals_stride, const float* uvs, uint32_t uvs_stride, uint32_t num_threads,
+                   zyg_mesh** out);
+void zyg_mesh_free(zyg_mesh* mesh);
+
+enum {
+    ZYG_MESH_BINARY_NODES = 0, /* 32-byte nodes, src/core/scene/bvh/node.zig:9-20 */
+    ZYG_MESH_TRIANGLES    = 1, /* u32[3] per BVH-order triangle, triangle.zig:6-10 */
+    ZYG_MESH_ORIGINAL     = 2, /* u32 per BVH-order triangle: index in the caller's triangle list */
+    ZYG_MESH_POSITIONS    = 3, /* f32[3] per vertex + 1 pad float, triangle_data.zig:49,54 */
+    ZYG_MESH_NORMALS      = 4, /* u16[2] per vertex, oct-encoded snorm16 */
+    ZYG_MESH_UVS          = 5, /* f32[2] per vertex */
+    ZYG_MESH_PARTS        = 6, /* u16 per BVH-order triangle */
+    ZYG_MESH_WIDE_NODES   = 7, /* 80-byte device nodes */
+    ZYG_MESH_WIDE_TRIS    = 8  /* 48-byte device triangle records */
+};
+
+/* Read-only view of one of the arrays above; valid until zyg_mesh_free. */
+const void* zyg_mesh_data(const zyg_mesh* mesh, int which, uint64_t* num_bytes);
+
+typedef struct ZygMeshInfo {
+    uint32_t num_source_triangles;
+    uint32_t num_tree_triangles; /* >= source: spatial splits duplicate references */
+    uint32_t num_vertices;
+    uint32_t num_binary_nodes;
+    uint32_t num_wide_nodes;
+    uint32_t wide_max_depth;
+    uint32_t num_degenerate_leaves;
+    uint32_t num_leaf_order_fixups;
+    float    aabb_min[3];
+    float    aabb_max[3];
+} ZygMeshInfo;
+
+int zyg_mesh_info(const zyg_mesh* mesh, ZygMeshInfo* info);
+
+/* ---- device -------------------------------------------------------------------------------- */
+
+typedef struct zygpu_device zygpu_device;
+
+int  zygpu_create(int device_ordinal, zygpu_device** out);
+void zygpu_destroy(zygpu_device* dev);
+
+/* Uploads the compiled mesh (wide layout + reference layout). Returns a mesh id >= 0. */
+int zygpu_upload_mesh(zygpu_device* dev, const zyg_mesh* mesh);
+
+/* 32-byte ray: origin, min_t, direction, max_t (object space of the mesh; src/base/math/ray.zig). */
+typedef struct ZygpuRay {
+    float origin[3];
+    float min_t;
+    float direction[3];
+    float max_t;
+} ZygpuRay;
+
+/* 16-byte closest-hit record (src/core/scene/shape/intersection.zig:46-61). primitive is the
+ * BVH-order triangle index (0xFFFFFFFF = miss, then t = max_t). */
+typedef struct ZygpuHit {
+    float    t, u, v;
+    uint32_t primitive;
+} ZygpuHit;
+
+enum {
+    ZYGPU_CLOSEST        = 0, /* TriangleTree.intersect,  triangle_tree.zig:46-109 — wide BVH */
+    ZYGPU_ANY            = 1, /* TriangleTree.intersectP, triangle_tree.zig:197-242 — wide BVH */
+    ZYGPU_CLOSEST_BINARY = 2, /* same, visiting the 32-byte reference nodes in reference order */
+    ZYGPU_ANY_BINARY     = 3
+};
+
+typedef struct ZygpuTraceCounters {
+    uint64_t nodes;     /* node records fetched (80 B wide / 32 B binary) */
+    uint64_t triangles; /* triangle tests */
+    uint64_t rays;
+    uint64_t max_stack;
+} ZygpuTraceCounters;
+
+/* Host buffers: copies rays in, traces, copies results out (chunked and overlapped on internal
+ * streams). `out` is ZygpuHit[n] for the closest modes and uint32_t[n] (1 = occluded) for any-hit. */
+int zygpu_trace_batch(zygpu_device* dev, int mesh, int mode, const ZygpuRay* rays, uint64_t n, void* out);
+
+/* Device buffers, asynchronous on `stream` (a CUstream / cudaStream_t; NULL = default stream).
+ * If `counters` is non-NULL the instrumented kernel runs, the call synchronises the stream and
+ * writes fetch counts for this batch. */
+int zygpu_trace_batch_device(zygpu_device* dev, int mesh, int mode, const void* d_rays, uint64_t n, void* d_out,
+                             void* stream, ZygpuTraceCounters* counters);
+
+const char* zygpu_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ZYGPU_H */

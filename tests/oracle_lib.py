@@ -1,0 +1,82 @@
+"""ctypes loader for the CPU oracle (oracle/libzyg_oracle.so). Test infrastructure only."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_PATH = os.path.join(ORACLE_DIR, "libzyg_oracle.so")
+
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("min_t", "<f4"), ("direction", "<f4", 3), ("max_t", "<f4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("primitive", "<u4")])
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(ORACLE_PATH):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    lib = C.CDLL(ORACLE_PATH)
+    vp, u64 = C.c_void_p, C.c_uint64
+    lib.zo_trace_closest.argtypes = [vp, vp, vp, vp, u64, vp, C.c_uint32, C.POINTER(u64), C.POINTER(u64)]
+    lib.zo_trace_closest.restype = None
+    lib.zo_trace_any.argtypes = [vp, vp, vp, vp, u64, vp, C.c_uint32]
+    lib.zo_trace_any.restype = None
+    lib.zo_brute_closest.argtypes = [vp, C.c_uint32, vp, vp, u64, vp, vp, C.c_uint32]
+    lib.zo_brute_closest.restype = None
+    lib.zo_pcg32_uints.argtypes = [u64, u64, C.c_uint32, vp]
+    lib.zo_pcg32_uints.restype = None
+    lib.zo_pcg32_floats.argtypes = [u64, u64, C.c_uint32, vp]
+    lib.zo_pcg32_floats.restype = None
+    _lib = lib
+    return lib
+
+
+def _p(a: np.ndarray) -> int:
+    assert a.flags.c_contiguous
+    return a.ctypes.data
+
+
+def trace_closest(nodes, triangles, positions, rays, threads=0, count=False):
+    lib = load()
+    out = np.empty(rays.shape[0], HIT_DTYPE)
+    vn, tt = C.c_uint64(), C.c_uint64()
+    lib.zo_trace_closest(_p(nodes), _p(triangles), _p(positions), _p(rays), rays.shape[0], _p(out), threads,
+                         C.byref(vn) if count else None, C.byref(tt) if count else None)
+    return (out, vn.value, tt.value) if count else out
+
+
+def trace_any(nodes, triangles, positions, rays, threads=0):
+    lib = load()
+    out = np.empty(rays.shape[0], np.uint32)
+    lib.zo_trace_any(_p(nodes), _p(triangles), _p(positions), _p(rays), rays.shape[0], _p(out), threads)
+    return out
+
+
+def brute_closest(triangles, positions, rays, threads=0):
+    lib = load()
+    out = np.empty(rays.shape[0], HIT_DTYPE)
+    ties = np.empty(rays.shape[0], np.uint32)
+    lib.zo_brute_closest(_p(triangles), triangles.size // 3, _p(positions), _p(rays), rays.shape[0], _p(out), _p(ties),
+                         threads)
+    return out, ties
+
+
+def pcg32_uints(state, sequence, n):
+    out = np.empty(n, np.uint32)
+    load().zo_pcg32_uints(state, sequence, n, _p(out))
+    return out
+
+
+def pcg32_floats(state, sequence, n):
+    out = np.empty(n, np.float32)
+    load().zo_pcg32_floats(state, sequence, n, _p(out))
+    return out

@@ -1,0 +1,443 @@
+#include "trace.cuh"
+
+#include <cfloat>
+
+namespace zygpu {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Reference arithmetic (strict fp32; this file is built with -fmad=false)
+// ---------------------------------------------------------------------------------------------
+
+struct V3 {
+    float x, y, z;
+};
+
+__device__ __forceinline__ V3 sub3(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+
+// src/base/math/vector4.zig:36-39 : (x + y) + z
+__device__ __forceinline__ float dot3(V3 a, V3 b) {
+    const float x = a.x * b.x, y = a.y * b.y, z = a.z * b.z;
+    return (x + y) + z;
+}
+
+// src/base/math/vector4.zig:73-92 : one FMA per lane
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+    return {__fmaf_rn(b.z, a.y, -(a.z * b.y)), __fmaf_rn(b.x, a.z, -(a.x * b.z)), __fmaf_rn(b.y, a.x, -(a.y * b.x))};
+}
+
+// src/base/math/util.zig:17-29 (x86 branch)
+__device__ __forceinline__ float zmin(float x, float y) { return x < y ? x : y; }
+__device__ __forceinline__ float zmax(float x, float y) { return y < x ? x : y; }
+
+struct RayT {
+    V3    o, d, inv_d;
+    float tmin, tmax;
+};
+
+// src/core/scene/shape/triangle/triangle.zig:26-52 with e1/e2 hoisted (same fp32 subtractions).
+__device__ __forceinline__ bool intersectTriangle(const RayT& ray, V3 a, V3 e1, V3 e2, float& ht, float& hu, float& hv) {
+    const V3 tvec = sub3(ray.o, a);
+    const V3 pvec = cross3(ray.d, e2);
+    const V3 qvec = cross3(tvec, e1);
+
+    const float e1_d_pv = dot3(e1, pvec);
+    const float tv_d_pv = dot3(tvec, pvec);
+    const float di_d_qv = dot3(ray.d, qvec);
+    const float e2_d_qv = dot3(e2, qvec);
+
+    const float inv_det = __fdiv_rn(1.f, e1_d_pv);
+
+    const float u     = tv_d_pv * inv_det;
+    const float v     = di_d_qv * inv_det;
+    const float hit_t = e2_d_qv * inv_det;
+
+    const float uv = u + v;
+
+    if (u >= 0.f && 1.f >= u && v >= 0.f && 1.f >= uv && hit_t >= ray.tmin && ray.tmax >= hit_t) {
+        ht = hit_t;
+        hu = u;
+        hv = v;
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ RayT loadRay(const RayIn* rays, uint32_t i) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rays) + 2 * size_t(i) + 1);
+    RayT         r;
+    r.o     = {a.x, a.y, a.z};
+    r.tmin  = a.w;
+    r.d     = {b.x, b.y, b.z};
+    r.tmax  = b.w;
+    // src/base/math/ray.zig:11-20 : reciprocal3 is a true division (vector4.zig:62-64)
+    r.inv_d = {__fdiv_rn(1.f, b.x), __fdiv_rn(1.f, b.y), __fdiv_rn(1.f, b.z)};
+    return r;
+}
+
+template <bool Count>
+struct Tally {
+    uint32_t nodes = 0, tris = 0, stack = 0;
+    __device__ __forceinline__ void node() {
+        if (Count) ++nodes;
+    }
+    __device__ __forceinline__ void tri() {
+        if (Count) ++tris;
+    }
+    __device__ __forceinline__ void depth(uint32_t d) {
+        if (Count) stack = d > stack ? d : stack;
+    }
+    __device__ void flush(TraceCounters* c) {
+        if (!Count) return;
+        unsigned long long n = nodes, t = tris;
+        uint32_t           s = stack;
+        for (int o = 16; o > 0; o >>= 1) {
+            n += __shfl_down_sync(0xffffffffu, n, o);
+            t += __shfl_down_sync(0xffffffffu, t, o);
+            const uint32_t so = __shfl_down_sync(0xffffffffu, s, o);
+            s                 = so > s ? so : s;
+        }
+        if (0 == (threadIdx.x & 31)) {
+            atomicAdd(&c->nodes, n);
+            atomicAdd(&c->triangles, t);
+            atomicMax(&c->max_stack, (unsigned long long)s);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Order-exact binary traversal
+// ---------------------------------------------------------------------------------------------
+
+// src/core/scene/bvh/node.zig:73-87
+__device__ __forceinline__ float intersectNode(const float4 nmin, const float4 nmax, const RayT& ray) {
+    const float lx = (nmin.x - ray.o.x) * ray.inv_d.x, ly = (nmin.y - ray.o.y) * ray.inv_d.y,
+                lz = (nmin.z - ray.o.z) * ray.inv_d.z;
+    const float ux = (nmax.x - ray.o.x) * ray.inv_d.x, uy = (nmax.y - ray.o.y) * ray.inv_d.y,
+                uz = (nmax.z - ray.o.z) * ray.inv_d.z;
+
+    const float t0x = zmin(lx, ux), t0y = zmin(ly, uy), t0z = zmin(lz, uz);
+    const float t1x = zmax(lx, ux), t1y = zmax(ly, uy), t1z = zmax(lz, uz);
+
+    // hmax4 / hmin4, vector4.zig:163-175
+    const float tboxmin = zmax(t0x, zmax(t0y, zmax(t0z, ray.tmin)));
+    const float tboxmax = zmin(t1x, zmin(t1y, zmin(t1z, ray.tmax)));
+
+    return tboxmin <= tboxmax ? tboxmin : FLT_MAX;
+}
+
+constexpr uint32_t kBinaryStack = 127;  // src/core/scene/bvh/node_stack.zig:2
+constexpr uint32_t kEnd         = 0xFFFFFFFFu;
+
+template <bool AnyHit, bool Count>
+__global__ void __launch_bounds__(128)
+    traceBinary(MeshDevice mesh, const RayIn* __restrict__ rays, void* __restrict__ out, uint32_t n,
+                TraceCounters* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    Tally<Count>   tally;
+    if (i < n) {
+        RayT ray = loadRay(rays, i);
+
+        uint32_t stack[kBinaryStack];
+        uint32_t end = 0;
+        uint32_t node = 0;
+
+        float    ht = 0.f, hu = 0.f, hv = 0.f;
+        uint32_t primitive = kEnd;
+        bool     occluded  = false;
+
+        while (kEnd != node) {
+            const float4 nmin = __ldg(mesh.binary_nodes + 2 * size_t(node));
+            const float4 nmax = __ldg(mesh.binary_nodes + 2 * size_t(node) + 1);
+            tally.node();
+
+            const uint32_t num = __float_as_uint(nmax.w);
+            if (0 != num) {
+                uint32_t       p = __float_as_uint(nmin.w);
+                const uint32_t e = p + num;
+                for (; p < e; ++p) {
+                    // triangle_data.zig:62-78 : index triple, then three position loads
+                    const uint32_t ia = __ldg(mesh.triangles + 3 * size_t(p) + 0);
+                    const uint32_t ib = __ldg(mesh.triangles + 3 * size_t(p) + 1);
+                    const uint32_t ic = __ldg(mesh.triangles + 3 * size_t(p) + 2);
+                    const float*   pa = mesh.positions + 3 * size_t(ia);
+                    const float*   pb = mesh.positions + 3 * size_t(ib);
+                    const float*   pc = mesh.positions + 3 * size_t(ic);
+                    const V3       a  = {__ldg(pa), __ldg(pa + 1), __ldg(pa + 2)};
+                    const V3       b  = {__ldg(pb), __ldg(pb + 1), __ldg(pb + 2)};
+                    const V3       c  = {__ldg(pc), __ldg(pc + 1), __ldg(pc + 2)};
+                    tally.tri();
+                    float t, u, v;
+                    if (intersectTriangle(ray, a, sub3(b, a), sub3(c, a), t, u, v)) {
+                        if (AnyHit) {
+                            occluded = true;
+                            break;
+                        }
+                        ray.tmax  = t;
+                        ht        = t;
+                        hu        = u;
+                        hv        = v;
+                        primitive = p;
+                    }
+                }
+                if (AnyHit && occluded) break;
+                node = 0 == end ? kEnd : stack[--end];
+                continue;
+            }
+
+            uint32_t a = __float_as_uint(nmin.w);
+            uint32_t b = a + 1;
+
+            const float4 amin = __ldg(mesh.binary_nodes + 2 * size_t(a));
+            const float4 amax = __ldg(mesh.binary_nodes + 2 * size_t(a) + 1);
+            const float4 bmin = __ldg(mesh.binary_nodes + 2 * size_t(b));
+            const float4 bmax = __ldg(mesh.binary_nodes + 2 * size_t(b) + 1);
+
+            float dista = intersectNode(amin, amax, ray);
+            float distb = intersectNode(bmin, bmax, ray);
+
+            if (dista > distb) {
+                const uint32_t tn = a;
+                a                 = b;
+                b                 = tn;
+                const float td    = dista;
+                dista             = distb;
+                distb             = td;
+            }
+
+            if (FLT_MAX == dista) {
+                node = 0 == end ? kEnd : stack[--end];
+            } else {
+                node = a;
+                if (FLT_MAX != distb) {
+                    stack[end++] = b;
+                    tally.depth(end);
+                }
+            }
+        }
+
+        if (AnyHit) {
+            reinterpret_cast<uint32_t*>(out)[i] = occluded ? 1u : 0u;
+        } else {
+            float4 h;
+            h.x = kEnd == primitive ? ray.tmax : ht;
+            h.y = hu;
+            h.z = hv;
+            h.w = __uint_as_float(primitive);
+            reinterpret_cast<float4*>(out)[i] = h;
+        }
+    }
+    tally.flush(counters);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wide traversal
+// ---------------------------------------------------------------------------------------------
+
+constexpr uint32_t kWideStack = 48;
+
+__device__ __forceinline__ float byteToFloat(uint32_t word, int byte) { return float((word >> (8 * byte)) & 0xffu); }
+
+template <bool AnyHit, bool Count>
+__global__ void __launch_bounds__(128)
+    traceWide(MeshDevice mesh, const RayIn* __restrict__ rays, void* __restrict__ out, uint32_t n,
+              TraceCounters* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    Tally<Count>   tally;
+    if (i < n) {
+        RayT ray = loadRay(rays, i);
+
+        // octant: slot bit 2 <-> x, bit 1 <-> y, bit 0 <-> z; children further along the ray get lower priority
+        const bool     px     = !signbit(ray.d.x);
+        const bool     py     = !signbit(ray.d.y);
+        const bool     pz     = !signbit(ray.d.z);
+        const uint32_t octinv = (px ? 4u : 0u) | (py ? 2u : 0u) | (pz ? 1u : 0u);
+
+        uint2    stack[kWideStack];
+        uint32_t sp = 0;
+
+        // The root (node 0) is entered as the only hit child of a virtual parent whose inner children
+        // start at index 0: bit 31 set, imask 0 -> rank 0.
+        uint2 node_group = make_uint2(0u, 0x80000000u);
+        uint2 tri_group  = make_uint2(0u, 0u);
+
+        float    ht = 0.f, hu = 0.f, hv = 0.f;
+        uint32_t primitive = kEnd;
+        bool     occluded  = false;
+
+        for (;;) {
+            if (node_group.y > 0x00FFFFFFu) {
+                // node groups carry (child_base, hits << 24 | imask); take the highest-priority hit child
+                const uint32_t hits  = node_group.y;
+                const uint32_t gmask = hits & 0xffu;
+                const uint32_t bit   = 31u - __clz(hits);
+                node_group.y         = hits & ~(1u << bit);
+                const uint32_t slot  = (bit - 24u) ^ octinv;
+                const uint32_t rank  = __popc(gmask & ((1u << slot) - 1u));
+                const uint32_t node_index = node_group.x + rank;
+                if (node_group.y > 0x00FFFFFFu) {
+                    stack[sp++] = node_group;
+                    tally.depth(sp);
+                }
+
+                const float4* np = mesh.wide_nodes + 5 * size_t(node_index);
+                const float4  n0 = __ldg(np + 0);
+                const float4  n1 = __ldg(np + 1);
+                const float4  n2 = __ldg(np + 2);
+                const float4  n3 = __ldg(np + 3);
+                const float4  n4 = __ldg(np + 4);
+                tally.node();
+
+                const uint32_t ew    = __float_as_uint(n0.w);
+                const uint32_t imask = ew >> 24;
+
+                const float idx = __uint_as_float((ew & 0xffu) << 23) * ray.inv_d.x;
+                const float idy = __uint_as_float(((ew >> 8) & 0xffu) << 23) * ray.inv_d.y;
+                const float idz = __uint_as_float(((ew >> 16) & 0xffu) << 23) * ray.inv_d.z;
+
+                const float orx = (n0.x - ray.o.x) * ray.inv_d.x;
+                const float ory = (n0.y - ray.o.y) * ray.inv_d.y;
+                const float orz = (n0.z - ray.o.z) * ray.inv_d.z;
+
+                // Conservative slack: the quantised slab arithmetic associates differently from the
+                // reference's (min - o) * inv_d; widen each interval by a few ulps of its largest term so
+                // no child the exact test would accept is ever dropped.
+                constexpr float kSlack = 4.76837158e-7f;  // 2^-21
+                const float     pdx = kSlack * (fabsf(orx) + 256.f * fabsf(idx));
+                const float     pdy = kSlack * (fabsf(ory) + 256.f * fabsf(idy));
+                const float     pdz = kSlack * (fabsf(orz) + 256.f * fabsf(idz));
+
+                const float olx = orx - pdx, ohx = orx + pdx;
+                const float oly = ory - pdy, ohy = ory + pdy;
+                const float olz = orz - pdz, ohz = orz + pdz;
+
+                // quantised planes: near = lo when the ray travels in +axis, else hi
+                const uint32_t qlox[2] = {__float_as_uint(n2.x), __float_as_uint(n2.y)};
+                const uint32_t qloy[2] = {__float_as_uint(n2.z), __float_as_uint(n2.w)};
+                const uint32_t qloz[2] = {__float_as_uint(n3.x), __float_as_uint(n3.y)};
+                const uint32_t qhix[2] = {__float_as_uint(n3.z), __float_as_uint(n3.w)};
+                const uint32_t qhiy[2] = {__float_as_uint(n4.x), __float_as_uint(n4.y)};
+                const uint32_t qhiz[2] = {__float_as_uint(n4.z), __float_as_uint(n4.w)};
+                const uint32_t meta[2] = {__float_as_uint(n1.z), __float_as_uint(n1.w)};
+
+                uint32_t hitmask = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t nx = px ? qlox[h] : qhix[h], fx = px ? qhix[h] : qlox[h];
+                    const uint32_t ny = py ? qloy[h] : qhiy[h], fy = py ? qhiy[h] : qloy[h];
+                    const uint32_t nz = pz ? qloz[h] : qhiz[h], fz = pz ? qhiz[h] : qloz[h];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float tminx = fmaf(byteToFloat(nx, j), idx, olx);
+                        const float tminy = fmaf(byteToFloat(ny, j), idy, oly);
+                        const float tminz = fmaf(byteToFloat(nz, j), idz, olz);
+                        const float tmaxx = fmaf(byteToFloat(fx, j), idx, ohx);
+                        const float tmaxy = fmaf(byteToFloat(fy, j), idy, ohy);
+                        const float tmaxz = fmaf(byteToFloat(fz, j), idz, ohz);
+
+                        const float tmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, ray.tmin));
+                        const float tmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, ray.tmax));
+
+                        if (tmin <= tmax) {
+                            const uint32_t m          = (meta[h] >> (8 * j)) & 0xffu;
+                            const uint32_t child_bits = m >> 5;
+                            uint32_t       bit_index  = m & 31u;
+                            if (bit_index >= 24u) bit_index ^= octinv;
+                            hitmask |= child_bits << bit_index;
+                        }
+                    }
+                }
+
+                node_group.x = __float_as_uint(n1.x);
+                node_group.y = (hitmask & 0xFF000000u) | imask;
+                tri_group.x  = __float_as_uint(n1.y);
+                tri_group.y  = hitmask & 0x00FFFFFFu;
+            } else {
+                tri_group    = node_group;
+                node_group.y = 0;
+            }
+
+            while (0 != tri_group.y) {
+                const uint32_t bit = 31u - __clz(tri_group.y);
+                tri_group.y &= ~(1u << bit);
+
+                const float4* tp = mesh.wide_tris + 3 * size_t(tri_group.x + bit);
+                const float4  t0 = __ldg(tp + 0);
+                const float4  t1 = __ldg(tp + 1);
+                const float4  t2 = __ldg(tp + 2);
+                tally.tri();
+
+                float t, u, v;
+                if (intersectTriangle(ray, {t0.x, t0.y, t0.z}, {t1.x, t1.y, t1.z}, {t2.x, t2.y, t2.z}, t, u, v)) {
+                    if (AnyHit) {
+                        occluded = true;
+                        break;
+                    }
+                    ray.tmax  = t;
+                    ht        = t;
+                    hu        = u;
+                    hv        = v;
+                    primitive = __float_as_uint(t0.w);
+                }
+            }
+            if (AnyHit && occluded) break;
+
+            if (node_group.y <= 0x00FFFFFFu) {
+                if (0 == sp) break;
+                node_group = stack[--sp];
+            }
+        }
+
+        if (AnyHit) {
+            reinterpret_cast<uint32_t*>(out)[i] = occluded ? 1u : 0u;
+        } else {
+            float4 h;
+            h.x = kEnd == primitive ? ray.tmax : ht;
+            h.y = hu;
+            h.z = hv;
+            h.w = __uint_as_float(primitive);
+            reinterpret_cast<float4*>(out)[i] = h;
+        }
+    }
+    tally.flush(counters);
+}
+
+template <bool AnyHit, bool Count>
+cudaError_t launchOne(const MeshDevice& mesh, bool wide, const RayIn* rays, void* out, uint32_t n,
+                      TraceCounters* counters, cudaStream_t stream) {
+    if (0 == n) return cudaSuccess;
+    const uint32_t block = 128;
+    const uint32_t grid  = (n + block - 1) / block;
+    if (wide) {
+        traceWide<AnyHit, Count><<<grid, block, 0, stream>>>(mesh, rays, out, n, counters);
+    } else {
+        traceBinary<AnyHit, Count><<<grid, block, 0, stream>>>(mesh, rays, out, n, counters);
+    }
+    return cudaGetLastError();
+}
+
+__global__ void addRays(TraceCounters* c, unsigned long long n) { c->rays += n; }
+
+}  // namespace
+
+cudaError_t launchTrace(const MeshDevice& mesh, int mode, const RayIn* rays, void* out, uint32_t n,
+                        TraceCounters* counters, cudaStream_t stream) {
+    const bool wide = kClosestWide == mode || kAnyWide == mode;
+    const bool any  = kAnyWide == mode || kAnyBinary == mode;
+    if (mode < 0 || mode > 3) return cudaErrorInvalidValue;
+
+    cudaError_t err;
+    if (counters) {
+        addRays<<<1, 1, 0, stream>>>(counters, n);
+        err = any ? launchOne<true, true>(mesh, wide, rays, out, n, counters, stream)
+                  : launchOne<false, true>(mesh, wide, rays, out, n, counters, stream);
+    } else {
+        err = any ? launchOne<true, false>(mesh, wide, rays, out, n, nullptr, stream)
+                  : launchOne<false, false>(mesh, wide, rays, out, n, nullptr, stream);
+    }
+    return err;
+}
+
+}  // namespace zygpu

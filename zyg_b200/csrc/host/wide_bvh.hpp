@@ -1,0 +1,56 @@
+// Device layout of a triangle BVH: 8-wide nodes with 8-bit quantised child boxes + 48-byte
+// triangle records. Derived ("flattened on upload") from the reference-order binary tree, so the
+// set of triangles and their clip regions is the reference's; only the visiting order changes.
+//
+// Node, 80 bytes = five 16-byte loads:
+//   +0   float  p[3]        origin (min corner) of the quantisation grid
+//   +12  u8     e[3]        biased exponents: cell size = 2^(e-127) per axis
+//   +15  u8     imask       bit s set: slot s holds an inner node
+//   +16  u32    child_base  index of the first inner child; inner children are consecutive in slot order
+//   +20  u32    tri_base    index of the first triangle record referenced by leaf slots
+//   +24  u8     meta[8]     inner: 0b001_11sss (s = slot); leaf: unary count (1..3) << 5 | first triangle offset;
+//                           empty: 0
+//   +32  u8     qlo[3][8]   quantised lower bounds, x then y then z, one byte per slot
+//   +56  u8     qhi[3][8]   quantised upper bounds
+// Slots are assigned so that `slot ^ octant(ray)` visits children roughly front to back.
+//
+// Triangle record, 48 bytes = three 16-byte loads: a, e1 = b - a, e2 = c - a (same fp32 subtractions
+// the reference does per test, triangle.zig:27-28), `primitive` = index into the reference-order
+// triangle list, `original` = index into the caller's triangle list.
+#pragma once
+
+#include "triangle_tree.hpp"
+
+namespace zyg {
+
+struct WideNode {
+    float    p[3];
+    uint8_t  e[3];
+    uint8_t  imask;
+    uint32_t child_base;
+    uint32_t tri_base;
+    uint8_t  meta[8];
+    uint8_t  qlo[3][8];
+    uint8_t  qhi[3][8];
+};
+static_assert(sizeof(WideNode) == 80, "wide node must be five 16-byte words");
+
+struct TriRecord {
+    float    a[3];
+    uint32_t primitive;
+    float    e1[3];
+    uint32_t original;
+    float    e2[3];
+    uint32_t part;
+};
+static_assert(sizeof(TriRecord) == 48, "triangle record must be three 16-byte words");
+
+struct WideBvh {
+    std::vector<WideNode>  nodes;
+    std::vector<TriRecord> triangles;
+    uint32_t               max_depth = 0;  // in wide nodes, root = 1
+};
+
+void buildWideBvh(const TriangleTree& tree, WideBvh& out);
+
+}  // namespace zyg

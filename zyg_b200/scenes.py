@@ -1,0 +1,165 @@
+"""Procedural inputs for the BASELINE.json configs (no assets ship with the reference).
+
+Everything is deterministic numpy; meshes are handed to the C ABI exactly the way
+``src/capi-test/test.py:200-235`` feeds ``su_triangle_mesh_create``.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .lib import RAY_DTYPE, RAY_MAX_T
+
+# ----------------------------------------------------------------------------------------------
+# value-noise displaced sphere (config 2: 1000 x 500 quads -> 1 000 000 triangles)
+# ----------------------------------------------------------------------------------------------
+
+
+def _hash3(ix: np.ndarray, iy: np.ndarray, iz: np.ndarray, seed: int) -> np.ndarray:
+    """Integer lattice hash -> float32 in [0, 1)."""
+    with np.errstate(over="ignore"):
+        h = (ix.astype(np.uint32) * np.uint32(0x8DA6B343)) ^ (iy.astype(np.uint32) * np.uint32(0xD8163841)) ^ (
+            iz.astype(np.uint32) * np.uint32(0xCB1AB31F)) ^ np.uint32(seed)
+        h ^= h >> np.uint32(16)
+        h *= np.uint32(0x7FEB352D)
+        h ^= h >> np.uint32(15)
+        h *= np.uint32(0x846CA68B)
+        h ^= h >> np.uint32(16)
+    return (h >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def _value_noise(p: np.ndarray, seed: int) -> np.ndarray:
+    f = np.floor(p)
+    i = f.astype(np.int64)
+    t = (p - f).astype(np.float32)
+    t = t * t * (np.float32(3.0) - np.float32(2.0) * t)
+    ix, iy, iz = i[:, 0], i[:, 1], i[:, 2]
+    out = np.zeros(p.shape[0], np.float32)
+    for dx in (0, 1):
+        wx = t[:, 0] if dx else (1 - t[:, 0])
+        for dy in (0, 1):
+            wy = t[:, 1] if dy else (1 - t[:, 1])
+            for dz in (0, 1):
+                wz = t[:, 2] if dz else (1 - t[:, 2])
+                out += wx * wy * wz * _hash3(ix + dx, iy + dy, iz + dz, seed)
+    return out
+
+
+def fbm(p: np.ndarray, seed: int, octaves: int = 3) -> np.ndarray:
+    amp, freq, total = 0.5, 4.0, np.zeros(p.shape[0], np.float32)
+    for o in range(octaves):
+        total += np.float32(amp) * (_value_noise(p * freq, seed + o) * 2 - 1)
+        amp *= 0.5
+        freq *= 2.0
+    return total
+
+
+def displaced_sphere(nu: int = 1000, nv: int = 500, radius: float = 1.0, amplitude: float = 0.05,
+                     seed: int = 0x5EED0001):
+    """Lat-long grid of ``nu x nv`` quads -> ``2 nu nv`` triangles, ``(nu + 1)(nv + 1)`` vertices.
+
+    Returns ``(positions f32[n,3], normals f32[n,3], uvs f32[n,2], indices u32[m,3])``.
+    """
+    u = np.linspace(0.0, 1.0, nu + 1)
+    v = np.linspace(0.0, 1.0, nv + 1)
+    uu, vv = np.meshgrid(u, v, indexing="xy")  # (nv + 1, nu + 1)
+    phi = uu * 2 * np.pi
+    theta = vv * np.pi
+    d = np.stack([np.sin(theta) * np.cos(phi), np.cos(theta), np.sin(theta) * np.sin(phi)], axis=-1).reshape(-1, 3)
+    # seam: make u = 1 reuse the direction of u = 0 so the displacement is continuous
+    d = d.reshape(nv + 1, nu + 1, 3)
+    d[:, nu, :] = d[:, 0, :]
+    d = d.reshape(-1, 3)
+    r = radius + amplitude * fbm(d.astype(np.float64), seed)
+    positions = (d * r[:, None]).astype(np.float32)
+    normals = d.astype(np.float32)
+    uvs = np.stack([uu.reshape(-1), vv.reshape(-1)], axis=-1).astype(np.float32)
+
+    j, i = np.meshgrid(np.arange(nv), np.arange(nu), indexing="ij")
+    a = (j * (nu + 1) + i).reshape(-1)
+    b = a + 1
+    c = a + (nu + 1)
+    e = c + 1
+    indices = np.empty((a.size * 2, 3), np.uint32)
+    indices[0::2] = np.stack([a, c, b], axis=-1)
+    indices[1::2] = np.stack([b, c, e], axis=-1)
+    return positions, normals, uvs, indices
+
+
+# ----------------------------------------------------------------------------------------------
+# ray batches
+# ----------------------------------------------------------------------------------------------
+
+
+def primary_rays(width: int, height: int, eye=(0.0, 0.0, -3.0), fov_deg: float = 40.0) -> np.ndarray:
+    """Pinhole rays through pixel centres, row-major, looking down +z (coherent batch)."""
+    rays = np.empty(width * height, RAY_DTYPE)
+    z = 0.5 * width / np.tan(0.5 * np.radians(fov_deg))
+    x = (np.arange(width, dtype=np.float64) + 0.5) - 0.5 * width
+    y = 0.5 * height - (np.arange(height, dtype=np.float64) + 0.5)
+    xx, yy = np.meshgrid(x, y, indexing="xy")
+    d = np.stack([xx, yy, np.full_like(xx, z)], axis=-1).reshape(-1, 3)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["origin"] = np.asarray(eye, np.float32)
+    rays["min_t"] = 0.0
+    rays["direction"] = d.astype(np.float32)
+    rays["max_t"] = RAY_MAX_T
+    return rays
+
+
+class PCG32:
+    """Vectorised rnd.Generator (src/base/random/generator.zig:1-47): one stream per array lane."""
+
+    MULT = np.uint64(6364136223846793005)
+
+    def __init__(self, state: int, sequence: np.ndarray):
+        seq = np.asarray(sequence, dtype=np.uint64)
+        self.inc = (seq << np.uint64(1)) | np.uint64(1)
+        self.state = np.zeros_like(seq)
+        self.uint()
+        with np.errstate(over="ignore"):
+            self.state = self.state + np.uint64(state)
+        self.uint()
+
+    def uint(self) -> np.ndarray:
+        old = self.state
+        with np.errstate(over="ignore"):
+            self.state = old * self.MULT + self.inc
+        xrs = (((old >> np.uint64(18)) ^ old) >> np.uint64(27)).astype(np.uint32)
+        rot = (old >> np.uint64(59)).astype(np.uint32)
+        return (xrs >> rot) | (xrs << ((np.uint32(0) - rot) & np.uint32(31)))
+
+    def float(self) -> np.ndarray:
+        bits = (self.uint() & np.uint32(0x007FFFFF)) | np.uint32(0x3F800000)
+        return bits.view(np.float32) - np.float32(1.0)
+
+
+def _sphere_uniform(u: np.ndarray, v: np.ndarray) -> np.ndarray:
+    z = 1.0 - 2.0 * u.astype(np.float64)
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    phi = v.astype(np.float64) * (2.0 * np.pi)
+    return np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=-1)
+
+
+def random_rays(n: int, radius: float = 1.5, shadow: bool = False, first: int = 0, chunk: int = 1 << 21) -> np.ndarray:
+    """Incoherent batch: ray i draws from ``Generator.start(0, first + i)``.
+
+    origin = radius * cbrt(u0) * sphere(u1, u2); closest: direction = sphere(u3, u4), max_t = RayMaxT;
+    shadow: second point from (u3, u4, u5) the same way, direction = p1 - p0 (unnormalised), max_t = 1.
+    """
+    rays = np.empty(n, RAY_DTYPE)
+    for b in range(0, n, chunk):
+        e = min(n, b + chunk)
+        g = PCG32(0, np.arange(first + b, first + e, dtype=np.uint64))
+        u = [g.float() for _ in range(6 if shadow else 5)]
+        p0 = radius * np.cbrt(u[0].astype(np.float64))[:, None] * _sphere_uniform(u[1], u[2])
+        rays["origin"][b:e] = p0.astype(np.float32)
+        rays["min_t"][b:e] = 0.0
+        if shadow:
+            p1 = radius * np.cbrt(u[3].astype(np.float64))[:, None] * _sphere_uniform(u[4], u[5])
+            rays["direction"][b:e] = (p1 - p0).astype(np.float32)
+            rays["max_t"][b:e] = 1.0
+        else:
+            rays["direction"][b:e] = _sphere_uniform(u[3], u[4]).astype(np.float32)
+            rays["max_t"][b:e] = RAY_MAX_T
+    return rays
