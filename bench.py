@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json config 2: ray-intersection microbench on the 1M-triangle displaced sphere.
+
+One step = one pass of the traversal hot path over the synthetic batch of this rank:
+    closest-hit over 16 777 216 primary rays      (coherent, 4096 x 4096 pinhole)
+  + closest-hit over 16 777 216 incoherent rays   (PCG32 origins in the ball, uniform directions)
+  + any-hit     over 16 777 216 shadow segments   (same origins, segment to a second point)
+`value` = rays of all ranks / device time (CUDA events, max over ranks), inputs resident in HBM.
+`e2e`   = same step through zygpu_trace_batch with pinned HOST buffers (H2D + D2H inside).
+`--impl reference` times the CPU restatement of zyg's own path (oracle/) on the host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PRIMARY_RES = 4096
+N_RAYS = PRIMARY_RES * PRIMARY_RES
+MESH_QUADS = (1000, 500)
+WORKLOAD = "config2: 1M-triangle displaced sphere; 16.8M primary + 16.8M incoherent closest-hit + 16.8M shadow any-hit rays"
+CLASSES = ("primary_closest", "incoherent_closest", "shadow_any")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def build_inputs(rank: int, n_rays: int, res: int):
+    from zyg_b200 import lib, scenes
+
+    t0 = time.time()
+    positions, normals, uvs, indices = scenes.displaced_sphere(*MESH_QUADS)
+    mesh = lib.Mesh(positions, indices, normals, uvs)
+    info = mesh.info()
+    log(f"[rank {rank}] mesh: {info.num_source_triangles} triangles -> {info.num_tree_triangles} references, "
+        f"{info.num_binary_nodes} binary / {info.num_wide_nodes} wide nodes, built in {time.time() - t0:.1f}s")
+    t0 = time.time()
+    rays = {
+        "primary_closest": scenes.primary_rays(res, res),
+        "incoherent_closest": scenes.random_rays(n_rays, first=rank * n_rays),
+        "shadow_any": scenes.random_rays(n_rays, shadow=True, first=rank * n_rays),
+    }
+    log(f"[rank {rank}] rays generated in {time.time() - t0:.1f}s")
+    return mesh, rays
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+
+    oracle_lib.load()
+    return oracle_lib
+
+
+def cpu_step(oracle, arrays, sample):
+    nodes, tris, pos = arrays
+    t0 = time.perf_counter()
+    oracle.trace_closest(nodes, tris, pos, sample["primary_closest"])
+    oracle.trace_closest(nodes, tris, pos, sample["incoherent_closest"])
+    oracle.trace_any(nodes, tris, pos, sample["shadow_any"])
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """CPU arm: zyg's own traversal (restated in oracle/, the reference is Zig and cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from zyg_b200 import lib
+
+    oracle = load_oracle()
+    mesh, rays = build_inputs(0, N_RAYS // 4, PRIMARY_RES // 2)
+    arrays = tuple(mesh.data(w) for w in (lib.MESH_BINARY_NODES, lib.MESH_TRIANGLES, lib.MESH_POSITIONS))
+    n = sum(r.shape[0] for r in rays.values())
+    for _ in range(args.warmup):
+        cpu_step(oracle, arrays, rays)
+    times = [cpu_step(oracle, arrays, rays) for _ in range(args.steps)]
+    dt = sum(times)
+    value = n * args.steps / dt / 1e6
+    cores = os.cpu_count()
+    sample = f"per step: {PRIMARY_RES // 2}^2 primary + {N_RAYS // 4} incoherent + {N_RAYS // 4} shadow rays (1/4 of the workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": "traversal_throughput", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step": n, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="zyg_b200", choices=["zyg_b200", "reference"])
+    ap.add_argument("--rays", type=int, default=PRIMARY_RES, help="primary resolution r (r*r rays per class)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from zyg_b200 import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    res = args.rays
+    n_rays = res * res
+    mesh, rays = build_inputs(rank, n_rays, res)
+    dev = lib.Device(local)
+    mid = dev.upload_mesh(mesh)
+    modes = {"primary_closest": lib.CLOSEST, "incoherent_closest": lib.CLOSEST, "shadow_any": lib.ANY}
+
+    # resident inputs / outputs (torch is the allocator and the stream owner; kernels are ours)
+    d_rays = {k: torch.from_numpy(v.view(np.float32).reshape(-1, 8)).cuda() for k, v in rays.items()}
+    d_out = {k: torch.empty((n_rays, 1 if modes[k] == lib.ANY else 4), dtype=torch.float32, device="cuda")
+             for k in CLASSES}
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch(k, counters=None):
+        dev.trace_batch_ptr(mid, modes[k], d_rays[k].data_ptr(), n_rays, d_out[k].data_ptr(), host=False,
+                            stream=stream, counters=counters)
+
+    # fetch counts from the instrumented build of the same kernels on the same batch
+    bytes_per_ray = {}
+    fetches = {}
+    for k in CLASSES:
+        c = lib.TraceCounters()
+        launch(k, c)
+        out_b = 4 if modes[k] == lib.ANY else 16
+        bytes_per_ray[k] = 32 + out_b + (c.nodes * 80 + c.triangles * 64) / n_rays
+        fetches[k] = {"nodes_per_ray": c.nodes / n_rays, "tris_per_ray": c.triangles / n_rays,
+                      "bytes_per_ray": bytes_per_ray[k], "max_stack": int(c.max_stack)}
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        for k in CLASSES:
+            launch(k)
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(CLASSES) + 1)] for _ in range(args.steps)]
+    for s in range(args.steps):
+        ev[s][0].record()
+        for i, k in enumerate(CLASSES):
+            launch(k)
+            ev[s][i + 1].record()
+    barrier()
+    total_ms = ev[0][0].elapsed_time(ev[-1][-1])
+    class_ms = {k: sum(ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)) / args.steps
+                for i, k in enumerate(CLASSES)}
+    launches = args.steps * len(CLASSES)
+
+    # end to end: pinned host buffers through the public C-ABI call, copies inside the timed region
+    h_rays = {k: torch.from_numpy(v.view(np.float32).reshape(-1, 8)).pin_memory() for k, v in rays.items()}
+    h_out = {k: torch.empty((n_rays, 1 if modes[k] == lib.ANY else 4), dtype=torch.float32).pin_memory()
+             for k in CLASSES}
+
+    def e2e_step():
+        for k in CLASSES:
+            dev.trace_batch_ptr(mid, modes[k], h_rays[k].data_ptr(), n_rays, h_out[k].data_ptr(), host=True)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = t.tolist()
+
+    rays_per_step = n_rays * len(CLASSES) * world
+    value = rays_per_step * args.steps / (total_ms * 1e-3) / 1e6
+    e2e_value = rays_per_step * args.steps / e2e_s / 1e6
+    h2d = n_rays * 32 * len(CLASSES)
+    d2h = n_rays * (16 + 16 + 4)
+
+    # spot parity of what was just timed (rank 0): device result == host-path result
+    if rank == 0:
+        k = "incoherent_closest"
+        assert torch.equal(d_out[k][: 1 << 16].cpu().view(torch.int32), h_out[k][: 1 << 16].view(torch.int32)), \
+            "device and host entry points disagree"
+
+    peak, peak_src = peak_hbm()
+    dom = max(CLASSES, key=lambda k: class_ms[k])
+    achieved = bytes_per_ray[dom] * n_rays / (class_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom)
+
+    result = {
+        "metric": "traversal_throughput", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n_rays * len(CLASSES), "mesh_triangles": 1000000,
+                   "l2": "inputs larger than L2 (512 MiB of rays per class); the 66 MB BVH is L2-resident by nature",
+                   "parallelism": f"replicated scene, independent ray batches x{world}"},
+        "classes": {k: {"mrays_s": n_rays / (class_ms[k] * 1e-3) / 1e6, "ms": class_ms[k], **fetches[k]}
+                    for k in CLASSES},
+        "roofline": {"bound": "hbm", "kernel": f"traceWide ({dom})", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "note": "algorithmic bytes = 32 B ray + hit record + counted 80 B node and 64 B triangle fetches"},
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        oracle = load_oracle()
+        arrays = tuple(mesh.data(w) for w in (lib.MESH_BINARY_NODES, lib.MESH_TRIANGLES, lib.MESH_POSITIONS))
+        stride = max(1, n_rays // (1 << 22))
+        sample = {k: np.ascontiguousarray(v[::stride]) for k, v in rays.items()}
+        ns = sum(v.shape[0] for v in sample.values())
+        cpu_step(oracle, arrays, {k: v[: 1 << 16] for k, v in sample.items()})
+        reps, dt = 0, 0.0
+        while dt < 10.0 and reps < 8:
+            dt += cpu_step(oracle, arrays, sample)
+            reps += 1
+        result["cpu_baseline"] = {"value": ns * reps / dt / 1e6, "unit": "Mrays/s", "cores": os.cpu_count(),
+                                  "kind": "port",
+                                  "sample": f"every {stride}th ray of each class ({ns} rays) x {reps} passes, "
+                                            f"oracle/ restatement of zyg's traversal, std::thread per core"}
+        # parity of the timed output against the oracle on the sample
+        ref = oracle.trace_closest(*arrays, sample["incoherent_closest"][: 1 << 18])
+        got = h_out["incoherent_closest"].numpy().view(lib.HIT_DTYPE).reshape(-1)[::stride][: 1 << 18]
+        assert np.array_equal(ref["t"].view(np.uint32), got["t"].view(np.uint32)), "timed output differs from oracle"
+
+    if rank == 0:
+        print(json.dumps(result))
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,7 +42,7 @@ enum {
     ZYG_MESH_UVS          = 5, /* f32[2] per vertex */
     ZYG_MESH_PARTS        = 6, /* u16 per BVH-order triangle */
     ZYG_MESH_WIDE_NODES   = 7, /* 80-byte device nodes */
-    ZYG_MESH_WIDE_TRIS    = 8  /* 48-byte device triangle records */
+    ZYG_MESH_WIDE_TRIS    = 8  /* 64-byte device triangle records */
 };
 
 /* Read-only view of one of the arrays above; valid until zyg_mesh_free. */

@@ -188,4 +188,11 @@ def test_wide_layout_is_conservative_and_complete(sphere_mesh):
         assert rank == bin(int(w["imask"][i])).count("1")
     assert seen_nodes.all() and seen_tris.all()
     assert np.array_equal(np.sort(recs["primitive"]), np.arange(info.num_tree_triangles))
-    assert np.array_equal(recs["original"], mesh.data(lib.MESH_ORIGINAL)[recs["primitive"]])
+    # every record carries the exact box of the reference leaf that owns its triangle (the gate)
+    nodes = mesh.data(lib.MESH_BINARY_NODES)
+    leaves = np.nonzero(nodes["max_data"] != 0)[0]
+    start_sorted = leaves[np.argsort(nodes["min_data"][leaves])]
+    owner = np.repeat(start_sorted, nodes["max_data"][start_sorted])  # tree-order triangle -> leaf node
+    gate_min = np.stack([recs["leaf_min_x"], recs["leaf_min_y"], recs["leaf_min_z"]], -1)
+    assert np.array_equal(gate_min, nodes["min"][owner[recs["primitive"]]])
+    assert np.array_equal(recs["leaf_max"], nodes["max"][owner[recs["primitive"]]])

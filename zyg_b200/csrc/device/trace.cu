@@ -255,6 +255,14 @@ __global__ void __launch_bounds__(128)
         const bool     pz     = !signbit(ray.d.z);
         const uint32_t octinv = (px ? 4u : 0u) | (py ? 2u : 0u) | (pz ? 1u : 0u);
 
+        // Reciprocal direction for the quantised (culling-only) slab test, clamped to a finite magnitude:
+        // a zero direction component would otherwise turn q * inf + (p - o) * inf into NaNs that switch the
+        // axis off, and an axis-parallel ray would walk every node in its slab. With +-2^80 a ray parallel
+        // to a slab gets (-huge, +huge) when inside and an empty interval when outside, as it should.
+        constexpr float kBig = 1.2089258e24f;  // 2^80
+        const V3        cid  = {fminf(fmaxf(ray.inv_d.x, -kBig), kBig), fminf(fmaxf(ray.inv_d.y, -kBig), kBig),
+                                fminf(fmaxf(ray.inv_d.z, -kBig), kBig)};
+
         uint2    stack[kWideStack];
         uint32_t sp = 0;
 
@@ -293,13 +301,13 @@ __global__ void __launch_bounds__(128)
                 const uint32_t ew    = __float_as_uint(n0.w);
                 const uint32_t imask = ew >> 24;
 
-                const float idx = __uint_as_float((ew & 0xffu) << 23) * ray.inv_d.x;
-                const float idy = __uint_as_float(((ew >> 8) & 0xffu) << 23) * ray.inv_d.y;
-                const float idz = __uint_as_float(((ew >> 16) & 0xffu) << 23) * ray.inv_d.z;
+                const float idx = __uint_as_float((ew & 0xffu) << 23) * cid.x;
+                const float idy = __uint_as_float(((ew >> 8) & 0xffu) << 23) * cid.y;
+                const float idz = __uint_as_float(((ew >> 16) & 0xffu) << 23) * cid.z;
 
-                const float orx = (n0.x - ray.o.x) * ray.inv_d.x;
-                const float ory = (n0.y - ray.o.y) * ray.inv_d.y;
-                const float orz = (n0.z - ray.o.z) * ray.inv_d.z;
+                const float orx = (n0.x - ray.o.x) * cid.x;
+                const float ory = (n0.y - ray.o.y) * cid.y;
+                const float orz = (n0.z - ray.o.z) * cid.z;
 
                 // Conservative slack: the quantised slab arithmetic associates differently from the
                 // reference's (min - o) * inv_d; widen each interval by a few ulps of its largest term so
@@ -363,11 +371,18 @@ __global__ void __launch_bounds__(128)
                 const uint32_t bit = 31u - __clz(tri_group.y);
                 tri_group.y &= ~(1u << bit);
 
-                const float4* tp = mesh.wide_tris + 3 * size_t(tri_group.x + bit);
+                const float4* tp = mesh.wide_tris + 4 * size_t(tri_group.x + bit);
                 const float4  t0 = __ldg(tp + 0);
                 const float4  t1 = __ldg(tp + 1);
                 const float4  t2 = __ldg(tp + 2);
+                const float4  t3 = __ldg(tp + 3);
                 tally.tri();
+
+                // Gate with the reference's own (non-watertight) slab test on the reference leaf box:
+                // the reference never tests a triangle whose leaf box it rejected.
+                if (FLT_MAX == intersectNode(make_float4(t1.w, t2.w, t3.x, 0.f), make_float4(t3.y, t3.z, t3.w, 0.f), ray)) {
+                    continue;
+                }
 
                 float t, u, v;
                 if (intersectTriangle(ray, {t0.x, t0.y, t0.z}, {t1.x, t1.y, t1.z}, {t2.x, t2.y, t2.z}, t, u, v)) {

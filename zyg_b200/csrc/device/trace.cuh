@@ -1,7 +1,7 @@
 // Ray / triangle-BVH traversal kernels for sm_100a.
 //
 // Two families over the same mesh:
-//  * `Wide*`  — product path: 8-wide quantised nodes (host/wide_bvh.hpp), 48-byte triangle records,
+//  * `Wide*`  — product path: 8-wide quantised nodes (host/wide_bvh.hpp), 64-byte triangle records,
 //               per-lane traversal with a node-group / triangle-group stack.
 //  * `Binary*` — order-exact restatement of TriangleTree.intersect / intersectP
 //               (src/core/scene/shape/triangle/triangle_tree.zig:46-109, 197-242) over the uploaded
@@ -27,7 +27,7 @@ struct HitOut {  // 16 bytes: include/zygpu.h ZygpuHit
 
 struct MeshDevice {
     const float4*   wide_nodes;    // 5 per node
-    const float4*   wide_tris;     // 3 per record
+    const float4*   wide_tris;     // 4 per record
     const float4*   binary_nodes;  // 2 per node
     const uint32_t* triangles;     // 3 per BVH-order triangle
     const float*    positions;     // 3 per vertex (+1 pad)

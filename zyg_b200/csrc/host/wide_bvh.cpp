@@ -32,6 +32,7 @@ struct ANode {
     int32_t  right = -1;
     uint32_t first = 0;  // into `leaf_prims`
     uint32_t count = 0;
+    Box      leaf_box;  // leaves: exact box of the reference leaf (the gate), see wide_bvh.hpp
 };
 
 struct Augment {
@@ -67,8 +68,9 @@ struct Augment {
 
         const size_t n = end - begin;
         if (n <= 3) {
-            nodes[id].first = uint32_t(leaf_prims.size());
-            nodes[id].count = uint32_t(n);
+            nodes[id].first    = uint32_t(leaf_prims.size());
+            nodes[id].count    = uint32_t(n);
+            nodes[id].leaf_box = clip;
             for (size_t i = begin; i < end; ++i) leaf_prims.push_back(prims[i]);
             return id;
         }
@@ -91,6 +93,15 @@ struct Augment {
         return id;
     }
 
+    void setGate(int32_t id, const Box& gate) {
+        if (nodes[id].left < 0) {
+            nodes[id].leaf_box = gate;
+        } else {
+            setGate(nodes[id].left, gate);
+            setGate(nodes[id].right, gate);
+        }
+    }
+
     int32_t convert(uint32_t n) {
         // iterative post-order would be nicer; depth is bounded by the binary tree depth (< 128, the
         // reference's own traversal stack limit node_stack.zig:2), so recursion is safe here.
@@ -101,6 +112,24 @@ struct Augment {
             box.hi[i] = node.max[i];
         }
         if (0 != node.numIndices()) {
+            if (0 == n) {
+                // A tree that is a single leaf: the reference tests its triangles without any box test
+                // (triangle_tree.zig:57-72), so the gate must always pass.
+                for (int i = 0; i < 3; ++i) {
+                    box.lo[i] = -INFINITY;
+                    box.hi[i] = INFINITY;
+                }
+                Box tight;
+                for (int i = 0; i < 3; ++i) {
+                    tight.lo[i] = node.min[i];
+                    tight.hi[i] = node.max[i];
+                }
+                std::vector<uint32_t> prims(node.numIndices());
+                for (uint32_t i = 0; i < node.numIndices(); ++i) prims[i] = node.indicesStart() + i;
+                const int32_t id = makeLeafTree(prims, 0, prims.size(), tight);
+                setGate(id, box);
+                return id;
+            }
             std::vector<uint32_t> prims(node.numIndices());
             for (uint32_t i = 0; i < node.numIndices(); ++i) prims[i] = node.indicesStart() + i;
             return makeLeafTree(prims, 0, prims.size(), box);
@@ -141,7 +170,7 @@ void buildWideBvh(const TriangleTree& tree, WideBvh& out) {
     out.nodes.emplace_back();
     queue.push_back({root, 0, 1});
 
-    auto emitTriangle = [&](uint32_t prim) {
+    auto emitTriangle = [&](uint32_t prim, const Box& gate) {
         TriRecord    r;
         const float* a = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + 0]) * 3];
         const float* b = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + 1]) * 3];
@@ -151,9 +180,11 @@ void buildWideBvh(const TriangleTree& tree, WideBvh& out) {
             r.e1[i] = b[i] - a[i];
             r.e2[i] = c[i] - a[i];
         }
-        r.primitive = prim;
-        r.original  = tree.original[prim];
-        r.part      = tree.triangle_parts[prim];
+        r.primitive  = prim;
+        r.leaf_min_x = gate.lo[0];
+        r.leaf_min_y = gate.lo[1];
+        r.leaf_min_z = gate.lo[2];
+        for (int i = 0; i < 3; ++i) r.leaf_max[i] = gate.hi[i];
         out.triangles.push_back(r);
     };
 
@@ -275,7 +306,7 @@ void buildWideBvh(const TriangleTree& tree, WideBvh& out) {
             } else {
                 const uint32_t unary = (1u << ch.count) - 1u;  // 1 -> 0b001, 2 -> 0b011, 3 -> 0b111
                 node.meta[s]         = uint8_t((unary << 5) | tri_offset);
-                for (uint32_t i = 0; i < ch.count; ++i) emitTriangle(aug.leaf_prims[ch.first + i]);
+                for (uint32_t i = 0; i < ch.count; ++i) emitTriangle(aug.leaf_prims[ch.first + i], ch.leaf_box);
                 tri_offset += ch.count;
             }
         }

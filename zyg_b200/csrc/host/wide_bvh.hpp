@@ -1,4 +1,4 @@
-// Device layout of a triangle BVH: 8-wide nodes with 8-bit quantised child boxes + 48-byte
+// Device layout of a triangle BVH: 8-wide nodes with 8-bit quantised child boxes + 64-byte
 // triangle records. Derived ("flattened on upload") from the reference-order binary tree, so the
 // set of triangles and their clip regions is the reference's; only the visiting order changes.
 //
@@ -14,9 +14,13 @@
 //   +56  u8     qhi[3][8]   quantised upper bounds
 // Slots are assigned so that `slot ^ octant(ray)` visits children roughly front to back.
 //
-// Triangle record, 48 bytes = three 16-byte loads: a, e1 = b - a, e2 = c - a (same fp32 subtractions
-// the reference does per test, triangle.zig:27-28), `primitive` = index into the reference-order
-// triangle list, `original` = index into the caller's triangle list.
+// Triangle record, 64 bytes = four 16-byte loads (two whole 32-byte sectors): a, e1 = b - a,
+// e2 = c - a (the same fp32 subtractions the reference does per test, triangle.zig:27-28),
+// `primitive` = index into the reference-order triangle list, and the exact fp32 box of the
+// reference leaf the triangle sits in. The kernels gate every triangle test with the reference's own
+// slab test on that box (node.zig:73-87): the reference only ever tests a triangle after its leaf box
+// passed, and the box test is not watertight against the triangle test, so without the gate the wide
+// path would report hits the reference misses (rays through shared edges of axis-aligned geometry).
 #pragma once
 
 #include "triangle_tree.hpp"
@@ -39,11 +43,13 @@ struct TriRecord {
     float    a[3];
     uint32_t primitive;
     float    e1[3];
-    uint32_t original;
+    float    leaf_min_x;
     float    e2[3];
-    uint32_t part;
+    float    leaf_min_y;
+    float    leaf_min_z;
+    float    leaf_max[3];
 };
-static_assert(sizeof(TriRecord) == 48, "triangle record must be three 16-byte words");
+static_assert(sizeof(TriRecord) == 64, "triangle record must be four 16-byte words");
 
 struct WideBvh {
     std::vector<WideNode>  nodes;

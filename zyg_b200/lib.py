@@ -97,8 +97,9 @@ class Mesh:
         MESH_UVS: np.dtype("<f4"),
         MESH_PARTS: np.dtype("<u2"),
         MESH_WIDE_NODES: np.dtype("u1"),
-        MESH_WIDE_TRIS: np.dtype([("a", "<f4", 3), ("primitive", "<u4"), ("e1", "<f4", 3), ("original", "<u4"),
-                                  ("e2", "<f4", 3), ("part", "<u4")]),
+        MESH_WIDE_TRIS: np.dtype([("a", "<f4", 3), ("primitive", "<u4"), ("e1", "<f4", 3), ("leaf_min_x", "<f4"),
+                                  ("e2", "<f4", 3), ("leaf_min_y", "<f4"), ("leaf_min_z", "<f4"),
+                                  ("leaf_max", "<f4", 3)]),
     }
 
     def __init__(self, positions, indices=None, normals=None, uvs=None, parts=None, num_threads: int = 0):
