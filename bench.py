@@ -46,11 +46,20 @@ def build_inputs(rank: int, n_rays: int, res: int):
     log(f"[rank {rank}] mesh: {info.num_source_triangles} triangles -> {info.num_tree_triangles} references, "
         f"{info.num_binary_nodes} binary / {info.num_wide_nodes} wide nodes, built in {time.time() - t0:.1f}s")
     t0 = time.time()
-    rays = {
-        "primary_closest": scenes.primary_rays(res, res),
-        "incoherent_closest": scenes.random_rays(n_rays, first=rank * n_rays),
-        "shadow_any": scenes.random_rays(n_rays, shadow=True, first=rank * n_rays),
-    }
+    cache = os.environ.get("ZYG_BENCH_CACHE")  # optional: reuse generated rays across tuning runs
+    path = os.path.join(cache, f"rays_{res}_{n_rays}_{rank}.npy") if cache else None
+    if path and os.path.exists(path):
+        packed = np.load(path)
+        rays = {k: packed[i] for i, k in enumerate(CLASSES)}
+    else:
+        rays = {
+            "primary_closest": scenes.primary_rays(res, res),
+            "incoherent_closest": scenes.random_rays(n_rays, first=rank * n_rays),
+            "shadow_any": scenes.random_rays(n_rays, shadow=True, first=rank * n_rays),
+        }
+        if path:
+            os.makedirs(cache, exist_ok=True)
+            np.save(path, np.stack([rays[k] for k in CLASSES]))
     log(f"[rank {rank}] rays generated in {time.time() - t0:.1f}s")
     return mesh, rays
 

@@ -55,6 +55,12 @@ struct zygpu_device {
     void*                     d_rays[kStreams]  = {};
     void*                     d_out[kStreams]   = {};
     zygpu::TraceCounters*     d_counters        = nullptr;
+
+    // work counters of the persistent kernels: one per in-flight launch, handed out round-robin
+    static constexpr int kWorkCounters = 64;
+    uint32_t*            d_work        = nullptr;
+    int                  next_work     = 0;
+    uint32_t*            workCounter() { return d_work + (next_work++ % kWorkCounters); }
 };
 
 extern "C" {
@@ -176,6 +182,7 @@ int zygpu_create(int device_ordinal, zygpu_device** out) {
         CUDA_OK(cudaMalloc(&dev->d_out[s], zygpu_device::kChunkRays * sizeof(ZygpuHit)));
     }
     CUDA_OK(cudaMalloc(&dev->d_counters, sizeof(zygpu::TraceCounters)));
+    CUDA_OK(cudaMalloc(&dev->d_work, zygpu_device::kWorkCounters * sizeof(uint32_t)));
     *out = dev.release();
     return 0;
 }
@@ -193,6 +200,7 @@ void zygpu_destroy(zygpu_device* dev) {
         if (dev->streams[s]) cudaStreamDestroy(dev->streams[s]);
     }
     cudaFree(dev->d_counters);
+    cudaFree(dev->d_work);
     delete dev;
 }
 
@@ -233,7 +241,7 @@ int zygpu_trace_batch_device(zygpu_device* dev, int mesh, int mode, const void* 
     if (counters) CUDA_OK(cudaMemsetAsync(dev->d_counters, 0, sizeof(zygpu::TraceCounters), s));
 
     CUDA_OK(zygpu::launchTrace(dev->meshes[mesh].view, mode, static_cast<const zygpu::RayIn*>(d_rays), d_out,
-                               uint32_t(n), counters ? dev->d_counters : nullptr, s));
+                               uint32_t(n), counters ? dev->d_counters : nullptr, dev->workCounter(), s));
 
     if (counters) {
         zygpu::TraceCounters h;
@@ -264,7 +272,7 @@ int zygpu_trace_batch(zygpu_device* dev, int mesh, int mode, const ZygpuRay* ray
 
         CUDA_OK(cudaMemcpyAsync(dev->d_rays[s], rays + done, count * sizeof(ZygpuRay), cudaMemcpyHostToDevice, st));
         CUDA_OK(zygpu::launchTrace(dev->meshes[mesh].view, mode, static_cast<const zygpu::RayIn*>(dev->d_rays[s]),
-                                   dev->d_out[s], uint32_t(count), nullptr, st));
+                                   dev->d_out[s], uint32_t(count), nullptr, dev->workCounter(), st));
         CUDA_OK(cudaMemcpyAsync(static_cast<char*>(out) + done * out_bytes, dev->d_out[s], count * out_bytes,
                                 cudaMemcpyDeviceToHost, st));
         done += count;

@@ -51,7 +51,9 @@ enum TraceMode : int {
 
 // Launches on `stream`. `out` is HitOut[n] for closest modes, uint32_t[n] (1 = occluded) for any-hit.
 // `counters` may be null; when set the instrumented variant runs (slower) and accumulates into it.
+// `work_counter` is one device word the persistent wide kernel hands ray blocks out from (reset on
+// `stream` before the launch); it must not be shared by launches that can run concurrently.
 cudaError_t launchTrace(const MeshDevice& mesh, int mode, const RayIn* rays, void* out, uint32_t n,
-                        TraceCounters* counters, cudaStream_t stream);
+                        TraceCounters* counters, uint32_t* work_counter, cudaStream_t stream);
 
 }  // namespace zygpu
