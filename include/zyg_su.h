@@ -1,0 +1,88 @@
+/* zyg_su.h — zyg's own C API (libzyg's `su_*` functions, src/capi/capi.zig:57-738) served by the B200 backend.
+ *
+ * A client of libzyg.so (src/capi-test/test.py, src/blender-plugin/engine.py) can load libzyg_b200.so
+ * instead: same symbols, same argument meaning, same return convention (0 or a non-negative id on
+ * success, -1 failure / not initialised, -3 bad material id, -4 material update failed). One
+ * process-global engine, single caller thread (capi.zig:55).
+ *
+ * Scope of this round: static scenes, perspective camera, PTMIS, the built-in shapes
+ * Rectangle / Cube / Sphere and triangle meshes, materials Substitute / Light (uniform parameters).
+ * Entry points outside that scope exist and return -1 (image, AOV, exporter and animation calls).
+ */
+#ifndef ZYG_SU_H
+#define ZYG_SU_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#include "zygpu_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int32_t su_init(void);                                                    /* capi.zig:57  */
+int32_t su_release(void);                                                 /* :116 */
+int32_t su_mount(const char* folder);                                     /* :131 (accepted, unused) */
+int32_t su_perspective_camera_create(uint32_t width, uint32_t height);    /* :143 -> camera entity id */
+int32_t su_camera_set_fov(float fov);                                     /* :169 (radians) */
+int32_t su_camera_sensor_dimensions(int32_t* dimensions);                 /* :178 */
+int32_t su_exporters_create(const char* json);                            /* :189 (-1: out of scope) */
+int32_t su_aovs_create(const char* json);                                 /* :202 (-1: out of scope) */
+int32_t su_sampler_create(uint32_t num_samples);                          /* :215 (returns -1 even on success, like the reference) */
+int32_t su_integrators_create(const char* json);                          /* :223 */
+int32_t su_image_create(uint32_t id, uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height,
+                        uint32_t depth, uint32_t pixel_stride, const uint8_t* data); /* :236 (-1: out of scope) */
+int32_t su_image_update(uint32_t id, uint32_t pixel_stride, const uint8_t* data);   /* :300 (-1) */
+int32_t su_material_create(uint32_t id, const char* json);                /* :342 -> material id */
+int32_t su_material_update(uint32_t id, const char* json);                /* :355 */
+int32_t su_triangle_mesh_create(uint32_t id, uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles,
+                                const uint32_t* indices, uint32_t num_vertices, const float* positions,
+                                uint32_t positions_stride, const float* normals, uint32_t normals_stride,
+                                const float* tangents, uint32_t tangents_stride, const float* uvs, uint32_t uvs_stride,
+                                bool async);                              /* :379 -> shape id */
+int32_t su_prop_create(uint32_t shape, uint32_t num_materials, const uint32_t* materials); /* :425 -> prop id */
+int32_t su_prop_create_instance(uint32_t entity);                         /* :457 (-1: instancing is a later row) */
+int32_t su_light_create(uint32_t prop);                                   /* :471 */
+int32_t su_prop_set_transformation(uint32_t prop, const float* trafo);    /* :485 (row-major 4x4, rows = basis vectors, last row = position) */
+int32_t su_prop_set_transformation_frame(uint32_t prop, uint32_t frame, const float* trafo); /* :506 (frame 0 only) */
+int32_t su_prop_set_visibility(uint32_t prop, uint32_t in_camera, uint32_t in_reflection, uint32_t in_sss); /* :535 */
+int32_t su_render_frame(uint32_t frame);                                  /* :548 */
+int32_t su_export_frame(void);                                            /* :569 (-1: out of scope) */
+int32_t su_start_frame(uint32_t frame);                                   /* :581 */
+int32_t su_render_iterations(uint32_t num_steps);                         /* :602 */
+int32_t su_resolve_frame(uint32_t aov);                                   /* :613 */
+int32_t su_resolve_frame_to_buffer(uint32_t aov, uint32_t width, uint32_t height, float* buffer); /* :626 */
+int32_t su_copy_framebuffer(uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height,
+                            uint8_t* destination);                        /* :643 */
+int32_t su_register_log(void (*post)(uint32_t level, const char* text));  /* :726 */
+int32_t su_register_progress(void (*start)(uint32_t resolution), void (*tick)(void)); /* :731 */
+
+/* ---- extensions (not in libzyg): what a take / scene file sets and the C API cannot ---------------- */
+
+/* The take's "sensor" block (src/cli/take_loader.zig:186-232): {"clamp":{...},"filter":{"Mitchell":{}}}.
+ * Without this call the sensor is libzyg's default: Mitchell radius 2, no clamp (take.zig:59-64). */
+int32_t zyg_su_sensor_create(const char* json);
+/* su_prop_create for an entity of type "Light", which the scene loader creates un-occluding unless told
+ * otherwise (src/util/scene_loader.zig:249,365-366). */
+int32_t zyg_su_prop_create_unoccluding(uint32_t shape, uint32_t num_materials, const uint32_t* materials);
+/* Thin-lens parameters of the take's camera block (camera_perspective.zig:200-240). */
+int32_t zyg_su_camera_set_lens(float aperture_radius, float focus_distance);
+/* CUDA device used by the render calls (default 0). */
+int32_t zyg_su_set_device(int32_t ordinal);
+/* su_render_frame for a sample range: Driver.render(camera, frame, iteration, num_samples), the CLI's
+ * --sample / --num-samples (src/cli/options.zig:88-91). Clears the film first like renderFrameForward. */
+int32_t zyg_su_render_frame_range(uint32_t frame, uint32_t iteration, uint32_t num_samples);
+/* Runs Scene.compile + camera.update and returns the flattened records (valid until the next su_* call
+ * that edits the scene). Needs no GPU. */
+int32_t zyg_su_compile(const struct ZygpuScene** scene, const struct ZygpuView** view);
+/* The device the engine renders on (a zygpu_device*), NULL before the first render call. */
+void* zyg_su_device(void);
+/* Read access to the registered meshes by shape id (>= 7). */
+const struct zyg_mesh* zyg_su_mesh(uint32_t shape);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ZYG_SU_H */

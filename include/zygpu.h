@@ -13,6 +13,8 @@
 
 #include <stdint.h>
 
+#include "zygpu_scene.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -111,6 +113,40 @@ int zygpu_trace_batch(zygpu_device* dev, int mesh, int mode, const ZygpuRay* ray
  * writes fetch counts for this batch. */
 int zygpu_trace_batch_device(zygpu_device* dev, int mesh, int mode, const void* d_rays, uint64_t n, void* d_out,
                              void* stream, ZygpuTraceCounters* counters);
+
+/* ---- forward surface-integration pass --------------------------------------------------------
+ * Replaces Driver.renderFrameForward / renderFrameIterationForward (src/core/rendering/driver.zig:309-348):
+ * the host compiles its scene as before (Scene.compile, camera.update), hands the flattened result over,
+ * and the per-pixel PathtracerMIS recursion runs as wavefront stages on the device. */
+
+/* Copies the compiled scene to the device (meshes referenced by the scene are uploaded on first use). */
+int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene);
+/* Camera, integrator, sampler and sensor settings; (re)allocates the film when the resolution changes. */
+int zygpu_set_view(zygpu_device* dev, const ZygpuView* view);
+/* Opaque.clear(0), buffer_opaque.zig:23-27. */
+int zygpu_clear_film(zygpu_device* dev);
+/* Adds samples [iteration, iteration + num_samples) of every pixel to the film: Driver.renderIterations
+ * (driver.zig:182-187) called once per sample, which is the progressive API's schedule and reseeds the PCG
+ * stream of the depth >= 3 sampler per sample (worker.zig:143). Asynchronous on the device's render stream. */
+int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples);
+/* Sensor.resolveTonemap (Linear) into a host RGBA fp32 buffer of num_pixels pixels; synchronises. */
+int zygpu_resolve(zygpu_device* dev, float* rgba, uint32_t num_pixels);
+/* The weighted-sum film itself: Pack4f per pixel (sum w*rgb, sum w), buffer_opaque.zig:12. */
+int   zygpu_download_film(zygpu_device* dev, float* film, uint32_t num_pixels);
+int   zygpu_upload_film(zygpu_device* dev, const float* film, uint32_t num_pixels);
+/* Device pointer of the film for the multi-GPU reduce (one ncclReduce(sum, fp32) per frame). */
+void* zygpu_film_device(zygpu_device* dev, uint64_t* num_floats);
+int   zygpu_synchronize(zygpu_device* dev);
+
+typedef struct ZygpuRenderStats {
+    uint64_t camera_samples;  /* path samples started */
+    uint64_t closest_rays;    /* Scene.intersect calls */
+    uint64_t shadow_rays;     /* Scene.visibility calls */
+    uint64_t kernel_launches; /* launches of this library's kernels */
+    uint64_t passes;
+} ZygpuRenderStats;
+/* Totals since the last zygpu_clear_film; synchronises the render stream. */
+int zygpu_render_stats(zygpu_device* dev, ZygpuRenderStats* stats);
 
 const char* zygpu_last_error(void);
 

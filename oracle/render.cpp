@@ -1,0 +1,1539 @@
+// ORACLE — test infrastructure only (see zmath.hpp). CPU restatement of the reference's forward
+// surface-integration pass over the flattened scene of include/zygpu_scene.h:
+//   Worker.render                        src/core/rendering/worker.zig:104-168
+//   Sensor.cameraSample / addSample      src/core/rendering/sensor/sensor.zig:152-385, 559-628
+//   Perspective.generateVertex           src/core/camera/camera_perspective.zig:124-150
+//   PathtracerMIS.li & friends           src/core/rendering/integrator/surface/pathtracer_mis.zig:37-341
+//   helpers                              src/core/rendering/integrator/helper.zig
+//   Vertex / Pool                        src/core/scene/vertex.zig
+//   Context / Scene queries              src/core/scene/context.zig:54-73, scene.zig:225-252, 592-634
+//   PropBvh                              src/core/scene/prop/prop_tree.zig:56-116, 185-240, 302-356
+//   Prop                                 src/core/scene/prop/prop.zig:163-264
+//   Rectangle / Cube / Sphere            src/core/scene/shape/{rectangle,cube,sphere}.zig
+//   Light / light tree                   src/core/scene/light/light.zig, light_tree.zig:65-227, 346-517
+// PARITY UNPINNED: the reference has no tests or fixtures for this path and cannot be built here.
+// Scope of this restatement: static scenes, no volumes / media, opaque film, no AOVs, no shadow catchers.
+#include "zmaterial.hpp"
+#include "ztree.hpp"
+#include "zyg_oracle.h"
+
+#include <atomic>
+#include <thread>
+#include <vector>
+
+namespace zo {
+
+namespace {
+
+struct Intersection {  // shape/intersection.zig:46-61
+    float    t, u, v;
+    uint32_t primitive;
+    Trafo    trafo;
+};
+
+struct Fragment {  // shape/intersection.zig:63-124 (event is always .Pass without volumes)
+    Intersection isec;
+    uint32_t     prop, part;
+    Vec4f        p, geo_n, t, b, n, uvw;
+
+    bool  hit() const { return ZYGPU_NULL != prop; }
+    float offset() const { return uvw[3]; }
+    bool  sameHemisphere(Vec4f v) const { return dot3(geo_n, v) > 0.f; }
+    Vec4f offsetP(Vec4f v) const {  // :112-116
+        const Vec4f nn = sameHemisphere(v) ? geo_n : -geo_n;
+        return offsetRay(mulAdd(splat(offset()), nn, p), nn);
+    }
+    Ray offsetRayTo(Vec4f dir) const { return Ray::init(offsetP(dir), dir, 0.f, RayMaxT); }  // :118-120
+};
+
+struct Depth {  // shape/probe.zig:7-22
+    uint16_t surface = 0, volume = 0;
+    uint32_t total() const { return uint32_t(surface) + volume; }
+};
+
+struct State {  // vertex.zig:19-43
+    bool primary_ray = true, transparent = true, singular = true, specular = false, translucent = false,
+         started_specular = false;
+
+    void update(const bxdf::Path& path) {
+        if (bxdf::Scattering::Specular == path.scattering) {
+            specular = true;
+            singular = path.singular();
+            if (primary_ray) started_specular = true;
+        } else if (bxdf::Event::Straight != path.event) {
+            specular    = false;
+            singular    = false;
+            primary_ray = false;
+        }
+    }
+};
+
+struct Vertex {  // vertex.zig:45-85
+    Ray   ray;
+    Depth probe_depth;
+
+    State    state;
+    Depth    depth;
+    float    bxdf_pdf               = 0.f;
+    float    reg_alpha              = 0.f;
+    float    split_weight           = 1.f;
+    float    light_split_threshold  = 0.f;
+    uint32_t path_count             = 1;
+    Vec4f    throughput             = splat(1.f);
+    Vec4f    origin;
+    Vec4f    geo_n = splat(0.f);
+};
+
+struct IValue {  // helper.zig:6-20
+    Vec4f emission = splat(0.f), direct = splat(0.f), indirect = splat(0.f);
+    void  add(Vec4f value, uint32_t depth, uint32_t direct_cutoff, bool is_emission, bool singular) {
+        if (is_emission) {
+            emission = emission + value;
+        } else if (singular || depth < direct_cutoff) {
+            direct = direct + value;
+        } else {
+            indirect = indirect + value;
+        }
+    }
+};
+
+constexpr float LowThreshold = 0.00000001f;  // helper.zig:29
+
+inline float splitThreshold(float split_threshold, Depth depth) {  // helper.zig:33-39
+    const uint32_t total_depth = depth.total();
+    return min(total_depth < 4 ? split_threshold : LowThreshold, split_threshold);
+}
+inline float powerHeuristic(float f_pdf, float g_pdf) {  // helper.zig:64-67
+    const float f2 = f_pdf * f_pdf;
+    return f2 / std::fmaf(g_pdf, g_pdf, f2);
+}
+inline float predividedPowerHeuristic(float f_pdf, float g_pdf) {  // helper.zig:70-73
+    const float f2 = f_pdf * f_pdf;
+    return f_pdf / std::fmaf(g_pdf, g_pdf, f2);
+}
+inline bool russianRoulette(Vec4f& throughput, float r) {  // helper.zig:75-89
+    const float mx                       = hmax3(throughput);
+    const float continuation_probability = mx / 0.1f;
+    if (continuation_probability < 1.f) {
+        if (r >= continuation_probability) return true;
+        throughput = throughput / splat(continuation_probability);
+    }
+    return false;
+}
+
+struct SampleTo {  // shape/sample.zig:10-32
+    Vec4f p, n, wi, uvw;
+    float pdf() const { return p[3]; }
+};
+
+struct LightPick {
+    uint32_t offset;
+    float    pdf;
+};
+
+// ---- shapes ----------------------------------------------------------------------------------
+
+namespace rectangle {
+
+bool intersect(const Ray& ray, const Trafo& trafo, Intersection& isec) {  // rectangle.zig:30-62
+    const Vec4f n     = trafo.r[2];
+    const float d     = dot3(n, trafo.position);
+    const float hit_t = -(dot3(n, ray.origin) - d) / dot3(n, ray.direction);
+
+    if (hit_t >= ray.min_t && ray.max_t >= hit_t) {
+        const Vec4f p = ray.point(hit_t);
+        const Vec4f k = p - trafo.position;
+        const Vec4f t = -trafo.r[0];
+
+        const float u = dot3(t, k) / (0.5f * trafo.scaleX());
+        if (u > 1.f || u < -1.f) return false;
+
+        const Vec4f b = -trafo.r[1];
+        const float v = dot3(b, k) / (0.5f * trafo.scaleY());
+        if (v > 1.f || v < -1.f) return false;
+
+        isec.u         = u;
+        isec.v         = v;
+        isec.t         = hit_t;
+        isec.primitive = 0;
+        isec.trafo     = trafo;
+        return true;
+    }
+    return false;
+}
+
+void fragment(const Ray& ray, Fragment& frag) {  // :102-124
+    const Vec4f p = ray.point(frag.isec.t);
+    const Vec4f n = frag.isec.trafo.r[2];
+    const Vec4f t = -frag.isec.trafo.r[0];
+    const Vec4f b = -frag.isec.trafo.r[1];
+
+    frag.p     = p;
+    frag.t     = t;
+    frag.b     = b;
+    frag.n     = n;
+    frag.geo_n = n;
+    if (frag.isec.trafo.scaleZ() < 0.f) {
+        const Vec4f k = p - frag.isec.trafo.position;
+        const float u = dot3(t, k) * 2.f;
+        const float v = dot3(b, k) * 2.f;
+        frag.uvw      = {{0.5f * (u + 1.f), 0.5f * (v + 1.f), 0.f, 0.f}};
+    } else {
+        frag.uvw = {{0.5f * (frag.isec.u + 1.f), 0.5f * (frag.isec.v + 1.f), 0.f, 0.f}};
+    }
+    frag.part = 0;
+}
+
+bool intersectP(const Ray& ray, const Trafo& trafo) {  // :126-152
+    Intersection unused;
+    return intersect(ray, trafo, unused);
+}
+
+// C. Ureña, M. Fajardo, A. King: An Area-Preserving Parametrization for Spherical Rectangles. rectangle.zig:199-303
+struct SphQuad {
+    Vec4f o, x, y, z;
+    float z0, x0, y0, x1, y1, b0, b1, k, S;
+
+    static SphQuad init(Vec4f scale, Vec4f o) {
+        const Vec4f s  = {{-0.5f * scale[0], -0.5f * scale[1], 0.f, 0.f}};
+        const Vec4f ex = {{scale[0], 0.f, 0.f, 0.f}};
+        const Vec4f ey = {{0.f, scale[1], 0.f, 0.f}};
+
+        SphQuad q;
+        q.o             = o;
+        const float exl = length3(ex);
+        const float eyl = length3(ey);
+        q.x             = ex / splat(exl);
+        q.y             = ey / splat(eyl);
+        q.z             = cross3(q.x, q.y);
+        const Vec4f d   = s - o;
+        q.z0            = dot3(d, q.z);
+        if (q.z0 > 0.f) {
+            q.z  = -q.z;
+            q.z0 = -q.z0;
+        }
+        q.x0 = dot3(d, q.x);
+        q.y0 = dot3(d, q.y);
+        q.x1 = q.x0 + exl;
+        q.y1 = q.y0 + eyl;
+
+        const Vec4f v00 = {{q.x0, q.y0, q.z0, 0.f}};
+        const Vec4f v01 = {{q.x0, q.y1, q.z0, 0.f}};
+        const Vec4f v10 = {{q.x1, q.y0, q.z0, 0.f}};
+        const Vec4f v11 = {{q.x1, q.y1, q.z0, 0.f}};
+
+        const Vec4f n0 = normalize3(cross3(v00, v10));
+        const Vec4f n1 = normalize3(cross3(v10, v11));
+        const Vec4f n2 = normalize3(cross3(v11, v01));
+        const Vec4f n3 = normalize3(cross3(v01, v00));
+
+        const float g0 = std::acos(-dot3(n0, n1));
+        const float g1 = std::acos(-dot3(n1, n2));
+        const float g2 = std::acos(-dot3(n2, n3));
+        const float g3 = std::acos(-dot3(n3, n0));
+
+        q.b0 = n0[2];
+        q.b1 = n2[2];
+        q.k  = 2.f * kPi - g2 - g3;
+        q.S  = g0 + g1 - q.k;
+        return q;
+    }
+
+    Vec4f sample(const float uv[2]) const {
+        const float au = uv[0] * S + k;
+        const float fu = (std::cos(au) * b0 - b1) / std::sin(au);
+        float       cu = 1.f / std::sqrt(fu * fu + b0 * b0) * (fu > 0.f ? 1.f : -1.f);
+        cu             = cu < -1.f ? -1.f : (cu > 1.f ? 1.f : cu);  // std.math.clamp
+
+        float xu = -(cu * z0) / std::sqrt(1.f - cu * cu);
+        xu       = xu < x0 ? x0 : (xu > x1 ? x1 : xu);
+
+        const float d   = std::sqrt(xu * xu + z0 * z0);
+        const float h0  = y0 / std::sqrt(d * d + y0 * y0);
+        const float h1  = y1 / std::sqrt(d * d + y1 * y1);
+        const float hv  = h0 + uv[1] * (h1 - h0);
+        const float hv2 = hv * hv;
+        uint32_t    eb  = 0x35800000u;
+        float       eps;
+        std::memcpy(&eps, &eb, 4);
+        const float yv = hv2 < 1.f - eps ? ((hv * d) / std::sqrt(1.f - hv2)) : y1;
+
+        return o + splat(xu) * x + splat(yv) * y + splat(z0) * z;
+    }
+
+    float pdf(Vec4f scale) const {
+        const Vec4f lp                      = o;
+        const float sqr_dist                = squaredLength3(lp);
+        const float area                    = scale[0] * scale[1];
+        const float diff_solid_angle_numer  = area * std::fabs(lp[2]);
+        const float diff_solid_angle_denom  = sqr_dist * std::sqrt(sqr_dist);
+        return diff_solid_angle_numer > diff_solid_angle_denom * safe::DotMin ? (1.f / S)
+                                                                               : (diff_solid_angle_denom / diff_solid_angle_numer);
+    }
+};
+
+// std.math.clamp asserts lower <= upper; with a degenerate quad the reference would trap in debug builds
+// and is unspecified in release builds. The scenes used here never reach that case.
+
+// Rectangle.sampleTo, rectangle.zig:305-397 (UseSphericalSampling = true)
+uint32_t sampleTo(Vec4f p, Vec4f n, const Trafo& trafo, bool two_sided, bool total_sphere, uint32_t num_samples,
+                  Sampler& sampler, SampleTo* buffer) {
+    const float nsf   = float(num_samples);
+    const Vec4f scale = trafo.scale();
+
+    const Vec4f   lp    = trafo.worldToFramePoint(p);
+    const SphQuad squad = SphQuad::init(scale, lp);
+
+    const float sample_pdf = nsf * squad.pdf(scale);
+
+    uint32_t current_sample = 0;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        const Vec2f uv = sampler.sample2D();
+
+        const Vec4f ls  = squad.sample(uv.v);
+        const Vec4f ws  = trafo.frameToWorldPoint(ls);
+        const Vec4f dir = normalize3(ws - p);
+
+        Vec4f wn = trafo.r[2];
+        if (two_sided && dot3(wn, dir) > 0.f) wn = -wn;
+
+        if (-dot3(wn, dir) < safe::DotMin || 0.f == squad.S || (dot3(dir, n) <= 0.f && !total_sphere)) continue;
+
+        buffer[current_sample++] = {{{ws[0], ws[1], ws[2], sample_pdf}}, wn, dir, {{uv[0], uv[1], 0.f, 0.f}}};
+    }
+    return current_sample;
+}
+
+// Rectangle.pdf, rectangle.zig:554-575
+float pdf(Vec4f p, const Fragment& frag, uint32_t num_samples) {
+    const float   nsf   = float(num_samples);
+    const Vec4f   scale = frag.isec.trafo.scale();
+    const Vec4f   lp    = frag.isec.trafo.worldToFramePoint(p);
+    const SphQuad squad = SphQuad::init(scale, lp);
+    return nsf * squad.pdf(scale);
+}
+
+}  // namespace rectangle
+
+namespace cube {
+
+const AABB kUnit = {{{{-0.5f, -0.5f, -0.5f, -0.5f}}, {{0.5f, 0.5f, 0.5f, 0.5f}}}};
+
+float aabbIntersectP(const AABB& box, const Ray& ray) {  // aabb.zig:62-84
+    const Vec4f lower = (box.bounds[0] - ray.origin) * ray.inv_direction;
+    const Vec4f upper = (box.bounds[1] - ray.origin) * ray.inv_direction;
+    const Vec4f t0    = min4(lower, upper);
+    const Vec4f t1    = max4(lower, upper);
+
+    const float imin = max(max(t0[0], t0[1]), t0[2]);
+    const float imax = min(min(t1[0], t1[1]), t1[2]);
+
+    const float tboxmin = max(imin, ray.min_t);
+    const float tboxmax = min(imax, ray.max_t);
+
+    if (tboxmin <= tboxmax) return imin < ray.min_t ? imax : imin;
+    return FLT_MAX;
+}
+
+bool intersect(const Ray& ray, const Trafo& trafo, Intersection& isec) {  // cube.zig:24-38
+    const Ray   local_ray = trafo.worldToObjectRay(ray);
+    const float hit_t     = aabbIntersectP(kUnit, local_ray);
+    if (hit_t < ray.max_t) {
+        isec.t         = hit_t;
+        isec.primitive = 0;
+        isec.trafo     = trafo;
+        return true;
+    }
+    return false;
+}
+
+void fragment(const Ray& ray, Fragment& frag) {  // cube.zig:40-62
+    const float hit_t = frag.isec.t;
+    frag.p            = ray.point(hit_t);
+
+    const Ray   local_ray = frag.isec.trafo.worldToObjectRay(ray);
+    const Vec4f local_p   = local_ray.point(hit_t);
+    Vec4f       distance;
+    for (int i = 0; i < 4; ++i) distance[i] = std::fabs(0.5f - std::fabs(local_p[i]));
+
+    const uint32_t i = indexMinComponent3(distance);
+    const float    s = std::copysign(1.f, local_p[int(i)]);
+    const Vec4f    n = splat(s) * frag.isec.trafo.r[i];
+
+    frag.part  = 0;
+    frag.geo_n = n;
+    frag.n     = n;
+    frag.uvw   = splat(0.f);
+    orthonormalBasis3(n, frag.t, frag.b);
+}
+
+bool intersectP(const Ray& ray, const Trafo& trafo) {  // cube.zig:64-69
+    const Ray local_ray = trafo.worldToObjectRay(ray);
+    return kUnit.intersect(local_ray);
+}
+
+}  // namespace cube
+
+namespace sphere {
+
+bool intersect(const Ray& ray, const Trafo& trafo, Intersection& isec) {  // sphere.zig:28-62
+    const float idl = 1.f / length3(ray.direction);
+    const Vec4f nd  = ray.direction * splat(idl);
+
+    const Vec4f v = trafo.position - ray.origin;
+    const float b = dot3(nd, v);
+
+    const Vec4f remedy_term  = v - splat(b) * nd;
+    const float radius       = 0.5f * trafo.scaleX();
+    const float discriminant = radius * radius - dot3(remedy_term, remedy_term);
+
+    if (discriminant > 0.f) {
+        const float dist = std::sqrt(discriminant);
+
+        const float t0 = (b - dist) * idl;
+        if (t0 >= ray.min_t && ray.max_t >= t0) {
+            isec.t         = t0;
+            isec.primitive = 0;
+            isec.trafo     = trafo;
+            return true;
+        }
+        const float t1 = (b + dist) * idl;
+        if (t1 >= ray.min_t && ray.max_t >= t1) {
+            isec.t         = t1;
+            isec.primitive = 0;
+            isec.trafo     = trafo;
+            return true;
+        }
+    }
+    return false;
+}
+
+void fragment(const Ray& ray, Fragment& frag) {  // sphere.zig:64-92
+    const Vec4f p = ray.point(frag.isec.t);
+    const Vec4f n = normalize3(p - frag.isec.trafo.position);
+
+    frag.p     = p;
+    frag.geo_n = n;
+    frag.n     = n;
+    frag.part  = 0;
+
+    const Vec4f xyz   = normalize3(frag.isec.trafo.worldToObjectNormal(n));
+    const float phi   = -std::atan2(xyz[0], xyz[2]) + kPi;
+    const float theta = std::acos(xyz[1]);
+
+    const float sin_phi   = std::sin(phi);
+    const float cos_phi   = std::cos(phi);
+    const float sin_theta = max(std::sin(theta), 0.00001f);
+
+    const Vec4f t = normalize3(frag.isec.trafo.objectToWorldNormal({{sin_theta * cos_phi, 0.f, sin_theta * sin_phi, 0.f}}));
+
+    frag.t   = t;
+    frag.b   = -cross3(t, n);
+    frag.uvw = {{phi * (0.5f * kPiInv), theta * kPiInv, 0.f, 0.f}};
+}
+
+bool intersectP(const Ray& ray, const Trafo& trafo) {
+    Intersection unused;
+    return intersect(ray, trafo, unused);
+}
+
+}  // namespace sphere
+
+// ---- scene -----------------------------------------------------------------------------------
+
+struct Scene {
+    const ZygpuScene& s;
+    const ZygpuView&  view;
+    GgxLuts           luts;
+
+    Scene(const ZygpuScene& scene, const ZygpuView& v) : s(scene), view(v), luts(scene.ggx_luts) {}
+
+    const ZygpuMaterial& propMaterial(uint32_t prop, uint32_t part) const {  // scene.zig:529-532
+        return s.materials[s.material_ids[s.props[prop].parts_start + part]];
+    }
+    uint32_t propLightId(uint32_t prop, uint32_t part) const { return s.light_ids[s.props[prop].parts_start + part]; }
+    Trafo    propTrafo(uint32_t prop) const { return Trafo::load(s.trafos[prop]); }
+    AABB     propAabb(uint32_t prop) const { return {{load4(s.aabbs[prop].min), load4(s.aabbs[prop].max)}}; }
+
+    static bool visible(uint32_t flags, uint32_t depth_surface) {  // prop.zig:38-48, sss = false
+        return 0 == depth_surface ? 0 != (flags & ZYG_PROP_VISIBLE_IN_CAMERA) : 0 != (flags & ZYG_PROP_VISIBLE_IN_REFLECTION);
+    }
+
+    float shapeArea(uint32_t shape, Vec4f scale) const {  // shape.zig:143-156
+        switch (shape) {
+            case ZYG_SHAPE_RECTANGLE: return scale[0] * scale[1];
+            case ZYG_SHAPE_SPHERE: return (4.f * kPi) * pow2(0.5f * scale[0]);
+            default: return 0.f;
+        }
+    }
+
+    bool shapeIntersect(uint32_t shape, const Ray& ray, const Trafo& trafo, Intersection& isec) const {  // shape.zig:165-179
+        switch (shape) {
+            case ZYG_SHAPE_CUBE: return cube::intersect(ray, trafo, isec);
+            case ZYG_SHAPE_RECTANGLE: return rectangle::intersect(ray, trafo, isec);
+            case ZYG_SHAPE_SPHERE: return sphere::intersect(ray, trafo, isec);
+            default: return false;
+        }
+    }
+    bool shapeIntersectP(uint32_t shape, const Ray& ray, const Trafo& trafo) const {  // shape.zig:221-233
+        switch (shape) {
+            case ZYG_SHAPE_CUBE: return cube::intersectP(ray, trafo);
+            case ZYG_SHAPE_RECTANGLE: return rectangle::intersectP(ray, trafo);
+            case ZYG_SHAPE_SPHERE: return sphere::intersectP(ray, trafo);
+            default: return false;
+        }
+    }
+    void shapeFragment(uint32_t shape, const Ray& ray, Fragment& frag) const {  // shape.zig:205-219
+        switch (shape) {
+            case ZYG_SHAPE_CUBE: cube::fragment(ray, frag); break;
+            case ZYG_SHAPE_RECTANGLE: rectangle::fragment(ray, frag); break;
+            case ZYG_SHAPE_SPHERE: sphere::fragment(ray, frag); break;
+            default: break;
+        }
+    }
+
+    // Prop.intersect, prop.zig:163-197
+    bool propIntersect(uint32_t entity, const Ray& ray, uint32_t depth_surface, Intersection& isec) const {
+        const ZygpuProp& prop = s.props[entity];
+        if (!visible(prop.flags, depth_surface)) return false;
+        if (!propAabb(entity).intersect(ray)) return false;
+        return shapeIntersect(prop.shape, ray, propTrafo(entity), isec);
+    }
+
+    // Prop.visibility, prop.zig:199-237 (no masks): true = unoccluded
+    bool propVisibility(uint32_t entity, const Ray& ray) const {
+        const ZygpuProp& prop = s.props[entity];
+        if (0 == (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW)) return true;
+        if (!propAabb(entity).intersect(ray)) return true;
+        return !shapeIntersectP(prop.shape, ray, propTrafo(entity));
+    }
+
+    static float nodeIntersect(const ZygpuBvhNode& node, const Ray& ray) {  // node.zig:73-87
+        const Node* n = reinterpret_cast<const Node*>(&node);
+        return n->intersect(ray);
+    }
+
+    // PropBvh.intersect, prop_tree.zig:56-116
+    bool intersect(Ray& ray, uint32_t depth_surface, Fragment& frag) const {
+        const ZygpuPropTree& tree = s.solid_bvh;
+
+        NodeStack stack;
+        uint32_t  n = 0 == tree.num_nodes ? NodeStack::End : 0;
+
+        Intersection isec{};
+        uint32_t     prop = ZYGPU_NULL;
+
+        while (NodeStack::End != n) {
+            const ZygpuBvhNode& node = tree.nodes[n];
+
+            const uint32_t num = node.num_indices;
+            if (0 != num) {
+                const uint32_t start = node.children_or_start;
+                for (uint32_t i = start; i < start + num; ++i) {
+                    const uint32_t p = tree.indices[i];
+                    if (propIntersect(p, ray, depth_surface, isec)) {
+                        ray.max_t = isec.t;
+                        prop      = p;
+                    }
+                }
+                n = stack.pop();
+                continue;
+            }
+
+            uint32_t a = node.children_or_start;
+            uint32_t b = a + 1;
+
+            float dista = nodeIntersect(tree.nodes[a], ray);
+            float distb = nodeIntersect(tree.nodes[b], ray);
+            if (dista > distb) {
+                std::swap(a, b);
+                std::swap(dista, distb);
+            }
+            if (FLT_MAX == dista) {
+                n = stack.pop();
+            } else {
+                n = a;
+                if (FLT_MAX != distb) stack.push(b);
+            }
+        }
+
+        const bool hit = ZYGPU_NULL != prop;
+        if (hit) {
+            frag.isec = isec;
+            shapeFragment(s.props[prop].shape, ray, frag);
+        }
+        frag.prop = prop;
+        return hit;
+    }
+
+    // PropBvh.visibility, prop_tree.zig:185-240; Scene.visibility scene.zig:229-235 (no volume props)
+    bool visibility(const Ray& ray) const {
+        const ZygpuPropTree& tree = s.solid_bvh;
+
+        NodeStack stack;
+        uint32_t  n = 0 == tree.num_nodes ? NodeStack::End : 0;
+
+        while (NodeStack::End != n) {
+            const ZygpuBvhNode& node = tree.nodes[n];
+
+            const uint32_t num = node.num_indices;
+            if (0 != num) {
+                const uint32_t start = node.children_or_start;
+                for (uint32_t i = start; i < start + num; ++i) {
+                    if (!propVisibility(tree.indices[i], ray)) return false;
+                }
+                n = stack.pop();
+                continue;
+            }
+
+            uint32_t a = node.children_or_start;
+            uint32_t b = a + 1;
+
+            float dista = nodeIntersect(tree.nodes[a], ray);
+            float distb = nodeIntersect(tree.nodes[b], ray);
+            if (dista > distb) {
+                std::swap(a, b);
+                std::swap(dista, distb);
+            }
+            if (FLT_MAX == dista) {
+                n = stack.pop();
+            } else {
+                n = a;
+                if (FLT_MAX != distb) stack.push(b);
+            }
+        }
+        return true;
+    }
+
+    // ---- lights ----
+
+    uint32_t lightNumSamples(const ZygpuLight& l, float split_threshold) const {  // shape_sampler.zig:35-41
+        if (split_threshold <= LowThreshold) return 1;
+        return l.num_samples;
+    }
+
+    struct LightProperties {  // light.zig:25-30, scene.zig:664-674
+        Vec4f sphere, cone;
+        float power;
+        bool  two_sided;
+    };
+    LightProperties lightProperties(uint32_t light_id) const {
+        const ZygpuAabb& box = s.light_aabbs[light_id];
+        const Vec4f      pos = splat(0.5f) * (load4(box.min) + load4(box.max));
+        return {{{pos[0], pos[1], pos[2], box.max[3]}}, load4(s.light_cones + 4 * light_id), box.min[3],
+                0 != s.lights[light_id].two_sided};
+    }
+
+    static float clampedCosSub(float cos_a, float cos_b, float sin_a, float sin_b) {  // light_tree.zig:217-220
+        const float angle = std::fmaf(cos_a, cos_b, sin_a * sin_b);
+        return cos_a > cos_b ? 1.f : angle;
+    }
+    static float clampedSinSub(float cos_a, float cos_b, float sin_a, float sin_b) {  // :222-225
+        const float angle = std::fmaf(sin_a, cos_b, -sin_b * cos_a);
+        return cos_a > cos_b ? 0.f : angle;
+    }
+
+    // light_tree.zig:173-215
+    static float importance(Vec4f p, Vec4f n, Vec4f center, Vec4f cone, float radius, float power, bool two_sided,
+                            bool total_sphere) {
+        const Vec4f axis = p - center;
+        const float l    = length3(axis);
+        const Vec4f na   = axis / splat(l);
+        const Vec4f da   = cone;
+
+        const float sin_cu   = min(radius / l, 1.f);
+        const float cos_cone = cone[3];
+        const float cos_a    = safe::absDotC(da, na, two_sided);
+        const float cos_n    = max(-dot3(n, na), 0.f);
+
+        const Vec4f sa = {{sin_cu, cos_cone, cos_a, cos_n}};
+        const Vec4f sb = max4(mulAdd(sa, -sa, splat(1.f)), splat(0.f));
+        Vec4f       sr;
+        for (int i = 0; i < 4; ++i) sr[i] = std::sqrt(sb[i]);
+
+        const float cos_cu   = sr[0];
+        const float sin_cone = sr[1];
+        const float sin_a    = sr[2];
+        const float sin_n    = sr[3];
+
+        const float ta = clampedCosSub(cos_a, cos_cone, sin_a, sin_cone);
+        const float tb = clampedSinSub(cos_a, cos_cone, sin_a, sin_cone);
+        const float tc = clampedCosSub(ta, cos_cu, tb, sin_cu);
+        const float tn = clampedCosSub(cos_n, cos_cu, sin_n, sin_cu);
+
+        const float ra = total_sphere ? 1.f : tn;
+        const float rb = max(tc, 0.f);
+
+        const float clamped_dist = max(l, 0.5f * radius);
+        const float rc           = power / (clamped_dist * clamped_dist);
+
+        return max(ra * rb * rc, 0.f);
+    }
+
+    float lightWeight(Vec4f p, Vec4f n, bool total_sphere, uint32_t light) const {  // light_tree.zig:227-233
+        const LightProperties props = lightProperties(light);
+        return importance(p, n, props.sphere, props.cone, props.sphere[3], props.power, props.two_sided, total_sphere);
+    }
+
+    struct LNode {  // light_tree.Node over the flattened record
+        const ZygpuLightNode& r;
+        bool                  hasChildren() const { return 0 != (r.meta & 1u); }
+        bool                  twoSided() const { return 0 != (r.meta & 2u); }
+        uint32_t              childrenOrLight() const { return r.meta >> 2; }
+    };
+
+    static Vec4f unorm16ToFloat(const uint16_t v[4]) {  // encoding.zig:49-58
+        const float k = 1.f / 65535.f;
+        return {{float(v[0]) * k, float(v[1]) * k, float(v[2]) * k, float(v[3]) * k}};
+    }
+    static Vec4f snorm16ToFloat(const uint16_t v[4]) {  // encoding.zig:71-80
+        Vec4f r;
+        for (int i = 0; i < 4; ++i) r[i] = std::fmaf(float(v[i]), 1.f / 32768.f, -1.f);
+        return r;
+    }
+
+    Vec4f nodeCenter(const ZygpuLightNode& node) const {  // light_tree.zig:39-42
+        const Vec4f t = unorm16ToFloat(node.center);
+        return lerp(load4(s.light_tree.bounds.min), load4(s.light_tree.bounds.max), t);
+    }
+    float nodeWeight(const ZygpuLightNode& node, Vec4f p, Vec4f n, bool total_sphere) const {  // :57-63
+        const Vec4f center = nodeCenter(node);
+        const Vec4f cone   = snorm16ToFloat(node.cone);
+        return importance(p, n, center, cone, center[3], node.power, 0 != (node.meta & 2u), total_sphere);
+    }
+    bool nodeSplit(const ZygpuLightNode& node, Vec4f p, float threshold) const {  // :65-89
+        const Vec4f center = nodeCenter(node);
+        const float r      = center[3];
+        const float d      = min(distance3(p, center), 1.0e6f);
+        const float a      = max(d - r, 0.001f);
+        const float b      = d + r;
+
+        const float eg  = 1.f / (a * b);
+        const float eg2 = eg * eg;
+        const float a3  = a * a * a;
+        const float b3  = b * b * b;
+        const float e2g = (b3 - a3) / (3.f * (b - a) * a3 * b3);
+        const float vg  = e2g - eg2;
+
+        const float ve = node.variance;
+        const float ee = node.power;
+        const float s2 = max(ve * vg + ve * eg2 + ee * ee * vg, 0.f);
+        const float ns = 1.f / (1.f + std::sqrt(s2));
+        return ns < threshold;
+    }
+
+    // Node.randomLight, light_tree.zig:91-145
+    LightPick nodeRandomLight(const ZygpuLightNode& node, Vec4f p, Vec4f n, bool total_sphere, float random) const {
+        const uint32_t* light_mapping = s.light_tree.light_mapping;
+        const uint32_t  num_lights    = node.num_lights;
+        const uint32_t  light         = node.meta >> 2;
+
+        if (1 == num_lights) return {light_mapping[light], 1.f};
+
+        uint32_t front = light;
+        uint32_t back  = light + num_lights - 1;
+
+        float w_front = lightWeight(p, n, total_sphere, light_mapping[front]);
+        float w_back  = lightWeight(p, n, total_sphere, light_mapping[back]);
+
+        float w_sum_front = w_front;
+        float w_sum_back  = w_back;
+        float w_sum       = 0.f;
+
+        while (front != back) {
+            w_sum = w_sum_front + w_sum_back;
+            if (w_sum_front <= random * w_sum) {
+                front += 1;
+                if (front != back) {
+                    w_front = lightWeight(p, n, total_sphere, light_mapping[front]);
+                    w_sum_front += w_front;
+                } else {
+                    w_front = w_back;
+                }
+            } else {
+                back -= 1;
+                if (front != back) {
+                    w_back = lightWeight(p, n, total_sphere, light_mapping[back]);
+                    w_sum_back += w_back;
+                }
+            }
+        }
+        if (0.f == w_sum) return {0, 0.f};
+        return {light_mapping[front], w_front / w_sum};
+    }
+
+    // Node.pdf, light_tree.zig:147-170
+    float nodePdf(const ZygpuLightNode& node, Vec4f p, Vec4f n, bool total_sphere, uint32_t id) const {
+        const uint32_t num_lights = node.num_lights;
+        if (1 == num_lights) return 1.f;
+
+        const uint32_t light = node.meta >> 2;
+        const uint32_t end   = light + num_lights;
+
+        float w_id = 0.f;
+        float sum  = 0.f;
+        for (uint32_t i = light; i < end; ++i) {
+            const float lw = lightWeight(p, n, total_sphere, s.light_tree.light_mapping[i]);
+            sum += lw;
+            if (id == i) w_id = lw;
+        }
+        if (0.f == sum) return 0.f;
+        return w_id / sum;
+    }
+
+    // Tree.randomLight, light_tree.zig:346-447. Infinite lights go through a Distribution1D the scenes in scope
+    // never populate with more than MaxLights - 1 entries, so only the split_infinite branch and the empty
+    // distribution are restated.
+    uint32_t randomLight(Vec4f p, Vec4f n, bool total_sphere, float random, float split_threshold, LightPick* buffer) const {
+        const ZygpuLightTree& tree = s.light_tree;
+
+        uint32_t current_light = 0;
+
+        float          ip                  = 0.f;
+        const uint32_t num_infinite_lights = tree.num_infinite_lights;
+        const bool     split               = split_threshold > 0.f;
+
+        if (split && num_infinite_lights < 64 - 1) {
+            for (uint32_t i = 0; i < num_infinite_lights; ++i) buffer[current_light++] = {tree.light_mapping[i], 1.f};
+        } else {
+            ip = tree.infinite_weight;
+            if (random < tree.infinite_guard) {
+                // infinite_light_distribution.sampleDiscrete — single infinite light only
+                buffer[0] = {tree.light_mapping[0], 1.f * ip};
+                return 1;
+            }
+        }
+
+        if (0 == tree.num_nodes) return current_light;
+
+        const float    pd              = 1.f - ip;
+        const uint32_t max_split_depth = tree.max_split_depth;
+
+        struct Value {
+            float    pdf, random;
+            uint32_t node, depth;
+        };
+        Value    stack[12];  // TraversalStackT(MaxSplitDepth)
+        uint32_t end = 0;
+
+        Value t{pd, (random - ip) / pd, 0, split ? 0 : max_split_depth};
+        stack[end++] = t;
+
+        auto pop = [&]() {
+            end -= 1;
+            return stack[end];
+        };
+
+        while (end > 0) {
+            const ZygpuLightNode& node = tree.nodes[t.node];
+
+            if (0 != (node.meta & 1u)) {
+                const bool do_split = t.depth < max_split_depth && nodeSplit(node, p, split_threshold);
+
+                const uint32_t c0 = node.meta >> 2;
+                const uint32_t c1 = c0 + 1;
+
+                if (do_split) {
+                    t.depth += 1;
+                    t.node       = c0;
+                    stack[end++] = {t.pdf, t.random, c1, t.depth};
+                } else {
+                    t.depth = max_split_depth;
+
+                    float p0 = nodeWeight(tree.nodes[c0], p, n, total_sphere);
+                    float p1 = nodeWeight(tree.nodes[c1], p, n, total_sphere);
+
+                    const float pt = p0 + p1;
+                    if (0.f == pt) {
+                        t = pop();
+                        continue;
+                    }
+
+                    p0 /= pt;
+                    p1 /= pt;
+
+                    if (t.random < p0) {
+                        t.node = c0;
+                        t.pdf *= p0;
+                        t.random /= p0;
+                    } else {
+                        t.node = c1;
+                        t.pdf *= p1;
+                        t.random = min((t.random - p0) / p1, 1.f);
+                    }
+                }
+            } else {
+                const LightPick pick = nodeRandomLight(node, p, n, total_sphere, t.random);
+                if (pick.pdf > 0.f) buffer[current_light++] = {pick.offset, pick.pdf * t.pdf};
+                t = pop();
+            }
+        }
+        return current_light;
+    }
+
+    // Tree.pdf, light_tree.zig:449-517
+    float lightTreePdf(Vec4f p, Vec4f n, bool total_sphere, float split_threshold, uint32_t id) const {
+        const ZygpuLightTree& tree = s.light_tree;
+
+        const uint32_t lo                  = tree.light_orders[id];
+        const uint32_t num_infinite_lights = tree.num_infinite_lights;
+        const bool     split               = split_threshold > 0.f;
+        const bool     split_infinite      = split && num_infinite_lights < 64 - 1;
+
+        if (lo < tree.infinite_end) {
+            if (split_infinite) return 1.f;
+            return tree.infinite_weight * 1.f;  // single infinite light: pdfI == 1
+        }
+        if (0 == tree.num_nodes) return 0.f;
+
+        const float    ip              = split_infinite ? 0.f : tree.infinite_weight;
+        const uint32_t max_split_depth = tree.max_split_depth;
+
+        float    pd    = 1.f - ip;
+        uint32_t nid   = 0;
+        uint32_t depth = split ? 0 : max_split_depth;
+        for (;;) {
+            const ZygpuLightNode& node = tree.nodes[nid];
+            if (0 != (node.meta & 1u)) {
+                const bool     do_split = depth < max_split_depth && nodeSplit(node, p, split_threshold);
+                const uint32_t c0       = node.meta >> 2;
+                const uint32_t c1       = c0 + 1;
+                const uint32_t middle   = tree.node_middles[nid];
+                if (do_split) {
+                    depth += 1;
+                    nid = lo < middle ? c0 : c1;
+                } else {
+                    depth          = max_split_depth;
+                    const float p0 = nodeWeight(tree.nodes[c0], p, n, total_sphere);
+                    const float p1 = nodeWeight(tree.nodes[c1], p, n, total_sphere);
+                    const float pt = p0 + p1;
+                    if (0.f == pt) return 0.f;
+                    if (lo < middle) {
+                        nid = c0;
+                        pd *= p0 / pt;
+                    } else {
+                        nid = c1;
+                        pd *= p1 / pt;
+                    }
+                }
+            } else {
+                return pd * nodePdf(node, p, n, total_sphere, lo);
+            }
+        }
+    }
+
+    // Light.sampleTo -> Shape.sampleTo, light.zig:87-106, 163-190; shape.zig:301-338
+    uint32_t lightSampleTo(const ZygpuLight& l, Vec4f p, Vec4f n, const Trafo& trafo, bool total_sphere,
+                           float split_threshold, Sampler& sampler, SampleTo* buffer) const {
+        const uint32_t num_samples = lightNumSamples(l, split_threshold);
+        switch (s.props[l.prop].shape) {
+            case ZYG_SHAPE_RECTANGLE:
+                return rectangle::sampleTo(p, n, trafo, 0 != l.two_sided, total_sphere, num_samples, sampler, buffer);
+            default: return 0;
+        }
+    }
+
+    // Shape.shadowRay, shape.zig:401-416 (finite shapes)
+    static Ray shadowRay(Vec4f origin, const SampleTo& sample) {
+        const Vec4f light_pos   = offsetRay(sample.p, sample.n);
+        const Vec4f shadow_axis = light_pos - origin;
+        const float shadow_len  = length3(shadow_axis);
+        return Ray::init(origin, shadow_axis / splat(shadow_len), 0.f, shadow_len);
+    }
+
+    // Material.evaluateRadiance, material.zig:194-207 for {Light, Substitute (uncoated)}
+    Vec4f materialRadiance(const ZygpuMaterial& m, Vec4f wi, const Trafo& trafo, uint32_t prop, bool in_camera) const {
+        const float area = 0.f != m.emission_normalize ? shapeArea(s.props[prop].shape, trafo.scale()) : 1.f;
+        return emittanceRadiance(m, wi, trafo, area, in_camera);
+    }
+};
+
+// ---- integrator ------------------------------------------------------------------------------
+
+struct Worker {
+    const Scene& scene;
+    Generator    rng;
+    Sampler      samplers[2];
+
+    explicit Worker(const Scene& sc) : scene(sc) {
+        samplers[0].is_sobol = ZYG_SAMPLER_SOBOL == sc.view.sampler;
+        samplers[0].rng      = &rng;
+        samplers[1].is_sobol = false;
+        samplers[1].rng      = &rng;
+    }
+
+    Sampler& pickSampler(uint32_t bounce) { return bounce < 3 ? samplers[0] : samplers[1]; }  // worker.zig:201-207
+
+    // Scene.lightPdf, scene.zig:624-634
+    float lightPdf(const Vertex& vertex, const Fragment& frag) const {
+        const uint32_t light_id = scene.propLightId(frag.prop, frag.part);
+        if (vertex.state.singular || ZYGPU_NULL == light_id) return 1.f;
+
+        const float select_pdf = scene.lightTreePdf(vertex.origin, vertex.geo_n, vertex.state.translucent,
+                                                    vertex.light_split_threshold, light_id);
+
+        // Light.pdf -> Shape.pdf, light.zig:149-157, shape.zig:469-492
+        const ZygpuLight& l          = scene.s.lights[light_id];
+        float             sample_pdf = 0.f;
+        switch (scene.s.props[l.prop].shape) {
+            case ZYG_SHAPE_RECTANGLE:
+                sample_pdf = rectangle::pdf(vertex.origin, frag, scene.lightNumSamples(l, vertex.light_split_threshold));
+                break;
+            default: break;
+        }
+        return powerHeuristic(vertex.bxdf_pdf, sample_pdf * select_pdf);
+    }
+
+    // Vertex.evaluateRadiance, vertex.zig:183-212
+    Vec4f evaluateRadiance(const Vertex& vertex, const Fragment& frag, Sampler& sampler) const {
+        const Vec4f          wo = -vertex.ray.direction;
+        const ZygpuMaterial& m  = scene.propMaterial(frag.prop, frag.part);
+        if (0 == (m.flags & ZYG_MATERIAL_EMISSIVE) || (0 == (m.flags & ZYG_MATERIAL_TWO_SIDED) && !frag.sameHemisphere(wo))) {
+            return splat(0.f);
+        }
+
+        (void)sampler.sample1D();  // rs.stochastic_r
+
+        const bool  in_camera = 0 == vertex.probe_depth.total();
+        const Vec4f energy    = scene.materialRadiance(m, wo, frag.isec.trafo, frag.prop, in_camera);
+        const float weight    = lightPdf(vertex, frag);
+        return splat(weight) * energy;
+    }
+
+    // Context.emission -> PropBvh.emission -> Prop.emission -> Shape.emission, prop_tree.zig:302-356,
+    // prop.zig:239-264, rectangle.zig:188-196
+    Vec4f emission(const Vertex& vertex, Sampler& sampler) const {
+        const ZygpuPropTree& tree = scene.s.unoccluding_bvh;
+
+        NodeStack stack;
+        uint32_t  n = 0 == tree.num_nodes ? NodeStack::End : 0;
+
+        Vec4f energy = splat(0.f);
+
+        while (NodeStack::End != n) {
+            const ZygpuBvhNode& node = tree.nodes[n];
+            const uint32_t      num  = node.num_indices;
+            if (0 != num) {
+                const uint32_t start = node.children_or_start;
+                for (uint32_t i = start; i < start + num; ++i) energy = energy + propEmission(tree.indices[i], vertex, sampler);
+                n = stack.pop();
+                continue;
+            }
+
+            uint32_t a = node.children_or_start;
+            uint32_t b = a + 1;
+
+            float dista = Scene::nodeIntersect(tree.nodes[a], vertex.ray);
+            float distb = Scene::nodeIntersect(tree.nodes[b], vertex.ray);
+            if (dista > distb) {
+                std::swap(a, b);
+                std::swap(dista, distb);
+            }
+            if (FLT_MAX == dista) {
+                n = stack.pop();
+            } else {
+                n = a;
+                if (FLT_MAX != distb) stack.push(b);
+            }
+        }
+        return energy;
+    }
+
+    Vec4f propEmission(uint32_t entity, const Vertex& vertex, Sampler& sampler) const {
+        const ZygpuProp& prop = scene.s.props[entity];
+        if (!Scene::visible(prop.flags, vertex.probe_depth.surface)) return splat(0.f);
+        if (!scene.propAabb(entity).intersect(vertex.ray)) return splat(0.f);
+
+        Fragment frag;
+        frag.isec.trafo = scene.propTrafo(entity);
+        frag.prop       = entity;
+
+        switch (prop.shape) {
+            case ZYG_SHAPE_RECTANGLE:
+                if (!rectangle::intersect(vertex.ray, frag.isec.trafo, frag.isec)) return splat(0.f);
+                rectangle::fragment(vertex.ray, frag);
+                return evaluateRadiance(vertex, frag, sampler);
+            default: return splat(0.f);  // shape.zig:283-299; Sphere / mesh emitters are not in scope yet
+        }
+    }
+
+    // PathtracerMIS.connectLight, pathtracer_mis.zig:280-341 (no shadow catchers; infinite props evaluated on escape)
+    Vec4f connectLight(Vertex& vertex, const Fragment& frag, Sampler& sampler) const {
+        if (0 == scene.view.caustics_path && vertex.state.specular && !vertex.state.primary_ray) return splat(0.f);
+
+        vertex.light_split_threshold = splitThreshold(scene.view.split_threshold, vertex.depth);
+
+        Vec4f result = splat(0.f);
+        if (frag.hit()) result = evaluateRadiance(vertex, frag, sampler);
+
+        result = result + emission(vertex, sampler);
+
+        // infinite_props: none of the shapes in scope (Canopy / Distant come with the sky configs)
+        return result;
+    }
+
+    // Vertex.sample, vertex.zig:137-181 + Material.sample, material.zig:184-194
+    MaterialSample vertexSample(const Vertex& vertex, const Fragment& frag, Sampler& sampler, bool caustics) const {
+        const Vec4f          wo = -vertex.ray.direction;
+        const ZygpuMaterial& m  = scene.propMaterial(frag.prop, frag.part);
+
+        Renderstate rs;
+        rs.trafo = frag.isec.trafo;
+        rs.p     = frag.p;
+        rs.t     = frag.t;
+        rs.b     = frag.b;
+        if (0 != (m.flags & ZYG_MATERIAL_TWO_SIDED) && !frag.sameHemisphere(wo)) {
+            rs.geo_n = -frag.geo_n;
+            rs.n     = -frag.n;
+        } else {
+            rs.geo_n = frag.geo_n;
+            rs.n     = frag.n;
+        }
+        rs.origin           = vertex.origin;
+        rs.uvw              = frag.uvw;
+        rs.stochastic_r     = sampler.sample1D();
+        rs.ior              = 1.f;  // empty medium stack: Stack.topIor / peekIor
+        rs.reg_weight       = scene.view.regularize_roughness;
+        rs.reg_alpha        = vertex.reg_alpha;
+        rs.prop             = frag.prop;
+        rs.part             = frag.part;
+        rs.primary          = vertex.state.primary_ray;
+        rs.caustics         = caustics;
+        rs.highest_priority = -128;
+
+        switch (m.type) {
+            case ZYG_MATERIAL_SUBSTITUTE: return substituteSample(m, wo, rs, scene.view.specular_threshold, scene.luts);
+            default: return lightSample(wo, rs);
+        }
+    }
+
+    // PathtracerMIS.evaluateLight, pathtracer_mis.zig:214-278
+    Vec4f evaluateLight(const LightPick& light_pick, const Vertex& vertex, const Fragment& frag, const MaterialSample& mat_sample,
+                        uint32_t max_material_splits, Sampler& sampler) const {
+        const Vec4f p           = frag.p;
+        const Vec4f gn          = mat_sample.super.geo_n;
+        const bool  translucent = mat_sample.isTranslucent();
+
+        const ZygpuLight& light = scene.s.lights[light_pick.offset];
+        const Trafo       trafo = scene.propTrafo(light.prop);
+
+        Vec4f occluded = splat(0.f);
+
+        SampleTo       samples[64];
+        const uint32_t num = scene.lightSampleTo(light, p, gn, trafo, translucent, vertex.light_split_threshold, sampler, samples);
+
+        for (uint32_t i = 0; i < num; ++i) {
+            const SampleTo& light_sample = samples[i];
+
+            const Ray shadow = Scene::shadowRay(frag.offsetP(light_sample.wi), light_sample);
+            if (!scene.visibility(shadow)) continue;
+
+            // Light.evaluateTo, light.zig:119-132
+            (void)sampler.sample1D();
+            const ZygpuMaterial& lm       = scene.propMaterial(light.prop, light.part);
+            const Vec4f          radiance = scene.materialRadiance(lm, light_sample.wi, trafo, light.prop, false);
+
+            const bxdf::Result bxdf_result = mat_sample.evaluate(light_sample.wi, max_material_splits, false);
+
+            const float light_pdf = light_sample.pdf() * light_pick.pdf;
+            const float weight    = predividedPowerHeuristic(light_pdf, bxdf_result.pdf);
+
+            occluded = occluded + splat(weight) * radiance * bxdf_result.reflection;
+        }
+        return occluded;
+    }
+
+    // PathtracerMIS.sampleLights, pathtracer_mis.zig:174-212
+    Vec4f sampleLights(const Vertex& vertex, const Fragment& frag, const MaterialSample& mat_sample, uint32_t max_material_splits,
+                       Sampler& sampler) const {
+        Vec4f result = splat(0.f);
+        if (!mat_sample.canEvaluate()) return result;
+
+        const Vec4f p           = frag.p;
+        const Vec4f n           = mat_sample.super.geo_n;
+        const bool  translucent = mat_sample.isTranslucent();
+
+        const float select = sampler.sample1D();
+
+        LightPick      lights[64];
+        const uint32_t num = scene.randomLight(p, n, translucent, select, vertex.light_split_threshold, lights);
+        for (uint32_t i = 0; i < num; ++i) {
+            result = result + evaluateLight(lights[i], vertex, frag, mat_sample, max_material_splits, sampler);
+        }
+        return result;
+    }
+
+    static uint32_t maxSplits(const Vertex& v, uint32_t depth) {  // vertex.zig:306-309
+        const uint32_t m = 4 / v.path_count;
+        return m - (v.state.primary_ray ? 0 : std::min(depth, m - 1));
+    }
+
+    // PathtracerMIS.li, pathtracer_mis.zig:37-172. The uniform-parameter Substitute never returns more than one
+    // bxdf sample (substitute_sample.zig:147-234), so the pool degenerates into a loop over one vertex.
+    IValue li(Vertex vertex) {
+        IValue result;
+
+        std::vector<Vertex> current{vertex}, next;
+
+        while (!current.empty()) {
+            next.clear();
+            for (Vertex& v : current) step(v, result, next);
+            current.swap(next);
+        }
+        result.direct[3] = 0.f;
+        return result;
+    }
+
+    void step(Vertex& vertex, IValue& result, std::vector<Vertex>& next) {
+        const uint32_t max_depth_surface = scene.view.max_depth_surface;
+        const uint32_t max_depth_volume  = scene.view.max_depth_volume;
+
+        const uint32_t total_depth = vertex.probe_depth.total();
+        Sampler&       sampler     = pickSampler(total_depth);
+
+        // Context.nextEvent, context.zig:54-69 (empty medium stack, no volume props)
+        Fragment frag;
+        {
+            const Vec4f origin = vertex.ray.origin;
+            scene.intersect(vertex.ray, vertex.probe_depth.surface, frag);
+            const float dif_t = distance3(origin, vertex.ray.origin);
+            vertex.ray.origin = origin;
+            vertex.ray.max_t += dif_t;
+        }
+
+        const Vec4f this_light       = connectLight(vertex, frag, sampler);
+        const Vec4f split_weight     = splat(vertex.split_weight);
+        Vec4f       split_throughput = vertex.throughput * split_weight;
+
+        result.add(split_throughput * this_light, total_depth, 2, 0 == total_depth, vertex.state.singular);
+
+        if (!frag.hit() || vertex.probe_depth.surface >= max_depth_surface || vertex.probe_depth.volume >= max_depth_volume) {
+            return;
+        }
+
+        if (russianRoulette(vertex.throughput, sampler.sample1D())) return;
+
+        const bool           caustics   = !vertex.state.primary_ray ? 0 != scene.view.caustics_path : true;
+        const MaterialSample mat_sample = vertexSample(vertex, frag, sampler, caustics);
+
+        split_throughput = vertex.throughput * split_weight;
+
+        vertex.light_split_threshold = splitThreshold(scene.view.split_threshold, vertex.probe_depth);
+        const uint32_t max_splits    = maxSplits(vertex, total_depth);
+        const Vec4f    next_light    = sampleLights(vertex, frag, mat_sample, max_splits, sampler);
+
+        result.add(split_throughput * next_light, total_depth, 1, false, false);
+
+        bxdf::Sample   bxdf_samples[4];
+        const uint32_t path_count = mat_sample.sample(sampler, max_splits, bxdf_samples);
+
+        if (0 == path_count) vertex.throughput = splat(0.f);
+
+        for (uint32_t i = 0; i < path_count; ++i) {
+            const bxdf::Sample& sample_result = bxdf_samples[i];
+
+            Vertex next_vertex       = vertex;
+            next_vertex.path_count   = vertex.path_count * path_count;
+            next_vertex.split_weight = vertex.split_weight * sample_result.split_weight;
+
+            const bxdf::Path path = sample_result.path;
+            next_vertex.state.update(path);
+
+            if (bxdf::Event::Straight != path.event) {
+                next_vertex.state.translucent = mat_sample.isTranslucent();
+                next_vertex.depth             = next_vertex.probe_depth;
+                next_vertex.bxdf_pdf          = sample_result.pdf;
+                next_vertex.origin            = frag.p;
+                next_vertex.geo_n             = mat_sample.super.geo_n;
+                next_vertex.reg_alpha         = path.reg_alpha;
+            }
+
+            next_vertex.throughput = next_vertex.throughput * (sample_result.reflection / splat(sample_result.pdf));
+
+            next_vertex.ray = frag.offsetRayTo(sample_result.wi);
+            next_vertex.probe_depth.surface += 1;  // Probe.Depth.increment, no subsurface
+
+            next_vertex.state.transparent =
+                next_vertex.state.transparent && (bxdf::Event::Transmission == path.event || bxdf::Event::Straight == path.event);
+
+            next.push_back(next_vertex);
+        }
+
+        sampler.incrementPadding();
+    }
+};
+
+// ---- sensor ----------------------------------------------------------------------------------
+
+inline Vec4f clampColor(Vec4f color, float mx) {  // sensor.zig:615-624
+    const float mc = hmax3(color);
+    if (mc > mx) {
+        const float r = mx / mc;
+        return splat(r) * color;
+    }
+    return color;
+}
+
+struct Film {
+    float*           pixels;  // Pack4f per pixel, weight in w
+    const ZygpuView& view;
+
+    float eval(float s) const {  // sensor.zig:626-628 + InterpolatedFunction1DN.eval
+        const float    x      = std::fabs(s);
+        const float    cx     = min(x, view.filter_range_end);
+        const float    o      = cx * view.filter_inverse_interval;
+        const uint32_t offset = uint32_t(o);
+        const float    t      = o - float(offset);
+        return lerp(view.filter[offset], view.filter[std::min(offset + 1, 29u)], t);
+    }
+
+    void addPixel(uint32_t i, Vec4f color, float weight, bool atomic) const {  // buffer_opaque.zig:39-55
+        const Vec4f wc = splat(weight) * color;
+        float*      v  = pixels + size_t(i) * 4;
+        if (atomic) {
+            std::atomic_ref<float>(v[0]).fetch_add(wc[0], std::memory_order_relaxed);
+            std::atomic_ref<float>(v[1]).fetch_add(wc[1], std::memory_order_relaxed);
+            std::atomic_ref<float>(v[2]).fetch_add(wc[2], std::memory_order_relaxed);
+            std::atomic_ref<float>(v[3]).fetch_add(weight, std::memory_order_relaxed);
+        } else {
+            v[0] += wc[0];
+            v[1] += wc[1];
+            v[2] += wc[2];
+            v[3] += weight;
+        }
+    }
+
+    void add(int32_t px, int32_t py, float weight, Vec4f color, const int32_t bounds[4], const int32_t isolated[4]) const {  // :559-574
+        if (uint32_t(px - bounds[0]) <= uint32_t(bounds[2]) && uint32_t(py - bounds[1]) <= uint32_t(bounds[3])) {
+            const uint32_t i    = uint32_t(view.resolution[0] * py + px);
+            const bool     iso  = uint32_t(px - isolated[0]) <= uint32_t(isolated[2]) && uint32_t(py - isolated[1]) <= uint32_t(isolated[3]);
+            addPixel(i, color, weight, !iso);
+        }
+    }
+
+    // Sensor.addSample, sensor.zig:168-385 (opaque, no AOV)
+    void addSample(int32_t x, int32_t y, const float pixel_uv[2], const IValue& value, const int32_t bounds[4],
+                   const int32_t isolated[4]) const {
+        const Vec4f emission = clampColor(value.emission, view.clamp_emission);
+        const Vec4f direct   = clampColor(value.direct, view.clamp_direct);
+        const Vec4f indirect = clampColor(value.indirect, view.clamp_indirect);
+        const Vec4f summed   = emission + direct + indirect;
+        const Vec4f composed = {{summed[0], summed[1], summed[2], value.direct[3]}};
+
+        const float ox = pixel_uv[0] - 0.5f;
+        const float oy = pixel_uv[1] - 0.5f;
+
+        const int32_t r = view.filter_radius_int;
+        if (0 == r) {
+            addPixel(uint32_t(view.resolution[0] * y + x), composed, 1.f, false);
+            return;
+        }
+        // r = 1: weights eval(o + 1), eval(o), eval(o - 1); r = 2: eval(o + 2) ... eval(o - 2); rows outer, columns inner.
+        float wx[5], wy[5];
+        for (int32_t i = 0; i <= 2 * r; ++i) {
+            wx[i] = eval(ox + float(r - i));
+            wy[i] = eval(oy + float(r - i));
+        }
+        for (int32_t j = 0; j <= 2 * r; ++j) {
+            for (int32_t i = 0; i <= 2 * r; ++i) add(x - r + i, y - r + j, wx[i] * wy[j], composed, bounds, isolated);
+        }
+    }
+};
+
+// Perspective.generateVertex, camera_perspective.zig:124-150 (static camera: the shutter time only costs a draw)
+Vertex generateVertex(const ZygpuView& view, int32_t px, int32_t py, const float pixel_uv[2], const float lens_uv[2]) {
+    const float c0 = float(px) + pixel_uv[0];
+    const float c1 = float(py) + pixel_uv[1];
+
+    Vec4f direction = load4(view.left_top) + load4(view.d_x) * splat(c0) + load4(view.d_y) * splat(c1);
+    Vec4f origin;
+
+    if (view.aperture_radius > 0.f) {
+        float lens[2];
+        diskConcentric(lens_uv, lens);  // Aperture.sample, aperture.zig:46-53 (no shape texture)
+        origin            = {{lens[0] * view.aperture_radius, lens[1] * view.aperture_radius, 0.f, 0.f}};
+        const Vec4f t     = splat(view.focus_distance / direction[2]);
+        const Vec4f focus = t * direction;
+        direction         = focus - origin;
+    } else {
+        origin = load4(view.eye_offset);
+    }
+
+    const Trafo trafo       = Trafo::load(view.camera_trafo);
+    const Vec4f origin_w    = trafo.objectToWorldPoint(origin);
+    const Vec4f direction_w = trafo.objectToWorldVector(normalize3(direction));
+
+    Vertex v;
+    v.ray    = Ray::init(origin_w, direction_w, 0.f, RayMaxT);
+    v.origin = origin_w;  // Vertex.init, vertex.zig:67-85
+    return v;
+}
+
+// Worker.render, worker.zig:104-168, for one tile
+void renderTile(Worker& worker, const Film& film, const int32_t tile[4], uint32_t iteration, uint32_t num_samples,
+                uint32_t num_expected_samples) {
+    const ZygpuView& view = worker.scene.view;
+
+    const int32_t crop[4]     = {view.crop[0], view.crop[1], view.crop[2] - (view.crop[0] + 1), view.crop[3] - (view.crop[1] + 1)};
+    const int32_t fr          = view.filter_radius_int;
+    const int32_t isolated[4] = {tile[0] + fr, tile[1] + fr, (tile[2] - fr) - (tile[0] + fr), (tile[3] - fr) - (tile[1] + fr)};
+
+    const int32_t  r0 = view.resolution[0] + 2 * fr;
+    const int32_t  r1 = view.resolution[1] + 2 * fr;
+    const uint32_t a  = uint32_t(r0) * uint32_t(r1);
+    const uint64_t o  = uint64_t(iteration) * a;
+    const uint32_t so = iteration / num_expected_samples;
+
+    for (int32_t y = tile[1]; y <= tile[3]; ++y) {
+        const uint32_t pixel_n = uint32_t((y + fr) * r0);
+        for (int32_t x = tile[0]; x <= tile[2]; ++x) {
+            const uint32_t pixel_id = pixel_n + uint32_t(x + fr);
+
+            worker.rng.start(0, uint64_t(pixel_id) + o);
+
+            const uint64_t sample_index = uint64_t(pixel_id) * uint64_t(num_expected_samples) + uint64_t(iteration);
+            const uint32_t tsi          = uint32_t(sample_index);
+            const uint32_t seed         = uint32_t(sample_index >> 32) + so;
+
+            worker.samplers[0].startPixel(tsi, seed);
+
+            for (uint32_t s = 0; s < num_samples; ++s) {
+                // Sensor.cameraSample, sensor.zig:152-166
+                const Vec4f s4 = worker.samplers[0].sample4D();
+                (void)worker.samplers[0].sample1D();  // time
+                worker.samplers[0].incrementPadding();
+
+                const float pixel_uv[2] = {s4[0], s4[1]};
+                const float lens_uv[2]  = {s4[2], s4[3]};
+
+                const Vertex vertex = generateVertex(view, x, y, pixel_uv, lens_uv);
+                const IValue ivalue = worker.li(vertex);
+
+                film.addSample(x, y, pixel_uv, ivalue, crop, isolated);
+
+                worker.samplers[0].incrementSample();
+            }
+        }
+    }
+}
+
+}  // namespace
+
+}  // namespace zo
+
+extern "C" {
+
+// Driver.renderFrameIterationForward over the whole crop (driver.zig:338-348): samples [iteration, iteration +
+// num_samples) of every pixel are added to `film` (Pack4f per pixel of the full resolution, weight in w; not cleared).
+// per_sample_iterations != 0 renders the range as num_samples calls of (iteration + k, 1) — the progressive API's
+// schedule (capi.zig:602-609), which reseeds the PCG stream per sample (worker.zig:143) and is what the device does.
+void zo_render(const ZygpuScene* scene, const ZygpuView* view, uint32_t iteration, uint32_t num_samples,
+               int per_sample_iterations, float* film_pixels, uint32_t threads) {
+    using namespace zo;
+
+    const Scene sc(*scene, *view);
+    const Film  film{film_pixels, *view};
+
+    const int32_t fr   = view->filter_radius_int;
+    const int32_t td   = 32;  // Worker.TileDimensions
+    const int32_t ntx  = (view->crop[2] - view->crop[0] + td - 1) / td;
+    const int32_t nty  = (view->crop[3] - view->crop[1] + td - 1) / td;
+    const int32_t nt   = ntx * nty;
+
+    if (0 == threads) threads = std::max(1u, std::thread::hardware_concurrency());
+
+    const uint32_t passes        = per_sample_iterations ? num_samples : 1;
+    const uint32_t pass_samples  = per_sample_iterations ? 1 : num_samples;
+
+    for (uint32_t pass = 0; pass < passes; ++pass) {
+        std::atomic<int32_t> current{0};
+
+        auto work = [&]() {
+            Worker worker(sc);
+            for (;;) {
+                const int32_t c = current.fetch_add(1, std::memory_order_relaxed);
+                if (c >= nt) return;
+                // TileQueue.pop, tile_queue.zig:47-87 (row-major instead of the generalised Hilbert order: the order
+                // only decides which thread renders a tile)
+                int32_t start[2] = {(c % ntx) * td + view->crop[0], (c / ntx) * td + view->crop[1]};
+                int32_t end[2]   = {std::min(start[0] + td, view->crop[2]), std::min(start[1] + td, view->crop[3])};
+                if (fr > 0) {
+                    if (view->crop[1] == start[1]) start[1] -= fr;
+                    if (view->crop[3] == end[1]) end[1] += fr;
+                    if (view->crop[0] == start[0]) start[0] -= fr;
+                    if (view->crop[2] == end[0]) end[0] += fr;
+                }
+                const int32_t tile[4] = {start[0], start[1], end[0] - 1, end[1] - 1};
+                renderTile(worker, film, tile, iteration + pass, pass_samples, view->spp_total);
+            }
+        };
+
+        if (threads <= 1) {
+            work();
+        } else {
+            std::vector<std::thread> pool;
+            for (uint32_t t = 0; t < threads; ++t) pool.emplace_back(work);
+            for (auto& t : pool) t.join();
+        }
+    }
+}
+
+// Opaque.resolveTonemap with the Linear tonemapper, buffer_opaque.zig:73-79, tonemapper.zig:36-39, aces.zig:19-27
+void zo_resolve(const ZygpuView* view, const float* film_pixels, uint32_t num_pixels, float* rgba) {
+    using namespace zo;
+    for (uint32_t i = 0; i < num_pixels; ++i) {
+        const float* p = film_pixels + size_t(i) * 4;
+        Vec4f        color = Vec4f{{p[0], p[1], p[2], 0.f}} / splat(p[3]);
+        for (int k = 0; k < 4; ++k) color[k] = std::fabs(color[k]);
+        const Vec4f scaled = splat(view->exposure_factor) * color;
+        const Vec4f srgb   = Vec4f{{1.70505155f, -0.13025714f, -0.02400328f, 0.f}} * splat(scaled[0]) +
+                           Vec4f{{-0.62179068f, 1.14080289f, -0.12896877f, 0.f}} * splat(scaled[1]) +
+                           Vec4f{{-0.08325840f, -0.01054853f, 1.15297171f, 0.f}} * splat(scaled[2]);
+        rgba[size_t(i) * 4 + 0] = srgb[0];
+        rgba[size_t(i) * 4 + 1] = srgb[1];
+        rgba[size_t(i) * 4 + 2] = srgb[2];
+        rgba[size_t(i) * 4 + 3] = 1.f;
+    }
+}
+
+// integrate_micro_directional_albedo of the reference's LUT generator (ggx_integrate.zig:27-57) through this
+// oracle's ggx::iso::reflect: lets tests pin the GGX restatement against the E_m table the reference ships.
+float zo_ggx_micro_directional_albedo(float alpha, float n_dot_wo, uint32_t num_samples) {
+    using namespace zo;
+    if (0.f == alpha) return 1.f;
+    const float            calpha = max(alpha, ggx::MinAlpha);
+    const fresnel::Schlick schlick{splat(1.f)};
+    const Frame            frame{{{1.f, 0.f, 0.f, 0.f}}, {{0.f, 1.f, 0.f, 0.f}}, {{0.f, 0.f, 1.f, 0.f}}};
+    const Vec4f            wo = {{std::sqrt(1.f - n_dot_wo * n_dot_wo), 0.f, n_dot_wo, 0.f}};
+
+    float accum = 0.f;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        // math.hammersley(i, num_samples, 0), sample_distribution.zig:3-18
+        uint32_t bits = i;
+        bits          = (bits << 16) | (bits >> 16);
+        bits          = ((bits & 0x55555555u) << 1) | ((bits & 0xAAAAAAAAu) >> 1);
+        bits          = ((bits & 0x33333333u) << 2) | ((bits & 0xCCCCCCCCu) >> 2);
+        bits          = ((bits & 0x0F0F0F0Fu) << 4) | ((bits & 0xF0F0F0F0u) >> 4);
+        bits          = ((bits & 0x00FF00FFu) << 8) | ((bits & 0xFF00FF00u) >> 8);
+        const float xi[2] = {float(i) / float(num_samples), float(bits) * 2.3283064365386963e-10f};
+
+        bxdf::Sample     result;
+        const ggx::Micro micro = ggx::iso::reflect(wo, n_dot_wo, calpha, 0.f, xi, schlick, frame, result);
+        accum += ((micro.n_dot_wi * result.reflection[0]) / result.pdf) / float(num_samples);
+    }
+    return accum;
+}
+
+// Sobol.sample1D stream: startPixel(sample, seed) then n draws with incrementPadding every `pad_every` draws (0 = never).
+void zo_sobol_stream(uint32_t sample, uint32_t seed, uint32_t n, uint32_t pad_every, float* out) {
+    zo::Sobol s;
+    s.startPixel(sample, seed);
+    for (uint32_t i = 0; i < n; ++i) {
+        out[i] = s.sample1D();
+        if (pad_every && 0 == (i + 1) % pad_every) s.incrementPadding();
+    }
+}
+
+void zo_sobol_directions(uint32_t* out) { std::memcpy(out, zo::sobolDirections().d, sizeof(uint32_t) * 160); }
+
+}  // extern "C"

@@ -1,0 +1,519 @@
+// ORACLE — test infrastructure only (see zmath.hpp). Material side of the reference, uniform-parameter
+// subset:
+//   bxdf.Result / Sample / Path     src/core/scene/material/bxdf.zig
+//   sample Base                     src/core/scene/material/sample_base.zig
+//   fresnel.Schlick                 src/core/scene/material/fresnel.zig:5-29
+//   ggx.Iso / Aniso, dspbrMicroEc   src/core/scene/material/ggx.zig
+//   diffuse.Micro                   src/core/scene/material/diffuse.zig:42-116
+//   Substitute Material.sample      src/core/scene/material/substitute/substitute_material.zig:114-221
+//   Substitute Sample               src/core/scene/material/substitute/substitute_sample.zig:38-410
+//   Light material / Emittance      src/core/scene/material/light/light_material.zig, light/emittance.zig:29-59
+#pragma once
+
+#include "zsampler.hpp"
+#include "zscene.hpp"
+
+namespace zo {
+
+namespace bxdf {
+
+struct Result {
+    Vec4f reflection;
+    float pdf;
+    static Result empty() { return {splat(0.f), 0.f}; }
+};
+
+enum class Scattering : uint8_t { Diffuse, Glossy, Specular, None };
+enum class Event : uint8_t { Reflection, Transmission, Straight };
+
+struct Path {  // bxdf.zig:42-73
+    float      reg_alpha;
+    Scattering scattering;
+    Event      event;
+
+    static Path diffuseReflection() { return {1.f, Scattering::Diffuse, Event::Reflection}; }
+    static Path singularReflection() { return {0.f, Scattering::Specular, Event::Reflection}; }
+    static Path singularTransmission() { return {0.f, Scattering::Specular, Event::Transmission}; }
+    static Path reflection(float alpha, float specular_threshold) {
+        return {alpha, alpha <= specular_threshold ? Scattering::Specular : Scattering::Glossy, Event::Reflection};
+    }
+    static Path transmission(float alpha, float specular_threshold) {
+        return {alpha, alpha <= specular_threshold ? Scattering::Specular : Scattering::Glossy, Event::Transmission};
+    }
+    bool singular() const { return 0.f == reg_alpha; }
+};
+
+struct Sample {  // bxdf.zig:75-82
+    Vec4f reflection;
+    Vec4f wi;
+    float pdf;
+    float split_weight;
+    float wavelength;
+    Path  path;
+};
+
+}  // namespace bxdf
+
+struct Renderstate {  // renderstate.zig:10-37 — the fields the in-scope materials read
+    Trafo trafo;
+    Vec4f p, geo_n, t, b, n, origin, uvw;
+    float stochastic_r;
+    float ior;
+    float reg_weight;
+    float reg_alpha;
+    uint32_t prop, part;
+    bool     primary;
+    bool     caustics;
+    int8_t   highest_priority;
+
+    // renderstate.zig:58-68
+    void regularizeAlpha(const float alpha[2], float specular_threshold, float out[2]) const {
+        const float weight = reg_weight;
+        if (0.f == weight || (alpha[0] <= specular_threshold && !caustics)) {
+            out[0] = alpha[0];
+            out[1] = alpha[1];
+            return;
+        }
+        const float k = 1.f - weight * reg_alpha;
+        out[0]        = 1.f - ((1.f - alpha[0]) * k);
+        out[1]        = 1.f - ((1.f - alpha[1]) * k);
+    }
+};
+
+struct SampleBase {  // sample_base.zig:14-104
+    Frame frame;
+    Vec4f geo_n, n, wo;
+    float alpha[2];
+    bool  translucent = false, can_evaluate = false, avoid_caustics = false, volumetric = false;
+
+    bool sameHemisphere(Vec4f v) const { return dot3(geo_n, v) > 0.f; }
+    bool avoidCausticsForce(bool force) const { return force || avoid_caustics; }
+};
+
+namespace fresnel {
+struct Schlick {  // fresnel.zig:9-29
+    Vec4f f0;
+    Vec4f f(float wo_dot_h) const { return mulAdd(splat(pow5(1.f - wo_dot_h)), splat(1.f) - f0, f0); }
+    static float IorToF0(float n0, float n1) {
+        const float t = (n0 - n1) / (n0 + n1);
+        return t * t;
+    }
+};
+}  // namespace fresnel
+
+namespace ggx {
+
+constexpr float MinRoughness = 0.01314f;                     // ggx.zig:14
+constexpr float MinAlpha     = MinRoughness * MinRoughness;  // :15
+
+inline float clampRoughness(float roughness) { return max(roughness, MinRoughness); }  // :48-50
+
+struct Micro {
+    Vec4f h;
+    float n_dot_wi, h_dot_wi;
+};
+
+inline float pdfVisible(float d, float g1_wo) { return (0.5f * d) / g1_wo; }  // :437-439
+
+// ggx.zig:34-46
+inline Vec4f dspbrMicroEc(const GgxLuts& luts, Vec4f f0, float n_dot_wi, float n_dot_wo, float alpha) {
+    const float e_wo  = luts.eM(n_dot_wo, alpha);
+    const float e_wi  = luts.eM(n_dot_wi, alpha);
+    const float e_avg = luts.eMAvg(alpha);
+
+    const float m = ((1.f - e_wo) * (1.f - e_wi)) / (kPi * (1.f - e_avg));
+
+    const Vec4f f_avg = mulAdd(splat(20.f / 21.f), f0, splat(1.f / 21.f));
+    const Vec4f f     = ((f_avg * f_avg) * splat(e_avg)) / mulAdd(-f_avg, splat(1.f - e_avg), splat(1.f));
+    return splat(m) * f;
+}
+
+// Aniso.sample, ggx.zig:393-409 (Dupuy & Benyoub spherical caps)
+inline Vec4f sampleVndf(Vec4f wo, const float alpha[2], const float xi[2], const Frame& frame, float& n_dot_h) {
+    const Vec4f wo_l = frame.worldToFrame(wo);
+    const Vec4f v    = normalize3({{alpha[0] * wo_l[0], alpha[1] * wo_l[1], wo_l[2], 0.f}});
+
+    const float phi       = (2.f * kPi) * xi[0];
+    const float z         = std::fmaf(1.f - xi[1], 1.f + v[2], -v[2]);
+    const float sin_theta = std::sqrt(saturate(1.f - z * z));
+    const float x         = sin_theta * std::cos(phi);
+    const float y         = sin_theta * std::sin(phi);
+
+    const Vec4f h = Vec4f{{x, y, z, 0.f}} + v;
+    const Vec4f m = normalize3({{alpha[0] * h[0], alpha[1] * h[1], h[2], 0.f}});
+
+    n_dot_h = safe::clamp(m[2]);
+    return frame.frameToWorld(m);
+}
+
+namespace iso {
+inline float distribution(float n_dot_h, float a2) {  // :235-238
+    const float d = std::fmaf(n_dot_h * n_dot_h, a2 - 1.f, 1.f);
+    return a2 / (kPi * d * d);
+}
+inline void visibilityAndG1Wo(float n_dot_wi, float n_dot_wo, float alpha2, float out[2]) {  // :240-250
+    const float t_wi = std::sqrt(std::fmaf(1.f - alpha2, n_dot_wi * n_dot_wi, alpha2));
+    const float t_wo = std::sqrt(std::fmaf(1.f - alpha2, n_dot_wo * n_dot_wo, alpha2));
+    out[0]           = 0.5f / (n_dot_wi * t_wo + n_dot_wo * t_wi);
+    out[1]           = t_wo + n_dot_wo;
+}
+
+// Iso.reflectionF, :73-95
+inline bxdf::Result reflection(Vec4f h, Vec4f n, float n_dot_wi, float n_dot_wo, float wo_dot_h, float alpha,
+                               const fresnel::Schlick& fr) {
+    const float alpha2  = alpha * alpha;
+    const float n_dot_h = saturate(dot3(n, h));
+    const float d       = distribution(n_dot_h, alpha2);
+    float       g[2];
+    visibilityAndG1Wo(n_dot_wi, n_dot_wo, alpha2, g);
+    const Vec4f f = fr.f(wo_dot_h);
+    return {splat(d * g[0]) * f, pdfVisible(d, g[1])};
+}
+
+// Iso.reflect, :97-126
+inline Micro reflect(Vec4f wo, float n_dot_wo, float alpha, float specular_threshold, const float xi[2],
+                     const fresnel::Schlick& fr, const Frame& frame, bxdf::Sample& result) {
+    float       n_dot_h;
+    const float a[2] = {alpha, alpha};
+    const Vec4f h    = sampleVndf(wo, a, xi, frame, n_dot_h);
+
+    const float wo_dot_h = safe::clampDot(wo, h);
+    const Vec4f wi       = normalize3(mulAdd(splat(2.f * wo_dot_h), h, -wo));
+
+    const float n_dot_wi = frame.clampNdot(wi);
+    const float alpha2   = alpha * alpha;
+
+    const float d = distribution(n_dot_h, alpha2);
+    float       g[2];
+    visibilityAndG1Wo(n_dot_wi, n_dot_wo, alpha2, g);
+    const Vec4f f = fr.f(wo_dot_h);
+
+    result.reflection = splat(d * g[0]) * f;
+    result.wi         = wi;
+    result.pdf        = pdfVisible(d, g[1]);
+    result.path       = bxdf::Path::reflection(alpha, specular_threshold);
+    return {h, n_dot_wi, wo_dot_h};
+}
+}  // namespace iso
+
+namespace aniso {
+inline float distribution(float n_dot_h, float x_dot_h, float y_dot_h, const float a[2]) {  // :411-419
+    const float a2x = a[0] * a[0];
+    const float a2y = a[1] * a[1];
+    const float x   = (x_dot_h * x_dot_h) / a2x;
+    const float y   = (y_dot_h * y_dot_h) / a2y;
+    const float d   = (x + y) + (n_dot_h * n_dot_h);
+    return 1.f / (kPi * (a[0] * a[1]) * (d * d));
+}
+inline void visibilityAndG1Wo(float t_dot_wi, float t_dot_wo, float b_dot_wi, float b_dot_wo, float n_dot_wi,
+                              float n_dot_wo, const float a[2], float out[2]) {  // :421-434
+    const float t_wo = length3({{a[0] * t_dot_wo, a[1] * b_dot_wo, n_dot_wo, 0.f}});
+    const float t_wi = length3({{a[0] * t_dot_wi, a[1] * b_dot_wi, n_dot_wi, 0.f}});
+    out[0]           = 0.5f / (n_dot_wi * t_wo + n_dot_wo * t_wi);
+    out[1]           = t_wo + n_dot_wo;
+}
+
+// Aniso.reflectionF, :268-305
+inline bxdf::Result reflection(Vec4f wi, Vec4f wo, Vec4f h, float n_dot_wi, float n_dot_wo, float wo_dot_h,
+                               const float alpha[2], const fresnel::Schlick& fr, const Frame& frame) {
+    if (alpha[0] == alpha[1]) return iso::reflection(h, frame.z, n_dot_wi, n_dot_wo, wo_dot_h, alpha[0], fr);
+
+    const float n_dot_h = saturate(dot3(frame.z, h));
+    const float x_dot_h = dot3(frame.x, h);
+    const float y_dot_h = dot3(frame.y, h);
+    const float d       = distribution(n_dot_h, x_dot_h, y_dot_h, alpha);
+
+    float g[2];
+    visibilityAndG1Wo(dot3(frame.x, wi), dot3(frame.x, wo), dot3(frame.y, wi), dot3(frame.y, wo), n_dot_wi, n_dot_wo,
+                      alpha, g);
+    const Vec4f f = fr.f(wo_dot_h);
+    return {splat(d * g[0]) * f, pdfVisible(d, g[1])};
+}
+
+// Aniso.reflect, :307-353
+inline Micro reflect(Vec4f wo, float n_dot_wo, const float alpha[2], float specular_threshold, const float xi[2],
+                     const fresnel::Schlick& fr, const Frame& frame, bxdf::Sample& result) {
+    if (alpha[0] == alpha[1]) return iso::reflect(wo, n_dot_wo, alpha[0], specular_threshold, xi, fr, frame, result);
+
+    float       n_dot_h;
+    const Vec4f h = sampleVndf(wo, alpha, xi, frame, n_dot_h);
+
+    const float x_dot_h  = dot3(frame.x, h);
+    const float y_dot_h  = dot3(frame.y, h);
+    const float wo_dot_h = safe::clampDot(wo, h);
+    const Vec4f wi       = normalize3(mulAdd(splat(2.f * wo_dot_h), h, -wo));
+    const float n_dot_wi = frame.clampNdot(wi);
+
+    const float d = distribution(n_dot_h, x_dot_h, y_dot_h, alpha);
+    float       g[2];
+    visibilityAndG1Wo(dot3(frame.x, wi), dot3(frame.x, wo), dot3(frame.y, wi), dot3(frame.y, wo), n_dot_wi, n_dot_wo,
+                      alpha, g);
+    const Vec4f f = fr.f(wo_dot_h);
+
+    result.reflection = splat(d * g[0]) * f;
+    result.wi         = wi;
+    result.pdf        = pdfVisible(d, g[1]);
+    result.path       = bxdf::Path::reflection(alpha[1], specular_threshold);
+    return {h, n_dot_wi, wo_dot_h};
+}
+}  // namespace aniso
+
+}  // namespace ggx
+
+namespace diffuse {  // diffuse.zig:42-116
+inline float estimateContribution(const GgxLuts& luts, float /*n_dot_wo*/, float alpha, float f0, float albedo) {
+    const float e_avg = luts.eAvg(alpha, f0);
+    const float a     = e_avg;
+    const float b     = 1.f / (kPi * (1.f - e_avg)) * albedo;
+    return b / (a + b);
+}
+inline Vec4f evaluate(const GgxLuts& luts, Vec4f color, float n_dot_wi, float n_dot_wo, float alpha, float f0) {
+    const float e_wo  = luts.e(n_dot_wo, alpha, f0);
+    const float e_wi  = luts.e(n_dot_wi, alpha, f0);
+    const float e_avg = luts.eAvg(alpha, f0);
+    return splat(((1.f - e_wo) * (1.f - e_wi)) / (kPi * (1.f - e_avg))) * color;
+}
+inline bxdf::Result reflection(const GgxLuts& luts, Vec4f color, float f0, float n_dot_wi, float n_dot_wo, float alpha) {
+    return {evaluate(luts, color, n_dot_wi, n_dot_wo, alpha, f0), n_dot_wi * kPiInv};
+}
+inline ggx::Micro reflect(const GgxLuts& luts, Vec4f color, float f0, Vec4f wo, float n_dot_wo, const Frame& frame,
+                          float alpha, const float xi[2], bxdf::Sample& result) {
+    const Vec4f is = hemisphereCosine(xi);
+    const Vec4f wi = normalize3(frame.frameToWorld(is));
+    const Vec4f h  = normalize3(wo + wi);
+
+    const float h_dot_wi = safe::clampDot(h, wi);
+    const float n_dot_wi = frame.clampNdot(wi);
+
+    result.reflection = evaluate(luts, color, n_dot_wi, n_dot_wo, alpha, f0);
+    result.wi         = wi;
+    result.pdf        = n_dot_wi * kPiInv;
+    result.path       = bxdf::Path::diffuseReflection();
+    return {h, n_dot_wi, h_dot_wi};
+}
+}  // namespace diffuse
+
+// Material sample of the Material union restricted to {Substitute surface, Light}: material_sample.zig.
+struct MaterialSample {
+    enum Kind { Light, Substitute } kind;
+
+    SampleBase super;
+
+    // Substitute, substitute_sample.zig:20-36
+    Vec4f albedo, f0;
+    float metallic, specular, specular_threshold, opacity;
+
+    const GgxLuts* luts;
+
+    bool canEvaluate() const { return super.can_evaluate; }
+    bool isTranslucent() const { return super.translucent; }
+
+    // substitute_sample.zig:236-278
+    bxdf::Result baseEvaluate(Vec4f wi, Vec4f wo, Vec4f h, float wo_dot_h, bool force_disable_caustics) const {
+        const Frame& frame = super.frame;
+        const float* alpha = super.alpha;
+
+        const float n_dot_wi = frame.clampNdot(wi);
+        const float n_dot_wo = frame.clampAbsNdot(wo);
+
+        bxdf::Result d  = bxdf::Result::empty();
+        float        dw = 0.f;
+
+        if (1.f != metallic) {
+            const Vec4f a   = splat(opacity) * albedo;
+            const float f0m = hmax3(f0);
+            d               = diffuse::reflection(*luts, a, f0m, n_dot_wi, n_dot_wo, alpha[1]);
+            const float am  = hmax3(albedo);
+            dw              = diffuse::estimateContribution(*luts, n_dot_wo, alpha[1], f0m, am);
+        }
+
+        if (super.avoidCausticsForce(force_disable_caustics) && alpha[1] <= specular_threshold) {
+            return {splat(n_dot_wi) * d.reflection, dw * d.pdf};
+        }
+
+        const float            s = specular;
+        const fresnel::Schlick schlick{f0};
+
+        const bxdf::Result gg  = ggx::aniso::reflection(wi, wo, h, n_dot_wi, n_dot_wo, wo_dot_h, alpha, schlick, frame);
+        const Vec4f        mms = ggx::dspbrMicroEc(*luts, f0, n_dot_wi, n_dot_wo, alpha[1]);
+
+        const float pdf = dw * d.pdf + (1.f - dw) * gg.pdf;
+        return {splat(n_dot_wi) * (d.reflection + splat(s) * (gg.reflection + mms)), pdf};
+    }
+
+    // material_sample.zig:56-62 -> substitute_sample.zig:88-145 (surface, opaque, uncoated)
+    bxdf::Result evaluate(Vec4f wi, uint32_t /*max_splits*/, bool force_disable_caustics) const {
+        if (Light == kind) return {splat(0.f), 0.f};
+
+        const Vec4f wo = super.wo;
+        if (!super.sameHemisphere(wo)) return bxdf::Result::empty();
+
+        const Vec4f h        = normalize3(wo + wi);
+        const float wo_dot_h = safe::clampDot(wo, h);
+        return baseEvaluate(wi, wo, h, wo_dot_h, force_disable_caustics);
+    }
+
+    // substitute_sample.zig:338-361
+    void diffuseSample(float diffuse_weight, const float xi[2], bxdf::Sample& result) const {
+        const Vec4f  wo    = super.wo;
+        const Frame& frame = super.frame;
+        const float* alpha = super.alpha;
+
+        const float n_dot_wo = frame.clampAbsNdot(wo);
+
+        const Vec4f      a     = splat(opacity) * albedo;
+        const float      f0m   = hmax3(f0);
+        const ggx::Micro micro = diffuse::reflect(*luts, a, f0m, wo, n_dot_wo, frame, alpha[1], xi, result);
+
+        const fresnel::Schlick schlick{f0};
+        const bxdf::Result     gg =
+            ggx::aniso::reflection(result.wi, wo, micro.h, micro.n_dot_wi, n_dot_wo, micro.h_dot_wi, alpha, schlick, frame);
+        const Vec4f mms = ggx::dspbrMicroEc(*luts, f0, micro.n_dot_wi, frame.clampNdot(wo), alpha[1]);
+
+        const float s     = specular;
+        result.reflection = splat(micro.n_dot_wi) * (result.reflection + splat(s) * (gg.reflection + mms));
+        result.pdf        = diffuse_weight * result.pdf + (1.f - diffuse_weight) * gg.pdf;
+    }
+
+    // substitute_sample.zig:363-410 (no flakes)
+    void glossSample(float diffuse_weight, const float xi[2], bxdf::Sample& result) const {
+        const Vec4f  wo    = super.wo;
+        const Frame& frame = super.frame;
+        const float* alpha = super.alpha;
+        const float  s     = specular;
+
+        const float            n_dot_wo = frame.clampAbsNdot(wo);
+        const fresnel::Schlick schlick{f0};
+
+        const ggx::Micro micro = ggx::aniso::reflect(wo, n_dot_wo, alpha, specular_threshold, xi, schlick, frame, result);
+        const Vec4f      mms   = ggx::dspbrMicroEc(*luts, f0, micro.n_dot_wi, frame.clampNdot(wo), alpha[1]);
+
+        bxdf::Result d = bxdf::Result::empty();
+        if (diffuse_weight > 0.f) {
+            const Vec4f a   = splat(opacity) * albedo;
+            const float f0m = hmax3(f0);
+            d               = diffuse::reflection(*luts, a, f0m, micro.n_dot_wi, n_dot_wo, alpha[1]);
+        }
+
+        result.reflection = splat(micro.n_dot_wi) * (splat(s) * (result.reflection + mms) + d.reflection);
+        result.pdf        = (1.f - diffuse_weight) * result.pdf + diffuse_weight * d.pdf;
+    }
+
+    // substitute_sample.zig:280-302
+    void baseSample(Sampler& sampler, bxdf::Sample& result) const {
+        float dw = 0.f;
+        if (1.f != metallic) {
+            const float n_dot_wo = super.frame.clampAbsNdot(super.wo);
+            const float f0m      = hmax3(f0);
+            const float am       = hmax3(albedo);
+            dw                   = diffuse::estimateContribution(*luts, n_dot_wo, super.alpha[1], f0m, am);
+        }
+
+        const Vec4f s3    = sampler.sample3D();
+        const float p     = s3[0];
+        const float xi[2] = {s3[1], s3[2]};
+        if (p < dw) {
+            diffuseSample(dw, xi, result);
+        } else {
+            glossSample(dw, xi, result);
+        }
+    }
+
+    // material_sample.zig:64-78 -> substitute_sample.zig:147-234 (surface, opaque, uncoated). Returns the count.
+    uint32_t sample(Sampler& sampler, uint32_t /*max_splits*/, bxdf::Sample buffer[4]) const {
+        if (Light == kind) return 0;
+
+        if (!super.sameHemisphere(super.wo)) return 0;
+
+        bxdf::Sample& result = buffer[0];
+        result.split_weight  = 1.f;
+        result.wavelength    = 0.f;
+
+        baseSample(sampler, result);
+
+        if (0.f == result.pdf) return 0;
+        return 1;
+    }
+};
+
+// Emittance.radiance, emittance.zig:29-59 (uniform emission map, no profile)
+inline Vec4f emittanceRadiance(const ZygpuMaterial& m, Vec4f wi, const Trafo& trafo, float area, bool in_camera) {
+    if (-dot3(wi, trafo.r[2]) < m.emission_cos_a) return splat(0.f);
+
+    const float factor    = in_camera ? m.emission_camera_weight : 1.f;
+    const Vec4f intensity = load4(m.emission) * Vec4f{{1.f, 1.f, 1.f, 0.f}};  // value * uniform1(1.0) map
+
+    if (0.f != m.emission_normalize) return splat(factor / area) * intensity;
+    return splat(factor) * intensity;
+}
+
+// Substitute Material.sample, substitute_material.zig:114-221, uniform textures, no coating / flakes / normal map.
+inline MaterialSample substituteSample(const ZygpuMaterial& m, Vec4f wo, const Renderstate& rs, float specular_threshold,
+                                       const GgxLuts& luts) {
+    const Vec4f color     = load4(m.color);
+    const float roughness = ggx::clampRoughness(m.roughness);
+    const float metallic  = m.metallic;
+    const float specular  = m.specular;
+
+    float alpha[2];  // anisotropicAlpha, :299-306
+    if (m.anisotropy > 0.f) {
+        const float rv = ggx::clampRoughness(roughness * (1.f - m.anisotropy));
+        alpha[0]       = roughness * roughness;
+        alpha[1]       = rv * rv;
+    } else {
+        alpha[0] = alpha[1] = roughness * roughness;
+    }
+
+    const float ior       = m.ior;
+    const float ior_outer = rs.ior;  // coating_thickness == 0
+
+    // Surface.init, substitute_sample.zig:38-78
+    MaterialSample r;
+    r.kind = MaterialSample::Substitute;
+    r.luts = &luts;
+
+    const Vec4f c = splat(1.f - metallic) * color;
+    float       reg_alpha[2];
+    rs.regularizeAlpha(alpha, specular_threshold, reg_alpha);
+    const float ior_medium = rs.ior;
+
+    r.super.geo_n          = rs.geo_n;
+    r.super.n              = rs.n;
+    r.super.wo             = wo;
+    r.super.alpha[0]       = reg_alpha[0];
+    r.super.alpha[1]       = reg_alpha[1];
+    r.super.can_evaluate   = ior != ior_medium;
+    r.super.avoid_caustics = !rs.caustics;
+    r.super.translucent    = false;
+    r.super.volumetric     = false;
+
+    const float f0 = fresnel::Schlick::IorToF0(ior, ior_outer);
+
+    r.albedo             = c;
+    r.f0                 = lerp(splat(f0), color, splat(metallic));
+    r.metallic           = metallic;
+    r.specular           = specular;
+    r.specular_threshold = specular_threshold;
+    r.opacity            = 1.f;  // 1 - 0.5 * translucency
+
+    r.super.frame = {rs.t, rs.b, rs.n};
+    return r;
+}
+
+// light_material.zig:108-110 -> light_sample.zig:10-12 (Base.initTBN, can_evaluate = false)
+inline MaterialSample lightSample(Vec4f wo, const Renderstate& rs) {
+    MaterialSample r;
+    r.kind                 = MaterialSample::Light;
+    r.luts                 = nullptr;
+    r.super.frame          = {rs.t, rs.b, rs.n};
+    r.super.geo_n          = rs.geo_n;
+    r.super.n              = rs.n;
+    r.super.wo             = wo;
+    r.super.alpha[0]       = 0.f;
+    r.super.alpha[1]       = 0.f;
+    r.super.can_evaluate   = false;
+    r.super.avoid_caustics = !rs.caustics;
+    return r;
+}
+
+}  // namespace zo

@@ -43,6 +43,22 @@ void zo_brute_closest(const uint32_t* triangles, uint32_t num_triangles, const f
 void zo_pcg32_uints(uint64_t state, uint64_t sequence, uint32_t n, uint32_t* out);
 void zo_pcg32_floats(uint64_t state, uint64_t sequence, uint32_t n, float* out);
 
+/* ---- forward surface-integration pass (render.cpp) ---- */
+struct ZygpuScene;
+struct ZygpuView;
+
+/* Adds samples [iteration, iteration + num_samples) of every pixel to `film` (Pack4f per pixel of the full
+ * resolution, weight sum in w). per_sample_iterations != 0: num_samples calls of (iteration + k, 1), the
+ * progressive API's schedule, which is the one the device implements. threads = 0: all cores. */
+void zo_render(const struct ZygpuScene* scene, const struct ZygpuView* view, uint32_t iteration, uint32_t num_samples,
+               int per_sample_iterations, float* film, uint32_t threads);
+/* Opaque.resolveTonemap, Linear tonemapper. */
+void zo_resolve(const struct ZygpuView* view, const float* film, uint32_t num_pixels, float* rgba);
+
+float zo_ggx_micro_directional_albedo(float alpha, float n_dot_wo, uint32_t num_samples);
+void  zo_sobol_stream(uint32_t sample, uint32_t seed, uint32_t n, uint32_t pad_every, float* out);
+void  zo_sobol_directions(uint32_t* out160);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,380 @@
+// zyg's C API (src/capi/capi.zig) over the host scene model and the device ABI (include/zyg_su.h).
+// One process-global engine like the reference (capi.zig:55). No compute happens here: render calls
+// compile the scene on the host and launch the device passes through zygpu_*.
+#include "../../../include/zyg_su.h"
+#include "../../../include/zygpu.h"
+
+#include "../host/mesh_handle.hpp"
+#include "../host/scene_model.hpp"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Engine {
+    zyg::SceneModel scene;
+
+    std::vector<zyg_mesh*> meshes;  // owned
+
+    zygpu_device* device         = nullptr;
+    int           device_ordinal = 0;
+
+    uint32_t frame     = 0;
+    uint32_t iteration = 0;
+
+    std::vector<float> target;  // Driver.target: resolved RGBA of the last su_resolve_frame
+
+    void (*log_post)(uint32_t, const char*) = nullptr;
+    void (*progress_start)(uint32_t)        = nullptr;
+    void (*progress_tick)()                 = nullptr;
+
+    ~Engine() {
+        if (device) zygpu_destroy(device);
+        for (zyg_mesh* m : meshes) zyg_mesh_free(m);
+    }
+};
+
+std::unique_ptr<Engine> g_engine;
+
+enum LogLevel : uint32_t { Info = 0, Warning = 1, Error = 2 };  // log.zig:5-7
+
+void logf(uint32_t level, const char* fmt, ...) {
+    char    buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (g_engine && g_engine->log_post) {
+        g_engine->log_post(level, buf);
+    } else if (level >= Warning) {
+        std::fprintf(stderr, "%s: %s\n", Warning == level ? "Warning" : "Error", buf);
+    }
+}
+
+bool parse(const char* text, zyg::json::Value& out) {
+    if (!text) return false;
+    zyg::json::Parser p(text);
+    return p.parse(out);
+}
+
+// Scene.compile + upload + view, the host half of Driver.startFrame (driver.zig:154-180)
+int prepareFrame(Engine& e) {
+    std::string error;
+    if (!e.scene.compile(error)) {
+        logf(Error, "%s", error.c_str());
+        return -1;
+    }
+    if (!e.device) {
+        if (0 != zygpu_create(e.device_ordinal, &e.device)) {
+            e.device = nullptr;
+            logf(Error, "%s", zygpu_last_error());
+            return -1;
+        }
+    }
+    if (0 != zygpu_upload_scene(e.device, &e.scene.scene()) || 0 != zygpu_set_view(e.device, &e.scene.view())) {
+        logf(Error, "%s", zygpu_last_error());
+        return -1;
+    }
+    return 0;
+}
+
+int renderRange(Engine& e, uint32_t frame, uint32_t iteration, uint32_t num_samples) {
+    if (0 != prepareFrame(e)) return -1;
+    e.frame = frame;
+
+    const uint32_t spp = num_samples > 0 ? num_samples : e.scene.samplesPerPixel();  // driver.zig:141-142
+
+    // renderFrameForward, driver.zig:309-336: clear, then every tile; the progressor ticks once per tile
+    const uint32_t tiles = ((e.scene.width() + 31) / 32) * ((e.scene.height() + 31) / 32);
+    if (e.progress_start) e.progress_start(tiles);
+
+    if (0 != zygpu_clear_film(e.device) || 0 != zygpu_render(e.device, iteration, spp) || 0 != zygpu_synchronize(e.device)) {
+        logf(Error, "%s", zygpu_last_error());
+        return -1;
+    }
+    if (e.progress_tick) {
+        for (uint32_t t = 0; t < tiles; ++t) e.progress_tick();
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t su_init(void) {
+    if (g_engine) return -1;
+    g_engine.reset(new Engine);
+    g_engine->scene.setSamplesPerPixel(1);  // capi.zig:104
+    return 0;
+}
+
+int32_t su_release(void) {
+    if (!g_engine) return -1;
+    g_engine.reset();
+    return 0;
+}
+
+int32_t su_mount(const char*) { return g_engine ? 0 : -1; }
+
+int32_t su_perspective_camera_create(uint32_t width, uint32_t height) {
+    if (!g_engine) return -1;
+    g_engine->scene.setCamera(width, height);
+    return int32_t(g_engine->scene.cameraEntity());
+}
+
+int32_t su_camera_set_fov(float fov) {
+    if (!g_engine) return -1;
+    g_engine->scene.setFov(fov);
+    return 0;
+}
+
+int32_t su_camera_sensor_dimensions(int32_t* dimensions) {
+    if (!g_engine || !dimensions) return -1;
+    dimensions[0] = int32_t(g_engine->scene.width());
+    dimensions[1] = int32_t(g_engine->scene.height());
+    return 0;
+}
+
+int32_t su_exporters_create(const char*) { return -1; }
+int32_t su_aovs_create(const char*) { return -1; }
+
+int32_t su_sampler_create(uint32_t num_samples) {
+    if (g_engine) g_engine->scene.setSamplesPerPixel(num_samples);
+    return -1;  // capi.zig:215-221 returns -1 on every path
+}
+
+int32_t su_integrators_create(const char* json) {
+    if (!g_engine) return -1;
+    zyg::json::Value v;
+    if (!parse(json, v)) return -1;
+    g_engine->scene.loadIntegrators(v);
+    return 0;
+}
+
+int32_t su_image_create(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, const uint8_t*) { return -1; }
+int32_t su_image_update(uint32_t, uint32_t, const uint8_t*) { return -1; }
+
+int32_t su_material_create(uint32_t /*id*/, const char* json) {
+    if (!g_engine) return -1;
+    zyg::json::Value v;
+    if (!parse(json, v)) return -1;
+    return g_engine->scene.createMaterial(v);
+}
+
+int32_t su_material_update(uint32_t id, const char* json) {
+    if (!g_engine) return -1;
+    zyg::json::Value v;
+    if (!parse(json, v)) return -1;
+    if (id >= g_engine->scene.numMaterials()) return -3;
+    return g_engine->scene.updateMaterial(id, v) ? 0 : -4;
+}
+
+int32_t su_triangle_mesh_create(uint32_t /*id*/, uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles,
+                                const uint32_t* indices, uint32_t num_vertices, const float* positions,
+                                uint32_t positions_stride, const float* normals, uint32_t normals_stride,
+                                const float* /*tangents*/, uint32_t /*tangents_stride*/, const float* uvs,
+                                uint32_t uvs_stride, bool /*async*/) {
+    if (!g_engine) return -1;
+    if (num_triangles < 1 || num_vertices < 1 || !positions) return -1;  // capi.zig:398-408
+
+    // The BVH is built before the call returns; the reference defers it to its async thread and joins at the
+    // next commitAsync (capi.zig:415-417, 550), which leaves nothing observable to a caller.
+    zyg_mesh* mesh = nullptr;
+    if (0 != zyg_mesh_build(num_parts, parts, num_triangles, indices, num_vertices, positions, positions_stride, normals,
+                            normals_stride, uvs, uvs_stride, 0, &mesh)) {
+        logf(Error, "%s", zygpu_last_error());
+        return -1;
+    }
+    g_engine->meshes.push_back(mesh);
+    return int32_t(g_engine->scene.addMesh(mesh, num_parts > 0 ? num_parts : 1));
+}
+
+static int32_t propCreate(uint32_t shape, uint32_t num_materials, const uint32_t* materials, bool unoccluding) {
+    if (!g_engine) return -1;
+    zyg::SceneModel& scene = g_engine->scene;
+    if (shape >= scene.numShapes()) return -1;
+
+    // capi.zig:431-449: out-of-range ids and missing entries fall back to the debug material
+    std::vector<uint32_t> mats;
+    for (uint32_t i = 0; i < num_materials; ++i) {
+        mats.push_back(materials[i] >= scene.numMaterials() ? scene.fallbackMaterial() : materials[i]);
+    }
+    if (mats.empty()) mats.push_back(scene.fallbackMaterial());
+    return int32_t(scene.createPropShape(shape, mats.data(), uint32_t(mats.size()), unoccluding));
+}
+
+int32_t su_prop_create(uint32_t shape, uint32_t num_materials, const uint32_t* materials) {
+    return propCreate(shape, num_materials, materials, false);
+}
+
+int32_t zyg_su_prop_create_unoccluding(uint32_t shape, uint32_t num_materials, const uint32_t* materials) {
+    return propCreate(shape, num_materials, materials, true);
+}
+
+int32_t su_prop_create_instance(uint32_t) { return -1; }
+
+int32_t su_light_create(uint32_t prop) {
+    if (!g_engine) return -1;
+    return g_engine->scene.createLight(prop) ? 0 : -1;
+}
+
+int32_t su_prop_set_transformation(uint32_t prop, const float* trafo) {
+    if (!g_engine || !trafo) return -1;
+    zyg::Transformation t;
+    zyg::decomposeMatrix(trafo, t);
+    return g_engine->scene.setWorldTransformation(prop, t) ? 0 : -1;
+}
+
+int32_t su_prop_set_transformation_frame(uint32_t prop, uint32_t frame, const float* trafo) {
+    if (0 != frame) return -1;  // static scenes only
+    return su_prop_set_transformation(prop, trafo);
+}
+
+int32_t su_prop_set_visibility(uint32_t prop, uint32_t in_camera, uint32_t in_reflection, uint32_t in_sss) {
+    if (!g_engine) return -1;
+    return g_engine->scene.setVisibility(prop, in_camera > 0, in_reflection > 0, in_sss > 0) ? 0 : -1;
+}
+
+int32_t su_render_frame(uint32_t frame) {
+    if (!g_engine) return -1;
+    return renderRange(*g_engine, frame, 0, 0);  // driver.render(0, frame, 0, 0), capi.zig:559
+}
+
+int32_t zyg_su_render_frame_range(uint32_t frame, uint32_t iteration, uint32_t num_samples) {
+    if (!g_engine) return -1;
+    return renderRange(*g_engine, frame, iteration, num_samples);
+}
+
+int32_t su_export_frame(void) { return -1; }
+
+int32_t su_start_frame(uint32_t frame) {
+    if (!g_engine) return -1;
+    Engine& e = *g_engine;
+    if (0 != prepareFrame(e)) return -1;
+    e.frame     = frame;
+    e.iteration = 0;
+    return 0 == zygpu_clear_film(e.device) ? 0 : -1;  // startFrame(progressive = true), driver.zig:175-179
+}
+
+int32_t su_render_iterations(uint32_t num_steps) {
+    if (!g_engine || !g_engine->device) return -1;
+    Engine& e = *g_engine;
+    if (0 != zygpu_render(e.device, e.iteration, num_steps)) {
+        logf(Error, "%s", zygpu_last_error());
+        return -1;
+    }
+    e.iteration += num_steps;
+    return 0;
+}
+
+int32_t su_resolve_frame(uint32_t aov) {
+    if (!g_engine || !g_engine->device) return -1;
+    Engine& e = *g_engine;
+    if (aov < 12) return -2;  // AOV classes are inactive (aov_value.zig; capi.zig:620)
+    const uint32_t n = e.scene.width() * e.scene.height();
+    e.target.resize(size_t(n) * 4);
+    return 0 == zygpu_resolve(e.device, e.target.data(), n) ? 0 : -1;
+}
+
+int32_t su_resolve_frame_to_buffer(uint32_t aov, uint32_t width, uint32_t height, float* buffer) {
+    if (!g_engine || !g_engine->device || !buffer) return -1;
+    Engine& e = *g_engine;
+    if (aov < 12) return -2;
+    const uint32_t n = std::min(width * height, e.scene.width() * e.scene.height());  // capi.zig:628
+    return 0 == zygpu_resolve(e.device, buffer, n) ? 0 : -1;
+}
+
+// CopyFramebufferContext, capi.zig:662-724: the resolved target as UInt8 sRGB-gamma or Float32, 3 or 4 channels
+int32_t su_copy_framebuffer(uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height, uint8_t* destination) {
+    if (!g_engine || !destination) return -1;
+    Engine&        e = *g_engine;
+    const uint32_t w = std::min(width, e.scene.width());
+    const uint32_t h = std::min(height, e.scene.height());
+    if (e.target.size() < size_t(e.scene.width()) * e.scene.height() * 4) return -1;
+
+    auto linearToGamma = [](float c) -> float {  // spectrum/srgb.zig linearToGamma
+        if (c <= 0.f) return 0.f;
+        if (c < 0.0031308f) return 12.92f * c;
+        if (c < 1.f) return 1.055f * std::pow(c, 1.f / 2.4f) - 0.055f;
+        return 1.f;
+    };
+
+    for (uint32_t y = 0; y < h; ++y) {
+        for (uint32_t x = 0; x < w; ++x) {
+            const float* src = e.target.data() + (size_t(y) * e.scene.width() + x) * 4;
+            const size_t o   = (size_t(y) * width + x) * num_channels;
+            if (0 == format) {  // UInt8
+                for (uint32_t c = 0; c < num_channels; ++c) {
+                    const float v      = c < 3 ? linearToGamma(src[c]) : src[3];
+                    destination[o + c] = uint8_t(v * 255.f + 0.5f);
+                }
+            } else if (4 == format) {  // Float32
+                float* dst = reinterpret_cast<float*>(destination) + o;
+                for (uint32_t c = 0; c < num_channels; ++c) dst[c] = src[c];
+            } else {
+                return -1;
+            }
+        }
+    }
+    return 0;
+}
+
+int32_t su_register_log(void (*post)(uint32_t, const char*)) {
+    if (!g_engine) return -1;
+    g_engine->log_post = post;
+    return 0;
+}
+
+int32_t su_register_progress(void (*start)(uint32_t), void (*tick)(void)) {
+    if (!g_engine) return -1;
+    g_engine->progress_start = start;
+    g_engine->progress_tick  = tick;
+    return 0;
+}
+
+int32_t zyg_su_sensor_create(const char* json) {
+    if (!g_engine) return -1;
+    zyg::json::Value v;
+    if (!parse(json, v)) return -1;
+    g_engine->scene.loadSensor(v);
+    return 0;
+}
+
+int32_t zyg_su_camera_set_lens(float aperture_radius, float focus_distance) {
+    if (!g_engine) return -1;
+    g_engine->scene.setLens(aperture_radius, focus_distance);
+    return 0;
+}
+
+int32_t zyg_su_set_device(int32_t ordinal) {
+    if (!g_engine || g_engine->device) return -1;
+    g_engine->device_ordinal = ordinal;
+    return 0;
+}
+
+int32_t zyg_su_compile(const ZygpuScene** scene, const ZygpuView** view) {
+    if (!g_engine) return -1;
+    std::string error;
+    if (!g_engine->scene.compile(error)) {
+        logf(Error, "%s", error.c_str());
+        return -1;
+    }
+    if (scene) *scene = &g_engine->scene.scene();
+    if (view) *view = &g_engine->scene.view();
+    return 0;
+}
+
+void* zyg_su_device(void) { return g_engine ? g_engine->device : nullptr; }
+
+const zyg_mesh* zyg_su_mesh(uint32_t shape) {
+    if (!g_engine || shape < 7 || shape - 7 >= g_engine->meshes.size()) return nullptr;
+    return g_engine->meshes[shape - 7];
+}
+
+}  // extern "C"

@@ -2,6 +2,7 @@
 #include "../../../include/zygpu.h"
 
 #include "../device/trace.cuh"
+#include "../host/mesh_handle.hpp"
 #include "../host/wide_bvh.hpp"
 
 #include <algorithm>
@@ -34,10 +35,6 @@ int fail(const char* fmt, ...) {
 
 }  // namespace
 
-struct zyg_mesh {
-    zyg::TriangleTree tree;
-    zyg::WideBvh      wide;
-};
 
 struct DeviceMesh {
     zygpu::MeshDevice view{};

@@ -1,0 +1,884 @@
+#include "scene_model.hpp"
+
+#include "bvh_builder.hpp"
+#include "mesh_handle.hpp"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+
+namespace zyg {
+
+namespace {
+
+constexpr float kPi = 3.14159265358979323846f;
+
+constexpr float kMinRoughness = 0.01314f;  // ggx.zig:14
+constexpr float kMinAlpha     = kMinRoughness * kMinRoughness;
+
+inline float degreesToRadians(float d) { return d * (kPi / 180.f); }  // math.zig:114-116
+
+Mat3x3 mulMat(const Mat3x3& a, const Mat3x3& b) {  // matrix3x3.zig:104-116
+    Mat3x3 m;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) m.r[i][j] = a.r[i][0] * b.r[0][j] + a.r[i][1] * b.r[1][j] + a.r[i][2] * b.r[2][j];
+        m.r[i][3] = 0.f;
+    }
+    return m;
+}
+
+Mat3x3 init9(float m00, float m01, float m02, float m10, float m11, float m12, float m20, float m21, float m22) {
+    return {{{{m00, m01, m02, 0.f}}, {{m10, m11, m12, 0.f}}, {{m20, m21, m22, 0.f}}}};
+}
+
+struct Mat4x4 {
+    Vec4f r[4];
+};
+
+Mat4x4 compose(const Mat3x3& basis, Vec4f scale, Vec4f origin) {  // matrix4x4.zig:88-107
+    Mat4x4 m;
+    for (int i = 0; i < 3; ++i) {
+        m.r[i] = {{basis.r[i][0] * scale[i], basis.r[i][1] * scale[i], basis.r[i][2] * scale[i], 0.f}};
+    }
+    m.r[3] = {{origin[0], origin[1], origin[2], 1.f}};
+    return m;
+}
+
+AABB transformAabb(const AABB& box, const Mat4x4& m) {  // aabb.zig:147-166
+    const Vec4f xa = m.r[0] * splat(box.b[0][0]);
+    const Vec4f xb = m.r[0] * splat(box.b[1][0]);
+    const Vec4f ya = m.r[1] * splat(box.b[0][1]);
+    const Vec4f yb = m.r[1] * splat(box.b[1][1]);
+    const Vec4f za = m.r[2] * splat(box.b[0][2]);
+    const Vec4f zb = m.r[2] * splat(box.b[1][2]);
+    const Vec4f mw = m.r[3];
+    return {{min4(xa, xb) + min4(ya, yb) + min4(za, zb) + mw, max4(xa, xb) + max4(ya, yb) + max4(za, zb) + mw}};
+}
+
+Vec4f transformVector(const Mat3x3& m, Vec4f v) {  // matrix3x3.zig:118-131
+    Vec4f result = splat(v[0]) * m.r[0];
+    result       = mulAdd(splat(v[1]), m.r[1], result);
+    return mulAdd(splat(v[2]), m.r[2], result);
+}
+
+ZygpuAabb packAabb(const AABB& b) {
+    ZygpuAabb r;
+    for (int i = 0; i < 4; ++i) {
+        r.min[i] = b.b[0][i];
+        r.max[i] = b.b[1][i];
+    }
+    return r;
+}
+
+Vec4f readVec4f3(const json::Value& v) {  // json.zig:128-138
+    if (json::Value::Array == v.kind && v.array.size() >= 3) {
+        return {{float(v.array[0].number), float(v.array[1].number), float(v.array[2].number), 0.f}};
+    }
+    return splat(float(v.number));
+}
+
+Vec4f readColor(const json::Value& v) {  // json.zig:251-278 (array / number / {"sRGB": ...})
+    if (json::Value::Object == v.kind) {
+        Vec4f rgb = splat(0.f);
+        if (const json::Value* s = v.get("sRGB")) rgb = readVec4f3(*s);
+        return sRGBtoAP1(rgb);
+    }
+    return sRGBtoAP1(readVec4f3(v));
+}
+
+ZygpuMaterial defaultMaterial(uint32_t type) {
+    ZygpuMaterial m{};
+    m.type                   = type;
+    m.flags                  = 0;
+    m.priority               = 0;
+    m.emission_num_samples   = 1;
+    m.emission_cos_a         = -1.f;
+    m.emission_camera_weight = 1.f;
+    m.emission_normalize     = 0.f;
+    m.specular               = 1.f;
+    m.ior                    = 1.f;
+    switch (type) {
+        case ZYG_MATERIAL_SUBSTITUTE:  // substitute_material.zig:41-67
+            m.color[0] = m.color[1] = m.color[2] = 0.5f;
+            m.roughness = 0.8f;
+            m.ior       = 1.46f;
+            break;
+        case ZYG_MATERIAL_LIGHT:  // light_material.zig:44
+            m.emission[0] = m.emission[1] = m.emission[2] = m.emission[3] = 1.f;
+            break;
+        case ZYG_MATERIAL_GLASS:  // glass_material.zig:28-36
+            m.ior                  = 1.46f;
+            m.roughness            = 0.f;
+            m.attenuation_distance = 1.f;
+            break;
+        default: break;
+    }
+    return m;
+}
+
+// loadEmittance, material_provider.zig:412-436 (no profile, no maps)
+void loadEmittance(const json::Value& j, ZygpuMaterial& m) {
+    Vec4f color = splat(1.f);
+    if (const json::Value* s = j.get("spectrum")) color = readColor(*s);
+    const float value = json::readFloatMember(j, "value", 1.f);
+
+    m.emission_normalize = json::readBoolMember(j, "normalize", false) ? 1.f : 0.f;
+    for (int i = 0; i < 4; ++i) m.emission[i] = value * color[i];
+    // profile_angle = degrees(pi) when there is no profile (emittance.zig:77-80)
+    const float profile_angle = kPi * (180.f / kPi);
+    m.emission_cos_a          = std::cos(degreesToRadians(json::readFloatMember(j, "angle", profile_angle)));
+    m.emission_camera_weight  = json::readFloatMember(j, "camera_weight", 1.f);
+    m.emission_num_samples    = std::min(json::readUIntMember(j, "num_samples", 1), 64u);
+}
+
+bool anyGreaterZero3(const float v[4]) { return v[0] > 0.f || v[1] > 0.f || v[2] > 0.f; }
+
+}  // namespace
+
+Vec4f sRGBtoAP1(Vec4f srgb) {
+    const Vec4f r = splat(srgb[0]), g = splat(srgb[1]), b = splat(srgb[2]);
+    return Vec4f{{0.61309732f, 0.07019422f, 0.02061560f, 0.f}} * r + Vec4f{{0.33952285f, 0.91635557f, 0.10956983f, 0.f}} * g +
+           Vec4f{{0.04737928f, 0.01345259f, 0.86981512f, 0.f}} * b;
+}
+
+Mat3x3 quaternionToMat3x3(Vec4f q) {
+    const Vec4f tq = q + q;
+    const float xy = tq[1] * q[0];
+    const float xz = tq[2] * q[0];
+    const float yz = tq[1] * q[2];
+    const Vec4f w  = tq * splat(q[3]);
+
+    const Vec4f a = {{q[3], q[0], q[3], q[1]}};
+    const Vec4f b = {{q[1], q[2], q[0], q[2]}};
+    const Vec4f t = (a + b) * (a - b);
+
+    return init9(t[0] + t[1], xy - w[2], xz + w[1], xy + w[2], t[2] + t[3], yz - w[0], xz - w[1], yz + w[0], t[2] - t[3]);
+}
+
+Vec4f quaternionFromMat3x3(const Mat3x3& m) {
+    float t;
+    Vec4f q;
+    if (m.r[2][2] < 0.f) {
+        if (m.r[0][0] > m.r[1][1]) {
+            t = 1.f + m.r[0][0] - m.r[1][1] - m.r[2][2];
+            q = {{t, m.r[0][1] + m.r[1][0], m.r[2][0] + m.r[0][2], m.r[2][1] - m.r[1][2]}};
+        } else {
+            t = 1.f - m.r[0][0] + m.r[1][1] - m.r[2][2];
+            q = {{m.r[0][1] + m.r[1][0], t, m.r[1][2] + m.r[2][1], m.r[0][2] - m.r[2][0]}};
+        }
+    } else {
+        if (m.r[0][0] < -m.r[1][1]) {
+            t = 1.f - m.r[0][0] - m.r[1][1] + m.r[2][2];
+            q = {{m.r[2][0] + m.r[0][2], m.r[1][2] + m.r[2][1], t, m.r[1][0] - m.r[0][1]}};
+        } else {
+            t = 1.f + m.r[0][0] + m.r[1][1] + m.r[2][2];
+            q = {{m.r[2][1] - m.r[1][2], m.r[0][2] - m.r[2][0], m.r[1][0] - m.r[0][1], t}};
+        }
+    }
+    return q * splat(0.5f / std::sqrt(t));
+}
+
+Mat3x3 rotationFromEulerDegrees(Vec4f xyz) {
+    const float ax = degreesToRadians(xyz[0]), ay = degreesToRadians(xyz[1]), az = degreesToRadians(xyz[2]);
+    const float cx = std::cos(ax), sx = std::sin(ax);
+    const float cy = std::cos(ay), sy = std::sin(ay);
+    const float cz = std::cos(az), sz = std::sin(az);
+    const Mat3x3 rot_x = init9(1.f, 0.f, 0.f, 0.f, cx, -sx, 0.f, sx, cx);  // matrix3x3.zig:31-50
+    const Mat3x3 rot_y = init9(cy, 0.f, sy, 0.f, 1.f, 0.f, -sy, 0.f, cy);
+    const Mat3x3 rot_z = init9(cz, -sz, 0.f, sz, cz, 0.f, 0.f, 0.f, 1.f);
+    return mulMat(mulMat(rot_z, rot_x), rot_y);
+}
+
+void decomposeMatrix(const float m[16], Transformation& out) {
+    const Vec4f mx = {{m[0], m[1], m[2], m[3]}};
+    const Vec4f my = {{m[4], m[5], m[6], m[7]}};
+    const Vec4f mz = {{m[8], m[9], m[10], m[11]}};
+    const float sx = length3(mx), sy = length3(my), sz = length3(mz);
+    const Mat3x3 basis = {{mx / splat(sx), my / splat(sy), mz / splat(sz)}};
+    out.scale    = {{sx, sy, sz, 0.f}};
+    out.position = {{m[12], m[13], m[14], m[15]}};
+    out.rotation = quaternionFromMat3x3(basis);
+}
+
+const std::vector<float>& ggxLuts(std::string& error) {
+    static std::vector<float> luts;
+    static std::string        load_error;
+    static bool               tried = false;
+    if (!tried) {
+        tried = true;
+        Dl_info info;
+        std::string dir = ".";
+        if (dladdr(reinterpret_cast<const void*>(&sRGBtoAP1), &info) && info.dli_fname) {
+            const std::string path = info.dli_fname;
+            const size_t      s    = path.find_last_of('/');
+            if (std::string::npos != s) dir = path.substr(0, s);
+        }
+        const std::string file = dir + "/data/ggx_luts.f32";
+        if (FILE* f = std::fopen(file.c_str(), "rb")) {
+            luts.resize(ZYGPU_GGX_LUT_FLOATS);
+            const size_t n = std::fread(luts.data(), sizeof(float), luts.size(), f);
+            std::fclose(f);
+            if (n != luts.size()) {
+                luts.clear();
+                load_error = file + ": truncated";
+            }
+        } else {
+            load_error = file + ": cannot open";
+        }
+    }
+    error = load_error;
+    return luts;
+}
+
+SceneModel::SceneModel() : specular_threshold_(kMinAlpha) {
+    clamp_[0] = clamp_[1] = clamp_[2] = FLT_MAX;
+    // createFallbackMaterial, material_provider.zig:127-129: a Debug material at id 0 (capi.zig:94-101)
+    materials_.push_back(defaultMaterial(ZYG_MATERIAL_DEBUG));
+}
+
+bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
+    if (id >= materials_.size()) return false;
+    const json::Value* rendering = material.get("rendering");
+    if (!rendering || json::Value::Object != rendering->kind) return false;
+
+    ZygpuMaterial& m = materials_[id];
+
+    for (const auto& entry : rendering->object) {
+        const json::Value& v = entry.second;
+        if ("Light" == entry.first && ZYG_MATERIAL_LIGHT == m.type) {  // updateLight, material_provider.zig:233-244
+            for (const auto& e : v.object) {
+                if ("emittance" == e.first) {
+                    loadEmittance(e.second, m);
+                } else if ("two_sided" == e.first) {
+                    m.flags = e.second.boolean ? (m.flags | ZYG_MATERIAL_TWO_SIDED) : (m.flags & ~ZYG_MATERIAL_TWO_SIDED);
+                }
+            }
+        } else if ("Substitute" == entry.first && ZYG_MATERIAL_SUBSTITUTE == m.type) {  // updateSubstitute, :254-330
+            for (const auto& e : v.object) {
+                const std::string& k = e.first;
+                if ("color" == k) {
+                    const Vec4f c = readColor(e.second);
+                    for (int i = 0; i < 4; ++i) m.color[i] = c[i];
+                } else if ("emittance" == k) {
+                    loadEmittance(e.second, m);
+                } else if ("roughness" == k) {
+                    m.roughness = float(e.second.number);
+                } else if ("metallic" == k) {
+                    m.metallic = float(e.second.number);
+                } else if ("specular" == k) {
+                    m.specular = float(e.second.number);
+                } else if ("anisotropy" == k) {
+                    m.anisotropy = float(e.second.number);
+                } else if ("ior" == k) {
+                    m.ior = float(e.second.number);
+                } else if ("priority" == k) {
+                    m.priority = int32_t(e.second.number);
+                } else if ("two_sided" == k) {
+                    m.flags = e.second.boolean ? (m.flags | ZYG_MATERIAL_TWO_SIDED) : (m.flags & ~ZYG_MATERIAL_TWO_SIDED);
+                }
+            }
+        } else if ("Glass" == entry.first && ZYG_MATERIAL_GLASS == m.type) {  // updateGlass, :165-196
+            Vec4f attenuation_color = splat(1.f);
+            for (const auto& e : v.object) {
+                const std::string& k = e.first;
+                if ("color" == k || "attenuation_color" == k) {
+                    attenuation_color = readColor(e.second);
+                } else if ("attenuation_distance" == k) {
+                    m.attenuation_distance = float(e.second.number);
+                } else if ("roughness" == k) {
+                    m.roughness = float(e.second.number);
+                } else if ("specular" == k) {
+                    m.specular = float(e.second.number);
+                } else if ("priority" == k) {
+                    m.priority = int32_t(e.second.number);
+                } else if ("ior" == k) {
+                    m.ior = float(e.second.number);
+                } else if ("abbe" == k) {
+                    m.abbe = float(e.second.number);
+                } else if ("thickness" == k) {
+                    m.thickness = float(e.second.number);
+                }
+            }
+            // Glass.setVolumetric -> attenuationCoefficient, collision_coefficients.zig:35-44
+            for (int i = 0; i < 3; ++i) {
+                const float c = fmin_(fmax_(attenuation_color[i], 0.01f), 0.991102f);
+                m.color[i]    = 0.f == m.attenuation_distance ? 0.f : -std::log(c) / m.attenuation_distance;
+            }
+        }
+    }
+
+    // Material.commit: light_material.zig:46-52, substitute_material.zig:69-83
+    if (ZYG_MATERIAL_LIGHT == m.type || ZYG_MATERIAL_SUBSTITUTE == m.type) {
+        m.flags = anyGreaterZero3(m.emission) ? (m.flags | ZYG_MATERIAL_EMISSIVE) : (m.flags & ~ZYG_MATERIAL_EMISSIVE);
+    }
+    if (ZYG_MATERIAL_SUBSTITUTE == m.type) {
+        m.flags = m.roughness <= specular_threshold_ ? (m.flags | ZYG_MATERIAL_CAUSTIC) : (m.flags & ~ZYG_MATERIAL_CAUSTIC);
+    }
+    if (ZYG_MATERIAL_GLASS == m.type) {  // glass_material.zig:38-45
+        m.flags = m.roughness * m.roughness <= specular_threshold_ ? (m.flags | ZYG_MATERIAL_CAUSTIC) : (m.flags & ~ZYG_MATERIAL_CAUSTIC);
+        m.flags = m.thickness > 0.f ? (m.flags | ZYG_MATERIAL_TWO_SIDED) : (m.flags & ~ZYG_MATERIAL_TWO_SIDED);
+    }
+    return true;
+}
+
+int SceneModel::createMaterial(const json::Value& material) {
+    const json::Value* rendering = material.get("rendering");
+    if (!rendering || json::Value::Object != rendering->kind) return -1;  // Error.NoRenderNode
+
+    for (const auto& entry : rendering->object) {
+        uint32_t type;
+        if ("Debug" == entry.first) {
+            type = ZYG_MATERIAL_DEBUG;
+        } else if ("Glass" == entry.first) {
+            type = ZYG_MATERIAL_GLASS;
+        } else if ("Light" == entry.first) {
+            type = ZYG_MATERIAL_LIGHT;
+        } else if ("Substitute" == entry.first) {
+            type = ZYG_MATERIAL_SUBSTITUTE;
+        } else {
+            continue;
+        }
+        materials_.push_back(defaultMaterial(type));
+        updateMaterial(uint32_t(materials_.size() - 1), material);
+        return int(materials_.size() - 1);
+    }
+    return -1;  // Error.UnknownMaterial
+}
+
+uint32_t SceneModel::addMesh(const zyg_mesh* mesh, uint32_t num_parts) {
+    meshes_.push_back({mesh, num_parts});
+    return 7 + uint32_t(meshes_.size() - 1);
+}
+
+bool SceneModel::shapeFinite(uint32_t shape) const {  // shape.zig:94-99
+    return !(ZYG_SHAPE_CANOPY == shape || ZYG_SHAPE_DISTANT == shape || ZYG_SHAPE_DOME == shape);
+}
+
+uint32_t SceneModel::createEntity() {
+    PropRec p;
+    p.shape = ZYG_SHAPE_DISTANT;  // scene.zig:257
+    props_.push_back(p);
+    world_.push_back(Transformation{});
+    return uint32_t(props_.size() - 1);
+}
+
+uint32_t SceneModel::createPropShape(uint32_t shape_id, const uint32_t* materials, uint32_t num_materials, bool unoccluding) {
+    PropRec p;
+    p.shape = shape_id;
+
+    // Prop.configureShape, prop.zig:94-135
+    bool pure_emissive = true;
+    bool mono          = num_materials > 0;
+    for (uint32_t i = 0; i < num_materials; ++i) {
+        const ZygpuMaterial& m = materials_[materials[i]];
+        if (ZYG_MATERIAL_LIGHT != m.type) pure_emissive = false;
+        if (materials[i] != materials[0]) mono = false;
+    }
+    const bool volumetric = shapeFinite(shape_id) && mono && materials_[materials[0]].ior < 1.f;
+    p.solid               = !volumetric;
+    if (unoccluding && shapeFinite(shape_id) && pure_emissive) p.flags |= ZYG_PROP_UNOCCLUDING;
+
+    const uint32_t num_parts = shape_id >= 7 ? meshes_[shape_id - 7].num_parts : 1;
+    p.parts_start            = uint32_t(material_ids_.size());
+    for (uint32_t i = 0; i < num_parts; ++i) {
+        material_ids_.push_back(num_materials > 0 ? materials[std::min(i, num_materials - 1)] : 0);
+        light_ids_.push_back(ZYGPU_NULL);
+    }
+
+    props_.push_back(p);
+    world_.push_back(Transformation{});
+    const uint32_t id = uint32_t(props_.size() - 1);
+
+    // Scene.classifyProp, scene.zig:322-340
+    if (p.solid) {
+        if (shapeFinite(shape_id)) {
+            (0 != (p.flags & ZYG_PROP_UNOCCLUDING) ? unoccluding_props_ : finite_props_).push_back(id);
+        } else {
+            infinite_props_.push_back(id);
+        }
+    }
+    return id;
+}
+
+bool SceneModel::createLight(uint32_t entity) {  // scene.zig:342-372
+    if (entity >= props_.size()) return false;
+    const PropRec& p         = props_[entity];
+    const uint32_t num_parts = p.shape >= 7 ? meshes_[p.shape - 7].num_parts : 1;
+    for (uint32_t i = 0; i < num_parts; ++i) {
+        const ZygpuMaterial& m = materials_[material_ids_[p.parts_start + i]];
+        if (0 == (m.flags & ZYG_MATERIAL_EMISSIVE)) continue;
+        ZygpuLight l{};
+        l.prop        = entity;
+        l.part        = i;
+        l.light_class = ZYG_LIGHT_PROP;  // no emission image maps in scope
+        l.two_sided   = 0 != (m.flags & ZYG_MATERIAL_TWO_SIDED);
+        l.num_samples = m.emission_num_samples;
+        lights_.push_back(l);
+    }
+    return true;
+}
+
+bool SceneModel::setWorldTransformation(uint32_t entity, const Transformation& t) {
+    if (entity >= props_.size()) return false;
+    world_[entity] = t;
+    return true;
+}
+
+bool SceneModel::setVisibility(uint32_t entity, bool in_camera, bool in_reflection, bool /*in_sss*/) {  // prop.zig:78-91
+    if (entity >= props_.size()) return false;
+    uint32_t& f = props_[entity].flags;
+    f &= ~(ZYG_PROP_VISIBLE_IN_CAMERA | ZYG_PROP_VISIBLE_IN_REFLECTION | ZYG_PROP_VISIBLE_IN_SHADOW);
+    if (in_camera) f |= ZYG_PROP_VISIBLE_IN_CAMERA;
+    if (in_reflection) f |= ZYG_PROP_VISIBLE_IN_REFLECTION | ZYG_PROP_VISIBLE_IN_SHADOW;
+    return true;
+}
+
+void SceneModel::setCamera(uint32_t width, uint32_t height) {  // capi.zig:143-167
+    resolution_[0] = int32_t(width);
+    resolution_[1] = int32_t(height);
+    fov_           = degreesToRadians(80.f);
+    if (ZYGPU_NULL == camera_entity_) camera_entity_ = createEntity();
+}
+
+void SceneModel::loadIntegrators(const json::Value& value) {
+    if (const json::Value* st = value.get("specular_threshold")) {
+        const float s       = float(st->number);
+        specular_threshold_ = s * s;
+    }
+    const json::Value* surface = value.get("surface");
+    if (!surface || json::Value::Object != surface->kind) return;
+    for (const auto& entry : surface->object) {
+        if ("PTMIS" != entry.first) continue;  // only PathtracerMIS is implemented
+        const json::Value& v   = entry.second;
+        regularize_roughness_  = json::readFloatMember(v, "regularize_roughness", 0.f);
+        caustics_path_         = json::readBoolMember(v, "caustics", true);
+        max_depth_surface_     = 16;  // take.zig:77
+        max_depth_volume_      = 256;
+        if (const json::Value* d = v.get("depth")) {  // loadDepth reads "surface" for both, take.zig:254-261
+            max_depth_surface_ = json::readUIntMember(*d, "surface", 16) & 0xFFFFu;
+            max_depth_volume_  = json::readUIntMember(*d, "surface", 256) & 0xFFFFu;
+        }
+        float st = 0.5f;  // take.zig:263-271
+        if (const json::Value* ls = v.get("light_sampling")) {
+            st = json::readFloatMember(*ls, "split_threshold", 0.5f);
+            st = st < 0.f ? 0.f : (st > 1.f ? 1.f : st);
+        }
+        const float st2  = st * st;
+        split_threshold_ = st2 * st2;
+        ptmis_           = true;
+    }
+}
+
+void SceneModel::loadSensor(const json::Value& value) {
+    clamp_[0] = clamp_[1] = clamp_[2] = FLT_MAX;
+    if (const json::Value* c = value.get("clamp")) {
+        if (json::Value::Object == c->kind) {
+            clamp_[0] = json::readFloatMember(*c, "emission", clamp_[0]);
+            clamp_[1] = json::readFloatMember(*c, "direct", clamp_[1]);
+            clamp_[2] = json::readFloatMember(*c, "indirect", clamp_[2]);
+        }
+    }
+    filter_kind_   = FilterKind::None;
+    filter_radius_ = 0.f;
+    if (const json::Value* f = value.get("filter")) {
+        for (const auto& entry : f->object) {
+            if ("Blackman" == entry.first) {
+                filter_kind_   = FilterKind::Blackman;
+                filter_radius_ = 2.f;
+                break;
+            }
+            if ("Mitchell" == entry.first) {
+                filter_kind_   = FilterKind::Mitchell;
+                filter_radius_ = 2.f;
+                break;
+            }
+        }
+    }
+}
+
+void SceneModel::loadSampler(const json::Value& value) {
+    sampler_ = ZYG_SAMPLER_SOBOL;
+    for (const auto& entry : value.object) {
+        spp_ = json::readUIntMember(entry.second, "samples_per_pixel", 1);
+        if ("Random" == entry.first) {
+            sampler_ = ZYG_SAMPLER_RANDOM;
+            return;
+        }
+    }
+}
+
+AABB SceneModel::shapeAabb(uint32_t shape) const {  // shape.zig:108-115
+    switch (shape) {
+        case ZYG_SHAPE_CANOPY:
+        case ZYG_SHAPE_DISTANT:
+        case ZYG_SHAPE_DOME: return AABB::empty();
+        case ZYG_SHAPE_DISK:
+        case ZYG_SHAPE_RECTANGLE: return {{{{-0.5f, -0.5f, 0.f, 0.f}}, {{0.5f, 0.5f, 0.f, 0.f}}}};
+        case ZYG_SHAPE_CUBE:
+        case ZYG_SHAPE_SPHERE: return {{splat(-0.5f), splat(0.5f)}};
+        default: return meshes_[shape - 7].mesh->tree.aabb();
+    }
+}
+
+// PropBvhBuilder.build + serialize, prop_tree_builder.zig:24-96
+void SceneModel::buildPropTree(const std::vector<uint32_t>& indices, std::vector<ZygpuBvhNode>& nodes,
+                               std::vector<uint32_t>& out_indices) {
+    nodes.clear();
+    out_indices.clear();
+    if (indices.empty()) return;
+
+    std::vector<Reference> references(indices.size());
+    AABB                   bounds = AABB::empty();
+    for (size_t i = 0; i < indices.size(); ++i) {
+        const ZygpuAabb& b  = flat_aabbs_[indices[i]];
+        const Vec4f      mi = {{b.min[0], b.min[1], b.min[2], b.min[3]}};
+        const Vec4f      ma = {{b.max[0], b.max[1], b.max[2], b.max[3]}};
+        references[i].set(mi, ma, indices[i]);
+        bounds.mergeAssign({{mi, ma}});
+    }
+
+    BuildResult build;
+    buildBinaryBvh(std::move(references), bounds, 16, 64, 4, 0, build);
+
+    nodes.assign(build.build_nodes.size(), ZygpuBvhNode{});
+    out_indices.assign(build.reference_ids.size(), 0);
+
+    struct Item {
+        uint32_t src, dst;
+    };
+    uint32_t          current_node = 1, current_prop = 0;
+    std::vector<Item> stack{{0, 0}};
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        const BvhNode& node = build.build_nodes[it.src];
+        ZygpuBvhNode   n;
+        for (int k = 0; k < 3; ++k) {
+            n.min[k] = node.min[k];
+            n.max[k] = node.max[k];
+        }
+        if (0 == node.numIndices()) {
+            const uint32_t child0 = current_node;
+            n.children_or_start   = child0;
+            n.num_indices         = 0;
+            current_node += 2;
+            stack.push_back({node.children() + 1, child0 + 1});
+            stack.push_back({node.children(), child0});
+        } else {
+            const uint32_t num  = node.numIndices();
+            n.children_or_start = current_prop;
+            n.num_indices       = num;
+            for (uint32_t k = 0; k < num; ++k) out_indices[current_prop + k] = build.reference_ids[node.children() + k];
+            current_prop += num;
+        }
+        nodes[it.dst] = n;
+    }
+}
+
+// LightTreeBuilder.build, light_tree_builder.zig:281-376. Only the degenerate tree over at most one finite
+// light is produced so far (one leaf holding that light); scenes with more lights are rejected at compile.
+bool SceneModel::buildLightTree(std::string& error) {
+    const uint32_t num_lights = uint32_t(lights_.size());
+    light_mapping_.assign(num_lights, 0);
+    light_orders_.assign(num_lights, 0);
+    light_nodes_.clear();
+    light_node_middles_.clear();
+
+    uint32_t lm = 0, order = 0;
+    for (uint32_t l = 0; l < num_lights; ++l) {
+        if (!shapeFinite(props_[lights_[l].prop].shape)) light_mapping_[lm++] = l;
+    }
+    const uint32_t num_infinite = lm;
+    for (uint32_t l = 0; l < num_lights; ++l) {
+        if (shapeFinite(props_[lights_[l].prop].shape)) light_mapping_[lm++] = l;
+    }
+    float infinite_total_power = 0.f;
+    for (uint32_t i = 0; i < num_infinite; ++i) {
+        light_orders_[light_mapping_[i]] = order++;
+        infinite_total_power += light_aabbs_[light_mapping_[i]].min[3];
+    }
+    const uint32_t num_finite = num_lights - num_infinite;
+    if (num_finite > 1 || num_infinite > 1) {
+        error = "light tree over more than one finite / infinite light is not implemented yet";
+        return false;
+    }
+
+    ZygpuLightTree& t     = flat_.light_tree;
+    t                     = ZygpuLightTree{};
+    t.infinite_end        = order;
+    t.max_split_depth     = 10;  // Tree.MaxSplitDepth
+    t.num_lights          = num_lights;
+    t.num_infinite_lights = num_infinite;
+
+    float finite_power = 0.f;
+    if (1 == num_finite) {
+        const uint32_t   l   = light_mapping_[num_infinite];
+        const ZygpuAabb& box = light_aabbs_[l];
+        light_orders_[l]     = order++;
+        finite_power         = box.min[3];
+
+        ZygpuLightNode node{};
+        node.power      = finite_power;
+        node.variance   = 0.f;
+        node.meta       = (0u << 2) | (lights_[l].two_sided ? 2u : 0u);  // leaf, children_or_light = 0 (offset into light_mapping)
+        node.num_lights = 1;
+        // a single-light leaf never reads center / cone (light_tree.zig:100-104, 155-159)
+        light_nodes_.push_back(node);
+        light_node_middles_.push_back(0);
+        t.bounds = box;
+        // countPotentialLights over a lone leaf: split_lights[0] = {1, 0} -> max_split_depth = 0
+        t.max_split_depth = 0;
+        // children_or_light indexes light_mapping, which lists infinite lights first
+        light_nodes_[0].meta = (num_infinite << 2) | (lights_[l].two_sided ? 2u : 0u);
+    }
+    t.num_nodes = uint32_t(light_nodes_.size());
+
+    const float p0 = infinite_total_power;
+    const float p1 = finite_power;
+    const float pt = p0 + p1;
+    t.infinite_weight = (0 == num_lights || 0.f == pt) ? 0.f : p0 / pt;
+    t.infinite_guard  = 0 == num_finite ? (0 == num_infinite ? 0.f : 1.1f) : t.infinite_weight;
+
+    t.nodes         = light_nodes_.data();
+    t.node_middles  = light_node_middles_.data();
+    t.light_orders  = light_orders_.data();
+    t.light_mapping = light_mapping_.data();
+    return true;
+}
+
+bool SceneModel::compile(std::string& error) {
+    if (ZYGPU_NULL == camera_entity_) {
+        error = "no camera";  // Error.NoCameraProp, driver.zig:122-124
+        return false;
+    }
+    const std::vector<float>& luts = ggxLuts(error);
+    if (luts.empty()) return false;
+
+    const uint32_t num_props = uint32_t(props_.size());
+    const Vec4f    origin    = world_[camera_entity_].position;  // Scene.propWorldPosition, driver.zig:163
+
+    flat_props_.resize(num_props);
+    flat_trafos_.resize(num_props);
+    flat_aabbs_.resize(num_props);
+
+    for (uint32_t i = 0; i < num_props; ++i) {
+        const PropRec&        p = props_[i];
+        const Transformation& t = world_[i];
+
+        // ComposedTransformation.init, composed_transformation.zig:19-31
+        Mat3x3 rot  = quaternionToMat3x3(t.rotation);
+        rot.r[0][3] = t.scale[0];
+        rot.r[1][3] = t.scale[1];
+        rot.r[2][3] = t.scale[2];
+
+        // Space.calculateWorldBounds, space.zig:60-97 (static prop)
+        const Vec4f scale  = {{t.scale[0], t.scale[1], t.scale[2], 1.f}};
+        AABB        bounds = transformAabb(shapeAabb(p.shape), compose(rot, scale, t.position));
+        bounds.translate(-origin);
+        bounds.cacheRadius();
+        flat_aabbs_[i] = packAabb(bounds);
+
+        // Space.transformationAtMaybeStatic, space.zig:103-111
+        ZygpuTrafo& ft = flat_trafos_[i];
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 4; ++c) ft.r[r][c] = rot.r[r][c];
+        }
+        const Vec4f pos = t.position + (-origin);
+        for (int c = 0; c < 4; ++c) ft.position[c] = pos[c];
+
+        ZygpuProp& fp  = flat_props_[i];
+        fp.shape       = p.shape >= 7 ? ZYG_SHAPE_TRIANGLE_MESH : p.shape;
+        fp.mesh        = p.shape >= 7 ? p.shape - 7 : ZYGPU_NULL;
+        fp.flags       = p.flags;
+        fp.parts_start = p.parts_start;
+    }
+
+    buildPropTree(finite_props_, solid_nodes_, solid_indices_);
+    buildPropTree(unoccluding_props_, unocc_nodes_, unocc_indices_);
+
+    // Scene.propPrepareSampling, scene.zig:402-497 (static props, analytic shapes)
+    const uint32_t num_lights = uint32_t(lights_.size());
+    light_aabbs_.resize(num_lights);
+    light_cones_.resize(size_t(num_lights) * 4);
+    for (uint32_t l = 0; l < num_lights; ++l) {
+        const ZygpuLight&     light = lights_[l];
+        const PropRec&        p     = props_[light.prop];
+        const Transformation& t     = world_[light.prop];
+
+        light_ids_[p.parts_start + light.part] = l;
+
+        Mat3x3 rot  = quaternionToMat3x3(t.rotation);
+        rot.r[0][3] = t.scale[0];
+        rot.r[1][3] = t.scale[1];
+        rot.r[2][3] = t.scale[2];
+        const Vec4f scale = {{t.scale[0], t.scale[1], t.scale[2], 1.f}};
+        const Vec4f pos   = t.position + (-origin);
+
+        AABB bb = transformAabb(shapeAabb(p.shape), compose(rot, scale, pos));
+        bb.cacheRadius();
+
+        // shape.cone(), shape.zig:117-122
+        const bool  flat_shape = ZYG_SHAPE_DISK == p.shape || ZYG_SHAPE_RECTANGLE == p.shape || ZYG_SHAPE_DISTANT == p.shape;
+        const Vec4f part_cone  = {{0.f, 0.f, 1.f, flat_shape ? 1.f : -1.f}};
+        const Vec4f tc         = transformVector(rot, part_cone);
+        light_cones_[l * 4 + 0] = tc[0];
+        light_cones_[l * 4 + 1] = tc[1];
+        light_cones_[l * 4 + 2] = tc[2];
+        light_cones_[l * 4 + 3] = part_cone[3];
+
+        // shape.area, shape.zig:143-156
+        float extent = 0.f;
+        switch (p.shape) {
+            case ZYG_SHAPE_RECTANGLE: extent = scale[0] * scale[1]; break;
+            case ZYG_SHAPE_SPHERE: extent = (4.f * kPi) * ((0.5f * scale[0]) * (0.5f * scale[0])); break;
+            case ZYG_SHAPE_CUBE: extent = 2.f * (scale[0] * scale[1] + scale[0] * scale[2] + scale[1] * scale[2]); break;
+            case ZYG_SHAPE_DISK: extent = kPi * ((0.5f * scale[0]) * (0.5f * scale[0])); break;
+            default: break;
+        }
+
+        // Emittance.totalEmission (emittance.zig:61-71) of the average radiance (= emittance value for uniform
+        // emission), then Light.power (light.zig:65-75; finite lights)
+        const ZygpuMaterial& m     = materials_[material_ids_[p.parts_start + light.part]];
+        Vec4f                power = {{m.emission[0], m.emission[1], m.emission[2], 0.f}};
+        if (extent <= 0.f) {
+            power = splat(0.f);
+        } else if (0.f == m.emission_normalize) {
+            power = power * splat(extent);
+        }
+        bb.b[0][3] = fmax_(power[0], fmax_(power[1], power[2]));  // hmax3
+        light_aabbs_[l] = packAabb(bb);
+    }
+
+    flat_ = ZygpuScene{};
+    if (!buildLightTree(error)) return false;
+
+    flat_meshes_.clear();
+    for (const MeshRec& m : meshes_) flat_meshes_.push_back(m.mesh);
+
+    flat_.num_props          = num_props;
+    flat_.num_parts          = uint32_t(material_ids_.size());
+    flat_.num_materials      = uint32_t(materials_.size());
+    flat_.num_lights         = num_lights;
+    flat_.num_infinite_props = uint32_t(infinite_props_.size());
+    flat_.num_meshes         = uint32_t(flat_meshes_.size());
+    flat_.props              = flat_props_.data();
+    flat_.trafos             = flat_trafos_.data();
+    flat_.aabbs              = flat_aabbs_.data();
+    flat_.material_ids       = material_ids_.data();
+    flat_.light_ids          = light_ids_.data();
+    flat_.materials          = materials_.data();
+    flat_.lights             = lights_.data();
+    flat_.light_aabbs        = light_aabbs_.data();
+    flat_.light_cones        = light_cones_.data();
+    flat_.solid_bvh          = {uint32_t(solid_nodes_.size()), uint32_t(solid_indices_.size()), solid_nodes_.data(), solid_indices_.data()};
+    flat_.unoccluding_bvh    = {uint32_t(unocc_nodes_.size()), uint32_t(unocc_indices_.size()), unocc_nodes_.data(), unocc_indices_.data()};
+    flat_.infinite_props     = infinite_props_.data();
+    flat_.meshes             = flat_meshes_.data();
+    flat_.ggx_luts           = luts.data();
+
+    // ---- view ----
+    ZygpuView& v    = view_;
+    v               = ZygpuView{};
+    v.resolution[0] = resolution_[0];
+    v.resolution[1] = resolution_[1];
+    v.crop[0] = v.crop[1] = 0;
+    v.crop[2]             = resolution_[0];
+    v.crop[3]             = resolution_[1];
+
+    {  // Perspective.update, camera_perspective.zig:79-122 (mono)
+        const float fr0   = float(resolution_[0]);
+        const float fr1   = float(resolution_[1]);
+        const float ratio = fr1 / fr0;
+        const float z     = 1.f / std::tan(0.5f * fov_);
+
+        const Vec4f left_top    = {{-1.f, ratio, z, 0.f}};
+        const Vec4f right_top   = {{1.f, ratio, z, 0.f}};
+        const Vec4f left_bottom = {{-1.f, -ratio, z, 0.f}};
+        const Vec4f d_x         = (right_top - left_top) / splat(fr0);
+        const Vec4f d_y         = (left_bottom - left_top) / splat(fr1);
+        for (int c = 0; c < 4; ++c) {
+            v.left_top[c]   = left_top[c];
+            v.d_x[c]        = d_x[c];
+            v.d_y[c]        = d_y[c];
+            v.eye_offset[c] = 0.f;
+        }
+    }
+    v.camera_trafo    = flat_trafos_[camera_entity_];
+    v.aperture_radius = aperture_radius_;
+    v.focus_distance  = focus_distance_;
+
+    v.sampler   = sampler_;
+    v.spp_total = spp_;
+
+    v.max_depth_surface    = max_depth_surface_;
+    v.max_depth_volume     = max_depth_volume_;
+    v.split_threshold      = split_threshold_;
+    v.regularize_roughness = regularize_roughness_;
+    v.caustics_path        = caustics_path_ ? 1u : 0u;
+    v.specular_threshold   = specular_threshold_;
+
+    v.clamp_emission = clamp_[0];
+    v.clamp_direct   = clamp_[1];
+    v.clamp_indirect = clamp_[2];
+
+    {  // Sensor.init, sensor.zig:106-124 + InterpolatedFunction1DN.init, interpolated_function.zig:100-120
+        const float radius      = filter_radius_;
+        v.filter_radius_int     = int32_t(std::ceil(radius));
+        const float interval    = (radius - 0.f) / float(30 - 1);
+        v.filter_range_end      = radius;
+        v.filter_inverse_interval = 1.f / interval;
+
+        auto evalFilter = [&](float x) -> float {
+            if (FilterKind::Mitchell == filter_kind_) {  // sensor.zig:42-58
+                const float b = 1.f / 3.f, c = 1.f / 3.f;
+                const float xx = x * x;
+                if (x > 1.f) {
+                    return ((-b - 6.f * c) * xx * x + (6.f * b + 30.f * c) * xx + (-12.f * b - 48.f * c) * x + (8.f * b + 24.f * c)) / 6.f;
+                }
+                return ((12.f - 9.f * b - 6.f * c) * xx * x + (-18.f + 12.f * b + 6.f * c) * xx + (6.f - 2.f * b)) / 6.f;
+            }
+            // Blackman, sensor.zig:27-40
+            const float a0 = 0.35875f, a1 = 0.48829f, a2 = 0.14128f, a3 = 0.01168f;
+            const float b  = (kPi * (x + radius)) / radius;
+            return a0 - a1 * std::cos(b) + a2 * std::cos(2.f * b) - a3 * std::cos(3.f * b);
+        };
+
+        float s = 0.f;
+        for (int i = 0; i < 30; ++i) {
+            v.filter[i] = evalFilter(s);
+            s += interval;
+        }
+
+        if (radius > 0.f) {
+            auto eval = [&](float x) -> float {  // InterpolatedFunction1DN.eval, :131-143
+                const float    cx     = fmin_(std::fabs(x), v.filter_range_end);
+                const float    o      = cx * v.filter_inverse_interval;
+                const uint32_t offset = uint32_t(o);
+                const float    t      = o - float(offset);
+                const float    u      = 1.f - t;
+                return std::fmaf(u, v.filter[offset], t * v.filter[std::min(offset + 1, 29u)]);
+            };
+            // Sensor.integral(64, radius), sensor.zig:630-645
+            const float ival = radius / 64.f;
+            float       x    = 0.5f * ival;
+            float       sum  = 0.f;
+            for (int i = 0; i < 64; ++i) {
+                const float a = eval(x) * ival;
+                sum += a;
+                x += ival;
+            }
+            const float scale = 1.f / (sum + sum);
+            for (int i = 0; i < 30; ++i) v.filter[i] *= scale;
+        }
+    }
+    v.exposure_factor = 1.f;  // Tonemapper.init(.Linear, 0.0): exp2(0)
+
+    if (!ptmis_) {
+        error = "only the PTMIS surface integrator is implemented: call su_integrators_create with {\"surface\":{\"PTMIS\":{}}}";
+        return false;
+    }
+    return true;
+}
+
+}  // namespace zyg

@@ -1,0 +1,156 @@
+// Host-side scene model of the backend: what a zyg host keeps between su_* calls (Scene, Take.View,
+// the material / shape resources) reduced to the parts the surface-integration path consumes, plus
+// `compile`, which flattens it into the ZygpuScene / ZygpuView arrays of include/zygpu_scene.h.
+//
+// Mirrors, for static scenes:
+//   Scene.createEntity / createPropShape / createLight / classifyProp   src/core/scene/scene.zig:254-380
+//   Scene.compile, propPrepareSampling                                  scene.zig:185-223, 402-497
+//   Space.calculateWorldBounds / transformationAtMaybeStatic            src/core/scene/space.zig:60-111
+//   Prop.configureShape / setVisibility                                 src/core/scene/prop/prop.zig:78-135
+//   PropBvhBuilder                                                      src/core/scene/prop/prop_tree_builder.zig
+//   material JSON                                                       src/core/scene/material/material_provider.zig
+//   View.loadIntegrators, Sensor.init, Perspective.update               take.zig:131-271, sensor.zig:106-124,
+//                                                                       camera_perspective.zig:79-122
+#pragma once
+
+#include "../../../include/zygpu_scene.h"
+#include "json.hpp"
+#include "zmath.hpp"
+
+#include <string>
+#include <vector>
+
+struct zyg_mesh;
+
+namespace zyg {
+
+struct Transformation {  // src/base/math/transformation.zig
+    Vec4f position{{0.f, 0.f, 0.f, 0.f}};
+    Vec4f scale{{1.f, 1.f, 1.f, 1.f}};
+    Vec4f rotation{{0.f, 0.f, 0.f, 1.f}};  // quaternion
+};
+
+struct Mat3x3 {
+    Vec4f r[3];
+};
+
+Mat3x3 quaternionToMat3x3(Vec4f q);                    // quaternion.zig:73-112
+Vec4f  quaternionFromMat3x3(const Mat3x3& m);          // quaternion.zig:14-37
+Mat3x3 rotationFromEulerDegrees(Vec4f xyz);            // json.zig:169-175 (createRotationMatrix)
+void   decomposeMatrix(const float m[16], Transformation& out);  // matrix4x4.zig:109-121 + capi.zig:485-503
+Vec4f  sRGBtoAP1(Vec4f srgb);                          // src/base/spectrum/aces.zig:9-17
+
+enum class FilterKind { None, Blackman, Mitchell };
+
+class SceneModel {
+  public:
+    SceneModel();
+
+    // ---- resources ----
+    // `rendering` is the JSON object holding one of "Substitute" / "Light" / "Glass" / "Debug"
+    // (material_provider.zig:131-161). Returns the material id or -1.
+    int  createMaterial(const json::Value& material);
+    bool updateMaterial(uint32_t id, const json::Value& material);
+    // Registers a compiled mesh as a shape resource; returns the shape id (>= 7).
+    uint32_t addMesh(const zyg_mesh* mesh, uint32_t num_parts);
+    uint32_t numShapes() const { return 7 + uint32_t(meshes_.size()); }
+    uint32_t numMaterials() const { return uint32_t(materials_.size()); }
+    uint32_t fallbackMaterial() const { return 0; }
+
+    // ---- scene ----
+    uint32_t createEntity();  // scene.zig:254-260
+    uint32_t createPropShape(uint32_t shape_id, const uint32_t* materials, uint32_t num_materials, bool unoccluding);
+    bool     createLight(uint32_t entity);
+    bool     setWorldTransformation(uint32_t entity, const Transformation& t);
+    bool     setVisibility(uint32_t entity, bool in_camera, bool in_reflection, bool in_sss);
+    uint32_t numProps() const { return uint32_t(props_.size()); }
+
+    // ---- view ----
+    void setCamera(uint32_t width, uint32_t height);  // su_perspective_camera_create
+    void setFov(float radians) { fov_ = radians; }
+    void setLens(float aperture_radius, float focus_distance) {
+        aperture_radius_ = aperture_radius;
+        focus_distance_  = focus_distance;
+    }
+    void setSamplesPerPixel(uint32_t spp) { spp_ = spp; }
+    void loadIntegrators(const json::Value& value);  // take.zig:131-148
+    void loadSensor(const json::Value& value);       // take_loader.zig:186-232
+    void loadSampler(const json::Value& value);      // take_loader.zig:142-158
+    uint32_t cameraEntity() const { return camera_entity_; }
+    uint32_t width() const { return uint32_t(resolution_[0]); }
+    uint32_t height() const { return uint32_t(resolution_[1]); }
+    uint32_t samplesPerPixel() const { return spp_; }
+
+    // Scene.compile + camera.update for the current camera position. The returned records point into
+    // storage owned by the model and stay valid until the next compile or edit.
+    bool compile(std::string& error);
+
+    const ZygpuScene& scene() const { return flat_; }
+    const ZygpuView&  view() const { return view_; }
+
+  private:
+    struct PropRec {
+        uint32_t shape       = ZYGPU_NULL;
+        uint32_t flags       = ZYG_PROP_VISIBLE_IN_CAMERA | ZYG_PROP_VISIBLE_IN_REFLECTION | ZYG_PROP_VISIBLE_IN_SHADOW;
+        uint32_t parts_start = 0;
+        bool     solid       = true;
+        bool     classified  = false;
+    };
+    struct MeshRec {
+        const zyg_mesh* mesh;
+        uint32_t        num_parts;
+    };
+
+    bool shapeFinite(uint32_t shape) const;
+    AABB shapeAabb(uint32_t shape) const;
+    void buildPropTree(const std::vector<uint32_t>& indices, std::vector<ZygpuBvhNode>& nodes, std::vector<uint32_t>& out_indices);
+    bool buildLightTree(std::string& error);
+
+    std::vector<ZygpuMaterial>  materials_;
+    std::vector<MeshRec>        meshes_;
+    std::vector<PropRec>        props_;
+    std::vector<Transformation> world_;
+    std::vector<uint32_t>       material_ids_, light_ids_;
+    std::vector<ZygpuLight>     lights_;
+    std::vector<uint32_t>       finite_props_, infinite_props_, unoccluding_props_;
+
+    // view
+    int32_t  resolution_[2]   = {0, 0};
+    float    fov_             = 0.f;
+    float    aperture_radius_ = 0.f;
+    float    focus_distance_  = 0.f;
+    uint32_t camera_entity_   = ZYGPU_NULL;
+    uint32_t spp_             = 1;
+    uint32_t sampler_         = ZYG_SAMPLER_SOBOL;
+
+    uint32_t max_depth_surface_ = 1, max_depth_volume_ = 1;  // take.zig:43-52 (default AOV integrator)
+    float    split_threshold_   = 0.f;
+    float    regularize_roughness_ = 0.f;
+    bool     caustics_path_     = true;
+    bool     ptmis_             = false;
+    float    specular_threshold_;
+
+    FilterKind filter_kind_   = FilterKind::Mitchell;  // take.zig:59-64
+    float      filter_radius_ = 2.f;
+    float      clamp_[3];
+
+    // flattened output
+    std::vector<ZygpuProp>      flat_props_;
+    std::vector<ZygpuTrafo>     flat_trafos_;
+    std::vector<ZygpuAabb>      flat_aabbs_;
+    std::vector<ZygpuAabb>      light_aabbs_;
+    std::vector<float>          light_cones_;
+    std::vector<ZygpuBvhNode>   solid_nodes_, unocc_nodes_;
+    std::vector<uint32_t>       solid_indices_, unocc_indices_;
+    std::vector<ZygpuLightNode> light_nodes_;
+    std::vector<uint32_t>       light_node_middles_, light_orders_, light_mapping_;
+    std::vector<const zyg_mesh*> flat_meshes_;
+    std::vector<float>          luts_;
+    ZygpuScene                  flat_{};
+    ZygpuView                   view_{};
+};
+
+// Locates and reads zyg_b200/data/ggx_luts.f32 (next to the shared library). Empty on failure.
+const std::vector<float>& ggxLuts(std::string& error);
+
+}  // namespace zyg

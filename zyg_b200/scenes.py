@@ -163,3 +163,53 @@ def random_rays(n: int, radius: float = 1.5, shadow: bool = False, first: int = 
             rays["direction"][b:e] = _sphere_uniform(u[3], u[4]).astype(np.float32)
             rays["max_t"][b:e] = RAY_MAX_T
     return rays
+
+
+# ---- config 1: Cornell box through the su_* API ------------------------------------------
+
+def cornell_box(width=512, height=512, spp=64, max_depth=8, filter_name=None, unoccluding_light=True,
+                roughness=1.0, light_value=17.0):
+    """Builds BASELINE config 1 through zyg's C API (``zyg_b200.su``): classic box x in [-1,1], y in [0,2],
+    z in [-1,1], open towards -z; five Rectangle walls, one 0.5 x 0.5 Rectangle light under the ceiling, two
+    rotated Cube props; camera at (0,1,-3.9) looking down +z with a 39 degree horizontal field of view.
+    The engine must not be initialised yet; the caller releases it with ``su.release()``."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(39.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.0, -3.9)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth},
+                                                 "light_sampling": {"split_threshold": 0.5}, "caustics": True}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    def substitute(color):
+        return su.material_create({"rendering": {"Substitute": {"color": list(color), "roughness": roughness,
+                                                                  "metallic": 0.0}}})
+
+    white = substitute((0.73, 0.73, 0.73))
+    red = substitute((0.65, 0.05, 0.05))
+    green = substitute((0.12, 0.45, 0.15))
+    light = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": [1.0, 1.0, 1.0], "value": light_value}}}})
+
+    walls = [
+        (white, (0.0, 0.0, 0.0), (90.0, 0.0, 0.0)),    # floor, normal +y
+        (white, (0.0, 2.0, 0.0), (-90.0, 0.0, 0.0)),   # ceiling, normal -y
+        (white, (0.0, 1.0, 1.0), (0.0, 180.0, 0.0)),   # back wall, normal -z
+        (red, (-1.0, 1.0, 0.0), (0.0, -90.0, 0.0)),    # left wall, normal +x
+        (green, (1.0, 1.0, 0.0), (0.0, 90.0, 0.0)),    # right wall, normal -x
+    ]
+    for material, position, rotation in walls:
+        prop = su.prop_create(su.RECTANGLE, [material])
+        su.prop_set_transformation(prop, su.transformation(position, (2.0, 2.0, 1.0), rotation))
+
+    tall = su.prop_create(su.CUBE, [white])
+    su.prop_set_transformation(tall, su.transformation((-0.35, 0.6, 0.3), (0.6, 1.2, 0.6), (0.0, 17.0, 0.0)))
+    short = su.prop_create(su.CUBE, [white])
+    su.prop_set_transformation(short, su.transformation((0.35, 0.3, -0.3), (0.6, 0.6, 0.6), (0.0, -17.0, 0.0)))
+
+    lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=unoccluding_light)
+    su.prop_set_transformation(lamp, su.transformation((0.0, 1.98, 0.0), (0.5, 0.5, 1.0), (-90.0, 0.0, 0.0)))
+    su.light_create(lamp)
+    return camera

@@ -1,0 +1,185 @@
+"""ctypes mirror of zyg's C API (``su_*``, include/zyg_su.h) as served by ``libzyg_b200.so``.
+
+Written the way ``src/capi-test/test.py`` drives ``libzyg.so``: module-level functions over one
+process-global engine, JSON strings for materials and integrators, 4x4 row-major matrices for
+transformations. No compute happens in Python.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import lib as _lib
+
+CANOPY, CUBE, DISK, DISTANT, DOME, RECTANGLE, SPHERE = range(7)  # src/core/resource/manager.zig:36-44
+
+_bound = None
+
+
+def _su() -> C.CDLL:
+    global _bound
+    if _bound is not None:
+        return _bound
+    lib = _lib.load_library()
+    u32, i32, f32, vp, cp = C.c_uint32, C.c_int32, C.c_float, C.c_void_p, C.c_char_p
+    sig = {
+        "su_init": [], "su_release": [], "su_mount": [cp],
+        "su_perspective_camera_create": [u32, u32], "su_camera_set_fov": [f32], "su_camera_sensor_dimensions": [vp],
+        "su_exporters_create": [cp], "su_aovs_create": [cp], "su_sampler_create": [u32], "su_integrators_create": [cp],
+        "su_image_create": [u32, u32, u32, u32, u32, u32, u32, vp], "su_image_update": [u32, u32, vp],
+        "su_material_create": [u32, cp], "su_material_update": [u32, cp],
+        "su_triangle_mesh_create": [u32, u32, vp, u32, vp, u32, vp, u32, vp, u32, vp, u32, vp, u32, C.c_bool],
+        "su_prop_create": [u32, u32, vp], "su_prop_create_instance": [u32], "su_light_create": [u32],
+        "su_prop_set_transformation": [u32, vp], "su_prop_set_transformation_frame": [u32, u32, vp],
+        "su_prop_set_visibility": [u32, u32, u32, u32],
+        "su_render_frame": [u32], "su_export_frame": [], "su_start_frame": [u32], "su_render_iterations": [u32],
+        "su_resolve_frame": [u32], "su_resolve_frame_to_buffer": [u32, u32, u32, vp],
+        "su_copy_framebuffer": [u32, u32, u32, u32, vp], "su_register_log": [vp], "su_register_progress": [vp, vp],
+        "zyg_su_sensor_create": [cp], "zyg_su_prop_create_unoccluding": [u32, u32, vp],
+        "zyg_su_camera_set_lens": [f32, f32], "zyg_su_set_device": [i32],
+        "zyg_su_render_frame_range": [u32, u32, u32], "zyg_su_compile": [vp, vp],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = i32
+    lib.zyg_su_device.argtypes = []
+    lib.zyg_su_device.restype = vp
+    lib.zyg_su_mesh.argtypes = [u32]
+    lib.zyg_su_mesh.restype = vp
+    _bound = lib
+    return lib
+
+
+class SuError(RuntimeError):
+    pass
+
+
+def _ok(rc: int, what: str) -> int:
+    if rc < 0:
+        raise SuError(f"{what} returned {rc}: {_su().zygpu_last_error().decode()}")
+    return rc
+
+
+def init():
+    _ok(_su().su_init(), "su_init")
+
+
+def release():
+    return _su().su_release()
+
+
+def perspective_camera_create(width: int, height: int) -> int:
+    return _ok(_su().su_perspective_camera_create(width, height), "su_perspective_camera_create")
+
+
+def camera_set_fov(radians: float):
+    _ok(_su().su_camera_set_fov(radians), "su_camera_set_fov")
+
+
+def camera_set_lens(aperture_radius: float, focus_distance: float):
+    _ok(_su().zyg_su_camera_set_lens(aperture_radius, focus_distance), "zyg_su_camera_set_lens")
+
+
+def sampler_create(spp: int):
+    _su().su_sampler_create(spp)  # returns -1 even on success (capi.zig:215-221)
+
+
+def integrators_create(desc: dict):
+    _ok(_su().su_integrators_create(json.dumps(desc).encode()), "su_integrators_create")
+
+
+def sensor_create(desc: dict):
+    _ok(_su().zyg_su_sensor_create(json.dumps(desc).encode()), "zyg_su_sensor_create")
+
+
+def material_create(desc: dict) -> int:
+    return _ok(_su().su_material_create(0xFFFFFFFF, json.dumps(desc).encode()), "su_material_create")
+
+
+def material_update(material: int, desc: dict):
+    _ok(_su().su_material_update(material, json.dumps(desc).encode()), "su_material_update")
+
+
+def triangle_mesh_create(positions, indices, normals=None, uvs=None, parts=None) -> int:
+    positions = np.ascontiguousarray(positions, np.float32)
+    indices = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+    nv, nt = positions.shape[0], indices.size // 3
+    normals = None if normals is None else np.ascontiguousarray(normals, np.float32)
+    uvs = None if uvs is None else np.ascontiguousarray(uvs, np.float32)
+    parts = None if parts is None else np.ascontiguousarray(parts, np.uint32).reshape(-1)
+    return _ok(_su().su_triangle_mesh_create(
+        0xFFFFFFFF, 0 if parts is None else parts.size // 3, None if parts is None else parts.ctypes.data, nt,
+        indices.ctypes.data, nv, positions.ctypes.data, 3, None if normals is None else normals.ctypes.data, 3, None, 0,
+        None if uvs is None else uvs.ctypes.data, 2, False), "su_triangle_mesh_create")
+
+
+def prop_create(shape: int, materials, unoccluding: bool = False) -> int:
+    mats = np.ascontiguousarray(materials, np.uint32)
+    fn = _su().zyg_su_prop_create_unoccluding if unoccluding else _su().su_prop_create
+    return _ok(fn(shape, mats.size, mats.ctypes.data), "su_prop_create")
+
+
+def light_create(prop: int):
+    _ok(_su().su_light_create(prop), "su_light_create")
+
+
+def prop_set_transformation(prop: int, matrix):
+    m = np.ascontiguousarray(matrix, np.float32).reshape(16)
+    _ok(_su().su_prop_set_transformation(prop, m.ctypes.data), "su_prop_set_transformation")
+
+
+def prop_set_visibility(prop: int, in_camera: bool, in_reflection: bool, in_sss: bool = False):
+    _ok(_su().su_prop_set_visibility(prop, int(in_camera), int(in_reflection), int(in_sss)), "su_prop_set_visibility")
+
+
+def render_frame(frame: int = 0):
+    _ok(_su().su_render_frame(frame), "su_render_frame")
+
+
+def render_frame_range(frame: int, iteration: int, num_samples: int):
+    _ok(_su().zyg_su_render_frame_range(frame, iteration, num_samples), "zyg_su_render_frame_range")
+
+
+def start_frame(frame: int = 0):
+    _ok(_su().su_start_frame(frame), "su_start_frame")
+
+
+def render_iterations(n: int):
+    _ok(_su().su_render_iterations(n), "su_render_iterations")
+
+
+def resolve_frame_to_buffer(width: int, height: int) -> np.ndarray:
+    out = np.empty((height, width, 4), np.float32)
+    _ok(_su().su_resolve_frame_to_buffer(0xFFFFFFFF, width, height, out.ctypes.data), "su_resolve_frame_to_buffer")
+    return out
+
+
+def compile_scene():
+    """Scene.compile + camera.update on the host. Returns (ZygpuScene*, ZygpuView*) as integers for the
+    oracle and the device ABI; valid until the scene is edited."""
+    scene, view = C.c_void_p(), C.c_void_p()
+    _ok(_su().zyg_su_compile(C.byref(scene), C.byref(view)), "zyg_su_compile")
+    return scene.value, view.value
+
+
+def device_handle():
+    return _su().zyg_su_device()
+
+
+def transformation(position=(0, 0, 0), scale=(1, 1, 1), rotation_deg=(0, 0, 0)) -> np.ndarray:
+    """Row-major 4x4 in the layout su_prop_set_transformation expects: rows 0-2 = scaled basis vectors, row 3 =
+    position. The rotation follows json.createRotationMatrix (src/base/json.zig:169-175): Rz * Rx * Ry."""
+    ax, ay, az = np.radians(np.asarray(rotation_deg, np.float64))
+    rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+    rot = rz @ rx @ ry
+    m = np.zeros((4, 4), np.float32)
+    m[:3, :3] = (rot * np.asarray(scale, np.float64)[:, None]).astype(np.float32)
+    m[3, :3] = position
+    m[3, 3] = 1
+    return m
