@@ -1,0 +1,85 @@
+// Shared state behind the opaque `zygpu_device` handle (include/zygpu.h) and the error helpers of the C ABI.
+#pragma once
+
+#include "../../../include/zygpu.h"
+
+#include "../device/render.cuh"
+#include "../device/trace.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+inline std::string& zygpuError() {
+    thread_local std::string error;
+    return error;
+}
+
+inline int fail(const char* fmt, ...) {
+    char    buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    zygpuError() = buf;
+    return -1;
+}
+
+#define CUDA_OK(expr)                                                                    \
+    do {                                                                                 \
+        const cudaError_t e_ = (expr);                                                   \
+        if (cudaSuccess != e_) return fail("%s: %s", #expr, cudaGetErrorString(e_));     \
+    } while (0)
+
+struct DeviceMesh {
+    zygpu::MeshDevice  view{};
+    zygpu::MeshShading shading{};
+    const zyg_mesh*    source     = nullptr;
+    void*              buffers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+// Everything the render entry points keep on the device (capi/zygpu_render.cu).
+struct RenderState {
+    std::vector<void*> scene_buffers;  // freed on the next upload
+    zygpu::SceneDevice scene{};
+    bool               has_scene = false;
+    ZygpuView          view{};
+    bool               has_view = false;
+
+    zygpu::PathState   paths{};
+    std::vector<void*> path_buffers;
+    uint32_t           max_light_samples = 1;  // shadow records one path may need
+
+    float4*  film        = nullptr;
+    float4*  resolved    = nullptr;
+    uint32_t film_pixels = 0;
+
+    cudaStream_t stream = nullptr;
+
+    ZygpuRenderStats stats{};
+};
+
+struct zygpu_device {
+    int                     ordinal = 0;
+    std::vector<DeviceMesh> meshes;
+
+    // staging for the host-buffer entry point
+    static constexpr int      kStreams    = 3;
+    static constexpr uint64_t kChunkRays  = 1u << 20;
+    cudaStream_t              streams[kStreams] = {};
+    void*                     d_rays[kStreams]  = {};
+    void*                     d_out[kStreams]   = {};
+    zygpu::TraceCounters*     d_counters        = nullptr;
+
+    // work counters of the persistent kernels: one per in-flight launch, handed out round-robin
+    static constexpr int kWorkCounters = 64;
+    uint32_t*            d_work        = nullptr;
+    int                  next_work     = 0;
+    uint32_t*            workCounter() { return d_work + (next_work++ % kWorkCounters); }
+
+    RenderState render;
+};
+
+void zygpuReleaseRender(zygpu_device* dev);
+

@@ -1,7 +1,7 @@
 // C-ABI of the device backend (include/zygpu.h). CUDA runtime API underneath; no torch types.
 #include "../../../include/zygpu.h"
 
-#include "../device/trace.cuh"
+#include "device_state.hpp"
 #include "../host/mesh_handle.hpp"
 #include "../host/wide_bvh.hpp"
 
@@ -13,56 +13,11 @@
 #include <thread>
 #include <vector>
 
-namespace {
 
-thread_local std::string g_error;
-
-int fail(const char* fmt, ...) {
-    char    buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    g_error = buf;
-    return -1;
-}
-
-#define CUDA_OK(expr)                                                                    \
-    do {                                                                                 \
-        const cudaError_t e_ = (expr);                                                   \
-        if (cudaSuccess != e_) return fail("%s: %s", #expr, cudaGetErrorString(e_));     \
-    } while (0)
-
-}  // namespace
-
-
-struct DeviceMesh {
-    zygpu::MeshDevice view{};
-    void*             buffers[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-};
-
-struct zygpu_device {
-    int                     ordinal = 0;
-    std::vector<DeviceMesh> meshes;
-
-    // staging for the host-buffer entry point
-    static constexpr int      kStreams    = 3;
-    static constexpr uint64_t kChunkRays  = 1u << 20;
-    cudaStream_t              streams[kStreams] = {};
-    void*                     d_rays[kStreams]  = {};
-    void*                     d_out[kStreams]   = {};
-    zygpu::TraceCounters*     d_counters        = nullptr;
-
-    // work counters of the persistent kernels: one per in-flight launch, handed out round-robin
-    static constexpr int kWorkCounters = 64;
-    uint32_t*            d_work        = nullptr;
-    int                  next_work     = 0;
-    uint32_t*            workCounter() { return d_work + (next_work++ % kWorkCounters); }
-};
 
 extern "C" {
 
-const char* zygpu_last_error(void) { return g_error.c_str(); }
+const char* zygpu_last_error(void) { return zygpuError().c_str(); }
 
 int zyg_mesh_build(uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles, const uint32_t* indices,
                    uint32_t num_vertices, const float* positions, uint32_t positions_stride, const float* normals,
@@ -198,6 +153,7 @@ void zygpu_destroy(zygpu_device* dev) {
     }
     cudaFree(dev->d_counters);
     cudaFree(dev->d_work);
+    zygpuReleaseRender(dev);
     delete dev;
 }
 
@@ -209,13 +165,22 @@ int zygpu_upload_mesh(zygpu_device* dev, const zyg_mesh* mesh) {
     const auto& t = mesh->tree;
     const auto& w = mesh->wide;
 
-    const void*  src[5]   = {w.nodes.data(), w.triangles.data(), t.nodes.data(), t.triangles.data(), t.positions.data()};
-    const size_t bytes[5] = {w.nodes.size() * sizeof(zyg::WideNode), w.triangles.size() * sizeof(zyg::TriRecord),
-                             t.nodes.size() * sizeof(zyg::BvhNode), t.triangles.size() * 4, t.positions.size() * 4};
-    for (int i = 0; i < 5; ++i) {
+    // an already uploaded mesh keeps its id
+    for (size_t i = 0; i < dev->meshes.size(); ++i) {
+        if (dev->meshes[i].source == mesh) return int(i);
+    }
+
+    const void*  src[8]   = {w.nodes.data(),     w.triangles.data(), t.nodes.data(), t.triangles.data(),
+                             t.positions.data(), t.normals.data(),   t.uvs.data(),   t.triangle_parts.data()};
+    const size_t bytes[8] = {w.nodes.size() * sizeof(zyg::WideNode), w.triangles.size() * sizeof(zyg::TriRecord),
+                             t.nodes.size() * sizeof(zyg::BvhNode),  t.triangles.size() * 4,
+                             t.positions.size() * 4,                 t.normals.size() * 2,
+                             t.uvs.size() * 4,                       t.triangle_parts.size() * 2};
+    for (int i = 0; i < 8; ++i) {
         CUDA_OK(cudaMalloc(&dm.buffers[i], std::max<size_t>(bytes[i], 16)));
         CUDA_OK(cudaMemcpy(dm.buffers[i], src[i], bytes[i], cudaMemcpyHostToDevice));
     }
+    dm.source              = mesh;
     dm.view.wide_nodes     = static_cast<const float4*>(dm.buffers[0]);
     dm.view.wide_tris      = static_cast<const float4*>(dm.buffers[1]);
     dm.view.binary_nodes   = static_cast<const float4*>(dm.buffers[2]);
@@ -223,6 +188,11 @@ int zygpu_upload_mesh(zygpu_device* dev, const zyg_mesh* mesh) {
     dm.view.positions      = static_cast<const float*>(dm.buffers[4]);
     dm.view.num_wide_nodes = uint32_t(w.nodes.size());
     dm.view.num_tris       = uint32_t(w.triangles.size());
+    dm.shading.triangles   = dm.view.triangles;
+    dm.shading.positions   = dm.view.positions;
+    dm.shading.normals     = static_cast<const uint16_t*>(dm.buffers[5]);
+    dm.shading.uvs         = static_cast<const float*>(dm.buffers[6]);
+    dm.shading.parts       = static_cast<const uint16_t*>(dm.buffers[7]);
 
     dev->meshes.push_back(dm);
     return int(dev->meshes.size() - 1);

@@ -1,14 +1,315 @@
-// placeholder until the device passes land
-#include "../../../include/zygpu.h"
-extern "C" {
-int zygpu_upload_scene(zygpu_device*, const ZygpuScene*) { return -1; }
-int zygpu_set_view(zygpu_device*, const ZygpuView*) { return -1; }
-int zygpu_clear_film(zygpu_device*) { return -1; }
-int zygpu_render(zygpu_device*, uint32_t, uint32_t) { return -1; }
-int zygpu_resolve(zygpu_device*, float*, uint32_t) { return -1; }
-int zygpu_download_film(zygpu_device*, float*, uint32_t) { return -1; }
-int zygpu_upload_film(zygpu_device*, const float*, uint32_t) { return -1; }
-void* zygpu_film_device(zygpu_device*, uint64_t*) { return nullptr; }
-int zygpu_synchronize(zygpu_device*) { return -1; }
-int zygpu_render_stats(zygpu_device*, ZygpuRenderStats*) { return -1; }
+// Render entry points of the device ABI (include/zygpu.h): scene / view upload and the pass loop that
+// strings the wavefront stages of device/render.cu together. Replaces Driver.renderFrameForward /
+// renderFrameIterationForward (src/core/rendering/driver.zig:309-348).
+#include "device_state.hpp"
+
+#include "../host/mesh_handle.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace {
+
+template <typename T>
+int uploadArray(RenderState& r, const T* host, size_t count, const T** device) {
+    void* d = nullptr;
+    CUDA_OK(cudaMalloc(&d, std::max<size_t>(count * sizeof(T), 16)));
+    r.scene_buffers.push_back(d);
+    if (count > 0) CUDA_OK(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *device = static_cast<const T*>(d);
+    return 0;
 }
+
+void freeAll(std::vector<void*>& buffers) {
+    for (void* b : buffers) cudaFree(b);
+    buffers.clear();
+}
+
+template <typename T>
+int allocPath(RenderState& r, T** out, size_t count) {
+    void* d = nullptr;
+    CUDA_OK(cudaMalloc(&d, std::max<size_t>(count * sizeof(T), 16)));
+    r.path_buffers.push_back(d);
+    *out = static_cast<T*>(d);
+    return 0;
+}
+
+// Path slots per pass: enough to fill the machine several times over, small enough to stay a modest share of HBM.
+uint32_t targetPathsPerPass() {
+    const char* v = getenv("ZYGPU_PATHS_PER_PASS");
+    return v ? uint32_t(std::max(1, atoi(v))) : (4u << 20);
+}
+
+int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride) {
+    if (r.paths.capacity >= capacity && r.paths.shadow_stride == shadow_stride) return 0;
+    freeAll(r.path_buffers);
+    zygpu::PathState& p = r.paths;
+    p                   = zygpu::PathState{};
+    if (0 != allocPath(r, &p.ray_o, capacity) || 0 != allocPath(r, &p.ray_d, capacity) || 0 != allocPath(r, &p.thr, capacity) ||
+        0 != allocPath(r, &p.prev_p, capacity) || 0 != allocPath(r, &p.prev_n, capacity) || 0 != allocPath(r, &p.hit, capacity) ||
+        0 != allocPath(r, &p.acc_e, capacity) || 0 != allocPath(r, &p.acc_d, capacity) || 0 != allocPath(r, &p.acc_i, capacity) ||
+        0 != allocPath(r, &p.smp, capacity) || 0 != allocPath(r, &p.rng, capacity) ||
+        0 != allocPath(r, &p.sh_o, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_p, size_t(capacity) * shadow_stride) ||
+        0 != allocPath(r, &p.sh_wi, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_n, capacity) ||
+        0 != allocPath(r, &p.queue_a, capacity) || 0 != allocPath(r, &p.queue_b, capacity) || 0 != allocPath(r, &p.counters, 8)) {
+        return -1;
+    }
+    CUDA_OK(cudaMemset(p.counters, 0, 8 * sizeof(uint32_t)));
+    p.capacity      = capacity;
+    p.shadow_stride = shadow_stride;
+    return 0;
+}
+
+}  // namespace
+
+void zygpuReleaseRender(zygpu_device* dev) {
+    RenderState& r = dev->render;
+    freeAll(r.scene_buffers);
+    freeAll(r.path_buffers);
+    cudaFree(r.film);
+    cudaFree(r.resolved);
+    if (r.stream) cudaStreamDestroy(r.stream);
+    r = RenderState{};
+}
+
+extern "C" {
+
+int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
+    if (!dev || !scene) return fail("zygpu_upload_scene: null argument");
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    RenderState& r = dev->render;
+    if (!r.stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+        CUDA_OK(zygpu::uploadSobolDirections());
+    }
+    CUDA_OK(cudaStreamSynchronize(r.stream));
+    freeAll(r.scene_buffers);
+    r.has_scene = false;
+
+    if (!scene->ggx_luts) return fail("zygpu_upload_scene: scene carries no GGX tables");
+
+    zygpu::SceneDevice& d = r.scene;
+    d                     = zygpu::SceneDevice{};
+
+    const float4* f4 = nullptr;
+    if (0 != uploadArray(r, scene->props, scene->num_props, &d.props)) return -1;
+    if (0 != uploadArray(r, reinterpret_cast<const float4*>(scene->trafos), size_t(scene->num_props) * 4, &f4)) return -1;
+    d.trafos = f4;
+    if (0 != uploadArray(r, reinterpret_cast<const float4*>(scene->aabbs), size_t(scene->num_props) * 2, &f4)) return -1;
+    d.aabbs = f4;
+    if (0 != uploadArray(r, scene->material_ids, scene->num_parts, &d.material_ids)) return -1;
+    if (0 != uploadArray(r, scene->light_ids, scene->num_parts, &d.light_ids)) return -1;
+    if (0 != uploadArray(r, scene->materials, scene->num_materials, &d.materials)) return -1;
+    if (0 != uploadArray(r, scene->lights, scene->num_lights, &d.lights)) return -1;
+    if (0 != uploadArray(r, reinterpret_cast<const float4*>(scene->light_aabbs), size_t(scene->num_lights) * 2, &f4)) return -1;
+    d.light_aabbs = f4;
+    if (0 != uploadArray(r, reinterpret_cast<const float4*>(scene->light_cones), scene->num_lights, &f4)) return -1;
+    d.light_cones = f4;
+
+    const ZygpuLightTree& lt = scene->light_tree;
+    if (0 != uploadArray(r, lt.nodes, lt.num_nodes, &d.lt_nodes)) return -1;
+    if (0 != uploadArray(r, lt.node_middles, lt.num_nodes, &d.lt_middles)) return -1;
+    if (0 != uploadArray(r, lt.light_orders, lt.num_lights, &d.lt_orders)) return -1;
+    if (0 != uploadArray(r, lt.light_mapping, lt.num_lights, &d.lt_mapping)) return -1;
+    d.lt_bounds_min      = make_float4(lt.bounds.min[0], lt.bounds.min[1], lt.bounds.min[2], lt.bounds.min[3]);
+    d.lt_bounds_max      = make_float4(lt.bounds.max[0], lt.bounds.max[1], lt.bounds.max[2], lt.bounds.max[3]);
+    d.lt_infinite_weight = lt.infinite_weight;
+    d.lt_infinite_guard  = lt.infinite_guard;
+    d.lt_infinite_end    = lt.infinite_end;
+    d.lt_max_split_depth = lt.max_split_depth;
+    d.lt_num_infinite    = lt.num_infinite_lights;
+    d.lt_num_nodes       = lt.num_nodes;
+
+    if (0 != uploadArray(r, reinterpret_cast<const float4*>(scene->solid_bvh.nodes), size_t(scene->solid_bvh.num_nodes) * 2, &f4)) return -1;
+    d.solid_nodes = f4;
+    if (0 != uploadArray(r, scene->solid_bvh.indices, scene->solid_bvh.num_indices, &d.solid_indices)) return -1;
+    d.num_solid_nodes = scene->solid_bvh.num_nodes;
+    if (0 != uploadArray(r, reinterpret_cast<const float4*>(scene->unoccluding_bvh.nodes), size_t(scene->unoccluding_bvh.num_nodes) * 2, &f4)) return -1;
+    d.unocc_nodes = f4;
+    if (0 != uploadArray(r, scene->unoccluding_bvh.indices, scene->unoccluding_bvh.num_indices, &d.unocc_indices)) return -1;
+    d.num_unocc_nodes = scene->unoccluding_bvh.num_nodes;
+
+    // meshes: uploaded once per zyg_mesh, referenced through a per-scene table
+    std::vector<zygpu::MeshDevice>  mesh_views(scene->num_meshes);
+    std::vector<zygpu::MeshShading> mesh_shading(scene->num_meshes);
+    for (uint32_t m = 0; m < scene->num_meshes; ++m) {
+        const int id = zygpu_upload_mesh(dev, scene->meshes[m]);
+        if (id < 0) return -1;
+        mesh_views[m]   = dev->meshes[size_t(id)].view;
+        mesh_shading[m] = dev->meshes[size_t(id)].shading;
+    }
+    if (0 != uploadArray(r, mesh_views.data(), mesh_views.size(), &d.meshes)) return -1;
+    if (0 != uploadArray(r, mesh_shading.data(), mesh_shading.size(), &d.mesh_shading)) return -1;
+
+    if (0 != uploadArray(r, scene->ggx_luts, size_t(ZYGPU_GGX_LUT_FLOATS), &d.luts)) return -1;
+
+    // shadow records one path vertex can need: every light the tree may return times its sample count
+    // (Tree.potentialMaxLights, light_tree.zig:331-344), capped like the reference's buffers (64 picks x 64 samples)
+    uint64_t potential = 0;
+    for (uint32_t l = 0; l < scene->num_lights; ++l) potential += std::max(1u, scene->lights[l].num_samples);
+    r.max_light_samples = uint32_t(std::min<uint64_t>(std::max<uint64_t>(potential, 1), 64u * 64u));
+
+    r.has_scene = true;
+    return 0;
+}
+
+int zygpu_set_view(zygpu_device* dev, const ZygpuView* view) {
+    if (!dev || !view) return fail("zygpu_set_view: null argument");
+    if (view->resolution[0] <= 0 || view->resolution[1] <= 0) return fail("zygpu_set_view: empty resolution");
+    if (view->filter_radius_int < 0 || view->filter_radius_int > 2) return fail("zygpu_set_view: filter radius must be 0, 1 or 2");
+    if (view->max_depth_surface > 255) return fail("zygpu_set_view: max surface depth above 255");
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    RenderState& r = dev->render;
+    if (!r.stream) {
+        CUDA_OK(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+        CUDA_OK(zygpu::uploadSobolDirections());
+    }
+    CUDA_OK(cudaStreamSynchronize(r.stream));
+
+    const uint32_t pixels = uint32_t(view->resolution[0]) * uint32_t(view->resolution[1]);
+    if (pixels != r.film_pixels) {  // Sensor.resize, sensor.zig:128-150
+        cudaFree(r.film);
+        cudaFree(r.resolved);
+        r.film = r.resolved = nullptr;
+        CUDA_OK(cudaMalloc(&r.film, size_t(pixels) * sizeof(float4)));
+        CUDA_OK(cudaMalloc(&r.resolved, size_t(pixels) * sizeof(float4)));
+        CUDA_OK(cudaMemset(r.film, 0, size_t(pixels) * sizeof(float4)));
+        r.film_pixels = pixels;
+    }
+    r.view     = *view;
+    r.has_view = true;
+    return 0;
+}
+
+int zygpu_clear_film(zygpu_device* dev) {
+    if (!dev || !dev->render.film) return fail("zygpu_clear_film: no view set");
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    RenderState& r = dev->render;
+    CUDA_OK(cudaMemsetAsync(r.film, 0, size_t(r.film_pixels) * sizeof(float4), r.stream));
+    if (r.paths.counters) CUDA_OK(cudaMemsetAsync(r.paths.counters, 0, 8 * sizeof(uint32_t), r.stream));
+    r.stats = ZygpuRenderStats{};
+    return 0;
+}
+
+int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
+    if (!dev) return fail("zygpu_render: null device");
+    RenderState& r = dev->render;
+    if (!r.has_scene || !r.has_view) return fail("zygpu_render: upload a scene and set a view first");
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+
+    const ZygpuView& view = r.view;
+    const uint32_t   fr   = uint32_t(view.filter_radius_int);
+    const uint32_t   pw   = uint32_t(view.resolution[0]) + 2 * fr;
+    const uint32_t   ph   = uint32_t(view.resolution[1]) + 2 * fr;
+    const uint64_t   padded = uint64_t(pw) * ph;
+    if (padded > 0xFFFFFFFFull) return fail("zygpu_render: resolution too large");
+
+    const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(num_samples, targetPathsPerPass() / padded)));
+    const uint64_t capacity = padded * per_pass;
+    if (capacity > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
+    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples)) return -1;
+
+    for (uint32_t done = 0; done < num_samples;) {
+        const uint32_t k = std::min(per_pass, num_samples - done);
+
+        zygpu::PassParams pass;
+        pass.iteration       = iteration + done;
+        pass.samples_in_pass = k;
+        pass.padded_w        = pw;
+        pass.padded_h        = ph;
+        pass.num_paths       = uint32_t(padded) * k;
+
+        CUDA_OK(zygpu::launchGenerate(view, r.paths, pass, r.stream));
+        r.stats.kernel_launches += 1;
+
+        // one bounce = extend, shade_a, shadow, shade_b (+ queue swap); depth max_depth_surface is the last vertex
+        // that can be reached (pathtracer_mis.zig:76-86), so max_depth + 1 extend / shade_a rounds
+        for (uint32_t bounce = 0; bounce <= view.max_depth_surface; ++bounce) {
+            CUDA_OK(zygpu::launchExtend(r.scene, r.paths, pass.num_paths, r.stream));
+            CUDA_OK(zygpu::launchShadeA(r.scene, view, r.paths, pass, pass.num_paths, r.stream));
+            r.stats.kernel_launches += 2;
+            if (bounce == view.max_depth_surface) break;
+            CUDA_OK(zygpu::launchShadow(r.scene, r.paths, pass.num_paths, r.stream));
+            CUDA_OK(zygpu::launchShadeB(r.scene, view, r.paths, pass, pass.num_paths, r.stream));
+            r.stats.kernel_launches += 3;
+        }
+
+        CUDA_OK(zygpu::launchFilm(view, r.paths, pass, r.film, r.stream));
+        r.stats.kernel_launches += 1;
+
+        r.stats.camera_samples += uint64_t(view.crop[2] - view.crop[0] + 2 * fr) * uint64_t(view.crop[3] - view.crop[1] + 2 * fr) * k;
+        r.stats.passes += 1;
+        done += k;
+    }
+    return 0;
+}
+
+int zygpu_synchronize(zygpu_device* dev) {
+    if (!dev) return fail("zygpu_synchronize: null device");
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    if (dev->render.stream) CUDA_OK(cudaStreamSynchronize(dev->render.stream));
+    if (dev->render.paths.counters) {
+        uint32_t overflow = 0;
+        CUDA_OK(cudaMemcpy(&overflow, dev->render.paths.counters + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (0 != overflow) return fail("zygpu_render: a path vertex produced more light samples than the %u reserved", dev->render.max_light_samples);
+    }
+    return 0;
+}
+
+int zygpu_resolve(zygpu_device* dev, float* rgba, uint32_t num_pixels) {
+    if (!dev || !rgba) return fail("zygpu_resolve: null argument");
+    RenderState& r = dev->render;
+    if (!r.film) return fail("zygpu_resolve: no view set");
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    const uint32_t n = std::min(num_pixels, r.film_pixels);
+    CUDA_OK(zygpu::launchResolve(r.view, r.film, r.resolved, n, r.stream));
+    r.stats.kernel_launches += 1;
+    CUDA_OK(cudaMemcpyAsync(rgba, r.resolved, size_t(n) * sizeof(float4), cudaMemcpyDeviceToHost, r.stream));
+    CUDA_OK(cudaStreamSynchronize(r.stream));
+    return 0;
+}
+
+int zygpu_download_film(zygpu_device* dev, float* film, uint32_t num_pixels) {
+    if (!dev || !film) return fail("zygpu_download_film: null argument");
+    RenderState& r = dev->render;
+    if (!r.film) return fail("zygpu_download_film: no view set");
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    const uint32_t n = std::min(num_pixels, r.film_pixels);
+    CUDA_OK(cudaMemcpyAsync(film, r.film, size_t(n) * sizeof(float4), cudaMemcpyDeviceToHost, r.stream));
+    CUDA_OK(cudaStreamSynchronize(r.stream));
+    return 0;
+}
+
+int zygpu_upload_film(zygpu_device* dev, const float* film, uint32_t num_pixels) {
+    if (!dev || !film) return fail("zygpu_upload_film: null argument");
+    RenderState& r = dev->render;
+    if (!r.film) return fail("zygpu_upload_film: no view set");
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    const uint32_t n = std::min(num_pixels, r.film_pixels);
+    CUDA_OK(cudaMemcpyAsync(r.film, film, size_t(n) * sizeof(float4), cudaMemcpyHostToDevice, r.stream));
+    CUDA_OK(cudaStreamSynchronize(r.stream));
+    return 0;
+}
+
+void* zygpu_film_device(zygpu_device* dev, uint64_t* num_floats) {
+    if (!dev || !dev->render.film) return nullptr;
+    if (num_floats) *num_floats = uint64_t(dev->render.film_pixels) * 4;
+    return dev->render.film;
+}
+
+int zygpu_render_stats(zygpu_device* dev, ZygpuRenderStats* stats) {
+    if (!dev || !stats) return fail("zygpu_render_stats: null argument");
+    RenderState& r = dev->render;
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    if (r.stream) CUDA_OK(cudaStreamSynchronize(r.stream));
+    *stats = r.stats;
+    if (r.paths.counters) {
+        uint32_t c[8];
+        CUDA_OK(cudaMemcpy(c, r.paths.counters, sizeof(c), cudaMemcpyDeviceToHost));
+        stats->closest_rays = c[5];
+        stats->shadow_rays  = c[6];
+    }
+    return 0;
+}
+
+}  // extern "C"

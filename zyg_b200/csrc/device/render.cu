@@ -1,0 +1,1322 @@
+#include "shading.cuh"
+
+#include <algorithm>
+
+namespace zygpu {
+
+namespace {
+
+constexpr uint32_t kBlock = 128;
+
+// ---- state packing ---------------------------------------------------------------------------
+
+enum : uint32_t {  // Vertex.State, vertex.zig:19-28
+    kPrimaryRay      = 1u << 0,
+    kTransparent     = 1u << 1,
+    kSingular        = 1u << 2,
+    kSpecular        = 1u << 3,
+    kTranslucent     = 1u << 4,
+    kStartedSpecular = 1u << 5,
+};
+
+__device__ __forceinline__ uint32_t packFlags(uint32_t state, uint32_t probe_depth, uint32_t vertex_depth) {
+    return state | (probe_depth << 8) | (vertex_depth << 16);
+}
+
+constexpr float kLowThreshold = 0.00000001f;  // helper.zig:29
+
+__device__ __forceinline__ float splitThreshold(float threshold, uint32_t total_depth) {  // helper.zig:33-39
+    return zmin(total_depth < 4 ? threshold : kLowThreshold, threshold);
+}
+__device__ __forceinline__ float powerHeuristic(float f_pdf, float g_pdf) {  // helper.zig:64-67
+    const float f2 = f_pdf * f_pdf;
+    return __fdiv_rn(f2, __fmaf_rn(g_pdf, g_pdf, f2));
+}
+__device__ __forceinline__ float predividedPowerHeuristic(float f_pdf, float g_pdf) {  // helper.zig:70-73
+    const float f2 = f_pdf * f_pdf;
+    return __fdiv_rn(f_pdf, __fmaf_rn(g_pdf, g_pdf, f2));
+}
+
+// ---- per-slot sampler state ------------------------------------------------------------------
+
+struct SlotId {
+    uint32_t pixel_id;   // over the padded resolution, worker.zig:127-141
+    uint32_t iteration;  // absolute sample number
+};
+
+__device__ __forceinline__ SlotId slotId(uint32_t slot, const PassParams& pass) {
+    const uint32_t padded = pass.padded_w * pass.padded_h;
+    const uint32_t s      = slot / padded;
+    return {slot - s * padded, pass.iteration + s};
+}
+
+// worker.zig:143-149 with num_samples = 1 per iteration (Driver.renderIterations(iteration, 1))
+__device__ __forceinline__ void seedSamplers(const SlotId id, const PassParams& pass, uint32_t spp_total, SobolD& sobol, PcgD& rng) {
+    const uint32_t a = pass.padded_w * pass.padded_h;
+    const uint64_t o = uint64_t(id.iteration) * a;
+    rng.start(0, uint64_t(id.pixel_id) + o);
+
+    const uint64_t sample_index = uint64_t(id.pixel_id) * uint64_t(spp_total) + uint64_t(id.iteration);
+    const uint32_t tsi          = uint32_t(sample_index);
+    const uint32_t seed         = uint32_t(sample_index >> 32) + id.iteration / spp_total;
+    sobol.startPixel(tsi, seed);
+}
+
+__device__ __forceinline__ void loadSampler(const PathState& st, uint32_t slot, const PassParams& pass, uint32_t spp_total,
+                                            uint32_t total_depth, SamplerD& sampler, uint32_t& aux) {
+    const SlotId id = slotId(slot, pass);
+    const uint4  s  = st.smp[slot];
+    aux             = s.w;
+    sampler.use_sobol = total_depth < 3;  // pickSampler; a Random take sampler is handled by the caller (view.sampler)
+    const uint64_t sample_index = uint64_t(id.pixel_id) * uint64_t(spp_total) + uint64_t(id.iteration);
+    if (sampler.use_sobol) {
+        sampler.sobol.restore(uint32_t(sample_index), s.x, s.y, s.z);
+    } else {
+        sampler.sobol.sample     = uint32_t(sample_index);
+        sampler.sobol.block_seed = s.x;
+        sampler.sobol.run_seed   = s.y;
+        sampler.sobol.dimension  = s.z;
+    }
+    const uint2 r     = st.rng[slot];
+    sampler.rng.state = (uint64_t(r.y) << 32) | r.x;
+    const uint64_t a  = uint64_t(pass.padded_w) * pass.padded_h;
+    sampler.rng.inc   = ((uint64_t(id.pixel_id) + uint64_t(id.iteration) * a) << 1) | 1;
+}
+
+__device__ __forceinline__ void storeSampler(const PathState& st, uint32_t slot, const SamplerD& sampler, uint32_t aux) {
+    st.smp[slot] = make_uint4(sampler.sobol.block_seed, sampler.sobol.run_seed, sampler.sobol.dimension, aux);
+    st.rng[slot] = make_uint2(uint32_t(sampler.rng.state), uint32_t(sampler.rng.state >> 32));
+}
+
+// ---- queues ----------------------------------------------------------------------------------
+
+// Warp-aggregated append: one atomic per warp.
+__device__ __forceinline__ void queuePush(uint32_t* queue, uint32_t* counter, bool push, uint32_t value) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, push);
+    if (0 == mask) return;
+    const uint32_t lane   = threadIdx.x & 31u;
+    const uint32_t leader = __ffs(mask) - 1;
+    uint32_t       base   = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (push) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+// ---- scene queries ---------------------------------------------------------------------------
+
+__device__ __forceinline__ bool propVisible(uint32_t flags, uint32_t depth_surface) {  // prop.zig:38-48
+    return 0 == depth_surface ? 0 != (flags & ZYG_PROP_VISIBLE_IN_CAMERA) : 0 != (flags & ZYG_PROP_VISIBLE_IN_REFLECTION);
+}
+
+__device__ __forceinline__ bool aabbIntersect(const float4* aabbs, uint32_t i, const RayT& ray) {  // aabb.zig:46-60
+    return FLT_MAX != intersectNode(__ldg(aabbs + 2 * size_t(i)), __ldg(aabbs + 2 * size_t(i) + 1), ray);
+}
+
+__device__ __forceinline__ float shapeArea(uint32_t shape, V3 scale) {  // shape.zig:143-156
+    switch (shape) {
+        case ZYG_SHAPE_RECTANGLE: return scale.x * scale.y;
+        case ZYG_SHAPE_SPHERE: return (4.f * kPi) * ((0.5f * scale.x) * (0.5f * scale.x));
+        default: return 0.f;
+    }
+}
+
+// Prop.intersect + Shape.intersect, prop.zig:163-197, shape.zig:165-179
+__device__ __forceinline__ bool propIntersect(const SceneDevice& sc, uint32_t entity, RayT& ray, uint32_t depth_surface, HitD& isec) {
+    const ZygpuProp prop = sc.props[entity];
+    if (!propVisible(prop.flags, depth_surface)) return false;
+    if (!aabbIntersect(sc.aabbs, entity, ray)) return false;
+    const TrafoD trafo = loadTrafo(sc.trafos, entity);
+    switch (prop.shape) {
+        case ZYG_SHAPE_CUBE: return cubeIntersect(ray, trafo, isec);
+        case ZYG_SHAPE_RECTANGLE: return rectangleIntersect(ray, trafo, isec);
+        case ZYG_SHAPE_SPHERE: return sphereIntersect(ray, trafo, isec);
+        case ZYG_SHAPE_TRIANGLE_MESH: {
+            // TriangleTree.intersect, triangle_tree.zig:46-109: the ray goes to object space un-normalised, so t is shared
+            WideRay w;
+            w.ray = worldToObjectRay(trafo, ray);
+            setupWideRay(w);
+            float    ht, hu, hv;
+            uint32_t prim;
+            if (traverseWide<false>(sc.meshes[prop.mesh], w, ht, hu, hv, prim)) {
+                isec = {ht, hu, hv, prim};
+                return true;
+            }
+            return false;
+        }
+        default: return false;
+    }
+}
+
+// Prop.visibility, prop.zig:199-237 (no masks): true = unoccluded
+__device__ __forceinline__ bool propVisibility(const SceneDevice& sc, uint32_t entity, const RayT& ray) {
+    const ZygpuProp prop = sc.props[entity];
+    if (0 == (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW)) return true;
+    if (!aabbIntersect(sc.aabbs, entity, ray)) return true;
+    const TrafoD trafo = loadTrafo(sc.trafos, entity);
+    switch (prop.shape) {
+        case ZYG_SHAPE_CUBE: return !cubeIntersectP(ray, trafo);
+        case ZYG_SHAPE_RECTANGLE: {
+            HitD unused;
+            return !rectangleIntersect(ray, trafo, unused);
+        }
+        case ZYG_SHAPE_SPHERE: {
+            HitD unused;
+            return !sphereIntersect(ray, trafo, unused);
+        }
+        case ZYG_SHAPE_TRIANGLE_MESH: {
+            WideRay w;
+            w.ray = worldToObjectRay(trafo, ray);
+            setupWideRay(w);
+            float    ht, hu, hv;
+            uint32_t prim;
+            return !traverseWide<true>(sc.meshes[prop.mesh], w, ht, hu, hv, prim);
+        }
+        default: return true;
+    }
+}
+
+constexpr uint32_t kPropStack = 32;  // prop trees are shallow; the reference's NodeStack holds 127
+
+// PropBvh.intersect, prop_tree.zig:56-116: reference order, so equal-t ties resolve like the reference.
+__device__ __forceinline__ uint32_t sceneIntersect(const SceneDevice& sc, RayT& ray, uint32_t depth_surface, HitD& isec) {
+    uint32_t stack[kPropStack];
+    uint32_t end = 0;
+    uint32_t n   = 0 == sc.num_solid_nodes ? kEnd : 0;
+
+    uint32_t prop = kEnd;
+
+    while (kEnd != n) {
+        const float4 nmin = __ldg(sc.solid_nodes + 2 * size_t(n));
+        const float4 nmax = __ldg(sc.solid_nodes + 2 * size_t(n) + 1);
+
+        const uint32_t num = __float_as_uint(nmax.w);
+        if (0 != num) {
+            const uint32_t start = __float_as_uint(nmin.w);
+            for (uint32_t i = start; i < start + num; ++i) {
+                const uint32_t p = __ldg(sc.solid_indices + i);
+                HitD           h;
+                if (propIntersect(sc, p, ray, depth_surface, h)) {
+                    ray.tmax = h.t;
+                    isec     = h;
+                    prop     = p;
+                }
+            }
+            n = 0 == end ? kEnd : stack[--end];
+            continue;
+        }
+
+        uint32_t a = __float_as_uint(nmin.w);
+        uint32_t b = a + 1;
+
+        float dista = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(a)), __ldg(sc.solid_nodes + 2 * size_t(a) + 1), ray);
+        float distb = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(b)), __ldg(sc.solid_nodes + 2 * size_t(b) + 1), ray);
+        if (dista > distb) {
+            const uint32_t tn = a;
+            a                 = b;
+            b                 = tn;
+            const float td    = dista;
+            dista             = distb;
+            distb             = td;
+        }
+        if (FLT_MAX == dista) {
+            n = 0 == end ? kEnd : stack[--end];
+        } else {
+            n = a;
+            if (FLT_MAX != distb) stack[end++] = b;
+        }
+    }
+    return prop;
+}
+
+// PropBvh.visibility, prop_tree.zig:185-240
+__device__ __forceinline__ bool sceneVisibility(const SceneDevice& sc, const RayT& ray) {
+    uint32_t stack[kPropStack];
+    uint32_t end = 0;
+    uint32_t n   = 0 == sc.num_solid_nodes ? kEnd : 0;
+
+    while (kEnd != n) {
+        const float4 nmin = __ldg(sc.solid_nodes + 2 * size_t(n));
+        const float4 nmax = __ldg(sc.solid_nodes + 2 * size_t(n) + 1);
+
+        const uint32_t num = __float_as_uint(nmax.w);
+        if (0 != num) {
+            const uint32_t start = __float_as_uint(nmin.w);
+            for (uint32_t i = start; i < start + num; ++i) {
+                if (!propVisibility(sc, __ldg(sc.solid_indices + i), ray)) return false;
+            }
+            n = 0 == end ? kEnd : stack[--end];
+            continue;
+        }
+
+        uint32_t a = __float_as_uint(nmin.w);
+        uint32_t b = a + 1;
+
+        float dista = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(a)), __ldg(sc.solid_nodes + 2 * size_t(a) + 1), ray);
+        float distb = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(b)), __ldg(sc.solid_nodes + 2 * size_t(b) + 1), ray);
+        if (dista > distb) {
+            const uint32_t tn = a;
+            a                 = b;
+            b                 = tn;
+            const float td    = dista;
+            dista             = distb;
+            distb             = td;
+        }
+        if (FLT_MAX == dista) {
+            n = 0 == end ? kEnd : stack[--end];
+        } else {
+            n = a;
+            if (FLT_MAX != distb) stack[end++] = b;
+        }
+    }
+    return true;
+}
+
+// Shape.fragment, shape.zig:205-219
+__device__ __forceinline__ void shapeFragment(const SceneDevice& sc, uint32_t prop, const RayT& ray, const HitD& isec, FragD& frag) {
+    frag.prop  = prop;
+    frag.trafo = loadTrafo(sc.trafos, prop);
+    switch (sc.props[prop].shape) {
+        case ZYG_SHAPE_CUBE: cubeFragment(ray, isec, frag); break;
+        case ZYG_SHAPE_RECTANGLE: rectangleFragment(ray, isec, frag); break;
+        case ZYG_SHAPE_SPHERE: sphereFragment(ray, isec, frag); break;
+        default: break;
+    }
+}
+
+// ---- lights ----------------------------------------------------------------------------------
+
+struct VertexD {  // the parts of Vertex (vertex.zig:45-64) the light code reads
+    RayT     ray;
+    V3       origin, geo_n;
+    float    bxdf_pdf, light_split_threshold;
+    uint32_t state, probe_depth;
+};
+
+__device__ __forceinline__ uint32_t lightNumSamples(const ZygpuLight& l, float split_threshold) {  // shape_sampler.zig:35-41
+    return split_threshold <= kLowThreshold ? 1u : l.num_samples;
+}
+
+// C. Ureña, M. Fajardo, A. King: An Area-Preserving Parametrization for Spherical Rectangles. rectangle.zig:199-303
+struct SphQuadD {
+    V3    o, x, y, z;
+    float z0, x0, y0, x1, y1, b0, b1, k, S;
+
+    __device__ void init(V3 scale, V3 origin) {
+        const V3 s  = {-0.5f * scale.x, -0.5f * scale.y, 0.f};
+        const V3 ex = {scale.x, 0.f, 0.f};
+        const V3 ey = {0.f, scale.y, 0.f};
+
+        o               = origin;
+        const float exl = length3(ex);
+        const float eyl = length3(ey);
+        x               = divs3(ex, exl);
+        y               = divs3(ey, eyl);
+        z               = cross3(x, y);
+        const V3 d      = sub3(s, o);
+        z0              = dot3(d, z);
+        if (z0 > 0.f) {
+            z  = neg3(z);
+            z0 = -z0;
+        }
+        x0 = dot3(d, x);
+        y0 = dot3(d, y);
+        x1 = x0 + exl;
+        y1 = y0 + eyl;
+
+        const V3 v00 = {x0, y0, z0}, v01 = {x0, y1, z0}, v10 = {x1, y0, z0}, v11 = {x1, y1, z0};
+
+        const V3 n0 = normalize3(cross3(v00, v10));
+        const V3 n1 = normalize3(cross3(v10, v11));
+        const V3 n2 = normalize3(cross3(v11, v01));
+        const V3 n3 = normalize3(cross3(v01, v00));
+
+        const float g0 = acosf(-dot3(n0, n1));
+        const float g1 = acosf(-dot3(n1, n2));
+        const float g2 = acosf(-dot3(n2, n3));
+        const float g3 = acosf(-dot3(n3, n0));
+
+        b0 = n0.z;
+        b1 = n2.z;
+        k  = 2.f * kPi - g2 - g3;
+        S  = g0 + g1 - k;
+    }
+
+    __device__ V3 sample(float u0, float u1) const {
+        const float au = u0 * S + k;
+        float       sa, ca;
+        sincosf(au, &sa, &ca);
+        const float fu = __fdiv_rn(ca * b0 - b1, sa);
+        float       cu = __fdiv_rn(1.f, __fsqrt_rn(fu * fu + b0 * b0)) * (fu > 0.f ? 1.f : -1.f);
+        cu             = cu < -1.f ? -1.f : (cu > 1.f ? 1.f : cu);
+
+        float xu = __fdiv_rn(-(cu * z0), __fsqrt_rn(1.f - cu * cu));
+        xu       = xu < x0 ? x0 : (xu > x1 ? x1 : xu);
+
+        const float d   = __fsqrt_rn(xu * xu + z0 * z0);
+        const float h0  = __fdiv_rn(y0, __fsqrt_rn(d * d + y0 * y0));
+        const float h1  = __fdiv_rn(y1, __fsqrt_rn(d * d + y1 * y1));
+        const float hv  = h0 + u1 * (h1 - h0);
+        const float hv2 = hv * hv;
+        const float eps = __uint_as_float(0x35800000u);
+        const float yv  = hv2 < 1.f - eps ? __fdiv_rn(hv * d, __fsqrt_rn(1.f - hv2)) : y1;
+
+        return add3(add3(add3(o, scale3(xu, x)), scale3(yv, y)), scale3(z0, z));
+    }
+
+    __device__ float pdf(V3 scale) const {
+        const float sqr_dist = squaredLength3(o);
+        const float area     = scale.x * scale.y;
+        const float numer    = area * fabsf(o.z);
+        const float denom    = sqr_dist * __fsqrt_rn(sqr_dist);
+        return numer > denom * kDotMin ? __fdiv_rn(1.f, S) : __fdiv_rn(denom, numer);
+    }
+};
+
+struct LightPropsD {  // light.zig:25-30, scene.zig:664-674
+    V3    center;
+    float radius;
+    V3    cone_axis;
+    float cone_cos;
+    float power;
+    bool  two_sided;
+};
+
+__device__ __forceinline__ LightPropsD lightProperties(const SceneDevice& sc, uint32_t light_id) {
+    const float4 mi   = __ldg(sc.light_aabbs + 2 * size_t(light_id));
+    const float4 ma   = __ldg(sc.light_aabbs + 2 * size_t(light_id) + 1);
+    const float4 cone = __ldg(sc.light_cones + light_id);
+    return {{0.5f * (mi.x + ma.x), 0.5f * (mi.y + ma.y), 0.5f * (mi.z + ma.z)}, ma.w, {cone.x, cone.y, cone.z}, cone.w, mi.w,
+            0 != sc.lights[light_id].two_sided};
+}
+
+__device__ __forceinline__ float clampedCosSub(float cos_a, float cos_b, float sin_a, float sin_b) {  // light_tree.zig:217-220
+    const float angle = __fmaf_rn(cos_a, cos_b, sin_a * sin_b);
+    return cos_a > cos_b ? 1.f : angle;
+}
+__device__ __forceinline__ float clampedSinSub(float cos_a, float cos_b, float sin_a, float sin_b) {  // :222-225
+    const float angle = __fmaf_rn(sin_a, cos_b, -sin_b * cos_a);
+    return cos_a > cos_b ? 0.f : angle;
+}
+
+// light_tree.zig:173-215
+__device__ float lightImportance(V3 p, V3 n, V3 center, V3 cone_axis, float cos_cone, float radius, float power, bool two_sided,
+                                 bool total_sphere) {
+    const V3    axis = sub3(p, center);
+    const float l    = length3(axis);
+    const V3    na   = divs3(axis, l);
+
+    const float sin_cu = zmin(__fdiv_rn(radius, l), 1.f);
+    const float dca    = dot3(cone_axis, na);
+    const float cos_a  = two_sided ? fabsf(dca) : dca;
+    const float cos_n  = zmax(-dot3(n, na), 0.f);
+
+    const float cos_cu   = __fsqrt_rn(zmax(__fmaf_rn(sin_cu, -sin_cu, 1.f), 0.f));
+    const float sin_cone = __fsqrt_rn(zmax(__fmaf_rn(cos_cone, -cos_cone, 1.f), 0.f));
+    const float sin_a    = __fsqrt_rn(zmax(__fmaf_rn(cos_a, -cos_a, 1.f), 0.f));
+    const float sin_n    = __fsqrt_rn(zmax(__fmaf_rn(cos_n, -cos_n, 1.f), 0.f));
+
+    const float ta = clampedCosSub(cos_a, cos_cone, sin_a, sin_cone);
+    const float tb = clampedSinSub(cos_a, cos_cone, sin_a, sin_cone);
+    const float tc = clampedCosSub(ta, cos_cu, tb, sin_cu);
+    const float tn = clampedCosSub(cos_n, cos_cu, sin_n, sin_cu);
+
+    const float ra = total_sphere ? 1.f : tn;
+    const float rb = zmax(tc, 0.f);
+
+    const float clamped_dist = zmax(l, 0.5f * radius);
+    const float rc           = __fdiv_rn(power, clamped_dist * clamped_dist);
+
+    return zmax(ra * rb * rc, 0.f);
+}
+
+__device__ float lightWeight(const SceneDevice& sc, V3 p, V3 n, bool total_sphere, uint32_t light) {  // light_tree.zig:227-233
+    const LightPropsD lp = lightProperties(sc, light);
+    return lightImportance(p, n, lp.center, lp.cone_axis, lp.cone_cos, lp.radius, lp.power, lp.two_sided, total_sphere);
+}
+
+struct LightNodeD {
+    V3       center;
+    float    radius;
+    V3       cone_axis;
+    float    cone_cos;
+    float    power, variance;
+    uint32_t meta, num_lights;
+};
+
+__device__ __forceinline__ LightNodeD loadLightNode(const SceneDevice& sc, uint32_t i) {  // light_tree.zig:25-42
+    const uint4* p  = reinterpret_cast<const uint4*>(sc.lt_nodes + i);
+    const uint4  a  = __ldg(p);
+    const uint4  b  = __ldg(p + 1);
+    const float  ku = 1.f / 65535.f;
+    const float  tx = float(a.x & 0xffffu) * ku, ty = float(a.x >> 16) * ku, tz = float(a.y & 0xffffu) * ku, tw = float(a.y >> 16) * ku;
+    LightNodeD   n;
+    n.center    = {zlerp(sc.lt_bounds_min.x, sc.lt_bounds_max.x, tx), zlerp(sc.lt_bounds_min.y, sc.lt_bounds_max.y, ty),
+                   zlerp(sc.lt_bounds_min.z, sc.lt_bounds_max.z, tz)};
+    n.radius    = zlerp(sc.lt_bounds_min.w, sc.lt_bounds_max.w, tw);
+    n.cone_axis = {__fmaf_rn(float(a.z & 0xffffu), 1.f / 32768.f, -1.f), __fmaf_rn(float(a.z >> 16), 1.f / 32768.f, -1.f),
+                   __fmaf_rn(float(a.w & 0xffffu), 1.f / 32768.f, -1.f)};
+    n.cone_cos  = __fmaf_rn(float(a.w >> 16), 1.f / 32768.f, -1.f);
+    n.power     = __uint_as_float(b.x);
+    n.variance  = __uint_as_float(b.y);
+    n.meta      = b.z;
+    n.num_lights = b.w;
+    return n;
+}
+
+__device__ float lightNodeWeight(const LightNodeD& node, V3 p, V3 n, bool total_sphere) {  // light_tree.zig:57-63
+    return lightImportance(p, n, node.center, node.cone_axis, node.cone_cos, node.radius, node.power, 0 != (node.meta & 2u), total_sphere);
+}
+
+__device__ bool lightNodeSplit(const LightNodeD& node, V3 p, float threshold) {  // light_tree.zig:65-89
+    const float r = node.radius;
+    const float d = zmin(length3(sub3(p, node.center)), 1.0e6f);
+    const float a = zmax(d - r, 0.001f);
+    const float b = d + r;
+
+    const float eg  = __fdiv_rn(1.f, a * b);
+    const float eg2 = eg * eg;
+    const float a3  = a * a * a;
+    const float b3  = b * b * b;
+    const float e2g = __fdiv_rn(b3 - a3, 3.f * (b - a) * a3 * b3);
+    const float vg  = e2g - eg2;
+
+    const float ve = node.variance;
+    const float ee = node.power;
+    const float s2 = zmax(ve * vg + ve * eg2 + ee * ee * vg, 0.f);
+    const float ns = __fdiv_rn(1.f, 1.f + __fsqrt_rn(s2));
+    return ns < threshold;
+}
+
+struct LightPickD {
+    uint32_t offset;
+    float    pdf;
+};
+
+// Node.randomLight, light_tree.zig:91-145
+__device__ LightPickD lightNodeRandomLight(const SceneDevice& sc, const LightNodeD& node, V3 p, V3 n, bool total_sphere, float random) {
+    const uint32_t num_lights = node.num_lights;
+    const uint32_t light      = node.meta >> 2;
+    if (1 == num_lights) return {__ldg(sc.lt_mapping + light), 1.f};
+
+    uint32_t front = light;
+    uint32_t back  = light + num_lights - 1;
+
+    float w_front = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + front));
+    float w_back  = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + back));
+
+    float w_sum_front = w_front;
+    float w_sum_back  = w_back;
+    float w_sum       = 0.f;
+
+    while (front != back) {
+        w_sum = w_sum_front + w_sum_back;
+        if (w_sum_front <= random * w_sum) {
+            front += 1;
+            if (front != back) {
+                w_front = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + front));
+                w_sum_front += w_front;
+            } else {
+                w_front = w_back;
+            }
+        } else {
+            back -= 1;
+            if (front != back) {
+                w_back = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + back));
+                w_sum_back += w_back;
+            }
+        }
+    }
+    if (0.f == w_sum) return {0, 0.f};
+    return {__ldg(sc.lt_mapping + front), __fdiv_rn(w_front, w_sum)};
+}
+
+// Node.pdf, light_tree.zig:147-170
+__device__ float lightNodePdf(const SceneDevice& sc, const LightNodeD& node, V3 p, V3 n, bool total_sphere, uint32_t id) {
+    const uint32_t num_lights = node.num_lights;
+    if (1 == num_lights) return 1.f;
+    const uint32_t light = node.meta >> 2;
+    const uint32_t end   = light + num_lights;
+    float          w_id = 0.f, sum = 0.f;
+    for (uint32_t i = light; i < end; ++i) {
+        const float lw = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + i));
+        sum += lw;
+        if (id == i) w_id = lw;
+    }
+    if (0.f == sum) return 0.f;
+    return __fdiv_rn(w_id, sum);
+}
+
+constexpr uint32_t kMaxLightPicks = 64;  // Tree.MaxLights
+
+// Tree.randomLight, light_tree.zig:346-447. `emit` is called for every pick in the reference's order.
+template <typename Emit>
+__device__ void lightTreeRandomLight(const SceneDevice& sc, V3 p, V3 n, bool total_sphere, float random, float split_threshold, Emit&& emit) {
+    float      ip    = 0.f;
+    const bool split = split_threshold > 0.f;
+
+    if (split && sc.lt_num_infinite < kMaxLightPicks - 1) {
+        for (uint32_t i = 0; i < sc.lt_num_infinite; ++i) emit(LightPickD{__ldg(sc.lt_mapping + i), 1.f});
+    } else {
+        ip = sc.lt_infinite_weight;
+        if (random < sc.lt_infinite_guard) {
+            emit(LightPickD{__ldg(sc.lt_mapping), 1.f * ip});  // single infinite light: sampleDiscrete -> (0, 1)
+            return;
+        }
+    }
+    if (0 == sc.lt_num_nodes) return;
+
+    const float    pd              = 1.f - ip;
+    const uint32_t max_split_depth = sc.lt_max_split_depth;
+
+    struct Value {
+        float    pdf, random;
+        uint32_t node, depth;
+    };
+    Value    stack[12];
+    uint32_t end = 0;
+
+    Value t{pd, __fdiv_rn(random - ip, pd), 0, split ? 0 : max_split_depth};
+    stack[end++] = t;
+
+    while (end > 0) {
+        const LightNodeD node = loadLightNode(sc, t.node);
+        if (0 != (node.meta & 1u)) {
+            const bool     do_split = t.depth < max_split_depth && lightNodeSplit(node, p, split_threshold);
+            const uint32_t c0       = node.meta >> 2;
+            const uint32_t c1       = c0 + 1;
+            if (do_split) {
+                t.depth += 1;
+                t.node       = c0;
+                stack[end++] = {t.pdf, t.random, c1, t.depth};
+            } else {
+                t.depth = max_split_depth;
+
+                float p0 = lightNodeWeight(loadLightNode(sc, c0), p, n, total_sphere);
+                float p1 = lightNodeWeight(loadLightNode(sc, c1), p, n, total_sphere);
+
+                const float pt = p0 + p1;
+                if (0.f == pt) {
+                    t = stack[--end];
+                    continue;
+                }
+                p0 = __fdiv_rn(p0, pt);
+                p1 = __fdiv_rn(p1, pt);
+                if (t.random < p0) {
+                    t.node = c0;
+                    t.pdf *= p0;
+                    t.random = __fdiv_rn(t.random, p0);
+                } else {
+                    t.node = c1;
+                    t.pdf *= p1;
+                    t.random = zmin(__fdiv_rn(t.random - p0, p1), 1.f);
+                }
+            }
+        } else {
+            const LightPickD pick = lightNodeRandomLight(sc, node, p, n, total_sphere, t.random);
+            if (pick.pdf > 0.f) emit(LightPickD{pick.offset, pick.pdf * t.pdf});
+            t = stack[--end];
+        }
+    }
+}
+
+// Tree.pdf, light_tree.zig:449-517
+__device__ float lightTreePdf(const SceneDevice& sc, V3 p, V3 n, bool total_sphere, float split_threshold, uint32_t id) {
+    const uint32_t lo             = __ldg(sc.lt_orders + id);
+    const bool     split          = split_threshold > 0.f;
+    const bool     split_infinite = split && sc.lt_num_infinite < kMaxLightPicks - 1;
+
+    if (lo < sc.lt_infinite_end) return split_infinite ? 1.f : sc.lt_infinite_weight * 1.f;
+    if (0 == sc.lt_num_nodes) return 0.f;
+
+    const float    ip              = split_infinite ? 0.f : sc.lt_infinite_weight;
+    const uint32_t max_split_depth = sc.lt_max_split_depth;
+
+    float    pd    = 1.f - ip;
+    uint32_t nid   = 0;
+    uint32_t depth = split ? 0 : max_split_depth;
+    for (;;) {
+        const LightNodeD node = loadLightNode(sc, nid);
+        if (0 != (node.meta & 1u)) {
+            const bool     do_split = depth < max_split_depth && lightNodeSplit(node, p, split_threshold);
+            const uint32_t c0       = node.meta >> 2;
+            const uint32_t c1       = c0 + 1;
+            const uint32_t middle   = __ldg(sc.lt_middles + nid);
+            if (do_split) {
+                depth += 1;
+                nid = lo < middle ? c0 : c1;
+            } else {
+                depth          = max_split_depth;
+                const float p0 = lightNodeWeight(loadLightNode(sc, c0), p, n, total_sphere);
+                const float p1 = lightNodeWeight(loadLightNode(sc, c1), p, n, total_sphere);
+                const float pt = p0 + p1;
+                if (0.f == pt) return 0.f;
+                if (lo < middle) {
+                    nid = c0;
+                    pd *= __fdiv_rn(p0, pt);
+                } else {
+                    nid = c1;
+                    pd *= __fdiv_rn(p1, pt);
+                }
+            }
+        } else {
+            return pd * lightNodePdf(sc, node, p, n, total_sphere, lo);
+        }
+    }
+}
+
+// Scene.lightPdf, scene.zig:624-634 (+ Light.pdf -> Shape.pdf, light.zig:149-157, shape.zig:469-492, rectangle.zig:554-575)
+__device__ float sceneLightPdf(const SceneDevice& sc, const VertexD& vertex, const FragD& frag) {
+    const uint32_t light_id = __ldg(sc.light_ids + sc.props[frag.prop].parts_start + frag.part);
+    if (0 != (vertex.state & kSingular) || ZYGPU_NULL == light_id) return 1.f;
+
+    const float select_pdf =
+        lightTreePdf(sc, vertex.origin, vertex.geo_n, 0 != (vertex.state & kTranslucent), vertex.light_split_threshold, light_id);
+
+    const ZygpuLight l          = sc.lights[light_id];
+    float            sample_pdf = 0.f;
+    if (ZYG_SHAPE_RECTANGLE == sc.props[l.prop].shape) {
+        const float nsf = float(lightNumSamples(l, vertex.light_split_threshold));
+        SphQuadD    squad;
+        squad.init(frag.trafo.scale, frag.trafo.worldToFramePoint(vertex.origin));
+        sample_pdf = nsf * squad.pdf(frag.trafo.scale);
+    }
+    return powerHeuristic(vertex.bxdf_pdf, sample_pdf * select_pdf);
+}
+
+// Vertex.evaluateRadiance, vertex.zig:183-212
+__device__ V3 evaluateRadiance(const SceneDevice& sc, const VertexD& vertex, const FragD& frag, SamplerD& sampler) {
+    const V3            wo = neg3(vertex.ray.d);
+    const ZygpuMaterial m  = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
+    if (0 == (m.flags & ZYG_MATERIAL_EMISSIVE) || (0 == (m.flags & ZYG_MATERIAL_TWO_SIDED) && !frag.sameHemisphere(wo))) {
+        return splat3(0.f);
+    }
+    (void)sampler.sample1D();  // rs.stochastic_r
+
+    const bool  in_camera = 0 == vertex.probe_depth;
+    const float area      = 0.f != m.emission_normalize ? shapeArea(sc.props[frag.prop].shape, frag.trafo.scale) : 1.f;
+    const V3    energy    = emittanceRadiance(m, wo, frag.trafo, area, in_camera);
+    const float weight    = sceneLightPdf(sc, vertex, frag);
+    return scale3(weight, energy);
+}
+
+// Prop.emission + Shape.emission, prop.zig:239-264, shape.zig:283-299, rectangle.zig:188-196
+__device__ V3 propEmission(const SceneDevice& sc, uint32_t entity, const VertexD& vertex, SamplerD& sampler) {
+    const ZygpuProp prop = sc.props[entity];
+    if (!propVisible(prop.flags, vertex.probe_depth)) return splat3(0.f);
+    if (!aabbIntersect(sc.aabbs, entity, vertex.ray)) return splat3(0.f);
+    if (ZYG_SHAPE_RECTANGLE != prop.shape) return splat3(0.f);
+
+    FragD frag;
+    frag.prop  = entity;
+    frag.trafo = loadTrafo(sc.trafos, entity);
+    HitD isec;
+    if (!rectangleIntersect(vertex.ray, frag.trafo, isec)) return splat3(0.f);
+    rectangleFragment(vertex.ray, isec, frag);
+    return evaluateRadiance(sc, vertex, frag, sampler);
+}
+
+// Context.emission -> PropBvh.emission, prop_tree.zig:302-356: every un-occluding emitter crossed before the hit
+__device__ V3 unoccludingEmission(const SceneDevice& sc, const VertexD& vertex, SamplerD& sampler) {
+    uint32_t stack[kPropStack];
+    uint32_t end = 0;
+    uint32_t n   = 0 == sc.num_unocc_nodes ? kEnd : 0;
+
+    V3 energy = splat3(0.f);
+
+    while (kEnd != n) {
+        const float4 nmin = __ldg(sc.unocc_nodes + 2 * size_t(n));
+        const float4 nmax = __ldg(sc.unocc_nodes + 2 * size_t(n) + 1);
+
+        const uint32_t num = __float_as_uint(nmax.w);
+        if (0 != num) {
+            const uint32_t start = __float_as_uint(nmin.w);
+            for (uint32_t i = start; i < start + num; ++i) {
+                energy = add3(energy, propEmission(sc, __ldg(sc.unocc_indices + i), vertex, sampler));
+            }
+            n = 0 == end ? kEnd : stack[--end];
+            continue;
+        }
+
+        uint32_t a = __float_as_uint(nmin.w);
+        uint32_t b = a + 1;
+
+        float dista = intersectNode(__ldg(sc.unocc_nodes + 2 * size_t(a)), __ldg(sc.unocc_nodes + 2 * size_t(a) + 1), vertex.ray);
+        float distb = intersectNode(__ldg(sc.unocc_nodes + 2 * size_t(b)), __ldg(sc.unocc_nodes + 2 * size_t(b) + 1), vertex.ray);
+        if (dista > distb) {
+            const uint32_t tn = a;
+            a                 = b;
+            b                 = tn;
+            const float td    = dista;
+            dista             = distb;
+            distb             = td;
+        }
+        if (FLT_MAX == dista) {
+            n = 0 == end ? kEnd : stack[--end];
+        } else {
+            n = a;
+            if (FLT_MAX != distb) stack[end++] = b;
+        }
+    }
+    return energy;
+}
+
+// ---- accumulation (IValue.add, helper.zig:11-19) ---------------------------------------------
+
+__device__ __forceinline__ void ivalueAdd(const PathState& st, uint32_t slot, V3 value, uint32_t depth, uint32_t direct_cutoff,
+                                          bool is_emission, bool singular) {
+    float4* target = is_emission ? st.acc_e : ((singular || depth < direct_cutoff) ? st.acc_d : st.acc_i);
+    float4  a      = target[slot];
+    a.x += value.x;
+    a.y += value.y;
+    a.z += value.z;
+    target[slot] = a;
+}
+
+// ---- stage kernels ---------------------------------------------------------------------------
+
+// Worker.render per sample: Sensor.cameraSample (sensor.zig:152-166) + Perspective.generateVertex
+// (camera_perspective.zig:124-150) + Vertex.init (vertex.zig:67-85)
+__global__ void __launch_bounds__(kBlock) generateKernel(ZygpuView view, PathState st, PassParams pass) {
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < pass.num_paths; slot += gridDim.x * blockDim.x) {
+        const SlotId id = slotId(slot, pass);
+
+        SamplerD sampler;
+        sampler.use_sobol = ZYG_SAMPLER_SOBOL == view.sampler;
+        seedSamplers(id, pass, view.spp_total, sampler.sobol, sampler.rng);
+
+        const int32_t fr = view.filter_radius_int;
+        const int32_t px = int32_t(id.pixel_id % pass.padded_w) - fr;
+        const int32_t py = int32_t(id.pixel_id / pass.padded_w) - fr;
+
+        float s4[4];
+        if (sampler.use_sobol) {  // sample4D
+            if (sampler.sobol.dimension >= 2) sampler.sobol.incrementSeed();
+            const uint32_t d       = sampler.sobol.dimension;
+            sampler.sobol.dimension = d + 4;
+            s4[0] = sampler.sobol.buffer[d];
+            s4[1] = sampler.sobol.buffer[d + 1];
+            s4[2] = sampler.sobol.buffer[d + 2];
+            s4[3] = sampler.sobol.buffer[d + 3];
+        } else {
+            for (int i = 0; i < 4; ++i) s4[i] = sampler.rng.randomFloat();
+        }
+        (void)sampler.sample1D();  // shutter time: static scenes
+        sampler.incrementPadding();
+
+        const float c0 = float(px) + s4[0];
+        const float c1 = float(py) + s4[1];
+
+        const V3 left_top = {view.left_top[0], view.left_top[1], view.left_top[2]};
+        const V3 d_x      = {view.d_x[0], view.d_x[1], view.d_x[2]};
+        const V3 d_y      = {view.d_y[0], view.d_y[1], view.d_y[2]};
+
+        V3 direction = add3(add3(left_top, scale3(c0, d_x)), scale3(c1, d_y));
+        V3 origin;
+        if (view.aperture_radius > 0.f) {
+            float lx, ly;
+            diskConcentric(s4[2], s4[3], lx, ly);  // Aperture.sample, aperture.zig:46-53
+            origin         = {lx * view.aperture_radius, ly * view.aperture_radius, 0.f};
+            const float t  = __fdiv_rn(view.focus_distance, direction.z);
+            const V3 focus = scale3(t, direction);
+            direction      = sub3(focus, origin);
+        } else {
+            origin = {view.eye_offset[0], view.eye_offset[1], view.eye_offset[2]};
+        }
+
+        const TrafoD trafo = {{view.camera_trafo.r[0][0], view.camera_trafo.r[0][1], view.camera_trafo.r[0][2]},
+                              {view.camera_trafo.r[1][0], view.camera_trafo.r[1][1], view.camera_trafo.r[1][2]},
+                              {view.camera_trafo.r[2][0], view.camera_trafo.r[2][1], view.camera_trafo.r[2][2]},
+                              {view.camera_trafo.r[0][3], view.camera_trafo.r[1][3], view.camera_trafo.r[2][3]},
+                              {view.camera_trafo.position[0], view.camera_trafo.position[1], view.camera_trafo.position[2]}};
+
+        const V3 origin_w    = trafo.objectToWorldPoint(origin);
+        const V3 direction_w = trafo.objectToWorldVector(normalize3(direction));
+
+        const uint32_t state = kPrimaryRay | kTransparent | kSingular;
+        st.ray_o[slot]  = make_float4(origin_w.x, origin_w.y, origin_w.z, __uint_as_float(packFlags(state, 0, 0)));
+        st.ray_d[slot]  = make_float4(direction_w.x, direction_w.y, direction_w.z, kRayMaxT);
+        st.thr[slot]    = make_float4(1.f, 1.f, 1.f, 0.f);
+        st.prev_p[slot] = make_float4(origin_w.x, origin_w.y, origin_w.z, 0.f);
+        st.prev_n[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        st.acc_e[slot]  = make_float4(0.f, 0.f, 0.f, s4[0]);
+        st.acc_d[slot]  = make_float4(0.f, 0.f, 0.f, s4[1]);
+        st.acc_i[slot]  = make_float4(0.f, 0.f, 0.f, 0.f);
+        storeSampler(st, slot, sampler, 0);
+        st.queue_a[slot] = slot;
+    }
+    if (0 == blockIdx.x && 0 == threadIdx.x) {
+        st.counters[0] = pass.num_paths;
+        st.counters[1] = 0;
+        st.counters[4] = 0;
+    }
+}
+
+// Context.nextEvent -> Scene.intersect, context.zig:54-69, scene.zig:225-227
+__global__ void __launch_bounds__(kBlock) extendKernel(SceneDevice sc, PathState st) {
+    const uint32_t count = st.counters[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = st.queue_a[i];
+        const float4   o    = st.ray_o[slot];
+        float4         d    = st.ray_d[slot];
+
+        RayT           ray           = makeRay({o.x, o.y, o.z}, {d.x, d.y, d.z}, 0.f, d.w);
+        const uint32_t depth_surface = (__float_as_uint(o.w) >> 8) & 0xffu;
+
+        HitD           isec = {0.f, 0.f, 0.f, 0};
+        const uint32_t prop = sceneIntersect(sc, ray, depth_surface, isec);
+
+        d.w             = ray.tmax;  // probe.ray.max_t = isec.t (prop_tree.zig:77); unchanged on a miss
+        st.ray_d[slot]  = d;
+        st.hit[slot]    = make_float4(isec.u, isec.v, __uint_as_float(isec.primitive), __uint_as_float(prop));
+    }
+    if (0 == blockIdx.x && 0 == threadIdx.x) atomicAdd(&st.counters[5], count);  // statistics: closest-hit rays
+}
+
+struct LoadedVertex {
+    VertexD  v;
+    V3       throughput;
+    float    reg_alpha;
+    uint32_t vertex_depth;
+    HitD     isec;
+    uint32_t prop;
+};
+
+__device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t slot) {
+    const float4 o  = st.ray_o[slot];
+    const float4 d  = st.ray_d[slot];
+    const float4 t  = st.thr[slot];
+    const float4 pp = st.prev_p[slot];
+    const float4 pn = st.prev_n[slot];
+    const float4 h  = st.hit[slot];
+
+    LoadedVertex    r;
+    const uint32_t  flags = __float_as_uint(o.w);
+    r.v.ray               = makeRay({o.x, o.y, o.z}, {d.x, d.y, d.z}, 0.f, d.w);
+    r.v.origin            = {pp.x, pp.y, pp.z};
+    r.v.geo_n             = {pn.x, pn.y, pn.z};
+    r.v.bxdf_pdf          = t.w;
+    r.v.light_split_threshold = pn.w;
+    r.v.state             = flags & 0xffu;
+    r.v.probe_depth       = (flags >> 8) & 0xffu;
+    r.vertex_depth        = (flags >> 16) & 0xffu;
+    r.throughput          = {t.x, t.y, t.z};
+    r.reg_alpha           = pp.w;
+    r.isec                = {d.w, h.x, h.y, __float_as_uint(h.z)};
+    r.prop                = __float_as_uint(h.w);
+    return r;
+}
+
+// PathtracerMIS.li up to the shadow rays: connectLight (pathtracer_mis.zig:280-341), termination (:76-86), Russian
+// roulette (:88, helper.zig:75-89), Vertex.sample (:93), sampleLights / evaluateLight up to the visibility test
+// (:174-250).
+__global__ void __launch_bounds__(kBlock) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass) {
+    const uint32_t count = st.counters[0];
+    const uint32_t iters = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t i      = it * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
+        bool           alive  = false;
+        uint32_t       slot   = 0;
+        if (i < count) {
+            slot            = st.queue_a[i];
+            LoadedVertex lv = loadVertex(st, slot);
+            VertexD&     vertex = lv.v;
+
+            const uint32_t total_depth = vertex.probe_depth;
+            const bool     hit         = kEnd != lv.prop;
+
+            SamplerD sampler;
+            uint32_t aux;
+            loadSampler(st, slot, pass, view.spp_total, total_depth, sampler, aux);
+            if (ZYG_SAMPLER_SOBOL != view.sampler) sampler.use_sobol = false;
+
+            FragD frag;
+            frag.prop = kEnd;
+            if (hit) shapeFragment(sc, lv.prop, vertex.ray, lv.isec, frag);
+
+            // connectLight
+            V3 this_light = splat3(0.f);
+            if (!(0 == view.caustics_path && 0 != (vertex.state & kSpecular) && 0 == (vertex.state & kPrimaryRay))) {
+                vertex.light_split_threshold = splitThreshold(view.split_threshold, lv.vertex_depth);
+                if (hit) this_light = evaluateRadiance(sc, vertex, frag, sampler);
+                this_light = add3(this_light, unoccludingEmission(sc, vertex, sampler));
+            }
+
+            const V3 split_throughput = scale3(1.f, lv.throughput);  // split_weight == 1
+            ivalueAdd(st, slot, mul3(split_throughput, this_light), total_depth, 2, 0 == total_depth, 0 != (vertex.state & kSingular));
+
+            bool terminate = !hit || vertex.probe_depth >= view.max_depth_surface || 0 >= view.max_depth_volume;
+
+            if (!terminate) {
+                // russianRoulette
+                const float r  = sampler.sample1D();
+                const float mx = hmax3(lv.throughput);
+                const float q  = __fdiv_rn(mx, 0.1f);
+                if (q < 1.f) {
+                    if (r >= q) {
+                        terminate = true;
+                    } else {
+                        lv.throughput = divs3(lv.throughput, q);
+                    }
+                }
+            }
+
+            if (!terminate) {
+                const bool caustics = 0 == (vertex.state & kPrimaryRay) ? 0 != view.caustics_path : true;  // causticsResolve, :343-349
+
+                const V3            wo = neg3(vertex.ray.d);
+                const ZygpuMaterial m  = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
+                (void)sampler.sample1D();  // rs.stochastic_r, vertex.zig:165
+                const MatSampleD mat_sample = materialSample(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics, view.specular_threshold);
+
+                vertex.light_split_threshold = splitThreshold(view.split_threshold, vertex.probe_depth);
+
+                // sampleLights. Every path owns `shadow_stride` consecutive shadow records (slot * stride + k): picks and
+                // their samples are generated in the reference's order and stored in that order.
+                uint32_t num_records = 0;
+                if (mat_sample.can_evaluate) {
+                    const V3    p           = frag.p;
+                    const V3    n           = mat_sample.geo_n;
+                    const bool  translucent = mat_sample.translucent;
+                    const float select      = sampler.sample1D();
+
+                    lightTreeRandomLight(sc, p, n, translucent, select, vertex.light_split_threshold, [&](LightPickD pick) {
+                        const ZygpuLight light = sc.lights[pick.offset];
+                        const TrafoD     trafo = loadTrafo(sc.trafos, light.prop);
+                        if (ZYG_SHAPE_RECTANGLE != sc.props[light.prop].shape) return;
+
+                        // Rectangle.sampleTo, rectangle.zig:305-357
+                        const uint32_t ns  = lightNumSamples(light, vertex.light_split_threshold);
+                        const float    nsf = float(ns);
+                        SphQuadD       squad;
+                        squad.init(trafo.scale, trafo.worldToFramePoint(p));
+                        const float sample_pdf = nsf * squad.pdf(trafo.scale);
+
+                        for (uint32_t k = 0; k < ns; ++k) {
+                            float u0, u1;
+                            sampler.sample2D(u0, u1);
+
+                            const V3 ls  = squad.sample(u0, u1);
+                            const V3 ws  = trafo.frameToWorldPoint(ls);
+                            const V3 dir = normalize3(sub3(ws, p));
+
+                            V3 wn = trafo.r2;
+                            if (0 != light.two_sided && dot3(wn, dir) > 0.f) wn = neg3(wn);
+
+                            if (-dot3(wn, dir) < kDotMin || 0.f == squad.S || (dot3(dir, n) <= 0.f && !translucent)) continue;
+
+                            if (num_records < st.shadow_stride) {
+                                const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+                                const V3     origin    = frag.offsetP(dir);
+                                const V3     light_pos = offsetRay(ws, wn);  // Shape.shadowRay, shape.zig:401-416
+                                st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, sample_pdf * pick.pdf);
+                                st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+                                st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                                num_records += 1;
+                            } else {
+                                st.counters[3] = 1;  // more light samples than the host reserved: reported by zygpu_render
+                            }
+                        }
+                    });
+                }
+
+                st.sh_n[slot] = num_records;
+                st.thr[slot]  = make_float4(lv.throughput.x, lv.throughput.y, lv.throughput.z, vertex.bxdf_pdf);
+                alive         = true;
+            }
+            storeSampler(st, slot, sampler, aux);
+        }
+        queuePush(st.queue_b, &st.counters[1], alive, slot);
+    }
+}
+
+// Scene.visibility for every shadow-ray record of the surviving paths, scene.zig:229-235 (no volume props)
+__global__ void __launch_bounds__(kBlock) shadowKernel(SceneDevice sc, PathState st) {
+    const uint32_t count  = st.counters[1];
+    const uint32_t stride = st.shadow_stride;
+    const uint64_t items  = uint64_t(count) * stride;
+    uint32_t       traced = 0;
+    for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t slot = st.queue_b[uint32_t(i / stride)];
+        const uint32_t k    = uint32_t(i % stride);
+        if (k >= st.sh_n[slot]) continue;
+        const size_t rec = size_t(slot) * stride + k;
+
+        const float4 o = st.sh_o[rec];
+        const float4 p = st.sh_p[rec];
+
+        const V3    origin      = {o.x, o.y, o.z};
+        const V3    shadow_axis = sub3({p.x, p.y, p.z}, origin);
+        const float shadow_len  = length3(shadow_axis);
+        const RayT  ray         = makeRay(origin, divs3(shadow_axis, shadow_len), 0.f, shadow_len);
+
+        st.sh_wi[rec].w = sceneVisibility(sc, ray) ? 1.f : 0.f;
+        traced += 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
+    if (0 == (threadIdx.x & 31u) && 0 != traced) atomicAdd(&st.counters[6], traced);  // statistics: shadow rays
+}
+
+// The rest of PathtracerMIS.li: evaluateLight after the visibility test (pathtracer_mis.zig:252-277), the direct-light
+// add (:116-117), mat_sample.sample and the next vertex (:121-166).
+__global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass) {
+    const uint32_t count = st.counters[1];
+    const LutsD    luts{sc.luts};
+    const uint32_t iters = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t i     = it * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
+        bool           alive = false;
+        uint32_t       slot  = 0;
+        if (i < count) {
+            slot                  = st.queue_b[i];
+            LoadedVertex   lv     = loadVertex(st, slot);
+            const VertexD& vertex = lv.v;
+
+            const uint32_t total_depth = vertex.probe_depth;
+
+            SamplerD sampler;
+            uint32_t aux;
+            loadSampler(st, slot, pass, view.spp_total, total_depth, sampler, aux);
+            if (ZYG_SAMPLER_SOBOL != view.sampler) sampler.use_sobol = false;
+
+            FragD frag;
+            shapeFragment(sc, lv.prop, vertex.ray, lv.isec, frag);
+
+            const bool          caustics   = 0 == (vertex.state & kPrimaryRay) ? 0 != view.caustics_path : true;
+            const V3            wo         = neg3(vertex.ray.d);
+            const ZygpuMaterial m          = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
+            const MatSampleD    mat_sample = materialSample(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics, view.specular_threshold);
+
+            // evaluateLight for the visible records
+            V3             next_light = splat3(0.f);
+            const uint32_t num        = st.sh_n[slot];
+            for (uint32_t k = 0; k < num; ++k) {
+                const size_t rec = size_t(slot) * st.shadow_stride + k;
+                const float4 wi4 = st.sh_wi[rec];
+                if (0.f == wi4.w) continue;
+                const float4 o4 = st.sh_o[rec];
+                const float4 p4 = st.sh_p[rec];
+                const V3     wi = {wi4.x, wi4.y, wi4.z};
+
+                // Light.evaluateTo, light.zig:119-132
+                (void)sampler.sample1D();
+                const uint32_t      light_id = __float_as_uint(p4.w);
+                const ZygpuLight    light    = sc.lights[light_id];
+                const TrafoD        ltrafo   = loadTrafo(sc.trafos, light.prop);
+                const ZygpuMaterial lm       = sc.materials[__ldg(sc.material_ids + sc.props[light.prop].parts_start + light.part)];
+                const float area     = 0.f != lm.emission_normalize ? shapeArea(sc.props[light.prop].shape, ltrafo.scale) : 1.f;
+                const V3    radiance = emittanceRadiance(lm, wi, ltrafo, area, false);
+
+                const BxdfResult bxdf_result = mat_sample.evaluate(luts, wi);
+
+                const float light_pdf = o4.w;
+                const float weight    = predividedPowerHeuristic(light_pdf, bxdf_result.pdf);
+
+                next_light = add3(next_light, mul3(scale3(weight, radiance), bxdf_result.reflection));
+            }
+
+            const V3 split_throughput = scale3(1.f, lv.throughput);
+            ivalueAdd(st, slot, mul3(split_throughput, next_light), total_depth, 1, false, false);
+
+            BxdfSample     sample_result;
+            const uint32_t path_count = mat_sample.sample(luts, sampler, sample_result);
+
+            if (0 != path_count) {
+                // Vertex.State.update, vertex.zig:30-43
+                uint32_t state = vertex.state;
+                if (kScatterSpecular == sample_result.scattering) {
+                    state |= kSpecular;
+                    state = 0.f == sample_result.reg_alpha ? (state | kSingular) : (state & ~kSingular);
+                    if (0 != (state & kPrimaryRay)) state |= kStartedSpecular;
+                } else if (kEventStraight != sample_result.event) {
+                    state &= ~(kSpecular | kSingular | kPrimaryRay);
+                }
+
+                uint32_t vertex_depth = lv.vertex_depth;
+                float    bxdf_pdf     = vertex.bxdf_pdf;
+                V3       origin       = vertex.origin;
+                V3       geo_n        = vertex.geo_n;
+                float    reg_alpha    = lv.reg_alpha;
+                if (kEventStraight != sample_result.event) {
+                    state        = mat_sample.translucent ? (state | kTranslucent) : (state & ~kTranslucent);
+                    vertex_depth = vertex.probe_depth;
+                    bxdf_pdf     = sample_result.pdf;
+                    origin       = frag.p;
+                    geo_n        = mat_sample.geo_n;
+                    reg_alpha    = sample_result.reg_alpha;
+                }
+
+                const V3 throughput = mul3(lv.throughput, divs3(sample_result.reflection, sample_result.pdf));
+
+                const V3 next_o = frag.offsetP(sample_result.wi);  // Fragment.offsetRay, intersection.zig:118-120
+
+                if (!(kEventTransmission == sample_result.event || kEventStraight == sample_result.event)) state &= ~kTransparent;
+
+                st.ray_o[slot]  = make_float4(next_o.x, next_o.y, next_o.z, __uint_as_float(packFlags(state, vertex.probe_depth + 1, vertex_depth)));
+                st.ray_d[slot]  = make_float4(sample_result.wi.x, sample_result.wi.y, sample_result.wi.z, kRayMaxT);
+                st.thr[slot]    = make_float4(throughput.x, throughput.y, throughput.z, bxdf_pdf);
+                st.prev_p[slot] = make_float4(origin.x, origin.y, origin.z, reg_alpha);
+                st.prev_n[slot] = make_float4(geo_n.x, geo_n.y, geo_n.z, 0.f);
+                alive           = true;
+            }
+            sampler.incrementPadding();
+            storeSampler(st, slot, sampler, 0);
+        }
+        queuePush(st.queue_a, &st.counters[4], alive, slot);
+    }
+}
+
+__global__ void advanceKernel(PathState st) {
+    st.counters[0] = st.counters[4];
+    st.counters[1] = 0;
+    st.counters[4] = 0;
+}
+
+// Sensor.addSample for every sample of the pass, gathered per film pixel (sensor.zig:168-385, buffer_opaque.zig:39-45).
+__device__ __forceinline__ V3 clampColor(V3 color, float mx) {  // sensor.zig:615-624
+    const float mc = hmax3(color);
+    if (mc > mx) return scale3(__fdiv_rn(mx, mc), color);
+    return color;
+}
+
+__device__ __forceinline__ float filterEval(const ZygpuView& view, float s) {  // sensor.zig:626-628
+    const float    cx     = zmin(fabsf(s), view.filter_range_end);
+    const float    o      = cx * view.filter_inverse_interval;
+    const uint32_t offset = uint32_t(o);
+    const float    t      = o - float(offset);
+    return zlerp(view.filter[offset], view.filter[min(offset + 1, 29u)], t);
+}
+
+__global__ void __launch_bounds__(kBlock) filmKernel(ZygpuView view, PathState st, PassParams pass, float4* film) {
+    const int32_t  w  = view.resolution[0];
+    const int32_t  h  = view.resolution[1];
+    const int32_t  fr = view.filter_radius_int;
+    const uint32_t padded = pass.padded_w * pass.padded_h;
+
+    for (uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < uint32_t(w * h); pixel += gridDim.x * blockDim.x) {
+        const int32_t x = int32_t(pixel % uint32_t(w));
+        const int32_t y = int32_t(pixel / uint32_t(w));
+        // Sensor.add bounds test: pixels outside the crop receive nothing (sensor.zig:559-562)
+        if (x < view.crop[0] || x >= view.crop[2] || y < view.crop[1] || y >= view.crop[3]) continue;
+
+        float4 value = film[pixel];
+
+        for (uint32_t s = 0; s < pass.samples_in_pass; ++s) {
+            for (int32_t dy = -fr; dy <= fr; ++dy) {
+                for (int32_t dx = -fr; dx <= fr; ++dx) {
+                    // the sample's pixel q = (x + dx, y + dy) must have been rendered: crop extended by the filter radius
+                    const int32_t qx = x + dx, qy = y + dy;
+                    if (qx < view.crop[0] - fr || qx >= view.crop[2] + fr || qy < view.crop[1] - fr || qy >= view.crop[3] + fr) continue;
+                    const uint32_t slot = s * padded + uint32_t(qy + fr) * pass.padded_w + uint32_t(qx + fr);
+
+                    const float4 e  = st.acc_e[slot];
+                    const float4 d  = st.acc_d[slot];
+                    const float4 in = st.acc_i[slot];
+
+                    const V3 emission = clampColor({e.x, e.y, e.z}, view.clamp_emission);
+                    const V3 direct   = clampColor({d.x, d.y, d.z}, view.clamp_direct);
+                    const V3 indirect = clampColor({in.x, in.y, in.z}, view.clamp_indirect);
+                    const V3 composed = add3(add3(emission, direct), indirect);
+
+                    float weight = 1.f;
+                    if (fr > 0) {
+                        const float ox = e.w - 0.5f;
+                        const float oy = d.w - 0.5f;
+                        weight         = filterEval(view, ox + float(dx)) * filterEval(view, oy + float(dy));
+                    }
+                    // Opaque.addPixel
+                    value.x += weight * composed.x;
+                    value.y += weight * composed.y;
+                    value.z += weight * composed.z;
+                    value.w += weight;
+                }
+            }
+        }
+        film[pixel] = value;
+    }
+}
+
+// Opaque.resolveTonemap with the Linear tonemapper, buffer_opaque.zig:73-79, tonemapper.zig:36-39, aces.zig:19-27
+__global__ void __launch_bounds__(kBlock) resolveKernel(ZygpuView view, const float4* film, float4* rgba, uint32_t num_pixels) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels; i += gridDim.x * blockDim.x) {
+        const float4 p = film[i];
+        const V3     c = {fabsf(__fdiv_rn(p.x, p.w)), fabsf(__fdiv_rn(p.y, p.w)), fabsf(__fdiv_rn(p.z, p.w))};
+        const V3     s = scale3(view.exposure_factor, c);
+        const V3     srgb = add3(add3(scale3(s.x, {1.70505155f, -0.13025714f, -0.02400328f}), scale3(s.y, {-0.62179068f, 1.14080289f, -0.12896877f})),
+                                 scale3(s.z, {-0.08325840f, -0.01054853f, 1.15297171f}));
+        rgba[i] = make_float4(srgb.x, srgb.y, srgb.z, 1.f);
+    }
+}
+
+int numSms() {
+    static int sms = 0;
+    if (0 == sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+// Grid-stride launches: a multiple of the SM count, never more blocks than there is work.
+uint32_t gridFor(uint32_t items, uint32_t blocks_per_sm) {
+    const uint32_t needed = (items + kBlock - 1) / kBlock;
+    return std::max(1u, std::min(needed, uint32_t(numSms()) * blocks_per_sm));
+}
+
+}  // namespace
+
+cudaError_t uploadSobolDirections() {
+    // Joe & Kuo direction numbers (new-joe-kuo-6.21201) for dimensions 1-5: degree s, coefficients a, initial m_i.
+    static const uint32_t S[5]    = {0, 1, 2, 3, 3};
+    static const uint32_t A[5]    = {0, 0, 1, 1, 2};
+    static const uint32_t M[5][3] = {{0, 0, 0}, {1, 0, 0}, {1, 3, 0}, {1, 3, 1}, {1, 1, 1}};
+    uint32_t              d[5][32];
+    for (uint32_t i = 0; i < 32; ++i) d[0][i] = 1u << (31 - i);
+    for (uint32_t j = 1; j < 5; ++j) {
+        const uint32_t s = S[j];
+        for (uint32_t i = 0; i < 32; ++i) {
+            if (i < s) {
+                d[j][i] = M[j][i] << (31 - i);
+            } else {
+                uint32_t v = d[j][i - s] ^ (d[j][i - s] >> s);
+                for (uint32_t k = 1; k < s; ++k) v ^= ((A[j] >> (s - 1 - k)) & 1u) * d[j][i - k];
+                d[j][i] = v;
+            }
+        }
+    }
+    return cudaMemcpyToSymbol(c_sobol_directions, d, sizeof(d));
+}
+
+cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const PassParams& pass, cudaStream_t stream) {
+    generateKernel<<<gridFor(pass.num_paths, 16), kBlock, 0, stream>>>(view, st, pass);
+    return cudaGetLastError();
+}
+cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream) {
+    extendKernel<<<gridFor(max_items, 16), kBlock, 0, stream>>>(scene, st);
+    return cudaGetLastError();
+}
+cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
+                         cudaStream_t stream) {
+    shadeAKernel<<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass);
+    return cudaGetLastError();
+}
+cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream) {
+    shadowKernel<<<gridFor(max_items, 16), kBlock, 0, stream>>>(scene, st);
+    return cudaGetLastError();
+}
+cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
+                         cudaStream_t stream) {
+    shadeBKernel<<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass);
+    advanceKernel<<<1, 1, 0, stream>>>(st);
+    return cudaGetLastError();
+}
+cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream) {
+    filmKernel<<<gridFor(uint32_t(view.resolution[0] * view.resolution[1]), 16), kBlock, 0, stream>>>(view, st, pass, film);
+    return cudaGetLastError();
+}
+cudaError_t launchResolve(const ZygpuView& view, const float4* film, float4* rgba, uint32_t num_pixels, cudaStream_t stream) {
+    resolveKernel<<<gridFor(num_pixels, 16), kBlock, 0, stream>>>(view, film, rgba, num_pixels);
+    return cudaGetLastError();
+}
+
+}  // namespace zygpu

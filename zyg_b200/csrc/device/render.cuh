@@ -1,0 +1,117 @@
+// Wavefront stages of the forward surface-integration pass (PathtracerMIS) for sm_100a.
+//
+// The per-pixel recursion of the reference (Worker.render -> PathtracerMIS.li, src/core/rendering/worker.zig:
+// 104-168, integrator/surface/pathtracer_mis.zig:37-172) is cut into stages that each run over a compacted
+// queue of path slots; path state lives in SoA arrays of 16-byte words in HBM:
+//
+//   generate   camera sample + ray for `samples_in_pass` samples of every (padded) pixel      -> queue A
+//   extend     closest hit: prop tree -> analytic shape / 8-wide mesh BVH                      A
+//   shade_a    emission at the hit + un-occluding emitter gather, termination, Russian roulette,
+//              material setup, light picks and light samples -> shadow-ray records             A -> queue B
+//   shadow     any-hit visibility of every shadow-ray record
+//   shade_b    NEE contributions of the visible records, BSDF sample, next ray                 B -> queue A
+//   film       per-pixel weighted sum over the pass's samples (gather, no atomics)
+//
+// shade_a / shade_b are split at the shadow ray because the reference draws the light's stochastic
+// number only after the shadow test passed (light.zig:127, pathtracer_mis.zig:252-260): keeping that
+// order keeps every path on the sampler dimensions the CPU path uses.
+#pragma once
+
+#include "../../../include/zygpu_scene.h"
+#include "trace.cuh"
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zygpu {
+
+struct MeshShading {  // hit-point reconstruction data of one mesh
+    const uint32_t* triangles;  // 3 per BVH-order triangle
+    const float*    positions;  // 3 per vertex
+    const uint16_t* normals;    // 2 per vertex, oct snorm16
+    const float*    uvs;        // 2 per vertex
+    const uint16_t* parts;      // per BVH-order triangle
+};
+
+struct SceneDevice {
+    const ZygpuProp*     props;
+    const float4*        trafos;  // 4 per prop
+    const float4*        aabbs;   // 2 per prop
+    const uint32_t*      material_ids;
+    const uint32_t*      light_ids;
+    const ZygpuMaterial* materials;
+
+    const ZygpuLight* lights;
+    const float4*     light_aabbs;  // 2 per light
+    const float4*     light_cones;
+
+    // light tree
+    const ZygpuLightNode* lt_nodes;
+    const uint32_t*       lt_middles;
+    const uint32_t*       lt_orders;
+    const uint32_t*       lt_mapping;
+    float4                lt_bounds_min, lt_bounds_max;
+    float                 lt_infinite_weight, lt_infinite_guard;
+    uint32_t              lt_infinite_end, lt_max_split_depth, lt_num_infinite, lt_num_nodes;
+
+    const float4*   solid_nodes;  // 2 per node
+    const uint32_t* solid_indices;
+    uint32_t        num_solid_nodes;
+    const float4*   unocc_nodes;
+    const uint32_t* unocc_indices;
+    uint32_t        num_unocc_nodes;
+
+    const MeshDevice*  meshes;
+    const MeshShading* mesh_shading;
+
+    const float* luts;  // ZygpuScene.ggx_luts
+};
+
+struct PathState {
+    float4* ray_o;   // origin xyz | flags: state bits 0-7, probe depth 8-15, vertex.depth 16-23
+    float4* ray_d;   // direction xyz | max_t (after extend: hit t)
+    float4* thr;     // throughput rgb | bxdf_pdf
+    float4* prev_p;  // vertex.origin xyz | reg_alpha
+    float4* prev_n;  // vertex.geo_n xyz | light_split_threshold
+    float4* hit;     // u, v | primitive | prop
+    float4* acc_e;   // emission rgb | pixel_uv.x
+    float4* acc_d;   // direct rgb | pixel_uv.y
+    float4* acc_i;   // indirect rgb | -
+    uint4*  smp;     // Sobol: block seed, run seed, dimension | -
+    uint2*  rng;     // PCG state
+
+    // shadow-ray records, written by shade_a: path `slot` owns records [slot * shadow_stride, +sh_n[slot])
+    float4*   sh_o;   // origin xyz | light pdf (sample pdf * pick pdf)
+    float4*   sh_p;   // offset light position xyz | light id
+    float4*   sh_wi;  // light_sample.wi xyz | visible (written by shadow)
+    uint32_t* sh_n;   // per path: number of records
+
+    uint32_t* queue_a;
+    uint32_t* queue_b;
+    uint32_t* counters;  // [0] |A|, [1] |B|, [3] shadow overflow flag, [4] |next A|, [5] closest rays, [6] shadow rays
+
+    uint32_t capacity;       // path slots
+    uint32_t shadow_stride;  // shadow records reserved per path
+};
+
+struct PassParams {
+    uint32_t iteration;        // first sample of the pass
+    uint32_t samples_in_pass;  // k
+    uint32_t padded_w, padded_h;
+    uint32_t num_paths;  // k * padded_w * padded_h
+};
+
+cudaError_t uploadSobolDirections();
+
+cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const PassParams& pass, cudaStream_t stream);
+// The queue lengths live on the device; the grids are sized for `max_items` and exit early.
+cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream);
+cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
+                         uint32_t max_items, cudaStream_t stream);
+cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream);
+cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
+                         uint32_t max_items, cudaStream_t stream);
+cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream);
+cudaError_t launchResolve(const ZygpuView& view, const float4* film, float4* rgba, uint32_t num_pixels, cudaStream_t stream);
+
+}  // namespace zygpu

@@ -1,0 +1,699 @@
+// Device restatement of the shading side of the reference for the render stages (render.cu):
+// samplers, analytic shapes, Substitute / Light materials, light tree, light sampling.
+// Every function names the reference code it follows; arithmetic order is the reference's
+// (see zmath.cuh for the fp rules).
+#pragma once
+
+#include "render.cuh"
+#include "zmath.cuh"
+
+namespace zygpu {
+
+// ---- samplers --------------------------------------------------------------------------------
+
+__constant__ uint32_t c_sobol_directions[5][32];  // src/core/sampler/sobol.zig:194-245, regenerated (render.cu)
+
+__device__ __forceinline__ uint32_t sobolHash(uint32_t i) {  // sobol.zig:107-124
+    uint32_t x = i ^ (i >> 16);
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t hashCombine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
+__device__ __forceinline__ uint32_t laineKarras(uint32_t i, uint32_t seed) {  // sobol.zig:142-174
+    uint32_t x = i ^ (i * 0x3d20adeau);
+    x += seed;
+    x *= (seed >> 16) | 1u;
+    x ^= x * 0x05526c56u;
+    x ^= x * 0x53a22864u;
+    return x;
+}
+__device__ __forceinline__ uint32_t nestedUniformScramble(uint32_t x, uint32_t seed) {  // :136-140
+    return __brev(laineKarras(__brev(x), seed));
+}
+
+struct SobolD {  // sobol.zig:8-105
+    float    buffer[5];
+    uint32_t sample, dimension, block_seed, run_seed;
+
+    __device__ void fill(uint32_t s) {  // incrementSeed body, :36-56
+        const float    S = 1.f / 4294967296.f;
+        const uint32_t i = nestedUniformScramble(sample, s);
+        uint32_t       x0 = 0, x1 = 0, x2 = 0, x3 = 0, x4 = 0;
+        for (uint32_t bit = 0, idx = i; 0 != idx; ++bit, idx >>= 1) {  // sobol5, :176-192
+            const uint32_t mask = idx & 1u;
+            x0 ^= mask * c_sobol_directions[0][bit];
+            x1 ^= mask * c_sobol_directions[1][bit];
+            x2 ^= mask * c_sobol_directions[2][bit];
+            x3 ^= mask * c_sobol_directions[3][bit];
+            x4 ^= mask * c_sobol_directions[4][bit];
+        }
+        buffer[0] = __uint2float_rn(nestedUniformScramble(x0, hashCombine(s, 0))) * S;
+        buffer[1] = __uint2float_rn(nestedUniformScramble(x1, hashCombine(s, 1))) * S;
+        buffer[2] = __uint2float_rn(nestedUniformScramble(x2, hashCombine(s, 2))) * S;
+        buffer[3] = __uint2float_rn(nestedUniformScramble(x3, hashCombine(s, 3))) * S;
+        buffer[4] = __uint2float_rn(nestedUniformScramble(x4, hashCombine(s, 4))) * S;
+    }
+    __device__ void incrementSeed() {
+        block_seed = run_seed;
+        fill(block_seed);
+        run_seed  = sobolHash(block_seed + 1);
+        dimension = 0;
+    }
+    __device__ void startPixel(uint32_t s, uint32_t seed) {
+        sample     = s;
+        dimension  = 5;
+        run_seed   = sobolHash(seed);
+        block_seed = run_seed;
+    }
+    // state carried between stages: (block_seed, run_seed, dimension); the buffer is rebuilt on demand
+    __device__ void restore(uint32_t s, uint32_t bseed, uint32_t rseed, uint32_t dim) {
+        sample     = s;
+        block_seed = bseed;
+        run_seed   = rseed;
+        dimension  = dim;
+        if (dim < 5) fill(bseed);
+    }
+};
+
+struct PcgD {  // src/base/random/generator.zig
+    uint64_t state, inc;
+
+    __device__ uint32_t randomUint() {
+        const uint64_t old = state;
+        state              = old * 6364136223846793005ull + inc;
+        const uint32_t xrs = uint32_t(((old >> 18) ^ old) >> 27);
+        const uint32_t rot = uint32_t(old >> 59);
+        return (xrs >> rot) | (xrs << ((0u - rot) & 31));
+    }
+    __device__ void start(uint64_t s, uint64_t sequence) {
+        state = 0;
+        inc   = (sequence << 1) | 1;
+        randomUint();
+        state += s;
+        randomUint();
+    }
+    __device__ float randomFloat() { return __uint_as_float((randomUint() & 0x007FFFFFu) | 0x3F800000u) - 1.f; }
+};
+
+struct SamplerD {  // sampler.zig:17-74 (+ Worker.pickSampler, worker.zig:201-207)
+    bool   use_sobol;
+    SobolD sobol;
+    PcgD   rng;
+
+    __device__ float sample1D() {
+        if (!use_sobol) return rng.randomFloat();
+        if (sobol.dimension >= 5) sobol.incrementSeed();
+        return sobol.buffer[sobol.dimension++];
+    }
+    __device__ void sample2D(float& a, float& b) {
+        if (!use_sobol) {
+            a = rng.randomFloat();
+            b = rng.randomFloat();
+            return;
+        }
+        if (sobol.dimension >= 4) sobol.incrementSeed();
+        const uint32_t d = sobol.dimension;
+        sobol.dimension  = d + 2;
+        a                = sobol.buffer[d];
+        b                = sobol.buffer[d + 1];
+    }
+    __device__ V3 sample3D() {
+        if (!use_sobol) {
+            V3 r;
+            r.x = rng.randomFloat();
+            r.y = rng.randomFloat();
+            r.z = rng.randomFloat();
+            return r;
+        }
+        if (sobol.dimension >= 3) sobol.incrementSeed();
+        const uint32_t d = sobol.dimension;
+        sobol.dimension  = d + 3;
+        return {sobol.buffer[d], sobol.buffer[d + 1], sobol.buffer[d + 2]};
+    }
+    __device__ void incrementPadding() {
+        if (use_sobol) sobol.dimension = 5;
+    }
+};
+
+// ---- shapes ----------------------------------------------------------------------------------
+
+struct HitD {  // shape/intersection.zig:46-61 (trafo is re-read from the prop)
+    float    t, u, v;
+    uint32_t primitive;
+};
+
+struct FragD {  // shape/intersection.zig:63-124
+    V3       p, geo_n, t, b, n;
+    float    u, v;  // uvw[0..1]; uvw[3] (ray offset) is 0 for every shape in scope
+    uint32_t prop, part;
+    TrafoD   trafo;
+
+    __device__ bool sameHemisphere(V3 w) const { return dot3(geo_n, w) > 0.f; }
+    __device__ V3   offsetP(V3 w) const {  // :112-116, offset() == 0: @mulAdd(0, n, p) == p
+        const V3 nn = sameHemisphere(w) ? geo_n : neg3(geo_n);
+        return offsetRay(fmas3(0.f, nn, p), nn);
+    }
+};
+
+// Rectangle.intersect, rectangle.zig:30-62
+__device__ __forceinline__ bool rectangleIntersect(const RayT& ray, const TrafoD& trafo, HitD& isec) {
+    const V3    n     = trafo.r2;
+    const float d     = dot3(n, trafo.position);
+    const float hit_t = __fdiv_rn(-(dot3(n, ray.o) - d), dot3(n, ray.d));
+
+    if (hit_t >= ray.tmin && ray.tmax >= hit_t) {
+        const V3 p = rayPoint(ray, hit_t);
+        const V3 k = sub3(p, trafo.position);
+        const V3 t = neg3(trafo.r0);
+
+        const float u = __fdiv_rn(dot3(t, k), 0.5f * trafo.scale.x);
+        if (u > 1.f || u < -1.f) return false;
+
+        const V3    b = neg3(trafo.r1);
+        const float v = __fdiv_rn(dot3(b, k), 0.5f * trafo.scale.y);
+        if (v > 1.f || v < -1.f) return false;
+
+        isec.u         = u;
+        isec.v         = v;
+        isec.t         = hit_t;
+        isec.primitive = 0;
+        return true;
+    }
+    return false;
+}
+
+// Rectangle.fragment, rectangle.zig:102-124
+__device__ __forceinline__ void rectangleFragment(const RayT& ray, const HitD& isec, FragD& frag) {
+    const V3 p = rayPoint(ray, isec.t);
+    const V3 n = frag.trafo.r2;
+    const V3 t = neg3(frag.trafo.r0);
+    const V3 b = neg3(frag.trafo.r1);
+
+    frag.p     = p;
+    frag.t     = t;
+    frag.b     = b;
+    frag.n     = n;
+    frag.geo_n = n;
+    if (frag.trafo.scale.z < 0.f) {
+        const V3    k = sub3(p, frag.trafo.position);
+        const float u = dot3(t, k) * 2.f;
+        const float v = dot3(b, k) * 2.f;
+        frag.u        = 0.5f * (u + 1.f);
+        frag.v        = 0.5f * (v + 1.f);
+    } else {
+        frag.u = 0.5f * (isec.u + 1.f);
+        frag.v = 0.5f * (isec.v + 1.f);
+    }
+    frag.part = 0;
+}
+
+// AABB.intersectP on the unit cube, aabb.zig:62-84
+__device__ __forceinline__ float unitCubeIntersectP(const RayT& ray) {
+    const float lx = (-0.5f - ray.o.x) * ray.inv_d.x, ly = (-0.5f - ray.o.y) * ray.inv_d.y, lz = (-0.5f - ray.o.z) * ray.inv_d.z;
+    const float ux = (0.5f - ray.o.x) * ray.inv_d.x, uy = (0.5f - ray.o.y) * ray.inv_d.y, uz = (0.5f - ray.o.z) * ray.inv_d.z;
+
+    const float t0x = zmin(lx, ux), t0y = zmin(ly, uy), t0z = zmin(lz, uz);
+    const float t1x = zmax(lx, ux), t1y = zmax(ly, uy), t1z = zmax(lz, uz);
+
+    const float imin = zmax(zmax(t0x, t0y), t0z);
+    const float imax = zmin(zmin(t1x, t1y), t1z);
+
+    const float tboxmin = zmax(imin, ray.tmin);
+    const float tboxmax = zmin(imax, ray.tmax);
+
+    if (tboxmin <= tboxmax) return imin < ray.tmin ? imax : imin;
+    return FLT_MAX;
+}
+
+__device__ __forceinline__ RayT worldToObjectRay(const TrafoD& trafo, const RayT& ray) {  // composed_transformation.zig:119-126
+    return makeRay(trafo.worldToObjectPoint(ray.o), trafo.worldToObjectVector(ray.d), ray.tmin, ray.tmax);
+}
+
+// Cube.intersect, cube.zig:24-38
+__device__ __forceinline__ bool cubeIntersect(const RayT& ray, const TrafoD& trafo, HitD& isec) {
+    const RayT  local_ray = worldToObjectRay(trafo, ray);
+    const float hit_t     = unitCubeIntersectP(local_ray);
+    if (hit_t < ray.tmax) {
+        isec.t         = hit_t;
+        isec.primitive = 0;
+        return true;
+    }
+    return false;
+}
+
+// Cube.fragment, cube.zig:40-62
+__device__ __forceinline__ void cubeFragment(const RayT& ray, const HitD& isec, FragD& frag) {
+    const float hit_t = isec.t;
+    frag.p            = rayPoint(ray, hit_t);
+
+    const RayT local_ray = worldToObjectRay(frag.trafo, ray);
+    const V3   local_p   = rayPoint(local_ray, hit_t);
+    const V3   distance  = {fabsf(0.5f - fabsf(local_p.x)), fabsf(0.5f - fabsf(local_p.y)), fabsf(0.5f - fabsf(local_p.z))};
+
+    // indexMinComponent3, vector4.zig:181-187
+    uint32_t i;
+    if (distance.x < distance.y) {
+        i = distance.x < distance.z ? 0 : 2;
+    } else {
+        i = distance.y < distance.z ? 1 : 2;
+    }
+    const float lp = 0 == i ? local_p.x : (1 == i ? local_p.y : local_p.z);
+    const V3    ri = 0 == i ? frag.trafo.r0 : (1 == i ? frag.trafo.r1 : frag.trafo.r2);
+    const float s  = copysignf(1.f, lp);
+    const V3    n  = scale3(s, ri);
+
+    frag.part  = 0;
+    frag.geo_n = n;
+    frag.n     = n;
+    frag.u     = 0.f;
+    frag.v     = 0.f;
+    orthonormalBasis3(n, frag.t, frag.b);
+}
+
+// Cube.intersectP, cube.zig:64-69 -> AABB.intersect, aabb.zig:46-60
+__device__ __forceinline__ bool cubeIntersectP(const RayT& ray, const TrafoD& trafo) {
+    const RayT r = worldToObjectRay(trafo, ray);
+    return FLT_MAX != intersectNode(make_float4(-0.5f, -0.5f, -0.5f, 0.f), make_float4(0.5f, 0.5f, 0.5f, 0.f), r);
+}
+
+// Sphere.intersect, sphere.zig:28-62
+__device__ __forceinline__ bool sphereIntersect(const RayT& ray, const TrafoD& trafo, HitD& isec) {
+    const float idl = __fdiv_rn(1.f, length3(ray.d));
+    const V3    nd  = scale3(idl, ray.d);
+
+    const V3    v = sub3(trafo.position, ray.o);
+    const float b = dot3(nd, v);
+
+    const V3    remedy_term  = sub3(v, scale3(b, nd));
+    const float radius       = 0.5f * trafo.scale.x;
+    const float discriminant = radius * radius - dot3(remedy_term, remedy_term);
+
+    if (discriminant > 0.f) {
+        const float dist = __fsqrt_rn(discriminant);
+        const float t0   = (b - dist) * idl;
+        if (t0 >= ray.tmin && ray.tmax >= t0) {
+            isec.t         = t0;
+            isec.primitive = 0;
+            return true;
+        }
+        const float t1 = (b + dist) * idl;
+        if (t1 >= ray.tmin && ray.tmax >= t1) {
+            isec.t         = t1;
+            isec.primitive = 0;
+            return true;
+        }
+    }
+    return false;
+}
+
+// Sphere.fragment, sphere.zig:64-92
+__device__ __forceinline__ void sphereFragment(const RayT& ray, const HitD& isec, FragD& frag) {
+    const V3 p = rayPoint(ray, isec.t);
+    const V3 n = normalize3(sub3(p, frag.trafo.position));
+
+    frag.p     = p;
+    frag.geo_n = n;
+    frag.n     = n;
+    frag.part  = 0;
+
+    const V3    xyz   = normalize3(frag.trafo.worldToObjectNormal(n));
+    const float phi   = -atan2f(xyz.x, xyz.z) + kPi;
+    const float theta = acosf(xyz.y);
+
+    float sin_phi, cos_phi;
+    sincosf(phi, &sin_phi, &cos_phi);
+    const float sin_theta = zmax(sinf(theta), 0.00001f);
+
+    const V3 t = normalize3(frag.trafo.objectToWorldNormal({sin_theta * cos_phi, 0.f, sin_theta * sin_phi}));
+
+    frag.t = t;
+    frag.b = neg3(cross3(t, n));
+    frag.u = phi * (0.5f * kPiInv);
+    frag.v = theta * kPiInv;
+}
+
+// ---- materials -------------------------------------------------------------------------------
+
+struct LutsD {  // ggx_integral.zig tables in the order of ZygpuScene.ggx_luts
+    const float* base;
+    __device__ float eM(float n_dot, float alpha) const { return lut2(base, 32, 32, n_dot, alpha); }
+    __device__ float eMAvg(float alpha) const { return lut1(base + 1024, 32, alpha); }
+    __device__ float e(float n_dot, float alpha, float f0) const { return lut3(base + 1056, 16, 16, 16, n_dot, alpha, f0); }
+    __device__ float eAvg(float alpha, float f0) const { return lut2(base + 1056 + 4096, 16, 16, alpha, f0); }
+};
+
+struct BxdfResult {  // bxdf.zig:8-19
+    V3    reflection;
+    float pdf;
+};
+
+enum : uint32_t { kScatterDiffuse = 0, kScatterGlossy = 1, kScatterSpecular = 2, kScatterNone = 3 };
+enum : uint32_t { kEventReflection = 0, kEventTransmission = 1, kEventStraight = 2 };
+
+struct BxdfSample {  // bxdf.zig:75-82
+    V3       reflection, wi;
+    float    pdf;
+    float    reg_alpha;  // Path
+    uint32_t scattering, event;
+};
+
+constexpr float kMinRoughness = 0.01314f;  // ggx.zig:14
+
+__device__ __forceinline__ V3 schlickF(V3 f0, float wo_dot_h) {  // fresnel.zig:16-18
+    const float p = pow5(1.f - wo_dot_h);
+    return {__fmaf_rn(p, 1.f - f0.x, f0.x), __fmaf_rn(p, 1.f - f0.y, f0.y), __fmaf_rn(p, 1.f - f0.z, f0.z)};
+}
+
+__device__ __forceinline__ float pdfVisible(float d, float g1_wo) { return __fdiv_rn(0.5f * d, g1_wo); }  // ggx.zig:437-439
+
+// ggx.zig:34-46
+__device__ __forceinline__ V3 dspbrMicroEc(const LutsD& luts, V3 f0, float n_dot_wi, float n_dot_wo, float alpha) {
+    const float e_wo  = luts.eM(n_dot_wo, alpha);
+    const float e_wi  = luts.eM(n_dot_wi, alpha);
+    const float e_avg = luts.eMAvg(alpha);
+
+    const float m = __fdiv_rn((1.f - e_wo) * (1.f - e_wi), kPi * (1.f - e_avg));
+
+    const V3 f_avg = {__fmaf_rn(20.f / 21.f, f0.x, 1.f / 21.f), __fmaf_rn(20.f / 21.f, f0.y, 1.f / 21.f), __fmaf_rn(20.f / 21.f, f0.z, 1.f / 21.f)};
+    const float om = 1.f - e_avg;
+    const V3 f = {__fdiv_rn((f_avg.x * f_avg.x) * e_avg, __fmaf_rn(-f_avg.x, om, 1.f)),
+                  __fdiv_rn((f_avg.y * f_avg.y) * e_avg, __fmaf_rn(-f_avg.y, om, 1.f)),
+                  __fdiv_rn((f_avg.z * f_avg.z) * e_avg, __fmaf_rn(-f_avg.z, om, 1.f))};
+    return scale3(m, f);
+}
+
+// Aniso.sample, ggx.zig:393-409
+__device__ __forceinline__ V3 sampleVndf(V3 wo, float ax, float ay, float xi0, float xi1, const FrameD& frame, float& n_dot_h) {
+    const V3 wo_l = frame.worldToFrame(wo);
+    const V3 v    = normalize3({ax * wo_l.x, ay * wo_l.y, wo_l.z});
+
+    const float phi       = (2.f * kPi) * xi0;
+    const float z         = __fmaf_rn(1.f - xi1, 1.f + v.z, -v.z);
+    const float sin_theta = __fsqrt_rn(saturate(1.f - z * z));
+    float       sp, cp;
+    sincosf(phi, &sp, &cp);
+    const float x = sin_theta * cp;
+    const float y = sin_theta * sp;
+
+    const V3 h = add3({x, y, z}, v);
+    const V3 m = normalize3({ax * h.x, ay * h.y, h.z});
+
+    n_dot_h = safeClamp(m.z);
+    return frame.frameToWorld(m);
+}
+
+__device__ __forceinline__ float isoDistribution(float n_dot_h, float a2) {  // ggx.zig:235-238
+    const float d = __fmaf_rn(n_dot_h * n_dot_h, a2 - 1.f, 1.f);
+    return __fdiv_rn(a2, kPi * d * d);
+}
+__device__ __forceinline__ void isoVisibilityAndG1Wo(float n_dot_wi, float n_dot_wo, float alpha2, float& vis, float& g1) {  // :240-250
+    const float t_wi = __fsqrt_rn(__fmaf_rn(1.f - alpha2, n_dot_wi * n_dot_wi, alpha2));
+    const float t_wo = __fsqrt_rn(__fmaf_rn(1.f - alpha2, n_dot_wo * n_dot_wo, alpha2));
+    vis              = __fdiv_rn(0.5f, n_dot_wi * t_wo + n_dot_wo * t_wi);
+    g1               = t_wo + n_dot_wo;
+}
+__device__ __forceinline__ float anisoDistribution(float n_dot_h, float x_dot_h, float y_dot_h, float ax, float ay) {  // :411-419
+    const float x = __fdiv_rn(x_dot_h * x_dot_h, ax * ax);
+    const float y = __fdiv_rn(y_dot_h * y_dot_h, ay * ay);
+    const float d = (x + y) + (n_dot_h * n_dot_h);
+    return __fdiv_rn(1.f, kPi * (ax * ay) * (d * d));
+}
+__device__ __forceinline__ void anisoVisibilityAndG1Wo(float t_dot_wi, float t_dot_wo, float b_dot_wi, float b_dot_wo, float n_dot_wi,
+                                                       float n_dot_wo, float ax, float ay, float& vis, float& g1) {  // :421-434
+    const float t_wo = length3({ax * t_dot_wo, ay * b_dot_wo, n_dot_wo});
+    const float t_wi = length3({ax * t_dot_wi, ay * b_dot_wi, n_dot_wi});
+    vis              = __fdiv_rn(0.5f, n_dot_wi * t_wo + n_dot_wo * t_wi);
+    g1               = t_wo + n_dot_wo;
+}
+
+// Aniso.reflectionF (-> Iso.reflectionF when isotropic), ggx.zig:268-305, 73-95
+__device__ __forceinline__ BxdfResult ggxReflection(V3 wi, V3 wo, V3 h, float n_dot_wi, float n_dot_wo, float wo_dot_h, float ax,
+                                                    float ay, V3 f0, const FrameD& frame) {
+    float d, vis, g1;
+    if (ax == ay) {
+        const float alpha2  = ax * ax;
+        const float n_dot_h = saturate(dot3(frame.z, h));
+        d                   = isoDistribution(n_dot_h, alpha2);
+        isoVisibilityAndG1Wo(n_dot_wi, n_dot_wo, alpha2, vis, g1);
+    } else {
+        const float n_dot_h = saturate(dot3(frame.z, h));
+        const float x_dot_h = dot3(frame.x, h);
+        const float y_dot_h = dot3(frame.y, h);
+        d                   = anisoDistribution(n_dot_h, x_dot_h, y_dot_h, ax, ay);
+        anisoVisibilityAndG1Wo(dot3(frame.x, wi), dot3(frame.x, wo), dot3(frame.y, wi), dot3(frame.y, wo), n_dot_wi, n_dot_wo, ax, ay,
+                               vis, g1);
+    }
+    const V3 f = schlickF(f0, wo_dot_h);
+    return {scale3(d * vis, f), pdfVisible(d, g1)};
+}
+
+struct MicroD {  // ggx.zig:52-56
+    V3    h;
+    float n_dot_wi, h_dot_wi;
+};
+
+// Aniso.reflect (-> Iso.reflect when isotropic), ggx.zig:307-353, 97-126
+__device__ __forceinline__ MicroD ggxReflect(V3 wo, float n_dot_wo, float ax, float ay, float specular_threshold, float xi0, float xi1,
+                                             V3 f0, const FrameD& frame, BxdfSample& result) {
+    float    n_dot_h;
+    const V3 h = sampleVndf(wo, ax, ay, xi0, xi1, frame, n_dot_h);
+
+    float x_dot_h = 0.f, y_dot_h = 0.f;
+    if (ax != ay) {
+        x_dot_h = dot3(frame.x, h);
+        y_dot_h = dot3(frame.y, h);
+    }
+
+    const float wo_dot_h = clampDot(wo, h);
+    const V3    wi       = normalize3(fmas3(2.f * wo_dot_h, h, neg3(wo)));
+    const float n_dot_wi = frame.clampNdot(wi);
+
+    float d, vis, g1;
+    if (ax == ay) {
+        const float alpha2 = ax * ax;
+        d                  = isoDistribution(n_dot_h, alpha2);
+        isoVisibilityAndG1Wo(n_dot_wi, n_dot_wo, alpha2, vis, g1);
+    } else {
+        d = anisoDistribution(n_dot_h, x_dot_h, y_dot_h, ax, ay);
+        anisoVisibilityAndG1Wo(dot3(frame.x, wi), dot3(frame.x, wo), dot3(frame.y, wi), dot3(frame.y, wo), n_dot_wi, n_dot_wo, ax, ay,
+                               vis, g1);
+    }
+    const V3 f = schlickF(f0, wo_dot_h);
+
+    result.reflection = scale3(d * vis, f);
+    result.wi         = wi;
+    result.pdf        = pdfVisible(d, g1);
+    const float a     = ax == ay ? ax : ay;  // Path.reflection(alpha | alpha[1], threshold)
+    result.reg_alpha  = a;
+    result.scattering = a <= specular_threshold ? kScatterSpecular : kScatterGlossy;
+    result.event      = kEventReflection;
+    return {h, n_dot_wi, wo_dot_h};
+}
+
+// diffuse.Micro, diffuse.zig:42-116
+__device__ __forceinline__ float diffuseEstimateContribution(const LutsD& luts, float alpha, float f0, float albedo) {
+    const float e_avg = luts.eAvg(alpha, f0);
+    const float a     = e_avg;
+    const float b     = __fdiv_rn(1.f, kPi * (1.f - e_avg)) * albedo;
+    return __fdiv_rn(b, a + b);
+}
+__device__ __forceinline__ V3 diffuseEvaluate(const LutsD& luts, V3 color, float n_dot_wi, float n_dot_wo, float alpha, float f0) {
+    const float e_wo  = luts.e(n_dot_wo, alpha, f0);
+    const float e_wi  = luts.e(n_dot_wi, alpha, f0);
+    const float e_avg = luts.eAvg(alpha, f0);
+    return scale3(__fdiv_rn((1.f - e_wo) * (1.f - e_wi), kPi * (1.f - e_avg)), color);
+}
+
+// Material sample of {Substitute surface, Light}: material_sample.zig + substitute_sample.zig:20-410
+struct MatSampleD {
+    bool   is_light;
+    bool   can_evaluate, avoid_caustics, translucent;
+    FrameD frame;
+    V3     geo_n, n, wo;
+    float  ax, ay;
+    V3     albedo, f0;
+    float  metallic, specular, specular_threshold, opacity;
+
+    __device__ bool sameHemisphere(V3 v) const { return dot3(geo_n, v) > 0.f; }
+
+    // substitute_sample.zig:236-278
+    __device__ BxdfResult baseEvaluate(const LutsD& luts, V3 wi, V3 h, float wo_dot_h, bool force_disable_caustics) const {
+        const float n_dot_wi = frame.clampNdot(wi);
+        const float n_dot_wo = frame.clampAbsNdot(wo);
+
+        BxdfResult d  = {splat3(0.f), 0.f};
+        float      dw = 0.f;
+
+        if (1.f != metallic) {
+            const V3    a   = scale3(opacity, albedo);
+            const float f0m = hmax3(f0);
+            d               = {diffuseEvaluate(luts, a, n_dot_wi, n_dot_wo, ay, f0m), n_dot_wi * kPiInv};
+            const float am  = hmax3(albedo);
+            dw              = diffuseEstimateContribution(luts, ay, f0m, am);
+        }
+
+        if ((force_disable_caustics || avoid_caustics) && ay <= specular_threshold) {
+            return {scale3(n_dot_wi, d.reflection), dw * d.pdf};
+        }
+
+        const BxdfResult gg  = ggxReflection(wi, wo, h, n_dot_wi, n_dot_wo, wo_dot_h, ax, ay, f0, frame);
+        const V3         mms = dspbrMicroEc(luts, f0, n_dot_wi, n_dot_wo, ay);
+
+        const float pdf = dw * d.pdf + (1.f - dw) * gg.pdf;
+        return {scale3(n_dot_wi, add3(d.reflection, scale3(specular, add3(gg.reflection, mms)))), pdf};
+    }
+
+    // material_sample.zig:56-62 -> substitute_sample.zig:88-145
+    __device__ BxdfResult evaluate(const LutsD& luts, V3 wi) const {
+        if (is_light) return {splat3(0.f), 0.f};
+        if (!sameHemisphere(wo)) return {splat3(0.f), 0.f};
+        const V3    h        = normalize3(add3(wo, wi));
+        const float wo_dot_h = clampDot(wo, h);
+        return baseEvaluate(luts, wi, h, wo_dot_h, false);
+    }
+
+    // substitute_sample.zig:338-361
+    __device__ void diffuseSample(const LutsD& luts, float diffuse_weight, float xi0, float xi1, BxdfSample& result) const {
+        const float n_dot_wo = frame.clampAbsNdot(wo);
+        const V3    a        = scale3(opacity, albedo);
+        const float f0m      = hmax3(f0);
+
+        // diffuse.Micro.reflect, diffuse.zig:82-106
+        const V3 is = hemisphereCosine(xi0, xi1);
+        const V3 wi = normalize3(frame.frameToWorld(is));
+        const V3 h  = normalize3(add3(wo, wi));
+
+        const float h_dot_wi = clampDot(h, wi);
+        const float n_dot_wi = frame.clampNdot(wi);
+
+        result.reflection = diffuseEvaluate(luts, a, n_dot_wi, n_dot_wo, ay, f0m);
+        result.wi         = wi;
+        result.pdf        = n_dot_wi * kPiInv;
+        result.reg_alpha  = 1.f;  // Path.diffuseReflection
+        result.scattering = kScatterDiffuse;
+        result.event      = kEventReflection;
+
+        const BxdfResult gg  = ggxReflection(wi, wo, h, n_dot_wi, n_dot_wo, h_dot_wi, ax, ay, f0, frame);
+        const V3         mms = dspbrMicroEc(luts, f0, n_dot_wi, frame.clampNdot(wo), ay);
+
+        result.reflection = scale3(n_dot_wi, add3(result.reflection, scale3(specular, add3(gg.reflection, mms))));
+        result.pdf        = diffuse_weight * result.pdf + (1.f - diffuse_weight) * gg.pdf;
+    }
+
+    // substitute_sample.zig:363-410 (no flakes)
+    __device__ void glossSample(const LutsD& luts, float diffuse_weight, float xi0, float xi1, BxdfSample& result) const {
+        const float n_dot_wo = frame.clampAbsNdot(wo);
+
+        const MicroD micro = ggxReflect(wo, n_dot_wo, ax, ay, specular_threshold, xi0, xi1, f0, frame, result);
+        const V3     mms   = dspbrMicroEc(luts, f0, micro.n_dot_wi, frame.clampNdot(wo), ay);
+
+        BxdfResult d = {splat3(0.f), 0.f};
+        if (diffuse_weight > 0.f) {
+            const V3    a   = scale3(opacity, albedo);
+            const float f0m = hmax3(f0);
+            d               = {diffuseEvaluate(luts, a, micro.n_dot_wi, n_dot_wo, ay, f0m), micro.n_dot_wi * kPiInv};
+        }
+
+        result.reflection = scale3(micro.n_dot_wi, add3(scale3(specular, add3(result.reflection, mms)), d.reflection));
+        result.pdf        = (1.f - diffuse_weight) * result.pdf + diffuse_weight * d.pdf;
+    }
+
+    // material_sample.zig:64-78 -> substitute_sample.zig:147-234, 280-302. Returns the number of samples (0 or 1).
+    __device__ uint32_t sample(const LutsD& luts, SamplerD& sampler, BxdfSample& result) const {
+        if (is_light) return 0;
+        if (!sameHemisphere(wo)) return 0;
+
+        float dw = 0.f;
+        if (1.f != metallic) {
+            const float f0m = hmax3(f0);
+            const float am  = hmax3(albedo);
+            dw              = diffuseEstimateContribution(luts, ay, f0m, am);
+        }
+
+        const V3    s3 = sampler.sample3D();
+        const float p  = s3.x;
+        if (p < dw) {
+            diffuseSample(luts, dw, s3.y, s3.z, result);
+        } else {
+            glossSample(luts, dw, s3.y, s3.z, result);
+        }
+        if (0.f == result.pdf) return 0;
+        return 1;
+    }
+};
+
+// Emittance.radiance, emittance.zig:29-59 (uniform emission, no profile)
+__device__ __forceinline__ V3 emittanceRadiance(const ZygpuMaterial& m, V3 wi, const TrafoD& trafo, float area, bool in_camera) {
+    if (-dot3(wi, trafo.r2) < m.emission_cos_a) return splat3(0.f);
+    const float factor    = in_camera ? m.emission_camera_weight : 1.f;
+    const V3    intensity = {m.emission[0] * 1.f, m.emission[1] * 1.f, m.emission[2] * 1.f};
+    if (0.f != m.emission_normalize) return scale3(__fdiv_rn(factor, area), intensity);
+    return scale3(factor, intensity);
+}
+
+// Vertex.sample + Material.sample, vertex.zig:137-181, material.zig:184-194, substitute_material.zig:114-221
+__device__ __forceinline__ MatSampleD materialSample(const ZygpuMaterial& m, const FragD& frag, V3 wo, float reg_weight, float reg_alpha,
+                                                     bool caustics, float specular_threshold) {
+    MatSampleD r;
+    r.wo = wo;
+    if (0 != (m.flags & ZYG_MATERIAL_TWO_SIDED) && !frag.sameHemisphere(wo)) {
+        r.geo_n = neg3(frag.geo_n);
+        r.n     = neg3(frag.n);
+    } else {
+        r.geo_n = frag.geo_n;
+        r.n     = frag.n;
+    }
+    r.frame          = {frag.t, frag.b, r.n};
+    r.avoid_caustics = !caustics;
+    r.translucent    = false;
+
+    if (ZYG_MATERIAL_SUBSTITUTE != m.type) {  // Light (and Debug): Base.initTBN(rs, wo, 0, 0, false)
+        r.is_light     = true;
+        r.can_evaluate = false;
+        r.ax = r.ay = 0.f;
+        return r;
+    }
+    r.is_light = false;
+
+    const V3    color     = {m.color[0], m.color[1], m.color[2]};
+    const float roughness = zmax(m.roughness, kMinRoughness);
+    const float metallic  = m.metallic;
+
+    float ax, ay;  // anisotropicAlpha, substitute_material.zig:299-306
+    if (m.anisotropy > 0.f) {
+        const float rv = zmax(roughness * (1.f - m.anisotropy), kMinRoughness);
+        ax             = roughness * roughness;
+        ay             = rv * rv;
+    } else {
+        ax = ay = roughness * roughness;
+    }
+
+    const float ior_medium = 1.f;  // empty medium stack
+    const float ior_outer  = ior_medium;
+
+    // Renderstate.regularizeAlpha, renderstate.zig:58-68
+    if (!(0.f == reg_weight || (ax <= specular_threshold && !caustics))) {
+        const float k = 1.f - reg_weight * reg_alpha;
+        ax            = 1.f - ((1.f - ax) * k);
+        ay            = 1.f - ((1.f - ay) * k);
+    }
+    r.ax           = ax;
+    r.ay           = ay;
+    r.can_evaluate = m.ior != ior_medium;
+
+    const float t  = __fdiv_rn(m.ior - ior_outer, m.ior + ior_outer);  // Schlick.IorToF0
+    const float f0 = t * t;
+
+    r.albedo             = scale3(1.f - metallic, color);
+    r.f0                 = lerp3(splat3(f0), color, splat3(metallic));
+    r.metallic           = metallic;
+    r.specular           = m.specular;
+    r.specular_threshold = specular_threshold;
+    r.opacity            = 1.f;
+    return r;
+}
+
+}  // namespace zygpu
