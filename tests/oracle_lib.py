@@ -80,3 +80,55 @@ def pcg32_floats(state, sequence, n):
     out = np.empty(n, np.float32)
     load().zo_pcg32_floats(state, sequence, n, _p(out))
     return out
+
+
+# ---- forward surface-integration pass (oracle/render.cpp) ---------------------------------------------
+
+def _bind_render(lib):
+    if getattr(lib, "_render_bound", False):
+        return lib
+    vp, u32 = C.c_void_p, C.c_uint32
+    lib.zo_render.argtypes = [vp, vp, u32, u32, C.c_int, vp, u32]
+    lib.zo_render.restype = None
+    lib.zo_resolve.argtypes = [vp, vp, u32, vp]
+    lib.zo_resolve.restype = None
+    lib.zo_ggx_micro_directional_albedo.argtypes = [C.c_float, C.c_float, u32]
+    lib.zo_ggx_micro_directional_albedo.restype = C.c_float
+    lib.zo_sobol_stream.argtypes = [u32, u32, u32, u32, vp]
+    lib.zo_sobol_stream.restype = None
+    lib.zo_sobol_directions.argtypes = [vp]
+    lib.zo_sobol_directions.restype = None
+    lib._render_bound = True
+    return lib
+
+
+def render(scene, view, width, height, iteration, num_samples, per_sample_iterations=True, threads=0, film=None):
+    """zo_render over the flattened scene (pointers from zyg_b200.su.compile_scene). Returns the film (H, W, 4)."""
+    lib = _bind_render(load())
+    if film is None:
+        film = np.zeros((height, width, 4), np.float32)
+    lib.zo_render(scene, view, iteration, num_samples, 1 if per_sample_iterations else 0, _p(film), threads)
+    return film
+
+
+def resolve(view, film):
+    lib = _bind_render(load())
+    out = np.empty_like(film)
+    lib.zo_resolve(view, _p(film), film.shape[0] * film.shape[1], _p(out))
+    return out
+
+
+def ggx_micro_directional_albedo(alpha, n_dot_wo, num_samples=1024):
+    return _bind_render(load()).zo_ggx_micro_directional_albedo(alpha, n_dot_wo, num_samples)
+
+
+def sobol_stream(sample, seed, n, pad_every=0):
+    out = np.empty(n, np.float32)
+    _bind_render(load()).zo_sobol_stream(sample, seed, n, pad_every, _p(out))
+    return out
+
+
+def sobol_directions():
+    out = np.empty((5, 32), np.uint32)
+    _bind_render(load()).zo_sobol_directions(_p(out))
+    return out

@@ -30,3 +30,56 @@ def test_host_pcg32_matches_oracle():
     draws = np.stack([g.uint() for _ in range(16)], axis=1)
     for row, s in zip(draws, seqs):
         assert np.array_equal(row, oracle.pcg32_uints(0, int(s), 16))
+
+
+# ---- golden data the reference ships for the shading path -----------------------------------------------
+# tests/golden/sobol_directions.npy and zyg_b200/data/ggx_luts.f32 are extracted from the reference by
+# tools/extract_reference_tables.py (data tables, not code).
+
+import os  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sobol_directions_match_reference_table():
+    """The oracle regenerates the direction numbers from the Joe-Kuo recurrence; sobol.zig:194-245 is the pin."""
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "sobol_directions.npy"))
+    assert np.array_equal(oracle.sobol_directions(), golden)
+
+
+def test_ggx_restatement_reproduces_reference_E_m_table():
+    """ggx_integral.zig's E_m table is integrate_micro_directional_albedo (ggx_integrate.zig:27-57, 207-255) over
+    ggx.Iso.reflect with 1024 Hammersley points. Recomputing it through the oracle's VNDF sampling, distribution,
+    visibility and pdf pins that code against numbers the reference holds (printed with 8 decimals)."""
+    luts = np.fromfile(os.path.join(ROOT, "zyg_b200", "data", "ggx_luts.f32"), np.float32)
+    e_m = luts[:1024].reshape(32, 32)
+    step = np.float32(1.0 / 31.0)
+    got = np.empty((32, 32), np.float32)
+    alpha = np.float32(0.0)
+    for a in range(32):
+        n_dot_wo = np.float32(0.0)
+        for i in range(32):
+            got[a, i] = oracle.ggx_micro_directional_albedo(float(alpha), float(n_dot_wo))
+            n_dot_wo = np.float32(n_dot_wo + step)
+        alpha = np.float32(alpha + step)
+    assert np.abs(got - e_m).max() < 5e-7
+
+
+def test_sobol_owen_scrambled_stratification():
+    """Nested uniform scrambling keeps the (0, m, 1)-net property: the first 2^m samples of a dimension fall into
+    distinct strata of width 2^-m (sobol.zig:36-60)."""
+    for seed in (0, 1, 77):
+        for m in (4, 6, 8):
+            n = 1 << m
+            firsts = np.array([oracle.sobol_stream(s, seed, 5) for s in range(n)])
+            for dim in range(5):
+                strata = np.floor(firsts[:, dim].astype(np.float64) * n).astype(int)
+                assert len(set(strata.tolist())) == n, (seed, m, dim)
+
+
+def test_sobol_padding_blocks_differ():
+    a = oracle.sobol_stream(5, 0, 10)
+    b = oracle.sobol_stream(5, 0, 10, pad_every=5)
+    assert np.array_equal(a, b)  # a refill after 5 draws happens with or without incrementPadding
+    c = oracle.sobol_stream(5, 0, 6, pad_every=1)
+    assert len(set(c.tolist())) == 6 and c[1] != a[1]  # padding after every draw: each draw is dim 0 of a new block

@@ -1,0 +1,153 @@
+"""Parity of the device's wavefront PathtracerMIS with the CPU oracle on BASELINE config 1 (Cornell box), through
+zyg's C API (su_*). The oracle is the checker only.
+
+Bar (BASELINE.json north_star): renders statistically indistinguishable from the CPU path, RMSE at the tested spp
+within 1 % of the CPU path's RMSE. Because the device keeps every path on the CPU path's sampler dimensions
+(device/render.cuh), the comparison can be much tighter than statistical: per-pixel agreement to fp32 rounding of the
+libm-dependent functions (sin / cos / acos differ by an ulp between glibc and CUDA), except for the few paths where
+such an ulp flips a discrete decision (Russian roulette, a hit at a silhouette edge)."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as oracle
+from zyg_b200 import lib, scenes, su
+
+pytestmark = pytest.mark.gpu
+
+
+def download_film(width, height):
+    L = lib.load_library()
+    L.zygpu_download_film.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    film = np.zeros((height, width, 4), np.float32)
+    assert 0 == L.zygpu_download_film(su.device_handle(), film.ctypes.data, width * height), L.zygpu_last_error()
+    return film
+
+
+def rel_error(a, b):
+    d = np.abs(a[..., :3] - b[..., :3]).sum(-1)
+    return d / np.maximum(np.abs(b[..., :3]).sum(-1), 1e-6)
+
+
+@pytest.fixture()
+def engine():
+    su.release()
+    yield
+    su.release()
+
+
+@pytest.mark.parametrize("filter_name", [None, "Mitchell", "Blackman"])
+def test_cornell_matches_oracle_per_pixel(engine, filter_name):
+    w, spp = 128, 16
+    scenes.cornell_box(w, w, spp=spp, filter_name=filter_name)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+
+    if filter_name is None:
+        assert np.array_equal(gpu[..., 3], ref[..., 3])  # weights: exactly spp
+    else:
+        assert np.abs(gpu[..., 3] - ref[..., 3]).max() < 1e-3 * spp
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 2e-6
+    assert (rel > 1e-3).mean() < 2e-3, "more than 0.2 % of the pixels carry a path that diverged"
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 1e-4
+
+
+def test_cornell_full_config(engine):
+    """BASELINE configs[0]: 512 x 512, 64 spp, max 8 bounces."""
+    w, spp = 512, 64
+    scenes.cornell_box(w, w, spp=spp)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 2e-6 and (rel > 1e-3).mean() < 1e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 1e-5
+
+    rgba = su.resolve_frame_to_buffer(w, w)
+    want = oracle.resolve(view, gpu)
+    assert np.allclose(rgba, want, rtol=1e-6, atol=1e-7)
+
+
+def test_rmse_against_high_spp_reference(engine):
+    """RMSE(device, 64 spp) within 1 % of RMSE(CPU path, 64 spp) against a 4096-spp CPU reference, and the error
+    falls at the CPU path's rate between 16 and 64 spp."""
+    w = 64
+    scenes.cornell_box(w, w, spp=4096)
+    scene, view = su.compile_scene()
+    truth = oracle.render(scene, view, w, w, 64, 4032)  # samples disjoint from the ones under test
+    truth = truth[..., :3] / truth[..., 3:4]
+
+    def rmse(film):
+        img = film[..., :3] / film[..., 3:4]
+        return float(np.sqrt(np.mean((img - truth) ** 2)))
+
+    errs = {}
+    for spp in (16, 64):
+        ref = oracle.render(scene, view, w, w, 0, spp)
+        su.render_frame_range(0, 0, spp)
+        gpu = download_film(w, w)
+        errs[spp] = (rmse(gpu), rmse(ref))
+        assert abs(errs[spp][0] - errs[spp][1]) / errs[spp][1] < 0.01
+    slope_gpu = np.log(errs[16][0] / errs[64][0]) / np.log(4.0)
+    slope_ref = np.log(errs[16][1] / errs[64][1]) / np.log(4.0)
+    assert abs(slope_gpu - slope_ref) < 0.02 and slope_gpu > 0.35
+
+
+def test_sample_ranges_accumulate_bit_exactly(engine):
+    """su_start_frame + su_render_iterations (capi.zig:581-611) adds sample ranges into the film; because every
+    sample is seeded from its absolute index the result is bit-identical to one su_render_frame."""
+    w, spp = 96, 12
+    scenes.cornell_box(w, w, spp=spp, filter_name="Mitchell")
+    su.render_frame(0)
+    whole = download_film(w, w)
+    su.start_frame(0)
+    for n in (1, 4, 7):
+        su.render_iterations(n)
+    su._ok(lib.load_library().zygpu_synchronize(su.device_handle()), "zygpu_synchronize")
+    parts = download_film(w, w)
+    assert whole.tobytes() == parts.tobytes()
+
+
+def test_sample_range_split_sums_to_whole(engine):
+    """The multi-GPU schedule: disjoint sample ranges rendered into separate films and summed equal
+    the single-device film up to fp32 summation order."""
+    w, spp = 96, 16
+    scenes.cornell_box(w, w, spp=spp)
+    su.render_frame(0)
+    whole = download_film(w, w)
+    total = np.zeros_like(whole)
+    for g in range(4):
+        su.render_frame_range(0, g * 4, 4)
+        total += download_film(w, w)
+    assert np.array_equal(total[..., 3], whole[..., 3])
+    assert np.allclose(total, whole, rtol=2e-6, atol=1e-6)
+
+
+def test_small_pass_size_gives_identical_film(engine, monkeypatch):
+    """The number of samples traced per pass is a scheduling choice; it must not change the film."""
+    w, spp = 64, 8
+    scenes.cornell_box(w, w, spp=spp)
+    su.render_frame(0)
+    a = download_film(w, w)
+    monkeypatch.setenv("ZYGPU_PATHS_PER_PASS", str(w * w * 3))
+    su.render_frame(0)
+    b = download_film(w, w)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_depth_zero_and_random_sampler(engine):
+    """Edge cases: max depth 1 (direct light only) and the Random sampler (sampler.zig:17-74) agree with the oracle."""
+    w, spp = 64, 8
+    scenes.cornell_box(w, w, spp=spp, max_depth=1)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert (rel_error(gpu, ref) > 1e-3).mean() < 2e-3
