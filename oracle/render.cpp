@@ -439,14 +439,102 @@ bool intersectP(const Ray& ray, const Trafo& trafo) {
 
 }  // namespace sphere
 
+namespace mesh {
+
+// Mesh.fragment, triangle_mesh.zig:310-335 + Data.interpolateData / normal, triangle_data.zig:106-149
+void fragment(const ZoMesh& m, Fragment& frag) {
+    const uint32_t prim = frag.isec.primitive;
+    frag.part           = m.parts[prim];
+
+    const float hit_u = frag.isec.u;
+    const float hit_v = frag.isec.v;
+
+    const uint32_t* tri = m.triangles + size_t(prim) * 3;
+
+    auto position = [&](uint32_t i) -> Vec4f { return {{m.positions[size_t(i) * 3], m.positions[size_t(i) * 3 + 1], m.positions[size_t(i) * 3 + 2], 0.f}}; };
+    auto shadingNormal = [&](uint32_t i) -> Vec4f {  // enc.decompressNormal, encoding.zig:91-108
+        const float o0 = std::fmaf(float(m.normals[size_t(i) * 2]), 1.f / 32768.f, -1.f);
+        const float o1 = std::fmaf(float(m.normals[size_t(i) * 2 + 1]), 1.f / 32768.f, -1.f);
+        Vec4f       v  = {{o0, o1, -1.f + std::fabs(o0) + std::fabs(o1), 0.f}};
+        const float t  = max(v[2], 0.f);
+        v[0] += v[0] > 0.f ? -t : t;
+        v[1] += v[1] > 0.f ? -t : t;
+        return normalize3(v);
+    };
+    auto interpolate3 = [](Vec4f a, Vec4f b, Vec4f c, float u, float v) -> Vec4f {  // triangle.zig:142-149
+        const float w     = 1.f - u - v;
+        const Vec4f temp0 = mulAdd(b, splat(u), c * splat(v));
+        return mulAdd(a, splat(w), temp0);
+    };
+
+    const Vec4f pa = position(tri[0]);
+    const Vec4f pb = position(tri[1]);
+    const Vec4f pc = position(tri[2]);
+
+    const Vec4f geo_n = normalize3(cross3(pb - pa, pc - pa));
+    frag.geo_n        = frag.isec.trafo.objectToWorldNormal(geo_n);
+
+    const Vec4f p = interpolate3(pa, pb, pc, hit_u, hit_v);
+
+    const float uva[2] = {m.uvs[size_t(tri[0]) * 2], m.uvs[size_t(tri[0]) * 2 + 1]};
+    const float uvb[2] = {m.uvs[size_t(tri[1]) * 2], m.uvs[size_t(tri[1]) * 2 + 1]};
+    const float uvc[2] = {m.uvs[size_t(tri[2]) * 2], m.uvs[size_t(tri[2]) * 2 + 1]};
+    const float w      = 1.f - hit_u - hit_v;  // triangle.zig:133-140
+    const float uv[2]  = {std::fmaf(uva[0], w, std::fmaf(uvb[0], hit_u, uvc[0] * hit_v)),
+                          std::fmaf(uva[1], w, std::fmaf(uvb[1], hit_u, uvc[1] * hit_v))};
+
+    const Vec4f nb = shadingNormal(tri[1]);
+    const Vec4f na = shadingNormal(tri[0]);
+    const Vec4f nc = shadingNormal(tri[2]);
+    const Vec4f ni = normalize3(interpolate3(na, nb, nc, hit_u, hit_v));
+
+    // triangle.positionDifferentials, triangle.zig:102-131
+    const float duv02[2]    = {uva[0] - uvc[0], uva[1] - uvc[1]};
+    const float duv12[2]    = {uvb[0] - uvc[0], uvb[1] - uvc[1]};
+    const float determinant = duv02[0] * duv12[1] - duv02[1] * duv12[0];
+
+    Vec4f       dpdu, dpdv;
+    const Vec4f dp02 = pa - pc;
+    const Vec4f dp12 = pb - pc;
+    if (0.f == std::fabs(determinant)) {
+        const Vec4f ng = normalize3(cross3(pc - pa, pb - pa));
+        if (std::fabs(ng[0]) > std::fabs(ng[1])) {
+            dpdu = Vec4f{{-ng[2], 0.f, ng[0], 0.f}} / splat(std::sqrt(ng[0] * ng[0] + ng[2] * ng[2]));
+        } else {
+            dpdu = Vec4f{{0.f, ng[2], -ng[1], 0.f}} / splat(std::sqrt(ng[1] * ng[1] + ng[2] * ng[2]));
+        }
+        dpdv = cross3(ng, dpdu);
+    } else {
+        const float invdet = 1.f / determinant;
+        dpdu               = splat(invdet) * mulAdd(splat(duv12[1]), dp02, splat(-duv02[1]) * dp12);
+        dpdv               = splat(invdet) * mulAdd(splat(-duv12[0]), dp02, splat(duv02[0]) * dp12);
+    }
+
+    const Vec4f t = normalize3(gramSchmidt(dpdu, ni));
+    const Vec4f b = normalize3(gramSchmidt(dpdv, ni));
+
+    frag.p   = frag.isec.trafo.objectToWorldPoint(p);
+    frag.t   = frag.isec.trafo.objectToWorldNormal(t);
+    frag.b   = frag.isec.trafo.objectToWorldNormal(b);
+    frag.n   = frag.isec.trafo.objectToWorldNormal(ni);
+    frag.uvw = {{uv[0], uv[1], 0.f, 0.f}};
+}
+
+}  // namespace mesh
+
 // ---- scene -----------------------------------------------------------------------------------
 
 struct Scene {
     const ZygpuScene& s;
     const ZygpuView&  view;
     GgxLuts           luts;
+    const ZoMesh*     meshes;  // indexed by ZygpuProp.mesh
 
-    Scene(const ZygpuScene& scene, const ZygpuView& v) : s(scene), view(v), luts(scene.ggx_luts) {}
+    Scene(const ZygpuScene& scene, const ZygpuView& v, const ZoMesh* ms) : s(scene), view(v), luts(scene.ggx_luts), meshes(ms) {}
+
+    Mesh treeOf(uint32_t mesh) const {
+        return {static_cast<const Node*>(meshes[mesh].nodes), meshes[mesh].triangles, meshes[mesh].positions};
+    }
 
     const ZygpuMaterial& propMaterial(uint32_t prop, uint32_t part) const {  // scene.zig:529-532
         return s.materials[s.material_ids[s.props[prop].parts_start + part]];
@@ -467,24 +555,38 @@ struct Scene {
         }
     }
 
-    bool shapeIntersect(uint32_t shape, const Ray& ray, const Trafo& trafo, Intersection& isec) const {  // shape.zig:165-179
+    bool shapeIntersect(uint32_t shape, uint32_t mesh_id, const Ray& ray, const Trafo& trafo, Intersection& isec) const {  // shape.zig:165-179
         switch (shape) {
+            case ZYG_SHAPE_TRIANGLE_MESH: {  // TriangleTree.intersect, triangle_tree.zig:46-109
+                ZoHit h;
+                if (treeOf(mesh_id).intersect(trafo.worldToObjectRay(ray), h, nullptr, nullptr)) {
+                    isec.t         = h.t;
+                    isec.u         = h.u;
+                    isec.v         = h.v;
+                    isec.primitive = h.primitive;
+                    isec.trafo     = trafo;
+                    return true;
+                }
+                return false;
+            }
             case ZYG_SHAPE_CUBE: return cube::intersect(ray, trafo, isec);
             case ZYG_SHAPE_RECTANGLE: return rectangle::intersect(ray, trafo, isec);
             case ZYG_SHAPE_SPHERE: return sphere::intersect(ray, trafo, isec);
             default: return false;
         }
     }
-    bool shapeIntersectP(uint32_t shape, const Ray& ray, const Trafo& trafo) const {  // shape.zig:221-233
+    bool shapeIntersectP(uint32_t shape, uint32_t mesh_id, const Ray& ray, const Trafo& trafo) const {  // shape.zig:221-233
         switch (shape) {
+            case ZYG_SHAPE_TRIANGLE_MESH: return treeOf(mesh_id).intersectP(trafo.worldToObjectRay(ray));  // triangle_mesh.zig:337-340
             case ZYG_SHAPE_CUBE: return cube::intersectP(ray, trafo);
             case ZYG_SHAPE_RECTANGLE: return rectangle::intersectP(ray, trafo);
             case ZYG_SHAPE_SPHERE: return sphere::intersectP(ray, trafo);
             default: return false;
         }
     }
-    void shapeFragment(uint32_t shape, const Ray& ray, Fragment& frag) const {  // shape.zig:205-219
+    void shapeFragment(uint32_t shape, uint32_t mesh_id, const Ray& ray, Fragment& frag) const {  // shape.zig:205-219
         switch (shape) {
+            case ZYG_SHAPE_TRIANGLE_MESH: mesh::fragment(meshes[mesh_id], frag); break;
             case ZYG_SHAPE_CUBE: cube::fragment(ray, frag); break;
             case ZYG_SHAPE_RECTANGLE: rectangle::fragment(ray, frag); break;
             case ZYG_SHAPE_SPHERE: sphere::fragment(ray, frag); break;
@@ -497,7 +599,7 @@ struct Scene {
         const ZygpuProp& prop = s.props[entity];
         if (!visible(prop.flags, depth_surface)) return false;
         if (!propAabb(entity).intersect(ray)) return false;
-        return shapeIntersect(prop.shape, ray, propTrafo(entity), isec);
+        return shapeIntersect(prop.shape, prop.mesh, ray, propTrafo(entity), isec);
     }
 
     // Prop.visibility, prop.zig:199-237 (no masks): true = unoccluded
@@ -505,7 +607,7 @@ struct Scene {
         const ZygpuProp& prop = s.props[entity];
         if (0 == (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW)) return true;
         if (!propAabb(entity).intersect(ray)) return true;
-        return !shapeIntersectP(prop.shape, ray, propTrafo(entity));
+        return !shapeIntersectP(prop.shape, prop.mesh, ray, propTrafo(entity));
     }
 
     static float nodeIntersect(const ZygpuBvhNode& node, const Ray& ray) {  // node.zig:73-87
@@ -560,7 +662,7 @@ struct Scene {
         const bool hit = ZYGPU_NULL != prop;
         if (hit) {
             frag.isec = isec;
-            shapeFragment(s.props[prop].shape, ray, frag);
+            shapeFragment(s.props[prop].shape, s.props[prop].mesh, ray, frag);
         }
         frag.prop = prop;
         return hit;
@@ -1427,11 +1529,11 @@ extern "C" {
 // num_samples) of every pixel are added to `film` (Pack4f per pixel of the full resolution, weight in w; not cleared).
 // per_sample_iterations != 0 renders the range as num_samples calls of (iteration + k, 1) — the progressive API's
 // schedule (capi.zig:602-609), which reseeds the PCG stream per sample (worker.zig:143) and is what the device does.
-void zo_render(const ZygpuScene* scene, const ZygpuView* view, uint32_t iteration, uint32_t num_samples,
+void zo_render(const ZygpuScene* scene, const ZygpuView* view, const ZoMesh* meshes, uint32_t iteration, uint32_t num_samples,
                int per_sample_iterations, float* film_pixels, uint32_t threads) {
     using namespace zo;
 
-    const Scene sc(*scene, *view);
+    const Scene sc(*scene, *view, meshes);
     const Film  film{film_pixels, *view};
 
     const int32_t fr   = view->filter_radius_int;

@@ -50,8 +50,19 @@ struct ZygpuView;
 /* Adds samples [iteration, iteration + num_samples) of every pixel to `film` (Pack4f per pixel of the full
  * resolution, weight sum in w). per_sample_iterations != 0: num_samples calls of (iteration + k, 1), the
  * progressive API's schedule, which is the one the device implements. threads = 0: all cores. */
-void zo_render(const struct ZygpuScene* scene, const struct ZygpuView* view, uint32_t iteration, uint32_t num_samples,
-               int per_sample_iterations, float* film, uint32_t threads);
+/* Host arrays of one compiled triangle mesh in the reference's layout (what zyg_mesh_data returns). */
+typedef struct ZoMesh {
+    const void*     nodes;     /* 32-byte bvh.Node */
+    const uint32_t* triangles; /* 3 per tree-order triangle */
+    const float*    positions; /* 3 per vertex */
+    const uint16_t* normals;   /* 2 per vertex, oct snorm16 */
+    const float*    uvs;       /* 2 per vertex */
+    const uint16_t* parts;     /* per tree-order triangle */
+} ZoMesh;
+
+/* `meshes` is indexed by ZygpuProp.mesh (NULL when the scene has none). */
+void zo_render(const struct ZygpuScene* scene, const struct ZygpuView* view, const ZoMesh* meshes, uint32_t iteration,
+               uint32_t num_samples, int per_sample_iterations, float* film, uint32_t threads);
 /* Opaque.resolveTonemap, Linear tonemapper. */
 void zo_resolve(const struct ZygpuView* view, const float* film, uint32_t num_pixels, float* rgba);
 

@@ -88,7 +88,7 @@ def _bind_render(lib):
     if getattr(lib, "_render_bound", False):
         return lib
     vp, u32 = C.c_void_p, C.c_uint32
-    lib.zo_render.argtypes = [vp, vp, u32, u32, C.c_int, vp, u32]
+    lib.zo_render.argtypes = [vp, vp, vp, u32, u32, C.c_int, vp, u32]
     lib.zo_render.restype = None
     lib.zo_resolve.argtypes = [vp, vp, u32, vp]
     lib.zo_resolve.restype = None
@@ -102,12 +102,37 @@ def _bind_render(lib):
     return lib
 
 
-def render(scene, view, width, height, iteration, num_samples, per_sample_iterations=True, threads=0, film=None):
+class ZoMesh(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("triangles", C.c_void_p), ("positions", C.c_void_p), ("normals", C.c_void_p),
+                ("uvs", C.c_void_p), ("parts", C.c_void_p)]
+
+
+def mesh_table(num_meshes):
+    """ZoMesh[num_meshes] over the host arrays of the engine's compiled meshes (shape ids 7..), for zo_render."""
+    from zyg_b200 import lib as zlib, su
+
+    if 0 == num_meshes:
+        return None
+    L = zlib.load_library()
+    table = (ZoMesh * num_meshes)()
+    which = (zlib.MESH_BINARY_NODES, zlib.MESH_TRIANGLES, zlib.MESH_POSITIONS, zlib.MESH_NORMALS, zlib.MESH_UVS,
+             zlib.MESH_PARTS)
+    for i in range(num_meshes):
+        handle = su._su().zyg_su_mesh(7 + i)
+        assert handle, f"no mesh registered as shape {7 + i}"
+        ptrs = [L.zyg_mesh_data(handle, w, None) for w in which]
+        table[i] = ZoMesh(*ptrs)
+    return table
+
+
+def render(scene, view, width, height, iteration, num_samples, per_sample_iterations=True, threads=0, film=None,
+           num_meshes=0):
     """zo_render over the flattened scene (pointers from zyg_b200.su.compile_scene). Returns the film (H, W, 4)."""
     lib = _bind_render(load())
     if film is None:
         film = np.zeros((height, width, 4), np.float32)
-    lib.zo_render(scene, view, iteration, num_samples, 1 if per_sample_iterations else 0, _p(film), threads)
+    table = mesh_table(num_meshes)
+    lib.zo_render(scene, view, table, iteration, num_samples, 1 if per_sample_iterations else 0, _p(film), threads)
     return film
 
 

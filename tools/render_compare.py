@@ -16,13 +16,7 @@ from png import write_png  # noqa: E402
 from zyg_b200 import scenes, su  # noqa: E402
 
 
-def oracle_lib():
-    o = C.CDLL(os.path.join(ROOT, "oracle", "libzyg_oracle.so"))
-    o.zo_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32]
-    o.zo_render.restype = None
-    o.zo_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
-    o.zo_resolve.restype = None
-    return o
+import oracle_lib as oracle  # noqa: E402
 
 
 def main():
@@ -32,13 +26,16 @@ def main():
     out = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
 
-    scenes.cornell_box(w, w, spp=spp, filter_name=filt)
+    which = os.environ.get("SCENE", "cornell")
+    num_meshes = 0
+    if "cornell" == which:
+        scenes.cornell_box(w, w, spp=spp, filter_name=filt)
+    else:
+        num_meshes = scenes.sphere_scene(w, w, spp=spp, filter_name=filt, quads=tuple(int(q) for q in os.environ.get("QUADS", "200,100").split(",")))
     scene, view = su.compile_scene()
 
-    o = oracle_lib()
-    film_ref = np.zeros((w, w, 4), np.float32)
     t = time.time()
-    o.zo_render(scene, view, 0, spp, 1, film_ref.ctypes.data, 0)
+    film_ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=num_meshes)
     t_ref = time.time() - t
 
     t = time.time()
@@ -55,8 +52,7 @@ def main():
     assert 0 == L.zygpu_download_film(su.device_handle(), film_gpu.ctypes.data, w * w)
     rgba = su.resolve_frame_to_buffer(w, w)
     write_png(os.path.join(out, "cornell_gpu.png"), rgba)
-    rgba_ref = np.zeros((w, w, 4), np.float32)
-    o.zo_resolve(view, film_ref.ctypes.data, w * w, rgba_ref.ctypes.data)
+    rgba_ref = oracle.resolve(view, film_ref)
     write_png(os.path.join(out, "cornell_ref.png"), rgba_ref)
 
     d = np.abs(film_gpu - film_ref)

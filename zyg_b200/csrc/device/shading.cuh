@@ -335,6 +335,86 @@ __device__ __forceinline__ void sphereFragment(const RayT& ray, const HitD& isec
     frag.v = theta * kPiInv;
 }
 
+// Mesh.fragment, triangle_mesh.zig:310-335 + Data.interpolateData / normal, triangle_data.zig:106-149
+__device__ __forceinline__ V3 decompressNormal(const uint16_t* normals, uint32_t i) {  // encoding.zig:91-108
+    const uint32_t packed = __ldg(reinterpret_cast<const uint32_t*>(normals) + i);
+    const float    o0     = __fmaf_rn(float(packed & 0xffffu), 1.f / 32768.f, -1.f);
+    const float    o1     = __fmaf_rn(float(packed >> 16), 1.f / 32768.f, -1.f);
+    V3             v      = {o0, o1, -1.f + fabsf(o0) + fabsf(o1)};
+    const float    t      = zmax(v.z, 0.f);
+    v.x += v.x > 0.f ? -t : t;
+    v.y += v.y > 0.f ? -t : t;
+    return normalize3(v);
+}
+
+__device__ __forceinline__ V3 interpolate3(V3 a, V3 b, V3 c, float u, float v) {  // triangle.zig:142-149
+    const float w     = 1.f - u - v;
+    const V3    temp0 = fma3(b, splat3(u), scale3(v, c));
+    return fma3(a, splat3(w), temp0);
+}
+
+__device__ __forceinline__ V3 gramSchmidt(V3 v, V3 w) { return fmas3(-dot3(v, w), w, v); }  // vector4.zig:120-122
+
+__device__ __forceinline__ void meshFragment(const MeshShading& m, const HitD& isec, FragD& frag) {
+    const uint32_t prim = isec.primitive;
+    frag.part           = __ldg(m.parts + prim);
+
+    const uint32_t ia = __ldg(m.triangles + 3 * size_t(prim) + 0);
+    const uint32_t ib = __ldg(m.triangles + 3 * size_t(prim) + 1);
+    const uint32_t ic = __ldg(m.triangles + 3 * size_t(prim) + 2);
+
+    const V3 pa = {__ldg(m.positions + 3 * size_t(ia)), __ldg(m.positions + 3 * size_t(ia) + 1), __ldg(m.positions + 3 * size_t(ia) + 2)};
+    const V3 pb = {__ldg(m.positions + 3 * size_t(ib)), __ldg(m.positions + 3 * size_t(ib) + 1), __ldg(m.positions + 3 * size_t(ib) + 2)};
+    const V3 pc = {__ldg(m.positions + 3 * size_t(ic)), __ldg(m.positions + 3 * size_t(ic) + 1), __ldg(m.positions + 3 * size_t(ic) + 2)};
+
+    const V3 geo_n = normalize3(cross3(sub3(pb, pa), sub3(pc, pa)));
+    frag.geo_n     = frag.trafo.objectToWorldNormal(geo_n);
+
+    const V3 p = interpolate3(pa, pb, pc, isec.u, isec.v);
+
+    const float2 uva = __ldg(reinterpret_cast<const float2*>(m.uvs) + ia);
+    const float2 uvb = __ldg(reinterpret_cast<const float2*>(m.uvs) + ib);
+    const float2 uvc = __ldg(reinterpret_cast<const float2*>(m.uvs) + ic);
+    const float  w   = 1.f - isec.u - isec.v;  // triangle.zig:133-140
+    frag.u           = __fmaf_rn(uva.x, w, __fmaf_rn(uvb.x, isec.u, uvc.x * isec.v));
+    frag.v           = __fmaf_rn(uva.y, w, __fmaf_rn(uvb.y, isec.u, uvc.y * isec.v));
+
+    const V3 nb = decompressNormal(m.normals, ib);
+    const V3 na = decompressNormal(m.normals, ia);
+    const V3 nc = decompressNormal(m.normals, ic);
+    const V3 ni = normalize3(interpolate3(na, nb, nc, isec.u, isec.v));
+
+    // triangle.positionDifferentials, triangle.zig:102-131
+    const float duv02x = uva.x - uvc.x, duv02y = uva.y - uvc.y;
+    const float duv12x = uvb.x - uvc.x, duv12y = uvb.y - uvc.y;
+    const float determinant = duv02x * duv12y - duv02y * duv12x;
+
+    V3       dpdu, dpdv;
+    const V3 dp02 = sub3(pa, pc);
+    const V3 dp12 = sub3(pb, pc);
+    if (0.f == fabsf(determinant)) {
+        const V3 ng = normalize3(cross3(sub3(pc, pa), sub3(pb, pa)));
+        if (fabsf(ng.x) > fabsf(ng.y)) {
+            dpdu = divs3({-ng.z, 0.f, ng.x}, __fsqrt_rn(ng.x * ng.x + ng.z * ng.z));
+        } else {
+            dpdu = divs3({0.f, ng.z, -ng.y}, __fsqrt_rn(ng.y * ng.y + ng.z * ng.z));
+        }
+        dpdv = cross3(ng, dpdu);
+    } else {
+        const float invdet = __fdiv_rn(1.f, determinant);
+        dpdu               = scale3(invdet, fmas3(duv12y, dp02, scale3(-duv02y, dp12)));
+        dpdv               = scale3(invdet, fmas3(-duv12x, dp02, scale3(duv02x, dp12)));
+    }
+
+    const V3 t = normalize3(gramSchmidt(dpdu, ni));
+    const V3 b = normalize3(gramSchmidt(dpdv, ni));
+
+    frag.p = frag.trafo.objectToWorldPoint(p);
+    frag.t = frag.trafo.objectToWorldNormal(t);
+    frag.b = frag.trafo.objectToWorldNormal(b);
+    frag.n = frag.trafo.objectToWorldNormal(ni);
+}
+
 // ---- materials -------------------------------------------------------------------------------
 
 struct LutsD {  // ggx_integral.zig tables in the order of ZygpuScene.ggx_luts

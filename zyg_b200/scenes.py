@@ -213,3 +213,40 @@ def cornell_box(width=512, height=512, spp=64, max_depth=8, filter_name=None, un
     su.prop_set_transformation(lamp, su.transformation((0.0, 1.98, 0.0), (0.5, 0.5, 1.0), (-90.0, 0.0, 0.0)))
     su.light_create(lamp)
     return camera
+
+
+def sphere_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, quads=(1000, 500), metallic=0.0,
+                 roughness=0.6):
+    """The config-2 mesh (displaced sphere, 2 * quads[0] * quads[1] triangles) as a path-traced scene: the mesh sits
+    on a diffuse floor inside a large open room lit by one Rectangle light. Returns the number of meshes."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(40.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 0.0, -3.0)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    grey = su.material_create({"rendering": {"Substitute": {"color": [0.6, 0.6, 0.6], "roughness": 1.0}}})
+    body = su.material_create({"rendering": {"Substitute": {"color": [0.8, 0.45, 0.2], "roughness": roughness,
+                                                            "metallic": metallic}}})
+    light = su.material_create({"rendering": {"Light": {"emittance": {"value": 12.0}}}})
+
+    positions, normals, uvs, indices = displaced_sphere(*quads)
+    # displaced_sphere winds its triangles clockwise seen from outside; a one-sided Substitute needs the geometric
+    # normal (cross(b - a, c - a), triangle_data.zig:140-149) on the side of the shading normals
+    indices = np.ascontiguousarray(indices.reshape(-1, 3)[:, [0, 2, 1]])
+    shape = su.triangle_mesh_create(positions, indices, normals, uvs)
+    su.prop_create(shape, [body])
+
+    floor = su.prop_create(su.RECTANGLE, [grey])
+    su.prop_set_transformation(floor, su.transformation((0.0, -1.1, 0.0), (12.0, 12.0, 1.0), (90.0, 0.0, 0.0)))
+    wall = su.prop_create(su.RECTANGLE, [grey])
+    su.prop_set_transformation(wall, su.transformation((0.0, 2.0, 3.0), (12.0, 8.0, 1.0), (0.0, 180.0, 0.0)))
+
+    lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=True)
+    su.prop_set_transformation(lamp, su.transformation((1.5, 3.0, -1.0), (1.5, 1.5, 1.0), (-90.0, 0.0, 0.0)))
+    su.light_create(lamp)
+    return 1
