@@ -8,6 +8,11 @@ One step = one pass of the traversal hot path over the synthetic batch of this r
 `value` = rays of all ranks / device time (CUDA events, max over ranks), inputs resident in HBM.
 `e2e`   = same step through zygpu_trace_batch with pinned HOST buffers (H2D + D2H inside).
 `--impl reference` times the CPU restatement of zyg's own path (oracle/) on the host cores.
+
+The same JSON line carries `path_tracing`: path-samples/s of the wavefront PathtracerMIS pass (the other half of
+BASELINE.json's metric) on config 1 (Cornell box, 512 x 512 x 64 spp) and on the config-2 mesh as a lit scene
+(1M triangles, 1024 x 1024 x 16 spp), device-timed with the scene resident, next to the CPU path on a bounded sample.
+With N > 1 ranks the samples of the frame are split by range and the films reduced to rank 0 (strong scaling).
 """
 
 from __future__ import annotations
@@ -139,6 +144,23 @@ def run_reference(args):
     value = n * args.steps / dt / 1e6
     cores = os.cpu_count()
     sample = f"per step: {PRIMARY_RES // 2}^2 primary + {N_RAYS // 4} incoherent + {N_RAYS // 4} shadow rays (1/4 of the workload)"
+
+    # the CPU path of the forward pass on a bounded sample of the two render workloads
+    from zyg_b200 import su
+
+    path_tracing = {}
+    for name, (kind, width, spp, cpu_sample) in RENDER_SCENES.items():
+        cw, cspp = cpu_sample
+        num_meshes = build_render_scene(kind, cw, cspp)
+        scene, view = su.compile_scene()
+        oracle.render(scene, view, cw, cw, 0, 1, num_meshes=num_meshes)
+        t0 = time.perf_counter()
+        oracle.render(scene, view, cw, cw, 0, cspp, num_meshes=num_meshes)
+        dt_r = time.perf_counter() - t0
+        path_tracing[name] = {"path_samples_per_s": cw * cw * cspp / dt_r, "cores": cores,
+                              "sample": f"{cw}x{cw} x {cspp} spp of the same scene"}
+        su.release()
+
     print(json.dumps({
         "impl": "reference", "metric": "traversal_throughput", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -146,7 +168,125 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "rays_per_step": n, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "path_tracing": path_tracing,
     }))
+
+
+RENDER_SCENES = {
+    # name: (builder kwargs, width, spp, cpu sample (width, spp))
+    "cornell_512x512x64": ("cornell", 512, 64, (256, 16)),
+    "sphere1m_1024x1024x16": ("sphere", 1024, 16, (256, 8)),
+}
+
+
+def build_render_scene(kind, width, spp):
+    from zyg_b200 import scenes, su
+
+    su.release()
+    if "cornell" == kind:
+        scenes.cornell_box(width, width, spp=spp)
+        return 0
+    return scenes.sphere_scene(width, width, spp=spp, quads=MESH_QUADS)
+
+
+def bench_render(args, rank, world, local):
+    """Path-samples/s of the device pass: per step clear + this rank's sample range + film reduce to rank 0."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from zyg_b200 import lib, multi, su
+
+    L = lib.load_library()
+    L.zygpu_clear_film.argtypes = [C.c_void_p]
+    L.zygpu_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    L.zygpu_synchronize.argtypes = [C.c_void_p]
+
+    class Stats(C.Structure):
+        _fields_ = [(n, C.c_uint64) for n in ("camera_samples", "closest_rays", "shadow_rays", "kernel_launches", "passes")]
+
+    L.zygpu_render_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+
+    out = {}
+    launches = 0
+    for name, (kind, width, spp, cpu_sample) in RENDER_SCENES.items():
+        num_meshes = build_render_scene(kind, width, spp)
+        su._ok(su._su().zyg_su_set_device(local), "zyg_su_set_device")
+        su.start_frame(0)  # Scene.compile + upload + clear (not timed: resident-scene number)
+        dev = su.device_handle()
+        stream = multi.render_stream()
+        first, count = multi.sample_range(rank, world, spp)
+        film = multi.device_film_tensor(width, width)
+
+        def step():
+            su._ok(L.zygpu_clear_film(dev), "zygpu_clear_film")
+            if count > 0:
+                su._ok(L.zygpu_render(dev, first, count), "zygpu_render")
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+
+        def barrier():
+            su._ok(L.zygpu_synchronize(dev), "zygpu_synchronize")
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record()
+        for _ in range(args.steps):
+            step()
+        with torch.cuda.stream(stream):
+            e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        st = Stats()
+        L.zygpu_render_stats(dev, C.byref(st))
+
+        # end to end through zyg's C API: su_render_frame (host compile + upload + pass) + su_resolve_frame_to_buffer
+        t0 = time.perf_counter()
+        if count > 0:
+            su.render_frame_range(0, first, count)
+        rgba = su.resolve_frame_to_buffer(width, width)
+        e2e_s = time.perf_counter() - t0
+
+        if world > 1:
+            t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, e2e_s = t.tolist()
+
+        samples = width * width * spp
+        entry = {
+            "path_samples_per_s": samples * args.steps / (ms * 1e-3), "ms_per_frame": ms / args.steps,
+            "resolution": [width, width], "spp": spp, "samples_per_frame": samples,
+            "closest_rays_per_sample": st.closest_rays / max(1, st.camera_samples),
+            "shadow_rays_per_sample": st.shadow_rays / max(1, st.camera_samples),
+            "mrays_per_s": (st.closest_rays + st.shadow_rays) / max(1, st.camera_samples) * samples * args.steps / (ms * 1e-3) / 1e6,
+            "e2e_path_samples_per_s": samples / e2e_s, "e2e_d2h_bytes": int(rgba.nbytes),
+            "scaling": "strong (sample-range split, film reduce to rank 0)" if world > 1 else "single device",
+        }
+        launches += int(st.kernel_launches)
+
+        if rank == 0 and world == 1 and not args.no_cpu:
+            oracle = load_oracle()
+            cw, cspp = cpu_sample
+            build_render_scene(kind, cw, cspp)
+            scene, view = su.compile_scene()
+            oracle.render(scene, view, cw, cw, 0, 1, num_meshes=num_meshes)
+            t0 = time.perf_counter()
+            oracle.render(scene, view, cw, cw, 0, cspp, num_meshes=num_meshes)
+            dt = time.perf_counter() - t0
+            entry["cpu_baseline"] = {"value": cw * cw * cspp / dt, "unit": "path-samples/s", "cores": os.cpu_count(), "kind": "port",
+                                     "sample": f"{cw}x{cw} x {cspp} spp of the same scene, oracle/ restatement of zyg's PathtracerMIS"}
+        su.release()
+        out[name] = entry
+    return out, launches
 
 
 def main():
@@ -157,6 +297,7 @@ def main():
     ap.add_argument("--impl", default="zyg_b200", choices=["zyg_b200", "reference"])
     ap.add_argument("--rays", type=int, default=PRIMARY_RES, help="primary resolution r (r*r rays per class)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-render", action="store_true", help="skip the path_tracing section")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -289,6 +430,13 @@ def main():
         "clocks": clocks,
     }
 
+    if not args.no_render:
+        dev.close()
+        dev = None
+        render, render_launches = bench_render(args, rank, world, local)
+        result["path_tracing"] = render
+        result["gpu_launches"] = launches + render_launches
+
     if rank == 0 and world == 1 and not args.no_cpu:
         oracle = load_oracle()
         arrays = tuple(mesh.data(w) for w in (lib.MESH_BINARY_NODES, lib.MESH_TRIANGLES, lib.MESH_POSITIONS))
@@ -311,7 +459,8 @@ def main():
 
     if rank == 0:
         print(json.dumps(result))
-    dev.close()
+    if dev is not None:
+        dev.close()
     if world > 1:
         dist.destroy_process_group()
 

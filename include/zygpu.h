@@ -137,6 +137,9 @@ int   zygpu_upload_film(zygpu_device* dev, const float* film, uint32_t num_pixel
 /* Device pointer of the film for the multi-GPU reduce (one ncclReduce(sum, fp32) per frame). */
 void* zygpu_film_device(zygpu_device* dev, uint64_t* num_floats);
 int   zygpu_synchronize(zygpu_device* dev);
+/* The CUDA stream (cudaStream_t) the render calls are enqueued on, for events and for ordering a collective after a
+ * pass. NULL before the first zygpu_upload_scene / zygpu_set_view. */
+void* zygpu_render_stream(zygpu_device* dev);
 
 typedef struct ZygpuRenderStats {
     uint64_t camera_samples;  /* path samples started */

@@ -43,7 +43,8 @@ struct DeviceMesh {
 struct RenderState {
     std::vector<void*> scene_buffers;  // freed on the next upload
     zygpu::SceneDevice scene{};
-    bool               has_scene = false;
+    bool               has_scene  = false;
+    bool               has_meshes = false;
     ZygpuView          view{};
     bool               has_view = false;
 

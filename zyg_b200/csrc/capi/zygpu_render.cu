@@ -37,7 +37,7 @@ int allocPath(RenderState& r, T** out, size_t count) {
 // Path slots per pass: enough to fill the machine several times over, small enough to stay a modest share of HBM.
 uint32_t targetPathsPerPass() {
     const char* v = getenv("ZYGPU_PATHS_PER_PASS");
-    return v ? uint32_t(std::max(1, atoi(v))) : (4u << 20);
+    return v ? uint32_t(std::max(1, atoi(v))) : (16u << 20);
 }
 
 int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride) {
@@ -51,10 +51,11 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride) {
         0 != allocPath(r, &p.smp, capacity) || 0 != allocPath(r, &p.rng, capacity) ||
         0 != allocPath(r, &p.sh_o, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_p, size_t(capacity) * shadow_stride) ||
         0 != allocPath(r, &p.sh_wi, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_n, capacity) ||
-        0 != allocPath(r, &p.queue_a, capacity) || 0 != allocPath(r, &p.queue_b, capacity) || 0 != allocPath(r, &p.counters, 8)) {
+        0 != allocPath(r, &p.ml_props, size_t(capacity) * shadow_stride * 8) || 0 != allocPath(r, &p.ml_count, size_t(capacity) * shadow_stride) ||
+        0 != allocPath(r, &p.queue_m, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.queue_a, capacity) || 0 != allocPath(r, &p.queue_b, capacity) || 0 != allocPath(r, &p.counters, 16)) {
         return -1;
     }
-    CUDA_OK(cudaMemset(p.counters, 0, 8 * sizeof(uint32_t)));
+    CUDA_OK(cudaMemset(p.counters, 0, 16 * sizeof(uint32_t)));
     p.capacity      = capacity;
     p.shadow_stride = shadow_stride;
     return 0;
@@ -149,7 +150,8 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     for (uint32_t l = 0; l < scene->num_lights; ++l) potential += std::max(1u, scene->lights[l].num_samples);
     r.max_light_samples = uint32_t(std::min<uint64_t>(std::max<uint64_t>(potential, 1), 64u * 64u));
 
-    r.has_scene = true;
+    r.has_meshes = scene->num_meshes > 0;
+    r.has_scene  = true;
     return 0;
 }
 
@@ -186,7 +188,7 @@ int zygpu_clear_film(zygpu_device* dev) {
     CUDA_OK(cudaSetDevice(dev->ordinal));
     RenderState& r = dev->render;
     CUDA_OK(cudaMemsetAsync(r.film, 0, size_t(r.film_pixels) * sizeof(float4), r.stream));
-    if (r.paths.counters) CUDA_OK(cudaMemsetAsync(r.paths.counters, 0, 8 * sizeof(uint32_t), r.stream));
+    if (r.paths.counters) CUDA_OK(cudaMemsetAsync(r.paths.counters, 0, 16 * sizeof(uint32_t), r.stream));
     r.stats = ZygpuRenderStats{};
     return 0;
 }
@@ -209,6 +211,9 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
     if (capacity > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
     if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples)) return -1;
 
+    // extend / shadow are one kernel each (prop-tree walk) plus the persistent mesh kernel when the scene has meshes
+    const uint32_t trace_extra = r.has_meshes ? 1 : 0;
+
     for (uint32_t done = 0; done < num_samples;) {
         const uint32_t k = std::min(per_pass, num_samples - done);
 
@@ -225,13 +230,13 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
         // one bounce = extend, shade_a, shadow, shade_b (+ queue swap); depth max_depth_surface is the last vertex
         // that can be reached (pathtracer_mis.zig:76-86), so max_depth + 1 extend / shade_a rounds
         for (uint32_t bounce = 0; bounce <= view.max_depth_surface; ++bounce) {
-            CUDA_OK(zygpu::launchExtend(r.scene, r.paths, pass.num_paths, r.stream));
+            CUDA_OK(zygpu::launchExtend(r.scene, r.paths, pass.num_paths, r.has_meshes, r.stream));
             CUDA_OK(zygpu::launchShadeA(r.scene, view, r.paths, pass, pass.num_paths, r.stream));
-            r.stats.kernel_launches += 2;
+            r.stats.kernel_launches += 2 + trace_extra;
             if (bounce == view.max_depth_surface) break;
-            CUDA_OK(zygpu::launchShadow(r.scene, r.paths, pass.num_paths, r.stream));
+            CUDA_OK(zygpu::launchShadow(r.scene, r.paths, pass.num_paths, r.has_meshes, r.stream));
             CUDA_OK(zygpu::launchShadeB(r.scene, view, r.paths, pass, pass.num_paths, r.stream));
-            r.stats.kernel_launches += 3;
+            r.stats.kernel_launches += 3 + trace_extra;  // shadow, shade_b, queue swap
         }
 
         CUDA_OK(zygpu::launchFilm(view, r.paths, pass, r.film, r.stream));
@@ -296,6 +301,8 @@ void* zygpu_film_device(zygpu_device* dev, uint64_t* num_floats) {
     if (num_floats) *num_floats = uint64_t(dev->render.film_pixels) * 4;
     return dev->render.film;
 }
+
+void* zygpu_render_stream(zygpu_device* dev) { return dev ? dev->render.stream : nullptr; }
 
 int zygpu_render_stats(zygpu_device* dev, ZygpuRenderStats* stats) {
     if (!dev || !stats) return fail("zygpu_render_stats: null argument");

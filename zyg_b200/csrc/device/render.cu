@@ -1,6 +1,7 @@
 #include "shading.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace zygpu {
 
@@ -269,6 +270,343 @@ __device__ __forceinline__ bool sceneVisibility(const SceneDevice& sc, const Ray
         }
     }
     return true;
+}
+
+// ---- two-level traversal, product path ---------------------------------------------------------
+//
+// The extend and shadow stages run as two kernels each:
+//
+//   top    one thread per ray walks the prop tree in the reference's order (binary nodes, near child first, leaf props in
+//          order: prop_tree.zig:56-116, 185-240). Analytic props are tested where they are met; a triangle-mesh prop whose
+//          world box the ray hits is appended to the ray's candidate list instead of being entered. Rays with candidates
+//          go to the mesh queue. All threads do the same short walk, so the warps stay full.
+//   mesh   persistent kernel over the mesh queue: a lane takes a ray, moves it into the object space of its next candidate
+//          (re-testing the world box against the shrunken max_t first) and traverses the 8-wide BVH. Warps run the
+//          lock-step loop of trace.cu's persistent kernel — NODE steps and TRIANGLE steps over the lanes that have that
+//          kind of work, postponing triangle groups — and lanes whose ray ran out of candidates are refilled from the
+//          queue (one global atomic per 1024 items), so incoherent bounces keep their lanes busy.
+//
+// Relative to the reference only the order in which props are tested changes (all analytic props of the walk first, then
+// the meshes in walk order): the closest hit is the same except for equal-t ties between different props.
+
+constexpr uint32_t kMeshCandidates = 8;  // per ray; further meshes are traversed inline by the top kernel
+constexpr uint32_t kScenePoolItems = 1024;
+
+struct SceneTraceTuning {
+    uint32_t fetch_idle;  // refill when at least this many lanes are idle
+    uint32_t tri_num, tri_den;
+};
+
+template <bool AnyHit>
+__device__ __forceinline__ RayT loadTraceRay(const PathState& st, uint32_t item, uint32_t& depth_surface) {
+    if (AnyHit) {  // Shape.shadowRay, shape.zig:401-416: the record holds both end points
+        const float4 o           = st.sh_o[item];
+        const float4 p           = st.sh_p[item];
+        const V3     origin      = {o.x, o.y, o.z};
+        const V3     shadow_axis = sub3({p.x, p.y, p.z}, origin);
+        const float  shadow_len  = length3(shadow_axis);
+        depth_surface            = 0;
+        return makeRay(origin, divs3(shadow_axis, shadow_len), 0.f, shadow_len);
+    }
+    const float4 o = st.ray_o[item];
+    const float4 d = st.ray_d[item];
+    depth_surface  = (__float_as_uint(o.w) >> 8) & 0xffu;
+    return makeRay({o.x, o.y, o.z}, {d.x, d.y, d.z}, 0.f, d.w);
+}
+
+// Item ids: closest-hit rays are identified by their path slot, shadow rays by their record (slot * stride + k).
+template <bool AnyHit>
+__global__ void __launch_bounds__(kBlock) topKernel(SceneDevice sc, PathState st) {
+    const uint32_t stride = st.shadow_stride;
+    const uint64_t total  = AnyHit ? uint64_t(st.counters[1]) * stride : uint64_t(st.counters[0]);
+    const uint32_t count  = uint32_t(total < 0xFFFFFFFFull ? total : 0xFFFFFFFFull);
+    const uint32_t iters  = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    uint32_t       traced = 0;
+
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t i       = it * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
+        bool           to_mesh = false;
+        uint32_t       item    = 0;
+        bool           valid   = i < count;
+        if (valid) {
+            if (AnyHit) {
+                const uint32_t slot = st.queue_b[i / stride];
+                const uint32_t k    = i % stride;
+                valid               = k < st.sh_n[slot];
+                item                = slot * stride + k;
+            } else {
+                item = st.queue_a[i];
+            }
+        }
+        if (valid) {
+            traced += 1;
+            uint32_t depth_surface;
+            RayT     ray = loadTraceRay<AnyHit>(st, item, depth_surface);
+
+            uint32_t stack[kPropStack];
+            uint32_t end = 0;
+            uint32_t n   = 0 == sc.num_solid_nodes ? kEnd : 0;
+
+            HitD     isec       = {0.f, 0.f, 0.f, 0};
+            uint32_t hit_prop   = kEnd;
+            bool     occluded   = false;
+            uint32_t candidates = 0;
+
+            while (kEnd != n && !(AnyHit && occluded)) {
+                const float4 nmin = __ldg(sc.solid_nodes + 2 * size_t(n));
+                const float4 nmax = __ldg(sc.solid_nodes + 2 * size_t(n) + 1);
+
+                const uint32_t num = __float_as_uint(nmax.w);
+                if (0 != num) {
+                    const uint32_t start = __float_as_uint(nmin.w);
+                    for (uint32_t li = start; li < start + num; ++li) {
+                        const uint32_t  p    = __ldg(sc.solid_indices + li);
+                        const ZygpuProp prop = sc.props[p];
+                        if (ZYG_SHAPE_TRIANGLE_MESH == prop.shape && candidates < kMeshCandidates) {
+                            // Prop.intersect / Prop.visibility up to the shape call, prop.zig:176-183, 212-218
+                            if (AnyHit ? 0 == (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW) : !propVisible(prop.flags, depth_surface)) continue;
+                            if (!aabbIntersect(sc.aabbs, p, ray)) continue;
+                            st.ml_props[size_t(item) * kMeshCandidates + candidates] = p;
+                            candidates += 1;
+                            continue;
+                        }
+                        if (AnyHit) {
+                            if (!propVisibility(sc, p, ray)) {
+                                occluded = true;
+                                break;
+                            }
+                        } else {
+                            HitD h;
+                            if (propIntersect(sc, p, ray, depth_surface, h)) {
+                                ray.tmax = h.t;
+                                isec     = h;
+                                hit_prop = p;
+                            }
+                        }
+                    }
+                    n = 0 == end ? kEnd : stack[--end];
+                    continue;
+                }
+
+                uint32_t a = __float_as_uint(nmin.w);
+                uint32_t b = a + 1;
+
+                float dista = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(a)), __ldg(sc.solid_nodes + 2 * size_t(a) + 1), ray);
+                float distb = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(b)), __ldg(sc.solid_nodes + 2 * size_t(b) + 1), ray);
+                if (dista > distb) {
+                    const uint32_t tn = a;
+                    a                 = b;
+                    b                 = tn;
+                    const float td    = dista;
+                    dista             = distb;
+                    distb             = td;
+                }
+                if (FLT_MAX == dista) {
+                    n = 0 == end ? kEnd : stack[--end];
+                } else {
+                    n = a;
+                    if (FLT_MAX != distb) stack[end++] = b;
+                }
+            }
+
+            if (AnyHit) {
+                st.sh_wi[item].w = occluded ? 0.f : 1.f;
+                to_mesh          = !occluded && 0 != candidates;
+            } else {
+                st.ray_d[item].w = ray.tmax;
+                st.hit[item]     = make_float4(isec.u, isec.v, __uint_as_float(isec.primitive), __uint_as_float(hit_prop));
+                to_mesh          = 0 != candidates;
+            }
+            if (to_mesh) st.ml_count[item] = candidates;
+        }
+        queuePush(st.queue_m, &st.counters[2], to_mesh, item);
+    }
+    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
+    if (0 == (threadIdx.x & 31u) && 0 != traced) atomicAdd(&st.counters[AnyHit ? 6 : 5], traced);
+}
+
+template <bool AnyHit>
+__global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathState st, uint32_t* __restrict__ work_counter,
+                                                           SceneTraceTuning tune) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    const uint32_t     lane  = threadIdx.x & 31u;
+    const uint32_t     n     = st.counters[2];
+
+    // Queue items are handed out in pools: large pools keep the atomic cold on big queues, small pools spread a short
+    // queue (late bounces) over all resident warps instead of leaving it to a few.
+    const uint32_t warps      = gridDim.x * (blockDim.x / 32u);
+    const uint32_t pool_items = max(32u, min(kScenePoolItems, (n / (warps * 4u)) & ~31u));
+
+    uint32_t pool_next = 0, pool_end = 0;
+    bool     exhausted = false;
+
+    bool     has_ray = false;  // the lane owns a ray (between candidates or inside a mesh)
+    bool     in_mesh = false;
+    uint32_t item    = 0;
+    float    tmax    = 0.f;  // world max_t == object max_t
+    uint32_t cand_i = 0, cand_n = 0;
+    uint32_t cur_prop = 0;
+    uint32_t hit_prop = kEnd;
+    bool     occluded = false;
+    MeshDevice mesh;  // of the mesh the lane is inside: only the two wide arrays are read
+    mesh.wide_nodes = nullptr;
+    mesh.wide_tris  = nullptr;
+
+    WideRay  w;
+    uint2    stack[kWideStack];
+    uint32_t sp         = 0;
+    uint2    node_group = make_uint2(0u, 0u);
+    uint2    tri_group  = make_uint2(0u, 0u);
+    float    ht = 0.f, hu = 0.f, hv = 0.f;
+    uint32_t primitive = kEnd;
+
+    for (;;) {
+        // ---- refill idle lanes
+        uint32_t idle = __ballot_sync(kFull, !has_ray);
+        while (0 != idle && !exhausted) {
+            if (pool_next >= pool_end) {
+                uint32_t base = 0;
+                if (0 == lane) base = atomicAdd(work_counter, pool_items);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= n) {
+                    exhausted = true;
+                    break;
+                }
+                pool_next = base;
+                pool_end  = min(base + pool_items, n);
+            }
+            const uint32_t avail = pool_end - pool_next;
+            const uint32_t rank  = __popc(idle & ((1u << lane) - 1u));
+            if (!has_ray && rank < avail) {
+                item     = st.queue_m[pool_next + rank];
+                cand_i   = 0;
+                cand_n   = st.ml_count[item];
+                has_ray  = true;
+                in_mesh  = false;
+                hit_prop = kEnd;
+                occluded = false;
+                tmax     = AnyHit ? 0.f : st.ray_d[item].w;
+            }
+            pool_next += min(avail, (uint32_t)__popc(idle));
+            idle = __ballot_sync(kFull, !has_ray);
+        }
+        if (kFull == idle) break;
+
+        // ---- lanes between candidates: enter the next mesh or retire
+        while (has_ray && !in_mesh) {
+            if (cand_i == cand_n || (AnyHit && occluded)) {
+                if (AnyHit) {
+                    if (occluded) st.sh_wi[item].w = 0.f;
+                } else if (kEnd != hit_prop) {
+                    st.ray_d[item].w = tmax;
+                    st.hit[item]     = make_float4(hu, hv, __uint_as_float(primitive), __uint_as_float(hit_prop));
+                }
+                has_ray = false;
+                break;
+            }
+            const uint32_t p = st.ml_props[size_t(item) * kMeshCandidates + cand_i];
+            cand_i += 1;
+
+            uint32_t depth_surface;
+            RayT     ray = loadTraceRay<AnyHit>(st, item, depth_surface);
+            if (!AnyHit) ray.tmax = tmax;
+            if (0 != cand_i - 1 && !aabbIntersect(sc.aabbs, p, ray)) continue;  // the first candidate was tested by the top kernel
+
+            const TrafoD trafo = loadTrafo(sc.trafos, p);
+            w.ray              = worldToObjectRay(trafo, ray);  // triangle_tree.zig:49: t is shared with world space
+            setupWideRay(w);
+            cur_prop = p;
+            {
+                const MeshDevice* m = sc.meshes + sc.props[p].mesh;
+                mesh.wide_nodes     = m->wide_nodes;
+                mesh.wide_tris      = m->wide_tris;
+            }
+            in_mesh    = true;
+            sp         = 0;
+            node_group = make_uint2(0u, 0x80000000u);
+            tri_group  = make_uint2(0u, 0u);
+        }
+
+        // ---- lock-step NODE / TRIANGLE steps over the lanes inside a mesh
+        for (;;) {
+            const bool     ready_node = in_mesh && node_group.y > 0x00FFFFFFu;
+            const bool     ready_tri  = in_mesh && 0 != tri_group.y;
+            const uint32_t mn         = __ballot_sync(kFull, ready_node);
+            const uint32_t mt         = __ballot_sync(kFull, ready_tri);
+            const uint32_t cn = __popc(mn), ct = __popc(mt);
+            if (0 == cn && 0 == ct) break;
+
+            if (0 != ct && (0 == cn || ct * tune.tri_den >= cn * tune.tri_num)) {
+                if (ready_tri) {
+                    const uint32_t bit = 31u - __clz(tri_group.y);
+                    tri_group.y &= ~(1u << bit);
+                    float    t, u, v;
+                    uint32_t prim;
+                    if (testWideTriangle(mesh, w.ray, tri_group.x + bit, t, u, v, prim)) {
+                        if (AnyHit) {
+                            occluded     = true;
+                            sp           = 0;
+                            node_group.y = 0;
+                            tri_group.y  = 0;
+                        } else {
+                            w.ray.tmax = t;
+                            tmax       = t;  // probe.ray.max_t = isec.t, prop_tree.zig:77
+                            hu         = u;
+                            hv         = v;
+                            primitive  = prim;
+                            hit_prop   = cur_prop;
+                        }
+                    }
+                }
+            } else if (ready_node) {
+                const uint32_t hits  = node_group.y;
+                const uint32_t gmask = hits & 0xffu;
+                const uint32_t bit   = 31u - __clz(hits);
+                node_group.y         = hits & ~(1u << bit);
+                const uint32_t slot  = (bit - 24u) ^ w.octinv;
+                const uint32_t rank  = __popc(gmask & ((1u << slot) - 1u));
+                const uint32_t node_index = node_group.x + rank;
+                if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
+                if (0 != tri_group.y) stack[sp++] = tri_group;
+
+                const float4* np = mesh.wide_nodes + 5 * size_t(node_index);
+                const float4  n0 = __ldg(np + 0);
+                const float4  n1 = __ldg(np + 1);
+                const float4  n2 = __ldg(np + 2);
+                const float4  n3 = __ldg(np + 3);
+                const float4  n4 = __ldg(np + 4);
+
+                const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
+
+                node_group.x = __float_as_uint(n1.x);
+                node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
+                tri_group.x  = __float_as_uint(n1.y);
+                tri_group.y  = hitmask & 0x00FFFFFFu;
+            }
+
+            // lanes that ran dry pop their stack or leave the mesh
+            if (in_mesh && node_group.y <= 0x00FFFFFFu && 0 == tri_group.y) {
+                if (0 == sp) {
+                    in_mesh = false;
+                } else {
+                    const uint2 e = stack[--sp];
+                    if (e.y > 0x00FFFFFFu) {
+                        node_group = e;
+                    } else {
+                        tri_group = e;
+                    }
+                }
+            }
+
+            const uint32_t inside = __popc(__ballot_sync(kFull, in_mesh));
+            if (0 == inside) break;
+            if (32u - inside >= tune.fetch_idle) {
+                // enough lanes left their mesh: let them move on / be refilled, unless nothing is left for them to do
+                const uint32_t waiting = __ballot_sync(kFull, has_ray && !in_mesh);
+                if (0 != waiting || !exhausted) break;
+            }
+        }
+    }
 }
 
 // Shape.fragment, shape.zig:205-219
@@ -1292,7 +1630,61 @@ cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const Pas
     generateKernel<<<gridFor(pass.num_paths, 16), kBlock, 0, stream>>>(view, st, pass);
     return cudaGetLastError();
 }
-cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream) {
+namespace {
+
+int envInt(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : fallback;
+}
+
+struct SceneTraceConfig {
+    int              variant;  // 0: one thread per ray (extendKernel / shadowKernel), 1: top kernel + persistent mesh kernel
+    SceneTraceTuning tune;
+    int              blocks_per_sm;
+};
+
+const SceneTraceConfig& sceneTraceConfig() {
+    static const SceneTraceConfig cfg = [] {
+        SceneTraceConfig c;
+        c.variant         = envInt("ZYGPU_SCENE_TRACE", 1);
+        c.tune.fetch_idle = uint32_t(envInt("ZYGPU_SCENE_FETCH_IDLE", 6));
+        c.tune.tri_num    = uint32_t(envInt("ZYGPU_TRI_NUM", 1));
+        c.tune.tri_den    = uint32_t(envInt("ZYGPU_TRI_DEN", 2));
+        c.blocks_per_sm   = envInt("ZYGPU_SCENE_BLOCKS_PER_SM", 0);
+        return c;
+    }();
+    return cfg;
+}
+
+template <bool AnyHit>
+cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
+    const SceneTraceConfig& cfg = sceneTraceConfig();
+    // counters[2] = mesh queue length, counters[8] = work counter of the persistent kernel
+    cudaError_t err = cudaMemsetAsync(st.counters + 2, 0, sizeof(uint32_t), stream);
+    if (cudaSuccess != err) return err;
+    topKernel<AnyHit><<<gridFor(max_items, 16), kBlock, 0, stream>>>(scene, st);
+    err = cudaGetLastError();
+    if (cudaSuccess != err || !has_meshes) return err;
+
+    static int resident = 0;
+    if (0 == resident) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, meshTracePersistent<AnyHit>, 128, 0);
+        if (cfg.blocks_per_sm > 0) per_sm = std::min(per_sm, cfg.blocks_per_sm);
+        resident = std::max(per_sm, 1) * numSms();
+    }
+    const uint32_t needed = (max_items + 127) / 128;
+    const uint32_t grid   = std::max(1u, std::min<uint32_t>(uint32_t(resident), needed));
+    err                   = cudaMemsetAsync(st.counters + 8, 0, sizeof(uint32_t), stream);
+    if (cudaSuccess != err) return err;
+    meshTracePersistent<AnyHit><<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, cfg.tune);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
+    if (0 != sceneTraceConfig().variant) return launchSceneTrace<false>(scene, st, max_items, has_meshes, stream);
     extendKernel<<<gridFor(max_items, 16), kBlock, 0, stream>>>(scene, st);
     return cudaGetLastError();
 }
@@ -1301,7 +1693,8 @@ cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const 
     shadeAKernel<<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass);
     return cudaGetLastError();
 }
-cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream) {
+cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
+    if (0 != sceneTraceConfig().variant) return launchSceneTrace<true>(scene, st, max_items * st.shadow_stride, has_meshes, stream);
     shadowKernel<<<gridFor(max_items, 16), kBlock, 0, stream>>>(scene, st);
     return cudaGetLastError();
 }

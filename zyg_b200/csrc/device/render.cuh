@@ -86,9 +86,15 @@ struct PathState {
     float4*   sh_wi;  // light_sample.wi xyz | visible (written by shadow)
     uint32_t* sh_n;   // per path: number of records
 
+    // mesh candidates collected by the top kernels, per trace item (closest: path slot, shadow: record)
+    uint32_t* ml_props;  // 8 per item
+    uint32_t* ml_count;
+    uint32_t* queue_m;  // items with candidates
+
     uint32_t* queue_a;
     uint32_t* queue_b;
-    uint32_t* counters;  // [0] |A|, [1] |B|, [3] shadow overflow flag, [4] |next A|, [5] closest rays, [6] shadow rays
+    uint32_t* counters;  // [0] |A|, [1] |B|, [2] |mesh queue|, [3] shadow overflow flag, [4] |next A|, [5] closest rays, [6] shadow rays,
+                         // [8] work counter of the persistent mesh kernel (16 words in all)
 
     uint32_t capacity;       // path slots
     uint32_t shadow_stride;  // shadow records reserved per path
@@ -105,10 +111,10 @@ cudaError_t uploadSobolDirections();
 
 cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const PassParams& pass, cudaStream_t stream);
 // The queue lengths live on the device; the grids are sized for `max_items` and exit early.
-cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream);
+cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream);
 cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
                          uint32_t max_items, cudaStream_t stream);
-cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream);
+cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream);
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
                          uint32_t max_items, cudaStream_t stream);
 cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream);
