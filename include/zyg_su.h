@@ -7,7 +7,7 @@
  *
  * Scope of this round: static scenes, perspective camera, PTMIS, the built-in shapes
  * Rectangle / Cube / Sphere and triangle meshes, materials Substitute / Light (uniform parameters).
- * Entry points outside that scope exist and return -1 (image, AOV, exporter and animation calls).
+ * Entry points outside that scope exist and return -1 (image, AOV, exporter and animation-frame calls).
  */
 #ifndef ZYG_SU_H
 #define ZYG_SU_H
@@ -42,7 +42,7 @@ int32_t su_triangle_mesh_create(uint32_t id, uint32_t num_parts, const uint32_t*
                                 const float* tangents, uint32_t tangents_stride, const float* uvs, uint32_t uvs_stride,
                                 bool async);                              /* :379 -> shape id */
 int32_t su_prop_create(uint32_t shape, uint32_t num_materials, const uint32_t* materials); /* :425 -> prop id */
-int32_t su_prop_create_instance(uint32_t entity);                         /* :457 (-1: instancing is a later row) */
+int32_t su_prop_create_instance(uint32_t entity);                         /* :457 -> prop id sharing the shape and materials */
 int32_t su_light_create(uint32_t prop);                                   /* :471 */
 int32_t su_prop_set_transformation(uint32_t prop, const float* trafo);    /* :485 (row-major 4x4, rows = basis vectors, last row = position) */
 int32_t su_prop_set_transformation_frame(uint32_t prop, uint32_t frame, const float* trafo); /* :506 (frame 0 only) */

@@ -179,3 +179,19 @@ def test_metal_mesh_matches_oracle(engine):
     gpu = download_film(w, w)
     rel = rel_error(gpu, ref)
     assert np.median(rel) < 1e-5 and (rel > 1e-3).mean() < 1e-2
+
+
+def test_instanced_scene_matches_oracle(engine):
+    """su_prop_create_instance (capi.zig:457-469): 256 instances of 4 meshes with their own transformations, three
+    material kinds; the prop tree has ~130 nodes, rays collect several mesh candidates."""
+    w, spp = 96, 8
+    n = scenes.instanced_scene(w, w, spp=spp, grid=(16, 16), prototypes=4, quads=(40, 20))
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 1e-5
+    assert (rel > 1e-3).mean() < 1e-2
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 5e-4

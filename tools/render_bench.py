@@ -51,5 +51,9 @@ if __name__ == "__main__":
     reps = int(os.environ.get("REPS", "3"))
     if which in ("all", "cornell"):
         run("cornell", lambda: scenes.cornell_box(512, 512, spp=64), 512, 64, reps)
+    if which in ("all", "instanced"):
+        g = int(os.environ.get("GRID", "100"))
+        run("instanced", lambda: scenes.instanced_scene(1024, 1024, spp=16, grid=(g, g), prototypes=int(os.environ.get("PROTOS", "20")),
+                                                        quads=tuple(int(q) for q in os.environ.get("QUADS", "500,250").split(","))), 1024, 16, reps)
     if which in ("all", "sphere"):
         run("sphere1M", lambda: scenes.sphere_scene(1024, 1024, spp=16, quads=(1000, 500)), 1024, 16, reps)

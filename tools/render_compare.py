@@ -30,6 +30,10 @@ def main():
     num_meshes = 0
     if "cornell" == which:
         scenes.cornell_box(w, w, spp=spp, filter_name=filt)
+    elif "instanced" == which:
+        g = int(os.environ.get("GRID", "24"))
+        num_meshes = scenes.instanced_scene(w, w, spp=spp, filter_name=filt, grid=(g, g), prototypes=int(os.environ.get("PROTOS", "4")),
+                                            quads=tuple(int(q) for q in os.environ.get("QUADS", "60,30").split(",")))
     else:
         num_meshes = scenes.sphere_scene(w, w, spp=spp, filter_name=filt, quads=tuple(int(q) for q in os.environ.get("QUADS", "200,100").split(",")))
     scene, view = su.compile_scene()

@@ -217,7 +217,10 @@ int32_t zyg_su_prop_create_unoccluding(uint32_t shape, uint32_t num_materials, c
     return propCreate(shape, num_materials, materials, true);
 }
 
-int32_t su_prop_create_instance(uint32_t) { return -1; }
+int32_t su_prop_create_instance(uint32_t entity) {
+    if (!g_engine) return -1;
+    return g_engine->scene.createPropInstance(entity);
+}
 
 int32_t su_light_create(uint32_t prop) {
     if (!g_engine) return -1;

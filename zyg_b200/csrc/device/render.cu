@@ -176,7 +176,7 @@ __device__ __forceinline__ bool propVisibility(const SceneDevice& sc, uint32_t e
     }
 }
 
-constexpr uint32_t kPropStack = 32;  // prop trees are shallow; the reference's NodeStack holds 127
+constexpr uint32_t kPropStack = 64;  // prop trees are shallow; the reference's NodeStack holds 127
 
 // PropBvh.intersect, prop_tree.zig:56-116: reference order, so equal-t ties resolve like the reference.
 __device__ __forceinline__ uint32_t sceneIntersect(const SceneDevice& sc, RayT& ray, uint32_t depth_surface, HitD& isec) {

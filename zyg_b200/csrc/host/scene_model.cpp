@@ -401,6 +401,22 @@ uint32_t SceneModel::createPropShape(uint32_t shape_id, const uint32_t* material
     return id;
 }
 
+int SceneModel::createPropInstance(uint32_t entity) {
+    if (entity >= props_.size()) return -1;
+    const PropRec p = props_[entity];  // same shape, materials and parts; its own transformation
+    props_.push_back(p);
+    world_.push_back(Transformation{});
+    const uint32_t id = uint32_t(props_.size() - 1);
+    if (p.solid) {  // Scene.classifyProp
+        if (shapeFinite(p.shape)) {
+            (0 != (p.flags & ZYG_PROP_UNOCCLUDING) ? unoccluding_props_ : finite_props_).push_back(id);
+        } else {
+            infinite_props_.push_back(id);
+        }
+    }
+    return int(id);
+}
+
 bool SceneModel::createLight(uint32_t entity) {  // scene.zig:342-372
     if (entity >= props_.size()) return false;
     const PropRec& p         = props_[entity];
@@ -688,7 +704,7 @@ bool SceneModel::compile(std::string& error) {
         for (int c = 0; c < 4; ++c) ft.position[c] = pos[c];
 
         ZygpuProp& fp  = flat_props_[i];
-        fp.shape       = p.shape >= 7 ? ZYG_SHAPE_TRIANGLE_MESH : p.shape;
+        fp.shape       = p.shape >= 7 ? uint32_t(ZYG_SHAPE_TRIANGLE_MESH) : p.shape;
         fp.mesh        = p.shape >= 7 ? p.shape - 7 : ZYGPU_NULL;
         fp.flags       = p.flags;
         fp.parts_start = p.parts_start;

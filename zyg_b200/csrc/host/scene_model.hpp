@@ -60,6 +60,7 @@ class SceneModel {
     // ---- scene ----
     uint32_t createEntity();  // scene.zig:254-260
     uint32_t createPropShape(uint32_t shape_id, const uint32_t* materials, uint32_t num_materials, bool unoccluding);
+    int      createPropInstance(uint32_t entity);  // scene.zig:310-320
     bool     createLight(uint32_t entity);
     bool     setWorldTransformation(uint32_t entity, const Transformation& t);
     bool     setVisibility(uint32_t entity, bool in_camera, bool in_reflection, bool in_sss);

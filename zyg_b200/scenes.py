@@ -250,3 +250,64 @@ def sphere_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, q
     su.prop_set_transformation(lamp, su.transformation((1.5, 3.0, -1.0), (1.5, 1.5, 1.0), (-90.0, 0.0, 0.0)))
     su.light_create(lamp)
     return 1
+
+
+def instanced_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, grid=(32, 32), prototypes=4,
+                    quads=(100, 50), seed=3):
+    """Config-3 style scene through the C API: `prototypes` displaced-sphere meshes (seeds 1..), instanced
+    grid[0] x grid[1] times with su_prop_create_instance on a jittered grid (uniform scale 0.3-0.6, random Y rotation,
+    PCG32 stream `seed`), a ground Rectangle and one Rectangle light. Materials go by prototype: diffuse, rough metal,
+    glossy dielectric, diffuse. Returns the number of meshes."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(50.0)))
+    extent = 0.5 * max(grid)
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 0.45 * extent, -1.15 * extent),
+                                                         rotation_deg=(-28.0, 0.0, 0.0)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    ground = su.material_create({"rendering": {"Substitute": {"color": [0.55, 0.55, 0.5], "roughness": 1.0}}})
+    palette = [
+        {"color": [0.7, 0.25, 0.2], "roughness": 1.0, "metallic": 0.0},
+        {"color": [1.0, 0.77, 0.34], "roughness": 0.3, "metallic": 1.0},
+        {"color": [0.2, 0.5, 0.75], "roughness": 0.15, "metallic": 0.0},
+        {"color": [0.3, 0.65, 0.3], "roughness": 0.6, "metallic": 0.0},
+    ]
+    materials = [su.material_create({"rendering": {"Substitute": palette[i % len(palette)]}}) for i in range(prototypes)]
+    light = su.material_create({"rendering": {"Light": {"emittance": {"value": 40.0}}}})
+
+    protos = []
+    for i in range(prototypes):
+        positions, normals, uvs, indices = displaced_sphere(*quads, seed=0x5EED0001 + i)
+        indices = np.ascontiguousarray(indices.reshape(-1, 3)[:, [0, 2, 1]])
+        shape = su.triangle_mesh_create(positions, indices, normals, uvs)
+        protos.append(su.prop_create(shape, [materials[i]]))
+
+    rng = PCG32(0, np.array([seed], np.uint64))
+    count = 0
+    for gy in range(grid[1]):
+        for gx in range(grid[0]):
+            r = [float(rng.float()[0]) for _ in range(5)]
+            proto = protos[int(r[0] * prototypes) % prototypes]
+            prop = su.prop_create_instance(proto)
+            scale = 0.3 + 0.3 * r[1]
+            x = (gx + 0.5 + 0.6 * (r[2] - 0.5)) - 0.5 * grid[0]
+            z = (gy + 0.5 + 0.6 * (r[3] - 0.5)) - 0.5 * grid[1]
+            su.prop_set_transformation(prop, su.transformation((x, 1.05 * scale, z), (scale, scale, scale),
+                                                               (0.0, 360.0 * r[4], 0.0)))
+            count += 1
+    # the prototypes themselves stay out of the picture (they are props too: park them below the ground, invisible)
+    for proto in protos:
+        su.prop_set_transformation(proto, su.transformation((0.0, -50.0, 0.0), (0.01, 0.01, 0.01)))
+        su.prop_set_visibility(proto, False, False)
+
+    floor = su.prop_create(su.RECTANGLE, [ground])
+    su.prop_set_transformation(floor, su.transformation((0.0, 0.0, 0.0), (3.0 * max(grid), 3.0 * max(grid), 1.0), (90.0, 0.0, 0.0)))
+    lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=True)
+    su.prop_set_transformation(lamp, su.transformation((0.25 * extent, 1.2 * extent, 0.0), (0.6 * extent, 0.6 * extent, 1.0), (-90.0, 0.0, 0.0)))
+    su.light_create(lamp)
+    return prototypes

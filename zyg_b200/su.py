@@ -123,6 +123,10 @@ def prop_create(shape: int, materials, unoccluding: bool = False) -> int:
     return _ok(fn(shape, mats.size, mats.ctypes.data), "su_prop_create")
 
 
+def prop_create_instance(entity: int) -> int:
+    return _ok(_su().su_prop_create_instance(entity), "su_prop_create_instance")
+
+
 def light_create(prop: int):
     _ok(_su().su_light_create(prop), "su_light_create")
 
