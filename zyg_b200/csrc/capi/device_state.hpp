@@ -35,7 +35,7 @@ inline int fail(const char* fmt, ...) {
 struct DeviceMesh {
     zygpu::MeshDevice  view{};
     zygpu::MeshShading shading{};
-    const zyg_mesh*    source     = nullptr;
+    uint64_t           source     = 0;  // zyg_mesh::serial
     void*              buffers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

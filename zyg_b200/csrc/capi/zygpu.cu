@@ -167,7 +167,7 @@ int zygpu_upload_mesh(zygpu_device* dev, const zyg_mesh* mesh) {
 
     // an already uploaded mesh keeps its id
     for (size_t i = 0; i < dev->meshes.size(); ++i) {
-        if (dev->meshes[i].source == mesh) return int(i);
+        if (dev->meshes[i].source == mesh->serial) return int(i);
     }
 
     const void*  src[8]   = {w.nodes.data(),     w.triangles.data(), t.nodes.data(), t.triangles.data(),
@@ -180,7 +180,7 @@ int zygpu_upload_mesh(zygpu_device* dev, const zyg_mesh* mesh) {
         CUDA_OK(cudaMalloc(&dm.buffers[i], std::max<size_t>(bytes[i], 16)));
         CUDA_OK(cudaMemcpy(dm.buffers[i], src[i], bytes[i], cudaMemcpyHostToDevice));
     }
-    dm.source              = mesh;
+    dm.source              = mesh->serial;
     dm.view.wide_nodes     = static_cast<const float4*>(dm.buffers[0]);
     dm.view.wide_tris      = static_cast<const float4*>(dm.buffers[1]);
     dm.view.binary_nodes   = static_cast<const float4*>(dm.buffers[2]);
