@@ -18,6 +18,8 @@
 #include "zyg_oracle.h"
 
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -68,6 +70,75 @@ struct State {  // vertex.zig:19-43
     }
 };
 
+struct MediumStack {  // prop/medium.zig:30-153; the collision coefficients are the material's (Glass: absorption, no scattering)
+    static constexpr uint32_t NumEntries = 4;
+    struct Medium {
+        uint32_t prop, part;
+        float    ior;
+        int8_t   priority;
+        Vec4f    cc_a;
+        bool     matches(uint32_t p, uint32_t pa) const { return prop == p && part == pa; }
+    };
+    uint32_t index = 0;
+    Medium   m_stack[NumEntries];
+
+    bool          empty() const { return 0 == index; }
+    const Medium& top() const { return m_stack[index - 1]; }
+    Vec4f         topCC() const {
+        int8_t   priority = -128;
+        uint32_t highest  = 0;
+        for (uint32_t i = 0; i < index; ++i) {
+            const int8_t lp = m_stack[i].priority;
+            if (lp >= priority) {
+                priority = lp;
+                highest  = i;
+            }
+        }
+        return m_stack[highest].cc_a;
+    }
+    int8_t highestPriority() const {
+        int8_t priority = -128;
+        for (uint32_t i = 0; i < index; ++i) priority = std::max(priority, m_stack[i].priority);
+        return priority;
+    }
+    float topIor() const { return index > 0 ? m_stack[index - 1].ior : 1.f; }
+    float peekIor(uint32_t prop, uint32_t part) const {
+        if (index <= 1) return 1.f;
+        const uint32_t back = index - 1;
+        return m_stack[back].matches(prop, part) ? m_stack[back - 1].ior : m_stack[back].ior;
+    }
+    void push(uint32_t prop, uint32_t part, Vec4f cc_a, float ior, int8_t priority) {
+        if (index < NumEntries - 1) {
+            m_stack[index] = {prop, part, ior, priority, cc_a};
+            index += 1;
+        }
+    }
+    void remove(uint32_t prop, uint32_t part) {
+        const int32_t back = int32_t(index) - 1;
+        for (int32_t i = back; i >= 0; --i) {
+            if (m_stack[i].matches(prop, part)) {
+                for (int32_t j = i; j < back; ++j) m_stack[j] = m_stack[j + 1];
+                index -= 1;
+                return;
+            }
+        }
+    }
+};
+
+// ray_offset.zig:29-31
+inline float offsetF(float t) {
+    const float origin      = 1.f / 32.f;
+    const float float_scale = 1.f / 65536.f;
+    const float int_scale   = 256.f;
+    if (t < origin) return t + float_scale;
+    int32_t i;
+    std::memcpy(&i, &t, 4);
+    i = int32_t(uint32_t(i) + uint32_t(int32_t(int_scale)));
+    float r;
+    std::memcpy(&r, &i, 4);
+    return r;
+}
+
 struct Vertex {  // vertex.zig:45-85
     Ray   ray;
     Depth probe_depth;
@@ -82,6 +153,8 @@ struct Vertex {  // vertex.zig:45-85
     Vec4f    throughput             = splat(1.f);
     Vec4f    origin;
     Vec4f    geo_n = splat(0.f);
+
+    MediumStack mediums;
 };
 
 struct IValue {  // helper.zig:6-20
@@ -1056,6 +1129,7 @@ struct Worker {
     const Scene& scene;
     Generator    rng;
     Sampler      samplers[2];
+    bool         debug = false;  // ZO_DEBUG_PIXEL="x,y": print the vertices of that pixel's paths (diagnostics)
 
     explicit Worker(const Scene& sc) : scene(sc) {
         samplers[0].is_sobol = ZYG_SAMPLER_SOBOL == sc.view.sampler;
@@ -1194,17 +1268,18 @@ struct Worker {
         rs.origin           = vertex.origin;
         rs.uvw              = frag.uvw;
         rs.stochastic_r     = sampler.sample1D();
-        rs.ior              = 1.f;  // empty medium stack: Stack.topIor / peekIor
+        rs.ior = frag.sameHemisphere(wo) ? vertex.mediums.topIor() : vertex.mediums.peekIor(frag.prop, frag.part);  // Vertex.iorOutside
         rs.reg_weight       = scene.view.regularize_roughness;
         rs.reg_alpha        = vertex.reg_alpha;
         rs.prop             = frag.prop;
         rs.part             = frag.part;
         rs.primary          = vertex.state.primary_ray;
         rs.caustics         = caustics;
-        rs.highest_priority = -128;
+        rs.highest_priority = vertex.mediums.highestPriority();
 
         switch (m.type) {
             case ZYG_MATERIAL_SUBSTITUTE: return substituteSample(m, wo, rs, scene.view.specular_threshold, scene.luts);
+            case ZYG_MATERIAL_GLASS: return glassSample(m, wo, rs, scene.view.specular_threshold, scene.luts);
             default: return lightSample(wo, rs);
         }
     }
@@ -1293,14 +1368,36 @@ struct Worker {
         const uint32_t total_depth = vertex.probe_depth.total();
         Sampler&       sampler     = pickSampler(total_depth);
 
-        // Context.nextEvent, context.zig:54-69 (empty medium stack, no volume props)
+        // Context.nextEvent, context.zig:54-69 (no volume props)
         Fragment frag;
-        {
+        if (!vertex.mediums.empty()) {
+            // VolumeIntegrator.integrate, volume_integrator.zig:84-130, for a homogeneous, non-scattering medium (the
+            // "glass" case of propScatter, :51-66): clip the ray to the medium prop's box, intersect, absorb
+            const MediumStack::Medium& medium    = vertex.mediums.top();
+            const float                ray_max_t = vertex.ray.max_t;
+            const float                limit     = cube::aabbIntersectP(scene.propAabb(medium.prop), vertex.ray);
+            vertex.ray.max_t                     = min(offsetF(limit), ray_max_t);
+            scene.intersect(vertex.ray, vertex.probe_depth.surface, frag);
+            if (frag.hit()) {
+                const float d     = vertex.ray.max_t;
+                const Vec4f cc_a  = vertex.mediums.topCC();
+                const Vec4f x     = splat(-(d - vertex.ray.min_t)) * cc_a;
+                const Vec4f tr    = {{std::exp(x[0]), std::exp(x[1]), std::exp(x[2]), std::exp(x[3])}};  // attenuation3
+                vertex.throughput = vertex.throughput * tr;
+            }
+        } else {
             const Vec4f origin = vertex.ray.origin;
             scene.intersect(vertex.ray, vertex.probe_depth.surface, frag);
             const float dif_t = distance3(origin, vertex.ray.origin);
             vertex.ray.origin = origin;
             vertex.ray.max_t += dif_t;
+        }
+
+        if (debug) {
+            std::printf("[zo] depth %u pc %u sw %g state p%d s%d sg%d | hit prop %u t %.9g media %u | thr %.9g %.9g %.9g | rng %llx\n", total_depth,
+                        vertex.path_count, vertex.split_weight, vertex.state.primary_ray, vertex.state.specular, vertex.state.singular,
+                        frag.prop, vertex.ray.max_t, vertex.mediums.index, vertex.throughput[0], vertex.throughput[1], vertex.throughput[2],
+                        (unsigned long long)rng.state);
         }
 
         const Vec4f this_light       = connectLight(vertex, frag, sampler);
@@ -1330,6 +1427,12 @@ struct Worker {
         const uint32_t path_count = mat_sample.sample(sampler, max_splits, bxdf_samples);
 
         if (0 == path_count) vertex.throughput = splat(0.f);
+        if (debug) {
+            for (uint32_t i = 0; i < path_count; ++i) {
+                std::printf("[zo]   sample %u/%u event %d sw %g pdf %g wi %.9g %.9g %.9g\n", i, path_count, int(bxdf_samples[i].path.event),
+                            bxdf_samples[i].split_weight, bxdf_samples[i].pdf, bxdf_samples[i].wi[0], bxdf_samples[i].wi[1], bxdf_samples[i].wi[2]);
+            }
+        }
 
         for (uint32_t i = 0; i < path_count; ++i) {
             const bxdf::Sample& sample_result = bxdf_samples[i];
@@ -1354,6 +1457,15 @@ struct Worker {
 
             next_vertex.ray = frag.offsetRayTo(sample_result.wi);
             next_vertex.probe_depth.surface += 1;  // Probe.Depth.increment, no subsurface
+
+            if (bxdf::Event::Transmission == path.event) {  // Vertex.interfaceChange, vertex.zig:95-110
+                if (frag.sameHemisphere(sample_result.wi)) {
+                    next_vertex.mediums.remove(frag.prop, frag.part);
+                } else {
+                    const ZygpuMaterial& material = scene.propMaterial(frag.prop, frag.part);
+                    next_vertex.mediums.push(frag.prop, frag.part, load4(material.color), material.ior, int8_t(material.priority));
+                }
+            }
 
             next_vertex.state.transparent =
                 next_vertex.state.transparent && (bxdf::Event::Transmission == path.event || bxdf::Event::Straight == path.event);
@@ -1492,6 +1604,13 @@ void renderTile(Worker& worker, const Film& film, const int32_t tile[4], uint32_
             const uint32_t pixel_id = pixel_n + uint32_t(x + fr);
 
             worker.rng.start(0, uint64_t(pixel_id) + o);
+            {
+                const char* dbg = std::getenv("ZO_DEBUG_PIXEL");
+                int                dx = -1, dy = -1;
+                if (dbg) std::sscanf(dbg, "%d,%d", &dx, &dy);
+                worker.debug = dbg && x == dx && y == dy;
+                if (worker.debug) std::printf("[zo] pixel %d %d iteration %u\n", x, y, iteration);
+            }
 
             const uint64_t sample_index = uint64_t(pixel_id) * uint64_t(num_expected_samples) + uint64_t(iteration);
             const uint32_t tsi          = uint32_t(sample_index);
@@ -1624,6 +1743,51 @@ float zo_ggx_micro_directional_albedo(float alpha, float n_dot_wo, uint32_t num_
         accum += ((micro.n_dot_wi * result.reflection[0]) / result.pdf) / float(num_samples);
     }
     return accum;
+}
+
+// integrate_f_s_ss of the reference's LUT generator (ggx_integrate.zig:134-205) through this oracle's VNDF sampling,
+// reflectNoFresnel / refractNoFresnel and schlick1: lets tests pin the rough-dielectric lobes of Glass against the E_s
+// table the reference ships (ggx_integral.zig:1045-1046 ff.).
+float zo_ggx_f_s_ss(float alpha, float f0, float ior_t, float n_dot_wo, uint32_t num_samples) {
+    using namespace zo;
+    if (alpha < ggx::MinAlpha || ior_t <= 1.f) return 1.f;
+    const Frame frame{{{1.f, 0.f, 0.f, 0.f}}, {{0.f, 1.f, 0.f, 0.f}}, {{0.f, 0.f, 1.f, 0.f}}};
+    const float cn_dot_wo = safe::clamp(n_dot_wo);
+    const Vec4f wo        = {{std::sqrt(1.f - cn_dot_wo * cn_dot_wo), 0.f, cn_dot_wo, 0.f}};
+    const IoR   ior{ior_t, 1.f};
+
+    float accum = 0.f;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        uint32_t bits = i;  // math.hammersley(i, num_samples, 0), sample_distribution.zig:3-18
+        bits          = (bits << 16) | (bits >> 16);
+        bits          = ((bits & 0x55555555u) << 1) | ((bits & 0xAAAAAAAAu) >> 1);
+        bits          = ((bits & 0x33333333u) << 2) | ((bits & 0xCCCCCCCCu) >> 2);
+        bits          = ((bits & 0x0F0F0F0Fu) << 4) | ((bits & 0xF0F0F0F0u) >> 4);
+        bits          = ((bits & 0x00FF00FFu) << 8) | ((bits & 0xFF00FF00u) >> 8);
+        const float xi[2] = {float(i) / float(num_samples), float(bits) * 2.3283064365386963e-10f};
+
+        float       n_dot_h;
+        const float a2[2] = {alpha, alpha};
+        const Vec4f h     = ggx::sampleVndf(wo, a2, xi, frame, n_dot_h);
+
+        const float wo_dot_h = safe::clampDot(wo, h);
+        const float eta      = ior.eta_i / ior.eta_t;
+        const float sint2    = (eta * eta) * (1.f - wo_dot_h * wo_dot_h);
+        const float wi_dot_h = std::sqrt(1.f - sint2);
+        const float cos_x    = ior.eta_i > ior.eta_t ? wi_dot_h : wo_dot_h;
+        const float f        = fresnel::schlick1(cos_x, f0);
+
+        bxdf::Sample result;
+        {
+            const float n_dot_wi = ggx::iso::reflectNoFresnel(wo, h, cn_dot_wo, n_dot_h, wo_dot_h, alpha, 0.f, frame, result);
+            accum += (min(n_dot_wi, n_dot_wo) * f * result.reflection[0]) / result.pdf;
+        }
+        {
+            const float n_dot_wi = ggx::iso::refractNoFresnel(wo, h, cn_dot_wo, n_dot_h, -wi_dot_h, -wo_dot_h, alpha, 0.f, ior, frame, result);
+            accum += (n_dot_wi * (1.f - f) * result.reflection[0]) / result.pdf;
+        }
+    }
+    return accum / float(num_samples);
 }
 
 // Sobol.sample1D stream: startPixel(sample, seed) then n draws with incrementPadding every `pad_every` draws (0 = never).

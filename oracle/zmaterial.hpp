@@ -8,6 +8,8 @@
 //   Substitute Material.sample      src/core/scene/material/substitute/substitute_material.zig:114-221
 //   Substitute Sample               src/core/scene/material/substitute/substitute_sample.zig:38-410
 //   Light material / Emittance      src/core/scene/material/light/light_material.zig, light/emittance.zig:29-59
+//   Glass Material.sample / Sample  src/core/scene/material/glass/glass_material.zig:46-73, glass_sample.zig:32-537
+//                                   (thick glass: thickness == 0, abbe == 0)
 #pragma once
 
 #include "zsampler.hpp"
@@ -84,7 +86,7 @@ struct SampleBase {  // sample_base.zig:14-104
     Frame frame;
     Vec4f geo_n, n, wo;
     float alpha[2];
-    bool  translucent = false, can_evaluate = false, avoid_caustics = false, volumetric = false;
+    bool  translucent = false, can_evaluate = false, avoid_caustics = false, volumetric = false, lower_priority = false;
 
     bool sameHemisphere(Vec4f v) const { return dot3(geo_n, v) > 0.f; }
     bool avoidCausticsForce(bool force) const { return force || avoid_caustics; }
@@ -99,7 +101,22 @@ struct Schlick {  // fresnel.zig:9-29
         return t * t;
     }
 };
+inline float schlick1(float wo_dot_h, float f0) { return std::fmaf(pow5(1.f - wo_dot_h), 1.f - f0, f0); }  // fresnel.zig:5-7
+inline float dielectric(float cos_theta_i, float cos_theta_t, float eta_i, float eta_t) {  // fresnel.zig:31-43
+    const float t0  = eta_t * cos_theta_i;
+    const float t1  = eta_i * cos_theta_t;
+    const float r_p = (t0 - t1) / (t0 + t1);
+    const float t2  = eta_i * cos_theta_i;
+    const float t3  = eta_t * cos_theta_t;
+    const float r_o = (t2 - t3) / (t2 + t3);
+    return 0.5f * (r_p * r_p + r_o * r_o);
+}
 }  // namespace fresnel
+
+struct IoR {  // sample_base.zig:106-117
+    float eta_t, eta_i;
+    IoR   swapped(bool same_side) const { return same_side ? *this : IoR{eta_i, eta_t}; }
+};
 
 namespace ggx {
 
@@ -127,6 +144,9 @@ inline Vec4f dspbrMicroEc(const GgxLuts& luts, Vec4f f0, float n_dot_wi, float n
     const Vec4f f     = ((f_avg * f_avg) * splat(e_avg)) / mulAdd(-f_avg, splat(1.f - e_avg), splat(1.f));
     return splat(m) * f;
 }
+
+// ggx.zig:30-32; E_s_inverse_max_f0 = 4 (ggx_integral.zig:1045)
+inline float ilmEpDielectric(const GgxLuts& luts, float n_dot_wo, float alpha, float f0) { return 1.f / luts.eS(n_dot_wo, alpha, f0 * 4.f); }
 
 // Aniso.sample, ggx.zig:393-409 (Dupuy & Benyoub spherical caps)
 inline Vec4f sampleVndf(Vec4f wo, const float alpha[2], const float xi[2], const Frame& frame, float& n_dot_h) {
@@ -193,6 +213,110 @@ inline Micro reflect(Vec4f wo, float n_dot_wo, float alpha, float specular_thres
     result.pdf        = pdfVisible(d, g[1]);
     result.path       = bxdf::Path::reflection(alpha, specular_threshold);
     return {h, n_dot_wi, wo_dot_h};
+}
+
+inline float gSmithCorrelated(float n_dot_wi, float n_dot_wo, float alpha2) {  // :252-257
+    const float a = n_dot_wo * std::sqrt(std::fmaf(1.f - alpha2, n_dot_wi * n_dot_wi, alpha2));
+    const float b = n_dot_wi * std::sqrt(std::fmaf(1.f - alpha2, n_dot_wo * n_dot_wo, alpha2));
+    return (2.f * n_dot_wi * n_dot_wo) / (a + b);
+}
+inline float gGgx(float n_dot_v, float alpha2) {  // :447-449
+    return (2.f * n_dot_v) / (n_dot_v + std::sqrt(alpha2 + (1.f - alpha2) * (n_dot_v * n_dot_v)));
+}
+inline float pdfVisibleRefract(float n_dot_wo, float wo_dot_h, float d, float alpha2) {  // :441-445
+    const float g1 = gGgx(n_dot_wo, alpha2);
+    return g1 * wo_dot_h * d / n_dot_wo;
+}
+
+struct ResultF {
+    bxdf::Result r;
+    float        f;  // fresnel term, lane 0
+};
+
+// Iso.reflectionF with a scalar f0, :73-95
+inline ResultF reflectionF(Vec4f h, Vec4f n, float n_dot_wi, float n_dot_wo, float wo_dot_h, float alpha, float f0) {
+    const float alpha2  = alpha * alpha;
+    const float n_dot_h = saturate(dot3(n, h));
+    const float d       = distribution(n_dot_h, alpha2);
+    float       g[2];
+    visibilityAndG1Wo(n_dot_wi, n_dot_wo, alpha2, g);
+    const float f = fresnel::schlick1(wo_dot_h, f0);
+    return {{splat(d * g[0]) * splat(f), pdfVisible(d, g[1])}, f};
+}
+
+// Iso.refractionF, :128-159
+inline ResultF refractionF(float n_dot_wi, float n_dot_wo, float wi_dot_h, float wo_dot_h, float n_dot_h, float alpha, IoR ior,
+                           float f0) {
+    const float alpha2 = alpha * alpha;
+
+    const float abs_wi_dot_h = safe::clampAbs(wi_dot_h);
+    const float abs_wo_dot_h = safe::clampAbs(wo_dot_h);
+
+    const float d = distribution(n_dot_h, alpha2);
+    const float g = gSmithCorrelated(n_dot_wi, n_dot_wo, alpha2);
+
+    const float cos_x = ior.eta_i > ior.eta_t ? abs_wi_dot_h : abs_wo_dot_h;
+    const float f     = 1.f - fresnel::schlick1(cos_x, f0);
+
+    const float sqr_eta_t = ior.eta_t * ior.eta_t;
+
+    const float factor = (abs_wi_dot_h * abs_wo_dot_h) / (n_dot_wi * n_dot_wo);
+    const float denom  = pow2(ior.eta_i * wo_dot_h + ior.eta_t * wi_dot_h);
+
+    const float refr = d * g * f;
+    const float refl = (factor * sqr_eta_t / denom) * refr;
+
+    const float pdf = pdfVisibleRefract(n_dot_wo, abs_wo_dot_h, d, alpha2);
+    return {{splat(refl), pdf * (abs_wi_dot_h * sqr_eta_t / denom)}, f};
+}
+
+// Iso.reflectNoFresnel, :161-187
+inline float reflectNoFresnel(Vec4f wo, Vec4f h, float n_dot_wo, float n_dot_h, float wo_dot_h, float alpha, float specular_threshold,
+                              const Frame& frame, bxdf::Sample& result) {
+    const Vec4f wi = normalize3(mulAdd(splat(2.f * wo_dot_h), h, -wo));
+
+    const float n_dot_wi = frame.clampNdot(wi);
+    const float alpha2   = alpha * alpha;
+
+    const float d = distribution(n_dot_h, alpha2);
+    float       g[2];
+    visibilityAndG1Wo(n_dot_wi, n_dot_wo, alpha2, g);
+
+    result.reflection = splat(d * g[0]);
+    result.wi         = wi;
+    result.pdf        = pdfVisible(d, g[1]);
+    result.path       = bxdf::Path::reflection(alpha, specular_threshold);
+    return n_dot_wi;
+}
+
+// Iso.refractNoFresnel, :189-233
+inline float refractNoFresnel(Vec4f wo, Vec4f h, float n_dot_wo, float n_dot_h, float wi_dot_h, float wo_dot_h, float alpha,
+                              float specular_threshold, IoR ior, const Frame& frame, bxdf::Sample& result) {
+    const float eta = ior.eta_i / ior.eta_t;
+
+    const float abs_wi_dot_h = safe::clampAbs(wi_dot_h);
+    const float abs_wo_dot_h = safe::clampAbs(wo_dot_h);
+
+    const Vec4f wi = normalize3(splat(std::fmaf(eta, abs_wo_dot_h, -abs_wi_dot_h)) * h - splat(eta) * wo);
+
+    const float n_dot_wi = frame.clampAbsNdot(wi);
+
+    const float alpha2 = alpha * alpha;
+
+    const float d = distribution(n_dot_h, alpha2);
+    const float g = gSmithCorrelated(n_dot_wi, n_dot_wo, alpha2);
+
+    const float refr      = d * g;
+    const float factor    = (abs_wi_dot_h * abs_wo_dot_h) / (n_dot_wi * n_dot_wo);
+    const float denom     = pow2(ior.eta_i * wo_dot_h + ior.eta_t * wi_dot_h);
+    const float sqr_eta_t = ior.eta_t * ior.eta_t;
+    const float pdf       = pdfVisibleRefract(n_dot_wo, abs_wo_dot_h, d, alpha2);
+
+    result.reflection = splat((factor * sqr_eta_t / denom) * refr);
+    result.wi         = wi;
+    result.pdf        = pdf * (abs_wi_dot_h * sqr_eta_t / denom);
+    result.path       = bxdf::Path::transmission(alpha, specular_threshold);
+    return n_dot_wi;
 }
 }  // namespace iso
 
@@ -295,13 +419,17 @@ inline ggx::Micro reflect(const GgxLuts& luts, Vec4f color, float f0, Vec4f wo, 
 
 // Material sample of the Material union restricted to {Substitute surface, Light}: material_sample.zig.
 struct MaterialSample {
-    enum Kind { Light, Substitute } kind;
+    enum Kind { Light, Substitute, Glass } kind;
 
     SampleBase super;
 
     // Substitute, substitute_sample.zig:20-36
     Vec4f albedo, f0;
     float metallic, specular, specular_threshold, opacity;
+
+    // Glass, glass_sample.zig:20-30 (abbe == 0, thickness == 0)
+    Vec4f absorption_coef;
+    float ior, ior_outside, glass_f0;
 
     const GgxLuts* luts;
 
@@ -342,8 +470,9 @@ struct MaterialSample {
     }
 
     // material_sample.zig:56-62 -> substitute_sample.zig:88-145 (surface, opaque, uncoated)
-    bxdf::Result evaluate(Vec4f wi, uint32_t /*max_splits*/, bool force_disable_caustics) const {
+    bxdf::Result evaluate(Vec4f wi, uint32_t max_splits, bool force_disable_caustics) const {
         if (Light == kind) return {splat(0.f), 0.f};
+        if (Glass == kind) return glassEvaluate(wi, max_splits, force_disable_caustics);
 
         const Vec4f wo = super.wo;
         if (!super.sameHemisphere(wo)) return bxdf::Result::empty();
@@ -420,8 +549,9 @@ struct MaterialSample {
     }
 
     // material_sample.zig:64-78 -> substitute_sample.zig:147-234 (surface, opaque, uncoated). Returns the count.
-    uint32_t sample(Sampler& sampler, uint32_t /*max_splits*/, bxdf::Sample buffer[4]) const {
+    uint32_t sample(Sampler& sampler, uint32_t max_splits, bxdf::Sample buffer[4]) const {
         if (Light == kind) return 0;
+        if (Glass == kind) return glassSample(sampler, max_splits, buffer);
 
         if (!super.sameHemisphere(super.wo)) return 0;
 
@@ -432,6 +562,213 @@ struct MaterialSample {
         baseSample(sampler, result);
 
         if (0.f == result.pdf) return 0;
+        return 1;
+    }
+
+    // ---- Glass, glass_sample.zig ----
+
+    // Sample.evaluate, :68-152
+    bxdf::Result glassEvaluate(Vec4f wi, uint32_t max_splits, bool force_disable_caustics) const {
+        const float alpha = super.alpha[0];
+        const bool  rough = alpha > 0.f;
+
+        if (ior == ior_outside || !rough || super.lower_priority ||
+            (super.avoidCausticsForce(force_disable_caustics) && alpha <= specular_threshold)) {
+            return bxdf::Result::empty();
+        }
+
+        const Frame& frame = super.frame;
+        const bool   split = max_splits > 1;
+        const float  s     = specular;
+        const Vec4f  wo    = super.wo;
+
+        if (!super.sameHemisphere(wo)) {
+            const IoR   io{ior_outside, ior};  // eta_i = self.ior, eta_t = self.ior_outside
+            const Vec4f h = -normalize3(splat(io.eta_t) * wi + splat(io.eta_i) * wo);
+
+            const float wi_dot_h = dot3(wi, h);
+            if (wi_dot_h <= 0.f) return bxdf::Result::empty();
+
+            const float wo_dot_h = dot3(wo, h);
+            const float eta      = io.eta_i / io.eta_t;
+            const float sint2    = (eta * eta) * (1.f - wo_dot_h * wo_dot_h);
+            if (sint2 >= 1.f) return bxdf::Result::empty();
+
+            const float n_dot_wi = frame.clampNdot(wi);
+            const float n_dot_wo = frame.clampAbsNdot(wo);
+            const float n_dot_h  = saturate(frame.nDot(h));
+
+            const ggx::iso::ResultF gg   = ggx::iso::refractionF(n_dot_wi, n_dot_wo, wi_dot_h, wo_dot_h, n_dot_h, alpha, io, glass_f0);
+            const float             comp = ggx::ilmEpDielectric(*luts, n_dot_wo, alpha, glass_f0);
+
+            const float split_pdf = split ? 1.f : gg.f;
+            return {splat(min(n_dot_wi, n_dot_wo) * comp * s) * gg.r.reflection, split_pdf * gg.r.pdf};
+        } else if (super.sameHemisphere(wi)) {
+            const float n_dot_wi = frame.clampNdot(wi);
+            const float n_dot_wo = frame.clampAbsNdot(wo);
+
+            const Vec4f h        = normalize3(wo + wi);
+            const float wo_dot_h = safe::clampDot(wo, h);
+
+            const ggx::iso::ResultF gg   = ggx::iso::reflectionF(h, frame.z, n_dot_wi, n_dot_wo, wo_dot_h, alpha, glass_f0);
+            const float             comp = ggx::ilmEpDielectric(*luts, n_dot_wo, alpha, glass_f0);
+
+            const float split_pdf = split ? 1.f : gg.f;
+            return {splat(n_dot_wi * comp * s) * gg.r.reflection, split_pdf * gg.r.pdf};
+        }
+        return bxdf::Result::empty();
+    }
+
+    // Sample.sample, :167-200 (thickness == 0, abbe == 0)
+    uint32_t glassSample(Sampler& sampler, uint32_t max_splits, bxdf::Sample buffer[4]) const {
+        const bool split = max_splits > 1;
+        if (super.alpha[0] > 0.f) return glassRoughSample(sampler, split, buffer);
+        return glassSpecularSample(sampler, split, buffer);
+    }
+
+    static bxdf::Sample glassReflect(Vec4f wo, Vec4f n, float n_dot_wo, float split_weight, float specular) {  // :429-438
+        return {splat(specular) * splat(1.f), normalize3(splat(2.f * n_dot_wo) * n - wo), 1.f, split_weight, 0.f,
+                bxdf::Path::singularReflection()};
+    }
+    static bxdf::Sample thickSpecularRefract(Vec4f wo, Vec4f n, float n_dot_wo, float n_dot_t, float eta, float split_weight) {  // :519-537
+        return {splat(1.f), normalize3(splat(eta * n_dot_wo - n_dot_t) * n - splat(eta) * wo), 1.f, split_weight, 0.f,
+                bxdf::Path::singularTransmission()};
+    }
+
+    // specularSample, :202-284 (Thin = false, weight = 1)
+    uint32_t glassSpecularSample(Sampler& sampler, bool split, bxdf::Sample buffer[4]) const {
+        float eta_i = ior_outside;
+        float eta_t = ior;
+
+        const Vec4f wo = super.wo;
+
+        if (eta_i == eta_t || super.lower_priority) {
+            buffer[0] = {splat(1.f), -wo, 1.f, 1.f, 0.f, bxdf::Path::singularTransmission()};
+            return 1;
+        }
+
+        Vec4f n = super.frame.z;
+        if (!super.sameHemisphere(wo)) {
+            n = -n;
+            std::swap(eta_i, eta_t);
+        }
+
+        const float n_dot_wo = min(std::fabs(dot3(n, wo)), 1.f);
+        const float eta      = eta_i / eta_t;
+        const float sint2    = (eta * eta) * (1.f - n_dot_wo * n_dot_wo);
+
+        const float s = specular;
+
+        float n_dot_t, f;
+        if (sint2 >= 1.f) {
+            n_dot_t = 0.f;
+            f       = 1.f;
+        } else {
+            n_dot_t = std::sqrt(1.f - sint2);
+            f       = fresnel::dielectric(n_dot_wo, n_dot_t, eta_i, eta_t);
+        }
+
+        if (split) {
+            buffer[0] = glassReflect(wo, n, n_dot_wo, f, s);
+            if (1.f == f) return 1;
+            buffer[1] = thickSpecularRefract(wo, n, n_dot_wo, n_dot_t, eta, 1.f - f);
+            return 2;
+        }
+        const float p = sampler.sample1D();
+        if (p <= f) {
+            buffer[0] = glassReflect(wo, n, n_dot_wo, 1.f, s);
+        } else {
+            buffer[0] = thickSpecularRefract(wo, n, n_dot_wo, n_dot_t, eta, 1.f);
+        }
+        return 1;
+    }
+
+    // roughRefract, :440-503 (Thin = false)
+    float roughRefract(bool same_side, const Frame& frame, Vec4f wo, Vec4f h, float n_dot_wo, float n_dot_h, float wi_dot_h,
+                       float wo_dot_h, float alpha, IoR io, bxdf::Sample& result) const {
+        const float r_wo_dot_h = same_side ? -wo_dot_h : wo_dot_h;
+        return ggx::iso::refractNoFresnel(wo, h, n_dot_wo, n_dot_h, -wi_dot_h, r_wo_dot_h, alpha, specular_threshold, io, frame, result);
+    }
+
+    // roughSample, :286-427 (Thin = false, weight = 1)
+    uint32_t glassRoughSample(Sampler& sampler, bool split, bxdf::Sample buffer[4]) const {
+        const IoR quo_ior{ior, ior_outside};  // eta_i = ior_outside, eta_t = ior_t
+
+        const Vec4f wo = super.wo;
+
+        if (std::fabs(quo_ior.eta_i - quo_ior.eta_t) <= 2.e-7f || super.lower_priority) {
+            buffer[0] = {splat(1.f), -wo, 1.f, 1.f, 0.f, bxdf::Path::singularTransmission()};
+            return 1;
+        }
+
+        const float alpha = super.alpha[0];
+
+        const bool same_side = super.sameHemisphere(wo);
+
+        const Frame frame = super.frame.swapped(same_side);
+        const IoR   io    = quo_ior.swapped(same_side);
+
+        const Vec4f s3    = sampler.sample3D();
+        const float xi[2] = {s3[1], s3[2]};
+
+        float       n_dot_h;
+        const Vec4f h = ggx::sampleVndf(wo, super.alpha, xi, frame, n_dot_h);
+
+        const float n_dot_wo = frame.clampAbsNdot(wo);
+        const float wo_dot_h = safe::clampDot(wo, h);
+
+        const float eta   = io.eta_i / io.eta_t;
+        const float sint2 = (eta * eta) * (1.f - wo_dot_h * wo_dot_h);
+
+        const float s = specular;
+
+        float wi_dot_h, f;
+        if (sint2 >= 1.f) {
+            wi_dot_h = 0.f;
+            f        = 1.f;
+        } else {
+            wi_dot_h          = std::sqrt(1.f - sint2);
+            const float cos_x = io.eta_i > io.eta_t ? wi_dot_h : wo_dot_h;
+            f                 = fresnel::schlick1(cos_x, glass_f0);
+        }
+
+        if (split) {
+            const float ep = ggx::ilmEpDielectric(*luts, n_dot_wo, alpha, glass_f0);
+            {
+                const float n_dot_wi = ggx::iso::reflectNoFresnel(wo, h, n_dot_wo, n_dot_h, wo_dot_h, alpha, specular_threshold, frame, buffer[0]);
+                buffer[0].reflection   = buffer[0].reflection * (splat(n_dot_wi * ep * s) * splat(1.f));
+                buffer[0].split_weight = f;
+                buffer[0].wavelength   = 0.f;
+            }
+            if (1.f == f) return 1;
+            {
+                const float n_dot_wi = roughRefract(same_side, frame, wo, h, n_dot_wo, n_dot_h, wi_dot_h, wo_dot_h, alpha, io, buffer[1]);
+                if (n_dot_wi < 0.f) return 1;
+                buffer[1].reflection   = buffer[1].reflection * (splat(n_dot_wi * ep) * splat(1.f));
+                buffer[1].split_weight = 1.f - f;
+                buffer[1].wavelength   = 0.f;
+            }
+            return 2;
+        }
+
+        bxdf::Sample& result = buffer[0];
+
+        const float ep = ggx::ilmEpDielectric(*luts, n_dot_wo, alpha, glass_f0);
+
+        const float p = s3[0];
+        if (p <= f) {
+            const float n_dot_wi = ggx::iso::reflectNoFresnel(wo, h, n_dot_wo, n_dot_h, wo_dot_h, alpha, specular_threshold, frame, result);
+            result.reflection    = result.reflection * (splat(f * n_dot_wi * ep * s) * splat(1.f));
+            result.pdf *= f;
+        } else {
+            const float n_dot_wi = roughRefract(same_side, frame, wo, h, n_dot_wo, n_dot_h, wi_dot_h, wo_dot_h, alpha, io, result);
+            if (n_dot_wi < 0.f) return 0;
+            const float omf   = 1.f - f;
+            result.reflection = result.reflection * (splat(omf * n_dot_wi * ep) * splat(1.f));
+            result.pdf *= omf;
+        }
+        result.split_weight = 1.f;
+        result.wavelength   = 0.f;
         return 1;
     }
 };
@@ -498,6 +835,41 @@ inline MaterialSample substituteSample(const ZygpuMaterial& m, Vec4f wo, const R
 
     r.super.frame = {rs.t, rs.b, rs.n};
     return r;
+}
+
+// Glass Material.sample, glass_material.zig:46-73 + Sample.init, glass_sample.zig:32-66 (uniform roughness, no normal map)
+inline MaterialSample glassSample(const ZygpuMaterial& m, Vec4f wo, const Renderstate& rs, float specular_threshold, const GgxLuts& luts) {
+    const float raw_r = m.roughness;
+    const float r     = 0.f == raw_r ? 0.f : ggx::clampRoughness(raw_r);
+
+    const float alpha[2] = {r * r, r * r};
+    float       reg_alpha[2];
+    rs.regularizeAlpha(alpha, specular_threshold, reg_alpha);
+    const bool  rough       = reg_alpha[0] > 0.f;
+    const float ior_outside = rs.ior;
+
+    MaterialSample s;
+    s.kind = MaterialSample::Glass;
+    s.luts = &luts;
+
+    s.super.geo_n          = rs.geo_n;
+    s.super.n              = rs.n;
+    s.super.wo             = wo;
+    s.super.alpha[0]       = reg_alpha[0];
+    s.super.alpha[1]       = reg_alpha[1];
+    s.super.can_evaluate   = rough && m.ior != ior_outside;
+    s.super.avoid_caustics = !rs.caustics;
+    s.super.lower_priority = int8_t(m.priority) < rs.highest_priority;
+    s.super.translucent    = m.thickness > 0.f;
+    s.super.frame          = {rs.t, rs.b, rs.n};
+
+    s.absorption_coef    = load4(m.color);
+    s.ior                = m.ior;
+    s.ior_outside        = ior_outside;
+    s.glass_f0           = rough ? fresnel::Schlick::IorToF0(m.ior, ior_outside) : 0.f;
+    s.specular           = m.specular;
+    s.specular_threshold = specular_threshold;
+    return s;
 }
 
 // light_material.zig:108-110 -> light_sample.zig:10-12 (Base.initTBN, can_evaluate = false)

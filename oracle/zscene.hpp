@@ -103,6 +103,8 @@ struct Frame {  // frame.zig
         const Vec4f n = v * z;
         return {{t[0] + t[1] + t[2], b[0] + b[1] + b[2], n[0] + n[1] + n[2], 0.f}};
     }
+    Frame swapped(bool same_side) const { return same_side ? *this : Frame{x, y, -z}; }  // :15-21
+    float nDot(Vec4f v) const { return dot3(z, v); }
     float clampNdot(Vec4f v) const { return safe::clampDot(z, v); }
     float clampAbsNdot(Vec4f v) const { return safe::clampAbsDot(z, v); }
 };
@@ -235,6 +237,7 @@ struct GgxLuts {
     float eMAvg(float alpha) const { return lut1(E_m_avg, 32, alpha); }
     float e(float n_dot, float alpha, float f0) const { return lut3(E, 16, 16, 16, n_dot, alpha, f0); }
     float eAvg(float alpha, float f0) const { return lut2(E_avg, 16, 16, alpha, f0); }
+    float eS(float n_dot, float alpha, float f0) const { return lut3(E_s, 16, 16, 16, n_dot, alpha, f0); }
 };
 
 }  // namespace zo

@@ -67,6 +67,7 @@ void zo_render(const struct ZygpuScene* scene, const struct ZygpuView* view, con
 void zo_resolve(const struct ZygpuView* view, const float* film, uint32_t num_pixels, float* rgba);
 
 float zo_ggx_micro_directional_albedo(float alpha, float n_dot_wo, uint32_t num_samples);
+float zo_ggx_f_s_ss(float alpha, float f0, float ior_t, float n_dot_wo, uint32_t num_samples);
 void  zo_sobol_stream(uint32_t sample, uint32_t seed, uint32_t n, uint32_t pad_every, float* out);
 void  zo_sobol_directions(uint32_t* out160);
 

@@ -94,6 +94,8 @@ def _bind_render(lib):
     lib.zo_resolve.restype = None
     lib.zo_ggx_micro_directional_albedo.argtypes = [C.c_float, C.c_float, u32]
     lib.zo_ggx_micro_directional_albedo.restype = C.c_float
+    lib.zo_ggx_f_s_ss.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, u32]
+    lib.zo_ggx_f_s_ss.restype = C.c_float
     lib.zo_sobol_stream.argtypes = [u32, u32, u32, u32, vp]
     lib.zo_sobol_stream.restype = None
     lib.zo_sobol_directions.argtypes = [vp]
@@ -145,6 +147,10 @@ def resolve(view, film):
 
 def ggx_micro_directional_albedo(alpha, n_dot_wo, num_samples=1024):
     return _bind_render(load()).zo_ggx_micro_directional_albedo(alpha, n_dot_wo, num_samples)
+
+
+def ggx_f_s_ss(alpha, f0, ior_t, n_dot_wo, num_samples=1024):
+    return _bind_render(load()).zo_ggx_f_s_ss(alpha, f0, ior_t, n_dot_wo, num_samples)
 
 
 def sobol_stream(sample, seed, n, pad_every=0):

@@ -65,6 +65,31 @@ def test_ggx_restatement_reproduces_reference_E_m_table():
     assert np.abs(got - e_m).max() < 5e-7
 
 
+def test_glass_lobes_reproduce_reference_E_s_table():
+    """ggx_integral.zig's E_s table is integrate_f_s_ss (ggx_integrate.zig:134-205, 422-484): reflectNoFresnel +
+    refractNoFresnel over the VNDF samples of 1024 Hammersley points, weighted by schlick1, for ior = F0ToIor(f0).
+    Recomputing it through the oracle pins the rough-dielectric lobes Glass samples and evaluates
+    (ggx.zig:161-233, 252-257, 441-449) against numbers the reference holds."""
+    luts = np.fromfile(os.path.join(ROOT, "zyg_b200", "data", "ggx_luts.f32"), np.float32)
+    e_s = luts[1056 + 4096 + 256:].reshape(16, 16, 16)
+    one, two = np.float32(1.0), np.float32(2.0)
+    step = np.float32(1.0 / 15.0)
+    got = np.empty((16, 16, 16), np.float32)
+    f0 = np.float32(0.0)
+    for z in range(16):
+        r = np.sqrt(f0, dtype=np.float32)
+        ior = np.float32(((-f0 - one) / (f0 - one)) - ((two * r) / ((r - one) * (r + one))))  # Schlick.F0ToIor, fresnel.zig:25-28
+        alpha = np.float32(0.0)
+        for a in range(16):
+            n_dot_wo = np.float32(0.0)
+            for i in range(16):
+                got[z, a, i] = oracle.ggx_f_s_ss(float(alpha), float(f0), float(ior), float(n_dot_wo))
+                n_dot_wo = np.float32(n_dot_wo + step)
+            alpha = np.float32(alpha + step)
+        f0 = np.float32(f0 + np.float32(0.25) * step)
+    assert np.abs(got - e_s).max() < 5e-7
+
+
 def test_sobol_owen_scrambled_stratification():
     """Nested uniform scrambling keeps the (0, m, 1)-net property: the first 2^m samples of a dimension fall into
     distinct strata of width 2^-m (sobol.zig:36-60)."""

@@ -195,3 +195,21 @@ def test_instanced_scene_matches_oracle(engine):
     assert np.median(rel) < 1e-5
     assert (rel > 1e-3).mean() < 1e-2
     assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 5e-4
+
+
+@pytest.mark.parametrize("roughness", [0.0, 0.25])
+def test_glass_matches_oracle(engine, roughness):
+    """Glass (glass_sample.zig): reflection + refraction split while max_splits allows (up to 4 vertices per camera
+    sample, processed in the reference's pool order so they draw the same sampler dimensions), the medium stack with
+    two nested dielectrics of different priority, Beer-Lambert absorption inside (volume_integrator.zig:51-66)."""
+    w, spp = 128, 16
+    scenes.cornell_box(w, w, spp=spp, glass={"roughness": roughness})
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6
+    assert (rel > 1e-3).mean() < 5e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4

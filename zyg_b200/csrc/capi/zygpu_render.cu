@@ -40,24 +40,32 @@ uint32_t targetPathsPerPass() {
     return v ? uint32_t(std::max(1, atoi(v))) : (16u << 20);
 }
 
-int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride) {
-    if (r.paths.capacity >= capacity && r.paths.shadow_stride == shadow_stride) return 0;
+// `lanes` vertex records per slot (1, or 4 when a material of the scene can split a path); trace items are vertex ids for
+// closest-hit rays and shadow records for any-hit rays, so the per-item arrays hold max(lanes, shadow_stride) per slot.
+int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint32_t lanes) {
+    if (r.paths.capacity >= capacity && r.paths.shadow_stride == shadow_stride && r.paths.lanes == lanes) return 0;
     freeAll(r.path_buffers);
     zygpu::PathState& p = r.paths;
     p                   = zygpu::PathState{};
-    if (0 != allocPath(r, &p.ray_o, capacity) || 0 != allocPath(r, &p.ray_d, capacity) || 0 != allocPath(r, &p.thr, capacity) ||
-        0 != allocPath(r, &p.prev_p, capacity) || 0 != allocPath(r, &p.prev_n, capacity) || 0 != allocPath(r, &p.hit, capacity) ||
+    const size_t vertices = size_t(capacity) * lanes;
+    const size_t items    = size_t(capacity) * std::max(shadow_stride, lanes);
+    if (0 != allocPath(r, &p.ray_o, vertices) || 0 != allocPath(r, &p.ray_d, vertices) || 0 != allocPath(r, &p.thr, vertices) ||
+        0 != allocPath(r, &p.prev_p, vertices) || 0 != allocPath(r, &p.prev_n, vertices) || 0 != allocPath(r, &p.hit, vertices) ||
         0 != allocPath(r, &p.acc_e, capacity) || 0 != allocPath(r, &p.acc_d, capacity) || 0 != allocPath(r, &p.acc_i, capacity) ||
         0 != allocPath(r, &p.smp, capacity) || 0 != allocPath(r, &p.rng, capacity) ||
         0 != allocPath(r, &p.sh_o, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_p, size_t(capacity) * shadow_stride) ||
         0 != allocPath(r, &p.sh_wi, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_n, capacity) ||
-        0 != allocPath(r, &p.ml_props, size_t(capacity) * shadow_stride * 8) || 0 != allocPath(r, &p.ml_count, size_t(capacity) * shadow_stride) ||
-        0 != allocPath(r, &p.queue_m, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.queue_a, capacity) || 0 != allocPath(r, &p.queue_b, capacity) || 0 != allocPath(r, &p.counters, 16)) {
+        0 != allocPath(r, &p.ml_props, items * 8) || 0 != allocPath(r, &p.ml_count, items) ||
+        0 != allocPath(r, &p.queue_m, items) || 0 != allocPath(r, &p.queue_a, capacity) || 0 != allocPath(r, &p.queue_b, capacity) || 0 != allocPath(r, &p.counters, 16)) {
+        return -1;
+    }
+    if (lanes > 1 && (0 != allocPath(r, &p.med, vertices) || 0 != allocPath(r, &p.queue_t, vertices) || 0 != allocPath(r, &p.queue_s, capacity))) {
         return -1;
     }
     CUDA_OK(cudaMemset(p.counters, 0, 16 * sizeof(uint32_t)));
     p.capacity      = capacity;
     p.shadow_stride = shadow_stride;
+    p.lanes         = lanes;
     return 0;
 }
 
@@ -150,6 +158,17 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     for (uint32_t l = 0; l < scene->num_lights; ++l) potential += std::max(1u, scene->lights[l].num_samples);
     r.max_light_samples = uint32_t(std::min<uint64_t>(std::max<uint64_t>(potential, 1), 64u * 64u));
 
+    // Glass splits a path into its reflected and refracted branch (glass_sample.zig:256-269, 350-395): such scenes run with
+    // Pool.NumVertices vertex records per camera sample and one shade round per record
+    r.can_split = false;
+    for (uint32_t m = 0; m < scene->num_materials; ++m) {
+        const ZygpuMaterial& mat = scene->materials[m];
+        if (ZYG_MATERIAL_GLASS == mat.type) {
+            if (mat.thickness > 0.f || 0.f != mat.abbe) return fail("zygpu_upload_scene: thin (thickness > 0) and dispersive (abbe != 0) Glass are not supported");
+            r.can_split = true;
+        }
+        if (mat.priority < -127 || mat.priority > 127) return fail("zygpu_upload_scene: material priority outside i8");
+    }
     r.has_meshes = scene->num_meshes > 0;
     r.has_scene  = true;
     return 0;
@@ -209,7 +228,10 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
     const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(num_samples, targetPathsPerPass() / padded)));
     const uint64_t capacity = padded * per_pass;
     if (capacity > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
-    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples)) return -1;
+    const uint32_t lanes = r.can_split ? 4 : 1;
+    if (capacity * lanes > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
+    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples, lanes)) return -1;
+    const uint32_t rounds = lanes;
 
     // extend / shadow are one kernel each (prop-tree walk) plus the persistent mesh kernel when the scene has meshes
     const uint32_t trace_extra = r.has_meshes ? 1 : 0;
@@ -223,6 +245,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
         pass.padded_w        = pw;
         pass.padded_h        = ph;
         pass.num_paths       = uint32_t(padded) * k;
+        pass.debug_slot      = getenv("ZYGPU_DEBUG_SLOT") ? uint32_t(strtoul(getenv("ZYGPU_DEBUG_SLOT"), nullptr, 10)) : 0xFFFFFFFFu;
 
         CUDA_OK(zygpu::launchGenerate(view, r.paths, pass, r.stream));
         r.stats.kernel_launches += 1;
@@ -230,13 +253,32 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
         // one bounce = extend, shade_a, shadow, shade_b (+ queue swap); depth max_depth_surface is the last vertex
         // that can be reached (pathtracer_mis.zig:76-86), so max_depth + 1 extend / shade_a rounds
         for (uint32_t bounce = 0; bounce <= view.max_depth_surface; ++bounce) {
-            CUDA_OK(zygpu::launchExtend(r.scene, r.paths, pass.num_paths, r.has_meshes, r.stream));
-            CUDA_OK(zygpu::launchShadeA(r.scene, view, r.paths, pass, pass.num_paths, r.stream));
-            r.stats.kernel_launches += 2 + trace_extra;
-            if (bounce == view.max_depth_surface) break;
-            CUDA_OK(zygpu::launchShadow(r.scene, r.paths, pass.num_paths, r.has_meshes, r.stream));
-            CUDA_OK(zygpu::launchShadeB(r.scene, view, r.paths, pass, pass.num_paths, r.stream));
-            r.stats.kernel_launches += 3 + trace_extra;  // shadow, shade_b, queue swap
+            const bool last = bounce == view.max_depth_surface;
+            // all vertices of the generation are extended at once (no sampler draws in between) ...
+            CUDA_OK(zygpu::launchExtend(r.scene, r.paths, pass.num_paths * lanes, r.has_meshes, r.stream));
+            r.stats.kernel_launches += 1 + trace_extra;
+            if (lanes > 1) {
+                CUDA_OK(zygpu::launchBeginGeneration(r.paths, r.stream));
+                r.stats.kernel_launches += 1;
+            }
+            // ... and shaded in rounds: round k handles the k-th vertex of every camera sample, because the vertices of a
+            // sample share its sampler and draw from it in turn (VertexPool.consume order)
+            for (uint32_t round = 0; round < rounds; ++round) {
+                if (round > 0) {
+                    CUDA_OK(zygpu::launchBeginRound(r.paths, r.stream));
+                    r.stats.kernel_launches += 1;
+                }
+                CUDA_OK(zygpu::launchShadeA(r.scene, view, r.paths, pass, pass.num_paths, round, r.stream));
+                r.stats.kernel_launches += 1;
+                if (last) continue;
+                CUDA_OK(zygpu::launchShadow(r.scene, r.paths, pass.num_paths, r.has_meshes, r.stream));
+                CUDA_OK(zygpu::launchShadeB(r.scene, view, r.paths, pass, pass.num_paths, round, r.stream));
+                r.stats.kernel_launches += 2 + trace_extra + (1 == lanes ? 1 : 0);  // shadow, shade_b (+ queue swap)
+            }
+            if (lanes > 1) {
+                CUDA_OK(zygpu::launchEndGeneration(r.paths, r.stream));
+                r.stats.kernel_launches += 1;
+            }
         }
 
         CUDA_OK(zygpu::launchFilm(view, r.paths, pass, r.film, r.stream));

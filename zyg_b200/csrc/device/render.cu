@@ -1,6 +1,7 @@
 #include "shading.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 namespace zygpu {
@@ -20,8 +21,65 @@ enum : uint32_t {  // Vertex.State, vertex.zig:19-28
     kStartedSpecular = 1u << 5,
 };
 
-__device__ __forceinline__ uint32_t packFlags(uint32_t state, uint32_t probe_depth, uint32_t vertex_depth) {
-    return state | (probe_depth << 8) | (vertex_depth << 16);
+__device__ __forceinline__ uint32_t packFlags(uint32_t state, uint32_t probe_depth, uint32_t vertex_depth, uint32_t path_count_log2 = 0,
+                                              uint32_t num_media = 0) {
+    return state | (probe_depth << 8) | (vertex_depth << 16) | (path_count_log2 << 24) | (num_media << 26);
+}
+
+// ---- vertex pool of one camera sample (Pool, vertex.zig:215-310) -------------------------------
+//
+// One word per slot: bits 0-7 lanes of the current generation in processing order (2 bits each), 8-10 their number,
+// 11-18 / 19-21 the same for the next generation, 22-25 lanes in use. path_count bounds the live vertices by 4.
+
+__device__ __forceinline__ uint32_t poolCurCount(uint32_t m) { return (m >> 8) & 7u; }
+__device__ __forceinline__ uint32_t poolCurLane(uint32_t m, uint32_t k) { return (m >> (2 * k)) & 3u; }
+__device__ __forceinline__ uint32_t poolNextCount(uint32_t m) { return (m >> 19) & 7u; }
+__device__ __forceinline__ uint32_t poolSwap(uint32_t m) { return (m & 0x03C00000u) | ((m >> 11) & 0x7FFu); }
+__device__ __forceinline__ uint32_t poolFree(uint32_t m, uint32_t lane) { return m & ~(1u << (22 + lane)); }
+__device__ __forceinline__ uint32_t poolAlloc(uint32_t m) { return uint32_t(__ffs(int(~(m >> 22) & 0xFu))) - 1u; }  // 0xFFFFFFFF when full
+__device__ __forceinline__ uint32_t poolAppendNext(uint32_t m, uint32_t lane) {
+    const uint32_t n = poolNextCount(m);
+    return (m | (lane << (11 + 2 * n)) | (1u << (22 + lane))) + (1u << 19);
+}
+constexpr uint32_t kPoolFirst = (1u << 19) | (1u << 22);  // after generate: lane 0 is the next generation
+
+// ---- medium stack (Stack, prop/medium.zig:30-153) ----------------------------------------------
+
+struct MediaD {
+    uint32_t count;
+    uint32_t prop[3];  // Num_entries - 1 entries can be pushed (:117-131)
+    uint32_t part[3];
+};
+
+__device__ __forceinline__ MediaD unpackMedia(uint4 w, uint32_t count) {
+    return {count, {w.x, w.y, w.z}, {w.w & 0xffu, (w.w >> 8) & 0xffu, (w.w >> 16) & 0xffu}};
+}
+__device__ __forceinline__ uint4 packMedia(const MediaD& m) {
+    return make_uint4(m.prop[0], m.prop[1], m.prop[2], m.part[0] | (m.part[1] << 8) | (m.part[2] << 16));
+}
+__device__ __forceinline__ void mediaPush(MediaD& m, uint32_t prop, uint32_t part) {
+    if (m.count < 3) {
+        m.prop[m.count] = prop;
+        m.part[m.count] = part;
+        m.count += 1;
+    }
+}
+__device__ __forceinline__ void mediaRemove(MediaD& m, uint32_t prop, uint32_t part) {
+    for (int i = int(m.count) - 1; i >= 0; --i) {
+        if (m.prop[i] == prop && m.part[i] == part) {
+            for (int j = i; j < int(m.count) - 1; ++j) {
+                m.prop[j] = m.prop[j + 1];
+                m.part[j] = m.part[j + 1];
+            }
+            m.count -= 1;
+            return;
+        }
+    }
+}
+
+// ray_offset.zig:29-31
+__device__ __forceinline__ float offsetF(float t) {
+    return t < (1.f / 32.f) ? t + (1.f / 65536.f) : __int_as_float(int(uint32_t(__float_as_int(t)) + 256u));
 }
 
 constexpr float kLowThreshold = 0.00000001f;  // helper.zig:29
@@ -63,11 +121,9 @@ __device__ __forceinline__ void seedSamplers(const SlotId id, const PassParams& 
     sobol.startPixel(tsi, seed);
 }
 
-__device__ __forceinline__ void loadSampler(const PathState& st, uint32_t slot, const PassParams& pass, uint32_t spp_total,
-                                            uint32_t total_depth, SamplerD& sampler, uint32_t& aux) {
+__device__ __forceinline__ void loadSampler(const PathState& st, uint32_t slot, uint4 s, const PassParams& pass, uint32_t spp_total,
+                                            uint32_t total_depth, SamplerD& sampler) {
     const SlotId id = slotId(slot, pass);
-    const uint4  s  = st.smp[slot];
-    aux             = s.w;
     sampler.use_sobol = total_depth < 3;  // pickSampler; a Random take sampler is handled by the caller (view.sampler)
     const uint64_t sample_index = uint64_t(id.pixel_id) * uint64_t(spp_total) + uint64_t(id.iteration);
     if (sampler.use_sobol) {
@@ -111,6 +167,31 @@ __device__ __forceinline__ bool propVisible(uint32_t flags, uint32_t depth_surfa
 
 __device__ __forceinline__ bool aabbIntersect(const float4* aabbs, uint32_t i, const RayT& ray) {  // aabb.zig:46-60
     return FLT_MAX != intersectNode(__ldg(aabbs + 2 * size_t(i)), __ldg(aabbs + 2 * size_t(i) + 1), ray);
+}
+
+// AABB.intersectP, aabb.zig:62-84
+__device__ __forceinline__ float aabbIntersectP(float4 mi, float4 ma, const RayT& ray) {
+    const float lx = (mi.x - ray.o.x) * ray.inv_d.x, ly = (mi.y - ray.o.y) * ray.inv_d.y, lz = (mi.z - ray.o.z) * ray.inv_d.z;
+    const float ux = (ma.x - ray.o.x) * ray.inv_d.x, uy = (ma.y - ray.o.y) * ray.inv_d.y, uz = (ma.z - ray.o.z) * ray.inv_d.z;
+
+    const float imin = zmax(zmax(zmin(lx, ux), zmin(ly, uy)), zmin(lz, uz));
+    const float imax = zmin(zmin(zmax(lx, ux), zmax(ly, uy)), zmax(lz, uz));
+
+    const float tboxmin = zmax(imin, ray.tmin);
+    const float tboxmax = zmin(imax, ray.tmax);
+
+    if (tboxmin <= tboxmax) return imin < ray.tmin ? imax : imin;
+    return FLT_MAX;
+}
+
+// VolumeIntegrator.integrate, volume_integrator.zig:97-99: a vertex inside a medium only looks as far as the medium prop's box
+__device__ __forceinline__ void clipToMedium(const SceneDevice& sc, const PathState& st, uint32_t vertex_id, uint32_t flags, RayT& ray) {
+    const uint32_t num_media = (flags >> 26) & 3u;
+    if (nullptr == st.med || 0 == num_media) return;
+    const uint4    w    = st.med[vertex_id];
+    const uint32_t prop = 1 == num_media ? w.x : (2 == num_media ? w.y : w.z);
+    const float    limit = aabbIntersectP(__ldg(sc.aabbs + 2 * size_t(prop)), __ldg(sc.aabbs + 2 * size_t(prop) + 1), ray);
+    ray.tmax             = zmin(offsetF(limit), ray.tmax);
 }
 
 __device__ __forceinline__ float shapeArea(uint32_t shape, V3 scale) {  // shape.zig:143-156
@@ -298,7 +379,7 @@ struct SceneTraceTuning {
 };
 
 template <bool AnyHit>
-__device__ __forceinline__ RayT loadTraceRay(const PathState& st, uint32_t item, uint32_t& depth_surface) {
+__device__ __forceinline__ RayT loadTraceRay(const PathState& st, uint32_t item, uint32_t& depth_surface, uint32_t* flags_out = nullptr) {
     if (AnyHit) {  // Shape.shadowRay, shape.zig:401-416: the record holds both end points
         const float4 o           = st.sh_o[item];
         const float4 p           = st.sh_p[item];
@@ -311,6 +392,7 @@ __device__ __forceinline__ RayT loadTraceRay(const PathState& st, uint32_t item,
     const float4 o = st.ray_o[item];
     const float4 d = st.ray_d[item];
     depth_surface  = (__float_as_uint(o.w) >> 8) & 0xffu;
+    if (flags_out) *flags_out = __float_as_uint(o.w);
     return makeRay({o.x, o.y, o.z}, {d.x, d.y, d.z}, 0.f, d.w);
 }
 
@@ -318,7 +400,8 @@ __device__ __forceinline__ RayT loadTraceRay(const PathState& st, uint32_t item,
 template <bool AnyHit>
 __global__ void __launch_bounds__(kBlock) topKernel(SceneDevice sc, PathState st) {
     const uint32_t stride = st.shadow_stride;
-    const uint64_t total  = AnyHit ? uint64_t(st.counters[1]) * stride : uint64_t(st.counters[0]);
+    const uint32_t* __restrict__ closest_queue = st.lanes > 1 ? st.queue_t : st.queue_a;
+    const uint64_t total = AnyHit ? uint64_t(st.counters[1]) * stride : uint64_t(st.counters[st.lanes > 1 ? 7 : 0]);
     const uint32_t count  = uint32_t(total < 0xFFFFFFFFull ? total : 0xFFFFFFFFull);
     const uint32_t iters  = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     uint32_t       traced = 0;
@@ -335,13 +418,14 @@ __global__ void __launch_bounds__(kBlock) topKernel(SceneDevice sc, PathState st
                 valid               = k < st.sh_n[slot];
                 item                = slot * stride + k;
             } else {
-                item = st.queue_a[i];
+                item = closest_queue[i];
             }
         }
         if (valid) {
             traced += 1;
-            uint32_t depth_surface;
-            RayT     ray = loadTraceRay<AnyHit>(st, item, depth_surface);
+            uint32_t depth_surface, flags = 0;
+            RayT     ray = loadTraceRay<AnyHit>(st, item, depth_surface, &flags);
+            if (!AnyHit) clipToMedium(sc, st, item, flags, ray);
 
             uint32_t stack[kPropStack];
             uint32_t end = 0;
@@ -1176,30 +1260,35 @@ __global__ void __launch_bounds__(kBlock) generateKernel(ZygpuView view, PathSta
         st.ray_d[slot]  = make_float4(direction_w.x, direction_w.y, direction_w.z, kRayMaxT);
         st.thr[slot]    = make_float4(1.f, 1.f, 1.f, 0.f);
         st.prev_p[slot] = make_float4(origin_w.x, origin_w.y, origin_w.z, 0.f);
-        st.prev_n[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        st.prev_n[slot] = make_float4(0.f, 0.f, 0.f, 1.f);  // split_weight = 1
         st.acc_e[slot]  = make_float4(0.f, 0.f, 0.f, s4[0]);
         st.acc_d[slot]  = make_float4(0.f, 0.f, 0.f, s4[1]);
         st.acc_i[slot]  = make_float4(0.f, 0.f, 0.f, 0.f);
-        storeSampler(st, slot, sampler, 0);
+        storeSampler(st, slot, sampler, kPoolFirst);  // the camera vertex sits in lane 0 (vertex id == slot)
         st.queue_a[slot] = slot;
+        if (st.lanes > 1) st.queue_t[slot] = slot;
     }
     if (0 == blockIdx.x && 0 == threadIdx.x) {
         st.counters[0] = pass.num_paths;
         st.counters[1] = 0;
         st.counters[4] = 0;
+        st.counters[7] = pass.num_paths;
+        st.counters[9] = 0;
     }
 }
 
 // Context.nextEvent -> Scene.intersect, context.zig:54-69, scene.zig:225-227
 __global__ void __launch_bounds__(kBlock) extendKernel(SceneDevice sc, PathState st) {
-    const uint32_t count = st.counters[0];
+    const uint32_t count = st.counters[st.lanes > 1 ? 7 : 0];
+    const uint32_t* __restrict__ queue = st.lanes > 1 ? st.queue_t : st.queue_a;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = st.queue_a[i];
+        const uint32_t slot = queue[i];  // vertex id
         const float4   o    = st.ray_o[slot];
         float4         d    = st.ray_d[slot];
 
         RayT           ray           = makeRay({o.x, o.y, o.z}, {d.x, d.y, d.z}, 0.f, d.w);
         const uint32_t depth_surface = (__float_as_uint(o.w) >> 8) & 0xffu;
+        clipToMedium(sc, st, slot, __float_as_uint(o.w), ray);
 
         HitD           isec = {0.f, 0.f, 0.f, 0};
         const uint32_t prop = sceneIntersect(sc, ray, depth_surface, isec);
@@ -1211,16 +1300,44 @@ __global__ void __launch_bounds__(kBlock) extendKernel(SceneDevice sc, PathState
     if (0 == blockIdx.x && 0 == threadIdx.x) atomicAdd(&st.counters[5], count);  // statistics: closest-hit rays
 }
 
+__device__ __forceinline__ const ZygpuMaterial& propMaterial(const SceneDevice& sc, uint32_t prop, uint32_t part) {
+    return sc.materials[__ldg(sc.material_ids + sc.props[prop].parts_start + part)];
+}
+
+// Vertex.iorOutside (vertex.zig:87-93) and Stack.highestPriority (medium.zig:74-82) for Vertex.sample
+__device__ __forceinline__ void mediaForSample(const SceneDevice& sc, const MediaD& media, const FragD& frag, V3 wo, float& ior_outside,
+                                               int& highest_priority) {
+    ior_outside      = 1.f;
+    highest_priority = -128;
+    if (0 == media.count) return;
+    for (uint32_t i = 0; i < media.count; ++i) highest_priority = max(highest_priority, propMaterial(sc, media.prop[i], media.part[i]).priority);
+    const uint32_t back = media.count - 1;
+    if (frag.sameHemisphere(wo)) {  // Stack.topIor
+        ior_outside = propMaterial(sc, media.prop[back], media.part[back]).ior;
+    } else if (media.count > 1) {  // Stack.peekIor
+        const uint32_t i = (media.prop[back] == frag.prop && media.part[back] == frag.part) ? back - 1 : back;
+        ior_outside      = propMaterial(sc, media.prop[i], media.part[i]).ior;
+    }
+}
+
+// Pool.maxSplits, vertex.zig:306-309
+__device__ __forceinline__ uint32_t maxSplits(uint32_t path_count_log2, bool primary_ray, uint32_t depth) {
+    const uint32_t m = 4u >> path_count_log2;
+    return m - (primary_ray ? 0u : min(depth, m - 1u));
+}
+
 struct LoadedVertex {
     VertexD  v;
     V3       throughput;
     float    reg_alpha;
+    float    split_weight;
     uint32_t vertex_depth;
+    uint32_t path_count_log2, num_media;
     HitD     isec;
     uint32_t prop;
 };
 
-__device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t slot) {
+__device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t slot /* vertex id */) {
     const float4 o  = st.ray_o[slot];
     const float4 d  = st.ray_d[slot];
     const float4 t  = st.thr[slot];
@@ -1234,10 +1351,13 @@ __device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t
     r.v.origin            = {pp.x, pp.y, pp.z};
     r.v.geo_n             = {pn.x, pn.y, pn.z};
     r.v.bxdf_pdf          = t.w;
-    r.v.light_split_threshold = pn.w;
+    r.v.light_split_threshold = 0.f;  // set by the stages before it is read
+    r.split_weight        = pn.w;
     r.v.state             = flags & 0xffu;
     r.v.probe_depth       = (flags >> 8) & 0xffu;
     r.vertex_depth        = (flags >> 16) & 0xffu;
+    r.path_count_log2     = (flags >> 24) & 3u;
+    r.num_media           = (flags >> 26) & 3u;
     r.throughput          = {t.x, t.y, t.z};
     r.reg_alpha           = pp.w;
     r.isec                = {d.w, h.x, h.y, __float_as_uint(h.z)};
@@ -1248,29 +1368,74 @@ __device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t
 // PathtracerMIS.li up to the shadow rays: connectLight (pathtracer_mis.zig:280-341), termination (:76-86), Russian
 // roulette (:88, helper.zig:75-89), Vertex.sample (:93), sampleLights / evaluateLight up to the visibility test
 // (:174-250).
-__global__ void __launch_bounds__(kBlock) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass) {
-    const uint32_t count = st.counters[0];
-    const uint32_t iters = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+template <bool Split>
+__global__ void __launch_bounds__(kBlock) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
+    const bool      later = Split && round > 0;
+    const uint32_t  count = later ? st.counters[9] : st.counters[0];
+    const uint32_t* __restrict__ queue = later ? st.queue_s : st.queue_a;
+    const uint32_t  iters = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t it = 0; it < iters; ++it) {
         const uint32_t i      = it * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
         bool           alive  = false;
+        bool           multi  = false;
         uint32_t       slot   = 0;
         if (i < count) {
-            slot            = st.queue_a[i];
-            LoadedVertex lv = loadVertex(st, slot);
+            slot            = queue[i];
+            const uint4 smp = st.smp[slot];
+            uint32_t    pool = smp.w;
+            uint32_t    lane = 0;
+            bool        mine = true;  // the slot has a vertex for this round
+            if (Split) {
+                if (0 == round) {
+                    pool  = poolSwap(pool);
+                    multi = poolCurCount(pool) > 1;
+                }
+                mine = poolCurCount(pool) > round;
+                lane = poolCurLane(pool, round);
+            }
+            if (mine) {
+            const uint32_t vid = lane * st.capacity + slot;
+            LoadedVertex lv = loadVertex(st, vid);
             VertexD&     vertex = lv.v;
 
             const uint32_t total_depth = vertex.probe_depth;
             const bool     hit         = kEnd != lv.prop;
 
             SamplerD sampler;
-            uint32_t aux;
-            loadSampler(st, slot, pass, view.spp_total, total_depth, sampler, aux);
+            loadSampler(st, slot, smp, pass, view.spp_total, total_depth, sampler);
             if (ZYG_SAMPLER_SOBOL != view.sampler) sampler.use_sobol = false;
 
             FragD frag;
             frag.prop = kEnd;
             if (hit) shapeFragment(sc, lv.prop, vertex.ray, lv.isec, frag);
+
+            // Context.nextEvent inside a medium: VolumeIntegrator.integrate -> propScatter, the "glass" case
+            // (volume_integrator.zig:51-66, 84-130): throughput *= exp(-mu_a * d); topCC = the highest-priority medium
+            MediaD media{0, {0, 0, 0}, {0, 0, 0}};
+            if (Split && 0 != lv.num_media) {
+                media = unpackMedia(st.med[vid], lv.num_media);
+                if (hit) {
+                    int      priority = -128;
+                    uint32_t highest  = 0;
+                    for (uint32_t m = 0; m < media.count; ++m) {
+                        const int lp = propMaterial(sc, media.prop[m], media.part[m]).priority;
+                        if (lp >= priority) {
+                            priority = lp;
+                            highest  = m;
+                        }
+                    }
+                    const ZygpuMaterial& mm = propMaterial(sc, media.prop[highest], media.part[highest]);
+                    const float          nd = -(vertex.ray.tmax - vertex.ray.tmin);
+                    lv.throughput = mul3(lv.throughput, {expf(nd * mm.color[0]), expf(nd * mm.color[1]), expf(nd * mm.color[2])});
+                }
+            }
+
+            if (slot == pass.debug_slot) {
+                printf("[gpu] depth %u pc %u sw %g state p%d s%d sg%d | hit prop %u t %.9g media %u | thr %.9g %.9g %.9g | rng %llx round %u lane %u\n",
+                       total_depth, 1u << lv.path_count_log2, lv.split_weight, int(0 != (vertex.state & kPrimaryRay)),
+                       int(0 != (vertex.state & kSpecular)), int(0 != (vertex.state & kSingular)), lv.prop, vertex.ray.tmax, lv.num_media,
+                       lv.throughput.x, lv.throughput.y, lv.throughput.z, (unsigned long long)sampler.rng.state, round, lane);
+            }
 
             // connectLight
             V3 this_light = splat3(0.f);
@@ -1280,7 +1445,7 @@ __global__ void __launch_bounds__(kBlock) shadeAKernel(SceneDevice sc, ZygpuView
                 this_light = add3(this_light, unoccludingEmission(sc, vertex, sampler));
             }
 
-            const V3 split_throughput = scale3(1.f, lv.throughput);  // split_weight == 1
+            const V3 split_throughput = scale3(lv.split_weight, lv.throughput);
             ivalueAdd(st, slot, mul3(split_throughput, this_light), total_depth, 2, 0 == total_depth, 0 != (vertex.state & kSingular));
 
             bool terminate = !hit || vertex.probe_depth >= view.max_depth_surface || 0 >= view.max_depth_volume;
@@ -1305,7 +1470,11 @@ __global__ void __launch_bounds__(kBlock) shadeAKernel(SceneDevice sc, ZygpuView
                 const V3            wo = neg3(vertex.ray.d);
                 const ZygpuMaterial m  = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
                 (void)sampler.sample1D();  // rs.stochastic_r, vertex.zig:165
-                const MatSampleD mat_sample = materialSample(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics, view.specular_threshold);
+                float ior_outside      = 1.f;
+                int   highest_priority = -128;
+                if (Split) mediaForSample(sc, media, frag, wo, ior_outside, highest_priority);
+                const MatSampleD mat_sample = materialSample(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics,
+                                                             view.specular_threshold, ior_outside, highest_priority);
 
                 vertex.light_split_threshold = splitThreshold(view.split_threshold, vertex.probe_depth);
 
@@ -1359,12 +1528,15 @@ __global__ void __launch_bounds__(kBlock) shadeAKernel(SceneDevice sc, ZygpuView
                 }
 
                 st.sh_n[slot] = num_records;
-                st.thr[slot]  = make_float4(lv.throughput.x, lv.throughput.y, lv.throughput.z, vertex.bxdf_pdf);
+                st.thr[vid]   = make_float4(lv.throughput.x, lv.throughput.y, lv.throughput.z, vertex.bxdf_pdf);
                 alive         = true;
             }
-            storeSampler(st, slot, sampler, aux);
+            if (Split && !alive) pool = poolFree(pool, lane);
+            storeSampler(st, slot, sampler, pool);
+            }
         }
         queuePush(st.queue_b, &st.counters[1], alive, slot);
+        if (Split && 0 == round) queuePush(st.queue_s, &st.counters[9], multi, slot);
     }
 }
 
@@ -1397,33 +1569,48 @@ __global__ void __launch_bounds__(kBlock) shadowKernel(SceneDevice sc, PathState
 
 // The rest of PathtracerMIS.li: evaluateLight after the visibility test (pathtracer_mis.zig:252-277), the direct-light
 // add (:116-117), mat_sample.sample and the next vertex (:121-166).
-__global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass) {
+template <bool Split>
+__global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
     const uint32_t count = st.counters[1];
     const LutsD    luts{sc.luts};
     const uint32_t iters = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t it = 0; it < iters; ++it) {
         const uint32_t i     = it * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
-        bool           alive = false;
+        bool           alive = false;  // the slot got its first vertex of the next generation
         uint32_t       slot  = 0;
+        uint32_t       child_id[2] = {0, 0};
+        bool           child_on[2] = {false, false};
         if (i < count) {
-            slot                  = st.queue_b[i];
-            LoadedVertex   lv     = loadVertex(st, slot);
+            slot                 = st.queue_b[i];
+            const uint4    smp   = st.smp[slot];
+            uint32_t       pool  = smp.w;
+            const uint32_t lane  = Split ? poolCurLane(pool, round) : 0;
+            const uint32_t vid   = lane * st.capacity + slot;
+            LoadedVertex   lv     = loadVertex(st, vid);
             const VertexD& vertex = lv.v;
 
             const uint32_t total_depth = vertex.probe_depth;
 
             SamplerD sampler;
-            uint32_t aux;
-            loadSampler(st, slot, pass, view.spp_total, total_depth, sampler, aux);
+            loadSampler(st, slot, smp, pass, view.spp_total, total_depth, sampler);
             if (ZYG_SAMPLER_SOBOL != view.sampler) sampler.use_sobol = false;
 
             FragD frag;
             shapeFragment(sc, lv.prop, vertex.ray, lv.isec, frag);
 
+            MediaD media{0, {0, 0, 0}, {0, 0, 0}};
+            if (Split && 0 != lv.num_media) media = unpackMedia(st.med[vid], lv.num_media);
+
             const bool          caustics   = 0 == (vertex.state & kPrimaryRay) ? 0 != view.caustics_path : true;
             const V3            wo         = neg3(vertex.ray.d);
             const ZygpuMaterial m          = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
-            const MatSampleD    mat_sample = materialSample(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics, view.specular_threshold);
+            float               ior_outside      = 1.f;
+            int                 highest_priority = -128;
+            if (Split) mediaForSample(sc, media, frag, wo, ior_outside, highest_priority);
+            const MatSampleD mat_sample = materialSample(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics,
+                                                         view.specular_threshold, ior_outside, highest_priority);
+
+            const uint32_t max_splits = Split ? maxSplits(lv.path_count_log2, 0 != (vertex.state & kPrimaryRay), total_depth) : 1;
 
             // evaluateLight for the visible records
             V3             next_light = splat3(0.f);
@@ -1445,7 +1632,7 @@ __global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView
                 const float area     = 0.f != lm.emission_normalize ? shapeArea(sc.props[light.prop].shape, ltrafo.scale) : 1.f;
                 const V3    radiance = emittanceRadiance(lm, wi, ltrafo, area, false);
 
-                const BxdfResult bxdf_result = mat_sample.evaluate(luts, wi);
+                const BxdfResult bxdf_result = mat_sample.evaluate(luts, wi, max_splits);
 
                 const float light_pdf = o4.w;
                 const float weight    = predividedPowerHeuristic(light_pdf, bxdf_result.pdf);
@@ -1453,13 +1640,23 @@ __global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView
                 next_light = add3(next_light, mul3(scale3(weight, radiance), bxdf_result.reflection));
             }
 
-            const V3 split_throughput = scale3(1.f, lv.throughput);
+            const V3 split_throughput = scale3(lv.split_weight, lv.throughput);
             ivalueAdd(st, slot, mul3(split_throughput, next_light), total_depth, 1, false, false);
 
-            BxdfSample     sample_result;
-            const uint32_t path_count = mat_sample.sample(luts, sampler, sample_result);
+            BxdfSample     sample_results[2];
+            const uint32_t path_count = mat_sample.sample(luts, sampler, max_splits, sample_results);
 
-            if (0 != path_count) {
+            if (Split) pool = poolFree(pool, lane);  // the parent lives in registers from here on
+            if (slot == pass.debug_slot) {
+                for (uint32_t c = 0; c < path_count; ++c) {
+                    printf("[gpu]   sample %u/%u event %u sw %g pdf %g wi %.9g %.9g %.9g\n", c, path_count, sample_results[c].event,
+                           sample_results[c].split_weight, sample_results[c].pdf, sample_results[c].wi.x, sample_results[c].wi.y, sample_results[c].wi.z);
+                }
+            }
+
+            for (uint32_t c = 0; c < path_count; ++c) {
+                const BxdfSample& sample_result = sample_results[c];
+
                 // Vertex.State.update, vertex.zig:30-43
                 uint32_t state = vertex.state;
                 if (kScatterSpecular == sample_result.scattering) {
@@ -1490,24 +1687,64 @@ __global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView
 
                 if (!(kEventTransmission == sample_result.event || kEventStraight == sample_result.event)) state &= ~kTransparent;
 
-                st.ray_o[slot]  = make_float4(next_o.x, next_o.y, next_o.z, __uint_as_float(packFlags(state, vertex.probe_depth + 1, vertex_depth)));
-                st.ray_d[slot]  = make_float4(sample_result.wi.x, sample_result.wi.y, sample_result.wi.z, kRayMaxT);
-                st.thr[slot]    = make_float4(throughput.x, throughput.y, throughput.z, bxdf_pdf);
-                st.prev_p[slot] = make_float4(origin.x, origin.y, origin.z, reg_alpha);
-                st.prev_n[slot] = make_float4(geo_n.x, geo_n.y, geo_n.z, 0.f);
-                alive           = true;
+                uint32_t cvid = vid;
+                uint32_t pcl2 = 0, num_media = 0;
+                if (Split) {
+                    const uint32_t clane = poolAlloc(pool);
+                    if (clane > 3u) break;  // cannot happen: path_count keeps the live vertices of a sample at 4 or fewer
+                    alive = alive || 0 == poolNextCount(pool);
+                    pool  = poolAppendNext(pool, clane);
+                    cvid  = clane * st.capacity + slot;
+
+                    pcl2 = lv.path_count_log2 + (path_count > 1 ? 1u : 0u);  // path_count *= number of samples (1 or 2)
+
+                    MediaD next_media = media;
+                    if (kEventTransmission == sample_result.event) {  // Vertex.interfaceChange, vertex.zig:95-110
+                        if (frag.sameHemisphere(sample_result.wi)) {
+                            mediaRemove(next_media, frag.prop, frag.part);
+                        } else {
+                            mediaPush(next_media, frag.prop, frag.part);
+                        }
+                    }
+                    num_media    = next_media.count;
+                    st.med[cvid] = packMedia(next_media);
+                    child_id[c]  = cvid;
+                    child_on[c]  = true;
+                } else {
+                    alive = true;
+                }
+
+                st.ray_o[cvid]  = make_float4(next_o.x, next_o.y, next_o.z,
+                                              __uint_as_float(packFlags(state, vertex.probe_depth + 1, vertex_depth, pcl2, num_media)));
+                st.ray_d[cvid]  = make_float4(sample_result.wi.x, sample_result.wi.y, sample_result.wi.z, kRayMaxT);
+                st.thr[cvid]    = make_float4(throughput.x, throughput.y, throughput.z, bxdf_pdf);
+                st.prev_p[cvid] = make_float4(origin.x, origin.y, origin.z, reg_alpha);
+                st.prev_n[cvid] = make_float4(geo_n.x, geo_n.y, geo_n.z, lv.split_weight * sample_result.split_weight);
             }
             sampler.incrementPadding();
-            storeSampler(st, slot, sampler, 0);
+            storeSampler(st, slot, sampler, pool);
         }
         queuePush(st.queue_a, &st.counters[4], alive, slot);
+        if (Split) {
+            queuePush(st.queue_t, &st.counters[7], child_on[0], child_id[0]);
+            queuePush(st.queue_t, &st.counters[7], child_on[1], child_id[1]);
+        }
     }
 }
 
+// Counter bookkeeping between the stages (single thread; the queue lengths never leave the device).
+__global__ void beginGenerationKernel(PathState st) {  // after extend: the trace queue is consumed, nothing is queued yet
+    st.counters[1] = 0;
+    st.counters[4] = 0;
+    st.counters[7] = 0;
+    st.counters[9] = 0;
+}
+__global__ void beginRoundKernel(PathState st) { st.counters[1] = 0; }
 __global__ void advanceKernel(PathState st) {
     st.counters[0] = st.counters[4];
     st.counters[1] = 0;
     st.counters[4] = 0;
+    st.counters[9] = 0;
 }
 
 // Sensor.addSample for every sample of the pass, gathered per film pixel (sensor.zig:168-385, buffer_opaque.zig:39-45).
@@ -1689,8 +1926,24 @@ cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t
     return cudaGetLastError();
 }
 cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
-                         cudaStream_t stream) {
-    shadeAKernel<<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass);
+                         uint32_t round, cudaStream_t stream) {
+    if (st.lanes > 1) {
+        shadeAKernel<true><<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass, round);
+    } else {
+        shadeAKernel<false><<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass, 0);
+    }
+    return cudaGetLastError();
+}
+cudaError_t launchBeginGeneration(const PathState& st, cudaStream_t stream) {
+    beginGenerationKernel<<<1, 1, 0, stream>>>(st);
+    return cudaGetLastError();
+}
+cudaError_t launchBeginRound(const PathState& st, cudaStream_t stream) {
+    beginRoundKernel<<<1, 1, 0, stream>>>(st);
+    return cudaGetLastError();
+}
+cudaError_t launchEndGeneration(const PathState& st, cudaStream_t stream) {
+    advanceKernel<<<1, 1, 0, stream>>>(st);
     return cudaGetLastError();
 }
 cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
@@ -1699,9 +1952,13 @@ cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t
     return cudaGetLastError();
 }
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
-                         cudaStream_t stream) {
-    shadeBKernel<<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass);
-    advanceKernel<<<1, 1, 0, stream>>>(st);
+                         uint32_t round, cudaStream_t stream) {
+    if (st.lanes > 1) {
+        shadeBKernel<true><<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass, round);
+    } else {
+        shadeBKernel<false><<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass, 0);
+        advanceKernel<<<1, 1, 0, stream>>>(st);
+    }
     return cudaGetLastError();
 }
 cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream) {

@@ -68,16 +68,21 @@ struct SceneDevice {
 };
 
 struct PathState {
-    float4* ray_o;   // origin xyz | flags: state bits 0-7, probe depth 8-15, vertex.depth 16-23
+    // Per path vertex. A camera sample ("slot") owns `lanes` vertex records: 1 when no material of the scene can split a
+    // path, 4 (= Pool.NumVertices, vertex.zig:216) when one can (Glass). Vertex id = lane * capacity + slot.
+    float4* ray_o;   // origin xyz | flags: state bits 0-7, probe depth 8-15, vertex.depth 16-23, log2(path_count) 24-25, media 26-27
     float4* ray_d;   // direction xyz | max_t (after extend: hit t)
     float4* thr;     // throughput rgb | bxdf_pdf
     float4* prev_p;  // vertex.origin xyz | reg_alpha
-    float4* prev_n;  // vertex.geo_n xyz | light_split_threshold
+    float4* prev_n;  // vertex.geo_n xyz | split_weight
     float4* hit;     // u, v | primitive | prop
+    uint4*  med;     // medium stack (prop/medium.zig:30-153): props of the up to 3 entries | their parts, 8 bits each; null when lanes == 1
+
+    // Per camera sample.
     float4* acc_e;   // emission rgb | pixel_uv.x
     float4* acc_d;   // direct rgb | pixel_uv.y
     float4* acc_i;   // indirect rgb | -
-    uint4*  smp;     // Sobol: block seed, run seed, dimension | -
+    uint4*  smp;     // Sobol: block seed, run seed, dimension | vertex-pool word (lanes of the current / next generation)
     uint2*  rng;     // PCG state
 
     // shadow-ray records, written by shade_a: path `slot` owns records [slot * shadow_stride, +sh_n[slot])
@@ -91,13 +96,16 @@ struct PathState {
     uint32_t* ml_count;
     uint32_t* queue_m;  // items with candidates
 
-    uint32_t* queue_a;
-    uint32_t* queue_b;
+    uint32_t* queue_a;   // slots with at least one vertex in the current generation
+    uint32_t* queue_b;   // slots whose vertex of the current round survived shade_a
+    uint32_t* queue_t;   // lanes > 1: vertex ids to extend (lanes == 1: the slots of queue_a are the vertex ids)
+    uint32_t* queue_s;   // lanes > 1: slots with more than one vertex in the current generation
     uint32_t* counters;  // [0] |A|, [1] |B|, [2] |mesh queue|, [3] shadow overflow flag, [4] |next A|, [5] closest rays, [6] shadow rays,
-                         // [8] work counter of the persistent mesh kernel (16 words in all)
+                         // [7] |T|, [8] work counter of the persistent mesh kernel, [9] |S| (16 words in all)
 
     uint32_t capacity;       // path slots
     uint32_t shadow_stride;  // shadow records reserved per path
+    uint32_t lanes;          // vertex records per slot: 1 or 4
 };
 
 struct PassParams {
@@ -105,6 +113,7 @@ struct PassParams {
     uint32_t samples_in_pass;  // k
     uint32_t padded_w, padded_h;
     uint32_t num_paths;  // k * padded_w * padded_h
+    uint32_t debug_slot; // ZYGPU_DEBUG_SLOT: the shade stages print the vertices of this slot (diagnostics); 0xFFFFFFFF = off
 };
 
 cudaError_t uploadSobolDirections();
@@ -112,11 +121,16 @@ cudaError_t uploadSobolDirections();
 cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const PassParams& pass, cudaStream_t stream);
 // The queue lengths live on the device; the grids are sized for `max_items` and exit early.
 cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream);
+// `round` = which vertex of each slot's current generation the shade stages work on: the vertices of one camera sample share
+// its sampler and are processed in the reference's order (VertexPool.consume, vertex.zig:232-283), so rounds are sequential.
+cudaError_t launchBeginGeneration(const PathState& st, cudaStream_t stream);
+cudaError_t launchBeginRound(const PathState& st, cudaStream_t stream);
+cudaError_t launchEndGeneration(const PathState& st, cudaStream_t stream);
 cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
-                         uint32_t max_items, cudaStream_t stream);
+                         uint32_t max_items, uint32_t round, cudaStream_t stream);
 cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream);
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
-                         uint32_t max_items, cudaStream_t stream);
+                         uint32_t max_items, uint32_t round, cudaStream_t stream);
 cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream);
 cudaError_t launchResolve(const ZygpuView& view, const float4* film, float4* rgba, uint32_t num_pixels, cudaStream_t stream);
 

@@ -423,6 +423,7 @@ struct LutsD {  // ggx_integral.zig tables in the order of ZygpuScene.ggx_luts
     __device__ float eMAvg(float alpha) const { return lut1(base + 1024, 32, alpha); }
     __device__ float e(float n_dot, float alpha, float f0) const { return lut3(base + 1056, 16, 16, 16, n_dot, alpha, f0); }
     __device__ float eAvg(float alpha, float f0) const { return lut2(base + 1056 + 4096, 16, 16, alpha, f0); }
+    __device__ float eS(float n_dot, float alpha, float f0) const { return lut3(base + 1056 + 4096 + 256, 16, 16, 16, n_dot, alpha, f0); }
 };
 
 struct BxdfResult {  // bxdf.zig:8-19
@@ -436,6 +437,7 @@ enum : uint32_t { kEventReflection = 0, kEventTransmission = 1, kEventStraight =
 struct BxdfSample {  // bxdf.zig:75-82
     V3       reflection, wi;
     float    pdf;
+    float    split_weight;
     float    reg_alpha;  // Path
     uint32_t scattering, event;
 };
@@ -587,9 +589,121 @@ __device__ __forceinline__ V3 diffuseEvaluate(const LutsD& luts, V3 color, float
     return scale3(__fdiv_rn((1.f - e_wo) * (1.f - e_wi), kPi * (1.f - e_avg)), color);
 }
 
-// Material sample of {Substitute surface, Light}: material_sample.zig + substitute_sample.zig:20-410
+
+// ---- Glass helpers: fresnel.zig:5-7, 31-43; ggx.zig:30-32, 128-257, 441-449 --------------------------------------
+
+__device__ __forceinline__ float safeClampAbs(float x) { return zclamp(fabsf(x), kDotMin, 1.f); }
+__device__ __forceinline__ float schlick1(float wo_dot_h, float f0) { return __fmaf_rn(pow5(1.f - wo_dot_h), 1.f - f0, f0); }
+__device__ __forceinline__ float fresnelDielectric(float cos_theta_i, float cos_theta_t, float eta_i, float eta_t) {
+    const float t0  = eta_t * cos_theta_i;
+    const float t1  = eta_i * cos_theta_t;
+    const float r_p = __fdiv_rn(t0 - t1, t0 + t1);
+    const float t2  = eta_i * cos_theta_i;
+    const float t3  = eta_t * cos_theta_t;
+    const float r_o = __fdiv_rn(t2 - t3, t2 + t3);
+    return 0.5f * (r_p * r_p + r_o * r_o);
+}
+__device__ __forceinline__ float ilmEpDielectric(const LutsD& luts, float n_dot_wo, float alpha, float f0) {
+    return __fdiv_rn(1.f, luts.eS(n_dot_wo, alpha, f0 * 4.f));
+}
+__device__ __forceinline__ float gSmithCorrelated(float n_dot_wi, float n_dot_wo, float alpha2) {
+    const float a = n_dot_wo * __fsqrt_rn(__fmaf_rn(1.f - alpha2, n_dot_wi * n_dot_wi, alpha2));
+    const float b = n_dot_wi * __fsqrt_rn(__fmaf_rn(1.f - alpha2, n_dot_wo * n_dot_wo, alpha2));
+    return __fdiv_rn(2.f * n_dot_wi * n_dot_wo, a + b);
+}
+__device__ __forceinline__ float pdfVisibleRefract(float n_dot_wo, float wo_dot_h, float d, float alpha2) {
+    const float g1 = __fdiv_rn(2.f * n_dot_wo, n_dot_wo + __fsqrt_rn(alpha2 + (1.f - alpha2) * (n_dot_wo * n_dot_wo)));
+    return __fdiv_rn(g1 * wo_dot_h * d, n_dot_wo);
+}
+
+struct IorD {  // sample_base.zig:106-117
+    float eta_t, eta_i;
+};
+
+// Iso.refractionF, ggx.zig:128-159: returns the reflection scalar, pdf and the fresnel term
+__device__ __forceinline__ void isoRefractionF(float n_dot_wi, float n_dot_wo, float wi_dot_h, float wo_dot_h, float n_dot_h, float alpha,
+                                               IorD ior, float f0, float& refl, float& pdf, float& f) {
+    const float alpha2       = alpha * alpha;
+    const float abs_wi_dot_h = safeClampAbs(wi_dot_h);
+    const float abs_wo_dot_h = safeClampAbs(wo_dot_h);
+
+    const float d = isoDistribution(n_dot_h, alpha2);
+    const float g = gSmithCorrelated(n_dot_wi, n_dot_wo, alpha2);
+
+    const float cos_x = ior.eta_i > ior.eta_t ? abs_wi_dot_h : abs_wo_dot_h;
+    f                 = 1.f - schlick1(cos_x, f0);
+
+    const float sqr_eta_t = ior.eta_t * ior.eta_t;
+    const float factor    = __fdiv_rn(abs_wi_dot_h * abs_wo_dot_h, n_dot_wi * n_dot_wo);
+    const float sum       = ior.eta_i * wo_dot_h + ior.eta_t * wi_dot_h;
+    const float denom     = sum * sum;
+
+    const float refr = d * g * f;
+    refl             = __fdiv_rn(factor * sqr_eta_t, denom) * refr;
+
+    const float p = pdfVisibleRefract(n_dot_wo, abs_wo_dot_h, d, alpha2);
+    pdf           = p * __fdiv_rn(abs_wi_dot_h * sqr_eta_t, denom);
+}
+
+// Iso.reflectNoFresnel, ggx.zig:161-187
+__device__ __forceinline__ float isoReflectNoFresnel(V3 wo, V3 h, float n_dot_wo, float n_dot_h, float wo_dot_h, float alpha,
+                                                     float specular_threshold, const FrameD& frame, BxdfSample& result) {
+    const V3    wi       = normalize3(fmas3(2.f * wo_dot_h, h, neg3(wo)));
+    const float n_dot_wi = frame.clampNdot(wi);
+    const float alpha2   = alpha * alpha;
+
+    const float d = isoDistribution(n_dot_h, alpha2);
+    float       vis, g1;
+    isoVisibilityAndG1Wo(n_dot_wi, n_dot_wo, alpha2, vis, g1);
+
+    result.reflection = splat3(d * vis);
+    result.wi         = wi;
+    result.pdf        = pdfVisible(d, g1);
+    result.reg_alpha  = alpha;
+    result.scattering = alpha <= specular_threshold ? kScatterSpecular : kScatterGlossy;
+    result.event      = kEventReflection;
+    return n_dot_wi;
+}
+
+// Iso.refractNoFresnel, ggx.zig:189-233
+__device__ __forceinline__ float isoRefractNoFresnel(V3 wo, V3 h, float n_dot_wo, float n_dot_h, float wi_dot_h, float wo_dot_h, float alpha,
+                                                     float specular_threshold, IorD ior, const FrameD& frame, BxdfSample& result) {
+    const float eta = __fdiv_rn(ior.eta_i, ior.eta_t);
+
+    const float abs_wi_dot_h = safeClampAbs(wi_dot_h);
+    const float abs_wo_dot_h = safeClampAbs(wo_dot_h);
+
+    const V3 wi = normalize3(sub3(scale3(__fmaf_rn(eta, abs_wo_dot_h, -abs_wi_dot_h), h), scale3(eta, wo)));
+
+    const float n_dot_wi = frame.clampAbsNdot(wi);
+    const float alpha2   = alpha * alpha;
+
+    const float d = isoDistribution(n_dot_h, alpha2);
+    const float g = gSmithCorrelated(n_dot_wi, n_dot_wo, alpha2);
+
+    const float refr      = d * g;
+    const float factor    = __fdiv_rn(abs_wi_dot_h * abs_wo_dot_h, n_dot_wi * n_dot_wo);
+    const float sum       = ior.eta_i * wo_dot_h + ior.eta_t * wi_dot_h;
+    const float denom     = sum * sum;
+    const float sqr_eta_t = ior.eta_t * ior.eta_t;
+    const float pdf       = pdfVisibleRefract(n_dot_wo, abs_wo_dot_h, d, alpha2);
+
+    result.reflection = splat3(__fdiv_rn(factor * sqr_eta_t, denom) * refr);
+    result.wi         = wi;
+    result.pdf        = pdf * __fdiv_rn(abs_wi_dot_h * sqr_eta_t, denom);
+    result.reg_alpha  = alpha;
+    result.scattering = alpha <= specular_threshold ? kScatterSpecular : kScatterGlossy;
+    result.event      = kEventTransmission;
+    return n_dot_wi;
+}
+
+enum : uint32_t { kSampleLight = 0, kSampleSubstitute = 1, kSampleGlass = 2 };
+
+// Material sample of {Substitute surface, Light, Glass}: material_sample.zig, substitute_sample.zig:20-410, glass_sample.zig:20-537
 struct MatSampleD {
-    bool   is_light;
+    uint32_t kind;
+    bool   lower_priority;
+    float  ior, ior_outside, glass_f0;  // Glass
     bool   can_evaluate, avoid_caustics, translucent;
     FrameD frame;
     V3     geo_n, n, wo;
@@ -627,8 +741,9 @@ struct MatSampleD {
     }
 
     // material_sample.zig:56-62 -> substitute_sample.zig:88-145
-    __device__ BxdfResult evaluate(const LutsD& luts, V3 wi) const {
-        if (is_light) return {splat3(0.f), 0.f};
+    __device__ BxdfResult evaluate(const LutsD& luts, V3 wi, uint32_t max_splits) const {
+        if (kSampleLight == kind) return {splat3(0.f), 0.f};
+        if (kSampleGlass == kind) return glassEvaluate(luts, wi, max_splits);
         if (!sameHemisphere(wo)) return {splat3(0.f), 0.f};
         const V3    h        = normalize3(add3(wo, wi));
         const float wo_dot_h = clampDot(wo, h);
@@ -682,9 +797,12 @@ struct MatSampleD {
     }
 
     // material_sample.zig:64-78 -> substitute_sample.zig:147-234, 280-302. Returns the number of samples (0 or 1).
-    __device__ uint32_t sample(const LutsD& luts, SamplerD& sampler, BxdfSample& result) const {
-        if (is_light) return 0;
+    __device__ uint32_t sample(const LutsD& luts, SamplerD& sampler, uint32_t max_splits, BxdfSample* results) const {
+        if (kSampleLight == kind) return 0;
+        if (kSampleGlass == kind) return glassSample(luts, sampler, max_splits, results);
         if (!sameHemisphere(wo)) return 0;
+        BxdfSample& result  = results[0];
+        result.split_weight = 1.f;
 
         float dw = 0.f;
         if (1.f != metallic) {
@@ -703,6 +821,206 @@ struct MatSampleD {
         if (0.f == result.pdf) return 0;
         return 1;
     }
+
+    // ---- Glass (thickness == 0, abbe == 0) ----
+
+    // Sample.evaluate, glass_sample.zig:68-152 (force_disable_caustics = false)
+    __device__ BxdfResult glassEvaluate(const LutsD& luts, V3 wi, uint32_t max_splits) const {
+        const float alpha = ax;
+        const bool  rough = alpha > 0.f;
+        if (ior == ior_outside || !rough || lower_priority || (avoid_caustics && alpha <= specular_threshold)) return {splat3(0.f), 0.f};
+
+        const bool  split = max_splits > 1;
+        const float s     = specular;
+
+        if (!sameHemisphere(wo)) {
+            const IorD io{ior_outside, ior};  // eta_i = self.ior, eta_t = self.ior_outside
+            const V3   h = neg3(normalize3(add3(scale3(io.eta_t, wi), scale3(io.eta_i, wo))));
+
+            const float wi_dot_h = dot3(wi, h);
+            if (wi_dot_h <= 0.f) return {splat3(0.f), 0.f};
+
+            const float wo_dot_h = dot3(wo, h);
+            const float eta      = __fdiv_rn(io.eta_i, io.eta_t);
+            const float sint2    = (eta * eta) * (1.f - wo_dot_h * wo_dot_h);
+            if (sint2 >= 1.f) return {splat3(0.f), 0.f};
+
+            const float n_dot_wi = frame.clampNdot(wi);
+            const float n_dot_wo = frame.clampAbsNdot(wo);
+            const float n_dot_h  = saturate(dot3(frame.z, h));
+
+            float refl, pdf, f;
+            isoRefractionF(n_dot_wi, n_dot_wo, wi_dot_h, wo_dot_h, n_dot_h, alpha, io, glass_f0, refl, pdf, f);
+            const float comp = ilmEpDielectric(luts, n_dot_wo, alpha, glass_f0);
+
+            const float split_pdf = split ? 1.f : f;
+            return {splat3((zmin(n_dot_wi, n_dot_wo) * comp * s) * refl), split_pdf * pdf};
+        } else if (sameHemisphere(wi)) {
+            const float n_dot_wi = frame.clampNdot(wi);
+            const float n_dot_wo = frame.clampAbsNdot(wo);
+
+            const V3    h        = normalize3(add3(wo, wi));
+            const float wo_dot_h = clampDot(wo, h);
+
+            // Iso.reflectionF, ggx.zig:73-95
+            const float alpha2  = alpha * alpha;
+            const float n_dot_h = saturate(dot3(frame.z, h));
+            const float d       = isoDistribution(n_dot_h, alpha2);
+            float       vis, g1;
+            isoVisibilityAndG1Wo(n_dot_wi, n_dot_wo, alpha2, vis, g1);
+            const float f    = schlick1(wo_dot_h, glass_f0);
+            const float refl = (d * vis) * f;
+            const float pdf  = pdfVisible(d, g1);
+
+            const float comp = ilmEpDielectric(luts, n_dot_wo, alpha, glass_f0);
+
+            const float split_pdf = split ? 1.f : f;
+            return {splat3((n_dot_wi * comp * s) * refl), split_pdf * pdf};
+        }
+        return {splat3(0.f), 0.f};
+    }
+
+    __device__ static BxdfSample singular(V3 reflection, V3 wi, float split_weight, uint32_t event) {
+        BxdfSample r;
+        r.reflection   = reflection;
+        r.wi           = wi;
+        r.pdf          = 1.f;
+        r.split_weight = split_weight;
+        r.reg_alpha    = 0.f;
+        r.scattering   = kScatterSpecular;
+        r.event        = event;
+        return r;
+    }
+
+    // specularSample, glass_sample.zig:202-284 (Thin = false, weight = 1)
+    __device__ uint32_t glassSpecularSample(SamplerD& sampler, bool split, BxdfSample* buffer) const {
+        float eta_i = ior_outside;
+        float eta_t = ior;
+
+        if (eta_i == eta_t || lower_priority) {
+            buffer[0] = singular(splat3(1.f), neg3(wo), 1.f, kEventTransmission);
+            return 1;
+        }
+
+        V3 nn = frame.z;
+        if (!sameHemisphere(wo)) {
+            nn            = neg3(nn);
+            const float t = eta_i;
+            eta_i         = eta_t;
+            eta_t         = t;
+        }
+
+        const float n_dot_wo = zmin(fabsf(dot3(nn, wo)), 1.f);
+        const float eta      = __fdiv_rn(eta_i, eta_t);
+        const float sint2    = (eta * eta) * (1.f - n_dot_wo * n_dot_wo);
+
+        float n_dot_t, f;
+        if (sint2 >= 1.f) {
+            n_dot_t = 0.f;
+            f       = 1.f;
+        } else {
+            n_dot_t = __fsqrt_rn(1.f - sint2);
+            f       = fresnelDielectric(n_dot_wo, n_dot_t, eta_i, eta_t);
+        }
+
+        const V3 reflected = normalize3(sub3(scale3(2.f * n_dot_wo, nn), wo));                             // reflect, :429-438
+        const V3 refracted = normalize3(sub3(scale3(eta * n_dot_wo - n_dot_t, nn), scale3(eta, wo)));     // thickSpecularRefract, :519-537
+
+        if (split) {
+            buffer[0] = singular(splat3(specular), reflected, f, kEventReflection);
+            if (1.f == f) return 1;
+            buffer[1] = singular(splat3(1.f), refracted, 1.f - f, kEventTransmission);
+            return 2;
+        }
+        const float p = sampler.sample1D();
+        if (p <= f) {
+            buffer[0] = singular(splat3(specular), reflected, 1.f, kEventReflection);
+        } else {
+            buffer[0] = singular(splat3(1.f), refracted, 1.f, kEventTransmission);
+        }
+        return 1;
+    }
+
+    // roughSample, glass_sample.zig:286-427 (Thin = false, weight = 1)
+    __device__ uint32_t glassRoughSample(const LutsD& luts, SamplerD& sampler, bool split, BxdfSample* buffer) const {
+        const IorD quo_ior{ior, ior_outside};  // eta_i = ior_outside, eta_t = ior
+
+        if (fabsf(quo_ior.eta_i - quo_ior.eta_t) <= 2.e-7f || lower_priority) {
+            buffer[0] = singular(splat3(1.f), neg3(wo), 1.f, kEventTransmission);
+            return 1;
+        }
+
+        const float alpha     = ax;
+        const bool  same_side = sameHemisphere(wo);
+
+        const FrameD fr = same_side ? frame : FrameD{frame.x, frame.y, neg3(frame.z)};
+        const IorD   io = same_side ? quo_ior : IorD{quo_ior.eta_i, quo_ior.eta_t};
+
+        const V3 s3 = sampler.sample3D();
+
+        float    n_dot_h;
+        const V3 h = sampleVndf(wo, ax, ay, s3.y, s3.z, fr, n_dot_h);
+
+        const float n_dot_wo = fr.clampAbsNdot(wo);
+        const float wo_dot_h = clampDot(wo, h);
+
+        const float eta   = __fdiv_rn(io.eta_i, io.eta_t);
+        const float sint2 = (eta * eta) * (1.f - wo_dot_h * wo_dot_h);
+
+        const float s = specular;
+
+        float wi_dot_h, f;
+        if (sint2 >= 1.f) {
+            wi_dot_h = 0.f;
+            f        = 1.f;
+        } else {
+            wi_dot_h          = __fsqrt_rn(1.f - sint2);
+            const float cos_x = io.eta_i > io.eta_t ? wi_dot_h : wo_dot_h;
+            f                 = schlick1(cos_x, glass_f0);
+        }
+
+        const float ep         = ilmEpDielectric(luts, n_dot_wo, alpha, glass_f0);
+        const float r_wo_dot_h = same_side ? -wo_dot_h : wo_dot_h;  // roughRefract, :440-503 (Thin = false)
+
+        if (split) {
+            {
+                const float n_dot_wi   = isoReflectNoFresnel(wo, h, n_dot_wo, n_dot_h, wo_dot_h, alpha, specular_threshold, fr, buffer[0]);
+                buffer[0].reflection   = mul3(buffer[0].reflection, splat3(n_dot_wi * ep * s));
+                buffer[0].split_weight = f;
+            }
+            if (1.f == f) return 1;
+            {
+                const float n_dot_wi = isoRefractNoFresnel(wo, h, n_dot_wo, n_dot_h, -wi_dot_h, r_wo_dot_h, alpha, specular_threshold, io, fr, buffer[1]);
+                if (n_dot_wi < 0.f) return 1;
+                buffer[1].reflection   = mul3(buffer[1].reflection, splat3(n_dot_wi * ep));
+                buffer[1].split_weight = 1.f - f;
+            }
+            return 2;
+        }
+
+        BxdfSample& result = buffer[0];
+        const float p      = s3.x;
+        if (p <= f) {
+            const float n_dot_wi = isoReflectNoFresnel(wo, h, n_dot_wo, n_dot_h, wo_dot_h, alpha, specular_threshold, fr, result);
+            result.reflection    = mul3(result.reflection, splat3(f * n_dot_wi * ep * s));
+            result.pdf *= f;
+        } else {
+            const float n_dot_wi = isoRefractNoFresnel(wo, h, n_dot_wo, n_dot_h, -wi_dot_h, r_wo_dot_h, alpha, specular_threshold, io, fr, result);
+            if (n_dot_wi < 0.f) return 0;
+            const float omf   = 1.f - f;
+            result.reflection = mul3(result.reflection, splat3(omf * n_dot_wi * ep));
+            result.pdf *= omf;
+        }
+        result.split_weight = 1.f;
+        return 1;
+    }
+
+    // Sample.sample, glass_sample.zig:167-200
+    __device__ uint32_t glassSample(const LutsD& luts, SamplerD& sampler, uint32_t max_splits, BxdfSample* buffer) const {
+        const bool split = max_splits > 1;
+        if (ax > 0.f) return glassRoughSample(luts, sampler, split, buffer);
+        return glassSpecularSample(sampler, split, buffer);
+    }
 };
 
 // Emittance.radiance, emittance.zig:29-59 (uniform emission, no profile)
@@ -716,9 +1034,11 @@ __device__ __forceinline__ V3 emittanceRadiance(const ZygpuMaterial& m, V3 wi, c
 
 // Vertex.sample + Material.sample, vertex.zig:137-181, material.zig:184-194, substitute_material.zig:114-221
 __device__ __forceinline__ MatSampleD materialSample(const ZygpuMaterial& m, const FragD& frag, V3 wo, float reg_weight, float reg_alpha,
-                                                     bool caustics, float specular_threshold) {
+                                                     bool caustics, float specular_threshold, float ior_outside = 1.f,
+                                                     int highest_priority = -128) {
     MatSampleD r;
-    r.wo = wo;
+    r.wo             = wo;
+    r.lower_priority = m.priority < highest_priority;
     if (0 != (m.flags & ZYG_MATERIAL_TWO_SIDED) && !frag.sameHemisphere(wo)) {
         r.geo_n = neg3(frag.geo_n);
         r.n     = neg3(frag.n);
@@ -730,13 +1050,34 @@ __device__ __forceinline__ MatSampleD materialSample(const ZygpuMaterial& m, con
     r.avoid_caustics = !caustics;
     r.translucent    = false;
 
+    if (ZYG_MATERIAL_GLASS == m.type) {  // glass_material.zig:46-73, glass_sample.zig:32-66
+        const float rr = 0.f == m.roughness ? 0.f : zmax(m.roughness, kMinRoughness);
+        float       a  = rr * rr;
+        if (!(0.f == reg_weight || (a <= specular_threshold && !caustics))) {  // Renderstate.regularizeAlpha
+            const float k = 1.f - reg_weight * reg_alpha;
+            a             = 1.f - ((1.f - a) * k);
+        }
+        const bool rough = a > 0.f;
+
+        r.kind               = kSampleGlass;
+        r.ax = r.ay          = a;
+        r.can_evaluate       = rough && m.ior != ior_outside;
+        r.translucent        = m.thickness > 0.f;
+        r.ior                = m.ior;
+        r.ior_outside        = ior_outside;
+        const float t        = __fdiv_rn(m.ior - ior_outside, m.ior + ior_outside);
+        r.glass_f0           = rough ? t * t : 0.f;
+        r.specular           = m.specular;
+        r.specular_threshold = specular_threshold;
+        return r;
+    }
     if (ZYG_MATERIAL_SUBSTITUTE != m.type) {  // Light (and Debug): Base.initTBN(rs, wo, 0, 0, false)
-        r.is_light     = true;
+        r.kind         = kSampleLight;
         r.can_evaluate = false;
         r.ax = r.ay = 0.f;
         return r;
     }
-    r.is_light = false;
+    r.kind = kSampleSubstitute;
 
     const V3    color     = {m.color[0], m.color[1], m.color[2]};
     const float roughness = zmax(m.roughness, kMinRoughness);
@@ -751,7 +1092,7 @@ __device__ __forceinline__ MatSampleD materialSample(const ZygpuMaterial& m, con
         ax = ay = roughness * roughness;
     }
 
-    const float ior_medium = 1.f;  // empty medium stack
+    const float ior_medium = ior_outside;  // rs.ior: Vertex.iorOutside, vertex.zig:87-93
     const float ior_outer  = ior_medium;
 
     // Renderstate.regularizeAlpha, renderstate.zig:58-68

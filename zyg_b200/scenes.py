@@ -168,10 +168,12 @@ def random_rays(n: int, radius: float = 1.5, shadow: bool = False, first: int = 
 # ---- config 1: Cornell box through the su_* API ------------------------------------------
 
 def cornell_box(width=512, height=512, spp=64, max_depth=8, filter_name=None, unoccluding_light=True,
-                roughness=1.0, light_value=17.0):
+                roughness=1.0, light_value=17.0, glass=None):
     """Builds BASELINE config 1 through zyg's C API (``zyg_b200.su``): classic box x in [-1,1], y in [0,2],
     z in [-1,1], open towards -z; five Rectangle walls, one 0.5 x 0.5 Rectangle light under the ceiling, two
     rotated Cube props; camera at (0,1,-3.9) looking down +z with a 39 degree horizontal field of view.
+    ``glass`` = a Glass parameter dict (e.g. ``{"ior": 1.5, "roughness": 0.0}``) turns the short box into glass and puts
+    a glass ball (higher priority, different ior) half sunk into its top, so paths split, nest media and absorb.
     The engine must not be initialised yet; the caller releases it with ``su.release()``."""
     from . import su
 
@@ -206,8 +208,22 @@ def cornell_box(width=512, height=512, spp=64, max_depth=8, filter_name=None, un
 
     tall = su.prop_create(su.CUBE, [white])
     su.prop_set_transformation(tall, su.transformation((-0.35, 0.6, 0.3), (0.6, 1.2, 0.6), (0.0, 17.0, 0.0)))
-    short = su.prop_create(su.CUBE, [white])
-    su.prop_set_transformation(short, su.transformation((0.35, 0.3, -0.3), (0.6, 0.6, 0.6), (0.0, -17.0, 0.0)))
+    short_material = white
+    if glass is not None:
+        params = {"ior": 1.5, "roughness": 0.0, "attenuation_color": [0.6, 0.9, 0.7], "attenuation_distance": 0.5}
+        params.update(glass)
+        short_material = su.material_create({"rendering": {"Glass": params}})
+        ball_params = dict(params, ior=1.33, priority=1, attenuation_color=[0.9, 0.5, 0.4], attenuation_distance=0.25)
+        if not params.get("no_ball"):
+            ball_material = su.material_create({"rendering": {"Glass": ball_params}})
+            ball = su.prop_create(su.SPHERE, [ball_material])
+            su.prop_set_transformation(ball, su.transformation((0.35, 0.6, -0.3), (0.4, 0.4, 0.4)))
+        if params.get("no_cube"):
+            short_material = white
+    short = su.prop_create(su.CUBE, [short_material])
+    # a glass box is lifted off the floor: seen from inside, a bottom face coincident with the floor is an equal-t tie
+    # that the last ulp of the ray direction decides
+    su.prop_set_transformation(short, su.transformation((0.35, 0.3 if glass is None else 0.302, -0.3), (0.6, 0.6, 0.6), (0.0, -17.0, 0.0)))
 
     lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=unoccluding_light)
     su.prop_set_transformation(lamp, su.transformation((0.0, 1.98, 0.0), (0.5, 0.5, 1.0), (-90.0, 0.0, 0.0)))
