@@ -1200,11 +1200,14 @@ __device__ __forceinline__ void ivalueAdd(const PathState& st, uint32_t slot, V3
 // Worker.render per sample: Sensor.cameraSample (sensor.zig:152-166) + Perspective.generateVertex
 // (camera_perspective.zig:124-150) + Vertex.init (vertex.zig:67-85)
 __global__ void __launch_bounds__(kBlock) generateKernel(ZygpuView view, PathState st, PassParams pass) {
+    __shared__ uint32_t sobol_tables[kSobolTableWords];
+    loadSobolTables(sobol_tables);
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < pass.num_paths; slot += gridDim.x * blockDim.x) {
         const SlotId id = slotId(slot, pass);
 
         SamplerD sampler;
-        sampler.use_sobol = ZYG_SAMPLER_SOBOL == view.sampler;
+        sampler.sobol.tables = sobol_tables;
+        sampler.use_sobol    = ZYG_SAMPLER_SOBOL == view.sampler;
         seedSamplers(id, pass, view.spp_total, sampler.sobol, sampler.rng);
 
         const int32_t fr = view.filter_radius_int;
@@ -1369,7 +1372,9 @@ __device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t
 // roulette (:88, helper.zig:75-89), Vertex.sample (:93), sampleLights / evaluateLight up to the visibility test
 // (:174-250).
 template <bool Split>
-__global__ void __launch_bounds__(kBlock) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
+__global__ void __launch_bounds__(kBlock, 4) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
+    __shared__ uint32_t sobol_tables[kSobolTableWords];
+    loadSobolTables(sobol_tables);
     const bool      later = Split && round > 0;
     const uint32_t  count = later ? st.counters[9] : st.counters[0];
     const uint32_t* __restrict__ queue = later ? st.queue_s : st.queue_a;
@@ -1402,6 +1407,7 @@ __global__ void __launch_bounds__(kBlock) shadeAKernel(SceneDevice sc, ZygpuView
             const bool     hit         = kEnd != lv.prop;
 
             SamplerD sampler;
+            sampler.sobol.tables = sobol_tables;
             loadSampler(st, slot, smp, pass, view.spp_total, total_depth, sampler);
             if (ZYG_SAMPLER_SOBOL != view.sampler) sampler.use_sobol = false;
 
@@ -1473,8 +1479,8 @@ __global__ void __launch_bounds__(kBlock) shadeAKernel(SceneDevice sc, ZygpuView
                 float ior_outside      = 1.f;
                 int   highest_priority = -128;
                 if (Split) mediaForSample(sc, media, frag, wo, ior_outside, highest_priority);
-                const MatSampleD mat_sample = materialSample(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics,
-                                                             view.specular_threshold, ior_outside, highest_priority);
+                const MatSampleD mat_sample = materialSample<Split>(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics,
+                                                                    view.specular_threshold, ior_outside, highest_priority);
 
                 vertex.light_split_threshold = splitThreshold(view.split_threshold, vertex.probe_depth);
 
@@ -1570,7 +1576,9 @@ __global__ void __launch_bounds__(kBlock) shadowKernel(SceneDevice sc, PathState
 // The rest of PathtracerMIS.li: evaluateLight after the visibility test (pathtracer_mis.zig:252-277), the direct-light
 // add (:116-117), mat_sample.sample and the next vertex (:121-166).
 template <bool Split>
-__global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
+__global__ void __launch_bounds__(kBlock, Split ? 3 : 4) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
+    __shared__ uint32_t sobol_tables[kSobolTableWords];
+    loadSobolTables(sobol_tables);
     const uint32_t count = st.counters[1];
     const LutsD    luts{sc.luts};
     const uint32_t iters = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
@@ -1592,6 +1600,7 @@ __global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView
             const uint32_t total_depth = vertex.probe_depth;
 
             SamplerD sampler;
+            sampler.sobol.tables = sobol_tables;
             loadSampler(st, slot, smp, pass, view.spp_total, total_depth, sampler);
             if (ZYG_SAMPLER_SOBOL != view.sampler) sampler.use_sobol = false;
 
@@ -1607,8 +1616,8 @@ __global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView
             float               ior_outside      = 1.f;
             int                 highest_priority = -128;
             if (Split) mediaForSample(sc, media, frag, wo, ior_outside, highest_priority);
-            const MatSampleD mat_sample = materialSample(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics,
-                                                         view.specular_threshold, ior_outside, highest_priority);
+            const MatSampleD mat_sample = materialSample<Split>(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics,
+                                                                view.specular_threshold, ior_outside, highest_priority);
 
             const uint32_t max_splits = Split ? maxSplits(lv.path_count_log2, 0 != (vertex.state & kPrimaryRay), total_depth) : 1;
 
@@ -1632,7 +1641,7 @@ __global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView
                 const float area     = 0.f != lm.emission_normalize ? shapeArea(sc.props[light.prop].shape, ltrafo.scale) : 1.f;
                 const V3    radiance = emittanceRadiance(lm, wi, ltrafo, area, false);
 
-                const BxdfResult bxdf_result = mat_sample.evaluate(luts, wi, max_splits);
+                const BxdfResult bxdf_result = mat_sample.template evaluate<Split>(luts, wi, max_splits);
 
                 const float light_pdf = o4.w;
                 const float weight    = predividedPowerHeuristic(light_pdf, bxdf_result.pdf);
@@ -1643,8 +1652,8 @@ __global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView
             const V3 split_throughput = scale3(lv.split_weight, lv.throughput);
             ivalueAdd(st, slot, mul3(split_throughput, next_light), total_depth, 1, false, false);
 
-            BxdfSample     sample_results[2];
-            const uint32_t path_count = mat_sample.sample(luts, sampler, max_splits, sample_results);
+            BxdfSample     sample_results[Split ? 2 : 1];
+            const uint32_t path_count = mat_sample.template sample<Split>(luts, sampler, max_splits, sample_results);
 
             if (Split) pool = poolFree(pool, lane);  // the parent lives in registers from here on
             if (slot == pass.debug_slot) {
@@ -1654,7 +1663,7 @@ __global__ void __launch_bounds__(kBlock) shadeBKernel(SceneDevice sc, ZygpuView
                 }
             }
 
-            for (uint32_t c = 0; c < path_count; ++c) {
+            for (uint32_t c = 0; c < (Split ? path_count : min(path_count, 1u)); ++c) {
                 const BxdfSample& sample_result = sample_results[c];
 
                 // Vertex.State.update, vertex.zig:30-43
@@ -1860,7 +1869,19 @@ cudaError_t uploadSobolDirections() {
             }
         }
     }
-    return cudaMemcpyToSymbol(c_sobol_directions, d, sizeof(d));
+    static uint32_t tables[kSobolTableWords];
+    for (uint32_t byte = 0; byte < 4; ++byte) {
+        for (uint32_t dim = 0; dim < 5; ++dim) {
+            for (uint32_t value = 0; value < 256; ++value) {
+                uint32_t x = 0;
+                for (uint32_t j = 0; j < 8; ++j) {
+                    if (0 != ((value >> j) & 1u)) x ^= d[dim][8 * byte + j];
+                }
+                tables[(byte * 5 + dim) * 256 + value] = x;
+            }
+        }
+    }
+    return cudaMemcpyToSymbol(d_sobol_tables, tables, sizeof(tables));
 }
 
 cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const PassParams& pass, cudaStream_t stream) {

@@ -11,7 +11,17 @@ namespace zygpu {
 
 // ---- samplers --------------------------------------------------------------------------------
 
-__constant__ uint32_t c_sobol_directions[5][32];  // src/core/sampler/sobol.zig:194-245, regenerated (render.cu)
+// sobol5 (sobol.zig:176-192) XORs one direction number per set bit of the index. The device folds the 32 direction numbers of a
+// dimension (sobol.zig:194-245, regenerated in render.cu) into four 256-entry tables, one per byte of the index:
+// table[(byte * 5 + dim) * 256 + value] = XOR of the directions of the bits set in `value`. Same integers, 20 lookups per block.
+constexpr uint32_t kSobolTableWords = 4 * 5 * 256;
+__device__ uint32_t d_sobol_tables[kSobolTableWords];
+
+// Copies the tables into the block's shared memory; every thread of the block must call it once before sampling.
+__device__ __forceinline__ void loadSobolTables(uint32_t* shared_tables) {
+    for (uint32_t i = threadIdx.x; i < kSobolTableWords; i += blockDim.x) shared_tables[i] = d_sobol_tables[i];
+    __syncthreads();
+}
 
 __device__ __forceinline__ uint32_t sobolHash(uint32_t i) {  // sobol.zig:107-124
     uint32_t x = i ^ (i >> 16);
@@ -35,21 +45,23 @@ __device__ __forceinline__ uint32_t nestedUniformScramble(uint32_t x, uint32_t s
 }
 
 struct SobolD {  // sobol.zig:8-105
-    float    buffer[5];
-    uint32_t sample, dimension, block_seed, run_seed;
+    float           buffer[5];
+    uint32_t        sample, dimension, block_seed, run_seed;
+    const uint32_t* tables;  // shared-memory copy of d_sobol_tables
 
     __device__ void fill(uint32_t s) {  // incrementSeed body, :36-56
         const float    S = 1.f / 4294967296.f;
         const uint32_t i = nestedUniformScramble(sample, s);
-        uint32_t       x0 = 0, x1 = 0, x2 = 0, x3 = 0, x4 = 0;
-        for (uint32_t bit = 0, idx = i; 0 != idx; ++bit, idx >>= 1) {  // sobol5, :176-192
-            const uint32_t mask = idx & 1u;
-            x0 ^= mask * c_sobol_directions[0][bit];
-            x1 ^= mask * c_sobol_directions[1][bit];
-            x2 ^= mask * c_sobol_directions[2][bit];
-            x3 ^= mask * c_sobol_directions[3][bit];
-            x4 ^= mask * c_sobol_directions[4][bit];
-        }
+        // sobol5, :176-192, a byte of the index at a time
+        const uint32_t* t0 = tables + (i & 0xffu);
+        const uint32_t* t1 = tables + 5 * 256 + ((i >> 8) & 0xffu);
+        const uint32_t* t2 = tables + 10 * 256 + ((i >> 16) & 0xffu);
+        const uint32_t* t3 = tables + 15 * 256 + (i >> 24);
+        const uint32_t  x0 = t0[0] ^ t1[0] ^ t2[0] ^ t3[0];
+        const uint32_t  x1 = t0[256] ^ t1[256] ^ t2[256] ^ t3[256];
+        const uint32_t  x2 = t0[512] ^ t1[512] ^ t2[512] ^ t3[512];
+        const uint32_t  x3 = t0[768] ^ t1[768] ^ t2[768] ^ t3[768];
+        const uint32_t  x4 = t0[1024] ^ t1[1024] ^ t2[1024] ^ t3[1024];
         buffer[0] = __uint2float_rn(nestedUniformScramble(x0, hashCombine(s, 0))) * S;
         buffer[1] = __uint2float_rn(nestedUniformScramble(x1, hashCombine(s, 1))) * S;
         buffer[2] = __uint2float_rn(nestedUniformScramble(x2, hashCombine(s, 2))) * S;
@@ -741,9 +753,11 @@ struct MatSampleD {
     }
 
     // material_sample.zig:56-62 -> substitute_sample.zig:88-145
+    // `Glass` = the scene holds Glass materials (compiled out otherwise)
+    template <bool Glass>
     __device__ BxdfResult evaluate(const LutsD& luts, V3 wi, uint32_t max_splits) const {
         if (kSampleLight == kind) return {splat3(0.f), 0.f};
-        if (kSampleGlass == kind) return glassEvaluate(luts, wi, max_splits);
+        if (Glass && kSampleGlass == kind) return glassEvaluate(luts, wi, max_splits);
         if (!sameHemisphere(wo)) return {splat3(0.f), 0.f};
         const V3    h        = normalize3(add3(wo, wi));
         const float wo_dot_h = clampDot(wo, h);
@@ -797,9 +811,10 @@ struct MatSampleD {
     }
 
     // material_sample.zig:64-78 -> substitute_sample.zig:147-234, 280-302. Returns the number of samples (0 or 1).
+    template <bool Glass>
     __device__ uint32_t sample(const LutsD& luts, SamplerD& sampler, uint32_t max_splits, BxdfSample* results) const {
         if (kSampleLight == kind) return 0;
-        if (kSampleGlass == kind) return glassSample(luts, sampler, max_splits, results);
+        if (Glass && kSampleGlass == kind) return glassSample(luts, sampler, max_splits, results);
         if (!sameHemisphere(wo)) return 0;
         BxdfSample& result  = results[0];
         result.split_weight = 1.f;
@@ -1033,6 +1048,7 @@ __device__ __forceinline__ V3 emittanceRadiance(const ZygpuMaterial& m, V3 wi, c
 }
 
 // Vertex.sample + Material.sample, vertex.zig:137-181, material.zig:184-194, substitute_material.zig:114-221
+template <bool Glass>
 __device__ __forceinline__ MatSampleD materialSample(const ZygpuMaterial& m, const FragD& frag, V3 wo, float reg_weight, float reg_alpha,
                                                      bool caustics, float specular_threshold, float ior_outside = 1.f,
                                                      int highest_priority = -128) {
@@ -1050,7 +1066,7 @@ __device__ __forceinline__ MatSampleD materialSample(const ZygpuMaterial& m, con
     r.avoid_caustics = !caustics;
     r.translucent    = false;
 
-    if (ZYG_MATERIAL_GLASS == m.type) {  // glass_material.zig:46-73, glass_sample.zig:32-66
+    if (Glass && ZYG_MATERIAL_GLASS == m.type) {  // glass_material.zig:46-73, glass_sample.zig:32-66
         const float rr = 0.f == m.roughness ? 0.f : zmax(m.roughness, kMinRoughness);
         float       a  = rr * rr;
         if (!(0.f == reg_weight || (a <= specular_threshold && !caustics))) {  // Renderstate.regularizeAlpha
