@@ -9,6 +9,9 @@ namespace zygpu {
 namespace {
 
 constexpr uint32_t kBlock = 128;
+#ifndef ZYGPU_SHADE_BLOCKS
+#define ZYGPU_SHADE_BLOCKS 4  // resident blocks per SM the shade kernels are compiled for (128 registers)
+#endif
 
 // ---- state packing ---------------------------------------------------------------------------
 
@@ -1372,7 +1375,7 @@ __device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t
 // roulette (:88, helper.zig:75-89), Vertex.sample (:93), sampleLights / evaluateLight up to the visibility test
 // (:174-250).
 template <bool Split>
-__global__ void __launch_bounds__(kBlock, 4) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
+__global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
     __shared__ uint32_t sobol_tables[kSobolTableWords];
     loadSobolTables(sobol_tables);
     const bool      later = Split && round > 0;
@@ -1576,7 +1579,7 @@ __global__ void __launch_bounds__(kBlock) shadowKernel(SceneDevice sc, PathState
 // The rest of PathtracerMIS.li: evaluateLight after the visibility test (pathtracer_mis.zig:252-277), the direct-light
 // add (:116-117), mat_sample.sample and the next vertex (:121-166).
 template <bool Split>
-__global__ void __launch_bounds__(kBlock, Split ? 3 : 4) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
+__global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
     __shared__ uint32_t sobol_tables[kSobolTableWords];
     loadSobolTables(sobol_tables);
     const uint32_t count = st.counters[1];
