@@ -1125,6 +1125,8 @@ struct Scene {
 
 // ---- integrator ------------------------------------------------------------------------------
 
+bool g_wavefront_light_order = false;  // zo_set_wavefront_light_order
+
 struct Worker {
     const Scene& scene;
     Generator    rng;
@@ -1334,8 +1336,56 @@ struct Worker {
 
         LightPick      lights[64];
         const uint32_t num = scene.randomLight(p, n, translucent, select, vertex.light_split_threshold, lights);
+        if (g_wavefront_light_order) return sampleLightsWavefront(lights, num, vertex, frag, mat_sample, max_material_splits, sampler);
         for (uint32_t i = 0; i < num; ++i) {
             result = result + evaluateLight(lights[i], vertex, frag, mat_sample, max_material_splits, sampler);
+        }
+        return result;
+    }
+
+    // The same estimator with the sampler draws regrouped the way a wavefront has to take them: first the light samples of
+    // every pick (Light.sampleTo), then - after all shadow rays - one draw per visible sample (Light.evaluateTo, light.zig:127).
+    // The reference interleaves the two per light sample; with one pick and one sample both orders coincide. The device
+    // implements this order; tests compare it with this variant per pixel and the two variants with each other statistically.
+    Vec4f sampleLightsWavefront(const LightPick* lights, uint32_t num, const Vertex& vertex, const Fragment& frag,
+                                const MaterialSample& mat_sample, uint32_t max_material_splits, Sampler& sampler) const {
+        const Vec4f p           = frag.p;
+        const Vec4f gn          = mat_sample.super.geo_n;
+        const bool  translucent = mat_sample.isTranslucent();
+
+        struct Record {
+            SampleTo sample;
+            uint32_t light;
+            float    pick_pdf;
+        };
+        std::vector<Record> records;
+        for (uint32_t i = 0; i < num; ++i) {
+            const ZygpuLight& light = scene.s.lights[lights[i].offset];
+            const Trafo       trafo = scene.propTrafo(light.prop);
+            SampleTo          samples[64];
+            const uint32_t    n = scene.lightSampleTo(light, p, gn, trafo, translucent, vertex.light_split_threshold, sampler, samples);
+            for (uint32_t k = 0; k < n; ++k) records.push_back({samples[k], lights[i].offset, lights[i].pdf});
+        }
+
+        // the device adds the records in order (with one sample per pick this is the reference's summation order too)
+        Vec4f result = splat(0.f);
+        for (const Record& r : records) {
+            const ZygpuLight& light = scene.s.lights[r.light];
+            const Trafo       trafo = scene.propTrafo(light.prop);
+
+            const Ray shadow = Scene::shadowRay(frag.offsetP(r.sample.wi), r.sample);
+            if (!scene.visibility(shadow)) continue;
+
+            (void)sampler.sample1D();  // Light.evaluateTo
+            const ZygpuMaterial& lm       = scene.propMaterial(light.prop, light.part);
+            const Vec4f          radiance = scene.materialRadiance(lm, r.sample.wi, trafo, light.prop, false);
+
+            const bxdf::Result bxdf_result = mat_sample.evaluate(r.sample.wi, max_material_splits, false);
+
+            const float light_pdf = r.sample.pdf() * r.pick_pdf;
+            const float weight    = predividedPowerHeuristic(light_pdf, bxdf_result.pdf);
+
+            result = result + splat(weight) * radiance * bxdf_result.reflection;
         }
         return result;
     }
@@ -1698,6 +1748,27 @@ void zo_render(const ZygpuScene* scene, const ZygpuView* view, const ZoMesh* mes
         }
     }
 }
+
+// Tree.randomLight / Tree.pdf (light_tree.zig:346-517) over the scene's light tree, for the host-side tests of the builder:
+// picks[2 * i] = light id, picks[2 * i + 1] = pdf. Returns the number of picks.
+uint32_t zo_light_tree_random(const ZygpuScene* scene, const ZygpuView* view, const float p[3], const float n[3], int total_sphere,
+                              float random, float split_threshold, float* picks) {
+    const zo::Scene sc(*scene, *view, nullptr);
+    zo::LightPick   buffer[64];
+    const uint32_t  num = sc.randomLight({{p[0], p[1], p[2], 0.f}}, {{n[0], n[1], n[2], 0.f}}, 0 != total_sphere, random, split_threshold, buffer);
+    for (uint32_t i = 0; i < num; ++i) {
+        picks[2 * i]     = float(buffer[i].offset);
+        picks[2 * i + 1] = buffer[i].pdf;
+    }
+    return num;
+}
+float zo_light_tree_pdf(const ZygpuScene* scene, const ZygpuView* view, const float p[3], const float n[3], int total_sphere,
+                        float split_threshold, uint32_t light) {
+    const zo::Scene sc(*scene, *view, nullptr);
+    return sc.lightTreePdf({{p[0], p[1], p[2], 0.f}}, {{n[0], n[1], n[2], 0.f}}, 0 != total_sphere, split_threshold, light);
+}
+
+void zo_set_wavefront_light_order(int on) { zo::g_wavefront_light_order = 0 != on; }
 
 // Opaque.resolveTonemap with the Linear tonemapper, buffer_opaque.zig:73-79, tonemapper.zig:36-39, aces.zig:19-27
 void zo_resolve(const ZygpuView* view, const float* film_pixels, uint32_t num_pixels, float* rgba) {

@@ -63,6 +63,15 @@ typedef struct ZoMesh {
 /* `meshes` is indexed by ZygpuProp.mesh (NULL when the scene has none). */
 void zo_render(const struct ZygpuScene* scene, const struct ZygpuView* view, const ZoMesh* meshes, uint32_t iteration,
                uint32_t num_samples, int per_sample_iterations, float* film, uint32_t threads);
+/* 0 (default): sampler draws in the reference's order. 1: the draws of PathtracerMIS.sampleLights regrouped the way the
+ * device takes them (all light samples of a vertex, then one draw per visible sample); identical when a vertex takes one
+ * light sample. */
+void zo_set_wavefront_light_order(int on);
+/* Tree.randomLight / Tree.pdf (light_tree.zig:346-517) over the compiled scene's light tree. picks = (light id, pdf) pairs. */
+uint32_t zo_light_tree_random(const struct ZygpuScene* scene, const struct ZygpuView* view, const float p[3], const float n[3],
+                              int total_sphere, float random, float split_threshold, float* picks);
+float    zo_light_tree_pdf(const struct ZygpuScene* scene, const struct ZygpuView* view, const float p[3], const float n[3],
+                           int total_sphere, float split_threshold, uint32_t light);
 /* Opaque.resolveTonemap, Linear tonemapper. */
 void zo_resolve(const struct ZygpuView* view, const float* film, uint32_t num_pixels, float* rgba);
 

@@ -96,6 +96,12 @@ def _bind_render(lib):
     lib.zo_ggx_micro_directional_albedo.restype = C.c_float
     lib.zo_ggx_f_s_ss.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, u32]
     lib.zo_ggx_f_s_ss.restype = C.c_float
+    lib.zo_set_wavefront_light_order.argtypes = [C.c_int]
+    lib.zo_set_wavefront_light_order.restype = None
+    lib.zo_light_tree_random.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, vp]
+    lib.zo_light_tree_random.restype = u32
+    lib.zo_light_tree_pdf.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, u32]
+    lib.zo_light_tree_pdf.restype = C.c_float
     lib.zo_sobol_stream.argtypes = [u32, u32, u32, u32, vp]
     lib.zo_sobol_stream.restype = None
     lib.zo_sobol_directions.argtypes = [vp]
@@ -128,9 +134,11 @@ def mesh_table(num_meshes):
 
 
 def render(scene, view, width, height, iteration, num_samples, per_sample_iterations=True, threads=0, film=None,
-           num_meshes=0):
-    """zo_render over the flattened scene (pointers from zyg_b200.su.compile_scene). Returns the film (H, W, 4)."""
+           num_meshes=0, wavefront_light_order=False):
+    """zo_render over the flattened scene (pointers from zyg_b200.su.compile_scene). Returns the film (H, W, 4).
+    wavefront_light_order: take the sampler draws of sampleLights in the device's order (see zyg_oracle.h)."""
     lib = _bind_render(load())
+    lib.zo_set_wavefront_light_order(1 if wavefront_light_order else 0)
     if film is None:
         film = np.zeros((height, width, 4), np.float32)
     table = mesh_table(num_meshes)
@@ -151,6 +159,21 @@ def ggx_micro_directional_albedo(alpha, n_dot_wo, num_samples=1024):
 
 def ggx_f_s_ss(alpha, f0, ior_t, n_dot_wo, num_samples=1024):
     return _bind_render(load()).zo_ggx_f_s_ss(alpha, f0, ior_t, n_dot_wo, num_samples)
+
+
+def light_tree_random(scene, view, p, n, random, split_threshold, total_sphere=False):
+    """Tree.randomLight: list of (light id, pdf)."""
+    lib = _bind_render(load())
+    p, n = np.asarray(p, np.float32), np.asarray(n, np.float32)
+    picks = np.zeros(128, np.float32)
+    num = lib.zo_light_tree_random(scene, view, _p(p), _p(n), int(total_sphere), random, split_threshold, _p(picks))
+    return [(int(picks[2 * i]), float(picks[2 * i + 1])) for i in range(num)]
+
+
+def light_tree_pdf(scene, view, p, n, split_threshold, light, total_sphere=False):
+    lib = _bind_render(load())
+    p, n = np.asarray(p, np.float32), np.asarray(n, np.float32)
+    return float(lib.zo_light_tree_pdf(scene, view, _p(p), _p(n), int(total_sphere), split_threshold, light))
 
 
 def sobol_stream(sample, seed, n, pad_every=0):

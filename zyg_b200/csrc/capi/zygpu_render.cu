@@ -155,8 +155,13 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     // shadow records one path vertex can need: every light the tree may return times its sample count
     // (Tree.potentialMaxLights, light_tree.zig:331-344), capped like the reference's buffers (64 picks x 64 samples)
     uint64_t potential = 0;
-    for (uint32_t l = 0; l < scene->num_lights; ++l) potential += std::max(1u, scene->lights[l].num_samples);
-    r.max_light_samples = uint32_t(std::min<uint64_t>(std::max<uint64_t>(potential, 1), 64u * 64u));
+    uint32_t most      = 1;
+    for (uint32_t l = 0; l < scene->num_lights; ++l) {
+        potential += std::max(1u, scene->lights[l].num_samples);
+        most = std::max(most, scene->lights[l].num_samples);
+    }
+    // the tree returns at most Tree.MaxLights = 64 picks (light_tree.zig:249), each with up to `most` samples
+    r.max_light_samples = uint32_t(std::min<uint64_t>(std::max<uint64_t>(potential, 1), 64ull * std::min(most, 64u)));
 
     // Glass splits a path into its reflected and refracted branch (glass_sample.zig:256-269, 350-395): such scenes run with
     // Pool.NumVertices vertex records per camera sample and one shade round per record
@@ -225,7 +230,9 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
     const uint64_t   padded = uint64_t(pw) * ph;
     if (padded > 0xFFFFFFFFull) return fail("zygpu_render: resolution too large");
 
-    const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(num_samples, targetPathsPerPass() / padded)));
+    // a pass holds at most 64 Mi shadow records (3 GiB): scenes whose vertices can sample many lights trace fewer paths per pass
+    const uint64_t target   = std::min<uint64_t>(targetPathsPerPass(), std::max<uint64_t>(padded, (64ull << 20) / r.max_light_samples));
+    const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(num_samples, target / padded)));
     const uint64_t capacity = padded * per_pass;
     if (capacity > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
     const uint32_t lanes = r.can_split ? 4 : 1;

@@ -1,5 +1,7 @@
 #include "scene_model.hpp"
 
+#include "light_tree_builder.hpp"
+
 #include "bvh_builder.hpp"
 #include "mesh_handle.hpp"
 
@@ -592,8 +594,7 @@ void SceneModel::buildPropTree(const std::vector<uint32_t>& indices, std::vector
     }
 }
 
-// LightTreeBuilder.build, light_tree_builder.zig:281-376. Only the degenerate tree over at most one finite
-// light is produced so far (one leaf holding that light); scenes with more lights are rejected at compile.
+// LightTreeBuilder.build, light_tree_builder.zig:281-376
 bool SceneModel::buildLightTree(std::string& error) {
     const uint32_t num_lights = uint32_t(lights_.size());
     light_mapping_.assign(num_lights, 0);
@@ -614,45 +615,48 @@ bool SceneModel::buildLightTree(std::string& error) {
         light_orders_[light_mapping_[i]] = order++;
         infinite_total_power += light_aabbs_[light_mapping_[i]].min[3];
     }
-    const uint32_t num_finite = num_lights - num_infinite;
-    if (num_finite > 1 || num_infinite > 1) {
-        error = "light tree over more than one finite / infinite light is not implemented yet";
+    if (num_infinite > 1) {
+        error = "more than one infinite light (Tree.infinite_light_distribution) is not implemented yet";
         return false;
     }
 
     ZygpuLightTree& t     = flat_.light_tree;
     t                     = ZygpuLightTree{};
     t.infinite_end        = order;
-    t.max_split_depth     = 10;  // Tree.MaxSplitDepth
     t.num_lights          = num_lights;
     t.num_infinite_lights = num_infinite;
 
-    float finite_power = 0.f;
-    if (1 == num_finite) {
-        const uint32_t   l   = light_mapping_[num_infinite];
-        const ZygpuAabb& box = light_aabbs_[l];
-        light_orders_[l]     = order++;
-        finite_power         = box.min[3];
-
-        ZygpuLightNode node{};
-        node.power      = finite_power;
-        node.variance   = 0.f;
-        node.meta       = (0u << 2) | (lights_[l].two_sided ? 2u : 0u);  // leaf, children_or_light = 0 (offset into light_mapping)
-        node.num_lights = 1;
-        // a single-light leaf never reads center / cone (light_tree.zig:100-104, 155-159)
-        light_nodes_.push_back(node);
-        light_node_middles_.push_back(0);
-        t.bounds = box;
-        // countPotentialLights over a lone leaf: split_lights[0] = {1, 0} -> max_split_depth = 0
-        t.max_split_depth = 0;
-        // children_or_light indexes light_mapping, which lists infinite lights first
-        light_nodes_[0].meta = (num_infinite << 2) | (lights_[l].two_sided ? 2u : 0u);
+    // what the builder reads of a light: Scene.lightAabb / lightCone / lightPower / lightTwoSided, scene.zig:650-664
+    std::vector<AABB>    aabbs(num_lights);
+    std::vector<Vec4f>   cones(num_lights);
+    std::vector<float>   powers(num_lights);
+    std::vector<uint8_t> two_sided(num_lights);
+    for (uint32_t l = 0; l < num_lights; ++l) {
+        const ZygpuAabb& b = light_aabbs_[l];
+        aabbs[l]           = {{{{b.min[0], b.min[1], b.min[2], b.min[3]}}, {{b.max[0], b.max[1], b.max[2], b.max[3]}}}};
+        cones[l]           = {{light_cones_[l * 4], light_cones_[l * 4 + 1], light_cones_[l * 4 + 2], light_cones_[l * 4 + 3]}};
+        powers[l]          = b.min[3];
+        two_sided[l]       = lights_[l].two_sided ? 1 : 0;
     }
-    t.num_nodes = uint32_t(light_nodes_.size());
+    const LightSet set{aabbs.data(), cones.data(), powers.data(), two_sided.data(), false, false};
 
-    const float p0 = infinite_total_power;
-    const float p1 = finite_power;
-    const float pt = p0 + p1;
+    LightTreeResult tree;
+    zyg::buildLightTree(set, light_mapping_, num_infinite, order, light_orders_, tree);
+    light_nodes_        = std::move(tree.nodes);
+    light_node_middles_ = std::move(tree.node_middles);
+    t.max_split_depth   = tree.max_split_depth;
+    t.num_nodes         = uint32_t(light_nodes_.size());
+    if (t.num_nodes > 0) {
+        for (int k = 0; k < 4; ++k) {
+            t.bounds.min[k] = tree.bounds.b[0][k];
+            t.bounds.max[k] = tree.bounds.b[1][k];
+        }
+    }
+
+    const uint32_t num_finite = num_lights - num_infinite;
+    const float    p0         = infinite_total_power;
+    const float    p1         = 0 == num_finite ? 0.f : tree.root_power;
+    const float    pt         = p0 + p1;
     t.infinite_weight = (0 == num_lights || 0.f == pt) ? 0.f : p0 / pt;
     t.infinite_guard  = 0 == num_finite ? (0 == num_infinite ? 0.f : 1.1f) : t.infinite_weight;
 

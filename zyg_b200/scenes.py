@@ -268,6 +268,49 @@ def sphere_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, q
     return 1
 
 
+def many_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=64, seed=5, filter_name=None,
+                      split_threshold=0.5, unoccluding=True):
+    """A closed room (6 x 3 x 6) with `num_lights` small Rectangle lights of random position, orientation, size, colour
+    and power (a quarter of them two-sided), a few diffuse and glossy cubes: the light tree has many nodes, the adaptive
+    split returns several picks near the lights and one far away."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(70.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.4, -2.8)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth},
+                                                 "light_sampling": {"split_threshold": split_threshold}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    wall = su.material_create({"rendering": {"Substitute": {"color": [0.7, 0.7, 0.7], "roughness": 1.0}}})
+    glossy = su.material_create({"rendering": {"Substitute": {"color": [0.8, 0.6, 0.3], "roughness": 0.35, "metallic": 1.0}}})
+    for position, scale, rotation in [((0, 0, 0), (6, 6, 1), (90, 0, 0)), ((0, 3, 0), (6, 6, 1), (-90, 0, 0)),
+                                      ((0, 1.5, 3), (6, 3, 1), (0, 180, 0)), ((0, 1.5, -3), (6, 3, 1), (0, 0, 0)),
+                                      ((-3, 1.5, 0), (6, 3, 1), (0, -90, 0)), ((3, 1.5, 0), (6, 3, 1), (0, 90, 0))]:
+        prop = su.prop_create(su.RECTANGLE, [wall])
+        su.prop_set_transformation(prop, su.transformation(tuple(map(float, position)), tuple(map(float, scale)), tuple(map(float, rotation))))
+    for k, (x, z) in enumerate([(-1.2, 0.8), (0.2, 1.6), (1.4, 0.2)]):
+        cube = su.prop_create(su.CUBE, [glossy if 1 == k else wall])
+        su.prop_set_transformation(cube, su.transformation((x, 0.4, z), (0.8, 0.8, 0.8), (0.0, 25.0 * k, 0.0)))
+
+    rng = PCG32(0, np.array([seed], np.uint64))
+    for i in range(num_lights):
+        r = [float(rng.float()[0]) for _ in range(10)]
+        colour = [0.3 + 0.7 * r[0], 0.3 + 0.7 * r[1], 0.3 + 0.7 * r[2]]
+        params = {"emittance": {"spectrum": colour, "value": 3.0 + 27.0 * r[3] * r[3]}}
+        if 0 == i % 4:
+            params["two_sided"] = True
+        material = su.material_create({"rendering": {"Light": params}})
+        lamp = su.prop_create(su.RECTANGLE, [material], unoccluding=unoccluding)
+        size = 0.1 + 0.3 * r[4]
+        su.prop_set_transformation(lamp, su.transformation((-2.7 + 5.4 * r[5], 0.3 + 2.5 * r[6], -2.7 + 5.4 * r[7]), (size, size, 1.0),
+                                                           (-90.0 + 120.0 * (r[8] - 0.5), 360.0 * r[9], 0.0)))
+        su.light_create(lamp)
+    return camera
+
+
 def instanced_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, grid=(32, 32), prototypes=4,
                     quads=(100, 50), seed=3):
     """Config-3 style scene through the C API: `prototypes` displaced-sphere meshes (seeds 1..), instanced
