@@ -512,6 +512,70 @@ bool intersectP(const Ray& ray, const Trafo& trafo) {
 
 }  // namespace sphere
 
+namespace distant {  // shape/distant.zig:22-146
+
+float solidAngle(float radius) { return (2.f * kPi) * (1.f - std::sqrt(1.f / (radius * radius + 1.f))); }  // :143-145
+
+bool intersect(const Ray& ray, const Trafo& trafo, Intersection& isec) {  // :22-54
+    const float radius = trafo.scaleX();
+    const Vec4f n      = trafo.r[2];
+    const float b      = dot3(n, ray.direction);
+    if (b > 0.f || ray.max_t < RayMaxT || radius <= 0.f) return false;
+
+    const float det = (b * b) - dot3(n, n) + (radius * radius);
+    if (det >= 0.f) {
+        const Vec4f k  = ray.direction - n;
+        const Vec4f sk = k / splat(radius);
+        isec.u         = dot3(trafo.r[0], sk);
+        isec.v         = dot3(trafo.r[1], sk);
+        isec.primitive = 0;
+        isec.t         = RayMaxT;
+        isec.trafo     = trafo;
+        return true;
+    }
+    return false;
+}
+
+void fragment(const Ray& ray, Fragment& frag) {  // :56-76
+    frag.p       = splat(RayMaxT) * ray.direction;
+    const Vec4f n = frag.isec.trafo.r[2];
+    frag.geo_n   = n;
+    frag.t       = frag.isec.trafo.r[0];
+    frag.b       = frag.isec.trafo.r[1];
+    frag.n       = n;
+    frag.uvw     = {{(frag.isec.u + 1.f) * 0.5f, (frag.isec.v + 1.f) * 0.5f, 0.f, 0.f}};
+    frag.part    = 0;
+}
+
+uint32_t sampleTo(Vec4f n, const Trafo& trafo, bool total_sphere, Sampler& sampler, SampleTo* buffer) {  // :78-107
+    const float radius = trafo.scaleX();
+    if (radius <= 0.f) return 0;
+
+    const Vec2f r2 = sampler.sample2D();
+    float       xy[2];
+    diskConcentric(r2.v, xy);
+
+    const Vec4f ls = {{xy[0], xy[1], 0.f, 0.f}};
+    // Mat3x3.transformVector, matrix3x3.zig:113-127 (the rotation rows carry the scale in lane 3, which is not read)
+    Vec4f tv = splat(ls[0]) * trafo.r[0];
+    tv       = mulAdd(splat(ls[1]), trafo.r[1], tv);
+    tv       = mulAdd(splat(ls[2]), trafo.r[2], tv);
+    const Vec4f ws  = splat(radius) * tv;
+    const Vec4f dir = normalize3(ws - trafo.r[2]);
+
+    if (dot3(dir, n) <= 0.f && !total_sphere) return 0;
+
+    const float solid_angle = solidAngle(radius);
+    const Vec4f p           = splat(RayMaxT) * dir;
+    buffer[0].p             = {{p[0], p[1], p[2], 1.f / solid_angle}};
+    buffer[0].n             = trafo.r[2];
+    buffer[0].wi            = dir;
+    buffer[0].uvw           = splat(0.f);
+    return 1;
+}
+
+}  // namespace distant
+
 namespace mesh {
 
 // Mesh.fragment, triangle_mesh.zig:310-335 + Data.interpolateData / normal, triangle_data.zig:106-149
@@ -624,6 +688,7 @@ struct Scene {
         switch (shape) {
             case ZYG_SHAPE_RECTANGLE: return scale[0] * scale[1];
             case ZYG_SHAPE_SPHERE: return (4.f * kPi) * pow2(0.5f * scale[0]);
+            case ZYG_SHAPE_DISTANT: return distant::solidAngle(scale[0]);  // "the solid angle, not the area", shape.zig:146-148
             default: return 0.f;
         }
     }
@@ -645,6 +710,7 @@ struct Scene {
             case ZYG_SHAPE_CUBE: return cube::intersect(ray, trafo, isec);
             case ZYG_SHAPE_RECTANGLE: return rectangle::intersect(ray, trafo, isec);
             case ZYG_SHAPE_SPHERE: return sphere::intersect(ray, trafo, isec);
+            case ZYG_SHAPE_DISTANT: return distant::intersect(ray, trafo, isec);
             default: return false;
         }
     }
@@ -663,6 +729,7 @@ struct Scene {
             case ZYG_SHAPE_CUBE: cube::fragment(ray, frag); break;
             case ZYG_SHAPE_RECTANGLE: rectangle::fragment(ray, frag); break;
             case ZYG_SHAPE_SPHERE: sphere::fragment(ray, frag); break;
+            case ZYG_SHAPE_DISTANT: distant::fragment(ray, frag); break;
             default: break;
         }
     }
@@ -1104,12 +1171,19 @@ struct Scene {
         switch (s.props[l.prop].shape) {
             case ZYG_SHAPE_RECTANGLE:
                 return rectangle::sampleTo(p, n, trafo, 0 != l.two_sided, total_sphere, num_samples, sampler, buffer);
+            case ZYG_SHAPE_DISTANT: return distant::sampleTo(n, trafo, total_sphere, sampler, buffer);
             default: return 0;
         }
     }
 
-    // Shape.shadowRay, shape.zig:401-416 (finite shapes)
-    static Ray shadowRay(Vec4f origin, const SampleTo& sample) {
+    bool lightFinite(const ZygpuLight& l) const {  // Shape.finite, shape.zig:94-99
+        const uint32_t shape = s.props[l.prop].shape;
+        return !(ZYG_SHAPE_CANOPY == shape || ZYG_SHAPE_DISTANT == shape || ZYG_SHAPE_DOME == shape);
+    }
+
+    // Shape.shadowRay, shape.zig:401-416
+    static Ray shadowRay(Vec4f origin, const SampleTo& sample, bool finite = true) {
+        if (!finite) return Ray::init(origin, sample.wi, 0.f, RayMaxT);
         const Vec4f light_pos   = offsetRay(sample.p, sample.n);
         const Vec4f shadow_axis = light_pos - origin;
         const float shadow_len  = length3(shadow_axis);
@@ -1157,6 +1231,7 @@ struct Worker {
             case ZYG_SHAPE_RECTANGLE:
                 sample_pdf = rectangle::pdf(vertex.origin, frag, scene.lightNumSamples(l, vertex.light_split_threshold));
                 break;
+            case ZYG_SHAPE_DISTANT: sample_pdf = 1.f / distant::solidAngle(frag.isec.trafo.scaleX()); break;  // distant.zig:139-141
             default: break;
         }
         return powerHeuristic(vertex.bxdf_pdf, sample_pdf * select_pdf);
@@ -1246,7 +1321,16 @@ struct Worker {
 
         result = result + emission(vertex, sampler);
 
-        // infinite_props: none of the shapes in scope (Canopy / Distant come with the sky configs)
+        if (RayMaxT == vertex.ray.max_t) {  // :313-338
+            for (uint32_t i = 0; i < scene.s.num_infinite_props; ++i) {
+                const uint32_t prop = scene.s.infinite_props[i];
+                Fragment       light_frag;
+                if (!scene.propIntersect(prop, vertex.ray, vertex.probe_depth.surface, light_frag.isec)) continue;
+                light_frag.prop = prop;
+                scene.shapeFragment(scene.s.props[prop].shape, scene.s.props[prop].mesh, vertex.ray, light_frag);
+                result = result + evaluateRadiance(vertex, light_frag, sampler);
+            }
+        }
         return result;
     }
 
@@ -1304,7 +1388,7 @@ struct Worker {
         for (uint32_t i = 0; i < num; ++i) {
             const SampleTo& light_sample = samples[i];
 
-            const Ray shadow = Scene::shadowRay(frag.offsetP(light_sample.wi), light_sample);
+            const Ray shadow = Scene::shadowRay(frag.offsetP(light_sample.wi), light_sample, scene.lightFinite(light));
             if (!scene.visibility(shadow)) continue;
 
             // Light.evaluateTo, light.zig:119-132
@@ -1373,7 +1457,7 @@ struct Worker {
             const ZygpuLight& light = scene.s.lights[r.light];
             const Trafo       trafo = scene.propTrafo(light.prop);
 
-            const Ray shadow = Scene::shadowRay(frag.offsetP(r.sample.wi), r.sample);
+            const Ray shadow = Scene::shadowRay(frag.offsetP(r.sample.wi), r.sample, scene.lightFinite(light));
             if (!scene.visibility(shadow)) continue;
 
             (void)sampler.sample1D();  // Light.evaluateTo

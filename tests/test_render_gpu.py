@@ -234,3 +234,25 @@ def test_many_lights_match_oracle(engine, num_lights, split_threshold):
     assert np.median(rel) < 1e-4
     assert (rel > 1e-2).mean() < 1e-2
     assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 1e-4
+
+
+def test_distant_light_matches_oracle(engine):
+    """A Distant light (distant.zig:22-146) next to a Rectangle light: the infinite-light branch of the light tree
+    (light_tree.zig:353-371), shadow rays that run to RayMaxT (shape.zig:401-403), emission met on escape through
+    Scene.infinite_props (pathtracer_mis.zig:313-338) weighted with Distant.pdf."""
+    w, spp = 96, 16
+    n = scenes.sphere_scene(w, w, spp=spp, quads=(100, 50), sun=600.0)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n, wavefront_light_order=True)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6 and (rel > 1e-3).mean() < 5e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 1e-4
+    # the sun matters: the same scene without it is darker
+    su.release()
+    scenes.sphere_scene(w, w, spp=spp, quads=(100, 50))
+    scene, view = su.compile_scene()
+    dark = oracle.render(scene, view, w, w, 0, 4, num_meshes=n)
+    assert ref[..., :3].sum() / ref[..., 3].sum() > 1.2 * dark[..., :3].sum() / dark[..., 3].sum()

@@ -138,6 +138,9 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     if (0 != uploadArray(r, scene->unoccluding_bvh.indices, scene->unoccluding_bvh.num_indices, &d.unocc_indices)) return -1;
     d.num_unocc_nodes = scene->unoccluding_bvh.num_nodes;
 
+    if (0 != uploadArray(r, scene->infinite_props, scene->num_infinite_props, &d.infinite_props)) return -1;
+    d.num_infinite_props = scene->num_infinite_props;
+
     // meshes: uploaded once per zyg_mesh, referenced through a per-scene table
     std::vector<zygpu::MeshDevice>  mesh_views(scene->num_meshes);
     std::vector<zygpu::MeshShading> mesh_shading(scene->num_meshes);

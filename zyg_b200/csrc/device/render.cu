@@ -201,6 +201,7 @@ __device__ __forceinline__ float shapeArea(uint32_t shape, V3 scale) {  // shape
     switch (shape) {
         case ZYG_SHAPE_RECTANGLE: return scale.x * scale.y;
         case ZYG_SHAPE_SPHERE: return (4.f * kPi) * ((0.5f * scale.x) * (0.5f * scale.x));
+        case ZYG_SHAPE_DISTANT: return distantSolidAngle(scale.x);
         default: return 0.f;
     }
 }
@@ -387,6 +388,11 @@ __device__ __forceinline__ RayT loadTraceRay(const PathState& st, uint32_t item,
         const float4 o           = st.sh_o[item];
         const float4 p           = st.sh_p[item];
         const V3     origin      = {o.x, o.y, o.z};
+        depth_surface            = 0;
+        if (0 != (__float_as_uint(p.w) & 0x80000000u)) {  // Shape.shadowRay for Canopy / Distant / Dome
+            const float4 wi = st.sh_wi[item];
+            return makeRay(origin, {wi.x, wi.y, wi.z}, 0.f, kRayMaxT);
+        }
         const V3     shadow_axis = sub3({p.x, p.y, p.z}, origin);
         const float  shadow_len  = length3(shadow_axis);
         depth_surface            = 0;
@@ -704,6 +710,7 @@ __device__ __forceinline__ void shapeFragment(const SceneDevice& sc, uint32_t pr
         case ZYG_SHAPE_CUBE: cubeFragment(ray, isec, frag); break;
         case ZYG_SHAPE_RECTANGLE: rectangleFragment(ray, isec, frag); break;
         case ZYG_SHAPE_SPHERE: sphereFragment(ray, isec, frag); break;
+        case ZYG_SHAPE_DISTANT: distantFragment(ray, isec, frag); break;
         case ZYG_SHAPE_TRIANGLE_MESH: meshFragment(sc.mesh_shading[sc.props[prop].mesh], isec, frag); break;
         default: break;
     }
@@ -1105,6 +1112,8 @@ __device__ float sceneLightPdf(const SceneDevice& sc, const VertexD& vertex, con
         SphQuadD    squad;
         squad.init(frag.trafo.scale, frag.trafo.worldToFramePoint(vertex.origin));
         sample_pdf = nsf * squad.pdf(frag.trafo.scale);
+    } else if (ZYG_SHAPE_DISTANT == sc.props[l.prop].shape) {  // Distant.pdf, distant.zig:139-141
+        sample_pdf = __fdiv_rn(1.f, distantSolidAngle(frag.trafo.scale.x));
     }
     return powerHeuristic(vertex.bxdf_pdf, sample_pdf * select_pdf);
 }
@@ -1452,6 +1461,20 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                 vertex.light_split_threshold = splitThreshold(view.split_threshold, lv.vertex_depth);
                 if (hit) this_light = evaluateRadiance(sc, vertex, frag, sampler);
                 this_light = add3(this_light, unoccludingEmission(sc, vertex, sampler));
+                if (kRayMaxT == vertex.ray.tmax) {  // the ray left the scene: infinite props, pathtracer_mis.zig:313-338
+                    for (uint32_t k = 0; k < sc.num_infinite_props; ++k) {
+                        const uint32_t  entity = __ldg(sc.infinite_props + k);
+                        const ZygpuProp iprop  = sc.props[entity];
+                        if (!propVisible(iprop.flags, vertex.probe_depth) || !aabbIntersect(sc.aabbs, entity, vertex.ray)) continue;
+                        FragD light_frag;
+                        light_frag.prop  = entity;
+                        light_frag.trafo = loadTrafo(sc.trafos, entity);
+                        HitD isec;
+                        if (ZYG_SHAPE_DISTANT != iprop.shape || !distantIntersect(vertex.ray, light_frag.trafo, isec)) continue;
+                        distantFragment(vertex.ray, isec, light_frag);
+                        this_light = add3(this_light, evaluateRadiance(sc, vertex, light_frag, sampler));
+                    }
+                }
             }
 
             const V3 split_throughput = scale3(lv.split_weight, lv.throughput);
@@ -1499,7 +1522,31 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                     lightTreeRandomLight(sc, p, n, translucent, select, vertex.light_split_threshold, [&](LightPickD pick) {
                         const ZygpuLight light = sc.lights[pick.offset];
                         const TrafoD     trafo = loadTrafo(sc.trafos, light.prop);
-                        if (ZYG_SHAPE_RECTANGLE != sc.props[light.prop].shape) return;
+                        const uint32_t   shape = sc.props[light.prop].shape;
+                        if (ZYG_SHAPE_DISTANT == shape) {  // Distant.sampleTo, distant.zig:78-107
+                            const float radius = trafo.scale.x;
+                            if (radius <= 0.f) return;
+                            float u0, u1;
+                            sampler.sample2D(u0, u1);
+                            float lx, ly;
+                            diskConcentric(u0, u1, lx, ly);
+                            const V3 ws  = scale3(radius, trafo.transformVector({lx, ly, 0.f}));
+                            const V3 dir = normalize3(sub3(ws, trafo.r2));
+                            if (dot3(dir, n) <= 0.f && !translucent) return;
+                            if (num_records < st.shadow_stride) {
+                                const size_t rec    = size_t(slot) * st.shadow_stride + num_records;
+                                const V3     origin = frag.offsetP(dir);
+                                const float  pdf    = __fdiv_rn(1.f, distantSolidAngle(radius));
+                                st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, pdf * pick.pdf);
+                                st.sh_p[rec]  = make_float4(0.f, 0.f, 0.f, __uint_as_float(pick.offset | 0x80000000u));
+                                st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                                num_records += 1;
+                            } else {
+                                st.counters[3] = 1;
+                            }
+                            return;
+                        }
+                        if (ZYG_SHAPE_RECTANGLE != shape) return;
 
                         // Rectangle.sampleTo, rectangle.zig:305-357
                         const uint32_t ns  = lightNumSamples(light, vertex.light_split_threshold);
@@ -1564,10 +1611,8 @@ __global__ void __launch_bounds__(kBlock) shadowKernel(SceneDevice sc, PathState
         const float4 o = st.sh_o[rec];
         const float4 p = st.sh_p[rec];
 
-        const V3    origin      = {o.x, o.y, o.z};
-        const V3    shadow_axis = sub3({p.x, p.y, p.z}, origin);
-        const float shadow_len  = length3(shadow_axis);
-        const RayT  ray         = makeRay(origin, divs3(shadow_axis, shadow_len), 0.f, shadow_len);
+        uint32_t   unused;
+        const RayT ray = loadTraceRay<true>(st, uint32_t(rec), unused);
 
         st.sh_wi[rec].w = sceneVisibility(sc, ray) ? 1.f : 0.f;
         traced += 1;
@@ -1637,7 +1682,7 @@ __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeB
 
                 // Light.evaluateTo, light.zig:119-132
                 (void)sampler.sample1D();
-                const uint32_t      light_id = __float_as_uint(p4.w);
+                const uint32_t      light_id = __float_as_uint(p4.w) & 0x7FFFFFFFu;
                 const ZygpuLight    light    = sc.lights[light_id];
                 const TrafoD        ltrafo   = loadTrafo(sc.trafos, light.prop);
                 const ZygpuMaterial lm       = sc.materials[__ldg(sc.material_ids + sc.props[light.prop].parts_start + light.part)];

@@ -61,6 +61,9 @@ struct SceneDevice {
     const uint32_t* unocc_indices;
     uint32_t        num_unocc_nodes;
 
+    const uint32_t* infinite_props;  // Scene.infinite_props (Distant): met only by rays that leave the scene
+    uint32_t        num_infinite_props;
+
     const MeshDevice*  meshes;
     const MeshShading* mesh_shading;
 
@@ -87,7 +90,7 @@ struct PathState {
 
     // shadow-ray records, written by shade_a: path `slot` owns records [slot * shadow_stride, +sh_n[slot])
     float4*   sh_o;   // origin xyz | light pdf (sample pdf * pick pdf)
-    float4*   sh_p;   // offset light position xyz | light id
+    float4*   sh_p;   // offset light position xyz | light id (bit 31: infinite light, the ray runs along wi to RayMaxT)
     float4*   sh_wi;  // light_sample.wi xyz | visible (written by shadow)
     uint32_t* sh_n;   // per path: number of records
 

@@ -347,6 +347,38 @@ __device__ __forceinline__ void sphereFragment(const RayT& ray, const HitD& isec
     frag.v = theta * kPiInv;
 }
 
+// Distant, shape/distant.zig:22-76, 139-145
+__device__ __forceinline__ float distantSolidAngle(float radius) {
+    return (2.f * kPi) * (1.f - __fsqrt_rn(__fdiv_rn(1.f, radius * radius + 1.f)));
+}
+__device__ __forceinline__ bool distantIntersect(const RayT& ray, const TrafoD& trafo, HitD& isec) {
+    const float radius = trafo.scale.x;
+    const V3    n      = trafo.r2;
+    const float b      = dot3(n, ray.d);
+    if (b > 0.f || ray.tmax < kRayMaxT || radius <= 0.f) return false;
+
+    const float det = (b * b) - dot3(n, n) + (radius * radius);
+    if (det >= 0.f) {
+        const V3 sk    = divs3(sub3(ray.d, n), radius);
+        isec.u         = dot3(trafo.r0, sk);
+        isec.v         = dot3(trafo.r1, sk);
+        isec.primitive = 0;
+        isec.t         = kRayMaxT;
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void distantFragment(const RayT& ray, const HitD& isec, FragD& frag) {
+    frag.p     = scale3(kRayMaxT, ray.d);
+    frag.geo_n = frag.trafo.r2;
+    frag.t     = frag.trafo.r0;
+    frag.b     = frag.trafo.r1;
+    frag.n     = frag.trafo.r2;
+    frag.u     = (isec.u + 1.f) * 0.5f;
+    frag.v     = (isec.v + 1.f) * 0.5f;
+    frag.part  = 0;
+}
+
 // Mesh.fragment, triangle_mesh.zig:310-335 + Data.interpolateData / normal, triangle_data.zig:106-149
 __device__ __forceinline__ V3 decompressNormal(const uint16_t* normals, uint32_t i) {  // encoding.zig:91-108
     const uint32_t packed = __ldg(reinterpret_cast<const uint32_t*>(normals) + i);

@@ -754,6 +754,9 @@ bool SceneModel::compile(std::string& error) {
             case ZYG_SHAPE_SPHERE: extent = (4.f * kPi) * ((0.5f * scale[0]) * (0.5f * scale[0])); break;
             case ZYG_SHAPE_CUBE: extent = 2.f * (scale[0] * scale[1] + scale[0] * scale[2] + scale[1] * scale[2]); break;
             case ZYG_SHAPE_DISK: extent = kPi * ((0.5f * scale[0]) * (0.5f * scale[0])); break;
+            case ZYG_SHAPE_DISTANT:  // Distant.solidAngle, distant.zig:143-145
+                extent = (2.f * kPi) * (1.f - std::sqrt(1.f / (scale[0] * scale[0] + 1.f)));
+                break;
             default: break;
         }
 
@@ -765,6 +768,13 @@ bool SceneModel::compile(std::string& error) {
             power = splat(0.f);
         } else if (0.f == m.emission_normalize) {
             power = power * splat(extent);
+        }
+        if (!shapeFinite(p.shape) && !solid_nodes_.empty()) {
+            // Light.power, light.zig:65-75: an infinite light's power scales with the squared extent of the scene box
+            // (Scene.aabb = the root of the solid prop tree, scene.zig:173-175)
+            const ZygpuBvhNode& root   = solid_nodes_[0];
+            const Vec4f         box_extent = {{root.max[0] - root.min[0], root.max[1] - root.min[1], root.max[2] - root.min[2], 0.f}};
+            power                          = splat(dot3(box_extent, box_extent)) * power;
         }
         bb.b[0][3] = fmax_(power[0], fmax_(power[1], power[2]));  // hmax3
         light_aabbs_[l] = packAabb(bb);

@@ -232,7 +232,7 @@ def cornell_box(width=512, height=512, spp=64, max_depth=8, filter_name=None, un
 
 
 def sphere_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, quads=(1000, 500), metallic=0.0,
-                 roughness=0.6):
+                 roughness=0.6, sun=None):
     """The config-2 mesh (displaced sphere, 2 * quads[0] * quads[1] triangles) as a path-traced scene: the mesh sits
     on a diffuse floor inside a large open room lit by one Rectangle light. Returns the number of meshes."""
     from . import su
@@ -265,6 +265,12 @@ def sphere_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, q
     lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=True)
     su.prop_set_transformation(lamp, su.transformation((1.5, 3.0, -1.0), (1.5, 1.5, 1.0), (-90.0, 0.0, 0.0)))
     su.light_create(lamp)
+    if sun is not None:
+        # a Distant light (shape id 3): the prop's -z axis points at the sun, scale.x = tan of its angular radius
+        sun_material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": [1.0, 0.9, 0.75], "value": float(sun)}}}})
+        sun_prop = su.prop_create(su.DISTANT, [sun_material])
+        su.prop_set_transformation(sun_prop, su.transformation((0.0, 0.0, 0.0), (0.05, 0.05, 0.05), (55.0, -35.0, 0.0)))
+        su.light_create(sun_prop)
     return 1
 
 
