@@ -241,7 +241,7 @@ def test_distant_light_matches_oracle(engine):
     (light_tree.zig:353-371), shadow rays that run to RayMaxT (shape.zig:401-403), emission met on escape through
     Scene.infinite_props (pathtracer_mis.zig:313-338) weighted with Distant.pdf."""
     w, spp = 96, 16
-    n = scenes.sphere_scene(w, w, spp=spp, quads=(100, 50), sun=600.0)
+    n = scenes.sphere_scene(w, w, spp=spp, quads=(100, 50), sun=150.0)
     scene, view = su.compile_scene()
     ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n, wavefront_light_order=True)
     su.render_frame(0)

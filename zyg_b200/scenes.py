@@ -269,7 +269,7 @@ def sphere_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, q
         # a Distant light (shape id 3): the prop's -z axis points at the sun, scale.x = tan of its angular radius
         sun_material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": [1.0, 0.9, 0.75], "value": float(sun)}}}})
         sun_prop = su.prop_create(su.DISTANT, [sun_material])
-        su.prop_set_transformation(sun_prop, su.transformation((0.0, 0.0, 0.0), (0.05, 0.05, 0.05), (55.0, -35.0, 0.0)))
+        su.prop_set_transformation(sun_prop, su.transformation((0.0, 0.0, 0.0), (0.05, 0.05, 0.05), (-55.0, -35.0, 0.0)))
         su.light_create(sun_prop)
     return 1
 
