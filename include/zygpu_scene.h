@@ -120,7 +120,8 @@ typedef struct ZygpuLight {
     uint32_t light_class;
     uint32_t two_sided;
     uint32_t num_samples; /* ShapeSampler.num_samples (shape_sampler.zig:33) */
-    uint32_t pad[3];
+    uint32_t sampler;     /* Light.sampler: index into ZygpuScene.mesh_samplers for a triangle-mesh light, else ZYGPU_NULL */
+    uint32_t pad[2];
 } ZygpuLight;
 
 /* light_tree.Node (src/core/scene/light/light_tree.zig:25-37). 32 bytes. */
@@ -132,6 +133,23 @@ typedef struct ZygpuLightNode {
     uint32_t meta; /* bit0 has_children, bit1 two_sided, bits 2..31 children_or_light */
     uint32_t num_lights;
 } ZygpuLightNode;
+
+/* shape_sampler.MeshImpl (src/core/scene/shape/shape_sampler.zig:149-262) of one emissive mesh part with its
+ * PrimitiveTree (light_tree.zig:520-719): what Mesh.sampleTo / Mesh.pdf (triangle_mesh.zig:492-608, 662-703) read. */
+typedef struct ZygpuMeshSampler {
+    ZygpuAabb bounds; /* PrimitiveTree.bounds: box of the emitting triangles (object space), radius cached in max[3] */
+    uint32_t  num_triangles; /* triangles of the part */
+    uint32_t  num_nodes;
+    uint32_t  two_sided;
+    uint32_t  mesh; /* index into ZygpuScene.meshes */
+    const struct ZygpuLightNode* nodes;
+    const uint32_t* node_middles;
+    const uint32_t* light_orders;      /* per part triangle */
+    const uint32_t* light_mapping;     /* tree order -> part triangle */
+    const uint32_t* triangle_mapping;  /* part triangle -> BVH-order triangle (Part.triangle_mapping) */
+    const float*    triangle_pdfs;     /* Distribution1D.pdfI per part triangle (relative area) */
+    const uint32_t* primitive_mapping; /* BVH-order triangle -> index within its part (Mesh.primitive_mapping) */
+} ZygpuMeshSampler;
 
 typedef struct ZygpuLightTree {
     ZygpuAabb             bounds;
@@ -185,6 +203,10 @@ typedef struct ZygpuScene {
     const uint32_t* infinite_props;
 
     const struct zyg_mesh* const* meshes; /* compiled meshes referenced by ZygpuProp.mesh */
+
+    uint32_t                num_mesh_samplers;
+    const ZygpuMeshSampler* mesh_samplers; /* referenced by ZygpuLight.sampler */
+    const float*            mesh_part_areas; /* Part.area (object space) per ZygpuScene part entry (material_ids index), 0 for analytic shapes */
 
     /* ggx_integral.zig tables, concatenated: E_m[32*32], E_m_avg[32], E[16^3], E_avg[16*16], E_s[16^3]. */
     const float* ggx_luts;

@@ -657,6 +657,108 @@ void fragment(const ZoMesh& m, Fragment& frag) {
     frag.uvw = {{uv[0], uv[1], 0.f, 0.f}};
 }
 
+// triangle_mesh.zig:390-394
+inline Vec4f orthogonalize(Vec4f a, Vec4f b) { return normalize3(mulAdd(splat(-dot3(a, b)), a, b)); }
+
+// triangle.barycentricCoords, triangle.zig:82-100
+inline void barycentricCoords(Vec4f dir, Vec4f a, Vec4f b, Vec4f c, float uv[2]) {
+    const Vec4f e1      = b - a;
+    const Vec4f e2      = c - a;
+    const Vec4f tvec    = -a;
+    const Vec4f pvec    = cross3(dir, e2);
+    const Vec4f qvec    = cross3(tvec, e1);
+    const float e1_d_pv = dot3(e1, pvec);
+    const float tv_d_pv = dot3(tvec, pvec);
+    const float di_d_qv = dot3(dir, qvec);
+    const float inv_det = 1.f / e1_d_pv;
+    uv[0]               = tv_d_pv * inv_det;
+    uv[1]               = di_d_qv * inv_det;
+}
+
+struct SphericalSample {
+    Vec4f dir;
+    float uv[2];
+    float pdf;
+};
+
+inline float sphericalArea(Vec4f A, Vec4f B, Vec4f C, float& cos_alpha, float& alpha) {
+    const Vec4f BA = orthogonalize(A, B - A);
+    const Vec4f CA = orthogonalize(A, C - A);
+    const Vec4f AB = orthogonalize(B, A - B);
+    const Vec4f CB = orthogonalize(B, C - B);
+    const Vec4f BC = orthogonalize(C, B - C);
+    const Vec4f AC = orthogonalize(C, A - C);
+    cos_alpha         = clamp(dot3(BA, CA), -1.f, 1.f);
+    alpha             = std::acos(cos_alpha);
+    const float beta  = std::acos(clamp(dot3(AB, CB), -1.f, 1.f));
+    const float gamma = std::acos(clamp(dot3(BC, AC), -1.f, 1.f));
+    return alpha + beta + gamma - kPi;
+}
+
+// Stratified Sampling of Spherical Triangles, James Arvo. triangle_mesh.zig:402-462
+inline bool sampleSpherical(Vec4f pos, Vec4f pa, Vec4f pb, Vec4f pc, const float r2[2], SphericalSample& out) {
+    const Vec4f pap = pa - pos;
+    const Vec4f pbp = pb - pos;
+    const Vec4f pcp = pc - pos;
+
+    const Vec4f A = normalize3(pap);
+    const Vec4f B = normalize3(pbp);
+    const Vec4f C = normalize3(pcp);
+
+    float       cos_alpha, alpha;
+    const float sarea = sphericalArea(A, B, C, cos_alpha, alpha);
+    if (0.f == sarea) return false;
+
+    const float cos_c = clamp(dot3(A, B), -1.f, 1.f);
+
+    const float area_S      = r2[0] * sarea;
+    const float angle_delta = area_S - alpha;
+    const float p           = std::sin(angle_delta);
+    const float q           = std::cos(angle_delta);
+
+    const float sin_alpha = std::sqrt(1.f - cos_alpha * cos_alpha);
+    const float u         = q - cos_alpha;
+    const float v         = p + sin_alpha * cos_c;
+
+    const float s   = clamp(((v * q - u * p) * cos_alpha - v) / ((v * p + u * q) * sin_alpha), -1.f, 1.f);
+    const Vec4f C_s = splat(s) * A + splat(std::sqrt(1.f - s * s)) * orthogonalize(A, C);
+
+    const float cs_b = dot3(C_s, B);
+    const float z    = 1.f - r2[1] * (1.f - cs_b);
+    const Vec4f P    = splat(z) * B + splat(std::sqrt(1.f - z * z)) * orthogonalize(B, C_s);
+
+    out.dir = P;
+    barycentricCoords(P, pap, pbp, pcp, out.uv);
+    out.pdf = 1.f / sarea;
+    return true;
+}
+
+inline float pdfSpherical(Vec4f pos, Vec4f pa, Vec4f pb, Vec4f pc) {  // :464-487
+    float       cos_alpha, alpha;
+    const float sarea = sphericalArea(normalize3(pa - pos), normalize3(pb - pos), normalize3(pc - pos), cos_alpha, alpha);
+    return 1.f / sarea;
+}
+
+inline void triangleUniform(const float uv[2], float out[2]) {  // sampling.zig:39-47 (E. Heitz)
+    if (uv[1] > uv[0]) {
+        const float x = 0.5f * uv[0];
+        out[0]        = x;
+        out[1]        = uv[1] - x;
+        return;
+    }
+    const float y = 0.5f * uv[1];
+    out[0]        = uv[0] - y;
+    out[1]        = y;
+}
+
+inline Vec4f interpolate3(Vec4f a, Vec4f b, Vec4f c, float u, float v) {  // triangle.zig:142-149
+    const float w     = 1.f - u - v;
+    const Vec4f temp0 = mulAdd(b, splat(u), splat(v) * c);
+    return mulAdd(a, splat(w), temp0);
+}
+
+constexpr float AreaDistanceRatio = 0.001f;  // :489
+
 }  // namespace mesh
 
 // ---- scene -----------------------------------------------------------------------------------
@@ -912,8 +1014,42 @@ struct Scene {
         return max(ra * rb * rc, 0.f);
     }
 
-    float lightWeight(Vec4f p, Vec4f n, bool total_sphere, uint32_t light) const {  // light_tree.zig:227-233
-        const LightProperties props = lightProperties(light);
+    // The tree a traversal runs over: the scene's (lights = scene lights) or the PrimitiveTree of a mesh sampler (lights =
+    // the emitting triangles of the part).
+    struct TreeRef {
+        const ZygpuLightNode*   nodes;
+        const uint32_t*         node_middles;
+        const uint32_t*         light_orders;
+        const uint32_t*         light_mapping;
+        Vec4f                   bounds_min, bounds_max;
+        const ZygpuMeshSampler* sampler;  // null for the scene tree
+    };
+    TreeRef sceneTree() const {
+        const ZygpuLightTree& t = s.light_tree;
+        return {t.nodes, t.node_middles, t.light_orders, t.light_mapping, load4(t.bounds.min), load4(t.bounds.max), nullptr};
+    }
+    static TreeRef primitiveTree(const ZygpuMeshSampler& m) {
+        return {m.nodes, m.node_middles, m.light_orders, m.light_mapping, load4(m.bounds.min), load4(m.bounds.max), &m};
+    }
+
+    // MeshImpl.lightProperties, shape_sampler.zig:198-226
+    LightProperties meshLightProperties(const ZygpuMeshSampler& m, uint32_t light) const {
+        const uint32_t global = m.triangle_mapping[light];
+        const Mesh     tree   = treeOf(m.mesh);
+        const Vec4f    a = tree.position(tree.triangles[3 * size_t(global)]), b = tree.position(tree.triangles[3 * size_t(global) + 1]),
+                    c = tree.position(tree.triangles[3 * size_t(global) + 2]);
+
+        const Vec4f center = (a + b + c) / splat(3.f);
+        const float sra    = squaredLength3(a - center);
+        const float srb    = squaredLength3(b - center);
+        const float src    = squaredLength3(c - center);
+        const float radius = std::sqrt(max(sra, max(srb, src)));
+        const Vec4f nn     = normalize3(cross3(b - a, c - a));
+        return {{{center[0], center[1], center[2], radius}}, {{nn[0], nn[1], nn[2], 1.f}}, m.triangle_pdfs[light], 0 != m.two_sided};
+    }
+
+    float lightWeight(const TreeRef& tr, Vec4f p, Vec4f n, bool total_sphere, uint32_t light) const {  // light_tree.zig:227-233
+        const LightProperties props = tr.sampler ? meshLightProperties(*tr.sampler, light) : lightProperties(light);
         return importance(p, n, props.sphere, props.cone, props.sphere[3], props.power, props.two_sided, total_sphere);
     }
 
@@ -934,17 +1070,17 @@ struct Scene {
         return r;
     }
 
-    Vec4f nodeCenter(const ZygpuLightNode& node) const {  // light_tree.zig:39-42
+    static Vec4f nodeCenter(const TreeRef& tr, const ZygpuLightNode& node) {  // light_tree.zig:39-42
         const Vec4f t = unorm16ToFloat(node.center);
-        return lerp(load4(s.light_tree.bounds.min), load4(s.light_tree.bounds.max), t);
+        return lerp(tr.bounds_min, tr.bounds_max, t);
     }
-    float nodeWeight(const ZygpuLightNode& node, Vec4f p, Vec4f n, bool total_sphere) const {  // :57-63
-        const Vec4f center = nodeCenter(node);
+    float nodeWeight(const TreeRef& tr, const ZygpuLightNode& node, Vec4f p, Vec4f n, bool total_sphere) const {  // :57-63
+        const Vec4f center = nodeCenter(tr, node);
         const Vec4f cone   = snorm16ToFloat(node.cone);
         return importance(p, n, center, cone, center[3], node.power, 0 != (node.meta & 2u), total_sphere);
     }
-    bool nodeSplit(const ZygpuLightNode& node, Vec4f p, float threshold) const {  // :65-89
-        const Vec4f center = nodeCenter(node);
+    bool nodeSplit(const TreeRef& tr, const ZygpuLightNode& node, Vec4f p, float threshold) const {  // :65-89
+        const Vec4f center = nodeCenter(tr, node);
         const float r      = center[3];
         const float d      = min(distance3(p, center), 1.0e6f);
         const float a      = max(d - r, 0.001f);
@@ -965,8 +1101,8 @@ struct Scene {
     }
 
     // Node.randomLight, light_tree.zig:91-145
-    LightPick nodeRandomLight(const ZygpuLightNode& node, Vec4f p, Vec4f n, bool total_sphere, float random) const {
-        const uint32_t* light_mapping = s.light_tree.light_mapping;
+    LightPick nodeRandomLight(const TreeRef& tr, const ZygpuLightNode& node, Vec4f p, Vec4f n, bool total_sphere, float random) const {
+        const uint32_t* light_mapping = tr.light_mapping;
         const uint32_t  num_lights    = node.num_lights;
         const uint32_t  light         = node.meta >> 2;
 
@@ -975,8 +1111,8 @@ struct Scene {
         uint32_t front = light;
         uint32_t back  = light + num_lights - 1;
 
-        float w_front = lightWeight(p, n, total_sphere, light_mapping[front]);
-        float w_back  = lightWeight(p, n, total_sphere, light_mapping[back]);
+        float w_front = lightWeight(tr, p, n, total_sphere, light_mapping[front]);
+        float w_back  = lightWeight(tr, p, n, total_sphere, light_mapping[back]);
 
         float w_sum_front = w_front;
         float w_sum_back  = w_back;
@@ -987,7 +1123,7 @@ struct Scene {
             if (w_sum_front <= random * w_sum) {
                 front += 1;
                 if (front != back) {
-                    w_front = lightWeight(p, n, total_sphere, light_mapping[front]);
+                    w_front = lightWeight(tr, p, n, total_sphere, light_mapping[front]);
                     w_sum_front += w_front;
                 } else {
                     w_front = w_back;
@@ -995,7 +1131,7 @@ struct Scene {
             } else {
                 back -= 1;
                 if (front != back) {
-                    w_back = lightWeight(p, n, total_sphere, light_mapping[back]);
+                    w_back = lightWeight(tr, p, n, total_sphere, light_mapping[back]);
                     w_sum_back += w_back;
                 }
             }
@@ -1005,7 +1141,7 @@ struct Scene {
     }
 
     // Node.pdf, light_tree.zig:147-170
-    float nodePdf(const ZygpuLightNode& node, Vec4f p, Vec4f n, bool total_sphere, uint32_t id) const {
+    float nodePdf(const TreeRef& tr, const ZygpuLightNode& node, Vec4f p, Vec4f n, bool total_sphere, uint32_t id) const {
         const uint32_t num_lights = node.num_lights;
         if (1 == num_lights) return 1.f;
 
@@ -1015,7 +1151,7 @@ struct Scene {
         float w_id = 0.f;
         float sum  = 0.f;
         for (uint32_t i = light; i < end; ++i) {
-            const float lw = lightWeight(p, n, total_sphere, s.light_tree.light_mapping[i]);
+            const float lw = lightWeight(tr, p, n, total_sphere, tr.light_mapping[i]);
             sum += lw;
             if (id == i) w_id = lw;
         }
@@ -1028,6 +1164,7 @@ struct Scene {
     // distribution are restated.
     uint32_t randomLight(Vec4f p, Vec4f n, bool total_sphere, float random, float split_threshold, LightPick* buffer) const {
         const ZygpuLightTree& tree = s.light_tree;
+        const TreeRef         tr   = sceneTree();
 
         uint32_t current_light = 0;
 
@@ -1070,7 +1207,7 @@ struct Scene {
             const ZygpuLightNode& node = tree.nodes[t.node];
 
             if (0 != (node.meta & 1u)) {
-                const bool do_split = t.depth < max_split_depth && nodeSplit(node, p, split_threshold);
+                const bool do_split = t.depth < max_split_depth && nodeSplit(tr, node, p, split_threshold);
 
                 const uint32_t c0 = node.meta >> 2;
                 const uint32_t c1 = c0 + 1;
@@ -1082,8 +1219,8 @@ struct Scene {
                 } else {
                     t.depth = max_split_depth;
 
-                    float p0 = nodeWeight(tree.nodes[c0], p, n, total_sphere);
-                    float p1 = nodeWeight(tree.nodes[c1], p, n, total_sphere);
+                    float p0 = nodeWeight(tr, tree.nodes[c0], p, n, total_sphere);
+                    float p1 = nodeWeight(tr, tree.nodes[c1], p, n, total_sphere);
 
                     const float pt = p0 + p1;
                     if (0.f == pt) {
@@ -1105,7 +1242,7 @@ struct Scene {
                     }
                 }
             } else {
-                const LightPick pick = nodeRandomLight(node, p, n, total_sphere, t.random);
+                const LightPick pick = nodeRandomLight(tr, node, p, n, total_sphere, t.random);
                 if (pick.pdf > 0.f) buffer[current_light++] = {pick.offset, pick.pdf * t.pdf};
                 t = pop();
             }
@@ -1116,6 +1253,7 @@ struct Scene {
     // Tree.pdf, light_tree.zig:449-517
     float lightTreePdf(Vec4f p, Vec4f n, bool total_sphere, float split_threshold, uint32_t id) const {
         const ZygpuLightTree& tree = s.light_tree;
+        const TreeRef         tr   = sceneTree();
 
         const uint32_t lo                  = tree.light_orders[id];
         const uint32_t num_infinite_lights = tree.num_infinite_lights;
@@ -1137,7 +1275,7 @@ struct Scene {
         for (;;) {
             const ZygpuLightNode& node = tree.nodes[nid];
             if (0 != (node.meta & 1u)) {
-                const bool     do_split = depth < max_split_depth && nodeSplit(node, p, split_threshold);
+                const bool     do_split = depth < max_split_depth && nodeSplit(tr, node, p, split_threshold);
                 const uint32_t c0       = node.meta >> 2;
                 const uint32_t c1       = c0 + 1;
                 const uint32_t middle   = tree.node_middles[nid];
@@ -1146,8 +1284,8 @@ struct Scene {
                     nid = lo < middle ? c0 : c1;
                 } else {
                     depth          = max_split_depth;
-                    const float p0 = nodeWeight(tree.nodes[c0], p, n, total_sphere);
-                    const float p1 = nodeWeight(tree.nodes[c1], p, n, total_sphere);
+                    const float p0 = nodeWeight(tr, tree.nodes[c0], p, n, total_sphere);
+                    const float p1 = nodeWeight(tr, tree.nodes[c1], p, n, total_sphere);
                     const float pt = p0 + p1;
                     if (0.f == pt) return 0.f;
                     if (lo < middle) {
@@ -1159,12 +1297,119 @@ struct Scene {
                     }
                 }
             } else {
-                return pd * nodePdf(node, p, n, total_sphere, lo);
+                return pd * nodePdf(tr, node, p, n, total_sphere, lo);
             }
         }
     }
 
     // Light.sampleTo -> Shape.sampleTo, light.zig:87-106, 163-190; shape.zig:301-338
+    // PrimitiveTree.randomLight, light_tree.zig:577-650
+    uint32_t primitiveRandomLight(const ZygpuMeshSampler& m, Vec4f p, Vec4f n, bool total_sphere, float random, float split_threshold,
+                                  LightPick* buffer) const {
+        constexpr uint32_t MaxSplitDepth = 6;
+        const TreeRef      tr            = primitiveTree(m);
+
+        uint32_t   current_light = 0;
+        const bool split         = split_threshold > 0.f;
+
+        struct Value {
+            float    pdf, random;
+            uint32_t node, depth;
+        };
+        Value    stack[MaxSplitDepth + 1];
+        uint32_t end = 0;
+
+        Value t{1.f, random, 0, split ? 0 : MaxSplitDepth};
+        stack[end++] = t;
+
+        auto pop = [&]() {
+            end -= 1;
+            return stack[end];
+        };
+
+        while (end > 0) {
+            const ZygpuLightNode& node = tr.nodes[t.node];
+            if (0 != (node.meta & 1u)) {
+                const bool     do_split = t.depth < MaxSplitDepth && nodeSplit(tr, node, p, split_threshold);
+                const uint32_t c0       = node.meta >> 2;
+                const uint32_t c1       = c0 + 1;
+                if (do_split) {
+                    t.depth += 1;
+                    t.node       = c0;
+                    stack[end++] = {t.pdf, t.random, c1, t.depth};
+                } else {
+                    t.depth = MaxSplitDepth;
+
+                    float p0 = nodeWeight(tr, tr.nodes[c0], p, n, total_sphere);
+                    float p1 = nodeWeight(tr, tr.nodes[c1], p, n, total_sphere);
+
+                    const float pt = p0 + p1;
+                    if (0.f == pt) {
+                        t = pop();
+                        continue;
+                    }
+                    p0 /= pt;
+                    p1 /= pt;
+                    if (t.random < p0) {
+                        t.node = c0;
+                        t.pdf *= p0;
+                        t.random /= p0;
+                    } else {
+                        t.node = c1;
+                        t.pdf *= p1;
+                        t.random = min((t.random - p0) / p1, 1.f);
+                    }
+                }
+            } else {
+                const LightPick pick = nodeRandomLight(tr, node, p, n, total_sphere, t.random);
+                if (pick.pdf > 0.f) buffer[current_light++] = {pick.offset, pick.pdf * t.pdf};
+                t = pop();
+            }
+        }
+        return current_light;
+    }
+
+    // PrimitiveTree.pdf, light_tree.zig:652-719
+    float primitivePdf(const ZygpuMeshSampler& m, Vec4f p, Vec4f n, bool total_sphere, float split_threshold, uint32_t id) const {
+        constexpr uint32_t MaxSplitDepth = 6;
+        const TreeRef      tr            = primitiveTree(m);
+
+        const uint32_t lo    = tr.light_orders[id];
+        const bool     split = split_threshold > 0.f;
+
+        float    pd    = 1.f;
+        uint32_t nid   = 0;
+        uint32_t depth = split ? 0 : MaxSplitDepth;
+        for (;;) {
+            const ZygpuLightNode& node = tr.nodes[nid];
+            if (0 != (node.meta & 1u)) {
+                const bool     do_split = depth < MaxSplitDepth && nodeSplit(tr, node, p, split_threshold);
+                const uint32_t c0       = node.meta >> 2;
+                const uint32_t c1       = c0 + 1;
+                const uint32_t middle   = tr.node_middles[nid];
+                if (do_split) {
+                    depth += 1;
+                    nid = lo < middle ? c0 : c1;
+                } else {
+                    depth          = MaxSplitDepth;
+                    const float p0 = nodeWeight(tr, tr.nodes[c0], p, n, total_sphere);
+                    const float p1 = nodeWeight(tr, tr.nodes[c1], p, n, total_sphere);
+                    const float pt = p0 + p1;
+                    if (0.f == pt) return 0.f;
+                    if (lo < middle) {
+                        nid = c0;
+                        pd *= p0 / pt;
+                    } else {
+                        nid = c1;
+                        pd *= p1 / pt;
+                    }
+                }
+            } else {
+                return pd * nodePdf(tr, node, p, n, total_sphere, lo);
+            }
+        }
+    }
+
     uint32_t lightSampleTo(const ZygpuLight& l, Vec4f p, Vec4f n, const Trafo& trafo, bool total_sphere,
                            float split_threshold, Sampler& sampler, SampleTo* buffer) const {
         const uint32_t num_samples = lightNumSamples(l, split_threshold);
@@ -1172,8 +1417,125 @@ struct Scene {
             case ZYG_SHAPE_RECTANGLE:
                 return rectangle::sampleTo(p, n, trafo, 0 != l.two_sided, total_sphere, num_samples, sampler, buffer);
             case ZYG_SHAPE_DISTANT: return distant::sampleTo(n, trafo, total_sphere, sampler, buffer);
+            case ZYG_SHAPE_TRIANGLE_MESH:
+                return meshSampleTo(s.mesh_samplers[l.sampler], p, n, trafo, 0 != l.two_sided, total_sphere, split_threshold, sampler, buffer);
             default: return 0;
         }
+    }
+
+    // Mesh.sampleTo, triangle_mesh.zig:492-608
+    uint32_t meshSampleTo(const ZygpuMeshSampler& m, Vec4f p, Vec4f n, const Trafo& trafo, bool two_sided, bool total_sphere,
+                          float split_threshold, Sampler& sampler, SampleTo* buffer) const {
+        const Vec4f op = trafo.worldToObjectPoint(p);
+        const Vec4f on = trafo.worldToObjectNormal(n);
+
+        const Vec4f scale         = trafo.scale();
+        const Vec4f scale_squared = scale * scale;
+
+        const Mesh tree = treeOf(m.mesh);
+
+        LightPick      samples[64];
+        const uint32_t num = primitiveRandomLight(m, op, on, total_sphere, sampler.sample1D(), split_threshold, samples);
+
+        uint32_t current_sample = 0;
+        for (uint32_t i = 0; i < num; ++i) {
+            const LightPick& sp     = samples[i];
+            const uint32_t   global = m.triangle_mapping[sp.offset];
+
+            const Vec4f a = tree.position(tree.triangles[3 * size_t(global)]);
+            const Vec4f b = tree.position(tree.triangles[3 * size_t(global) + 1]);
+            const Vec4f c = tree.position(tree.triangles[3 * size_t(global) + 2]);
+
+            const Vec4f e1 = b - a;
+            const Vec4f e2 = c - a;
+
+            const Vec4f cross_axis = cross3(e1, e2);
+
+            const Vec4f ca  = scale_squared * cross_axis;
+            const float lca = length3(ca);
+            const Vec4f sn  = ca / splat(lca);
+            Vec4f       wn  = trafo.objectToWorldNormal(sn);
+
+            const float tri_area = 0.5f * lca;
+
+            const Vec4f center = (a + b + c) / splat(3.f);
+
+            Vec4f dir, v;
+            float bary_uv[2];
+            float sample_pdf, n_dot_dir;
+
+            if (tri_area / distance3(center, op) > mesh::AreaDistanceRatio) {
+                const Vec2f           r2 = sampler.sample2D();
+                mesh::SphericalSample sample;
+                if (!mesh::sampleSpherical(op, a, b, c, r2.v, sample)) continue;
+                if (dot3(sample.dir, on) <= 0.f && !total_sphere) continue;
+
+                bary_uv[0] = sample.uv[0];
+                bary_uv[1] = sample.uv[1];
+
+                dir = trafo.objectToWorldNormal(sample.dir);
+
+                const Vec4f sv = mesh::interpolate3(a, b, c, bary_uv[0], bary_uv[1]);
+                v              = trafo.objectToWorldPoint(sv);
+                sample_pdf     = sp.pdf * sample.pdf;
+
+                if (two_sided && dot3(wn, dir) > 0.f) wn = -wn;
+                n_dot_dir = -dot3(wn, dir);
+            } else {
+                const Vec2f r2 = sampler.sample2D();
+                mesh::triangleUniform(r2.v, bary_uv);
+
+                const Vec4f sv = mesh::interpolate3(a, b, c, bary_uv[0], bary_uv[1]);
+                v              = trafo.objectToWorldPoint(sv);
+
+                const Vec4f axis = v - p;
+                const float sl   = squaredLength3(axis);
+                const float d    = std::sqrt(sl);
+                dir              = axis / splat(d);
+
+                if (dot3(dir, n) <= 0.f && !total_sphere) continue;
+                if (two_sided && dot3(wn, dir) > 0.f) wn = -wn;
+
+                n_dot_dir  = -dot3(wn, dir);
+                sample_pdf = (sp.pdf * sl) / (n_dot_dir * tri_area);
+            }
+
+            if (n_dot_dir < safe::DotMin) continue;
+
+            SampleTo& out = buffer[current_sample++];
+            out.p         = {{v[0], v[1], v[2], sample_pdf}};
+            out.n         = wn;
+            out.wi        = dir;
+            out.uvw       = splat(0.f);  // interpolated uv: only read by emission maps
+        }
+        return current_sample;
+    }
+
+    // Mesh.pdf, triangle_mesh.zig:662-703
+    float meshPdf(const ZygpuMeshSampler& m, Vec4f dir, Vec4f p, Vec4f n, const Fragment& frag, bool total_sphere, float split_threshold) const {
+        const float n_dot_dir = std::fabs(dot3(frag.geo_n, dir));
+
+        const Vec4f op = frag.isec.trafo.worldToObjectPoint(p);
+        const Vec4f on = frag.isec.trafo.worldToObjectNormal(n);
+
+        const uint32_t pm      = m.primitive_mapping[frag.isec.primitive];
+        const float    tri_pdf = primitivePdf(m, op, on, total_sphere, split_threshold, pm);
+
+        const Mesh  tree = treeOf(m.mesh);
+        const Vec4f a    = tree.position(tree.triangles[3 * size_t(frag.isec.primitive)]);
+        const Vec4f b    = tree.position(tree.triangles[3 * size_t(frag.isec.primitive) + 1]);
+        const Vec4f c    = tree.position(tree.triangles[3 * size_t(frag.isec.primitive) + 2]);
+
+        const Vec4f cross_axis = cross3(b - a, c - a);
+        const Vec4f scale      = frag.isec.trafo.scale();
+        const Vec4f ca         = (scale * scale) * cross_axis;
+        const float tri_area   = 0.5f * length3(ca);
+
+        const Vec4f center = (a + b + c) / splat(3.f);
+
+        if (tri_area / distance3(center, op) > mesh::AreaDistanceRatio) return tri_pdf * mesh::pdfSpherical(op, a, b, c);
+        const float sl = squaredDistance3(p, frag.p);
+        return (tri_pdf * sl) / (n_dot_dir * tri_area);
     }
 
     bool lightFinite(const ZygpuLight& l) const {  // Shape.finite, shape.zig:94-99
@@ -1191,8 +1553,14 @@ struct Scene {
     }
 
     // Material.evaluateRadiance, material.zig:194-207 for {Light, Substitute (uncoated)}
-    Vec4f materialRadiance(const ZygpuMaterial& m, Vec4f wi, const Trafo& trafo, uint32_t prop, bool in_camera) const {
-        const float area = 0.f != m.emission_normalize ? shapeArea(s.props[prop].shape, trafo.scale()) : 1.f;
+    Vec4f materialRadiance(const ZygpuMaterial& m, Vec4f wi, const Trafo& trafo, uint32_t prop, bool in_camera, uint32_t part = 0) const {
+        float area = 1.f;
+        if (0.f != m.emission_normalize) {
+            const Vec4f scale = trafo.scale();
+            area = ZYG_SHAPE_TRIANGLE_MESH == s.props[prop].shape
+                       ? s.mesh_part_areas[s.props[prop].parts_start + part] * (scale[0] * scale[1])  // Mesh.area, triangle_mesh.zig:283-286
+                       : shapeArea(s.props[prop].shape, scale);
+        }
         return emittanceRadiance(m, wi, trafo, area, in_camera);
     }
 };
@@ -1232,6 +1600,10 @@ struct Worker {
                 sample_pdf = rectangle::pdf(vertex.origin, frag, scene.lightNumSamples(l, vertex.light_split_threshold));
                 break;
             case ZYG_SHAPE_DISTANT: sample_pdf = 1.f / distant::solidAngle(frag.isec.trafo.scaleX()); break;  // distant.zig:139-141
+            case ZYG_SHAPE_TRIANGLE_MESH:
+                sample_pdf = scene.meshPdf(scene.s.mesh_samplers[l.sampler], vertex.ray.direction, vertex.origin, vertex.geo_n, frag,
+                                           vertex.state.translucent, vertex.light_split_threshold);
+                break;
             default: break;
         }
         return powerHeuristic(vertex.bxdf_pdf, sample_pdf * select_pdf);
@@ -1248,7 +1620,7 @@ struct Worker {
         (void)sampler.sample1D();  // rs.stochastic_r
 
         const bool  in_camera = 0 == vertex.probe_depth.total();
-        const Vec4f energy    = scene.materialRadiance(m, wo, frag.isec.trafo, frag.prop, in_camera);
+        const Vec4f energy    = scene.materialRadiance(m, wo, frag.isec.trafo, frag.prop, in_camera, frag.part);
         const float weight    = lightPdf(vertex, frag);
         return splat(weight) * energy;
     }
@@ -1394,7 +1766,7 @@ struct Worker {
             // Light.evaluateTo, light.zig:119-132
             (void)sampler.sample1D();
             const ZygpuMaterial& lm       = scene.propMaterial(light.prop, light.part);
-            const Vec4f          radiance = scene.materialRadiance(lm, light_sample.wi, trafo, light.prop, false);
+            const Vec4f          radiance = scene.materialRadiance(lm, light_sample.wi, trafo, light.prop, false, light.part);
 
             const bxdf::Result bxdf_result = mat_sample.evaluate(light_sample.wi, max_material_splits, false);
 
@@ -1462,7 +1834,7 @@ struct Worker {
 
             (void)sampler.sample1D();  // Light.evaluateTo
             const ZygpuMaterial& lm       = scene.propMaterial(light.prop, light.part);
-            const Vec4f          radiance = scene.materialRadiance(lm, r.sample.wi, trafo, light.prop, false);
+            const Vec4f          radiance = scene.materialRadiance(lm, r.sample.wi, trafo, light.prop, false, light.part);
 
             const bxdf::Result bxdf_result = mat_sample.evaluate(r.sample.wi, max_material_splits, false);
 

@@ -155,16 +155,50 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
 
     if (0 != uploadArray(r, scene->ggx_luts, size_t(ZYGPU_GGX_LUT_FLOATS), &d.luts)) return -1;
 
+    // mesh-light samplers (shape_sampler.MeshImpl + PrimitiveTree)
+    std::vector<zygpu::MeshSamplerDevice> samplers(scene->num_mesh_samplers);
+    for (uint32_t i = 0; i < scene->num_mesh_samplers; ++i) {
+        const ZygpuMeshSampler&   ms = scene->mesh_samplers[i];
+        zygpu::MeshSamplerDevice& sd = samplers[i];
+        if (ms.mesh >= scene->num_meshes) return fail("zygpu_upload_scene: mesh sampler %u references mesh %u", i, ms.mesh);
+        sd.bounds_min    = make_float4(ms.bounds.min[0], ms.bounds.min[1], ms.bounds.min[2], ms.bounds.min[3]);
+        sd.bounds_max    = make_float4(ms.bounds.max[0], ms.bounds.max[1], ms.bounds.max[2], ms.bounds.max[3]);
+        sd.num_triangles = ms.num_triangles;
+        sd.num_nodes     = ms.num_nodes;
+        sd.two_sided     = ms.two_sided;
+        sd.mesh          = ms.mesh;
+        const uint32_t tree_triangles = uint32_t(scene->meshes[ms.mesh]->tree.numTriangles());
+        if (0 != uploadArray(r, ms.nodes, ms.num_nodes, &sd.nodes) || 0 != uploadArray(r, ms.node_middles, ms.num_nodes, &sd.node_middles) ||
+            0 != uploadArray(r, ms.light_orders, ms.num_triangles, &sd.light_orders) ||
+            0 != uploadArray(r, ms.light_mapping, ms.num_triangles, &sd.light_mapping) ||
+            0 != uploadArray(r, ms.triangle_mapping, ms.num_triangles, &sd.triangle_mapping) ||
+            0 != uploadArray(r, ms.triangle_pdfs, ms.num_triangles, &sd.triangle_pdfs) ||
+            0 != uploadArray(r, ms.primitive_mapping, tree_triangles, &sd.primitive_mapping)) {
+            return -1;
+        }
+    }
+    if (0 != uploadArray(r, samplers.data(), samplers.size(), &d.mesh_samplers)) return -1;
+    d.num_mesh_samplers = scene->num_mesh_samplers;
+    if (0 != uploadArray(r, scene->mesh_part_areas, scene->mesh_part_areas ? scene->num_parts : 0, &d.mesh_part_areas)) return -1;
+
     // shadow records one path vertex can need: every light the tree may return times its sample count
     // (Tree.potentialMaxLights, light_tree.zig:331-344), capped like the reference's buffers (64 picks x 64 samples)
     uint64_t potential = 0;
     uint32_t most      = 1;
     for (uint32_t l = 0; l < scene->num_lights; ++l) {
-        potential += std::max(1u, scene->lights[l].num_samples);
-        most = std::max(most, scene->lights[l].num_samples);
+        // Light.potentialMaxSamples, light.zig:77-85: a mesh light can return a sample per leaf its primitive tree splits into
+        // (2^6 = Shape.MaxSamples); the budget below assumes 8, zygpu_synchronize reports a vertex that needed more
+        const uint32_t n = ZYGPU_NULL != scene->lights[l].sampler ? 8u : std::max(1u, scene->lights[l].num_samples);
+        potential += n;
+        most = std::max(most, n);
     }
     // the tree returns at most Tree.MaxLights = 64 picks (light_tree.zig:249), each with up to `most` samples
     r.max_light_samples = uint32_t(std::min<uint64_t>(std::max<uint64_t>(potential, 1), 64ull * std::min(most, 64u)));
+    {  // records are reserved per path slot: keep the reservation moderate (ZYGPU_MAX_LIGHT_SAMPLES overrides)
+        const char*    v   = getenv("ZYGPU_MAX_LIGHT_SAMPLES");
+        const uint32_t cap = v ? uint32_t(std::max(1, atoi(v))) : 128u;
+        r.max_light_samples = std::min(r.max_light_samples, cap);
+    }
 
     // Glass splits a path into its reflected and refracted branch (glass_sample.zig:256-269, 350-395): such scenes run with
     // Pool.NumVertices vertex records per camera sample and one shade round per record

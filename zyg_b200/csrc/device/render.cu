@@ -704,8 +704,9 @@ __global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathS
 
 // Shape.fragment, shape.zig:205-219
 __device__ __forceinline__ void shapeFragment(const SceneDevice& sc, uint32_t prop, const RayT& ray, const HitD& isec, FragD& frag) {
-    frag.prop  = prop;
-    frag.trafo = loadTrafo(sc.trafos, prop);
+    frag.prop      = prop;
+    frag.primitive = isec.primitive;
+    frag.trafo     = loadTrafo(sc.trafos, prop);
     switch (sc.props[prop].shape) {
         case ZYG_SHAPE_CUBE: cubeFragment(ray, isec, frag); break;
         case ZYG_SHAPE_RECTANGLE: rectangleFragment(ray, isec, frag); break;
@@ -862,8 +863,48 @@ __device__ float lightImportance(V3 p, V3 n, V3 center, V3 cone_axis, float cos_
     return zmax(ra * rb * rc, 0.f);
 }
 
-__device__ float lightWeight(const SceneDevice& sc, V3 p, V3 n, bool total_sphere, uint32_t light) {  // light_tree.zig:227-233
-    const LightPropsD lp = lightProperties(sc, light);
+// The tree a traversal runs over: the scene's (lights = scene lights) or the PrimitiveTree of a mesh sampler (lights = the
+// emitting triangles of the part, light_tree.zig:520-719).
+struct TreeD {
+    const ZygpuLightNode*    nodes;
+    const uint32_t*          middles;
+    const uint32_t*          orders;
+    const uint32_t*          mapping;
+    float4                   bounds_min, bounds_max;
+    const MeshSamplerDevice* sampler;  // null for the scene tree
+};
+
+__device__ __forceinline__ TreeD sceneTree(const SceneDevice& sc) {
+    return {sc.lt_nodes, sc.lt_middles, sc.lt_orders, sc.lt_mapping, sc.lt_bounds_min, sc.lt_bounds_max, nullptr};
+}
+__device__ __forceinline__ TreeD primitiveTree(const MeshSamplerDevice& m) {
+    return {m.nodes, m.node_middles, m.light_orders, m.light_mapping, m.bounds_min, m.bounds_max, &m};
+}
+
+__device__ __forceinline__ V3 meshPosition(const MeshDevice& mesh, uint32_t index) {
+    return {__ldg(mesh.positions + 3 * size_t(index)), __ldg(mesh.positions + 3 * size_t(index) + 1), __ldg(mesh.positions + 3 * size_t(index) + 2)};
+}
+__device__ __forceinline__ void meshTriangle(const MeshDevice& mesh, uint32_t t, V3& a, V3& b, V3& c) {
+    a = meshPosition(mesh, __ldg(mesh.triangles + 3 * size_t(t)));
+    b = meshPosition(mesh, __ldg(mesh.triangles + 3 * size_t(t) + 1));
+    c = meshPosition(mesh, __ldg(mesh.triangles + 3 * size_t(t) + 2));
+}
+
+// MeshImpl.lightProperties, shape_sampler.zig:198-226
+__device__ LightPropsD meshLightProperties(const SceneDevice& sc, const MeshSamplerDevice& m, uint32_t light) {
+    V3 a, b, c;
+    meshTriangle(sc.meshes[m.mesh], __ldg(m.triangle_mapping + light), a, b, c);
+    const V3    center = divs3(add3(add3(a, b), c), 3.f);
+    const float sra    = squaredLength3(sub3(a, center));
+    const float srb    = squaredLength3(sub3(b, center));
+    const float src    = squaredLength3(sub3(c, center));
+    const float radius = __fsqrt_rn(zmax(sra, zmax(srb, src)));
+    const V3    nn     = normalize3(cross3(sub3(b, a), sub3(c, a)));
+    return {center, radius, nn, 1.f, __ldg(m.triangle_pdfs + light), 0 != m.two_sided};
+}
+
+__device__ float lightWeight(const SceneDevice& sc, const TreeD& tr, V3 p, V3 n, bool total_sphere, uint32_t light) {  // light_tree.zig:227-233
+    const LightPropsD lp = tr.sampler ? meshLightProperties(sc, *tr.sampler, light) : lightProperties(sc, light);
     return lightImportance(p, n, lp.center, lp.cone_axis, lp.cone_cos, lp.radius, lp.power, lp.two_sided, total_sphere);
 }
 
@@ -876,16 +917,16 @@ struct LightNodeD {
     uint32_t meta, num_lights;
 };
 
-__device__ __forceinline__ LightNodeD loadLightNode(const SceneDevice& sc, uint32_t i) {  // light_tree.zig:25-42
-    const uint4* p  = reinterpret_cast<const uint4*>(sc.lt_nodes + i);
+__device__ __forceinline__ LightNodeD loadLightNode(const TreeD& sc, uint32_t i) {  // light_tree.zig:25-42
+    const uint4* p  = reinterpret_cast<const uint4*>(sc.nodes + i);
     const uint4  a  = __ldg(p);
     const uint4  b  = __ldg(p + 1);
     const float  ku = 1.f / 65535.f;
     const float  tx = float(a.x & 0xffffu) * ku, ty = float(a.x >> 16) * ku, tz = float(a.y & 0xffffu) * ku, tw = float(a.y >> 16) * ku;
     LightNodeD   n;
-    n.center    = {zlerp(sc.lt_bounds_min.x, sc.lt_bounds_max.x, tx), zlerp(sc.lt_bounds_min.y, sc.lt_bounds_max.y, ty),
-                   zlerp(sc.lt_bounds_min.z, sc.lt_bounds_max.z, tz)};
-    n.radius    = zlerp(sc.lt_bounds_min.w, sc.lt_bounds_max.w, tw);
+    n.center    = {zlerp(sc.bounds_min.x, sc.bounds_max.x, tx), zlerp(sc.bounds_min.y, sc.bounds_max.y, ty),
+                   zlerp(sc.bounds_min.z, sc.bounds_max.z, tz)};
+    n.radius    = zlerp(sc.bounds_min.w, sc.bounds_max.w, tw);
     n.cone_axis = {__fmaf_rn(float(a.z & 0xffffu), 1.f / 32768.f, -1.f), __fmaf_rn(float(a.z >> 16), 1.f / 32768.f, -1.f),
                    __fmaf_rn(float(a.w & 0xffffu), 1.f / 32768.f, -1.f)};
     n.cone_cos  = __fmaf_rn(float(a.w >> 16), 1.f / 32768.f, -1.f);
@@ -926,16 +967,17 @@ struct LightPickD {
 };
 
 // Node.randomLight, light_tree.zig:91-145
-__device__ LightPickD lightNodeRandomLight(const SceneDevice& sc, const LightNodeD& node, V3 p, V3 n, bool total_sphere, float random) {
+__device__ LightPickD lightNodeRandomLight(const SceneDevice& sc, const TreeD& tr, const LightNodeD& node, V3 p, V3 n, bool total_sphere,
+                                           float random) {
     const uint32_t num_lights = node.num_lights;
     const uint32_t light      = node.meta >> 2;
-    if (1 == num_lights) return {__ldg(sc.lt_mapping + light), 1.f};
+    if (1 == num_lights) return {__ldg(tr.mapping + light), 1.f};
 
     uint32_t front = light;
     uint32_t back  = light + num_lights - 1;
 
-    float w_front = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + front));
-    float w_back  = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + back));
+    float w_front = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + front));
+    float w_back  = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + back));
 
     float w_sum_front = w_front;
     float w_sum_back  = w_back;
@@ -946,7 +988,7 @@ __device__ LightPickD lightNodeRandomLight(const SceneDevice& sc, const LightNod
         if (w_sum_front <= random * w_sum) {
             front += 1;
             if (front != back) {
-                w_front = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + front));
+                w_front = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + front));
                 w_sum_front += w_front;
             } else {
                 w_front = w_back;
@@ -954,24 +996,24 @@ __device__ LightPickD lightNodeRandomLight(const SceneDevice& sc, const LightNod
         } else {
             back -= 1;
             if (front != back) {
-                w_back = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + back));
+                w_back = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + back));
                 w_sum_back += w_back;
             }
         }
     }
     if (0.f == w_sum) return {0, 0.f};
-    return {__ldg(sc.lt_mapping + front), __fdiv_rn(w_front, w_sum)};
+    return {__ldg(tr.mapping + front), __fdiv_rn(w_front, w_sum)};
 }
 
 // Node.pdf, light_tree.zig:147-170
-__device__ float lightNodePdf(const SceneDevice& sc, const LightNodeD& node, V3 p, V3 n, bool total_sphere, uint32_t id) {
+__device__ float lightNodePdf(const SceneDevice& sc, const TreeD& tr, const LightNodeD& node, V3 p, V3 n, bool total_sphere, uint32_t id) {
     const uint32_t num_lights = node.num_lights;
     if (1 == num_lights) return 1.f;
     const uint32_t light = node.meta >> 2;
     const uint32_t end   = light + num_lights;
     float          w_id = 0.f, sum = 0.f;
     for (uint32_t i = light; i < end; ++i) {
-        const float lw = lightWeight(sc, p, n, total_sphere, __ldg(sc.lt_mapping + i));
+        const float lw = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + i));
         sum += lw;
         if (id == i) w_id = lw;
     }
@@ -984,8 +1026,9 @@ constexpr uint32_t kMaxLightPicks = 64;  // Tree.MaxLights
 // Tree.randomLight, light_tree.zig:346-447. `emit` is called for every pick in the reference's order.
 template <typename Emit>
 __device__ void lightTreeRandomLight(const SceneDevice& sc, V3 p, V3 n, bool total_sphere, float random, float split_threshold, Emit&& emit) {
-    float      ip    = 0.f;
-    const bool split = split_threshold > 0.f;
+    float       ip    = 0.f;
+    const bool  split = split_threshold > 0.f;
+    const TreeD tr    = sceneTree(sc);
 
     if (split && sc.lt_num_infinite < kMaxLightPicks - 1) {
         for (uint32_t i = 0; i < sc.lt_num_infinite; ++i) emit(LightPickD{__ldg(sc.lt_mapping + i), 1.f});
@@ -1012,7 +1055,7 @@ __device__ void lightTreeRandomLight(const SceneDevice& sc, V3 p, V3 n, bool tot
     stack[end++] = t;
 
     while (end > 0) {
-        const LightNodeD node = loadLightNode(sc, t.node);
+        const LightNodeD node = loadLightNode(tr, t.node);
         if (0 != (node.meta & 1u)) {
             const bool     do_split = t.depth < max_split_depth && lightNodeSplit(node, p, split_threshold);
             const uint32_t c0       = node.meta >> 2;
@@ -1024,8 +1067,8 @@ __device__ void lightTreeRandomLight(const SceneDevice& sc, V3 p, V3 n, bool tot
             } else {
                 t.depth = max_split_depth;
 
-                float p0 = lightNodeWeight(loadLightNode(sc, c0), p, n, total_sphere);
-                float p1 = lightNodeWeight(loadLightNode(sc, c1), p, n, total_sphere);
+                float p0 = lightNodeWeight(loadLightNode(tr, c0), p, n, total_sphere);
+                float p1 = lightNodeWeight(loadLightNode(tr, c1), p, n, total_sphere);
 
                 const float pt = p0 + p1;
                 if (0.f == pt) {
@@ -1045,15 +1088,116 @@ __device__ void lightTreeRandomLight(const SceneDevice& sc, V3 p, V3 n, bool tot
                 }
             }
         } else {
-            const LightPickD pick = lightNodeRandomLight(sc, node, p, n, total_sphere, t.random);
+            const LightPickD pick = lightNodeRandomLight(sc, tr, node, p, n, total_sphere, t.random);
             if (pick.pdf > 0.f) emit(LightPickD{pick.offset, pick.pdf * t.pdf});
             t = stack[--end];
         }
     }
 }
 
+// PrimitiveTree.randomLight, light_tree.zig:577-650. `emit` receives (part triangle, pdf) in the reference's order.
+template <typename Emit>
+__device__ void primitiveTreeRandomLight(const SceneDevice& sc, const MeshSamplerDevice& m, V3 p, V3 n, bool total_sphere, float random,
+                                         float split_threshold, Emit&& emit) {
+    constexpr uint32_t kMaxSplitDepth = 6;
+    const TreeD        tr             = primitiveTree(m);
+    const bool         split          = split_threshold > 0.f;
+
+    struct Value {
+        float    pdf, random;
+        uint32_t node, depth;
+    };
+    Value    stack[kMaxSplitDepth + 1];
+    uint32_t end = 0;
+
+    Value t{1.f, random, 0, split ? 0 : kMaxSplitDepth};
+    stack[end++] = t;
+
+    while (end > 0) {
+        const LightNodeD node = loadLightNode(tr, t.node);
+        if (0 != (node.meta & 1u)) {
+            const bool     do_split = t.depth < kMaxSplitDepth && lightNodeSplit(node, p, split_threshold);
+            const uint32_t c0       = node.meta >> 2;
+            const uint32_t c1       = c0 + 1;
+            if (do_split) {
+                t.depth += 1;
+                t.node       = c0;
+                stack[end++] = {t.pdf, t.random, c1, t.depth};
+            } else {
+                t.depth = kMaxSplitDepth;
+
+                float p0 = lightNodeWeight(loadLightNode(tr, c0), p, n, total_sphere);
+                float p1 = lightNodeWeight(loadLightNode(tr, c1), p, n, total_sphere);
+
+                const float pt = p0 + p1;
+                if (0.f == pt) {
+                    t = stack[--end];
+                    continue;
+                }
+                p0 = __fdiv_rn(p0, pt);
+                p1 = __fdiv_rn(p1, pt);
+                if (t.random < p0) {
+                    t.node = c0;
+                    t.pdf *= p0;
+                    t.random = __fdiv_rn(t.random, p0);
+                } else {
+                    t.node = c1;
+                    t.pdf *= p1;
+                    t.random = zmin(__fdiv_rn(t.random - p0, p1), 1.f);
+                }
+            }
+        } else {
+            const LightPickD pick = lightNodeRandomLight(sc, tr, node, p, n, total_sphere, t.random);
+            if (pick.pdf > 0.f) emit(LightPickD{pick.offset, pick.pdf * t.pdf});
+            t = stack[--end];
+        }
+    }
+}
+
+// PrimitiveTree.pdf, light_tree.zig:652-719
+__device__ float primitiveTreePdf(const SceneDevice& sc, const MeshSamplerDevice& m, V3 p, V3 n, bool total_sphere, float split_threshold,
+                                  uint32_t id) {
+    constexpr uint32_t kMaxSplitDepth = 6;
+    const TreeD        tr             = primitiveTree(m);
+    const uint32_t     lo             = __ldg(tr.orders + id);
+    const bool         split          = split_threshold > 0.f;
+
+    float    pd    = 1.f;
+    uint32_t nid   = 0;
+    uint32_t depth = split ? 0 : kMaxSplitDepth;
+    for (;;) {
+        const LightNodeD node = loadLightNode(tr, nid);
+        if (0 != (node.meta & 1u)) {
+            const bool     do_split = depth < kMaxSplitDepth && lightNodeSplit(node, p, split_threshold);
+            const uint32_t c0       = node.meta >> 2;
+            const uint32_t c1       = c0 + 1;
+            const uint32_t middle   = __ldg(tr.middles + nid);
+            if (do_split) {
+                depth += 1;
+                nid = lo < middle ? c0 : c1;
+            } else {
+                depth          = kMaxSplitDepth;
+                const float p0 = lightNodeWeight(loadLightNode(tr, c0), p, n, total_sphere);
+                const float p1 = lightNodeWeight(loadLightNode(tr, c1), p, n, total_sphere);
+                const float pt = p0 + p1;
+                if (0.f == pt) return 0.f;
+                if (lo < middle) {
+                    nid = c0;
+                    pd *= __fdiv_rn(p0, pt);
+                } else {
+                    nid = c1;
+                    pd *= __fdiv_rn(p1, pt);
+                }
+            }
+        } else {
+            return pd * lightNodePdf(sc, tr, node, p, n, total_sphere, lo);
+        }
+    }
+}
+
 // Tree.pdf, light_tree.zig:449-517
 __device__ float lightTreePdf(const SceneDevice& sc, V3 p, V3 n, bool total_sphere, float split_threshold, uint32_t id) {
+    const TreeD    tr             = sceneTree(sc);
     const uint32_t lo             = __ldg(sc.lt_orders + id);
     const bool     split          = split_threshold > 0.f;
     const bool     split_infinite = split && sc.lt_num_infinite < kMaxLightPicks - 1;
@@ -1068,7 +1212,7 @@ __device__ float lightTreePdf(const SceneDevice& sc, V3 p, V3 n, bool total_sphe
     uint32_t nid   = 0;
     uint32_t depth = split ? 0 : max_split_depth;
     for (;;) {
-        const LightNodeD node = loadLightNode(sc, nid);
+        const LightNodeD node = loadLightNode(tr, nid);
         if (0 != (node.meta & 1u)) {
             const bool     do_split = depth < max_split_depth && lightNodeSplit(node, p, split_threshold);
             const uint32_t c0       = node.meta >> 2;
@@ -1079,8 +1223,8 @@ __device__ float lightTreePdf(const SceneDevice& sc, V3 p, V3 n, bool total_sphe
                 nid = lo < middle ? c0 : c1;
             } else {
                 depth          = max_split_depth;
-                const float p0 = lightNodeWeight(loadLightNode(sc, c0), p, n, total_sphere);
-                const float p1 = lightNodeWeight(loadLightNode(sc, c1), p, n, total_sphere);
+                const float p0 = lightNodeWeight(loadLightNode(tr, c0), p, n, total_sphere);
+                const float p1 = lightNodeWeight(loadLightNode(tr, c1), p, n, total_sphere);
                 const float pt = p0 + p1;
                 if (0.f == pt) return 0.f;
                 if (lo < middle) {
@@ -1092,12 +1236,103 @@ __device__ float lightTreePdf(const SceneDevice& sc, V3 p, V3 n, bool total_sphe
                 }
             }
         } else {
-            return pd * lightNodePdf(sc, node, p, n, total_sphere, lo);
+            return pd * lightNodePdf(sc, tr, node, p, n, total_sphere, lo);
         }
     }
 }
 
+// Mesh.pdf, triangle_mesh.zig:662-703. Kept out of line: scenes without mesh lights should not pay its registers.
+__device__ __noinline__ float meshLightPdf(const SceneDevice& sc, const MeshSamplerDevice& m, const VertexD& vertex, const FragD& frag) {
+    const float n_dot_dir = fabsf(dot3(frag.geo_n, vertex.ray.d));
+
+    const V3 op = frag.trafo.worldToObjectPoint(vertex.origin);
+    const V3 on = frag.trafo.worldToObjectNormal(vertex.geo_n);
+
+    const uint32_t pm      = __ldg(m.primitive_mapping + frag.primitive);
+    const float    tri_pdf = primitiveTreePdf(sc, m, op, on, 0 != (vertex.state & kTranslucent), vertex.light_split_threshold, pm);
+
+    V3 a, b, c;
+    meshTriangle(sc.meshes[m.mesh], frag.primitive, a, b, c);
+    const V3    ca       = mul3(mul3(frag.trafo.scale, frag.trafo.scale), cross3(sub3(b, a), sub3(c, a)));
+    const float tri_area = 0.5f * length3(ca);
+    const V3    center   = divs3(add3(add3(a, b), c), 3.f);
+
+    if (__fdiv_rn(tri_area, length3(sub3(center, op))) > kAreaDistanceRatio) return tri_pdf * pdfSpherical(op, a, b, c);
+    const float sl = squaredLength3(sub3(vertex.origin, frag.p));
+    return __fdiv_rn(tri_pdf * sl, n_dot_dir * tri_area);
+}
+
+// Mesh.sampleTo, triangle_mesh.zig:492-608: appends the shadow records of one picked mesh light, returns the new record count.
+// Kept out of line for the same reason.
+__device__ __noinline__ uint32_t meshLightSampleTo(const SceneDevice& sc, const PathState& st, uint32_t slot, const ZygpuLight& light,
+                                                   LightPickD pick, const TrafoD& trafo, const FragD& frag, V3 n, bool translucent,
+                                                   float split_threshold, SamplerD& sampler, uint32_t num_records) {
+    const MeshSamplerDevice& m  = sc.mesh_samplers[light.sampler];
+    const V3                 p  = frag.p;
+    const V3                 op = trafo.worldToObjectPoint(p);
+    const V3                 on = trafo.worldToObjectNormal(n);
+    const V3    scale_squared   = mul3(trafo.scale, trafo.scale);
+    const float r1              = sampler.sample1D();
+    primitiveTreeRandomLight(sc, m, op, on, translucent, r1, split_threshold, [&](LightPickD sp) {
+        V3 a, b, c;
+        meshTriangle(sc.meshes[m.mesh], __ldg(m.triangle_mapping + sp.offset), a, b, c);
+
+        const V3    ca  = mul3(scale_squared, cross3(sub3(b, a), sub3(c, a)));
+        const float lca = length3(ca);
+        V3          wn  = trafo.objectToWorldNormal(divs3(ca, lca));
+
+        const float tri_area = 0.5f * lca;
+        const V3    center   = divs3(add3(add3(a, b), c), 3.f);
+
+        float u0, u1;
+        sampler.sample2D(u0, u1);
+
+        V3    dir, v;
+        float sample_pdf, n_dot_dir;
+        if (__fdiv_rn(tri_area, length3(sub3(center, op))) > kAreaDistanceRatio) {
+            V3    sdir;
+            float bu, bv, spdf;
+            if (!sampleSpherical(op, a, b, c, u0, u1, sdir, bu, bv, spdf)) return;
+            if (dot3(sdir, on) <= 0.f && !translucent) return;
+            dir        = trafo.objectToWorldNormal(sdir);
+            v          = trafo.objectToWorldPoint(interpolate3(a, b, c, bu, bv));
+            sample_pdf = sp.pdf * spdf;
+            if (0 != light.two_sided && dot3(wn, dir) > 0.f) wn = neg3(wn);
+            n_dot_dir = -dot3(wn, dir);
+        } else {
+            float bu, bv;
+            triangleUniform(u0, u1, bu, bv);
+            v = trafo.objectToWorldPoint(interpolate3(a, b, c, bu, bv));
+
+            const V3    axis = sub3(v, p);
+            const float sl   = squaredLength3(axis);
+            const float d    = __fsqrt_rn(sl);
+            dir              = divs3(axis, d);
+            if (dot3(dir, n) <= 0.f && !translucent) return;
+            if (0 != light.two_sided && dot3(wn, dir) > 0.f) wn = neg3(wn);
+            n_dot_dir  = -dot3(wn, dir);
+            sample_pdf = __fdiv_rn(sp.pdf * sl, n_dot_dir * tri_area);
+        }
+        if (n_dot_dir < kDotMin) return;
+
+        if (num_records < st.shadow_stride) {
+            const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+            const V3     origin    = frag.offsetP(dir);
+            const V3     light_pos = offsetRay(v, wn);
+            st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, sample_pdf * pick.pdf);
+            st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+            st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+            num_records += 1;
+        } else {
+            st.counters[3] = 1;
+        }
+    });
+    return num_records;
+}
+
 // Scene.lightPdf, scene.zig:624-634 (+ Light.pdf -> Shape.pdf, light.zig:149-157, shape.zig:469-492, rectangle.zig:554-575)
+// `MeshLights`: the scene has triangle-mesh lights (their sampling code is compiled out otherwise)
+template <bool MeshLights>
 __device__ float sceneLightPdf(const SceneDevice& sc, const VertexD& vertex, const FragD& frag) {
     const uint32_t light_id = __ldg(sc.light_ids + sc.props[frag.prop].parts_start + frag.part);
     if (0 != (vertex.state & kSingular) || ZYGPU_NULL == light_id) return 1.f;
@@ -1114,11 +1349,14 @@ __device__ float sceneLightPdf(const SceneDevice& sc, const VertexD& vertex, con
         sample_pdf = nsf * squad.pdf(frag.trafo.scale);
     } else if (ZYG_SHAPE_DISTANT == sc.props[l.prop].shape) {  // Distant.pdf, distant.zig:139-141
         sample_pdf = __fdiv_rn(1.f, distantSolidAngle(frag.trafo.scale.x));
+    } else if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == sc.props[l.prop].shape && ZYGPU_NULL != l.sampler) {
+        sample_pdf = meshLightPdf(sc, sc.mesh_samplers[l.sampler], vertex, frag);
     }
     return powerHeuristic(vertex.bxdf_pdf, sample_pdf * select_pdf);
 }
 
 // Vertex.evaluateRadiance, vertex.zig:183-212
+template <bool MeshLights>
 __device__ V3 evaluateRadiance(const SceneDevice& sc, const VertexD& vertex, const FragD& frag, SamplerD& sampler) {
     const V3            wo = neg3(vertex.ray.d);
     const ZygpuMaterial m  = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
@@ -1130,11 +1368,12 @@ __device__ V3 evaluateRadiance(const SceneDevice& sc, const VertexD& vertex, con
     const bool  in_camera = 0 == vertex.probe_depth;
     const float area      = 0.f != m.emission_normalize ? shapeArea(sc.props[frag.prop].shape, frag.trafo.scale) : 1.f;
     const V3    energy    = emittanceRadiance(m, wo, frag.trafo, area, in_camera);
-    const float weight    = sceneLightPdf(sc, vertex, frag);
+    const float weight    = sceneLightPdf<MeshLights>(sc, vertex, frag);
     return scale3(weight, energy);
 }
 
 // Prop.emission + Shape.emission, prop.zig:239-264, shape.zig:283-299, rectangle.zig:188-196
+template <bool MeshLights>
 __device__ V3 propEmission(const SceneDevice& sc, uint32_t entity, const VertexD& vertex, SamplerD& sampler) {
     const ZygpuProp prop = sc.props[entity];
     if (!propVisible(prop.flags, vertex.probe_depth)) return splat3(0.f);
@@ -1147,10 +1386,11 @@ __device__ V3 propEmission(const SceneDevice& sc, uint32_t entity, const VertexD
     HitD isec;
     if (!rectangleIntersect(vertex.ray, frag.trafo, isec)) return splat3(0.f);
     rectangleFragment(vertex.ray, isec, frag);
-    return evaluateRadiance(sc, vertex, frag, sampler);
+    return evaluateRadiance<MeshLights>(sc, vertex, frag, sampler);
 }
 
 // Context.emission -> PropBvh.emission, prop_tree.zig:302-356: every un-occluding emitter crossed before the hit
+template <bool MeshLights>
 __device__ V3 unoccludingEmission(const SceneDevice& sc, const VertexD& vertex, SamplerD& sampler) {
     uint32_t stack[kPropStack];
     uint32_t end = 0;
@@ -1166,7 +1406,7 @@ __device__ V3 unoccludingEmission(const SceneDevice& sc, const VertexD& vertex, 
         if (0 != num) {
             const uint32_t start = __float_as_uint(nmin.w);
             for (uint32_t i = start; i < start + num; ++i) {
-                energy = add3(energy, propEmission(sc, __ldg(sc.unocc_indices + i), vertex, sampler));
+                energy = add3(energy, propEmission<MeshLights>(sc, __ldg(sc.unocc_indices + i), vertex, sampler));
             }
             n = 0 == end ? kEnd : stack[--end];
             continue;
@@ -1383,8 +1623,14 @@ __device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t
 // PathtracerMIS.li up to the shadow rays: connectLight (pathtracer_mis.zig:280-341), termination (:76-86), Russian
 // roulette (:88, helper.zig:75-89), Vertex.sample (:93), sampleLights / evaluateLight up to the visibility test
 // (:174-250).
-template <bool Split>
+// Features the scene needs of shade_a; what it does not need is compiled out (each costs registers in the hottest kernel).
+enum : uint32_t { kFeatureSplit = 1, kFeatureMeshLights = 2, kFeatureInfiniteLights = 4 };
+
+template <uint32_t Features>
 __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
+    constexpr bool Split      = 0 != (Features & kFeatureSplit);
+    constexpr bool MeshLights = 0 != (Features & kFeatureMeshLights);
+    constexpr bool Infinite   = 0 != (Features & kFeatureInfiniteLights);
     __shared__ uint32_t sobol_tables[kSobolTableWords];
     loadSobolTables(sobol_tables);
     const bool      later = Split && round > 0;
@@ -1459,9 +1705,9 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
             V3 this_light = splat3(0.f);
             if (!(0 == view.caustics_path && 0 != (vertex.state & kSpecular) && 0 == (vertex.state & kPrimaryRay))) {
                 vertex.light_split_threshold = splitThreshold(view.split_threshold, lv.vertex_depth);
-                if (hit) this_light = evaluateRadiance(sc, vertex, frag, sampler);
-                this_light = add3(this_light, unoccludingEmission(sc, vertex, sampler));
-                if (kRayMaxT == vertex.ray.tmax) {  // the ray left the scene: infinite props, pathtracer_mis.zig:313-338
+                if (hit) this_light = evaluateRadiance<MeshLights>(sc, vertex, frag, sampler);
+                this_light = add3(this_light, unoccludingEmission<MeshLights>(sc, vertex, sampler));
+                if (Infinite && kRayMaxT == vertex.ray.tmax) {  // the ray left the scene: infinite props, pathtracer_mis.zig:313-338
                     for (uint32_t k = 0; k < sc.num_infinite_props; ++k) {
                         const uint32_t  entity = __ldg(sc.infinite_props + k);
                         const ZygpuProp iprop  = sc.props[entity];
@@ -1472,7 +1718,7 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                         HitD isec;
                         if (ZYG_SHAPE_DISTANT != iprop.shape || !distantIntersect(vertex.ray, light_frag.trafo, isec)) continue;
                         distantFragment(vertex.ray, isec, light_frag);
-                        this_light = add3(this_light, evaluateRadiance(sc, vertex, light_frag, sampler));
+                        this_light = add3(this_light, evaluateRadiance<MeshLights>(sc, vertex, light_frag, sampler));
                     }
                 }
             }
@@ -1523,7 +1769,7 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                         const ZygpuLight light = sc.lights[pick.offset];
                         const TrafoD     trafo = loadTrafo(sc.trafos, light.prop);
                         const uint32_t   shape = sc.props[light.prop].shape;
-                        if (ZYG_SHAPE_DISTANT == shape) {  // Distant.sampleTo, distant.zig:78-107
+                        if (Infinite && ZYG_SHAPE_DISTANT == shape) {  // Distant.sampleTo, distant.zig:78-107
                             const float radius = trafo.scale.x;
                             if (radius <= 0.f) return;
                             float u0, u1;
@@ -1544,6 +1790,11 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                             } else {
                                 st.counters[3] = 1;
                             }
+                            return;
+                        }
+                        if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == shape && ZYGPU_NULL != light.sampler) {
+                            num_records = meshLightSampleTo(sc, st, slot, light, pick, trafo, frag, n, translucent,
+                                                            vertex.light_split_threshold, sampler, num_records);
                             return;
                         }
                         if (ZYG_SHAPE_RECTANGLE != shape) return;
@@ -1996,10 +2247,19 @@ cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t
 }
 cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
                          uint32_t round, cudaStream_t stream) {
-    if (st.lanes > 1) {
-        shadeAKernel<true><<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass, round);
-    } else {
-        shadeAKernel<false><<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass, 0);
+    const uint32_t features = (st.lanes > 1 ? kFeatureSplit : 0u) | (scene.num_mesh_samplers > 0 ? kFeatureMeshLights : 0u) |
+                              (scene.num_infinite_props > 0 ? kFeatureInfiniteLights : 0u);
+    const uint32_t grid = gridFor(max_items, 8);
+    if (st.lanes <= 1) round = 0;
+    switch (features) {
+        case 0: shadeAKernel<0><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 1: shadeAKernel<1><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 2: shadeAKernel<2><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 3: shadeAKernel<3><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 4: shadeAKernel<4><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 5: shadeAKernel<5><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 6: shadeAKernel<6><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        default: shadeAKernel<7><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
     }
     return cudaGetLastError();
 }

@@ -33,6 +33,18 @@ struct MeshShading {  // hit-point reconstruction data of one mesh
     const uint16_t* parts;      // per BVH-order triangle
 };
 
+struct MeshSamplerDevice {  // ZygpuMeshSampler with device pointers
+    float4                bounds_min, bounds_max;
+    uint32_t              num_triangles, num_nodes, two_sided, mesh;
+    const ZygpuLightNode* nodes;
+    const uint32_t*       node_middles;
+    const uint32_t*       light_orders;
+    const uint32_t*       light_mapping;
+    const uint32_t*       triangle_mapping;
+    const float*          triangle_pdfs;
+    const uint32_t*       primitive_mapping;
+};
+
 struct SceneDevice {
     const ZygpuProp*     props;
     const float4*        trafos;  // 4 per prop
@@ -60,6 +72,10 @@ struct SceneDevice {
     const float4*   unocc_nodes;
     const uint32_t* unocc_indices;
     uint32_t        num_unocc_nodes;
+
+    const MeshSamplerDevice* mesh_samplers;    // by ZygpuLight.sampler
+    uint32_t                 num_mesh_samplers;
+    const float*             mesh_part_areas;  // Part.area per part entry
 
     const uint32_t* infinite_props;  // Scene.infinite_props (Distant): met only by rays that leave the scene
     uint32_t        num_infinite_props;

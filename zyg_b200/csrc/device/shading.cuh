@@ -160,7 +160,7 @@ struct HitD {  // shape/intersection.zig:46-61 (trafo is re-read from the prop)
 struct FragD {  // shape/intersection.zig:63-124
     V3       p, geo_n, t, b, n;
     float    u, v;  // uvw[0..1]; uvw[3] (ray offset) is 0 for every shape in scope
-    uint32_t prop, part;
+    uint32_t prop, part, primitive;
     TrafoD   trafo;
 
     __device__ bool sameHemisphere(V3 w) const { return dot3(geo_n, w) > 0.f; }
@@ -458,6 +458,94 @@ __device__ __forceinline__ void meshFragment(const MeshShading& m, const HitD& i
     frag.b = frag.trafo.objectToWorldNormal(b);
     frag.n = frag.trafo.objectToWorldNormal(ni);
 }
+
+// ---- mesh light sampling: triangle_mesh.zig:390-487, triangle.zig:82-100, sampling.zig:39-47 -----------------------
+
+__device__ __forceinline__ V3 orthogonalize(V3 a, V3 b) { return normalize3(fmas3(-dot3(a, b), a, b)); }
+
+__device__ __forceinline__ void barycentricCoords(V3 dir, V3 a, V3 b, V3 c, float& u, float& v) {
+    const V3    e1      = sub3(b, a);
+    const V3    e2      = sub3(c, a);
+    const V3    tvec    = neg3(a);
+    const V3    pvec    = cross3(dir, e2);
+    const V3    qvec    = cross3(tvec, e1);
+    const float e1_d_pv = dot3(e1, pvec);
+    const float tv_d_pv = dot3(tvec, pvec);
+    const float di_d_qv = dot3(dir, qvec);
+    const float inv_det = __fdiv_rn(1.f, e1_d_pv);
+    u                   = tv_d_pv * inv_det;
+    v                   = di_d_qv * inv_det;
+}
+
+__device__ __forceinline__ float sphericalArea(V3 A, V3 B, V3 C, float& cos_alpha, float& alpha) {
+    const V3 BA = orthogonalize(A, sub3(B, A));
+    const V3 CA = orthogonalize(A, sub3(C, A));
+    const V3 AB = orthogonalize(B, sub3(A, B));
+    const V3 CB = orthogonalize(B, sub3(C, B));
+    const V3 BC = orthogonalize(C, sub3(B, C));
+    const V3 AC = orthogonalize(C, sub3(A, C));
+    cos_alpha         = zclamp(dot3(BA, CA), -1.f, 1.f);
+    alpha             = acosf(cos_alpha);
+    const float beta  = acosf(zclamp(dot3(AB, CB), -1.f, 1.f));
+    const float gamma = acosf(zclamp(dot3(BC, AC), -1.f, 1.f));
+    return alpha + beta + gamma - kPi;
+}
+
+// Stratified Sampling of Spherical Triangles, James Arvo
+__device__ __forceinline__ bool sampleSpherical(V3 pos, V3 pa, V3 pb, V3 pc, float r0, float r1, V3& dir, float& bu, float& bv, float& pdf) {
+    const V3 pap = sub3(pa, pos);
+    const V3 pbp = sub3(pb, pos);
+    const V3 pcp = sub3(pc, pos);
+
+    const V3 A = normalize3(pap);
+    const V3 B = normalize3(pbp);
+    const V3 C = normalize3(pcp);
+
+    float       cos_alpha, alpha;
+    const float sarea = sphericalArea(A, B, C, cos_alpha, alpha);
+    if (0.f == sarea) return false;
+
+    const float cos_c = zclamp(dot3(A, B), -1.f, 1.f);
+
+    const float area_S      = r0 * sarea;
+    const float angle_delta = area_S - alpha;
+    const float p           = sinf(angle_delta);
+    const float q           = cosf(angle_delta);
+
+    const float sin_alpha = __fsqrt_rn(1.f - cos_alpha * cos_alpha);
+    const float u         = q - cos_alpha;
+    const float v         = p + sin_alpha * cos_c;
+
+    const float s   = zclamp(__fdiv_rn((v * q - u * p) * cos_alpha - v, (v * p + u * q) * sin_alpha), -1.f, 1.f);
+    const V3    C_s = add3(scale3(s, A), scale3(__fsqrt_rn(1.f - s * s), orthogonalize(A, C)));
+
+    const float cs_b = dot3(C_s, B);
+    const float z    = 1.f - r1 * (1.f - cs_b);
+    const V3    P    = add3(scale3(z, B), scale3(__fsqrt_rn(1.f - z * z), orthogonalize(B, C_s)));
+
+    dir = P;
+    barycentricCoords(P, pap, pbp, pcp, bu, bv);
+    pdf = __fdiv_rn(1.f, sarea);
+    return true;
+}
+
+__device__ __forceinline__ float pdfSpherical(V3 pos, V3 pa, V3 pb, V3 pc) {
+    float       cos_alpha, alpha;
+    const float sarea = sphericalArea(normalize3(sub3(pa, pos)), normalize3(sub3(pb, pos)), normalize3(sub3(pc, pos)), cos_alpha, alpha);
+    return __fdiv_rn(1.f, sarea);
+}
+
+__device__ __forceinline__ void triangleUniform(float u0, float u1, float& x, float& y) {  // E. Heitz
+    if (u1 > u0) {
+        x = 0.5f * u0;
+        y = u1 - x;
+        return;
+    }
+    y = 0.5f * u1;
+    x = u0 - y;
+}
+
+constexpr float kAreaDistanceRatio = 0.001f;  // triangle_mesh.zig:489
 
 // ---- materials -------------------------------------------------------------------------------
 

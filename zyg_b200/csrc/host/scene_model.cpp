@@ -349,7 +349,7 @@ int SceneModel::createMaterial(const json::Value& material) {
 }
 
 uint32_t SceneModel::addMesh(const zyg_mesh* mesh, uint32_t num_parts) {
-    meshes_.push_back({mesh, num_parts});
+    meshes_.push_back({mesh, num_parts, {}, {}});
     return 7 + uint32_t(meshes_.size() - 1);
 }
 
@@ -721,12 +721,37 @@ bool SceneModel::compile(std::string& error) {
     const uint32_t num_lights = uint32_t(lights_.size());
     light_aabbs_.resize(num_lights);
     light_cones_.resize(size_t(num_lights) * 4);
+    flat_part_areas_.assign(material_ids_.size(), 0.f);
     for (uint32_t l = 0; l < num_lights; ++l) {
-        const ZygpuLight&     light = lights_[l];
+        ZygpuLight&           light = lights_[l];
         const PropRec&        p     = props_[light.prop];
         const Transformation& t     = world_[light.prop];
 
         light_ids_[p.parts_start + light.part] = l;
+
+        // ShapeSamplerCache.prepareSampling -> Mesh.prepareSampling -> Part.configure (triangle_mesh.zig:57-149, 722-746)
+        light.sampler                 = ZYGPU_NULL;
+        const MeshSamplerData* mesh_sampler = nullptr;
+        if (p.shape >= 7) {
+            MeshRec& mr = meshes_[p.shape - 7];
+            if (mr.primitive_mapping.empty()) meshPartTables(mr.mesh->tree, mr.primitive_mapping, mr.part_areas);
+            for (size_t k = 0; k < samplers_.size(); ++k) {
+                if (samplers_[k]->mesh == p.shape - 7 && samplers_[k]->part == light.part && samplers_[k]->two_sided == (0 != light.two_sided)) {
+                    light.sampler = uint32_t(k);
+                }
+            }
+            if (ZYGPU_NULL == light.sampler) {
+                samplers_.push_back(std::make_unique<SamplerRec>());
+                SamplerRec& rec = *samplers_.back();
+                rec.mesh        = p.shape - 7;
+                rec.part        = light.part;
+                rec.two_sided   = 0 != light.two_sided;
+                buildMeshSampler(mr.mesh->tree, light.part, rec.two_sided, rec.data);
+                light.sampler = uint32_t(samplers_.size() - 1);
+            }
+            mesh_sampler = &samplers_[light.sampler]->data;
+            for (uint32_t k = 0; k < mr.num_parts; ++k) flat_part_areas_[p.parts_start + k] = mr.part_areas[k];
+        }
 
         Mat3x3 rot  = quaternionToMat3x3(t.rotation);
         rot.r[0][3] = t.scale[0];
@@ -735,12 +760,13 @@ bool SceneModel::compile(std::string& error) {
         const Vec4f scale = {{t.scale[0], t.scale[1], t.scale[2], 1.f}};
         const Vec4f pos   = t.position + (-origin);
 
-        AABB bb = transformAabb(shapeAabb(p.shape), compose(rot, scale, pos));
+        // sampler.impl.aabb / cone: the emitting triangles' for a mesh part, the shape's otherwise (shape_sampler.zig:105-117)
+        AABB bb = transformAabb(mesh_sampler ? mesh_sampler->aabb : shapeAabb(p.shape), compose(rot, scale, pos));
         bb.cacheRadius();
 
         // shape.cone(), shape.zig:117-122
         const bool  flat_shape = ZYG_SHAPE_DISK == p.shape || ZYG_SHAPE_RECTANGLE == p.shape || ZYG_SHAPE_DISTANT == p.shape;
-        const Vec4f part_cone  = {{0.f, 0.f, 1.f, flat_shape ? 1.f : -1.f}};
+        const Vec4f part_cone  = mesh_sampler ? mesh_sampler->cone : Vec4f{{0.f, 0.f, 1.f, flat_shape ? 1.f : -1.f}};
         const Vec4f tc         = transformVector(rot, part_cone);
         light_cones_[l * 4 + 0] = tc[0];
         light_cones_[l * 4 + 1] = tc[1];
@@ -757,7 +783,9 @@ bool SceneModel::compile(std::string& error) {
             case ZYG_SHAPE_DISTANT:  // Distant.solidAngle, distant.zig:143-145
                 extent = (2.f * kPi) * (1.f - std::sqrt(1.f / (scale[0] * scale[0] + 1.f)));
                 break;
-            default: break;
+            default:  // Mesh.area, triangle_mesh.zig:283-286
+                if (p.shape >= 7) extent = meshes_[p.shape - 7].part_areas[light.part] * (scale[0] * scale[1]);
+                break;
         }
 
         // Emittance.totalEmission (emittance.zig:61-71) of the average radiance (= emittance value for uniform
@@ -786,6 +814,28 @@ bool SceneModel::compile(std::string& error) {
     flat_meshes_.clear();
     for (const MeshRec& m : meshes_) flat_meshes_.push_back(m.mesh);
 
+    flat_samplers_.clear();
+    for (const auto& rec : samplers_) {
+        const MeshSamplerData& d = rec->data;
+        ZygpuMeshSampler       ms{};
+        for (int k = 0; k < 4; ++k) {
+            ms.bounds.min[k] = d.tree.bounds.b[0][k];
+            ms.bounds.max[k] = d.tree.bounds.b[1][k];
+        }
+        ms.num_triangles     = uint32_t(d.triangle_mapping.size());
+        ms.num_nodes         = uint32_t(d.tree.nodes.size());
+        ms.two_sided         = d.two_sided ? 1 : 0;
+        ms.mesh              = rec->mesh;
+        ms.nodes             = d.tree.nodes.data();
+        ms.node_middles      = d.tree.node_middles.data();
+        ms.light_orders      = d.tree.light_orders.data();
+        ms.light_mapping     = d.tree.light_mapping.data();
+        ms.triangle_mapping  = d.triangle_mapping.data();
+        ms.triangle_pdfs     = d.triangle_pdfs.data();
+        ms.primitive_mapping = meshes_[rec->mesh].primitive_mapping.data();
+        flat_samplers_.push_back(ms);
+    }
+
     flat_.num_props          = num_props;
     flat_.num_parts          = uint32_t(material_ids_.size());
     flat_.num_materials      = uint32_t(materials_.size());
@@ -804,6 +854,9 @@ bool SceneModel::compile(std::string& error) {
     flat_.solid_bvh          = {uint32_t(solid_nodes_.size()), uint32_t(solid_indices_.size()), solid_nodes_.data(), solid_indices_.data()};
     flat_.unoccluding_bvh    = {uint32_t(unocc_nodes_.size()), uint32_t(unocc_indices_.size()), unocc_nodes_.data(), unocc_indices_.data()};
     flat_.infinite_props     = infinite_props_.data();
+    flat_.num_mesh_samplers  = uint32_t(flat_samplers_.size());
+    flat_.mesh_samplers      = flat_samplers_.data();
+    flat_.mesh_part_areas    = flat_part_areas_.data();
     flat_.meshes             = flat_meshes_.data();
     flat_.ggx_luts           = luts.data();
 

@@ -13,6 +13,10 @@
 //                                                                       camera_perspective.zig:79-122
 #pragma once
 
+#include "mesh_sampler.hpp"
+
+#include <memory>
+
 #include "../../../include/zygpu_scene.h"
 #include "json.hpp"
 #include "zmath.hpp"
@@ -100,6 +104,14 @@ class SceneModel {
     struct MeshRec {
         const zyg_mesh* mesh;
         uint32_t        num_parts;
+        // Mesh.prepareSampling / calculateAreas products, filled when a part of the mesh first becomes a light
+        std::vector<uint32_t> primitive_mapping;
+        std::vector<float>    part_areas;
+    };
+    struct SamplerRec {  // ShapeSamplerCache entry (shape_sampler_cache.zig:131-172), keyed by mesh, part and sidedness
+        uint32_t        mesh, part;
+        bool            two_sided;
+        MeshSamplerData data;
     };
 
     bool shapeFinite(uint32_t shape) const;
@@ -146,6 +158,9 @@ class SceneModel {
     std::vector<ZygpuLightNode> light_nodes_;
     std::vector<uint32_t>       light_node_middles_, light_orders_, light_mapping_;
     std::vector<const zyg_mesh*> flat_meshes_;
+    std::vector<std::unique_ptr<SamplerRec>> samplers_;
+    std::vector<ZygpuMeshSampler>            flat_samplers_;
+    std::vector<float>                       flat_part_areas_;
     std::vector<float>          luts_;
     ZygpuScene                  flat_{};
     ZygpuView                   view_{};

@@ -317,6 +317,69 @@ def many_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=64,
     return camera
 
 
+def icosahedron():
+    """Unit icosahedron: (positions f32[12,3], indices u32[20,3]), counter-clockwise seen from outside."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], np.float64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6],
+                  [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10],
+                  [8, 6, 7], [9, 8, 1]], np.uint32)
+    return v.astype(np.float32), f
+
+
+def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24, seed=11, filter_name=None,
+                      split_threshold=0.5, big_light_quads=(24, 12)):
+    """Config-4 style: a closed room lit only by emissive triangle meshes - `num_lights` small icosahedra (20 triangles,
+    radius 0.05-0.12, instances of one mesh with PCG-random colour and power) and one larger emissive displaced sphere
+    with many triangles, so both the scene light tree and the per-part primitive trees (spherical-triangle sampling near,
+    area sampling far) are exercised. Returns the number of meshes (2)."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(70.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.4, -2.8)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth},
+                                                 "light_sampling": {"split_threshold": split_threshold}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    wall = su.material_create({"rendering": {"Substitute": {"color": [0.7, 0.7, 0.7], "roughness": 1.0}}})
+    glossy = su.material_create({"rendering": {"Substitute": {"color": [0.8, 0.6, 0.3], "roughness": 0.35, "metallic": 1.0}}})
+    for position, scale, rotation in [((0, 0, 0), (6, 6, 1), (90, 0, 0)), ((0, 3, 0), (6, 6, 1), (-90, 0, 0)),
+                                      ((0, 1.5, 3), (6, 3, 1), (0, 180, 0)), ((0, 1.5, -3), (6, 3, 1), (0, 0, 0)),
+                                      ((-3, 1.5, 0), (6, 3, 1), (0, -90, 0)), ((3, 1.5, 0), (6, 3, 1), (0, 90, 0))]:
+        prop = su.prop_create(su.RECTANGLE, [wall])
+        su.prop_set_transformation(prop, su.transformation(tuple(map(float, position)), tuple(map(float, scale)), tuple(map(float, rotation))))
+    for k, (x, z) in enumerate([(-1.2, 0.8), (1.4, 0.2)]):
+        cube = su.prop_create(su.CUBE, [glossy if 1 == k else wall])
+        su.prop_set_transformation(cube, su.transformation((x, 0.4, z), (0.8, 0.8, 0.8), (0.0, 25.0 * k, 0.0)))
+
+    positions, indices = icosahedron()
+    ico = su.triangle_mesh_create(positions, indices, positions.copy(), np.zeros((positions.shape[0], 2), np.float32))
+    rng = PCG32(0, np.array([seed], np.uint64))
+    for i in range(num_lights):
+        r = [float(rng.float()[0]) for _ in range(8)]
+        colour = [0.3 + 0.7 * r[0], 0.3 + 0.7 * r[1], 0.3 + 0.7 * r[2]]
+        material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": colour, "value": 10.0 + 60.0 * r[3] * r[3]}}}})
+        lamp = su.prop_create(ico, [material])
+        radius = 0.05 + 0.07 * r[4]
+        su.prop_set_transformation(lamp, su.transformation((-2.6 + 5.2 * r[5], 0.4 + 2.3 * r[6], -2.6 + 5.2 * r[7]), (radius, radius, radius),
+                                                           (0.0, 360.0 * r[0], 0.0)))
+        su.light_create(lamp)
+
+    bp, bn, buv, bi = displaced_sphere(*big_light_quads, seed=0x5EED0042)
+    bi = np.ascontiguousarray(bi.reshape(-1, 3)[:, [0, 2, 1]])
+    big = su.triangle_mesh_create(bp, bi, bn, buv)
+    big_material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": [1.0, 0.85, 0.6], "value": 4.0}}}})
+    big_prop = su.prop_create(big, [big_material])
+    su.prop_set_transformation(big_prop, su.transformation((0.2, 0.45, 1.5), (0.45, 0.45, 0.45), (0.0, 30.0, 0.0)))
+    su.light_create(big_prop)
+    return 2
+
+
 def instanced_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, grid=(32, 32), prototypes=4,
                     quads=(100, 50), seed=3):
     """Config-3 style scene through the C API: `prototypes` displaced-sphere meshes (seeds 1..), instanced
