@@ -182,12 +182,13 @@ def test_metal_mesh_matches_oracle(engine):
 
 
 def test_instanced_scene_matches_oracle(engine):
-    """su_prop_create_instance (capi.zig:457-469): 256 instances of 4 meshes with their own transformations, three
-    material kinds; the prop tree has ~130 nodes, rays collect several mesh candidates."""
+    """su_prop_create_instance (capi.zig:457-469): 256 instances of 6 meshes with their own transformations, the three
+    material kinds of BASELINE config 3 (diffuse, rough metal, glass with interior absorption) under a Rectangle light and
+    a Distant sun; the prop tree has ~130 nodes, rays collect several mesh candidates, glass meshes split paths."""
     w, spp = 96, 8
-    n = scenes.instanced_scene(w, w, spp=spp, grid=(16, 16), prototypes=4, quads=(40, 20))
+    n = scenes.instanced_scene(w, w, spp=spp, grid=(16, 16), prototypes=6, quads=(40, 20), sun=60.0)
     scene, view = su.compile_scene()
-    ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n)
+    ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n, wavefront_light_order=True)
     su.render_frame(0)
     gpu = download_film(w, w)
     assert np.array_equal(gpu[..., 3], ref[..., 3])

@@ -381,11 +381,12 @@ def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24,
 
 
 def instanced_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, grid=(32, 32), prototypes=4,
-                    quads=(100, 50), seed=3):
+                    quads=(100, 50), seed=3, glass=True, sun=None):
     """Config-3 style scene through the C API: `prototypes` displaced-sphere meshes (seeds 1..), instanced
     grid[0] x grid[1] times with su_prop_create_instance on a jittered grid (uniform scale 0.3-0.6, random Y rotation,
-    PCG32 stream `seed`), a ground Rectangle and one Rectangle light. Materials go by prototype: diffuse, rough metal,
-    glossy dielectric, diffuse. Returns the number of meshes."""
+    PCG32 stream `seed`), a ground Rectangle, one Rectangle light and optionally a Distant sun. Materials go by prototype
+    id mod 3 like BASELINE config 3: diffuse Substitute, gold-like rough metal, Glass (ior 1.5, smooth, attenuation
+    distance 1; a glossy dielectric Substitute when `glass` is off). Returns the number of meshes."""
     from . import su
 
     su.init()
@@ -400,12 +401,12 @@ def instanced_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None
 
     ground = su.material_create({"rendering": {"Substitute": {"color": [0.55, 0.55, 0.5], "roughness": 1.0}}})
     palette = [
-        {"color": [0.7, 0.25, 0.2], "roughness": 1.0, "metallic": 0.0},
-        {"color": [1.0, 0.77, 0.34], "roughness": 0.3, "metallic": 1.0},
-        {"color": [0.2, 0.5, 0.75], "roughness": 0.15, "metallic": 0.0},
-        {"color": [0.3, 0.65, 0.3], "roughness": 0.6, "metallic": 0.0},
+        {"Substitute": {"color": [0.7, 0.25, 0.2], "roughness": 1.0, "metallic": 0.0}},
+        {"Substitute": {"color": [1.0, 0.77, 0.34], "roughness": 0.3, "metallic": 1.0}},
+        {"Glass": {"ior": 1.5, "roughness": 0.0, "attenuation_color": [0.75, 0.9, 0.95], "attenuation_distance": 1.0}} if glass
+        else {"Substitute": {"color": [0.2, 0.5, 0.75], "roughness": 0.15, "metallic": 0.0}},
     ]
-    materials = [su.material_create({"rendering": {"Substitute": palette[i % len(palette)]}}) for i in range(prototypes)]
+    materials = [su.material_create({"rendering": palette[i % len(palette)]}) for i in range(prototypes)]
     light = su.material_create({"rendering": {"Light": {"emittance": {"value": 40.0}}}})
 
     protos = []
@@ -438,4 +439,9 @@ def instanced_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None
     lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=True)
     su.prop_set_transformation(lamp, su.transformation((0.25 * extent, 1.2 * extent, 0.0), (0.6 * extent, 0.6 * extent, 1.0), (-90.0, 0.0, 0.0)))
     su.light_create(lamp)
+    if sun is not None:
+        sun_material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": [1.0, 0.9, 0.75], "value": float(sun)}}}})
+        sun_prop = su.prop_create(su.DISTANT, [sun_material])
+        su.prop_set_transformation(sun_prop, su.transformation((0.0, 0.0, 0.0), (0.05, 0.05, 0.05), (-55.0, -35.0, 0.0)))
+        su.light_create(sun_prop)
     return prototypes
