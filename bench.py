@@ -149,16 +149,16 @@ def run_reference(args):
     from zyg_b200 import su
 
     path_tracing = {}
-    for name, (kind, width, spp, cpu_sample) in RENDER_SCENES.items():
-        cw, cspp = cpu_sample
-        num_meshes = build_render_scene(kind, cw, cspp)
+    for name, (builder, kwargs, width, height, spp, cpu_spp) in RENDER_SCENES.items():
+        if args.scenes and name not in args.scenes:
+            continue
+        num_meshes = build_render_scene(builder, kwargs, width, height, spp)
         scene, view = su.compile_scene()
-        oracle.render(scene, view, cw, cw, 0, 1, num_meshes=num_meshes)
         t0 = time.perf_counter()
-        oracle.render(scene, view, cw, cw, 0, cspp, num_meshes=num_meshes)
+        oracle.render(scene, view, width, height, 0, cpu_spp, num_meshes=num_meshes)
         dt_r = time.perf_counter() - t0
-        path_tracing[name] = {"path_samples_per_s": cw * cw * cspp / dt_r, "cores": cores,
-                              "sample": f"{cw}x{cw} x {cspp} spp of the same scene"}
+        path_tracing[name] = {"path_samples_per_s": width * height * cpu_spp / dt_r, "cores": cores,
+                              "sample": f"{width}x{height} x {cpu_spp} spp of the same scene"}
         su.release()
 
     print(json.dumps({
@@ -172,21 +172,31 @@ def run_reference(args):
     }))
 
 
+# The forward pass on the BASELINE.json configs: name -> (scene builder, kwargs, width, height, spp per step, spp of the CPU
+# sample). The CPU path renders the same compiled scene at the same resolution with fewer samples per pixel.
 RENDER_SCENES = {
-    # name: (builder kwargs, width, spp, cpu sample (width, spp))
-    "cornell_512x512x64": ("cornell", 512, 64, (256, 16)),
-    "sphere1m_1024x1024x16": ("sphere", 1024, 16, (256, 8)),
+    # configs[0]: Cornell box 512 x 512 x 64 spp, PathtracerMIS, max 8 bounces
+    "config1_cornell_512x512x64": ("cornell_box", {}, 512, 512, 64, 8),
+    # the configs[1] mesh (1M triangles) as a lit scene
+    "sphere1m_1024x1024x16": ("sphere_scene", {"quads": MESH_QUADS}, 1024, 1024, 16, 2),
+    # configs[2]: 20 x 250k-triangle prototypes = 5M triangles, 10k prop instances, diffuse + rough metal + glass, Rectangle
+    # light + Distant sun, 1920 x 1080 (8 of the 256 spp per step)
+    "config3_instanced5m_1920x1080x8": ("instanced_scene", {"grid": (100, 100), "prototypes": 20, "quads": (500, 250), "sun": 60.0},
+                                        1920, 1080, 8, 1),
+    # configs[3] without the sky image: 1000 emissive icosahedron meshes + a 576-triangle emitter in a room with 200k triangles
+    # of diffuse geometry, Distant sun, light-tree sampling with split threshold 0.5, 1920 x 1080 (4 of the 1024 spp per step)
+    "config4_meshlights1k_1920x1080x4": ("mesh_lights_scene", {"num_lights": 1000, "geometry_quads": (400, 250), "sun": 15.0, "max_depth": 8},
+                                         1920, 1080, 4, 1),
 }
+MESH_SCENES = ("sphere_scene", "instanced_scene", "mesh_lights_scene")
 
 
-def build_render_scene(kind, width, spp):
+def build_render_scene(builder, kwargs, width, height, spp):
     from zyg_b200 import scenes, su
 
     su.release()
-    if "cornell" == kind:
-        scenes.cornell_box(width, width, spp=spp)
-        return 0
-    return scenes.sphere_scene(width, width, spp=spp, quads=MESH_QUADS)
+    r = getattr(scenes, builder)(width, height, spp=spp, **kwargs)
+    return r if builder in MESH_SCENES else 0
 
 
 def bench_render(args, rank, world, local):
@@ -210,14 +220,18 @@ def bench_render(args, rank, world, local):
 
     out = {}
     launches = 0
-    for name, (kind, width, spp, cpu_sample) in RENDER_SCENES.items():
-        num_meshes = build_render_scene(kind, width, spp)
+    for name, (builder, kwargs, width, height, spp, cpu_spp) in RENDER_SCENES.items():
+        if args.scenes and name not in args.scenes:
+            continue
+        t_build = time.time()
+        num_meshes = build_render_scene(builder, kwargs, width, height, spp)
         su._ok(su._su().zyg_su_set_device(local), "zyg_su_set_device")
         su.start_frame(0)  # Scene.compile + upload + clear (not timed: resident-scene number)
         dev = su.device_handle()
         stream = multi.render_stream()
         first, count = multi.sample_range(rank, world, spp)
-        film = multi.device_film_tensor(width, width)
+        film = multi.device_film_tensor(width, height)
+        log(f"[rank {rank}] {name}: scene built, compiled and uploaded in {time.time() - t_build:.1f}s")
 
         def step():
             su._ok(L.zygpu_clear_film(dev), "zygpu_clear_film")
@@ -253,7 +267,7 @@ def bench_render(args, rank, world, local):
         t0 = time.perf_counter()
         if count > 0:
             su.render_frame_range(0, first, count)
-        rgba = su.resolve_frame_to_buffer(width, width)
+        rgba = su.resolve_frame_to_buffer(width, height)
         e2e_s = time.perf_counter() - t0
 
         if world > 1:
@@ -261,10 +275,10 @@ def bench_render(args, rank, world, local):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, e2e_s = t.tolist()
 
-        samples = width * width * spp
+        samples = width * height * spp
         entry = {
             "path_samples_per_s": samples * args.steps / (ms * 1e-3), "ms_per_frame": ms / args.steps,
-            "resolution": [width, width], "spp": spp, "samples_per_frame": samples,
+            "resolution": [width, height], "spp": spp, "samples_per_frame": samples,
             "closest_rays_per_sample": st.closest_rays / max(1, st.camera_samples),
             "shadow_rays_per_sample": st.shadow_rays / max(1, st.camera_samples),
             "mrays_per_s": (st.closest_rays + st.shadow_rays) / max(1, st.camera_samples) * samples * args.steps / (ms * 1e-3) / 1e6,
@@ -275,15 +289,12 @@ def bench_render(args, rank, world, local):
 
         if rank == 0 and world == 1 and not args.no_cpu:
             oracle = load_oracle()
-            cw, cspp = cpu_sample
-            build_render_scene(kind, cw, cspp)
             scene, view = su.compile_scene()
-            oracle.render(scene, view, cw, cw, 0, 1, num_meshes=num_meshes)
             t0 = time.perf_counter()
-            oracle.render(scene, view, cw, cw, 0, cspp, num_meshes=num_meshes)
+            oracle.render(scene, view, width, height, 0, cpu_spp, num_meshes=num_meshes)
             dt = time.perf_counter() - t0
-            entry["cpu_baseline"] = {"value": cw * cw * cspp / dt, "unit": "path-samples/s", "cores": os.cpu_count(), "kind": "port",
-                                     "sample": f"{cw}x{cw} x {cspp} spp of the same scene, oracle/ restatement of zyg's PathtracerMIS"}
+            entry["cpu_baseline"] = {"value": width * height * cpu_spp / dt, "unit": "path-samples/s", "cores": os.cpu_count(), "kind": "port",
+                                     "sample": f"{width}x{height} x {cpu_spp} spp of the same scene, oracle/ restatement of zyg's PathtracerMIS"}
         su.release()
         out[name] = entry
     return out, launches
@@ -298,6 +309,7 @@ def main():
     ap.add_argument("--rays", type=int, default=PRIMARY_RES, help="primary resolution r (r*r rays per class)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-render", action="store_true", help="skip the path_tracing section")
+    ap.add_argument("--scenes", nargs="*", default=None, help="path_tracing scenes to run (default: all of RENDER_SCENES)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

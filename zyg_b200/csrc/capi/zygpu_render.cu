@@ -62,6 +62,7 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint3
     if (lanes > 1 && (0 != allocPath(r, &p.med, vertices) || 0 != allocPath(r, &p.queue_t, vertices) || 0 != allocPath(r, &p.queue_s, capacity))) {
         return -1;
     }
+    if (shadow_stride > 1 && 0 != allocPath(r, &p.queue_r, size_t(capacity) * shadow_stride)) return -1;
     CUDA_OK(cudaMemset(p.counters, 0, 16 * sizeof(uint32_t)));
     p.capacity      = capacity;
     p.shadow_stride = shadow_stride;

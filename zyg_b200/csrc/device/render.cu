@@ -410,7 +410,9 @@ template <bool AnyHit>
 __global__ void __launch_bounds__(kBlock) topKernel(SceneDevice sc, PathState st) {
     const uint32_t stride = st.shadow_stride;
     const uint32_t* __restrict__ closest_queue = st.lanes > 1 ? st.queue_t : st.queue_a;
-    const uint64_t total = AnyHit ? uint64_t(st.counters[1]) * stride : uint64_t(st.counters[st.lanes > 1 ? 7 : 0]);
+    const bool     compact = AnyHit && nullptr != st.queue_r;  // shadow records listed in queue_r instead of stride per slot
+    const uint64_t total   = AnyHit ? (compact ? uint64_t(st.counters[10]) : uint64_t(st.counters[1]) * stride)
+                                    : uint64_t(st.counters[st.lanes > 1 ? 7 : 0]);
     const uint32_t count  = uint32_t(total < 0xFFFFFFFFull ? total : 0xFFFFFFFFull);
     const uint32_t iters  = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     uint32_t       traced = 0;
@@ -421,7 +423,9 @@ __global__ void __launch_bounds__(kBlock) topKernel(SceneDevice sc, PathState st
         uint32_t       item    = 0;
         bool           valid   = i < count;
         if (valid) {
-            if (AnyHit) {
+            if (compact) {
+                item = st.queue_r[i];
+            } else if (AnyHit) {
                 const uint32_t slot = st.queue_b[i / stride];
                 const uint32_t k    = i % stride;
                 valid               = k < st.sh_n[slot];
@@ -1527,8 +1531,9 @@ __global__ void __launch_bounds__(kBlock) generateKernel(ZygpuView view, PathSta
         st.counters[0] = pass.num_paths;
         st.counters[1] = 0;
         st.counters[4] = 0;
-        st.counters[7] = pass.num_paths;
-        st.counters[9] = 0;
+        st.counters[7]  = pass.num_paths;
+        st.counters[9]  = 0;
+        st.counters[10] = 0;
     }
 }
 
@@ -1837,6 +1842,10 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                 st.sh_n[slot] = num_records;
                 st.thr[vid]   = make_float4(lv.throughput.x, lv.throughput.y, lv.throughput.z, vertex.bxdf_pdf);
                 alive         = true;
+                if (nullptr != st.queue_r && 0 != num_records) {
+                    const uint32_t base = atomicAdd(&st.counters[10], num_records);
+                    for (uint32_t k = 0; k < num_records; ++k) st.queue_r[base + k] = slot * st.shadow_stride + k;
+                }
             }
             if (Split && !alive) pool = poolFree(pool, lane);
             storeSampler(st, slot, sampler, pool);
@@ -2042,17 +2051,22 @@ __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeB
 
 // Counter bookkeeping between the stages (single thread; the queue lengths never leave the device).
 __global__ void beginGenerationKernel(PathState st) {  // after extend: the trace queue is consumed, nothing is queued yet
-    st.counters[1] = 0;
-    st.counters[4] = 0;
-    st.counters[7] = 0;
-    st.counters[9] = 0;
+    st.counters[1]  = 0;
+    st.counters[4]  = 0;
+    st.counters[7]  = 0;
+    st.counters[9]  = 0;
+    st.counters[10] = 0;
 }
-__global__ void beginRoundKernel(PathState st) { st.counters[1] = 0; }
+__global__ void beginRoundKernel(PathState st) {
+    st.counters[1]  = 0;
+    st.counters[10] = 0;
+}
 __global__ void advanceKernel(PathState st) {
     st.counters[0] = st.counters[4];
     st.counters[1] = 0;
-    st.counters[4] = 0;
-    st.counters[9] = 0;
+    st.counters[4]  = 0;
+    st.counters[9]  = 0;
+    st.counters[10] = 0;
 }
 
 // Sensor.addSample for every sample of the pass, gathered per film pixel (sensor.zig:168-385, buffer_opaque.zig:39-45).

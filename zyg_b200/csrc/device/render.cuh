@@ -119,8 +119,9 @@ struct PathState {
     uint32_t* queue_b;   // slots whose vertex of the current round survived shade_a
     uint32_t* queue_t;   // lanes > 1: vertex ids to extend (lanes == 1: the slots of queue_a are the vertex ids)
     uint32_t* queue_s;   // lanes > 1: slots with more than one vertex in the current generation
+    uint32_t* queue_r;   // shadow_stride > 1: the shadow records written by shade_a, compacted (null: every slot has one record)
     uint32_t* counters;  // [0] |A|, [1] |B|, [2] |mesh queue|, [3] shadow overflow flag, [4] |next A|, [5] closest rays, [6] shadow rays,
-                         // [7] |T|, [8] work counter of the persistent mesh kernel, [9] |S| (16 words in all)
+                         // [7] |T|, [8] work counter of the persistent mesh kernel, [9] |S|, [10] |R| (16 words in all)
 
     uint32_t capacity;       // path slots
     uint32_t shadow_stride;  // shadow records reserved per path

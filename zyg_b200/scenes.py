@@ -330,11 +330,12 @@ def icosahedron():
 
 
 def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24, seed=11, filter_name=None,
-                      split_threshold=0.5, big_light_quads=(24, 12)):
+                      split_threshold=0.5, big_light_quads=(24, 12), geometry_quads=None, sun=None):
     """Config-4 style: a closed room lit only by emissive triangle meshes - `num_lights` small icosahedra (20 triangles,
     radius 0.05-0.12, instances of one mesh with PCG-random colour and power) and one larger emissive displaced sphere
     with many triangles, so both the scene light tree and the per-part primitive trees (spherical-triangle sampling near,
-    area sampling far) are exercised. Returns the number of meshes (2)."""
+    area sampling far) are exercised. `geometry_quads` adds a diffuse displaced sphere of 2 * nu * nv triangles (config 4: 200 k
+    triangles of diffuse geometry), `sun` a Distant light. Returns the number of meshes."""
     from . import su
 
     su.init()
@@ -348,9 +349,12 @@ def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24,
 
     wall = su.material_create({"rendering": {"Substitute": {"color": [0.7, 0.7, 0.7], "roughness": 1.0}}})
     glossy = su.material_create({"rendering": {"Substitute": {"color": [0.8, 0.6, 0.3], "roughness": 0.35, "metallic": 1.0}}})
-    for position, scale, rotation in [((0, 0, 0), (6, 6, 1), (90, 0, 0)), ((0, 3, 0), (6, 6, 1), (-90, 0, 0)),
-                                      ((0, 1.5, 3), (6, 3, 1), (0, 180, 0)), ((0, 1.5, -3), (6, 3, 1), (0, 0, 0)),
-                                      ((-3, 1.5, 0), (6, 3, 1), (0, -90, 0)), ((3, 1.5, 0), (6, 3, 1), (0, 90, 0))]:
+    walls = [((0, 0, 0), (6, 6, 1), (90, 0, 0)), ((0, 3, 0), (6, 6, 1), (-90, 0, 0)),
+             ((0, 1.5, 3), (6, 3, 1), (0, 180, 0)), ((0, 1.5, -3), (6, 3, 1), (0, 0, 0)),
+             ((-3, 1.5, 0), (6, 3, 1), (0, -90, 0)), ((3, 1.5, 0), (6, 3, 1), (0, 90, 0))]
+    if sun is not None:
+        del walls[1]  # no ceiling: the sun (and escaping paths) get in and out
+    for position, scale, rotation in walls:
         prop = su.prop_create(su.RECTANGLE, [wall])
         su.prop_set_transformation(prop, su.transformation(tuple(map(float, position)), tuple(map(float, scale)), tuple(map(float, rotation))))
     for k, (x, z) in enumerate([(-1.2, 0.8), (1.4, 0.2)]):
@@ -363,7 +367,7 @@ def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24,
     for i in range(num_lights):
         r = [float(rng.float()[0]) for _ in range(8)]
         colour = [0.3 + 0.7 * r[0], 0.3 + 0.7 * r[1], 0.3 + 0.7 * r[2]]
-        material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": colour, "value": 10.0 + 60.0 * r[3] * r[3]}}}})
+        material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": colour, "value": (10.0 + 60.0 * r[3] * r[3]) * min(1.0, 24.0 / num_lights)}}}})
         lamp = su.prop_create(ico, [material])
         radius = 0.05 + 0.07 * r[4]
         su.prop_set_transformation(lamp, su.transformation((-2.6 + 5.2 * r[5], 0.4 + 2.3 * r[6], -2.6 + 5.2 * r[7]), (radius, radius, radius),
@@ -377,7 +381,20 @@ def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24,
     big_prop = su.prop_create(big, [big_material])
     su.prop_set_transformation(big_prop, su.transformation((0.2, 0.45, 1.5), (0.45, 0.45, 0.45), (0.0, 30.0, 0.0)))
     su.light_create(big_prop)
-    return 2
+    num_meshes = 2
+    if geometry_quads is not None:
+        gp, gn, guv, gi = displaced_sphere(*geometry_quads, seed=0x5EED0077, amplitude=0.12)
+        gi = np.ascontiguousarray(gi.reshape(-1, 3)[:, [0, 2, 1]])
+        geometry = su.triangle_mesh_create(gp, gi, gn, guv)
+        geometry_prop = su.prop_create(geometry, [wall])
+        su.prop_set_transformation(geometry_prop, su.transformation((-0.6, 0.9, 1.2), (0.9, 0.9, 0.9), (0.0, 0.0, 0.0)))
+        num_meshes += 1
+    if sun is not None:
+        sun_material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": [1.0, 0.9, 0.75], "value": float(sun)}}}})
+        sun_prop = su.prop_create(su.DISTANT, [sun_material])
+        su.prop_set_transformation(sun_prop, su.transformation((0.0, 0.0, 0.0), (0.05, 0.05, 0.05), (-70.0, -20.0, 0.0)))
+        su.light_create(sun_prop)
+    return num_meshes
 
 
 def instanced_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, grid=(32, 32), prototypes=4,
