@@ -325,8 +325,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
+    # rank 0 prints exactly one JSON line on stdout: everything else that writes to fd 1 while the bench runs (NCCL's version
+    # banner, library chatter) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     res = args.rays
@@ -471,7 +475,8 @@ def main():
         assert np.array_equal(ref["t"].view(np.uint32), got["t"].view(np.uint32)), "timed output differs from oracle"
 
     if rank == 0:
-        print(json.dumps(result))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(result) + "\n").encode())
     if dev is not None:
         dev.close()
     if world > 1:

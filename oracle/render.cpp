@@ -1678,7 +1678,27 @@ struct Worker {
                 if (!rectangle::intersect(vertex.ray, frag.isec.trafo, frag.isec)) return splat(0.f);
                 rectangle::fragment(vertex.ray, frag);
                 return evaluateRadiance(vertex, frag, sampler);
-            default: return splat(0.f);  // shape.zig:283-299; Sphere / mesh emitters are not in scope yet
+            case ZYG_SHAPE_TRIANGLE_MESH: {  // Mesh.emission -> Tree.emission, triangle_mesh.zig:379-388, triangle_tree.zig:405-477
+                const Ray    local_ray = frag.isec.trafo.worldToObjectRay(vertex.ray);
+                const Mesh   tree      = scene.treeOf(prop.mesh);
+                const ZoMesh& zm       = scene.meshes[prop.mesh];
+                Vec4f        energy    = splat(0.f);
+                tree.allHits(local_ray, [&](uint32_t i, const Hit& hit) {
+                    frag.isec.t         = hit.t;
+                    frag.isec.u         = hit.u;
+                    frag.isec.v         = hit.v;
+                    frag.isec.primitive = i;
+                    frag.part           = zm.parts[i];
+                    const Vec4f a = tree.position(tree.triangles[3 * size_t(i)]), b = tree.position(tree.triangles[3 * size_t(i) + 1]),
+                                c = tree.position(tree.triangles[3 * size_t(i) + 2]);
+                    frag.p     = frag.isec.trafo.objectToWorldPoint(mesh::interpolate3(a, b, c, hit.u, hit.v));
+                    frag.geo_n = frag.isec.trafo.objectToWorldNormal(normalize3(cross3(b - a, c - a)));
+                    frag.uvw   = splat(0.f);  // interpolated uv: only read by emission maps
+                    energy     = energy + evaluateRadiance(vertex, frag, sampler);
+                });
+                return energy;
+            }
+            default: return splat(0.f);  // shape.zig:283-299; Sphere emitters are not in scope yet
         }
     }
 

@@ -154,6 +154,41 @@ struct Mesh {
         return true;
     }
 
+    // The traversal of Tree.emission, triangle_tree.zig:405-477: every triangle the (fixed) ray interval hits, in tree order.
+    template <typename Visit>
+    void allHits(const Ray& ray, Visit&& visit) const {
+        NodeStack stack;
+        uint32_t  n = 0;
+        while (NodeStack::End != n) {
+            const Node&    node = nodes[n];
+            const uint32_t num  = node.numIndices();
+            if (0 != num) {
+                uint32_t       i = node.indicesStart();
+                const uint32_t e = i + num;
+                for (; i < e; ++i) {
+                    Hit hit;
+                    if (intersectIndexed(ray, i, hit)) visit(i, hit);
+                }
+                n = stack.pop();
+                continue;
+            }
+            uint32_t a = node.children();
+            uint32_t b = a + 1;
+            float dista = nodes[a].intersect(ray);
+            float distb = nodes[b].intersect(ray);
+            if (dista > distb) {
+                std::swap(a, b);
+                std::swap(dista, distb);
+            }
+            if (FLT_MAX == dista) {
+                n = stack.pop();
+            } else {
+                n = a;
+                if (FLT_MAX != distb) stack.push(b);
+            }
+        }
+    }
+
     // triangle_tree.zig:197-242
     bool intersectP(const Ray& ray) const {
         NodeStack stack;
