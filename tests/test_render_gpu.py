@@ -259,14 +259,15 @@ def test_distant_light_matches_oracle(engine):
     assert ref[..., :3].sum() / ref[..., 3].sum() > 1.2 * dark[..., :3].sum() / dark[..., 3].sum()
 
 
-@pytest.mark.parametrize("split_threshold", [0.5, 0.0])
-def test_mesh_lights_match_oracle(engine, split_threshold):
+@pytest.mark.parametrize("split_threshold,unoccluding", [(0.5, False), (0.0, False), (0.5, True)])
+def test_mesh_lights_match_oracle(engine, split_threshold, unoccluding):
     """Emissive triangle meshes (config 4 style): 24 icosahedra + one 576-triangle emitter. Part.configure and the
     per-part PrimitiveTree on the host (triangle_mesh.zig:57-149, light_tree_builder.zig:378-428), Mesh.sampleTo with
     Arvo's spherical-triangle sampling near and area sampling far (triangle_mesh.zig:402-608), Mesh.pdf through the
-    primitive mapping for emitter hits (:662-703)."""
+    primitive mapping for emitter hits (:662-703). Un-occluding mesh emitters (what a scene file's Light entities are by
+    default) are gathered by the all-hits traversal of TriangleTree.emission (triangle_tree.zig:405-477)."""
     w, spp = 96, 16
-    n = scenes.mesh_lights_scene(w, w, spp=spp, split_threshold=split_threshold)
+    n = scenes.mesh_lights_scene(w, w, spp=spp, split_threshold=split_threshold, unoccluding=unoccluding)
     scene, view = su.compile_scene()
     ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n, wavefront_light_order=True)
     su.render_frame(0)

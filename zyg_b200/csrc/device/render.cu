@@ -1376,12 +1376,75 @@ __device__ V3 evaluateRadiance(const SceneDevice& sc, const VertexD& vertex, con
     return scale3(weight, energy);
 }
 
+// Mesh.emission -> Tree.emission, triangle_mesh.zig:379-388, triangle_tree.zig:405-477: every triangle of an un-occluding mesh
+// emitter the segment crosses, visited in the reference's order (binary tree, near child first) because each hit draws from
+// the sampler.
+template <bool MeshLights>
+__device__ __noinline__ V3 meshEmission(const SceneDevice& sc, uint32_t entity, const ZygpuProp& prop, const VertexD& vertex, SamplerD& sampler) {
+    FragD frag;
+    frag.prop  = entity;
+    frag.trafo = loadTrafo(sc.trafos, entity);
+    frag.t = frag.b = frag.n = splat3(0.f);
+    frag.u = frag.v = 0.f;
+
+    const MeshDevice&  mesh  = sc.meshes[prop.mesh];
+    const MeshShading& shade = sc.mesh_shading[prop.mesh];
+    const RayT         ray   = worldToObjectRay(frag.trafo, vertex.ray);
+
+    uint32_t stack[64];
+    uint32_t end = 0;
+    uint32_t n   = 0;
+    V3       energy = splat3(0.f);
+
+    while (kEnd != n) {
+        const float4 nmin = __ldg(mesh.binary_nodes + 2 * size_t(n));
+        const float4 nmax = __ldg(mesh.binary_nodes + 2 * size_t(n) + 1);
+        const uint32_t num = __float_as_uint(nmax.w);
+        if (0 != num) {
+            const uint32_t start = __float_as_uint(nmin.w);
+            for (uint32_t i = start; i < start + num; ++i) {
+                V3 a, b, c;
+                meshTriangle(mesh, i, a, b, c);
+                float ht, hu, hv;
+                if (!intersectTriangle(ray, a, sub3(b, a), sub3(c, a), ht, hu, hv)) continue;
+                frag.primitive = i;
+                frag.part      = __ldg(shade.parts + i);
+                frag.p         = frag.trafo.objectToWorldPoint(interpolate3(a, b, c, hu, hv));
+                frag.geo_n     = frag.trafo.objectToWorldNormal(normalize3(cross3(sub3(b, a), sub3(c, a))));
+                energy         = add3(energy, evaluateRadiance<MeshLights>(sc, vertex, frag, sampler));
+            }
+            n = 0 == end ? kEnd : stack[--end];
+            continue;
+        }
+        uint32_t a = __float_as_uint(nmin.w);
+        uint32_t b = a + 1;
+        float dista = intersectNode(__ldg(mesh.binary_nodes + 2 * size_t(a)), __ldg(mesh.binary_nodes + 2 * size_t(a) + 1), ray);
+        float distb = intersectNode(__ldg(mesh.binary_nodes + 2 * size_t(b)), __ldg(mesh.binary_nodes + 2 * size_t(b) + 1), ray);
+        if (dista > distb) {
+            const uint32_t tn = a;
+            a                 = b;
+            b                 = tn;
+            const float td    = dista;
+            dista             = distb;
+            distb             = td;
+        }
+        if (FLT_MAX == dista) {
+            n = 0 == end ? kEnd : stack[--end];
+        } else {
+            n = a;
+            if (FLT_MAX != distb && end < 64) stack[end++] = b;
+        }
+    }
+    return energy;
+}
+
 // Prop.emission + Shape.emission, prop.zig:239-264, shape.zig:283-299, rectangle.zig:188-196
 template <bool MeshLights>
 __device__ V3 propEmission(const SceneDevice& sc, uint32_t entity, const VertexD& vertex, SamplerD& sampler) {
     const ZygpuProp prop = sc.props[entity];
     if (!propVisible(prop.flags, vertex.probe_depth)) return splat3(0.f);
     if (!aabbIntersect(sc.aabbs, entity, vertex.ray)) return splat3(0.f);
+    if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == prop.shape) return meshEmission<MeshLights>(sc, entity, prop, vertex, sampler);
     if (ZYG_SHAPE_RECTANGLE != prop.shape) return splat3(0.f);
 
     FragD frag;

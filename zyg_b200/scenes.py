@@ -330,7 +330,7 @@ def icosahedron():
 
 
 def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24, seed=11, filter_name=None,
-                      split_threshold=0.5, big_light_quads=(24, 12), geometry_quads=None, sun=None):
+                      split_threshold=0.5, big_light_quads=(24, 12), geometry_quads=None, sun=None, unoccluding=False):
     """Config-4 style: a closed room lit only by emissive triangle meshes - `num_lights` small icosahedra (20 triangles,
     radius 0.05-0.12, instances of one mesh with PCG-random colour and power) and one larger emissive displaced sphere
     with many triangles, so both the scene light tree and the per-part primitive trees (spherical-triangle sampling near,
@@ -368,7 +368,7 @@ def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24,
         r = [float(rng.float()[0]) for _ in range(8)]
         colour = [0.3 + 0.7 * r[0], 0.3 + 0.7 * r[1], 0.3 + 0.7 * r[2]]
         material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": colour, "value": (10.0 + 60.0 * r[3] * r[3]) * min(1.0, 24.0 / num_lights)}}}})
-        lamp = su.prop_create(ico, [material])
+        lamp = su.prop_create(ico, [material], unoccluding=unoccluding)  # scene files make Light entities un-occluding by default
         radius = 0.05 + 0.07 * r[4]
         su.prop_set_transformation(lamp, su.transformation((-2.6 + 5.2 * r[5], 0.4 + 2.3 * r[6], -2.6 + 5.2 * r[7]), (radius, radius, radius),
                                                            (0.0, 360.0 * r[0], 0.0)))
