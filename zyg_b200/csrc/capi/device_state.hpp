@@ -45,6 +45,7 @@ struct RenderState {
     zygpu::SceneDevice scene{};
     bool               has_scene  = false;
     bool               has_meshes = false;
+    bool               deferred_lights = false;  // light selection / sampling in the persistent light kernels
     bool               can_split  = false;  // a material can split paths: 4 vertex records per camera sample
     ZygpuView          view{};
     bool               has_view = false;

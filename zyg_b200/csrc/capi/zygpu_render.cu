@@ -42,8 +42,11 @@ uint32_t targetPathsPerPass() {
 
 // `lanes` vertex records per slot (1, or 4 when a material of the scene can split a path); trace items are vertex ids for
 // closest-hit rays and shadow records for any-hit rays, so the per-item arrays hold max(lanes, shadow_stride) per slot.
-int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint32_t lanes) {
-    if (r.paths.capacity >= capacity && r.paths.shadow_stride == shadow_stride && r.paths.lanes == lanes) return 0;
+int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint32_t lanes, bool deferred_lights) {
+    if (r.paths.capacity >= capacity && r.paths.shadow_stride == shadow_stride && r.paths.lanes == lanes &&
+        (nullptr != r.paths.queue_l) == deferred_lights) {
+        return 0;
+    }
     freeAll(r.path_buffers);
     zygpu::PathState& p = r.paths;
     p                   = zygpu::PathState{};
@@ -63,6 +66,11 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint3
         return -1;
     }
     if (shadow_stride > 1 && 0 != allocPath(r, &p.queue_r, size_t(capacity) * shadow_stride)) return -1;
+    if (deferred_lights && (0 != allocPath(r, &p.ls_p, capacity) || 0 != allocPath(r, &p.ls_g, capacity) ||
+                            0 != allocPath(r, &p.picks, size_t(capacity) * 64) || 0 != allocPath(r, &p.pick_n, capacity) ||
+                            0 != allocPath(r, &p.queue_l, capacity))) {
+        return -1;
+    }
     CUDA_OK(cudaMemset(p.counters, 0, 16 * sizeof(uint32_t)));
     p.capacity      = capacity;
     p.shadow_stride = shadow_stride;
@@ -212,6 +220,11 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
         }
         if (mat.priority < -127 || mat.priority > 127) return fail("zygpu_upload_scene: material priority outside i8");
     }
+    // with many lights the light selection / sampling of a vertex varies from one tree descent to dozens of picks: such
+    // scenes run it in the persistent light kernels instead of inside shade_a (ZYGPU_DEFERRED_LIGHTS=0/1 overrides)
+    r.deferred_lights = scene->num_lights >= 8;
+    if (const char* v = getenv("ZYGPU_DEFERRED_LIGHTS")) r.deferred_lights = 0 != atoi(v);
+
     r.has_meshes = scene->num_meshes > 0;
     r.has_scene  = true;
     return 0;
@@ -275,7 +288,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
     if (capacity > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
     const uint32_t lanes = r.can_split ? 4 : 1;
     if (capacity * lanes > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
-    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples, lanes)) return -1;
+    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples, lanes, r.deferred_lights)) return -1;
     const uint32_t rounds = lanes;
 
     // extend / shadow are one kernel each (prop-tree walk) plus the persistent mesh kernel when the scene has meshes
@@ -316,6 +329,10 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
                 CUDA_OK(zygpu::launchShadeA(r.scene, view, r.paths, pass, pass.num_paths, round, r.stream));
                 r.stats.kernel_launches += 1;
                 if (last) continue;
+                if (r.deferred_lights) {
+                    CUDA_OK(zygpu::launchLightStages(r.scene, view, r.paths, pass, pass.num_paths, r.stream));
+                    r.stats.kernel_launches += 2;
+                }
                 CUDA_OK(zygpu::launchShadow(r.scene, r.paths, pass.num_paths, r.has_meshes, r.stream));
                 CUDA_OK(zygpu::launchShadeB(r.scene, view, r.paths, pass, pass.num_paths, round, r.stream));
                 r.stats.kernel_launches += 2 + trace_extra + (1 == lanes ? 1 : 0);  // shadow, shade_b (+ queue swap)

@@ -1597,6 +1597,7 @@ __global__ void __launch_bounds__(kBlock) generateKernel(ZygpuView view, PathSta
         st.counters[7]  = pass.num_paths;
         st.counters[9]  = 0;
         st.counters[10] = 0;
+        st.counters[11] = 0;
     }
 }
 
@@ -1692,13 +1693,14 @@ __device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t
 // roulette (:88, helper.zig:75-89), Vertex.sample (:93), sampleLights / evaluateLight up to the visibility test
 // (:174-250).
 // Features the scene needs of shade_a; what it does not need is compiled out (each costs registers in the hottest kernel).
-enum : uint32_t { kFeatureSplit = 1, kFeatureMeshLights = 2, kFeatureInfiniteLights = 4 };
+enum : uint32_t { kFeatureSplit = 1, kFeatureMeshLights = 2, kFeatureInfiniteLights = 4, kFeatureDeferredLights = 8 };
 
 template <uint32_t Features>
 __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
     constexpr bool Split      = 0 != (Features & kFeatureSplit);
     constexpr bool MeshLights = 0 != (Features & kFeatureMeshLights);
     constexpr bool Infinite   = 0 != (Features & kFeatureInfiniteLights);
+    constexpr bool Deferred   = 0 != (Features & kFeatureDeferredLights);  // light selection and sampling run in the light kernels
     __shared__ uint32_t sobol_tables[kSobolTableWords];
     loadSobolTables(sobol_tables);
     const bool      later = Split && round > 0;
@@ -1827,7 +1829,16 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                 // sampleLights. Every path owns `shadow_stride` consecutive shadow records (slot * stride + k): picks and
                 // their samples are generated in the reference's order and stored in that order.
                 uint32_t num_records = 0;
-                if (mat_sample.can_evaluate) {
+                bool     request     = false;
+                if (Deferred && mat_sample.can_evaluate) {
+                    const float    select = sampler.sample1D();
+                    const uint32_t bits   = (mat_sample.translucent ? 1u : 0u) | (dot3(mat_sample.geo_n, frag.geo_n) < 0.f ? 2u : 0u) |
+                                          (vertex.light_split_threshold != view.split_threshold ? 4u : 0u) | (total_depth << 8);
+                    st.ls_p[slot] = make_float4(frag.p.x, frag.p.y, frag.p.z, select);
+                    st.ls_g[slot] = make_float4(frag.geo_n.x, frag.geo_n.y, frag.geo_n.z, __uint_as_float(bits));
+                    request       = true;
+                }
+                if (!Deferred && mat_sample.can_evaluate) {
                     const V3    p           = frag.p;
                     const V3    n           = mat_sample.geo_n;
                     const bool  translucent = mat_sample.translucent;
@@ -1909,6 +1920,7 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                     const uint32_t base = atomicAdd(&st.counters[10], num_records);
                     for (uint32_t k = 0; k < num_records; ++k) st.queue_r[base + k] = slot * st.shadow_stride + k;
                 }
+                if (Deferred && request) st.queue_l[atomicAdd(&st.counters[11], 1u)] = slot;
             }
             if (Split && !alive) pool = poolFree(pool, lane);
             storeSampler(st, slot, sampler, pool);
@@ -1916,6 +1928,275 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
         }
         queuePush(st.queue_b, &st.counters[1], alive, slot);
         if (Split && 0 == round) queuePush(st.queue_s, &st.counters[9], multi, slot);
+    }
+}
+
+// ---- deferred light sampling ---------------------------------------------------------------------------------------
+//
+// With many lights the work of PathtracerMIS.sampleLights varies wildly between vertices: far from the lights the tree is
+// descended once, near them the adaptive split returns dozens of picks, and a picked mesh light descends its own tree. Inside
+// shade_a a warp would wait for its slowest lane (measured: 2.8 of 32 lanes active). So shade_a only leaves a request, and
+// two persistent kernels whose lanes fetch new work as soon as they finish do the rest:
+//
+//   lightSelectPersistent   Tree.randomLight (light_tree.zig:346-447), one tree node per step and lane -> picks
+//   lightSamplePersistent   Light.sampleTo for one pick per step and lane, in pick order -> shadow records
+//
+// The sampler is only touched by the second kernel, pick by pick in the reference's order, so the stream of a vertex is the
+// one the inline path produces.
+
+__device__ __forceinline__ V3 offsetPoint(V3 p, V3 geo_n, V3 w) {  // Fragment.offsetP with offset() == 0, intersection.zig:112-116
+    const V3 nn = dot3(geo_n, w) > 0.f ? geo_n : neg3(geo_n);
+    return offsetRay(fmas3(0.f, nn, p), nn);
+}
+
+__global__ void __launch_bounds__(128) lightSelectPersistent(SceneDevice sc, ZygpuView view, PathState st, uint32_t* __restrict__ work_counter) {
+    constexpr uint32_t kFull   = 0xffffffffu;
+    const uint32_t     lane    = threadIdx.x & 31u;
+    const uint32_t     n_items = st.counters[11];
+    const TreeD        tr      = sceneTree(sc);
+
+    struct Value {
+        float    pdf, random;
+        uint32_t node, depth;
+    };
+
+    bool     active = false, exhausted = false;
+    uint32_t slot = 0, num_picks = 0, end = 0;
+    V3       p = {0.f, 0.f, 0.f}, n = {0.f, 0.f, 0.f};
+    bool     total_sphere = false;
+    float    threshold    = 0.f;
+    Value    t{0.f, 0.f, 0, 0};
+    Value    stack[12];
+
+    const uint32_t max_split_depth = sc.lt_max_split_depth;
+
+    for (;;) {
+        const uint32_t idle = __ballot_sync(kFull, !active);
+        if (0 != idle && !exhausted) {
+            uint32_t base = 0;
+            if (lane == uint32_t(__ffs(int(idle))) - 1u) base = atomicAdd(work_counter, uint32_t(__popc(idle)));
+            base = __shfl_sync(kFull, base, __ffs(int(idle)) - 1);
+            if (base + uint32_t(__popc(idle)) >= n_items) exhausted = true;
+            const uint32_t index = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
+            if (!active && index < n_items) {
+                slot              = st.queue_l[index];
+                const float4 lp   = st.ls_p[slot];
+                const float4 lg   = st.ls_g[slot];
+                const uint32_t fl = __float_as_uint(lg.w);
+                p                 = {lp.x, lp.y, lp.z};
+                n                 = 0 != (fl & 2u) ? V3{-lg.x, -lg.y, -lg.z} : V3{lg.x, lg.y, lg.z};
+                total_sphere      = 0 != (fl & 1u);
+                threshold         = 0 != (fl & 4u) ? kLowThreshold : view.split_threshold;
+                const float random = lp.w;
+                num_picks          = 0;
+                end                = 0;
+
+                // Tree.randomLight up to the descent, light_tree.zig:353-381
+                float      ip    = 0.f;
+                const bool split = threshold > 0.f;
+                bool       done  = false;
+                if (split && sc.lt_num_infinite < kMaxLightPicks - 1) {
+                    for (uint32_t i = 0; i < sc.lt_num_infinite; ++i) {
+                        st.picks[size_t(slot) * kMaxLightPicks + num_picks++] = make_uint2(__ldg(sc.lt_mapping + i), __float_as_uint(1.f));
+                    }
+                } else {
+                    ip = sc.lt_infinite_weight;
+                    if (random < sc.lt_infinite_guard) {
+                        st.picks[size_t(slot) * kMaxLightPicks + num_picks++] = make_uint2(__ldg(sc.lt_mapping), __float_as_uint(1.f * ip));
+                        done = true;
+                    }
+                }
+                if (done || 0 == sc.lt_num_nodes) {
+                    st.pick_n[slot] = num_picks;
+                } else {
+                    const float pd = 1.f - ip;
+                    t              = {pd, __fdiv_rn(random - ip, pd), 0, split ? 0 : max_split_depth};
+                    stack[end++]   = t;
+                    active         = true;
+                }
+            }
+        }
+        if (0 == __ballot_sync(kFull, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        if (active) {  // one iteration of the descent loop, light_tree.zig:396-444
+            const LightNodeD node = loadLightNode(tr, t.node);
+            if (0 != (node.meta & 1u)) {
+                const bool     do_split = t.depth < max_split_depth && lightNodeSplit(node, p, threshold);
+                const uint32_t c0       = node.meta >> 2;
+                const uint32_t c1       = c0 + 1;
+                if (do_split) {
+                    t.depth += 1;
+                    t.node       = c0;
+                    stack[end++] = {t.pdf, t.random, c1, t.depth};
+                } else {
+                    t.depth = max_split_depth;
+
+                    float p0 = lightNodeWeight(loadLightNode(tr, c0), p, n, total_sphere);
+                    float p1 = lightNodeWeight(loadLightNode(tr, c1), p, n, total_sphere);
+
+                    const float pt = p0 + p1;
+                    if (0.f == pt) {
+                        t = stack[--end];
+                    } else {
+                        p0 = __fdiv_rn(p0, pt);
+                        p1 = __fdiv_rn(p1, pt);
+                        if (t.random < p0) {
+                            t.node = c0;
+                            t.pdf *= p0;
+                            t.random = __fdiv_rn(t.random, p0);
+                        } else {
+                            t.node = c1;
+                            t.pdf *= p1;
+                            t.random = zmin(__fdiv_rn(t.random - p0, p1), 1.f);
+                        }
+                    }
+                }
+            } else {
+                const LightPickD pick = lightNodeRandomLight(sc, tr, node, p, n, total_sphere, t.random);
+                if (pick.pdf > 0.f && num_picks < kMaxLightPicks) {
+                    st.picks[size_t(slot) * kMaxLightPicks + num_picks++] = make_uint2(pick.offset, __float_as_uint(pick.pdf * t.pdf));
+                }
+                t = stack[--end];
+            }
+            if (0 == end) {  // `while (!stack.empty())`: the entry pushed first is popped last
+                st.pick_n[slot] = num_picks;
+                active          = false;
+            }
+        }
+    }
+}
+
+template <bool MeshLights, bool Infinite>
+__global__ void __launch_bounds__(128) lightSamplePersistent(SceneDevice sc, ZygpuView view, PathState st, PassParams pass,
+                                                             uint32_t* __restrict__ work_counter) {
+    __shared__ uint32_t sobol_tables[kSobolTableWords];
+    loadSobolTables(sobol_tables);
+
+    constexpr uint32_t kFull   = 0xffffffffu;
+    const uint32_t     lane    = threadIdx.x & 31u;
+    const uint32_t     n_items = st.counters[11];
+
+    bool     active = false, exhausted = false;
+    uint32_t slot = 0, pick_i = 0, pick_count = 0, num_records = 0;
+    V3       p = {0.f, 0.f, 0.f}, geo_n = {0.f, 0.f, 0.f}, n = {0.f, 0.f, 0.f};
+    bool     translucent = false;
+    float    threshold   = 0.f;
+    uint32_t pool_word   = 0;
+    SamplerD sampler;
+    sampler.sobol.tables = sobol_tables;
+
+    for (;;) {
+        const uint32_t idle = __ballot_sync(kFull, !active);
+        if (0 != idle && !exhausted) {
+            uint32_t base = 0;
+            if (lane == uint32_t(__ffs(int(idle))) - 1u) base = atomicAdd(work_counter, uint32_t(__popc(idle)));
+            base = __shfl_sync(kFull, base, __ffs(int(idle)) - 1);
+            if (base + uint32_t(__popc(idle)) >= n_items) exhausted = true;
+            const uint32_t index = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
+            if (!active && index < n_items) {
+                slot              = st.queue_l[index];
+                const float4 lp   = st.ls_p[slot];
+                const float4 lg   = st.ls_g[slot];
+                const uint32_t fl = __float_as_uint(lg.w);
+                p                 = {lp.x, lp.y, lp.z};
+                geo_n             = {lg.x, lg.y, lg.z};
+                n                 = 0 != (fl & 2u) ? neg3(geo_n) : geo_n;
+                translucent       = 0 != (fl & 1u);
+                threshold         = 0 != (fl & 4u) ? kLowThreshold : view.split_threshold;
+                pick_i            = 0;
+                pick_count        = st.pick_n[slot];
+                num_records       = 0;
+                const uint4 smp   = st.smp[slot];
+                pool_word         = smp.w;
+                loadSampler(st, slot, smp, pass, view.spp_total, (fl >> 8) & 0xffu, sampler);
+                if (ZYG_SAMPLER_SOBOL != view.sampler) sampler.use_sobol = false;
+                active = true;
+            }
+        }
+        if (0 == __ballot_sync(kFull, active)) {
+            if (exhausted) break;
+            continue;
+        }
+        if (active && pick_i < pick_count) {  // Light.sampleTo for one pick, pathtracer_mis.zig:214-250
+            const uint2      pk = st.picks[size_t(slot) * kMaxLightPicks + pick_i];
+            const LightPickD pick{pk.x, __uint_as_float(pk.y)};
+            pick_i += 1;
+
+            const ZygpuLight light = sc.lights[pick.offset];
+            const TrafoD     trafo = loadTrafo(sc.trafos, light.prop);
+            const uint32_t   shape = sc.props[light.prop].shape;
+            if (Infinite && ZYG_SHAPE_DISTANT == shape) {  // Distant.sampleTo, distant.zig:78-107
+                const float radius = trafo.scale.x;
+                if (radius > 0.f) {
+                    float u0, u1;
+                    sampler.sample2D(u0, u1);
+                    float lx, ly;
+                    diskConcentric(u0, u1, lx, ly);
+                    const V3 ws  = scale3(radius, trafo.transformVector({lx, ly, 0.f}));
+                    const V3 dir = normalize3(sub3(ws, trafo.r2));
+                    if (!(dot3(dir, n) <= 0.f && !translucent)) {
+                        if (num_records < st.shadow_stride) {
+                            const size_t rec    = size_t(slot) * st.shadow_stride + num_records;
+                            const V3     origin = offsetPoint(p, geo_n, dir);
+                            const float  pdf    = __fdiv_rn(1.f, distantSolidAngle(radius));
+                            st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, pdf * pick.pdf);
+                            st.sh_p[rec]  = make_float4(0.f, 0.f, 0.f, __uint_as_float(pick.offset | 0x80000000u));
+                            st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                            num_records += 1;
+                        } else {
+                            st.counters[3] = 1;
+                        }
+                    }
+                }
+            } else if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == shape && ZYGPU_NULL != light.sampler) {
+                FragD frag;  // meshLightSampleTo reads the shading point and offsets from it
+                frag.p      = p;
+                frag.geo_n  = geo_n;
+                num_records = meshLightSampleTo(sc, st, slot, light, pick, trafo, frag, n, translucent, threshold, sampler, num_records);
+            } else if (ZYG_SHAPE_RECTANGLE == shape) {  // Rectangle.sampleTo, rectangle.zig:305-357
+                const uint32_t ns  = lightNumSamples(light, threshold);
+                const float    nsf = float(ns);
+                SphQuadD       squad;
+                squad.init(trafo.scale, trafo.worldToFramePoint(p));
+                const float sample_pdf = nsf * squad.pdf(trafo.scale);
+                for (uint32_t k = 0; k < ns; ++k) {
+                    float u0, u1;
+                    sampler.sample2D(u0, u1);
+
+                    const V3 ls  = squad.sample(u0, u1);
+                    const V3 ws  = trafo.frameToWorldPoint(ls);
+                    const V3 dir = normalize3(sub3(ws, p));
+
+                    V3 wn = trafo.r2;
+                    if (0 != light.two_sided && dot3(wn, dir) > 0.f) wn = neg3(wn);
+
+                    if (-dot3(wn, dir) < kDotMin || 0.f == squad.S || (dot3(dir, n) <= 0.f && !translucent)) continue;
+
+                    if (num_records < st.shadow_stride) {
+                        const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+                        const V3     origin    = offsetPoint(p, geo_n, dir);
+                        const V3     light_pos = offsetRay(ws, wn);
+                        st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, sample_pdf * pick.pdf);
+                        st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+                        st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                        num_records += 1;
+                    } else {
+                        st.counters[3] = 1;
+                    }
+                }
+            }
+        }
+        if (active && pick_i >= pick_count) {
+            st.sh_n[slot] = num_records;
+            storeSampler(st, slot, sampler, pool_word);
+            if (nullptr != st.queue_r && 0 != num_records) {
+                const uint32_t base = atomicAdd(&st.counters[10], num_records);
+                for (uint32_t k = 0; k < num_records; ++k) st.queue_r[base + k] = slot * st.shadow_stride + k;
+            }
+            active = false;
+        }
     }
 }
 
@@ -2119,10 +2400,12 @@ __global__ void beginGenerationKernel(PathState st) {  // after extend: the trac
     st.counters[7]  = 0;
     st.counters[9]  = 0;
     st.counters[10] = 0;
+    st.counters[11] = 0;
 }
 __global__ void beginRoundKernel(PathState st) {
     st.counters[1]  = 0;
     st.counters[10] = 0;
+    st.counters[11] = 0;
 }
 __global__ void advanceKernel(PathState st) {
     st.counters[0] = st.counters[4];
@@ -2130,6 +2413,7 @@ __global__ void advanceKernel(PathState st) {
     st.counters[4]  = 0;
     st.counters[9]  = 0;
     st.counters[10] = 0;
+    st.counters[11] = 0;
 }
 
 // Sensor.addSample for every sample of the pass, gathered per film pixel (sensor.zig:168-385, buffer_opaque.zig:39-45).
@@ -2325,7 +2609,7 @@ cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t
 cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
                          uint32_t round, cudaStream_t stream) {
     const uint32_t features = (st.lanes > 1 ? kFeatureSplit : 0u) | (scene.num_mesh_samplers > 0 ? kFeatureMeshLights : 0u) |
-                              (scene.num_infinite_props > 0 ? kFeatureInfiniteLights : 0u);
+                              (scene.num_infinite_props > 0 ? kFeatureInfiniteLights : 0u) | (nullptr != st.queue_l ? kFeatureDeferredLights : 0u);
     const uint32_t grid = gridFor(max_items, 8);
     if (st.lanes <= 1) round = 0;
     switch (features) {
@@ -2336,7 +2620,45 @@ cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const 
         case 4: shadeAKernel<4><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
         case 5: shadeAKernel<5><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
         case 6: shadeAKernel<6><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        default: shadeAKernel<7><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 7: shadeAKernel<7><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 8: shadeAKernel<8><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 9: shadeAKernel<9><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 10: shadeAKernel<10><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 11: shadeAKernel<11><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 12: shadeAKernel<12><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 13: shadeAKernel<13><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        case 14: shadeAKernel<14><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        default: shadeAKernel<15><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launchLightStages(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
+                              cudaStream_t stream) {
+    if (nullptr == st.queue_l) return cudaSuccess;
+    cudaError_t err = cudaMemsetAsync(st.counters + 12, 0, 2 * sizeof(uint32_t), stream);
+    if (cudaSuccess != err) return err;
+
+    static int resident_select = 0, resident_sample = 0;
+    if (0 == resident_select) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lightSelectPersistent, 128, 0);
+        resident_select = std::max(per_sm, 1) * numSms();
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lightSamplePersistent<true, true>, 128, 0);
+        resident_sample = std::max(per_sm, 1) * numSms();
+    }
+    const uint32_t needed = (max_items + 127) / 128;
+    lightSelectPersistent<<<std::max(1u, std::min<uint32_t>(uint32_t(resident_select), needed)), 128, 0, stream>>>(scene, view, st, st.counters + 12);
+
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(uint32_t(resident_sample), needed));
+    const bool     ml = scene.num_mesh_samplers > 0, inf = scene.num_infinite_props > 0;
+    if (ml && inf) {
+        lightSamplePersistent<true, true><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+    } else if (ml) {
+        lightSamplePersistent<true, false><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+    } else if (inf) {
+        lightSamplePersistent<false, true><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+    } else {
+        lightSamplePersistent<false, false><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
     }
     return cudaGetLastError();
 }

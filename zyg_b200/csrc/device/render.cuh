@@ -110,6 +110,15 @@ struct PathState {
     float4*   sh_wi;  // light_sample.wi xyz | visible (written by shadow)
     uint32_t* sh_n;   // per path: number of records
 
+    // deferred light sampling (scenes with many lights; null otherwise): shade_a leaves the request, the persistent
+    // light kernels turn it into picks and shadow records
+    float4*   ls_p;     // shading point xyz | the light-selection random number
+    float4*   ls_g;     // Fragment.geo_n xyz | bit 0 translucent, bit 1 the material sample's geo_n is -geo_n, bit 2 low split
+                        // threshold, bits 8-15 total depth
+    uint2*    picks;    // 64 per slot: light id, pdf
+    uint32_t* pick_n;   // per slot
+    uint32_t* queue_l;  // slots with a request
+
     // mesh candidates collected by the top kernels, per trace item (closest: path slot, shadow: record)
     uint32_t* ml_props;  // 8 per item
     uint32_t* ml_count;
@@ -121,7 +130,8 @@ struct PathState {
     uint32_t* queue_s;   // lanes > 1: slots with more than one vertex in the current generation
     uint32_t* queue_r;   // shadow_stride > 1: the shadow records written by shade_a, compacted (null: every slot has one record)
     uint32_t* counters;  // [0] |A|, [1] |B|, [2] |mesh queue|, [3] shadow overflow flag, [4] |next A|, [5] closest rays, [6] shadow rays,
-                         // [7] |T|, [8] work counter of the persistent mesh kernel, [9] |S|, [10] |R| (16 words in all)
+                         // [7] |T|, [8] work counter of the persistent mesh kernel, [9] |S|, [10] |R|, [11] |L|, [12] / [13] work counters of the
+                         // persistent light kernels (16 words in all)
 
     uint32_t capacity;       // path slots
     uint32_t shadow_stride;  // shadow records reserved per path
@@ -148,6 +158,9 @@ cudaError_t launchBeginRound(const PathState& st, cudaStream_t stream);
 cudaError_t launchEndGeneration(const PathState& st, cudaStream_t stream);
 cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
                          uint32_t max_items, uint32_t round, cudaStream_t stream);
+// Deferred light sampling between shade_a and the shadow stage (PathState.queue_l non-null).
+cudaError_t launchLightStages(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
+                              cudaStream_t stream);
 cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream);
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
                          uint32_t max_items, uint32_t round, cudaStream_t stream);
