@@ -105,7 +105,7 @@ typedef struct ZygpuMaterial {
     float attenuation_distance;
     float thickness;
     float abbe;
-    float pad;
+    uint32_t emission_map; /* Emittance.emission_map when it is an image: index into ZygpuScene.image_samplers, else ZYGPU_NULL */
 } ZygpuMaterial;
 
 enum { /* Light.Class (src/core/scene/light/light.zig:34-40) */
@@ -120,7 +120,8 @@ typedef struct ZygpuLight {
     uint32_t light_class;
     uint32_t two_sided;
     uint32_t num_samples; /* ShapeSampler.num_samples (shape_sampler.zig:33) */
-    uint32_t sampler;     /* Light.sampler: index into ZygpuScene.mesh_samplers for a triangle-mesh light, else ZYGPU_NULL */
+    uint32_t sampler;     /* Light.sampler: index into ZygpuScene.mesh_samplers for a triangle-mesh light, into
+                             ZygpuScene.image_samplers for a ZYG_LIGHT_PROP_IMAGE light, else ZYGPU_NULL */
     uint32_t pad[2];
 } ZygpuLight;
 
@@ -151,6 +152,23 @@ typedef struct ZygpuMeshSampler {
     const uint32_t* primitive_mapping; /* BVH-order triangle -> index within its part (Mesh.primitive_mapping) */
 } ZygpuMeshSampler;
 
+/* An emission image with its importance-sampling tables: Texture (Float3 image + sampler_mode.zig Mode) and
+ * shape_sampler.ImageImpl (shape_sampler.zig:128-152) = Distribution2D (src/base/math/distribution_2d.zig) over the
+ * MIS-compensated luminance (light_material.zig:54-119, 248-272). The CDFs are the reference's arrays
+ * (Distribution1D.precomputePdfCdf, distribution_1d.zig:93-131); its lookup tables (initLut) only accelerate the linear
+ * search and are rebuilt by whoever wants them. */
+typedef struct ZygpuImageSampler {
+    uint32_t width, height;
+    uint32_t address_u, address_v; /* Texture.Mode.Address: 0 Clamp, 1 Repeat */
+    uint32_t filter;               /* Texture.Mode.Filter: 0 Nearest, 1 LinearStochastic */
+    float    total_weight;         /* ImageImpl.total_weight = sum of Shape.uvWeight over the texels */
+    float    scale[2];             /* Texture.data.image.scale */
+    const float* pixels;           /* width * height RGB triples (ACEScg) */
+    const float* marginal_cdf;     /* height + 1 */
+    const float* conditional_cdf;  /* height rows of width + 1 */
+    const float* conditional_integral; /* height; 0 => that row is the degenerate distribution {1, 1} (distribution_1d.zig:99-110) */
+} ZygpuImageSampler;
+
 typedef struct ZygpuLightTree {
     ZygpuAabb             bounds;
     float                 infinite_weight;
@@ -165,6 +183,7 @@ typedef struct ZygpuLightTree {
     const uint32_t*       node_middles;
     const uint32_t*       light_orders;
     const uint32_t*       light_mapping;
+    const float*          infinite_cdf; /* Tree.infinite_light_distribution.cdf: num_infinite_lights + 1 entries (light_tree.zig:273) */
 } ZygpuLightTree;
 
 /* PropBvh.Tree (src/core/scene/prop/prop_tree.zig:31-36). */
@@ -207,6 +226,9 @@ typedef struct ZygpuScene {
     uint32_t                num_mesh_samplers;
     const ZygpuMeshSampler* mesh_samplers; /* referenced by ZygpuLight.sampler */
     const float*            mesh_part_areas; /* Part.area (object space) per ZygpuScene part entry (material_ids index), 0 for analytic shapes */
+
+    uint32_t                 num_image_samplers;
+    const ZygpuImageSampler* image_samplers; /* referenced by ZygpuMaterial.emission_map and ZygpuLight.sampler */
 
     /* ggx_integral.zig tables, concatenated: E_m[32*32], E_m_avg[32], E[16^3], E_avg[16*16], E_s[16^3]. */
     const float* ggx_luts;

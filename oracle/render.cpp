@@ -576,6 +576,221 @@ uint32_t sampleTo(Vec4f n, const Trafo& trafo, bool total_sphere, Sampler& sampl
 
 }  // namespace distant
 
+// ---- emission images: Distribution1D / Distribution2D / ImageImpl / texture lookup ------------
+namespace image {
+
+// Distribution1D over a ZygpuImageSampler cdf row. The lookup table is the reference's accelerator for its linear search
+// (initLut / map / search, distribution_1d.zig:133-165, 250-258), rebuilt here from the cdf.
+struct Distribution1D {
+    const float*          cdf = nullptr;
+    uint32_t              size = 0;  // entries of cdf
+    std::vector<uint32_t> lut;
+    float                 lut_range = 0.f;
+
+    void configure(const float* c, uint32_t num_data) {  // configure + initLut
+        cdf  = c;
+        size = num_data + 1;
+        uint32_t lut_size = num_data / 16;
+        lut_size          = std::min(std::max(lut_size, 1u), size);
+        lut.assign(lut_size + 1, 0u);
+        lut_range = float(lut_size);
+        lut[0]    = 1;
+        uint32_t border = 0;
+        for (uint32_t i = 1; i < size; ++i) {
+            const uint32_t mapped = map(cdf[i]);
+            if (mapped > border) {
+                for (uint32_t k = border + 1; k <= mapped && k < lut.size(); ++k) lut[k] = i;
+                border = mapped;
+            }
+        }
+    }
+    uint32_t map(float s) const { return uint32_t(s * lut_range); }
+    uint32_t sample(float r) const {  // :50-54
+        const uint32_t bucket = map(r);
+        uint32_t       i      = lut[bucket];
+        const uint32_t end    = size - 1;
+        for (; i < end; ++i) {
+            if (cdf[i] >= r) return i - 1;
+        }
+        return end - 1;
+    }
+    void sampleDiscrete(float r, uint32_t& offset, float& pdf) const {  // :56-60
+        offset = sample(r);
+        pdf    = cdf[offset + 1] - cdf[offset];
+    }
+    void sampleContinuous(float r, float& offset, float& pdf) const {  // :62-75
+        const uint32_t o = sample(r);
+        const float    c = cdf[o + 1];
+        const float    v = c - cdf[o];
+        if (0.f == v) {
+            offset = 0.f;
+            pdf    = 0.f;
+            return;
+        }
+        const float t = (c - r) / v;
+        offset        = (float(o) + t) / float(size - 1);
+        pdf           = v;
+    }
+    float pdfI(uint32_t index) const { return cdf[index + 1] - cdf[index]; }
+    float pdfF(float u) const {  // :81-86
+        const uint32_t len = size;
+        const uint32_t o   = std::min(uint32_t(u * float(len - 1)), len - 2);
+        return cdf[o + 1] - cdf[o];
+    }
+};
+
+struct Sampler2D {  // shape_sampler.ImageImpl + Distribution2D, shape_sampler.zig:128-152, distribution_2d.zig:67-87
+    const ZygpuImageSampler*    img = nullptr;
+    Distribution1D              marginal;
+    std::vector<Distribution1D> conditional;
+
+    explicit Sampler2D(const ZygpuImageSampler& is) : img(&is), conditional(is.height) {
+        marginal.configure(is.marginal_cdf, is.height);
+        for (uint32_t y = 0; y < is.height; ++y) conditional[y].configure(is.conditional_cdf + size_t(y) * (is.width + 1), is.width);
+    }
+    static float address(uint32_t mode, float x) {  // sampler_mode.zig:21-26
+        return 0 == mode ? clamp(x, 0.f, 1.f) : x - std::floor(x);
+    }
+    static int32_t coord(uint32_t mode, int32_t c, int32_t end) {  // :35-40, 76-80
+        if (0 == mode) return std::max(std::min(c, end - 1), 0);
+        const int32_t m = c % end;
+        return m < 0 ? m + end : m;
+    }
+    void sample(float r0, float r1, float uv[2], float& pdf) const {  // ImageImpl.sample
+        float v, vp, u, up;
+        marginal.sampleContinuous(r1, v, vp);
+        const uint32_t n = uint32_t(conditional.size());
+        const uint32_t c = std::min(uint32_t(v * float(n)), n - 1);
+        conditional[c].sampleContinuous(r0, u, up);
+        uv[0] = u;
+        uv[1] = v;
+        pdf   = (up * vp) * img->total_weight;
+    }
+    float pdf(float u, float v) const {  // ImageImpl.pdf
+        const float    au = address(img->address_u, u), av = address(img->address_v, v);
+        const float    v_pdf = marginal.pdfF(av);
+        const uint32_t n     = uint32_t(conditional.size());
+        const uint32_t c     = std::min(uint32_t(av * float(n)), n - 1);
+        return (conditional[c].pdfF(au) * v_pdf) * img->total_weight;
+    }
+    // ts.sample2D_3 for an image texture, texture_sampler.zig:63-79, 99-124 (Nearest), 126-170 (LinearStochastic)
+    Vec4f texel(float u, float v, float r) const {
+        const int32_t d[2] = {int32_t(img->width), int32_t(img->height)};
+        const float   st[2] = {img->scale[0] * u, img->scale[1] * v};
+        int32_t       xy[2];
+        if (0 == img->filter) {
+            xy[0] = std::min(int32_t(address(img->address_u, st[0]) * float(d[0])), d[0] - 1);
+            xy[1] = std::min(int32_t(address(img->address_v, st[1]) * float(d[1])), d[1] - 1);
+        } else {
+            const float mst[2] = {address(img->address_u, st[0]) * float(d[0]) - 0.5f, address(img->address_v, st[1]) * float(d[1]) - 0.5f};
+            const float fst[2] = {std::floor(mst[0]), std::floor(mst[1])};
+            const float w[2]   = {mst[0] - fst[0], mst[1] - fst[1]};
+            const float omw[2] = {1.f - w[0], 1.f - w[1]};
+            xy[0]              = int32_t(fst[0]);
+            xy[1]              = int32_t(fst[1]);
+            int32_t index      = 0;
+            float   threshold  = omw[0] * omw[1];
+            index += r > threshold ? 1 : 0;
+            threshold = std::fmaf(w[0], omw[1], threshold);
+            index += r > threshold ? 1 : 0;
+            threshold = std::fmaf(omw[0], w[1], threshold);
+            index += r > threshold ? 1 : 0;
+            xy[0] += index & 1;
+            xy[1] += (index & 2) >> 1;
+            xy[0] = coord(img->address_u, xy[0], d[0]);
+            xy[1] = coord(img->address_v, xy[1], d[1]);
+        }
+        const float* px = img->pixels + 3 * (size_t(xy[1]) * img->width + xy[0]);
+        return {{px[0], px[1], px[2], 0.f}};
+    }
+};
+
+}  // namespace image
+
+namespace canopy {  // shape/canopy.zig
+
+constexpr float Eps = -0.0005f;
+
+bool intersect(const Ray& ray, const Trafo& trafo, Intersection& isec) {  // :27-39
+    if (ray.max_t < RayMaxT || dot3(ray.direction, trafo.r[2]) < Eps) return false;
+    isec.primitive = 0;
+    isec.t         = RayMaxT;
+    isec.u = isec.v = 0.f;
+    isec.trafo     = trafo;
+    return true;
+}
+
+void hemisphereToDiskEquidistant(Vec4f dir, float disk[2]) {  // :164-177
+    const float colatitude = std::acos(dir[2]);
+    const float longitude  = std::atan2(-dir[1], dir[0]);
+    const float r          = colatitude * (kPiInv * 2.f);
+    const float sin_lon    = std::sin(longitude);
+    const float cos_lon    = std::cos(longitude);
+    disk[0]                = r * cos_lon;
+    disk[1]                = r * sin_lon;
+}
+
+Vec4f diskToHemisphereEquidistant(const float uv[2]) {  // :179-202
+    const float longitude  = std::atan2(-uv[1], uv[0]);
+    const float r          = std::sqrt(uv[0] * uv[0] + uv[1] * uv[1]);
+    const float colatitude = r * (kPi / 2.f);
+    const float sin_col    = std::sin(colatitude);
+    const float cos_col    = std::cos(colatitude);
+    const float sin_lon    = std::sin(longitude);
+    const float cos_lon    = std::cos(longitude);
+    return {{sin_col * cos_lon, sin_col * sin_lon, cos_col, 0.f}};
+}
+
+void fragment(const Ray& ray, Fragment& frag) {  // :41-62
+    const Trafo& trafo = frag.isec.trafo;
+    // Mat3x3.transformVectorTransposed, matrix3x3.zig
+    const Vec4f d   = ray.direction;
+    const Vec4f xyz = normalize3(Vec4f{{dot3(d, trafo.r[0]), dot3(d, trafo.r[1]), dot3(d, trafo.r[2]), 0.f}});
+    float       disk[2];
+    hemisphereToDiskEquidistant(xyz, disk);
+    frag.uvw = {{0.5f * disk[0] + 0.5f, 0.5f * disk[1] + 0.5f, 0.f, 0.f}};
+
+    const Vec4f dir = {{d[0], d[1], d[2], 0.f}};
+    frag.p          = splat(RayMaxT) * dir;
+    const Vec4f n   = -dir;
+    frag.geo_n      = n;
+    frag.t          = trafo.r[0];
+    frag.b          = trafo.r[1];
+    frag.n          = n;
+    frag.part       = 0;
+}
+
+// Canopy.sampleMaterialTo, :94-131
+uint32_t sampleMaterialTo(Vec4f n, const Trafo& trafo, bool total_sphere, const image::Sampler2D& shape_sampler, Sampler& sampler,
+                          SampleTo* buffer) {
+    const Vec2f r2 = sampler.sample2D();
+    float       uv[2], pdf;
+    shape_sampler.sample(r2.v[0], r2.v[1], uv, pdf);
+    if (0.f == pdf) return 0;
+
+    const float disk[2] = {2.f * uv[0] - 1.f, 2.f * uv[1] - 1.f};
+    const float z       = disk[0] * disk[0] + disk[1] * disk[1];
+    if (z > 1.f) return 0;
+
+    const Vec4f dir_l = diskToHemisphereEquidistant(disk);
+    // Mat3x3.transformVector, matrix3x3.zig:113-127
+    Vec4f dir = splat(dir_l[0]) * trafo.r[0];
+    dir       = mulAdd(splat(dir_l[1]), trafo.r[1], dir);
+    dir       = mulAdd(splat(dir_l[2]), trafo.r[2], dir);
+    dir[3]    = 0.f;
+
+    if (dot3(dir, n) <= 0.f && !total_sphere) return 0;
+
+    const Vec4f p = splat(RayMaxT) * dir;
+    buffer[0].p   = {{p[0], p[1], p[2], pdf / (2.f * kPi)}};
+    buffer[0].n   = -dir;
+    buffer[0].wi  = dir;
+    buffer[0].uvw = {{uv[0], uv[1], 0.f, 0.f}};
+    return 1;
+}
+
+}  // namespace canopy
+
 namespace mesh {
 
 // Mesh.fragment, triangle_mesh.zig:310-335 + Data.interpolateData / normal, triangle_data.zig:106-149
@@ -769,7 +984,16 @@ struct Scene {
     GgxLuts           luts;
     const ZoMesh*     meshes;  // indexed by ZygpuProp.mesh
 
-    Scene(const ZygpuScene& scene, const ZygpuView& v, const ZoMesh* ms) : s(scene), view(v), luts(scene.ggx_luts), meshes(ms) {}
+    std::vector<image::Sampler2D> image_samplers;  // shape_sampler.ImageImpl per ZygpuImageSampler
+    image::Distribution1D         infinite_light_distribution;  // light_tree.zig:273
+
+    Scene(const ZygpuScene& scene, const ZygpuView& v, const ZoMesh* ms) : s(scene), view(v), luts(scene.ggx_luts), meshes(ms) {
+        image_samplers.reserve(scene.num_image_samplers);
+        for (uint32_t i = 0; i < scene.num_image_samplers; ++i) image_samplers.emplace_back(scene.image_samplers[i]);
+        if (scene.light_tree.num_infinite_lights > 0 && scene.light_tree.infinite_cdf) {
+            infinite_light_distribution.configure(scene.light_tree.infinite_cdf, scene.light_tree.num_infinite_lights);
+        }
+    }
 
     Mesh treeOf(uint32_t mesh) const {
         return {static_cast<const Node*>(meshes[mesh].nodes), meshes[mesh].triangles, meshes[mesh].positions};
@@ -791,6 +1015,7 @@ struct Scene {
             case ZYG_SHAPE_RECTANGLE: return scale[0] * scale[1];
             case ZYG_SHAPE_SPHERE: return (4.f * kPi) * pow2(0.5f * scale[0]);
             case ZYG_SHAPE_DISTANT: return distant::solidAngle(scale[0]);  // "the solid angle, not the area", shape.zig:146-148
+            case ZYG_SHAPE_CANOPY: return 2.f * kPi;
             default: return 0.f;
         }
     }
@@ -813,6 +1038,7 @@ struct Scene {
             case ZYG_SHAPE_RECTANGLE: return rectangle::intersect(ray, trafo, isec);
             case ZYG_SHAPE_SPHERE: return sphere::intersect(ray, trafo, isec);
             case ZYG_SHAPE_DISTANT: return distant::intersect(ray, trafo, isec);
+            case ZYG_SHAPE_CANOPY: return canopy::intersect(ray, trafo, isec);
             default: return false;
         }
     }
@@ -832,6 +1058,7 @@ struct Scene {
             case ZYG_SHAPE_RECTANGLE: rectangle::fragment(ray, frag); break;
             case ZYG_SHAPE_SPHERE: sphere::fragment(ray, frag); break;
             case ZYG_SHAPE_DISTANT: distant::fragment(ray, frag); break;
+            case ZYG_SHAPE_CANOPY: canopy::fragment(ray, frag); break;
             default: break;
         }
     }
@@ -1177,8 +1404,10 @@ struct Scene {
         } else {
             ip = tree.infinite_weight;
             if (random < tree.infinite_guard) {
-                // infinite_light_distribution.sampleDiscrete — single infinite light only
-                buffer[0] = {tree.light_mapping[0], 1.f * ip};
+                uint32_t l_offset;
+                float    l_pdf;
+                infinite_light_distribution.sampleDiscrete(random, l_offset, l_pdf);
+                buffer[0] = {tree.light_mapping[l_offset], l_pdf * ip};
                 return 1;
             }
         }
@@ -1262,7 +1491,7 @@ struct Scene {
 
         if (lo < tree.infinite_end) {
             if (split_infinite) return 1.f;
-            return tree.infinite_weight * 1.f;  // single infinite light: pdfI == 1
+            return tree.infinite_weight * infinite_light_distribution.pdfI(lo);
         }
         if (0 == tree.num_nodes) return 0.f;
 
@@ -1417,6 +1646,9 @@ struct Scene {
             case ZYG_SHAPE_RECTANGLE:
                 return rectangle::sampleTo(p, n, trafo, 0 != l.two_sided, total_sphere, num_samples, sampler, buffer);
             case ZYG_SHAPE_DISTANT: return distant::sampleTo(n, trafo, total_sphere, sampler, buffer);
+            case ZYG_SHAPE_CANOPY:  // Light.propSampleMaterialTo -> Shape.sampleMaterialTo, light.zig:191-215, shape.zig:348-371
+                if (ZYG_LIGHT_PROP_IMAGE != l.light_class) return 0;  // Canopy.sampleTo (uniform sky) is not in scope
+                return canopy::sampleMaterialTo(n, trafo, total_sphere, image_samplers[l.sampler], sampler, buffer);
             case ZYG_SHAPE_TRIANGLE_MESH:
                 return meshSampleTo(s.mesh_samplers[l.sampler], p, n, trafo, 0 != l.two_sided, total_sphere, split_threshold, sampler, buffer);
             default: return 0;
@@ -1553,7 +1785,18 @@ struct Scene {
     }
 
     // Material.evaluateRadiance, material.zig:194-207 for {Light, Substitute (uncoated)}
-    Vec4f materialRadiance(const ZygpuMaterial& m, Vec4f wi, const Trafo& trafo, uint32_t prop, bool in_camera, uint32_t part = 0) const {
+    Vec4f materialRadiance(const ZygpuMaterial& m, Vec4f wi, const Trafo& trafo, uint32_t prop, bool in_camera, uint32_t part,
+                           Vec4f uvw, float stochastic_r) const {
+        if (ZYGPU_NULL != m.emission_map) {  // Emittance.radiance with an image emission_map, emittance.zig:29-59
+            if (-dot3(wi, trafo.r[2]) < m.emission_cos_a) return splat(0.f);
+            const float factor    = in_camera ? m.emission_camera_weight : 1.f;
+            const Vec4f intensity = load4(m.emission) * image_samplers[m.emission_map].texel(uvw[0], uvw[1], stochastic_r);
+            if (0.f != m.emission_normalize) {
+                const Vec4f scale = trafo.scale();
+                return splat(factor / shapeArea(s.props[prop].shape, scale)) * intensity;
+            }
+            return splat(factor) * intensity;
+        }
         float area = 1.f;
         if (0.f != m.emission_normalize) {
             const Vec4f scale = trafo.scale();
@@ -1600,6 +1843,9 @@ struct Worker {
                 sample_pdf = rectangle::pdf(vertex.origin, frag, scene.lightNumSamples(l, vertex.light_split_threshold));
                 break;
             case ZYG_SHAPE_DISTANT: sample_pdf = 1.f / distant::solidAngle(frag.isec.trafo.scaleX()); break;  // distant.zig:139-141
+            case ZYG_SHAPE_CANOPY:  // Light.propMaterialPdf -> Shape.materialPdf, light.zig:371-374, shape.zig:519
+                if (ZYG_LIGHT_PROP_IMAGE == l.light_class) sample_pdf = scene.image_samplers[l.sampler].pdf(frag.uvw[0], frag.uvw[1]) / (2.f * kPi);
+                break;
             case ZYG_SHAPE_TRIANGLE_MESH:
                 sample_pdf = scene.meshPdf(scene.s.mesh_samplers[l.sampler], vertex.ray.direction, vertex.origin, vertex.geo_n, frag,
                                            vertex.state.translucent, vertex.light_split_threshold);
@@ -1617,10 +1863,10 @@ struct Worker {
             return splat(0.f);
         }
 
-        (void)sampler.sample1D();  // rs.stochastic_r
+        const float stochastic_r = sampler.sample1D();  // rs.stochastic_r
 
         const bool  in_camera = 0 == vertex.probe_depth.total();
-        const Vec4f energy    = scene.materialRadiance(m, wo, frag.isec.trafo, frag.prop, in_camera, frag.part);
+        const Vec4f energy    = scene.materialRadiance(m, wo, frag.isec.trafo, frag.prop, in_camera, frag.part, frag.uvw, stochastic_r);
         const float weight    = lightPdf(vertex, frag);
         return splat(weight) * energy;
     }
@@ -1784,9 +2030,9 @@ struct Worker {
             if (!scene.visibility(shadow)) continue;
 
             // Light.evaluateTo, light.zig:119-132
-            (void)sampler.sample1D();
+            const float          stochastic_r = sampler.sample1D();
             const ZygpuMaterial& lm       = scene.propMaterial(light.prop, light.part);
-            const Vec4f          radiance = scene.materialRadiance(lm, light_sample.wi, trafo, light.prop, false, light.part);
+            const Vec4f          radiance = scene.materialRadiance(lm, light_sample.wi, trafo, light.prop, false, light.part, light_sample.uvw, stochastic_r);
 
             const bxdf::Result bxdf_result = mat_sample.evaluate(light_sample.wi, max_material_splits, false);
 
@@ -1852,9 +2098,9 @@ struct Worker {
             const Ray shadow = Scene::shadowRay(frag.offsetP(r.sample.wi), r.sample, scene.lightFinite(light));
             if (!scene.visibility(shadow)) continue;
 
-            (void)sampler.sample1D();  // Light.evaluateTo
+            const float          stochastic_r = sampler.sample1D();  // Light.evaluateTo
             const ZygpuMaterial& lm       = scene.propMaterial(light.prop, light.part);
-            const Vec4f          radiance = scene.materialRadiance(lm, r.sample.wi, trafo, light.prop, false, light.part);
+            const Vec4f          radiance = scene.materialRadiance(lm, r.sample.wi, trafo, light.prop, false, light.part, r.sample.uvw, stochastic_r);
 
             const bxdf::Result bxdf_result = mat_sample.evaluate(r.sample.wi, max_material_splits, false);
 
@@ -2242,6 +2488,27 @@ float zo_light_tree_pdf(const ZygpuScene* scene, const ZygpuView* view, const fl
                         float split_threshold, uint32_t light) {
     const zo::Scene sc(*scene, *view, nullptr);
     return sc.lightTreePdf({{p[0], p[1], p[2], 0.f}}, {{n[0], n[1], n[2], 0.f}}, 0 != total_sphere, split_threshold, light);
+}
+
+// ImageImpl.sample / pdf / ts.sample2D_3 of image sampler `index` of the compiled scene (shape_sampler.zig:128-152)
+void zo_image_sample(const ZygpuScene* scene, uint32_t index, uint32_t n, const float* r2, float* uv_pdf) {
+    const zo::image::Sampler2D sampler(scene->image_samplers[index]);
+    for (uint32_t i = 0; i < n; ++i) {
+        float uv[2], pdf;
+        sampler.sample(r2[2 * i], r2[2 * i + 1], uv, pdf);
+        uv_pdf[3 * i] = uv[0], uv_pdf[3 * i + 1] = uv[1], uv_pdf[3 * i + 2] = pdf;
+    }
+}
+void zo_image_pdf(const ZygpuScene* scene, uint32_t index, uint32_t n, const float* uv, float* pdf) {
+    const zo::image::Sampler2D sampler(scene->image_samplers[index]);
+    for (uint32_t i = 0; i < n; ++i) pdf[i] = sampler.pdf(uv[2 * i], uv[2 * i + 1]);
+}
+void zo_image_texel(const ZygpuScene* scene, uint32_t index, uint32_t n, const float* uvr, float* rgb) {
+    const zo::image::Sampler2D sampler(scene->image_samplers[index]);
+    for (uint32_t i = 0; i < n; ++i) {
+        const zo::Vec4f c = sampler.texel(uvr[3 * i], uvr[3 * i + 1], uvr[3 * i + 2]);
+        rgb[3 * i] = c[0], rgb[3 * i + 1] = c[1], rgb[3 * i + 2] = c[2];
+    }
 }
 
 void zo_set_wavefront_light_order(int on) { zo::g_wavefront_light_order = 0 != on; }

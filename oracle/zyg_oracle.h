@@ -72,6 +72,11 @@ uint32_t zo_light_tree_random(const struct ZygpuScene* scene, const struct Zygpu
                               int total_sphere, float random, float split_threshold, float* picks);
 float    zo_light_tree_pdf(const struct ZygpuScene* scene, const struct ZygpuView* view, const float p[3], const float n[3],
                            int total_sphere, float split_threshold, uint32_t light);
+/* shape_sampler.ImageImpl of ZygpuScene.image_samplers[index]: sample (r2 pairs -> u, v, pdf triples), pdf (uv pairs),
+ * and the texture lookup ts.sample2D_3 (u, v, stochastic_r triples -> rgb). */
+void zo_image_sample(const struct ZygpuScene* scene, uint32_t index, uint32_t n, const float* r2, float* uv_pdf);
+void zo_image_pdf(const struct ZygpuScene* scene, uint32_t index, uint32_t n, const float* uv, float* pdf);
+void zo_image_texel(const struct ZygpuScene* scene, uint32_t index, uint32_t n, const float* uvr, float* rgb);
 /* Opaque.resolveTonemap, Linear tonemapper. */
 void zo_resolve(const struct ZygpuView* view, const float* film, uint32_t num_pixels, float* rgba);
 

@@ -102,6 +102,9 @@ def _bind_render(lib):
     lib.zo_light_tree_random.restype = u32
     lib.zo_light_tree_pdf.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, u32]
     lib.zo_light_tree_pdf.restype = C.c_float
+    for fn in (lib.zo_image_sample, lib.zo_image_pdf, lib.zo_image_texel):
+        fn.argtypes = [vp, u32, u32, vp, vp]
+        fn.restype = None
     lib.zo_sobol_stream.argtypes = [u32, u32, u32, u32, vp]
     lib.zo_sobol_stream.restype = None
     lib.zo_sobol_directions.argtypes = [vp]
@@ -144,6 +147,27 @@ def render(scene, view, width, height, iteration, num_samples, per_sample_iterat
     table = mesh_table(num_meshes)
     lib.zo_render(scene, view, table, iteration, num_samples, 1 if per_sample_iterations else 0, _p(film), threads)
     return film
+
+
+def image_sample(scene, index, r2):
+    r2 = np.ascontiguousarray(r2, np.float32)
+    out = np.empty((r2.shape[0], 3), np.float32)
+    _bind_render(load()).zo_image_sample(scene, index, r2.shape[0], _p(r2), _p(out))
+    return out
+
+
+def image_pdf(scene, index, uv):
+    uv = np.ascontiguousarray(uv, np.float32)
+    out = np.empty(uv.shape[0], np.float32)
+    _bind_render(load()).zo_image_pdf(scene, index, uv.shape[0], _p(uv), _p(out))
+    return out
+
+
+def image_texel(scene, index, uvr):
+    uvr = np.ascontiguousarray(uvr, np.float32)
+    out = np.empty((uvr.shape[0], 3), np.float32)
+    _bind_render(load()).zo_image_texel(scene, index, uvr.shape[0], _p(uvr), _p(out))
+    return out
 
 
 def resolve(view, film):

@@ -157,8 +157,16 @@ int32_t su_integrators_create(const char* json) {
     return 0;
 }
 
-int32_t su_image_create(uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, const uint8_t*) { return -1; }
-int32_t su_image_update(uint32_t, uint32_t, const uint8_t*) { return -1; }
+int32_t su_image_create(uint32_t id, uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height, uint32_t depth,
+                        uint32_t pixel_stride, const uint8_t* data) {
+    if (!g_engine) return -1;
+    return g_engine->scene.createImage(id, format, num_channels, width, height, depth, pixel_stride, data);
+}
+
+int32_t su_image_update(uint32_t id, uint32_t pixel_stride, const uint8_t* data) {
+    if (!g_engine) return -1;
+    return g_engine->scene.updateImage(id, pixel_stride, data);
+}
 
 int32_t su_material_create(uint32_t /*id*/, const char* json) {
     if (!g_engine) return -1;

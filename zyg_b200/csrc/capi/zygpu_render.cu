@@ -137,6 +137,8 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     d.lt_max_split_depth = lt.max_split_depth;
     d.lt_num_infinite    = lt.num_infinite_lights;
     d.lt_num_nodes       = lt.num_nodes;
+    if (lt.num_infinite_lights > 0 && !lt.infinite_cdf) return fail("zygpu_upload_scene: light tree carries no infinite_cdf");
+    if (0 != uploadArray(r, lt.infinite_cdf, lt.num_infinite_lights > 0 ? size_t(lt.num_infinite_lights) + 1 : 0, &d.lt_infinite_cdf)) return -1;
 
     if (0 != uploadArray(r, reinterpret_cast<const float4*>(scene->solid_bvh.nodes), size_t(scene->solid_bvh.num_nodes) * 2, &f4)) return -1;
     d.solid_nodes = f4;
@@ -189,6 +191,40 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     if (0 != uploadArray(r, samplers.data(), samplers.size(), &d.mesh_samplers)) return -1;
     d.num_mesh_samplers = scene->num_mesh_samplers;
     if (0 != uploadArray(r, scene->mesh_part_areas, scene->mesh_part_areas ? scene->num_parts : 0, &d.mesh_part_areas)) return -1;
+
+    // emission images with their Distribution2D rows (shape_sampler.ImageImpl)
+    std::vector<zygpu::ImageSamplerDevice> image_samplers(scene->num_image_samplers);
+    for (uint32_t i = 0; i < scene->num_image_samplers; ++i) {
+        const ZygpuImageSampler&   is = scene->image_samplers[i];
+        zygpu::ImageSamplerDevice& id = image_samplers[i];
+        if (0 == is.width || 0 == is.height || !is.pixels || !is.marginal_cdf || !is.conditional_cdf) {
+            return fail("zygpu_upload_scene: image sampler %u is incomplete", i);
+        }
+        id.width        = is.width;
+        id.height       = is.height;
+        id.address_u    = is.address_u;
+        id.address_v    = is.address_v;
+        id.filter       = is.filter;
+        id.total_weight = is.total_weight;
+        id.scale_u      = is.scale[0];
+        id.scale_v      = is.scale[1];
+        // the same image may back several samplers (one per uv-weight class): upload its pixels once
+        id.pixels = nullptr;
+        for (uint32_t k = 0; k < i; ++k) {
+            if (scene->image_samplers[k].pixels == is.pixels) id.pixels = image_samplers[k].pixels;
+        }
+        if (!id.pixels && 0 != uploadArray(r, is.pixels, size_t(is.width) * is.height * 3, &id.pixels)) return -1;
+        if (0 != uploadArray(r, is.marginal_cdf, size_t(is.height) + 1, &id.marginal_cdf) ||
+            0 != uploadArray(r, is.conditional_cdf, size_t(is.height) * (is.width + 1), &id.conditional_cdf)) {
+            return -1;
+        }
+    }
+    if (0 != uploadArray(r, image_samplers.data(), image_samplers.size(), &d.image_samplers)) return -1;
+    for (uint32_t m = 0; m < scene->num_materials; ++m) {
+        if (ZYGPU_NULL != scene->materials[m].emission_map && scene->materials[m].emission_map >= scene->num_image_samplers) {
+            return fail("zygpu_upload_scene: material %u references image sampler %u", m, scene->materials[m].emission_map);
+        }
+    }
 
     // shadow records one path vertex can need: every light the tree may return times its sample count
     // (Tree.potentialMaxLights, light_tree.zig:331-344), capped like the reference's buffers (64 picks x 64 samples)

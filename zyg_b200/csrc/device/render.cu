@@ -202,6 +202,7 @@ __device__ __forceinline__ float shapeArea(uint32_t shape, V3 scale) {  // shape
         case ZYG_SHAPE_RECTANGLE: return scale.x * scale.y;
         case ZYG_SHAPE_SPHERE: return (4.f * kPi) * ((0.5f * scale.x) * (0.5f * scale.x));
         case ZYG_SHAPE_DISTANT: return distantSolidAngle(scale.x);
+        case ZYG_SHAPE_CANOPY: return 2.f * kPi;
         default: return 0.f;
     }
 }
@@ -716,6 +717,7 @@ __device__ __forceinline__ void shapeFragment(const SceneDevice& sc, uint32_t pr
         case ZYG_SHAPE_RECTANGLE: rectangleFragment(ray, isec, frag); break;
         case ZYG_SHAPE_SPHERE: sphereFragment(ray, isec, frag); break;
         case ZYG_SHAPE_DISTANT: distantFragment(ray, isec, frag); break;
+        case ZYG_SHAPE_CANOPY: canopyFragment(ray, frag); break;
         case ZYG_SHAPE_TRIANGLE_MESH: meshFragment(sc.mesh_shading[sc.props[prop].mesh], isec, frag); break;
         default: break;
     }
@@ -1039,7 +1041,9 @@ __device__ void lightTreeRandomLight(const SceneDevice& sc, V3 p, V3 n, bool tot
     } else {
         ip = sc.lt_infinite_weight;
         if (random < sc.lt_infinite_guard) {
-            emit(LightPickD{__ldg(sc.lt_mapping), 1.f * ip});  // single infinite light: sampleDiscrete -> (0, 1)
+            // infinite_light_distribution.sampleDiscrete(random), distribution_1d.zig:56-60
+            const uint32_t l = dist1dSample(sc.lt_infinite_cdf, sc.lt_num_infinite + 1, random);
+            emit(LightPickD{__ldg(sc.lt_mapping + l), (__ldg(sc.lt_infinite_cdf + l + 1) - __ldg(sc.lt_infinite_cdf + l)) * ip});
             return;
         }
     }
@@ -1206,7 +1210,9 @@ __device__ float lightTreePdf(const SceneDevice& sc, V3 p, V3 n, bool total_sphe
     const bool     split          = split_threshold > 0.f;
     const bool     split_infinite = split && sc.lt_num_infinite < kMaxLightPicks - 1;
 
-    if (lo < sc.lt_infinite_end) return split_infinite ? 1.f : sc.lt_infinite_weight * 1.f;
+    if (lo < sc.lt_infinite_end) {  // infinite_weight * infinite_light_distribution.pdfI(lo)
+        return split_infinite ? 1.f : sc.lt_infinite_weight * (__ldg(sc.lt_infinite_cdf + lo + 1) - __ldg(sc.lt_infinite_cdf + lo));
+    }
     if (0 == sc.lt_num_nodes) return 0.f;
 
     const float    ip              = split_infinite ? 0.f : sc.lt_infinite_weight;
@@ -1353,6 +1359,8 @@ __device__ float sceneLightPdf(const SceneDevice& sc, const VertexD& vertex, con
         sample_pdf = nsf * squad.pdf(frag.trafo.scale);
     } else if (ZYG_SHAPE_DISTANT == sc.props[l.prop].shape) {  // Distant.pdf, distant.zig:139-141
         sample_pdf = __fdiv_rn(1.f, distantSolidAngle(frag.trafo.scale.x));
+    } else if (ZYG_SHAPE_CANOPY == sc.props[l.prop].shape) {  // Light.propMaterialPdf -> Shape.materialPdf, shape.zig:519
+        if (ZYG_LIGHT_PROP_IMAGE == l.light_class) sample_pdf = __fdiv_rn(imagePdf(sc.image_samplers[l.sampler], frag.u, frag.v), 2.f * kPi);
     } else if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == sc.props[l.prop].shape && ZYGPU_NULL != l.sampler) {
         sample_pdf = meshLightPdf(sc, sc.mesh_samplers[l.sampler], vertex, frag);
     }
@@ -1367,11 +1375,14 @@ __device__ V3 evaluateRadiance(const SceneDevice& sc, const VertexD& vertex, con
     if (0 == (m.flags & ZYG_MATERIAL_EMISSIVE) || (0 == (m.flags & ZYG_MATERIAL_TWO_SIDED) && !frag.sameHemisphere(wo))) {
         return splat3(0.f);
     }
-    (void)sampler.sample1D();  // rs.stochastic_r
+    const float stochastic_r = sampler.sample1D();  // rs.stochastic_r
 
     const bool  in_camera = 0 == vertex.probe_depth;
     const float area      = 0.f != m.emission_normalize ? shapeArea(sc.props[frag.prop].shape, frag.trafo.scale) : 1.f;
-    const V3    energy    = emittanceRadiance(m, wo, frag.trafo, area, in_camera);
+    const V3    energy    = ZYGPU_NULL != m.emission_map
+                                ? emittanceRadianceMapped(m, wo, frag.trafo, area, in_camera,
+                                                          imageTexel(sc.image_samplers[m.emission_map], frag.u, frag.v, stochastic_r))
+                                : emittanceRadiance(m, wo, frag.trafo, area, in_camera);
     const float weight    = sceneLightPdf<MeshLights>(sc, vertex, frag);
     return scale3(weight, energy);
 }
@@ -1786,8 +1797,15 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                         light_frag.prop  = entity;
                         light_frag.trafo = loadTrafo(sc.trafos, entity);
                         HitD isec;
-                        if (ZYG_SHAPE_DISTANT != iprop.shape || !distantIntersect(vertex.ray, light_frag.trafo, isec)) continue;
-                        distantFragment(vertex.ray, isec, light_frag);
+                        if (ZYG_SHAPE_DISTANT == iprop.shape) {
+                            if (!distantIntersect(vertex.ray, light_frag.trafo, isec)) continue;
+                            distantFragment(vertex.ray, isec, light_frag);
+                        } else if (ZYG_SHAPE_CANOPY == iprop.shape) {
+                            if (!canopyIntersect(vertex.ray, light_frag.trafo, isec)) continue;
+                            canopyFragment(vertex.ray, light_frag);
+                        } else {
+                            continue;
+                        }
                         this_light = add3(this_light, evaluateRadiance<MeshLights>(sc, vertex, light_frag, sampler));
                     }
                 }
@@ -1864,6 +1882,25 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                                 const float  pdf    = __fdiv_rn(1.f, distantSolidAngle(radius));
                                 st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, pdf * pick.pdf);
                                 st.sh_p[rec]  = make_float4(0.f, 0.f, 0.f, __uint_as_float(pick.offset | 0x80000000u));
+                                st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                                num_records += 1;
+                            } else {
+                                st.counters[3] = 1;
+                            }
+                            return;
+                        }
+                        if (Infinite && ZYG_SHAPE_CANOPY == shape) {  // Canopy.sampleMaterialTo, canopy.zig:94-131
+                            if (ZYG_LIGHT_PROP_IMAGE != light.light_class) return;
+                            float u0, u1;
+                            sampler.sample2D(u0, u1);
+                            V3    dir;
+                            float su, sv, pdf;
+                            if (!canopySampleMaterialTo(sc.image_samplers[light.sampler], trafo, n, translucent, u0, u1, dir, su, sv, pdf)) return;
+                            if (num_records < st.shadow_stride) {
+                                const size_t rec    = size_t(slot) * st.shadow_stride + num_records;
+                                const V3     origin = frag.offsetP(dir);
+                                st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, pdf * pick.pdf);
+                                st.sh_p[rec]  = make_float4(su, sv, 0.f, __uint_as_float(pick.offset | 0x80000000u));  // uvw of the sample
                                 st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
                                 num_records += 1;
                             } else {
@@ -2002,7 +2039,9 @@ __global__ void __launch_bounds__(128) lightSelectPersistent(SceneDevice sc, Zyg
                 } else {
                     ip = sc.lt_infinite_weight;
                     if (random < sc.lt_infinite_guard) {
-                        st.picks[size_t(slot) * kMaxLightPicks + num_picks++] = make_uint2(__ldg(sc.lt_mapping), __float_as_uint(1.f * ip));
+                        const uint32_t l  = dist1dSample(sc.lt_infinite_cdf, sc.lt_num_infinite + 1, random);
+                        const float    lp = __ldg(sc.lt_infinite_cdf + l + 1) - __ldg(sc.lt_infinite_cdf + l);
+                        st.picks[size_t(slot) * kMaxLightPicks + num_picks++] = make_uint2(__ldg(sc.lt_mapping + l), __float_as_uint(lp * ip));
                         done = true;
                     }
                 }
@@ -2150,6 +2189,25 @@ __global__ void __launch_bounds__(128) lightSamplePersistent(SceneDevice sc, Zyg
                         }
                     }
                 }
+            } else if (Infinite && ZYG_SHAPE_CANOPY == shape) {  // Canopy.sampleMaterialTo, canopy.zig:94-131
+                if (ZYG_LIGHT_PROP_IMAGE == light.light_class) {
+                    float u0, u1;
+                    sampler.sample2D(u0, u1);
+                    V3    dir;
+                    float su, sv, pdf;
+                    if (canopySampleMaterialTo(sc.image_samplers[light.sampler], trafo, n, translucent, u0, u1, dir, su, sv, pdf)) {
+                        if (num_records < st.shadow_stride) {
+                            const size_t rec    = size_t(slot) * st.shadow_stride + num_records;
+                            const V3     origin = offsetPoint(p, geo_n, dir);
+                            st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, pdf * pick.pdf);
+                            st.sh_p[rec]  = make_float4(su, sv, 0.f, __uint_as_float(pick.offset | 0x80000000u));
+                            st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                            num_records += 1;
+                        } else {
+                            st.counters[3] = 1;
+                        }
+                    }
+                }
             } else if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == shape && ZYGPU_NULL != light.sampler) {
                 FragD frag;  // meshLightSampleTo reads the shading point and offsets from it
                 frag.p      = p;
@@ -2285,13 +2343,17 @@ __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeB
                 const V3     wi = {wi4.x, wi4.y, wi4.z};
 
                 // Light.evaluateTo, light.zig:119-132
-                (void)sampler.sample1D();
+                const float         stochastic_r = sampler.sample1D();
                 const uint32_t      light_id = __float_as_uint(p4.w) & 0x7FFFFFFFu;
                 const ZygpuLight    light    = sc.lights[light_id];
                 const TrafoD        ltrafo   = loadTrafo(sc.trafos, light.prop);
                 const ZygpuMaterial lm       = sc.materials[__ldg(sc.material_ids + sc.props[light.prop].parts_start + light.part)];
                 const float area     = 0.f != lm.emission_normalize ? shapeArea(sc.props[light.prop].shape, ltrafo.scale) : 1.f;
-                const V3    radiance = emittanceRadiance(lm, wi, ltrafo, area, false);
+                // an image-mapped (PROP_IMAGE) light left the uvw of its sample in the record's position lanes
+                const V3    radiance = ZYGPU_NULL != lm.emission_map
+                                           ? emittanceRadianceMapped(lm, wi, ltrafo, area, false,
+                                                                     imageTexel(sc.image_samplers[lm.emission_map], p4.x, p4.y, stochastic_r))
+                                           : emittanceRadiance(lm, wi, ltrafo, area, false);
 
                 const BxdfResult bxdf_result = mat_sample.template evaluate<Split>(luts, wi, max_splits);
 

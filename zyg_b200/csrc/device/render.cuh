@@ -45,6 +45,15 @@ struct MeshSamplerDevice {  // ZygpuMeshSampler with device pointers
     const uint32_t*       primitive_mapping;
 };
 
+// ZygpuImageSampler on the device: the emission image and the cdf rows of its Distribution2D.
+struct ImageSamplerDevice {
+    uint32_t     width, height, address_u, address_v, filter;
+    float        total_weight, scale_u, scale_v;
+    const float* pixels;
+    const float* marginal_cdf;
+    const float* conditional_cdf;
+};
+
 struct SceneDevice {
     const ZygpuProp*     props;
     const float4*        trafos;  // 4 per prop
@@ -65,6 +74,7 @@ struct SceneDevice {
     float4                lt_bounds_min, lt_bounds_max;
     float                 lt_infinite_weight, lt_infinite_guard;
     uint32_t              lt_infinite_end, lt_max_split_depth, lt_num_infinite, lt_num_nodes;
+    const float*          lt_infinite_cdf;  // Tree.infinite_light_distribution.cdf
 
     const float4*   solid_nodes;  // 2 per node
     const uint32_t* solid_indices;
@@ -77,7 +87,9 @@ struct SceneDevice {
     uint32_t                 num_mesh_samplers;
     const float*             mesh_part_areas;  // Part.area per part entry
 
-    const uint32_t* infinite_props;  // Scene.infinite_props (Distant): met only by rays that leave the scene
+    const ImageSamplerDevice* image_samplers;  // by ZygpuMaterial.emission_map / ZygpuLight.sampler (PROP_IMAGE lights)
+
+    const uint32_t* infinite_props;  // Scene.infinite_props (Distant, Canopy): met only by rays that leave the scene
     uint32_t        num_infinite_props;
 
     const MeshDevice*  meshes;

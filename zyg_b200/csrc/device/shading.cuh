@@ -347,6 +347,135 @@ __device__ __forceinline__ void sphereFragment(const RayT& ray, const HitD& isec
     frag.v = theta * kPiInv;
 }
 
+// ---- emission images --------------------------------------------------------------------------------------------------
+// Distribution1D.sample, distribution_1d.zig:50-54, 250-258: the first i in [1, size - 1) with cdf[i] >= r (else size - 1),
+// minus one. The reference walks there linearly from a lookup-table start; the cdf is non-decreasing on that range, so a
+// binary search lands on the same entry.
+__device__ __forceinline__ uint32_t dist1dSample(const float* __restrict__ cdf, uint32_t size, float r) {
+    uint32_t lo = 1, hi = size - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(cdf + mid) >= r) {
+            hi = mid;
+        } else {
+            lo = mid + 1;
+        }
+    }
+    return lo - 1;
+}
+__device__ __forceinline__ void dist1dSampleContinuous(const float* __restrict__ cdf, uint32_t size, float r, float& offset, float& pdf) {  // :62-75
+    const uint32_t o = dist1dSample(cdf, size, r);
+    const float    c = __ldg(cdf + o + 1);
+    const float    v = c - __ldg(cdf + o);
+    if (0.f == v) {
+        offset = 0.f;
+        pdf    = 0.f;
+        return;
+    }
+    const float t = __fdiv_rn(c - r, v);
+    offset        = __fdiv_rn(float(o) + t, float(size - 1));
+    pdf           = v;
+}
+__device__ __forceinline__ float dist1dPdfF(const float* __restrict__ cdf, uint32_t size, float u) {  // :81-86
+    const uint32_t o = min(uint32_t(u * float(size - 1)), size - 2);
+    return __ldg(cdf + o + 1) - __ldg(cdf + o);
+}
+__device__ __forceinline__ float textureAddress(uint32_t mode, float x) {  // sampler_mode.zig:21-26
+    return 0 == mode ? zmin(zmax(x, 0.f), 1.f) : x - floorf(x);
+}
+__device__ __forceinline__ int32_t textureCoord(uint32_t mode, int32_t c, int32_t end) {  // :35-40, 76-80
+    if (0 == mode) return max(min(c, end - 1), 0);
+    const int32_t m = c % end;
+    return m < 0 ? m + end : m;
+}
+// ImageImpl.sample / pdf, shape_sampler.zig:128-152 over Distribution2D.sampleContinuous / pdf, distribution_2d.zig:67-87
+__device__ __forceinline__ void imageSample(const ImageSamplerDevice& is, float r0, float r1, float& u, float& v, float& pdf) {
+    float vp, up;
+    dist1dSampleContinuous(is.marginal_cdf, is.height + 1, r1, v, vp);
+    const uint32_t c = min(uint32_t(v * float(is.height)), is.height - 1);
+    dist1dSampleContinuous(is.conditional_cdf + size_t(c) * (is.width + 1), is.width + 1, r0, u, up);
+    pdf = (up * vp) * is.total_weight;
+}
+__device__ __forceinline__ float imagePdf(const ImageSamplerDevice& is, float u, float v) {
+    const float    au = textureAddress(is.address_u, u), av = textureAddress(is.address_v, v);
+    const float    v_pdf = dist1dPdfF(is.marginal_cdf, is.height + 1, av);
+    const uint32_t c     = min(uint32_t(av * float(is.height)), is.height - 1);
+    return (dist1dPdfF(is.conditional_cdf + size_t(c) * (is.width + 1), is.width + 1, au) * v_pdf) * is.total_weight;
+}
+// ts.sample2D_3 of an image texture, texture_sampler.zig:63-79; Nearest2D.map :99-124, LinearStochastic2D.map :126-170
+__device__ __forceinline__ V3 imageTexel(const ImageSamplerDevice& is, float u, float v, float r) {
+    const int32_t dx = int32_t(is.width), dy = int32_t(is.height);
+    const float   s = is.scale_u * u, t = is.scale_v * v;
+    int32_t       x, y;
+    if (0 == is.filter) {
+        x = min(int32_t(textureAddress(is.address_u, s) * float(dx)), dx - 1);
+        y = min(int32_t(textureAddress(is.address_v, t) * float(dy)), dy - 1);
+    } else {
+        const float ms = textureAddress(is.address_u, s) * float(dx) - 0.5f, mt = textureAddress(is.address_v, t) * float(dy) - 0.5f;
+        const float fs = floorf(ms), ft = floorf(mt);
+        const float w0 = ms - fs, w1 = mt - ft;
+        const float o0 = 1.f - w0, o1 = 1.f - w1;
+        x              = int32_t(fs);
+        y              = int32_t(ft);
+        int32_t index     = 0;
+        float   threshold = o0 * o1;
+        index += r > threshold ? 1 : 0;
+        threshold = __fmaf_rn(w0, o1, threshold);
+        index += r > threshold ? 1 : 0;
+        threshold = __fmaf_rn(o0, w1, threshold);
+        index += r > threshold ? 1 : 0;
+        x = textureCoord(is.address_u, x + (index & 1), dx);
+        y = textureCoord(is.address_v, y + ((index & 2) >> 1), dy);
+    }
+    const float* px = is.pixels + 3 * (size_t(y) * is.width + size_t(x));
+    return {__ldg(px), __ldg(px + 1), __ldg(px + 2)};
+}
+
+// Canopy, shape/canopy.zig:24-62, 164-202
+__device__ __forceinline__ bool canopyIntersect(const RayT& ray, const TrafoD& trafo, HitD& isec) {
+    if (ray.tmax < kRayMaxT || dot3(ray.d, trafo.r2) < -0.0005f) return false;
+    isec.u = isec.v = 0.f;
+    isec.primitive  = 0;
+    isec.t          = kRayMaxT;
+    return true;
+}
+__device__ __forceinline__ void canopyFragment(const RayT& ray, FragD& frag) {
+    const V3    xyz        = normalize3(frag.trafo.transformVectorTransposed(ray.d));
+    const float colatitude = acosf(xyz.z);
+    const float longitude  = atan2f(-xyz.y, xyz.x);
+    const float r          = colatitude * (kPiInv * 2.f);
+    const float dx = r * cosf(longitude), dy = r * sinf(longitude);
+    frag.u     = 0.5f * dx + 0.5f;
+    frag.v     = 0.5f * dy + 0.5f;
+    frag.p     = scale3(kRayMaxT, ray.d);
+    frag.geo_n = neg3(ray.d);
+    frag.t     = frag.trafo.r0;
+    frag.b     = frag.trafo.r1;
+    frag.n     = neg3(ray.d);
+    frag.part  = 0;
+}
+__device__ __forceinline__ V3 canopyDiskToHemisphere(float ux, float uy) {
+    const float longitude  = atan2f(-uy, ux);
+    const float r          = __fsqrt_rn(ux * ux + uy * uy);
+    const float colatitude = r * (kPi / 2.f);
+    const float sin_col = sinf(colatitude), cos_col = cosf(colatitude);
+    const float sin_lon = sinf(longitude), cos_lon = cosf(longitude);
+    return {sin_col * cos_lon, sin_col * sin_lon, cos_col};
+}
+// Canopy.sampleMaterialTo, canopy.zig:94-131: false = no sample. `pdf` excludes the light pick.
+__device__ __forceinline__ bool canopySampleMaterialTo(const ImageSamplerDevice& is, const TrafoD& trafo, V3 n, bool total_sphere, float r0,
+                                                       float r1, V3& dir, float& u, float& v, float& pdf) {
+    float ipdf;
+    imageSample(is, r0, r1, u, v, ipdf);
+    if (0.f == ipdf) return false;
+    const float dx = 2.f * u - 1.f, dy = 2.f * v - 1.f;
+    if (dx * dx + dy * dy > 1.f) return false;
+    dir = trafo.transformVector(canopyDiskToHemisphere(dx, dy));
+    if (dot3(dir, n) <= 0.f && !total_sphere) return false;
+    pdf = __fdiv_rn(ipdf, 2.f * kPi);
+    return true;
+}
+
 // Distant, shape/distant.zig:22-76, 139-145
 __device__ __forceinline__ float distantSolidAngle(float radius) {
     return (2.f * kPi) * (1.f - __fsqrt_rn(__fdiv_rn(1.f, radius * radius + 1.f)));
@@ -1163,6 +1292,15 @@ __device__ __forceinline__ V3 emittanceRadiance(const ZygpuMaterial& m, V3 wi, c
     if (-dot3(wi, trafo.r2) < m.emission_cos_a) return splat3(0.f);
     const float factor    = in_camera ? m.emission_camera_weight : 1.f;
     const V3    intensity = {m.emission[0] * 1.f, m.emission[1] * 1.f, m.emission[2] * 1.f};
+    if (0.f != m.emission_normalize) return scale3(__fdiv_rn(factor, area), intensity);
+    return scale3(factor, intensity);
+}
+
+// the same with an image emission_map: `texel` = ts.sample2D_3(emission_map, rs, ...), emittance.zig:48
+__device__ __forceinline__ V3 emittanceRadianceMapped(const ZygpuMaterial& m, V3 wi, const TrafoD& trafo, float area, bool in_camera, V3 texel) {
+    if (-dot3(wi, trafo.r2) < m.emission_cos_a) return splat3(0.f);
+    const float factor    = in_camera ? m.emission_camera_weight : 1.f;
+    const V3    intensity = {m.emission[0] * texel.x, m.emission[1] * texel.y, m.emission[2] * texel.z};
     if (0.f != m.emission_normalize) return scale3(__fdiv_rn(factor, area), intensity);
     return scale3(factor, intensity);
 }

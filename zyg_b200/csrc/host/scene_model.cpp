@@ -8,7 +8,9 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstring>
 
 namespace zyg {
 
@@ -100,6 +102,7 @@ ZygpuMaterial defaultMaterial(uint32_t type) {
     m.emission_normalize     = 0.f;
     m.specular               = 1.f;
     m.ior                    = 1.f;
+    m.emission_map           = ZYGPU_NULL;
     switch (type) {
         case ZYG_MATERIAL_SUBSTITUTE:  // substitute_material.zig:41-67
             m.color[0] = m.color[1] = m.color[2] = 0.5f;
@@ -119,8 +122,41 @@ ZygpuMaterial defaultMaterial(uint32_t type) {
     return m;
 }
 
-// loadEmittance, material_provider.zig:412-436 (no profile, no maps)
-void loadEmittance(const json::Value& j, ZygpuMaterial& m) {
+uint32_t readAddress(const json::Value& v) {  // material_provider.zig:624-632
+    return (json::Value::String == v.kind && "Clamp" == v.string) ? 0u : 1u;
+}
+
+// loadEmittance, material_provider.zig:412-436 (no profile; `emission_map` as an image resource: TextureDescriptor "id" +
+// "sampler" + "scale", :440-476, 579-600, 634-678)
+void loadEmittance(const json::Value& j, ZygpuMaterial& m, uint32_t& map_image, uint32_t mode[3], float map_scale[2]) {
+    if (const json::Value* em = j.get("emission_map")) {
+        if (json::Value::Object == em->kind) {
+            if (const json::Value* id = em->get("id")) map_image = uint32_t(id->number);
+            if (const json::Value* sa = em->get("sampler")) {
+                if (const json::Value* f = sa->get("filter")) {
+                    if (json::Value::String == f->kind && "Nearest" == f->string) mode[2] = 0;
+                    if (json::Value::String == f->kind && "Linear" == f->string) mode[2] = 1;
+                }
+                if (const json::Value* a = sa->get("address")) {
+                    if (json::Value::Array == a->kind && a->array.size() >= 2) {
+                        mode[0] = readAddress(a->array[0]);
+                        mode[1] = readAddress(a->array[1]);
+                    } else {
+                        mode[0] = mode[1] = readAddress(*a);
+                    }
+                }
+            }
+            if (const json::Value* sc = em->get("scale")) {
+                if (json::Value::Array == sc->kind && sc->array.size() >= 2) {
+                    map_scale[0] = float(sc->array[0].number);
+                    map_scale[1] = float(sc->array[1].number);
+                } else {
+                    map_scale[0] = map_scale[1] = float(sc->number);
+                }
+            }
+        }
+    }
+
     Vec4f color = splat(1.f);
     if (const json::Value* s = j.get("spectrum")) color = readColor(*s);
     const float value = json::readFloatMember(j, "value", 1.f);
@@ -237,6 +273,7 @@ SceneModel::SceneModel() : specular_threshold_(kMinAlpha) {
     clamp_[0] = clamp_[1] = clamp_[2] = FLT_MAX;
     // createFallbackMaterial, material_provider.zig:127-129: a Debug material at id 0 (capi.zig:94-101)
     materials_.push_back(defaultMaterial(ZYG_MATERIAL_DEBUG));
+    emission_maps_.push_back(EmissionMapRec{});
 }
 
 bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
@@ -251,7 +288,12 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
         if ("Light" == entry.first && ZYG_MATERIAL_LIGHT == m.type) {  // updateLight, material_provider.zig:233-244
             for (const auto& e : v.object) {
                 if ("emittance" == e.first) {
-                    loadEmittance(e.second, m);
+                    EmissionMapRec& em = emission_maps_[id];
+                    uint32_t mode[3]   = {em.address_u, em.address_v, em.filter};
+                    loadEmittance(e.second, m, em.image, mode, em.scale);
+                    em.address_u = mode[0];
+                    em.address_v = mode[1];
+                    em.filter    = mode[2];
                 } else if ("two_sided" == e.first) {
                     m.flags = e.second.boolean ? (m.flags | ZYG_MATERIAL_TWO_SIDED) : (m.flags & ~ZYG_MATERIAL_TWO_SIDED);
                 }
@@ -263,7 +305,9 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
                     const Vec4f c = readColor(e.second);
                     for (int i = 0; i < 4; ++i) m.color[i] = c[i];
                 } else if ("emittance" == k) {
-                    loadEmittance(e.second, m);
+                    EmissionMapRec em;  // Substitute emission maps are not in scope: parsed and dropped
+                    uint32_t       mode[3] = {1, 1, 1};
+                    loadEmittance(e.second, m, em.image, mode, em.scale);
                 } else if ("roughness" == k) {
                     m.roughness = float(e.second.number);
                 } else if ("metallic" == k) {
@@ -342,10 +386,140 @@ int SceneModel::createMaterial(const json::Value& material) {
             continue;
         }
         materials_.push_back(defaultMaterial(type));
+        emission_maps_.push_back(EmissionMapRec{});
         updateMaterial(uint32_t(materials_.size() - 1), material);
         return int(materials_.size() - 1);
     }
     return -1;  // Error.UnknownMaterial
+}
+
+int SceneModel::createImage(uint32_t id, uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height, uint32_t depth,
+                            uint32_t pixel_stride, const uint8_t* data) {
+    // capi.zig:29-35 Format: UInt8 0, UInt16 1, UInt32 2, Float16 3, Float32 4
+    const uint32_t bpc = 0 == format ? 1u : ((1 == format || 3 == format) ? 2u : 4u);
+    if (3 != num_channels || !(0 == format || 4 == format) || 0 == width || 0 == height || 1 != depth || !data) return -1;
+    ImageRec img;
+    img.width  = width;
+    img.height = height;
+    img.format = format;
+    img.pixels.assign(size_t(width) * height * 3, 0.f);
+    // Cache.store, resource/cache.zig: an id inside the cache replaces that entry, anything else appends
+    uint32_t slot = id < images_.size() ? id : uint32_t(images_.size());
+    if (slot == images_.size()) images_.push_back(ImageRec{});
+    images_[slot] = std::move(img);
+    if (bpc * num_channels == pixel_stride) updateImage(slot, pixel_stride, data);  // capi.zig:262-264: other strides leave the pixels unset
+    return int(slot);
+}
+
+int SceneModel::updateImage(uint32_t id, uint32_t pixel_stride, const uint8_t* data) {
+    if (id >= images_.size() || !data) return -1;
+    ImageRec&      img = images_[id];
+    const size_t   n   = size_t(img.width) * img.height;
+    const uint32_t bpp = (0 == img.format ? 1u : 4u) * 3u;
+    if (bpp != pixel_stride) return 0;  // capi.zig:322: silently ignored
+    if (4 == img.format) {
+        std::memcpy(img.pixels.data(), data, n * 12);
+    } else {  // Texture.Byte3_sRGB: cachedSrgbToFloat3 then sRGB -> AP1 (texture.zig:196-199, srgb.zig:28-38)
+        float table[256];
+        for (int i = 0; i < 256; ++i) {
+            const float c = float(i) / 255.f;
+            table[i]      = c <= 0.f ? 0.f : (c < 0.04045f ? c / 12.92f : (c < 1.f ? std::pow((c + 0.055f) / 1.055f, 2.4f) : 1.f));
+        }
+        for (size_t i = 0; i < n; ++i) {
+            const Vec4f c = sRGBtoAP1({{table[data[3 * i]], table[data[3 * i + 1]], table[data[3 * i + 2]], 0.f}});
+            img.pixels[3 * i] = c[0], img.pixels[3 * i + 1] = c[1], img.pixels[3 * i + 2] = c[2];
+        }
+    }
+    return 0;
+}
+
+namespace {
+
+// Distribution1D.precomputePdfCdf, distribution_1d.zig:93-131. Returns the integral; `cdf` has n + 1 entries (a zero
+// integral leaves the caller's degenerate row, see ZygpuImageSampler.conditional_integral).
+float precomputeCdf(const float* data, size_t n, float* cdf) {
+    float integral = 0.f;
+    for (size_t i = 0; i < n; ++i) integral += data[i];
+    if (0.f == integral) {
+        for (size_t i = 0; i <= n; ++i) cdf[i] = 1.f;
+        return 0.f;
+    }
+    const float ii = 1.f / integral;
+    float       p  = 0.f;
+    cdf[0]         = 0.f;
+    for (size_t i = 0; i + 1 < n; ++i) {
+        const float c = std::fmaf(data[i], ii, p);
+        cdf[i + 1]    = c;
+        p             = c;
+    }
+    cdf[n] = 1.f;
+    return integral;
+}
+
+}  // namespace
+
+uint32_t SceneModel::uvWeightClass(uint32_t shape) {  // Shape.uvWeight, shape.zig:535-542
+    return ZYG_SHAPE_CANOPY == shape ? 1u : (ZYG_SHAPE_DOME == shape ? 2u : 0u);
+}
+
+// light_material.Material.prepareSampling, light_material.zig:54-119 + LuminanceContext / DistributionContext, :206-272
+// (rows are summed in order on one thread; the reference adds per-thread partial sums)
+uint32_t SceneModel::imageSampler(uint32_t material, uint32_t shape) {
+    const uint32_t wc = uvWeightClass(shape);
+    for (size_t i = 0; i < image_samplers_.size(); ++i) {
+        if (image_samplers_[i]->material == material && image_samplers_[i]->weight_class == wc) return uint32_t(i);
+    }
+    const EmissionMapRec& em  = emission_maps_[material];
+    const ImageRec&       img = images_[em.image];
+    const uint32_t        w = img.width, h = img.height;
+
+    auto rec          = std::make_unique<ImageSamplerRec>();
+    rec->material     = material;
+    rec->weight_class = wc;
+
+    std::vector<float> luminance(size_t(w) * h);
+    const float        idf[2] = {1.f / float(w), 1.f / float(h)};
+    Vec4f              avg    = splat(0.f);
+    for (uint32_t y = 0; y < h; ++y) {
+        const float v = idf[1] * (float(y) + 0.5f);
+        for (uint32_t x = 0; x < w; ++x) {
+            const float u         = idf[0] * (float(x) + 0.5f);
+            float       uv_weight = 1.f;
+            if (1 == wc) {  // Canopy.uvWeight, canopy.zig:133-141
+                const float dx = 2.f * u - 1.f, dy = 2.f * v - 1.f;
+                uv_weight      = (dx * dx + dy * dy) > 1.f ? 0.f : 1.f;
+            } else if (2 == wc) {
+                uv_weight = std::sin(v * kPi);
+            }
+            const float* px = &img.pixels[3 * (size_t(y) * w + x)];
+            const Vec4f  wr = {{uv_weight * px[0], uv_weight * px[1], uv_weight * px[2], 0.f}};
+            avg             = avg + Vec4f{{wr[0], wr[1], wr[2], uv_weight}};
+            luminance[size_t(y) * w + x] = fmax_(wr[0], fmax_(wr[1], wr[2]));
+        }
+    }
+    const Vec4f average_emission = avg / splat(avg[3]);
+    const ZygpuMaterial& m       = materials_[material];
+    rec->total_weight            = avg[3];
+    rec->average_emission        = Vec4f{{m.emission[0], m.emission[1], m.emission[2], m.emission[3]}} * average_emission;
+
+    // MIS compensation (:248-272)
+    const float al = 0.6f * fmax_(average_emission[0], fmax_(average_emission[1], average_emission[2]));
+    rec->conditional_cdf.resize(size_t(h) * (w + 1));
+    rec->conditional_integral.resize(h);
+    for (uint32_t y = 0; y < h; ++y) {
+        float* row = &luminance[size_t(y) * w];
+        for (uint32_t x = 0; x < w; ++x) {
+            const float l = row[x];
+            row[x]        = fmax_(l - al, fmin_(l, 0.0025f));
+        }
+        rec->conditional_integral[y] = precomputeCdf(row, w, &rec->conditional_cdf[size_t(y) * (w + 1)]);
+    }
+    // Distribution2D.configure, distribution_2d.zig:52-61
+    rec->marginal_cdf.resize(h + 1);
+    precomputeCdf(rec->conditional_integral.data(), h, rec->marginal_cdf.data());
+
+    image_samplers_.push_back(std::move(rec));
+    return uint32_t(image_samplers_.size() - 1);
 }
 
 uint32_t SceneModel::addMesh(const zyg_mesh* mesh, uint32_t num_parts) {
@@ -429,7 +603,7 @@ bool SceneModel::createLight(uint32_t entity) {  // scene.zig:342-372
         ZygpuLight l{};
         l.prop        = entity;
         l.part        = i;
-        l.light_class = ZYG_LIGHT_PROP;  // no emission image maps in scope
+        l.light_class = ZYG_LIGHT_PROP;  // becomes PROP_IMAGE in compile when the material has an emission image (scene.zig:356-366)
         l.two_sided   = 0 != (m.flags & ZYG_MATERIAL_TWO_SIDED);
         l.num_samples = m.emission_num_samples;
         lights_.push_back(l);
@@ -595,7 +769,7 @@ void SceneModel::buildPropTree(const std::vector<uint32_t>& indices, std::vector
 }
 
 // LightTreeBuilder.build, light_tree_builder.zig:281-376
-bool SceneModel::buildLightTree(std::string& error) {
+bool SceneModel::buildLightTree(std::string& /*error*/) {
     const uint32_t num_lights = uint32_t(lights_.size());
     light_mapping_.assign(num_lights, 0);
     light_orders_.assign(num_lights, 0);
@@ -615,9 +789,11 @@ bool SceneModel::buildLightTree(std::string& error) {
         light_orders_[light_mapping_[i]] = order++;
         infinite_total_power += light_aabbs_[light_mapping_[i]].min[3];
     }
-    if (num_infinite > 1) {
-        error = "more than one infinite light (Tree.infinite_light_distribution) is not implemented yet";
-        return false;
+    {  // Tree.infinite_light_distribution.configure(infinite_light_powers), light_tree_builder.zig:312-326
+        std::vector<float> powers(num_infinite);
+        for (uint32_t i = 0; i < num_infinite; ++i) powers[i] = light_aabbs_[light_mapping_[i]].min[3];
+        infinite_cdf_.assign(size_t(num_infinite) + 1, 1.f);
+        if (num_infinite > 0) precomputeCdf(powers.data(), num_infinite, infinite_cdf_.data());
     }
 
     ZygpuLightTree& t     = flat_.light_tree;
@@ -664,6 +840,7 @@ bool SceneModel::buildLightTree(std::string& error) {
     t.node_middles  = light_node_middles_.data();
     t.light_orders  = light_orders_.data();
     t.light_mapping = light_mapping_.data();
+    t.infinite_cdf  = infinite_cdf_.data();
     return true;
 }
 
@@ -722,6 +899,16 @@ bool SceneModel::compile(std::string& error) {
     light_aabbs_.resize(num_lights);
     light_cones_.resize(size_t(num_lights) * 4);
     flat_part_areas_.assign(material_ids_.size(), 0.f);
+    image_samplers_.clear();
+    for (size_t m = 0; m < materials_.size(); ++m) {
+        const EmissionMapRec& em = emission_maps_[m];
+        materials_[m].emission_map = ZYGPU_NULL;
+        if (ZYGPU_NULL == em.image) continue;
+        if (em.image >= images_.size()) {
+            error = "material " + std::to_string(m) + ": emission_map references image " + std::to_string(em.image) + " which does not exist";
+            return false;
+        }
+    }
     for (uint32_t l = 0; l < num_lights; ++l) {
         ZygpuLight&           light = lights_[l];
         const PropRec&        p     = props_[light.prop];
@@ -729,8 +916,18 @@ bool SceneModel::compile(std::string& error) {
 
         light_ids_[p.parts_start + light.part] = l;
 
+        // Scene.createLight, scene.zig:356-366: an analytic shape with an emission image is sampled through the image
+        const uint32_t        light_material = material_ids_[p.parts_start + light.part];
+        const ImageSamplerRec* image_sampler = nullptr;
+        light.light_class                    = ZYG_LIGHT_PROP;
+        if (p.shape < 7 && ZYGPU_NULL != emission_maps_[light_material].image) {
+            light.light_class = ZYG_LIGHT_PROP_IMAGE;
+            light.sampler     = imageSampler(light_material, p.shape);
+            image_sampler     = image_samplers_[light.sampler].get();
+        }
+
         // ShapeSamplerCache.prepareSampling -> Mesh.prepareSampling -> Part.configure (triangle_mesh.zig:57-149, 722-746)
-        light.sampler                 = ZYGPU_NULL;
+        if (!image_sampler) light.sampler = ZYGPU_NULL;
         const MeshSamplerData* mesh_sampler = nullptr;
         if (p.shape >= 7) {
             MeshRec& mr = meshes_[p.shape - 7];
@@ -783,6 +980,7 @@ bool SceneModel::compile(std::string& error) {
             case ZYG_SHAPE_DISTANT:  // Distant.solidAngle, distant.zig:143-145
                 extent = (2.f * kPi) * (1.f - std::sqrt(1.f / (scale[0] * scale[0] + 1.f)));
                 break;
+            case ZYG_SHAPE_CANOPY: extent = 2.f * kPi; break;
             default:  // Mesh.area, triangle_mesh.zig:283-286
                 if (p.shape >= 7) extent = meshes_[p.shape - 7].part_areas[light.part] * (scale[0] * scale[1]);
                 break;
@@ -792,6 +990,7 @@ bool SceneModel::compile(std::string& error) {
         // emission), then Light.power (light.zig:65-75; finite lights)
         const ZygpuMaterial& m     = materials_[material_ids_[p.parts_start + light.part]];
         Vec4f                power = {{m.emission[0], m.emission[1], m.emission[2], 0.f}};
+        if (image_sampler) power = image_sampler->average_emission;  // Sampler.averageEmission, shape_sampler.zig:43-48
         if (extent <= 0.f) {
             power = splat(0.f);
         } else if (0.f == m.emission_normalize) {
@@ -806,6 +1005,35 @@ bool SceneModel::compile(std::string& error) {
         }
         bb.b[0][3] = fmax_(power[0], fmax_(power[1], power[2]));  // hmax3
         light_aabbs_[l] = packAabb(bb);
+    }
+
+    // every material with an emission image gets (at least) the sampler of the plain uv weight for its texture lookups
+    for (size_t m = 0; m < materials_.size(); ++m) {
+        if (ZYGPU_NULL == emission_maps_[m].image) continue;
+        uint32_t first = ZYGPU_NULL;
+        for (size_t i = 0; i < image_samplers_.size() && ZYGPU_NULL == first; ++i) {
+            if (image_samplers_[i]->material == m) first = uint32_t(i);
+        }
+        materials_[m].emission_map = ZYGPU_NULL != first ? first : imageSampler(uint32_t(m), ZYG_SHAPE_RECTANGLE);
+    }
+    flat_image_samplers_.clear();
+    for (const auto& rec : image_samplers_) {
+        const EmissionMapRec& em  = emission_maps_[rec->material];
+        const ImageRec&       img = images_[em.image];
+        ZygpuImageSampler     is{};
+        is.width                = img.width;
+        is.height               = img.height;
+        is.address_u            = em.address_u;
+        is.address_v            = em.address_v;
+        is.filter               = em.filter;
+        is.total_weight         = rec->total_weight;
+        is.scale[0]             = em.scale[0];
+        is.scale[1]             = em.scale[1];
+        is.pixels               = img.pixels.data();
+        is.marginal_cdf         = rec->marginal_cdf.data();
+        is.conditional_cdf      = rec->conditional_cdf.data();
+        is.conditional_integral = rec->conditional_integral.data();
+        flat_image_samplers_.push_back(is);
     }
 
     flat_ = ZygpuScene{};
@@ -857,6 +1085,8 @@ bool SceneModel::compile(std::string& error) {
     flat_.num_mesh_samplers  = uint32_t(flat_samplers_.size());
     flat_.mesh_samplers      = flat_samplers_.data();
     flat_.mesh_part_areas    = flat_part_areas_.data();
+    flat_.num_image_samplers = uint32_t(flat_image_samplers_.size());
+    flat_.image_samplers     = flat_image_samplers_.data();
     flat_.meshes             = flat_meshes_.data();
     flat_.ggx_luts           = luts.data();
 

@@ -55,6 +55,11 @@ class SceneModel {
     // (material_provider.zig:131-161). Returns the material id or -1.
     int  createMaterial(const json::Value& material);
     bool updateMaterial(uint32_t id, const json::Value& material);
+    // su_image_create / su_image_update, capi.zig:236-340: the library copies the pixels. Float32 x 3 (image.Float3) and
+    // UInt8 x 3 (image.Byte3, read as sRGB like Texture.Byte3_sRGB) are the formats an emission map can have here.
+    int  createImage(uint32_t id, uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height, uint32_t depth,
+                     uint32_t pixel_stride, const uint8_t* data);
+    int  updateImage(uint32_t id, uint32_t pixel_stride, const uint8_t* data);
     // Registers a compiled mesh as a shape resource; returns the shape id (>= 7).
     uint32_t addMesh(const zyg_mesh* mesh, uint32_t num_parts);
     uint32_t numShapes() const { return 7 + uint32_t(meshes_.size()); }
@@ -114,12 +119,35 @@ class SceneModel {
         MeshSamplerData data;
     };
 
+    struct ImageRec {  // image.Float3 / image.Byte3
+        uint32_t           width = 0, height = 0, format = 0;
+        std::vector<float> pixels;  // RGB, ACEScg
+    };
+    struct EmissionMapRec {  // Emittance.emission_map when it is an image (Texture + Texture.Mode), per material
+        uint32_t image     = ZYGPU_NULL;
+        uint32_t address_u = 1, address_v = 1, filter = 1;  // Texture.DefaultMode: Repeat, Repeat, LinearStochastic
+        float    scale[2]  = {1.f, 1.f};
+    };
+    struct ImageSamplerRec {  // shape_sampler.ImageImpl of one (material, uv-weight class of the shape) pair
+        uint32_t           material, weight_class;
+        float              total_weight;
+        Vec4f              average_emission;
+        std::vector<float> marginal_cdf, conditional_cdf, conditional_integral;
+    };
+    static uint32_t uvWeightClass(uint32_t shape);
+    uint32_t        imageSampler(uint32_t material, uint32_t shape);
+
     bool shapeFinite(uint32_t shape) const;
     AABB shapeAabb(uint32_t shape) const;
     void buildPropTree(const std::vector<uint32_t>& indices, std::vector<ZygpuBvhNode>& nodes, std::vector<uint32_t>& out_indices);
     bool buildLightTree(std::string& error);
 
     std::vector<ZygpuMaterial>  materials_;
+    std::vector<EmissionMapRec> emission_maps_;  // per material
+    std::vector<ImageRec>       images_;
+    std::vector<std::unique_ptr<ImageSamplerRec>> image_samplers_;
+    std::vector<ZygpuImageSampler>                flat_image_samplers_;
+    std::vector<float>                            infinite_cdf_;
     std::vector<MeshRec>        meshes_;
     std::vector<PropRec>        props_;
     std::vector<Transformation> world_;

@@ -329,8 +329,86 @@ def icosahedron():
     return v.astype(np.float32), f
 
 
+def procedural_sky(size=1024, sun_rotation_deg=(-70.0, -20.0, 0.0), zenith=(0.25, 0.45, 1.0), horizon=(0.9, 0.95, 1.0), glow=6.0):
+    """A sky radiance image in the Canopy's mapping (equidistant hemisphere -> unit disk -> [0, 1]^2, canopy.zig:164-202), the
+    layout zyg bakes its own sky model into (sky.zig:44,176-343; the arpraguesky dataset is not shipped): zenith-to-horizon
+    gradient plus a glow around the sun direction, black outside the disk. Returns (size, size, 3) float32 (ACEScg)."""
+    c = (np.arange(size, dtype=np.float64) + 0.5) / size
+    u, v = np.meshgrid(c, c)
+    dx, dy = 2.0 * u - 1.0, 2.0 * v - 1.0
+    r = np.sqrt(dx * dx + dy * dy)
+    inside = r <= 1.0
+    colat = np.minimum(r, 1.0) * (np.pi / 2.0)
+    lon = np.arctan2(-dy, dx)
+    d = np.stack([np.sin(colat) * np.cos(lon), np.sin(colat) * np.sin(lon), np.cos(colat)], -1)  # canopy-local, z = up
+    # the sun points along -r[2] of its Distant prop (distant.zig:22-54); world -> canopy-local with the sky rotation (90, 0, 0)
+    from . import su
+
+    sun_dir = -su.transformation(rotation_deg=sun_rotation_deg)[2, :3].astype(np.float64)
+    sky_rot = su.transformation(rotation_deg=(90.0, 0.0, 0.0))[:3, :3].astype(np.float64)
+    sun_local = sky_rot @ sun_dir
+    t = np.cos(colat)[..., None] ** 0.6
+    img = (1.0 - t) * np.asarray(horizon) + t * np.asarray(zenith)
+    cos_sun = np.clip(d @ sun_local, -1.0, 1.0)
+    img = img * (0.35 + glow * np.exp((cos_sun - 1.0) * 40.0)[..., None])
+    img[~inside] = 0.0
+    return np.ascontiguousarray(img, np.float32)
+
+
+def add_sky(image: np.ndarray, value: float = 1.0):
+    """Sky dome the way sky.zig:57-66,121-131 sets it up, with a Light material carrying the image as its emission map
+    (the C API has no Sky material): Canopy prop rotated 90 degrees about X (z = up), clamped texture addressing."""
+    from . import su
+
+    sky_image = su.image_create(image)
+    material = su.material_create({"rendering": {"Light": {"emittance": {
+        "emission_map": {"id": sky_image, "sampler": {"address": "Clamp"}}, "value": float(value)}}}})
+    sky = su.prop_create(su.CANOPY, [material])
+    su.prop_set_transformation(sky, su.transformation(rotation_deg=(90.0, 0.0, 0.0)))
+    su.light_create(sky)
+    return sky
+
+
+def sky_scene(width=256, height=256, spp=16, max_depth=6, filter_name=None, sky_size=256, sun=8.0, sky_value=1.0, uniform_sky=None,
+              ground_albedo=0.5, objects=True, split_threshold=0.5):
+    """Open scene lit by an image-mapped Canopy sky (a PropImage light, importance-sampled through Distribution2D) and
+    optionally a Distant sun: two infinite lights, so Tree.infinite_light_distribution is exercised too. `uniform_sky` = L
+    replaces the image by a constant radiance L (furnace-style checks: a ground of albedo a shows a * L)."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(60.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.2, -4.0), rotation_deg=(-10.0, 0.0, 0.0)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth}, "light_sampling": {"split_threshold": split_threshold}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    ground = su.material_create({"rendering": {"Substitute": {"color": [ground_albedo] * 3, "roughness": 1.0}}})
+    g = su.prop_create(su.RECTANGLE, [ground])
+    su.prop_set_transformation(g, su.transformation((0.0, 0.0, 0.0), (400.0, 400.0, 1.0), (90.0, 0.0, 0.0)))
+    if objects:
+        red = su.material_create({"rendering": {"Substitute": {"color": [0.7, 0.2, 0.15], "roughness": 1.0}}})
+        gold = su.material_create({"rendering": {"Substitute": {"color": [0.9, 0.7, 0.3], "roughness": 0.3, "metallic": 1.0}}})
+        cube = su.prop_create(su.CUBE, [red])
+        su.prop_set_transformation(cube, su.transformation((-1.0, 0.5, 0.5), (1.0, 1.0, 1.0), (0.0, 30.0, 0.0)))
+        ball = su.prop_create(su.SPHERE, [gold])
+        su.prop_set_transformation(ball, su.transformation((1.1, 0.6, 0.0), (1.2, 1.2, 1.2)))
+    if uniform_sky is not None:
+        image = np.full((sky_size, sky_size, 3), float(uniform_sky), np.float32)
+    else:
+        image = procedural_sky(sky_size)
+    add_sky(image, sky_value)
+    if sun is not None:
+        sun_material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": [1.0, 0.9, 0.75], "value": float(sun) * 400.0}}}})
+        sun_prop = su.prop_create(su.DISTANT, [sun_material])
+        su.prop_set_transformation(sun_prop, su.transformation((0.0, 0.0, 0.0), (0.05, 0.05, 0.05), (-70.0, -20.0, 0.0)))
+        su.light_create(sun_prop)
+    return 0
+
+
 def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24, seed=11, filter_name=None,
-                      split_threshold=0.5, big_light_quads=(24, 12), geometry_quads=None, sun=None, unoccluding=False):
+                      split_threshold=0.5, big_light_quads=(24, 12), geometry_quads=None, sun=None, unoccluding=False, sky=None):
     """Config-4 style: a closed room lit only by emissive triangle meshes - `num_lights` small icosahedra (20 triangles,
     radius 0.05-0.12, instances of one mesh with PCG-random colour and power) and one larger emissive displaced sphere
     with many triangles, so both the scene light tree and the per-part primitive trees (spherical-triangle sampling near,
@@ -394,6 +472,8 @@ def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24,
         sun_prop = su.prop_create(su.DISTANT, [sun_material])
         su.prop_set_transformation(sun_prop, su.transformation((0.0, 0.0, 0.0), (0.05, 0.05, 0.05), (-70.0, -20.0, 0.0)))
         su.light_create(sun_prop)
+    if sky is not None:  # config 4: the sky dome (baked 1024^2 image on a Canopy) next to the sun
+        add_sky(procedural_sky(int(sky)), 1.0)
     return num_meshes
 
 

@@ -96,6 +96,19 @@ def sensor_create(desc: dict):
     _ok(_su().zyg_su_sensor_create(json.dumps(desc).encode()), "zyg_su_sensor_create")
 
 
+def image_create(pixels: np.ndarray) -> int:
+    """su_image_create for an (H, W, 3) float32 (Format.Float32) or uint8 (Format.UInt8, sRGB) array; the library copies."""
+    px = np.ascontiguousarray(pixels)
+    assert px.ndim == 3 and px.shape[2] == 3 and px.dtype in (np.float32, np.uint8)
+    fmt, bpc = (4, 4) if px.dtype == np.float32 else (0, 1)
+    return _ok(_su().su_image_create(0xFFFFFFFF, fmt, 3, px.shape[1], px.shape[0], 1, 3 * bpc, px.ctypes.data), "su_image_create")
+
+
+def image_update(image: int, pixels: np.ndarray):
+    px = np.ascontiguousarray(pixels)
+    _ok(_su().su_image_update(image, 3 * px.dtype.itemsize, px.ctypes.data), "su_image_update")
+
+
 def material_create(desc: dict) -> int:
     return _ok(_su().su_material_create(0xFFFFFFFF, json.dumps(desc).encode()), "su_material_create")
 
