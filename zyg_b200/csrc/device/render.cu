@@ -2107,8 +2107,14 @@ __global__ void __launch_bounds__(128) lightSelectPersistent(SceneDevice sc, Zyg
     }
 }
 
+// The kernel is long and branchy and its warps mostly wait for instruction fetch (ncu: no_instruction is the top stall, issue
+// slots 13 % busy at 122 registers / 4 blocks per SM): more resident warps hide that better than registers help, so it is
+// compiled for 8 blocks per SM (64 registers; measured 310 -> 265 ms per 4-spp pass of config 4, 12 and 16 blocks are slower).
+#ifndef ZYGPU_LIGHT_BLOCKS
+#define ZYGPU_LIGHT_BLOCKS 8
+#endif
 template <bool MeshLights, bool Infinite>
-__global__ void __launch_bounds__(128) lightSamplePersistent(SceneDevice sc, ZygpuView view, PathState st, PassParams pass,
+__global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent(SceneDevice sc, ZygpuView view, PathState st, PassParams pass,
                                                              uint32_t* __restrict__ work_counter) {
     __shared__ uint32_t sobol_tables[kSobolTableWords];
     loadSobolTables(sobol_tables);
