@@ -510,6 +510,69 @@ bool intersectP(const Ray& ray, const Trafo& trafo) {
     return intersect(ray, trafo, unused);
 }
 
+inline float conePdfUniform(float one_minus_cos_theta_max) {  // sampling.zig:103-106
+    return 1.f / ((2.f * kPi) * max(one_minus_cos_theta_max, 1.0e-20f));
+}
+
+// Sphere.sampleTo, sphere.zig:323-393
+uint32_t sampleTo(Vec4f p, Vec4f n, const Trafo& trafo, bool total_sphere, uint32_t num_samples, Sampler& sampler, SampleTo* buffer) {
+    const Vec4f v = trafo.position - p;
+    const float l = length3(v);
+    const float r = 0.5f * trafo.scaleX();
+    if (l <= (r + 0.0000001f)) return 0;
+
+    const Vec4f z     = splat(1.f / l) * v;
+    const Frame frame = Frame::init(z);
+    const float nsf   = float(num_samples);
+
+    uint32_t current_sample = 0;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        const float sin_theta_max           = r / l;
+        const float sin2_theta_max          = sin_theta_max * sin_theta_max;
+        const float cos_theta_max           = std::sqrt(1.f - sin2_theta_max);
+        float       one_minus_cos_theta_max = 1.f - cos_theta_max;
+
+        const Vec2f s2 = sampler.sample2D();
+
+        float cos_theta  = (cos_theta_max - 1.f) * s2[0] + 1.f;
+        float sin2_theta = 1.f - (cos_theta * cos_theta);
+        if (sin2_theta_max < 0.00068523f) {
+            sin2_theta              = sin2_theta_max * s2[0];
+            cos_theta               = std::sqrt(1.f - sin2_theta);
+            one_minus_cos_theta_max = 0.5f * sin2_theta_max;
+        }
+
+        const float cos_alpha = min(sin2_theta / sin_theta_max + cos_theta * std::sqrt(1.f - min(sin2_theta / sin2_theta_max, 1.f)), 1.f);
+        const float sin_alpha = std::sqrt(1.f - cos_alpha * cos_alpha);
+        const float phi       = s2[1] * (2.f * kPi);
+
+        // smpl.sphereDirection, sampling.zig:78-83
+        const float sin_phi = std::sin(phi), cos_phi = std::cos(phi);
+        const Vec4f w  = {{cos_phi * sin_alpha, sin_phi * sin_alpha, cos_alpha, 0.f}};
+        const Vec4f wn = frame.frameToWorld(-w);
+        const Vec4f lp = trafo.position + splat(r) * wn;
+        const Vec4f dir = normalize3(lp - p);
+        if (dot3(dir, n) <= 0.f && !total_sphere) continue;
+
+        SampleTo& out = buffer[current_sample++];
+        out.p         = {{lp[0], lp[1], lp[2], nsf * conePdfUniform(one_minus_cos_theta_max)}};
+        out.n         = wn;
+        out.wi        = dir;
+        out.uvw       = splat(0.f);
+    }
+    return current_sample;
+}
+
+// Sphere.pdf, sphere.zig:472-487
+float pdf(Vec4f p, const Trafo& trafo, uint32_t num_samples) {
+    const Vec4f v              = trafo.position - p;
+    const float l2             = squaredLength3(v);
+    const float r              = 0.5f * trafo.scaleX();
+    const float sin2_theta_max = (r * r) / l2;
+    const float one_minus_cos_theta_max = sin2_theta_max < 0.00068523f ? 0.5f * sin2_theta_max : 1.f - std::sqrt(max(1.f - sin2_theta_max, 0.f));
+    return float(num_samples) * conePdfUniform(one_minus_cos_theta_max);
+}
+
 }  // namespace sphere
 
 namespace distant {  // shape/distant.zig:22-146
@@ -1646,6 +1709,7 @@ struct Scene {
             case ZYG_SHAPE_RECTANGLE:
                 return rectangle::sampleTo(p, n, trafo, 0 != l.two_sided, total_sphere, num_samples, sampler, buffer);
             case ZYG_SHAPE_DISTANT: return distant::sampleTo(n, trafo, total_sphere, sampler, buffer);
+            case ZYG_SHAPE_SPHERE: return sphere::sampleTo(p, n, trafo, total_sphere, num_samples, sampler, buffer);
             case ZYG_SHAPE_CANOPY:  // Light.propSampleMaterialTo -> Shape.sampleMaterialTo, light.zig:191-215, shape.zig:348-371
                 if (ZYG_LIGHT_PROP_IMAGE != l.light_class) return 0;  // Canopy.sampleTo (uniform sky) is not in scope
                 return canopy::sampleMaterialTo(n, trafo, total_sphere, image_samplers[l.sampler], sampler, buffer);
@@ -1843,6 +1907,9 @@ struct Worker {
                 sample_pdf = rectangle::pdf(vertex.origin, frag, scene.lightNumSamples(l, vertex.light_split_threshold));
                 break;
             case ZYG_SHAPE_DISTANT: sample_pdf = 1.f / distant::solidAngle(frag.isec.trafo.scaleX()); break;  // distant.zig:139-141
+            case ZYG_SHAPE_SPHERE:
+                sample_pdf = sphere::pdf(vertex.origin, frag.isec.trafo, scene.lightNumSamples(l, vertex.light_split_threshold));
+                break;
             case ZYG_SHAPE_CANOPY:  // Light.propMaterialPdf -> Shape.materialPdf, light.zig:371-374, shape.zig:519
                 if (ZYG_LIGHT_PROP_IMAGE == l.light_class) sample_pdf = scene.image_samplers[l.sampler].pdf(frag.uvw[0], frag.uvw[1]) / (2.f * kPi);
                 break;
@@ -1944,7 +2011,11 @@ struct Worker {
                 });
                 return energy;
             }
-            default: return splat(0.f);  // shape.zig:283-299; Sphere emitters are not in scope yet
+            case ZYG_SHAPE_SPHERE:  // Sphere.emission, sphere.zig:271-279
+                if (!sphere::intersect(vertex.ray, frag.isec.trafo, frag.isec)) return splat(0.f);
+                sphere::fragment(vertex.ray, frag);
+                return evaluateRadiance(vertex, frag, sampler);
+            default: return splat(0.f);  // shape.zig:283-299
         }
     }
 

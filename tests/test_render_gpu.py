@@ -328,3 +328,21 @@ def test_mesh_lights_with_sky_match_oracle(engine):
     assert np.median(rel) < 2e-5
     assert (rel > 1e-2).mean() < 1e-2
     assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4
+
+
+@pytest.mark.parametrize("split_threshold,num_samples,deferred", [(0.5, 1, "0"), (0.5, 4, "0"), (0.0, 1, "0"), (0.5, 4, "1")])
+def test_sphere_lights_match_oracle(engine, monkeypatch, split_threshold, num_samples, deferred):
+    """Sphere lights (cone sampling of the visible cap, sphere.zig:323-393; pdf :472-487) as occluding props and as
+    un-occluding emitters gathered by Sphere.emission (:271-279), sampled inside shade_a and in the deferred light kernels."""
+    monkeypatch.setenv("ZYGPU_DEFERRED_LIGHTS", deferred)
+    w, spp = 128, 16
+    scenes.sphere_lights_scene(w, w, spp=spp, split_threshold=split_threshold, num_samples=num_samples)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp, wavefront_light_order=True)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6
+    assert (rel > 1e-2).mean() < 5e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4

@@ -153,3 +153,32 @@ def test_infinite_light_distribution_agrees_with_split(engine):
         film = oracle.render(scene, view, w, w, 0, spp)
         means.append((film[..., :3] / film[..., 3:4]).astype(np.float64).mean((0, 1)))
     assert np.allclose(means[0], means[1], rtol=0.01)
+
+
+def test_sphere_light_irradiance(engine):
+    """Sphere.sampleTo / pdf / emission pinned against the closed form: a diffuse sphere emitter of radiance L and radius r
+    whose centre is d above a diffuse plane gives the point below it the irradiance pi * L * (r / d)^2, i.e. the radiance
+    a * L * (r / d)^2 (times the Substitute lobe's directional albedo, within 2 % of 1)."""
+    L, a, r, d = 5.0, 0.5, 0.5, 2.0
+    for unoccluding in (False, True):
+        su.release()
+        su.init()
+        camera = su.perspective_camera_create(32, 32)
+        su.camera_set_fov(float(np.radians(2.0)))
+        su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.0, -3.0), rotation_deg=(-18.434949, 0.0, 0.0)))
+        su.sampler_create(256)
+        su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": 1}}}})
+        su.sensor_create({})
+        ground = su.material_create({"rendering": {"Substitute": {"color": [a] * 3, "roughness": 1.0}}})
+        g = su.prop_create(su.RECTANGLE, [ground])
+        su.prop_set_transformation(g, su.transformation((0.0, 0.0, 0.0), (100.0, 100.0, 1.0), (90.0, 0.0, 0.0)))
+        lamp_material = su.material_create({"rendering": {"Light": {"emittance": {"value": L}}}})
+        lamp = su.prop_create(su.SPHERE, [lamp_material], unoccluding=unoccluding)
+        su.prop_set_transformation(lamp, su.transformation((0.0, d, 0.0), (2 * r, 2 * r, 2 * r)))
+        su.light_create(lamp)
+        scene, view = su.compile_scene()
+        film = oracle.render(scene, view, 32, 32, 0, 256)
+        img = (film[..., :3] / film[..., 3:4]).astype(np.float64)
+        # sRGB (1,1,1) -> AP1 keeps grey: the film holds AP1 radiance; centre pixels look at the origin
+        got = img[12:20, 12:20].mean()
+        assert abs(got / (a * L * (r / d) ** 2) - 1.0) < 0.03, (unoccluding, got)

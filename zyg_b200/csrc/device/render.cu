@@ -1359,6 +1359,8 @@ __device__ float sceneLightPdf(const SceneDevice& sc, const VertexD& vertex, con
         sample_pdf = nsf * squad.pdf(frag.trafo.scale);
     } else if (ZYG_SHAPE_DISTANT == sc.props[l.prop].shape) {  // Distant.pdf, distant.zig:139-141
         sample_pdf = __fdiv_rn(1.f, distantSolidAngle(frag.trafo.scale.x));
+    } else if (ZYG_SHAPE_SPHERE == sc.props[l.prop].shape) {  // Sphere.pdf, sphere.zig:472-487
+        sample_pdf = float(lightNumSamples(l, vertex.light_split_threshold)) * sphereLightPdf(frag.trafo, vertex.origin);
     } else if (ZYG_SHAPE_CANOPY == sc.props[l.prop].shape) {  // Light.propMaterialPdf -> Shape.materialPdf, shape.zig:519
         if (ZYG_LIGHT_PROP_IMAGE == l.light_class) sample_pdf = __fdiv_rn(imagePdf(sc.image_samplers[l.sampler], frag.u, frag.v), 2.f * kPi);
     } else if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == sc.props[l.prop].shape && ZYGPU_NULL != l.sampler) {
@@ -1456,14 +1458,19 @@ __device__ V3 propEmission(const SceneDevice& sc, uint32_t entity, const VertexD
     if (!propVisible(prop.flags, vertex.probe_depth)) return splat3(0.f);
     if (!aabbIntersect(sc.aabbs, entity, vertex.ray)) return splat3(0.f);
     if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == prop.shape) return meshEmission<MeshLights>(sc, entity, prop, vertex, sampler);
-    if (ZYG_SHAPE_RECTANGLE != prop.shape) return splat3(0.f);
+    if (ZYG_SHAPE_RECTANGLE != prop.shape && ZYG_SHAPE_SPHERE != prop.shape) return splat3(0.f);
 
     FragD frag;
     frag.prop  = entity;
     frag.trafo = loadTrafo(sc.trafos, entity);
     HitD isec;
-    if (!rectangleIntersect(vertex.ray, frag.trafo, isec)) return splat3(0.f);
-    rectangleFragment(vertex.ray, isec, frag);
+    if (ZYG_SHAPE_SPHERE == prop.shape) {  // Sphere.emission, sphere.zig:271-279
+        if (!sphereIntersect(vertex.ray, frag.trafo, isec)) return splat3(0.f);
+        sphereFragment(vertex.ray, isec, frag);
+    } else {
+        if (!rectangleIntersect(vertex.ray, frag.trafo, isec)) return splat3(0.f);
+        rectangleFragment(vertex.ray, isec, frag);
+    }
     return evaluateRadiance<MeshLights>(sc, vertex, frag, sampler);
 }
 
@@ -1913,6 +1920,31 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                                                             vertex.light_split_threshold, sampler, num_records);
                             return;
                         }
+                        if (ZYG_SHAPE_SPHERE == shape) {  // Sphere.sampleTo, sphere.zig:323-393
+                            SphereLightD sl;
+                            sl.init(trafo, p);
+                            if (!sl.valid) return;
+                            const uint32_t ns = lightNumSamples(light, vertex.light_split_threshold);
+                            for (uint32_t k = 0; k < ns; ++k) {
+                                float u0, u1;
+                                sampler.sample2D(u0, u1);
+                                V3    lp, wn, dir;
+                                float pdf;
+                                if (!sl.sample(trafo, p, n, translucent, u0, u1, lp, wn, dir, pdf)) continue;
+                                if (num_records < st.shadow_stride) {
+                                    const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+                                    const V3     origin    = frag.offsetP(dir);
+                                    const V3     light_pos = offsetRay(lp, wn);
+                                    st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, (float(ns) * pdf) * pick.pdf);
+                                    st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+                                    st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                                    num_records += 1;
+                                } else {
+                                    st.counters[3] = 1;
+                                }
+                            }
+                            return;
+                        }
                         if (ZYG_SHAPE_RECTANGLE != shape) return;
 
                         // Rectangle.sampleTo, rectangle.zig:305-357
@@ -2219,6 +2251,28 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                 frag.p      = p;
                 frag.geo_n  = geo_n;
                 num_records = meshLightSampleTo(sc, st, slot, light, pick, trafo, frag, n, translucent, threshold, sampler, num_records);
+            } else if (ZYG_SHAPE_SPHERE == shape) {  // Sphere.sampleTo, sphere.zig:323-393
+                SphereLightD sl;
+                sl.init(trafo, p);
+                const uint32_t ns = sl.valid ? lightNumSamples(light, threshold) : 0;
+                for (uint32_t k = 0; k < ns; ++k) {
+                    float u0, u1;
+                    sampler.sample2D(u0, u1);
+                    V3    lp, wn, dir;
+                    float pdf;
+                    if (!sl.sample(trafo, p, n, translucent, u0, u1, lp, wn, dir, pdf)) continue;
+                    if (num_records < st.shadow_stride) {
+                        const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+                        const V3     origin    = offsetPoint(p, geo_n, dir);
+                        const V3     light_pos = offsetRay(lp, wn);
+                        st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, (float(ns) * pdf) * pick.pdf);
+                        st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+                        st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                        num_records += 1;
+                    } else {
+                        st.counters[3] = 1;
+                    }
+                }
             } else if (ZYG_SHAPE_RECTANGLE == shape) {  // Rectangle.sampleTo, rectangle.zig:305-357
                 const uint32_t ns  = lightNumSamples(light, threshold);
                 const float    nsf = float(ns);

@@ -347,6 +347,63 @@ __device__ __forceinline__ void sphereFragment(const RayT& ray, const HitD& isec
     frag.v = theta * kPiInv;
 }
 
+// Sphere as a light: Sphere.sampleTo / Sphere.pdf, sphere.zig:323-393, 472-487; smpl.conePdfUniform, sampling.zig:103-106
+__device__ __forceinline__ float conePdfUniform(float one_minus_cos_theta_max) {
+    return __fdiv_rn(1.f, (2.f * kPi) * zmax(one_minus_cos_theta_max, 1.0e-20f));
+}
+struct SphereLightD {
+    V3    z, tx, ty;  // Frame.init(z)
+    float l, r;
+    bool  valid;
+
+    __device__ void init(const TrafoD& trafo, V3 p) {
+        const V3 v = sub3(trafo.position, p);
+        l          = length3(v);
+        r          = 0.5f * trafo.scale.x;
+        valid      = !(l <= (r + 0.0000001f));
+        z          = scale3(__fdiv_rn(1.f, l), v);
+        orthonormalBasis3(z, tx, ty);
+    }
+    // one light sample: false when it faces away from n; pdf excludes the sample count and the light pick
+    __device__ bool sample(const TrafoD& trafo, V3 p, V3 n, bool total_sphere, float s0, float s1, V3& lp, V3& wn, V3& dir, float& pdf) const {
+        const float sin_theta_max           = __fdiv_rn(r, l);
+        const float sin2_theta_max          = sin_theta_max * sin_theta_max;
+        const float cos_theta_max           = __fsqrt_rn(1.f - sin2_theta_max);
+        float       one_minus_cos_theta_max = 1.f - cos_theta_max;
+
+        float cos_theta  = (cos_theta_max - 1.f) * s0 + 1.f;
+        float sin2_theta = 1.f - (cos_theta * cos_theta);
+        if (sin2_theta_max < 0.00068523f) {
+            sin2_theta              = sin2_theta_max * s0;
+            cos_theta               = __fsqrt_rn(1.f - sin2_theta);
+            one_minus_cos_theta_max = 0.5f * sin2_theta_max;
+        }
+        const float cos_alpha = zmin(__fdiv_rn(sin2_theta, sin_theta_max) +
+                                         cos_theta * __fsqrt_rn(1.f - zmin(__fdiv_rn(sin2_theta, sin2_theta_max), 1.f)),
+                                     1.f);
+        const float sin_alpha = __fsqrt_rn(1.f - cos_alpha * cos_alpha);
+        const float phi       = s1 * (2.f * kPi);
+        const float sin_phi = sinf(phi), cos_phi = cosf(phi);
+        const V3    w = {-(cos_phi * sin_alpha), -(sin_phi * sin_alpha), -cos_alpha};
+        const FrameD frame{tx, ty, z};
+        wn  = frame.frameToWorld(w);
+        lp  = add3(trafo.position, scale3(r, wn));
+        dir = normalize3(sub3(lp, p));
+        if (dot3(dir, n) <= 0.f && !total_sphere) return false;
+        pdf = conePdfUniform(one_minus_cos_theta_max);
+        return true;
+    }
+};
+__device__ __forceinline__ float sphereLightPdf(const TrafoD& trafo, V3 p) {
+    const V3    v              = sub3(trafo.position, p);
+    const float l2             = squaredLength3(v);
+    const float r              = 0.5f * trafo.scale.x;
+    const float sin2_theta_max = __fdiv_rn(r * r, l2);
+    const float one_minus_cos_theta_max =
+        sin2_theta_max < 0.00068523f ? 0.5f * sin2_theta_max : 1.f - __fsqrt_rn(zmax(1.f - sin2_theta_max, 0.f));
+    return conePdfUniform(one_minus_cos_theta_max);
+}
+
 // ---- emission images --------------------------------------------------------------------------------------------------
 // Distribution1D.sample, distribution_1d.zig:50-54, 250-258: the first i in [1, size - 1) with cdf[i] >= r (else size - 1),
 // minus one. The reference walks there linearly from a lookup-table start; the cdf is non-decreasing on that range, so a

@@ -317,6 +317,43 @@ def many_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=64,
     return camera
 
 
+def sphere_lights_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None, split_threshold=0.5, num_samples=1,
+                        unoccluding=(True, False, True)):
+    """A closed room lit by three Sphere lights (Sphere.sampleTo / pdf / emission, sphere.zig:271-279, 323-393, 472-487): a
+    large one close to the floor, a small one and a tiny far one (the small-angle branch of the cone sampling); each either
+    un-occluding (a scene file's default for Light entities: gathered by Prop.emission) or an ordinary occluding prop."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(70.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.4, -2.8)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth},
+                                                 "light_sampling": {"split_threshold": split_threshold}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    wall = su.material_create({"rendering": {"Substitute": {"color": [0.7, 0.7, 0.7], "roughness": 1.0}}})
+    glossy = su.material_create({"rendering": {"Substitute": {"color": [0.8, 0.6, 0.3], "roughness": 0.35, "metallic": 1.0}}})
+    walls = [((0, 0, 0), (6, 6, 1), (90, 0, 0)), ((0, 3, 0), (6, 6, 1), (-90, 0, 0)),
+             ((0, 1.5, 3), (6, 3, 1), (0, 180, 0)), ((0, 1.5, -3), (6, 3, 1), (0, 0, 0)),
+             ((-3, 1.5, 0), (6, 3, 1), (0, -90, 0)), ((3, 1.5, 0), (6, 3, 1), (0, 90, 0))]
+    for position, scale, rotation in walls:
+        prop = su.prop_create(su.RECTANGLE, [wall])
+        su.prop_set_transformation(prop, su.transformation(tuple(map(float, position)), tuple(map(float, scale)), tuple(map(float, rotation))))
+    for k, (x, z) in enumerate([(-1.2, 0.8), (1.4, 0.2)]):
+        cube = su.prop_create(su.CUBE, [glossy if 1 == k else wall])
+        su.prop_set_transformation(cube, su.transformation((x, 0.4, z), (0.8, 0.8, 0.8), (0.0, 25.0 * k, 0.0)))
+    lamps = [((0.3, 0.9, 1.4), 1.0, [1.0, 0.8, 0.6], 3.0), ((-1.6, 2.2, -0.5), 0.25, [0.6, 0.8, 1.0], 60.0),
+             ((2.4, 2.7, 2.5), 0.02, [1.0, 1.0, 1.0], 6000.0)]
+    for (position, diameter, colour, value), un in zip(lamps, unoccluding):
+        material = su.material_create({"rendering": {"Light": {"emittance": {"spectrum": colour, "value": value, "num_samples": num_samples}}}})
+        lamp = su.prop_create(su.SPHERE, [material], unoccluding=un)
+        su.prop_set_transformation(lamp, su.transformation(position, (diameter, diameter, diameter)))
+        su.light_create(lamp)
+    return 0
+
+
 def icosahedron():
     """Unit icosahedron: (positions f32[12,3], indices u32[20,3]), counter-clockwise seen from outside."""
     t = (1.0 + 5.0 ** 0.5) / 2.0
