@@ -150,7 +150,7 @@ def run_reference(args):
 
     path_tracing = {}
     for name, (builder, kwargs, width, height, spp, cpu_spp) in RENDER_SCENES.items():
-        if args.scenes and name not in args.scenes:
+        if (args.scenes and name not in args.scenes) or 0 == cpu_spp:
             continue
         num_meshes = build_render_scene(builder, kwargs, width, height, spp)
         scene, view = su.compile_scene()
@@ -183,6 +183,10 @@ RENDER_SCENES = {
     # light + Distant sun, 1920 x 1080 (8 of the 256 spp per step)
     "config3_instanced5m_1920x1080x8": ("instanced_scene", {"grid": (100, 100), "prototypes": 20, "quads": (500, 250), "sun": 60.0},
                                         1920, 1080, 8, 1),
+    # configs[4]: the instanced scene at 3840 x 2160, the frame's samples split by range over the ranks and the 132.7 MB film
+    # reduced to rank 0 (8 of the 4096 spp per step; 8 / N per GPU)
+    "config5_instanced5m_3840x2160x8": ("instanced_scene", {"grid": (100, 100), "prototypes": 20, "quads": (500, 250), "sun": 60.0},
+                                        3840, 2160, 8, 0),
     # configs[3]: 1000 emissive icosahedron meshes + a 576-triangle emitter in a room with 200k triangles of diffuse geometry,
     # sky = a 1024^2 radiance image on a Canopy (procedural: the arpraguesky dataset is not shipped) + Distant sun, light-tree
     # sampling with split threshold 0.5, 1920 x 1080 (4 of the 1024 spp per step)
@@ -271,10 +275,20 @@ def bench_render(args, rank, world, local):
         rgba = su.resolve_frame_to_buffer(width, height)
         e2e_s = time.perf_counter() - t0
 
-        if world > 1:
-            t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        reduce_ms = 0.0
+        if world > 1:  # the film reduce on its own (it is inside `ms` as well)
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                r0.record()
+                for _ in range(args.steps):
+                    dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+                r1.record()
+            barrier()
+            reduce_ms = r0.elapsed_time(r1) / args.steps
+            t = torch.tensor([ms, e2e_s, reduce_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, e2e_s = t.tolist()
+            ms, e2e_s, reduce_ms = t.tolist()
 
         samples = width * height * spp
         entry = {
@@ -284,11 +298,12 @@ def bench_render(args, rank, world, local):
             "shadow_rays_per_sample": st.shadow_rays / max(1, st.camera_samples),
             "mrays_per_s": (st.closest_rays + st.shadow_rays) / max(1, st.camera_samples) * samples * args.steps / (ms * 1e-3) / 1e6,
             "e2e_path_samples_per_s": samples / e2e_s, "e2e_d2h_bytes": int(rgba.nbytes),
+            "film_reduce_ms": reduce_ms, "film_bytes": width * height * 16,
             "scaling": "strong (sample-range split, film reduce to rank 0)" if world > 1 else "single device",
         }
         launches += int(st.kernel_launches)
 
-        if rank == 0 and world == 1 and not args.no_cpu:
+        if rank == 0 and world == 1 and not args.no_cpu and cpu_spp > 0:
             oracle = load_oracle()
             scene, view = su.compile_scene()
             t0 = time.perf_counter()
