@@ -66,6 +66,13 @@ int32_t zyg_su_sensor_create(const char* json);
 /* su_prop_create for an entity of type "Light", which the scene loader creates un-occluding unless told
  * otherwise (src/util/scene_loader.zig:249,365-366). */
 int32_t zyg_su_prop_create_unoccluding(uint32_t shape, uint32_t num_materials, const uint32_t* materials);
+/* An entity of type "Instancer" (src/util/scene_loader.zig:401-508, src/core/scene/prop/instancer.zig): `prototypes` are
+ * entities made with su_prop_create (they leave the scene's own prop tree, like is_prototype entities of a scene file);
+ * instance i places prototypes[prototype_indices[i]] with the 4x4 `transformations + 16 * i` (the layout of
+ * su_prop_set_transformation) relative to the returned entity, whose own transformation su_prop_set_transformation sets.
+ * The instancer is flattened at compile time: every instance becomes a prop of the two-level device layout. */
+int32_t zyg_su_instancer_create(uint32_t num_prototypes, const uint32_t* prototypes, uint32_t num_instances,
+                                const uint32_t* prototype_indices, const float* transformations);
 /* Thin-lens parameters of the take's camera block (camera_perspective.zig:200-240). */
 int32_t zyg_su_camera_set_lens(float aperture_radius, float focus_distance);
 /* CUDA device used by the render calls (default 0). */

@@ -346,3 +346,20 @@ def test_sphere_lights_match_oracle(engine, monkeypatch, split_threshold, num_sa
     assert np.median(rel) < 5e-6
     assert (rel > 1e-2).mean() < 5e-3
     assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4
+
+
+def test_instancer_matches_oracle(engine):
+    """A scene-file style Instancer entity (zyg_su_instancer_create) under a rotated / scaled / translated transformation:
+    flattened on the host into the two-level layout, traced and shaded like prop instances."""
+    w, spp = 128, 8
+    outer = su.transformation((0.4, 0.3, -0.2), (1.25, 1.25, 1.25), (0.0, 35.0, 0.0))
+    n = scenes.instanced_scene(w, w, spp=spp, grid=(16, 16), prototypes=3, quads=(40, 20), instancer=outer, sun=30.0)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n, wavefront_light_order=True)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6
+    assert (rel > 1e-2).mean() < 1e-2
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 5e-4

@@ -225,6 +225,14 @@ int32_t zyg_su_prop_create_unoccluding(uint32_t shape, uint32_t num_materials, c
     return propCreate(shape, num_materials, materials, true);
 }
 
+int32_t zyg_su_instancer_create(uint32_t num_prototypes, const uint32_t* prototypes, uint32_t num_instances,
+                                const uint32_t* prototype_indices, const float* transformations) {
+    if (!g_engine || (num_instances > 0 && !transformations)) return -1;
+    std::vector<zyg::Transformation> trafos(num_instances);
+    for (uint32_t i = 0; i < num_instances; ++i) zyg::decomposeMatrix(transformations + size_t(i) * 16, trafos[i]);
+    return g_engine->scene.createInstancer(prototypes, num_prototypes, prototype_indices, trafos.data(), num_instances);
+}
+
 int32_t su_prop_create_instance(uint32_t entity) {
     if (!g_engine) return -1;
     return g_engine->scene.createPropInstance(entity);

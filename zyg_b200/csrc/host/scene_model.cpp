@@ -593,6 +593,31 @@ int SceneModel::createPropInstance(uint32_t entity) {
     return int(id);
 }
 
+int SceneModel::createInstancer(const uint32_t* prototypes, uint32_t num_prototypes, const uint32_t* prototype_indices,
+                                const Transformation* transformations, uint32_t num_instances) {
+    if (0 == num_prototypes || !prototypes || (num_instances > 0 && (!prototype_indices || !transformations))) return -1;
+    for (uint32_t i = 0; i < num_prototypes; ++i) {
+        if (prototypes[i] >= props_.size() || ZYGPU_NULL == props_[prototypes[i]].parts_start) return -1;
+    }
+    // prototypes are loaded with is_prototype = true: they are not classified into the scene's own trees (scene.zig:299-301)
+    auto erase = [](std::vector<uint32_t>& v, uint32_t id) { v.erase(std::remove(v.begin(), v.end(), id), v.end()); };
+    for (uint32_t i = 0; i < num_prototypes; ++i) {
+        erase(finite_props_, prototypes[i]);
+        erase(unoccluding_props_, prototypes[i]);
+        erase(infinite_props_, prototypes[i]);
+    }
+    InstancerRec rec;
+    rec.entity = createEntity();
+    rec.prototypes.resize(num_instances);
+    rec.trafos.assign(transformations, transformations + num_instances);
+    for (uint32_t i = 0; i < num_instances; ++i) {
+        const uint32_t pi = prototype_indices[i] < num_prototypes ? prototype_indices[i] : 0;  // scene_loader.zig:453-456
+        rec.prototypes[i] = prototypes[pi];
+    }
+    instancers_.push_back(std::move(rec));
+    return int(instancers_.back().entity);
+}
+
 bool SceneModel::createLight(uint32_t entity) {  // scene.zig:342-372
     if (entity >= props_.size()) return false;
     const PropRec& p         = props_[entity];
@@ -852,26 +877,19 @@ bool SceneModel::compile(std::string& error) {
     const std::vector<float>& luts = ggxLuts(error);
     if (luts.empty()) return false;
 
-    const uint32_t num_props = uint32_t(props_.size());
-    const Vec4f    origin    = world_[camera_entity_].position;  // Scene.propWorldPosition, driver.zig:163
+    uint32_t num_props = uint32_t(props_.size());
+    for (const InstancerRec& ir : instancers_) num_props += uint32_t(ir.prototypes.size());
+    const Vec4f origin = world_[camera_entity_].position;  // Scene.propWorldPosition, driver.zig:163
 
     flat_props_.resize(num_props);
     flat_trafos_.resize(num_props);
     flat_aabbs_.resize(num_props);
 
-    for (uint32_t i = 0; i < num_props; ++i) {
-        const PropRec&        p = props_[i];
-        const Transformation& t = world_[i];
-
-        // ComposedTransformation.init, composed_transformation.zig:19-31
-        Mat3x3 rot  = quaternionToMat3x3(t.rotation);
-        rot.r[0][3] = t.scale[0];
-        rot.r[1][3] = t.scale[1];
-        rot.r[2][3] = t.scale[2];
-
+    // one flat prop from a composed transformation: rotation rows with the scale in lane 3, position in world space
+    auto emitProp = [&](uint32_t i, const PropRec& p, Mat3x3 rot, Vec4f position) {
         // Space.calculateWorldBounds, space.zig:60-97 (static prop)
-        const Vec4f scale  = {{t.scale[0], t.scale[1], t.scale[2], 1.f}};
-        AABB        bounds = transformAabb(shapeAabb(p.shape), compose(rot, scale, t.position));
+        const Vec4f scale  = {{rot.r[0][3], rot.r[1][3], rot.r[2][3], 1.f}};
+        AABB        bounds = transformAabb(shapeAabb(p.shape), compose(rot, scale, position));
         bounds.translate(-origin);
         bounds.cacheRadius();
         flat_aabbs_[i] = packAabb(bounds);
@@ -881,7 +899,7 @@ bool SceneModel::compile(std::string& error) {
         for (int r = 0; r < 3; ++r) {
             for (int c = 0; c < 4; ++c) ft.r[r][c] = rot.r[r][c];
         }
-        const Vec4f pos = t.position + (-origin);
+        const Vec4f pos = position + (-origin);
         for (int c = 0; c < 4; ++c) ft.position[c] = pos[c];
 
         ZygpuProp& fp  = flat_props_[i];
@@ -889,10 +907,52 @@ bool SceneModel::compile(std::string& error) {
         fp.mesh        = p.shape >= 7 ? p.shape - 7 : ZYGPU_NULL;
         fp.flags       = p.flags;
         fp.parts_start = p.parts_start;
+    };
+    auto composed = [](const Transformation& t) {  // ComposedTransformation.init, composed_transformation.zig:19-31
+        Mat3x3 rot  = quaternionToMat3x3(t.rotation);
+        rot.r[0][3] = t.scale[0];
+        rot.r[1][3] = t.scale[1];
+        rot.r[2][3] = t.scale[2];
+        return rot;
+    };
+
+    const uint32_t num_entities = uint32_t(props_.size());
+    for (uint32_t i = 0; i < num_entities; ++i) emitProp(i, props_[i], composed(world_[i]), world_[i].position);
+
+    // instancers: instance trafo = instancer.transform(instance) (instancer.zig:77-86, composed_transformation.zig:55-68)
+    flat_finite_      = finite_props_;
+    flat_unoccluding_ = unoccluding_props_;
+    uint32_t next     = num_entities;
+    for (const InstancerRec& ir : instancers_) {
+        const Transformation& st    = world_[ir.entity];
+        const Mat3x3          self  = composed(st);
+        const Vec4f           sscale = {{st.scale[0], st.scale[1], st.scale[2], 1.f}};
+        const Vec4f           a = self.r[0] * splat(sscale[0]), b = self.r[1] * splat(sscale[1]), c = self.r[2] * splat(sscale[2]);
+        for (size_t k = 0; k < ir.prototypes.size(); ++k) {
+            const Transformation& ot    = ir.trafos[k];
+            const Mat3x3          other = composed(ot);
+            Mat3x3                rot   = mulMat(other, self);
+            rot.r[0][3]                 = st.scale[0] * ot.scale[0];
+            rot.r[1][3]                 = st.scale[1] * ot.scale[1];
+            rot.r[2][3]                 = st.scale[2] * ot.scale[2];
+            // objectToWorldPoint(other.position), composed_transformation.zig:70-94
+            Vec4f pos = splat(ot.position[0]) * a;
+            pos       = mulAdd(splat(ot.position[1]), b, pos);
+            pos       = mulAdd(splat(ot.position[2]), c, pos);
+            pos       = pos + st.position;
+            pos[3]    = 0.f;
+
+            const PropRec& proto = props_[ir.prototypes[k]];
+            emitProp(next, proto, rot, pos);
+            if (proto.solid && shapeFinite(proto.shape)) {
+                (0 != (proto.flags & ZYG_PROP_UNOCCLUDING) ? flat_unoccluding_ : flat_finite_).push_back(next);
+            }
+            next += 1;
+        }
     }
 
-    buildPropTree(finite_props_, solid_nodes_, solid_indices_);
-    buildPropTree(unoccluding_props_, unocc_nodes_, unocc_indices_);
+    buildPropTree(flat_finite_, solid_nodes_, solid_indices_);
+    buildPropTree(flat_unoccluding_, unocc_nodes_, unocc_indices_);
 
     // Scene.propPrepareSampling, scene.zig:402-497 (static props, analytic shapes)
     const uint32_t num_lights = uint32_t(lights_.size());

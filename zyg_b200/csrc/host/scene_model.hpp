@@ -70,6 +70,12 @@ class SceneModel {
     uint32_t createEntity();  // scene.zig:254-260
     uint32_t createPropShape(uint32_t shape_id, const uint32_t* materials, uint32_t num_materials, bool unoccluding);
     int      createPropInstance(uint32_t entity);  // scene.zig:310-320
+    // scene_loader.loadInstancer + Scene.createPropInstancer (src/util/scene_loader.zig:401-508, scene.zig:292-304): the
+    // prototype entities leave the scene's own prop tree, every instance places one of them with a transformation relative to
+    // the instancer entity. Compile flattens the instancer: each instance becomes a prop with the composed transformation
+    // (ComposedTransformation.transform, composed_transformation.zig:55-68), so the device sees one two-level layout.
+    int      createInstancer(const uint32_t* prototypes, uint32_t num_prototypes, const uint32_t* prototype_indices,
+                             const Transformation* transformations, uint32_t num_instances);
     bool     createLight(uint32_t entity);
     bool     setWorldTransformation(uint32_t entity, const Transformation& t);
     bool     setVisibility(uint32_t entity, bool in_camera, bool in_reflection, bool in_sss);
@@ -119,6 +125,11 @@ class SceneModel {
         MeshSamplerData data;
     };
 
+    struct InstancerRec {  // prop/instancer.zig:22-50
+        uint32_t                    entity;
+        std::vector<uint32_t>       prototypes;  // per instance: the prototype entity
+        std::vector<Transformation> trafos;      // per instance, relative to the instancer entity
+    };
     struct ImageRec {  // image.Float3 / image.Byte3
         uint32_t           width = 0, height = 0, format = 0;
         std::vector<float> pixels;  // RGB, ACEScg
@@ -154,6 +165,8 @@ class SceneModel {
     std::vector<uint32_t>       material_ids_, light_ids_;
     std::vector<ZygpuLight>     lights_;
     std::vector<uint32_t>       finite_props_, infinite_props_, unoccluding_props_;
+    std::vector<InstancerRec>   instancers_;
+    std::vector<uint32_t>       flat_finite_, flat_unoccluding_;  // the classified lists with the instancers' instances appended
 
     // view
     int32_t  resolution_[2]   = {0, 0};

@@ -515,7 +515,7 @@ def mesh_lights_scene(width=256, height=256, spp=16, max_depth=6, num_lights=24,
 
 
 def instanced_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None, grid=(32, 32), prototypes=4,
-                    quads=(100, 50), seed=3, glass=True, sun=None):
+                    quads=(100, 50), seed=3, glass=True, sun=None, instancer=None):
     """Config-3 style scene through the C API: `prototypes` displaced-sphere meshes (seeds 1..), instanced
     grid[0] x grid[1] times with su_prop_create_instance on a jittered grid (uniform scale 0.3-0.6, random Y rotation,
     PCG32 stream `seed`), a ground Rectangle, one Rectangle light and optionally a Distant sun. Materials go by prototype
@@ -551,22 +551,30 @@ def instanced_scene(width=512, height=512, spp=16, max_depth=8, filter_name=None
         protos.append(su.prop_create(shape, [materials[i]]))
 
     rng = PCG32(0, np.array([seed], np.uint64))
-    count = 0
+    indices, matrices = [], []
     for gy in range(grid[1]):
         for gx in range(grid[0]):
             r = [float(rng.float()[0]) for _ in range(5)]
-            proto = protos[int(r[0] * prototypes) % prototypes]
-            prop = su.prop_create_instance(proto)
+            index = int(r[0] * prototypes) % prototypes
             scale = 0.3 + 0.3 * r[1]
             x = (gx + 0.5 + 0.6 * (r[2] - 0.5)) - 0.5 * grid[0]
             z = (gy + 0.5 + 0.6 * (r[3] - 0.5)) - 0.5 * grid[1]
-            su.prop_set_transformation(prop, su.transformation((x, 1.05 * scale, z), (scale, scale, scale),
-                                                               (0.0, 360.0 * r[4], 0.0)))
-            count += 1
-    # the prototypes themselves stay out of the picture (they are props too: park them below the ground, invisible)
-    for proto in protos:
-        su.prop_set_transformation(proto, su.transformation((0.0, -50.0, 0.0), (0.01, 0.01, 0.01)))
-        su.prop_set_visibility(proto, False, False)
+            matrix = su.transformation((x, 1.05 * scale, z), (scale, scale, scale), (0.0, 360.0 * r[4], 0.0))
+            if instancer is None:
+                su.prop_set_transformation(su.prop_create_instance(protos[index]), matrix)
+            else:
+                indices.append(index)
+                matrices.append(matrix)
+    if instancer is None:
+        # the prototypes themselves stay out of the picture (they are props too: park them below the ground, invisible)
+        for proto in protos:
+            su.prop_set_transformation(proto, su.transformation((0.0, -50.0, 0.0), (0.01, 0.01, 0.01)))
+            su.prop_set_visibility(proto, False, False)
+    else:
+        # a scene file's "Instancer" entity (scene_loader.zig:401-508): prototypes + instance transformations relative to the
+        # instancer, `instancer` = the instancer's own transformation (a 4x4 as su.transformation returns it)
+        entity = su.instancer_create(protos, indices, np.stack(matrices))
+        su.prop_set_transformation(entity, instancer)
 
     floor = su.prop_create(su.RECTANGLE, [ground])
     su.prop_set_transformation(floor, su.transformation((0.0, 0.0, 0.0), (3.0 * max(grid), 3.0 * max(grid), 1.0), (90.0, 0.0, 0.0)))

@@ -38,7 +38,7 @@ def _su() -> C.CDLL:
         "su_render_frame": [u32], "su_export_frame": [], "su_start_frame": [u32], "su_render_iterations": [u32],
         "su_resolve_frame": [u32], "su_resolve_frame_to_buffer": [u32, u32, u32, vp],
         "su_copy_framebuffer": [u32, u32, u32, u32, vp], "su_register_log": [vp], "su_register_progress": [vp, vp],
-        "zyg_su_sensor_create": [cp], "zyg_su_prop_create_unoccluding": [u32, u32, vp],
+        "zyg_su_sensor_create": [cp], "zyg_su_instancer_create": [u32, vp, u32, vp, vp], "zyg_su_prop_create_unoccluding": [u32, u32, vp],
         "zyg_su_camera_set_lens": [f32, f32], "zyg_su_set_device": [i32],
         "zyg_su_render_frame_range": [u32, u32, u32], "zyg_su_compile": [vp, vp],
     }
@@ -138,6 +138,17 @@ def prop_create(shape: int, materials, unoccluding: bool = False) -> int:
 
 def prop_create_instance(entity: int) -> int:
     return _ok(_su().su_prop_create_instance(entity), "su_prop_create_instance")
+
+
+def instancer_create(prototypes, prototype_indices, matrices) -> int:
+    """An "Instancer" entity (zyg_su_instancer_create): instance i = prototypes[prototype_indices[i]] placed with the 4x4
+    matrices[i] relative to the returned entity."""
+    protos = np.ascontiguousarray(prototypes, np.uint32)
+    idx = np.ascontiguousarray(prototype_indices, np.uint32)
+    m = np.ascontiguousarray(matrices, np.float32).reshape(-1, 16)
+    assert m.shape[0] == idx.size
+    return _ok(_su().zyg_su_instancer_create(protos.size, protos.ctypes.data, idx.size, idx.ctypes.data, m.ctypes.data),
+               "zyg_su_instancer_create")
 
 
 def light_create(prop: int):
