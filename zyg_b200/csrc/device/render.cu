@@ -407,8 +407,11 @@ __device__ __forceinline__ RayT loadTraceRay(const PathState& st, uint32_t item,
 }
 
 // Item ids: closest-hit rays are identified by their path slot, shadow rays by their record (slot * stride + k).
+#ifndef ZYGPU_TOP_BLOCKS
+#define ZYGPU_TOP_BLOCKS 6  // 80 registers: measured +4 % on the instanced scene over the unbounded 96-register build
+#endif
 template <bool AnyHit>
-__global__ void __launch_bounds__(kBlock) topKernel(SceneDevice sc, PathState st) {
+__global__ void __launch_bounds__(kBlock, ZYGPU_TOP_BLOCKS) topKernel(SceneDevice sc, PathState st) {
     const uint32_t stride = st.shadow_stride;
     const uint32_t* __restrict__ closest_queue = st.lanes > 1 ? st.queue_t : st.queue_a;
     const bool     compact = AnyHit && nullptr != st.queue_r;  // shadow records listed in queue_r instead of stride per slot
