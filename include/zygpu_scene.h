@@ -82,7 +82,8 @@ enum { /* material_base.zig:17-26 */
     ZYG_MATERIAL_EMISSIVE  = 1u << 3
 };
 
-/* Uniform-parameter subset of Substitute / Glass / Light. 96 bytes. */
+/* Substitute / Glass / Light parameters: uniform values plus the image maps in scope (emission map,
+ * Substitute colour map). 112 bytes. */
 typedef struct ZygpuMaterial {
     uint32_t type;  /* ZYG_MATERIAL_* */
     uint32_t flags; /* ZYG_MATERIAL_* bits */
@@ -106,6 +107,9 @@ typedef struct ZygpuMaterial {
     float thickness;
     float abbe;
     uint32_t emission_map; /* Emittance.emission_map when it is an image: index into ZygpuScene.image_samplers, else ZYGPU_NULL */
+
+    uint32_t color_map; /* Substitute.color when it is an image (substitute_material.zig:120): index into image_samplers, else ZYGPU_NULL */
+    uint32_t pad[3];
 } ZygpuMaterial;
 
 enum { /* Light.Class (src/core/scene/light/light.zig:34-40) */
@@ -164,7 +168,7 @@ typedef struct ZygpuImageSampler {
     float    total_weight;         /* ImageImpl.total_weight = sum of Shape.uvWeight over the texels */
     float    scale[2];             /* Texture.data.image.scale */
     const float* pixels;           /* width * height RGB triples (ACEScg) */
-    const float* marginal_cdf;     /* height + 1 */
+    const float* marginal_cdf;     /* height + 1; NULL (with the two arrays below) for an image that is only looked up, never sampled */
     const float* conditional_cdf;  /* height rows of width + 1 */
     const float* conditional_integral; /* height; 0 => that row is the degenerate distribution {1, 1} (distribution_1d.zig:99-110) */
 } ZygpuImageSampler;

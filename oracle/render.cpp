@@ -707,7 +707,8 @@ struct Sampler2D {  // shape_sampler.ImageImpl + Distribution2D, shape_sampler.z
     Distribution1D              marginal;
     std::vector<Distribution1D> conditional;
 
-    explicit Sampler2D(const ZygpuImageSampler& is) : img(&is), conditional(is.height) {
+    explicit Sampler2D(const ZygpuImageSampler& is) : img(&is), conditional(is.marginal_cdf ? is.height : 0) {
+        if (!is.marginal_cdf) return;  // an image that is only looked up (a colour map)
         marginal.configure(is.marginal_cdf, is.height);
         for (uint32_t y = 0; y < is.height; ++y) conditional[y].configure(is.conditional_cdf + size_t(y) * (is.width + 1), is.width);
     }
@@ -2073,7 +2074,14 @@ struct Worker {
         rs.highest_priority = vertex.mediums.highestPriority();
 
         switch (m.type) {
-            case ZYG_MATERIAL_SUBSTITUTE: return substituteSample(m, wo, rs, scene.view.specular_threshold, scene.luts);
+            case ZYG_MATERIAL_SUBSTITUTE: {
+                if (ZYGPU_NULL == m.color_map) return substituteSample(m, wo, rs, scene.view.specular_threshold, scene.luts);
+                // ts.sample2D_3(self.color, rs, ...), substitute_material.zig:120
+                ZygpuMaterial textured = m;
+                const Vec4f   c        = scene.image_samplers[m.color_map].texel(rs.uvw[0], rs.uvw[1], rs.stochastic_r);
+                textured.color[0] = c[0], textured.color[1] = c[1], textured.color[2] = c[2];
+                return substituteSample(textured, wo, rs, scene.view.specular_threshold, scene.luts);
+            }
             case ZYG_MATERIAL_GLASS: return glassSample(m, wo, rs, scene.view.specular_threshold, scene.luts);
             default: return lightSample(wo, rs);
         }

@@ -363,3 +363,21 @@ def test_instancer_matches_oracle(engine):
     assert np.median(rel) < 5e-6
     assert (rel > 1e-2).mean() < 1e-2
     assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 5e-4
+
+
+@pytest.mark.parametrize("nearest", [False, True])
+def test_colour_maps_match_oracle(engine, nearest):
+    """Substitute colour maps on a Rectangle (Repeat, scaled), a Cube (sRGB bytes, Clamp) and a triangle mesh (its uvs):
+    stochastic-bilinear / nearest texel lookups with the vertex's stochastic_r (texture_sampler.zig:99-170), the same texel in
+    shade_a and shade_b."""
+    w, spp = 128, 16
+    n = scenes.textured_scene(w, w, spp=spp, nearest=nearest)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6
+    assert (rel > 1e-2).mean() < 5e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4

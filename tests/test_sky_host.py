@@ -182,3 +182,23 @@ def test_sphere_light_irradiance(engine):
         # sRGB (1,1,1) -> AP1 keeps grey: the film holds AP1 radiance; centre pixels look at the origin
         got = img[12:20, 12:20].mean()
         assert abs(got / (a * L * (r / d) ** 2) - 1.0) < 0.03, (unoccluding, got)
+
+
+def test_constant_colour_map_equals_uniform_colour(engine, monkeypatch):
+    """Substitute colour maps (substitute_material.zig:120): images that hold one colour everywhere give the film of the
+    uniform-colour materials (the grey passes sRGB -> AP1 within an ulp), with either texture filter."""
+    films = {}
+    for key, nearest in (("linear", False), ("nearest", True)):
+        su.release()
+        monkeypatch.setattr(scenes, "checker_image", lambda size=64, cells=8, a=None, b=None, dtype=np.float32:
+                            np.full((size, size, 3), 0.5, np.float32))
+        n = scenes.textured_scene(64, 64, spp=8, nearest=nearest)
+        scene, view = su.compile_scene()
+        films[key] = oracle.render(scene, view, 64, 64, 0, 8, num_meshes=n)
+    monkeypatch.undo()
+    su.release()
+    n = scenes.textured_scene(64, 64, spp=8, uniform=(0.5, 0.5, 0.5))
+    scene, view = su.compile_scene()
+    plain = oracle.render(scene, view, 64, 64, 0, 8, num_meshes=n)
+    assert np.array_equal(films["linear"], films["nearest"])
+    assert np.allclose(films["linear"], plain, rtol=1e-4, atol=1e-6)

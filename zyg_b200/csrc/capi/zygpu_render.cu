@@ -42,9 +42,9 @@ uint32_t targetPathsPerPass() {
 
 // `lanes` vertex records per slot (1, or 4 when a material of the scene can split a path); trace items are vertex ids for
 // closest-hit rays and shadow records for any-hit rays, so the per-item arrays hold max(lanes, shadow_stride) per slot.
-int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint32_t lanes, bool deferred_lights) {
+int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint32_t lanes, bool deferred_lights, bool textures) {
     if (r.paths.capacity >= capacity && r.paths.shadow_stride == shadow_stride && r.paths.lanes == lanes &&
-        (nullptr != r.paths.queue_l) == deferred_lights) {
+        (nullptr != r.paths.queue_l) == deferred_lights && (nullptr != r.paths.stoch) == textures) {
         return 0;
     }
     freeAll(r.path_buffers);
@@ -66,6 +66,7 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint3
         return -1;
     }
     if (shadow_stride > 1 && 0 != allocPath(r, &p.queue_r, size_t(capacity) * shadow_stride)) return -1;
+    if (textures && 0 != allocPath(r, &p.stoch, vertices)) return -1;
     if (deferred_lights && (0 != allocPath(r, &p.ls_p, capacity) || 0 != allocPath(r, &p.ls_g, capacity) ||
                             0 != allocPath(r, &p.picks, size_t(capacity) * 64) || 0 != allocPath(r, &p.pick_n, capacity) ||
                             0 != allocPath(r, &p.queue_l, capacity))) {
@@ -192,12 +193,13 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     d.num_mesh_samplers = scene->num_mesh_samplers;
     if (0 != uploadArray(r, scene->mesh_part_areas, scene->mesh_part_areas ? scene->num_parts : 0, &d.mesh_part_areas)) return -1;
 
+    r.has_textures = false;
     // emission images with their Distribution2D rows (shape_sampler.ImageImpl)
     std::vector<zygpu::ImageSamplerDevice> image_samplers(scene->num_image_samplers);
     for (uint32_t i = 0; i < scene->num_image_samplers; ++i) {
         const ZygpuImageSampler&   is = scene->image_samplers[i];
         zygpu::ImageSamplerDevice& id = image_samplers[i];
-        if (0 == is.width || 0 == is.height || !is.pixels || !is.marginal_cdf || !is.conditional_cdf) {
+        if (0 == is.width || 0 == is.height || !is.pixels || (nullptr == is.marginal_cdf) != (nullptr == is.conditional_cdf)) {
             return fail("zygpu_upload_scene: image sampler %u is incomplete", i);
         }
         id.width        = is.width;
@@ -214,8 +216,9 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
             if (scene->image_samplers[k].pixels == is.pixels) id.pixels = image_samplers[k].pixels;
         }
         if (!id.pixels && 0 != uploadArray(r, is.pixels, size_t(is.width) * is.height * 3, &id.pixels)) return -1;
-        if (0 != uploadArray(r, is.marginal_cdf, size_t(is.height) + 1, &id.marginal_cdf) ||
-            0 != uploadArray(r, is.conditional_cdf, size_t(is.height) * (is.width + 1), &id.conditional_cdf)) {
+        id.marginal_cdf = id.conditional_cdf = nullptr;  // an image that is only looked up (a colour map) has no distribution
+        if (is.marginal_cdf && (0 != uploadArray(r, is.marginal_cdf, size_t(is.height) + 1, &id.marginal_cdf) ||
+                                0 != uploadArray(r, is.conditional_cdf, size_t(is.height) * (is.width + 1), &id.conditional_cdf))) {
             return -1;
         }
     }
@@ -224,6 +227,10 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
         if (ZYGPU_NULL != scene->materials[m].emission_map && scene->materials[m].emission_map >= scene->num_image_samplers) {
             return fail("zygpu_upload_scene: material %u references image sampler %u", m, scene->materials[m].emission_map);
         }
+        if (ZYGPU_NULL != scene->materials[m].color_map && scene->materials[m].color_map >= scene->num_image_samplers) {
+            return fail("zygpu_upload_scene: material %u references image sampler %u", m, scene->materials[m].color_map);
+        }
+        if (ZYGPU_NULL != scene->materials[m].color_map) r.has_textures = true;
     }
 
     // shadow records one path vertex can need: every light the tree may return times its sample count
@@ -247,7 +254,7 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
 
     // Glass splits a path into its reflected and refracted branch (glass_sample.zig:256-269, 350-395): such scenes run with
     // Pool.NumVertices vertex records per camera sample and one shade round per record
-    r.can_split = false;
+    r.can_split    = false;
     for (uint32_t m = 0; m < scene->num_materials; ++m) {
         const ZygpuMaterial& mat = scene->materials[m];
         if (ZYG_MATERIAL_GLASS == mat.type) {
@@ -324,7 +331,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
     if (capacity > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
     const uint32_t lanes = r.can_split ? 4 : 1;
     if (capacity * lanes > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
-    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples, lanes, r.deferred_lights)) return -1;
+    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples, lanes, r.deferred_lights, r.has_textures)) return -1;
     const uint32_t rounds = lanes;
 
     // extend / shadow are one kernel each (prop-tree walk) plus the persistent mesh kernel when the scene has meshes

@@ -1843,9 +1843,16 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
             if (!terminate) {
                 const bool caustics = 0 == (vertex.state & kPrimaryRay) ? 0 != view.caustics_path : true;  // causticsResolve, :343-349
 
-                const V3            wo = neg3(vertex.ray.d);
-                const ZygpuMaterial m  = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
-                (void)sampler.sample1D();  // rs.stochastic_r, vertex.zig:165
+                const V3      wo = neg3(vertex.ray.d);
+                ZygpuMaterial m  = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
+                const float   stochastic_r = sampler.sample1D();  // rs.stochastic_r, vertex.zig:165
+                if (nullptr != st.stoch) {
+                    st.stoch[vid] = stochastic_r;
+                    if (ZYGPU_NULL != m.color_map) {  // ts.sample2D_3(self.color, rs, ...), substitute_material.zig:120
+                        const V3 c = imageTexel(sc.image_samplers[m.color_map], frag.u, frag.v, stochastic_r);
+                        m.color[0] = c.x, m.color[1] = c.y, m.color[2] = c.z;
+                    }
+                }
                 float ior_outside      = 1.f;
                 int   highest_priority = -128;
                 if (Split) mediaForSample(sc, media, frag, wo, ior_outside, highest_priority);
@@ -2384,8 +2391,12 @@ __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeB
             if (Split && 0 != lv.num_media) media = unpackMedia(st.med[vid], lv.num_media);
 
             const bool          caustics   = 0 == (vertex.state & kPrimaryRay) ? 0 != view.caustics_path : true;
-            const V3            wo         = neg3(vertex.ray.d);
-            const ZygpuMaterial m          = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
+            const V3      wo = neg3(vertex.ray.d);
+            ZygpuMaterial m  = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
+            if (nullptr != st.stoch && ZYGPU_NULL != m.color_map) {  // the same texel shade_a's material sample read
+                const V3 c = imageTexel(sc.image_samplers[m.color_map], frag.u, frag.v, st.stoch[vid]);
+                m.color[0] = c.x, m.color[1] = c.y, m.color[2] = c.z;
+            }
             float               ior_outside      = 1.f;
             int                 highest_priority = -128;
             if (Split) mediaForSample(sc, media, frag, wo, ior_outside, highest_priority);

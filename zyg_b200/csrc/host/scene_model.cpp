@@ -103,6 +103,7 @@ ZygpuMaterial defaultMaterial(uint32_t type) {
     m.specular               = 1.f;
     m.ior                    = 1.f;
     m.emission_map           = ZYGPU_NULL;
+    m.color_map              = ZYGPU_NULL;
     switch (type) {
         case ZYG_MATERIAL_SUBSTITUTE:  // substitute_material.zig:41-67
             m.color[0] = m.color[1] = m.color[2] = 0.5f;
@@ -126,10 +127,9 @@ uint32_t readAddress(const json::Value& v) {  // material_provider.zig:624-632
     return (json::Value::String == v.kind && "Clamp" == v.string) ? 0u : 1u;
 }
 
-// loadEmittance, material_provider.zig:412-436 (no profile; `emission_map` as an image resource: TextureDescriptor "id" +
-// "sampler" + "scale", :440-476, 579-600, 634-678)
-void loadEmittance(const json::Value& j, ZygpuMaterial& m, uint32_t& map_image, uint32_t mode[3], float map_scale[2]) {
-    if (const json::Value* em = j.get("emission_map")) {
+// TextureDescriptor of an image resource: "id" + "sampler" + "scale" (material_provider.zig:440-476, 579-600, 634-678)
+void readTextureDescriptor(const json::Value* em, uint32_t& map_image, uint32_t mode[3], float map_scale[2]) {
+    {
         if (json::Value::Object == em->kind) {
             if (const json::Value* id = em->get("id")) map_image = uint32_t(id->number);
             if (const json::Value* sa = em->get("sampler")) {
@@ -156,6 +156,11 @@ void loadEmittance(const json::Value& j, ZygpuMaterial& m, uint32_t& map_image, 
             }
         }
     }
+}
+
+// loadEmittance, material_provider.zig:412-436 (no profile; `emission_map` as an image resource)
+void loadEmittance(const json::Value& j, ZygpuMaterial& m, uint32_t& map_image, uint32_t mode[3], float map_scale[2]) {
+    if (const json::Value* em = j.get("emission_map")) readTextureDescriptor(em, map_image, mode, map_scale);
 
     Vec4f color = splat(1.f);
     if (const json::Value* s = j.get("spectrum")) color = readColor(*s);
@@ -274,6 +279,7 @@ SceneModel::SceneModel() : specular_threshold_(kMinAlpha) {
     // createFallbackMaterial, material_provider.zig:127-129: a Debug material at id 0 (capi.zig:94-101)
     materials_.push_back(defaultMaterial(ZYG_MATERIAL_DEBUG));
     emission_maps_.push_back(EmissionMapRec{});
+    color_maps_.push_back(EmissionMapRec{});
 }
 
 bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
@@ -302,8 +308,20 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
             for (const auto& e : v.object) {
                 const std::string& k = e.first;
                 if ("color" == k) {
-                    const Vec4f c = readColor(e.second);
-                    for (int i = 0; i < 4; ++i) m.color[i] = c[i];
+                    // readValue(.Color): a texture description with an image id becomes the colour map, anything else a
+                    // uniform colour (material_provider.zig:741-776)
+                    EmissionMapRec& cm = color_maps_[id];
+                    cm                 = EmissionMapRec{};
+                    if (json::Value::Object == e.second.kind && e.second.get("id")) {
+                        uint32_t mode[3] = {cm.address_u, cm.address_v, cm.filter};
+                        readTextureDescriptor(&e.second, cm.image, mode, cm.scale);
+                        cm.address_u = mode[0];
+                        cm.address_v = mode[1];
+                        cm.filter    = mode[2];
+                    } else {
+                        const Vec4f c = readColor(e.second);
+                        for (int i = 0; i < 4; ++i) m.color[i] = c[i];
+                    }
                 } else if ("emittance" == k) {
                     EmissionMapRec em;  // Substitute emission maps are not in scope: parsed and dropped
                     uint32_t       mode[3] = {1, 1, 1};
@@ -387,6 +405,7 @@ int SceneModel::createMaterial(const json::Value& material) {
         }
         materials_.push_back(defaultMaterial(type));
         emission_maps_.push_back(EmissionMapRec{});
+        color_maps_.push_back(EmissionMapRec{});
         updateMaterial(uint32_t(materials_.size() - 1), material);
         return int(materials_.size() - 1);
     }
@@ -963,6 +982,11 @@ bool SceneModel::compile(std::string& error) {
     for (size_t m = 0; m < materials_.size(); ++m) {
         const EmissionMapRec& em = emission_maps_[m];
         materials_[m].emission_map = ZYGPU_NULL;
+        materials_[m].color_map    = ZYGPU_NULL;
+        if (ZYGPU_NULL != color_maps_[m].image && color_maps_[m].image >= images_.size()) {
+            error = "material " + std::to_string(m) + ": color references image " + std::to_string(color_maps_[m].image) + " which does not exist";
+            return false;
+        }
         if (ZYGPU_NULL == em.image) continue;
         if (em.image >= images_.size()) {
             error = "material " + std::to_string(m) + ": emission_map references image " + std::to_string(em.image) + " which does not exist";
@@ -1093,6 +1117,22 @@ bool SceneModel::compile(std::string& error) {
         is.marginal_cdf         = rec->marginal_cdf.data();
         is.conditional_cdf      = rec->conditional_cdf.data();
         is.conditional_integral = rec->conditional_integral.data();
+        flat_image_samplers_.push_back(is);
+    }
+    for (size_t m = 0; m < materials_.size(); ++m) {  // colour maps: looked up only (no distribution)
+        const EmissionMapRec& cm = color_maps_[m];
+        if (ZYGPU_NULL == cm.image) continue;
+        const ImageRec&   img = images_[cm.image];
+        ZygpuImageSampler is{};
+        is.width     = img.width;
+        is.height    = img.height;
+        is.address_u = cm.address_u;
+        is.address_v = cm.address_v;
+        is.filter    = cm.filter;
+        is.scale[0]  = cm.scale[0];
+        is.scale[1]  = cm.scale[1];
+        is.pixels    = img.pixels.data();
+        materials_[m].color_map = uint32_t(flat_image_samplers_.size());
         flat_image_samplers_.push_back(is);
     }
 

@@ -155,6 +155,7 @@ class SceneModel {
 
     std::vector<ZygpuMaterial>  materials_;
     std::vector<EmissionMapRec> emission_maps_;  // per material
+    std::vector<EmissionMapRec> color_maps_;     // per material: Substitute.color as an image texture
     std::vector<ImageRec>       images_;
     std::vector<std::unique_ptr<ImageSamplerRec>> image_samplers_;
     std::vector<ZygpuImageSampler>                flat_image_samplers_;

@@ -354,6 +354,58 @@ def sphere_lights_scene(width=128, height=128, spp=16, max_depth=6, filter_name=
     return 0
 
 
+def checker_image(size=64, cells=8, a=(0.8, 0.8, 0.8), b=(0.15, 0.3, 0.6), dtype=np.float32):
+    """A checkerboard colour texture: float32 RGB (ACEScg as is) or uint8 (read as sRGB like Texture.Byte3_sRGB)."""
+    i = np.arange(size) * cells // size
+    mask = ((i[:, None] + i[None, :]) & 1).astype(bool)
+    img = np.where(mask[..., None], np.asarray(a, np.float64), np.asarray(b, np.float64))
+    return (img * 255.0 + 0.5).astype(np.uint8) if dtype == np.uint8 else np.ascontiguousarray(img, np.float32)
+
+
+def textured_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None, quads=(48, 24), uniform=None, nearest=False):
+    """Substitute colour maps (substitute_material.zig:120, texture_sampler.zig:63-170): a float checker on the ground
+    (Repeat addressing, texture scale 4), an sRGB byte checker on a cube, a float checker on a displaced-sphere mesh through
+    its own uvs. `uniform` = (r, g, b) replaces every image by that constant colour (then the film must equal the one of plain
+    uniform-colour materials). Returns the number of meshes."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(55.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.6, -4.2), rotation_deg=(-14.0, 0.0, 0.0)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    sampler = {"filter": "Nearest"} if nearest else {}
+
+    def textured(image, roughness, metallic=0.0, scale=1.0, address="Repeat"):
+        if uniform is not None:
+            return su.material_create({"rendering": {"Substitute": {"color": {"sRGB": list(uniform)} if image.dtype == np.uint8 else list(uniform),
+                                                                    "roughness": roughness, "metallic": metallic}}})
+        iid = su.image_create(image)
+        return su.material_create({"rendering": {"Substitute": {
+            "color": {"id": iid, "scale": scale, "sampler": dict(sampler, address=address)}, "roughness": roughness, "metallic": metallic}}})
+
+    ground = textured(checker_image(64, 8), 1.0, scale=4.0)
+    g = su.prop_create(su.RECTANGLE, [ground])
+    su.prop_set_transformation(g, su.transformation((0.0, 0.0, 0.0), (12.0, 12.0, 1.0), (90.0, 0.0, 0.0)))
+    crate = textured(checker_image(32, 4, (0.9, 0.6, 0.2), (0.3, 0.1, 0.05), np.uint8), 0.6, address="Clamp")
+    cube = su.prop_create(su.CUBE, [crate])
+    su.prop_set_transformation(cube, su.transformation((-1.3, 0.5, 0.4), (1.0, 1.0, 1.0), (0.0, 30.0, 0.0)))
+    ball_material = textured(checker_image(128, 16, (0.9, 0.9, 0.9), (0.7, 0.1, 0.1)), 0.35, metallic=0.0)
+    positions, normals, uvs, indices = displaced_sphere(*quads, seed=0x5EED0009)
+    indices = np.ascontiguousarray(indices.reshape(-1, 3)[:, [0, 2, 1]])
+    ball = su.prop_create(su.triangle_mesh_create(positions, indices, normals, uvs), [ball_material])
+    su.prop_set_transformation(ball, su.transformation((1.2, 0.8, 0.0), (0.75, 0.75, 0.75), (0.0, 20.0, 0.0)))
+
+    light = su.material_create({"rendering": {"Light": {"emittance": {"value": 25.0}}}})
+    lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=True)
+    su.prop_set_transformation(lamp, su.transformation((0.0, 4.0, -0.5), (2.0, 2.0, 1.0), (-90.0, 0.0, 0.0)))
+    su.light_create(lamp)
+    return 1
+
+
 def icosahedron():
     """Unit icosahedron: (positions f32[12,3], indices u32[20,3]), counter-clockwise seen from outside."""
     t = (1.0 + 5.0 ** 0.5) / 2.0
