@@ -1254,8 +1254,9 @@ __device__ __forceinline__ float lightTreePdf(const SceneDevice& sc, V3 p, V3 n,
     }
 }
 
-// Mesh.pdf, triangle_mesh.zig:662-703. Kept out of line: scenes without mesh lights should not pay its registers.
-__device__ __noinline__ float meshLightPdf(const SceneDevice& sc, const MeshSamplerDevice& m, const VertexD& vertex, const FragD& frag) {
+// Mesh.pdf, triangle_mesh.zig:662-703. Inlined: only the MeshLights instances of the kernels contain it, and an out-of-line copy
+// taking the scene by reference makes every thread copy the kernel's parameter structs to local memory.
+__device__ __forceinline__ float meshLightPdf(const SceneDevice& sc, const MeshSamplerDevice& m, const VertexD& vertex, const FragD& frag) {
     const float n_dot_dir = fabsf(dot3(frag.geo_n, vertex.ray.d));
 
     const V3 op = frag.trafo.worldToObjectPoint(vertex.origin);
@@ -1276,8 +1277,8 @@ __device__ __noinline__ float meshLightPdf(const SceneDevice& sc, const MeshSamp
 }
 
 // Mesh.sampleTo, triangle_mesh.zig:492-608: appends the shadow records of one picked mesh light, returns the new record count.
-// Kept out of line for the same reason.
-__device__ __noinline__ uint32_t meshLightSampleTo(const SceneDevice& sc, const PathState& st, uint32_t slot, const ZygpuLight& light,
+// Inlined for the same reason.
+__device__ __forceinline__ uint32_t meshLightSampleTo(const SceneDevice& sc, const PathState& st, uint32_t slot, const ZygpuLight& light,
                                                    LightPickD pick, const TrafoD& trafo, const FragD& frag, V3 n, bool translucent,
                                                    float split_threshold, SamplerD& sampler, uint32_t num_records) {
     const MeshSamplerDevice& m  = sc.mesh_samplers[light.sampler];
@@ -1396,7 +1397,7 @@ __device__ __forceinline__ V3 evaluateRadiance(const SceneDevice& sc, const Vert
 // emitter the segment crosses, visited in the reference's order (binary tree, near child first) because each hit draws from
 // the sampler.
 template <bool MeshLights>
-__device__ __noinline__ V3 meshEmission(const SceneDevice& sc, uint32_t entity, const ZygpuProp& prop, const VertexD& vertex, SamplerD& sampler) {
+__device__ __forceinline__ V3 meshEmission(const SceneDevice& sc, uint32_t entity, const ZygpuProp& prop, const VertexD& vertex, SamplerD& sampler) {
     FragD frag;
     frag.prop  = entity;
     frag.trafo = loadTrafo(sc.trafos, entity);
