@@ -41,7 +41,11 @@ struct DeviceMesh {
 
 // Everything the render entry points keep on the device (capi/zygpu_render.cu).
 struct RenderState {
-    std::vector<void*> scene_buffers;  // freed on the next upload
+    // Device buffers of the uploaded scene, reused by the next upload in call order when they are large enough: a frame of the
+    // su_* API re-uploads the compiled scene, and a cudaFree / cudaMalloc cycle per array costs 0.1 - 1.5 s on some frames.
+    std::vector<void*>  scene_buffers;
+    std::vector<size_t> scene_buffer_bytes;
+    size_t              scene_buffer_cursor = 0;
     zygpu::SceneDevice scene{};
     bool               has_scene  = false;
     bool               has_meshes = false;

@@ -12,9 +12,21 @@ namespace {
 
 template <typename T>
 int uploadArray(RenderState& r, const T* host, size_t count, const T** device) {
-    void* d = nullptr;
-    CUDA_OK(cudaMalloc(&d, std::max<size_t>(count * sizeof(T), 16)));
-    r.scene_buffers.push_back(d);
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    const size_t slot  = r.scene_buffer_cursor++;
+    if (slot == r.scene_buffers.size()) {
+        r.scene_buffers.push_back(nullptr);
+        r.scene_buffer_bytes.push_back(0);
+    }
+    if (r.scene_buffer_bytes[slot] < bytes) {  // grow with some slack so that a scene that changes a little keeps its buffers
+        cudaFree(r.scene_buffers[slot]);
+        r.scene_buffers[slot]      = nullptr;
+        r.scene_buffer_bytes[slot] = 0;
+        const size_t capacity      = bytes + bytes / 8;
+        CUDA_OK(cudaMalloc(&r.scene_buffers[slot], capacity));
+        r.scene_buffer_bytes[slot] = capacity;
+    }
+    void* d = r.scene_buffers[slot];
     if (count > 0) CUDA_OK(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
     *device = static_cast<const T*>(d);
     return 0;
@@ -102,8 +114,8 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
         CUDA_OK(zygpu::uploadSobolDirections());
     }
     CUDA_OK(cudaStreamSynchronize(r.stream));
-    freeAll(r.scene_buffers);
-    r.has_scene = false;
+    r.scene_buffer_cursor = 0;  // the arrays below take the buffers of the previous upload in the same order
+    r.has_scene           = false;
 
     if (!scene->ggx_luts) return fail("zygpu_upload_scene: scene carries no GGX tables");
 
