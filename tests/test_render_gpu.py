@@ -381,3 +381,32 @@ def test_colour_maps_match_oracle(engine, nearest):
     assert np.median(rel) < 5e-6
     assert (rel > 1e-2).mean() < 5e-3
     assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4
+
+
+def test_empty_and_sky_only_scenes(engine):
+    """Edge cases of the scene compile and the stages: no props at all (every path escapes into nothing: a black film with
+    full weights), and a sky dome over no geometry (every pixel shows the sky's radiance, no shadow rays, empty prop trees)."""
+    w, spp = 64, 4
+    su.init()
+    su.perspective_camera_create(w, w)
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": 4}}}})
+    su.sensor_create({})
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], np.full((w, w), spp, np.float32)) and not gpu[..., :3].any()
+
+    su.release()
+    su.init()
+    camera = su.perspective_camera_create(w, w)
+    su.prop_set_transformation(camera, su.transformation(rotation_deg=(60.0, 0.0, 0.0)))  # look up
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": 4}}}})
+    su.sensor_create({})
+    scenes.add_sky(np.full((32, 32, 3), 1.5, np.float32))
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu, ref)
+    assert np.array_equal(gpu[..., :3], np.full((w, w, 3), 1.5 * spp, np.float32))
