@@ -1,5 +1,5 @@
-for L in libzyg_b200.so libzyg_b200_tb6.so libzyg_b200_tb8.so libzyg_b200_tb10.so; do echo $L
-SCENE=instanced_scene KW='{"grid":[100,100],"prototypes":20,"quads":[500,250],"sun":60.0}' ZYG_B200_LIB=$PWD/zyg_b200/$L python tools/render_scene.py 1920 1080 4 2
-SCENE=mesh_lights_scene KW='{"num_lights":1000,"geometry_quads":[400,250],"sun":15.0,"sky":1024,"max_depth":8}' ZYG_B200_LIB=$PWD/zyg_b200/$L python tools/render_scene.py 1920 1080 4 2
-SCENE=cornell_box ZYG_B200_LIB=$PWD/zyg_b200/$L python tools/render_scene.py 512 512 64 3
-done
+python -m pytest tests/test_render_gpu.py -x -q 2>&1 | tail -2
+SCENE=instanced_scene KW='{"grid":[100,100],"prototypes":20,"quads":[500,250],"sun":60.0}' python tools/render_scene.py 1920 1080 8 2
+SCENE=cornell_box KW='{}' python tools/render_scene.py 512 512 64 3
+SCENE=cornell_box KW='{}' python tools/render_scene.py 512 512 8 3
+SCENE=sphere_scene KW='{"quads":[1000,500]}' python tools/render_scene.py 1024 1024 4 3

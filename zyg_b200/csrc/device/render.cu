@@ -1723,9 +1723,10 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
     constexpr bool Infinite   = 0 != (Features & kFeatureInfiniteLights);
     constexpr bool Deferred   = 0 != (Features & kFeatureDeferredLights);  // light selection and sampling run in the light kernels
     __shared__ uint32_t sobol_tables[kSobolTableWords];
-    loadSobolTables(sobol_tables);
     const bool      later = Split && round > 0;
     const uint32_t  count = later ? st.counters[9] : st.counters[0];
+    if (blockIdx.x * blockDim.x >= count) return;  // no item of any iteration falls to this block: skip the 20 KB table load
+    loadSobolTables(sobol_tables);
     const uint32_t* __restrict__ queue = later ? st.queue_s : st.queue_a;
     const uint32_t  iters = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t it = 0; it < iters; ++it) {
@@ -2367,8 +2368,9 @@ __global__ void __launch_bounds__(kBlock) shadowKernel(SceneDevice sc, PathState
 template <bool Split>
 __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
     __shared__ uint32_t sobol_tables[kSobolTableWords];
-    loadSobolTables(sobol_tables);
     const uint32_t count = st.counters[1];
+    if (blockIdx.x * blockDim.x >= count) return;  // see shade_a
+    loadSobolTables(sobol_tables);
     const LutsD    luts{sc.luts};
     const uint32_t iters = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
     for (uint32_t it = 0; it < iters; ++it) {
