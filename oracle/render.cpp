@@ -2638,6 +2638,57 @@ float zo_ggx_micro_directional_albedo(float alpha, float n_dot_wo, uint32_t num_
     return accum;
 }
 
+// integrate_directional_albedo of the reference's LUT generator (ggx_integrate.zig:89-116): ggx.Iso.reflect with Schlick(f0)
+// plus the multi-scatter term dspbrMicroEc over the E_m / E_m_avg tables. Recomputing the E table through it pins Schlick,
+// dspbrMicroEc and the bilinear / linear table evaluation against numbers the reference holds.
+float zo_ggx_directional_albedo(const float* luts_base, float alpha, float f0, float n_dot_wo, uint32_t num_samples) {
+    using namespace zo;
+    const GgxLuts          luts(luts_base);
+    const float            calpha = max(alpha, ggx::MinAlpha);
+    const fresnel::Schlick schlick{splat(f0)};
+    const Frame            frame{{{1.f, 0.f, 0.f, 0.f}}, {{0.f, 1.f, 0.f, 0.f}}, {{0.f, 0.f, 1.f, 0.f}}};
+    const Vec4f            wo = {{std::sqrt(1.f - n_dot_wo * n_dot_wo), 0.f, n_dot_wo, 0.f}};
+
+    float accum = 0.f;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        uint32_t bits = i;
+        bits          = (bits << 16) | (bits >> 16);
+        bits          = ((bits & 0x55555555u) << 1) | ((bits & 0xAAAAAAAAu) >> 1);
+        bits          = ((bits & 0x33333333u) << 2) | ((bits & 0xCCCCCCCCu) >> 2);
+        bits          = ((bits & 0x0F0F0F0Fu) << 4) | ((bits & 0xF0F0F0F0u) >> 4);
+        bits          = ((bits & 0x00FF00FFu) << 8) | ((bits & 0xFF00FF00u) >> 8);
+        const float xi[2] = {float(i) / float(num_samples), float(bits) * 2.3283064365386963e-10f};
+
+        bxdf::Sample     result;
+        const ggx::Micro micro = ggx::iso::reflect(wo, n_dot_wo, calpha, 0.f, xi, schlick, frame, result);
+        const float      mms   = ggx::dspbrMicroEc(luts, splat(f0), micro.n_dot_wi, n_dot_wo, calpha)[0];
+        accum += ((micro.n_dot_wi * (result.reflection[0] + mms)) / result.pdf) / float(num_samples);
+    }
+    return min(accum, 1.f);
+}
+
+// integrate_average_albedo (ggx_integrate.zig:118-132): the cosine-weighted mean of the E table (trilinear evaluation).
+float zo_ggx_average_albedo(const float* luts_base, float alpha, float f0, uint32_t num_samples) {
+    using namespace zo;
+    const GgxLuts luts(luts_base);
+    float         accum = 0.f;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        uint32_t bits = i;
+        bits          = (bits << 16) | (bits >> 16);
+        bits          = ((bits & 0x55555555u) << 1) | ((bits & 0xAAAAAAAAu) >> 1);
+        bits          = ((bits & 0x33333333u) << 2) | ((bits & 0xCCCCCCCCu) >> 2);
+        bits          = ((bits & 0x0F0F0F0Fu) << 4) | ((bits & 0xF0F0F0F0u) >> 4);
+        bits          = ((bits & 0x00FF00FFu) << 8) | ((bits & 0xFF00FF00u) >> 8);
+        const float xi[2] = {float(i) / float(num_samples), float(bits) * 2.3283064365386963e-10f};
+        // smpl.hemisphereCosine(xi)[2], sampling.zig
+        float xy[2];
+        diskConcentric(xi, xy);
+        const float z = std::sqrt(max(0.f, 1.f - xy[0] * xy[0] - xy[1] * xy[1]));
+        accum += luts.e(z, alpha, f0) / float(num_samples);
+    }
+    return accum;
+}
+
 // integrate_f_s_ss of the reference's LUT generator (ggx_integrate.zig:134-205) through this oracle's VNDF sampling,
 // reflectNoFresnel / refractNoFresnel and schlick1: lets tests pin the rough-dielectric lobes of Glass against the E_s
 // table the reference ships (ggx_integral.zig:1045-1046 ff.).

@@ -82,6 +82,10 @@ void zo_resolve(const struct ZygpuView* view, const float* film, uint32_t num_pi
 
 float zo_ggx_micro_directional_albedo(float alpha, float n_dot_wo, uint32_t num_samples);
 float zo_ggx_f_s_ss(float alpha, float f0, float ior_t, float n_dot_wo, uint32_t num_samples);
+/* integrate_directional_albedo / integrate_average_albedo of the same generator (ggx_integrate.zig:89-132) over the shipped
+ * tables (`luts` = ZygpuScene.ggx_luts). */
+float zo_ggx_directional_albedo(const float* luts, float alpha, float f0, float n_dot_wo, uint32_t num_samples);
+float zo_ggx_average_albedo(const float* luts, float alpha, float f0, uint32_t num_samples);
 void  zo_sobol_stream(uint32_t sample, uint32_t seed, uint32_t n, uint32_t pad_every, float* out);
 void  zo_sobol_directions(uint32_t* out160);
 

@@ -96,6 +96,10 @@ def _bind_render(lib):
     lib.zo_ggx_micro_directional_albedo.restype = C.c_float
     lib.zo_ggx_f_s_ss.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, u32]
     lib.zo_ggx_f_s_ss.restype = C.c_float
+    lib.zo_ggx_directional_albedo.argtypes = [vp, C.c_float, C.c_float, C.c_float, u32]
+    lib.zo_ggx_directional_albedo.restype = C.c_float
+    lib.zo_ggx_average_albedo.argtypes = [vp, C.c_float, C.c_float, u32]
+    lib.zo_ggx_average_albedo.restype = C.c_float
     lib.zo_set_wavefront_light_order.argtypes = [C.c_int]
     lib.zo_set_wavefront_light_order.restype = None
     lib.zo_light_tree_random.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, vp]
@@ -179,6 +183,14 @@ def resolve(view, film):
 
 def ggx_micro_directional_albedo(alpha, n_dot_wo, num_samples=1024):
     return _bind_render(load()).zo_ggx_micro_directional_albedo(alpha, n_dot_wo, num_samples)
+
+
+def ggx_directional_albedo(luts, alpha, f0, n_dot_wo, num_samples=1024):
+    return _bind_render(load()).zo_ggx_directional_albedo(_p(luts), alpha, f0, n_dot_wo, num_samples)
+
+
+def ggx_average_albedo(luts, alpha, f0, num_samples=1024):
+    return _bind_render(load()).zo_ggx_average_albedo(_p(luts), alpha, f0, num_samples)
 
 
 def ggx_f_s_ss(alpha, f0, ior_t, n_dot_wo, num_samples=1024):

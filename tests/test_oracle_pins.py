@@ -108,3 +108,41 @@ def test_sobol_padding_blocks_differ():
     assert np.array_equal(a, b)  # a refill after 5 draws happens with or without incrementPadding
     c = oracle.sobol_stream(5, 0, 6, pad_every=1)
     assert len(set(c.tolist())) == 6 and c[1] != a[1]  # padding after every draw: each draw is dim 0 of a new block
+
+
+def test_multiscatter_term_reproduces_reference_E_table():
+    """ggx_integral.zig's E table is integrate_directional_albedo (ggx_integrate.zig:89-116, 300-368): ggx.Iso.reflect with
+    Schlick(f0) plus dspbrMicroEc over the E_m / E_m_avg tables, clamped to 1. Recomputing it through the oracle pins the
+    Schlick term, the multi-scatter compensation and the bilinear / linear table evaluation of the Substitute lobe."""
+    luts = np.fromfile(os.path.join(ROOT, "zyg_b200", "data", "ggx_luts.f32"), np.float32)
+    e = luts[1056:1056 + 4096].reshape(16, 16, 16)
+    step = np.float32(1.0 / 15.0)
+    got = np.empty((16, 16, 16), np.float32)
+    f0 = np.float32(0.0)
+    for z in range(16):
+        alpha = np.float32(0.0)
+        for a in range(16):
+            n_dot_wo = np.float32(0.0)
+            for i in range(16):
+                got[z, a, i] = oracle.ggx_directional_albedo(luts, float(alpha), float(f0), float(n_dot_wo))
+                n_dot_wo = np.float32(n_dot_wo + step)
+            alpha = np.float32(alpha + step)
+        f0 = np.float32(f0 + step)
+    assert np.abs(got - e).max() < 5e-7, np.abs(got - e).max()  # measured 2.4e-7, 2946 / 4096 entries equal at 8 decimals
+
+
+def test_trilinear_lookup_reproduces_reference_E_avg_table():
+    """E_avg is integrate_average_albedo (ggx_integrate.zig:118-132, 370-420): the mean of E.eval over 1024 cosine-distributed
+    Hammersley directions, capped at 0.9997 — a pin for InterpolatedFunction3D.eval and smpl.hemisphereCosine."""
+    luts = np.fromfile(os.path.join(ROOT, "zyg_b200", "data", "ggx_luts.f32"), np.float32)
+    e_avg = luts[1056 + 4096:1056 + 4096 + 256].reshape(16, 16)
+    step = np.float32(1.0 / 15.0)
+    got = np.empty((16, 16), np.float32)
+    f0 = np.float32(0.0)
+    for a in range(16):
+        alpha = np.float32(0.0)
+        for i in range(16):
+            got[a, i] = min(oracle.ggx_average_albedo(luts, float(alpha), float(f0)), np.float32(0.9997))
+            alpha = np.float32(alpha + step)
+        f0 = np.float32(f0 + step)
+    assert np.abs(got - e_avg).max() < 2e-7, np.abs(got - e_avg).max()  # measured 6e-8, 244 / 256 entries equal
