@@ -1540,7 +1540,7 @@ __device__ __forceinline__ void ivalueAdd(const PathState& st, uint32_t slot, V3
 // Worker.render per sample: Sensor.cameraSample (sensor.zig:152-166) + Perspective.generateVertex
 // (camera_perspective.zig:124-150) + Vertex.init (vertex.zig:67-85)
 __global__ void __launch_bounds__(kBlock) generateKernel(ZygpuView view, PathState st, PassParams pass) {
-    __shared__ uint32_t sobol_tables[kSobolTableWords];
+    __shared__ __align__(16) uint32_t sobol_tables[kSobolTableWords];
     loadSobolTables(sobol_tables);
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < pass.num_paths; slot += gridDim.x * blockDim.x) {
         const SlotId id = slotId(slot, pass);
@@ -1722,7 +1722,7 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
     constexpr bool MeshLights = 0 != (Features & kFeatureMeshLights);
     constexpr bool Infinite   = 0 != (Features & kFeatureInfiniteLights);
     constexpr bool Deferred   = 0 != (Features & kFeatureDeferredLights);  // light selection and sampling run in the light kernels
-    __shared__ uint32_t sobol_tables[kSobolTableWords];
+    __shared__ __align__(16) uint32_t sobol_tables[kSobolTableWords];
     const bool      later = Split && round > 0;
     const uint32_t  count = later ? st.counters[9] : st.counters[0];
     if (blockIdx.x * blockDim.x >= count) return;  // no item of any iteration falls to this block: skip the 20 KB table load
@@ -2168,7 +2168,7 @@ __global__ void __launch_bounds__(128) lightSelectPersistent(SceneDevice sc, Zyg
 template <bool MeshLights, bool Infinite>
 __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent(SceneDevice sc, ZygpuView view, PathState st, PassParams pass,
                                                              uint32_t* __restrict__ work_counter) {
-    __shared__ uint32_t sobol_tables[kSobolTableWords];
+    __shared__ __align__(16) uint32_t sobol_tables[kSobolTableWords];
     loadSobolTables(sobol_tables);
 
     constexpr uint32_t kFull   = 0xffffffffu;
@@ -2367,7 +2367,7 @@ __global__ void __launch_bounds__(kBlock) shadowKernel(SceneDevice sc, PathState
 // add (:116-117), mat_sample.sample and the next vertex (:121-166).
 template <bool Split>
 __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
-    __shared__ uint32_t sobol_tables[kSobolTableWords];
+    __shared__ __align__(16) uint32_t sobol_tables[kSobolTableWords];
     const uint32_t count = st.counters[1];
     if (blockIdx.x * blockDim.x >= count) return;  // see shade_a
     loadSobolTables(sobol_tables);
