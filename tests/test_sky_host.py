@@ -202,3 +202,24 @@ def test_constant_colour_map_equals_uniform_colour(engine, monkeypatch):
     plain = oracle.render(scene, view, 64, 64, 0, 8, num_meshes=n)
     assert np.array_equal(films["linear"], films["nearest"])
     assert np.allclose(films["linear"], plain, rtol=1e-4, atol=1e-6)
+
+
+def test_image_update_reaches_the_next_frame(engine):
+    """su_image_update (capi.zig:300-340) overwrites the library's copy of the pixels; the next compile rebuilds the
+    distribution from them."""
+    w, spp = 32, 8
+    su.init()
+    camera = su.perspective_camera_create(w, w)
+    su.prop_set_transformation(camera, su.transformation(rotation_deg=(60.0, 0.0, 0.0)))  # look up
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": 2}}}})
+    su.sensor_create({})
+    pixels = np.full((16, 16, 3), 2.0, np.float32)
+    scenes.add_sky(pixels)
+    scene, view = su.compile_scene()
+    a = oracle.render(scene, view, w, w, 0, spp)
+    assert np.array_equal(a[..., :3], np.full((w, w, 3), 2.0 * spp, np.float32))
+    su.image_update(0, np.full((16, 16, 3), 0.25, np.float32))
+    scene, view = su.compile_scene()
+    b = oracle.render(scene, view, w, w, 0, spp)
+    assert np.array_equal(b[..., :3], np.full((w, w, 3), 0.25 * spp, np.float32))
