@@ -2689,6 +2689,27 @@ float zo_ggx_average_albedo(const float* luts_base, float alpha, float f0, uint3
     return accum;
 }
 
+// integrate_micro_average_albedo (ggx_integrate.zig:59-73): the cosine-weighted mean of the E_m table (bilinear evaluation).
+float zo_ggx_micro_average_albedo(const float* luts_base, float alpha, uint32_t num_samples) {
+    using namespace zo;
+    const GgxLuts luts(luts_base);
+    float         accum = 0.f;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        uint32_t bits = i;
+        bits          = (bits << 16) | (bits >> 16);
+        bits          = ((bits & 0x55555555u) << 1) | ((bits & 0xAAAAAAAAu) >> 1);
+        bits          = ((bits & 0x33333333u) << 2) | ((bits & 0xCCCCCCCCu) >> 2);
+        bits          = ((bits & 0x0F0F0F0Fu) << 4) | ((bits & 0xF0F0F0F0u) >> 4);
+        bits          = ((bits & 0x00FF00FFu) << 8) | ((bits & 0xFF00FF00u) >> 8);
+        const float xi[2] = {float(i) / float(num_samples), float(bits) * 2.3283064365386963e-10f};
+        float       xy[2];
+        diskConcentric(xi, xy);
+        const float z = std::sqrt(max(0.f, 1.f - xy[0] * xy[0] - xy[1] * xy[1]));
+        accum += luts.eM(z, alpha) / float(num_samples);
+    }
+    return accum;
+}
+
 // integrate_f_s_ss of the reference's LUT generator (ggx_integrate.zig:134-205) through this oracle's VNDF sampling,
 // reflectNoFresnel / refractNoFresnel and schlick1: lets tests pin the rough-dielectric lobes of Glass against the E_s
 // table the reference ships (ggx_integral.zig:1045-1046 ff.).

@@ -86,6 +86,7 @@ float zo_ggx_f_s_ss(float alpha, float f0, float ior_t, float n_dot_wo, uint32_t
  * tables (`luts` = ZygpuScene.ggx_luts). */
 float zo_ggx_directional_albedo(const float* luts, float alpha, float f0, float n_dot_wo, uint32_t num_samples);
 float zo_ggx_average_albedo(const float* luts, float alpha, float f0, uint32_t num_samples);
+float zo_ggx_micro_average_albedo(const float* luts, float alpha, uint32_t num_samples); /* :59-73 */
 void  zo_sobol_stream(uint32_t sample, uint32_t seed, uint32_t n, uint32_t pad_every, float* out);
 void  zo_sobol_directions(uint32_t* out160);
 

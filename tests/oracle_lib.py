@@ -100,6 +100,8 @@ def _bind_render(lib):
     lib.zo_ggx_directional_albedo.restype = C.c_float
     lib.zo_ggx_average_albedo.argtypes = [vp, C.c_float, C.c_float, u32]
     lib.zo_ggx_average_albedo.restype = C.c_float
+    lib.zo_ggx_micro_average_albedo.argtypes = [vp, C.c_float, u32]
+    lib.zo_ggx_micro_average_albedo.restype = C.c_float
     lib.zo_set_wavefront_light_order.argtypes = [C.c_int]
     lib.zo_set_wavefront_light_order.restype = None
     lib.zo_light_tree_random.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, vp]
@@ -187,6 +189,10 @@ def ggx_micro_directional_albedo(alpha, n_dot_wo, num_samples=1024):
 
 def ggx_directional_albedo(luts, alpha, f0, n_dot_wo, num_samples=1024):
     return _bind_render(load()).zo_ggx_directional_albedo(_p(luts), alpha, f0, n_dot_wo, num_samples)
+
+
+def ggx_micro_average_albedo(luts, alpha, num_samples=1024):
+    return _bind_render(load()).zo_ggx_micro_average_albedo(_p(luts), alpha, num_samples)
 
 
 def ggx_average_albedo(luts, alpha, f0, num_samples=1024):

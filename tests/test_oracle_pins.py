@@ -146,3 +146,17 @@ def test_trilinear_lookup_reproduces_reference_E_avg_table():
             alpha = np.float32(alpha + step)
         f0 = np.float32(f0 + step)
     assert np.abs(got - e_avg).max() < 2e-7, np.abs(got - e_avg).max()  # measured 6e-8, 244 / 256 entries equal
+
+
+def test_bilinear_lookup_reproduces_reference_E_m_avg_table():
+    """E_m_avg is integrate_micro_average_albedo (ggx_integrate.zig:59-73, 259-298): the mean of E_m.eval over 1024
+    cosine-distributed Hammersley directions — a pin for InterpolatedFunction2D.eval."""
+    luts = np.fromfile(os.path.join(ROOT, "zyg_b200", "data", "ggx_luts.f32"), np.float32)
+    e_m_avg = luts[1024:1056]
+    step = np.float32(1.0 / 31.0)
+    alpha = np.float32(0.0)
+    got = np.empty(32, np.float32)
+    for a in range(32):
+        got[a] = oracle.ggx_micro_average_albedo(luts, float(alpha))
+        alpha = np.float32(alpha + step)
+    assert np.abs(got - e_m_avg).max() < 2e-7, np.abs(got - e_m_avg).max()
