@@ -189,9 +189,9 @@ RENDER_SCENES = {
                                         3840, 2160, 8, 0),
     # configs[3]: 1000 emissive icosahedron meshes + a 576-triangle emitter in a room with 200k triangles of diffuse geometry,
     # sky = a 1024^2 radiance image on a Canopy (procedural: the arpraguesky dataset is not shipped) + Distant sun, light-tree
-    # sampling with split threshold 0.5, 1920 x 1080 (4 of the 1024 spp per step)
-    "config4_meshlights1k_sky_1920x1080x4": ("mesh_lights_scene", {"num_lights": 1000, "geometry_quads": (400, 250), "sun": 15.0, "sky": 1024, "max_depth": 8},
-                                         1920, 1080, 4, 1),
+    # sampling with split threshold 0.5, 1920 x 1080 (8 of the 1024 spp per step, so that 8 ranks have a sample each)
+    "config4_meshlights1k_sky_1920x1080x8": ("mesh_lights_scene", {"num_lights": 1000, "geometry_quads": (400, 250), "sun": 15.0, "sky": 1024, "max_depth": 8},
+                                         1920, 1080, 8, 1),
 }
 MESH_SCENES = ("sphere_scene", "instanced_scene", "mesh_lights_scene")
 
