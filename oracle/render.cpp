@@ -771,7 +771,58 @@ struct Sampler2D {  // shape_sampler.ImageImpl + Distribution2D, shape_sampler.z
 
 }  // namespace image
 
+namespace rectangle {
+
+// Rectangle.sampleMaterialTo, rectangle.zig (image-mapped area light: texels picked through the material's Distribution2D)
+uint32_t sampleMaterialTo(Vec4f p, Vec4f n, const Trafo& trafo, bool two_sided, bool total_sphere, uint32_t num_samples,
+                          const image::Sampler2D& shape_sampler, Sampler& sampler, SampleTo* buffer) {
+    const float nsf   = float(num_samples);
+    const Vec4f scale = trafo.scale();
+    const float area  = scale[0] * scale[1];
+
+    uint32_t current_sample = 0;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        const Vec2f r2 = sampler.sample2D();
+        float       uv[2], rs_pdf;
+        shape_sampler.sample(r2.v[0], r2.v[1], uv, rs_pdf);
+        if (0.f == rs_pdf) continue;
+
+        const Vec4f ls   = {{-1.f * uv[0] + 0.5f, -1.f * uv[1] + 0.5f, 0.f, 0.f}};
+        const Vec4f ws   = trafo.objectToWorldPoint(ls);
+        const Vec4f axis = ws - p;
+
+        Vec4f wn = trafo.r[2];
+        if (two_sided && dot3(wn, axis) > 0.f) wn = -wn;
+
+        const float sl  = squaredLength3(axis);
+        const float t   = std::sqrt(sl);
+        const Vec4f dir = axis / splat(t);
+        const float c   = -dot3(wn, dir);
+        if (c < safe::DotMin || (dot3(dir, n) <= 0.f && !total_sphere)) continue;
+
+        SampleTo& out = buffer[current_sample++];
+        out.p         = {{ws[0], ws[1], ws[2], (nsf * rs_pdf * sl) / (c * area)}};
+        out.n         = wn;
+        out.wi        = dir;
+        out.uvw       = {{uv[0], uv[1], 0.f, 0.f}};
+    }
+    return current_sample;
+}
+
+// Rectangle.materialPdf
+float materialPdf(Vec4f dir, Vec4f p, const Fragment& frag, uint32_t num_samples, const image::Sampler2D& shape_sampler) {
+    const float c            = std::fabs(dot3(frag.isec.trafo.r[2], dir));
+    const Vec4f scale        = frag.isec.trafo.scale();
+    const float area         = scale[0] * scale[1];
+    const float sl           = squaredDistance3(p, frag.p);
+    const float material_pdf = shape_sampler.pdf(frag.uvw[0], frag.uvw[1]) * float(num_samples);
+    return (material_pdf * sl) / (c * area);
+}
+
+}  // namespace rectangle
+
 namespace canopy {  // shape/canopy.zig
+
 
 constexpr float Eps = -0.0005f;
 
@@ -1708,6 +1759,10 @@ struct Scene {
         const uint32_t num_samples = lightNumSamples(l, split_threshold);
         switch (s.props[l.prop].shape) {
             case ZYG_SHAPE_RECTANGLE:
+                if (ZYG_LIGHT_PROP_IMAGE == l.light_class) {
+                    return rectangle::sampleMaterialTo(p, n, trafo, 0 != l.two_sided, total_sphere, num_samples, image_samplers[l.sampler],
+                                                       sampler, buffer);
+                }
                 return rectangle::sampleTo(p, n, trafo, 0 != l.two_sided, total_sphere, num_samples, sampler, buffer);
             case ZYG_SHAPE_DISTANT: return distant::sampleTo(n, trafo, total_sphere, sampler, buffer);
             case ZYG_SHAPE_SPHERE: return sphere::sampleTo(p, n, trafo, total_sphere, num_samples, sampler, buffer);
@@ -1905,7 +1960,10 @@ struct Worker {
         float             sample_pdf = 0.f;
         switch (scene.s.props[l.prop].shape) {
             case ZYG_SHAPE_RECTANGLE:
-                sample_pdf = rectangle::pdf(vertex.origin, frag, scene.lightNumSamples(l, vertex.light_split_threshold));
+                sample_pdf = ZYG_LIGHT_PROP_IMAGE == l.light_class
+                                 ? rectangle::materialPdf(vertex.ray.direction, vertex.origin, frag,
+                                                          scene.lightNumSamples(l, vertex.light_split_threshold), scene.image_samplers[l.sampler])
+                                 : rectangle::pdf(vertex.origin, frag, scene.lightNumSamples(l, vertex.light_split_threshold));
                 break;
             case ZYG_SHAPE_DISTANT: sample_pdf = 1.f / distant::solidAngle(frag.isec.trafo.scaleX()); break;  // distant.zig:139-141
             case ZYG_SHAPE_SPHERE:

@@ -410,3 +410,21 @@ def test_empty_and_sky_only_scenes(engine):
     gpu = download_film(w, w)
     assert np.array_equal(gpu, ref)
     assert np.array_equal(gpu[..., :3], np.full((w, w, 3), 1.5 * spp, np.float32))
+
+
+@pytest.mark.parametrize("num_samples,two_sided,deferred", [(1, False, "0"), (3, True, "0"), (2, False, "1")])
+def test_image_mapped_rectangle_light_matches_oracle(engine, monkeypatch, num_samples, two_sided, deferred):
+    """A Rectangle light with an emission image (PropImage class on a finite shape): Rectangle.sampleMaterialTo / materialPdf,
+    the sample's uv carried in the shadow record for Light.evaluateTo, inline and deferred light sampling."""
+    monkeypatch.setenv("ZYGPU_DEFERRED_LIGHTS", deferred)
+    w, spp = 128, 16
+    scenes.image_light_scene(w, w, spp=spp, num_samples=num_samples, two_sided=two_sided)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp, wavefront_light_order=True)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6
+    assert (rel > 1e-2).mean() < 5e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4

@@ -223,3 +223,19 @@ def test_image_update_reaches_the_next_frame(engine):
     scene, view = su.compile_scene()
     b = oracle.render(scene, view, w, w, 0, spp)
     assert np.array_equal(b[..., :3], np.full((w, w, 3), 0.25 * spp, np.float32))
+
+
+def test_image_mapped_rectangle_light_agrees_with_uniform_light(engine):
+    """Rectangle.sampleMaterialTo / materialPdf with a constant emission image is an ordinary area light sampled through the
+    image's (then uniform) Distribution2D instead of the spherical rectangle: both estimators converge to the same image."""
+    w, spp = 48, 256
+    means = []
+    for image in (np.full((8, 8, 3), 1.0, np.float32), False):
+        su.release()
+        scenes.image_light_scene(w, w, spp=spp, image=image)
+        scene, view = su.compile_scene()
+        film = oracle.render(scene, view, w, w, 0, spp)
+        img = (film[..., :3] / film[..., 3:4]).astype(np.float64)
+        means.append(img.reshape(6, 8, 6, 8, 3).mean((1, 3)))
+    assert np.allclose(means[0], means[1], rtol=0.04)
+    assert abs(means[0].mean() / means[1].mean() - 1.0) < 0.01

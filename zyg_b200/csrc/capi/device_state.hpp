@@ -49,6 +49,7 @@ struct RenderState {
     zygpu::SceneDevice scene{};
     bool               has_scene  = false;
     bool               has_meshes = false;
+    bool               has_image_area_lights = false;  // a finite PROP_IMAGE light: shadow records carry the sample's uv
     bool               has_textures = false;  // a material reads an image per vertex: shade_a hands its stochastic_r to shade_b
     bool               deferred_lights = false;  // light selection / sampling in the persistent light kernels
     bool               can_split  = false;  // a material can split paths: 4 vertex records per camera sample

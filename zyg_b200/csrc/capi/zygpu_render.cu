@@ -54,9 +54,10 @@ uint32_t targetPathsPerPass() {
 
 // `lanes` vertex records per slot (1, or 4 when a material of the scene can split a path); trace items are vertex ids for
 // closest-hit rays and shadow records for any-hit rays, so the per-item arrays hold max(lanes, shadow_stride) per slot.
-int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint32_t lanes, bool deferred_lights, bool textures) {
+int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint32_t lanes, bool deferred_lights, bool textures, bool record_uvs) {
     if (r.paths.capacity >= capacity && r.paths.shadow_stride == shadow_stride && r.paths.lanes == lanes &&
-        (nullptr != r.paths.queue_l) == deferred_lights && (nullptr != r.paths.stoch) == textures) {
+        (nullptr != r.paths.queue_l) == deferred_lights && (nullptr != r.paths.stoch) == textures &&
+        (nullptr != r.paths.sh_uv) == record_uvs) {
         return 0;
     }
     freeAll(r.path_buffers);
@@ -79,6 +80,7 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint3
     }
     if (shadow_stride > 1 && 0 != allocPath(r, &p.queue_r, size_t(capacity) * shadow_stride)) return -1;
     if (textures && 0 != allocPath(r, &p.stoch, vertices)) return -1;
+    if (record_uvs && 0 != allocPath(r, &p.sh_uv, size_t(capacity) * shadow_stride)) return -1;
     if (deferred_lights && (0 != allocPath(r, &p.ls_p, capacity) || 0 != allocPath(r, &p.ls_g, capacity) ||
                             0 != allocPath(r, &p.picks, size_t(capacity) * 64) || 0 != allocPath(r, &p.pick_n, capacity) ||
                             0 != allocPath(r, &p.queue_l, capacity))) {
@@ -205,7 +207,18 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     d.num_mesh_samplers = scene->num_mesh_samplers;
     if (0 != uploadArray(r, scene->mesh_part_areas, scene->mesh_part_areas ? scene->num_parts : 0, &d.mesh_part_areas)) return -1;
 
-    r.has_textures = false;
+    r.has_textures          = false;
+    r.has_image_area_lights = false;
+    for (uint32_t l = 0; l < scene->num_lights; ++l) {
+        const ZygpuLight& light = scene->lights[l];
+        if (ZYG_LIGHT_PROP_IMAGE != light.light_class) continue;
+        const uint32_t shape = scene->props[light.prop].shape;
+        if (ZYG_SHAPE_CANOPY != shape && ZYG_SHAPE_RECTANGLE != shape) {
+            return fail("zygpu_upload_scene: light %u: image-mapped lights are supported on Canopy and Rectangle shapes", l);
+        }
+        if (light.sampler >= scene->num_image_samplers) return fail("zygpu_upload_scene: light %u references image sampler %u", l, light.sampler);
+        if (ZYG_SHAPE_RECTANGLE == shape) r.has_image_area_lights = true;
+    }
     // emission images with their Distribution2D rows (shape_sampler.ImageImpl)
     std::vector<zygpu::ImageSamplerDevice> image_samplers(scene->num_image_samplers);
     for (uint32_t i = 0; i < scene->num_image_samplers; ++i) {
@@ -343,7 +356,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
     if (capacity > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
     const uint32_t lanes = r.can_split ? 4 : 1;
     if (capacity * lanes > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
-    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples, lanes, r.deferred_lights, r.has_textures)) return -1;
+    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples, lanes, r.deferred_lights, r.has_textures, r.has_image_area_lights)) return -1;
     const uint32_t rounds = lanes;
 
     // extend / shadow are one kernel each (prop-tree walk) plus the persistent mesh kernel when the scene has meshes

@@ -1355,7 +1355,13 @@ __device__ __forceinline__ float sceneLightPdf(const SceneDevice& sc, const Vert
 
     const ZygpuLight l          = sc.lights[light_id];
     float            sample_pdf = 0.f;
-    if (ZYG_SHAPE_RECTANGLE == sc.props[l.prop].shape) {
+    if (ZYG_SHAPE_RECTANGLE == sc.props[l.prop].shape && ZYG_LIGHT_PROP_IMAGE == l.light_class) {  // Rectangle.materialPdf
+        const float c            = fabsf(dot3(frag.trafo.r2, vertex.ray.d));
+        const float area         = frag.trafo.scale.x * frag.trafo.scale.y;
+        const float sl           = squaredLength3(sub3(vertex.origin, frag.p));
+        const float material_pdf = imagePdf(sc.image_samplers[l.sampler], frag.u, frag.v) * float(lightNumSamples(l, vertex.light_split_threshold));
+        sample_pdf               = __fdiv_rn(material_pdf * sl, c * area);
+    } else if (ZYG_SHAPE_RECTANGLE == sc.props[l.prop].shape) {
         const float nsf = float(lightNumSamples(l, vertex.light_split_threshold));
         SphQuadD    squad;
         squad.init(frag.trafo.scale, frag.trafo.worldToFramePoint(vertex.origin));
@@ -1965,6 +1971,40 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                             }
                             continue;
                         }
+                        if (ZYG_SHAPE_RECTANGLE == shape && ZYG_LIGHT_PROP_IMAGE == light.light_class) {  // Rectangle.sampleMaterialTo
+                            const uint32_t            ns   = lightNumSamples(light, vertex.light_split_threshold);
+                            const ImageSamplerDevice& is   = sc.image_samplers[light.sampler];
+                            const float               area = trafo.scale.x * trafo.scale.y;
+                            for (uint32_t k = 0; k < ns; ++k) {
+                                float u0, u1;
+                                sampler.sample2D(u0, u1);
+                                float su, sv, rs_pdf;
+                                imageSample(is, u0, u1, su, sv, rs_pdf);
+                                if (0.f == rs_pdf) continue;
+                                const V3 ws   = trafo.objectToWorldPoint({-1.f * su + 0.5f, -1.f * sv + 0.5f, 0.f});
+                                const V3 axis = sub3(ws, p);
+                                V3       wn   = trafo.r2;
+                                if (0 != light.two_sided && dot3(wn, axis) > 0.f) wn = neg3(wn);
+                                const float sl  = squaredLength3(axis);
+                                const float t   = __fsqrt_rn(sl);
+                                const V3    dir = divs3(axis, t);
+                                const float c   = -dot3(wn, dir);
+                                if (c < kDotMin || (dot3(dir, n) <= 0.f && !translucent)) continue;
+                                if (num_records < st.shadow_stride) {
+                                    const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+                                    const V3     origin    = frag.offsetP(dir);
+                                    const V3     light_pos = offsetRay(ws, wn);
+                                    st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, __fdiv_rn(float(ns) * rs_pdf * sl, c * area) * pick.pdf);
+                                    st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+                                    st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                                    if (nullptr != st.sh_uv) st.sh_uv[rec] = make_float2(su, sv);
+                                    num_records += 1;
+                                } else {
+                                    st.counters[3] = 1;
+                                }
+                            }
+                            continue;
+                        }
                         if (ZYG_SHAPE_RECTANGLE != shape) continue;
 
                         // Rectangle.sampleTo, rectangle.zig:305-357
@@ -2293,6 +2333,38 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                         st.counters[3] = 1;
                     }
                 }
+            } else if (ZYG_SHAPE_RECTANGLE == shape && ZYG_LIGHT_PROP_IMAGE == light.light_class) {  // Rectangle.sampleMaterialTo
+                const uint32_t            ns   = lightNumSamples(light, threshold);
+                const ImageSamplerDevice& is   = sc.image_samplers[light.sampler];
+                const float               area = trafo.scale.x * trafo.scale.y;
+                for (uint32_t k = 0; k < ns; ++k) {
+                    float u0, u1;
+                    sampler.sample2D(u0, u1);
+                    float su, sv, rs_pdf;
+                    imageSample(is, u0, u1, su, sv, rs_pdf);
+                    if (0.f == rs_pdf) continue;
+                    const V3 ws   = trafo.objectToWorldPoint({-1.f * su + 0.5f, -1.f * sv + 0.5f, 0.f});
+                    const V3 axis = sub3(ws, p);
+                    V3       wn   = trafo.r2;
+                    if (0 != light.two_sided && dot3(wn, axis) > 0.f) wn = neg3(wn);
+                    const float sl  = squaredLength3(axis);
+                    const float t   = __fsqrt_rn(sl);
+                    const V3    dir = divs3(axis, t);
+                    const float c   = -dot3(wn, dir);
+                    if (c < kDotMin || (dot3(dir, n) <= 0.f && !translucent)) continue;
+                    if (num_records < st.shadow_stride) {
+                        const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+                        const V3     origin    = offsetPoint(p, geo_n, dir);
+                        const V3     light_pos = offsetRay(ws, wn);
+                        st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, __fdiv_rn(float(ns) * rs_pdf * sl, c * area) * pick.pdf);
+                        st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+                        st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                        if (nullptr != st.sh_uv) st.sh_uv[rec] = make_float2(su, sv);
+                        num_records += 1;
+                    } else {
+                        st.counters[3] = 1;
+                    }
+                }
             } else if (ZYG_SHAPE_RECTANGLE == shape) {  // Rectangle.sampleTo, rectangle.zig:305-357
                 const uint32_t ns  = lightNumSamples(light, threshold);
                 const float    nsf = float(ns);
@@ -2434,10 +2506,12 @@ __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeB
                 const TrafoD        ltrafo   = loadTrafo(sc.trafos, light.prop);
                 const ZygpuMaterial lm       = sc.materials[__ldg(sc.material_ids + sc.props[light.prop].parts_start + light.part)];
                 const float area     = 0.f != lm.emission_normalize ? shapeArea(sc.props[light.prop].shape, ltrafo.scale) : 1.f;
-                // an image-mapped (PROP_IMAGE) light left the uvw of its sample in the record's position lanes
+                // an image-mapped (PROP_IMAGE) light left the uvw of its sample in the record's position lanes (infinite lights:
+                // the lanes are free) or in sh_uv (finite lights)
+                const float2 luv = 0 != (__float_as_uint(p4.w) & 0x80000000u) || nullptr == st.sh_uv ? make_float2(p4.x, p4.y) : st.sh_uv[rec];
                 const V3    radiance = ZYGPU_NULL != lm.emission_map
                                            ? emittanceRadianceMapped(lm, wi, ltrafo, area, false,
-                                                                     imageTexel(sc.image_samplers[lm.emission_map], p4.x, p4.y, stochastic_r))
+                                                                     imageTexel(sc.image_samplers[lm.emission_map], luv.x, luv.y, stochastic_r))
                                            : emittanceRadiance(lm, wi, ltrafo, area, false);
 
                 const BxdfResult bxdf_result = mat_sample.template evaluate<Split>(luts, wi, max_splits);

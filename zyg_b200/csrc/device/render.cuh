@@ -121,6 +121,8 @@ struct PathState {
     float4*   sh_p;   // offset light position xyz | light id (bit 31: infinite light, the ray runs along wi to RayMaxT)
     float4*   sh_wi;  // light_sample.wi xyz | visible (written by shadow)
     uint32_t* sh_n;   // per path: number of records
+    float2*   sh_uv;  // per record: uvw of a light sample taken through the light's emission image (Rectangle.sampleMaterialTo), read
+                      // by Light.evaluateTo in shade_b; null unless the scene has an image-mapped finite light
     float*    stoch;  // per vertex: rs.stochastic_r of Vertex.sample (vertex.zig:165), drawn by shade_a and read again by shade_b
                       // for the material's image lookups; null when no material of the scene reads an image per vertex
 

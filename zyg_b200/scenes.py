@@ -406,6 +406,46 @@ def textured_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None,
     return 1
 
 
+def image_light_scene(width=128, height=128, spp=16, max_depth=5, filter_name=None, split_threshold=0.5, num_samples=1,
+                      image=None, value=6.0, two_sided=False, unoccluding=True):
+    """A closed room lit by a Rectangle whose Light material carries an emission image (a PropImage light on a finite shape:
+    Rectangle.sampleMaterialTo / materialPdf, texels picked through the material's Distribution2D) — a "stained-glass" ceiling
+    panel. `image` = None uses a colour checker; a constant image makes it an ordinary area light sampled another way."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(70.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.4, -2.8)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth},
+                                                 "light_sampling": {"split_threshold": split_threshold}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    wall = su.material_create({"rendering": {"Substitute": {"color": [0.7, 0.7, 0.7], "roughness": 1.0}}})
+    glossy = su.material_create({"rendering": {"Substitute": {"color": [0.8, 0.6, 0.3], "roughness": 0.35, "metallic": 1.0}}})
+    walls = [((0, 0, 0), (6, 6, 1), (90, 0, 0)), ((0, 3, 0), (6, 6, 1), (-90, 0, 0)),
+             ((0, 1.5, 3), (6, 3, 1), (0, 180, 0)), ((0, 1.5, -3), (6, 3, 1), (0, 0, 0)),
+             ((-3, 1.5, 0), (6, 3, 1), (0, -90, 0)), ((3, 1.5, 0), (6, 3, 1), (0, 90, 0))]
+    for position, scale, rotation in walls:
+        prop = su.prop_create(su.RECTANGLE, [wall])
+        su.prop_set_transformation(prop, su.transformation(tuple(map(float, position)), tuple(map(float, scale)), tuple(map(float, rotation))))
+    for k, (x, z) in enumerate([(-1.2, 0.8), (1.4, 0.2)]):
+        cube = su.prop_create(su.CUBE, [glossy if 1 == k else wall])
+        su.prop_set_transformation(cube, su.transformation((x, 0.4, z), (0.8, 0.8, 0.8), (0.0, 25.0 * k, 0.0)))
+
+    if image is None:
+        image = checker_image(32, 4, (1.0, 0.2, 0.1), (0.1, 0.3, 1.0))
+    emittance = {"value": float(value), "num_samples": num_samples}
+    if image is not False:  # False: a plain uniform Rectangle light (spherical-rectangle sampling) for comparison
+        emittance["emission_map"] = {"id": su.image_create(image), "sampler": {"address": "Clamp"}}
+    material = su.material_create({"rendering": {"Light": {"two_sided": two_sided, "emittance": emittance}}})
+    panel = su.prop_create(su.RECTANGLE, [material], unoccluding=unoccluding)
+    su.prop_set_transformation(panel, su.transformation((0.2, 2.6, 0.6), (2.2, 1.4, 1.0), (-90.0, 0.0, 20.0)))
+    su.light_create(panel)
+    return 0
+
+
 def icosahedron():
     """Unit icosahedron: (positions f32[12,3], indices u32[20,3]), counter-clockwise seen from outside."""
     t = (1.0 + 5.0 ** 0.5) / 2.0
