@@ -2723,6 +2723,17 @@ int numSms() {
     return sms;
 }
 
+// Blocks per SM of the shade launches (ZYGPU_SHADE_GRID overrides). Measured: exactly the resident 4 for the kernels without
+// path splits (Cornell 39.2 -> 37.1 ms: one table prologue per block, no second wave), 16 for the split kernels of glass scenes,
+// whose blocks finish unevenly (config 3: 389.8 ms with 4, 378.7 ms with 16).
+uint32_t shadeGrid(bool split) {
+    static const int v = [] {
+        const char* e = getenv("ZYGPU_SHADE_GRID");
+        return e ? std::max(1, atoi(e)) : 0;
+    }();
+    return 0 != v ? uint32_t(v) : (split ? 16u : 4u);
+}
+
 // Grid-stride launches: a multiple of the SM count, never more blocks than there is work.
 uint32_t gridFor(uint32_t items, uint32_t blocks_per_sm) {
     const uint32_t needed = (items + kBlock - 1) / kBlock;
@@ -2831,7 +2842,7 @@ cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const 
                          uint32_t round, cudaStream_t stream) {
     const uint32_t features = (st.lanes > 1 ? kFeatureSplit : 0u) | (scene.num_mesh_samplers > 0 ? kFeatureMeshLights : 0u) |
                               (scene.num_infinite_props > 0 ? kFeatureInfiniteLights : 0u) | (nullptr != st.queue_l ? kFeatureDeferredLights : 0u);
-    const uint32_t grid = gridFor(max_items, 8);
+    const uint32_t grid = gridFor(max_items, shadeGrid(st.lanes > 1));
     if (st.lanes <= 1) round = 0;
     switch (features) {
         case 0: shadeAKernel<0><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
@@ -2903,9 +2914,9 @@ cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
                          uint32_t round, cudaStream_t stream) {
     if (st.lanes > 1) {
-        shadeBKernel<true><<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass, round);
+        shadeBKernel<true><<<gridFor(max_items, shadeGrid(true)), kBlock, 0, stream>>>(scene, view, st, pass, round);
     } else {
-        shadeBKernel<false><<<gridFor(max_items, 8), kBlock, 0, stream>>>(scene, view, st, pass, 0);
+        shadeBKernel<false><<<gridFor(max_items, shadeGrid(false)), kBlock, 0, stream>>>(scene, view, st, pass, 0);
         advanceKernel<<<1, 1, 0, stream>>>(st);
     }
     return cudaGetLastError();
