@@ -90,6 +90,24 @@ float zo_ggx_micro_average_albedo(const float* luts, float alpha, uint32_t num_s
 void  zo_sobol_stream(uint32_t sample, uint32_t seed, uint32_t n, uint32_t pad_every, float* out);
 void  zo_sobol_directions(uint32_t* out160);
 
+/* ---- the oracle's own scene-compile builders (builders.cpp) -------------------------------------------------------
+ * Independent restatement of builder_base.zig / split_candidate.zig / triangle_tree_builder.zig / prop_tree_builder.zig /
+ * light_tree_builder.zig / Part.configure: tests compare every array with what the product's host builds (byte for byte),
+ * bench.py --impl reference builds its tree here. Handles are freed with zo_build_free; the *_data views are valid until then. */
+struct ZygpuAabb;
+void        zo_build_free(void* handle);
+void*       zo_mesh_build(uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles, const uint32_t* indices, uint32_t num_vertices,
+                          const float* positions, uint32_t positions_stride, const float* normals, uint32_t normals_stride,
+                          const float* uvs, uint32_t uvs_stride, uint32_t threads);
+const void* zo_mesh_data(const void* handle, int which, uint64_t* num_bytes);
+void*       zo_prop_tree_build(const uint32_t* indices, uint32_t num_indices, const struct ZygpuAabb* aabbs, uint32_t threads);
+const void* zo_prop_tree_data(const void* handle, int which, uint64_t* num_bytes);
+void*       zo_light_tree_build(uint32_t num_lights, const struct ZygpuAabb* aabbs, const float* cones, const uint8_t* two_sided,
+                                const uint8_t* finite);
+const void* zo_light_tree_data(const void* handle, int sampler, int which, uint64_t* num_bytes);
+void*       zo_mesh_sampler_build(const ZoMesh* mesh, uint32_t num_tree_triangles, uint32_t num_parts, uint32_t part, int two_sided);
+const void* zo_mesh_sampler_data(const void* handle, int which, uint64_t* num_bytes);
+
 #ifdef __cplusplus
 }
 #endif

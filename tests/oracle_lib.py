@@ -228,3 +228,123 @@ def sobol_directions():
     out = np.empty((5, 32), np.uint32)
     _bind_render(load()).zo_sobol_directions(_p(out))
     return out
+
+
+# ---- the oracle's own scene-compile builders (oracle/builders.cpp) -----------------------------------
+
+def _bind_builders(lib):
+    if getattr(lib, "_builders_bound", False):
+        return lib
+    vp, u32 = C.c_void_p, C.c_uint32
+    lib.zo_build_free.argtypes = [vp]
+    lib.zo_build_free.restype = None
+    lib.zo_mesh_build.argtypes = [u32, vp, u32, vp, u32, vp, u32, vp, u32, vp, u32, u32]
+    lib.zo_mesh_build.restype = vp
+    lib.zo_prop_tree_build.argtypes = [vp, u32, vp, u32]
+    lib.zo_prop_tree_build.restype = vp
+    lib.zo_light_tree_build.argtypes = [u32, vp, vp, vp, vp]
+    lib.zo_light_tree_build.restype = vp
+    lib.zo_mesh_sampler_build.argtypes = [vp, u32, u32, u32, C.c_int]
+    lib.zo_mesh_sampler_build.restype = vp
+    for fn in (lib.zo_mesh_data, lib.zo_prop_tree_data, lib.zo_mesh_sampler_data):
+        fn.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
+        fn.restype = vp
+    lib.zo_light_tree_data.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    lib.zo_light_tree_data.restype = vp
+    lib._builders_bound = True
+    return lib
+
+
+def _blob(fn, handle, *which):
+    n = C.c_uint64()
+    p = fn(handle, *which, C.byref(n))
+    if not p or 0 == n.value:
+        return b""
+    return C.string_at(p, n.value)
+
+
+MESH_NODE_DTYPE = np.dtype([("min", "<f4", 3), ("min_data", "<u4"), ("max", "<f4", 3), ("max_data", "<u4")])
+
+
+class BuiltMesh:
+    """A triangle tree built by the oracle's own builder (zo_mesh_build): same arrays, same numbering as zyg_mesh_data."""
+
+    NODES, TRIANGLES, ORIGINAL, POSITIONS, NORMALS, UVS, PARTS = range(7)
+    _dtypes = {0: MESH_NODE_DTYPE, 1: "<u4", 2: "<u4", 3: "<f4", 4: "<u2", 5: "<f4", 6: "<u2"}
+
+    def __init__(self, positions, indices, normals=None, uvs=None, parts=None, threads=0):
+        lib = _bind_builders(load())
+        positions = np.ascontiguousarray(positions, np.float32)
+        indices = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        normals = None if normals is None else np.ascontiguousarray(normals, np.float32)
+        uvs = None if uvs is None else np.ascontiguousarray(uvs, np.float32)
+        parts = None if parts is None else np.ascontiguousarray(parts, np.uint32).reshape(-1)
+        self._lib = lib
+        self.handle = lib.zo_mesh_build(0 if parts is None else parts.size // 3, None if parts is None else _p(parts),
+                                        indices.size // 3, _p(indices), positions.shape[0], _p(positions), 3,
+                                        None if normals is None else _p(normals), 3, None if uvs is None else _p(uvs), 2, threads)
+        self._cache = {}
+
+    def raw(self, which) -> bytes:
+        return _blob(self._lib.zo_mesh_data, self.handle, which)
+
+    def data(self, which) -> np.ndarray:
+        if which not in self._cache:
+            self._cache[which] = np.frombuffer(self.raw(which), self._dtypes[which]).copy()
+        return self._cache[which]
+
+    def diagnostics(self):
+        d = np.frombuffer(self.raw(100), np.uint32)
+        return {"leaf_offset_mismatches": int(d[0]), "unsplittable": int(d[1]), "task_root_leaves": int(d[2])}
+
+    def table(self):
+        """ZoMesh[1] over this mesh's arrays, for zo_render / zo_mesh_sampler_build."""
+        arrays = [self.data(w) for w in (self.NODES, self.TRIANGLES, self.POSITIONS, self.NORMALS, self.UVS, self.PARTS)]
+        self._keep = arrays
+        t = (ZoMesh * 1)()
+        t[0] = ZoMesh(*[_p(a) for a in arrays])
+        return t
+
+    def __del__(self):
+        try:
+            self._lib.zo_build_free(self.handle)
+        except Exception:
+            pass
+
+
+def build_prop_tree(indices, aabbs, threads=0):
+    """PropBvhBuilder.build over prop ids `indices` and the (N, 32-byte) world boxes: (nodes bytes, indices bytes)."""
+    lib = _bind_builders(load())
+    indices = np.ascontiguousarray(indices, np.uint32)
+    aabbs = np.ascontiguousarray(aabbs)
+    h = lib.zo_prop_tree_build(_p(indices), indices.size, _p(aabbs), threads)
+    out = _blob(lib.zo_prop_tree_data, h, 0), _blob(lib.zo_prop_tree_data, h, 1)
+    lib.zo_build_free(h)
+    return out
+
+
+LIGHT_TREE_PARTS = ("nodes", "middles", "orders", "mapping", "infinite_cdf", "floats", "uints")
+
+
+def build_light_tree(light_aabbs, light_cones, two_sided, finite):
+    """Builder.build over the scene lights: dict of raw byte strings per LIGHT_TREE_PARTS."""
+    lib = _bind_builders(load())
+    light_aabbs = np.ascontiguousarray(light_aabbs)
+    light_cones = np.ascontiguousarray(light_cones, np.float32)
+    two_sided = np.ascontiguousarray(two_sided, np.uint8)
+    finite = np.ascontiguousarray(finite, np.uint8)
+    h = lib.zo_light_tree_build(two_sided.size, _p(light_aabbs), _p(light_cones), _p(two_sided), _p(finite))
+    out = {name: _blob(lib.zo_light_tree_data, h, 0, i) for i, name in enumerate(LIGHT_TREE_PARTS)}
+    lib.zo_build_free(h)
+    return out
+
+
+def build_mesh_sampler(table, num_tree_triangles, num_parts, part, two_sided):
+    """Part.configure + Builder.buildPrimitive over a ZoMesh: dict with the sampler tables and its primitive tree."""
+    lib = _bind_builders(load())
+    h = lib.zo_mesh_sampler_build(table, num_tree_triangles, num_parts, part, int(two_sided))
+    out = {name: _blob(lib.zo_mesh_sampler_data, h, i)
+           for i, name in enumerate(("triangle_mapping", "triangle_pdfs", "primitive_mapping", "part_areas", "floats"))}
+    out["tree"] = {name: _blob(lib.zo_light_tree_data, h, 1, i) for i, name in enumerate(LIGHT_TREE_PARTS)}
+    lib.zo_build_free(h)
+    return out

@@ -695,13 +695,15 @@ void SceneModel::loadIntegrators(const json::Value& value) {
             max_depth_surface_ = json::readUIntMember(*d, "surface", 16) & 0xFFFFu;
             max_depth_volume_  = json::readUIntMember(*d, "surface", 256) & 0xFFFFu;
         }
-        float st = 0.5f;  // take.zig:263-271
+        // loadLightSampling, take.zig:263-271: without a "light_sampling" node the threshold is the raw default 0.5; only a
+        // value read from the node is clamped and raised to the 4th power
+        split_threshold_ = 0.5f;
         if (const json::Value* ls = v.get("light_sampling")) {
-            st = json::readFloatMember(*ls, "split_threshold", 0.5f);
-            st = st < 0.f ? 0.f : (st > 1.f ? 1.f : st);
+            float st = json::readFloatMember(*ls, "split_threshold", 0.5f);
+            st       = st < 0.f ? 0.f : (st > 1.f ? 1.f : st);
+            const float st2  = st * st;
+            split_threshold_ = st2 * st2;
         }
-        const float st2  = st * st;
-        split_threshold_ = st2 * st2;
         ptmis_           = true;
     }
 }
