@@ -5,9 +5,13 @@
  * success, -1 failure / not initialised, -3 bad material id, -4 material update failed). One
  * process-global engine, single caller thread (capi.zig:55).
  *
- * Scope of this round: static scenes, perspective camera, PTMIS, the built-in shapes
- * Rectangle / Cube / Sphere and triangle meshes, materials Substitute / Light (uniform parameters).
- * Entry points outside that scope exist and return -1 (image, AOV, exporter and animation-frame calls).
+ * Scope: static scenes, perspective camera (pinhole / thin lens), PTMIS, the built-in shapes Rectangle / Cube /
+ * Sphere / Canopy / Distant and triangle meshes (props, prop instances, instancers), materials Substitute / Glass / Light with
+ * uniform parameters, image colour maps and image emission maps (su_image_create: Float32 x 3 and UInt8 x 3). A scene that
+ * uses a Disk or Dome prop, thin or dispersive Glass is refused by the render calls (-1 and a log message) rather than rendered
+ * wrongly; unsupported material parameters are ignored with a warning through the log callback.
+ * Entry points outside that scope exist and return -1 (su_aovs_create, su_exporters_create, su_export_frame, animation frames
+ * other than 0).
  */
 #ifndef ZYG_SU_H
 #define ZYG_SU_H
@@ -32,15 +36,18 @@ int32_t su_aovs_create(const char* json);                                 /* :20
 int32_t su_sampler_create(uint32_t num_samples);                          /* :215 (returns -1 even on success, like the reference) */
 int32_t su_integrators_create(const char* json);                          /* :223 */
 int32_t su_image_create(uint32_t id, uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height,
-                        uint32_t depth, uint32_t pixel_stride, const uint8_t* data); /* :236 (-1: out of scope) */
-int32_t su_image_update(uint32_t id, uint32_t pixel_stride, const uint8_t* data);   /* :300 (-1) */
+                        uint32_t depth, uint32_t pixel_stride, const uint8_t* data); /* :236 -> image id (the pixels are copied) */
+int32_t su_image_update(uint32_t id, uint32_t pixel_stride, const uint8_t* data);   /* :300 */
 int32_t su_material_create(uint32_t id, const char* json);                /* :342 -> material id */
 int32_t su_material_update(uint32_t id, const char* json);                /* :355 */
 int32_t su_triangle_mesh_create(uint32_t id, uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles,
                                 const uint32_t* indices, uint32_t num_vertices, const float* positions,
                                 uint32_t positions_stride, const float* normals, uint32_t normals_stride,
                                 const float* tangents, uint32_t tangents_stride, const float* uvs, uint32_t uvs_stride,
-                                bool async);                              /* :379 -> shape id */
+                                bool async);                              /* :379 -> shape id. async: the BVH is built on a worker
+                                                                             thread that reads the caller's buffers until the next
+                                                                             su_render_frame / su_start_frame / mesh call joins it
+                                                                             (shape_provider.zig:299-303; commitAsync capi.zig:550) */
 int32_t su_prop_create(uint32_t shape, uint32_t num_materials, const uint32_t* materials); /* :425 -> prop id */
 int32_t su_prop_create_instance(uint32_t entity);                         /* :457 -> prop id sharing the shape and materials */
 int32_t su_light_create(uint32_t prop);                                   /* :471 */
@@ -51,12 +58,14 @@ int32_t su_render_frame(uint32_t frame);                                  /* :54
 int32_t su_export_frame(void);                                            /* :569 (-1: out of scope) */
 int32_t su_start_frame(uint32_t frame);                                   /* :581 */
 int32_t su_render_iterations(uint32_t num_steps);                         /* :602 */
-int32_t su_resolve_frame(uint32_t aov);                                   /* :613 */
+int32_t su_resolve_frame(uint32_t aov);                                   /* :613 (aov < 9 = AovValue.NumClasses: -2, the class is
+                                                                             inactive; anything else resolves the beauty) */
 int32_t su_resolve_frame_to_buffer(uint32_t aov, uint32_t width, uint32_t height, float* buffer); /* :626 */
 int32_t su_copy_framebuffer(uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height,
                             uint8_t* destination);                        /* :643 */
 int32_t su_register_log(void (*post)(uint32_t level, const char* text));  /* :726 */
-int32_t su_register_progress(void (*start)(uint32_t resolution), void (*tick)(void)); /* :731 */
+int32_t su_register_progress(void (*start)(uint32_t resolution), void (*tick)(void)); /* :731 (start(number of 32 x 32 tiles), then
+                                                                             that many ticks spread over the passes as they finish) */
 
 /* ---- extensions (not in libzyg): what a take / scene file sets and the C API cannot ---------------- */
 
@@ -75,6 +84,9 @@ int32_t zyg_su_instancer_create(uint32_t num_prototypes, const uint32_t* prototy
                                 const uint32_t* prototype_indices, const float* transformations);
 /* Thin-lens parameters of the take's camera block (camera_perspective.zig:200-240). */
 int32_t zyg_su_camera_set_lens(float aperture_radius, float focus_distance);
+/* The take's camera "crop": x0, y0, x1, y1 (x1 / y1 exclusive), clamped like Base.setResolution (camera_base.zig:32-41). Pixel
+ * ids and sampler seeds still run over the full resolution (worker.zig:127-141). x1 < 0 restores the full frame. */
+int32_t zyg_su_camera_set_crop(int32_t x0, int32_t y0, int32_t x1, int32_t y1);
 /* CUDA device used by the render calls (default 0). */
 int32_t zyg_su_set_device(int32_t ordinal);
 /* su_render_frame for a sample range: Driver.render(camera, frame, iteration, num_samples), the CLI's

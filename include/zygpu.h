@@ -137,6 +137,16 @@ int   zygpu_upload_film(zygpu_device* dev, const float* film, uint32_t num_pixel
 /* Device pointer of the film for the multi-GPU reduce (one ncclReduce(sum, fp32) per frame). */
 void* zygpu_film_device(zygpu_device* dev, uint64_t* num_floats);
 int   zygpu_synchronize(zygpu_device* dev);
+/* The film combine of the multi-GPU split: one ncclReduce(sum, fp32) of the W*H*4 film to `root`, enqueued
+ * on the render stream behind the passes. `nccl_comm` is the caller's ncclComm_t; the library resolves ncclReduce from the NCCL
+ * already loaded in the process, it does not link one. */
+int   zygpu_reduce_film(zygpu_device* dev, void* nccl_comm, int root);
+/* CUDA ordinal the device was created on. */
+int   zygpu_device_ordinal(zygpu_device* dev);
+/* Progress of the asynchronous zygpu_render calls since zygpu_create: passes enqueued and passes the device has finished
+ * (Progressor.tick granularity of the device path; driver.zig:305 ticks per tile). */
+uint32_t zygpu_passes_enqueued(zygpu_device* dev);
+uint32_t zygpu_passes_completed(zygpu_device* dev);
 /* The CUDA stream (cudaStream_t) the render calls are enqueued on, for events and for ordering a collective after a
  * pass. NULL before the first zygpu_upload_scene / zygpu_set_view. */
 void* zygpu_render_stream(zygpu_device* dev);
@@ -147,6 +157,7 @@ typedef struct ZygpuRenderStats {
     uint64_t shadow_rays;     /* Scene.visibility calls */
     uint64_t kernel_launches; /* launches of this library's kernels */
     uint64_t passes;
+    uint64_t overflow_retries; /* passes run again with a larger shadow-record reservation */
 } ZygpuRenderStats;
 /* Totals since the last zygpu_clear_film; synchronises the render stream. */
 int zygpu_render_stats(zygpu_device* dev, ZygpuRenderStats* stats);

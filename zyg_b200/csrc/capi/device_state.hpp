@@ -6,6 +6,7 @@
 #include "../device/render.cuh"
 #include "../device/trace.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -58,7 +59,8 @@ struct RenderState {
 
     zygpu::PathState   paths{};
     std::vector<void*> path_buffers;
-    uint32_t           max_light_samples = 1;  // shadow records one path may need
+    uint32_t           max_light_samples   = 1;  // shadow records reserved per path
+    uint32_t           worst_light_samples = 1;  // what a path vertex can need at most (Tree.potentialMaxLights)
 
     float4*  film        = nullptr;
     float4*  resolved    = nullptr;
@@ -67,6 +69,11 @@ struct RenderState {
     cudaStream_t stream = nullptr;
 
     ZygpuRenderStats stats{};
+    uint64_t         stats_carry[2] = {0, 0};  // closest / shadow rays counted by path buffers that were replaced since the clear
+
+    // progress: passes enqueued by zygpu_render / passes the device has finished (a host function on the stream counts them)
+    uint32_t              passes_enqueued = 0;
+    std::atomic<uint32_t> passes_completed{0};
 };
 
 struct zygpu_device {

@@ -11,7 +11,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <memory>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -27,6 +29,18 @@ struct Engine {
     uint32_t frame     = 0;
     uint32_t iteration = 0;
 
+    // Scene.compile + upload are skipped while nothing was edited since the last frame (driver.zig:154-180 recompiles every
+    // frame; the products are the same, so the device keeps them)
+    uint64_t uploaded_revision = ~0ull;
+
+    // su_triangle_mesh_create(async = true): the BVH is built on a worker thread and joined by the next call that needs a
+    // compiled scene or starts another build (one outstanding build, pool.zig:155-162; commitAsync, capi.zig:550,583)
+    std::thread async_build;
+    uint32_t    async_shape  = 0;
+    zyg_mesh*   async_mesh   = nullptr;
+    int         async_result = 0;
+    std::string async_error;
+
     std::vector<float> target;  // Driver.target: resolved RGBA of the last su_resolve_frame
 
     void (*log_post)(uint32_t, const char*) = nullptr;
@@ -34,6 +48,8 @@ struct Engine {
     void (*progress_tick)()                 = nullptr;
 
     ~Engine() {
+        if (async_build.joinable()) async_build.join();
+        if (async_mesh) zyg_mesh_free(async_mesh);
         if (device) zygpu_destroy(device);
         for (zyg_mesh* m : meshes) zyg_mesh_free(m);
     }
@@ -42,6 +58,8 @@ struct Engine {
 std::unique_ptr<Engine> g_engine;
 
 enum LogLevel : uint32_t { Info = 0, Warning = 1, Error = 2 };  // log.zig:5-7
+
+constexpr uint32_t kNumAovClasses = 9;  // AovValue.NumClasses, rendering/sensor/aov/aov_value.zig:10-44; capi.zig:615, 633
 
 void logf(uint32_t level, const char* fmt, ...) {
     char    buf[512];
@@ -62,13 +80,36 @@ bool parse(const char* text, zyg::json::Value& out) {
     return p.parse(out);
 }
 
-// Scene.compile + upload + view, the host half of Driver.startFrame (driver.zig:154-180)
-int prepareFrame(Engine& e) {
-    std::string error;
-    if (!e.scene.compile(error)) {
-        logf(Error, "%s", error.c_str());
+// commitAsync, capi.zig:550,583 / shape_provider.zig:127-144: the finished tree of an asynchronous build becomes the shape
+int commitAsync(Engine& e) {
+    if (!e.async_build.joinable()) return 0;
+    e.async_build.join();
+    if (0 != e.async_result || !e.async_mesh) {
+        logf(Error, "%s", e.async_error.c_str());  // the reference swallows the failure (shape_provider.zig:326-328); the shape stays empty
         return -1;
     }
+    e.meshes[e.async_shape - 7] = e.async_mesh;
+    e.scene.setMesh(e.async_shape, e.async_mesh);
+    e.async_mesh = nullptr;
+    return 0;
+}
+
+int compileScene(Engine& e) {
+    if (0 != commitAsync(e)) return -1;
+    std::string error;
+    const bool  ok = e.scene.compile(error);
+    for (const std::string& w : e.scene.warnings()) logf(Warning, "%s", w.c_str());
+    e.scene.warnings().clear();
+    if (!ok) logf(Error, "%s", error.c_str());
+    return ok ? 0 : -1;
+}
+
+// Scene.compile + upload + view, the host half of Driver.startFrame (driver.zig:154-180). The reference recompiles every frame;
+// the products only change when the scene was edited, so an unchanged scene keeps what the device already holds.
+int prepareFrame(Engine& e) {
+    if (0 != commitAsync(e)) return -1;
+    if (e.device && e.uploaded_revision == e.scene.revision()) return 0;
+    if (0 != compileScene(e)) return -1;
     if (!e.device) {
         if (0 != zygpu_create(e.device_ordinal, &e.device)) {
             e.device = nullptr;
@@ -80,7 +121,22 @@ int prepareFrame(Engine& e) {
         logf(Error, "%s", zygpu_last_error());
         return -1;
     }
+    e.uploaded_revision = e.scene.revision();
     return 0;
+}
+
+// Progressor.tick (progress.zig:3-25): the reference ticks once per finished tile (driver.zig:305). The device path has no
+// tiles; it finishes passes (all pixels x some samples), so the `tiles` ticks are spread over the passes as they complete.
+void tickWhileRendering(Engine& e, uint32_t tiles, uint32_t first_pass) {
+    const uint32_t total = zygpu_passes_enqueued(e.device) - first_pass;
+    uint32_t       ticked = 0;
+    for (;;) {
+        const uint32_t finished = zygpu_passes_completed(e.device) - first_pass;
+        const uint32_t due      = 0 == total ? tiles : uint32_t(uint64_t(tiles) * std::min(finished, total) / total);
+        for (; ticked < due; ++ticked) e.progress_tick();
+        if (finished >= total) break;
+        std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
 }
 
 int renderRange(Engine& e, uint32_t frame, uint32_t iteration, uint32_t num_samples) {
@@ -93,12 +149,15 @@ int renderRange(Engine& e, uint32_t frame, uint32_t iteration, uint32_t num_samp
     const uint32_t tiles = ((e.scene.width() + 31) / 32) * ((e.scene.height() + 31) / 32);
     if (e.progress_start) e.progress_start(tiles);
 
-    if (0 != zygpu_clear_film(e.device) || 0 != zygpu_render(e.device, iteration, spp) || 0 != zygpu_synchronize(e.device)) {
+    const uint32_t first_pass = zygpu_passes_enqueued(e.device);
+    if (0 != zygpu_clear_film(e.device) || 0 != zygpu_render(e.device, iteration, spp)) {
         logf(Error, "%s", zygpu_last_error());
         return -1;
     }
-    if (e.progress_tick) {
-        for (uint32_t t = 0; t < tiles; ++t) e.progress_tick();
+    if (e.progress_tick) tickWhileRendering(e, tiles, first_pass);
+    if (0 != zygpu_synchronize(e.device)) {
+        logf(Error, "%s", zygpu_last_error());
+        return -1;
     }
     return 0;
 }
@@ -187,12 +246,26 @@ int32_t su_triangle_mesh_create(uint32_t /*id*/, uint32_t num_parts, const uint3
                                 const uint32_t* indices, uint32_t num_vertices, const float* positions,
                                 uint32_t positions_stride, const float* normals, uint32_t normals_stride,
                                 const float* /*tangents*/, uint32_t /*tangents_stride*/, const float* uvs,
-                                uint32_t uvs_stride, bool /*async*/) {
+                                uint32_t uvs_stride, bool async) {
     if (!g_engine) return -1;
     if (num_triangles < 1 || num_vertices < 1 || !positions) return -1;  // capi.zig:398-408
 
-    // The BVH is built before the call returns; the reference defers it to its async thread and joins at the
-    // next commitAsync (capi.zig:415-417, 550), which leaves nothing observable to a caller.
+    Engine& e = *g_engine;
+    commitAsync(e);  // one outstanding build (pool.zig:155-162): a second request waits for the first
+    if (async) {
+        // shape_provider.zig:299-303, 847-913: the build reads the caller's buffers on the async thread; they must outlive the
+        // next call that commits (su_render_frame / su_start_frame / another mesh). The shape id is handed out at once.
+        e.meshes.push_back(nullptr);
+        e.async_shape  = e.scene.addMesh(nullptr, num_parts > 0 ? num_parts : 1);
+        e.async_result = 0;
+        e.async_build  = std::thread([=, &e] {
+            e.async_result = zyg_mesh_build(num_parts, parts, num_triangles, indices, num_vertices, positions, positions_stride, normals,
+                                            normals_stride, uvs, uvs_stride, 0, &e.async_mesh);
+            if (0 != e.async_result) e.async_error = zygpu_last_error();  // the error slot is per thread
+        });
+        return int32_t(e.async_shape);
+    }
+
     zyg_mesh* mesh = nullptr;
     if (0 != zyg_mesh_build(num_parts, parts, num_triangles, indices, num_vertices, positions, positions_stride, normals,
                             normals_stride, uvs, uvs_stride, 0, &mesh)) {
@@ -295,7 +368,7 @@ int32_t su_render_iterations(uint32_t num_steps) {
 int32_t su_resolve_frame(uint32_t aov) {
     if (!g_engine || !g_engine->device) return -1;
     Engine& e = *g_engine;
-    if (aov < 12) return -2;  // AOV classes are inactive (aov_value.zig; capi.zig:620)
+    if (aov < kNumAovClasses) return -2;  // the AOV classes are inactive (no su_aovs_create); anything above resolves the beauty
     const uint32_t n = e.scene.width() * e.scene.height();
     e.target.resize(size_t(n) * 4);
     return 0 == zygpu_resolve(e.device, e.target.data(), n) ? 0 : -1;
@@ -304,7 +377,7 @@ int32_t su_resolve_frame(uint32_t aov) {
 int32_t su_resolve_frame_to_buffer(uint32_t aov, uint32_t width, uint32_t height, float* buffer) {
     if (!g_engine || !g_engine->device || !buffer) return -1;
     Engine& e = *g_engine;
-    if (aov < 12) return -2;
+    if (aov < kNumAovClasses) return -2;
     const uint32_t n = std::min(width * height, e.scene.width() * e.scene.height());  // capi.zig:628
     return 0 == zygpu_resolve(e.device, buffer, n) ? 0 : -1;
 }
@@ -377,13 +450,16 @@ int32_t zyg_su_set_device(int32_t ordinal) {
     return 0;
 }
 
+int32_t zyg_su_camera_set_crop(int32_t x0, int32_t y0, int32_t x1, int32_t y1) {
+    if (!g_engine) return -1;
+    g_engine->scene.setCrop(x0, y0, x1, y1);
+    return 0;
+}
+
 int32_t zyg_su_compile(const ZygpuScene** scene, const ZygpuView** view) {
     if (!g_engine) return -1;
-    std::string error;
-    if (!g_engine->scene.compile(error)) {
-        logf(Error, "%s", error.c_str());
-        return -1;
-    }
+    if (0 != compileScene(*g_engine)) return -1;
+    g_engine->uploaded_revision = ~0ull;  // compile() rebuilt the arrays the last upload was made from
     if (scene) *scene = &g_engine->scene.scene();
     if (view) *view = &g_engine->scene.view();
     return 0;

@@ -6,7 +6,9 @@
 #include "../host/mesh_handle.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
+#include <dlfcn.h>
 
 namespace {
 
@@ -86,7 +88,7 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint3
                             0 != allocPath(r, &p.queue_l, capacity))) {
         return -1;
     }
-    CUDA_OK(cudaMemset(p.counters, 0, 16 * sizeof(uint32_t)));
+    CUDA_OK(cudaMemsetAsync(p.counters, 0, 16 * sizeof(uint32_t), r.stream));  // ordered before the pass (the stream is non-blocking)
     p.capacity      = capacity;
     p.shadow_stride = shadow_stride;
     p.lanes         = lanes;
@@ -101,8 +103,18 @@ void zygpuReleaseRender(zygpu_device* dev) {
     freeAll(r.path_buffers);
     cudaFree(r.film);
     cudaFree(r.resolved);
-    if (r.stream) cudaStreamDestroy(r.stream);
-    r = RenderState{};
+    if (r.stream) {
+        cudaStreamSynchronize(r.stream);  // host functions of finished passes still point at this state
+        cudaStreamDestroy(r.stream);
+    }
+    r.scene_buffer_bytes.clear();
+    r.scene_buffer_cursor = 0;
+    r.scene               = zygpu::SceneDevice{};
+    r.paths               = zygpu::PathState{};
+    r.has_scene = r.has_view = r.has_meshes = false;
+    r.film = r.resolved = nullptr;
+    r.film_pixels       = 0;
+    r.stream            = nullptr;
 }
 
 extern "C" {
@@ -260,18 +272,24 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
 
     // shadow records one path vertex can need: every light the tree may return times its sample count
     // (Tree.potentialMaxLights, light_tree.zig:331-344), capped like the reference's buffers (64 picks x 64 samples)
-    uint64_t potential = 0;
-    uint32_t most      = 1;
+    uint64_t potential = 0, worst = 0;
+    uint32_t most = 1, worst_most = 1;
     for (uint32_t l = 0; l < scene->num_lights; ++l) {
         // Light.potentialMaxSamples, light.zig:77-85: a mesh light can return a sample per leaf its primitive tree splits into
-        // (2^6 = Shape.MaxSamples); the budget below assumes 8, zygpu_synchronize reports a vertex that needed more
-        const uint32_t n = ZYGPU_NULL != scene->lights[l].sampler ? 8u : std::max(1u, scene->lights[l].num_samples);
+        // (2^6 = Shape.MaxSamples). The first reservation assumes 8; a pass in which a vertex needed more is run again with a
+        // larger one (zygpu_render), so no sample is ever dropped.
+        const bool     mesh = ZYGPU_NULL != scene->lights[l].sampler && ZYG_LIGHT_PROP_IMAGE != scene->lights[l].light_class;
+        const uint32_t n    = mesh ? 8u : std::max(1u, scene->lights[l].num_samples);
+        const uint32_t w    = mesh ? 64u : n;
         potential += n;
-        most = std::max(most, n);
+        worst += w;
+        most       = std::max(most, n);
+        worst_most = std::max(worst_most, w);
     }
     // the tree returns at most Tree.MaxLights = 64 picks (light_tree.zig:249), each with up to `most` samples
-    r.max_light_samples = uint32_t(std::min<uint64_t>(std::max<uint64_t>(potential, 1), 64ull * std::min(most, 64u)));
-    {  // records are reserved per path slot: keep the reservation moderate (ZYGPU_MAX_LIGHT_SAMPLES overrides)
+    r.max_light_samples   = uint32_t(std::min<uint64_t>(std::max<uint64_t>(potential, 1), 64ull * std::min(most, 64u)));
+    r.worst_light_samples = uint32_t(std::min<uint64_t>(std::max<uint64_t>(worst, 1), 64ull * std::min(worst_most, 64u)));
+    {  // records are reserved per path slot: keep the first reservation moderate (ZYGPU_MAX_LIGHT_SAMPLES overrides)
         const char*    v   = getenv("ZYGPU_MAX_LIGHT_SAMPLES");
         const uint32_t cap = v ? uint32_t(std::max(1, atoi(v))) : 128u;
         r.max_light_samples = std::min(r.max_light_samples, cap);
@@ -333,6 +351,7 @@ int zygpu_clear_film(zygpu_device* dev) {
     CUDA_OK(cudaMemsetAsync(r.film, 0, size_t(r.film_pixels) * sizeof(float4), r.stream));
     if (r.paths.counters) CUDA_OK(cudaMemsetAsync(r.paths.counters, 0, 16 * sizeof(uint32_t), r.stream));
     r.stats = ZygpuRenderStats{};
+    r.stats_carry[0] = r.stats_carry[1] = 0;
     return 0;
 }
 
@@ -349,18 +368,23 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
     const uint64_t   padded = uint64_t(pw) * ph;
     if (padded > 0xFFFFFFFFull) return fail("zygpu_render: resolution too large");
 
-    // a pass holds at most 64 Mi shadow records (3 GiB): scenes whose vertices can sample many lights trace fewer paths per pass
-    const uint64_t target   = std::min<uint64_t>(targetPathsPerPass(), std::max<uint64_t>(padded, (64ull << 20) / r.max_light_samples));
-    const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(num_samples, target / padded)));
-    const uint64_t capacity = padded * per_pass;
-    if (capacity > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
-    const uint32_t lanes = r.can_split ? 4 : 1;
-    if (capacity * lanes > 0xFFFFFFFFull) return fail("zygpu_render: pass too large");
-    if (0 != ensurePaths(r, uint32_t(capacity), r.max_light_samples, lanes, r.deferred_lights, r.has_textures, r.has_image_area_lights)) return -1;
+    const uint32_t lanes  = r.can_split ? 4 : 1;
     const uint32_t rounds = lanes;
-
     // extend / shadow are one kernel each (prop-tree walk) plus the persistent mesh kernel when the scene has meshes
     const uint32_t trace_extra = r.has_meshes ? 1 : 0;
+
+    // Samples per pass for the current shadow-record reservation: a pass holds at most 64 Mi shadow records (3 GiB), so scenes
+    // whose vertices can sample many lights trace fewer paths per pass. 0 = a single frame of paths does not fit.
+    auto samplesPerPass = [&]() -> uint32_t {
+        const uint64_t target   = std::min<uint64_t>(targetPathsPerPass(), std::max<uint64_t>(padded, (64ull << 20) / r.max_light_samples));
+        const uint32_t per_pass = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(num_samples, target / padded)));
+        const uint64_t capacity = padded * per_pass;
+        if (capacity * lanes > 0xFFFFFFFFull || capacity * r.max_light_samples > 0xFFFFFFFFull) return 0;  // 32-bit vertex / record ids
+        return per_pass;
+    };
+    uint32_t per_pass = samplesPerPass();
+    if (0 == per_pass) return fail("zygpu_render: %llu paths x %u shadow records per pass exceed the 32-bit record ids", (unsigned long long)padded, r.max_light_samples);
+    if (0 != ensurePaths(r, uint32_t(padded * per_pass), r.max_light_samples, lanes, r.deferred_lights, r.has_textures, r.has_image_area_lights)) return -1;
 
     for (uint32_t done = 0; done < num_samples;) {
         const uint32_t k = std::min(per_pass, num_samples - done);
@@ -411,13 +435,66 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
             }
         }
 
+        // A vertex that produced more light samples than a slot reserves sets counters[3] and drops the extra records. Where the
+        // reservation is below what the light tree can return (mesh lights, the 128-record cap) the flag is read before the pass
+        // reaches the film: an overflowed pass is discarded and run again with twice the reservation, so the film never sees a
+        // biased sample. Scenes whose reservation is exact skip the read and stay fully asynchronous.
+        if (r.max_light_samples < r.worst_light_samples) {
+            uint32_t c[8];
+            CUDA_OK(cudaMemcpyAsync(c, r.paths.counters, sizeof(c), cudaMemcpyDeviceToHost, r.stream));
+            CUDA_OK(cudaStreamSynchronize(r.stream));
+            if (0 != c[3]) {
+                r.stats_carry[0] += c[5];  // the ray counters restart with the new buffers
+                r.stats_carry[1] += c[6];
+                r.max_light_samples = std::min(r.worst_light_samples, r.max_light_samples * 2);
+                per_pass            = samplesPerPass();
+                if (0 == per_pass) return fail("zygpu_render: %llu paths x %u shadow records per pass exceed the 32-bit record ids", (unsigned long long)padded, r.max_light_samples);
+                if (0 != ensurePaths(r, uint32_t(padded * per_pass), r.max_light_samples, lanes, r.deferred_lights, r.has_textures, r.has_image_area_lights)) return -1;
+                r.stats.overflow_retries += 1;
+                continue;  // same `done`: the pass is rendered again
+            }
+        }
+
         CUDA_OK(zygpu::launchFilm(view, r.paths, pass, r.film, r.stream));
         r.stats.kernel_launches += 1;
 
         r.stats.camera_samples += uint64_t(view.crop[2] - view.crop[0] + 2 * fr) * uint64_t(view.crop[3] - view.crop[1] + 2 * fr) * k;
         r.stats.passes += 1;
+        r.passes_enqueued += 1;
+        CUDA_OK(cudaLaunchHostFunc(r.stream, [](void* counter) { static_cast<std::atomic<uint32_t>*>(counter)->fetch_add(1); }, &r.passes_completed));
         done += k;
     }
+    return 0;
+}
+
+uint32_t zygpu_passes_enqueued(zygpu_device* dev) { return dev ? dev->render.passes_enqueued : 0; }
+uint32_t zygpu_passes_completed(zygpu_device* dev) { return dev ? dev->render.passes_completed.load() : 0; }
+
+int zygpu_device_ordinal(zygpu_device* dev) { return dev ? dev->ordinal : -1; }
+
+// One ncclReduce(sum, fp32) of the weighted-sum film to `root`, enqueued on the render stream behind the passes. NCCL is not a
+// link-time dependency: the symbols are taken from the NCCL the process already loaded (the one that made `nccl_comm`).
+int zygpu_reduce_film(zygpu_device* dev, void* nccl_comm, int root) {
+    if (!dev || !nccl_comm) return fail("zygpu_reduce_film: null argument");
+    RenderState& r = dev->render;
+    if (!r.film) return fail("zygpu_reduce_film: no view set");
+    using ReduceFn = int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
+    using ErrorFn  = const char* (*)(int);
+    static ReduceFn reduce = nullptr;
+    static ErrorFn  error  = nullptr;
+    if (!reduce) {
+        void* sym = dlsym(RTLD_DEFAULT, "ncclReduce");
+        if (!sym) {
+            if (void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL)) sym = dlsym(h, "ncclReduce");
+        }
+        if (!sym) return fail("zygpu_reduce_film: no NCCL in this process (ncclReduce not found)");
+        reduce = reinterpret_cast<ReduceFn>(sym);
+        error  = reinterpret_cast<ErrorFn>(dlsym(RTLD_DEFAULT, "ncclGetErrorString"));
+    }
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    constexpr int kNcclFloat32 = 7, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t, nccl.h
+    const int rc = reduce(r.film, r.film, size_t(r.film_pixels) * 4, kNcclFloat32, kNcclSum, root, nccl_comm, r.stream);
+    if (0 != rc) return fail("zygpu_reduce_film: ncclReduce failed: %s", error ? error(rc) : "?");
     return 0;
 }
 
@@ -425,7 +502,7 @@ int zygpu_synchronize(zygpu_device* dev) {
     if (!dev) return fail("zygpu_synchronize: null device");
     CUDA_OK(cudaSetDevice(dev->ordinal));
     if (dev->render.stream) CUDA_OK(cudaStreamSynchronize(dev->render.stream));
-    if (dev->render.paths.counters) {
+    if (dev->render.paths.counters) {  // cannot happen any more (zygpu_render re-runs such a pass); kept as a tripwire
         uint32_t overflow = 0;
         CUDA_OK(cudaMemcpy(&overflow, dev->render.paths.counters + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (0 != overflow) return fail("zygpu_render: a path vertex produced more light samples than the %u reserved", dev->render.max_light_samples);
@@ -485,8 +562,8 @@ int zygpu_render_stats(zygpu_device* dev, ZygpuRenderStats* stats) {
     if (r.paths.counters) {
         uint32_t c[8];
         CUDA_OK(cudaMemcpy(c, r.paths.counters, sizeof(c), cudaMemcpyDeviceToHost));
-        stats->closest_rays = c[5];
-        stats->shadow_rays  = c[6];
+        stats->closest_rays = r.stats_carry[0] + c[5];
+        stats->shadow_rays  = r.stats_carry[1] + c[6];
     }
     return 0;
 }

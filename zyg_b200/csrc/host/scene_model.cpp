@@ -283,6 +283,7 @@ SceneModel::SceneModel() : specular_threshold_(kMinAlpha) {
 }
 
 bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
+    touch();
     if (id >= materials_.size()) return false;
     const json::Value* rendering = material.get("rendering");
     if (!rendering || json::Value::Object != rendering->kind) return false;
@@ -302,6 +303,8 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
                     em.filter    = mode[2];
                 } else if ("two_sided" == e.first) {
                     m.flags = e.second.boolean ? (m.flags | ZYG_MATERIAL_TWO_SIDED) : (m.flags & ~ZYG_MATERIAL_TWO_SIDED);
+                } else {
+                    warnings_.push_back("material " + std::to_string(id) + ": Light parameter \"" + e.first + "\" is not supported by the device path and is ignored");
                 }
             }
         } else if ("Substitute" == entry.first && ZYG_MATERIAL_SUBSTITUTE == m.type) {  // updateSubstitute, :254-330
@@ -340,6 +343,8 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
                     m.priority = int32_t(e.second.number);
                 } else if ("two_sided" == k) {
                     m.flags = e.second.boolean ? (m.flags | ZYG_MATERIAL_TWO_SIDED) : (m.flags & ~ZYG_MATERIAL_TWO_SIDED);
+                } else {  // coating, flakes, normal / surface / rotation / mask maps, attenuation, volumetric_anisotropy, ...
+                    warnings_.push_back("material " + std::to_string(id) + ": Substitute parameter \"" + k + "\" is not supported by the device path and is ignored");
                 }
             }
         } else if ("Glass" == entry.first && ZYG_MATERIAL_GLASS == m.type) {  // updateGlass, :165-196
@@ -362,6 +367,8 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
                     m.abbe = float(e.second.number);
                 } else if ("thickness" == k) {
                     m.thickness = float(e.second.number);
+                } else {
+                    warnings_.push_back("material " + std::to_string(id) + ": Glass parameter \"" + k + "\" is not supported by the device path and is ignored");
                 }
             }
             // Glass.setVolumetric -> attenuationCoefficient, collision_coefficients.zig:35-44
@@ -387,6 +394,7 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
 }
 
 int SceneModel::createMaterial(const json::Value& material) {
+    touch();
     const json::Value* rendering = material.get("rendering");
     if (!rendering || json::Value::Object != rendering->kind) return -1;  // Error.NoRenderNode
 
@@ -414,6 +422,7 @@ int SceneModel::createMaterial(const json::Value& material) {
 
 int SceneModel::createImage(uint32_t id, uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height, uint32_t depth,
                             uint32_t pixel_stride, const uint8_t* data) {
+    touch();
     // capi.zig:29-35 Format: UInt8 0, UInt16 1, UInt32 2, Float16 3, Float32 4
     const uint32_t bpc = 0 == format ? 1u : ((1 == format || 3 == format) ? 2u : 4u);
     if (3 != num_channels || !(0 == format || 4 == format) || 0 == width || 0 == height || 1 != depth || !data) return -1;
@@ -431,6 +440,7 @@ int SceneModel::createImage(uint32_t id, uint32_t format, uint32_t num_channels,
 }
 
 int SceneModel::updateImage(uint32_t id, uint32_t pixel_stride, const uint8_t* data) {
+    touch();
     if (id >= images_.size() || !data) return -1;
     ImageRec&      img = images_[id];
     const size_t   n   = size_t(img.width) * img.height;
@@ -542,6 +552,7 @@ uint32_t SceneModel::imageSampler(uint32_t material, uint32_t shape) {
 }
 
 uint32_t SceneModel::addMesh(const zyg_mesh* mesh, uint32_t num_parts) {
+    touch();
     meshes_.push_back({mesh, num_parts, {}, {}});
     return 7 + uint32_t(meshes_.size() - 1);
 }
@@ -551,6 +562,7 @@ bool SceneModel::shapeFinite(uint32_t shape) const {  // shape.zig:94-99
 }
 
 uint32_t SceneModel::createEntity() {
+    touch();
     PropRec p;
     p.shape = ZYG_SHAPE_DISTANT;  // scene.zig:257
     props_.push_back(p);
@@ -559,6 +571,7 @@ uint32_t SceneModel::createEntity() {
 }
 
 uint32_t SceneModel::createPropShape(uint32_t shape_id, const uint32_t* materials, uint32_t num_materials, bool unoccluding) {
+    touch();
     PropRec p;
     p.shape = shape_id;
 
@@ -597,6 +610,7 @@ uint32_t SceneModel::createPropShape(uint32_t shape_id, const uint32_t* material
 }
 
 int SceneModel::createPropInstance(uint32_t entity) {
+    touch();
     if (entity >= props_.size()) return -1;
     const PropRec p = props_[entity];  // same shape, materials and parts; its own transformation
     props_.push_back(p);
@@ -614,6 +628,7 @@ int SceneModel::createPropInstance(uint32_t entity) {
 
 int SceneModel::createInstancer(const uint32_t* prototypes, uint32_t num_prototypes, const uint32_t* prototype_indices,
                                 const Transformation* transformations, uint32_t num_instances) {
+    touch();
     if (0 == num_prototypes || !prototypes || (num_instances > 0 && (!prototype_indices || !transformations))) return -1;
     for (uint32_t i = 0; i < num_prototypes; ++i) {
         if (prototypes[i] >= props_.size() || ZYGPU_NULL == props_[prototypes[i]].parts_start) return -1;
@@ -638,6 +653,7 @@ int SceneModel::createInstancer(const uint32_t* prototypes, uint32_t num_prototy
 }
 
 bool SceneModel::createLight(uint32_t entity) {  // scene.zig:342-372
+    touch();
     if (entity >= props_.size()) return false;
     const PropRec& p         = props_[entity];
     const uint32_t num_parts = p.shape >= 7 ? meshes_[p.shape - 7].num_parts : 1;
@@ -656,12 +672,14 @@ bool SceneModel::createLight(uint32_t entity) {  // scene.zig:342-372
 }
 
 bool SceneModel::setWorldTransformation(uint32_t entity, const Transformation& t) {
+    touch();
     if (entity >= props_.size()) return false;
     world_[entity] = t;
     return true;
 }
 
 bool SceneModel::setVisibility(uint32_t entity, bool in_camera, bool in_reflection, bool /*in_sss*/) {  // prop.zig:78-91
+    touch();
     if (entity >= props_.size()) return false;
     uint32_t& f = props_[entity].flags;
     f &= ~(ZYG_PROP_VISIBLE_IN_CAMERA | ZYG_PROP_VISIBLE_IN_REFLECTION | ZYG_PROP_VISIBLE_IN_SHADOW);
@@ -671,6 +689,7 @@ bool SceneModel::setVisibility(uint32_t entity, bool in_camera, bool in_reflecti
 }
 
 void SceneModel::setCamera(uint32_t width, uint32_t height) {  // capi.zig:143-167
+    touch();
     resolution_[0] = int32_t(width);
     resolution_[1] = int32_t(height);
     fov_           = degreesToRadians(80.f);
@@ -678,6 +697,7 @@ void SceneModel::setCamera(uint32_t width, uint32_t height) {  // capi.zig:143-1
 }
 
 void SceneModel::loadIntegrators(const json::Value& value) {
+    touch();
     if (const json::Value* st = value.get("specular_threshold")) {
         const float s       = float(st->number);
         specular_threshold_ = s * s;
@@ -709,6 +729,7 @@ void SceneModel::loadIntegrators(const json::Value& value) {
 }
 
 void SceneModel::loadSensor(const json::Value& value) {
+    touch();
     clamp_[0] = clamp_[1] = clamp_[2] = FLT_MAX;
     if (const json::Value* c = value.get("clamp")) {
         if (json::Value::Object == c->kind) {
@@ -736,6 +757,7 @@ void SceneModel::loadSensor(const json::Value& value) {
 }
 
 void SceneModel::loadSampler(const json::Value& value) {
+    touch();
     sampler_ = ZYG_SAMPLER_SOBOL;
     for (const auto& entry : value.object) {
         spp_ = json::readUIntMember(entry.second, "samples_per_pixel", 1);
@@ -897,6 +919,31 @@ bool SceneModel::compile(std::string& error) {
     }
     const std::vector<float>& luts = ggxLuts(error);
     if (luts.empty()) return false;
+
+    // The device intersects Rectangle, Cube, Sphere, triangle meshes, Distant and Canopy. A Disk or Dome prop would be silently
+    // invisible (and black as a light): refuse the scene instead, like thin or dispersive Glass at upload.
+    for (const PropRec& p : props_) {
+        if (ZYGPU_NULL != p.shape && p.shape >= 7 && !meshes_[p.shape - 7].mesh) {
+            error = "shape " + std::to_string(p.shape) + " has no triangle tree (its build failed)";
+            return false;
+        }
+    }
+    for (const std::vector<uint32_t>* list : {&finite_props_, &unoccluding_props_, &infinite_props_}) {
+        for (uint32_t id : *list) {
+            if (ZYG_SHAPE_DISK == props_[id].shape || ZYG_SHAPE_DOME == props_[id].shape) {
+                error = "prop " + std::to_string(id) + ": the shapes Disk and Dome are not supported by the device path";
+                return false;
+            }
+        }
+    }
+    for (const InstancerRec& ir : instancers_) {
+        for (uint32_t proto : ir.prototypes) {
+            if (ZYG_SHAPE_DISK == props_[proto].shape || ZYG_SHAPE_DOME == props_[proto].shape) {
+                error = "prop " + std::to_string(proto) + ": the shapes Disk and Dome are not supported by the device path";
+                return false;
+            }
+        }
+    }
 
     uint32_t num_props = uint32_t(props_.size());
     for (const InstancerRec& ir : instancers_) num_props += uint32_t(ir.prototypes.size());
@@ -1197,9 +1244,17 @@ bool SceneModel::compile(std::string& error) {
     v               = ZygpuView{};
     v.resolution[0] = resolution_[0];
     v.resolution[1] = resolution_[1];
-    v.crop[0] = v.crop[1] = 0;
-    v.crop[2]             = resolution_[0];
-    v.crop[3]             = resolution_[1];
+    {  // Base.setResolution, camera_base.zig:32-41
+        int32_t cc[4] = {0, 0, resolution_[0], resolution_[1]};
+        if (crop_[2] >= 0) {
+            for (int k = 0; k < 4; ++k) cc[k] = std::max(crop_[k], 0);
+            cc[2] = std::min(cc[2], resolution_[0]);
+            cc[3] = std::min(cc[3], resolution_[1]);
+            cc[0] = std::min(cc[0], cc[2]);
+            cc[1] = std::min(cc[1], cc[3]);
+        }
+        for (int k = 0; k < 4; ++k) v.crop[k] = cc[k];
+    }
 
     {  // Perspective.update, camera_perspective.zig:79-122 (mono)
         const float fr0   = float(resolution_[0]);

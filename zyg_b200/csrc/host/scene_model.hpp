@@ -62,6 +62,15 @@ class SceneModel {
     int  updateImage(uint32_t id, uint32_t pixel_stride, const uint8_t* data);
     // Registers a compiled mesh as a shape resource; returns the shape id (>= 7).
     uint32_t addMesh(const zyg_mesh* mesh, uint32_t num_parts);
+    // The mesh of a shape registered with a null handle (an asynchronous build that has finished since).
+    void     setMesh(uint32_t shape, const zyg_mesh* mesh) {
+        meshes_[shape - 7].mesh = mesh;
+        touch();
+    }
+    // Messages about accepted but ignored input (unsupported material parameters); the caller logs and clears them.
+    std::vector<std::string>& warnings() { return warnings_; }
+    // Counts the edits: a caller that kept the products of compile() may skip the next compile while it is unchanged.
+    uint64_t revision() const { return revision_; }
     uint32_t numShapes() const { return 7 + uint32_t(meshes_.size()); }
     uint32_t numMaterials() const { return uint32_t(materials_.size()); }
     uint32_t fallbackMaterial() const { return 0; }
@@ -83,12 +92,25 @@ class SceneModel {
 
     // ---- view ----
     void setCamera(uint32_t width, uint32_t height);  // su_perspective_camera_create
-    void setFov(float radians) { fov_ = radians; }
+    void setFov(float radians) {
+        fov_ = radians;
+        touch();
+    }
     void setLens(float aperture_radius, float focus_distance) {
         aperture_radius_ = aperture_radius;
         focus_distance_  = focus_distance;
+        touch();
     }
-    void setSamplesPerPixel(uint32_t spp) { spp_ = spp; }
+    // The take's camera "crop" (take_loader.zig camera block -> Base.setResolution, camera_base.zig:32-41): x0, y0, x1, y1 with
+    // x1 / y1 exclusive; clamped to the resolution at compile time. A negative x1 restores the full frame.
+    void setCrop(int32_t x0, int32_t y0, int32_t x1, int32_t y1) {
+        crop_[0] = x0, crop_[1] = y0, crop_[2] = x1, crop_[3] = y1;
+        touch();
+    }
+    void setSamplesPerPixel(uint32_t spp) {
+        spp_ = spp;
+        touch();
+    }
     void loadIntegrators(const json::Value& value);  // take.zig:131-148
     void loadSensor(const json::Value& value);       // take_loader.zig:186-232
     void loadSampler(const json::Value& value);      // take_loader.zig:142-158
@@ -105,6 +127,11 @@ class SceneModel {
     const ZygpuView&  view() const { return view_; }
 
   private:
+    void touch() { revision_ += 1; }
+    std::vector<std::string> warnings_;
+    uint64_t revision_ = 0;
+    int32_t  crop_[4]  = {0, 0, -1, -1};
+
     struct PropRec {
         uint32_t shape       = ZYGPU_NULL;
         uint32_t flags       = ZYG_PROP_VISIBLE_IN_CAMERA | ZYG_PROP_VISIBLE_IN_REFLECTION | ZYG_PROP_VISIBLE_IN_SHADOW;

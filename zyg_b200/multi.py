@@ -5,8 +5,8 @@ zyg already exposes the split: ``Driver.render(camera, frame, iteration, num_sam
 (src/core/rendering/driver.zig:115,141-142, worker.zig:145-149; CLI ``--sample / --num-samples``, options.zig:88-91),
 and the film is a linear accumulator of (sum w*rgb, sum w) (buffer_opaque.zig:39-45). One process per GPU renders its
 range with the whole scene replicated; a single reduce(sum, fp32) of the W*H*4 film to rank 0 finishes the frame.
-torch.distributed is the plumbing (NCCL over NVLink for device films, gloo for the CPU tests); no kernel of this package
-takes part in the exchange.
+The reduce is the C ABI's ``zygpu_reduce_film(dev, ncclComm_t, root)`` (include/zygpu.h), which a Zig host calls the same way;
+torch.distributed only supplies the communicator here (and the gloo plumbing of the CPU tests).
 """
 
 from __future__ import annotations
@@ -46,7 +46,46 @@ def device_film_tensor(width: int, height: int):
     ptr = L.zygpu_film_device(su.device_handle(), C.byref(n))
     if not ptr or n.value != width * height * 4:
         raise RuntimeError("no device film of that size: call su.start_frame first")
-    return torch.as_tensor(_DeviceFilm(ptr, height, width), device=torch.device("cuda", torch.cuda.current_device()))
+    return torch.as_tensor(_DeviceFilm(ptr, height, width), device=torch.device("cuda", device_ordinal()))
+
+
+def device_ordinal() -> int:
+    """CUDA ordinal of the engine's device (zyg_su_set_device), independent of torch's current device."""
+    L = _lib.load_library()
+    L.zygpu_device_ordinal.argtypes = [C.c_void_p]
+    return int(L.zygpu_device_ordinal(su.device_handle()))
+
+
+def nccl_comm(group=None) -> int:
+    """The ncclComm_t of torch's NCCL process group for the engine's device (created by the first collective)."""
+    import torch
+    import torch.distributed as dist
+
+    device = torch.device("cuda", device_ordinal())
+    backend = (group or dist.distributed_c10d._get_default_group())._get_backend(device)
+    try:
+        ptr = backend._comm_ptr()
+    except Exception:
+        ptr = 0
+    if not ptr:  # communicators are made lazily: run one collective on this device first
+        dist.all_reduce(torch.zeros(1, device=device), group=group)
+        torch.cuda.synchronize(device)
+        ptr = backend._comm_ptr()
+    return int(ptr)
+
+
+def reduce_film(root: int = 0, group=None):
+    """zygpu_reduce_film: one ncclReduce(sum, fp32) of the device film to `root`, enqueued on the render stream behind the passes."""
+    L = _lib.load_library()
+    L.zygpu_reduce_film.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    su._ok(L.zygpu_reduce_film(su.device_handle(), nccl_comm(group), root), "zygpu_reduce_film")
+
+
+def synchronize():
+    """Waits for the render stream (passes and a reduce enqueued behind them)."""
+    L = _lib.load_library()
+    L.zygpu_synchronize.argtypes = [C.c_void_p]
+    su._ok(L.zygpu_synchronize(su.device_handle()), "zygpu_synchronize")
 
 
 def render_stream():
@@ -60,12 +99,10 @@ def render_stream():
 
 
 def render_frame_distributed(width: int, height: int, spp: int, rank: int, world: int, frame: int = 0, reduce: bool = True):
-    """su_start_frame + this rank's sample range + reduce to rank 0. Returns the film tensor (complete on rank 0).
+    """su_start_frame + this rank's sample range + reduce to rank 0. Returns the film tensor (complete on rank 0); the render
+    stream has been waited for, so the tensor can be read from any stream.
 
     The caller has built the same scene on every rank and initialised torch.distributed with the NCCL backend."""
-    import torch
-    import torch.distributed as dist
-
     su.start_frame(frame)
     first, count = sample_range(rank, world, spp)
     L = _lib.load_library()
@@ -74,9 +111,8 @@ def render_frame_distributed(width: int, height: int, spp: int, rank: int, world
         su._ok(L.zygpu_render(su.device_handle(), first, count), "zygpu_render")
     film = device_film_tensor(width, height)
     if reduce and world > 1:
-        stream = render_stream()
-        with torch.cuda.stream(stream):
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        reduce_film(0)
+    synchronize()
     return film
 
 

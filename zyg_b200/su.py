@@ -39,7 +39,7 @@ def _su() -> C.CDLL:
         "su_resolve_frame": [u32], "su_resolve_frame_to_buffer": [u32, u32, u32, vp],
         "su_copy_framebuffer": [u32, u32, u32, u32, vp], "su_register_log": [vp], "su_register_progress": [vp, vp],
         "zyg_su_sensor_create": [cp], "zyg_su_instancer_create": [u32, vp, u32, vp, vp], "zyg_su_prop_create_unoccluding": [u32, u32, vp],
-        "zyg_su_camera_set_lens": [f32, f32], "zyg_su_set_device": [i32],
+        "zyg_su_camera_set_lens": [f32, f32], "zyg_su_camera_set_crop": [i32, i32, i32, i32], "zyg_su_set_device": [i32],
         "zyg_su_render_frame_range": [u32, u32, u32], "zyg_su_compile": [vp, vp],
     }
     for name, argtypes in sig.items():
@@ -82,6 +82,10 @@ def camera_set_fov(radians: float):
 
 def camera_set_lens(aperture_radius: float, focus_distance: float):
     _ok(_su().zyg_su_camera_set_lens(aperture_radius, focus_distance), "zyg_su_camera_set_lens")
+
+
+def camera_set_crop(x0: int, y0: int, x1: int, y1: int):
+    _ok(_su().zyg_su_camera_set_crop(x0, y0, x1, y1), "zyg_su_camera_set_crop")
 
 
 def sampler_create(spp: int):
