@@ -162,6 +162,16 @@ typedef struct ZygpuRenderStats {
 /* Totals since the last zygpu_clear_film; synchronises the render stream. */
 int zygpu_render_stats(zygpu_device* dev, ZygpuRenderStats* stats);
 
+/* Instrumented render traversal (the counted fetches behind the roofline of the render path, SURVEY.md §8d "B_sample"): while
+ * counting is on the closest-hit and shadow traversal kernels count their 80-byte node, 64-byte triangle-record and 32-byte
+ * prop-record fetches and their warp-level steps. zygpu_set_counting(dev, on) also zeroes the counters. */
+typedef struct ZygpuTraversalCounts {
+    uint64_t nodes, triangles, props;                 /* records fetched (per lane) */
+    uint64_t node_steps, triangle_steps, prop_steps;  /* warp-level lock-step steps of each kind */
+} ZygpuTraversalCounts;
+int zygpu_set_counting(zygpu_device* dev, int on);
+int zygpu_traversal_counts(zygpu_device* dev, ZygpuTraversalCounts* closest, ZygpuTraversalCounts* shadow);
+
 const char* zygpu_last_error(void);
 
 #ifdef __cplusplus

@@ -76,28 +76,36 @@ def test_cornell_full_config(engine):
 
 
 def test_rmse_against_high_spp_reference(engine):
-    """RMSE(device, 64 spp) within 1 % of RMSE(CPU path, 64 spp) against a 4096-spp CPU reference, and the error
-    falls at the CPU path's rate between 16 and 64 spp."""
+    """north_star: "per-pixel mean relative error against a 16k-spp reference must converge at the reference's own rate, with
+    RMSE at the tested spp within 1 % of the reference's RMSE". RMSE(device) within 1 % of RMSE(CPU path) at 16, 64 and 256 spp
+    against a 16 384-spp CPU reference, the error falls at the CPU path's rate, and so does the mean relative error."""
     w = 64
-    scenes.cornell_box(w, w, spp=4096)
+    scenes.cornell_box(w, w, spp=16384 + 256)
     scene, view = su.compile_scene()
-    truth = oracle.render(scene, view, w, w, 64, 4032)  # samples disjoint from the ones under test
+    truth = oracle.render(scene, view, w, w, 256, 16384)  # samples disjoint from the ones under test
     truth = truth[..., :3] / truth[..., 3:4]
 
     def rmse(film):
         img = film[..., :3] / film[..., 3:4]
         return float(np.sqrt(np.mean((img - truth) ** 2)))
 
-    errs = {}
-    for spp in (16, 64):
+    def mre(film):  # per-pixel mean relative error
+        img = film[..., :3] / film[..., 3:4]
+        return float(np.mean(np.abs(img - truth).sum(-1) / np.maximum(truth.sum(-1), 1e-4)))
+
+    errs, rels = {}, {}
+    for spp in (16, 64, 256):
         ref = oracle.render(scene, view, w, w, 0, spp)
         su.render_frame_range(0, 0, spp)
         gpu = download_film(w, w)
         errs[spp] = (rmse(gpu), rmse(ref))
+        rels[spp] = (mre(gpu), mre(ref))
         assert abs(errs[spp][0] - errs[spp][1]) / errs[spp][1] < 0.01
-    slope_gpu = np.log(errs[16][0] / errs[64][0]) / np.log(4.0)
-    slope_ref = np.log(errs[16][1] / errs[64][1]) / np.log(4.0)
-    assert abs(slope_gpu - slope_ref) < 0.02 and slope_gpu > 0.35
+        assert abs(rels[spp][0] - rels[spp][1]) / rels[spp][1] < 0.01
+    for table in (errs, rels):
+        slope_gpu = np.log(table[16][0] / table[256][0]) / np.log(16.0)
+        slope_ref = np.log(table[16][1] / table[256][1]) / np.log(16.0)
+        assert abs(slope_gpu - slope_ref) < 0.02 and slope_gpu > 0.35
 
 
 def test_sample_ranges_accumulate_bit_exactly(engine):
@@ -463,3 +471,148 @@ def test_full_size_configs_by_properties(engine, builder, kwargs, spp):
     second = whole[..., :3] - first[..., :3]
     a, b = first[..., :3].astype(np.float64).mean(), second.astype(np.float64).mean()
     assert abs(a - b) / (0.5 * (a + b)) < 0.05
+
+
+def _compare(w, h, spp, num_meshes=0, wavefront=False, median=5e-6, tail=5e-3, mean=2e-4):
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, h, 0, spp, num_meshes=num_meshes, wavefront_light_order=wavefront)
+    su.render_frame(0)
+    gpu = download_film(w, h)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    lit = ref[..., 3] > 0
+    assert np.median(rel[lit]) < median
+    assert (rel[lit] > 1e-3).mean() < tail
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < mean
+    return gpu, ref
+
+
+def test_thin_lens_matches_oracle(engine):
+    """Perspective.generateVertex with a lens (camera_perspective.zig:124-150): Aperture.sample maps lens_uv to the disk
+    (aperture.zig:46-53), the ray starts on the lens and passes through the point of the pinhole ray at the focus distance.
+    The defocused film differs from the pinhole film and agrees with the oracle per pixel."""
+    w, spp = 128, 16
+    scenes.cornell_box(w, w, spp=spp)
+    su.render_frame(0)
+    pinhole = download_film(w, w)
+    su.camera_set_lens(0.08, 3.9)  # focused on the centre of the box
+    gpu, ref = _compare(w, w, spp)
+    blurred = rel_error(gpu, pinhole)
+    assert (blurred > 1e-2).mean() > 0.2, "the lens left most of the film unchanged"
+    # in focus (the plane z = 0 through the light) sharp features stay: the film is not simply a blur of everything
+    assert np.isfinite(gpu).all()
+
+
+def test_sensor_clamp_matches_oracle(engine):
+    """Sensor.clamp per component class before summation (sensor.zig:177-181, 615-624): emission, direct and indirect are
+    scaled down separately where their largest channel exceeds the limit."""
+    w, spp = 128, 16
+    scenes.cornell_box(w, w, spp=spp)
+    su.render_frame(0)
+    free = download_film(w, w)
+    su.sensor_create({"clamp": {"emission": 4.0, "direct": 0.4, "indirect": 0.1}})
+    gpu, ref = _compare(w, w, spp)
+    assert gpu[..., :3].sum() < 0.9 * free[..., :3].sum(), "the clamp removed no energy"
+    lamp = free[..., :3].max(-1) > 16.0 * spp  # pixels that only see the lamp: emission 17 clamped to 4
+    assert lamp.any() and np.allclose(gpu[lamp][:, :3].max(-1) / spp, 4.0, rtol=0.2)
+
+
+def test_visibility_flags_match_oracle(engine):
+    """Prop visibility by depth (prop.zig:38-48, 78-91): the tall box is hidden from the camera but still seen in reflections
+    and still casts shadows; the short box is hidden everywhere. su_prop_set_visibility, capi.zig:535-546."""
+    w, spp = 128, 16
+    scenes.cornell_box(w, w, spp=spp, roughness=1.0)
+    su.render_frame(0)
+    both = download_film(w, w)
+    tall, short = 6, 7  # entity ids: camera 0, walls 1-5, the two boxes, the lamp
+    su.prop_set_visibility(tall, False, True)
+    su.prop_set_visibility(short, False, False)
+    gpu, ref = _compare(w, w, spp)
+    changed = rel_error(gpu, both) > 1e-2
+    assert changed.mean() > 0.05
+    # where the tall box was seen directly the back wall shows now, still shadowed by the box's shadow-ray visibility
+    su.prop_set_visibility(tall, False, False)
+    su.render_frame(0)
+    gone = download_film(w, w)
+    assert (rel_error(gone, gpu) > 1e-2).mean() > 0.01, "shadow / reflection visibility of the hidden box had no effect"
+
+
+def test_ptmis_without_light_sampling_node_uses_raw_default(engine):
+    """loadLightSampling (take.zig:263-271): without a "light_sampling" node the split threshold is the raw 0.5, not 0.5^4 —
+    the reference's own capi-test/test.py passes PTMIS that way. Many lights make the threshold visible in the film."""
+    w, spp = 96, 8
+    scenes.many_lights_scene(w, w, spp=spp, num_lights=64)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": 6}}}})
+    gpu, ref = _compare(w, w, spp, wavefront=True, median=1e-4, tail=5e-2, mean=2e-4)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": 6}, "light_sampling": {"split_threshold": 0.5}}}})
+    su.render_frame(0)
+    explicit = download_film(w, w)
+    assert (rel_error(explicit, gpu) > 1e-3).mean() > 0.05, "0.5 and 0.5^4 gave the same film"
+
+
+def test_overflowed_pass_is_rerun_not_dropped(engine, monkeypatch):
+    """A vertex that produces more light samples than a slot reserves used to drop them (a darker film, rc 0 in the progressive
+    API). The pass is now discarded and run again with a larger reservation: the film equals the one of a generous reservation."""
+    w, spp = 64, 4
+    L = lib.load_library()
+
+    class Stats(C.Structure):
+        _fields_ = [(n, C.c_uint64) for n in ("camera_samples", "closest_rays", "shadow_rays", "kernel_launches", "passes", "overflow_retries")]
+
+    L.zygpu_render_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    films = {}
+    for cap in ("2", "512"):
+        su.release()
+        monkeypatch.setenv("ZYGPU_MAX_LIGHT_SAMPLES", cap)
+        scenes.mesh_lights_scene(w, w, spp=spp, num_lights=24)
+        su.start_frame(0)
+        su.render_iterations(spp)
+        films[cap] = download_film(w, w)
+        st = Stats()
+        assert 0 == L.zygpu_render_stats(su.device_handle(), C.byref(st))
+        assert (st.overflow_retries > 0) == ("2" == cap)
+    assert films["2"].tobytes() == films["512"].tobytes() or np.allclose(films["2"], films["512"], rtol=1e-5, atol=1e-6)
+
+
+def _crop_compare(w, h, crop, spp, num_meshes, median, tail):
+    """Device vs oracle on the window `crop` of a w x h frame; pixel ids and seeds run over the full resolution."""
+    su.camera_set_crop(*crop)
+    su.sampler_create(spp)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, h, 0, spp, num_meshes=num_meshes, wavefront_light_order=True)
+    su.render_frame(0)
+    gpu = download_film(w, h)
+    x0, y0, x1, y1 = crop
+    inside = np.zeros((h, w), bool)
+    inside[y0:y1, x0:x1] = True
+    assert not gpu[~inside].any() and not ref[~inside].any(), "samples landed outside the crop"
+    g, r = gpu[y0:y1, x0:x1], ref[y0:y1, x0:x1]
+    assert np.array_equal(g[..., 3], r[..., 3]) and (r[..., 3] == spp).all()
+    rel = rel_error(g, r)
+    assert np.median(rel) < median
+    assert (rel > 1e-2).mean() < tail
+    assert abs(g[..., :3].mean() - r[..., :3].mean()) / r[..., :3].mean() < 1e-3
+    return g, r
+
+
+def test_config3_and_config5_full_scene_crops_match_oracle(engine):
+    """BASELINE configs 3 and 5 at their full scene size — 20 prototypes x 250 k = 5 M triangles, 10 000 instances, diffuse /
+    rough metal / glass, Rectangle light + Distant sun — compared with the oracle per pixel on windows of the 1920 x 1080 and
+    3840 x 2160 frames (the oracle needs minutes for a whole frame). A traversal bug that needs the full TLAS depth or many
+    mesh candidates per ray shows here; the miniature scenes of the other tests cannot see it."""
+    kwargs = {"grid": (100, 100), "prototypes": 20, "quads": (500, 250), "sun": 60.0}
+    n = scenes.instanced_scene(1920, 1080, spp=2, **kwargs)
+    # a window across the horizon of the instance field (grazing rays cross many instances) and one near the camera
+    _crop_compare(1920, 1080, (640, 300, 1280, 480), 2, n, 1e-5, 2e-2)
+    _crop_compare(1920, 1080, (200, 800, 520, 980), 2, n, 1e-5, 2e-2)
+    su.perspective_camera_create(3840, 2160)  # config 5: the same scene at 4K
+    su.camera_set_fov(float(np.radians(50.0)))
+    _crop_compare(3840, 2160, (1700, 900, 2212, 1188), 1, n, 1e-5, 2e-2)
+
+
+def test_config4_full_scene_crop_matches_oracle(engine):
+    """BASELINE config 4 at full size: 1000 emissive icosahedra + a 576-triangle emitter + 200 k triangles of diffuse geometry,
+    sky image (1024^2) + sun, light-tree sampling with split threshold 0.5, on a window of the 1920 x 1080 frame."""
+    kwargs = {"num_lights": 1000, "geometry_quads": (400, 250), "sun": 15.0, "sky": 1024, "max_depth": 8}
+    n = scenes.mesh_lights_scene(1920, 1080, spp=2, **kwargs)
+    _crop_compare(1920, 1080, (700, 400, 1220, 680), 2, n, 5e-5, 3e-2)

@@ -68,6 +68,9 @@ struct RenderState {
 
     cudaStream_t stream = nullptr;
 
+    unsigned long long* tally    = nullptr;  // zygpu_set_counting: fetch / step counters of the instrumented traversal kernels
+    bool                counting = false;
+
     ZygpuRenderStats stats{};
     uint64_t         stats_carry[2] = {0, 0};  // closest / shadow rays counted by path buffers that were replaced since the clear
 

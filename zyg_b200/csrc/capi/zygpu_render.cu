@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cfloat>
+#include <cmath>
 #include <cstdlib>
 #include <dlfcn.h>
 
@@ -103,6 +105,9 @@ void zygpuReleaseRender(zygpu_device* dev) {
     freeAll(r.path_buffers);
     cudaFree(r.film);
     cudaFree(r.resolved);
+    cudaFree(r.tally);
+    r.tally    = nullptr;
+    r.counting = false;
     if (r.stream) {
         cudaStreamSynchronize(r.stream);  // host functions of finished passes still point at this state
         cudaStreamDestroy(r.stream);
@@ -175,6 +180,36 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     d.unocc_nodes = f4;
     if (0 != uploadArray(r, scene->unoccluding_bvh.indices, scene->unoccluding_bvh.num_indices, &d.unocc_indices)) return -1;
     d.num_unocc_nodes = scene->unoccluding_bvh.num_nodes;
+
+    {  // "flattened on upload": the solid prop tree in the 8-wide quantised layout the fused traversal kernel walks
+        // world-space bounding spheres of the mesh props: the mesh's object-space sphere through the prop's transformation
+        std::vector<float> spheres(size_t(scene->num_props) * 4, 0.f);
+        for (uint32_t p = 0; p < scene->num_props; ++p) {
+            float* s = &spheres[size_t(p) * 4];
+            s[3]     = FLT_MAX;
+            const ZygpuProp& prop = scene->props[p];
+            if (ZYG_SHAPE_TRIANGLE_MESH != prop.shape || prop.mesh >= scene->num_meshes) continue;
+            const zyg::WideBvh& wb = scene->meshes[prop.mesh]->wide;
+            const ZygpuTrafo&   t  = scene->trafos[p];
+            double              c[3] = {t.position[0], t.position[1], t.position[2]};
+            double              max_scale = 0.0;
+            for (int k = 0; k < 3; ++k) {
+                const double sk = t.r[k][3];
+                max_scale       = std::max(max_scale, std::fabs(sk));
+                for (int i = 0; i < 3; ++i) c[i] += double(wb.bound_center[k]) * sk * double(t.r[k][i]);
+            }
+            const double len = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+            for (int i = 0; i < 3; ++i) s[i] = float(c[i]);
+            // slack for the fp32 arithmetic of the device test and of the object-space traversal it stands in for
+            s[3] = float(double(wb.bound_radius) * max_scale * (1.0 + 1e-4) + 1e-5 * (len + 1.0));
+        }
+        zyg::WidePropBvh wide;
+        zyg::buildWidePropBvh(scene->solid_bvh.nodes, scene->solid_bvh.num_nodes, scene->solid_bvh.indices, scene->aabbs, spheres.data(), wide);
+        if (0 != uploadArray(r, reinterpret_cast<const float4*>(wide.nodes.data()), wide.nodes.size() * 5, &f4)) return -1;
+        d.tlas_nodes = f4;
+        if (0 != uploadArray(r, reinterpret_cast<const float4*>(wide.records.data()), wide.records.size() * 3, &f4)) return -1;
+        d.tlas_recs = f4;
+    }
 
     if (0 != uploadArray(r, scene->infinite_props, scene->num_infinite_props, &d.infinite_props)) return -1;
     d.num_infinite_props = scene->num_infinite_props;
@@ -371,7 +406,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
     const uint32_t lanes  = r.can_split ? 4 : 1;
     const uint32_t rounds = lanes;
     // extend / shadow are one kernel each (prop-tree walk) plus the persistent mesh kernel when the scene has meshes
-    const uint32_t trace_extra = r.has_meshes ? 1 : 0;
+    const uint32_t trace_extra = zygpu::sceneTraceLaunches(r.has_meshes) - 1;
 
     // Samples per pass for the current shadow-record reservation: a pass holds at most 64 Mi shadow records (3 GiB), so scenes
     // whose vertices can sample many lights trace fewer paths per pass. 0 = a single frame of paths does not fit.
@@ -397,6 +432,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
         pass.num_paths       = uint32_t(padded) * k;
         pass.debug_slot      = getenv("ZYGPU_DEBUG_SLOT") ? uint32_t(strtoul(getenv("ZYGPU_DEBUG_SLOT"), nullptr, 10)) : 0xFFFFFFFFu;
 
+        r.paths.tally = r.counting ? r.tally : nullptr;
         CUDA_OK(zygpu::launchGenerate(view, r.paths, pass, r.stream));
         r.stats.kernel_launches += 1;
 
@@ -463,6 +499,36 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
         r.passes_enqueued += 1;
         CUDA_OK(cudaLaunchHostFunc(r.stream, [](void* counter) { static_cast<std::atomic<uint32_t>*>(counter)->fetch_add(1); }, &r.passes_completed));
         done += k;
+    }
+    return 0;
+}
+
+// Instrumented traversal: counts the 80-byte node, 64-byte triangle-record and 32-byte prop-record fetches of
+// the render path's closest-hit and shadow traversal. The counting kernels are slower; timing runs leave it off.
+int zygpu_set_counting(zygpu_device* dev, int on) {
+    if (!dev) return fail("zygpu_set_counting: null device");
+    RenderState& r = dev->render;
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    if (on && !r.tally) {
+        CUDA_OK(cudaMalloc(&r.tally, 12 * sizeof(unsigned long long)));
+    }
+    if (r.tally) CUDA_OK(cudaMemset(r.tally, 0, 12 * sizeof(unsigned long long)));
+    r.counting = 0 != on;
+    return 0;
+}
+
+int zygpu_traversal_counts(zygpu_device* dev, ZygpuTraversalCounts* closest, ZygpuTraversalCounts* shadow) {
+    if (!dev || !closest || !shadow) return fail("zygpu_traversal_counts: null argument");
+    RenderState& r = dev->render;
+    if (!r.tally) return fail("zygpu_traversal_counts: counting was never enabled");
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    if (r.stream) CUDA_OK(cudaStreamSynchronize(r.stream));
+    unsigned long long c[12];
+    CUDA_OK(cudaMemcpy(c, r.tally, sizeof(c), cudaMemcpyDeviceToHost));
+    ZygpuTraversalCounts* out[2] = {closest, shadow};
+    for (int k = 0; k < 2; ++k) {
+        out[k]->nodes = c[6 * k], out[k]->triangles = c[6 * k + 1], out[k]->props = c[6 * k + 2];
+        out[k]->node_steps = c[6 * k + 3], out[k]->triangle_steps = c[6 * k + 4], out[k]->prop_steps = c[6 * k + 5];
     }
     return 0;
 }

@@ -710,6 +710,350 @@ __global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathS
     }
 }
 
+// ---- fused two-level traversal -------------------------------------------------------------------------------------
+//
+// One persistent kernel walks both levels of the "two-level layout for prop instances": the prop tree (PropBvh, prop_tree.zig:
+// 56-240) collapsed on upload into the same 80-byte 8-wide quantised nodes as the mesh trees, its leaf slots pointing at prop
+// records {prop id, exact box of the reference leaf}. A lane owns a ray from the trace queue until the ray is done; the warp
+// runs lock-step steps of three kinds, each over the lanes that have that kind of work:
+//
+//   NODE      test the eight quantised child boxes of one wide node — the same code for a lane in the prop tree and a lane
+//             inside a mesh, only the node array differs
+//   TRIANGLE  one gated triangle test (lanes inside a mesh)
+//   PROP      one prop record (lanes in the prop tree): reference leaf gate, visibility flags, the prop's world box against the
+//             current max_t (Prop.intersect up to the shape call, prop.zig:163-197), then an analytic shape in place or entry into
+//             a mesh: the ray goes to object space, the prop-tree work still pending is left on the lane's stack below the mesh's
+//
+// Children are visited front to back by octant, every test uses the ray's current max_t, so instances behind the closest hit
+// so far are culled at the node or at their world box; nothing but the result goes back to HBM (the former top kernel wrote
+// 8 candidate props per ray and the mesh kernel read them back). Relative to the reference only the order in which props are
+// tested changes: the closest hit is identical except for equal-t ties between different props.
+
+// Conservative: false only if the segment [tmin, tmax] of the ray cannot touch the sphere (xyz centre, w radius).
+__device__ __forceinline__ bool segmentMeetsSphere(const RayT& ray, float4 sphere) {
+    if (FLT_MAX == sphere.w) return true;
+    const V3    oc = {sphere.x - ray.o.x, sphere.y - ray.o.y, sphere.z - ray.o.z};
+    const float dd = dot3(ray.d, ray.d);
+    const float b  = dot3(oc, ray.d);
+    const float r2 = sphere.w * sphere.w;
+    const float oo = dot3(oc, oc);
+    if (oo <= r2) return true;  // the origin is inside
+    if (b <= 0.f) return false;  // outside and heading away
+    const float tc = __fdividef(b, dd);  // parameter of the closest approach
+    const V3    pv = {oc.x - tc * ray.d.x, oc.y - tc * ray.d.y, oc.z - tc * ray.d.z};
+    if (dot3(pv, pv) > r2 * 1.0001f) return false;
+    // the entry point is no nearer than tc - r / |d|
+    return tc - sphere.w * rsqrtf(dd) * 1.0001f <= ray.tmax;
+}
+
+struct SceneStepTuning {
+    uint32_t fetch_idle;  // refill when at least this many lanes are idle
+    uint32_t weight[4];   // NODE, TRIANGLE, PROP, ENTER: the step kind with the largest (ready lanes x weight) runs
+};
+
+template <bool AnyHit, bool Count>
+__global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, PathState st, uint32_t* __restrict__ work_counter,
+                                                            SceneStepTuning tune, unsigned long long* __restrict__ tally) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    const uint32_t     lane  = threadIdx.x & 31u;
+
+    // the trace queue: closest-hit rays are vertex ids, shadow rays are records (compact list, or `stride` slots per path)
+    const uint32_t stride = st.shadow_stride;
+    const uint32_t* __restrict__ closest_queue = st.lanes > 1 ? st.queue_t : st.queue_a;
+    const bool     compact = AnyHit && nullptr != st.queue_r;
+    const uint64_t total   = AnyHit ? (compact ? uint64_t(st.counters[10]) : uint64_t(st.counters[1]) * stride)
+                                    : uint64_t(st.counters[st.lanes > 1 ? 7 : 0]);
+    const uint32_t n       = uint32_t(total < 0xFFFFFFFFull ? total : 0xFFFFFFFFull);
+
+    const uint32_t warps      = gridDim.x * (blockDim.x / 32u);
+    const uint32_t pool_items = max(32u, min(kScenePoolItems, (n / (warps * 4u)) & ~31u));
+
+    uint32_t pool_next = 0, pool_end = 0;
+    bool     exhausted = false;
+
+    bool     has_ray = false;
+    bool     in_mesh = false;
+    uint32_t item    = 0;
+    uint32_t depth_surface = 0;
+    uint32_t enter_prop = kEnd;  // a mesh prop that passed the culling tests and waits for its ENTER step
+    uint32_t cur_prop = 0, hit_prop = kEnd;
+    bool     occluded = false;
+    const float4* nodes = sc.tlas_nodes;  // of the level the lane is in
+    const float4* recs  = sc.tlas_recs;
+
+    WideRay  w;
+    uint2    stack[kWideStack];
+    uint32_t sp = 0, sp_mesh = 0;  // sp_mesh: stack depth at mesh entry (the world ray and the prop-tree entries lie below)
+    uint2    node_group = make_uint2(0u, 0u);
+    uint2    tri_group  = make_uint2(0u, 0u);
+    float    hu = 0.f, hv = 0.f;
+    uint32_t primitive = 0;
+    uint32_t traced = 0, count_nodes = 0, count_tris = 0, count_props = 0;
+    uint32_t steps[3] = {0, 0, 0};  // instrumented build: warp-level NODE / TRIANGLE / PROP + ENTER steps
+
+    for (;;) {
+        // ---- refill idle lanes
+        uint32_t idle = __ballot_sync(kFull, !has_ray);
+        while (0 != idle && !exhausted) {
+            if (pool_next >= pool_end) {
+                uint32_t base = 0;
+                if (0 == lane) base = atomicAdd(work_counter, pool_items);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= n) {
+                    exhausted = true;
+                    break;
+                }
+                pool_next = base;
+                pool_end  = min(base + pool_items, n);
+            }
+            const uint32_t avail = pool_end - pool_next;
+            const uint32_t rank  = __popc(idle & ((1u << lane) - 1u));
+            if (!has_ray && rank < avail) {
+                const uint32_t i     = pool_next + rank;
+                bool           valid = true;
+                if (compact) {
+                    item = st.queue_r[i];
+                } else if (AnyHit) {
+                    const uint32_t slot = st.queue_b[i / stride];
+                    const uint32_t k    = i % stride;
+                    valid               = k < st.sh_n[slot];
+                    item                = slot * stride + k;
+                } else {
+                    item = closest_queue[i];
+                }
+                if (valid) {
+                    uint32_t flags = 0;
+                    w.ray          = loadTraceRay<AnyHit>(st, item, depth_surface, &flags);
+                    if (!AnyHit) clipToMedium(sc, st, item, flags, w.ray);
+                    setupWideRay(w);
+                    has_ray    = true;
+                    in_mesh    = false;
+                    enter_prop = kEnd;
+                    hit_prop   = kEnd;
+                    occluded   = false;
+                    nodes      = sc.tlas_nodes;
+                    recs       = sc.tlas_recs;
+                    sp         = 0;
+                    sp_mesh    = 0;
+                    node_group = make_uint2(0u, 0 != sc.num_solid_nodes ? 0x80000000u : 0u);  // root of the prop tree
+                    tri_group  = make_uint2(0u, 0u);
+                    hu = hv    = 0.f;
+                    primitive  = 0;
+                    traced += 1;
+                }
+            }
+            pool_next += min(avail, (uint32_t)__popc(idle));
+            idle = __ballot_sync(kFull, !has_ray);
+        }
+        if (kFull == idle) break;
+
+        // ---- lock-step steps until enough lanes ran out of work
+        for (;;) {
+            const bool     ready_enter = has_ray && kEnd != enter_prop;
+            const bool     ready_node  = has_ray && !ready_enter && node_group.y > 0x00FFFFFFu;
+            const bool     ready_leaf  = has_ray && !ready_enter && 0 != tri_group.y;
+            const uint32_t cn = __popc(__ballot_sync(kFull, ready_node)) * tune.weight[0];
+            const uint32_t ct = __popc(__ballot_sync(kFull, ready_leaf && in_mesh)) * tune.weight[1];
+            const uint32_t cp = __popc(__ballot_sync(kFull, ready_leaf && !in_mesh)) * tune.weight[2];
+            const uint32_t ce = __popc(__ballot_sync(kFull, ready_enter)) * tune.weight[3];
+            const uint32_t most = max(max(cn, ct), max(cp, ce));
+
+            if (0 != ce && ce == most) {
+                // ENTER step: the ray goes to the object space of the mesh (triangle_tree.zig:49: t is shared). The world ray and the
+                // prop-tree work still pending stay on the stack below the mesh's entries.
+                if (Count) steps[2] += 1;
+                if (ready_enter) {
+                    if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
+                    if (0 != tri_group.y) stack[sp++] = tri_group;
+                    stack[sp++] = make_uint2(__float_as_uint(w.ray.o.x), __float_as_uint(w.ray.o.y));
+                    stack[sp++] = make_uint2(__float_as_uint(w.ray.o.z), __float_as_uint(w.ray.d.x));
+                    stack[sp++] = make_uint2(__float_as_uint(w.ray.d.y), __float_as_uint(w.ray.d.z));
+                    stack[sp++] = make_uint2(__float_as_uint(w.ray.inv_d.x), __float_as_uint(w.ray.inv_d.y));
+                    stack[sp++] = make_uint2(__float_as_uint(w.ray.inv_d.z), 0u);
+                    sp_mesh     = sp;
+                    const TrafoD      trafo = loadTrafo(sc.trafos, enter_prop);
+                    const MeshDevice* m     = sc.meshes + sc.props[enter_prop].mesh;
+                    nodes                   = m->wide_nodes;
+                    recs                    = m->wide_tris;
+                    w.ray                   = worldToObjectRay(trafo, w.ray);
+                    setupWideRay(w);
+                    cur_prop   = enter_prop;
+                    enter_prop = kEnd;
+                    in_mesh    = true;
+                    node_group = make_uint2(0u, 0x80000000u);
+                    tri_group  = make_uint2(0u, 0u);
+                }
+            } else if (0 != cp && cp == most) {
+                // PROP step: a lane works through its pending prop records until a mesh prop survives the culling tests
+                if (Count) steps[2] += 1;
+                if (ready_leaf && !in_mesh) {
+                    do {
+                        const uint32_t bit = 31u - __clz(tri_group.y);
+                        tri_group.y &= ~(1u << bit);
+                        if (Count) count_props += 1;
+                        const float4* rp = recs + 3 * size_t(tri_group.x + bit);
+                        const float4  r0 = __ldg(rp);
+                        const float4  r1 = __ldg(rp + 1);
+                        const uint32_t  p    = __float_as_uint(r0.w);
+                        const ZygpuProp prop = sc.props[p];
+                        // the reference reaches a prop through its leaf's box (prop_tree.zig:86-104) ...
+                        bool enter = FLT_MAX != intersectNode(make_float4(r0.x, r0.y, r0.z, 0.f), make_float4(r1.x, r1.y, r1.z, 0.f), w.ray);
+                        // ... then Prop.intersect / Prop.visibility: flags, world box (prop.zig:176-183, 212-218)
+                        enter = enter && (AnyHit ? 0 != (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW) : propVisible(prop.flags, depth_surface));
+                        enter = enter && aabbIntersect(sc.aabbs, p, w.ray);
+                        if (!enter) continue;
+                        if (ZYG_SHAPE_TRIANGLE_MESH == prop.shape) {
+                            // culling only: every triangle of the instance lies inside its bounding sphere
+                            if (segmentMeetsSphere(w.ray, __ldg(rp + 2))) {
+                                enter_prop = p;
+                                break;
+                            }
+                            continue;
+                        }
+                        const TrafoD trafo = loadTrafo(sc.trafos, p);
+                        if (AnyHit) {
+                            bool hit = false;
+                            HitD unused;
+                            switch (prop.shape) {
+                                case ZYG_SHAPE_CUBE: hit = cubeIntersectP(w.ray, trafo); break;
+                                case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, unused); break;
+                                case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, unused); break;
+                                default: break;
+                            }
+                            if (hit) {
+                                occluded     = true;
+                                sp           = 0;
+                                node_group.y = 0;
+                                tri_group.y  = 0;
+                            }
+                        } else {
+                            HitD h;
+                            bool hit = false;
+                            switch (prop.shape) {
+                                case ZYG_SHAPE_CUBE: hit = cubeIntersect(w.ray, trafo, h); break;
+                                case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, h); break;
+                                case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, h); break;
+                                default: break;
+                            }
+                            if (hit) {
+                                w.ray.tmax = h.t;
+                                hu         = h.u;
+                                hv         = h.v;
+                                primitive  = h.primitive;
+                                hit_prop   = p;
+                            }
+                        }
+                    } while (0 != tri_group.y);
+                }
+            } else if (0 != ct && ct == most) {
+                // TRIANGLE step
+                if (Count) steps[1] += 1;
+                if (ready_leaf && in_mesh) {
+                    const uint32_t bit = 31u - __clz(tri_group.y);
+                    tri_group.y &= ~(1u << bit);
+                    if (Count) count_tris += 1;
+                    MeshDevice mesh;
+                    mesh.wide_tris = recs;
+                    float    t, u, v;
+                    uint32_t prim;
+                    if (testWideTriangle(mesh, w.ray, tri_group.x + bit, t, u, v, prim)) {
+                        if (AnyHit) {
+                            occluded     = true;
+                            in_mesh      = false;
+                            sp           = 0;
+                            node_group.y = 0;
+                            tri_group.y  = 0;
+                        } else {
+                            w.ray.tmax = t;  // probe.ray.max_t = isec.t, prop_tree.zig:77
+                            hu         = u;
+                            hv         = v;
+                            primitive  = prim;
+                            hit_prop   = cur_prop;
+                        }
+                    }
+                }
+            } else {
+                // NODE step: the same code for a lane in the prop tree and a lane inside a mesh
+                if (Count && 0 != cn) steps[0] += 1;
+                if (ready_node) {
+                    const uint32_t hits  = node_group.y;
+                    const uint32_t gmask = hits & 0xffu;
+                    const uint32_t bit   = 31u - __clz(hits);
+                    node_group.y         = hits & ~(1u << bit);
+                    const uint32_t slot  = (bit - 24u) ^ w.octinv;
+                    const uint32_t rank  = __popc(gmask & ((1u << slot) - 1u));
+                    const uint32_t node_index = node_group.x + rank;
+                    if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
+                    if (0 != tri_group.y) stack[sp++] = tri_group;
+                    if (Count) count_nodes += 1;
+
+                    const float4* np = nodes + 5 * size_t(node_index);
+                    const float4  n0 = __ldg(np + 0);
+                    const float4  n1 = __ldg(np + 1);
+                    const float4  n2 = __ldg(np + 2);
+                    const float4  n3 = __ldg(np + 3);
+                    const float4  n4 = __ldg(np + 4);
+
+                    const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
+
+                    node_group.x = __float_as_uint(n1.x);
+                    node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
+                    tri_group.x  = __float_as_uint(n1.y);
+                    tri_group.y  = hitmask & 0x00FFFFFFu;
+                }
+            }
+
+            // ---- lanes that ran dry pop their stack, leave the mesh or retire their ray
+            if (has_ray && kEnd == enter_prop && node_group.y <= 0x00FFFFFFu && 0 == tri_group.y) {
+                if (in_mesh && sp == sp_mesh) {
+                    // back to the prop tree: the world ray comes off the stack, max_t is the one found so far
+                    in_mesh        = false;
+                    const uint2 e4 = stack[--sp], e3 = stack[--sp], e2 = stack[--sp], e1 = stack[--sp], e0 = stack[--sp];
+                    w.ray.o        = {__uint_as_float(e0.x), __uint_as_float(e0.y), __uint_as_float(e1.x)};
+                    w.ray.d        = {__uint_as_float(e1.y), __uint_as_float(e2.x), __uint_as_float(e2.y)};
+                    w.ray.inv_d    = {__uint_as_float(e3.x), __uint_as_float(e3.y), __uint_as_float(e4.x)};
+                    setupWideRay(w);
+                    nodes = sc.tlas_nodes;
+                    recs  = sc.tlas_recs;
+                }
+                if (0 == sp) {
+                    if (AnyHit) {
+                        st.sh_wi[item].w = occluded ? 0.f : 1.f;
+                    } else {
+                        st.ray_d[item].w = w.ray.tmax;
+                        st.hit[item]     = make_float4(hu, hv, __uint_as_float(primitive), __uint_as_float(hit_prop));
+                    }
+                    has_ray = false;
+                } else if (!in_mesh || sp > sp_mesh) {
+                    const uint2 e = stack[--sp];
+                    if (e.y > 0x00FFFFFFu) {
+                        node_group = e;
+                    } else {
+                        tri_group = e;
+                    }
+                }
+            }
+
+            const uint32_t active = __ballot_sync(kFull, has_ray);
+            if (0 == active) break;
+            if (!exhausted && 32u - __popc(active) >= tune.fetch_idle) break;
+        }
+    }
+
+    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(kFull, traced, o);
+    if (0 == lane && 0 != traced) atomicAdd(&st.counters[AnyHit ? 6 : 5], traced);
+    if (Count) {
+        unsigned long long cnt[3] = {count_nodes, count_tris, count_props};
+        for (int k = 0; k < 3; ++k) {
+            for (int o = 16; o > 0; o >>= 1) cnt[k] += __shfl_down_sync(kFull, cnt[k], o);
+            if (0 == lane) atomicAdd(tally + (AnyHit ? 6 : 0) + k, cnt[k]);
+        }
+        if (0 == lane) {
+            for (int k = 0; k < 3; ++k) atomicAdd(tally + (AnyHit ? 6 : 0) + 3 + k, (unsigned long long)steps[k]);
+        }
+    }
+}
+
 // Shape.fragment, shape.zig:205-219
 __device__ __forceinline__ void shapeFragment(const SceneDevice& sc, uint32_t prop, const RayT& ray, const HitD& isec, FragD& frag) {
     frag.prop      = prop;
@@ -2798,15 +3142,22 @@ int envInt(const char* name, int fallback) {
 }
 
 struct SceneTraceConfig {
-    int              variant;  // 0: one thread per ray (extendKernel / shadowKernel), 1: top kernel + persistent mesh kernel
+    int              variant;  // 0: one thread per ray (extendKernel / shadowKernel), 1: top kernel + persistent mesh kernel,
+                               // 2: fused two-level persistent kernel for scenes with meshes (default)
     SceneTraceTuning tune;
+    SceneStepTuning  step;
     int              blocks_per_sm;
 };
 
 const SceneTraceConfig& sceneTraceConfig() {
     static const SceneTraceConfig cfg = [] {
         SceneTraceConfig c;
-        c.variant         = envInt("ZYGPU_SCENE_TRACE", 1);
+        c.variant         = envInt("ZYGPU_SCENE_TRACE", 2);
+        c.step.fetch_idle = uint32_t(envInt("ZYGPU_FUSED_FETCH_IDLE", 10));
+        c.step.weight[0]  = uint32_t(envInt("ZYGPU_W_NODE", 1));
+        c.step.weight[1]  = uint32_t(envInt("ZYGPU_W_TRI", 2));
+        c.step.weight[2]  = uint32_t(envInt("ZYGPU_W_PROP", 2));
+        c.step.weight[3]  = uint32_t(envInt("ZYGPU_W_ENTER", 2));
         c.tune.fetch_idle = uint32_t(envInt("ZYGPU_SCENE_FETCH_IDLE", 10));  // measured: 10 beats 6 by 1 - 2 % on the sphere and instanced scenes
         c.tune.tri_num    = uint32_t(envInt("ZYGPU_TRI_NUM", 1));
         c.tune.tri_den    = uint32_t(envInt("ZYGPU_TRI_DEN", 2));
@@ -2819,6 +3170,28 @@ const SceneTraceConfig& sceneTraceConfig() {
 template <bool AnyHit>
 cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
     const SceneTraceConfig& cfg = sceneTraceConfig();
+    if (2 == cfg.variant && has_meshes) {
+        static int resident = 0, resident_counted = 0;
+        if (0 == resident) {
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sceneTracePersistent<AnyHit, false>, 128, 0);
+            if (cfg.blocks_per_sm > 0) per_sm = std::min(per_sm, cfg.blocks_per_sm);
+            resident = std::max(per_sm, 1) * numSms();
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sceneTracePersistent<AnyHit, true>, 128, 0);
+            resident_counted = std::max(per_sm, 1) * numSms();
+        }
+        const bool     counted = nullptr != st.tally;
+        const uint32_t needed  = (max_items + 127) / 128;
+        const uint32_t grid    = std::max(1u, std::min<uint32_t>(uint32_t(counted ? resident_counted : resident), needed));
+        cudaError_t    err     = cudaMemsetAsync(st.counters + 8, 0, sizeof(uint32_t), stream);
+        if (cudaSuccess != err) return err;
+        if (counted) {
+            sceneTracePersistent<AnyHit, true><<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, cfg.step, st.tally);
+        } else {
+            sceneTracePersistent<AnyHit, false><<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, cfg.step, nullptr);
+        }
+        return cudaGetLastError();
+    }
     // counters[2] = mesh queue length, counters[8] = work counter of the persistent kernel
     cudaError_t err = cudaMemsetAsync(st.counters + 2, 0, sizeof(uint32_t), stream);
     if (cudaSuccess != err) return err;
@@ -2842,6 +3215,11 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
 }
 
 }  // namespace
+
+uint32_t sceneTraceLaunches(bool has_meshes) {  // kernels per extend / shadow stage
+    const int v = sceneTraceConfig().variant;
+    return (1 == v && has_meshes) ? 2u : 1u;
+}
 
 cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
     if (0 != sceneTraceConfig().variant) return launchSceneTrace<false>(scene, st, max_items, has_meshes, stream);

@@ -79,6 +79,8 @@ struct SceneDevice {
     const float4*   solid_nodes;  // 2 per node
     const uint32_t* solid_indices;
     uint32_t        num_solid_nodes;
+    const float4*   tlas_nodes;  // the solid prop tree in the 8-wide device layout (host/wide_bvh.hpp): 5 per node
+    const float4*   tlas_recs;   // prop records of its leaf slots: 2 per record
     const float4*   unocc_nodes;
     const uint32_t* unocc_indices;
     uint32_t        num_unocc_nodes;
@@ -145,6 +147,9 @@ struct PathState {
     uint32_t* queue_t;   // lanes > 1: vertex ids to extend (lanes == 1: the slots of queue_a are the vertex ids)
     uint32_t* queue_s;   // lanes > 1: slots with more than one vertex in the current generation
     uint32_t* queue_r;   // shadow_stride > 1: the shadow records written by shade_a, compacted (null: every slot has one record)
+    unsigned long long* tally;  // instrumented passes only (else null), 12 words: node / triangle / prop-record fetches and warp-level
+                                // NODE / TRIANGLE / PROP steps of the closest-hit ([0..5]) and shadow ([6..11]) traversal — the
+                                // counted bytes behind the render-path roofline and the lanes-per-step of the lock-step loop
     uint32_t* counters;  // [0] |A|, [1] |B|, [2] |mesh queue|, [3] shadow overflow flag, [4] |next A|, [5] closest rays, [6] shadow rays,
                          // [7] |T|, [8] work counter of the persistent mesh kernel, [9] |S|, [10] |R|, [11] |L|, [12] / [13] work counters of the
                          // persistent light kernels (16 words in all)
@@ -163,6 +168,7 @@ struct PassParams {
 };
 
 cudaError_t uploadSobolDirections();
+uint32_t    sceneTraceLaunches(bool has_meshes);  // kernels one extend / shadow stage launches (for the launch statistics)
 
 cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const PassParams& pass, cudaStream_t stream);
 // The queue lengths live on the device; the grids are sized for `max_items` and exit early.

@@ -35,20 +35,16 @@ struct ANode {
     Box      leaf_box;  // leaves: exact box of the reference leaf (the gate), see wide_bvh.hpp
 };
 
+// `ItemBox(item)` = the unclipped box of leaf item `item` (a BVH-order triangle, or a position in a prop tree's index list).
+template <typename ItemBox>
 struct Augment {
-    const TriangleTree&   tree;
+    const BvhNode*        binary_nodes;
+    ItemBox               itemBox;
     std::vector<ANode>    nodes;
-    std::vector<uint32_t> leaf_prims;  // BVH-order triangle ids
+    std::vector<uint32_t> leaf_prims;  // leaf items in leaf order
 
     Box triBox(uint32_t prim, const Box& clip) const {
-        Box b = Box::empty();
-        for (int k = 0; k < 3; ++k) {
-            const float* p = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + k]) * 3];
-            for (int i = 0; i < 3; ++i) {
-                b.lo[i] = std::min(b.lo[i], p[i]);
-                b.hi[i] = std::max(b.hi[i], p[i]);
-            }
-        }
+        Box b = itemBox(prim);
         for (int i = 0; i < 3; ++i) {
             b.lo[i] = std::max(b.lo[i], clip.lo[i]);
             b.hi[i] = std::min(b.hi[i], clip.hi[i]);
@@ -105,7 +101,7 @@ struct Augment {
     int32_t convert(uint32_t n) {
         // iterative post-order would be nicer; depth is bounded by the binary tree depth (< 128, the
         // reference's own traversal stack limit node_stack.zig:2), so recursion is safe here.
-        const BvhNode& node = tree.nodes[n];
+        const BvhNode& node = binary_nodes[n];
         Box            box;
         for (int i = 0; i < 3; ++i) {
             box.lo[i] = node.min[i];
@@ -147,51 +143,24 @@ struct Augment {
 
 inline float exp2i(int e) { return std::ldexp(1.f, e); }
 
-}  // namespace
-
-void buildWideBvh(const TriangleTree& tree, WideBvh& out) {
-    Augment aug{tree, {}, {}};
-    aug.nodes.reserve(tree.nodes.size() * 2);
-    aug.leaf_prims.reserve(tree.numTriangles());
-    const int32_t root = aug.convert(0);
-
-    out.nodes.clear();
-    out.triangles.clear();
-    out.nodes.reserve(tree.nodes.size() / 3 + 1);
-    out.triangles.reserve(tree.numTriangles());
-    out.max_depth = 0;
-
+// Collapses the augmented binary tree below `root` into 8-wide quantised nodes, breadth first. `emit(item, gate)` appends the
+// record of one leaf item (in slot order: records of a node's leaf slots are consecutive from `tri_base`); returns max depth.
+template <typename Aug, typename Emit>
+uint32_t collapseWide(const Aug& aug, int32_t root, std::vector<WideNode>& out_nodes, uint32_t& num_records, Emit&& emit) {
+    uint32_t max_depth = 0;
     struct Work {
         int32_t  anode;  // augmented node that becomes this wide node
         uint32_t wide;
         uint32_t depth;
     };
     std::deque<Work> queue;
-    out.nodes.emplace_back();
+    out_nodes.emplace_back();
     queue.push_back({root, 0, 1});
-
-    auto emitTriangle = [&](uint32_t prim, const Box& gate) {
-        TriRecord    r;
-        const float* a = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + 0]) * 3];
-        const float* b = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + 1]) * 3];
-        const float* c = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + 2]) * 3];
-        for (int i = 0; i < 3; ++i) {
-            r.a[i]  = a[i];
-            r.e1[i] = b[i] - a[i];
-            r.e2[i] = c[i] - a[i];
-        }
-        r.primitive  = prim;
-        r.leaf_min_x = gate.lo[0];
-        r.leaf_min_y = gate.lo[1];
-        r.leaf_min_z = gate.lo[2];
-        for (int i = 0; i < 3; ++i) r.leaf_max[i] = gate.hi[i];
-        out.triangles.push_back(r);
-    };
 
     while (!queue.empty()) {
         const Work w = queue.front();
         queue.pop_front();
-        out.max_depth = std::max(out.max_depth, w.depth);
+        max_depth = std::max(max_depth, w.depth);
 
         // 1. gather up to eight children by repeatedly opening the inner child with the largest area
         int32_t  children[8];
@@ -276,8 +245,8 @@ void buildWideBvh(const TriangleTree& tree, WideBvh& out) {
         for (uint32_t c = 0; c < num; ++c) child_in_slot[slot_of[c]] = int(c);
 
         // 4. fill slots in slot order (inner children and triangles are addressed by rank)
-        node.child_base = uint32_t(out.nodes.size());
-        node.tri_base   = uint32_t(out.triangles.size());
+        node.child_base = uint32_t(out_nodes.size());
+        node.tri_base   = num_records;
         uint32_t tri_offset = 0;
         for (int s = 0; s < 8; ++s) {
             const int c = child_in_slot[s];
@@ -300,20 +269,109 @@ void buildWideBvh(const TriangleTree& tree, WideBvh& out) {
             if (ch.left >= 0) {
                 node.imask |= uint8_t(1u << s);
                 node.meta[s] = uint8_t((1u << 5) | (24u + uint32_t(s)));
-                const uint32_t wi = uint32_t(out.nodes.size());
-                out.nodes.emplace_back();
+                const uint32_t wi = uint32_t(out_nodes.size());
+                out_nodes.emplace_back();
                 queue.push_back({children[c], wi, w.depth + 1});
             } else {
                 const uint32_t unary = (1u << ch.count) - 1u;  // 1 -> 0b001, 2 -> 0b011, 3 -> 0b111
                 node.meta[s]         = uint8_t((unary << 5) | tri_offset);
-                for (uint32_t i = 0; i < ch.count; ++i) emitTriangle(aug.leaf_prims[ch.first + i], ch.leaf_box);
+                for (uint32_t i = 0; i < ch.count; ++i) emit(aug.leaf_prims[ch.first + i], ch.leaf_box);
+                num_records += ch.count;
                 tri_offset += ch.count;
             }
         }
         for (int a = 0; a < 3; ++a) node.e[a] = uint8_t(ex[a] + 127);
 
-        out.nodes[w.wide] = node;
+        out_nodes[w.wide] = node;
     }
+    return max_depth;
+}
+
+}  // namespace
+
+void buildWideBvh(const TriangleTree& tree, WideBvh& out) {
+    auto item_box = [&tree](uint32_t prim) {
+        Box b = Box::empty();
+        for (int k = 0; k < 3; ++k) {
+            const float* p = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + k]) * 3];
+            for (int i = 0; i < 3; ++i) {
+                b.lo[i] = std::min(b.lo[i], p[i]);
+                b.hi[i] = std::max(b.hi[i], p[i]);
+            }
+        }
+        return b;
+    };
+    Augment<decltype(item_box)> aug{tree.nodes.data(), item_box, {}, {}};
+    aug.nodes.reserve(tree.nodes.size() * 2);
+    aug.leaf_prims.reserve(tree.numTriangles());
+    const int32_t root = aug.convert(0);
+
+    out.nodes.clear();
+    out.triangles.clear();
+    out.nodes.reserve(tree.nodes.size() / 3 + 1);
+    out.triangles.reserve(tree.numTriangles());
+
+    auto emitTriangle = [&](uint32_t prim, const Box& gate) {
+        TriRecord    r;
+        const float* a = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + 0]) * 3];
+        const float* b = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + 1]) * 3];
+        const float* c = &tree.positions[size_t(tree.triangles[size_t(prim) * 3 + 2]) * 3];
+        for (int i = 0; i < 3; ++i) {
+            r.a[i]  = a[i];
+            r.e1[i] = b[i] - a[i];
+            r.e2[i] = c[i] - a[i];
+        }
+        r.primitive  = prim;
+        r.leaf_min_x = gate.lo[0];
+        r.leaf_min_y = gate.lo[1];
+        r.leaf_min_z = gate.lo[2];
+        for (int i = 0; i < 3; ++i) r.leaf_max[i] = gate.hi[i];
+        out.triangles.push_back(r);
+    };
+    uint32_t num_records = 0;
+    out.max_depth        = collapseWide(aug, root, out.nodes, num_records, emitTriangle);
+
+    const BvhNode& top = tree.nodes[0];
+    double         c[3], r2 = 0.0;
+    for (int i = 0; i < 3; ++i) c[i] = 0.5 * (double(top.min[i]) + double(top.max[i]));
+    for (uint32_t index : tree.triangles) {
+        const float* p = &tree.positions[size_t(index) * 3];
+        double       d2 = 0.0;
+        for (int i = 0; i < 3; ++i) d2 += (double(p[i]) - c[i]) * (double(p[i]) - c[i]);
+        r2 = std::max(r2, d2);
+    }
+    for (int i = 0; i < 3; ++i) out.bound_center[i] = float(c[i]);
+    out.bound_radius = float(std::sqrt(r2) * (1.0 + 1e-6)) + FLT_MIN;
+}
+
+void buildWidePropBvh(const ZygpuBvhNode* nodes, uint32_t num_nodes, const uint32_t* indices, const ZygpuAabb* aabbs, const float* spheres,
+                      WidePropBvh& out) {
+    out.nodes.clear();
+    out.records.clear();
+    out.max_depth = 0;
+    if (0 == num_nodes) return;
+    static_assert(sizeof(ZygpuBvhNode) == sizeof(BvhNode), "the prop tree uses the bvh.Node layout");
+    auto item_box = [&](uint32_t position) {
+        const ZygpuAabb& b = aabbs[indices[position]];
+        return Box{{b.min[0], b.min[1], b.min[2]}, {b.max[0], b.max[1], b.max[2]}};
+    };
+    Augment<decltype(item_box)> aug{reinterpret_cast<const BvhNode*>(nodes), item_box, {}, {}};
+    aug.nodes.reserve(size_t(num_nodes) * 2);
+    const int32_t root = aug.convert(0);
+
+    auto emit = [&](uint32_t position, const Box& gate) {
+        PropRecord r;
+        for (int i = 0; i < 3; ++i) {
+            r.leaf_min[i] = gate.lo[i];
+            r.leaf_max[i] = gate.hi[i];
+        }
+        r.prop = indices[position];
+        r.pad  = 0;
+        for (int i = 0; i < 4; ++i) r.sphere[i] = spheres ? spheres[size_t(r.prop) * 4 + i] : (3 == i ? FLT_MAX : 0.f);
+        out.records.push_back(r);
+    };
+    uint32_t num_records = 0;
+    out.max_depth        = collapseWide(aug, root, out.nodes, num_records, emit);
 }
 
 }  // namespace zyg

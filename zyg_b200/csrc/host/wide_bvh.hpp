@@ -23,6 +23,7 @@
 // path would report hits the reference misses (rays through shared edges of axis-aligned geometry).
 #pragma once
 
+#include "../../../include/zygpu_scene.h"
 #include "triangle_tree.hpp"
 
 namespace zyg {
@@ -55,8 +56,35 @@ struct WideBvh {
     std::vector<WideNode>  nodes;
     std::vector<TriRecord> triangles;
     uint32_t               max_depth = 0;  // in wide nodes, root = 1
+    // bounding sphere of the referenced vertices around the centre of the root box (object space): an instance of the mesh is
+    // only entered by rays that pass its sphere (culling only: no triangle lies outside)
+    float bound_center[3] = {0.f, 0.f, 0.f};
+    float bound_radius    = 0.f;
 };
 
 void buildWideBvh(const TriangleTree& tree, WideBvh& out);
+
+// The same node format over a prop tree (PropBvh.Tree, prop_tree.zig:31-36): the "two-level layout for prop instances". Leaf
+// slots reference prop records instead of triangle records: the prop id and the exact box of the reference leaf the prop sits in
+// (a prop duplicated by a spatial split has one record per leaf). The kernels gate a prop with the reference's slab test on that
+// box, then test the prop's own world box like Prop.intersect does (prop.zig:163-197). 48 bytes = three 16-byte loads.
+struct PropRecord {
+    float    leaf_min[3];
+    uint32_t prop;
+    float    leaf_max[3];
+    uint32_t pad;
+    float    sphere[4];  // world-space bounding sphere of a mesh prop (centre, radius); radius FLT_MAX = no sphere test
+};
+static_assert(sizeof(PropRecord) == 48, "prop record must be three 16-byte words");
+
+struct WidePropBvh {
+    std::vector<WideNode>   nodes;
+    std::vector<PropRecord> records;
+    uint32_t                max_depth = 0;
+};
+
+// `spheres`: 4 floats per prop (world-space centre, radius; FLT_MAX radius for props without one), may be null.
+void buildWidePropBvh(const ZygpuBvhNode* nodes, uint32_t num_nodes, const uint32_t* indices, const ZygpuAabb* aabbs, const float* spheres,
+                      WidePropBvh& out);
 
 }  // namespace zyg
