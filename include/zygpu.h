@@ -43,7 +43,7 @@ enum {
     ZYG_MESH_NORMALS      = 4, /* u16[2] per vertex, oct-encoded snorm16 */
     ZYG_MESH_UVS          = 5, /* f32[2] per vertex */
     ZYG_MESH_PARTS        = 6, /* u16 per BVH-order triangle */
-    ZYG_MESH_WIDE_NODES   = 7, /* 80-byte device nodes */
+    ZYG_MESH_WIDE_NODES   = 7, /* 96-byte device nodes (80 bytes + padding to three 32-byte loads) */
     ZYG_MESH_WIDE_TRIS    = 8  /* 64-byte device triangle records */
 };
 
@@ -108,7 +108,8 @@ typedef struct ZygpuTraceCounters {
  * streams). `out` is ZygpuHit[n] for the closest modes and uint32_t[n] (1 = occluded) for any-hit. */
 int zygpu_trace_batch(zygpu_device* dev, int mesh, int mode, const ZygpuRay* rays, uint64_t n, void* out);
 
-/* Device buffers, asynchronous on `stream` (a CUstream / cudaStream_t; NULL = default stream).
+/* Device buffers, asynchronous on `stream` (a CUstream / cudaStream_t; NULL = default stream). Calls on one device share a
+ * scratch region for the traversal stacks: launches of different calls must not overlap on the device (use one stream).
  * If `counters` is non-NULL the instrumented kernel runs, the call synchronises the stream and
  * writes fetch counts for this batch. */
 int zygpu_trace_batch_device(zygpu_device* dev, int mesh, int mode, const void* d_rays, uint64_t n, void* d_out,

@@ -132,7 +132,7 @@ def test_small_and_ragged_meshes(shape):
 
 
 def decode_wide(mesh):
-    raw = mesh.data(lib.MESH_WIDE_NODES).reshape(-1, 80)
+    raw = mesh.data(lib.MESH_WIDE_NODES).reshape(-1, 96)  # 80 bytes of node + 16 bytes of padding
     p = raw[:, 0:12].copy().view("<f4").reshape(-1, 3)
     e = raw[:, 12:15].astype(np.int32) - 127
     imask = raw[:, 15]

@@ -97,6 +97,11 @@ struct zygpu_device {
     int                  next_work     = 0;
     uint32_t*            workCounter() { return d_work + (next_work++ % kWorkCounters); }
 
+    // traversal-stack scratch of the ray-pool kernels (device/trace.cu): [main region][one region per staging stream]
+    void*  d_stacks           = nullptr;
+    size_t stack_bytes_main   = 0;
+    size_t stack_bytes_stream = 0;
+
     RenderState render;
 };
 

@@ -135,6 +135,11 @@ int zygpu_create(int device_ordinal, zygpu_device** out) {
     }
     CUDA_OK(cudaMalloc(&dev->d_counters, sizeof(zygpu::TraceCounters)));
     CUDA_OK(cudaMalloc(&dev->d_work, zygpu_device::kWorkCounters * sizeof(uint32_t)));
+    // traversal stacks of the ray-pool kernel: one region for the device-buffer entry point (as many blocks as can be resident), one
+    // smaller region per staging stream of the host-buffer entry point (its chunk kernels run concurrently)
+    dev->stack_bytes_main   = zygpu::traceStackBytesPerBlock() * size_t(prop.multiProcessorCount) * 8;
+    dev->stack_bytes_stream = zygpu::traceStackBytesPerBlock() * size_t(prop.multiProcessorCount) * 4;
+    CUDA_OK(cudaMalloc(&dev->d_stacks, dev->stack_bytes_main + zygpu_device::kStreams * dev->stack_bytes_stream));
     *out = dev.release();
     return 0;
 }
@@ -153,6 +158,7 @@ void zygpu_destroy(zygpu_device* dev) {
     }
     cudaFree(dev->d_counters);
     cudaFree(dev->d_work);
+    cudaFree(dev->d_stacks);
     zygpuReleaseRender(dev);
     delete dev;
 }
@@ -208,7 +214,7 @@ int zygpu_trace_batch_device(zygpu_device* dev, int mesh, int mode, const void* 
     if (counters) CUDA_OK(cudaMemsetAsync(dev->d_counters, 0, sizeof(zygpu::TraceCounters), s));
 
     CUDA_OK(zygpu::launchTrace(dev->meshes[mesh].view, mode, static_cast<const zygpu::RayIn*>(d_rays), d_out,
-                               uint32_t(n), counters ? dev->d_counters : nullptr, dev->workCounter(), s));
+                               uint32_t(n), counters ? dev->d_counters : nullptr, dev->workCounter(), dev->d_stacks, dev->stack_bytes_main, s));
 
     if (counters) {
         zygpu::TraceCounters h;
@@ -239,7 +245,9 @@ int zygpu_trace_batch(zygpu_device* dev, int mesh, int mode, const ZygpuRay* ray
 
         CUDA_OK(cudaMemcpyAsync(dev->d_rays[s], rays + done, count * sizeof(ZygpuRay), cudaMemcpyHostToDevice, st));
         CUDA_OK(zygpu::launchTrace(dev->meshes[mesh].view, mode, static_cast<const zygpu::RayIn*>(dev->d_rays[s]),
-                                   dev->d_out[s], uint32_t(count), nullptr, dev->workCounter(), st));
+                                   dev->d_out[s], uint32_t(count), nullptr, dev->workCounter(),
+                                   static_cast<char*>(dev->d_stacks) + dev->stack_bytes_main + size_t(s) * dev->stack_bytes_stream,
+                                   dev->stack_bytes_stream, st));
         CUDA_OK(cudaMemcpyAsync(static_cast<char*>(out) + done * out_bytes, dev->d_out[s], count * out_bytes,
                                 cudaMemcpyDeviceToHost, st));
         done += count;

@@ -16,7 +16,7 @@ namespace {
 
 template <typename T>
 int uploadArray(RenderState& r, const T* host, size_t count, const T** device) {
-    const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 128);
     const size_t slot  = r.scene_buffer_cursor++;
     if (slot == r.scene_buffers.size()) {
         r.scene_buffers.push_back(nullptr);
@@ -205,9 +205,9 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
         }
         zyg::WidePropBvh wide;
         zyg::buildWidePropBvh(scene->solid_bvh.nodes, scene->solid_bvh.num_nodes, scene->solid_bvh.indices, scene->aabbs, spheres.data(), wide);
-        if (0 != uploadArray(r, reinterpret_cast<const float4*>(wide.nodes.data()), wide.nodes.size() * 5, &f4)) return -1;
+        if (0 != uploadArray(r, reinterpret_cast<const float4*>(wide.nodes.data()), wide.nodes.size() * (sizeof(zyg::WideNode) / 16), &f4)) return -1;
         d.tlas_nodes = f4;
-        if (0 != uploadArray(r, reinterpret_cast<const float4*>(wide.records.data()), wide.records.size() * 3, &f4)) return -1;
+        if (0 != uploadArray(r, reinterpret_cast<const float4*>(wide.records.data()), wide.records.size() * (sizeof(zyg::PropRecord) / 16), &f4)) return -1;
         d.tlas_recs = f4;
     }
 

@@ -375,6 +375,14 @@ __device__ __forceinline__ bool sceneVisibility(const SceneDevice& sc, const Ray
 // Relative to the reference only the order in which props are tested changes (all analytic props of the walk first, then
 // the meshes in walk order): the closest hit is the same except for equal-t ties between different props.
 
+// Equal-t ties. The reference accepts `hit_t <= max_t`, so of two hits at the same t the one tested later wins (triangle.zig:47,
+// prop_tree.zig:76-79) — later in ITS traversal order. The device visits nodes in another order, and in the lock-step kernels
+// the order even depends on the warp's votes; resolving ties by (prop id, primitive id), larger wins, makes the result
+// independent of the schedule (renders are bit-reproducible) and agrees with the reference inside a leaf, where later = larger.
+__device__ __forceinline__ bool closerOrLater(float t, float tmax, uint32_t prop, uint32_t prim, uint32_t hit_prop, uint32_t hit_prim) {
+    return kEnd == hit_prop || t < tmax || prop > hit_prop || (prop == hit_prop && prim > hit_prim);
+}
+
 constexpr uint32_t kMeshCandidates = 8;  // per ray; further meshes are traversed inline by the top kernel
 constexpr uint32_t kScenePoolItems = 1024;
 
@@ -649,7 +657,7 @@ __global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathS
                             sp           = 0;
                             node_group.y = 0;
                             tri_group.y  = 0;
-                        } else {
+                        } else if (closerOrLater(t, w.ray.tmax, cur_prop, prim, hit_prop, primitive)) {
                             w.ray.tmax = t;
                             tmax       = t;  // probe.ray.max_t = isec.t, prop_tree.zig:77
                             hu         = u;
@@ -670,12 +678,8 @@ __global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathS
                 if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
                 if (0 != tri_group.y) stack[sp++] = tri_group;
 
-                const float4* np = mesh.wide_nodes + 5 * size_t(node_index);
-                const float4  n0 = __ldg(np + 0);
-                const float4  n1 = __ldg(np + 1);
-                const float4  n2 = __ldg(np + 2);
-                const float4  n3 = __ldg(np + 3);
-                const float4  n4 = __ldg(np + 4);
+                const WideNodeRegs nd = loadWideNode(mesh.wide_nodes, node_index);
+                const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
 
                 const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
 
@@ -891,9 +895,9 @@ __global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, Path
                         const uint32_t bit = 31u - __clz(tri_group.y);
                         tri_group.y &= ~(1u << bit);
                         if (Count) count_props += 1;
-                        const float4* rp = recs + 3 * size_t(tri_group.x + bit);
-                        const float4  r0 = __ldg(rp);
-                        const float4  r1 = __ldg(rp + 1);
+                        const float4* rp = recs + 4 * size_t(tri_group.x + bit);
+                        const F8      rr = ldg256(rp);
+                        const float4  r0 = rr.lo, r1 = rr.hi;
                         const uint32_t  p    = __float_as_uint(r0.w);
                         const ZygpuProp prop = sc.props[p];
                         // the reference reaches a prop through its leaf's box (prop_tree.zig:86-104) ...
@@ -935,7 +939,7 @@ __global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, Path
                                 case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, h); break;
                                 default: break;
                             }
-                            if (hit) {
+                            if (hit && closerOrLater(h.t, w.ray.tmax, p, h.primitive, hit_prop, primitive)) {
                                 w.ray.tmax = h.t;
                                 hu         = h.u;
                                 hv         = h.v;
@@ -963,7 +967,7 @@ __global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, Path
                             sp           = 0;
                             node_group.y = 0;
                             tri_group.y  = 0;
-                        } else {
+                        } else if (closerOrLater(t, w.ray.tmax, cur_prop, prim, hit_prop, primitive)) {
                             w.ray.tmax = t;  // probe.ray.max_t = isec.t, prop_tree.zig:77
                             hu         = u;
                             hv         = v;
@@ -987,12 +991,8 @@ __global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, Path
                     if (0 != tri_group.y) stack[sp++] = tri_group;
                     if (Count) count_nodes += 1;
 
-                    const float4* np = nodes + 5 * size_t(node_index);
-                    const float4  n0 = __ldg(np + 0);
-                    const float4  n1 = __ldg(np + 1);
-                    const float4  n2 = __ldg(np + 2);
-                    const float4  n3 = __ldg(np + 3);
-                    const float4  n4 = __ldg(np + 4);
+                    const WideNodeRegs nd = loadWideNode(nodes, node_index);
+                    const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
 
                     const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
 
@@ -3170,7 +3170,9 @@ const SceneTraceConfig& sceneTraceConfig() {
 template <bool AnyHit>
 cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
     const SceneTraceConfig& cfg = sceneTraceConfig();
-    if (2 == cfg.variant && has_meshes) {
+    // a prop tree that is a single leaf (a mesh and a few analytic props) gains nothing from the fused walk: the thread-per-ray
+    // top kernel deals with it at full lane occupancy (measured on the 1M-triangle sphere scene: 48.2 ms against 51.4 ms fused)
+    if (2 == cfg.variant && has_meshes && scene.num_solid_nodes > 1) {
         static int resident = 0, resident_counted = 0;
         if (0 == resident) {
             int per_sm = 0;
@@ -3218,7 +3220,7 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
 
 uint32_t sceneTraceLaunches(bool has_meshes) {  // kernels per extend / shadow stage
     const int v = sceneTraceConfig().variant;
-    return (1 == v && has_meshes) ? 2u : 1u;
+    return (0 != v && has_meshes) ? 2u : 1u;  // upper bound: the fused kernel (variant 2, prop trees with inner nodes) is one launch
 }
 
 cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {

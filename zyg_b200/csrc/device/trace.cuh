@@ -53,7 +53,10 @@ enum TraceMode : int {
 // `counters` may be null; when set the instrumented variant runs (slower) and accumulates into it.
 // `work_counter` is one device word the persistent wide kernel hands ray blocks out from (reset on
 // `stream` before the launch); it must not be shared by launches that can run concurrently.
+// `stack_scratch`: device memory for the traversal stacks of the ray-pool kernel, traceStackBytesPerBlock() per resident block
+// (it launches at most as many blocks as fit); must not be shared by launches that can run concurrently. Null: lock-step kernel.
 cudaError_t launchTrace(const MeshDevice& mesh, int mode, const RayIn* rays, void* out, uint32_t n,
-                        TraceCounters* counters, uint32_t* work_counter, cudaStream_t stream);
+                        TraceCounters* counters, uint32_t* work_counter, void* stack_scratch, size_t stack_scratch_bytes, cudaStream_t stream);
+size_t      traceStackBytesPerBlock();
 
 }  // namespace zygpu

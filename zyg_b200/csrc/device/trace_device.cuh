@@ -120,6 +120,32 @@ __device__ __forceinline__ void setupWideRay(WideRay& w) {
              fminf(fmaxf(w.ray.inv_d.z, -kBig), kBig)};
 }
 
+// 256-bit global loads (LDG.E.256 on sm_100): the L1 handles one request per distinct 32-byte sector either way, so a record fetched
+// with 32-byte loads costs half the requests of 16-byte loads. Divergent node / triangle fetches are bound by that request rate
+// (profiles/r02: l1tex throughput 60 %+ with prefetches making it worse), not by bytes.
+struct F8 {
+    float4 lo, hi;
+};
+__device__ __forceinline__ F8 ldg256(const float4* p) {  // p must be 32-byte aligned
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+        : "l"(p));
+    return r;
+}
+
+constexpr uint32_t kWideNodeWords = 6;  // float4 per node: 80 bytes of node + 16 bytes of padding = three 32-byte loads
+
+struct WideNodeRegs {
+    float4 n0, n1, n2, n3, n4;
+};
+__device__ __forceinline__ WideNodeRegs loadWideNode(const float4* nodes, uint32_t index) {
+    const float4* np = nodes + kWideNodeWords * size_t(index);
+    const F8      a = ldg256(np), b = ldg256(np + 2);
+    const float4  c = __ldg(np + 4);
+    return {a.lo, a.hi, b.lo, b.hi, c};
+}
+
 // byte j of `word` -> 32768 + byte as a float, one PRMT and no int->float conversion (the XU pipe
 // was the busiest unit with I2F: profiles/r01_traceWide_a.md): 0x47000000 is 32768.0f and the byte
 // lands in mantissa bits 8..15, i.e. at weight 1.
@@ -204,10 +230,8 @@ __device__ __forceinline__ uint32_t testWideNode(const WideRay& w, float tmin_ra
 __device__ __forceinline__ bool testWideTriangle(const MeshDevice& mesh, const RayT& ray, uint32_t index, float& t,
                                                  float& u, float& v, uint32_t& primitive) {
     const float4* tp = mesh.wide_tris + 4 * size_t(index);
-    const float4  t0 = __ldg(tp + 0);
-    const float4  t1 = __ldg(tp + 1);
-    const float4  t2 = __ldg(tp + 2);
-    const float4  t3 = __ldg(tp + 3);
+    const F8      ta = ldg256(tp), tb = ldg256(tp + 2);
+    const float4  t0 = ta.lo, t1 = ta.hi, t2 = tb.lo, t3 = tb.hi;
 
     // Gate with the reference's own (non-watertight) slab test on the reference leaf box: the
     // reference never tests a triangle whose leaf box it rejected.
@@ -243,14 +267,10 @@ __device__ __forceinline__ bool traverseWide(const MeshDevice& mesh, WideRay& w,
             const uint32_t node_index = node_group.x + rank;
             if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
 
-            const float4* np = mesh.wide_nodes + 5 * size_t(node_index);
-            const float4  n0 = __ldg(np + 0);
-            const float4  n1 = __ldg(np + 1);
-            const float4  n2 = __ldg(np + 2);
-            const float4  n3 = __ldg(np + 3);
-            const float4  n4 = __ldg(np + 4);
+            const WideNodeRegs nd = loadWideNode(mesh.wide_nodes, node_index);
+            const float4 n0 = nd.n0, n1 = nd.n1;
 
-            const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
+            const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, nd.n0, nd.n1, nd.n2, nd.n3, nd.n4);
 
             node_group.x = __float_as_uint(n1.x);
             node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);

@@ -368,6 +368,7 @@ void buildWidePropBvh(const ZygpuBvhNode* nodes, uint32_t num_nodes, const uint3
         r.prop = indices[position];
         r.pad  = 0;
         for (int i = 0; i < 4; ++i) r.sphere[i] = spheres ? spheres[size_t(r.prop) * 4 + i] : (3 == i ? FLT_MAX : 0.f);
+        for (int i = 0; i < 4; ++i) r.pad2[i] = 0.f;
         out.records.push_back(r);
     };
     uint32_t num_records = 0;

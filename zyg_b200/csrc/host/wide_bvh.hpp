@@ -2,7 +2,7 @@
 // triangle records. Derived ("flattened on upload") from the reference-order binary tree, so the
 // set of triangles and their clip regions is the reference's; only the visiting order changes.
 //
-// Node, 80 bytes = five 16-byte loads:
+// Node, 80 bytes + 16 bytes of padding = three 32-byte loads (LDG.E.256):
 //   +0   float  p[3]        origin (min corner) of the quantisation grid
 //   +12  u8     e[3]        biased exponents: cell size = 2^(e-127) per axis
 //   +15  u8     imask       bit s set: slot s holds an inner node
@@ -37,8 +37,9 @@ struct WideNode {
     uint8_t  meta[8];
     uint8_t  qlo[3][8];
     uint8_t  qhi[3][8];
+    uint8_t  pad[16];  // to 96 bytes: a node is three aligned 32-byte (256-bit) loads on the device
 };
-static_assert(sizeof(WideNode) == 80, "wide node must be five 16-byte words");
+static_assert(sizeof(WideNode) == 96, "wide node must be three 32-byte words");
 
 struct TriRecord {
     float    a[3];
@@ -67,15 +68,16 @@ void buildWideBvh(const TriangleTree& tree, WideBvh& out);
 // The same node format over a prop tree (PropBvh.Tree, prop_tree.zig:31-36): the "two-level layout for prop instances". Leaf
 // slots reference prop records instead of triangle records: the prop id and the exact box of the reference leaf the prop sits in
 // (a prop duplicated by a spatial split has one record per leaf). The kernels gate a prop with the reference's slab test on that
-// box, then test the prop's own world box like Prop.intersect does (prop.zig:163-197). 48 bytes = three 16-byte loads.
+// box, then test the prop's own world box like Prop.intersect does (prop.zig:163-197). 64 bytes = two 32-byte loads.
 struct PropRecord {
     float    leaf_min[3];
     uint32_t prop;
     float    leaf_max[3];
     uint32_t pad;
     float    sphere[4];  // world-space bounding sphere of a mesh prop (centre, radius); radius FLT_MAX = no sphere test
+    float    pad2[4];
 };
-static_assert(sizeof(PropRecord) == 48, "prop record must be three 16-byte words");
+static_assert(sizeof(PropRecord) == 64, "prop record must be two 32-byte words");
 
 struct WidePropBvh {
     std::vector<WideNode>   nodes;
