@@ -126,16 +126,35 @@ def cpu_step(oracle, arrays, sample):
     return time.perf_counter() - t0
 
 
+def build_reference_inputs(n_rays: int, res: int):
+    """Mesh arrays for the CPU arm, built by the oracle's own restatement of zyg's BVH builder (oracle/builders.cpp): this
+    process never maps libzyg_b200.so. zyg_b200.scenes is plain numpy (procedural vertices and rays)."""
+    from zyg_b200 import scenes
+
+    oracle = load_oracle()
+    t0 = time.time()
+    positions, normals, uvs, indices = scenes.displaced_sphere(*MESH_QUADS)
+    mesh = oracle.BuiltMesh(positions, indices, normals, uvs)
+    arrays = tuple(mesh.data(w) for w in (mesh.NODES, mesh.TRIANGLES, mesh.POSITIONS))
+    log(f"[reference] mesh: {indices.shape[0]} triangles -> {arrays[1].size // 3} references, {arrays[0].size} binary nodes, "
+        f"built by oracle/builders.cpp in {time.time() - t0:.1f}s")
+    rays = {
+        "primary_closest": scenes.primary_rays(res, res),
+        "incoherent_closest": scenes.random_rays(n_rays),
+        "shadow_any": scenes.random_rays(n_rays, shadow=True),
+    }
+    return oracle, arrays, rays
+
+
 def run_reference(args):
-    """CPU arm: zyg's own traversal (restated in oracle/, the reference is Zig and cannot be built here)."""
+    """CPU arm: zyg's own traversal on the box's host cores (restated in oracle/: the reference is Zig and cannot be built
+    here), over a tree built by the oracle's own builder. The forward-pass legs need a compiled scene, which only the
+    product's host model produces: they run in a child process (`--impl reference-render`), so this process stays free of
+    libzyg_b200.so, and the child re-builds the scene's prop and light trees with the oracle's builders and compares."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from zyg_b200 import lib
-
-    oracle = load_oracle()
-    mesh, rays = build_inputs(0, N_RAYS // 4, PRIMARY_RES // 2)
-    arrays = tuple(mesh.data(w) for w in (lib.MESH_BINARY_NODES, lib.MESH_TRIANGLES, lib.MESH_POSITIONS))
+    oracle, arrays, rays = build_reference_inputs(N_RAYS // 4, PRIMARY_RES // 2)
     n = sum(r.shape[0] for r in rays.values())
     for _ in range(args.warmup):
         cpu_step(oracle, arrays, rays)
@@ -143,24 +162,23 @@ def run_reference(args):
     dt = sum(times)
     value = n * args.steps / dt / 1e6
     cores = os.cpu_count()
-    sample = f"per step: {PRIMARY_RES // 2}^2 primary + {N_RAYS // 4} incoherent + {N_RAYS // 4} shadow rays (1/4 of the workload)"
-
-    # the CPU path of the forward pass on a bounded sample of the two render workloads
-    from zyg_b200 import su
+    sample = (f"per step: {PRIMARY_RES // 2}^2 primary + {N_RAYS // 4} incoherent + {N_RAYS // 4} shadow rays (1/4 of the workload: "
+              f"a rate, so the ratio to the GPU arm stands), tree built by oracle/builders.cpp")
 
     path_tracing = {}
-    for name, (builder, kwargs, width, height, spp, cpu_spp) in RENDER_SCENES.items():
-        if (args.scenes and name not in args.scenes) or 0 == cpu_spp:
-            continue
-        num_meshes = build_render_scene(builder, kwargs, width, height, spp)
-        scene, view = su.compile_scene()
-        t0 = time.perf_counter()
-        oracle.render(scene, view, width, height, 0, cpu_spp, num_meshes=num_meshes)
-        dt_r = time.perf_counter() - t0
-        path_tracing[name] = {"path_samples_per_s": width * height * cpu_spp / dt_r, "cores": cores,
-                              "sample": f"{width}x{height} x {cpu_spp} spp of the same scene"}
-        su.release()
+    if not args.no_render:
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-render"]
+        if args.scenes:
+            cmd += ["--scenes"] + list(args.scenes)
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, text=True, env=env)
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if 0 == out.returncode and lines:
+            path_tracing = json.loads(lines[-1])
+        else:
+            path_tracing = {"unavailable": f"child process returned {out.returncode}"}
 
+    loaded = sorted({l.split()[-1] for l in open("/proc/self/maps") if l.rstrip().endswith(".so") and ("zyg" in l)})
     print(json.dumps({
         "impl": "reference", "metric": "traversal_throughput", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -168,8 +186,63 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "rays_per_step": n, "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "native_libraries": [os.path.basename(x) for x in loaded],
         "path_tracing": path_tracing,
     }))
+
+
+def run_reference_render(args):
+    """Child of the reference arm: the CPU path of the forward pass on a bounded sample of the render workloads. The scene is
+    compiled by the product's host model (there is no other source of a compiled scene); its prop trees and light tree are
+    re-built by the oracle's own builders and must be identical before the oracle renders."""
+    from zyg_b200 import su
+
+    oracle = load_oracle()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scene_view as sv
+
+    out = {}
+    cores = os.cpu_count()
+    for name, (builder, kwargs, width, height, spp, cpu_spp) in RENDER_SCENES.items():
+        if (args.scenes and name not in args.scenes) or 0 == cpu_spp:
+            continue
+        num_meshes = build_render_scene(builder, kwargs, width, height, spp)
+        scene, view = su.compile_scene()
+        identical = oracle_rebuild_matches(oracle, sv, scene)
+        t0 = time.perf_counter()
+        oracle.render(scene, view, width, height, 0, cpu_spp, num_meshes=num_meshes)
+        dt_r = time.perf_counter() - t0
+        out[name] = {"path_samples_per_s": width * height * cpu_spp / dt_r, "cores": cores,
+                     "sample": f"{width}x{height} x {cpu_spp} spp of the same scene",
+                     "scene_compiled_by": "product host model (child process)", "oracle_rebuilt_trees_identical": identical}
+        su.release()
+    print(json.dumps(out))
+
+
+def oracle_rebuild_matches(oracle, sv, scene_address) -> bool:
+    """Prop trees and the scene light tree of a compiled scene, re-built by oracle/builders.cpp from the scene's primary records."""
+    s = sv.scene_at(scene_address)
+    props = sv.view(s.props, sv.PROP_DTYPE, s.num_props)
+    aabbs = sv.view(s.aabbs, sv.AABB_DTYPE, s.num_props)
+    infinite = np.isin(props["shape"], (sv.SHAPE_CANOPY, sv.SHAPE_DISTANT, sv.SHAPE_DOME))
+    unocc = (props["flags"] & sv.PROP_UNOCCLUDING) != 0
+    ok = True
+    for tree, want in ((s.solid_bvh, False), (s.unoccluding_bvh, True)):
+        idx = sv.view(tree.indices, "<u4", tree.num_indices)
+        members = np.zeros(s.num_props, bool)
+        members[idx] = True
+        ids = np.nonzero(members & ~infinite & (unocc == want))[0].astype(np.uint32)
+        nodes, indices = oracle.build_prop_tree(ids, aabbs)
+        ok = ok and nodes == sv.view(tree.nodes, sv.NODE_DTYPE, tree.num_nodes).tobytes() and indices == idx.tobytes()
+    if s.num_lights > 0:
+        lights = sv.view(s.lights, sv.LIGHT_DTYPE, s.num_lights)
+        finite = ~np.isin(props["shape"][lights["prop"]], (sv.SHAPE_CANOPY, sv.SHAPE_DISTANT, sv.SHAPE_DOME))
+        mine = oracle.build_light_tree(sv.view(s.light_aabbs, sv.AABB_DTYPE, s.num_lights), sv.view(s.light_cones, "<f4", 4 * s.num_lights),
+                                       lights["two_sided"] != 0, finite)
+        t = s.light_tree
+        ok = ok and mine["nodes"] == sv.view(t.nodes, sv.LIGHT_NODE_DTYPE, t.num_nodes).tobytes()
+        ok = ok and mine["mapping"] == sv.view(t.light_mapping, "<u4", t.num_lights).tobytes()
+    return bool(ok)
 
 
 # The forward pass on the BASELINE.json configs: name -> (scene builder, kwargs, width, height, spp per step, spp of the CPU
@@ -195,6 +268,16 @@ RENDER_SCENES = {
 }
 MESH_SCENES = ("sphere_scene", "instanced_scene", "mesh_lights_scene")
 
+# Path-state traffic of the wavefront stages per ray, in bytes (the 16-byte SoA words of device/render.cuh):
+# a path vertex = one closest-hit ray: extend reads origin + direction (32) and writes max_t + hit (32); shade_a reads the six
+# vertex words (96), the sampler (24) and the accumulators it adds to (32 read + write), writes throughput (16) and sampler (24);
+# shade_b reads the vertex words again (96), sampler (24), accumulator (32), writes the next vertex (80) and sampler (24);
+# queue entries 3 x 4.
+STATE_BYTES_PER_VERTEX = 32 + 32 + (96 + 24 + 32 + 16 + 24) + (96 + 24 + 32 + 80 + 24) + 12
+# a shadow ray: shade_a writes the record (48), the shadow stage reads 32 of it and writes the visibility flag (4), shade_b reads it
+# (48); one queue entry
+STATE_BYTES_PER_SHADOW_RAY = 48 + 32 + 4 + 48 + 4
+
 
 def build_render_scene(builder, kwargs, width, height, spp):
     from zyg_b200 import scenes, su
@@ -219,9 +302,18 @@ def bench_render(args, rank, world, local):
     L.zygpu_synchronize.argtypes = [C.c_void_p]
 
     class Stats(C.Structure):
-        _fields_ = [(n, C.c_uint64) for n in ("camera_samples", "closest_rays", "shadow_rays", "kernel_launches", "passes")]
+        _fields_ = [(n, C.c_uint64) for n in ("camera_samples", "closest_rays", "shadow_rays", "kernel_launches", "passes", "overflow_retries")]
+
+    class Counts(C.Structure):
+        _fields_ = [(n, C.c_uint64) for n in ("nodes", "triangles", "props", "node_steps", "triangle_steps", "prop_steps")]
 
     L.zygpu_render_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.zygpu_set_counting.argtypes = [C.c_void_p, C.c_int]
+    L.zygpu_traversal_counts.argtypes = [C.c_void_p, C.POINTER(Counts), C.POINTER(Counts)]
+    L.zygpu_download_film.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    peak, peak_src = peak_hbm()
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
 
     out = {}
     launches = 0
@@ -243,8 +335,7 @@ def bench_render(args, rank, world, local):
             if count > 0:
                 su._ok(L.zygpu_render(dev, first, count), "zygpu_render")
             if world > 1:
-                with torch.cuda.stream(stream):
-                    dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+                multi.reduce_film(0)  # zygpu_reduce_film: ncclReduce(sum, fp32) on the render stream behind the passes
 
         def barrier():
             su._ok(L.zygpu_synchronize(dev), "zygpu_synchronize")
@@ -268,7 +359,12 @@ def bench_render(args, rank, world, local):
         st = Stats()
         L.zygpu_render_stats(dev, C.byref(st))
 
-        # end to end through zyg's C API: su_render_frame (host compile + upload + pass) + su_resolve_frame_to_buffer
+        # the film of the timed step, for the checks below (rank 0 holds the reduced film when world > 1)
+        timed_film = np.empty((height, width, 4), np.float32)
+        su._ok(L.zygpu_download_film(dev, timed_film.ctypes.data, width * height), "zygpu_download_film")
+
+        # end to end through zyg's C API: su_render_frame (scene unchanged since the last frame: no recompile, no upload) +
+        # su_resolve_frame_to_buffer (resolve on the device, RGBA fp32 to the host)
         t0 = time.perf_counter()
         if count > 0:
             su.render_frame_range(0, first, count)
@@ -282,7 +378,7 @@ def bench_render(args, rank, world, local):
             with torch.cuda.stream(stream):
                 r0.record()
                 for _ in range(args.steps):
-                    dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+                    multi.reduce_film(0)
                 r1.record()
             barrier()
             reduce_ms = r0.elapsed_time(r1) / args.steps
@@ -303,6 +399,46 @@ def bench_render(args, rank, world, local):
         }
         launches += int(st.kernel_launches)
 
+        # Roofline of the render path (SURVEY.md §8d "B_sample"): algorithmic bytes per path sample = counted traversal fetches
+        # of an instrumented pass over the same samples (80 B nodes, 64 B triangle records, 64 B prop records) + ray / hit /
+        # shadow-record / path-state traffic of the stages per ray + 16 B of film, times the measured samples/s.
+        if count > 0 and 0 == L.zygpu_set_counting(dev, 1):
+            su._ok(L.zygpu_clear_film(dev), "zygpu_clear_film")
+            su._ok(L.zygpu_render(dev, first, count), "zygpu_render")
+            a, b = Counts(), Counts()
+            st2 = Stats()
+            if 0 == L.zygpu_traversal_counts(dev, C.byref(a), C.byref(b)) and 0 == L.zygpu_render_stats(dev, C.byref(st2)):
+                mine = width * height * count
+                trav = ((a.nodes + b.nodes) * 80 + (a.triangles + b.triangles) * 64 + (a.props + b.props) * 64) / mine
+                state = (st2.closest_rays * STATE_BYTES_PER_VERTEX + st2.shadow_rays * STATE_BYTES_PER_SHADOW_RAY) / mine + 16
+                b_sample = trav + state
+                achieved = b_sample * entry["path_samples_per_s"] / 1e9
+                entry["roofline"] = {
+                    "bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                    "bytes_per_sample": b_sample, "traversal_bytes_per_sample": trav, "state_bytes_per_sample": state,
+                    "traffic": traffic.get(name), "peak_source": peak_src,
+                    "counted": "fused two-level kernel" if a.node_steps + b.node_steps > 0 else "top + mesh kernels are not instrumented: state bytes only",
+                    "nodes_per_closest_ray": a.nodes / max(1, st2.closest_rays), "tris_per_closest_ray": a.triangles / max(1, st2.closest_rays),
+                    "props_per_closest_ray": a.props / max(1, st2.closest_rays),
+                    "lanes_per_node_step": a.nodes / max(1, a.node_steps), "lanes_per_triangle_step": a.triangles / max(1, a.triangle_steps)}
+            L.zygpu_set_counting(dev, 0)
+
+        if world > 1:
+            # The NCCL film path checked where N GPUs exist: rank 0 renders all samples of the frame alone and compares with
+            # the film the ranks reduced (same samples, same seeds: equal up to fp32 summation order).
+            check = None
+            if 0 == rank:
+                su._ok(L.zygpu_clear_film(dev), "zygpu_clear_film")
+                su._ok(L.zygpu_render(dev, 0, spp), "zygpu_render")
+                alone = np.empty((height, width, 4), np.float32)
+                su._ok(L.zygpu_download_film(dev, alone.ctypes.data, width * height), "zygpu_download_film")
+                err = np.abs(timed_film - alone) / np.maximum(np.abs(alone), 1e-3)
+                check = {"allclose_2e-6": bool(np.allclose(timed_film, alone, rtol=2e-6, atol=1e-6)), "max_rel_error": float(err.max()),
+                         "weights_equal": bool(np.array_equal(timed_film[..., 3], alone[..., 3]))}
+                assert check["allclose_2e-6"], f"{name}: the reduced film differs from the single-GPU film: {check}"
+            entry["nccl_film_check"] = check
+            dist.barrier()
+
         if rank == 0 and world == 1 and not args.no_cpu and cpu_spp > 0:
             oracle = load_oracle()
             scene, view = su.compile_scene()
@@ -321,7 +457,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="zyg_b200", choices=["zyg_b200", "reference"])
+    ap.add_argument("--impl", default="zyg_b200", choices=["zyg_b200", "reference", "reference-render"])
     ap.add_argument("--rays", type=int, default=PRIMARY_RES, help="primary resolution r (r*r rays per class)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-render", action="store_true", help="skip the path_tracing section")
@@ -331,6 +467,8 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-render":
+        return run_reference_render(args)
 
     import torch
     import torch.distributed as dist

@@ -406,7 +406,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
     const uint32_t lanes  = r.can_split ? 4 : 1;
     const uint32_t rounds = lanes;
     // extend / shadow are one kernel each (prop-tree walk) plus the persistent mesh kernel when the scene has meshes
-    const uint32_t trace_extra = zygpu::sceneTraceLaunches(r.has_meshes) - 1;
+    const uint32_t trace_extra = zygpu::sceneTraceLaunches(r.has_meshes, r.scene.num_solid_nodes) - 1;
 
     // Samples per pass for the current shadow-record reservation: a pass holds at most 64 Mi shadow records (3 GiB), so scenes
     // whose vertices can sample many lights trace fewer paths per pass. 0 = a single frame of paths does not fit.

@@ -3172,7 +3172,8 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
     const SceneTraceConfig& cfg = sceneTraceConfig();
     // a prop tree that is a single leaf (a mesh and a few analytic props) gains nothing from the fused walk: the thread-per-ray
     // top kernel deals with it at full lane occupancy (measured on the 1M-triangle sphere scene: 48.2 ms against 51.4 ms fused)
-    if (2 == cfg.variant && has_meshes && scene.num_solid_nodes > 1) {
+    // (an instrumented pass always takes the fused kernel, the one that counts its fetches; the results are the same)
+    if ((2 == cfg.variant && has_meshes && scene.num_solid_nodes > 1) || nullptr != st.tally) {
         static int resident = 0, resident_counted = 0;
         if (0 == resident) {
             int per_sm = 0;
@@ -3218,9 +3219,10 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
 
 }  // namespace
 
-uint32_t sceneTraceLaunches(bool has_meshes) {  // kernels per extend / shadow stage
+uint32_t sceneTraceLaunches(bool has_meshes, uint32_t num_solid_nodes) {  // kernels per extend / shadow stage
     const int v = sceneTraceConfig().variant;
-    return (0 != v && has_meshes) ? 2u : 1u;  // upper bound: the fused kernel (variant 2, prop trees with inner nodes) is one launch
+    if (0 == v || !has_meshes) return 1u;
+    return (2 == v && num_solid_nodes > 1) ? 1u : 2u;  // fused kernel, or top kernel + mesh kernel
 }
 
 cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {

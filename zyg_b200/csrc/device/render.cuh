@@ -168,7 +168,7 @@ struct PassParams {
 };
 
 cudaError_t uploadSobolDirections();
-uint32_t    sceneTraceLaunches(bool has_meshes);  // kernels one extend / shadow stage launches (for the launch statistics)
+uint32_t    sceneTraceLaunches(bool has_meshes, uint32_t num_solid_nodes);  // kernels one extend / shadow stage launches (for the launch statistics)
 
 cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const PassParams& pass, cudaStream_t stream);
 // The queue lengths live on the device; the grids are sized for `max_items` and exit early.

@@ -663,7 +663,7 @@ const WideLaunchConfig& wideConfig() {
         c.pool.fetch_free = uint32_t(envInt("ZYGPU_POOL_FETCH_FREE", 32));
         c.pool.tri_num    = uint32_t(envInt("ZYGPU_POOL_TRI_NUM", 1));
         c.pool.tri_den    = uint32_t(envInt("ZYGPU_POOL_TRI_DEN", 1));
-        c.pool.prefetch   = uint32_t(envInt("ZYGPU_POOL_PREFETCH", 1));
+        c.pool.prefetch   = uint32_t(envInt("ZYGPU_POOL_PREFETCH", 0));  // measured: prefetch.global.L1 of the next record halves the incoherent rate (more L1 requests, the bound)
         c.tune.fetch_idle = uint32_t(envInt("ZYGPU_FETCH_IDLE", 6));
         c.tune.tri_num    = uint32_t(envInt("ZYGPU_TRI_NUM", 1));
         c.tune.tri_den    = uint32_t(envInt("ZYGPU_TRI_DEN", 2));
