@@ -553,6 +553,7 @@ __global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathS
     bool     in_mesh = false;
     uint32_t item    = 0;
     float    tmax    = 0.f;  // world max_t == object max_t
+    float    tmax0   = 0.f;  // the max_t the mesh walk started with (after the analytic props): the limit of the leaf gates
     uint32_t cand_i = 0, cand_n = 0;
     uint32_t cur_prop = 0;
     uint32_t hit_prop = kEnd;
@@ -595,6 +596,7 @@ __global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathS
                 hit_prop = kEnd;
                 occluded = false;
                 tmax     = AnyHit ? 0.f : st.ray_d[item].w;
+                tmax0    = tmax;
             }
             pool_next += min(avail, (uint32_t)__popc(idle));
             idle = __ballot_sync(kFull, !has_ray);
@@ -619,7 +621,8 @@ __global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathS
             uint32_t depth_surface;
             RayT     ray = loadTraceRay<AnyHit>(st, item, depth_surface);
             if (!AnyHit) ray.tmax = tmax;
-            if (0 != cand_i - 1 && !aabbIntersect(sc.aabbs, p, ray)) continue;  // the first candidate was tested by the top kernel
+            // (the first candidate was tested by the top kernel)
+            if (0 != cand_i - 1 && !gateBox(__ldg(sc.aabbs + 2 * size_t(p)), __ldg(sc.aabbs + 2 * size_t(p) + 1), ray, AnyHit ? ray.tmax : tmax0)) continue;
 
             const TrafoD trafo = loadTrafo(sc.trafos, p);
             w.ray              = worldToObjectRay(trafo, ray);  // triangle_tree.zig:49: t is shared with world space
@@ -651,7 +654,7 @@ __global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathS
                     tri_group.y &= ~(1u << bit);
                     float    t, u, v;
                     uint32_t prim;
-                    if (testWideTriangle(mesh, w.ray, tri_group.x + bit, t, u, v, prim)) {
+                    if (testWideTriangle(mesh, w.ray, AnyHit ? w.ray.tmax : tmax0, tri_group.x + bit, t, u, v, prim)) {
                         if (AnyHit) {
                             occluded     = true;
                             sp           = 0;
@@ -779,6 +782,7 @@ __global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, Path
     bool     in_mesh = false;
     uint32_t item    = 0;
     uint32_t depth_surface = 0;
+    float    tmax0      = 0.f;   // the max_t the ray started with: the limit of the reference's box gates (gateBox)
     uint32_t enter_prop = kEnd;  // a mesh prop that passed the culling tests and waits for its ENTER step
     uint32_t cur_prop = 0, hit_prop = kEnd;
     bool     occluded = false;
@@ -829,6 +833,7 @@ __global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, Path
                     uint32_t flags = 0;
                     w.ray          = loadTraceRay<AnyHit>(st, item, depth_surface, &flags);
                     if (!AnyHit) clipToMedium(sc, st, item, flags, w.ray);
+                    tmax0 = w.ray.tmax;
                     setupWideRay(w);
                     has_ray    = true;
                     in_mesh    = false;
@@ -901,10 +906,10 @@ __global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, Path
                         const uint32_t  p    = __float_as_uint(r0.w);
                         const ZygpuProp prop = sc.props[p];
                         // the reference reaches a prop through its leaf's box (prop_tree.zig:86-104) ...
-                        bool enter = FLT_MAX != intersectNode(make_float4(r0.x, r0.y, r0.z, 0.f), make_float4(r1.x, r1.y, r1.z, 0.f), w.ray);
+                        bool enter = gateBox(make_float4(r0.x, r0.y, r0.z, 0.f), make_float4(r1.x, r1.y, r1.z, 0.f), w.ray, tmax0);
                         // ... then Prop.intersect / Prop.visibility: flags, world box (prop.zig:176-183, 212-218)
                         enter = enter && (AnyHit ? 0 != (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW) : propVisible(prop.flags, depth_surface));
-                        enter = enter && aabbIntersect(sc.aabbs, p, w.ray);
+                        enter = enter && gateBox(__ldg(sc.aabbs + 2 * size_t(p)), __ldg(sc.aabbs + 2 * size_t(p) + 1), w.ray, tmax0);
                         if (!enter) continue;
                         if (ZYG_SHAPE_TRIANGLE_MESH == prop.shape) {
                             // culling only: every triangle of the instance lies inside its bounding sphere
@@ -960,7 +965,7 @@ __global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, Path
                     mesh.wide_tris = recs;
                     float    t, u, v;
                     uint32_t prim;
-                    if (testWideTriangle(mesh, w.ray, tri_group.x + bit, t, u, v, prim)) {
+                    if (testWideTriangle(mesh, w.ray, tmax0, tri_group.x + bit, t, u, v, prim)) {
                         if (AnyHit) {
                             occluded     = true;
                             in_mesh      = false;

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128)
 
                 float    t, u, v;
                 uint32_t prim;
-                if (testWideTriangle(mesh, w.ray, tri_group.x + bit, t, u, v, prim)) {
+                if (testWideTriangle(mesh, w.ray, w.ray.tmax, tri_group.x + bit, t, u, v, prim)) {
                     if (AnyHit) {
                         occluded = true;
                         break;
@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(128)
     bool     has_ray = false;
     uint32_t ray_index = 0;
     WideRay  w;
+    float    tmax0 = 0.f;  // the max_t the ray started with: the limit of the leaf gates (gateBox)
     uint2    stack[kWideStack];
     uint32_t sp         = 0;
     uint2    node_group = make_uint2(0u, 0u);
@@ -306,6 +307,7 @@ __global__ void __launch_bounds__(128)
             if (!has_ray && rank < avail) {
                 ray_index = pool_next + rank;
                 w.ray     = loadRay(rays, ray_index);
+                tmax0     = w.ray.tmax;
                 setupWideRay(w);
                 sp         = 0;
                 node_group = make_uint2(0u, 0x80000000u);  // root as the only hit child of a virtual parent
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(128)
                     tally.tri();
                     float    t, u, v;
                     uint32_t prim;
-                    if (testWideTriangle(mesh, w.ray, tri_group.x + bit, t, u, v, prim)) {
+                    if (testWideTriangle(mesh, w.ray, tmax0, tri_group.x + bit, t, u, v, prim)) {
                         if (AnyHit) {
                             // occluded: drop all remaining work of this ray
                             primitive    = 0;
@@ -434,6 +436,7 @@ struct RayPool {  // one per warp
     float4   c[kPoolSlots];  // inverse direction xyz | u of the hit
     uint4    g[kPoolSlots];  // node group | triangle group
     uint4    h[kPoolSlots];  // stack depth | ray index (kEnd: the slot is free) | primitive | v of the hit
+    float    t0[kPoolSlots];  // the max_t the ray started with: the limit of the leaf gates (gateBox)
     uint32_t assign[32];
 };
 
@@ -487,6 +490,7 @@ __global__ void __launch_bounds__(128)
                         pool.c[slot]         = make_float4(r.inv_d.x, r.inv_d.y, r.inv_d.z, 0.f);
                         pool.g[slot]         = make_uint4(0u, 0x80000000u, 0u, 0u);  // root as the only hit child of a virtual parent
                         pool.h[slot]         = make_uint4(0u, index, kEnd, 0u);
+                        pool.t0[slot]        = r.tmax;
                     }
                     const uint32_t taken = __ballot_sync(kFull, take);
                     pool_next += __popc(taken);
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(128)
                 tally.tri();
                 float    t, u, v;
                 uint32_t prim;
-                if (testWideTriangle(mesh, w.ray, tri_group.x + bit, t, u, v, prim)) {
+                if (testWideTriangle(mesh, w.ray, pool.t0[slot], tri_group.x + bit, t, u, v, prim)) {
                     if (AnyHit) {
                         h.z          = 0;  // occluded: drop all remaining work of this ray
                         sp           = 0;

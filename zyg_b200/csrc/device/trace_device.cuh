@@ -226,8 +226,22 @@ __device__ __forceinline__ uint32_t testWideNode(const WideRay& w, float tmin_ra
     return hitmask;
 }
 
-// One gated triangle test against record `index`; true on an accepted hit (fills t, u, v, primitive).
-__device__ __forceinline__ bool testWideTriangle(const MeshDevice& mesh, const RayT& ray, uint32_t index, float& t,
+// The reference's slab test (node.zig:73-87) against a box with the ray's max_t replaced by `gate_tmax`, then a conservative cull
+// against the ray's current max_t. Why two limits: the reference's own test is not watertight against the shape / triangle
+// test, so whether it passes can depend on max_t — and on the device the current max_t depends on the order in which the
+// lock-step schedule found earlier hits. Gating with the max_t the ray STARTED with makes the decision independent of the
+// schedule (equal-t ties included, see closerOrLater); the cull against the current max_t only drops boxes whose entry lies
+// beyond it by more than the rounding of the test, where no hit could be accepted or tie.
+__device__ __forceinline__ bool gateBox(const float4 bmin, const float4 bmax, const RayT& ray, float gate_tmax) {
+    RayT g        = ray;
+    g.tmax        = gate_tmax;
+    const float e = intersectNode(bmin, bmax, g);
+    return FLT_MAX != e && e * 0.9999995f <= ray.tmax;
+}
+
+// One gated triangle test against record `index`; true on an accepted hit (fills t, u, v, primitive). `gate_tmax`: the max_t
+// the ray started with (closest hit), or its max_t (any hit, where it never changes).
+__device__ __forceinline__ bool testWideTriangle(const MeshDevice& mesh, const RayT& ray, float gate_tmax, uint32_t index, float& t,
                                                  float& u, float& v, uint32_t& primitive) {
     const float4* tp = mesh.wide_tris + 4 * size_t(index);
     const F8      ta = ldg256(tp), tb = ldg256(tp + 2);
@@ -235,9 +249,7 @@ __device__ __forceinline__ bool testWideTriangle(const MeshDevice& mesh, const R
 
     // Gate with the reference's own (non-watertight) slab test on the reference leaf box: the
     // reference never tests a triangle whose leaf box it rejected.
-    if (FLT_MAX == intersectNode(make_float4(t1.w, t2.w, t3.x, 0.f), make_float4(t3.y, t3.z, t3.w, 0.f), ray)) {
-        return false;
-    }
+    if (!gateBox(make_float4(t1.w, t2.w, t3.x, 0.f), make_float4(t3.y, t3.z, t3.w, 0.f), ray, gate_tmax)) return false;
     primitive = __float_as_uint(t0.w);
     return intersectTriangle(ray, {t0.x, t0.y, t0.z}, {t1.x, t1.y, t1.z}, {t2.x, t2.y, t2.z}, t, u, v);
 }
@@ -287,7 +299,7 @@ __device__ __forceinline__ bool traverseWide(const MeshDevice& mesh, WideRay& w,
 
             float    t, u, v;
             uint32_t prim;
-            if (testWideTriangle(mesh, w.ray, tri_group.x + bit, t, u, v, prim)) {
+            if (testWideTriangle(mesh, w.ray, w.ray.tmax, tri_group.x + bit, t, u, v, prim)) {
                 if (AnyHit) return true;
                 w.ray.tmax = t;
                 ht         = t;
