@@ -10,8 +10,7 @@
  * uniform parameters, image colour maps and image emission maps (su_image_create: Float32 x 3 and UInt8 x 3). A scene that
  * uses a Disk or Dome prop, thin or dispersive Glass is refused by the render calls (-1 and a log message) rather than rendered
  * wrongly; unsupported material parameters are ignored with a warning through the log callback.
- * Entry points outside that scope exist and return -1 (su_aovs_create, su_exporters_create, su_export_frame, animation frames
- * other than 0).
+ * Entry points outside that scope exist and return -1 (su_aovs_create, animation frames other than 0).
  */
 #ifndef ZYG_SU_H
 #define ZYG_SU_H
@@ -31,7 +30,8 @@ int32_t su_mount(const char* folder);                                     /* :13
 int32_t su_perspective_camera_create(uint32_t width, uint32_t height);    /* :143 -> camera entity id */
 int32_t su_camera_set_fov(float fov);                                     /* :169 (radians) */
 int32_t su_camera_sensor_dimensions(int32_t* dimensions);                 /* :178 */
-int32_t su_exporters_create(const char* json);                            /* :189 (-1: out of scope) */
+int32_t su_exporters_create(const char* json);                            /* :189 {"Image":{"format":"PNG"|"EXR"|"RGBE","bitdepth":16|32,
+                                                                             "error_diffusion":bool}} (take.zig:303-331; "Video" skipped) */
 int32_t su_aovs_create(const char* json);                                 /* :202 (-1: out of scope) */
 int32_t su_sampler_create(uint32_t num_samples);                          /* :215 (returns -1 even on success, like the reference) */
 int32_t su_integrators_create(const char* json);                          /* :223 */
@@ -55,7 +55,9 @@ int32_t su_prop_set_transformation(uint32_t prop, const float* trafo);    /* :48
 int32_t su_prop_set_transformation_frame(uint32_t prop, uint32_t frame, const float* trafo); /* :506 (frame 0 only) */
 int32_t su_prop_set_visibility(uint32_t prop, uint32_t in_camera, uint32_t in_reflection, uint32_t in_sss); /* :535 */
 int32_t su_render_frame(uint32_t frame);                                  /* :548 */
-int32_t su_export_frame(void);                                            /* :569 (-1: out of scope) */
+int32_t su_export_frame(void);                                            /* :569 resolves the beauty and writes image_00_<frame:06>.<ext>
+                                                                             per exporter into the working directory
+                                                                             (exporting/image_sequence.zig:24-56) */
 int32_t su_start_frame(uint32_t frame);                                   /* :581 */
 int32_t su_render_iterations(uint32_t num_steps);                         /* :602 */
 int32_t su_resolve_frame(uint32_t aov);                                   /* :613 (aov < 9 = AovValue.NumClasses: -2, the class is
@@ -99,6 +101,11 @@ int32_t zyg_su_compile(const struct ZygpuScene** scene, const struct ZygpuView**
 void* zyg_su_device(void);
 /* Read access to the registered meshes by shape id (>= 7). */
 const struct zyg_mesh* zyg_su_mesh(uint32_t shape);
+/* The image codecs behind su_export_frame on a caller-owned RGBA float image (image/image_writer.zig:15-66). format: 0 PNG,
+ * 1 EXR, 2 RGBE; flags: bit 0 alpha channel (PNG / EXR), bit 1 EXR half floats, bit 2 PNG error diffusion; crop = x0, y0, x1, y1
+ * (exclusive) or NULL for the full frame. Host only, needs no engine and no GPU. */
+int32_t zyg_su_write_image(const char* path, uint32_t format, uint32_t flags, const float* rgba, int32_t width, int32_t height,
+                           const int32_t* crop);
 
 #ifdef __cplusplus
 }

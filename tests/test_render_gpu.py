@@ -613,3 +613,33 @@ def test_config4_full_scene_crop_matches_oracle(engine):
     kwargs = {"num_lights": 1000, "geometry_quads": (400, 250), "sun": 15.0, "sky": 1024, "max_depth": 8}
     n = scenes.mesh_lights_scene(1920, 1080, spp=2, **kwargs)
     _crop_compare(1920, 1080, (700, 400, 1220, 680), 2, n, 5e-5, 3e-2)
+
+
+def test_export_frame_writes_the_resolved_image(engine, tmp_path, monkeypatch):
+    """su_exporters_create + su_export_frame (capi.zig:189-200, 569-579; driver.zig:224-253): one file per exporter named
+    image_<camera:02>_<frame:06>.<ext>; the float EXR holds exactly what su_resolve_frame_to_buffer returns."""
+    from test_image_writer_host import read_exr, read_png, read_rgbe
+
+    w, h = 96, 64
+    scenes.cornell_box(w, h, spp=4)
+    monkeypatch.chdir(tmp_path)
+    su.exporters_create({"Image": {"format": "EXR", "bitdepth": 32}})
+    su.render_frame(7)
+    su.export_frame()
+    resolved = su.resolve_frame_to_buffer(w, h)
+    exr, names, window, _ = read_exr("image_00_000007.exr")
+    assert names == ["B", "G", "R"] and window == (0, 0, w - 1, h - 1)
+    assert np.array_equal(exr, resolved[..., [2, 1, 0]])
+
+    su.exporters_create({"Image": {"format": "PNG"}})
+    su.export_frame()
+    png = read_png("image_00_000007.png")
+    assert png.shape == (h, w, 3) and png.mean() > 5
+    srgb = np.zeros((h, w, 3), np.uint8)
+    su._su().su_resolve_frame(0xFFFFFFFF)
+    su._su().su_copy_framebuffer(0, 3, w, h, srgb.ctypes.data)
+    assert np.array_equal(png, srgb)
+
+    su.exporters_create({"Image": {"format": "RGBE"}})
+    su.export_frame()
+    assert read_rgbe("image_00_000007.hdr").shape == (h, w, 4)

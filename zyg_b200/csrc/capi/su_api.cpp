@@ -4,6 +4,7 @@
 #include "../../../include/zyg_su.h"
 #include "../../../include/zygpu.h"
 
+#include "../host/image_writer.hpp"
 #include "../host/mesh_handle.hpp"
 #include "../host/scene_model.hpp"
 
@@ -42,6 +43,14 @@ struct Engine {
     std::string async_error;
 
     std::vector<float> target;  // Driver.target: resolved RGBA of the last su_resolve_frame
+
+    // take.exporters (take.zig:303-331): the `Image` sinks of su_exporters_create
+    struct Exporter {
+        enum Format { PNG, EXR, RGBE } format = PNG;
+        bool half            = true;   // EXR "bitdepth": 16
+        bool error_diffusion = false;  // PNG
+    };
+    std::vector<Exporter> exporters;
 
     void (*log_post)(uint32_t, const char*) = nullptr;
     void (*progress_start)(uint32_t)        = nullptr;
@@ -200,7 +209,35 @@ int32_t su_camera_sensor_dimensions(int32_t* dimensions) {
     return 0;
 }
 
-int32_t su_exporters_create(const char*) { return -1; }
+// Take.loadExporters, take.zig:303-331 (capi.zig:189-200). `Video` (an ffmpeg pipe) is not an image codec: warned about and skipped.
+int32_t su_exporters_create(const char* json) {
+    if (!g_engine) return -1;
+    zyg::json::Value v;
+    if (!parse(json, v) || zyg::json::Value::Object != v.kind) return -1;
+    Engine& e = *g_engine;
+    e.exporters.clear();
+    for (const auto& entry : v.object) {
+        if ("Image" == entry.first) {
+            Engine::Exporter x;
+            const zyg::json::Value* fm = entry.second.get("format");
+            const std::string format = fm && zyg::json::Value::String == fm->kind ? fm->string : "PNG";
+            if ("EXR" == format) {
+                x.format = Engine::Exporter::EXR;
+                x.half   = 16 == zyg::json::readUIntMember(entry.second, "bitdepth", 16);
+            } else if ("RGBE" == format) {
+                x.format = Engine::Exporter::RGBE;
+            } else {
+                x.format          = Engine::Exporter::PNG;
+                x.error_diffusion = zyg::json::readBoolMember(entry.second, "error_diffusion", false);
+            }
+            e.exporters.push_back(x);
+        } else if ("Video" == entry.first) {
+            logf(Warning, "Video exporter (ffmpeg pipe) is not supported: skipped");
+        }
+    }
+    return 0;
+}
+
 int32_t su_aovs_create(const char*) { return -1; }
 
 int32_t su_sampler_create(uint32_t num_samples) {
@@ -343,7 +380,45 @@ int32_t zyg_su_render_frame_range(uint32_t frame, uint32_t iteration, uint32_t n
     return renderRange(*g_engine, frame, iteration, num_samples);
 }
 
-int32_t su_export_frame(void) { return -1; }
+// Driver.exportFrame + ImageSequence.write, driver.zig:224-253, exporting/image_sequence.zig:24-56: resolve the beauty, then one
+// file "image_<camera:02>_<frame:06>.<ext>" per exporter in the working directory. The Opaque sensor has no alpha channel
+// (buffer.zig:19-23); no AOV class is active.
+int32_t su_export_frame(void) {
+    if (!g_engine || !g_engine->device) return -1;
+    Engine&        e = *g_engine;
+    const uint32_t n = e.scene.width() * e.scene.height();
+    e.target.resize(size_t(n) * 4);
+    if (0 != zygpu_resolve(e.device, e.target.data(), n)) {
+        logf(Error, "%s", zygpu_last_error());
+        return -1;
+    }
+    const int32_t* crop = e.scene.view().crop;
+    for (const Engine::Exporter& x : e.exporters) {
+        std::vector<uint8_t> bytes;
+        const char*          ext = "png";
+        bool                 ok  = false;
+        switch (x.format) {
+            case Engine::Exporter::PNG:
+                ok = zyg::encodePng(bytes, e.target.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop, false, x.error_diffusion);
+                break;
+            case Engine::Exporter::EXR:
+                ext = "exr";
+                ok  = zyg::encodeExr(bytes, e.target.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop, false, x.half);
+                break;
+            case Engine::Exporter::RGBE:
+                ext = "hdr";
+                ok  = zyg::encodeRgbe(bytes, e.target.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop);
+                break;
+        }
+        char name[64];
+        std::snprintf(name, sizeof(name), "image_%02u_%06u.%s", 0u, e.frame, ext);
+        if (!ok || !zyg::writeFile(name, bytes)) {
+            logf(Error, "Exporting frame %u to %s failed", e.frame, name);
+            return -1;
+        }
+    }
+    return 0;
+}
 
 int32_t su_start_frame(uint32_t frame) {
     if (!g_engine) return -1;
@@ -470,6 +545,19 @@ void* zyg_su_device(void) { return g_engine ? g_engine->device : nullptr; }
 const zyg_mesh* zyg_su_mesh(uint32_t shape) {
     if (!g_engine || shape < 7 || shape - 7 >= g_engine->meshes.size()) return nullptr;
     return g_engine->meshes[shape - 7];
+}
+
+int32_t zyg_su_write_image(const char* path, uint32_t format, uint32_t flags, const float* rgba, int32_t width, int32_t height,
+                           const int32_t* crop) {
+    if (!path || !rgba || width < 1 || height < 1 || format > 2) return -1;
+    const int32_t full[4] = {0, 0, width, height};
+    const int32_t* c      = crop ? crop : full;
+    std::vector<uint8_t> bytes;
+    bool                 ok = false;
+    if (0 == format) ok = zyg::encodePng(bytes, rgba, width, height, c, 0 != (flags & 1u), 0 != (flags & 4u));
+    if (1 == format) ok = zyg::encodeExr(bytes, rgba, width, height, c, 0 != (flags & 1u), 0 != (flags & 2u));
+    if (2 == format) ok = zyg::encodeRgbe(bytes, rgba, width, height, c);
+    return ok && zyg::writeFile(path, bytes) ? 0 : -1;
 }
 
 }  // extern "C"

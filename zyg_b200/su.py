@@ -41,6 +41,7 @@ def _su() -> C.CDLL:
         "zyg_su_sensor_create": [cp], "zyg_su_instancer_create": [u32, vp, u32, vp, vp], "zyg_su_prop_create_unoccluding": [u32, u32, vp],
         "zyg_su_camera_set_lens": [f32, f32], "zyg_su_camera_set_crop": [i32, i32, i32, i32], "zyg_su_set_device": [i32],
         "zyg_su_render_frame_range": [u32, u32, u32], "zyg_su_compile": [vp, vp],
+        "zyg_su_write_image": [cp, u32, u32, vp, i32, i32, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -188,6 +189,28 @@ def resolve_frame_to_buffer(width: int, height: int) -> np.ndarray:
     out = np.empty((height, width, 4), np.float32)
     _ok(_su().su_resolve_frame_to_buffer(0xFFFFFFFF, width, height, out.ctypes.data), "su_resolve_frame_to_buffer")
     return out
+
+
+def exporters_create(desc: dict):
+    """The take's "export" block, e.g. {"Image": {"format": "EXR", "bitdepth": 32}} (take.zig:303-331)."""
+    _ok(_su().su_exporters_create(json.dumps(desc).encode()), "su_exporters_create")
+
+
+def export_frame():
+    """Writes image_00_<frame:06>.<ext> per exporter into the working directory (driver.zig:224-253)."""
+    _ok(_su().su_export_frame(), "su_export_frame")
+
+
+IMAGE_PNG, IMAGE_EXR, IMAGE_RGBE = 0, 1, 2
+IMAGE_ALPHA, IMAGE_HALF, IMAGE_ERROR_DIFFUSION = 1, 2, 4
+
+
+def write_image(path: str, fmt: int, rgba, flags: int = 0, crop=None):
+    """The codecs behind su_export_frame on a caller-owned (H, W, 4) float image; needs no engine and no GPU."""
+    img = np.ascontiguousarray(rgba, np.float32)
+    c = None if crop is None else np.ascontiguousarray(crop, np.int32)
+    _ok(_su().zyg_su_write_image(path.encode(), fmt, flags, img.ctypes.data, img.shape[1], img.shape[0],
+                                 None if c is None else c.ctypes.data), "zyg_su_write_image")
 
 
 def compile_scene():
