@@ -89,6 +89,14 @@ int32_t zyg_su_camera_set_lens(float aperture_radius, float focus_distance);
 /* The take's camera "crop": x0, y0, x1, y1 (x1 / y1 exclusive), clamped like Base.setResolution (camera_base.zig:32-41). Pixel
  * ids and sampler seeds still run over the full resolution (worker.zig:127-141). x1 < 0 restores the full frame. */
 int32_t zyg_su_camera_set_crop(int32_t x0, int32_t y0, int32_t x1, int32_t y1);
+/* Which builder su_triangle_mesh_create uses: 0 (default) the host's restatement of the reference's SAH /
+ * spatial-split build (reference-order tree, identical `primitive` ids), 1 the device LBVH build (zygpu_mesh_build: milliseconds
+ * instead of seconds per million triangles; meshes of fewer than 4 triangles still use the host). */
+int32_t zyg_su_set_mesh_builder(int32_t builder);
+/* Moved vertices of a registered mesh (same topology): refits its trees on the device (zygpu_mesh_refit). `normals` may be NULL.
+ * The next su_render_frame / su_start_frame compiles and uploads the scene again. */
+int32_t zyg_su_triangle_mesh_refit(uint32_t shape, const float* positions, uint32_t positions_stride, const float* normals,
+                                   uint32_t normals_stride);
 /* CUDA device used by the render calls (default 0). */
 int32_t zyg_su_set_device(int32_t ordinal);
 /* su_render_frame for a sample range: Driver.render(camera, frame, iteration, num_samples), the CLI's

@@ -75,6 +75,22 @@ void zygpu_destroy(zygpu_device* dev);
 /* Uploads the compiled mesh (wide layout + reference layout). Returns a mesh id >= 0. */
 int zygpu_upload_mesh(zygpu_device* dev, const zyg_mesh* mesh);
 
+/* ---- device BVH build / refit ------------------------------------------------
+ * zyg_mesh_build on the device: replaces builder_base.zig:65-283 + triangle_tree_builder.zig:33-207 for callers that want the
+ * first pixel sooner than the SAH / spatial-split build allows. The tree is an LBVH (60-bit Morton order, Karras' binary radix
+ * tree, leaves of at most three triangles) collapsed into the same 8-wide quantised nodes; triangles are not duplicated, so
+ * num_tree_triangles == num_source_triangles. The handle is an ordinary zyg_mesh (arrays copied back to the host): closest hits
+ * are the reference's up to equal-t ties and the leaf-box gate (a hit whose ray misses the box of its leaf is not reported, by
+ * either tree; the boxes differ). Needs at least 4 triangles. `device_ms` (may be NULL): CUDA-event time of the build. */
+int zygpu_mesh_build(zygpu_device* dev, uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles, const uint32_t* indices,
+                     uint32_t num_vertices, const float* positions, uint32_t positions_stride, const float* normals,
+                     uint32_t normals_stride, const float* uvs, uint32_t uvs_stride, zyg_mesh** out, float* device_ms);
+/* Same topology, moved vertices: refits the wide tree level by level from the leaves (triangle records, leaf gates, quantised
+ * child boxes), the boxes of the binary tree and the bounding sphere, on the device copy of the mesh (uploaded if it was not)
+ * and in the handle. `normals` may be NULL (kept). A scene that uses the mesh has to be compiled and uploaded again. */
+int zygpu_mesh_refit(zygpu_device* dev, zyg_mesh* mesh, const float* positions, uint32_t positions_stride, const float* normals,
+                     uint32_t normals_stride, float* device_ms);
+
 /* 32-byte ray: origin, min_t, direction, max_t (object space of the mesh; src/base/math/ray.zig). */
 typedef struct ZygpuRay {
     float origin[3];

@@ -30,6 +30,8 @@ struct Engine {
     uint32_t frame     = 0;
     uint32_t iteration = 0;
 
+    int mesh_builder = 0;  // zyg_su_set_mesh_builder: 0 host (reference-order SAH tree), 1 device (LBVH)
+
     // Scene.compile + upload are skipped while nothing was edited since the last frame (driver.zig:154-180 recompiles every
     // frame; the products are the same, so the device keeps them)
     uint64_t uploaded_revision = ~0ull;
@@ -289,6 +291,22 @@ int32_t su_triangle_mesh_create(uint32_t /*id*/, uint32_t num_parts, const uint3
 
     Engine& e = *g_engine;
     commitAsync(e);  // one outstanding build (pool.zig:155-162): a second request waits for the first
+    if (1 == e.mesh_builder && num_triangles >= 4) {
+        // the device build takes milliseconds: nothing to gain from the async thread
+        if (!e.device && 0 != zygpu_create(e.device_ordinal, &e.device)) {
+            e.device = nullptr;
+            logf(Error, "%s", zygpu_last_error());
+            return -1;
+        }
+        zyg_mesh* mesh = nullptr;
+        if (0 != zygpu_mesh_build(e.device, num_parts, parts, num_triangles, indices, num_vertices, positions, positions_stride, normals,
+                                  normals_stride, uvs, uvs_stride, &mesh, nullptr)) {
+            logf(Error, "%s", zygpu_last_error());
+            return -1;
+        }
+        e.meshes.push_back(mesh);
+        return int32_t(e.scene.addMesh(mesh, num_parts > 0 ? num_parts : 1));
+    }
     if (async) {
         // shape_provider.zig:299-303, 847-913: the build reads the caller's buffers on the async thread; they must outlive the
         // next call that commits (su_render_frame / su_start_frame / another mesh). The shape id is handed out at once.
@@ -522,6 +540,30 @@ int32_t zyg_su_camera_set_lens(float aperture_radius, float focus_distance) {
 int32_t zyg_su_set_device(int32_t ordinal) {
     if (!g_engine || g_engine->device) return -1;
     g_engine->device_ordinal = ordinal;
+    return 0;
+}
+
+int32_t zyg_su_set_mesh_builder(int32_t builder) {
+    if (!g_engine || builder < 0 || builder > 1) return -1;
+    g_engine->mesh_builder = builder;
+    return 0;
+}
+
+int32_t zyg_su_triangle_mesh_refit(uint32_t shape, const float* positions, uint32_t positions_stride, const float* normals,
+                                   uint32_t normals_stride) {
+    if (!g_engine || shape < 7 || shape - 7 >= g_engine->meshes.size() || !positions) return -1;
+    Engine& e = *g_engine;
+    if (0 != commitAsync(e) || !e.meshes[shape - 7]) return -1;
+    if (!e.device && 0 != zygpu_create(e.device_ordinal, &e.device)) {
+        e.device = nullptr;
+        logf(Error, "%s", zygpu_last_error());
+        return -1;
+    }
+    if (0 != zygpu_mesh_refit(e.device, e.meshes[shape - 7], positions, positions_stride, normals, normals_stride, nullptr)) {
+        logf(Error, "%s", zygpu_last_error());
+        return -1;
+    }
+    e.scene.setMesh(shape, e.meshes[shape - 7]);  // the bounds and areas changed: the next frame compiles and uploads again
     return 0;
 }
 

@@ -15,23 +15,15 @@
 
 
 
-extern "C" {
+namespace {
 
-const char* zygpu_last_error(void) { return zygpuError().c_str(); }
-
-int zyg_mesh_build(uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles, const uint32_t* indices,
-                   uint32_t num_vertices, const float* positions, uint32_t positions_stride, const float* normals,
-                   uint32_t normals_stride, const float* uvs, uint32_t uvs_stride, uint32_t num_threads,
-                   zyg_mesh** out) {
-    if (!out || !positions || 0 == num_triangles || 0 == num_vertices || positions_stride < 3) {
-        return fail("zyg_mesh_build: invalid arguments");
-    }
-
-    // shape_provider.zig:863-898 (buildDescAsync): triangles are filled part by part
-    std::vector<zyg::IndexTriangle> triangles(num_triangles);
-    const uint32_t                  empty_part[3] = {0, num_triangles * 3, 0};
-    const uint32_t*                 ps            = (num_parts > 0 && parts) ? parts : empty_part;
-    const uint32_t                  np            = num_parts > 0 ? num_parts : 1;
+// shape_provider.zig:863-898 (buildDescAsync): triangles are filled part by part
+int fillIndexTriangles(const char* who, uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles, const uint32_t* indices,
+                       uint32_t num_vertices, std::vector<zyg::IndexTriangle>& triangles, uint32_t& np) {
+    triangles.assign(num_triangles, zyg::IndexTriangle{{0, 0, 0}, 0});
+    const uint32_t  empty_part[3] = {0, num_triangles * 3, 0};
+    const uint32_t* ps            = (num_parts > 0 && parts) ? parts : empty_part;
+    np                            = num_parts > 0 ? num_parts : 1;
     for (uint32_t p = 0; p < np; ++p) {
         const uint32_t start_index = ps[p * 3 + 0];
         const uint32_t num_indices = ps[p * 3 + 1];
@@ -53,9 +45,29 @@ int zyg_mesh_build(uint32_t num_parts, const uint32_t* parts, uint32_t num_trian
     }
     for (const zyg::IndexTriangle& t : triangles) {
         if (t.i[0] >= num_vertices || t.i[1] >= num_vertices || t.i[2] >= num_vertices) {
-            return fail("zyg_mesh_build: vertex index out of range");
+            return fail("%s: vertex index out of range", who);
         }
     }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* zygpu_last_error(void) { return zygpuError().c_str(); }
+
+int zyg_mesh_build(uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles, const uint32_t* indices,
+                   uint32_t num_vertices, const float* positions, uint32_t positions_stride, const float* normals,
+                   uint32_t normals_stride, const float* uvs, uint32_t uvs_stride, uint32_t num_threads,
+                   zyg_mesh** out) {
+    if (!out || !positions || 0 == num_triangles || 0 == num_vertices || positions_stride < 3) {
+        return fail("zyg_mesh_build: invalid arguments");
+    }
+
+    std::vector<zyg::IndexTriangle> triangles;
+    uint32_t                        np = 1;
+    if (0 != fillIndexTriangles("zyg_mesh_build", num_parts, parts, num_triangles, indices, num_vertices, triangles, np)) return -1;
 
     if (0 == num_threads) num_threads = std::max(1u, std::thread::hardware_concurrency());
 

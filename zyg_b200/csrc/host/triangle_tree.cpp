@@ -80,6 +80,34 @@ struct Serializer {  // triangle_tree_builder.zig:166-207
 
 }  // namespace
 
+// triangle_data.zig:40-55 + vertex_buffer.zig:221-245 (CAPI.copy): packed positions (+1 pad float), oct-encoded normals, uvs
+void packVertexStreams(const VertexStreams& vertices, TriangleTree& tree) {
+    const uint32_t nv = vertices.num_vertices;
+    tree.num_vertices = nv;
+    tree.positions.assign(size_t(nv) * 3 + 1, 0.f);
+    tree.normals.assign(size_t(nv) * 2, 0);
+    tree.uvs.assign(size_t(nv) * 2, 0.f);
+    for (uint32_t i = 0; i < nv; ++i) {
+        const size_t s          = size_t(i) * vertices.positions_stride;
+        tree.positions[i * 3 + 0] = vertices.positions[s + 0];
+        tree.positions[i * 3 + 1] = vertices.positions[s + 1];
+        tree.positions[i * 3 + 2] = vertices.positions[s + 2];
+
+        Vec4f n = {{0.f, 0.f, 1.f, 0.f}};
+        if (vertices.normals) {
+            const size_t ns = size_t(i) * vertices.normals_stride;
+            n               = {{vertices.normals[ns + 0], vertices.normals[ns + 1], vertices.normals[ns + 2], 0.f}};
+        }
+        compressNormal(n, &tree.normals[size_t(i) * 2]);
+
+        if (vertices.uvs) {
+            const size_t us      = size_t(i) * vertices.uvs_stride;
+            tree.uvs[i * 2 + 0] = vertices.uvs[us + 0];
+            tree.uvs[i * 2 + 1] = vertices.uvs[us + 1];
+        }
+    }
+}
+
 void buildTriangleTree(const std::vector<IndexTriangle>& triangles, const VertexStreams& vertices,
                        uint32_t num_threads, TriangleTree& tree) {
     const uint32_t num_triangles = uint32_t(triangles.size());
@@ -118,29 +146,7 @@ void buildTriangleTree(const std::vector<IndexTriangle>& triangles, const Vertex
     tree.triangle_parts.assign(num_tree_triangles, 0);
     tree.original.assign(num_tree_triangles, 0);
 
-    // triangle_data.zig:40-55 + vertex_buffer.zig:221-245 (CAPI.copy)
-    tree.positions.assign(size_t(nv) * 3 + 1, 0.f);
-    tree.normals.assign(size_t(nv) * 2, 0);
-    tree.uvs.assign(size_t(nv) * 2, 0.f);
-    for (uint32_t i = 0; i < nv; ++i) {
-        const size_t s          = size_t(i) * vertices.positions_stride;
-        tree.positions[i * 3 + 0] = vertices.positions[s + 0];
-        tree.positions[i * 3 + 1] = vertices.positions[s + 1];
-        tree.positions[i * 3 + 2] = vertices.positions[s + 2];
-
-        Vec4f n = {{0.f, 0.f, 1.f, 0.f}};
-        if (vertices.normals) {
-            const size_t ns = size_t(i) * vertices.normals_stride;
-            n               = {{vertices.normals[ns + 0], vertices.normals[ns + 1], vertices.normals[ns + 2], 0.f}};
-        }
-        compressNormal(n, &tree.normals[size_t(i) * 2]);
-
-        if (vertices.uvs) {
-            const size_t us      = size_t(i) * vertices.uvs_stride;
-            tree.uvs[i * 2 + 0] = vertices.uvs[us + 0];
-            tree.uvs[i * 2 + 1] = vertices.uvs[us + 1];
-        }
-    }
+    packVertexStreams(vertices, tree);
 
     Serializer s{build, triangles, tree};
     s.current_node = 1;  // super.newNode() before serialize, triangle_tree_builder.zig:63

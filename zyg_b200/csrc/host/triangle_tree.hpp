@@ -47,6 +47,9 @@ struct VertexStreams {
     uint32_t     uvs_stride;
 };
 
+// Fills positions / normals / uvs and num_vertices of `tree` from the caller's streams.
+void packVertexStreams(const VertexStreams& vertices, TriangleTree& tree);
+
 // shape_provider.zig:915-924 (16 slices, sweep 64, 4 primitives) + triangle_tree_builder.zig:33-65.
 void buildTriangleTree(const std::vector<IndexTriangle>& triangles, const VertexStreams& vertices,
                        uint32_t num_threads, TriangleTree& tree);

@@ -69,6 +69,9 @@ def load_library() -> C.CDLL:
     lib.zygpu_destroy.argtypes = [vp]
     lib.zygpu_destroy.restype = None
     lib.zygpu_upload_mesh.argtypes = [vp, vp]
+    lib.zygpu_mesh_build.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, C.c_uint32, f32p, C.c_uint32, f32p, C.c_uint32,
+                                     f32p, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_float)]
+    lib.zygpu_mesh_refit.argtypes = [vp, vp, f32p, C.c_uint32, f32p, C.c_uint32, C.POINTER(C.c_float)]
     lib.zygpu_trace_batch.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint64, vp]
     lib.zygpu_trace_batch_device.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint64, vp, vp, C.POINTER(TraceCounters)]
     _lib = lib
@@ -102,7 +105,9 @@ class Mesh:
                                   ("leaf_max", "<f4", 3)]),
     }
 
-    def __init__(self, positions, indices=None, normals=None, uvs=None, parts=None, num_threads: int = 0):
+    def __init__(self, positions, indices=None, normals=None, uvs=None, parts=None, num_threads: int = 0, device=None):
+        """`device`: a Device -> the tree is built on the GPU (zygpu_mesh_build, an LBVH) instead of the host's reference-order
+        SAH build; `build_ms` then holds the CUDA-event time of the build."""
         lib = load_library()
         self._keep = []
 
@@ -126,9 +131,17 @@ class Mesh:
         num_parts = 0 if parts is None else parts.size // 3
 
         handle = C.c_void_p()
-        _check(lib.zyg_mesh_build(num_parts, _ptr(parts, C.c_uint32), num_triangles, _ptr(indices, C.c_uint32),
-                                  positions.shape[0], _ptr(positions, C.c_float), 3, _ptr(normals, C.c_float), 3,
-                                  _ptr(uvs, C.c_float), 2, num_threads, C.byref(handle)), "zyg_mesh_build")
+        self.build_ms = None
+        if device is not None:
+            ms = C.c_float()
+            _check(lib.zygpu_mesh_build(device.handle, num_parts, _ptr(parts, C.c_uint32), num_triangles, _ptr(indices, C.c_uint32),
+                                        positions.shape[0], _ptr(positions, C.c_float), 3, _ptr(normals, C.c_float), 3,
+                                        _ptr(uvs, C.c_float), 2, C.byref(handle), C.byref(ms)), "zygpu_mesh_build")
+            self.build_ms = ms.value
+        else:
+            _check(lib.zyg_mesh_build(num_parts, _ptr(parts, C.c_uint32), num_triangles, _ptr(indices, C.c_uint32),
+                                      positions.shape[0], _ptr(positions, C.c_float), 3, _ptr(normals, C.c_float), 3,
+                                      _ptr(uvs, C.c_float), 2, num_threads, C.byref(handle)), "zyg_mesh_build")
         self.handle = handle
         self._lib = lib
 
@@ -171,6 +184,15 @@ class Device:
 
     def upload_mesh(self, mesh: Mesh) -> int:
         return _check(self._lib.zygpu_upload_mesh(self.handle, mesh.handle), "zygpu_upload_mesh")
+
+    def refit_mesh(self, mesh: Mesh, positions, normals=None) -> float:
+        """Moved vertices, same topology (``zygpu_mesh_refit``); returns the CUDA-event time in ms."""
+        positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        normals = None if normals is None else np.ascontiguousarray(normals, np.float32)
+        ms = C.c_float()
+        _check(self._lib.zygpu_mesh_refit(self.handle, mesh.handle, _ptr(positions, C.c_float), 3, _ptr(normals, C.c_float), 3,
+                                          C.byref(ms)), "zygpu_mesh_refit")
+        return ms.value
 
     def trace_batch(self, mesh_id: int, mode: int, rays: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """Host buffers in, host buffers out (``zygpu_trace_batch``)."""

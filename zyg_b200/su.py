@@ -42,6 +42,7 @@ def _su() -> C.CDLL:
         "zyg_su_camera_set_lens": [f32, f32], "zyg_su_camera_set_crop": [i32, i32, i32, i32], "zyg_su_set_device": [i32],
         "zyg_su_render_frame_range": [u32, u32, u32], "zyg_su_compile": [vp, vp],
         "zyg_su_write_image": [cp, u32, u32, vp, i32, i32, vp],
+        "zyg_su_set_mesh_builder": [i32], "zyg_su_triangle_mesh_refit": [u32, vp, u32, vp, u32],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -65,8 +66,13 @@ def _ok(rc: int, what: str) -> int:
     return rc
 
 
+MESH_BUILDER = 0  # builder every new engine starts with (set_mesh_builder): scene helpers call init() themselves
+
+
 def init():
     _ok(_su().su_init(), "su_init")
+    if 0 != MESH_BUILDER:
+        _ok(_su().zyg_su_set_mesh_builder(MESH_BUILDER), "zyg_su_set_mesh_builder")
 
 
 def release():
@@ -189,6 +195,20 @@ def resolve_frame_to_buffer(width: int, height: int) -> np.ndarray:
     out = np.empty((height, width, 4), np.float32)
     _ok(_su().su_resolve_frame_to_buffer(0xFFFFFFFF, width, height, out.ctypes.data), "su_resolve_frame_to_buffer")
     return out
+
+
+HOST_BUILDER, DEVICE_BUILDER = 0, 1
+
+
+def set_mesh_builder(builder: int):
+    """0: host SAH build in reference order (default); 1: LBVH built on the device (zygpu_mesh_build)."""
+    _ok(_su().zyg_su_set_mesh_builder(builder), "zyg_su_set_mesh_builder")
+
+
+def triangle_mesh_refit(shape: int, positions, normals=None):
+    p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    n = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    _ok(_su().zyg_su_triangle_mesh_refit(shape, p.ctypes.data, 3, None if n is None else n.ctypes.data, 3), "zyg_su_triangle_mesh_refit")
 
 
 def exporters_create(desc: dict):
