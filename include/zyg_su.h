@@ -97,6 +97,9 @@ int32_t zyg_su_set_mesh_builder(int32_t builder);
  * The next su_render_frame / su_start_frame compiles and uploads the scene again. */
 int32_t zyg_su_triangle_mesh_refit(uint32_t shape, const float* positions, uint32_t positions_stride, const float* normals,
                                    uint32_t normals_stride);
+/* Which builder makes the light trees at compile time: 0 (default) the host's restatement of the reference's
+ * builder, 1 the device builder (zygpu_set_light_tree_builder) for trees of at least `min_lights` lights / emissive triangles. */
+int32_t zyg_su_set_light_tree_builder(int32_t builder, uint32_t min_lights);
 /* CUDA device used by the render calls (default 0). */
 int32_t zyg_su_set_device(int32_t ordinal);
 /* su_render_frame for a sample range: Driver.render(camera, frame, iteration, num_samples), the CLI's

@@ -91,6 +91,17 @@ int zygpu_mesh_build(zygpu_device* dev, uint32_t num_parts, const uint32_t* part
 int zygpu_mesh_refit(zygpu_device* dev, zyg_mesh* mesh, const float* positions, uint32_t positions_stride, const float* normals,
                      uint32_t normals_stride, float* device_ms);
 
+/* ---- device light-tree build --------------------------------------------------
+ * Replaces light_tree_builder.zig:281-428 (Builder.build for the scene's lights, Builder.buildPrimitive for the emissive triangles
+ * of a mesh part, i.e. the expensive half of Scene.propPrepareSampling, scene.zig:402-497) for trees of at least `min_lights`
+ * lights: while a device is installed, the host scene compile (zyg_su_compile / su_render_frame) and the mesh-light sampler build
+ * hand those trees to the GPU: Morton order over the light centres, Karras' radix tree, bounds / cone / power / variance / two-
+ * sidedness aggregated bottom-up, serialised into the reference's 32-byte light_tree.Node. The estimator is unchanged, the pdfs are
+ * those of another valid tree than the reference's cost-driven one. dev = NULL uninstalls. Process-global, like the su_* engine. */
+int zygpu_set_light_tree_builder(zygpu_device* dev, uint32_t min_lights);
+/* CUDA-event time spent in device light-tree builds since the last reset. */
+float zygpu_light_tree_build_ms(int reset);
+
 /* 32-byte ray: origin, min_t, direction, max_t (object space of the mesh; src/base/math/ray.zig). */
 typedef struct ZygpuRay {
     float origin[3];

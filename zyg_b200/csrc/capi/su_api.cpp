@@ -61,7 +61,10 @@ struct Engine {
     ~Engine() {
         if (async_build.joinable()) async_build.join();
         if (async_mesh) zyg_mesh_free(async_mesh);
-        if (device) zygpu_destroy(device);
+        if (device) {
+            zygpu_set_light_tree_builder(nullptr, 0);  // the builder hook must not outlive the device it builds on
+            zygpu_destroy(device);
+        }
         for (zyg_mesh* m : meshes) zyg_mesh_free(m);
     }
 };
@@ -547,6 +550,18 @@ int32_t zyg_su_set_mesh_builder(int32_t builder) {
     if (!g_engine || builder < 0 || builder > 1) return -1;
     g_engine->mesh_builder = builder;
     return 0;
+}
+
+int32_t zyg_su_set_light_tree_builder(int32_t builder, uint32_t min_lights) {
+    if (!g_engine || builder < 0 || builder > 1) return -1;
+    Engine& e = *g_engine;
+    if (0 == builder) return zygpu_set_light_tree_builder(nullptr, 0);
+    if (!e.device && 0 != zygpu_create(e.device_ordinal, &e.device)) {
+        e.device = nullptr;
+        logf(Error, "%s", zygpu_last_error());
+        return -1;
+    }
+    return zygpu_set_light_tree_builder(e.device, min_lights);
 }
 
 int32_t zyg_su_triangle_mesh_refit(uint32_t shape, const float* positions, uint32_t positions_stride, const float* normals,

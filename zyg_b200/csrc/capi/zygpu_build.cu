@@ -5,7 +5,9 @@
 
 #include "device_state.hpp"
 #include "../device/build.cuh"
+#include "../device/light_build.cuh"
 #include "../device/trace_device.cuh"
+#include "../host/light_tree_builder.hpp"
 #include "../host/mesh_handle.hpp"
 
 #include <algorithm>
@@ -63,9 +65,115 @@ uint32_t binaryDepth(const std::vector<zyg::BvhNode>& nodes) {
     return deepest;
 }
 
+// ---- light trees ---------------------------------------------------------------------------------------------------
+
+zygpu_device* g_light_device = nullptr;  // the device the host builder's hook builds on (zygpu_set_light_tree_builder)
+float         g_light_build_ms = 0.f;
+
+bool deviceLightTree(const zyg::LightSet& set, const uint32_t* lights, uint32_t num, uint32_t first_order, zyg::LightTreeResult& out,
+                     std::vector<uint32_t>& order) {
+    zygpu_device* dev = g_light_device;
+    if (!dev || num < 2) return false;
+    if (cudaSuccess != cudaSetDevice(dev->ordinal)) return false;
+    cudaStream_t stream = dev->streams[0];
+
+    // what the builder reads of a light, compacted to the lights of this tree
+    std::vector<float4>  lo(num), hi(num), cones(num);
+    std::vector<float>   powers(num);
+    std::vector<uint8_t> two_sided(num);
+    for (uint32_t i = 0; i < num; ++i) {
+        const uint32_t   l = lights[i];
+        const zyg::AABB& b = set.aabbs[l];
+        lo[i]              = make_float4(b.b[0][0], b.b[0][1], b.b[0][2], 0.f);
+        hi[i]              = make_float4(b.b[1][0], b.b[1][1], b.b[1][2], 0.f);
+        cones[i]           = make_float4(set.cones[l][0], set.cones[l][1], set.cones[l][2], set.cones[l][3]);
+        powers[i]          = set.powers[l];
+        two_sided[i]       = set.twoSided(l) ? 1 : 0;
+    }
+    DeviceBuffers          buffers;
+    zygpu::LightBuildInput in{};
+    float4 *               d_lo = nullptr, *d_hi = nullptr, *d_cones = nullptr;
+    float*                 d_powers = nullptr;
+    uint8_t*               d_two    = nullptr;
+    if (cudaSuccess != buffers.upload(d_lo, lo.data(), lo.size() * sizeof(float4), stream) ||
+        cudaSuccess != buffers.upload(d_hi, hi.data(), hi.size() * sizeof(float4), stream) ||
+        cudaSuccess != buffers.upload(d_cones, cones.data(), cones.size() * sizeof(float4), stream) ||
+        cudaSuccess != buffers.upload(d_powers, powers.data(), powers.size() * sizeof(float), stream) ||
+        cudaSuccess != buffers.upload(d_two, two_sided.data(), two_sided.size(), stream)) {
+        return false;
+    }
+    in.aabb_min      = d_lo;
+    in.aabb_max      = d_hi;
+    in.cones         = d_cones;
+    in.powers        = d_powers;
+    in.two_sided     = d_two;
+    in.num_lights    = num;
+    in.all_two_sided = set.all_two_sided;
+    in.primitive     = set.primitive;
+    in.first_order   = first_order;
+
+    zygpu::LightBuildOutput built;
+    if (cudaSuccess != zygpu::buildLightTreeOnDevice(in, built, stream)) {
+        zygpu::freeLightBuildOutput(built);
+        cudaGetLastError();
+        return false;
+    }
+    std::vector<ZygpuLightNode> slots(built.num_nodes);
+    std::vector<uint32_t>       slot_middles(built.num_nodes);
+    order.resize(num);
+    const bool copied =
+        cudaSuccess == cudaMemcpyAsync(slots.data(), built.nodes, slots.size() * sizeof(ZygpuLightNode), cudaMemcpyDeviceToHost, stream) &&
+        cudaSuccess == cudaMemcpyAsync(slot_middles.data(), built.node_middles, slot_middles.size() * 4, cudaMemcpyDeviceToHost, stream) &&
+        cudaSuccess == cudaMemcpyAsync(order.data(), built.order, order.size() * 4, cudaMemcpyDeviceToHost, stream) &&
+        cudaSuccess == cudaStreamSynchronize(stream);
+    g_light_build_ms += built.device_ms;
+    for (int a = 0; a < 3; ++a) {
+        out.bounds.b[0][a] = built.bounds_min[a];
+        out.bounds.b[1][a] = built.bounds_max[a];
+    }
+    out.bounds.b[0][3] = out.bounds.b[1][3] = 0.f;
+    out.root_power     = built.root_power;
+    zygpu::freeLightBuildOutput(built);
+    if (!copied) return false;
+
+    // the device leaves the slots of subtrees that became leaves unused: compact, keeping children adjacent (breadth first)
+    out.nodes.clear();
+    out.node_middles.clear();
+    out.nodes.reserve(slots.size());
+    std::vector<uint32_t> queue{0u};
+    out.nodes.push_back(slots[0]);
+    out.node_middles.push_back(slot_middles[0]);
+    for (size_t q = 0; q < queue.size(); ++q) {
+        const uint32_t       slot = queue[q];
+        const ZygpuLightNode n    = slots[slot];
+        if (0 == (n.meta & 1u)) continue;
+        const uint32_t c0    = n.meta >> 2;
+        const uint32_t new_c = uint32_t(out.nodes.size());
+        out.nodes[q].meta    = (n.meta & 3u) | (new_c << 2);
+        for (uint32_t k = 0; k < 2; ++k) {
+            out.nodes.push_back(slots[c0 + k]);
+            out.node_middles.push_back(slot_middles[c0 + k]);
+            queue.push_back(c0 + k);
+        }
+    }
+    return true;
+}
+
 }  // namespace
 
 extern "C" {
+
+int zygpu_set_light_tree_builder(zygpu_device* dev, uint32_t min_lights) {
+    g_light_device = dev;
+    zyg::setDeviceLightTreeBuilder(dev ? deviceLightTree : nullptr, min_lights);
+    return 0;
+}
+
+float zygpu_light_tree_build_ms(int reset) {
+    const float ms = g_light_build_ms;
+    if (reset) g_light_build_ms = 0.f;
+    return ms;
+}
 
 int zygpu_mesh_build(zygpu_device* dev, uint32_t num_parts, const uint32_t* parts, uint32_t num_triangles, const uint32_t* indices,
                      uint32_t num_vertices, const float* positions, uint32_t positions_stride, const float* normals,

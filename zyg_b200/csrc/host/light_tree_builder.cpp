@@ -436,6 +436,47 @@ Vec4f coneMerge(Vec4f a, Vec4f b) {
     return {{axis[0], axis[1], axis[2], std::cos(o_angle)}};
 }
 
+namespace {
+
+DeviceLightTreeFn g_device_builder     = nullptr;
+uint32_t          g_device_min_lights = 0;
+
+// BuildNode.countPotentialLights (:44-57) + the depth search of Builder.build (:350-361) on serialised nodes
+uint32_t maxSplitDepth(const std::vector<ZygpuLightNode>& nodes, uint32_t num_infinite) {
+    uint32_t split_lights[kLightTreeMaxSplitDepth][2] = {};
+    struct Item {
+        uint32_t node, depth;
+    };
+    std::vector<Item> stack{{0u, 0u}};
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        const ZygpuLightNode& n = nodes[it.node];
+        if (0 == (n.meta & 1u)) {
+            split_lights[it.depth][0] += 1;
+        } else {
+            split_lights[it.depth][1] += 2;
+            if (it.depth + 1 < kLightTreeMaxSplitDepth) {
+                stack.push_back({(n.meta >> 2) + 1, it.depth + 1});
+                stack.push_back({n.meta >> 2, it.depth + 1});
+            }
+        }
+    }
+    uint32_t num_split_lights = 0;
+    for (uint32_t i = 0; i < kLightTreeMaxSplitDepth; ++i) {
+        num_split_lights += split_lights[i][0];
+        if ((num_split_lights + split_lights[i][1]) > (kLightTreeMaxLights - num_infinite) || 0 == split_lights[i][1]) return i;
+    }
+    return kLightTreeMaxSplitDepth;
+}
+
+}  // namespace
+
+void setDeviceLightTreeBuilder(DeviceLightTreeFn fn, uint32_t min_lights) {
+    g_device_builder    = fn;
+    g_device_min_lights = min_lights;
+}
+
 void buildLightTree(const LightSet& set, std::vector<uint32_t>& mapping, uint32_t num_infinite, uint32_t first_order,
                     std::vector<uint32_t>& light_orders, LightTreeResult& out) {
     const uint32_t num_lights = uint32_t(mapping.size());
@@ -446,6 +487,25 @@ void buildLightTree(const LightSet& set, std::vector<uint32_t>& mapping, uint32_
     out.root_power      = 0.f;
     out.bounds          = AABB::empty();
     if (0 == num_finite) return;
+
+    if (g_device_builder && num_finite >= std::max(g_device_min_lights, 2u)) {
+        std::vector<uint32_t> order;
+        const std::vector<uint32_t> finite(mapping.begin() + num_infinite, mapping.end());
+        if (g_device_builder(set, finite.data(), num_finite, first_order, out, order)) {
+            for (uint32_t i = 0; i < num_finite; ++i) {
+                const uint32_t l          = finite[order[i]];
+                mapping[num_infinite + i] = l;
+                light_orders[l]           = first_order + i;
+            }
+            out.bounds.cacheRadius();
+            out.max_split_depth = maxSplitDepth(out.nodes, num_infinite);
+            return;
+        }
+        out = LightTreeResult{};
+        out.max_split_depth = kLightTreeMaxSplitDepth;
+        out.root_power      = 0.f;
+        out.bounds          = AABB::empty();
+    }
 
     Builder builder(set, mapping, light_orders);
     builder.light_order = first_order;
@@ -487,6 +547,23 @@ void buildPrimitiveLightTree(const LightSet& set, uint32_t num_triangles, const 
     for (uint32_t l = 0; l < num_triangles; ++l) out.light_mapping[l] = l;
     out.max_split_depth = 0;
     if (0 == num_triangles) return;
+
+    if (g_device_builder && num_triangles >= std::max(g_device_min_lights, 8u)) {
+        std::vector<uint32_t> order;
+        LightTreeResult       built;
+        if (g_device_builder(set, out.light_mapping.data(), num_triangles, 0, built, order)) {
+            built.light_mapping.resize(num_triangles);
+            built.light_orders.assign(num_triangles, 0);
+            for (uint32_t i = 0; i < num_triangles; ++i) {
+                built.light_mapping[i]      = order[i];
+                built.light_orders[order[i]] = i;
+            }
+            built.bounds.cacheRadius();
+            built.max_split_depth = 0;
+            out                   = std::move(built);
+            return;
+        }
+    }
 
     Builder builder(set, out.light_mapping, out.light_orders);
     builder.allocate(num_triangles, kPartSweepThreshold);

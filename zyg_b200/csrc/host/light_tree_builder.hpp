@@ -47,6 +47,13 @@ void buildLightTree(const LightSet& set, std::vector<uint32_t>& mapping, uint32_
 void buildPrimitiveLightTree(const LightSet& set, uint32_t num_triangles, const AABB& bounds, Vec4f cone, float total_power,
                              LightTreeResult& out);
 
+// Optional device builder (device/light_build.cu), installed by the C-ABI layer: builds the tree over
+// `lights[0..num)` (indices into `set`) and fills nodes / node_middles / bounds / root_power of `out` plus `order`: tree position ->
+// index into `lights`. Leaf and middle indices already include `first_order`. Returns false when it declines (then the host builds).
+using DeviceLightTreeFn = bool (*)(const LightSet& set, const uint32_t* lights, uint32_t num, uint32_t first_order, LightTreeResult& out,
+                                   std::vector<uint32_t>& order);
+void setDeviceLightTreeBuilder(DeviceLightTreeFn fn, uint32_t min_lights);
+
 Vec4f coneMerge(Vec4f a, Vec4f b);  // math.cone.merge, src/base/math/cone.zig:8-44
 
 }  // namespace zyg

@@ -42,7 +42,7 @@ def _su() -> C.CDLL:
         "zyg_su_camera_set_lens": [f32, f32], "zyg_su_camera_set_crop": [i32, i32, i32, i32], "zyg_su_set_device": [i32],
         "zyg_su_render_frame_range": [u32, u32, u32], "zyg_su_compile": [vp, vp],
         "zyg_su_write_image": [cp, u32, u32, vp, i32, i32, vp],
-        "zyg_su_set_mesh_builder": [i32], "zyg_su_triangle_mesh_refit": [u32, vp, u32, vp, u32],
+        "zyg_su_set_mesh_builder": [i32], "zyg_su_set_light_tree_builder": [i32, u32], "zyg_su_triangle_mesh_refit": [u32, vp, u32, vp, u32],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -66,13 +66,16 @@ def _ok(rc: int, what: str) -> int:
     return rc
 
 
-MESH_BUILDER = 0  # builder every new engine starts with (set_mesh_builder): scene helpers call init() themselves
+MESH_BUILDER = 0  # builders every new engine starts with (set_mesh_builder / set_light_tree_builder): the scene helpers call
+LIGHT_TREE_BUILDER = 0  # init() themselves
 
 
 def init():
     _ok(_su().su_init(), "su_init")
     if 0 != MESH_BUILDER:
         _ok(_su().zyg_su_set_mesh_builder(MESH_BUILDER), "zyg_su_set_mesh_builder")
+    if 0 != LIGHT_TREE_BUILDER:
+        _ok(_su().zyg_su_set_light_tree_builder(LIGHT_TREE_BUILDER, 0), "zyg_su_set_light_tree_builder")
 
 
 def release():
@@ -203,6 +206,11 @@ HOST_BUILDER, DEVICE_BUILDER = 0, 1
 def set_mesh_builder(builder: int):
     """0: host SAH build in reference order (default); 1: LBVH built on the device (zygpu_mesh_build)."""
     _ok(_su().zyg_su_set_mesh_builder(builder), "zyg_su_set_mesh_builder")
+
+
+def set_light_tree_builder(builder: int, min_lights: int = 0):
+    """0: host restatement of the reference's light-tree builder (default); 1: device builder for trees of >= min_lights lights."""
+    _ok(_su().zyg_su_set_light_tree_builder(builder, min_lights), "zyg_su_set_light_tree_builder")
 
 
 def triangle_mesh_refit(shape: int, positions, normals=None):
