@@ -1189,8 +1189,13 @@ __device__ __forceinline__ float clampedSinSub(float cos_a, float cos_b, float s
     return cos_a > cos_b ? 0.f : angle;
 }
 
-// light_tree.zig:173-215
-__device__ __forceinline__ float lightImportance(V3 p, V3 n, V3 center, V3 cone_axis, float cos_cone, float radius, float power, bool two_sided,
+// light_tree.zig:173-215. Out of line on purpose: every argument is a value (nothing forces kernel parameters into local memory), and the
+// tree code calls it from a dozen places - inlined, its IEEE divisions and square roots alone were a fifth of the shade kernels' code,
+// which are bound by instruction fetch (ncu: `no_instruction` next to `long_scoreboard`).
+#ifndef ZYGPU_IMPORTANCE_INLINE
+#define ZYGPU_IMPORTANCE_INLINE __noinline__
+#endif
+__device__ ZYGPU_IMPORTANCE_INLINE float lightImportance(V3 p, V3 n, V3 center, V3 cone_axis, float cos_cone, float radius, float power, bool two_sided,
                                  bool total_sphere) {
     const V3    axis = sub3(p, center);
     const float l    = length3(axis);
@@ -2554,9 +2559,15 @@ __global__ void __launch_bounds__(128) lightSelectPersistent(SceneDevice sc, Zyg
 #ifndef ZYGPU_LIGHT_BLOCKS
 #define ZYGPU_LIGHT_BLOCKS 8
 #endif
-template <bool MeshLights, bool Infinite>
+// Scenes with infinite lights run it twice: their picks come first in a vertex's list (Tree.randomLight, light_tree.zig:353-371), so
+// phase 1 takes the Distant / Canopy picks of every vertex and phase 2 the finite ones, each on the sampler state the other left.
+// A warp then works on one class of light at a time (and each instance holds half the code): lanes that fetch a new vertex no longer
+// start with a sky sample while their neighbours are inside a mesh light. Phase 0 = every pick in one launch.
+template <bool MeshLights, bool Infinite, int Phase>
 __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent(SceneDevice sc, ZygpuView view, PathState st, PassParams pass,
                                                              uint32_t* __restrict__ work_counter) {
+    constexpr bool kInfinitePicks = Infinite && 2 != Phase;  // this instance handles Distant / Canopy picks
+    constexpr bool kFinitePicks   = 1 != Phase;
     __shared__ __align__(16) uint32_t sobol_tables[kSobolTableWords];
     loadSobolTables(sobol_tables);
 
@@ -2591,9 +2602,10 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                 n                 = 0 != (fl & 2u) ? neg3(geo_n) : geo_n;
                 translucent       = 0 != (fl & 1u);
                 threshold         = 0 != (fl & 4u) ? kLowThreshold : view.split_threshold;
-                pick_i            = 0;
-                pick_count        = st.pick_n[slot];
-                num_records       = 0;
+                const uint32_t pn = st.pick_n[slot];
+                pick_i            = 2 == Phase ? pn >> 16 : 0u;  // phase 1 leaves the index of the first finite pick there
+                pick_count        = pn & 0xffffu;
+                num_records       = 2 == Phase ? st.sh_n[slot] : 0u;
                 const uint4 smp   = st.smp[slot];
                 pool_word         = smp.w;
                 loadSampler(st, slot, smp, pass, view.spp_total, (fl >> 8) & 0xffu, sampler);
@@ -2613,7 +2625,14 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
             const ZygpuLight light = sc.lights[pick.offset];
             const TrafoD     trafo = loadTrafo(sc.trafos, light.prop);
             const uint32_t   shape = sc.props[light.prop].shape;
-            if (Infinite && ZYG_SHAPE_DISTANT == shape) {  // Distant.sampleTo, distant.zig:78-107
+            if (1 == Phase && ZYG_SHAPE_DISTANT != shape && ZYG_SHAPE_CANOPY != shape) {
+                // the first finite pick ends phase 1: phase 2 resumes here
+                pick_i -= 1;
+                st.pick_n[slot] = pick_count | (pick_i << 16);
+                st.sh_n[slot]   = num_records;
+                storeSampler(st, slot, sampler, pool_word);
+                active = false;
+            } else if (kInfinitePicks && ZYG_SHAPE_DISTANT == shape) {  // Distant.sampleTo, distant.zig:78-107
                 const float radius = trafo.scale.x;
                 if (radius > 0.f) {
                     float u0, u1;
@@ -2636,7 +2655,7 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                         }
                     }
                 }
-            } else if (Infinite && ZYG_SHAPE_CANOPY == shape) {  // Canopy.sampleMaterialTo, canopy.zig:94-131
+            } else if (kInfinitePicks && ZYG_SHAPE_CANOPY == shape) {  // Canopy.sampleMaterialTo, canopy.zig:94-131
                 if (ZYG_LIGHT_PROP_IMAGE == light.light_class) {
                     float u0, u1;
                     sampler.sample2D(u0, u1);
@@ -2655,12 +2674,12 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                         }
                     }
                 }
-            } else if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == shape && ZYGPU_NULL != light.sampler) {
+            } else if (kFinitePicks && MeshLights && ZYG_SHAPE_TRIANGLE_MESH == shape && ZYGPU_NULL != light.sampler) {
                 FragD frag;  // meshLightSampleTo reads the shading point and offsets from it
                 frag.p      = p;
                 frag.geo_n  = geo_n;
                 num_records = meshLightSampleTo(sc, st, slot, light, pick, trafo, frag, n, translucent, threshold, sampler, num_records);
-            } else if (ZYG_SHAPE_SPHERE == shape) {  // Sphere.sampleTo, sphere.zig:323-393
+            } else if (kFinitePicks && ZYG_SHAPE_SPHERE == shape) {  // Sphere.sampleTo, sphere.zig:323-393
                 SphereLightD sl;
                 sl.init(trafo, p);
                 const uint32_t ns = sl.valid ? lightNumSamples(light, threshold) : 0;
@@ -2682,7 +2701,7 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                         st.counters[3] = 1;
                     }
                 }
-            } else if (ZYG_SHAPE_RECTANGLE == shape && ZYG_LIGHT_PROP_IMAGE == light.light_class) {  // Rectangle.sampleMaterialTo
+            } else if (kFinitePicks && ZYG_SHAPE_RECTANGLE == shape && ZYG_LIGHT_PROP_IMAGE == light.light_class) {  // Rectangle.sampleMaterialTo
                 const uint32_t            ns   = lightNumSamples(light, threshold);
                 const ImageSamplerDevice& is   = sc.image_samplers[light.sampler];
                 const float               area = trafo.scale.x * trafo.scale.y;
@@ -2714,7 +2733,7 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                         st.counters[3] = 1;
                     }
                 }
-            } else if (ZYG_SHAPE_RECTANGLE == shape) {  // Rectangle.sampleTo, rectangle.zig:305-357
+            } else if (kFinitePicks && ZYG_SHAPE_RECTANGLE == shape) {  // Rectangle.sampleTo, rectangle.zig:305-357
                 const uint32_t ns  = lightNumSamples(light, threshold);
                 const float    nsf = float(ns);
                 SphQuadD       squad;
@@ -2748,9 +2767,10 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
             }
         }
         if (active && pick_i >= pick_count) {
+            if (1 == Phase) st.pick_n[slot] = pick_count | (pick_count << 16);  // no finite pick: phase 2 only queues the records
             st.sh_n[slot] = num_records;
             storeSampler(st, slot, sampler, pool_word);
-            if (nullptr != st.queue_r && 0 != num_records) {
+            if (1 != Phase && nullptr != st.queue_r && 0 != num_records) {
                 const uint32_t base = atomicAdd(&st.counters[10], num_records);
                 for (uint32_t k = 0; k < num_records; ++k) st.queue_r[base + k] = slot * st.shadow_stride + k;
             }
@@ -3264,7 +3284,7 @@ cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const 
 cudaError_t launchLightStages(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
                               cudaStream_t stream) {
     if (nullptr == st.queue_l) return cudaSuccess;
-    cudaError_t err = cudaMemsetAsync(st.counters + 12, 0, 2 * sizeof(uint32_t), stream);
+    cudaError_t err = cudaMemsetAsync(st.counters + 12, 0, 3 * sizeof(uint32_t), stream);
     if (cudaSuccess != err) return err;
 
     static int resident_select = 0, resident_sample = 0;
@@ -3272,7 +3292,7 @@ cudaError_t launchLightStages(const SceneDevice& scene, const ZygpuView& view, c
         int per_sm = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lightSelectPersistent, 128, 0);
         resident_select = std::max(per_sm, 1) * numSms();
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lightSamplePersistent<true, true>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lightSamplePersistent<true, true, 0>, 128, 0);
         resident_sample = std::max(per_sm, 1) * numSms();
     }
     const uint32_t needed = (max_items + 127) / 128;
@@ -3280,14 +3300,21 @@ cudaError_t launchLightStages(const SceneDevice& scene, const ZygpuView& view, c
 
     const uint32_t grid = std::max(1u, std::min<uint32_t>(uint32_t(resident_sample), needed));
     const bool     ml = scene.num_mesh_samplers > 0, inf = scene.num_infinite_props > 0;
-    if (ml && inf) {
-        lightSamplePersistent<true, true><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+    static const bool phases = nullptr == getenv("ZYGPU_LIGHT_PHASES") || 0 != atoi(getenv("ZYGPU_LIGHT_PHASES"));
+    if (ml && inf && phases) {
+        lightSamplePersistent<true, true, 1><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+        lightSamplePersistent<true, true, 2><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 14);
+    } else if (ml && inf) {
+        lightSamplePersistent<true, true, 0><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
     } else if (ml) {
-        lightSamplePersistent<true, false><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+        lightSamplePersistent<true, false, 0><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+    } else if (inf && phases) {
+        lightSamplePersistent<false, true, 1><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+        lightSamplePersistent<false, true, 2><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 14);
     } else if (inf) {
-        lightSamplePersistent<false, true><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+        lightSamplePersistent<false, true, 0><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
     } else {
-        lightSamplePersistent<false, false><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
+        lightSamplePersistent<false, false, 0><<<grid, 128, 0, stream>>>(scene, view, st, pass, st.counters + 13);
     }
     return cudaGetLastError();
 }
