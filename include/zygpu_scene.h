@@ -83,7 +83,7 @@ enum { /* material_base.zig:17-26 */
 };
 
 /* Substitute / Glass / Light parameters: uniform values plus the image maps in scope (emission map,
- * Substitute colour map). 112 bytes. */
+ * Substitute colour, roughness, metallic and normal maps). 112 bytes. */
 typedef struct ZygpuMaterial {
     uint32_t type;  /* ZYG_MATERIAL_* */
     uint32_t flags; /* ZYG_MATERIAL_* bits */
@@ -109,7 +109,9 @@ typedef struct ZygpuMaterial {
     uint32_t emission_map; /* Emittance.emission_map when it is an image: index into ZygpuScene.image_samplers, else ZYGPU_NULL */
 
     uint32_t color_map; /* Substitute.color when it is an image (substitute_material.zig:120): index into image_samplers, else ZYGPU_NULL */
-    uint32_t pad[3];
+    uint32_t roughness_map; /* Substitute.roughness as an image (ts.sample2D_1, substitute_material.zig:122): first channel */
+    uint32_t metallic_map;  /* Substitute.metallic as an image (:123): first channel */
+    uint32_t normal_map;    /* Substitute.normal_map (hlp.sampleNormal, material_helper.zig:16-79): first two channels = tangent-space xy */
 } ZygpuMaterial;
 
 enum { /* Light.Class (src/core/scene/light/light.zig:34-40) */
@@ -167,7 +169,7 @@ typedef struct ZygpuImageSampler {
     uint32_t filter;               /* Texture.Mode.Filter: 0 Nearest, 1 LinearStochastic */
     float    total_weight;         /* ImageImpl.total_weight = sum of Shape.uvWeight over the texels */
     float    scale[2];             /* Texture.data.image.scale */
-    const float* pixels;           /* width * height RGB triples (ACEScg) */
+    const float* pixels;           /* width * height float triples: RGB (ACEScg); a 1- or 2-channel image fills the first channels */
     const float* marginal_cdf;     /* height + 1; NULL (with the two arrays below) for an image that is only looked up, never sampled */
     const float* conditional_cdf;  /* height rows of width + 1 */
     const float* conditional_integral; /* height; 0 => that row is the degenerate distribution {1, 1} (distribution_1d.zig:99-110) */

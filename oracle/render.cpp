@@ -2102,6 +2102,36 @@ struct Worker {
         return result;
     }
 
+    // hlp.sampleNormal, material_helper.zig:16-79 (tex_coord UV)
+    static Vec4f sampleNormal(Vec4f wo, const Renderstate& rs, float nx, float ny) {
+        const float nmz = std::sqrt(max(1.f - (nx * nx + ny * ny), 0.01f));
+        const Vec4f nm  = {{nx, ny, nmz, 0.f}};
+        // rs.tangentToWorld(nm), renderstate.zig:51-58
+        const Vec4f w = {{nm[0] * rs.t[0] + nm[1] * rs.b[0] + nm[2] * rs.n[0], nm[0] * rs.t[1] + nm[1] * rs.b[1] + nm[2] * rs.n[1],
+                          nm[0] * rs.t[2] + nm[1] * rs.b[2] + nm[2] * rs.n[2], 0.f}};
+        const Vec4f n = normalize3(w);
+
+        const Vec4f ng = rs.geo_n;
+        const Vec4f r  = reflect3(n, wo);
+        const float a  = dot3(ng, r);
+        if (a >= 0.f) return n;
+
+        const float cos_threshold = 0.0017453f;  // cos(89.9 degrees)
+        if (dot3(ng, wo) < cos_threshold) return ng;
+
+        const float b       = dot3(ng, n);
+        const float epsilon = 1e-4f;
+        Vec4f       tangent;
+        if (b > epsilon) {
+            const float distance_to_surface_along_normal = std::fabs(a) / b;
+            tangent = normalize3(r + splat(distance_to_surface_along_normal) * n);
+        } else {
+            tangent = n;
+        }
+        tangent = tangent + splat(epsilon) * ng;
+        return normalize3(wo + tangent);
+    }
+
     // Vertex.sample, vertex.zig:137-181 + Material.sample, material.zig:184-194
     MaterialSample vertexSample(const Vertex& vertex, const Fragment& frag, Sampler& sampler, bool caustics) const {
         const Vec4f          wo = -vertex.ray.direction;
@@ -2133,12 +2163,26 @@ struct Worker {
 
         switch (m.type) {
             case ZYG_MATERIAL_SUBSTITUTE: {
-                if (ZYGPU_NULL == m.color_map) return substituteSample(m, wo, rs, scene.view.specular_threshold, scene.luts);
-                // ts.sample2D_3(self.color, rs, ...), substitute_material.zig:120
+                if (ZYGPU_NULL == m.color_map && ZYGPU_NULL == m.roughness_map && ZYGPU_NULL == m.metallic_map && ZYGPU_NULL == m.normal_map) {
+                    return substituteSample(m, wo, rs, scene.view.specular_threshold, scene.luts);
+                }
                 ZygpuMaterial textured = m;
-                const Vec4f   c        = scene.image_samplers[m.color_map].texel(rs.uvw[0], rs.uvw[1], rs.stochastic_r);
-                textured.color[0] = c[0], textured.color[1] = c[1], textured.color[2] = c[2];
-                return substituteSample(textured, wo, rs, scene.view.specular_threshold, scene.luts);
+                auto texel = [&](uint32_t map) { return scene.image_samplers[map].texel(rs.uvw[0], rs.uvw[1], rs.stochastic_r); };
+                if (ZYGPU_NULL != m.color_map) {  // ts.sample2D_3(self.color, rs, ...), substitute_material.zig:120
+                    const Vec4f c = texel(m.color_map);
+                    textured.color[0] = c[0], textured.color[1] = c[1], textured.color[2] = c[2];
+                }
+                if (ZYGPU_NULL != m.roughness_map) textured.roughness = texel(m.roughness_map)[0];  // ts.sample2D_1(self.roughness), :122
+                if (ZYGPU_NULL != m.metallic_map) textured.metallic = texel(m.metallic_map)[0];     // :123
+                MaterialSample result = substituteSample(textured, wo, rs, scene.view.specular_threshold, scene.luts);
+                if (ZYGPU_NULL != m.normal_map) {  // :157-159
+                    const Vec4f xy = texel(m.normal_map);
+                    const Vec4f n  = sampleNormal(wo, rs, xy[0], xy[1]);
+                    Vec4f       t, b;
+                    orthonormalBasis3(n, t, b);
+                    result.super.frame = {t, b, n};
+                }
+                return result;
             }
             case ZYG_MATERIAL_GLASS: return glassSample(m, wo, rs, scene.view.specular_threshold, scene.luts);
             default: return lightSample(wo, rs);

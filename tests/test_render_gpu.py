@@ -643,3 +643,21 @@ def test_export_frame_writes_the_resolved_image(engine, tmp_path, monkeypatch):
     su.exporters_create({"Image": {"format": "RGBE"}})
     su.export_frame()
     assert read_rgbe("image_00_000007.hdr").shape == (h, w, 4)
+
+
+@pytest.mark.parametrize("nearest", [False, True])
+def test_surface_maps_match_oracle(engine, nearest):
+    """Substitute roughness, metallic and normal maps (substitute_material.zig:122-123, 157-159; hlp.sampleNormal,
+    material_helper.zig:16-79) from float and byte (unorm / snorm) images on a Rectangle, a Cube and a triangle mesh: every map of a
+    vertex is looked up with its one stochastic_r in shade_a and again in shade_b."""
+    w, spp = 128, 16
+    n = scenes.surface_maps_scene(w, w, spp=spp, nearest=nearest)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6
+    assert (rel > 1e-2).mean() < 5e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4

@@ -302,7 +302,10 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
         if (ZYGPU_NULL != scene->materials[m].color_map && scene->materials[m].color_map >= scene->num_image_samplers) {
             return fail("zygpu_upload_scene: material %u references image sampler %u", m, scene->materials[m].color_map);
         }
-        if (ZYGPU_NULL != scene->materials[m].color_map) r.has_textures = true;
+        const ZygpuMaterial& mat = scene->materials[m];
+        if (ZYGPU_NULL != mat.color_map || ZYGPU_NULL != mat.roughness_map || ZYGPU_NULL != mat.metallic_map || ZYGPU_NULL != mat.normal_map) {
+            r.has_textures = true;
+        }
     }
 
     // shadow records one path vertex can need: every light the tree may return times its sample count
@@ -345,6 +348,7 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     // scenes run it in the persistent light kernels instead of inside shade_a (ZYGPU_DEFERRED_LIGHTS=0/1 overrides)
     r.deferred_lights = scene->num_lights >= 8;
     if (const char* v = getenv("ZYGPU_DEFERRED_LIGHTS")) r.deferred_lights = 0 != atoi(v);
+    if (scene->num_mesh_samplers > 0) r.deferred_lights = true;  // triangle-mesh lights are only sampled by the light kernels
 
     r.has_meshes = scene->num_meshes > 0;
     r.has_scene  = true;

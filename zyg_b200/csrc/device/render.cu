@@ -2074,7 +2074,61 @@ __device__ __forceinline__ LoadedVertex loadVertex(const PathState& st, uint32_t
 // roulette (:88, helper.zig:75-89), Vertex.sample (:93), sampleLights / evaluateLight up to the visibility test
 // (:174-250).
 // Features the scene needs of shade_a; what it does not need is compiled out (each costs registers in the hottest kernel).
-enum : uint32_t { kFeatureSplit = 1, kFeatureMeshLights = 2, kFeatureInfiniteLights = 4, kFeatureDeferredLights = 8 };
+// kFeatureTextured: a material reads image maps per vertex (colour / roughness / metallic / normal): instances without it hold none of
+// that code (as a run-time branch it cost the map-free scenes 4 % through registers and code size)
+enum : uint32_t { kFeatureSplit = 1, kFeatureMeshLights = 2, kFeatureInfiniteLights = 4, kFeatureDeferredLights = 8, kFeatureTextured = 16 };
+
+
+// hlp.sampleNormal, material_helper.zig:16-79 for a UV-mapped normal map: the tangent-space normal of the map in the shading frame, then the
+// adaption that keeps the reflection of `wo` above the geometric surface.
+__device__ __forceinline__ V3 sampleNormal(V3 wo, V3 t, V3 b, V3 n, V3 geo_n, float nx, float ny) {
+    const float nz = __fsqrt_rn(zmax(1.f - (nx * nx + ny * ny), 0.01f));
+    // rs.tangentToWorld(nm), renderstate.zig:51-58
+    const V3 w  = {(nx * t.x + ny * b.x) + nz * n.x, (nx * t.y + ny * b.y) + nz * n.y, (nx * t.z + ny * b.z) + nz * n.z};
+    const V3 nn = normalize3(w);
+
+    const V3    r = sub3(scale3(2.f * dot3(wo, nn), nn), wo);  // math.reflect3(n, wo), vector4.zig:94-96
+    const float a = dot3(geo_n, r);
+    if (a >= 0.f) return nn;
+    if (dot3(geo_n, wo) < 0.0017453f) return geo_n;  // cos(89.9 degrees)
+
+    const float bb      = dot3(geo_n, nn);
+    const float epsilon = 1e-4f;
+    V3          tangent = nn;
+    if (bb > epsilon) {
+        const float distance = __fdiv_rn(fabsf(a), bb);
+        tangent              = normalize3(add3(r, scale3(distance, nn)));
+    }
+    tangent = add3(tangent, scale3(epsilon, geo_n));
+    return normalize3(add3(wo, tangent));
+}
+
+__device__ __forceinline__ V3 surfaceMapTexel(const ImageSamplerDevice* is, float u, float v, float r) { return imageTexel(*is, u, v, r); }
+
+// Material.sample with the image maps of a Substitute (substitute_material.zig:114-162): colour, roughness, metallic and the normal map are
+// all looked up with the vertex's one stochastic_r (texture_sampler.zig:22-76), so shade_b re-reads the texels shade_a read.
+template <bool Split, bool Textured>
+__device__ __forceinline__ MatSampleD texturedMaterialSample(const SceneDevice& sc, ZygpuMaterial& m, const FragD& frag, V3 wo,
+                                                             float stochastic_r, float reg_weight, float reg_alpha, bool caustics,
+                                                             float specular_threshold, float ior_outside, int highest_priority) {
+    if (Textured) {
+        if (ZYGPU_NULL != m.color_map) {  // ts.sample2D_3(self.color, rs, ...), :120
+            const V3 c = imageTexel(sc.image_samplers[m.color_map], frag.u, frag.v, stochastic_r);
+            m.color[0] = c.x, m.color[1] = c.y, m.color[2] = c.z;
+        }
+        if (ZYGPU_NULL != m.roughness_map) m.roughness = surfaceMapTexel(sc.image_samplers + m.roughness_map, frag.u, frag.v, stochastic_r).x;  // :122
+        if (ZYGPU_NULL != m.metallic_map) m.metallic = surfaceMapTexel(sc.image_samplers + m.metallic_map, frag.u, frag.v, stochastic_r).x;     // :123
+    }
+    MatSampleD r = materialSample<Split>(m, frag, wo, reg_weight, reg_alpha, caustics, specular_threshold, ior_outside, highest_priority);
+    if (Textured && ZYGPU_NULL != m.normal_map && kSampleSubstitute == r.kind) {  // :157-159: result.super.frame = Frame.init(n)
+        const V3 xy = surfaceMapTexel(sc.image_samplers + m.normal_map, frag.u, frag.v, stochastic_r);
+        const V3 n  = sampleNormal(wo, frag.t, frag.b, r.n, r.geo_n, xy.x, xy.y);
+        V3       t, b;
+        orthonormalBasis3(n, t, b);
+        r.frame = {t, b, n};
+    }
+    return r;
+}
 
 template <uint32_t Features>
 __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
@@ -2082,6 +2136,7 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
     constexpr bool MeshLights = 0 != (Features & kFeatureMeshLights);
     constexpr bool Infinite   = 0 != (Features & kFeatureInfiniteLights);
     constexpr bool Deferred   = 0 != (Features & kFeatureDeferredLights);  // light selection and sampling run in the light kernels
+    constexpr bool Textured   = 0 != (Features & kFeatureTextured);
     __shared__ __align__(16) uint32_t sobol_tables[kSobolTableWords];
     const bool      later = Split && round > 0;
     const uint32_t  count = later ? st.counters[9] : st.counters[0];
@@ -2207,18 +2262,12 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                 const V3      wo = neg3(vertex.ray.d);
                 ZygpuMaterial m  = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
                 const float   stochastic_r = sampler.sample1D();  // rs.stochastic_r, vertex.zig:165
-                if (nullptr != st.stoch) {
-                    st.stoch[vid] = stochastic_r;
-                    if (ZYGPU_NULL != m.color_map) {  // ts.sample2D_3(self.color, rs, ...), substitute_material.zig:120
-                        const V3 c = imageTexel(sc.image_samplers[m.color_map], frag.u, frag.v, stochastic_r);
-                        m.color[0] = c.x, m.color[1] = c.y, m.color[2] = c.z;
-                    }
-                }
+                if (Textured) st.stoch[vid] = stochastic_r;
                 float ior_outside      = 1.f;
                 int   highest_priority = -128;
                 if (Split) mediaForSample(sc, media, frag, wo, ior_outside, highest_priority);
-                const MatSampleD mat_sample = materialSample<Split>(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics,
-                                                                    view.specular_threshold, ior_outside, highest_priority);
+                const MatSampleD mat_sample = texturedMaterialSample<Split, Textured>(sc, m, frag, wo, stochastic_r, view.regularize_roughness, lv.reg_alpha,
+                                                                                      caustics, view.specular_threshold, ior_outside, highest_priority);
 
                 vertex.light_split_threshold = splitThreshold(view.split_threshold, vertex.probe_depth);
 
@@ -2806,7 +2855,7 @@ __global__ void __launch_bounds__(kBlock) shadowKernel(SceneDevice sc, PathState
 
 // The rest of PathtracerMIS.li: evaluateLight after the visibility test (pathtracer_mis.zig:252-277), the direct-light
 // add (:116-117), mat_sample.sample and the next vertex (:121-166).
-template <bool Split>
+template <bool Split, bool Textured>
 __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeBKernel(SceneDevice sc, ZygpuView view, PathState st, PassParams pass, uint32_t round) {
     __shared__ __align__(16) uint32_t sobol_tables[kSobolTableWords];
     const uint32_t count = st.counters[1];
@@ -2845,15 +2894,13 @@ __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeB
             const bool          caustics   = 0 == (vertex.state & kPrimaryRay) ? 0 != view.caustics_path : true;
             const V3      wo = neg3(vertex.ray.d);
             ZygpuMaterial m  = sc.materials[__ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part)];
-            if (nullptr != st.stoch && ZYGPU_NULL != m.color_map) {  // the same texel shade_a's material sample read
-                const V3 c = imageTexel(sc.image_samplers[m.color_map], frag.u, frag.v, st.stoch[vid]);
-                m.color[0] = c.x, m.color[1] = c.y, m.color[2] = c.z;
-            }
             float               ior_outside      = 1.f;
             int                 highest_priority = -128;
             if (Split) mediaForSample(sc, media, frag, wo, ior_outside, highest_priority);
-            const MatSampleD mat_sample = materialSample<Split>(m, frag, wo, view.regularize_roughness, lv.reg_alpha, caustics,
-                                                                view.specular_threshold, ior_outside, highest_priority);
+            // the same texels shade_a's material sample read
+            const MatSampleD mat_sample = texturedMaterialSample<Split, Textured>(sc, m, frag, wo, Textured ? st.stoch[vid] : 0.f, view.regularize_roughness,
+                                                                                  lv.reg_alpha, caustics, view.specular_threshold, ior_outside,
+                                                                                  highest_priority);
 
             const uint32_t max_splits = Split ? maxSplits(lv.path_count_log2, 0 != (vertex.state & kPrimaryRay), total_depth) : 1;
 
@@ -3257,28 +3304,23 @@ cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t
 }
 cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
                          uint32_t round, cudaStream_t stream) {
+    // triangle-mesh lights are always sampled by the light kernels (capi/zygpu_render.cu): no instance samples them inline
     const uint32_t features = (st.lanes > 1 ? kFeatureSplit : 0u) | (scene.num_mesh_samplers > 0 ? kFeatureMeshLights : 0u) |
-                              (scene.num_infinite_props > 0 ? kFeatureInfiniteLights : 0u) | (nullptr != st.queue_l ? kFeatureDeferredLights : 0u);
+                              (scene.num_infinite_props > 0 ? kFeatureInfiniteLights : 0u) | (nullptr != st.queue_l ? kFeatureDeferredLights : 0u) |
+                              (nullptr != st.stoch ? kFeatureTextured : 0u);
+    if (0 != (features & kFeatureMeshLights) && 0 == (features & kFeatureDeferredLights)) return cudaErrorInvalidValue;
     const uint32_t grid = gridFor(max_items, shadeGrid(st.lanes > 1));
     if (st.lanes <= 1) round = 0;
+#define ZYGPU_SHADE_A(F) \
+    case F: shadeAKernel<F><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
     switch (features) {
-        case 0: shadeAKernel<0><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 1: shadeAKernel<1><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 2: shadeAKernel<2><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 3: shadeAKernel<3><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 4: shadeAKernel<4><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 5: shadeAKernel<5><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 6: shadeAKernel<6><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 7: shadeAKernel<7><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 8: shadeAKernel<8><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 9: shadeAKernel<9><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 10: shadeAKernel<10><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 11: shadeAKernel<11><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 12: shadeAKernel<12><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 13: shadeAKernel<13><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        case 14: shadeAKernel<14><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
-        default: shadeAKernel<15><<<grid, kBlock, 0, stream>>>(scene, view, st, pass, round); break;
+        ZYGPU_SHADE_A(0) ZYGPU_SHADE_A(1) ZYGPU_SHADE_A(4) ZYGPU_SHADE_A(5) ZYGPU_SHADE_A(8) ZYGPU_SHADE_A(9) ZYGPU_SHADE_A(10) ZYGPU_SHADE_A(11)
+        ZYGPU_SHADE_A(12) ZYGPU_SHADE_A(13) ZYGPU_SHADE_A(14) ZYGPU_SHADE_A(15)
+        ZYGPU_SHADE_A(16) ZYGPU_SHADE_A(17) ZYGPU_SHADE_A(20) ZYGPU_SHADE_A(21) ZYGPU_SHADE_A(24) ZYGPU_SHADE_A(25) ZYGPU_SHADE_A(26) ZYGPU_SHADE_A(27)
+        ZYGPU_SHADE_A(28) ZYGPU_SHADE_A(29) ZYGPU_SHADE_A(30) ZYGPU_SHADE_A(31)
+        default: return cudaErrorInvalidValue;
     }
+#undef ZYGPU_SHADE_A
     return cudaGetLastError();
 }
 cudaError_t launchLightStages(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
@@ -3338,9 +3380,17 @@ cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
                          uint32_t round, cudaStream_t stream) {
     if (st.lanes > 1) {
-        shadeBKernel<true><<<gridFor(max_items, shadeGrid(true)), kBlock, 0, stream>>>(scene, view, st, pass, round);
+        if (nullptr != st.stoch) {
+            shadeBKernel<true, true><<<gridFor(max_items, shadeGrid(true)), kBlock, 0, stream>>>(scene, view, st, pass, round);
+        } else {
+            shadeBKernel<true, false><<<gridFor(max_items, shadeGrid(true)), kBlock, 0, stream>>>(scene, view, st, pass, round);
+        }
     } else {
-        shadeBKernel<false><<<gridFor(max_items, shadeGrid(false)), kBlock, 0, stream>>>(scene, view, st, pass, 0);
+        if (nullptr != st.stoch) {
+            shadeBKernel<false, true><<<gridFor(max_items, shadeGrid(false)), kBlock, 0, stream>>>(scene, view, st, pass, 0);
+        } else {
+            shadeBKernel<false, false><<<gridFor(max_items, shadeGrid(false)), kBlock, 0, stream>>>(scene, view, st, pass, 0);
+        }
         advanceKernel<<<1, 1, 0, stream>>>(st);
     }
     return cudaGetLastError();

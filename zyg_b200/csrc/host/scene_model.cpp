@@ -104,6 +104,7 @@ ZygpuMaterial defaultMaterial(uint32_t type) {
     m.ior                    = 1.f;
     m.emission_map           = ZYGPU_NULL;
     m.color_map              = ZYGPU_NULL;
+    m.roughness_map = m.metallic_map = m.normal_map = ZYGPU_NULL;
     switch (type) {
         case ZYG_MATERIAL_SUBSTITUTE:  // substitute_material.zig:41-67
             m.color[0] = m.color[1] = m.color[2] = 0.5f;
@@ -280,6 +281,7 @@ SceneModel::SceneModel() : specular_threshold_(kMinAlpha) {
     materials_.push_back(defaultMaterial(ZYG_MATERIAL_DEBUG));
     emission_maps_.push_back(EmissionMapRec{});
     color_maps_.push_back(EmissionMapRec{});
+    surface_maps_.push_back({});
 }
 
 bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
@@ -329,10 +331,22 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
                     EmissionMapRec em;  // Substitute emission maps are not in scope: parsed and dropped
                     uint32_t       mode[3] = {1, 1, 1};
                     loadEmittance(e.second, m, em.image, mode, em.scale);
-                } else if ("roughness" == k) {
-                    m.roughness = float(e.second.number);
-                } else if ("metallic" == k) {
-                    m.metallic = float(e.second.number);
+                } else if ("roughness" == k || "metallic" == k || "normal" == k) {
+                    // readValue(.Roughness / .Metallic / .Normal), material_provider.zig:269-287, 741-800: an image id makes it a map
+                    const int       slot = "roughness" == k ? kRoughnessMap : ("metallic" == k ? kMetallicMap : kNormalMap);
+                    EmissionMapRec& sm   = surface_maps_[id][slot];
+                    sm                   = EmissionMapRec{};
+                    if (json::Value::Object == e.second.kind && e.second.get("id")) {
+                        uint32_t mode[3] = {sm.address_u, sm.address_v, sm.filter};
+                        readTextureDescriptor(&e.second, sm.image, mode, sm.scale);
+                        sm.address_u = mode[0];
+                        sm.address_v = mode[1];
+                        sm.filter    = mode[2];
+                    } else if (kRoughnessMap == slot) {
+                        m.roughness = float(e.second.number);
+                    } else if (kMetallicMap == slot) {
+                        m.metallic = float(e.second.number);
+                    }  // a uniform "normal" is no normal map (Texture.initUniform2: isUniform, substitute_material.zig:157)
                 } else if ("specular" == k) {
                     m.specular = float(e.second.number);
                 } else if ("anisotropy" == k) {
@@ -343,7 +357,7 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
                     m.priority = int32_t(e.second.number);
                 } else if ("two_sided" == k) {
                     m.flags = e.second.boolean ? (m.flags | ZYG_MATERIAL_TWO_SIDED) : (m.flags & ~ZYG_MATERIAL_TWO_SIDED);
-                } else {  // coating, flakes, normal / surface / rotation / mask maps, attenuation, volumetric_anisotropy, ...
+                } else {  // coating, flakes, surface / rotation / mask maps, attenuation, volumetric_anisotropy, ...
                     warnings_.push_back("material " + std::to_string(id) + ": Substitute parameter \"" + k + "\" is not supported by the device path and is ignored");
                 }
             }
@@ -414,6 +428,7 @@ int SceneModel::createMaterial(const json::Value& material) {
         materials_.push_back(defaultMaterial(type));
         emission_maps_.push_back(EmissionMapRec{});
         color_maps_.push_back(EmissionMapRec{});
+        surface_maps_.push_back({});
         updateMaterial(uint32_t(materials_.size() - 1), material);
         return int(materials_.size() - 1);
     }
@@ -425,11 +440,13 @@ int SceneModel::createImage(uint32_t id, uint32_t format, uint32_t num_channels,
     touch();
     // capi.zig:29-35 Format: UInt8 0, UInt16 1, UInt32 2, Float16 3, Float32 4
     const uint32_t bpc = 0 == format ? 1u : ((1 == format || 3 == format) ? 2u : 4u);
-    if (3 != num_channels || !(0 == format || 4 == format) || 0 == width || 0 == height || 1 != depth || !data) return -1;
+    // capi.zig:268-284: UInt8 x 1 / 2 / 3 and Float32 x 1 / 2 / 3 (Float32 x 4 and volumes are outside the scope)
+    if (num_channels < 1 || num_channels > 3 || !(0 == format || 4 == format) || 0 == width || 0 == height || 1 != depth || !data) return -1;
     ImageRec img;
-    img.width  = width;
-    img.height = height;
-    img.format = format;
+    img.width    = width;
+    img.height   = height;
+    img.format   = format;
+    img.channels = num_channels;
     img.pixels.assign(size_t(width) * height * 3, 0.f);
     // Cache.store, resource/cache.zig: an id inside the cache replaces that entry, anything else appends
     uint32_t slot = id < images_.size() ? id : uint32_t(images_.size());
@@ -444,10 +461,21 @@ int SceneModel::updateImage(uint32_t id, uint32_t pixel_stride, const uint8_t* d
     if (id >= images_.size() || !data) return -1;
     ImageRec&      img = images_[id];
     const size_t   n   = size_t(img.width) * img.height;
-    const uint32_t bpp = (0 == img.format ? 1u : 4u) * 3u;
+    const uint32_t bpp = (0 == img.format ? 1u : 4u) * img.channels;
     if (bpp != pixel_stride) return 0;  // capi.zig:322: silently ignored
-    if (4 == img.format) {
+    if (4 == img.format && 3 == img.channels) {
         std::memcpy(img.pixels.data(), data, n * 12);
+    } else if (4 == img.format) {  // Float1 / Float2 (texture.zig:172, 183)
+        const float* src = reinterpret_cast<const float*>(data);
+        for (size_t i = 0; i < n; ++i) {
+            for (uint32_t c = 0; c < img.channels; ++c) img.pixels[3 * i + c] = src[img.channels * i + c];
+        }
+    } else if (1 == img.channels) {  // Texture.Byte1_unorm: enc.cachedUnormToFloat (encoding.zig:10-12)
+        for (size_t i = 0; i < n; ++i) img.pixels[3 * i] = float(data[i]) * (1.f / 255.f);
+    } else if (2 == img.channels) {
+        // Texture.Byte2_snorm: what createTexture makes of a Byte2 image used as a normal map (texture_provider.zig:72), the one use a
+        // two-channel image has on this path; enc.snorm8ToFloat (encoding.zig:18-20)
+        for (size_t i = 0; i < 2 * n; ++i) img.pixels[3 * (i / 2) + (i & 1)] = std::fmaf(float(data[i]), 1.f / 128.f, -1.f);
     } else {  // Texture.Byte3_sRGB: cachedSrgbToFloat3 then sRGB -> AP1 (texture.zig:196-199, srgb.zig:28-38)
         float table[256];
         for (int i = 0; i < 256; ++i) {
@@ -1032,6 +1060,22 @@ bool SceneModel::compile(std::string& error) {
         const EmissionMapRec& em = emission_maps_[m];
         materials_[m].emission_map = ZYGPU_NULL;
         materials_[m].color_map    = ZYGPU_NULL;
+        materials_[m].roughness_map = materials_[m].metallic_map = materials_[m].normal_map = ZYGPU_NULL;
+        static const char* const kMapName[kNumSurfaceMaps] = {"roughness", "metallic", "normal"};
+        for (int k = 0; k < kNumSurfaceMaps; ++k) {
+            const uint32_t image = surface_maps_[m][k].image;
+            if (ZYGPU_NULL == image) continue;
+            if (image >= images_.size()) {
+                error = "material " + std::to_string(m) + ": " + kMapName[k] + " references image " + std::to_string(image) + " which does not exist";
+                return false;
+            }
+            // texture.zig:166-186: a fetch with the wrong channel count returns zero; refuse instead of rendering something else
+            const uint32_t want = kNormalMap == k ? 2u : 1u;
+            if (images_[image].channels != want) {
+                error = "material " + std::to_string(m) + ": " + kMapName[k] + " map needs an image of " + std::to_string(want) + " channel(s)";
+                return false;
+            }
+        }
         if (ZYGPU_NULL != color_maps_[m].image && color_maps_[m].image >= images_.size()) {
             error = "material " + std::to_string(m) + ": color references image " + std::to_string(color_maps_[m].image) + " which does not exist";
             return false;
@@ -1183,6 +1227,25 @@ bool SceneModel::compile(std::string& error) {
         is.pixels    = img.pixels.data();
         materials_[m].color_map = uint32_t(flat_image_samplers_.size());
         flat_image_samplers_.push_back(is);
+    }
+    for (size_t m = 0; m < materials_.size(); ++m) {  // roughness / metallic / normal maps: looked up only
+        for (int k = 0; k < kNumSurfaceMaps; ++k) {
+            const EmissionMapRec& sm = surface_maps_[m][k];
+            if (ZYGPU_NULL == sm.image) continue;
+            const ImageRec&   img = images_[sm.image];
+            ZygpuImageSampler is{};
+            is.width     = img.width;
+            is.height    = img.height;
+            is.address_u = sm.address_u;
+            is.address_v = sm.address_v;
+            is.filter    = sm.filter;
+            is.scale[0]  = sm.scale[0];
+            is.scale[1]  = sm.scale[1];
+            is.pixels    = img.pixels.data();
+            uint32_t& slot = kRoughnessMap == k ? materials_[m].roughness_map : (kMetallicMap == k ? materials_[m].metallic_map : materials_[m].normal_map);
+            slot           = uint32_t(flat_image_samplers_.size());
+            flat_image_samplers_.push_back(is);
+        }
     }
 
     flat_ = ZygpuScene{};

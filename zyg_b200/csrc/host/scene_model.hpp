@@ -22,6 +22,7 @@
 #include "zmath.hpp"
 
 #include <string>
+#include <array>
 #include <vector>
 
 struct zyg_mesh;
@@ -157,9 +158,9 @@ class SceneModel {
         std::vector<uint32_t>       prototypes;  // per instance: the prototype entity
         std::vector<Transformation> trafos;      // per instance, relative to the instancer entity
     };
-    struct ImageRec {  // image.Float3 / image.Byte3
-        uint32_t           width = 0, height = 0, format = 0;
-        std::vector<float> pixels;  // RGB, ACEScg
+    struct ImageRec {  // image.Float1 / Float2 / Float3 / Byte1 / Byte2 / Byte3
+        uint32_t           width = 0, height = 0, format = 0, channels = 3;
+        std::vector<float> pixels;  // float triples: RGB in ACEScg, or the 1 / 2 channels of a scalar / normal map in the first slots
     };
     struct EmissionMapRec {  // Emittance.emission_map when it is an image (Texture + Texture.Mode), per material
         uint32_t image     = ZYGPU_NULL;
@@ -183,6 +184,8 @@ class SceneModel {
     std::vector<ZygpuMaterial>  materials_;
     std::vector<EmissionMapRec> emission_maps_;  // per material
     std::vector<EmissionMapRec> color_maps_;     // per material: Substitute.color as an image texture
+    enum { kRoughnessMap = 0, kMetallicMap = 1, kNormalMap = 2, kNumSurfaceMaps = 3 };
+    std::vector<std::array<EmissionMapRec, 3>> surface_maps_;  // per material: Substitute.roughness / metallic / normal_map as images
     std::vector<ImageRec>       images_;
     std::vector<std::unique_ptr<ImageSamplerRec>> image_samplers_;
     std::vector<ZygpuImageSampler>                flat_image_samplers_;

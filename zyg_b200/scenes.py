@@ -406,6 +406,75 @@ def textured_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None,
     return 1
 
 
+def bump_normal_map(size=64, waves=4.0, strength=0.5, dtype=np.float32):
+    """Tangent-space xy of the normals of a sinusoidal height field, (size, size, 2): float32, or uint8 snorm (enc.floatToSnorm8)."""
+    t = (np.arange(size) + 0.5) / size * (2.0 * np.pi * waves)
+    nx = -strength * np.cos(t)[None, :] * np.ones((size, 1))
+    ny = -strength * np.cos(t)[:, None] * np.ones((1, size))
+    xy = np.stack([nx, ny], -1)
+    xy /= np.sqrt(1.0 + (xy * xy).sum(-1, keepdims=True))
+    if dtype == np.uint8:
+        return ((xy + 1.0) * np.where(xy > 0.0, 127.5, 128.0)).astype(np.uint8)
+    return np.ascontiguousarray(xy, np.float32)
+
+
+def surface_maps_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None, quads=(48, 24), uniform=False, nearest=False,
+                       maps=("roughness", "metallic", "normal")):
+    """Substitute roughness, metallic and normal maps (substitute_material.zig:122-123, 157-159; material_helper.zig:16-79): a ground
+    plane with a float roughness ramp and a byte (snorm) normal map, a cube with byte (unorm) roughness and metallic checkers, a
+    displaced-sphere mesh with a float normal map over its own uvs and a metallic map. `uniform` replaces every map by the constant it
+    averages to (a flat normal map is no map). Returns the number of meshes."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(55.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.6, -4.2), rotation_deg=(-14.0, 0.0, 0.0)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+    sampler = {"filter": "Nearest"} if nearest else {}
+
+    def mapped(kind, image, constant, scale=1.0, address="Repeat"):
+        if uniform or kind not in maps:
+            return constant
+        return {"id": su.image_create(image), "scale": scale, "sampler": dict(sampler, address=address)}
+
+    def material(color, roughness, metallic, normal=None):
+        desc = {"color": color, "roughness": roughness, "metallic": metallic}
+        if isinstance(normal, dict):
+            desc["normal"] = normal
+        return su.material_create({"rendering": {"Substitute": desc}})
+
+    ramp = np.ascontiguousarray(np.tile(np.linspace(0.08, 0.9, 64, dtype=np.float32)[None, :], (64, 1)))
+    ground = material([0.6, 0.6, 0.55], mapped("roughness", ramp, 0.49, scale=3.0), 0.0,
+                      mapped("normal", bump_normal_map(64, 4.0, 0.6, np.uint8), None, scale=6.0))
+    g = su.prop_create(su.RECTANGLE, [ground])
+    su.prop_set_transformation(g, su.transformation((0.0, 0.0, 0.0), (12.0, 12.0, 1.0), (90.0, 0.0, 0.0)))
+
+    i = np.arange(32) * 4 // 32
+    checker = ((i[:, None] + i[None, :]) & 1).astype(np.uint8)
+    crate = material([0.9, 0.6, 0.2], mapped("roughness", (60 + 150 * checker).astype(np.uint8), 0.53, address="Clamp"),
+                     mapped("metallic", (255 * checker).astype(np.uint8), 0.5, address="Clamp"))
+    cube = su.prop_create(su.CUBE, [crate])
+    su.prop_set_transformation(cube, su.transformation((-1.3, 0.5, 0.4), (1.0, 1.0, 1.0), (0.0, 30.0, 0.0)))
+
+    j = np.arange(128) * 16 // 128
+    spots = (((j[:, None] + j[None, :]) & 1) * 1.0).astype(np.float32)
+    ball_material = material([0.8, 0.75, 0.7], 0.3, mapped("metallic", spots, 0.5),
+                             mapped("normal", bump_normal_map(128, 12.0, 0.8), None))
+    positions, normals, uvs, indices = displaced_sphere(*quads, seed=0x5EED0009)
+    indices = np.ascontiguousarray(indices.reshape(-1, 3)[:, [0, 2, 1]])
+    ball = su.prop_create(su.triangle_mesh_create(positions, indices, normals, uvs), [ball_material])
+    su.prop_set_transformation(ball, su.transformation((1.2, 0.8, 0.0), (0.75, 0.75, 0.75), (0.0, 20.0, 0.0)))
+
+    light = su.material_create({"rendering": {"Light": {"emittance": {"value": 25.0}}}})
+    lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=True)
+    su.prop_set_transformation(lamp, su.transformation((0.0, 4.0, -0.5), (2.0, 2.0, 1.0), (-90.0, 0.0, 0.0)))
+    su.light_create(lamp)
+    return 1
+
+
 def image_light_scene(width=128, height=128, spp=16, max_depth=5, filter_name=None, split_threshold=0.5, num_samples=1,
                       image=None, value=6.0, two_sided=False, unoccluding=True):
     """A closed room lit by a Rectangle whose Light material carries an emission image (a PropImage light on a finite shape:

@@ -111,16 +111,20 @@ def sensor_create(desc: dict):
 
 
 def image_create(pixels: np.ndarray) -> int:
-    """su_image_create for an (H, W, 3) float32 (Format.Float32) or uint8 (Format.UInt8, sRGB) array; the library copies."""
+    """su_image_create for an (H, W, C) float32 (Format.Float32) or uint8 (Format.UInt8) array, C = 1, 2 or 3 ((H, W) = one channel);
+    the library copies. uint8 x 3 is read as sRGB, x 1 as unorm (roughness / metallic maps), x 2 as snorm (normal maps)."""
     px = np.ascontiguousarray(pixels)
-    assert px.ndim == 3 and px.shape[2] == 3 and px.dtype in (np.float32, np.uint8)
+    if 2 == px.ndim:
+        px = px[..., None]
+    assert px.ndim == 3 and 1 <= px.shape[2] <= 3 and px.dtype in (np.float32, np.uint8)
     fmt, bpc = (4, 4) if px.dtype == np.float32 else (0, 1)
-    return _ok(_su().su_image_create(0xFFFFFFFF, fmt, 3, px.shape[1], px.shape[0], 1, 3 * bpc, px.ctypes.data), "su_image_create")
+    return _ok(_su().su_image_create(0xFFFFFFFF, fmt, px.shape[2], px.shape[1], px.shape[0], 1, px.shape[2] * bpc, px.ctypes.data), "su_image_create")
 
 
 def image_update(image: int, pixels: np.ndarray):
     px = np.ascontiguousarray(pixels)
-    _ok(_su().su_image_update(image, 3 * px.dtype.itemsize, px.ctypes.data), "su_image_update")
+    channels = 1 if 2 == px.ndim else px.shape[2]
+    _ok(_su().su_image_update(image, channels * px.dtype.itemsize, px.ctypes.data), "su_image_update")
 
 
 def material_create(desc: dict) -> int:
