@@ -13,15 +13,17 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OBJ = os.path.join(ROOT, "zyg_b200", "csrc", "build", "device_render.o")
-LOG = os.path.join(ROOT, "zyg_b200", "csrc", "build", "device_render.ptxas.log")
+BUILD = os.path.join(ROOT, "zyg_b200", "csrc", "build")
+OBJS = [os.path.join(BUILD, "device_render.o"), os.path.join(BUILD, "device_render_trace.o")]  # shading stages, traversal stages
+LOGS = [o[:-2] + ".ptxas.log" for o in OBJS]
+OBJ = OBJS[0]
 
-pytestmark = pytest.mark.skipif(not (os.path.exists(OBJ) and shutil.which("cuobjdump") and shutil.which("c++filt")),
+pytestmark = pytest.mark.skipif(not (all(os.path.exists(o) for o in OBJS) and shutil.which("cuobjdump") and shutil.which("c++filt")),
                                 reason="needs the built device_render.o and the CUDA binary utilities")
 
 
 def kernels():
-    sass = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True, check=True).stdout
+    sass = "".join(subprocess.run(["cuobjdump", "-sass", o], capture_output=True, text=True, check=True).stdout for o in OBJS)
     out, name, n = {}, None, 0
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)
@@ -47,7 +49,7 @@ def test_kernel_parameters_stay_out_of_local_memory():
 
 
 def test_hot_shade_kernels_do_not_spill():
-    text = open(LOG).read()
+    text = "".join(open(log).read() for log in LOGS)
     entries = re.findall(r"Compiling entry function '([^']+)' for 'sm_100a'\n.*\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads",
                          text)
     names = subprocess.run(["c++filt"], input="\n".join(e[0] for e in entries), capture_output=True, text=True, check=True).stdout.splitlines()

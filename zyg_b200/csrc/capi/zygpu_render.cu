@@ -76,7 +76,7 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint3
         0 != allocPath(r, &p.sh_o, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_p, size_t(capacity) * shadow_stride) ||
         0 != allocPath(r, &p.sh_wi, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_n, capacity) ||
         0 != allocPath(r, &p.ml_props, items * 8) || 0 != allocPath(r, &p.ml_count, items) ||
-        0 != allocPath(r, &p.queue_m, items) || 0 != allocPath(r, &p.queue_a, capacity) || 0 != allocPath(r, &p.queue_b, capacity) || 0 != allocPath(r, &p.counters, 16)) {
+        0 != allocPath(r, &p.queue_m, items) || 0 != allocPath(r, &p.sort_bins, zygpu::kSortBins + 1) || 0 != allocPath(r, &p.queue_a, capacity) || 0 != allocPath(r, &p.queue_b, capacity) || 0 != allocPath(r, &p.counters, 16)) {
         return -1;
     }
     if (lanes > 1 && (0 != allocPath(r, &p.med, vertices) || 0 != allocPath(r, &p.queue_t, vertices) || 0 != allocPath(r, &p.queue_s, capacity))) {
@@ -180,6 +180,28 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     d.unocc_nodes = f4;
     if (0 != uploadArray(r, scene->unoccluding_bvh.indices, scene->unoccluding_bvh.num_indices, &d.unocc_indices)) return -1;
     d.num_unocc_nodes = scene->unoccluding_bvh.num_nodes;
+
+    {  // the grid of the ray sort: 32 x 8 x 32 cells over the box of the finite props (y is up in zyg's scenes: the thin axis)
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (uint32_t p = 0; p < scene->num_props; ++p) {
+            const ZygpuAabb& b = scene->aabbs[p];
+            bool finite = true;
+            for (int a = 0; a < 3; ++a) finite = finite && std::fabs(b.min[a]) < 1e30f && std::fabs(b.max[a]) < 1e30f && b.min[a] <= b.max[a];
+            if (!finite) continue;
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = std::min(lo[a], b.min[a]);
+                hi[a] = std::max(hi[a], b.max[a]);
+            }
+        }
+        const float cells[3] = {32.f, 8.f, 32.f};
+        float       per[3];
+        for (int a = 0; a < 3; ++a) {
+            if (!(lo[a] <= hi[a])) lo[a] = hi[a] = 0.f;
+            per[a] = hi[a] > lo[a] ? cells[a] / (hi[a] - lo[a]) : 0.f;
+        }
+        d.world_lo    = make_float4(lo[0], lo[1], lo[2], 0.f);
+        d.world_cells = make_float4(per[0], per[1], per[2], 0.f);
+    }
 
     {  // "flattened on upload": the solid prop tree in the 8-wide quantised layout the fused traversal kernel walks
         // world-space bounding spheres of the mesh props: the mesh's object-space sphere through the prop's transformation
@@ -445,7 +467,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
         for (uint32_t bounce = 0; bounce <= view.max_depth_surface; ++bounce) {
             const bool last = bounce == view.max_depth_surface;
             // all vertices of the generation are extended at once (no sampler draws in between) ...
-            CUDA_OK(zygpu::launchExtend(r.scene, r.paths, pass.num_paths * lanes, r.has_meshes, r.stream));
+            CUDA_OK(zygpu::launchExtend(r.scene, r.paths, pass.num_paths * lanes, r.has_meshes, bounce, r.stream));
             r.stats.kernel_launches += 1 + trace_extra;
             if (lanes > 1) {
                 CUDA_OK(zygpu::launchBeginGeneration(r.paths, r.stream));
@@ -465,7 +487,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
                     CUDA_OK(zygpu::launchLightStages(r.scene, view, r.paths, pass, pass.num_paths, r.stream));
                     r.stats.kernel_launches += 2;
                 }
-                CUDA_OK(zygpu::launchShadow(r.scene, r.paths, pass.num_paths, r.has_meshes, r.stream));
+                CUDA_OK(zygpu::launchShadow(r.scene, r.paths, pass.num_paths, r.has_meshes, bounce, r.stream));
                 CUDA_OK(zygpu::launchShadeB(r.scene, view, r.paths, pass, pass.num_paths, round, r.stream));
                 r.stats.kernel_launches += 2 + trace_extra + (1 == lanes ? 1 : 0);  // shadow, shade_b (+ queue swap)
             }

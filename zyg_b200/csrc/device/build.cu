@@ -521,17 +521,68 @@ void freeMeshBuildOutput(MeshBuildOutput& out) {
     out = MeshBuildOutput{};
 }
 
+namespace {
+// bump allocator over one cudaMalloc
+struct Arena {
+    char*  base = nullptr;
+    size_t size = 0, used = 0;
+    ~Arena() { cudaFree(base); }
+    static size_t padded(size_t bytes) { return (std::max<size_t>(bytes, 16) + 255) & ~size_t(255); }
+    template <typename T>
+    void reserve(size_t count) { size += padded(count * sizeof(T)); }
+    template <typename T>
+    cudaError_t take(T*& p, size_t count) {
+        const size_t bytes = padded(count * sizeof(T));
+        if (used + bytes > size) return cudaErrorMemoryAllocation;
+        p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return cudaSuccess;
+    }
+};
+}  // namespace
+
 cudaError_t buildMeshOnDevice(const MeshBuildInput& in, MeshBuildOutput& out, cudaStream_t stream) {
     const uint32_t n = in.num_triangles;
     if (n < 4) return cudaErrorInvalidValue;
 
-    std::vector<void*> scratch;
-    struct Cleanup {
-        std::vector<void*>& s;
-        ~Cleanup() {
-            for (void* p : s) cudaFree(p);
-        }
-    } cleanup{scratch};
+    // All scratch comes out of one allocation and the six arrays that outlive the build are made before the clock starts: ~35 cudaMalloc
+    // calls inside the timed region cost 10 - 50 ms for a million triangles, against 1.6 ms of kernels (profiles/r02_build_launches.md).
+    Arena arena;
+    std::vector<void*> scratch;  // unused: the outputs belong to the caller (freeMeshBuildOutput), everything else to the arena
+    auto deviceAlloc = [&arena](auto*& p, size_t count, std::vector<void*>&, bool keep = false) -> cudaError_t {
+        using T = std::remove_reference_t<decltype(*p)>;
+        if (!keep) return arena.take(p, count);
+        void*             raw = nullptr;
+        const cudaError_t e   = cudaMalloc(&raw, std::max<size_t>(count * sizeof(T), 16));
+        if (cudaSuccess == e) p = static_cast<T*>(raw);
+        return e;
+    };
+
+    size_t sort_bytes = 0, scan_bytes = 0;
+    BUILD_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                             (uint32_t*)nullptr, int(n), 0, 60, stream));
+    BUILD_OK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, int(n) + 1, stream));
+    for (int k = 0; k < 6; ++k) arena.reserve<float4>(n);           // tri_lo / hi, sorted_lo / hi, h.lo / hi
+    arena.reserve<Bounds>(1);
+    arena.reserve<uint32_t>(8);
+    for (int k = 0; k < 2; ++k) arena.reserve<uint64_t>(n);         // keys
+    for (int k = 0; k < 2; ++k) arena.reserve<uint32_t>(n);         // vals
+    arena.reserve<char>(sort_bytes);
+    for (int k = 0; k < 7; ++k) arena.reserve<uint32_t>(n);         // h.left / right / first / last / parent / leaf_parent / flags
+    for (int k = 0; k < 2; ++k) arena.reserve<LevelItem>(n);
+    arena.reserve<Gathered>(n);
+    for (int k = 0; k < 2; ++k) arena.reserve<uint64_t>(size_t(n) + 1);
+    arena.reserve<char>(scan_bytes);
+    arena.size += 64 * 256;  // slack for members whose type is wider than assumed above
+    BUILD_OK(cudaMalloc(reinterpret_cast<void**>(&arena.base), arena.size));
+
+    BUILD_OK(deviceAlloc(out.triangles, size_t(n) * 3, scratch, true));
+    BUILD_OK(deviceAlloc(out.original, n, scratch, true));
+    BUILD_OK(deviceAlloc(out.triangle_parts, n, scratch, true));
+    out.num_binary_nodes = 2 * n - 1;
+    BUILD_OK(deviceAlloc(out.binary_nodes, size_t(out.num_binary_nodes) * 2, scratch, true));
+    BUILD_OK(deviceAlloc(out.wide_nodes, size_t(n) * 6, scratch, true));
+    BUILD_OK(deviceAlloc(out.wide_tris, size_t(n) * 4, scratch, true));
 
     cudaEvent_t ev0, ev1;
     BUILD_OK(cudaEventCreate(&ev0));
@@ -558,16 +609,11 @@ cudaError_t buildMeshOnDevice(const MeshBuildInput& in, MeshBuildOutput& out, cu
     initBoundsKernel<<<1, 32, 0, stream>>>(bounds, counters, 8);
     triangleBoundsKernel<<<blocksFor(n), kThreads, 0, stream>>>(in, tri_lo, tri_hi, bounds);
     mortonKernel<<<blocksFor(n), kThreads, 0, stream>>>(n, tri_lo, tri_hi, bounds, keys, vals);
-    size_t sort_bytes = 0;
-    BUILD_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, keys, keys_sorted, vals, vals_sorted, int(n), 0, 60, stream));
     char* sort_tmp;
     BUILD_OK(deviceAlloc(sort_tmp, sort_bytes, scratch));
     BUILD_OK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, keys, keys_sorted, vals, vals_sorted, int(n), 0, 60, stream));
 
     // 2. tree-order triangle arrays
-    BUILD_OK(deviceAlloc(out.triangles, size_t(n) * 3, scratch, true));
-    BUILD_OK(deviceAlloc(out.original, n, scratch, true));
-    BUILD_OK(deviceAlloc(out.triangle_parts, n, scratch, true));
     gatherKernel<<<blocksFor(n), kThreads, 0, stream>>>(in, vals_sorted, tri_lo, tri_hi, out.triangles, out.original, out.triangle_parts, sorted_lo,
                                                         sorted_hi);
 
@@ -587,14 +633,10 @@ cudaError_t buildMeshOnDevice(const MeshBuildInput& in, MeshBuildOutput& out, cu
     fitKernel<<<blocksFor(n), kThreads, 0, stream>>>(int(n), h, sorted_lo, sorted_hi);
 
     // 4. reference-layout binary nodes
-    out.num_binary_nodes = 2 * n - 1;
-    BUILD_OK(deviceAlloc(out.binary_nodes, size_t(out.num_binary_nodes) * 2, scratch, true));
     BUILD_OK(cudaMemsetAsync(out.binary_nodes, 0, size_t(out.num_binary_nodes) * 2 * sizeof(float4), stream));
     emitBinaryKernel<<<blocksFor(2 * uint64_t(n) - 1), kThreads, 0, stream>>>(int(n), h, sorted_lo, sorted_hi, out.binary_nodes, counters);
 
     // 5. wide collapse, level by level: every wide node is an internal node of more than three triangles, so n bounds their number
-    BUILD_OK(deviceAlloc(out.wide_nodes, size_t(n) * 6, scratch, true));
-    BUILD_OK(deviceAlloc(out.wide_tris, size_t(n) * 4, scratch, true));
     LevelItem *items, *next_items;
     Gathered*  gathered;
     uint64_t * counts, *offsets;
@@ -603,8 +645,6 @@ cudaError_t buildMeshOnDevice(const MeshBuildInput& in, MeshBuildOutput& out, cu
     BUILD_OK(deviceAlloc(gathered, n, scratch));
     BUILD_OK(deviceAlloc(counts, size_t(n) + 1, scratch));
     BUILD_OK(deviceAlloc(offsets, size_t(n) + 1, scratch));
-    size_t scan_bytes = 0;
-    BUILD_OK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, offsets, int(n) + 1, stream));
     char* scan_tmp;
     BUILD_OK(deviceAlloc(scan_tmp, scan_bytes, scratch));
 

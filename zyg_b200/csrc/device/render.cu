@@ -1,1063 +1,8 @@
-#include "shading.cuh"
-
-#include <algorithm>
-#include <cstdio>
-#include <cstdlib>
+#include "render_common.cuh"
 
 namespace zygpu {
 
 namespace {
-
-constexpr uint32_t kBlock = 128;
-#ifndef ZYGPU_SHADE_BLOCKS
-#define ZYGPU_SHADE_BLOCKS 4  // resident blocks per SM the shade kernels are compiled for (128 registers)
-#endif
-
-// ---- state packing ---------------------------------------------------------------------------
-
-enum : uint32_t {  // Vertex.State, vertex.zig:19-28
-    kPrimaryRay      = 1u << 0,
-    kTransparent     = 1u << 1,
-    kSingular        = 1u << 2,
-    kSpecular        = 1u << 3,
-    kTranslucent     = 1u << 4,
-    kStartedSpecular = 1u << 5,
-};
-
-__device__ __forceinline__ uint32_t packFlags(uint32_t state, uint32_t probe_depth, uint32_t vertex_depth, uint32_t path_count_log2 = 0,
-                                              uint32_t num_media = 0) {
-    return state | (probe_depth << 8) | (vertex_depth << 16) | (path_count_log2 << 24) | (num_media << 26);
-}
-
-// ---- vertex pool of one camera sample (Pool, vertex.zig:215-310) -------------------------------
-//
-// One word per slot: bits 0-7 lanes of the current generation in processing order (2 bits each), 8-10 their number,
-// 11-18 / 19-21 the same for the next generation, 22-25 lanes in use. path_count bounds the live vertices by 4.
-
-__device__ __forceinline__ uint32_t poolCurCount(uint32_t m) { return (m >> 8) & 7u; }
-__device__ __forceinline__ uint32_t poolCurLane(uint32_t m, uint32_t k) { return (m >> (2 * k)) & 3u; }
-__device__ __forceinline__ uint32_t poolNextCount(uint32_t m) { return (m >> 19) & 7u; }
-__device__ __forceinline__ uint32_t poolSwap(uint32_t m) { return (m & 0x03C00000u) | ((m >> 11) & 0x7FFu); }
-__device__ __forceinline__ uint32_t poolFree(uint32_t m, uint32_t lane) { return m & ~(1u << (22 + lane)); }
-__device__ __forceinline__ uint32_t poolAlloc(uint32_t m) { return uint32_t(__ffs(int(~(m >> 22) & 0xFu))) - 1u; }  // 0xFFFFFFFF when full
-__device__ __forceinline__ uint32_t poolAppendNext(uint32_t m, uint32_t lane) {
-    const uint32_t n = poolNextCount(m);
-    return (m | (lane << (11 + 2 * n)) | (1u << (22 + lane))) + (1u << 19);
-}
-constexpr uint32_t kPoolFirst = (1u << 19) | (1u << 22);  // after generate: lane 0 is the next generation
-
-// ---- medium stack (Stack, prop/medium.zig:30-153) ----------------------------------------------
-
-struct MediaD {
-    uint32_t count;
-    uint32_t prop[3];  // Num_entries - 1 entries can be pushed (:117-131)
-    uint32_t part[3];
-};
-
-__device__ __forceinline__ MediaD unpackMedia(uint4 w, uint32_t count) {
-    return {count, {w.x, w.y, w.z}, {w.w & 0xffu, (w.w >> 8) & 0xffu, (w.w >> 16) & 0xffu}};
-}
-__device__ __forceinline__ uint4 packMedia(const MediaD& m) {
-    return make_uint4(m.prop[0], m.prop[1], m.prop[2], m.part[0] | (m.part[1] << 8) | (m.part[2] << 16));
-}
-__device__ __forceinline__ void mediaPush(MediaD& m, uint32_t prop, uint32_t part) {
-    if (m.count < 3) {
-        m.prop[m.count] = prop;
-        m.part[m.count] = part;
-        m.count += 1;
-    }
-}
-__device__ __forceinline__ void mediaRemove(MediaD& m, uint32_t prop, uint32_t part) {
-    for (int i = int(m.count) - 1; i >= 0; --i) {
-        if (m.prop[i] == prop && m.part[i] == part) {
-            for (int j = i; j < int(m.count) - 1; ++j) {
-                m.prop[j] = m.prop[j + 1];
-                m.part[j] = m.part[j + 1];
-            }
-            m.count -= 1;
-            return;
-        }
-    }
-}
-
-// ray_offset.zig:29-31
-__device__ __forceinline__ float offsetF(float t) {
-    return t < (1.f / 32.f) ? t + (1.f / 65536.f) : __int_as_float(int(uint32_t(__float_as_int(t)) + 256u));
-}
-
-constexpr float kLowThreshold = 0.00000001f;  // helper.zig:29
-
-__device__ __forceinline__ float splitThreshold(float threshold, uint32_t total_depth) {  // helper.zig:33-39
-    return zmin(total_depth < 4 ? threshold : kLowThreshold, threshold);
-}
-__device__ __forceinline__ float powerHeuristic(float f_pdf, float g_pdf) {  // helper.zig:64-67
-    const float f2 = f_pdf * f_pdf;
-    return __fdiv_rn(f2, __fmaf_rn(g_pdf, g_pdf, f2));
-}
-__device__ __forceinline__ float predividedPowerHeuristic(float f_pdf, float g_pdf) {  // helper.zig:70-73
-    const float f2 = f_pdf * f_pdf;
-    return __fdiv_rn(f_pdf, __fmaf_rn(g_pdf, g_pdf, f2));
-}
-
-// ---- per-slot sampler state ------------------------------------------------------------------
-
-struct SlotId {
-    uint32_t pixel_id;   // over the padded resolution, worker.zig:127-141
-    uint32_t iteration;  // absolute sample number
-};
-
-__device__ __forceinline__ SlotId slotId(uint32_t slot, const PassParams& pass) {
-    const uint32_t padded = pass.padded_w * pass.padded_h;
-    const uint32_t s      = slot / padded;
-    return {slot - s * padded, pass.iteration + s};
-}
-
-// worker.zig:143-149 with num_samples = 1 per iteration (Driver.renderIterations(iteration, 1))
-__device__ __forceinline__ void seedSamplers(const SlotId id, const PassParams& pass, uint32_t spp_total, SobolD& sobol, PcgD& rng) {
-    const uint32_t a = pass.padded_w * pass.padded_h;
-    const uint64_t o = uint64_t(id.iteration) * a;
-    rng.start(0, uint64_t(id.pixel_id) + o);
-
-    const uint64_t sample_index = uint64_t(id.pixel_id) * uint64_t(spp_total) + uint64_t(id.iteration);
-    const uint32_t tsi          = uint32_t(sample_index);
-    const uint32_t seed         = uint32_t(sample_index >> 32) + id.iteration / spp_total;
-    sobol.startPixel(tsi, seed);
-}
-
-__device__ __forceinline__ void loadSampler(const PathState& st, uint32_t slot, uint4 s, const PassParams& pass, uint32_t spp_total,
-                                            uint32_t total_depth, SamplerD& sampler) {
-    const SlotId id = slotId(slot, pass);
-    sampler.use_sobol = total_depth < 3;  // pickSampler; a Random take sampler is handled by the caller (view.sampler)
-    const uint64_t sample_index = uint64_t(id.pixel_id) * uint64_t(spp_total) + uint64_t(id.iteration);
-    if (sampler.use_sobol) {
-        sampler.sobol.restore(uint32_t(sample_index), s.x, s.y, s.z);
-    } else {
-        sampler.sobol.sample     = uint32_t(sample_index);
-        sampler.sobol.block_seed = s.x;
-        sampler.sobol.run_seed   = s.y;
-        sampler.sobol.dimension  = s.z;
-    }
-    const uint2 r     = st.rng[slot];
-    sampler.rng.state = (uint64_t(r.y) << 32) | r.x;
-    const uint64_t a  = uint64_t(pass.padded_w) * pass.padded_h;
-    sampler.rng.inc   = ((uint64_t(id.pixel_id) + uint64_t(id.iteration) * a) << 1) | 1;
-}
-
-__device__ __forceinline__ void storeSampler(const PathState& st, uint32_t slot, const SamplerD& sampler, uint32_t aux) {
-    st.smp[slot] = make_uint4(sampler.sobol.block_seed, sampler.sobol.run_seed, sampler.sobol.dimension, aux);
-    st.rng[slot] = make_uint2(uint32_t(sampler.rng.state), uint32_t(sampler.rng.state >> 32));
-}
-
-// ---- queues ----------------------------------------------------------------------------------
-
-// Warp-aggregated append: one atomic per warp.
-__device__ __forceinline__ void queuePush(uint32_t* queue, uint32_t* counter, bool push, uint32_t value) {
-    const uint32_t mask = __ballot_sync(0xffffffffu, push);
-    if (0 == mask) return;
-    const uint32_t lane   = threadIdx.x & 31u;
-    const uint32_t leader = __ffs(mask) - 1;
-    uint32_t       base   = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (push) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
-}
-
-// ---- scene queries ---------------------------------------------------------------------------
-
-__device__ __forceinline__ bool propVisible(uint32_t flags, uint32_t depth_surface) {  // prop.zig:38-48
-    return 0 == depth_surface ? 0 != (flags & ZYG_PROP_VISIBLE_IN_CAMERA) : 0 != (flags & ZYG_PROP_VISIBLE_IN_REFLECTION);
-}
-
-__device__ __forceinline__ bool aabbIntersect(const float4* aabbs, uint32_t i, const RayT& ray) {  // aabb.zig:46-60
-    return FLT_MAX != intersectNode(__ldg(aabbs + 2 * size_t(i)), __ldg(aabbs + 2 * size_t(i) + 1), ray);
-}
-
-// AABB.intersectP, aabb.zig:62-84
-__device__ __forceinline__ float aabbIntersectP(float4 mi, float4 ma, const RayT& ray) {
-    const float lx = (mi.x - ray.o.x) * ray.inv_d.x, ly = (mi.y - ray.o.y) * ray.inv_d.y, lz = (mi.z - ray.o.z) * ray.inv_d.z;
-    const float ux = (ma.x - ray.o.x) * ray.inv_d.x, uy = (ma.y - ray.o.y) * ray.inv_d.y, uz = (ma.z - ray.o.z) * ray.inv_d.z;
-
-    const float imin = zmax(zmax(zmin(lx, ux), zmin(ly, uy)), zmin(lz, uz));
-    const float imax = zmin(zmin(zmax(lx, ux), zmax(ly, uy)), zmax(lz, uz));
-
-    const float tboxmin = zmax(imin, ray.tmin);
-    const float tboxmax = zmin(imax, ray.tmax);
-
-    if (tboxmin <= tboxmax) return imin < ray.tmin ? imax : imin;
-    return FLT_MAX;
-}
-
-// VolumeIntegrator.integrate, volume_integrator.zig:97-99: a vertex inside a medium only looks as far as the medium prop's box
-__device__ __forceinline__ void clipToMedium(const SceneDevice& sc, const PathState& st, uint32_t vertex_id, uint32_t flags, RayT& ray) {
-    const uint32_t num_media = (flags >> 26) & 3u;
-    if (nullptr == st.med || 0 == num_media) return;
-    const uint4    w    = st.med[vertex_id];
-    const uint32_t prop = 1 == num_media ? w.x : (2 == num_media ? w.y : w.z);
-    const float    limit = aabbIntersectP(__ldg(sc.aabbs + 2 * size_t(prop)), __ldg(sc.aabbs + 2 * size_t(prop) + 1), ray);
-    ray.tmax             = zmin(offsetF(limit), ray.tmax);
-}
-
-__device__ __forceinline__ float shapeArea(uint32_t shape, V3 scale) {  // shape.zig:143-156
-    switch (shape) {
-        case ZYG_SHAPE_RECTANGLE: return scale.x * scale.y;
-        case ZYG_SHAPE_SPHERE: return (4.f * kPi) * ((0.5f * scale.x) * (0.5f * scale.x));
-        case ZYG_SHAPE_DISTANT: return distantSolidAngle(scale.x);
-        case ZYG_SHAPE_CANOPY: return 2.f * kPi;
-        default: return 0.f;
-    }
-}
-
-// Prop.intersect + Shape.intersect, prop.zig:163-197, shape.zig:165-179
-__device__ __forceinline__ bool propIntersect(const SceneDevice& sc, uint32_t entity, RayT& ray, uint32_t depth_surface, HitD& isec) {
-    const ZygpuProp prop = sc.props[entity];
-    if (!propVisible(prop.flags, depth_surface)) return false;
-    if (!aabbIntersect(sc.aabbs, entity, ray)) return false;
-    const TrafoD trafo = loadTrafo(sc.trafos, entity);
-    switch (prop.shape) {
-        case ZYG_SHAPE_CUBE: return cubeIntersect(ray, trafo, isec);
-        case ZYG_SHAPE_RECTANGLE: return rectangleIntersect(ray, trafo, isec);
-        case ZYG_SHAPE_SPHERE: return sphereIntersect(ray, trafo, isec);
-        case ZYG_SHAPE_TRIANGLE_MESH: {
-            // TriangleTree.intersect, triangle_tree.zig:46-109: the ray goes to object space un-normalised, so t is shared
-            WideRay w;
-            w.ray = worldToObjectRay(trafo, ray);
-            setupWideRay(w);
-            float    ht, hu, hv;
-            uint32_t prim;
-            if (traverseWide<false>(sc.meshes[prop.mesh], w, ht, hu, hv, prim)) {
-                isec = {ht, hu, hv, prim};
-                return true;
-            }
-            return false;
-        }
-        default: return false;
-    }
-}
-
-// Prop.visibility, prop.zig:199-237 (no masks): true = unoccluded
-__device__ __forceinline__ bool propVisibility(const SceneDevice& sc, uint32_t entity, const RayT& ray) {
-    const ZygpuProp prop = sc.props[entity];
-    if (0 == (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW)) return true;
-    if (!aabbIntersect(sc.aabbs, entity, ray)) return true;
-    const TrafoD trafo = loadTrafo(sc.trafos, entity);
-    switch (prop.shape) {
-        case ZYG_SHAPE_CUBE: return !cubeIntersectP(ray, trafo);
-        case ZYG_SHAPE_RECTANGLE: {
-            HitD unused;
-            return !rectangleIntersect(ray, trafo, unused);
-        }
-        case ZYG_SHAPE_SPHERE: {
-            HitD unused;
-            return !sphereIntersect(ray, trafo, unused);
-        }
-        case ZYG_SHAPE_TRIANGLE_MESH: {
-            WideRay w;
-            w.ray = worldToObjectRay(trafo, ray);
-            setupWideRay(w);
-            float    ht, hu, hv;
-            uint32_t prim;
-            return !traverseWide<true>(sc.meshes[prop.mesh], w, ht, hu, hv, prim);
-        }
-        default: return true;
-    }
-}
-
-constexpr uint32_t kPropStack = 64;  // prop trees are shallow; the reference's NodeStack holds 127
-
-// PropBvh.intersect, prop_tree.zig:56-116: reference order, so equal-t ties resolve like the reference.
-__device__ __forceinline__ uint32_t sceneIntersect(const SceneDevice& sc, RayT& ray, uint32_t depth_surface, HitD& isec) {
-    uint32_t stack[kPropStack];
-    uint32_t end = 0;
-    uint32_t n   = 0 == sc.num_solid_nodes ? kEnd : 0;
-
-    uint32_t prop = kEnd;
-
-    while (kEnd != n) {
-        const float4 nmin = __ldg(sc.solid_nodes + 2 * size_t(n));
-        const float4 nmax = __ldg(sc.solid_nodes + 2 * size_t(n) + 1);
-
-        const uint32_t num = __float_as_uint(nmax.w);
-        if (0 != num) {
-            const uint32_t start = __float_as_uint(nmin.w);
-            for (uint32_t i = start; i < start + num; ++i) {
-                const uint32_t p = __ldg(sc.solid_indices + i);
-                HitD           h;
-                if (propIntersect(sc, p, ray, depth_surface, h)) {
-                    ray.tmax = h.t;
-                    isec     = h;
-                    prop     = p;
-                }
-            }
-            n = 0 == end ? kEnd : stack[--end];
-            continue;
-        }
-
-        uint32_t a = __float_as_uint(nmin.w);
-        uint32_t b = a + 1;
-
-        float dista = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(a)), __ldg(sc.solid_nodes + 2 * size_t(a) + 1), ray);
-        float distb = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(b)), __ldg(sc.solid_nodes + 2 * size_t(b) + 1), ray);
-        if (dista > distb) {
-            const uint32_t tn = a;
-            a                 = b;
-            b                 = tn;
-            const float td    = dista;
-            dista             = distb;
-            distb             = td;
-        }
-        if (FLT_MAX == dista) {
-            n = 0 == end ? kEnd : stack[--end];
-        } else {
-            n = a;
-            if (FLT_MAX != distb) stack[end++] = b;
-        }
-    }
-    return prop;
-}
-
-// PropBvh.visibility, prop_tree.zig:185-240
-__device__ __forceinline__ bool sceneVisibility(const SceneDevice& sc, const RayT& ray) {
-    uint32_t stack[kPropStack];
-    uint32_t end = 0;
-    uint32_t n   = 0 == sc.num_solid_nodes ? kEnd : 0;
-
-    while (kEnd != n) {
-        const float4 nmin = __ldg(sc.solid_nodes + 2 * size_t(n));
-        const float4 nmax = __ldg(sc.solid_nodes + 2 * size_t(n) + 1);
-
-        const uint32_t num = __float_as_uint(nmax.w);
-        if (0 != num) {
-            const uint32_t start = __float_as_uint(nmin.w);
-            for (uint32_t i = start; i < start + num; ++i) {
-                if (!propVisibility(sc, __ldg(sc.solid_indices + i), ray)) return false;
-            }
-            n = 0 == end ? kEnd : stack[--end];
-            continue;
-        }
-
-        uint32_t a = __float_as_uint(nmin.w);
-        uint32_t b = a + 1;
-
-        float dista = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(a)), __ldg(sc.solid_nodes + 2 * size_t(a) + 1), ray);
-        float distb = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(b)), __ldg(sc.solid_nodes + 2 * size_t(b) + 1), ray);
-        if (dista > distb) {
-            const uint32_t tn = a;
-            a                 = b;
-            b                 = tn;
-            const float td    = dista;
-            dista             = distb;
-            distb             = td;
-        }
-        if (FLT_MAX == dista) {
-            n = 0 == end ? kEnd : stack[--end];
-        } else {
-            n = a;
-            if (FLT_MAX != distb) stack[end++] = b;
-        }
-    }
-    return true;
-}
-
-// ---- two-level traversal, product path ---------------------------------------------------------
-//
-// The extend and shadow stages run as two kernels each:
-//
-//   top    one thread per ray walks the prop tree in the reference's order (binary nodes, near child first, leaf props in
-//          order: prop_tree.zig:56-116, 185-240). Analytic props are tested where they are met; a triangle-mesh prop whose
-//          world box the ray hits is appended to the ray's candidate list instead of being entered. Rays with candidates
-//          go to the mesh queue. All threads do the same short walk, so the warps stay full.
-//   mesh   persistent kernel over the mesh queue: a lane takes a ray, moves it into the object space of its next candidate
-//          (re-testing the world box against the shrunken max_t first) and traverses the 8-wide BVH. Warps run the
-//          lock-step loop of trace.cu's persistent kernel — NODE steps and TRIANGLE steps over the lanes that have that
-//          kind of work, postponing triangle groups — and lanes whose ray ran out of candidates are refilled from the
-//          queue (one global atomic per 1024 items), so incoherent bounces keep their lanes busy.
-//
-// Relative to the reference only the order in which props are tested changes (all analytic props of the walk first, then
-// the meshes in walk order): the closest hit is the same except for equal-t ties between different props.
-
-// Equal-t ties. The reference accepts `hit_t <= max_t`, so of two hits at the same t the one tested later wins (triangle.zig:47,
-// prop_tree.zig:76-79) — later in ITS traversal order. The device visits nodes in another order, and in the lock-step kernels
-// the order even depends on the warp's votes; resolving ties by (prop id, primitive id), larger wins, makes the result
-// independent of the schedule (renders are bit-reproducible) and agrees with the reference inside a leaf, where later = larger.
-__device__ __forceinline__ bool closerOrLater(float t, float tmax, uint32_t prop, uint32_t prim, uint32_t hit_prop, uint32_t hit_prim) {
-    return kEnd == hit_prop || t < tmax || prop > hit_prop || (prop == hit_prop && prim > hit_prim);
-}
-
-constexpr uint32_t kMeshCandidates = 8;  // per ray; further meshes are traversed inline by the top kernel
-constexpr uint32_t kScenePoolItems = 1024;
-
-struct SceneTraceTuning {
-    uint32_t fetch_idle;  // refill when at least this many lanes are idle
-    uint32_t tri_num, tri_den;
-};
-
-template <bool AnyHit>
-__device__ __forceinline__ RayT loadTraceRay(const PathState& st, uint32_t item, uint32_t& depth_surface, uint32_t* flags_out = nullptr) {
-    if (AnyHit) {  // Shape.shadowRay, shape.zig:401-416: the record holds both end points
-        const float4 o           = st.sh_o[item];
-        const float4 p           = st.sh_p[item];
-        const V3     origin      = {o.x, o.y, o.z};
-        depth_surface            = 0;
-        if (0 != (__float_as_uint(p.w) & 0x80000000u)) {  // Shape.shadowRay for Canopy / Distant / Dome
-            const float4 wi = st.sh_wi[item];
-            return makeRay(origin, {wi.x, wi.y, wi.z}, 0.f, kRayMaxT);
-        }
-        const V3     shadow_axis = sub3({p.x, p.y, p.z}, origin);
-        const float  shadow_len  = length3(shadow_axis);
-        depth_surface            = 0;
-        return makeRay(origin, divs3(shadow_axis, shadow_len), 0.f, shadow_len);
-    }
-    const float4 o = st.ray_o[item];
-    const float4 d = st.ray_d[item];
-    depth_surface  = (__float_as_uint(o.w) >> 8) & 0xffu;
-    if (flags_out) *flags_out = __float_as_uint(o.w);
-    return makeRay({o.x, o.y, o.z}, {d.x, d.y, d.z}, 0.f, d.w);
-}
-
-// Item ids: closest-hit rays are identified by their path slot, shadow rays by their record (slot * stride + k).
-#ifndef ZYGPU_TOP_BLOCKS
-#define ZYGPU_TOP_BLOCKS 6  // 80 registers: measured +4 % on the instanced scene over the unbounded 96-register build
-#endif
-template <bool AnyHit>
-__global__ void __launch_bounds__(kBlock, ZYGPU_TOP_BLOCKS) topKernel(SceneDevice sc, PathState st) {
-    const uint32_t stride = st.shadow_stride;
-    const uint32_t* __restrict__ closest_queue = st.lanes > 1 ? st.queue_t : st.queue_a;
-    const bool     compact = AnyHit && nullptr != st.queue_r;  // shadow records listed in queue_r instead of stride per slot
-    const uint64_t total   = AnyHit ? (compact ? uint64_t(st.counters[10]) : uint64_t(st.counters[1]) * stride)
-                                    : uint64_t(st.counters[st.lanes > 1 ? 7 : 0]);
-    const uint32_t count  = uint32_t(total < 0xFFFFFFFFull ? total : 0xFFFFFFFFull);
-    const uint32_t iters  = (count + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
-    uint32_t       traced = 0;
-
-    for (uint32_t it = 0; it < iters; ++it) {
-        const uint32_t i       = it * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
-        bool           to_mesh = false;
-        uint32_t       item    = 0;
-        bool           valid   = i < count;
-        if (valid) {
-            if (compact) {
-                item = st.queue_r[i];
-            } else if (AnyHit) {
-                const uint32_t slot = st.queue_b[i / stride];
-                const uint32_t k    = i % stride;
-                valid               = k < st.sh_n[slot];
-                item                = slot * stride + k;
-            } else {
-                item = closest_queue[i];
-            }
-        }
-        if (valid) {
-            traced += 1;
-            uint32_t depth_surface, flags = 0;
-            RayT     ray = loadTraceRay<AnyHit>(st, item, depth_surface, &flags);
-            if (!AnyHit) clipToMedium(sc, st, item, flags, ray);
-
-            uint32_t stack[kPropStack];
-            uint32_t end = 0;
-            uint32_t n   = 0 == sc.num_solid_nodes ? kEnd : 0;
-
-            HitD     isec       = {0.f, 0.f, 0.f, 0};
-            uint32_t hit_prop   = kEnd;
-            bool     occluded   = false;
-            uint32_t candidates = 0;
-
-            while (kEnd != n && !(AnyHit && occluded)) {
-                const float4 nmin = __ldg(sc.solid_nodes + 2 * size_t(n));
-                const float4 nmax = __ldg(sc.solid_nodes + 2 * size_t(n) + 1);
-
-                const uint32_t num = __float_as_uint(nmax.w);
-                if (0 != num) {
-                    const uint32_t start = __float_as_uint(nmin.w);
-                    for (uint32_t li = start; li < start + num; ++li) {
-                        const uint32_t  p    = __ldg(sc.solid_indices + li);
-                        const ZygpuProp prop = sc.props[p];
-                        if (ZYG_SHAPE_TRIANGLE_MESH == prop.shape && candidates < kMeshCandidates) {
-                            // Prop.intersect / Prop.visibility up to the shape call, prop.zig:176-183, 212-218
-                            if (AnyHit ? 0 == (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW) : !propVisible(prop.flags, depth_surface)) continue;
-                            if (!aabbIntersect(sc.aabbs, p, ray)) continue;
-                            st.ml_props[size_t(item) * kMeshCandidates + candidates] = p;
-                            candidates += 1;
-                            continue;
-                        }
-                        if (AnyHit) {
-                            if (!propVisibility(sc, p, ray)) {
-                                occluded = true;
-                                break;
-                            }
-                        } else {
-                            HitD h;
-                            if (propIntersect(sc, p, ray, depth_surface, h)) {
-                                ray.tmax = h.t;
-                                isec     = h;
-                                hit_prop = p;
-                            }
-                        }
-                    }
-                    n = 0 == end ? kEnd : stack[--end];
-                    continue;
-                }
-
-                uint32_t a = __float_as_uint(nmin.w);
-                uint32_t b = a + 1;
-
-                float dista = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(a)), __ldg(sc.solid_nodes + 2 * size_t(a) + 1), ray);
-                float distb = intersectNode(__ldg(sc.solid_nodes + 2 * size_t(b)), __ldg(sc.solid_nodes + 2 * size_t(b) + 1), ray);
-                if (dista > distb) {
-                    const uint32_t tn = a;
-                    a                 = b;
-                    b                 = tn;
-                    const float td    = dista;
-                    dista             = distb;
-                    distb             = td;
-                }
-                if (FLT_MAX == dista) {
-                    n = 0 == end ? kEnd : stack[--end];
-                } else {
-                    n = a;
-                    if (FLT_MAX != distb) stack[end++] = b;
-                }
-            }
-
-            if (AnyHit) {
-                st.sh_wi[item].w = occluded ? 0.f : 1.f;
-                to_mesh          = !occluded && 0 != candidates;
-            } else {
-                st.ray_d[item].w = ray.tmax;
-                st.hit[item]     = make_float4(isec.u, isec.v, __uint_as_float(isec.primitive), __uint_as_float(hit_prop));
-                to_mesh          = 0 != candidates;
-            }
-            if (to_mesh) st.ml_count[item] = candidates;
-        }
-        queuePush(st.queue_m, &st.counters[2], to_mesh, item);
-    }
-    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
-    if (0 == (threadIdx.x & 31u) && 0 != traced) atomicAdd(&st.counters[AnyHit ? 6 : 5], traced);
-}
-
-template <bool AnyHit>
-__global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathState st, uint32_t* __restrict__ work_counter,
-                                                           SceneTraceTuning tune) {
-    constexpr uint32_t kFull = 0xffffffffu;
-    const uint32_t     lane  = threadIdx.x & 31u;
-    const uint32_t     n     = st.counters[2];
-
-    // Queue items are handed out in pools: large pools keep the atomic cold on big queues, small pools spread a short
-    // queue (late bounces) over all resident warps instead of leaving it to a few.
-    const uint32_t warps      = gridDim.x * (blockDim.x / 32u);
-    const uint32_t pool_items = max(32u, min(kScenePoolItems, (n / (warps * 4u)) & ~31u));
-
-    uint32_t pool_next = 0, pool_end = 0;
-    bool     exhausted = false;
-
-    bool     has_ray = false;  // the lane owns a ray (between candidates or inside a mesh)
-    bool     in_mesh = false;
-    uint32_t item    = 0;
-    float    tmax    = 0.f;  // world max_t == object max_t
-    float    tmax0   = 0.f;  // the max_t the mesh walk started with (after the analytic props): the limit of the leaf gates
-    uint32_t cand_i = 0, cand_n = 0;
-    uint32_t cur_prop = 0;
-    uint32_t hit_prop = kEnd;
-    bool     occluded = false;
-    MeshDevice mesh;  // of the mesh the lane is inside: only the two wide arrays are read
-    mesh.wide_nodes = nullptr;
-    mesh.wide_tris  = nullptr;
-
-    WideRay  w;
-    uint2    stack[kWideStack];
-    uint32_t sp         = 0;
-    uint2    node_group = make_uint2(0u, 0u);
-    uint2    tri_group  = make_uint2(0u, 0u);
-    float    ht = 0.f, hu = 0.f, hv = 0.f;
-    uint32_t primitive = kEnd;
-
-    for (;;) {
-        // ---- refill idle lanes
-        uint32_t idle = __ballot_sync(kFull, !has_ray);
-        while (0 != idle && !exhausted) {
-            if (pool_next >= pool_end) {
-                uint32_t base = 0;
-                if (0 == lane) base = atomicAdd(work_counter, pool_items);
-                base = __shfl_sync(kFull, base, 0);
-                if (base >= n) {
-                    exhausted = true;
-                    break;
-                }
-                pool_next = base;
-                pool_end  = min(base + pool_items, n);
-            }
-            const uint32_t avail = pool_end - pool_next;
-            const uint32_t rank  = __popc(idle & ((1u << lane) - 1u));
-            if (!has_ray && rank < avail) {
-                item     = st.queue_m[pool_next + rank];
-                cand_i   = 0;
-                cand_n   = st.ml_count[item];
-                has_ray  = true;
-                in_mesh  = false;
-                hit_prop = kEnd;
-                occluded = false;
-                tmax     = AnyHit ? 0.f : st.ray_d[item].w;
-                tmax0    = tmax;
-            }
-            pool_next += min(avail, (uint32_t)__popc(idle));
-            idle = __ballot_sync(kFull, !has_ray);
-        }
-        if (kFull == idle) break;
-
-        // ---- lanes between candidates: enter the next mesh or retire
-        while (has_ray && !in_mesh) {
-            if (cand_i == cand_n || (AnyHit && occluded)) {
-                if (AnyHit) {
-                    if (occluded) st.sh_wi[item].w = 0.f;
-                } else if (kEnd != hit_prop) {
-                    st.ray_d[item].w = tmax;
-                    st.hit[item]     = make_float4(hu, hv, __uint_as_float(primitive), __uint_as_float(hit_prop));
-                }
-                has_ray = false;
-                break;
-            }
-            const uint32_t p = st.ml_props[size_t(item) * kMeshCandidates + cand_i];
-            cand_i += 1;
-
-            uint32_t depth_surface;
-            RayT     ray = loadTraceRay<AnyHit>(st, item, depth_surface);
-            if (!AnyHit) ray.tmax = tmax;
-            // (the first candidate was tested by the top kernel)
-            if (0 != cand_i - 1 && !gateBox(__ldg(sc.aabbs + 2 * size_t(p)), __ldg(sc.aabbs + 2 * size_t(p) + 1), ray, AnyHit ? ray.tmax : tmax0)) continue;
-
-            const TrafoD trafo = loadTrafo(sc.trafos, p);
-            w.ray              = worldToObjectRay(trafo, ray);  // triangle_tree.zig:49: t is shared with world space
-            setupWideRay(w);
-            cur_prop = p;
-            {
-                const MeshDevice* m = sc.meshes + sc.props[p].mesh;
-                mesh.wide_nodes     = m->wide_nodes;
-                mesh.wide_tris      = m->wide_tris;
-            }
-            in_mesh    = true;
-            sp         = 0;
-            node_group = make_uint2(0u, 0x80000000u);
-            tri_group  = make_uint2(0u, 0u);
-        }
-
-        // ---- lock-step NODE / TRIANGLE steps over the lanes inside a mesh
-        for (;;) {
-            const bool     ready_node = in_mesh && node_group.y > 0x00FFFFFFu;
-            const bool     ready_tri  = in_mesh && 0 != tri_group.y;
-            const uint32_t mn         = __ballot_sync(kFull, ready_node);
-            const uint32_t mt         = __ballot_sync(kFull, ready_tri);
-            const uint32_t cn = __popc(mn), ct = __popc(mt);
-            if (0 == cn && 0 == ct) break;
-
-            if (0 != ct && (0 == cn || ct * tune.tri_den >= cn * tune.tri_num)) {
-                if (ready_tri) {
-                    const uint32_t bit = 31u - __clz(tri_group.y);
-                    tri_group.y &= ~(1u << bit);
-                    float    t, u, v;
-                    uint32_t prim;
-                    if (testWideTriangle(mesh, w.ray, AnyHit ? w.ray.tmax : tmax0, tri_group.x + bit, t, u, v, prim)) {
-                        if (AnyHit) {
-                            occluded     = true;
-                            sp           = 0;
-                            node_group.y = 0;
-                            tri_group.y  = 0;
-                        } else if (closerOrLater(t, w.ray.tmax, cur_prop, prim, hit_prop, primitive)) {
-                            w.ray.tmax = t;
-                            tmax       = t;  // probe.ray.max_t = isec.t, prop_tree.zig:77
-                            hu         = u;
-                            hv         = v;
-                            primitive  = prim;
-                            hit_prop   = cur_prop;
-                        }
-                    }
-                }
-            } else if (ready_node) {
-                const uint32_t hits  = node_group.y;
-                const uint32_t gmask = hits & 0xffu;
-                const uint32_t bit   = 31u - __clz(hits);
-                node_group.y         = hits & ~(1u << bit);
-                const uint32_t slot  = (bit - 24u) ^ w.octinv;
-                const uint32_t rank  = __popc(gmask & ((1u << slot) - 1u));
-                const uint32_t node_index = node_group.x + rank;
-                if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
-                if (0 != tri_group.y) stack[sp++] = tri_group;
-
-                const WideNodeRegs nd = loadWideNode(mesh.wide_nodes, node_index);
-                const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
-
-                const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
-
-                node_group.x = __float_as_uint(n1.x);
-                node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
-                tri_group.x  = __float_as_uint(n1.y);
-                tri_group.y  = hitmask & 0x00FFFFFFu;
-            }
-
-            // lanes that ran dry pop their stack or leave the mesh
-            if (in_mesh && node_group.y <= 0x00FFFFFFu && 0 == tri_group.y) {
-                if (0 == sp) {
-                    in_mesh = false;
-                } else {
-                    const uint2 e = stack[--sp];
-                    if (e.y > 0x00FFFFFFu) {
-                        node_group = e;
-                    } else {
-                        tri_group = e;
-                    }
-                }
-            }
-
-            const uint32_t inside = __popc(__ballot_sync(kFull, in_mesh));
-            if (0 == inside) break;
-            if (32u - inside >= tune.fetch_idle) {
-                // enough lanes left their mesh: let them move on / be refilled, unless nothing is left for them to do
-                const uint32_t waiting = __ballot_sync(kFull, has_ray && !in_mesh);
-                if (0 != waiting || !exhausted) break;
-            }
-        }
-    }
-}
-
-// ---- fused two-level traversal -------------------------------------------------------------------------------------
-//
-// One persistent kernel walks both levels of the "two-level layout for prop instances": the prop tree (PropBvh, prop_tree.zig:
-// 56-240) collapsed on upload into the same 80-byte 8-wide quantised nodes as the mesh trees, its leaf slots pointing at prop
-// records {prop id, exact box of the reference leaf}. A lane owns a ray from the trace queue until the ray is done; the warp
-// runs lock-step steps of three kinds, each over the lanes that have that kind of work:
-//
-//   NODE      test the eight quantised child boxes of one wide node — the same code for a lane in the prop tree and a lane
-//             inside a mesh, only the node array differs
-//   TRIANGLE  one gated triangle test (lanes inside a mesh)
-//   PROP      one prop record (lanes in the prop tree): reference leaf gate, visibility flags, the prop's world box against the
-//             current max_t (Prop.intersect up to the shape call, prop.zig:163-197), then an analytic shape in place or entry into
-//             a mesh: the ray goes to object space, the prop-tree work still pending is left on the lane's stack below the mesh's
-//
-// Children are visited front to back by octant, every test uses the ray's current max_t, so instances behind the closest hit
-// so far are culled at the node or at their world box; nothing but the result goes back to HBM (the former top kernel wrote
-// 8 candidate props per ray and the mesh kernel read them back). Relative to the reference only the order in which props are
-// tested changes: the closest hit is identical except for equal-t ties between different props.
-
-// Conservative: false only if the segment [tmin, tmax] of the ray cannot touch the sphere (xyz centre, w radius).
-__device__ __forceinline__ bool segmentMeetsSphere(const RayT& ray, float4 sphere) {
-    if (FLT_MAX == sphere.w) return true;
-    const V3    oc = {sphere.x - ray.o.x, sphere.y - ray.o.y, sphere.z - ray.o.z};
-    const float dd = dot3(ray.d, ray.d);
-    const float b  = dot3(oc, ray.d);
-    const float r2 = sphere.w * sphere.w;
-    const float oo = dot3(oc, oc);
-    if (oo <= r2) return true;  // the origin is inside
-    if (b <= 0.f) return false;  // outside and heading away
-    const float tc = __fdividef(b, dd);  // parameter of the closest approach
-    const V3    pv = {oc.x - tc * ray.d.x, oc.y - tc * ray.d.y, oc.z - tc * ray.d.z};
-    if (dot3(pv, pv) > r2 * 1.0001f) return false;
-    // the entry point is no nearer than tc - r / |d|
-    return tc - sphere.w * rsqrtf(dd) * 1.0001f <= ray.tmax;
-}
-
-struct SceneStepTuning {
-    uint32_t fetch_idle;  // refill when at least this many lanes are idle
-    uint32_t weight[4];   // NODE, TRIANGLE, PROP, ENTER: the step kind with the largest (ready lanes x weight) runs
-};
-
-template <bool AnyHit, bool Count>
-__global__ void __launch_bounds__(128) sceneTracePersistent(SceneDevice sc, PathState st, uint32_t* __restrict__ work_counter,
-                                                            SceneStepTuning tune, unsigned long long* __restrict__ tally) {
-    constexpr uint32_t kFull = 0xffffffffu;
-    const uint32_t     lane  = threadIdx.x & 31u;
-
-    // the trace queue: closest-hit rays are vertex ids, shadow rays are records (compact list, or `stride` slots per path)
-    const uint32_t stride = st.shadow_stride;
-    const uint32_t* __restrict__ closest_queue = st.lanes > 1 ? st.queue_t : st.queue_a;
-    const bool     compact = AnyHit && nullptr != st.queue_r;
-    const uint64_t total   = AnyHit ? (compact ? uint64_t(st.counters[10]) : uint64_t(st.counters[1]) * stride)
-                                    : uint64_t(st.counters[st.lanes > 1 ? 7 : 0]);
-    const uint32_t n       = uint32_t(total < 0xFFFFFFFFull ? total : 0xFFFFFFFFull);
-
-    const uint32_t warps      = gridDim.x * (blockDim.x / 32u);
-    const uint32_t pool_items = max(32u, min(kScenePoolItems, (n / (warps * 4u)) & ~31u));
-
-    uint32_t pool_next = 0, pool_end = 0;
-    bool     exhausted = false;
-
-    bool     has_ray = false;
-    bool     in_mesh = false;
-    uint32_t item    = 0;
-    uint32_t depth_surface = 0;
-    float    tmax0      = 0.f;   // the max_t the ray started with: the limit of the reference's box gates (gateBox)
-    uint32_t enter_prop = kEnd;  // a mesh prop that passed the culling tests and waits for its ENTER step
-    uint32_t cur_prop = 0, hit_prop = kEnd;
-    bool     occluded = false;
-    const float4* nodes = sc.tlas_nodes;  // of the level the lane is in
-    const float4* recs  = sc.tlas_recs;
-
-    WideRay  w;
-    uint2    stack[kWideStack];
-    uint32_t sp = 0, sp_mesh = 0;  // sp_mesh: stack depth at mesh entry (the world ray and the prop-tree entries lie below)
-    uint2    node_group = make_uint2(0u, 0u);
-    uint2    tri_group  = make_uint2(0u, 0u);
-    float    hu = 0.f, hv = 0.f;
-    uint32_t primitive = 0;
-    uint32_t traced = 0, count_nodes = 0, count_tris = 0, count_props = 0;
-    uint32_t steps[3] = {0, 0, 0};  // instrumented build: warp-level NODE / TRIANGLE / PROP + ENTER steps
-
-    for (;;) {
-        // ---- refill idle lanes
-        uint32_t idle = __ballot_sync(kFull, !has_ray);
-        while (0 != idle && !exhausted) {
-            if (pool_next >= pool_end) {
-                uint32_t base = 0;
-                if (0 == lane) base = atomicAdd(work_counter, pool_items);
-                base = __shfl_sync(kFull, base, 0);
-                if (base >= n) {
-                    exhausted = true;
-                    break;
-                }
-                pool_next = base;
-                pool_end  = min(base + pool_items, n);
-            }
-            const uint32_t avail = pool_end - pool_next;
-            const uint32_t rank  = __popc(idle & ((1u << lane) - 1u));
-            if (!has_ray && rank < avail) {
-                const uint32_t i     = pool_next + rank;
-                bool           valid = true;
-                if (compact) {
-                    item = st.queue_r[i];
-                } else if (AnyHit) {
-                    const uint32_t slot = st.queue_b[i / stride];
-                    const uint32_t k    = i % stride;
-                    valid               = k < st.sh_n[slot];
-                    item                = slot * stride + k;
-                } else {
-                    item = closest_queue[i];
-                }
-                if (valid) {
-                    uint32_t flags = 0;
-                    w.ray          = loadTraceRay<AnyHit>(st, item, depth_surface, &flags);
-                    if (!AnyHit) clipToMedium(sc, st, item, flags, w.ray);
-                    tmax0 = w.ray.tmax;
-                    setupWideRay(w);
-                    has_ray    = true;
-                    in_mesh    = false;
-                    enter_prop = kEnd;
-                    hit_prop   = kEnd;
-                    occluded   = false;
-                    nodes      = sc.tlas_nodes;
-                    recs       = sc.tlas_recs;
-                    sp         = 0;
-                    sp_mesh    = 0;
-                    node_group = make_uint2(0u, 0 != sc.num_solid_nodes ? 0x80000000u : 0u);  // root of the prop tree
-                    tri_group  = make_uint2(0u, 0u);
-                    hu = hv    = 0.f;
-                    primitive  = 0;
-                    traced += 1;
-                }
-            }
-            pool_next += min(avail, (uint32_t)__popc(idle));
-            idle = __ballot_sync(kFull, !has_ray);
-        }
-        if (kFull == idle) break;
-
-        // ---- lock-step steps until enough lanes ran out of work
-        for (;;) {
-            const bool     ready_enter = has_ray && kEnd != enter_prop;
-            const bool     ready_node  = has_ray && !ready_enter && node_group.y > 0x00FFFFFFu;
-            const bool     ready_leaf  = has_ray && !ready_enter && 0 != tri_group.y;
-            const uint32_t cn = __popc(__ballot_sync(kFull, ready_node)) * tune.weight[0];
-            const uint32_t ct = __popc(__ballot_sync(kFull, ready_leaf && in_mesh)) * tune.weight[1];
-            const uint32_t cp = __popc(__ballot_sync(kFull, ready_leaf && !in_mesh)) * tune.weight[2];
-            const uint32_t ce = __popc(__ballot_sync(kFull, ready_enter)) * tune.weight[3];
-            const uint32_t most = max(max(cn, ct), max(cp, ce));
-
-            if (0 != ce && ce == most) {
-                // ENTER step: the ray goes to the object space of the mesh (triangle_tree.zig:49: t is shared). The world ray and the
-                // prop-tree work still pending stay on the stack below the mesh's entries.
-                if (Count) steps[2] += 1;
-                if (ready_enter) {
-                    if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
-                    if (0 != tri_group.y) stack[sp++] = tri_group;
-                    stack[sp++] = make_uint2(__float_as_uint(w.ray.o.x), __float_as_uint(w.ray.o.y));
-                    stack[sp++] = make_uint2(__float_as_uint(w.ray.o.z), __float_as_uint(w.ray.d.x));
-                    stack[sp++] = make_uint2(__float_as_uint(w.ray.d.y), __float_as_uint(w.ray.d.z));
-                    stack[sp++] = make_uint2(__float_as_uint(w.ray.inv_d.x), __float_as_uint(w.ray.inv_d.y));
-                    stack[sp++] = make_uint2(__float_as_uint(w.ray.inv_d.z), 0u);
-                    sp_mesh     = sp;
-                    const TrafoD      trafo = loadTrafo(sc.trafos, enter_prop);
-                    const MeshDevice* m     = sc.meshes + sc.props[enter_prop].mesh;
-                    nodes                   = m->wide_nodes;
-                    recs                    = m->wide_tris;
-                    w.ray                   = worldToObjectRay(trafo, w.ray);
-                    setupWideRay(w);
-                    cur_prop   = enter_prop;
-                    enter_prop = kEnd;
-                    in_mesh    = true;
-                    node_group = make_uint2(0u, 0x80000000u);
-                    tri_group  = make_uint2(0u, 0u);
-                }
-            } else if (0 != cp && cp == most) {
-                // PROP step: a lane works through its pending prop records until a mesh prop survives the culling tests
-                if (Count) steps[2] += 1;
-                if (ready_leaf && !in_mesh) {
-                    do {
-                        const uint32_t bit = 31u - __clz(tri_group.y);
-                        tri_group.y &= ~(1u << bit);
-                        if (Count) count_props += 1;
-                        const float4* rp = recs + 4 * size_t(tri_group.x + bit);
-                        const F8      rr = ldg256(rp);
-                        const float4  r0 = rr.lo, r1 = rr.hi;
-                        const uint32_t  p    = __float_as_uint(r0.w);
-                        const ZygpuProp prop = sc.props[p];
-                        // the reference reaches a prop through its leaf's box (prop_tree.zig:86-104) ...
-                        bool enter = gateBox(make_float4(r0.x, r0.y, r0.z, 0.f), make_float4(r1.x, r1.y, r1.z, 0.f), w.ray, tmax0);
-                        // ... then Prop.intersect / Prop.visibility: flags, world box (prop.zig:176-183, 212-218)
-                        enter = enter && (AnyHit ? 0 != (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW) : propVisible(prop.flags, depth_surface));
-                        enter = enter && gateBox(__ldg(sc.aabbs + 2 * size_t(p)), __ldg(sc.aabbs + 2 * size_t(p) + 1), w.ray, tmax0);
-                        if (!enter) continue;
-                        if (ZYG_SHAPE_TRIANGLE_MESH == prop.shape) {
-                            // culling only: every triangle of the instance lies inside its bounding sphere
-                            if (segmentMeetsSphere(w.ray, __ldg(rp + 2))) {
-                                enter_prop = p;
-                                break;
-                            }
-                            continue;
-                        }
-                        const TrafoD trafo = loadTrafo(sc.trafos, p);
-                        if (AnyHit) {
-                            bool hit = false;
-                            HitD unused;
-                            switch (prop.shape) {
-                                case ZYG_SHAPE_CUBE: hit = cubeIntersectP(w.ray, trafo); break;
-                                case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, unused); break;
-                                case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, unused); break;
-                                default: break;
-                            }
-                            if (hit) {
-                                occluded     = true;
-                                sp           = 0;
-                                node_group.y = 0;
-                                tri_group.y  = 0;
-                            }
-                        } else {
-                            HitD h;
-                            bool hit = false;
-                            switch (prop.shape) {
-                                case ZYG_SHAPE_CUBE: hit = cubeIntersect(w.ray, trafo, h); break;
-                                case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, h); break;
-                                case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, h); break;
-                                default: break;
-                            }
-                            if (hit && closerOrLater(h.t, w.ray.tmax, p, h.primitive, hit_prop, primitive)) {
-                                w.ray.tmax = h.t;
-                                hu         = h.u;
-                                hv         = h.v;
-                                primitive  = h.primitive;
-                                hit_prop   = p;
-                            }
-                        }
-                    } while (0 != tri_group.y);
-                }
-            } else if (0 != ct && ct == most) {
-                // TRIANGLE step
-                if (Count) steps[1] += 1;
-                if (ready_leaf && in_mesh) {
-                    const uint32_t bit = 31u - __clz(tri_group.y);
-                    tri_group.y &= ~(1u << bit);
-                    if (Count) count_tris += 1;
-                    MeshDevice mesh;
-                    mesh.wide_tris = recs;
-                    float    t, u, v;
-                    uint32_t prim;
-                    if (testWideTriangle(mesh, w.ray, tmax0, tri_group.x + bit, t, u, v, prim)) {
-                        if (AnyHit) {
-                            occluded     = true;
-                            in_mesh      = false;
-                            sp           = 0;
-                            node_group.y = 0;
-                            tri_group.y  = 0;
-                        } else if (closerOrLater(t, w.ray.tmax, cur_prop, prim, hit_prop, primitive)) {
-                            w.ray.tmax = t;  // probe.ray.max_t = isec.t, prop_tree.zig:77
-                            hu         = u;
-                            hv         = v;
-                            primitive  = prim;
-                            hit_prop   = cur_prop;
-                        }
-                    }
-                }
-            } else {
-                // NODE step: the same code for a lane in the prop tree and a lane inside a mesh
-                if (Count && 0 != cn) steps[0] += 1;
-                if (ready_node) {
-                    const uint32_t hits  = node_group.y;
-                    const uint32_t gmask = hits & 0xffu;
-                    const uint32_t bit   = 31u - __clz(hits);
-                    node_group.y         = hits & ~(1u << bit);
-                    const uint32_t slot  = (bit - 24u) ^ w.octinv;
-                    const uint32_t rank  = __popc(gmask & ((1u << slot) - 1u));
-                    const uint32_t node_index = node_group.x + rank;
-                    if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
-                    if (0 != tri_group.y) stack[sp++] = tri_group;
-                    if (Count) count_nodes += 1;
-
-                    const WideNodeRegs nd = loadWideNode(nodes, node_index);
-                    const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
-
-                    const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
-
-                    node_group.x = __float_as_uint(n1.x);
-                    node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
-                    tri_group.x  = __float_as_uint(n1.y);
-                    tri_group.y  = hitmask & 0x00FFFFFFu;
-                }
-            }
-
-            // ---- lanes that ran dry pop their stack, leave the mesh or retire their ray
-            if (has_ray && kEnd == enter_prop && node_group.y <= 0x00FFFFFFu && 0 == tri_group.y) {
-                if (in_mesh && sp == sp_mesh) {
-                    // back to the prop tree: the world ray comes off the stack, max_t is the one found so far
-                    in_mesh        = false;
-                    const uint2 e4 = stack[--sp], e3 = stack[--sp], e2 = stack[--sp], e1 = stack[--sp], e0 = stack[--sp];
-                    w.ray.o        = {__uint_as_float(e0.x), __uint_as_float(e0.y), __uint_as_float(e1.x)};
-                    w.ray.d        = {__uint_as_float(e1.y), __uint_as_float(e2.x), __uint_as_float(e2.y)};
-                    w.ray.inv_d    = {__uint_as_float(e3.x), __uint_as_float(e3.y), __uint_as_float(e4.x)};
-                    setupWideRay(w);
-                    nodes = sc.tlas_nodes;
-                    recs  = sc.tlas_recs;
-                }
-                if (0 == sp) {
-                    if (AnyHit) {
-                        st.sh_wi[item].w = occluded ? 0.f : 1.f;
-                    } else {
-                        st.ray_d[item].w = w.ray.tmax;
-                        st.hit[item]     = make_float4(hu, hv, __uint_as_float(primitive), __uint_as_float(hit_prop));
-                    }
-                    has_ray = false;
-                } else if (!in_mesh || sp > sp_mesh) {
-                    const uint2 e = stack[--sp];
-                    if (e.y > 0x00FFFFFFu) {
-                        node_group = e;
-                    } else {
-                        tri_group = e;
-                    }
-                }
-            }
-
-            const uint32_t active = __ballot_sync(kFull, has_ray);
-            if (0 == active) break;
-            if (!exhausted && 32u - __popc(active) >= tune.fetch_idle) break;
-        }
-    }
-
-    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(kFull, traced, o);
-    if (0 == lane && 0 != traced) atomicAdd(&st.counters[AnyHit ? 6 : 5], traced);
-    if (Count) {
-        unsigned long long cnt[3] = {count_nodes, count_tris, count_props};
-        for (int k = 0; k < 3; ++k) {
-            for (int o = 16; o > 0; o >>= 1) cnt[k] += __shfl_down_sync(kFull, cnt[k], o);
-            if (0 == lane) atomicAdd(tally + (AnyHit ? 6 : 0) + k, cnt[k]);
-        }
-        if (0 == lane) {
-            for (int k = 0; k < 3; ++k) atomicAdd(tally + (AnyHit ? 6 : 0) + 3 + k, (unsigned long long)steps[k]);
-        }
-    }
-}
 
 // Shape.fragment, shape.zig:205-219
 __device__ __forceinline__ void shapeFragment(const SceneDevice& sc, uint32_t prop, const RayT& ray, const HitD& isec, FragD& frag) {
@@ -1982,29 +927,6 @@ __global__ void __launch_bounds__(kBlock) generateKernel(ZygpuView view, PathSta
     }
 }
 
-// Context.nextEvent -> Scene.intersect, context.zig:54-69, scene.zig:225-227
-__global__ void __launch_bounds__(kBlock) extendKernel(SceneDevice sc, PathState st) {
-    const uint32_t count = st.counters[st.lanes > 1 ? 7 : 0];
-    const uint32_t* __restrict__ queue = st.lanes > 1 ? st.queue_t : st.queue_a;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = queue[i];  // vertex id
-        const float4   o    = st.ray_o[slot];
-        float4         d    = st.ray_d[slot];
-
-        RayT           ray           = makeRay({o.x, o.y, o.z}, {d.x, d.y, d.z}, 0.f, d.w);
-        const uint32_t depth_surface = (__float_as_uint(o.w) >> 8) & 0xffu;
-        clipToMedium(sc, st, slot, __float_as_uint(o.w), ray);
-
-        HitD           isec = {0.f, 0.f, 0.f, 0};
-        const uint32_t prop = sceneIntersect(sc, ray, depth_surface, isec);
-
-        d.w             = ray.tmax;  // probe.ray.max_t = isec.t (prop_tree.zig:77); unchanged on a miss
-        st.ray_d[slot]  = d;
-        st.hit[slot]    = make_float4(isec.u, isec.v, __uint_as_float(isec.primitive), __uint_as_float(prop));
-    }
-    if (0 == blockIdx.x && 0 == threadIdx.x) atomicAdd(&st.counters[5], count);  // statistics: closest-hit rays
-}
-
 __device__ __forceinline__ const ZygpuMaterial& propMaterial(const SceneDevice& sc, uint32_t prop, uint32_t part) {
     return sc.materials[__ldg(sc.material_ids + sc.props[prop].parts_start + part)];
 }
@@ -2828,31 +1750,6 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
     }
 }
 
-// Scene.visibility for every shadow-ray record of the surviving paths, scene.zig:229-235 (no volume props)
-__global__ void __launch_bounds__(kBlock) shadowKernel(SceneDevice sc, PathState st) {
-    const uint32_t count  = st.counters[1];
-    const uint32_t stride = st.shadow_stride;
-    const uint64_t items  = uint64_t(count) * stride;
-    uint32_t       traced = 0;
-    for (uint64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += uint64_t(gridDim.x) * blockDim.x) {
-        const uint32_t slot = st.queue_b[uint32_t(i / stride)];
-        const uint32_t k    = uint32_t(i % stride);
-        if (k >= st.sh_n[slot]) continue;
-        const size_t rec = size_t(slot) * stride + k;
-
-        const float4 o = st.sh_o[rec];
-        const float4 p = st.sh_p[rec];
-
-        uint32_t   unused;
-        const RayT ray = loadTraceRay<true>(st, uint32_t(rec), unused);
-
-        st.sh_wi[rec].w = sceneVisibility(sc, ray) ? 1.f : 0.f;
-        traced += 1;
-    }
-    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(0xffffffffu, traced, o);
-    if (0 == (threadIdx.x & 31u) && 0 != traced) atomicAdd(&st.counters[6], traced);  // statistics: shadow rays
-}
-
 // The rest of PathtracerMIS.li: evaluateLight after the visibility test (pathtracer_mis.zig:252-277), the direct-light
 // add (:116-117), mat_sample.sample and the next vertex (:121-166).
 template <bool Split, bool Textured>
@@ -3129,43 +2026,6 @@ __global__ void __launch_bounds__(kBlock) resolveKernel(ZygpuView view, const fl
     }
 }
 
-int numSms() {
-    static int sms = 0;
-    if (0 == sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return sms;
-}
-
-// Blocks per SM of the shade launches (ZYGPU_SHADE_GRID overrides). Measured: exactly the resident 4 for the kernels without
-// path splits (Cornell 39.2 -> 37.1 ms: one table prologue per block, no second wave), 16 for the split kernels of glass scenes,
-// whose blocks finish unevenly (config 3: 389.8 ms with 4, 378.7 ms with 16).
-uint32_t shadeGrid(bool split) {
-    static const int v = [] {
-        const char* e = getenv("ZYGPU_SHADE_GRID");
-        return e ? std::max(1, atoi(e)) : 0;
-    }();
-    return 0 != v ? uint32_t(v) : (split ? 16u : 4u);
-}
-
-// Blocks per SM of the grid-stride walk kernels (top / extend / shadow; ZYGPU_WALK_GRID overrides). They have no per-block
-// prologue, so many short blocks even out the uneven walks: 64 measured 1 - 2 % faster than 16 on configs 1, 3 and 4.
-uint32_t walkGrid() {
-    static const uint32_t v = [] {
-        const char* e = getenv("ZYGPU_WALK_GRID");
-        return e ? uint32_t(std::max(1, atoi(e))) : 64u;
-    }();
-    return v;
-}
-
-// Grid-stride launches: a multiple of the SM count, never more blocks than there is work.
-uint32_t gridFor(uint32_t items, uint32_t blocks_per_sm) {
-    const uint32_t needed = (items + kBlock - 1) / kBlock;
-    return std::max(1u, std::min(needed, uint32_t(numSms()) * blocks_per_sm));
-}
-
 }  // namespace
 
 cudaError_t uploadSobolDirections() {
@@ -3204,102 +2064,6 @@ cudaError_t uploadSobolDirections() {
 
 cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const PassParams& pass, cudaStream_t stream) {
     generateKernel<<<gridFor(pass.num_paths, 16), kBlock, 0, stream>>>(view, st, pass);
-    return cudaGetLastError();
-}
-namespace {
-
-int envInt(const char* name, int fallback) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : fallback;
-}
-
-struct SceneTraceConfig {
-    int              variant;  // 0: one thread per ray (extendKernel / shadowKernel), 1: top kernel + persistent mesh kernel,
-                               // 2: fused two-level persistent kernel for scenes with meshes (default)
-    SceneTraceTuning tune;
-    SceneStepTuning  step;
-    int              blocks_per_sm;
-};
-
-const SceneTraceConfig& sceneTraceConfig() {
-    static const SceneTraceConfig cfg = [] {
-        SceneTraceConfig c;
-        c.variant         = envInt("ZYGPU_SCENE_TRACE", 2);
-        c.step.fetch_idle = uint32_t(envInt("ZYGPU_FUSED_FETCH_IDLE", 10));
-        c.step.weight[0]  = uint32_t(envInt("ZYGPU_W_NODE", 1));
-        c.step.weight[1]  = uint32_t(envInt("ZYGPU_W_TRI", 2));
-        c.step.weight[2]  = uint32_t(envInt("ZYGPU_W_PROP", 2));
-        c.step.weight[3]  = uint32_t(envInt("ZYGPU_W_ENTER", 2));
-        c.tune.fetch_idle = uint32_t(envInt("ZYGPU_SCENE_FETCH_IDLE", 10));  // measured: 10 beats 6 by 1 - 2 % on the sphere and instanced scenes
-        c.tune.tri_num    = uint32_t(envInt("ZYGPU_TRI_NUM", 1));
-        c.tune.tri_den    = uint32_t(envInt("ZYGPU_TRI_DEN", 2));
-        c.blocks_per_sm   = envInt("ZYGPU_SCENE_BLOCKS_PER_SM", 0);
-        return c;
-    }();
-    return cfg;
-}
-
-template <bool AnyHit>
-cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
-    const SceneTraceConfig& cfg = sceneTraceConfig();
-    // a prop tree that is a single leaf (a mesh and a few analytic props) gains nothing from the fused walk: the thread-per-ray
-    // top kernel deals with it at full lane occupancy (measured on the 1M-triangle sphere scene: 48.2 ms against 51.4 ms fused)
-    // (an instrumented pass always takes the fused kernel, the one that counts its fetches; the results are the same)
-    if ((2 == cfg.variant && has_meshes && scene.num_solid_nodes > 1) || nullptr != st.tally) {
-        static int resident = 0, resident_counted = 0;
-        if (0 == resident) {
-            int per_sm = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sceneTracePersistent<AnyHit, false>, 128, 0);
-            if (cfg.blocks_per_sm > 0) per_sm = std::min(per_sm, cfg.blocks_per_sm);
-            resident = std::max(per_sm, 1) * numSms();
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sceneTracePersistent<AnyHit, true>, 128, 0);
-            resident_counted = std::max(per_sm, 1) * numSms();
-        }
-        const bool     counted = nullptr != st.tally;
-        const uint32_t needed  = (max_items + 127) / 128;
-        const uint32_t grid    = std::max(1u, std::min<uint32_t>(uint32_t(counted ? resident_counted : resident), needed));
-        cudaError_t    err     = cudaMemsetAsync(st.counters + 8, 0, sizeof(uint32_t), stream);
-        if (cudaSuccess != err) return err;
-        if (counted) {
-            sceneTracePersistent<AnyHit, true><<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, cfg.step, st.tally);
-        } else {
-            sceneTracePersistent<AnyHit, false><<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, cfg.step, nullptr);
-        }
-        return cudaGetLastError();
-    }
-    // counters[2] = mesh queue length, counters[8] = work counter of the persistent kernel
-    cudaError_t err = cudaMemsetAsync(st.counters + 2, 0, sizeof(uint32_t), stream);
-    if (cudaSuccess != err) return err;
-    topKernel<AnyHit><<<gridFor(max_items, walkGrid()), kBlock, 0, stream>>>(scene, st);
-    err = cudaGetLastError();
-    if (cudaSuccess != err || !has_meshes) return err;
-
-    static int resident = 0;
-    if (0 == resident) {
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, meshTracePersistent<AnyHit>, 128, 0);
-        if (cfg.blocks_per_sm > 0) per_sm = std::min(per_sm, cfg.blocks_per_sm);
-        resident = std::max(per_sm, 1) * numSms();
-    }
-    const uint32_t needed = (max_items + 127) / 128;
-    const uint32_t grid   = std::max(1u, std::min<uint32_t>(uint32_t(resident), needed));
-    err                   = cudaMemsetAsync(st.counters + 8, 0, sizeof(uint32_t), stream);
-    if (cudaSuccess != err) return err;
-    meshTracePersistent<AnyHit><<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, cfg.tune);
-    return cudaGetLastError();
-}
-
-}  // namespace
-
-uint32_t sceneTraceLaunches(bool has_meshes, uint32_t num_solid_nodes) {  // kernels per extend / shadow stage
-    const int v = sceneTraceConfig().variant;
-    if (0 == v || !has_meshes) return 1u;
-    return (2 == v && num_solid_nodes > 1) ? 1u : 2u;  // fused kernel, or top kernel + mesh kernel
-}
-
-cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
-    if (0 != sceneTraceConfig().variant) return launchSceneTrace<false>(scene, st, max_items, has_meshes, stream);
-    extendKernel<<<gridFor(max_items, walkGrid()), kBlock, 0, stream>>>(scene, st);
     return cudaGetLastError();
 }
 cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
@@ -3370,11 +2134,6 @@ cudaError_t launchBeginRound(const PathState& st, cudaStream_t stream) {
 }
 cudaError_t launchEndGeneration(const PathState& st, cudaStream_t stream) {
     advanceKernel<<<1, 1, 0, stream>>>(st);
-    return cudaGetLastError();
-}
-cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream) {
-    if (0 != sceneTraceConfig().variant) return launchSceneTrace<true>(scene, st, max_items * st.shadow_stride, has_meshes, stream);
-    shadowKernel<<<gridFor(max_items, walkGrid()), kBlock, 0, stream>>>(scene, st);
     return cudaGetLastError();
 }
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,

@@ -98,7 +98,12 @@ struct SceneDevice {
     const MeshShading* mesh_shading;
 
     const float* luts;  // ZygpuScene.ggx_luts
+
+    float4 world_lo;     // lower corner of the box around the finite props and, per axis, cells per unit length: the ray-sort grid
+    float4 world_cells;  // (device/render_trace.cu, sortKeyKernel)
 };
+
+constexpr uint32_t kSortBins = 1u << 16;  // keys of the ray sort (device/render_trace.cu)
 
 struct PathState {
     // Per path vertex. A camera sample ("slot") owns `lanes` vertex records: 1 when no material of the scene can split a
@@ -140,7 +145,8 @@ struct PathState {
     // mesh candidates collected by the top kernels, per trace item (closest: path slot, shadow: record)
     uint32_t* ml_props;  // 8 per item
     uint32_t* ml_count;
-    uint32_t* queue_m;  // items with candidates
+    uint32_t* queue_m;  // items with candidates (fused traversal kernel: the trace items in ray-sort order)
+    uint32_t* sort_bins; // ray sort: one counter per key (kSortBins + 1), null when the pass does not sort
 
     uint32_t* queue_a;   // slots with at least one vertex in the current generation
     uint32_t* queue_b;   // slots whose vertex of the current round survived shade_a
@@ -152,7 +158,7 @@ struct PathState {
                                 // counted bytes behind the render-path roofline and the lanes-per-step of the lock-step loop
     uint32_t* counters;  // [0] |A|, [1] |B|, [2] |mesh queue|, [3] shadow overflow flag, [4] |next A|, [5] closest rays, [6] shadow rays,
                          // [7] |T|, [8] work counter of the persistent mesh kernel, [9] |S|, [10] |R|, [11] |L|, [12] / [13] work counters of the
-                         // persistent light kernels (16 words in all)
+                         // persistent light kernels, [15] sorted trace items (16 words in all)
 
     uint32_t capacity;       // path slots
     uint32_t shadow_stride;  // shadow records reserved per path
@@ -172,7 +178,8 @@ uint32_t    sceneTraceLaunches(bool has_meshes, uint32_t num_solid_nodes);  // k
 
 cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const PassParams& pass, cudaStream_t stream);
 // The queue lengths live on the device; the grids are sized for `max_items` and exit early.
-cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream);
+// `bounce`: the path depth of the stage (the ray sort skips the camera rays, which arrive in pixel order).
+cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, uint32_t bounce, cudaStream_t stream);
 // `round` = which vertex of each slot's current generation the shade stages work on: the vertices of one camera sample share
 // its sampler and are processed in the reference's order (VertexPool.consume, vertex.zig:232-283), so rounds are sequential.
 cudaError_t launchBeginGeneration(const PathState& st, cudaStream_t stream);
@@ -183,7 +190,7 @@ cudaError_t launchShadeA(const SceneDevice& scene, const ZygpuView& view, const 
 // Deferred light sampling between shade_a and the shadow stage (PathState.queue_l non-null).
 cudaError_t launchLightStages(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass, uint32_t max_items,
                               cudaStream_t stream);
-cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, cudaStream_t stream);
+cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, uint32_t bounce, cudaStream_t stream);
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
                          uint32_t max_items, uint32_t round, cudaStream_t stream);
 cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream);
