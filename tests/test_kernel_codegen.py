@@ -55,7 +55,7 @@ def test_hot_shade_kernels_do_not_spill():
     names = subprocess.run(["c++filt"], input="\n".join(e[0] for e in entries), capture_output=True, text=True, check=True).stdout.splitlines()
     spills = {n: int(e[2]) + int(e[3]) for n, e in zip(names, entries)}
     # shade_a calls the out-of-line lightImportance (device/render.cu): the values live across those calls are saved around them
-    for key, limit in (("shadeAKernel<0u>", 160), ("shadeBKernel<false, false>", 16), ("meshTracePersistent<true>", 16)):
+    for key, limit in (("shadeAKernel<0u>", 160), ("shadeBKernel<false, false>", 16), ("meshTracePersistent<true, 8>", 16)):
         match = [n for n in spills if key in n]
         assert match, key
         assert spills[match[0]] <= limit, f"{match[0]} spills {spills[match[0]]} bytes"

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-source-line instruction and stall-sample shares of one kernel from an .ncu-rep (needs -lineinfo).
-usage: tools/ncu_lines.py prof.ncu-rep [top N]"""
+usage: tools/ncu_lines.py prof.ncu-rep [top N] [stall]   ("stall": rank the lines by stall samples instead of instructions)"""
 import collections
 import csv
 import io
@@ -35,5 +35,7 @@ for r in rows:
     text[key] = r[1].strip()
 T, S = sum(inst.values()), sum(stall.values())
 print(f"total warp instructions {T}, stall samples {S}")
-for key, v in inst.most_common(top):
+ranked = stall if len(sys.argv) > 3 and "stall" == sys.argv[3] else inst
+for key, _ in ranked.most_common(top):
+    v = inst[key]
     print(f"{v / T * 100:5.1f}% inst {stall[key] / max(S, 1) * 100:5.1f}% stall  {key[0]}:{key[1]:<5d} {text[key][:110]}")

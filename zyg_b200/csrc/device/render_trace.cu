@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_TOP_BLOCKS) topKernel(SceneDevic
     if (0 == (threadIdx.x & 31u) && 0 != traced) atomicAdd(&st.counters[AnyHit ? 6 : 5], traced);
 }
 
-template <bool AnyHit>
-__global__ void __launch_bounds__(128) meshTracePersistent(SceneDevice sc, PathState st, uint32_t* __restrict__ work_counter,
+template <bool AnyHit, int MinBlocks>
+__global__ void __launch_bounds__(128, MinBlocks) meshTracePersistent(SceneDevice sc, PathState st, uint32_t* __restrict__ work_counter,
                                                            SceneTraceTuning tune) {
     constexpr uint32_t kFull = 0xffffffffu;
     const uint32_t     lane  = threadIdx.x & 31u;
@@ -344,21 +344,48 @@ __device__ __forceinline__ bool segmentMeetsSphere(const RayT& ray, float4 spher
     return tc - sphere.w * rsqrtf(dd) * 1.0001f <= ray.tmax;
 }
 
-// The record a lane reads in its next NODE step (96-byte node stride) or TRIANGLE / PROP step (64-byte records), asked of L1 early.
-__device__ __forceinline__ void prefetchNext(const float4* nodes, const float4* recs, uint2 node_group, uint2 tri_group, uint32_t octinv) {
-    if (node_group.y > 0x00FFFFFFu) {
-        const uint32_t bit  = 31u - __clz(node_group.y);
-        const uint32_t slot = (bit - 24u) ^ octinv;
-        const uint32_t rank = __popc(node_group.y & 0xffu & ((1u << slot) - 1u));
-        const char*    p    = reinterpret_cast<const char*>(nodes + kWideNodeWords * size_t(node_group.x + rank));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 64));
-    } else if (0 != tri_group.y) {
-        const uint32_t bit = 31u - __clz(tri_group.y);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(recs + 4 * size_t(tri_group.x + bit)));
+// Prefetches. The kernel waits on memory, not on bandwidth (DRAM 6 % busy, half of the stall samples on the first use of a loaded
+// record): a lane asks for the records it is going to read as soon as it knows which, without holding registers for them.
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// mode 1: the one record of the lane's next step, to L1; 2: every 64-byte record of the leaf slots just hit, to L2; 3: those and the
+// inner children that go to the stack; 4: like 2, to L1
+__device__ __forceinline__ void prefetchNext(uint32_t mode, const float4* nodes, const float4* recs, uint2 node_group, uint2 tri_group,
+                                             uint32_t octinv) {
+    if (1 == mode) {
+        if (node_group.y > 0x00FFFFFFu) {
+            const uint32_t bit  = 31u - __clz(node_group.y);
+            const uint32_t slot = (bit - 24u) ^ octinv;
+            const uint32_t rank = __popc(node_group.y & 0xffu & ((1u << slot) - 1u));
+            const char*    p    = reinterpret_cast<const char*>(nodes + kWideNodeWords * size_t(node_group.x + rank));
+            prefetchL1(p);
+            prefetchL1(p + 64);
+        } else if (0 != tri_group.y) {
+            prefetchL1(recs + 4 * size_t(tri_group.x + (31u - __clz(tri_group.y))));
+        }
+        return;
+    }
+    for (uint32_t m = tri_group.y; 0 != m; m &= m - 1u) {
+        const float4* p = recs + 4 * size_t(tri_group.x + uint32_t(__ffs(int(m))) - 1u);
+        if (4 == mode) {
+            prefetchL1(p);
+        } else {
+            prefetchL2(p);
+        }
+    }
+    if (3 == mode && node_group.y > 0x00FFFFFFu) {
+        uint32_t m = node_group.y >> 24;
+        m &= ~(1u << (31u - __clz(m)));  // the nearest child is read in the lane's next NODE step
+        for (; 0 != m; m &= m - 1u) {
+            const uint32_t slot = (uint32_t(__ffs(int(m))) - 1u) ^ octinv;
+            const uint32_t rank = __popc(node_group.y & 0xffu & ((1u << slot) - 1u));
+            const char*    p    = reinterpret_cast<const char*>(nodes + kWideNodeWords * size_t(node_group.x + rank));
+            prefetchL2(p);
+            prefetchL2(p + 64);
+        }
     }
 }
-
 
 // ---- ray sort ---------------------------------------------------------------------------------------------------------------------------
 // After the first bounce the rays of a warp start anywhere and point anywhere: they walk different instances, the lock-step loop runs
@@ -738,7 +765,7 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                     node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
                     tri_group.x  = __float_as_uint(n1.y);
                     tri_group.y  = hitmask & 0x00FFFFFFu;
-                    if (0 != tune.prefetch) prefetchNext(nodes, recs, node_group, tri_group, w.octinv);
+                    if (0 != tune.prefetch) prefetchNext(tune.prefetch, nodes, recs, node_group, tri_group, w.octinv);
                 }
             }
 
@@ -770,7 +797,7 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                     } else {
                         tri_group = e;
                     }
-                    if (0 != tune.prefetch) prefetchNext(nodes, recs, node_group, tri_group, w.octinv);
+                    if (1 == tune.prefetch) prefetchNext(1, nodes, recs, node_group, tri_group, w.octinv);
                 }
             }
 
@@ -851,6 +878,7 @@ struct SceneTraceConfig {
     SceneStepTuning  step;
     int              blocks_per_sm;
     int              min_blocks;
+    int              mesh_min_blocks;
     int              sort, sort_from, sort_mode;
 };
 
@@ -868,6 +896,7 @@ const SceneTraceConfig& sceneTraceConfig() {
         c.tune.tri_den    = uint32_t(envInt("ZYGPU_TRI_DEN", 2));
         c.blocks_per_sm   = envInt("ZYGPU_SCENE_BLOCKS_PER_SM", 0);
         c.min_blocks      = envInt("ZYGPU_SCENE_MIN_BLOCKS", 0);
+        c.mesh_min_blocks = envInt("ZYGPU_MESH_MIN_BLOCKS", 0);
         c.sort            = envInt("ZYGPU_RAY_SORT", 0);       // bit 0: closest-hit rays, bit 1: shadow rays
         c.sort_from       = envInt("ZYGPU_RAY_SORT_FROM", 1);  // first bounce that sorts
         c.sort_mode       = envInt("ZYGPU_RAY_SORT_MODE", 1);  // 1: (cell, octant), 2: (octant, cell)
@@ -886,8 +915,10 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
     // (an instrumented pass always takes the fused kernel, the one that counts its fetches; the results are the same)
     if ((2 == cfg.variant && has_meshes && scene.num_solid_nodes > 1) || nullptr != st.tally) {
         static int resident = 0, resident_counted = 0;
-        // resident blocks per SM the kernel is compiled for (ZYGPU_SCENE_MIN_BLOCKS): 5 -> 96 registers, 6 -> 80, 7 -> 72, 8 -> 64
-        const int  mb = 0 != cfg.min_blocks ? cfg.min_blocks : (AnyHit ? 7 : 5);
+        // resident blocks per SM the kernel is compiled for (ZYGPU_SCENE_MIN_BLOCKS): 5 -> 96 registers, 6 -> 80, 7 -> 72, 8 -> 64.
+        // Measured on config 3 (1920 x 1080 x 4 spp): 188.5 / 179.6 / 169.9 / 168.9 ms - the walk waits on memory (5 M triangles do not
+        // fit the L2), more resident warps cover more of it; config 4 does not care (profiles/r02_sweeps.md)
+        const int  mb = 0 != cfg.min_blocks ? cfg.min_blocks : 8;
         const auto fn = 8 == mb   ? sceneTracePersistent<AnyHit, false, 8>
                         : 7 == mb ? sceneTracePersistent<AnyHit, false, 7>
                         : 6 == mb ? sceneTracePersistent<AnyHit, false, 6>
@@ -930,10 +961,13 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
     err = cudaGetLastError();
     if (cudaSuccess != err || !has_meshes) return err;
 
+    // resident blocks per SM the mesh kernel is compiled for (ZYGPU_MESH_MIN_BLOCKS): 6 -> 80 registers, 7 -> 72, 8 -> 64
+    const int  mmb = 0 != cfg.mesh_min_blocks ? cfg.mesh_min_blocks : 8;  // sphere scene: 48.9 (6 / 7) -> 47.1 ms (8)
+    const auto mfn = 8 == mmb ? meshTracePersistent<AnyHit, 8> : (7 == mmb ? meshTracePersistent<AnyHit, 7> : meshTracePersistent<AnyHit, 6>);
     static int resident = 0;
     if (0 == resident) {
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, meshTracePersistent<AnyHit>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mfn, 128, 0);
         if (cfg.blocks_per_sm > 0) per_sm = std::min(per_sm, cfg.blocks_per_sm);
         resident = std::max(per_sm, 1) * numSms();
     }
@@ -941,7 +975,7 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
     const uint32_t grid   = std::max(1u, std::min<uint32_t>(uint32_t(resident), needed));
     err                   = cudaMemsetAsync(st.counters + 8, 0, sizeof(uint32_t), stream);
     if (cudaSuccess != err) return err;
-    meshTracePersistent<AnyHit><<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, cfg.tune);
+    mfn<<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, cfg.tune);
     return cudaGetLastError();
 }
 
