@@ -7,10 +7,11 @@
  *
  * Scope: static scenes, perspective camera (pinhole / thin lens), PTMIS, the built-in shapes Rectangle / Cube /
  * Sphere / Canopy / Distant and triangle meshes (props, prop instances, instancers), materials Substitute / Glass / Light with
- * uniform parameters, image colour maps and image emission maps (su_image_create: Float32 x 3 and UInt8 x 3). A scene that
+ * uniform parameters, image maps for colour / roughness / metallic / normal and emission (su_image_create: Float32 or UInt8 x 1, 2, 3),
+ * the nine AOV classes next to the beauty. A scene that
  * uses a Disk or Dome prop, thin or dispersive Glass is refused by the render calls (-1 and a log message) rather than rendered
  * wrongly; unsupported material parameters are ignored with a warning through the log callback.
- * Entry points outside that scope exist and return -1 (su_aovs_create, animation frames other than 0).
+ * Entry points outside that scope exist and return -1 (animation frames other than 0).
  */
 #ifndef ZYG_SU_H
 #define ZYG_SU_H
@@ -32,7 +33,9 @@ int32_t su_camera_set_fov(float fov);                                     /* :16
 int32_t su_camera_sensor_dimensions(int32_t* dimensions);                 /* :178 */
 int32_t su_exporters_create(const char* json);                            /* :189 {"Image":{"format":"PNG"|"EXR"|"RGBE","bitdepth":16|32,
                                                                              "error_diffusion":bool}} (take.zig:303-331; "Video" skipped) */
-int32_t su_aovs_create(const char* json);                                 /* :202 (-1: out of scope) */
+int32_t su_aovs_create(const char* json);                                 /* :202 {"Albedo":bool,"Depth":..,"MaterialId":..,"GeometricNormal":..,
+                                                                             "ShadingNormal":..,"Roughness":..,"Emission":..,"Direct":..,
+                                                                             "Indirect":..} sets / clears the class bits (take.zig:106-129) */
 int32_t su_sampler_create(uint32_t num_samples);                          /* :215 (returns -1 even on success, like the reference) */
 int32_t su_integrators_create(const char* json);                          /* :223 */
 int32_t su_image_create(uint32_t id, uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height,
@@ -60,8 +63,9 @@ int32_t su_export_frame(void);                                            /* :56
                                                                              (exporting/image_sequence.zig:24-56) */
 int32_t su_start_frame(uint32_t frame);                                   /* :581 */
 int32_t su_render_iterations(uint32_t num_steps);                         /* :602 */
-int32_t su_resolve_frame(uint32_t aov);                                   /* :613 (aov < 9 = AovValue.NumClasses: -2, the class is
-                                                                             inactive; anything else resolves the beauty) */
+int32_t su_resolve_frame(uint32_t aov);                                   /* :613 aov < 9 = AovValue.NumClasses: that class
+                                                                             (aov_buffer.zig:51-82), -2 when it is not recorded;
+                                                                             anything else resolves the beauty */
 int32_t su_resolve_frame_to_buffer(uint32_t aov, uint32_t width, uint32_t height, float* buffer); /* :626 */
 int32_t su_copy_framebuffer(uint32_t format, uint32_t num_channels, uint32_t width, uint32_t height,
                             uint8_t* destination);                        /* :643 */

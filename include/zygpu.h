@@ -159,6 +159,11 @@ int zygpu_clear_film(zygpu_device* dev);
 int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples);
 /* Sensor.resolveTonemap (Linear) into a host RGBA fp32 buffer of num_pixels pixels; synchronises. */
 int zygpu_resolve(zygpu_device* dev, float* rgba, uint32_t num_pixels);
+/* aov.Buffer.resolve (rendering/sensor/aov/aov_buffer.zig:51-82) of one AOV class (ZYG_AOV_*) the view records (ZygpuView.aov_slots):
+ * colours are |rgb| / weight in sRGB primaries, normals rgb / weight, Roughness x / weight, Depth and MaterialId the stored value;
+ * alpha 1. Returns -2 when the class is not active (Driver.resolveAovToBuffer, driver.zig:209-217). `download_layer` != 0 copies
+ * the unresolved Pack4f layer instead. The AOV layers stay on the device that rendered them: zygpu_reduce_film sums the beauty only. */
+int zygpu_resolve_aov(zygpu_device* dev, uint32_t aov_class, float* rgba, uint32_t num_pixels, int download_layer);
 /* The weighted-sum film itself: Pack4f per pixel (sum w*rgb, sum w), buffer_opaque.zig:12. */
 int   zygpu_download_film(zygpu_device* dev, float* film, uint32_t num_pixels);
 int   zygpu_upload_film(zygpu_device* dev, const float* film, uint32_t num_pixels);

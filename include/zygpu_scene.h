@@ -275,7 +275,22 @@ typedef struct ZygpuView {
     float   filter_inverse_interval;
     float   filter[30];      /* InterpolatedFunction1DN(30) samples, already normalised */
     float   exposure_factor; /* Tonemapper.exposure_factor, Linear class */
+
+    uint32_t aov_slots; /* aov.Factory.slots (rendering/sensor/aov/aov_value.zig:84-103): bit c = AOV class c is recorded */
 } ZygpuView;
+
+enum { /* aov.Value.Class, aov_value.zig:10-20 */
+    ZYG_AOV_ALBEDO           = 0,
+    ZYG_AOV_DEPTH            = 1,
+    ZYG_AOV_MATERIAL_ID      = 2,
+    ZYG_AOV_GEOMETRIC_NORMAL = 3,
+    ZYG_AOV_SHADING_NORMAL   = 4,
+    ZYG_AOV_ROUGHNESS        = 5,
+    ZYG_AOV_EMISSION         = 6,
+    ZYG_AOV_DIRECT           = 7,
+    ZYG_AOV_INDIRECT         = 8,
+    ZYG_AOV_NUM_CLASSES      = 9
+};
 
 #ifdef __cplusplus
 }

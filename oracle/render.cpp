@@ -1117,6 +1117,7 @@ struct Scene {
     const ZygpuMaterial& propMaterial(uint32_t prop, uint32_t part) const {  // scene.zig:529-532
         return s.materials[s.material_ids[s.props[prop].parts_start + part]];
     }
+    uint32_t propMaterialId(uint32_t prop, uint32_t part) const { return s.material_ids[s.props[prop].parts_start + part]; }  // scene.zig propMaterialId
     uint32_t propLightId(uint32_t prop, uint32_t part) const { return s.light_ids[s.props[prop].parts_start + part]; }
     Trafo    propTrafo(uint32_t prop) const { return Trafo::load(s.trafos[prop]); }
     AABB     propAabb(uint32_t prop) const { return {{load4(s.aabbs[prop].min), load4(s.aabbs[prop].max)}}; }
@@ -1932,10 +1933,27 @@ struct Scene {
 
 bool g_wavefront_light_order = false;  // zo_set_wavefront_light_order
 
+// aov.Value, rendering/sensor/aov/aov_value.zig:9-82 (Emission / Direct / Indirect need no slot: they are the IValue)
+struct AovValue {
+    uint32_t slots = 0;
+    Vec4f    values[6];
+
+    bool active() const { return 0 != slots; }
+    bool activeClass(uint32_t c) const { return 0 != (slots & (1u << c)); }
+    void clear() {
+        for (uint32_t c = 0; c < 6; ++c) {
+            if (activeClass(c)) values[c] = ZYG_AOV_DEPTH == c ? splat(std::numeric_limits<float>::max()) : splat(0.f);
+        }
+    }
+    void insert3(uint32_t c, Vec4f v) { values[c] = v; }
+    void insert1(uint32_t c, float v) { values[c][0] = v; }
+};
+
 struct Worker {
     const Scene& scene;
     Generator    rng;
     Sampler      samplers[2];
+    AovValue     aov;
     bool         debug = false;  // ZO_DEBUG_PIXEL="x,y": print the vertices of that pixel's paths (diagnostics)
 
     explicit Worker(const Scene& sc) : scene(sc) {
@@ -2293,6 +2311,26 @@ struct Worker {
         return result;
     }
 
+    // Worker.commonAOV, worker.zig:209-242
+    void commonAOV(const Vertex& vertex, const Fragment& frag, const MaterialSample& mat_sample) {
+        if (vertex.state.primary_ray && aov.activeClass(ZYG_AOV_ALBEDO) && mat_sample.canEvaluate()) {
+            // MaterialSample.aovAlbedo, material_sample.zig:38-45; Substitute: substitute_sample.zig:80-86 (no volumetric materials)
+            Vec4f albedo = splat(0.f);
+            if (MaterialSample::Substitute == mat_sample.kind) {
+                albedo = lerp(mat_sample.albedo, mat_sample.f0, splat(mat_sample.metallic));
+            } else if (MaterialSample::Glass == mat_sample.kind) {
+                albedo = splat(1.f);
+            }
+            aov.insert3(ZYG_AOV_ALBEDO, vertex.throughput * albedo);
+        }
+        if (vertex.probe_depth.surface > 0) return;
+        if (aov.activeClass(ZYG_AOV_GEOMETRIC_NORMAL)) aov.insert3(ZYG_AOV_GEOMETRIC_NORMAL, mat_sample.super.geo_n);
+        if (aov.activeClass(ZYG_AOV_SHADING_NORMAL)) aov.insert3(ZYG_AOV_SHADING_NORMAL, mat_sample.super.frame.z);
+        if (aov.activeClass(ZYG_AOV_ROUGHNESS)) aov.insert1(ZYG_AOV_ROUGHNESS, std::sqrt(mat_sample.super.alpha[0]));
+        if (aov.activeClass(ZYG_AOV_DEPTH)) aov.insert1(ZYG_AOV_DEPTH, vertex.ray.max_t);
+        if (aov.activeClass(ZYG_AOV_MATERIAL_ID)) aov.insert1(ZYG_AOV_MATERIAL_ID, float(1u + scene.propMaterialId(frag.prop, frag.part)));
+    }
+
     static uint32_t maxSplits(const Vertex& v, uint32_t depth) {  // vertex.zig:306-309
         const uint32_t m = 4 / v.path_count;
         return m - (v.state.primary_ray ? 0 : std::min(depth, m - 1));
@@ -2367,6 +2405,8 @@ struct Worker {
 
         const bool           caustics   = !vertex.state.primary_ray ? 0 != scene.view.caustics_path : true;
         const MaterialSample mat_sample = vertexSample(vertex, frag, sampler, caustics);
+
+        if (aov.active()) commonAOV(vertex, frag, mat_sample);  // pathtracer_mis.zig:95-97
 
         split_throughput = vertex.throughput * split_weight;
 
@@ -2444,6 +2484,7 @@ inline Vec4f clampColor(Vec4f color, float mx) {  // sensor.zig:615-624
 struct Film {
     float*           pixels;  // Pack4f per pixel, weight in w
     const ZygpuView& view;
+    float* const*    aov_layers = nullptr;  // aov.Buffer: ZYG_AOV_NUM_CLASSES Pack4f images, null where a class is inactive
 
     float eval(float s) const {  // sensor.zig:626-628 + InterpolatedFunction1DN.eval
         const float    x      = std::fabs(s);
@@ -2478,8 +2519,80 @@ struct Film {
         }
     }
 
-    // Sensor.addSample, sensor.zig:168-385 (opaque, no AOV)
-    void addSample(int32_t x, int32_t y, const float pixel_uv[2], const IValue& value, const int32_t bounds[4],
+    // aov.Buffer.addPixel / addPixelAtomic / lessPixel / overwritePixel, aov_buffer.zig:84-113
+    void addAovPixel(uint32_t i, uint32_t c, Vec4f value, float weight, bool atomic) const {
+        float* v = aov_layers[c] + size_t(i) * 4;
+        if (atomic) {
+            std::atomic_ref<float>(v[0]).fetch_add(weight * value[0], std::memory_order_relaxed);
+            std::atomic_ref<float>(v[1]).fetch_add(weight * value[1], std::memory_order_relaxed);
+            std::atomic_ref<float>(v[2]).fetch_add(weight * value[2], std::memory_order_relaxed);
+            std::atomic_ref<float>(v[3]).fetch_add(weight, std::memory_order_relaxed);
+        } else {
+            const Vec4f wc = splat(weight) * value;
+            v[0] += wc[0];
+            v[1] += wc[1];
+            v[2] += wc[2];
+            v[3] += weight;
+        }
+    }
+    // Sensor.addAov / lessAov / overwriteAov, sensor.zig:576-613
+    void addAov(int32_t px, int32_t py, uint32_t c, float weight, Vec4f value, const int32_t bounds[4], const int32_t isolated[4]) const {
+        if (uint32_t(px - bounds[0]) <= uint32_t(bounds[2]) && uint32_t(py - bounds[1]) <= uint32_t(bounds[3])) {
+            const uint32_t i   = uint32_t(view.resolution[0] * py + px);
+            const bool     iso = uint32_t(px - isolated[0]) <= uint32_t(isolated[2]) && uint32_t(py - isolated[1]) <= uint32_t(isolated[3]);
+            addAovPixel(i, c, value, weight, !iso);
+        }
+    }
+    void lessAov(int32_t px, int32_t py, uint32_t c, float value, const int32_t bounds[4]) const {
+        if (uint32_t(px - bounds[0]) <= uint32_t(bounds[2]) && uint32_t(py - bounds[1]) <= uint32_t(bounds[3])) {
+            float* v = aov_layers[c] + size_t(view.resolution[0] * py + px) * 4;
+            if (value < v[0]) v[0] = value;
+        }
+    }
+    void overwriteAov(int32_t px, int32_t py, uint32_t c, float weight, float value, const int32_t bounds[4]) const {
+        if (uint32_t(px - bounds[0]) <= uint32_t(bounds[2]) && uint32_t(py - bounds[1]) <= uint32_t(bounds[3])) {
+            float* v = aov_layers[c] + size_t(view.resolution[0] * py + px) * 4;
+            if (weight > v[3]) {
+                v[0] = value;
+                v[3] = weight;
+            }
+        }
+    }
+
+    // the AOV half of Sensor.addSample, sensor.zig:197-219, 244-275, 328-377
+    void addAovSample(int32_t x, int32_t y, const float* wx, const float* wy, Vec4f emission, Vec4f direct, Vec4f indirect,
+                      const AovValue& aov, const int32_t bounds[4], const int32_t isolated[4]) const {
+        const int32_t r = view.filter_radius_int;
+        for (uint32_t c = 0; c < ZYG_AOV_NUM_CLASSES; ++c) {
+            if (!aov.activeClass(c) || !aov_layers || !aov_layers[c]) continue;
+            const Vec4f avalue = ZYG_AOV_EMISSION == c ? emission : (ZYG_AOV_DIRECT == c ? direct : (ZYG_AOV_INDIRECT == c ? indirect : aov.values[c]));
+            if (0 == r) {
+                const uint32_t id = uint32_t(view.resolution[0] * y + x);
+                float*         v  = aov_layers[c] + size_t(id) * 4;
+                if (ZYG_AOV_DEPTH == c) {
+                    if (avalue[0] < v[0]) v[0] = avalue[0];
+                } else if (ZYG_AOV_MATERIAL_ID == c) {
+                    if (1.f > v[3]) {
+                        v[0] = avalue[0];
+                        v[3] = 1.f;
+                    }
+                } else {
+                    addAovPixel(id, c, avalue, 1.f, false);
+                }
+            } else if (ZYG_AOV_DEPTH == c) {
+                lessAov(x, y, c, avalue[0], bounds);
+            } else if (ZYG_AOV_MATERIAL_ID == c) {
+                overwriteAov(x, y, c, wx[r] * wy[r], avalue[0], bounds);
+            } else {
+                for (int32_t j = 0; j <= 2 * r; ++j) {
+                    for (int32_t i = 0; i <= 2 * r; ++i) addAov(x - r + i, y - r + j, c, wx[i] * wy[j], avalue, bounds, isolated);
+                }
+            }
+        }
+    }
+
+    // Sensor.addSample, sensor.zig:168-385
+    void addSample(int32_t x, int32_t y, const float pixel_uv[2], const IValue& value, const AovValue& aov, const int32_t bounds[4],
                    const int32_t isolated[4]) const {
         const Vec4f emission = clampColor(value.emission, view.clamp_emission);
         const Vec4f direct   = clampColor(value.direct, view.clamp_direct);
@@ -2493,6 +2606,7 @@ struct Film {
         const int32_t r = view.filter_radius_int;
         if (0 == r) {
             addPixel(uint32_t(view.resolution[0] * y + x), composed, 1.f, false);
+            if (aov.active()) addAovSample(x, y, nullptr, nullptr, emission, direct, indirect, aov, bounds, isolated);
             return;
         }
         // r = 1: weights eval(o + 1), eval(o), eval(o - 1); r = 2: eval(o + 2) ... eval(o - 2); rows outer, columns inner.
@@ -2504,6 +2618,7 @@ struct Film {
         for (int32_t j = 0; j <= 2 * r; ++j) {
             for (int32_t i = 0; i <= 2 * r; ++i) add(x - r + i, y - r + j, wx[i] * wy[j], composed, bounds, isolated);
         }
+        if (aov.active()) addAovSample(x, y, wx, wy, emission, direct, indirect, aov, bounds, isolated);
     }
 };
 
@@ -2580,10 +2695,12 @@ void renderTile(Worker& worker, const Film& film, const int32_t tile[4], uint32_
                 const float pixel_uv[2] = {s4[0], s4[1]};
                 const float lens_uv[2]  = {s4[2], s4[3]};
 
+                worker.aov.clear();  // worker.zig:155
+
                 const Vertex vertex = generateVertex(view, x, y, pixel_uv, lens_uv);
                 const IValue ivalue = worker.li(vertex);
 
-                film.addSample(x, y, pixel_uv, ivalue, crop, isolated);
+                film.addSample(x, y, pixel_uv, ivalue, worker.aov, crop, isolated);
 
                 worker.samplers[0].incrementSample();
             }
@@ -2603,10 +2720,18 @@ extern "C" {
 // schedule (capi.zig:602-609), which reseeds the PCG stream per sample (worker.zig:143) and is what the device does.
 void zo_render(const ZygpuScene* scene, const ZygpuView* view, const ZoMesh* meshes, uint32_t iteration, uint32_t num_samples,
                int per_sample_iterations, float* film_pixels, uint32_t threads) {
+    zo_render_aov(scene, view, meshes, iteration, num_samples, per_sample_iterations, film_pixels, nullptr, threads);
+}
+
+// zo_render that also fills the AOV layers of view->aov_slots: aov_layers[c] = Pack4f image of class c, cleared by the caller to the
+// class default (aov.Buffer.clear: Depth floatMax in xyz, 0 elsewhere, weight 0); entries of inactive classes may be null.
+void zo_render_aov(const ZygpuScene* scene, const ZygpuView* view, const ZoMesh* meshes, uint32_t iteration, uint32_t num_samples,
+                   int per_sample_iterations, float* film_pixels, float* const* aov_layers, uint32_t threads) {
     using namespace zo;
 
     const Scene sc(*scene, *view, meshes);
-    const Film  film{film_pixels, *view};
+    const Film  film{film_pixels, *view, aov_layers};
+    const uint32_t aov_slots = aov_layers ? view->aov_slots : 0u;
 
     const int32_t fr   = view->filter_radius_int;
     const int32_t td   = 32;  // Worker.TileDimensions
@@ -2624,6 +2749,7 @@ void zo_render(const ZygpuScene* scene, const ZygpuView* view, const ZoMesh* mes
 
         auto work = [&]() {
             Worker worker(sc);
+            worker.aov.slots = aov_slots;
             for (;;) {
                 const int32_t c = current.fetch_add(1, std::memory_order_relaxed);
                 if (c >= nt) return;
@@ -2709,6 +2835,28 @@ void zo_resolve(const ZygpuView* view, const float* film_pixels, uint32_t num_pi
         rgba[size_t(i) * 4 + 1] = srgb[1];
         rgba[size_t(i) * 4 + 2] = srgb[2];
         rgba[size_t(i) * 4 + 3] = 1.f;
+    }
+}
+
+// aov.Buffer.resolve, aov_buffer.zig:51-82
+void zo_resolve_aov(uint32_t aov_class, const float* layer, uint32_t num_pixels, float* rgba) {
+    using namespace zo;
+    for (uint32_t i = 0; i < num_pixels; ++i) {
+        const float* p = layer + size_t(i) * 4;
+        float*       o = rgba + size_t(i) * 4;
+        if (ZYG_AOV_ALBEDO == aov_class || aov_class >= ZYG_AOV_EMISSION) {
+            const Vec4f color = Vec4f{{std::fabs(p[0]), std::fabs(p[1]), std::fabs(p[2]), 0.f}} / splat(p[3]);
+            const Vec4f srgb  = Vec4f{{1.70505155f, -0.13025714f, -0.02400328f, 0.f}} * splat(color[0]) +
+                               Vec4f{{-0.62179068f, 1.14080289f, -0.12896877f, 0.f}} * splat(color[1]) +
+                               Vec4f{{-0.08325840f, -0.01054853f, 1.15297171f, 0.f}} * splat(color[2]);
+            o[0] = srgb[0], o[1] = srgb[1], o[2] = srgb[2], o[3] = 1.f;
+        } else if (ZYG_AOV_GEOMETRIC_NORMAL == aov_class || ZYG_AOV_SHADING_NORMAL == aov_class) {
+            o[0] = p[0] / p[3], o[1] = p[1] / p[3], o[2] = p[2] / p[3], o[3] = 1.f;
+        } else if (ZYG_AOV_ROUGHNESS == aov_class) {
+            o[0] = p[0] / p[3], o[1] = 0.f, o[2] = 0.f, o[3] = 1.f;
+        } else {
+            o[0] = p[0], o[1] = 0.f, o[2] = 0.f, o[3] = 1.f;
+        }
     }
 }
 

@@ -63,6 +63,13 @@ typedef struct ZoMesh {
 /* `meshes` is indexed by ZygpuProp.mesh (NULL when the scene has none). */
 void zo_render(const struct ZygpuScene* scene, const struct ZygpuView* view, const ZoMesh* meshes, uint32_t iteration,
                uint32_t num_samples, int per_sample_iterations, float* film, uint32_t threads);
+/* zo_render plus the AOV layers of view->aov_slots (Worker.commonAOV, worker.zig:209-242; Sensor.addSample's AOV half,
+ * sensor.zig:197-377): aov_layers[c] = Pack4f image of class c (ZYG_AOV_*), cleared by the caller to the class default
+ * (aov.Buffer.clear), null for inactive classes. */
+void zo_render_aov(const struct ZygpuScene* scene, const struct ZygpuView* view, const ZoMesh* meshes, uint32_t iteration,
+                   uint32_t num_samples, int per_sample_iterations, float* film, float* const* aov_layers, uint32_t threads);
+/* aov.Buffer.resolve (aov_buffer.zig:51-82) of one class. */
+void zo_resolve_aov(uint32_t aov_class, const float* layer, uint32_t num_pixels, float* rgba);
 /* 0 (default): sampler draws in the reference's order. 1: the draws of PathtracerMIS.sampleLights regrouped the way the
  * device takes them (all light samples of a vertex, then one draw per visible sample); identical when a vertex takes one
  * light sample. */

@@ -92,6 +92,10 @@ def _bind_render(lib):
     lib.zo_render.restype = None
     lib.zo_resolve.argtypes = [vp, vp, u32, vp]
     lib.zo_resolve.restype = None
+    lib.zo_render_aov.argtypes = [vp, vp, vp, u32, u32, C.c_int, vp, vp, u32]
+    lib.zo_render_aov.restype = None
+    lib.zo_resolve_aov.argtypes = [u32, vp, u32, vp]
+    lib.zo_resolve_aov.restype = None
     lib.zo_ggx_micro_directional_albedo.argtypes = [C.c_float, C.c_float, u32]
     lib.zo_ggx_micro_directional_albedo.restype = C.c_float
     lib.zo_ggx_f_s_ss.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, u32]
@@ -153,6 +157,33 @@ def render(scene, view, width, height, iteration, num_samples, per_sample_iterat
     table = mesh_table(num_meshes)
     lib.zo_render(scene, view, table, iteration, num_samples, 1 if per_sample_iterations else 0, _p(film), threads)
     return film
+
+
+AOV_CLASSES = ("Albedo", "Depth", "MaterialId", "GeometricNormal", "ShadingNormal", "Roughness", "Emission", "Direct", "Indirect")
+
+
+def render_aov(scene, view, width, height, iteration, num_samples, aov_slots, threads=0, num_meshes=0, wavefront_light_order=False):
+    """zo_render_aov: the film plus one Pack4f layer per class of `aov_slots` (the bit mask the view was compiled with), each cleared to
+    the class default first (aov.Buffer.clear). Returns (film, {class index: layer})."""
+    lib = _bind_render(load())
+    lib.zo_set_wavefront_light_order(1 if wavefront_light_order else 0)
+    film = np.zeros((height, width, 4), np.float32)
+    layers, table = {}, (C.c_void_p * len(AOV_CLASSES))()
+    for c in range(len(AOV_CLASSES)):
+        if aov_slots & (1 << c):
+            layer = np.zeros((height, width, 4), np.float32)
+            if 1 == c:
+                layer[..., :3] = np.finfo(np.float32).max
+            layers[c] = layer
+            table[c] = layer.ctypes.data
+    lib.zo_render_aov(scene, view, mesh_table(num_meshes), iteration, num_samples, 1, _p(film), table, threads)
+    return film, layers
+
+
+def resolve_aov(aov_class, layer):
+    out = np.empty_like(layer)
+    _bind_render(load()).zo_resolve_aov(aov_class, _p(layer), layer.shape[0] * layer.shape[1], _p(out))
+    return out
 
 
 def image_sample(scene, index, r2):

@@ -661,3 +661,55 @@ def test_surface_maps_match_oracle(engine, nearest):
     assert np.median(rel) < 5e-6
     assert (rel > 1e-2).mean() < 5e-3
     assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4
+
+
+def download_aov_layer(aov_class, width, height):
+    L = lib.load_library()
+    L.zygpu_resolve_aov.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int]
+    layer = np.zeros((height, width, 4), np.float32)
+    assert 0 == L.zygpu_resolve_aov(su.device_handle(), aov_class, layer.ctypes.data, width * height, 1), L.zygpu_last_error()
+    return layer
+
+
+@pytest.mark.parametrize("scene_name,filter_name", [("surface_maps", None), ("surface_maps", "Mitchell"), ("glass", None), ("mesh", "Blackman")])
+def test_aov_layers_match_oracle(engine, scene_name, filter_name):
+    """All nine AOV classes (Worker.commonAOV, worker.zig:209-242; Sensor.addSample, sensor.zig:197-377; aov.Buffer,
+    aov_buffer.zig) next to the beauty: the unresolved layers against the oracle's, then su_resolve_frame_to_buffer against
+    aov.Buffer.resolve. Glass: the albedo is the last primary-ray vertex's (split paths, pool order)."""
+    w, spp = 96, 8
+    n = 0
+    if "surface_maps" == scene_name:
+        n = scenes.surface_maps_scene(w, w, spp=spp, filter_name=filter_name)
+    elif "glass" == scene_name:
+        scenes.cornell_box(w, w, spp=spp, glass={"roughness": 0.0}, filter_name=filter_name)
+    else:
+        n = scenes.sphere_scene(w, w, spp=spp, quads=(96, 48), filter_name=filter_name)
+    su.aovs_create({name: True for name in oracle.AOV_CLASSES})
+    scene, view = su.compile_scene()
+    ref_film, ref = oracle.render_aov(scene, view, w, w, 0, spp, 0x1FF, num_meshes=n or 0)
+    su.render_frame(0)
+    gpu_film = download_film(w, w)
+    assert np.median(rel_error(gpu_film, ref_film)) < 5e-6
+
+    for c in range(9):
+        gpu = download_aov_layer(c, w, w)
+        name = oracle.AOV_CLASSES[c]
+        if c in (1, 2):  # Depth (min over the pixel's samples) and MaterialId (first sample of the largest centre weight): stored values
+            same = gpu[..., 0] == ref[c][..., 0]
+            assert same.mean() > 0.998, f"{name}: {100 * (1 - same.mean()):.3f} % of the pixels differ"
+            continue
+        assert np.allclose(gpu[..., 3], ref[c][..., 3], rtol=2e-6, atol=0), name
+        d = np.abs(gpu[..., :3] - ref[c][..., :3]).sum(-1)
+        scale = np.maximum(np.abs(ref[c][..., :3]).sum(-1), 1e-3)
+        assert np.median(d / scale) < 5e-6, name
+        assert (d / scale > 1e-2).mean() < 5e-3, name
+
+    # the C API: resolved classes, -2 for a class that is not recorded
+    for c in (0, 1, 3, 5, 7):
+        got = su.resolve_frame_to_buffer(w, w, c)
+        want = oracle.resolve_aov(c, download_aov_layer(c, w, w))
+        assert np.allclose(got, want, rtol=1e-6, atol=1e-7, equal_nan=True), oracle.AOV_CLASSES[c]
+    su.aovs_create({"Roughness": False})
+    su.render_frame(0)
+    assert -2 == su._su().su_resolve_frame_to_buffer(5, w, w, np.zeros((w, w, 4), np.float32).ctypes.data)
+    assert 0 == su._su().su_resolve_frame(0) and -2 == su._su().su_resolve_frame(5) and 0 == su._su().su_resolve_frame(9)

@@ -65,6 +65,7 @@ struct RenderState {
     float4*  film        = nullptr;
     float4*  resolved    = nullptr;
     uint32_t film_pixels = 0;
+    zygpu::AovFilm aov{};  // one layer per class of ZygpuView.aov_slots (aov.Buffer)
 
     cudaStream_t stream = nullptr;
 

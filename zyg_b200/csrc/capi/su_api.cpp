@@ -243,7 +243,14 @@ int32_t su_exporters_create(const char* json) {
     return 0;
 }
 
-int32_t su_aovs_create(const char*) { return -1; }
+// capi.zig:202-213 -> View.loadAOV (take.zig:106-129)
+int32_t su_aovs_create(const char* json) {
+    if (!g_engine) return -1;
+    zyg::json::Value v;
+    if (!parse(json, v)) return -1;
+    g_engine->scene.loadAovs(v);
+    return 0;
+}
 
 int32_t su_sampler_create(uint32_t num_samples) {
     if (g_engine) g_engine->scene.setSamplesPerPixel(num_samples);
@@ -464,17 +471,23 @@ int32_t su_render_iterations(uint32_t num_steps) {
 int32_t su_resolve_frame(uint32_t aov) {
     if (!g_engine || !g_engine->device) return -1;
     Engine& e = *g_engine;
-    if (aov < kNumAovClasses) return -2;  // the AOV classes are inactive (no su_aovs_create); anything above resolves the beauty
     const uint32_t n = e.scene.width() * e.scene.height();
     e.target.resize(size_t(n) * 4);
-    return 0 == zygpu_resolve(e.device, e.target.data(), n) ? 0 : -1;
+    if (aov < kNumAovClasses) {  // Driver.resolveAov, driver.zig:219-222: -2 when the class is not recorded
+        const int rc = zygpu_resolve_aov(e.device, aov, e.target.data(), n, 0);
+        return 0 == rc ? 0 : (-2 == rc ? -2 : -1);
+    }
+    return 0 == zygpu_resolve(e.device, e.target.data(), n) ? 0 : -1;  // anything above the classes resolves the beauty
 }
 
 int32_t su_resolve_frame_to_buffer(uint32_t aov, uint32_t width, uint32_t height, float* buffer) {
     if (!g_engine || !g_engine->device || !buffer) return -1;
     Engine& e = *g_engine;
-    if (aov < kNumAovClasses) return -2;
     const uint32_t n = std::min(width * height, e.scene.width() * e.scene.height());  // capi.zig:628
+    if (aov < kNumAovClasses) {
+        const int rc = zygpu_resolve_aov(e.device, aov, buffer, n, 0);
+        return 0 == rc ? 0 : (-2 == rc ? -2 : -1);
+    }
     return 0 == zygpu_resolve(e.device, buffer, n) ? 0 : -1;
 }
 

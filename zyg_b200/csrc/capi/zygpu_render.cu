@@ -59,9 +59,12 @@ uint32_t targetPathsPerPass() {
 // `lanes` vertex records per slot (1, or 4 when a material of the scene can split a path); trace items are vertex ids for
 // closest-hit rays and shadow records for any-hit rays, so the per-item arrays hold max(lanes, shadow_stride) per slot.
 int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint32_t lanes, bool deferred_lights, bool textures, bool record_uvs) {
+    // the per-sample AOV values are written by the shade_a instances that read image maps (one run-time test there, none in the others)
+    const bool aovs = 0 != r.view.aov_slots;
+    textures        = textures || aovs;
     if (r.paths.capacity >= capacity && r.paths.shadow_stride == shadow_stride && r.paths.lanes == lanes &&
         (nullptr != r.paths.queue_l) == deferred_lights && (nullptr != r.paths.stoch) == textures &&
-        (nullptr != r.paths.sh_uv) == record_uvs) {
+        (nullptr != r.paths.sh_uv) == record_uvs && (nullptr != r.paths.aov_misc) == aovs) {
         return 0;
     }
     freeAll(r.path_buffers);
@@ -84,6 +87,10 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint3
     }
     if (shadow_stride > 1 && 0 != allocPath(r, &p.queue_r, size_t(capacity) * shadow_stride)) return -1;
     if (textures && 0 != allocPath(r, &p.stoch, vertices)) return -1;
+    if (aovs && (0 != allocPath(r, &p.aov_albedo, capacity) || 0 != allocPath(r, &p.aov_gn, capacity) || 0 != allocPath(r, &p.aov_sn, capacity) ||
+                 0 != allocPath(r, &p.aov_misc, capacity))) {
+        return -1;
+    }
     if (record_uvs && 0 != allocPath(r, &p.sh_uv, size_t(capacity) * shadow_stride)) return -1;
     if (deferred_lights && (0 != allocPath(r, &p.ls_p, capacity) || 0 != allocPath(r, &p.ls_g, capacity) ||
                             0 != allocPath(r, &p.picks, size_t(capacity) * 64) || 0 != allocPath(r, &p.pick_n, capacity) ||
@@ -106,6 +113,10 @@ void zygpuReleaseRender(zygpu_device* dev) {
     cudaFree(r.film);
     cudaFree(r.resolved);
     cudaFree(r.tally);
+    for (float4*& layer : r.aov.layers) {
+        cudaFree(layer);
+        layer = nullptr;
+    }
     r.tally    = nullptr;
     r.counting = false;
     if (r.stream) {
@@ -398,8 +409,25 @@ int zygpu_set_view(zygpu_device* dev, const ZygpuView* view) {
         CUDA_OK(cudaMalloc(&r.film, size_t(pixels) * sizeof(float4)));
         CUDA_OK(cudaMalloc(&r.resolved, size_t(pixels) * sizeof(float4)));
         CUDA_OK(cudaMemset(r.film, 0, size_t(pixels) * sizeof(float4)));
+        for (float4*& layer : r.aov.layers) {
+            cudaFree(layer);
+            layer = nullptr;
+        }
         r.film_pixels = pixels;
     }
+    // aov.Buffer.resize, aov_buffer.zig:28-37: a layer per active class
+    bool new_layers = false;
+    for (uint32_t c = 0; c < ZYG_AOV_NUM_CLASSES; ++c) {
+        const bool active = 0 != (view->aov_slots & (1u << c));
+        if (active && !r.aov.layers[c]) {
+            CUDA_OK(cudaMalloc(&r.aov.layers[c], size_t(pixels) * sizeof(float4)));
+            new_layers = true;
+        } else if (!active && r.aov.layers[c]) {
+            cudaFree(r.aov.layers[c]);
+            r.aov.layers[c] = nullptr;
+        }
+    }
+    if (new_layers) CUDA_OK(zygpu::launchAovClear(r.aov, pixels, r.stream));
     r.view     = *view;
     r.has_view = true;
     return 0;
@@ -410,6 +438,7 @@ int zygpu_clear_film(zygpu_device* dev) {
     CUDA_OK(cudaSetDevice(dev->ordinal));
     RenderState& r = dev->render;
     CUDA_OK(cudaMemsetAsync(r.film, 0, size_t(r.film_pixels) * sizeof(float4), r.stream));
+    if (0 != r.view.aov_slots) CUDA_OK(zygpu::launchAovClear(r.aov, r.film_pixels, r.stream));
     if (r.paths.counters) CUDA_OK(cudaMemsetAsync(r.paths.counters, 0, 16 * sizeof(uint32_t), r.stream));
     r.stats = ZygpuRenderStats{};
     r.stats_carry[0] = r.stats_carry[1] = 0;
@@ -518,6 +547,10 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
         }
 
         CUDA_OK(zygpu::launchFilm(view, r.paths, pass, r.film, r.stream));
+        if (0 != view.aov_slots) {
+            CUDA_OK(zygpu::launchAovFilm(view, r.paths, pass, r.aov, r.stream));
+            r.stats.kernel_launches += 1;
+        }
         r.stats.kernel_launches += 1;
 
         r.stats.camera_samples += uint64_t(view.crop[2] - view.crop[0] + 2 * fr) * uint64_t(view.crop[3] - view.crop[1] + 2 * fr) * k;
@@ -611,6 +644,24 @@ int zygpu_resolve(zygpu_device* dev, float* rgba, uint32_t num_pixels) {
     CUDA_OK(zygpu::launchResolve(r.view, r.film, r.resolved, n, r.stream));
     r.stats.kernel_launches += 1;
     CUDA_OK(cudaMemcpyAsync(rgba, r.resolved, size_t(n) * sizeof(float4), cudaMemcpyDeviceToHost, r.stream));
+    CUDA_OK(cudaStreamSynchronize(r.stream));
+    return 0;
+}
+
+int zygpu_resolve_aov(zygpu_device* dev, uint32_t aov_class, float* rgba, uint32_t num_pixels, int download_layer) {
+    if (!dev || !rgba) return fail("zygpu_resolve_aov: null argument");
+    RenderState& r = dev->render;
+    if (!r.film) return fail("zygpu_resolve_aov: no view set");
+    if (aov_class >= ZYG_AOV_NUM_CLASSES || !r.aov.layers[aov_class]) return -2;  // the class is not active
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    const uint32_t n = std::min(num_pixels, r.film_pixels);
+    const float4*  src = r.aov.layers[aov_class];
+    if (0 == download_layer) {
+        CUDA_OK(zygpu::launchResolveAov(aov_class, r.aov.layers[aov_class], r.resolved, n, r.stream));
+        r.stats.kernel_launches += 1;
+        src = r.resolved;
+    }
+    CUDA_OK(cudaMemcpyAsync(rgba, src, size_t(n) * sizeof(float4), cudaMemcpyDeviceToHost, r.stream));
     CUDA_OK(cudaStreamSynchronize(r.stream));
     return 0;
 }

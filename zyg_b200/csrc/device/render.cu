@@ -912,6 +912,12 @@ __global__ void __launch_bounds__(kBlock) generateKernel(ZygpuView view, PathSta
         st.acc_e[slot]  = make_float4(0.f, 0.f, 0.f, s4[0]);
         st.acc_d[slot]  = make_float4(0.f, 0.f, 0.f, s4[1]);
         st.acc_i[slot]  = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nullptr != st.aov_misc) {  // aov.Value.clear, worker.zig:155: Depth starts at floatMax, everything else at 0
+            st.aov_albedo[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+            st.aov_gn[slot]     = make_float4(0.f, 0.f, 0.f, 0.f);
+            st.aov_sn[slot]     = make_float4(0.f, 0.f, 0.f, 0.f);
+            st.aov_misc[slot]   = make_float4(0.f, FLT_MAX, 0.f, 0.f);
+        }
         storeSampler(st, slot, sampler, kPoolFirst);  // the camera vertex sits in lane 0 (vertex id == slot)
         st.queue_a[slot] = slot;
         if (st.lanes > 1) st.queue_t[slot] = slot;
@@ -1190,6 +1196,28 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                 if (Split) mediaForSample(sc, media, frag, wo, ior_outside, highest_priority);
                 const MatSampleD mat_sample = texturedMaterialSample<Split, Textured>(sc, m, frag, wo, stochastic_r, view.regularize_roughness, lv.reg_alpha,
                                                                                       caustics, view.specular_threshold, ior_outside, highest_priority);
+
+                // Worker.commonAOV, worker.zig:209-242 (pathtracer_mis.zig:95-97). A view that records AOVs runs the Textured instances.
+                if (Textured && nullptr != st.aov_misc) {
+                    if (0 != (vertex.state & kPrimaryRay) && mat_sample.can_evaluate) {
+                        // MaterialSample.aovAlbedo, material_sample.zig:38-45; substitute_sample.zig:80-86
+                        V3 albedo = splat3(0.f);
+                        if (kSampleSubstitute == mat_sample.kind) {
+                            albedo = {zlerp(mat_sample.albedo.x, mat_sample.f0.x, mat_sample.metallic), zlerp(mat_sample.albedo.y, mat_sample.f0.y, mat_sample.metallic),
+                                      zlerp(mat_sample.albedo.z, mat_sample.f0.z, mat_sample.metallic)};
+                        } else if (kSampleGlass == mat_sample.kind) {
+                            albedo = splat3(1.f);
+                        }
+                        const V3 a          = mul3(lv.throughput, albedo);
+                        st.aov_albedo[slot] = make_float4(a.x, a.y, a.z, 0.f);
+                    }
+                    if (0 == vertex.probe_depth) {
+                        st.aov_gn[slot]   = make_float4(mat_sample.geo_n.x, mat_sample.geo_n.y, mat_sample.geo_n.z, 0.f);
+                        st.aov_sn[slot]   = make_float4(mat_sample.frame.z.x, mat_sample.frame.z.y, mat_sample.frame.z.z, 0.f);
+                        const uint32_t id = __ldg(sc.material_ids + sc.props[frag.prop].parts_start + frag.part);
+                        st.aov_misc[slot] = make_float4(__fsqrt_rn(mat_sample.ax), vertex.ray.tmax, float(1u + id), 0.f);
+                    }
+                }
 
                 vertex.light_split_threshold = splitThreshold(view.split_threshold, vertex.probe_depth);
 
@@ -2014,6 +2042,109 @@ __global__ void __launch_bounds__(kBlock) filmKernel(ZygpuView view, PathState s
     }
 }
 
+// The AOV half of Sensor.addSample (sensor.zig:197-219, 244-275, 328-377) on the gather layout of filmKernel: colour-like classes are
+// filtered sums (aov.Buffer.addPixel), Depth keeps the smallest value of the pixel's own samples (lessPixel), MaterialId the value of the
+// own sample with the largest centre weight, the first one on ties (overwritePixel: a thread sees its samples in sample order).
+__global__ void __launch_bounds__(kBlock) aovFilmKernel(ZygpuView view, PathState st, PassParams pass, AovFilm aov) {
+    const int32_t  w  = view.resolution[0];
+    const int32_t  h  = view.resolution[1];
+    const int32_t  fr = view.filter_radius_int;
+    const uint32_t padded = pass.padded_w * pass.padded_h;
+
+    for (uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < uint32_t(w * h); pixel += gridDim.x * blockDim.x) {
+        const int32_t x = int32_t(pixel % uint32_t(w));
+        const int32_t y = int32_t(pixel / uint32_t(w));
+        if (x < view.crop[0] || x >= view.crop[2] || y < view.crop[1] || y >= view.crop[3]) continue;
+
+        float4 value[ZYG_AOV_NUM_CLASSES];
+        for (uint32_t c = 0; c < ZYG_AOV_NUM_CLASSES; ++c) value[c] = nullptr != aov.layers[c] ? aov.layers[c][pixel] : make_float4(0.f, 0.f, 0.f, 0.f);
+
+        for (uint32_t s = 0; s < pass.samples_in_pass; ++s) {
+            for (int32_t dy = -fr; dy <= fr; ++dy) {
+                for (int32_t dx = -fr; dx <= fr; ++dx) {
+                    const int32_t qx = x + dx, qy = y + dy;
+                    if (qx < view.crop[0] - fr || qx >= view.crop[2] + fr || qy < view.crop[1] - fr || qy >= view.crop[3] + fr) continue;
+                    const uint32_t slot = s * padded + uint32_t(qy + fr) * pass.padded_w + uint32_t(qx + fr);
+
+                    const float4 e  = st.acc_e[slot];
+                    const float4 d  = st.acc_d[slot];
+                    const float4 in = st.acc_i[slot];
+
+                    float weight = 1.f;
+                    if (fr > 0) weight = filterEval(view, (e.w - 0.5f) + float(dx)) * filterEval(view, (d.w - 0.5f) + float(dy));
+
+                    auto add = [&](uint32_t c, V3 v) {
+                        value[c].x += weight * v.x;
+                        value[c].y += weight * v.y;
+                        value[c].z += weight * v.z;
+                        value[c].w += weight;
+                    };
+                    if (nullptr != aov.layers[ZYG_AOV_EMISSION]) add(ZYG_AOV_EMISSION, clampColor({e.x, e.y, e.z}, view.clamp_emission));
+                    if (nullptr != aov.layers[ZYG_AOV_DIRECT]) add(ZYG_AOV_DIRECT, clampColor({d.x, d.y, d.z}, view.clamp_direct));
+                    if (nullptr != aov.layers[ZYG_AOV_INDIRECT]) add(ZYG_AOV_INDIRECT, clampColor({in.x, in.y, in.z}, view.clamp_indirect));
+                    if (nullptr != aov.layers[ZYG_AOV_ALBEDO]) {
+                        const float4 a = st.aov_albedo[slot];
+                        add(ZYG_AOV_ALBEDO, {a.x, a.y, a.z});
+                    }
+                    if (nullptr != aov.layers[ZYG_AOV_GEOMETRIC_NORMAL]) {
+                        const float4 n = st.aov_gn[slot];
+                        add(ZYG_AOV_GEOMETRIC_NORMAL, {n.x, n.y, n.z});
+                    }
+                    if (nullptr != aov.layers[ZYG_AOV_SHADING_NORMAL]) {
+                        const float4 n = st.aov_sn[slot];
+                        add(ZYG_AOV_SHADING_NORMAL, {n.x, n.y, n.z});
+                    }
+                    const float4 misc = st.aov_misc[slot];
+                    // insert1 sets lane 0 only; lanes 1 and 2 keep the class default 0 (aov_value.zig:68-78)
+                    if (nullptr != aov.layers[ZYG_AOV_ROUGHNESS]) add(ZYG_AOV_ROUGHNESS, {misc.x, 0.f, 0.f});
+                    if (0 == dx && 0 == dy) {
+                        if (nullptr != aov.layers[ZYG_AOV_DEPTH] && misc.y < value[ZYG_AOV_DEPTH].x) value[ZYG_AOV_DEPTH].x = misc.y;
+                        if (nullptr != aov.layers[ZYG_AOV_MATERIAL_ID] && weight > value[ZYG_AOV_MATERIAL_ID].w) {
+                            value[ZYG_AOV_MATERIAL_ID].x = misc.z;
+                            value[ZYG_AOV_MATERIAL_ID].w = weight;
+                        }
+                    }
+                }
+            }
+        }
+        for (uint32_t c = 0; c < ZYG_AOV_NUM_CLASSES; ++c) {
+            if (nullptr != aov.layers[c]) aov.layers[c][pixel] = value[c];
+        }
+    }
+}
+
+// aov.Buffer.clear, aov_buffer.zig:39-49
+__global__ void __launch_bounds__(kBlock) aovClearKernel(AovFilm aov, uint32_t num_pixels) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels; i += gridDim.x * blockDim.x) {
+        for (uint32_t c = 0; c < ZYG_AOV_NUM_CLASSES; ++c) {
+            if (nullptr == aov.layers[c]) continue;
+            const float d    = ZYG_AOV_DEPTH == c ? FLT_MAX : 0.f;
+            aov.layers[c][i] = make_float4(d, d, d, 0.f);
+        }
+    }
+}
+
+// aov.Buffer.resolve, aov_buffer.zig:51-82, by Class.encoding (aov_value.zig:32-40)
+__global__ void __launch_bounds__(kBlock) resolveAovKernel(uint32_t aov_class, const float4* layer, float4* rgba, uint32_t num_pixels) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels; i += gridDim.x * blockDim.x) {
+        const float4 p = layer[i];
+        float4       out;
+        if (ZYG_AOV_ALBEDO == aov_class || aov_class >= ZYG_AOV_EMISSION) {  // Color: |rgb| / weight, AP1 -> sRGB
+            const V3 c    = {__fdiv_rn(fabsf(p.x), p.w), __fdiv_rn(fabsf(p.y), p.w), __fdiv_rn(fabsf(p.z), p.w)};
+            const V3 srgb = add3(add3(scale3(c.x, {1.70505155f, -0.13025714f, -0.02400328f}), scale3(c.y, {-0.62179068f, 1.14080289f, -0.12896877f})),
+                                 scale3(c.z, {-0.08325840f, -0.01054853f, 1.15297171f}));
+            out           = make_float4(srgb.x, srgb.y, srgb.z, 1.f);
+        } else if (ZYG_AOV_GEOMETRIC_NORMAL == aov_class || ZYG_AOV_SHADING_NORMAL == aov_class) {  // Normal
+            out = make_float4(__fdiv_rn(p.x, p.w), __fdiv_rn(p.y, p.w), __fdiv_rn(p.z, p.w), 1.f);
+        } else if (ZYG_AOV_ROUGHNESS == aov_class) {  // Float
+            out = make_float4(__fdiv_rn(p.x, p.w), 0.f, 0.f, 1.f);
+        } else {  // Depth, Id
+            out = make_float4(p.x, 0.f, 0.f, 1.f);
+        }
+        rgba[i] = out;
+    }
+}
+
 // Opaque.resolveTonemap with the Linear tonemapper, buffer_opaque.zig:73-79, tonemapper.zig:36-39, aces.zig:19-27
 __global__ void __launch_bounds__(kBlock) resolveKernel(ZygpuView view, const float4* film, float4* rgba, uint32_t num_pixels) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels; i += gridDim.x * blockDim.x) {
@@ -2156,6 +2287,18 @@ cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const 
 }
 cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream) {
     filmKernel<<<gridFor(uint32_t(view.resolution[0] * view.resolution[1]), 16), kBlock, 0, stream>>>(view, st, pass, film);
+    return cudaGetLastError();
+}
+cudaError_t launchAovClear(const AovFilm& aov, uint32_t num_pixels, cudaStream_t stream) {
+    aovClearKernel<<<gridFor(num_pixels, 16), kBlock, 0, stream>>>(aov, num_pixels);
+    return cudaGetLastError();
+}
+cudaError_t launchAovFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, const AovFilm& aov, cudaStream_t stream) {
+    aovFilmKernel<<<gridFor(uint32_t(view.resolution[0] * view.resolution[1]), 16), kBlock, 0, stream>>>(view, st, pass, aov);
+    return cudaGetLastError();
+}
+cudaError_t launchResolveAov(uint32_t aov_class, const float4* layer, float4* rgba, uint32_t num_pixels, cudaStream_t stream) {
+    resolveAovKernel<<<gridFor(num_pixels, 16), kBlock, 0, stream>>>(aov_class, layer, rgba, num_pixels);
     return cudaGetLastError();
 }
 cudaError_t launchResolve(const ZygpuView& view, const float4* film, float4* rgba, uint32_t num_pixels, cudaStream_t stream) {

@@ -130,6 +130,12 @@ struct PathState {
     uint32_t* sh_n;   // per path: number of records
     float2*   sh_uv;  // per record: uvw of a light sample taken through the light's emission image (Rectangle.sampleMaterialTo), read
                       // by Light.evaluateTo in shade_b; null unless the scene has an image-mapped finite light
+    // AOV values of the camera sample (Worker.commonAOV, worker.zig:209-242; aov.Value): null unless the view records an AOV class
+    float4* aov_albedo;  // throughput * mat_sample.aovAlbedo() of the last primary-ray vertex
+    float4* aov_gn;      // geometric normal of the first hit
+    float4* aov_sn;      // shading normal of the first hit
+    float4* aov_misc;    // roughness | depth (FLT_MAX: nothing hit) | 1 + material id | -
+
     float*    stoch;  // per vertex: rs.stochastic_r of Vertex.sample (vertex.zig:165), drawn by shade_a and read again by shade_b
                       // for the material's image lookups; null when no material of the scene reads an image per vertex
 
@@ -194,6 +200,13 @@ cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
                          uint32_t max_items, uint32_t round, cudaStream_t stream);
 cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream);
+// The AOV layers of the sensor (aov.Buffer, rendering/sensor/aov/aov_buffer.zig): one Pack4f image per active class.
+struct AovFilm {
+    float4* layers[9];  // by aov.Value.Class; null = inactive
+};
+cudaError_t launchAovClear(const AovFilm& aov, uint32_t num_pixels, cudaStream_t stream);  // aov.Buffer.clear
+cudaError_t launchAovFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, const AovFilm& aov, cudaStream_t stream);
+cudaError_t launchResolveAov(uint32_t aov_class, const float4* layer, float4* rgba, uint32_t num_pixels, cudaStream_t stream);
 cudaError_t launchResolve(const ZygpuView& view, const float4* film, float4* rgba, uint32_t num_pixels, cudaStream_t stream);
 
 }  // namespace zygpu

@@ -784,6 +784,21 @@ void SceneModel::loadSensor(const json::Value& value) {
     }
 }
 
+// View.loadAOV, take.zig:106-129: {"Albedo": true, "Depth": true, ...} sets or clears the class bits; unknown keys are ignored
+void SceneModel::loadAovs(const json::Value& value) {
+    touch();
+    static const char* const kNames[ZYG_AOV_NUM_CLASSES] = {"Albedo",    "Depth",    "MaterialId", "GeometricNormal", "ShadingNormal",
+                                                            "Roughness", "Emission", "Direct",     "Indirect"};
+    if (json::Value::Object != value.kind) return;
+    for (const auto& entry : value.object) {
+        for (uint32_t c = 0; c < ZYG_AOV_NUM_CLASSES; ++c) {
+            if (entry.first != kNames[c]) continue;
+            const bool on = json::Value::Bool == entry.second.kind ? entry.second.boolean : false;  // json.readBool
+            aov_slots_    = on ? (aov_slots_ | (1u << c)) : (aov_slots_ & ~(1u << c));
+        }
+    }
+}
+
 void SceneModel::loadSampler(const json::Value& value) {
     touch();
     sampler_ = ZYG_SAMPLER_SOBOL;
@@ -1406,6 +1421,7 @@ bool SceneModel::compile(std::string& error) {
         }
     }
     v.exposure_factor = 1.f;  // Tonemapper.init(.Linear, 0.0): exp2(0)
+    v.aov_slots       = aov_slots_;
 
     if (!ptmis_) {
         error = "only the PTMIS surface integrator is implemented: call su_integrators_create with {\"surface\":{\"PTMIS\":{}}}";

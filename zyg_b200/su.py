@@ -198,10 +198,20 @@ def render_iterations(n: int):
     _ok(_su().su_render_iterations(n), "su_render_iterations")
 
 
-def resolve_frame_to_buffer(width: int, height: int) -> np.ndarray:
+def resolve_frame_to_buffer(width: int, height: int, aov: int = 0xFFFFFFFF) -> np.ndarray:
+    """su_resolve_frame_to_buffer: the beauty (any aov >= 9) or one AOV class (0..8, aov.Value.Class order); SuError(-2) when the
+    class is not recorded."""
     out = np.empty((height, width, 4), np.float32)
-    _ok(_su().su_resolve_frame_to_buffer(0xFFFFFFFF, width, height, out.ctypes.data), "su_resolve_frame_to_buffer")
+    _ok(_su().su_resolve_frame_to_buffer(aov, width, height, out.ctypes.data), "su_resolve_frame_to_buffer")
     return out
+
+
+AOV_ALBEDO, AOV_DEPTH, AOV_MATERIAL_ID, AOV_GEOMETRIC_NORMAL, AOV_SHADING_NORMAL, AOV_ROUGHNESS, AOV_EMISSION, AOV_DIRECT, AOV_INDIRECT = range(9)
+
+
+def aovs_create(desc: dict):
+    """The take's "aov" block, e.g. {"Albedo": true, "Depth": true} (View.loadAOV, take.zig:106-129)."""
+    _ok(_su().su_aovs_create(json.dumps(desc).encode()), "su_aovs_create")
 
 
 HOST_BUILDER, DEVICE_BUILDER = 0, 1
