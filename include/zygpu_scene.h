@@ -83,7 +83,7 @@ enum { /* material_base.zig:17-26 */
 };
 
 /* Substitute / Glass / Light parameters: uniform values plus the image maps in scope (emission map,
- * Substitute colour, roughness, metallic and normal maps). 112 bytes. */
+ * Substitute colour, roughness, metallic and normal maps) and the clear coat of a Substitute. 144 bytes. */
 typedef struct ZygpuMaterial {
     uint32_t type;  /* ZYG_MATERIAL_* */
     uint32_t flags; /* ZYG_MATERIAL_* bits */
@@ -112,6 +112,13 @@ typedef struct ZygpuMaterial {
     uint32_t roughness_map; /* Substitute.roughness as an image (ts.sample2D_1, substitute_material.zig:122): first channel */
     uint32_t metallic_map;  /* Substitute.metallic as an image (:123): first channel */
     uint32_t normal_map;    /* Substitute.normal_map (hlp.sampleNormal, material_helper.zig:16-79): first two channels = tangent-space xy */
+
+    /* Substitute "coating" (material_provider.zig:303-326, substitute_coating.zig): uniform parameters, scale 1 */
+    float coating_absorption[3]; /* coating_absorption_coef = attenuationCoefficient(color, attenuation_distance), substitute_material.zig:81-83 */
+    float coating_thickness;     /* 0: no coating */
+    float coating_ior;
+    float coating_roughness; /* un-clamped */
+    float pad[2];
 } ZygpuMaterial;
 
 enum { /* Light.Class (src/core/scene/light/light.zig:34-40) */

@@ -418,6 +418,61 @@ inline ggx::Micro reflect(const GgxLuts& luts, Vec4f color, float f0, Vec4f wo, 
 }  // namespace diffuse
 
 // Material sample of the Material union restricted to {Substitute surface, Light}: material_sample.zig.
+// Coating, substitute/substitute_coating.zig (the clear coat of a Substitute)
+struct Coating {
+    Vec4f n, absorption_coef;
+    float thickness = 0.f, f0 = 0.f, alpha = 0.f, weight = 0.f;
+
+    struct Result {
+        Vec4f reflection, attenuation;
+        float f, pdf;
+    };
+
+    static Vec4f attenuation3(Vec4f c, float distance) {  // collision_coefficients.zig:64-66
+        const Vec4f x = splat(-distance) * c;
+        return {{std::exp(x[0]), std::exp(x[1]), std::exp(x[2]), std::exp(x[3])}};
+    }
+    Vec4f singleAttenuation(float n_dot_wo) const {  // :92-100
+        const float d = thickness * (1.f / n_dot_wo);
+        return attenuation3(absorption_coef, d);
+    }
+    Vec4f attenuation(float n_dot_wi, float n_dot_wo) const {  // :102-108
+        const float f = weight * fresnel::schlick1(min(n_dot_wi, n_dot_wo), f0);
+        const float d = thickness * (1.f / n_dot_wi + 1.f / n_dot_wo);
+        return splat(1.f - f) * attenuation3(absorption_coef, d);
+    }
+    // :35-58
+    Result evaluate(const GgxLuts& luts, Vec4f wi, Vec4f wo, Vec4f h, float wo_dot_h, float specular_threshold, bool avoid_caustics) const {
+        const float n_dot_wi = safe::clampDot(n, wi);
+        const float n_dot_wo = safe::clampAbsDot(n, wo);
+        const Vec4f att      = attenuation(n_dot_wi, n_dot_wo);
+        if (avoid_caustics && alpha <= specular_threshold) return {splat(0.f), att, 0.f, 0.f};
+
+        const ggx::iso::ResultF gg = ggx::iso::reflectionF(h, n, n_dot_wi, n_dot_wo, wo_dot_h, alpha, f0);
+        const float             ep = ggx::ilmEpDielectric(luts, n_dot_wo, alpha, f0);
+        return {splat(ep * weight * n_dot_wi) * gg.r.reflection, att, gg.f, gg.r.pdf};
+    }
+    // :60-82
+    Vec4f reflect(const GgxLuts& luts, Vec4f wo, Vec4f h, float n_dot_wo, float n_dot_h, float wo_dot_h, float specular_threshold,
+                  bxdf::Sample& result) const {
+        Vec4f t, b;
+        orthonormalBasis3(n, t, b);
+        const float n_dot_wi = ggx::iso::reflectNoFresnel(wo, h, n_dot_wo, n_dot_h, wo_dot_h, alpha, specular_threshold, Frame{t, b, n}, result);
+        const float ep       = ggx::ilmEpDielectric(luts, n_dot_wo, alpha, f0);
+        result.reflection    = result.reflection * splat(ep * weight * n_dot_wi);
+        return attenuation(n_dot_wi, n_dot_wo);
+    }
+    // :84-90: Micro.n_dot_wi carries the Fresnel term
+    ggx::Micro sample(Vec4f wo, const float xi[2], float& n_dot_h) const {
+        Vec4f t, b;
+        orthonormalBasis3(n, t, b);
+        const float a[2]     = {alpha, alpha};
+        const Vec4f h        = ggx::sampleVndf(wo, a, xi, Frame{t, b, n}, n_dot_h);
+        const float wo_dot_h = safe::clampDot(wo, h);
+        return {h, fresnel::schlick1(wo_dot_h, f0), wo_dot_h};
+    }
+};
+
 struct MaterialSample {
     enum Kind { Light, Substitute, Glass } kind;
 
@@ -426,6 +481,7 @@ struct MaterialSample {
     // Substitute, substitute_sample.zig:20-36
     Vec4f albedo, f0;
     float metallic, specular, specular_threshold, opacity;
+    Coating coating;
 
     // Glass, glass_sample.zig:20-30 (abbe == 0, thickness == 0)
     Vec4f absorption_coef;
@@ -479,11 +535,17 @@ struct MaterialSample {
 
         const Vec4f h        = normalize3(wo + wi);
         const float wo_dot_h = safe::clampDot(wo, h);
-        return baseEvaluate(wi, wo, h, wo_dot_h, force_disable_caustics);
+        const bxdf::Result base_result = baseEvaluate(wi, wo, h, wo_dot_h, force_disable_caustics);
+        if (coating.thickness > 0.f) {  // :138-142
+            const Coating::Result c = coating.evaluate(*luts, wi, wo, h, wo_dot_h, specular_threshold, super.avoidCausticsForce(force_disable_caustics));
+            const float           pdf = c.f * c.pdf + (1.f - c.f) * base_result.pdf;
+            return {c.reflection + c.attenuation * base_result.reflection, pdf};
+        }
+        return base_result;
     }
 
     // substitute_sample.zig:338-361
-    void diffuseSample(float diffuse_weight, const float xi[2], bxdf::Sample& result) const {
+    ggx::Micro diffuseSample(float diffuse_weight, const float xi[2], bxdf::Sample& result) const {
         const Vec4f  wo    = super.wo;
         const Frame& frame = super.frame;
         const float* alpha = super.alpha;
@@ -502,10 +564,11 @@ struct MaterialSample {
         const float s     = specular;
         result.reflection = splat(micro.n_dot_wi) * (result.reflection + splat(s) * (gg.reflection + mms));
         result.pdf        = diffuse_weight * result.pdf + (1.f - diffuse_weight) * gg.pdf;
+        return micro;
     }
 
     // substitute_sample.zig:363-410 (no flakes)
-    void glossSample(float diffuse_weight, const float xi[2], bxdf::Sample& result) const {
+    ggx::Micro glossSample(float diffuse_weight, const float xi[2], bxdf::Sample& result) const {
         const Vec4f  wo    = super.wo;
         const Frame& frame = super.frame;
         const float* alpha = super.alpha;
@@ -526,6 +589,44 @@ struct MaterialSample {
 
         result.reflection = splat(micro.n_dot_wi) * (splat(s) * (result.reflection + mms) + d.reflection);
         result.pdf        = (1.f - diffuse_weight) * result.pdf + diffuse_weight * d.pdf;
+        return micro;
+    }
+
+    // substitute_sample.zig:304-336, 412-433
+    void coatingSample(Sampler& sampler, bxdf::Sample& result) const {
+        float       n_dot_h;
+        const Vec2f s2    = sampler.sample2D();
+        const float xi2[2] = {s2[0], s2[1]};
+        const ggx::Micro micro = coating.sample(super.wo, xi2, n_dot_h);
+        const float      f     = micro.n_dot_wi;
+
+        const Vec4f s3 = sampler.sample3D();
+        const float p  = s3[0];
+        if (p <= f) {
+            // coatingReflect
+            const Vec4f wo       = super.wo;
+            const float n_dot_wo = safe::clampAbsDot(coating.n, wo);
+            const Vec4f coating_attenuation = coating.reflect(*luts, wo, micro.h, n_dot_wo, n_dot_h, micro.h_dot_wi, specular_threshold, result);
+            const bxdf::Result base_result  = baseEvaluate(result.wi, wo, micro.h, micro.h_dot_wi, false);
+            result.reflection = (result.reflection * splat(f)) + coating_attenuation * base_result.reflection;
+            result.pdf        = f * result.pdf + (1.f - f) * base_result.pdf;
+        } else {
+            float dw = 0.f;
+            if (1.f != metallic) {
+                const float n_dot_wo = super.frame.clampAbsNdot(super.wo);
+                const float f0m      = hmax3(f0);
+                const float am       = hmax3(albedo);
+                dw                   = diffuse::estimateContribution(*luts, n_dot_wo, super.alpha[1], f0m, am);
+            }
+            const float xi[2] = {s3[1], s3[2]};
+            const float p1    = (p - f) / (1.f - f);
+            // coatingBaseSample
+            const ggx::Micro base_micro = p1 < dw ? diffuseSample(dw, xi, result) : glossSample(dw, xi, result);
+            const Coating::Result c =
+                coating.evaluate(*luts, result.wi, super.wo, base_micro.h, base_micro.h_dot_wi, specular_threshold, super.avoid_caustics);
+            result.reflection = c.attenuation * result.reflection + c.reflection;
+            result.pdf        = (1.f - f) * result.pdf + f * c.pdf;
+        }
     }
 
     // substitute_sample.zig:280-302
@@ -559,7 +660,11 @@ struct MaterialSample {
         result.split_weight  = 1.f;
         result.wavelength    = 0.f;
 
-        baseSample(sampler, result);
+        if (coating.thickness > 0.f) {
+            coatingSample(sampler, result);
+        } else {
+            baseSample(sampler, result);
+        }
 
         if (0.f == result.pdf) return 0;
         return 1;
@@ -801,8 +906,13 @@ inline MaterialSample substituteSample(const ZygpuMaterial& m, Vec4f wo, const R
         alpha[0] = alpha[1] = roughness * roughness;
     }
 
+    // coating_scale is the uniform 1: weight 1 (substitute_material.zig:128-134)
+    const float coating_thickness = 1.f * m.coating_thickness;
+    const float coating_weight    = 1.f;
+    const float coating_ior       = lerp(rs.ior, m.coating_ior, coating_weight);
+
     const float ior       = m.ior;
-    const float ior_outer = rs.ior;  // coating_thickness == 0
+    const float ior_outer = coating_thickness > 0.f ? coating_ior : rs.ior;
 
     // Surface.init, substitute_sample.zig:38-78
     MaterialSample r;
@@ -834,6 +944,20 @@ inline MaterialSample substituteSample(const ZygpuMaterial& m, Vec4f wo, const R
     r.opacity            = 1.f;  // 1 - 0.5 * translucency
 
     r.super.frame = {rs.t, rs.b, rs.n};
+
+    if (coating_thickness > 0.f) {  // :164-181. No coating normal map: n is the base frame's normal without a normal map (the two uniform
+        // textures are equal) and the interpolated normal with one (not equal, coating map uniform) - rs.n either way
+        r.coating.n               = rs.n;
+        const float cr            = ggx::clampRoughness(m.coating_roughness);
+        r.coating.absorption_coef = {{m.coating_absorption[0], m.coating_absorption[1], m.coating_absorption[2], 0.f}};
+        r.coating.thickness       = coating_thickness;
+        r.coating.f0              = fresnel::Schlick::IorToF0(coating_ior, rs.ior);
+        const float ca[2]         = {cr * cr, cr * cr};
+        float       reg[2];
+        rs.regularizeAlpha(ca, specular_threshold, reg);
+        r.coating.alpha  = reg[0];
+        r.coating.weight = coating_weight;
+    }
     return r;
 }
 

@@ -713,3 +713,21 @@ def test_aov_layers_match_oracle(engine, scene_name, filter_name):
     su.render_frame(0)
     assert -2 == su._su().su_resolve_frame_to_buffer(5, w, w, np.zeros((w, w, 4), np.float32).ctypes.data)
     assert 0 == su._su().su_resolve_frame(0) and -2 == su._su().su_resolve_frame(5) and 0 == su._su().su_resolve_frame(9)
+
+
+@pytest.mark.parametrize("normal_map", [True, False])
+def test_coated_substitutes_match_oracle(engine, normal_map):
+    """The clear coat (substitute_coating.zig; evaluate substitute_sample.zig:138-142, coatingSample :304-336, coatingReflect /
+    coatingBaseSample :412-433) over glossy, diffuse, metallic and normal-mapped anisotropic bases, on Rectangle, Cube, Sphere and a mesh:
+    the coat's two extra sampler draws per vertex, its Fresnel split, the absorption along both passes through the layer."""
+    w, spp = 128, 16
+    n = scenes.coated_scene(w, w, spp=spp, normal_map=normal_map)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp, num_meshes=n)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6
+    assert (rel > 1e-2).mean() < 5e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4

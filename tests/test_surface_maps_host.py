@@ -49,7 +49,7 @@ def test_material_records_point_at_their_maps(engine):
     scene, _ = su.compile_scene()
     s = sv.scene_at(scene)
     mats = sv.view(s.materials, np.dtype([("head", "<u4", 24), ("color_map", "<u4"), ("roughness_map", "<u4"), ("metallic_map", "<u4"),
-                                          ("normal_map", "<u4")]), s.num_materials)
+                                          ("normal_map", "<u4"), ("coating", "<f4", 8)]), s.num_materials)
     null = 0xFFFFFFFF
     used = [(int(m["roughness_map"]) != null, int(m["metallic_map"]) != null, int(m["normal_map"]) != null) for m in mats]
     assert (True, False, True) in used and (True, True, False) in used and (False, True, True) in used

@@ -339,6 +339,8 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
         if (ZYGPU_NULL != mat.color_map || ZYGPU_NULL != mat.roughness_map || ZYGPU_NULL != mat.metallic_map || ZYGPU_NULL != mat.normal_map) {
             r.has_textures = true;
         }
+        // a coated Substitute runs the same shade kernel instances (device/shading.cuh materialSample<Glass, Coated>)
+        if (ZYG_MATERIAL_SUBSTITUTE == mat.type && mat.coating_thickness > 0.f) r.has_textures = true;
     }
 
     // shadow records one path vertex can need: every light the tree may return times its sample count

@@ -1047,7 +1047,7 @@ __device__ __forceinline__ MatSampleD texturedMaterialSample(const SceneDevice& 
         if (ZYGPU_NULL != m.roughness_map) m.roughness = surfaceMapTexel(sc.image_samplers + m.roughness_map, frag.u, frag.v, stochastic_r).x;  // :122
         if (ZYGPU_NULL != m.metallic_map) m.metallic = surfaceMapTexel(sc.image_samplers + m.metallic_map, frag.u, frag.v, stochastic_r).x;     // :123
     }
-    MatSampleD r = materialSample<Split>(m, frag, wo, reg_weight, reg_alpha, caustics, specular_threshold, ior_outside, highest_priority);
+    MatSampleD r = materialSample<Split, Textured>(m, frag, wo, reg_weight, reg_alpha, caustics, specular_threshold, ior_outside, highest_priority);
     if (Textured && ZYGPU_NULL != m.normal_map && kSampleSubstitute == r.kind) {  // :157-159: result.super.frame = Frame.init(n)
         const V3 xy = surfaceMapTexel(sc.image_samplers + m.normal_map, frag.u, frag.v, stochastic_r);
         const V3 n  = sampleNormal(wo, frag.t, frag.b, r.n, r.geo_n, xy.x, xy.y);
@@ -1855,7 +1855,7 @@ __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeB
                                                                      imageTexel(sc.image_samplers[lm.emission_map], luv.x, luv.y, stochastic_r))
                                            : emittanceRadiance(lm, wi, ltrafo, area, false);
 
-                const BxdfResult bxdf_result = mat_sample.template evaluate<Split>(luts, wi, max_splits);
+                const BxdfResult bxdf_result = mat_sample.template evaluate<Split, Textured>(luts, wi, max_splits);
 
                 const float light_pdf = o4.w;
                 const float weight    = predividedPowerHeuristic(light_pdf, bxdf_result.pdf);
@@ -1867,7 +1867,7 @@ __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeB
             ivalueAdd(st, slot, mul3(split_throughput, next_light), total_depth, 1, false, false);
 
             BxdfSample     sample_results[Split ? 2 : 1];
-            const uint32_t path_count = mat_sample.template sample<Split>(luts, sampler, max_splits, sample_results);
+            const uint32_t path_count = mat_sample.template sample<Split, Textured>(luts, sampler, max_splits, sample_results);
 
             if (Split) pool = poolFree(pool, lane);  // the parent lives in registers from here on
             if (slot == pass.debug_slot) {

@@ -1032,8 +1032,52 @@ struct MatSampleD {
     float  ax, ay;
     V3     albedo, f0;
     float  metallic, specular, specular_threshold, opacity;
+    // Coating of a Substitute, substitute/substitute_coating.zig (weight 1: the scale texture is the uniform 1). Only the instances
+    // compiled with Coated = true (the ones that read image maps) look at these.
+    V3     coat_n, coat_absorption;
+    float  coat_thickness, coat_f0, coat_alpha;
 
     __device__ bool sameHemisphere(V3 v) const { return dot3(geo_n, v) > 0.f; }
+
+    struct CoatResult {
+        V3    reflection, attenuation;
+        float f, pdf;
+    };
+    __device__ V3 coatAttenuation3(float distance) const {  // ccoef.attenuation3, collision_coefficients.zig:64-66
+        const float nd = -distance;
+        return {expf(nd * coat_absorption.x), expf(nd * coat_absorption.y), expf(nd * coat_absorption.z)};
+    }
+    __device__ V3 coatAttenuation(float n_dot_wi, float n_dot_wo) const {  // substitute_coating.zig:102-108
+        const float f = 1.f * schlick1(zmin(n_dot_wi, n_dot_wo), coat_f0);
+        const float d = coat_thickness * (__fdiv_rn(1.f, n_dot_wi) + __fdiv_rn(1.f, n_dot_wo));
+        return scale3(1.f - f, coatAttenuation3(d));
+    }
+    // Coating.evaluate, :35-58
+    __device__ CoatResult coatEvaluate(const LutsD& luts, V3 wi, V3 h, float wo_dot_h, bool avoid) const {
+        const float n_dot_wi = clampDot(coat_n, wi);
+        const float n_dot_wo = clampAbsDot(coat_n, wo);
+        const V3    att      = coatAttenuation(n_dot_wi, n_dot_wo);
+        if (avoid && coat_alpha <= specular_threshold) return {splat3(0.f), att, 0.f, 0.f};
+        // ggx.Iso.reflectionF, ggx.zig:73-95
+        const float alpha2  = coat_alpha * coat_alpha;
+        const float n_dot_h = saturate(dot3(coat_n, h));
+        const float d       = isoDistribution(n_dot_h, alpha2);
+        float       vis, g1;
+        isoVisibilityAndG1Wo(n_dot_wi, n_dot_wo, alpha2, vis, g1);
+        const float f  = schlick1(wo_dot_h, coat_f0);
+        const float ep = ilmEpDielectric(luts, n_dot_wo, coat_alpha, coat_f0);
+        return {splat3(((ep * 1.f) * n_dot_wi) * ((d * vis) * f)), att, f, pdfVisible(d, g1)};
+    }
+    // Coating.reflect, :60-82
+    __device__ V3 coatReflect(const LutsD& luts, V3 h, float n_dot_wo, float n_dot_h, float wo_dot_h, BxdfSample& result) const {
+        FrameD cf;
+        cf.z = coat_n;
+        orthonormalBasis3(coat_n, cf.x, cf.y);
+        const float n_dot_wi = isoReflectNoFresnel(wo, h, n_dot_wo, n_dot_h, wo_dot_h, coat_alpha, specular_threshold, cf, result);
+        const float ep       = ilmEpDielectric(luts, n_dot_wo, coat_alpha, coat_f0);
+        result.reflection    = scale3((ep * 1.f) * n_dot_wi, result.reflection);
+        return coatAttenuation(n_dot_wi, n_dot_wo);
+    }
 
     // substitute_sample.zig:236-278
     __device__ BxdfResult baseEvaluate(const LutsD& luts, V3 wi, V3 h, float wo_dot_h, bool force_disable_caustics) const {
@@ -1064,18 +1108,24 @@ struct MatSampleD {
 
     // material_sample.zig:56-62 -> substitute_sample.zig:88-145
     // `Glass` = the scene holds Glass materials (compiled out otherwise)
-    template <bool Glass>
+    template <bool Glass, bool Coated = false>
     __device__ BxdfResult evaluate(const LutsD& luts, V3 wi, uint32_t max_splits) const {
         if (kSampleLight == kind) return {splat3(0.f), 0.f};
         if (Glass && kSampleGlass == kind) return glassEvaluate(luts, wi, max_splits);
         if (!sameHemisphere(wo)) return {splat3(0.f), 0.f};
         const V3    h        = normalize3(add3(wo, wi));
         const float wo_dot_h = clampDot(wo, h);
-        return baseEvaluate(luts, wi, h, wo_dot_h, false);
+        const BxdfResult base_result = baseEvaluate(luts, wi, h, wo_dot_h, false);
+        if (Coated && coat_thickness > 0.f) {  // substitute_sample.zig:138-142
+            const CoatResult c   = coatEvaluate(luts, wi, h, wo_dot_h, avoid_caustics);
+            const float      pdf = c.f * c.pdf + (1.f - c.f) * base_result.pdf;
+            return {add3(c.reflection, mul3(c.attenuation, base_result.reflection)), pdf};
+        }
+        return base_result;
     }
 
     // substitute_sample.zig:338-361
-    __device__ void diffuseSample(const LutsD& luts, float diffuse_weight, float xi0, float xi1, BxdfSample& result) const {
+    __device__ MicroD diffuseSample(const LutsD& luts, float diffuse_weight, float xi0, float xi1, BxdfSample& result) const {
         const float n_dot_wo = frame.clampAbsNdot(wo);
         const V3    a        = scale3(opacity, albedo);
         const float f0m      = hmax3(f0);
@@ -1100,10 +1150,11 @@ struct MatSampleD {
 
         result.reflection = scale3(n_dot_wi, add3(result.reflection, scale3(specular, add3(gg.reflection, mms))));
         result.pdf        = diffuse_weight * result.pdf + (1.f - diffuse_weight) * gg.pdf;
+        return {h, n_dot_wi, h_dot_wi};
     }
 
     // substitute_sample.zig:363-410 (no flakes)
-    __device__ void glossSample(const LutsD& luts, float diffuse_weight, float xi0, float xi1, BxdfSample& result) const {
+    __device__ MicroD glossSample(const LutsD& luts, float diffuse_weight, float xi0, float xi1, BxdfSample& result) const {
         const float n_dot_wo = frame.clampAbsNdot(wo);
 
         const MicroD micro = ggxReflect(wo, n_dot_wo, ax, ay, specular_threshold, xi0, xi1, f0, frame, result);
@@ -1118,16 +1169,51 @@ struct MatSampleD {
 
         result.reflection = scale3(micro.n_dot_wi, add3(scale3(specular, add3(result.reflection, mms)), d.reflection));
         result.pdf        = (1.f - diffuse_weight) * result.pdf + diffuse_weight * d.pdf;
+        return micro;
     }
 
     // material_sample.zig:64-78 -> substitute_sample.zig:147-234, 280-302. Returns the number of samples (0 or 1).
-    template <bool Glass>
+    template <bool Glass, bool Coated = false>
     __device__ uint32_t sample(const LutsD& luts, SamplerD& sampler, uint32_t max_splits, BxdfSample* results) const {
         if (kSampleLight == kind) return 0;
         if (Glass && kSampleGlass == kind) return glassSample(luts, sampler, max_splits, results);
         if (!sameHemisphere(wo)) return 0;
         BxdfSample& result  = results[0];
         result.split_weight = 1.f;
+
+        if (Coated && coat_thickness > 0.f) {  // coatingSample, substitute_sample.zig:304-336, 412-433
+            float xi0, xi1;
+            sampler.sample2D(xi0, xi1);
+            // Coating.sample, substitute_coating.zig:84-90
+            FrameD cf;
+            cf.z = coat_n;
+            orthonormalBasis3(coat_n, cf.x, cf.y);
+            float       n_dot_h;
+            const V3    h        = sampleVndf(wo, coat_alpha, coat_alpha, xi0, xi1, cf, n_dot_h);
+            const float h_dot_wi = clampDot(wo, h);
+            const float f        = schlick1(h_dot_wi, coat_f0);
+
+            const V3    s3 = sampler.sample3D();
+            const float p  = s3.x;
+            if (p <= f) {  // coatingReflect
+                const float n_dot_wo            = clampAbsDot(coat_n, wo);
+                const V3    coating_attenuation = coatReflect(luts, h, n_dot_wo, n_dot_h, h_dot_wi, result);
+                const BxdfResult base_result    = baseEvaluate(luts, result.wi, h, h_dot_wi, false);
+                result.reflection = add3(scale3(f, result.reflection), mul3(coating_attenuation, base_result.reflection));
+                result.pdf        = f * result.pdf + (1.f - f) * base_result.pdf;
+            } else {
+                float dw = 0.f;
+                if (1.f != metallic) dw = diffuseEstimateContribution(luts, ay, hmax3(f0), hmax3(albedo));
+                const float  p1    = __fdiv_rn(p - f, 1.f - f);
+                const MicroD micro = p1 < dw ? diffuseSample(luts, dw, s3.y, s3.z, result) : glossSample(luts, dw, s3.y, s3.z, result);
+                // coatingBaseSample
+                const CoatResult c = coatEvaluate(luts, result.wi, micro.h, micro.h_dot_wi, avoid_caustics);
+                result.reflection  = add3(mul3(c.attenuation, result.reflection), c.reflection);
+                result.pdf         = (1.f - f) * result.pdf + f * c.pdf;
+            }
+            if (0.f == result.pdf) return 0;
+            return 1;
+        }
 
         float dw = 0.f;
         if (1.f != metallic) {
@@ -1367,7 +1453,8 @@ __device__ __forceinline__ V3 emittanceRadianceMapped(const ZygpuMaterial& m, V3
 }
 
 // Vertex.sample + Material.sample, vertex.zig:137-181, material.zig:184-194, substitute_material.zig:114-221
-template <bool Glass>
+// `Coated`: the instance looks at the clear coat of a Substitute (the instances that read image maps; compiled out of the others)
+template <bool Glass, bool Coated = false>
 __device__ __forceinline__ MatSampleD materialSample(const ZygpuMaterial& m, const FragD& frag, V3 wo, float reg_weight, float reg_alpha,
                                                      bool caustics, float specular_threshold, float ior_outside = 1.f,
                                                      int highest_priority = -128) {
@@ -1428,7 +1515,11 @@ __device__ __forceinline__ MatSampleD materialSample(const ZygpuMaterial& m, con
     }
 
     const float ior_medium = ior_outside;  // rs.ior: Vertex.iorOutside, vertex.zig:87-93
-    const float ior_outer  = ior_medium;
+    // substitute_material.zig:128-134 with the uniform coating scale 1: weight 1
+    const bool  coated      = Coated && m.coating_thickness > 0.f;
+    const float coating_ior = zlerp(ior_medium, m.coating_ior, 1.f);
+    const float ior_outer   = coated ? coating_ior : ior_medium;
+    r.coat_thickness        = 0.f;
 
     // Renderstate.regularizeAlpha, renderstate.zig:58-68
     if (!(0.f == reg_weight || (ax <= specular_threshold && !caustics))) {
@@ -1449,6 +1540,21 @@ __device__ __forceinline__ MatSampleD materialSample(const ZygpuMaterial& m, con
     r.specular           = m.specular;
     r.specular_threshold = specular_threshold;
     r.opacity            = 1.f;
+
+    if (coated) {  // :164-181 (no coating normal map: the interpolated normal)
+        r.coat_n          = r.n;
+        r.coat_absorption = {m.coating_absorption[0], m.coating_absorption[1], m.coating_absorption[2]};
+        r.coat_thickness  = 1.f * m.coating_thickness;
+        const float ct    = __fdiv_rn(coating_ior - ior_medium, coating_ior + ior_medium);
+        r.coat_f0         = ct * ct;
+        const float cr    = zmax(m.coating_roughness, kMinRoughness);
+        float       ca    = cr * cr;
+        if (!(0.f == reg_weight || (ca <= specular_threshold && !caustics))) {
+            const float k = 1.f - reg_weight * reg_alpha;
+            ca            = 1.f - ((1.f - ca) * k);
+        }
+        r.coat_alpha = ca;
+    }
     return r;
 }
 

@@ -110,6 +110,8 @@ ZygpuMaterial defaultMaterial(uint32_t type) {
             m.color[0] = m.color[1] = m.color[2] = 0.5f;
             m.roughness = 0.8f;
             m.ior       = 1.46f;
+            m.coating_ior       = 1.5f;  // coating_thickness 0: no coat
+            m.coating_roughness = 0.2f;
             break;
         case ZYG_MATERIAL_LIGHT:  // light_material.zig:44
             m.emission[0] = m.emission[1] = m.emission[2] = m.emission[3] = 1.f;
@@ -347,6 +349,29 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
                     } else if (kMetallicMap == slot) {
                         m.metallic = float(e.second.number);
                     }  // a uniform "normal" is no normal map (Texture.initUniform2: isUniform, substitute_material.zig:157)
+                } else if ("coating" == k && json::Value::Object == e.second.kind) {  // material_provider.zig:303-326
+                    Vec4f coating_color{{1.f, 1.f, 1.f, 1.f}};
+                    float coating_attenuation_distance = 0.1f;
+                    for (const auto& c : e.second.object) {
+                        if ("color" == c.first) {
+                            coating_color = readColor(c.second);
+                        } else if ("attenuation_distance" == c.first) {
+                            coating_attenuation_distance = float(c.second.number);
+                        } else if ("ior" == c.first) {
+                            m.coating_ior = float(c.second.number);
+                        } else if ("roughness" == c.first && json::Value::Number == c.second.kind) {
+                            m.coating_roughness = float(c.second.number);
+                        } else if ("thickness" == c.first) {
+                            m.coating_thickness = float(c.second.number);
+                        } else {  // normal / scale / roughness maps of the coat
+                            warnings_.push_back("material " + std::to_string(id) + ": coating parameter \"" + c.first + "\" is not supported by the device path and is ignored");
+                        }
+                    }
+                    // setCoatingAttenuation -> attenuationCoefficient, collision_coefficients.zig:35-44
+                    for (int i = 0; i < 3; ++i) {
+                        const float c           = fmin_(fmax_(coating_color[i], 0.01f), 0.991102f);
+                        m.coating_absorption[i] = 0.f == coating_attenuation_distance ? 0.f : -std::log(c) / coating_attenuation_distance;
+                    }
                 } else if ("specular" == k) {
                     m.specular = float(e.second.number);
                 } else if ("anisotropy" == k) {
@@ -357,7 +382,7 @@ bool SceneModel::updateMaterial(uint32_t id, const json::Value& material) {
                     m.priority = int32_t(e.second.number);
                 } else if ("two_sided" == k) {
                     m.flags = e.second.boolean ? (m.flags | ZYG_MATERIAL_TWO_SIDED) : (m.flags & ~ZYG_MATERIAL_TWO_SIDED);
-                } else {  // coating, flakes, surface / rotation / mask maps, attenuation, volumetric_anisotropy, ...
+                } else {  // flakes, surface / rotation / mask maps, attenuation, volumetric_anisotropy, ...
                     warnings_.push_back("material " + std::to_string(id) + ": Substitute parameter \"" + k + "\" is not supported by the device path and is ignored");
                 }
             }
@@ -1076,6 +1101,11 @@ bool SceneModel::compile(std::string& error) {
         materials_[m].emission_map = ZYGPU_NULL;
         materials_[m].color_map    = ZYGPU_NULL;
         materials_[m].roughness_map = materials_[m].metallic_map = materials_[m].normal_map = ZYGPU_NULL;
+        if (ZYG_MATERIAL_SUBSTITUTE == materials_[m].type && materials_[m].coating_thickness > 0.f && 0 != (materials_[m].flags & ZYG_MATERIAL_EMISSIVE)) {
+            // substitute_material.zig:274-292 attenuates the emission by the coat: not on the device path, refused instead of rendered wrongly
+            error = "material " + std::to_string(m) + ": an emissive Substitute with a coating is not supported";
+            return false;
+        }
         static const char* const kMapName[kNumSurfaceMaps] = {"roughness", "metallic", "normal"};
         for (int k = 0; k < kNumSurfaceMaps; ++k) {
             const uint32_t image = surface_maps_[m][k].image;

@@ -475,6 +475,57 @@ def surface_maps_scene(width=128, height=128, spp=16, max_depth=6, filter_name=N
     return 1
 
 
+def coated_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None, quads=(48, 24), coated=True, thickness=0.02, normal_map=True):
+    """Clear-coated Substitutes (substitute_coating.zig, substitute_sample.zig:138-142, 304-336, 412-433): a glossy ground with a smooth
+    colourless coat, a diffuse cube under a thick amber coat (absorption along both passes through the layer), a rough-metal Sphere with
+    a rough coat, a mesh whose base has a normal map while the coat keeps the interpolated normal. `coated=False` renders the same
+    bases without their coats. Returns the number of meshes."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(55.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.6, -4.2), rotation_deg=(-14.0, 0.0, 0.0)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    def material(base, coating):
+        desc = dict(base)
+        if coated:
+            desc["coating"] = coating
+        return su.material_create({"rendering": {"Substitute": desc}})
+
+    ground = material({"color": [0.5, 0.05, 0.04], "roughness": 0.5, "metallic": 0.0},
+                      {"thickness": thickness, "roughness": 0.02, "ior": 1.5})
+    g = su.prop_create(su.RECTANGLE, [ground])
+    su.prop_set_transformation(g, su.transformation((0.0, 0.0, 0.0), (12.0, 12.0, 1.0), (90.0, 0.0, 0.0)))
+
+    amber = material({"color": [0.8, 0.8, 0.8], "roughness": 1.0, "metallic": 0.0},
+                     {"thickness": 10.0 * thickness, "roughness": 0.1, "ior": 1.6, "color": [0.9, 0.6, 0.15], "attenuation_distance": 0.1})
+    cube = su.prop_create(su.CUBE, [amber])
+    su.prop_set_transformation(cube, su.transformation((-1.3, 0.5, 0.4), (1.0, 1.0, 1.0), (0.0, 30.0, 0.0)))
+
+    metal = material({"color": [0.95, 0.64, 0.54], "roughness": 0.35, "metallic": 1.0}, {"thickness": thickness, "roughness": 0.3, "ior": 1.4})
+    ball = su.prop_create(su.SPHERE, [metal])
+    su.prop_set_transformation(ball, su.transformation((-0.1, 0.45, -1.2), (0.45, 0.45, 0.45)))
+
+    base = {"color": [0.1, 0.25, 0.6], "roughness": 0.4, "metallic": 0.0, "anisotropy": 0.5}
+    if normal_map:
+        base["normal"] = {"id": su.image_create(bump_normal_map(128, 12.0, 0.8))}
+    paint = material(base, {"thickness": thickness, "roughness": 0.05, "ior": 1.5})
+    positions, normals, uvs, indices = displaced_sphere(*quads, seed=0x5EED0009)
+    indices = np.ascontiguousarray(indices.reshape(-1, 3)[:, [0, 2, 1]])
+    mesh = su.prop_create(su.triangle_mesh_create(positions, indices, normals, uvs), [paint])
+    su.prop_set_transformation(mesh, su.transformation((1.2, 0.8, 0.0), (0.75, 0.75, 0.75), (0.0, 20.0, 0.0)))
+
+    light = su.material_create({"rendering": {"Light": {"emittance": {"value": 25.0}}}})
+    lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=True)
+    su.prop_set_transformation(lamp, su.transformation((0.0, 4.0, -0.5), (2.0, 2.0, 1.0), (-90.0, 0.0, 0.0)))
+    su.light_create(lamp)
+    return 1
+
+
 def image_light_scene(width=128, height=128, spp=16, max_depth=5, filter_name=None, split_threshold=0.5, num_samples=1,
                       image=None, value=6.0, two_sided=False, unoccluding=True):
     """A closed room lit by a Rectangle whose Light material carries an emission image (a PropImage light on a finite shape:
