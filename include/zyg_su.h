@@ -119,6 +119,9 @@ const struct zyg_mesh* zyg_su_mesh(uint32_t shape);
 /* The image codecs behind su_export_frame on a caller-owned RGBA float image (image/image_writer.zig:15-66). format: 0 PNG,
  * 1 EXR, 2 RGBE; flags: bit 0 alpha channel (PNG / EXR), bit 1 EXR half floats, bit 2 PNG error diffusion; crop = x0, y0, x1, y1
  * (exclusive) or NULL for the full frame. Host only, needs no engine and no GPU. */
+/* `it --denoise sigma` (src/it/denoise.zig) on the frame that was just rendered, from the device's own buffers: width * height RGBA
+ * like su_resolve_frame_to_buffer. -2 unless su_aovs_create switched on ShadingNormal and Albedo. */
+int32_t zyg_su_denoise_frame_to_buffer(float sigma, uint32_t width, uint32_t height, float* buffer);
 int32_t zyg_su_write_image(const char* path, uint32_t format, uint32_t flags, const float* rgba, int32_t width, int32_t height,
                            const int32_t* crop);
 

@@ -164,6 +164,11 @@ int zygpu_resolve(zygpu_device* dev, float* rgba, uint32_t num_pixels);
  * alpha 1. Returns -2 when the class is not active (Driver.resolveAovToBuffer, driver.zig:209-217). `download_layer` != 0 copies
  * the unresolved Pack4f layer instead. The AOV layers stay on the device that rendered them: zygpu_reduce_film sums the beauty only. */
 int zygpu_resolve_aov(zygpu_device* dev, uint32_t aov_class, float* rgba, uint32_t num_pixels, int download_layer);
+/* The `it` tool's denoise operator (src/it/denoise.zig; `it --denoise sigma`, options.zig:98-100) as a post kernel on the device: the
+ * beauty filtered with the normalised Gaussian of sigma (radius ceil(3 sigma)), each tap blended in by normal agreement, albedo
+ * distance and the local noise estimate; sRGB primaries, alpha 1, like the tool's output. Needs the ShadingNormal and Albedo classes
+ * in ZygpuView.aov_slots (the "_n" and "_albedo" files the tool looks for, operator.zig:70-93): -2 otherwise. Synchronises. */
+int zygpu_denoise(zygpu_device* dev, float sigma, float* rgba, uint32_t num_pixels);
 /* The weighted-sum film itself: Pack4f per pixel (sum w*rgb, sum w), buffer_opaque.zig:12. */
 int   zygpu_download_film(zygpu_device* dev, float* film, uint32_t num_pixels);
 int   zygpu_upload_film(zygpu_device* dev, const float* film, uint32_t num_pixels);

@@ -2838,6 +2838,82 @@ void zo_resolve(const ZygpuView* view, const float* film_pixels, uint32_t num_pi
     }
 }
 
+// Denoise.init + process + filter + estimateNoise, src/it/denoise.zig
+void zo_denoise(const ZygpuView* view, const float* film, const float* normal_layer, const float* albedo_layer, float sigma, float* rgba) {
+    using namespace zo;
+    const int32_t w = view->resolution[0], h = view->resolution[1];
+
+    const int32_t      radius = int32_t(std::ceil(3.f * sigma));  // :34-72
+    std::vector<float> weights;
+    float              wsum   = 0.f;
+    const float        sigma2 = sigma * sigma;
+    for (int32_t y = -radius; y <= radius; ++y) {
+        for (int32_t x = -radius; x <= radius; ++x) {
+            const float p = (float(x) * float(x) + float(y) * float(y)) / (2.f * sigma2);
+            weights.push_back(std::exp(-p));
+            wsum += weights.back();
+        }
+    }
+    for (float& g : weights) g /= wsum;
+
+    auto colorAt = [&](int32_t x, int32_t y) {  // Opaque.resolveTonemap (Linear) before the matrix to sRGB primaries
+        const float* p = film + (size_t(y) * size_t(w) + size_t(x)) * 4;
+        return splat(view->exposure_factor) * Vec4f{{std::fabs(p[0] / p[3]), std::fabs(p[1] / p[3]), std::fabs(p[2] / p[3]), 0.f}};
+    };
+    auto normalAt = [&](int32_t x, int32_t y) {
+        const float* p = normal_layer + (size_t(y) * size_t(w) + size_t(x)) * 4;
+        return Vec4f{{p[0] / p[3], p[1] / p[3], p[2] / p[3], 0.f}};
+    };
+    auto albedoAt = [&](int32_t x, int32_t y) {
+        const float* p = albedo_layer + (size_t(y) * size_t(w) + size_t(x)) * 4;
+        return Vec4f{{std::fabs(p[0]) / p[3], std::fabs(p[1]) / p[3], std::fabs(p[2]) / p[3], 0.f}};
+    };
+    auto luma = [](Vec4f c) { return std::pow(hmax3(c), 1.f / 2.2f); };
+
+    for (int32_t py = 0; py < h; ++py) {
+        for (int32_t px = 0; px < w; ++px) {
+            const Vec4f ref_color = colorAt(px, py), ref_n = normalAt(px, py), ref_albedo = albedoAt(px, py);
+
+            float sum = 0.f, l[9];  // estimateNoise, :375-451
+            for (int32_t y = -1, k = 0; y <= 1; ++y) {
+                for (int32_t x = -1; x <= 1; ++x, ++k) {
+                    l[k] = luma(colorAt(std::clamp(px + x, 0, w - 1), std::clamp(py + y, 0, h - 1)));
+                    sum += l[k];
+                }
+            }
+            const float norm = 1.f / 9.f;
+            const float mean = sum * norm;
+            float       dif_sum = 0.f;
+            for (int k = 0; k < 9; ++k) {
+                const float dif = l[k] - mean;
+                dif_sum += dif * dif;
+            }
+            const float std_dev        = std::sqrt(norm * dif_sum);
+            const float coef           = mean > 0.f ? std_dev / mean : 0.f;
+            const float noise_estimate = min(coef * 20.f * min(mean, 1.f), 1.f);
+
+            Vec4f    result = splat(0.f);  // filter, :175-246 (dd is overwritten with 1: the depth input has no effect)
+            uint32_t tap    = 0;
+            for (int32_t y = -radius; y <= radius; ++y) {
+                for (int32_t x = -radius; x <= radius; ++x) {
+                    const int32_t sx = std::clamp(px + x, 0, w - 1), sy = std::clamp(py + y, 0, h - 1);
+                    const float   weight      = weights[tap++];
+                    const float   dot_n       = saturate(dot3(ref_n, normalAt(sx, sy)));
+                    const float   dist_albedo = min(distance3(ref_albedo, albedoAt(sx, sy)), 1.f);
+                    const float   strength    = 1.f * (dot_n * dot_n) * (1.f - dist_albedo) * noise_estimate;
+                    const Vec4f   color       = lerp(ref_color, colorAt(sx, sy), splat(strength));
+                    result                    = result + splat(weight) * color;
+                }
+            }
+            const Vec4f srgb = Vec4f{{1.70505155f, -0.13025714f, -0.02400328f, 0.f}} * splat(result[0]) +
+                               Vec4f{{-0.62179068f, 1.14080289f, -0.12896877f, 0.f}} * splat(result[1]) +
+                               Vec4f{{-0.08325840f, -0.01054853f, 1.15297171f, 0.f}} * splat(result[2]);
+            float* o = rgba + (size_t(py) * size_t(w) + size_t(px)) * 4;
+            o[0] = srgb[0], o[1] = srgb[1], o[2] = srgb[2], o[3] = 1.f;
+        }
+    }
+}
+
 // aov.Buffer.resolve, aov_buffer.zig:51-82
 void zo_resolve_aov(uint32_t aov_class, const float* layer, uint32_t num_pixels, float* rgba) {
     using namespace zo;

@@ -70,6 +70,9 @@ void zo_render_aov(const struct ZygpuScene* scene, const struct ZygpuView* view,
                    uint32_t num_samples, int per_sample_iterations, float* film, float* const* aov_layers, uint32_t threads);
 /* aov.Buffer.resolve (aov_buffer.zig:51-82) of one class. */
 void zo_resolve_aov(uint32_t aov_class, const float* layer, uint32_t num_pixels, float* rgba);
+/* The `it` tool's denoise operator (src/it/denoise.zig:137-246, 375-451) over the unresolved film and the unresolved ShadingNormal and
+ * Albedo layers of a view (the colour in AP1, as the tool's loader leaves it): rgba = sRGB primaries, alpha 1. */
+void zo_denoise(const struct ZygpuView* view, const float* film, const float* normal_layer, const float* albedo_layer, float sigma, float* rgba);
 /* 0 (default): sampler draws in the reference's order. 1: the draws of PathtracerMIS.sampleLights regrouped the way the
  * device takes them (all light samples of a vertex, then one draw per visible sample); identical when a vertex takes one
  * light sample. */

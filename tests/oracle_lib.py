@@ -180,6 +180,15 @@ def render_aov(scene, view, width, height, iteration, num_samples, aov_slots, th
     return film, layers
 
 
+def denoise(view, film, normal_layer, albedo_layer, sigma):
+    lib = _bind_render(load())
+    lib.zo_denoise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    lib.zo_denoise.restype = None
+    out = np.empty_like(film)
+    lib.zo_denoise(view, _p(film), _p(normal_layer), _p(albedo_layer), sigma, _p(out))
+    return out
+
+
 def resolve_aov(aov_class, layer):
     out = np.empty_like(layer)
     _bind_render(load()).zo_resolve_aov(aov_class, _p(layer), layer.shape[0] * layer.shape[1], _p(out))

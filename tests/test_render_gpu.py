@@ -731,3 +731,22 @@ def test_coated_substitutes_match_oracle(engine, normal_map):
     assert np.median(rel) < 5e-6
     assert (rel > 1e-2).mean() < 5e-3
     assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4
+
+
+@pytest.mark.parametrize("sigma", [1.0, 0.6])
+def test_denoise_matches_oracle(engine, sigma):
+    """`it --denoise` as a post kernel (src/it/denoise.zig) over the device's film and its ShadingNormal / Albedo layers, against the
+    oracle's restatement fed with the very same buffers; -2 without those AOV classes."""
+    w, spp = 96, 4
+    n = scenes.surface_maps_scene(w, w, spp=spp)
+    scene, view = su.compile_scene()
+    su.render_frame(0)
+    assert -2 == su._su().zyg_su_denoise_frame_to_buffer(C.c_float(sigma), w, w, np.zeros((w, w, 4), np.float32).ctypes.data)
+    su.aovs_create({"Albedo": True, "ShadingNormal": True})
+    scene, view = su.compile_scene()
+    su.render_frame(0)
+    got = su.denoise_frame_to_buffer(sigma, w, w)
+    want = oracle.denoise(view, download_film(w, w), download_aov_layer(4, w, w), download_aov_layer(0, w, w), sigma)
+    assert np.allclose(got, want, rtol=2e-4, atol=2e-6)
+    plain = su.resolve_frame_to_buffer(w, w)
+    assert np.abs(got[..., :3] - plain[..., :3]).mean() > 1e-3  # it did something

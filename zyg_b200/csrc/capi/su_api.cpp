@@ -617,6 +617,15 @@ const zyg_mesh* zyg_su_mesh(uint32_t shape) {
     return g_engine->meshes[shape - 7];
 }
 
+int32_t zyg_su_denoise_frame_to_buffer(float sigma, uint32_t width, uint32_t height, float* buffer) {
+    if (!g_engine || !g_engine->device || !buffer) return -1;
+    Engine&        e  = *g_engine;
+    const uint32_t n  = std::min(width * height, e.scene.width() * e.scene.height());
+    const int      rc = zygpu_denoise(e.device, sigma, buffer, n);
+    if (-1 == rc) logf(Error, "%s", zygpu_last_error());
+    return 0 == rc ? 0 : (-2 == rc ? -2 : -1);
+}
+
 int32_t zyg_su_write_image(const char* path, uint32_t format, uint32_t flags, const float* rgba, int32_t width, int32_t height,
                            const int32_t* crop) {
     if (!path || !rgba || width < 1 || height < 1 || format > 2) return -1;

@@ -668,6 +668,41 @@ int zygpu_resolve_aov(zygpu_device* dev, uint32_t aov_class, float* rgba, uint32
     return 0;
 }
 
+int zygpu_denoise(zygpu_device* dev, float sigma, float* rgba, uint32_t num_pixels) {
+    if (!dev || !rgba) return fail("zygpu_denoise: null argument");
+    RenderState& r = dev->render;
+    if (!r.film) return fail("zygpu_denoise: no view set");
+    if (!(sigma > 0.f) || sigma > 16.f) return fail("zygpu_denoise: sigma must be in (0, 16]");
+    if (!r.aov.layers[ZYG_AOV_SHADING_NORMAL] || !r.aov.layers[ZYG_AOV_ALBEDO]) return -2;
+    CUDA_OK(cudaSetDevice(dev->ordinal));
+    // Denoise.init, denoise.zig:34-72
+    const int32_t      radius = int32_t(std::ceil(3.f * sigma));
+    std::vector<float> weights;
+    float              sum    = 0.f;
+    const float        sigma2 = sigma * sigma;
+    for (int32_t y = -radius; y <= radius; ++y) {
+        for (int32_t x = -radius; x <= radius; ++x) {
+            const float p = (float(x) * float(x) + float(y) * float(y)) / (2.f * sigma2);
+            weights.push_back(std::exp(-p));
+            sum += weights.back();
+        }
+    }
+    for (float& g : weights) g /= sum;
+    float* d_weights = nullptr;
+    CUDA_OK(cudaMalloc(&d_weights, weights.size() * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(d_weights, weights.data(), weights.size() * sizeof(float), cudaMemcpyHostToDevice, r.stream);
+    if (cudaSuccess == e) {
+        e = zygpu::launchDenoise(r.view, r.film, r.aov.layers[ZYG_AOV_SHADING_NORMAL], r.aov.layers[ZYG_AOV_ALBEDO], d_weights, radius, r.resolved, r.stream);
+    }
+    r.stats.kernel_launches += 1;
+    const uint32_t n = std::min(num_pixels, r.film_pixels);
+    if (cudaSuccess == e) e = cudaMemcpyAsync(rgba, r.resolved, size_t(n) * sizeof(float4), cudaMemcpyDeviceToHost, r.stream);
+    if (cudaSuccess == e) e = cudaStreamSynchronize(r.stream);
+    cudaFree(d_weights);
+    CUDA_OK(e);
+    return 0;
+}
+
 int zygpu_download_film(zygpu_device* dev, float* film, uint32_t num_pixels) {
     if (!dev || !film) return fail("zygpu_download_film: null argument");
     RenderState& r = dev->render;

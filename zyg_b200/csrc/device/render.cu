@@ -2145,6 +2145,82 @@ __global__ void __launch_bounds__(kBlock) resolveAovKernel(uint32_t aov_class, c
     }
 }
 
+// ---- denoise (src/it/denoise.zig) -------------------------------------------------------------------------------------------------------
+// The inputs `it denoise` reads from the exported files, taken from the buffers they were exported from: colour = the resolved beauty in
+// AP1 (Opaque.resolveTonemap without the matrix to sRGB primaries, which the tool's image loader undoes again), normal = the resolved
+// ShadingNormal layer ("_n"), albedo = the resolved Albedo layer in AP1. The depth input only feeds `dd`, which the reference overwrites
+// with 1 (denoise.zig:229-230): it is not read.
+__device__ __forceinline__ V3 denoiseColor(const ZygpuView& view, const float4* film, int32_t x, int32_t y) {
+    const float4 p = film[size_t(y) * size_t(view.resolution[0]) + size_t(x)];
+    return scale3(view.exposure_factor, {fabsf(__fdiv_rn(p.x, p.w)), fabsf(__fdiv_rn(p.y, p.w)), fabsf(__fdiv_rn(p.z, p.w))});
+}
+__device__ __forceinline__ float denoiseLuma(V3 c) { return powf(hmax3(c), 1.f / 2.2f); }
+
+__global__ void __launch_bounds__(kBlock) denoiseKernel(ZygpuView view, const float4* __restrict__ film, const float4* __restrict__ normal,
+                                                        const float4* __restrict__ albedo, const float* __restrict__ weights, int32_t radius,
+                                                        float4* __restrict__ rgba) {
+    const int32_t w = view.resolution[0], h = view.resolution[1];
+    for (uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x; pixel < uint32_t(w * h); pixel += gridDim.x * blockDim.x) {
+        const int32_t px = int32_t(pixel % uint32_t(w)), py = int32_t(pixel / uint32_t(w));
+
+        auto normalAt = [&](int32_t x, int32_t y) -> V3 {
+            const float4 p = normal[size_t(y) * size_t(w) + size_t(x)];
+            return {__fdiv_rn(p.x, p.w), __fdiv_rn(p.y, p.w), __fdiv_rn(p.z, p.w)};
+        };
+        auto albedoAt = [&](int32_t x, int32_t y) -> V3 {
+            const float4 p = albedo[size_t(y) * size_t(w) + size_t(x)];
+            return {__fdiv_rn(fabsf(p.x), p.w), __fdiv_rn(fabsf(p.y), p.w), __fdiv_rn(fabsf(p.z), p.w)};
+        };
+
+        const V3 ref_color  = denoiseColor(view, film, px, py);
+        const V3 ref_n      = normalAt(px, py);
+        const V3 ref_albedo = albedoAt(px, py);
+
+        // estimateNoise, :375-451: coefficient of variation of the 3 x 3 neighbourhood's gamma-encoded brightness
+        float sum = 0.f;
+        float l[9];
+        for (int32_t y = -1, k = 0; y <= 1; ++y) {
+            for (int32_t x = -1; x <= 1; ++x, ++k) {
+                l[k] = denoiseLuma(denoiseColor(view, film, min(max(px + x, 0), w - 1), min(max(py + y, 0), h - 1)));
+                sum += l[k];
+            }
+        }
+        const float norm    = __fdiv_rn(1.f, 9.f);
+        const float mean    = sum * norm;
+        float       dif_sum = 0.f;
+        for (int k = 0; k < 9; ++k) {
+            const float dif = l[k] - mean;
+            dif_sum += dif * dif;
+        }
+        const float std_dev        = __fsqrt_rn(norm * dif_sum);
+        const float coef           = mean > 0.f ? __fdiv_rn(std_dev, mean) : 0.f;
+        const float noise_estimate = zmin(coef * 20.f * zmin(mean, 1.f), 1.f);
+
+        // filter, :175-246
+        V3       result = splat3(0.f);
+        uint32_t tap    = 0;
+        for (int32_t y = -radius; y <= radius; ++y) {
+            for (int32_t x = -radius; x <= radius; ++x) {
+                const int32_t sx = min(max(px + x, 0), w - 1), sy = min(max(py + y, 0), h - 1);
+                const float   weight = weights[tap++];
+
+                const V3    f_n         = normalAt(sx, sy);
+                const V3    f_albedo    = albedoAt(sx, sy);
+                const float dot_n       = saturate(dot3(ref_n, f_n));
+                const V3    da          = sub3(ref_albedo, f_albedo);
+                const float dist_albedo = zmin(__fsqrt_rn(dot3(da, da)), 1.f);
+                const float strength    = 1.f * (dot_n * dot_n) * (1.f - dist_albedo) * noise_estimate;
+
+                const V3 color = lerp3(ref_color, denoiseColor(view, film, sx, sy), splat3(strength));
+                result         = add3(result, scale3(weight, color));
+            }
+        }
+        const V3 srgb = add3(add3(scale3(result.x, {1.70505155f, -0.13025714f, -0.02400328f}), scale3(result.y, {-0.62179068f, 1.14080289f, -0.12896877f})),
+                             scale3(result.z, {-0.08325840f, -0.01054853f, 1.15297171f}));
+        rgba[pixel]   = make_float4(srgb.x, srgb.y, srgb.z, 1.f);
+    }
+}
+
 // Opaque.resolveTonemap with the Linear tonemapper, buffer_opaque.zig:73-79, tonemapper.zig:36-39, aces.zig:19-27
 __global__ void __launch_bounds__(kBlock) resolveKernel(ZygpuView view, const float4* film, float4* rgba, uint32_t num_pixels) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels; i += gridDim.x * blockDim.x) {
@@ -2299,6 +2375,11 @@ cudaError_t launchAovFilm(const ZygpuView& view, const PathState& st, const Pass
 }
 cudaError_t launchResolveAov(uint32_t aov_class, const float4* layer, float4* rgba, uint32_t num_pixels, cudaStream_t stream) {
     resolveAovKernel<<<gridFor(num_pixels, 16), kBlock, 0, stream>>>(aov_class, layer, rgba, num_pixels);
+    return cudaGetLastError();
+}
+cudaError_t launchDenoise(const ZygpuView& view, const float4* film, const float4* normal, const float4* albedo, const float* weights, int32_t radius,
+                          float4* rgba, cudaStream_t stream) {
+    denoiseKernel<<<gridFor(uint32_t(view.resolution[0] * view.resolution[1]), 16), kBlock, 0, stream>>>(view, film, normal, albedo, weights, radius, rgba);
     return cudaGetLastError();
 }
 cudaError_t launchResolve(const ZygpuView& view, const float4* film, float4* rgba, uint32_t num_pixels, cudaStream_t stream) {

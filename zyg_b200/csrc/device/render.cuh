@@ -207,6 +207,10 @@ struct AovFilm {
 cudaError_t launchAovClear(const AovFilm& aov, uint32_t num_pixels, cudaStream_t stream);  // aov.Buffer.clear
 cudaError_t launchAovFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, const AovFilm& aov, cudaStream_t stream);
 cudaError_t launchResolveAov(uint32_t aov_class, const float4* layer, float4* rgba, uint32_t num_pixels, cudaStream_t stream);
+// The `it` tool's denoise operator (src/it/denoise.zig:137-246, 375-451) as a post kernel over the film and the ShadingNormal / Albedo
+// layers still on the device. `weights`: the normalised (2 radius + 1)^2 Gaussian of Denoise.init (:34-72).
+cudaError_t launchDenoise(const ZygpuView& view, const float4* film, const float4* normal, const float4* albedo, const float* weights, int32_t radius,
+                          float4* rgba, cudaStream_t stream);
 cudaError_t launchResolve(const ZygpuView& view, const float4* film, float4* rgba, uint32_t num_pixels, cudaStream_t stream);
 
 }  // namespace zygpu

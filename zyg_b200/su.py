@@ -209,6 +209,15 @@ def resolve_frame_to_buffer(width: int, height: int, aov: int = 0xFFFFFFFF) -> n
 AOV_ALBEDO, AOV_DEPTH, AOV_MATERIAL_ID, AOV_GEOMETRIC_NORMAL, AOV_SHADING_NORMAL, AOV_ROUGHNESS, AOV_EMISSION, AOV_DIRECT, AOV_INDIRECT = range(9)
 
 
+def denoise_frame_to_buffer(sigma: float, width: int, height: int) -> np.ndarray:
+    """zyg_su_denoise_frame_to_buffer: `it --denoise sigma` over the frame just rendered (needs the ShadingNormal and Albedo AOVs)."""
+    fn = _su().zyg_su_denoise_frame_to_buffer
+    fn.argtypes = [C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
+    out = np.empty((height, width, 4), np.float32)
+    _ok(fn(sigma, width, height, out.ctypes.data), "zyg_su_denoise_frame_to_buffer")
+    return out
+
+
 def aovs_create(desc: dict):
     """The take's "aov" block, e.g. {"Albedo": true, "Depth": true} (View.loadAOV, take.zig:106-129)."""
     _ok(_su().su_aovs_create(json.dumps(desc).encode()), "su_aovs_create")
