@@ -284,6 +284,8 @@ typedef struct ZygpuView {
     float   exposure_factor; /* Tonemapper.exposure_factor, Linear class */
 
     uint32_t aov_slots; /* aov.Factory.slots (rendering/sensor/aov/aov_value.zig:84-103): bit c = AOV class c is recorded */
+    uint32_t alpha_transparency; /* sensor "alpha_transparency" (take_loader.zig:194-196): the Transparent buffer keeps the alpha of
+                                    Pool.transparency (vertex.zig:243-268) next to the colour (buffer_transparent.zig) */
 } ZygpuView;
 
 enum { /* aov.Value.Class, aov_value.zig:10-20 */

@@ -2343,12 +2343,27 @@ struct Worker {
 
         std::vector<Vertex> current{vertex}, next;
 
+        // Pool.transparency, vertex.zig:243-268 (no shadow-catcher props): a vertex that ended without a successor adds what a
+        // see-through path lost on the way, or its whole weight
+        float transparency = 0.f;
+
         while (!current.empty()) {
             next.clear();
-            for (Vertex& v : current) step(v, result, next);
+            std::vector<bool> ended;
+            for (Vertex& v : current) {
+                const size_t before = next.size();
+                step(v, result, next);
+                ended.push_back(next.size() == before);
+            }
+            for (size_t i = 0; i < current.size(); ++i) {  // summed when the generation has been consumed, in buffer order
+                if (!ended[i]) continue;
+                const Vertex& v = current[i];
+                transparency += v.state.transparent ? max((1.f - average3(v.throughput)) * v.split_weight, 0.f) : v.split_weight;
+            }
             current.swap(next);
         }
         result.direct[3] = 0.f;
+        result.direct[3] += transparency;  // result.direct += vertices.transparency, pathtracer_mis.zig:169-170
         return result;
     }
 
@@ -2398,6 +2413,9 @@ struct Worker {
         result.add(split_throughput * this_light, total_depth, 2, 0 == total_depth, vertex.state.singular);
 
         if (!frag.hit() || vertex.probe_depth.surface >= max_depth_surface || vertex.probe_depth.volume >= max_depth_volume) {
+            if (vertex.state.transparent) {  // pathtracer_mis.zig:81-83
+                vertex.throughput = vertex.throughput * (splat(1.f) - Vec4f{{min(this_light[0], 1.f), min(this_light[1], 1.f), min(this_light[2], 1.f), min(this_light[3], 1.f)}});
+            }
             return;
         }
 
@@ -2485,6 +2503,7 @@ struct Film {
     float*           pixels;  // Pack4f per pixel, weight in w
     const ZygpuView& view;
     float* const*    aov_layers = nullptr;  // aov.Buffer: ZYG_AOV_NUM_CLASSES Pack4f images, null where a class is inactive
+    float*           alpha      = nullptr;  // Transparent buffer (buffer_transparent.zig): the fourth lane of `pixels`, sum of weight * alpha
 
     float eval(float s) const {  // sensor.zig:626-628 + InterpolatedFunction1DN.eval
         const float    x      = std::fabs(s);
@@ -2503,11 +2522,13 @@ struct Film {
             std::atomic_ref<float>(v[1]).fetch_add(wc[1], std::memory_order_relaxed);
             std::atomic_ref<float>(v[2]).fetch_add(wc[2], std::memory_order_relaxed);
             std::atomic_ref<float>(v[3]).fetch_add(weight, std::memory_order_relaxed);
+            if (alpha) std::atomic_ref<float>(alpha[i]).fetch_add(wc[3], std::memory_order_relaxed);  // Transparent.addPixelAtomic
         } else {
             v[0] += wc[0];
             v[1] += wc[1];
             v[2] += wc[2];
             v[3] += weight;
+            if (alpha) alpha[i] += wc[3];  // Transparent.addPixel, buffer_transparent.zig:45-54
         }
     }
 
@@ -2720,17 +2741,22 @@ extern "C" {
 // schedule (capi.zig:602-609), which reseeds the PCG stream per sample (worker.zig:143) and is what the device does.
 void zo_render(const ZygpuScene* scene, const ZygpuView* view, const ZoMesh* meshes, uint32_t iteration, uint32_t num_samples,
                int per_sample_iterations, float* film_pixels, uint32_t threads) {
-    zo_render_aov(scene, view, meshes, iteration, num_samples, per_sample_iterations, film_pixels, nullptr, threads);
+    zo_render_layers(scene, view, meshes, iteration, num_samples, per_sample_iterations, film_pixels, nullptr, nullptr, threads);
+}
+void zo_render_aov(const ZygpuScene* scene, const ZygpuView* view, const ZoMesh* meshes, uint32_t iteration, uint32_t num_samples,
+                   int per_sample_iterations, float* film_pixels, float* const* aov_layers, uint32_t threads) {
+    zo_render_layers(scene, view, meshes, iteration, num_samples, per_sample_iterations, film_pixels, aov_layers, nullptr, threads);
 }
 
 // zo_render that also fills the AOV layers of view->aov_slots: aov_layers[c] = Pack4f image of class c, cleared by the caller to the
 // class default (aov.Buffer.clear: Depth floatMax in xyz, 0 elsewhere, weight 0); entries of inactive classes may be null.
-void zo_render_aov(const ZygpuScene* scene, const ZygpuView* view, const ZoMesh* meshes, uint32_t iteration, uint32_t num_samples,
-                   int per_sample_iterations, float* film_pixels, float* const* aov_layers, uint32_t threads) {
+// `alpha` (one float per pixel, not cleared, may be null): the alpha lane of the Transparent sensor buffer, sum of weight * alpha.
+void zo_render_layers(const ZygpuScene* scene, const ZygpuView* view, const ZoMesh* meshes, uint32_t iteration, uint32_t num_samples,
+                      int per_sample_iterations, float* film_pixels, float* const* aov_layers, float* alpha, uint32_t threads) {
     using namespace zo;
 
     const Scene sc(*scene, *view, meshes);
-    const Film  film{film_pixels, *view, aov_layers};
+    const Film  film{film_pixels, *view, aov_layers, alpha};
     const uint32_t aov_slots = aov_layers ? view->aov_slots : 0u;
 
     const int32_t fr   = view->filter_radius_int;
@@ -2819,6 +2845,12 @@ void zo_image_texel(const ZygpuScene* scene, uint32_t index, uint32_t n, const f
 }
 
 void zo_set_wavefront_light_order(int on) { zo::g_wavefront_light_order = 0 != on; }
+
+// Transparent.resolveTonemap, buffer_transparent.zig:82-93
+void zo_resolve_transparent(const ZygpuView* view, const float* film_pixels, const float* alpha, uint32_t num_pixels, float* rgba) {
+    zo_resolve(view, film_pixels, num_pixels, rgba);
+    for (uint32_t i = 0; i < num_pixels; ++i) rgba[size_t(i) * 4 + 3] = std::fabs(alpha[i] / film_pixels[size_t(i) * 4 + 3]);
+}
 
 // Opaque.resolveTonemap with the Linear tonemapper, buffer_opaque.zig:73-79, tonemapper.zig:36-39, aces.zig:19-27
 void zo_resolve(const ZygpuView* view, const float* film_pixels, uint32_t num_pixels, float* rgba) {

@@ -68,6 +68,13 @@ void zo_render(const struct ZygpuScene* scene, const struct ZygpuView* view, con
  * (aov.Buffer.clear), null for inactive classes. */
 void zo_render_aov(const struct ZygpuScene* scene, const struct ZygpuView* view, const ZoMesh* meshes, uint32_t iteration,
                    uint32_t num_samples, int per_sample_iterations, float* film, float* const* aov_layers, uint32_t threads);
+/* ... and the alpha lane of the Transparent sensor buffer (buffer_transparent.zig; Pool.transparency, vertex.zig:243-268): `alpha` = one
+ * float per pixel, sum of weight * alpha, not cleared; null = Opaque. */
+void zo_render_layers(const struct ZygpuScene* scene, const struct ZygpuView* view, const ZoMesh* meshes, uint32_t iteration,
+                      uint32_t num_samples, int per_sample_iterations, float* film, float* const* aov_layers, float* alpha,
+                      uint32_t threads);
+/* Transparent.resolveTonemap (buffer_transparent.zig:82-93): zo_resolve with alpha = |alpha sum / weight|. */
+void zo_resolve_transparent(const struct ZygpuView* view, const float* film, const float* alpha, uint32_t num_pixels, float* rgba);
 /* aov.Buffer.resolve (aov_buffer.zig:51-82) of one class. */
 void zo_resolve_aov(uint32_t aov_class, const float* layer, uint32_t num_pixels, float* rgba);
 /* The `it` tool's denoise operator (src/it/denoise.zig:137-246, 375-451) over the unresolved film and the unresolved ShadingNormal and

@@ -180,6 +180,27 @@ def render_aov(scene, view, width, height, iteration, num_samples, aov_slots, th
     return film, layers
 
 
+def render_alpha(scene, view, width, height, iteration, num_samples, threads=0, num_meshes=0, wavefront_light_order=False):
+    """zo_render_layers with the Transparent buffer's alpha lane: returns (film, alpha sums (H, W))."""
+    lib = _bind_render(load())
+    lib.zo_render_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.zo_render_layers.restype = None
+    lib.zo_set_wavefront_light_order(1 if wavefront_light_order else 0)
+    film = np.zeros((height, width, 4), np.float32)
+    alpha = np.zeros((height, width), np.float32)
+    lib.zo_render_layers(scene, view, mesh_table(num_meshes), iteration, num_samples, 1, _p(film), None, _p(alpha), threads)
+    return film, alpha
+
+
+def resolve_transparent(view, film, alpha):
+    lib = _bind_render(load())
+    lib.zo_resolve_transparent.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.zo_resolve_transparent.restype = None
+    out = np.empty_like(film)
+    lib.zo_resolve_transparent(view, _p(film), _p(alpha), film.shape[0] * film.shape[1], _p(out))
+    return out
+
+
 def denoise(view, film, normal_layer, albedo_layer, sigma):
     lib = _bind_render(load())
     lib.zo_denoise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]

@@ -750,3 +750,37 @@ def test_denoise_matches_oracle(engine, sigma):
     assert np.allclose(got, want, rtol=2e-4, atol=2e-6)
     plain = su.resolve_frame_to_buffer(w, w)
     assert np.abs(got[..., :3] - plain[..., :3]).mean() > 1e-3  # it did something
+
+
+@pytest.mark.parametrize("scene_name,filter_name", [("glass", None), ("glass", "Mitchell"), ("sky", None), ("mesh", None)])
+def test_transparent_film_matches_oracle(engine, scene_name, filter_name, tmp_path, monkeypatch):
+    """Sensor "alpha_transparency" (buffer_transparent.zig): the alpha of Pool.transparency (vertex.zig:243-268) — see-through paths
+    through glass (Transmission keeps state.transparent), a sky that covers by its brightness, opaque hits — resolved next to the colour,
+    and written into the exported PNG."""
+    w, spp = 96, 8
+    n = 0
+    if "glass" == scene_name:
+        scenes.cornell_box(w, w, spp=spp, glass={"roughness": 0.0})
+    elif "sky" == scene_name:
+        scenes.sky_scene(w, w, spp=spp, sky_size=64, sun=None)
+    else:
+        n = scenes.sphere_scene(w, w, spp=spp, quads=(96, 48))
+    su.sensor_create({"alpha_transparency": True, "filter": {filter_name: {}}} if filter_name else {"alpha_transparency": True})
+    scene, view = su.compile_scene()
+    ref_film, ref_alpha = oracle.render_alpha(scene, view, w, w, 0, spp, num_meshes=n or 0)
+    want = oracle.resolve_transparent(view, ref_film, ref_alpha)
+    su.render_frame(0)
+    gpu_film = download_film(w, w)
+    assert np.median(rel_error(gpu_film, ref_film)) < 5e-6
+    got = su.resolve_frame_to_buffer(w, w)
+    d = np.abs(got[..., 3] - want[..., 3])
+    assert np.median(d) < 1e-6 and (d > 1e-3).mean() < 5e-3, f"alpha: median {np.median(d):.2e}, {100 * (d > 1e-3).mean():.3f} % off"
+    assert 0.02 < got[..., 3].mean() <= 1.0 + 1e-4 and (("sky" != scene_name) or got[..., 3].mean() < 0.99)
+
+    monkeypatch.chdir(tmp_path)
+    su.exporters_create({"Image": {"format": "PNG"}})
+    su.export_frame()
+    from test_image_writer_host import read_png
+    rgba = read_png("image_00_000000.png")
+    assert rgba.shape == (w, w, 4)
+    assert np.abs(rgba[..., 3].astype(np.float32) / 255.0 - np.clip(got[..., 3], 0.0, 1.0)).max() < 1.5 / 255.0

@@ -21,7 +21,7 @@ class View(C.Structure):
                 ("max_depth_surface", C.c_uint32), ("max_depth_volume", C.c_uint32), ("split_threshold", C.c_float),
                 ("regularize_roughness", C.c_float), ("caustics_path", C.c_uint32), ("specular_threshold", C.c_float),
                 ("clamp", C.c_float * 3), ("filter_radius_int", C.c_int32), ("filter_range_end", C.c_float),
-                ("filter_inverse_interval", C.c_float), ("filter", C.c_float * 30), ("exposure_factor", C.c_float), ("aov_slots", C.c_uint32)]
+                ("filter_inverse_interval", C.c_float), ("filter", C.c_float * 30), ("exposure_factor", C.c_float), ("aov_slots", C.c_uint32), ("alpha_transparency", C.c_uint32)]
 
 
 @pytest.fixture()

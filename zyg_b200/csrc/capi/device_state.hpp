@@ -65,6 +65,7 @@ struct RenderState {
     float4*  film        = nullptr;
     float4*  resolved    = nullptr;
     uint32_t film_pixels = 0;
+    float*   film_alpha  = nullptr;  // views with alpha_transparency: the alpha lane of the Transparent buffer (sum of weight * alpha)
     zygpu::AovFilm aov{};  // one layer per class of ZygpuView.aov_slots (aov.Buffer)
 
     cudaStream_t stream = nullptr;

@@ -409,8 +409,8 @@ int32_t zyg_su_render_frame_range(uint32_t frame, uint32_t iteration, uint32_t n
 }
 
 // Driver.exportFrame + ImageSequence.write, driver.zig:224-253, exporting/image_sequence.zig:24-56: resolve the beauty, then one
-// file "image_<camera:02>_<frame:06>.<ext>" per exporter in the working directory. The Opaque sensor has no alpha channel
-// (buffer.zig:19-23); no AOV class is active.
+// file "image_<camera:02>_<frame:06>.<ext>" per exporter in the working directory; with the Transparent sensor ("alpha_transparency")
+// PNG and EXR carry the alpha channel. The AOV layers are reached through su_resolve_frame[_to_buffer] (+ zyg_su_write_image).
 int32_t su_export_frame(void) {
     if (!g_engine || !g_engine->device) return -1;
     Engine&        e = *g_engine;
@@ -421,17 +421,18 @@ int32_t su_export_frame(void) {
         return -1;
     }
     const int32_t* crop = e.scene.view().crop;
+    const bool     alpha = e.scene.alphaTransparency();  // ImageSequence.alpha = sensor.class.alphaTransparency(), take.zig:311
     for (const Engine::Exporter& x : e.exporters) {
         std::vector<uint8_t> bytes;
         const char*          ext = "png";
         bool                 ok  = false;
         switch (x.format) {
             case Engine::Exporter::PNG:
-                ok = zyg::encodePng(bytes, e.target.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop, false, x.error_diffusion);
+                ok = zyg::encodePng(bytes, e.target.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop, alpha, x.error_diffusion);
                 break;
             case Engine::Exporter::EXR:
                 ext = "exr";
-                ok  = zyg::encodeExr(bytes, e.target.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop, false, x.half);
+                ok  = zyg::encodeExr(bytes, e.target.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop, alpha, x.half);
                 break;
             case Engine::Exporter::RGBE:
                 ext = "hdr";

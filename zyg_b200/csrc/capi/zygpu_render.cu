@@ -113,6 +113,8 @@ void zygpuReleaseRender(zygpu_device* dev) {
     cudaFree(r.film);
     cudaFree(r.resolved);
     cudaFree(r.tally);
+    cudaFree(r.film_alpha);
+    r.film_alpha = nullptr;
     for (float4*& layer : r.aov.layers) {
         cudaFree(layer);
         layer = nullptr;
@@ -415,7 +417,17 @@ int zygpu_set_view(zygpu_device* dev, const ZygpuView* view) {
             cudaFree(layer);
             layer = nullptr;
         }
+        cudaFree(r.film_alpha);
+        r.film_alpha  = nullptr;
         r.film_pixels = pixels;
+    }
+    // Sensor.Buffer.Class: Opaque or Transparent (buffer.zig:9-23)
+    if (0 != view->alpha_transparency && !r.film_alpha) {
+        CUDA_OK(cudaMalloc(&r.film_alpha, size_t(pixels) * sizeof(float)));
+        CUDA_OK(cudaMemsetAsync(r.film_alpha, 0, size_t(pixels) * sizeof(float), r.stream));
+    } else if (0 == view->alpha_transparency && r.film_alpha) {
+        cudaFree(r.film_alpha);
+        r.film_alpha = nullptr;
     }
     // aov.Buffer.resize, aov_buffer.zig:28-37: a layer per active class
     bool new_layers = false;
@@ -441,6 +453,7 @@ int zygpu_clear_film(zygpu_device* dev) {
     RenderState& r = dev->render;
     CUDA_OK(cudaMemsetAsync(r.film, 0, size_t(r.film_pixels) * sizeof(float4), r.stream));
     if (0 != r.view.aov_slots) CUDA_OK(zygpu::launchAovClear(r.aov, r.film_pixels, r.stream));
+    if (r.film_alpha) CUDA_OK(cudaMemsetAsync(r.film_alpha, 0, size_t(r.film_pixels) * sizeof(float), r.stream));
     if (r.paths.counters) CUDA_OK(cudaMemsetAsync(r.paths.counters, 0, 16 * sizeof(uint32_t), r.stream));
     r.stats = ZygpuRenderStats{};
     r.stats_carry[0] = r.stats_carry[1] = 0;
@@ -548,7 +561,7 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
             }
         }
 
-        CUDA_OK(zygpu::launchFilm(view, r.paths, pass, r.film, r.stream));
+        CUDA_OK(zygpu::launchFilm(view, r.paths, pass, r.film, r.film_alpha, r.stream));
         if (0 != view.aov_slots) {
             CUDA_OK(zygpu::launchAovFilm(view, r.paths, pass, r.aov, r.stream));
             r.stats.kernel_launches += 1;
@@ -622,6 +635,10 @@ int zygpu_reduce_film(zygpu_device* dev, void* nccl_comm, int root) {
     constexpr int kNcclFloat32 = 7, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t, nccl.h
     const int rc = reduce(r.film, r.film, size_t(r.film_pixels) * 4, kNcclFloat32, kNcclSum, root, nccl_comm, r.stream);
     if (0 != rc) return fail("zygpu_reduce_film: ncclReduce failed: %s", error ? error(rc) : "?");
+    if (r.film_alpha) {  // the Transparent buffer's alpha lane is a weighted sum like the colour
+        const int ra = reduce(r.film_alpha, r.film_alpha, size_t(r.film_pixels), kNcclFloat32, kNcclSum, root, nccl_comm, r.stream);
+        if (0 != ra) return fail("zygpu_reduce_film: ncclReduce (alpha) failed: %s", error ? error(ra) : "?");
+    }
     return 0;
 }
 
@@ -643,7 +660,7 @@ int zygpu_resolve(zygpu_device* dev, float* rgba, uint32_t num_pixels) {
     if (!r.film) return fail("zygpu_resolve: no view set");
     CUDA_OK(cudaSetDevice(dev->ordinal));
     const uint32_t n = std::min(num_pixels, r.film_pixels);
-    CUDA_OK(zygpu::launchResolve(r.view, r.film, r.resolved, n, r.stream));
+    CUDA_OK(zygpu::launchResolve(r.view, r.film, r.film_alpha, r.resolved, n, r.stream));
     r.stats.kernel_launches += 1;
     CUDA_OK(cudaMemcpyAsync(rgba, r.resolved, size_t(n) * sizeof(float4), cudaMemcpyDeviceToHost, r.stream));
     CUDA_OK(cudaStreamSynchronize(r.stream));

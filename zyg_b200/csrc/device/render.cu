@@ -840,6 +840,13 @@ __device__ __forceinline__ void ivalueAdd(const PathState& st, uint32_t slot, V3
     target[slot] = a;
 }
 
+// Pool.consume's bookkeeping for a vertex that ended without a successor (vertex.zig:243-268, no shadow catchers): a path that only went
+// straight on / through interfaces adds what it lost on the way, any other path its whole weight
+__device__ __forceinline__ void alphaAdd(const PathState& st, uint32_t slot, bool transparent, V3 throughput, float split_weight) {
+    const float avg = __fdiv_rn((throughput.x + throughput.y) + throughput.z, 3.f);
+    st.acc_i[slot].w += transparent ? zmax((1.f - avg) * split_weight, 0.f) : split_weight;
+}
+
 // ---- stage kernels ---------------------------------------------------------------------------
 
 // Worker.render per sample: Sensor.cameraSample (sensor.zig:152-166) + Perspective.generateVertex
@@ -1169,6 +1176,11 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
             ivalueAdd(st, slot, mul3(split_throughput, this_light), total_depth, 2, 0 == total_depth, 0 != (vertex.state & kSingular));
 
             bool terminate = !hit || vertex.probe_depth >= view.max_depth_surface || 0 >= view.max_depth_volume;
+            // pathtracer_mis.zig:75-84: what a see-through path meets at its end covers the background (only the alpha reads this)
+            V3 end_throughput = lv.throughput;
+            if (terminate && 0 != (vertex.state & kTransparent)) {
+                end_throughput = mul3(end_throughput, {1.f - zmin(this_light.x, 1.f), 1.f - zmin(this_light.y, 1.f), 1.f - zmin(this_light.z, 1.f)});
+            }
 
             if (!terminate) {
                 // russianRoulette
@@ -1405,6 +1417,7 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                 if (Deferred && request) st.queue_l[atomicAdd(&st.counters[11], 1u)] = slot;
             }
             if (Split && !alive) pool = poolFree(pool, lane);
+            if (!alive && 0 != view.alpha_transparency) alphaAdd(st, slot, 0 != (vertex.state & kTransparent), end_throughput, lv.split_weight);
             storeSampler(st, slot, sampler, pool);
             }
         }
@@ -1877,6 +1890,9 @@ __global__ void __launch_bounds__(kBlock, Split ? 3 : ZYGPU_SHADE_BLOCKS) shadeB
                 }
             }
 
+            // no sample: the vertex ends here (Pool.consume finds it terminated, vertex.zig:250-268)
+            if (0 == path_count && 0 != view.alpha_transparency) alphaAdd(st, slot, 0 != (vertex.state & kTransparent), lv.throughput, lv.split_weight);
+
             for (uint32_t c = 0; c < (Split ? path_count : min(path_count, 1u)); ++c) {
                 const BxdfSample& sample_result = sample_results[c];
 
@@ -1993,7 +2009,7 @@ __device__ __forceinline__ float filterEval(const ZygpuView& view, float s) {  /
     return zlerp(view.filter[offset], view.filter[min(offset + 1, 29u)], t);
 }
 
-__global__ void __launch_bounds__(kBlock) filmKernel(ZygpuView view, PathState st, PassParams pass, float4* film) {
+__global__ void __launch_bounds__(kBlock) filmKernel(ZygpuView view, PathState st, PassParams pass, float4* film, float* film_alpha) {
     const int32_t  w  = view.resolution[0];
     const int32_t  h  = view.resolution[1];
     const int32_t  fr = view.filter_radius_int;
@@ -2006,6 +2022,7 @@ __global__ void __launch_bounds__(kBlock) filmKernel(ZygpuView view, PathState s
         if (x < view.crop[0] || x >= view.crop[2] || y < view.crop[1] || y >= view.crop[3]) continue;
 
         float4 value = film[pixel];
+        float  alpha = nullptr != film_alpha ? film_alpha[pixel] : 0.f;
 
         for (uint32_t s = 0; s < pass.samples_in_pass; ++s) {
             for (int32_t dy = -fr; dy <= fr; ++dy) {
@@ -2035,10 +2052,12 @@ __global__ void __launch_bounds__(kBlock) filmKernel(ZygpuView view, PathState s
                     value.y += weight * composed.y;
                     value.z += weight * composed.z;
                     value.w += weight;
+                    alpha += weight * in.w;  // Transparent.addPixel: the fourth lane of the colour, buffer_transparent.zig:45-54
                 }
             }
         }
         film[pixel] = value;
+        if (nullptr != film_alpha) film_alpha[pixel] = alpha;
     }
 }
 
@@ -2222,14 +2241,15 @@ __global__ void __launch_bounds__(kBlock) denoiseKernel(ZygpuView view, const fl
 }
 
 // Opaque.resolveTonemap with the Linear tonemapper, buffer_opaque.zig:73-79, tonemapper.zig:36-39, aces.zig:19-27
-__global__ void __launch_bounds__(kBlock) resolveKernel(ZygpuView view, const float4* film, float4* rgba, uint32_t num_pixels) {
+// Transparent.resolveTonemap, buffer_transparent.zig:82-93: the same colour, alpha = |sum of weight * alpha / weight|
+__global__ void __launch_bounds__(kBlock) resolveKernel(ZygpuView view, const float4* film, const float* film_alpha, float4* rgba, uint32_t num_pixels) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < num_pixels; i += gridDim.x * blockDim.x) {
         const float4 p = film[i];
         const V3     c = {fabsf(__fdiv_rn(p.x, p.w)), fabsf(__fdiv_rn(p.y, p.w)), fabsf(__fdiv_rn(p.z, p.w))};
         const V3     s = scale3(view.exposure_factor, c);
         const V3     srgb = add3(add3(scale3(s.x, {1.70505155f, -0.13025714f, -0.02400328f}), scale3(s.y, {-0.62179068f, 1.14080289f, -0.12896877f})),
                                  scale3(s.z, {-0.08325840f, -0.01054853f, 1.15297171f}));
-        rgba[i] = make_float4(srgb.x, srgb.y, srgb.z, 1.f);
+        rgba[i] = make_float4(srgb.x, srgb.y, srgb.z, nullptr != film_alpha ? fabsf(__fdiv_rn(film_alpha[i], p.w)) : 1.f);
     }
 }
 
@@ -2361,8 +2381,8 @@ cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const 
     }
     return cudaGetLastError();
 }
-cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream) {
-    filmKernel<<<gridFor(uint32_t(view.resolution[0] * view.resolution[1]), 16), kBlock, 0, stream>>>(view, st, pass, film);
+cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, float* film_alpha, cudaStream_t stream) {
+    filmKernel<<<gridFor(uint32_t(view.resolution[0] * view.resolution[1]), 16), kBlock, 0, stream>>>(view, st, pass, film, film_alpha);
     return cudaGetLastError();
 }
 cudaError_t launchAovClear(const AovFilm& aov, uint32_t num_pixels, cudaStream_t stream) {
@@ -2382,8 +2402,8 @@ cudaError_t launchDenoise(const ZygpuView& view, const float4* film, const float
     denoiseKernel<<<gridFor(uint32_t(view.resolution[0] * view.resolution[1]), 16), kBlock, 0, stream>>>(view, film, normal, albedo, weights, radius, rgba);
     return cudaGetLastError();
 }
-cudaError_t launchResolve(const ZygpuView& view, const float4* film, float4* rgba, uint32_t num_pixels, cudaStream_t stream) {
-    resolveKernel<<<gridFor(num_pixels, 16), kBlock, 0, stream>>>(view, film, rgba, num_pixels);
+cudaError_t launchResolve(const ZygpuView& view, const float4* film, const float* film_alpha, float4* rgba, uint32_t num_pixels, cudaStream_t stream) {
+    resolveKernel<<<gridFor(num_pixels, 16), kBlock, 0, stream>>>(view, film, film_alpha, rgba, num_pixels);
     return cudaGetLastError();
 }
 

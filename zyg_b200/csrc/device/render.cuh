@@ -119,7 +119,7 @@ struct PathState {
     // Per camera sample.
     float4* acc_e;   // emission rgb | pixel_uv.x
     float4* acc_d;   // direct rgb | pixel_uv.y
-    float4* acc_i;   // indirect rgb | -
+    float4* acc_i;   // indirect rgb | alpha of the sample (Pool.transparency[3], vertex.zig:243-268; views with alpha_transparency)
     uint4*  smp;     // Sobol: block seed, run seed, dimension | vertex-pool word (lanes of the current / next generation)
     uint2*  rng;     // PCG state
 
@@ -199,7 +199,8 @@ cudaError_t launchLightStages(const SceneDevice& scene, const ZygpuView& view, c
 cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, uint32_t bounce, cudaStream_t stream);
 cudaError_t launchShadeB(const SceneDevice& scene, const ZygpuView& view, const PathState& st, const PassParams& pass,
                          uint32_t max_items, uint32_t round, cudaStream_t stream);
-cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, cudaStream_t stream);
+// `film_alpha`: the alpha lane of the Transparent buffer (sum of weight * alpha per pixel, buffer_transparent.zig:45-54), or null
+cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, float4* film, float* film_alpha, cudaStream_t stream);
 // The AOV layers of the sensor (aov.Buffer, rendering/sensor/aov/aov_buffer.zig): one Pack4f image per active class.
 struct AovFilm {
     float4* layers[9];  // by aov.Value.Class; null = inactive
@@ -211,6 +212,6 @@ cudaError_t launchResolveAov(uint32_t aov_class, const float4* layer, float4* rg
 // layers still on the device. `weights`: the normalised (2 radius + 1)^2 Gaussian of Denoise.init (:34-72).
 cudaError_t launchDenoise(const ZygpuView& view, const float4* film, const float4* normal, const float4* albedo, const float* weights, int32_t radius,
                           float4* rgba, cudaStream_t stream);
-cudaError_t launchResolve(const ZygpuView& view, const float4* film, float4* rgba, uint32_t num_pixels, cudaStream_t stream);
+cudaError_t launchResolve(const ZygpuView& view, const float4* film, const float* film_alpha, float4* rgba, uint32_t num_pixels, cudaStream_t stream);
 
 }  // namespace zygpu

@@ -791,8 +791,9 @@ void SceneModel::loadSensor(const json::Value& value) {
             clamp_[2] = json::readFloatMember(*c, "indirect", clamp_[2]);
         }
     }
-    filter_kind_   = FilterKind::None;
-    filter_radius_ = 0.f;
+    alpha_transparency_ = json::readBoolMember(value, "alpha_transparency", false);  // take_loader.zig:194-196
+    filter_kind_        = FilterKind::None;
+    filter_radius_      = 0.f;
     if (const json::Value* f = value.get("filter")) {
         for (const auto& entry : f->object) {
             if ("Blackman" == entry.first) {
@@ -1452,6 +1453,7 @@ bool SceneModel::compile(std::string& error) {
     }
     v.exposure_factor = 1.f;  // Tonemapper.init(.Linear, 0.0): exp2(0)
     v.aov_slots       = aov_slots_;
+    v.alpha_transparency = alpha_transparency_ ? 1u : 0u;
 
     if (!ptmis_) {
         error = "only the PTMIS surface integrator is implemented: call su_integrators_create with {\"surface\":{\"PTMIS\":{}}}";

@@ -117,6 +117,7 @@ class SceneModel {
     void loadSampler(const json::Value& value);      // take_loader.zig:142-158
     void loadAovs(const json::Value& value);         // View.loadAOV, take.zig:106-129
     uint32_t aovSlots() const { return aov_slots_; }
+    bool     alphaTransparency() const { return alpha_transparency_; }
     uint32_t cameraEntity() const { return camera_entity_; }
     uint32_t width() const { return uint32_t(resolution_[0]); }
     uint32_t height() const { return uint32_t(resolution_[1]); }
@@ -210,6 +211,7 @@ class SceneModel {
     uint32_t spp_             = 1;
     uint32_t sampler_         = ZYG_SAMPLER_SOBOL;
     uint32_t aov_slots_       = 0;  // aov.Factory.slots
+    bool     alpha_transparency_ = false;  // Sensor.Buffer.Class Transparent
 
     uint32_t max_depth_surface_ = 1, max_depth_volume_ = 1;  // take.zig:43-52 (default AOV integrator)
     float    split_threshold_   = 0.f;
