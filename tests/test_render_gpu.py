@@ -8,6 +8,7 @@ libm-dependent functions (sin / cos / acos differ by an ulp between glibc and CU
 such an ulp flips a discrete decision (Russian roulette, a hit at a silhouette edge)."""
 
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -16,6 +17,7 @@ import oracle_lib as oracle
 from zyg_b200 import lib, scenes, su
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def download_film(width, height):
@@ -784,3 +786,32 @@ def test_transparent_film_matches_oracle(engine, scene_name, filter_name, tmp_pa
     rgba = read_png("image_00_000000.png")
     assert rgba.shape == (w, w, 4)
     assert np.abs(rgba[..., 3].astype(np.float32) / 255.0 - np.clip(got[..., 3], 0.0, 1.0)).max() < 1.5 / 255.0
+
+
+def test_trace_kernel_variants_are_bit_identical(tmp_path):
+    """The fused traversal kernel with one ray per lane, its ray-pool variant and the ray sort in front of either walk the rays in
+    different orders and hand different rays to a warp: equal-t ties are resolved by ids and the box gates use the ray's initial max_t, so
+    the films are the same bytes (the tuning variables are read once per process: one process per variant)."""
+    import subprocess
+    import sys
+
+    script = (
+        "import sys, numpy as np, ctypes as C; sys.path.insert(0, %r)\n"
+        "from zyg_b200 import lib, scenes, su\n"
+        "w = 160\n"
+        "scenes.instanced_scene(w, w, spp=4, grid=(24, 24), prototypes=4, quads=(48, 24), sun=60.0)\n"
+        "su.render_frame(0)\n"
+        "L = lib.load_library(); L.zygpu_download_film.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]\n"
+        "film = np.zeros((w, w, 4), np.float32)\n"
+        "assert 0 == L.zygpu_download_film(su.device_handle(), film.ctypes.data, w * w)\n"
+        "np.save(sys.argv[1], film)\n" % ROOT)
+    films = {}
+    for name, env in (("lock_step", {"ZYGPU_SCENE_POOL": "0"}), ("pool", {"ZYGPU_SCENE_POOL": "1"}),
+                      ("pool_sorted", {"ZYGPU_SCENE_POOL": "1", "ZYGPU_RAY_SORT": "3", "ZYGPU_RAY_SORT_FROM": "0"}),
+                      ("two_kernels", {"ZYGPU_SCENE_TRACE": "1"})):
+        out = str(tmp_path / (name + ".npy"))
+        subprocess.run([sys.executable, "-c", script, out], check=True, env=dict(os.environ, **env), timeout=600)
+        films[name] = np.load(out)
+    assert films["lock_step"][..., :3].sum() > 0
+    for name in ("pool", "pool_sorted", "two_kernels"):
+        assert films[name].tobytes() == films["lock_step"].tobytes(), name

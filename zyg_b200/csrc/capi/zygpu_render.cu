@@ -79,7 +79,8 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint3
         0 != allocPath(r, &p.sh_o, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_p, size_t(capacity) * shadow_stride) ||
         0 != allocPath(r, &p.sh_wi, size_t(capacity) * shadow_stride) || 0 != allocPath(r, &p.sh_n, capacity) ||
         0 != allocPath(r, &p.ml_props, items * 8) || 0 != allocPath(r, &p.ml_count, items) ||
-        0 != allocPath(r, &p.queue_m, items) || 0 != allocPath(r, &p.sort_bins, zygpu::kSortBins + 1) || 0 != allocPath(r, &p.queue_a, capacity) || 0 != allocPath(r, &p.queue_b, capacity) || 0 != allocPath(r, &p.counters, 16)) {
+        0 != allocPath(r, &p.queue_m, items) || 0 != allocPath(r, &p.sort_bins, zygpu::kSortBins + 1) ||
+        0 != allocPath(r, &p.trace_stacks, size_t(zygpu::numSmsOfCurrentDevice()) * 8 * zygpu::kScenePoolStackWords) || 0 != allocPath(r, &p.queue_a, capacity) || 0 != allocPath(r, &p.queue_b, capacity) || 0 != allocPath(r, &p.counters, 16)) {
         return -1;
     }
     if (lanes > 1 && (0 != allocPath(r, &p.med, vertices) || 0 != allocPath(r, &p.queue_t, vertices) || 0 != allocPath(r, &p.queue_s, capacity))) {
@@ -98,6 +99,7 @@ int ensurePaths(RenderState& r, uint32_t capacity, uint32_t shadow_stride, uint3
         return -1;
     }
     CUDA_OK(cudaMemsetAsync(p.counters, 0, 16 * sizeof(uint32_t), r.stream));  // ordered before the pass (the stream is non-blocking)
+    p.trace_stack_blocks = uint32_t(zygpu::numSmsOfCurrentDevice()) * 8;
     p.capacity      = capacity;
     p.shadow_stride = shadow_stride;
     p.lanes         = lanes;

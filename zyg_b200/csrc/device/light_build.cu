@@ -289,10 +289,16 @@ __global__ void emitLightNodesKernel(LightBuildInput in, uint32_t max_leaf, Hier
     middles[slot] = middle;
 }
 
+// Scratch comes from the device's stream-ordered pool (kept across builds: a compile builds one tree per emissive mesh part): two dozen
+// cudaMalloc / cudaFree pairs per build cost 20 - 100 ms around well under a millisecond of kernels. The three arrays that outlive the
+// build are ordinary allocations.
+cudaStream_t g_alloc_stream = nullptr;
+
 template <typename T>
 cudaError_t lightAlloc(T*& p, size_t count, std::vector<void*>& scratch, bool keep = false) {
-    void*             raw = nullptr;
-    const cudaError_t e   = cudaMalloc(&raw, std::max<size_t>(count * sizeof(T), 16));
+    void*             raw   = nullptr;
+    const size_t      bytes = std::max<size_t>(count * sizeof(T), 16);
+    const cudaError_t e     = keep ? cudaMalloc(&raw, bytes) : cudaMallocAsync(&raw, bytes, g_alloc_stream);
     if (cudaSuccess != e) return e;
     p = static_cast<T*>(raw);
     if (!keep) scratch.push_back(raw);
@@ -314,13 +320,27 @@ cudaError_t buildLightTreeOnDevice(const LightBuildInput& in, LightBuildOutput& 
     const uint32_t n = in.num_lights;
     if (n < 2) return cudaErrorInvalidValue;
 
+    static bool pool_kept = false;
+    if (!pool_kept) {  // keep what the pool has handed out once instead of returning it to the driver at every synchronisation
+        int device = 0;
+        cudaGetDevice(&device);
+        cudaMemPool_t mem_pool = nullptr;
+        if (cudaSuccess == cudaDeviceGetDefaultMemPool(&mem_pool, device)) {
+            uint64_t threshold = ~0ull;
+            cudaMemPoolSetAttribute(mem_pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        pool_kept = true;
+    }
+    g_alloc_stream = stream;
+
     std::vector<void*> scratch;
     struct Cleanup {
         std::vector<void*>& s;
+        cudaStream_t        stream;
         ~Cleanup() {
-            for (void* p : s) cudaFree(p);
+            for (void* p : s) cudaFreeAsync(p, stream);
         }
-    } cleanup{scratch};
+    } cleanup{scratch, stream};
 
     cudaEvent_t ev0, ev1;
     BUILD_OK(cudaEventCreate(&ev0));

@@ -103,7 +103,8 @@ struct SceneDevice {
     float4 world_cells;  // (device/render_trace.cu, sortKeyKernel)
 };
 
-constexpr uint32_t kSortBins = 1u << 16;  // keys of the ray sort (device/render_trace.cu)
+constexpr uint32_t kSortBins = 1u << 16;
+constexpr uint32_t kScenePoolStackWords = 4u * 64u * 48u;  // per block: 4 warps x 64 pooled rays x kWideStack entries  // keys of the ray sort (device/render_trace.cu)
 
 struct PathState {
     // Per path vertex. A camera sample ("slot") owns `lanes` vertex records: 1 when no material of the scene can split a
@@ -153,6 +154,8 @@ struct PathState {
     uint32_t* ml_count;
     uint32_t* queue_m;  // items with candidates (fused traversal kernel: the trace items in ray-sort order)
     uint32_t* sort_bins; // ray sort: one counter per key (kSortBins + 1), null when the pass does not sort
+    uint2*    trace_stacks;        // ray-pool traversal kernel: kScenePoolStackWords entries per resident block (device/render_trace.cu)
+    uint32_t  trace_stack_blocks;  // blocks the scratch array is sized for
 
     uint32_t* queue_a;   // slots with at least one vertex in the current generation
     uint32_t* queue_b;   // slots whose vertex of the current round survived shade_a
@@ -179,6 +182,7 @@ struct PassParams {
     uint32_t debug_slot; // ZYGPU_DEBUG_SLOT: the shade stages print the vertices of this slot (diagnostics); 0xFFFFFFFF = off
 };
 
+int         numSmsOfCurrentDevice();
 cudaError_t uploadSobolDirections();
 uint32_t    sceneTraceLaunches(bool has_meshes, uint32_t num_solid_nodes);  // kernels one extend / shadow stage launches (for the launch statistics)
 

@@ -821,6 +821,378 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
     }
 }
 
+// ---- ray-pool variant of the fused kernel -------------------------------------------------------------------------------------------------
+// sceneTracePersistent keeps one ray per lane, so a step only uses the lanes whose ray wants that kind of step: 14 of 32 on the instanced
+// scene with its four kinds (profiles/r02_d_config3_sceneTrace_64reg.md). Here a warp keeps kScenePoolSlots rays in shared memory (the ray
+// in its current space, traversal groups, hit so far, level bookkeeping: 100 bytes per ray) and every step first hands the rays that are
+// ready for the chosen kind to the lanes, like traceWidePool does for ray batches (device/trace.cu). Per-ray stacks live in a global scratch
+// array. Same tests per ray, ties resolved by ids: the results are sceneTracePersistent's, bit for bit.
+constexpr uint32_t kScenePoolSlots = 64;
+
+struct ScenePool {  // one per warp
+    float4   a[kScenePoolSlots];   // origin xyz (world, or object space inside a mesh) | the max_t the ray started with
+    float4   b[kScenePoolSlots];   // direction xyz | max_t (the closest hit so far)
+    float4   c[kScenePoolSlots];   // inverse direction xyz | u of the hit
+    uint4    g[kScenePoolSlots];   // node group | triangle / prop-record group
+    uint4    h[kScenePoolSlots];   // stack depth | trace item (kEnd: the slot is free) | primitive (any hit: 1 = occluded) | v of the hit
+    uint4    s[kScenePoolSlots];   // stack depth at mesh entry | prop the ray is inside of (kEnd: prop tree) | prop waiting for ENTER | prop of the hit
+    uint32_t dm[kScenePoolSlots];  // depth.surface of the ray (bits 0-7) | mesh of the prop the ray is inside of (bits 8-31)
+    uint32_t ready[kScenePoolSlots];  // what the ray's next step is ready for: 1 NODE, 2 TRIANGLE, 4 PROP, 8 ENTER; 0: the slot is free
+    uint32_t assign[32];
+};
+
+template <bool AnyHit>
+__global__ void __launch_bounds__(128, 7) scenePoolTrace(SceneDevice sc, PathState st, uint32_t* __restrict__ work_counter, SceneStepTuning tune,
+                                                         uint2* __restrict__ stacks) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    __shared__ ScenePool pools[4];
+    ScenePool&           pool = pools[threadIdx.x >> 5];
+    const uint32_t       lane = threadIdx.x & 31u;
+    const uint32_t       lt   = (1u << lane) - 1u;
+    uint2* __restrict__  stk  = stacks + size_t(blockIdx.x * 4u + (threadIdx.x >> 5)) * kScenePoolSlots * kWideStack;
+
+    TraceItems items = traceItems<AnyHit>(st);
+    if (0 != tune.sorted) items.n = st.counters[15];
+    const uint32_t n = items.n;
+
+    const uint32_t warps      = gridDim.x * (blockDim.x / 32u);
+    const uint32_t pool_items = max(32u, min(kScenePoolItems, (n / (warps * 4u)) & ~31u));
+
+    for (uint32_t s = lane; s < kScenePoolSlots; s += 32) {
+        pool.g[s] = make_uint4(0u, 0u, 0u, 0u);
+        pool.h[s] = make_uint4(0u, kEnd, 0u, 0u);
+        pool.s[s] = make_uint4(0u, kEnd, kEnd, kEnd);
+        pool.ready[s] = 0u;
+    }
+    __syncwarp();
+
+    uint32_t occupied  = 0;  // warp-uniform
+    uint32_t pool_next = 0, pool_end = 0;
+    bool     exhausted = false;
+    uint32_t traced    = 0;
+
+    for (;;) {
+        // ---- refill free slots
+        if (!exhausted && kScenePoolSlots - occupied >= tune.fetch_idle) {
+            for (uint32_t half = 0; half < kScenePoolSlots / 32; ++half) {
+                const uint32_t slot = lane + 32u * half;
+                uint32_t       need = __ballot_sync(kFull, 0u == pool.ready[slot]);
+                while (0 != need && !exhausted) {
+                    if (pool_next >= pool_end) {
+                        uint32_t base = 0;
+                        if (0 == lane) base = atomicAdd(work_counter, pool_items);
+                        base = __shfl_sync(kFull, base, 0);
+                        if (base >= n) {
+                            exhausted = true;
+                            break;
+                        }
+                        pool_next = base;
+                        pool_end  = min(base + pool_items, n);
+                    }
+                    const uint32_t avail = pool_end - pool_next;
+                    const bool     take  = 0 != ((need >> lane) & 1u) && uint32_t(__popc(need & lt)) < avail;
+                    bool           valid = false;
+                    if (take) {
+                        const uint32_t i    = pool_next + uint32_t(__popc(need & lt));
+                        uint32_t       item = 0;
+                        if (0 != tune.sorted) {
+                            item  = st.queue_m[i];
+                            valid = true;
+                        } else {
+                            valid = traceItem<AnyHit>(st, items, i, item);
+                        }
+                        if (valid) {
+                            uint32_t depth_surface = 0, flags = 0;
+                            RayT     r             = loadTraceRay<AnyHit>(st, item, depth_surface, &flags);
+                            if (!AnyHit) clipToMedium(sc, st, item, flags, r);
+                            pool.a[slot]  = make_float4(r.o.x, r.o.y, r.o.z, r.tmax);
+                            pool.b[slot]  = make_float4(r.d.x, r.d.y, r.d.z, r.tmax);
+                            pool.c[slot]  = make_float4(r.inv_d.x, r.inv_d.y, r.inv_d.z, 0.f);
+                            pool.g[slot]  = make_uint4(0u, 0x80000000u, 0u, 0u);  // root of the prop tree
+                            pool.h[slot]  = make_uint4(0u, item, 0u, 0u);
+                            pool.s[slot]  = make_uint4(0u, kEnd, kEnd, kEnd);
+                            pool.dm[slot] = depth_surface & 0xffu;
+                            pool.ready[slot] = 1u;
+                            traced += 1;
+                        }
+                    }
+                    const uint32_t taken = __ballot_sync(kFull, take);
+                    pool_next += __popc(taken);
+                    occupied += __popc(__ballot_sync(kFull, valid));
+                    need &= ~taken;
+                }
+            }
+            __syncwarp();
+        }
+        if (0 == occupied) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- which rays are ready for which kind of step
+        uint32_t m_node[kScenePoolSlots / 32], m_tri[kScenePoolSlots / 32], m_prop[kScenePoolSlots / 32], m_enter[kScenePoolSlots / 32];
+        uint32_t cn = 0, ct = 0, cp = 0, ce = 0;
+#pragma unroll
+        for (uint32_t half = 0; half < kScenePoolSlots / 32; ++half) {
+            const uint32_t r = pool.ready[lane + 32u * half];
+            m_node[half]     = __ballot_sync(kFull, 0 != (r & 1u));
+            m_tri[half]      = __ballot_sync(kFull, 0 != (r & 2u));
+            m_prop[half]     = __ballot_sync(kFull, 0 != (r & 4u));
+            m_enter[half]    = __ballot_sync(kFull, 0 != (r & 8u));
+            cn += __popc(m_node[half]);
+            ct += __popc(m_tri[half]);
+            cp += __popc(m_prop[half]);
+            ce += __popc(m_enter[half]);
+        }
+        const uint32_t wn = min(cn, 32u) * tune.weight[0], wt = min(ct, 32u) * tune.weight[1], wp = min(cp, 32u) * tune.weight[2],
+                       we = min(ce, 32u) * tune.weight[3];
+        const uint32_t most = max(max(wn, wt), max(wp, we));
+        const uint32_t kind = (0 != we && we == most) ? 3u : ((0 != wp && wp == most) ? 2u : ((0 != wt && wt == most) ? 1u : 0u));
+
+        // ---- hand the first 32 ready rays to the lanes
+        uint32_t rank = 0;
+#pragma unroll
+        for (uint32_t half = 0; half < kScenePoolSlots / 32; ++half) {
+            const uint32_t m = 3u == kind ? m_enter[half] : (2u == kind ? m_prop[half] : (1u == kind ? m_tri[half] : m_node[half]));
+            if (0 != ((m >> lane) & 1u)) {
+                const uint32_t r = rank + uint32_t(__popc(m & lt));
+                if (r < 32u) pool.assign[r] = lane + 32u * half;
+            }
+            rank += __popc(m);
+        }
+        __syncwarp();
+        const bool     busy = lane < rank;
+        const uint32_t slot = busy ? pool.assign[lane] : 0u;
+
+        uint32_t retired = 0;
+        if (busy) {
+            const float4 ra = pool.a[slot];
+            const float4 rb = pool.b[slot];
+            const float4 rc = pool.c[slot];
+            const uint4  g  = pool.g[slot];
+            uint4        h  = pool.h[slot];
+            uint4        sv = pool.s[slot];
+            uint32_t     dm = pool.dm[slot];
+
+            WideRay w;
+            w.ray.o     = {ra.x, ra.y, ra.z};
+            w.ray.tmin  = 0.f;
+            w.ray.d     = {rb.x, rb.y, rb.z};
+            w.ray.tmax  = rb.w;
+            w.ray.inv_d = {rc.x, rc.y, rc.z};
+            setupWideRay(w);
+            const float tmax0 = ra.w;
+            float       hu    = rc.w;
+            uint2* __restrict__ stack = stk + size_t(slot) * kWideStack;
+
+            uint2    node_group = make_uint2(g.x, g.y);
+            uint2    tri_group  = make_uint2(g.z, g.w);
+            uint32_t sp         = h.x;
+            bool     in_mesh    = kEnd != sv.y;
+            // what has to go back to shared memory: the groups and the stack depth always, the rest when it changed
+            bool ray_dirty = false, hit_dirty = false, level_dirty = false;
+
+            const float4* nodes = sc.tlas_nodes;
+            const float4* recs  = sc.tlas_recs;
+            if (in_mesh) {
+                const MeshDevice* m = sc.meshes + (dm >> 8);
+                nodes               = m->wide_nodes;
+                recs                = m->wide_tris;
+            }
+
+            if (3u == kind) {
+                // ENTER: the world ray and the prop-tree work still pending stay on the stack below the mesh's entries
+                const uint32_t enter_prop = sv.z;
+                if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
+                if (0 != tri_group.y) stack[sp++] = tri_group;
+                stack[sp++] = make_uint2(__float_as_uint(w.ray.o.x), __float_as_uint(w.ray.o.y));
+                stack[sp++] = make_uint2(__float_as_uint(w.ray.o.z), __float_as_uint(w.ray.d.x));
+                stack[sp++] = make_uint2(__float_as_uint(w.ray.d.y), __float_as_uint(w.ray.d.z));
+                stack[sp++] = make_uint2(__float_as_uint(w.ray.inv_d.x), __float_as_uint(w.ray.inv_d.y));
+                stack[sp++] = make_uint2(__float_as_uint(w.ray.inv_d.z), 0u);
+                sv.x        = sp;
+                const TrafoD   trafo = loadTrafo(sc.trafos, enter_prop);
+                const uint32_t mesh  = sc.props[enter_prop].mesh;
+                w.ray                = worldToObjectRay(trafo, w.ray);
+                sv.y                 = enter_prop;
+                sv.z                 = kEnd;
+                dm                   = (dm & 0xffu) | (mesh << 8);
+                in_mesh              = true;
+                ray_dirty = level_dirty = true;
+                node_group           = make_uint2(0u, 0x80000000u);
+                tri_group            = make_uint2(0u, 0u);
+            } else if (2u == kind) {
+                // PROP: the ray works through its pending prop records until a mesh prop survives the culling tests
+                do {
+                    const uint32_t bit = 31u - __clz(tri_group.y);
+                    tri_group.y &= ~(1u << bit);
+                    const float4* rp = recs + 4 * size_t(tri_group.x + bit);
+                    const F8      rr = ldg256(rp);
+                    const float4  r0 = rr.lo, r1 = rr.hi;
+                    const uint32_t  p    = __float_as_uint(r0.w);
+                    const ZygpuProp prop = sc.props[p];
+                    bool enter = gateBox(make_float4(r0.x, r0.y, r0.z, 0.f), make_float4(r1.x, r1.y, r1.z, 0.f), w.ray, tmax0);
+                    enter = enter && (AnyHit ? 0 != (prop.flags & ZYG_PROP_VISIBLE_IN_SHADOW) : propVisible(prop.flags, dm & 0xffu));
+                    enter = enter && gateBox(__ldg(sc.aabbs + 2 * size_t(p)), __ldg(sc.aabbs + 2 * size_t(p) + 1), w.ray, tmax0);
+                    if (!enter) continue;
+                    if (ZYG_SHAPE_TRIANGLE_MESH == prop.shape) {
+                        if (segmentMeetsSphere(w.ray, __ldg(rp + 2))) {
+                            sv.z        = p;
+                            level_dirty = true;
+                            break;
+                        }
+                        continue;
+                    }
+                    const TrafoD trafo = loadTrafo(sc.trafos, p);
+                    if (AnyHit) {
+                        bool hit = false;
+                        HitD unused;
+                        switch (prop.shape) {
+                            case ZYG_SHAPE_CUBE: hit = cubeIntersectP(w.ray, trafo); break;
+                            case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, unused); break;
+                            case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, unused); break;
+                            default: break;
+                        }
+                        if (hit) {
+                            h.z          = 1u;
+                            hit_dirty    = true;
+                            sp           = 0;
+                            node_group.y = 0;
+                            tri_group.y  = 0;
+                        }
+                    } else {
+                        HitD hd;
+                        bool hit = false;
+                        switch (prop.shape) {
+                            case ZYG_SHAPE_CUBE: hit = cubeIntersect(w.ray, trafo, hd); break;
+                            case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, hd); break;
+                            case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, hd); break;
+                            default: break;
+                        }
+                        if (hit && closerOrLater(hd.t, w.ray.tmax, p, hd.primitive, sv.w, h.z)) {
+                            w.ray.tmax = hd.t;
+                            hu         = hd.u;
+                            h.w        = __float_as_uint(hd.v);
+                            h.z        = hd.primitive;
+                            sv.w       = p;
+                            hit_dirty = level_dirty = true;
+                        }
+                    }
+                } while (0 != tri_group.y);
+            } else if (1u == kind) {
+                // TRIANGLE
+                const uint32_t bit = 31u - __clz(tri_group.y);
+                tri_group.y &= ~(1u << bit);
+                MeshDevice mesh;
+                mesh.wide_tris = recs;
+                float    t, u, v;
+                uint32_t prim;
+                if (testWideTriangle(mesh, w.ray, tmax0, tri_group.x + bit, t, u, v, prim)) {
+                    if (AnyHit) {
+                        h.z          = 1u;
+                        hit_dirty = level_dirty = true;
+                        in_mesh      = false;
+                        sv.y         = kEnd;
+                        sp           = 0;
+                        node_group.y = 0;
+                        tri_group.y  = 0;
+                    } else if (closerOrLater(t, w.ray.tmax, sv.y, prim, sv.w, h.z)) {
+                        w.ray.tmax = t;
+                        hu         = u;
+                        h.w        = __float_as_uint(v);
+                        h.z        = prim;
+                        sv.w       = sv.y;
+                        hit_dirty = level_dirty = true;
+                    }
+                }
+            } else {
+                // NODE: the same code for a ray in the prop tree and a ray inside a mesh
+                const uint32_t hits  = node_group.y;
+                const uint32_t gmask = hits & 0xffu;
+                const uint32_t bit   = 31u - __clz(hits);
+                node_group.y         = hits & ~(1u << bit);
+                const uint32_t cslot = (bit - 24u) ^ w.octinv;
+                const uint32_t crank = __popc(gmask & ((1u << cslot) - 1u));
+                const uint32_t node_index = node_group.x + crank;
+                if (node_group.y > 0x00FFFFFFu) stack[sp++] = node_group;
+                if (0 != tri_group.y) stack[sp++] = tri_group;
+
+                const WideNodeRegs nd = loadWideNode(nodes, node_index);
+                const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
+                const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
+
+                node_group.x = __float_as_uint(n1.x);
+                node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
+                tri_group.x  = __float_as_uint(n1.y);
+                tri_group.y  = hitmask & 0x00FFFFFFu;
+            }
+
+            // ---- a ray that ran dry pops its stack, leaves the mesh or retires
+            if (kEnd == sv.z && node_group.y <= 0x00FFFFFFu && 0 == tri_group.y) {
+                if (in_mesh && sp == sv.x) {
+                    in_mesh        = false;
+                    sv.y           = kEnd;
+                    ray_dirty = level_dirty = true;
+                    const uint2 e4 = stack[--sp], e3 = stack[--sp], e2 = stack[--sp], e1 = stack[--sp], e0 = stack[--sp];
+                    w.ray.o        = {__uint_as_float(e0.x), __uint_as_float(e0.y), __uint_as_float(e1.x)};
+                    w.ray.d        = {__uint_as_float(e1.y), __uint_as_float(e2.x), __uint_as_float(e2.y)};
+                    w.ray.inv_d    = {__uint_as_float(e3.x), __uint_as_float(e3.y), __uint_as_float(e4.x)};
+                }
+                if (0 == sp) {
+                    const uint32_t item = h.y;
+                    if (AnyHit) {
+                        st.sh_wi[item].w = 0 != h.z ? 0.f : 1.f;
+                    } else {
+                        st.ray_d[item].w = w.ray.tmax;
+                        st.hit[item]     = make_float4(hu, __uint_as_float(h.w), __uint_as_float(h.z), __uint_as_float(sv.w));
+                    }
+                    h.y     = kEnd;
+                    retired = 1;
+                } else if (!in_mesh || sp > sv.x) {
+                    const uint2 e = stack[--sp];
+                    if (e.y > 0x00FFFFFFu) {
+                        node_group = e;
+                    } else {
+                        tri_group = e;
+                    }
+                }
+            }
+            if (ray_dirty) {
+                pool.a[slot]  = make_float4(w.ray.o.x, w.ray.o.y, w.ray.o.z, tmax0);
+                pool.b[slot]  = make_float4(w.ray.d.x, w.ray.d.y, w.ray.d.z, w.ray.tmax);
+                pool.c[slot]  = make_float4(w.ray.inv_d.x, w.ray.inv_d.y, w.ray.inv_d.z, hu);
+                pool.dm[slot] = dm;
+            } else if (hit_dirty) {
+                pool.b[slot].w = w.ray.tmax;
+                pool.c[slot].w = hu;
+            }
+            pool.g[slot] = make_uint4(node_group.x, node_group.y, tri_group.x, tri_group.y);
+            if (hit_dirty || 0 != retired) {
+                h.x          = sp;
+                pool.h[slot] = h;
+            } else {
+                pool.h[slot].x = sp;
+            }
+            if (level_dirty) pool.s[slot] = sv;
+            uint32_t ready = 0;
+            if (0 == retired) {
+                if (kEnd != sv.z) {
+                    ready = 8u;
+                } else {
+                    ready = (node_group.y > 0x00FFFFFFu ? 1u : 0u) | (0 != tri_group.y ? (in_mesh ? 2u : 4u) : 0u);
+                }
+            }
+            pool.ready[slot] = ready;
+        }
+        occupied -= __popc(__ballot_sync(kFull, 0 != retired));
+        __syncwarp();
+    }
+
+    for (int o = 16; o > 0; o >>= 1) traced += __shfl_down_sync(kFull, traced, o);
+    if (0 == lane && 0 != traced) atomicAdd(&st.counters[AnyHit ? 6 : 5], traced);
+}
+
+
 // Context.nextEvent -> Scene.intersect, context.zig:54-69, scene.zig:225-227
 __global__ void __launch_bounds__(kBlock) extendKernel(SceneDevice sc, PathState st) {
     const uint32_t count = st.counters[st.lanes > 1 ? 7 : 0];
@@ -879,6 +1251,7 @@ struct SceneTraceConfig {
     int              blocks_per_sm;
     int              min_blocks;
     int              mesh_min_blocks;
+    int              pool, pool_fetch_free;
     int              sort, sort_from, sort_mode;
 };
 
@@ -897,6 +1270,8 @@ const SceneTraceConfig& sceneTraceConfig() {
         c.blocks_per_sm   = envInt("ZYGPU_SCENE_BLOCKS_PER_SM", 0);
         c.min_blocks      = envInt("ZYGPU_SCENE_MIN_BLOCKS", 0);
         c.mesh_min_blocks = envInt("ZYGPU_MESH_MIN_BLOCKS", 0);
+        c.pool            = envInt("ZYGPU_SCENE_POOL", -1);  // the ray-pool variant of the fused kernel: 1 on, 0 off, -1 by prop-tree size
+        c.pool_fetch_free = envInt("ZYGPU_POOL_FETCH_FREE", 16);
         c.sort            = envInt("ZYGPU_RAY_SORT", 0);       // bit 0: closest-hit rays, bit 1: shadow rays
         c.sort_from       = envInt("ZYGPU_RAY_SORT_FROM", 1);  // first bounce that sorts
         c.sort_mode       = envInt("ZYGPU_RAY_SORT_MODE", 1);  // 1: (cell, octant), 2: (octant, cell)
@@ -947,7 +1322,22 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
             sortScanKernel<<<1, 1024, 0, stream>>>(st);
             sortScatterKernel<AnyHit><<<sort_grid, 256, 0, stream>>>(st);
         }
-        if (counted) {
+        // Measured (profiles/r02_sweeps.md): 20.6 instead of 14.0 active lanes per instruction on config 3, but 30 % more thread-level work for
+        // picking and moving the rays - 339.6 -> 322.3 ms per 8-spp frame there, 190.8 -> 200.2 ms on config 4, whose rays see few props. The
+        // variant is taken for large prop trees (ZYGPU_SCENE_POOL = 0 / 1 overrides).
+        const bool pooled = -1 == cfg.pool ? scene.num_solid_nodes >= 4096u : 0 != cfg.pool;
+        if (!counted && pooled && nullptr != st.trace_stacks && scene.num_solid_nodes > 1) {
+            // the ray-pool variant: rays ready for the same kind of step are handed to the lanes first
+            static int pool_resident = 0;
+            if (0 == pool_resident) {
+                int per_sm = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scenePoolTrace<AnyHit>, 128, 0);
+                pool_resident = std::max(per_sm, 1) * numSms();
+            }
+            const uint32_t pool_grid = std::max(1u, std::min<uint32_t>(std::min<uint32_t>(uint32_t(pool_resident), st.trace_stack_blocks), needed));
+            step.fetch_idle          = uint32_t(cfg.pool_fetch_free);
+            scenePoolTrace<AnyHit><<<pool_grid, 128, 0, stream>>>(scene, st, st.counters + 8, step, st.trace_stacks);
+        } else if (counted) {
             sceneTracePersistent<AnyHit, true, 5><<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, step, st.tally);
         } else {
             fn<<<grid, 128, 0, stream>>>(scene, st, st.counters + 8, step, nullptr);
@@ -980,6 +1370,8 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
 }
 
 }  // namespace
+
+int numSmsOfCurrentDevice() { return numSms(); }
 
 uint32_t sceneTraceLaunches(bool has_meshes, uint32_t num_solid_nodes) {  // kernels per extend / shadow stage
     const int v = sceneTraceConfig().variant;
