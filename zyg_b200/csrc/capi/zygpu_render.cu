@@ -246,6 +246,13 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
         d.tlas_nodes = f4;
         if (0 != uploadArray(r, reinterpret_cast<const float4*>(wide.records.data()), wide.records.size() * (sizeof(zyg::PropRecord) / 16), &f4)) return -1;
         d.tlas_recs = f4;
+        uint32_t mesh_depth = 0;
+        for (uint32_t m = 0; m < scene->num_meshes; ++m) mesh_depth = std::max(mesh_depth, scene->meshes[m]->wide.max_depth);
+        d.trace_stack_bound = 2 * (wide.max_depth + mesh_depth) + 6;
+        if (getenv("ZYGPU_DEBUG_TLAS")) {
+            fprintf(stderr, "[zygpu] prop tree: %zu wide nodes, depth %u; deepest mesh tree %u; stack bound %u\n", wide.nodes.size(), wide.max_depth,
+                    mesh_depth, d.trace_stack_bound);
+        }
     }
 
     if (0 != uploadArray(r, scene->infinite_props, scene->num_infinite_props, &d.infinite_props)) return -1;
@@ -513,6 +520,25 @@ int zygpu_render(zygpu_device* dev, uint32_t iteration, uint32_t num_samples) {
         for (uint32_t bounce = 0; bounce <= view.max_depth_surface; ++bounce) {
             const bool last = bounce == view.max_depth_surface;
             // all vertices of the generation are extended at once (no sampler draws in between) ...
+            static const bool verify_trace = nullptr != getenv("ZYGPU_VERIFY_TRACE");
+            if (verify_trace) {  // diagnostics: the fused walk against one thread per ray in the reference's order
+                const size_t bytes = size_t(r.paths.capacity) * lanes * sizeof(float4);
+                float4 *before = nullptr, *ta = nullptr, *ha = nullptr;
+                CUDA_OK(cudaMalloc(&before, bytes));
+                CUDA_OK(cudaMalloc(&ta, bytes));
+                CUDA_OK(cudaMalloc(&ha, bytes));
+                CUDA_OK(cudaMemcpyAsync(before, r.paths.ray_d, bytes, cudaMemcpyDeviceToDevice, r.stream));
+                CUDA_OK(zygpu::launchExtend(r.scene, r.paths, pass.num_paths * lanes, r.has_meshes, bounce, r.stream));
+                CUDA_OK(cudaMemcpyAsync(ta, r.paths.ray_d, bytes, cudaMemcpyDeviceToDevice, r.stream));
+                CUDA_OK(cudaMemcpyAsync(ha, r.paths.hit, bytes, cudaMemcpyDeviceToDevice, r.stream));
+                CUDA_OK(cudaMemcpyAsync(r.paths.ray_d, before, bytes, cudaMemcpyDeviceToDevice, r.stream));
+                CUDA_OK(zygpu::launchExtendReference(r.scene, r.paths, pass.num_paths * lanes, r.stream));
+                CUDA_OK(zygpu::launchCompareHits(r.paths, before, ta, ha, pass.num_paths * lanes, bounce, r.stream));
+                CUDA_OK(cudaStreamSynchronize(r.stream));
+                cudaFree(before);
+                cudaFree(ta);
+                cudaFree(ha);
+            } else
             CUDA_OK(zygpu::launchExtend(r.scene, r.paths, pass.num_paths * lanes, r.has_meshes, bounce, r.stream));
             r.stats.kernel_launches += 1 + trace_extra;
             if (lanes > 1) {

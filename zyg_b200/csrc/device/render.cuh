@@ -99,12 +99,18 @@ struct SceneDevice {
 
     const float* luts;  // ZygpuScene.ggx_luts
 
+    // What a ray's traversal stack can hold at most in the fused kernels: two entries (node group, postponed leaf group) per level of the
+    // prop tree and of the deepest mesh tree, the parked world ray (5), one spare. The one-ray-per-lane kernel keeps kWideStack (48)
+    // entries in local memory, the ray-pool kernel kScenePoolStack in global scratch; a scene beyond either takes the next variant.
+    uint32_t trace_stack_bound;
+
     float4 world_lo;     // lower corner of the box around the finite props and, per axis, cells per unit length: the ray-sort grid
     float4 world_cells;  // (device/render_trace.cu, sortKeyKernel)
 };
 
 constexpr uint32_t kSortBins = 1u << 16;
-constexpr uint32_t kScenePoolStackWords = 4u * 64u * 48u;  // per block: 4 warps x 64 pooled rays x kWideStack entries  // keys of the ray sort (device/render_trace.cu)
+constexpr uint32_t kScenePoolStack      = 96;  // traversal stack entries per pooled ray (global scratch: depth is cheap there)
+constexpr uint32_t kScenePoolStackWords = 4u * 64u * kScenePoolStack;  // per block: 4 warps x 64 pooled rays  // keys of the ray sort (device/render_trace.cu)
 
 struct PathState {
     // Per path vertex. A camera sample ("slot") owns `lanes` vertex records: 1 when no material of the scene can split a
@@ -190,6 +196,11 @@ cudaError_t launchGenerate(const ZygpuView& view, const PathState& st, const Pas
 // The queue lengths live on the device; the grids are sized for `max_items` and exit early.
 // `bounce`: the path depth of the stage (the ray sort skips the camera rays, which arrive in pixel order).
 cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, uint32_t bounce, cudaStream_t stream);
+// Diagnostics (ZYGPU_VERIFY_TRACE=1): the closest-hit stage once more with one thread per ray in the reference's prop order, and a
+// comparison of two result sets (prints the rays whose hits differ).
+cudaError_t launchExtendReference(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream);
+cudaError_t launchCompareHits(const PathState& st, const float4* ray_d_before, const float4* ray_d_a, const float4* hit_a, uint32_t max_items,
+                              uint32_t bounce, cudaStream_t stream);
 // `round` = which vertex of each slot's current generation the shade stages work on: the vertices of one camera sample share
 // its sampler and are processed in the reference's order (VertexPool.consume, vertex.zig:232-283), so rounds are sequential.
 cudaError_t launchBeginGeneration(const PathState& st, cudaStream_t stream);

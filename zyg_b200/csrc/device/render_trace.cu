@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(128, MinBlocks) meshTracePersistent(SceneDevic
                 const WideNodeRegs nd = loadWideNode(mesh.wide_nodes, node_index);
                 const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
 
-                const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
+                const uint32_t hitmask = testWideNode(w, w.ray.tmin, cullLimit(w.ray), n0, n1, n2, n3, n4);
 
                 node_group.x = __float_as_uint(n1.x);
                 node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
@@ -341,7 +341,7 @@ __device__ __forceinline__ bool segmentMeetsSphere(const RayT& ray, float4 spher
     const V3    pv = {oc.x - tc * ray.d.x, oc.y - tc * ray.d.y, oc.z - tc * ray.d.z};
     if (dot3(pv, pv) > r2 * 1.0001f) return false;
     // the entry point is no nearer than tc - r / |d|
-    return tc - sphere.w * rsqrtf(dd) * 1.0001f <= ray.tmax;
+    return tc - sphere.w * rsqrtf(dd) * 1.0001f <= cullLimit(ray);
 }
 
 // Prefetches. The kernel waits on memory, not on bandwidth (DRAM 6 % busy, half of the stall samples on the first use of a loaded
@@ -524,6 +524,7 @@ struct SceneStepTuning {
     uint32_t weight[4];   // NODE, TRIANGLE, PROP, ENTER: the step kind with the largest (ready lanes x weight) runs
     uint32_t prefetch;    // 1: a lane asks L1 for the node / record it will read in its next step as soon as it knows which
     uint32_t sorted;      // 1: the items come from queue_m in ray-sort order (counters[15] of them)
+    uint32_t debug_item;  // diagnostics (ZYGPU_DEBUG_TRACE_ITEM): the one-ray-per-lane kernel prints what this trace item does; kEnd = off
 };
 
 template <bool AnyHit, bool Count, int MinBlocks>
@@ -646,6 +647,12 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                     recs                    = m->wide_tris;
                     w.ray                   = worldToObjectRay(trafo, w.ray);
                     setupWideRay(w);
+                    if (!AnyHit && item == tune.debug_item) {
+                        printf("[trace] ENTER prop %u mesh %u sp %u | world o %.9g %.9g %.9g d %.9g %.9g %.9g tmax %.9g | object o %.9g %.9g %.9g d %.9g %.9g %.9g\n",
+                               enter_prop, sc.props[enter_prop].mesh, sp, __uint_as_float(stack[sp - 5].x), __uint_as_float(stack[sp - 5].y),
+                               __uint_as_float(stack[sp - 4].x), __uint_as_float(stack[sp - 4].y), __uint_as_float(stack[sp - 3].x),
+                               __uint_as_float(stack[sp - 3].y), w.ray.tmax, w.ray.o.x, w.ray.o.y, w.ray.o.z, w.ray.d.x, w.ray.d.y, w.ray.d.z);
+                    }
                     cur_prop   = enter_prop;
                     enter_prop = kEnd;
                     in_mesh    = true;
@@ -733,6 +740,10 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                             node_group.y = 0;
                             tri_group.y  = 0;
                         } else if (closerOrLater(t, w.ray.tmax, cur_prop, prim, hit_prop, primitive)) {
+                            if (item == tune.debug_item) {
+                                printf("[trace] HIT prop %u record %u prim %u t %.9g (max_t was %.9g) u %.9g v %.9g sp %u sp_mesh %u\n", cur_prop,
+                                       tri_group.x + bit, prim, t, w.ray.tmax, u, v, sp, sp_mesh);
+                            }
                             w.ray.tmax = t;  // probe.ray.max_t = isec.t, prop_tree.zig:77
                             hu         = u;
                             hv         = v;
@@ -759,7 +770,7 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                     const WideNodeRegs nd = loadWideNode(nodes, node_index);
                     const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
 
-                    const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
+                    const uint32_t hitmask = testWideNode(w, w.ray.tmin, cullLimit(w.ray), n0, n1, n2, n3, n4);
 
                     node_group.x = __float_as_uint(n1.x);
                     node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
@@ -778,6 +789,10 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                     w.ray.o        = {__uint_as_float(e0.x), __uint_as_float(e0.y), __uint_as_float(e1.x)};
                     w.ray.d        = {__uint_as_float(e1.y), __uint_as_float(e2.x), __uint_as_float(e2.y)};
                     w.ray.inv_d    = {__uint_as_float(e3.x), __uint_as_float(e3.y), __uint_as_float(e4.x)};
+                    if (!AnyHit && item == tune.debug_item) {
+                        printf("[trace] LEAVE prop %u sp %u | world o %.9g %.9g %.9g d %.9g %.9g %.9g tmax %.9g\n", cur_prop, sp, w.ray.o.x, w.ray.o.y,
+                               w.ray.o.z, w.ray.d.x, w.ray.d.y, w.ray.d.z, w.ray.tmax);
+                    }
                     setupWideRay(w);
                     nodes = sc.tlas_nodes;
                     recs  = sc.tlas_recs;
@@ -849,7 +864,7 @@ __global__ void __launch_bounds__(128, 7) scenePoolTrace(SceneDevice sc, PathSta
     ScenePool&           pool = pools[threadIdx.x >> 5];
     const uint32_t       lane = threadIdx.x & 31u;
     const uint32_t       lt   = (1u << lane) - 1u;
-    uint2* __restrict__  stk  = stacks + size_t(blockIdx.x * 4u + (threadIdx.x >> 5)) * kScenePoolSlots * kWideStack;
+    uint2* __restrict__  stk  = stacks + size_t(blockIdx.x * 4u + (threadIdx.x >> 5)) * kScenePoolSlots * kScenePoolStack;
 
     TraceItems items = traceItems<AnyHit>(st);
     if (0 != tune.sorted) items.n = st.counters[15];
@@ -983,7 +998,7 @@ __global__ void __launch_bounds__(128, 7) scenePoolTrace(SceneDevice sc, PathSta
             setupWideRay(w);
             const float tmax0 = ra.w;
             float       hu    = rc.w;
-            uint2* __restrict__ stack = stk + size_t(slot) * kWideStack;
+            uint2* __restrict__ stack = stk + size_t(slot) * kScenePoolStack;
 
             uint2    node_group = make_uint2(g.x, g.y);
             uint2    tri_group  = make_uint2(g.z, g.w);
@@ -1119,7 +1134,7 @@ __global__ void __launch_bounds__(128, 7) scenePoolTrace(SceneDevice sc, PathSta
 
                 const WideNodeRegs nd = loadWideNode(nodes, node_index);
                 const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
-                const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
+                const uint32_t hitmask = testWideNode(w, w.ray.tmin, cullLimit(w.ray), n0, n1, n2, n3, n4);
 
                 node_group.x = __float_as_uint(n1.x);
                 node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
@@ -1276,6 +1291,7 @@ const SceneTraceConfig& sceneTraceConfig() {
         c.sort_from       = envInt("ZYGPU_RAY_SORT_FROM", 1);  // first bounce that sorts
         c.sort_mode       = envInt("ZYGPU_RAY_SORT_MODE", 1);  // 1: (cell, octant), 2: (octant, cell)
         c.step.sorted     = 0;
+        c.step.debug_item = uint32_t(envInt("ZYGPU_DEBUG_TRACE_ITEM", -1));
         c.step.prefetch   = uint32_t(envInt("ZYGPU_SCENE_PREFETCH", 0));
         return c;
     }();
@@ -1288,7 +1304,10 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
     // a prop tree that is a single leaf (a mesh and a few analytic props) gains nothing from the fused walk: the thread-per-ray
     // top kernel deals with it at full lane occupancy (measured on the 1M-triangle sphere scene: 48.2 ms against 51.4 ms fused)
     // (an instrumented pass always takes the fused kernel, the one that counts its fetches; the results are the same)
-    if ((2 == cfg.variant && has_meshes && scene.num_solid_nodes > 1) || nullptr != st.tally) {
+    // (a scene whose trees are too deep for the fused kernels' stacks takes the two-kernel path, whose levels have a stack each)
+    const bool pool_fits  = scene.trace_stack_bound <= kScenePoolStack && nullptr != st.trace_stacks && nullptr == st.tally && 0 != cfg.pool;
+    const bool fused_fits = scene.trace_stack_bound <= kWideStack || pool_fits;
+    if ((2 == cfg.variant && has_meshes && scene.num_solid_nodes > 1 && fused_fits) || (nullptr != st.tally && scene.trace_stack_bound <= kWideStack)) {
         static int resident = 0, resident_counted = 0;
         // resident blocks per SM the kernel is compiled for (ZYGPU_SCENE_MIN_BLOCKS): 5 -> 96 registers, 6 -> 80, 7 -> 72, 8 -> 64.
         // Measured on config 3 (1920 x 1080 x 4 spp): 188.5 / 179.6 / 169.9 / 168.9 ms - the walk waits on memory (5 M triangles do not
@@ -1325,7 +1344,7 @@ cudaError_t launchSceneTrace(const SceneDevice& scene, const PathState& st, uint
         // Measured (profiles/r02_sweeps.md): 20.6 instead of 14.0 active lanes per instruction on config 3, but 30 % more thread-level work for
         // picking and moving the rays - 339.6 -> 322.3 ms per 8-spp frame there, 190.8 -> 200.2 ms on config 4, whose rays see few props. The
         // variant is taken for large prop trees (ZYGPU_SCENE_POOL = 0 / 1 overrides).
-        const bool pooled = -1 == cfg.pool ? scene.num_solid_nodes >= 4096u : 0 != cfg.pool;
+        const bool pooled = pool_fits && (scene.trace_stack_bound > kWideStack || (-1 == cfg.pool ? scene.num_solid_nodes >= 4096u : true));
         if (!counted && pooled && nullptr != st.trace_stacks && scene.num_solid_nodes > 1) {
             // the ray-pool variant: rays ready for the same kind of step are handed to the lanes first
             static int pool_resident = 0;
@@ -1384,6 +1403,36 @@ cudaError_t launchExtend(const SceneDevice& scene, const PathState& st, uint32_t
     extendKernel<<<gridFor(max_items, walkGrid()), kBlock, 0, stream>>>(scene, st);
     return cudaGetLastError();
 }
+cudaError_t launchExtendReference(const SceneDevice& scene, const PathState& st, uint32_t max_items, cudaStream_t stream) {
+    extendKernel<<<gridFor(max_items, walkGrid()), kBlock, 0, stream>>>(scene, st);
+    return cudaGetLastError();
+}
+
+namespace {
+__global__ void compareHitsKernel(PathState st, const float4* __restrict__ ray_d_before, const float4* __restrict__ ray_d_a,
+                                  const float4* __restrict__ hit_a, uint32_t bounce) {
+    const uint32_t count = st.counters[st.lanes > 1 ? 7 : 0];
+    const uint32_t* __restrict__ queue = st.lanes > 1 ? st.queue_t : st.queue_a;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t item = queue[i];
+        const float4   ha = hit_a[item], hb = st.hit[item];
+        const float    ta = ray_d_a[item].w, tb = st.ray_d[item].w;
+        if (__float_as_uint(ta) != __float_as_uint(tb) || __float_as_uint(ha.z) != __float_as_uint(hb.z) || __float_as_uint(ha.w) != __float_as_uint(hb.w)) {
+            const float4 o = st.ray_o[item], d = ray_d_before[item];
+            printf("[verify] bounce %u item %u o %.9g %.9g %.9g d %.9g %.9g %.9g max_t %.9g | fused t %.9g prim %u prop %u | reference t %.9g prim %u prop %u\n",
+                   bounce, item, o.x, o.y, o.z, d.x, d.y, d.z, d.w, ta, __float_as_uint(ha.z), __float_as_uint(ha.w), tb, __float_as_uint(hb.z),
+                   __float_as_uint(hb.w));
+        }
+    }
+}
+}  // namespace
+
+cudaError_t launchCompareHits(const PathState& st, const float4* ray_d_before, const float4* ray_d_a, const float4* hit_a, uint32_t max_items,
+                              uint32_t bounce, cudaStream_t stream) {
+    compareHitsKernel<<<gridFor(max_items, 16), kBlock, 0, stream>>>(st, ray_d_before, ray_d_a, hit_a, bounce);
+    return cudaGetLastError();
+}
+
 cudaError_t launchShadow(const SceneDevice& scene, const PathState& st, uint32_t max_items, bool has_meshes, uint32_t bounce, cudaStream_t stream) {
     if (0 != sceneTraceConfig().variant) return launchSceneTrace<true>(scene, st, max_items * st.shadow_stride, has_meshes, bounce, stream);
     shadowKernel<<<gridFor(max_items, walkGrid()), kBlock, 0, stream>>>(scene, st);

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(128)
                     const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
                     tally.node();
 
-                    const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
+                    const uint32_t hitmask = testWideNode(w, w.ray.tmin, cullLimit(w.ray), n0, n1, n2, n3, n4);
 
                     node_group.x = __float_as_uint(n1.x);
                     node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(128)
                 const float4 n0 = nd.n0, n1 = nd.n1, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
                 tally.node();
 
-                const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, n0, n1, n2, n3, n4);
+                const uint32_t hitmask = testWideNode(w, w.ray.tmin, cullLimit(w.ray), n0, n1, n2, n3, n4);
 
                 node_group.x = __float_as_uint(n1.x);
                 node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);

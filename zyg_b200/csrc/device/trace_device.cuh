@@ -232,11 +232,24 @@ __device__ __forceinline__ uint32_t testWideNode(const WideRay& w, float tmin_ra
 // lock-step schedule found earlier hits. Gating with the max_t the ray STARTED with makes the decision independent of the
 // schedule (equal-t ties included, see closerOrLater); the cull against the current max_t only drops boxes whose entry lies
 // beyond it by more than the rounding of the test, where no hit could be accepted or tie.
+// The limit of every cull against the ray's *current* max_t. How far max_t has come down when a box is met depends on the schedule, so
+// such a cull must never drop a box that could still hold a hit at or below the final max_t. A slab test's entry and Moeller-Trumbore's t
+// are rounded differently - the latter with errors relative to the distance between origin and triangle, not to t - so a hit can come out
+// slightly in front of its own box: with a margin of 5e-7 two paths of the 66 M of a 4K frame flipped between two near-equal hits from
+// run to run. 0.1 % and an absolute term in units of the origin's magnitude cost no measurable time.
+__device__ __forceinline__ float originScale(const RayT& ray) { return fabsf(ray.o.x) + fabsf(ray.o.y) + fabsf(ray.o.z) + 1.f; }
+__device__ __forceinline__ float cullLimit(const RayT& ray) { return fmaf(ray.tmax, 1.001f, 2e-5f * originScale(ray)); }
+
+// `entry`: where the ray enters the box (its min_t when it starts inside)
+__device__ __forceinline__ bool gateBox(const float4 bmin, const float4 bmax, const RayT& ray, float gate_tmax, float& entry) {
+    RayT g = ray;
+    g.tmax = gate_tmax;
+    entry  = intersectNode(bmin, bmax, g);
+    return FLT_MAX != entry && entry <= cullLimit(ray);
+}
 __device__ __forceinline__ bool gateBox(const float4 bmin, const float4 bmax, const RayT& ray, float gate_tmax) {
-    RayT g        = ray;
-    g.tmax        = gate_tmax;
-    const float e = intersectNode(bmin, bmax, g);
-    return FLT_MAX != e && e * 0.9999995f <= ray.tmax;
+    float entry;
+    return gateBox(bmin, bmax, ray, gate_tmax, entry);
 }
 
 // One gated triangle test against record `index`; true on an accepted hit (fills t, u, v, primitive). `gate_tmax`: the max_t
@@ -249,9 +262,16 @@ __device__ __forceinline__ bool testWideTriangle(const MeshDevice& mesh, const R
 
     // Gate with the reference's own (non-watertight) slab test on the reference leaf box: the
     // reference never tests a triangle whose leaf box it rejected.
-    if (!gateBox(make_float4(t1.w, t2.w, t3.x, 0.f), make_float4(t3.y, t3.z, t3.w, 0.f), ray, gate_tmax)) return false;
+    float entry;
+    if (!gateBox(make_float4(t1.w, t2.w, t3.x, 0.f), make_float4(t3.y, t3.z, t3.w, 0.f), ray, gate_tmax, entry)) return false;
     primitive = __float_as_uint(t0.w);
-    return intersectTriangle(ray, {t0.x, t0.y, t0.z}, {t1.x, t1.y, t1.z}, {t2.x, t2.y, t2.z}, t, u, v);
+    if (!intersectTriangle(ray, {t0.x, t0.y, t0.z}, {t1.x, t1.y, t1.z}, {t2.x, t2.y, t2.z}, t, u, v)) return false;
+    // A hit in front of its own leaf box is an artefact of a degenerate triangle (a pole of a lat-long sphere met exactly: every term of
+    // u, v and t rounds to 0 over a tiny determinant, "hit" at t = 0). The reference accepts it when its order happens to reach that leaf
+    // before a nearer real hit has culled it; a parallel walk has no such order, so whether the leaf is reached would depend on the
+    // schedule (two rays of the 66 M of a 4K frame of the instanced scene flipped from run to run). It is refused: no surface lies there.
+    // The tolerance is half the margin of cullLimit, so a hit that passes could never have been culled in another order.
+    return t >= fmaf(entry, 1.f - 5e-4f, -1e-5f * originScale(ray));
 }
 
 // One ray through one mesh, per-thread while-while loop over the wide layout (the body of the
@@ -282,7 +302,7 @@ __device__ __forceinline__ bool traverseWide(const MeshDevice& mesh, WideRay& w,
             const WideNodeRegs nd = loadWideNode(mesh.wide_nodes, node_index);
             const float4 n0 = nd.n0, n1 = nd.n1;
 
-            const uint32_t hitmask = testWideNode(w, w.ray.tmin, w.ray.tmax, nd.n0, nd.n1, nd.n2, nd.n3, nd.n4);
+            const uint32_t hitmask = testWideNode(w, w.ray.tmin, cullLimit(w.ray), nd.n0, nd.n1, nd.n2, nd.n3, nd.n4);
 
             node_group.x = __float_as_uint(n1.x);
             node_group.y = (hitmask & 0xFF000000u) | (__float_as_uint(n0.w) >> 24);
