@@ -815,3 +815,23 @@ def test_trace_kernel_variants_are_bit_identical(tmp_path):
     assert films["lock_step"][..., :3].sum() > 0
     for name in ("pool", "pool_sorted", "two_kernels"):
         assert films[name].tobytes() == films["lock_step"].tobytes(), name
+
+
+def test_4k_instanced_frame_is_reproducible(engine):
+    """BASELINE config 5's scene and resolution, 4 spp, three times: the films are the same bytes. Two of the 33 M paths used to flip from
+    run to run (a sliver triangle at a pole of a lat-long prototype met exactly reports a hit at t = 0; whether its leaf was reached
+    depended on how far max_t had come down, i.e. on the schedule) and failed the NCCL film check of the bench at 4K."""
+    w, h, spp = 3840, 2160, 4
+    scenes.instanced_scene(w, h, spp=spp, grid=(100, 100), prototypes=20, quads=(500, 250), sun=60.0)
+    L = lib.load_library()
+    L.zygpu_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    L.zygpu_clear_film.argtypes = [C.c_void_p]
+    su.start_frame(0)
+    dev = su.device_handle()
+    films = []
+    for _ in range(3):
+        assert 0 == L.zygpu_clear_film(dev)
+        assert 0 == L.zygpu_render(dev, 0, spp)
+        films.append(download_film(w, h))
+    assert films[0][..., 3].min() == spp
+    assert films[1].tobytes() == films[0].tobytes() and films[2].tobytes() == films[0].tobytes()
