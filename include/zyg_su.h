@@ -122,6 +122,8 @@ const struct zyg_mesh* zyg_su_mesh(uint32_t shape);
 /* `it --denoise sigma` (src/it/denoise.zig) on the frame that was just rendered, from the device's own buffers: width * height RGBA
  * like su_resolve_frame_to_buffer. -2 unless su_aovs_create switched on ShadingNormal and Albedo. */
 int32_t zyg_su_denoise_frame_to_buffer(float sigma, uint32_t width, uint32_t height, float* buffer);
+/* (flags: 1 alpha, 2 half floats (EXR), 4 error diffusion (PNG), bits 8-10 a Writer.Encoding other than colour: 2 Depth, 3 Id,
+ * 4 Normal, 5 Float - image_writer.zig:17-24, what su_export_frame uses for the AOV layers) */
 int32_t zyg_su_write_image(const char* path, uint32_t format, uint32_t flags, const float* rgba, int32_t width, int32_t height,
                            const int32_t* crop);
 

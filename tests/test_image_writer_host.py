@@ -44,7 +44,7 @@ def read_png(path):
         pos += 12 + n
     w, h, depth, colour, _, flt, interlace = header
     assert depth == 8 and flt == 0 and interlace == 0
-    ch = {2: 3, 6: 4}[colour]
+    ch = {0: 1, 2: 3, 6: 4}[colour]
     raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + w * ch)
     assert not raw[:, 0].any()  # filter type None on every scanline
     return raw[:, 1:].reshape(h, w, ch)
@@ -109,7 +109,7 @@ def read_exr(path):
     w, h = x1 - x0 + 1, y1 - y0 + 1
     blocks = (h + 15) // 16
     offsets = struct.unpack(f"<{blocks}Q", data[pos:pos + 8 * blocks])
-    dtype = {1: np.float16, 2: np.float32}[channels[0][1]]
+    dtype = {0: np.uint32, 1: np.float16, 2: np.float32}[channels[0][1]]
     out = np.zeros((h, w, len(channels)), np.float32)
     for b, off in enumerate(offsets):
         y, size = struct.unpack("<iI", data[off:off + 8])
@@ -129,7 +129,7 @@ def read_exr(path):
         else:
             raw = np.frombuffer(payload, np.uint8)
         planes = raw.view(dtype).reshape(rows, len(channels), w)
-        out[16 * b:16 * b + rows] = planes.transpose(0, 2, 1)
+        out[16 * b:16 * b + rows] = planes.transpose(0, 2, 1)  # (uint ids stay exact in float32 up to 2^24)
     return out, [c[0] for c in channels], (x0, y0, x1, y1), display
 
 
@@ -212,3 +212,69 @@ def test_rgbe_round_trip(tmp_path, width):
     # decoded radiance within the format's 1/128 relative precision of the brightest channel
     dec = got[..., :3].astype(np.float64) * np.exp2(got[..., 3].astype(np.float64) - 136)[..., None]
     assert np.all(np.abs(dec - rgb) <= v[..., None] / 100 + 1e-30)
+
+
+def aov_image(w=40, h=28, seed=3):
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w, 4), np.float32)
+    img[..., 0] = rng.uniform(2.0, 9.0, (h, w))      # depth / id / roughness live in the first lane
+    img[..., 1:3] = rng.uniform(-1.0, 1.0, (h, w, 2))
+    img[..., 3] = 1.0
+    return img
+
+
+def test_png_aov_encodings(tmp_path):
+    """Srgb.toSrgbBuffer for the AOV encodings (image/encoding/srgb.zig:225-277): Depth and Float as one grey channel, Id as a 24-bit
+    hash, Normal as 0.5 (n + 1)."""
+    img = aov_image()
+    unorm = lambda x: (np.clip(x, 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)  # enc.floatToUnorm8
+
+    path = str(tmp_path / "d.png")
+    img_d = img.copy()
+    img_d[3, 5, 0] = np.finfo(np.float32).max  # a pixel that saw nothing: excluded from the range, black
+    su.write_image(path, su.IMAGE_PNG, img_d, su.IMAGE_DEPTH)
+    got = read_png(path)
+    assert got.shape == (28, 40, 1)
+    d = img_d[..., 0]
+    lo, hi = d.min(), d[d < 2.0e9].max()
+    assert np.abs(got[..., 0].astype(int) - unorm(np.float32(1.0) - (d - lo) / (hi - lo)).astype(int)).max() <= 1 and 0 == got[3, 5, 0]
+
+    path = str(tmp_path / "f.png")
+    rough = img.copy()
+    rough[..., 0] = (rough[..., 0] - 2.0) / 7.0
+    su.write_image(path, su.IMAGE_PNG, rough, su.IMAGE_FLOAT)
+    got = read_png(path)
+    assert got.shape == (28, 40, 1) and np.abs(got[..., 0].astype(int) - unorm(rough[..., 0]).astype(int)).max() <= 1
+
+    path = str(tmp_path / "n.png")
+    nrm = img.copy()
+    nrm[..., 0] = np.sqrt(np.clip(1.0 - (nrm[..., 1:3] ** 2).sum(-1), 0.0, 1.0))
+    su.write_image(path, su.IMAGE_PNG, nrm, su.IMAGE_NORMAL)
+    got = read_png(path)
+    assert got.shape == (28, 40, 3) and np.abs(got.astype(int) - unorm(np.float32(0.5) * (nrm[..., :3] + np.float32(1.0))).astype(int)).max() <= 1
+
+    path = str(tmp_path / "i.png")
+    ids = img.copy()
+    ids[..., 0] = np.floor(ids[..., 0])
+    su.write_image(path, su.IMAGE_PNG, ids, su.IMAGE_ID)
+    got = read_png(path).astype(np.uint32)
+    mid = (ids[..., 0].astype(np.uint64) * 9795927 % (1 << 32)) % 16777216
+    assert np.array_equal((got[..., 0] << 16) | (got[..., 1] << 8) | got[..., 2], mid.astype(np.uint32))
+    assert len(np.unique(mid)) == len(np.unique(ids[..., 0]))  # different ids, different colours
+
+
+def test_exr_aov_encodings(tmp_path):
+    """exr_writer.zig:42-80, 449-469: Depth = one float channel Y (never half), Id = one uint channel Y, Normal = three channels."""
+    img = aov_image()
+    path = str(tmp_path / "d.exr")
+    su.write_image(path, su.IMAGE_EXR, img, su.IMAGE_DEPTH | su.IMAGE_HALF)
+    got, names, _, _ = read_exr(path)
+    assert names == ["Y"] and np.array_equal(got[..., 0], img[..., 0])
+    path = str(tmp_path / "i.exr")
+    su.write_image(path, su.IMAGE_EXR, img, su.IMAGE_ID)
+    got, names, _, _ = read_exr(path)
+    assert names == ["Y"] and np.array_equal(got[..., 0], np.floor(img[..., 0]))
+    path = str(tmp_path / "n.exr")
+    su.write_image(path, su.IMAGE_EXR, img, su.IMAGE_NORMAL)
+    got, names, _, _ = read_exr(path)
+    assert names == ["B", "G", "R"] and np.array_equal(got, img[..., [2, 1, 0]])

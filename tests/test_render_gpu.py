@@ -835,3 +835,29 @@ def test_4k_instanced_frame_is_reproducible(engine):
         films.append(download_film(w, h))
     assert films[0][..., 3].min() == spp
     assert films[1].tobytes() == films[0].tobytes() and films[2].tobytes() == films[0].tobytes()
+
+
+def test_export_frame_writes_the_aov_layers(engine, tmp_path, monkeypatch):
+    """Driver.exportFrame (driver.zig:224-253): after the beauty, one file per recorded AOV class and exporter, named and encoded by
+    its class (image_sequence.zig:36-78, aov_value.zig:32-40)."""
+    from test_image_writer_host import read_exr, read_png
+
+    w, h, spp = 48, 40, 4
+    scenes.cornell_box(w, h, spp=spp)
+    su.aovs_create({"Albedo": True, "Depth": True, "MaterialId": True, "ShadingNormal": True})
+    su.exporters_create({"Image": {"format": "EXR", "bitdepth": 32}})
+    monkeypatch.chdir(tmp_path)
+    su.render_frame(3)
+    su.export_frame()
+    import os as _os
+    assert sorted(_os.listdir(".")) == ["image_00_000003.exr", "image_00_000003_albedo.exr", "image_00_000003_depth.exr",
+                                        "image_00_000003_mat.exr", "image_00_000003_n.exr"]
+    depth, names, _, _ = read_exr("image_00_000003_depth.exr")
+    assert names == ["Y"] and np.array_equal(depth[..., 0], su.resolve_frame_to_buffer(w, h, su.AOV_DEPTH)[..., 0])
+    ids, names, _, _ = read_exr("image_00_000003_mat.exr")
+    assert names == ["Y"] and np.array_equal(ids[..., 0], su.resolve_frame_to_buffer(w, h, su.AOV_MATERIAL_ID)[..., 0])
+    normal, names, _, _ = read_exr("image_00_000003_n.exr")
+    assert names == ["B", "G", "R"] and np.array_equal(normal[..., ::-1], su.resolve_frame_to_buffer(w, h, su.AOV_SHADING_NORMAL)[..., :3], equal_nan=True)
+    su.exporters_create({"Image": {"format": "PNG"}})
+    su.export_frame()
+    assert read_png("image_00_000003_depth.png").shape == (h, w, 1) and read_png("image_00_000003_mat.png").shape == (h, w, 3)

@@ -410,7 +410,8 @@ int32_t zyg_su_render_frame_range(uint32_t frame, uint32_t iteration, uint32_t n
 
 // Driver.exportFrame + ImageSequence.write, driver.zig:224-253, exporting/image_sequence.zig:24-56: resolve the beauty, then one
 // file "image_<camera:02>_<frame:06>.<ext>" per exporter in the working directory; with the Transparent sensor ("alpha_transparency")
-// PNG and EXR carry the alpha channel. The AOV layers are reached through su_resolve_frame[_to_buffer] (+ zyg_su_write_image).
+// PNG and EXR carry the alpha channel. Every recorded AOV class follows as image_<..>_<frame><_albedo|_depth|_mat|_ng|_n|_r|_emission|
+// _direct|_indirect>.<ext> in the encoding of its class (aov_value.zig:32-40).
 int32_t su_export_frame(void) {
     if (!g_engine || !g_engine->device) return -1;
     Engine&        e = *g_engine;
@@ -422,6 +423,43 @@ int32_t su_export_frame(void) {
     }
     const int32_t* crop = e.scene.view().crop;
     const bool     alpha = e.scene.alphaTransparency();  // ImageSequence.alpha = sensor.class.alphaTransparency(), take.zig:311
+    // the beauty, then every recorded AOV class under its own name and encoding (driver.zig:231-250, image_sequence.zig:36-78)
+    static const char* const kAovExtension[kNumAovClasses] = {"_albedo", "_depth", "_mat", "_ng", "_n", "_r", "_emission", "_direct", "_indirect"};
+    static const zyg::Encoding kAovEncoding[kNumAovClasses] = {zyg::Encoding::Color, zyg::Encoding::Depth,  zyg::Encoding::Id,
+                                                               zyg::Encoding::Normal, zyg::Encoding::Normal, zyg::Encoding::Float,
+                                                               zyg::Encoding::Color, zyg::Encoding::Color,  zyg::Encoding::Color};
+    for (uint32_t aov = 0; aov < kNumAovClasses; ++aov) {
+        if (0 == (e.scene.aovSlots() & (1u << aov))) continue;
+        std::vector<float> layer(size_t(n) * 4);
+        if (0 != zygpu_resolve_aov(e.device, aov, layer.data(), n, 0)) {
+            logf(Error, "%s", zygpu_last_error());
+            return -1;
+        }
+        for (const Engine::Exporter& x : e.exporters) {
+            std::vector<uint8_t> bytes;
+            const char*          ext = "png";
+            bool                 ok  = false;
+            switch (x.format) {
+                case Engine::Exporter::PNG:
+                    ok = zyg::encodePngAs(bytes, layer.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop, kAovEncoding[aov], x.error_diffusion);
+                    break;
+                case Engine::Exporter::EXR:
+                    ext = "exr";
+                    ok  = zyg::encodeExrAs(bytes, layer.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop, kAovEncoding[aov], x.half);
+                    break;
+                case Engine::Exporter::RGBE:  // the RGBE writer has no notion of an encoding (rgbe_writer.zig): the resolved values as they are
+                    ext = "hdr";
+                    ok  = zyg::encodeRgbe(bytes, layer.data(), int32_t(e.scene.width()), int32_t(e.scene.height()), crop);
+                    break;
+            }
+            char name[64];
+            std::snprintf(name, sizeof(name), "image_%02u_%06u%s.%s", 0u, e.frame, kAovExtension[aov], ext);
+            if (!ok || !zyg::writeFile(name, bytes)) {
+                logf(Error, "Exporting frame %u to %s failed", e.frame, name);
+                return -1;
+            }
+        }
+    }
     for (const Engine::Exporter& x : e.exporters) {
         std::vector<uint8_t> bytes;
         const char*          ext = "png";
@@ -634,8 +672,10 @@ int32_t zyg_su_write_image(const char* path, uint32_t format, uint32_t flags, co
     const int32_t* c      = crop ? crop : full;
     std::vector<uint8_t> bytes;
     bool                 ok = false;
-    if (0 == format) ok = zyg::encodePng(bytes, rgba, width, height, c, 0 != (flags & 1u), 0 != (flags & 4u));
-    if (1 == format) ok = zyg::encodeExr(bytes, rgba, width, height, c, 0 != (flags & 1u), 0 != (flags & 2u));
+    const uint32_t      e        = (flags >> 8) & 7u;  // Writer.Encoding when not 0: Depth 2, Id 3, Normal 4, Float 5
+    const zyg::Encoding encoding = e > 1u && e <= 5u ? zyg::Encoding(e) : (0 != (flags & 1u) ? zyg::Encoding::ColorAlpha : zyg::Encoding::Color);
+    if (0 == format) ok = zyg::encodePngAs(bytes, rgba, width, height, c, encoding, 0 != (flags & 4u));
+    if (1 == format) ok = zyg::encodeExrAs(bytes, rgba, width, height, c, encoding, 0 != (flags & 2u));
     if (2 == format) ok = zyg::encodeRgbe(bytes, rgba, width, height, c);
     return ok && zyg::writeFile(path, bytes) ? 0 : -1;
 }

@@ -1,6 +1,7 @@
 #include "image_writer.hpp"
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -88,23 +89,60 @@ bool writeFile(const char* path, const std::vector<uint8_t>& bytes) {
 // Srgb.toSrgb + PngWriter.write, image/encoding/srgb.zig:34-230, png/png_writer.zig:33-61: the whole frame is written, pixels
 // outside the crop stay zero.
 bool encodePng(std::vector<uint8_t>& out, const float* rgba, int32_t width, int32_t height, const int32_t crop[4], bool alpha, bool error_diffusion) {
-    const uint32_t       channels = alpha ? 4u : 3u;
+    return encodePngAs(out, rgba, width, height, crop, alpha ? Encoding::ColorAlpha : Encoding::Color, error_diffusion);
+}
+
+bool encodePngAs(std::vector<uint8_t>& out, const float* rgba, int32_t width, int32_t height, const int32_t crop[4], Encoding encoding,
+                 bool error_diffusion) {
+    const bool     alpha    = Encoding::ColorAlpha == encoding;
+    const bool     color    = Encoding::Color == encoding || alpha;
+    const uint32_t channels = alpha ? 4u : ((Encoding::Depth == encoding || Encoding::Float == encoding) ? 1u : 3u);
     std::vector<uint8_t> pixels(size_t(width) * height * channels, 0);
+
+    float mind = FLT_MAX, maxd = 0.f;
+    if (Encoding::Depth == encoding) {  // srgb.zig:50-68 (the inner loop counts from crop[1]: kept as it is)
+        for (int32_t y = crop[1]; y < crop[3]; ++y) {
+            size_t i = size_t(y) * width + crop[0];
+            for (int32_t x = crop[1]; x < crop[2]; ++x, ++i) {
+                if (i >= size_t(width) * height) break;
+                const float depth = rgba[i * 4];
+                mind              = std::min(mind, depth);
+                if (depth < 2.14748313e+09f) maxd = std::max(maxd, depth);  // ro.RayMaxT
+            }
+        }
+    }
+    const float range = maxd - mind;
+    auto        saturate = [](float x) { return std::min(std::max(x, 0.f), 1.f); };
+
     for (int32_t y = crop[1]; y < crop[3]; ++y) {
         float err[4];
         for (float& e : err) e = goldenRatio(uint32_t(y)) - 0.5f;
         for (int32_t x = crop[0]; x < crop[2]; ++x) {
             const float* p = rgba + (size_t(y) * width + x) * 4;
             uint8_t*     o = &pixels[(size_t(y) * width + x) * channels];
-            float        color[4] = {linearToGamma(p[0]), linearToGamma(p[1]), linearToGamma(p[2]), std::min(p[3], 1.f)};
+            if (!color) {
+                if (Encoding::Depth == encoding) {
+                    o[0] = floatToUnorm8(saturate(1.f - (p[0] - mind) / range));
+                } else if (Encoding::Float == encoding) {
+                    o[0] = floatToUnorm8(saturate(p[0]));
+                } else if (Encoding::Id == encoding) {
+                    const uint32_t id  = uint32_t(p[0]);
+                    const uint32_t mid = (id * 9795927u) % 16777216u;
+                    o[0] = uint8_t(mid >> 16), o[1] = uint8_t(mid >> 8), o[2] = uint8_t(mid);
+                } else {  // Normal
+                    for (int c = 0; c < 3; ++c) o[c] = floatToUnorm8(saturate(0.5f * (p[c] + 1.f)));
+                }
+                continue;
+            }
+            float        color4[4] = {linearToGamma(p[0]), linearToGamma(p[1]), linearToGamma(p[2]), std::min(p[3], 1.f)};
             for (uint32_t c = 0; c < channels; ++c) {
                 if (error_diffusion) {
-                    const float   cf = 255.f * color[c];
+                    const float   cf = 255.f * color4[c];
                     const uint8_t ci = uint8_t(cf + err[c] + 0.5f);
                     err[c] += cf - float(ci);
                     o[c] = ci;
                 } else {
-                    o[c] = floatToUnorm8(color[c]);
+                    o[c] = floatToUnorm8(color4[c]);
                 }
             }
         }
@@ -127,7 +165,7 @@ bool encodePng(std::vector<uint8_t>& out, const float* rgba, int32_t width, int3
     put32be(ihdr, uint32_t(width));
     put32be(ihdr, uint32_t(height));
     ihdr.push_back(8);
-    ihdr.push_back(alpha ? 6 : 2);  // colour type: RGBA / RGB
+    ihdr.push_back(alpha ? 6 : (1 == channels ? 0 : 2));  // colour type: RGBA / grey / RGB
     ihdr.push_back(0);
     ihdr.push_back(0);
     ihdr.push_back(0);
@@ -140,8 +178,15 @@ bool encodePng(std::vector<uint8_t>& out, const float* rgba, int32_t width, int3
 // exr_writer.zig:24-164 (header) + :240-300, 330-400, 480-530 (ZIP blocks of 16 scanlines, planar A B G R per row, byte reorder +
 // delta predictor before deflate, a block that does not shrink is stored raw)
 bool encodeExr(std::vector<uint8_t>& out, const float* rgba, int32_t width, int32_t height, const int32_t crop[4], bool alpha, bool half) {
-    const uint32_t channels    = alpha ? 4u : 3u;
-    const uint32_t format      = half ? 1u : 2u;  // exr.Channel.Format: Uint 0, Half 1, Float 2
+    return encodeExrAs(out, rgba, width, height, crop, alpha ? Encoding::ColorAlpha : Encoding::Color, half);
+}
+
+bool encodeExrAs(std::vector<uint8_t>& out, const float* rgba, int32_t width, int32_t height, const int32_t crop[4], Encoding encoding, bool half_in) {
+    const bool     alpha       = Encoding::ColorAlpha == encoding;
+    const bool     single      = Encoding::Depth == encoding || Encoding::Id == encoding;  // exr_writer.zig:46-57
+    const bool     half        = half_in && !single;
+    const uint32_t channels    = alpha ? 4u : (single ? 1u : 3u);
+    const uint32_t format      = Encoding::Id == encoding ? 0u : (half ? 1u : 2u);  // exr.Channel.Format: Uint 0, Half 1, Float 2
     const uint32_t scalar_size = half ? 2u : 4u;
 
     out = {0x76, 0x2f, 0x31, 0x01, 2, 0, 0, 0};
@@ -156,9 +201,13 @@ bool encodeExr(std::vector<uint8_t>& out, const float* rgba, int32_t width, int3
     putString(out, "chlist");
     put<uint32_t>(out, channels * (2 + 4 + 4 + 4 + 4) + 1);
     if (alpha) channel("A");
-    channel("B");
-    channel("G");
-    channel("R");
+    if (channels >= 3) {
+        channel("B");
+        channel("G");
+        channel("R");
+    } else {
+        channel("Y");
+    }
     out.push_back(0);
 
     putString(out, "compression");
@@ -220,9 +269,12 @@ bool encodeExr(std::vector<uint8_t>& out, const float* rgba, int32_t width, int3
             for (uint32_t x = 0; x < w; ++x) {
                 const float* p = rgba + (size_t(y) * width + uint32_t(crop[0]) + x) * 4;
                 for (uint32_t c = 0; c < channels; ++c) {
-                    const float  v = p[channels - 1 - c];  // planes in the order (A) B G R
+                    const float  v = p[channels - 1 - c];  // planes in the order (A) B G R, or the one plane Y
                     const size_t o = (size_t(row) * w * channels + size_t(w) * c + x) * scalar_size;
-                    if (half) {
+                    if (0u == format) {  // blockUint, exr_writer.zig:449-469
+                        const uint32_t uv = uint32_t(v);
+                        std::memcpy(&block[o], &uv, 4);
+                    } else if (half) {
                         const uint16_t hv = floatToHalf(v);
                         std::memcpy(&block[o], &hv, 2);
                     } else {

@@ -254,6 +254,7 @@ def export_frame():
 
 IMAGE_PNG, IMAGE_EXR, IMAGE_RGBE = 0, 1, 2
 IMAGE_ALPHA, IMAGE_HALF, IMAGE_ERROR_DIFFUSION = 1, 2, 4
+IMAGE_DEPTH, IMAGE_ID, IMAGE_NORMAL, IMAGE_FLOAT = 2 << 8, 3 << 8, 4 << 8, 5 << 8  # Writer.Encoding of an AOV layer
 
 
 def write_image(path: str, fmt: int, rgba, flags: int = 0, crop=None):
