@@ -524,7 +524,8 @@ struct SceneStepTuning {
     uint32_t weight[4];   // NODE, TRIANGLE, PROP, ENTER: the step kind with the largest (ready lanes x weight) runs
     uint32_t prefetch;    // 1: a lane asks L1 for the node / record it will read in its next step as soon as it knows which
     uint32_t sorted;      // 1: the items come from queue_m in ray-sort order (counters[15] of them)
-    uint32_t debug_item;  // diagnostics (ZYGPU_DEBUG_TRACE_ITEM): the one-ray-per-lane kernel prints what this trace item does; kEnd = off
+    uint32_t debug_item;  // diagnostics (ZYGPU_DEBUG_TRACE_ITEM): the instrumented (zygpu_set_counting) one-ray-per-lane kernel prints what
+                          // this trace item does; kEnd = off. Only the counting instances carry the printf (it costs 200 bytes of stack).
 };
 
 template <bool AnyHit, bool Count, int MinBlocks>
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                     recs                    = m->wide_tris;
                     w.ray                   = worldToObjectRay(trafo, w.ray);
                     setupWideRay(w);
-                    if (!AnyHit && item == tune.debug_item) {
+                    if (Count && !AnyHit && item == tune.debug_item) {
                         printf("[trace] ENTER prop %u mesh %u sp %u | world o %.9g %.9g %.9g d %.9g %.9g %.9g tmax %.9g | object o %.9g %.9g %.9g d %.9g %.9g %.9g\n",
                                enter_prop, sc.props[enter_prop].mesh, sp, __uint_as_float(stack[sp - 5].x), __uint_as_float(stack[sp - 5].y),
                                __uint_as_float(stack[sp - 4].x), __uint_as_float(stack[sp - 4].y), __uint_as_float(stack[sp - 3].x),
@@ -740,7 +741,7 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                             node_group.y = 0;
                             tri_group.y  = 0;
                         } else if (closerOrLater(t, w.ray.tmax, cur_prop, prim, hit_prop, primitive)) {
-                            if (item == tune.debug_item) {
+                            if (Count && item == tune.debug_item) {
                                 printf("[trace] HIT prop %u record %u prim %u t %.9g (max_t was %.9g) u %.9g v %.9g sp %u sp_mesh %u\n", cur_prop,
                                        tri_group.x + bit, prim, t, w.ray.tmax, u, v, sp, sp_mesh);
                             }
@@ -789,7 +790,7 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                     w.ray.o        = {__uint_as_float(e0.x), __uint_as_float(e0.y), __uint_as_float(e1.x)};
                     w.ray.d        = {__uint_as_float(e1.y), __uint_as_float(e2.x), __uint_as_float(e2.y)};
                     w.ray.inv_d    = {__uint_as_float(e3.x), __uint_as_float(e3.y), __uint_as_float(e4.x)};
-                    if (!AnyHit && item == tune.debug_item) {
+                    if (Count && !AnyHit && item == tune.debug_item) {
                         printf("[trace] LEAVE prop %u sp %u | world o %.9g %.9g %.9g d %.9g %.9g %.9g tmax %.9g\n", cur_prop, sp, w.ray.o.x, w.ray.o.y,
                                w.ray.o.z, w.ray.d.x, w.ray.d.y, w.ray.d.z, w.ray.tmax);
                     }
