@@ -524,6 +524,7 @@ struct SceneStepTuning {
     uint32_t weight[4];   // NODE, TRIANGLE, PROP, ENTER: the step kind with the largest (ready lanes x weight) runs
     uint32_t prefetch;    // 1: a lane asks L1 for the node / record it will read in its next step as soon as it knows which
     uint32_t sorted;      // 1: the items come from queue_m in ray-sort order (counters[15] of them)
+    uint32_t repeat, repeat_lanes;  // ray-pool kernel: up to `repeat` steps of one kind per pick while `repeat_lanes` rays want another
     uint32_t debug_item;  // diagnostics (ZYGPU_DEBUG_TRACE_ITEM): the instrumented (zygpu_set_counting) one-ray-per-lane kernel prints what
                           // this trace item does; kEnd = off. Only the counting instances carry the printf (it costs 200 bytes of stack).
 };
@@ -980,34 +981,47 @@ __global__ void __launch_bounds__(128, 7) scenePoolTrace(SceneDevice sc, PathSta
         const bool     busy = lane < rank;
         const uint32_t slot = busy ? pool.assign[lane] : 0u;
 
+        // The rays stay in the lanes' registers while most of them want another step of the same kind (a NODE step usually leaves a ray
+        // with the next node group, a TRIANGLE step with the rest of its leaf): picking and moving rays costs about half a step.
         uint32_t retired = 0;
+        // (declared for all lanes: the repetition vote below is warp-wide)
+        WideRay  w;
+        float    tmax0 = 0.f, hu = 0.f;
+        uint2*   stack = stk;
+        uint2    node_group = make_uint2(0u, 0u), tri_group = make_uint2(0u, 0u);
+        uint32_t sp = 0, dm = 0;
+        bool     in_mesh = false, ray_dirty = false, hit_dirty = false, level_dirty = false;
+        uint4    h = make_uint4(0u, kEnd, 0u, 0u), sv = make_uint4(0u, kEnd, kEnd, kEnd);
+        uint32_t ready = 0;
         if (busy) {
             const float4 ra = pool.a[slot];
             const float4 rb = pool.b[slot];
             const float4 rc = pool.c[slot];
             const uint4  g  = pool.g[slot];
-            uint4        h  = pool.h[slot];
-            uint4        sv = pool.s[slot];
-            uint32_t     dm = pool.dm[slot];
+            h               = pool.h[slot];
+            sv              = pool.s[slot];
+            dm              = pool.dm[slot];
 
-            WideRay w;
             w.ray.o     = {ra.x, ra.y, ra.z};
             w.ray.tmin  = 0.f;
             w.ray.d     = {rb.x, rb.y, rb.z};
             w.ray.tmax  = rb.w;
             w.ray.inv_d = {rc.x, rc.y, rc.z};
-            setupWideRay(w);
-            const float tmax0 = ra.w;
-            float       hu    = rc.w;
-            uint2* __restrict__ stack = stk + size_t(slot) * kScenePoolStack;
+            tmax0 = ra.w;
+            hu    = rc.w;
+            stack = stk + size_t(slot) * kScenePoolStack;
 
-            uint2    node_group = make_uint2(g.x, g.y);
-            uint2    tri_group  = make_uint2(g.z, g.w);
-            uint32_t sp         = h.x;
-            bool     in_mesh    = kEnd != sv.y;
+            node_group = make_uint2(g.x, g.y);
+            tri_group  = make_uint2(g.z, g.w);
+            sp         = h.x;
+            in_mesh    = kEnd != sv.y;
             // what has to go back to shared memory: the groups and the stack depth always, the rest when it changed
-            bool ray_dirty = false, hit_dirty = false, level_dirty = false;
 
+        }
+        bool part = busy;
+        for (uint32_t rep = 0;; ++rep) {
+        if (part) {
+            setupWideRay(w);
             const float4* nodes = sc.tlas_nodes;
             const float4* recs  = sc.tlas_recs;
             if (in_mesh) {
@@ -1173,6 +1187,22 @@ __global__ void __launch_bounds__(128, 7) scenePoolTrace(SceneDevice sc, PathSta
                     }
                 }
             }
+            ready = 0;
+            if (0 == retired) {
+                if (kEnd != sv.z) {
+                    ready = 8u;
+                } else {
+                    ready = (node_group.y > 0x00FFFFFFu ? 1u : 0u) | (0 != tri_group.y ? (in_mesh ? 2u : 4u) : 0u);
+                }
+            }
+        }
+        // another step of the same kind while enough of the lanes' rays are ready for one
+        const bool     again = part && 0 != (ready & (1u << kind));
+        const uint32_t more  = __ballot_sync(kFull, again);
+        if (rep + 1u >= tune.repeat || uint32_t(__popc(more)) < tune.repeat_lanes) break;
+        part = again;
+        }
+        if (busy) {
             if (ray_dirty) {
                 pool.a[slot]  = make_float4(w.ray.o.x, w.ray.o.y, w.ray.o.z, tmax0);
                 pool.b[slot]  = make_float4(w.ray.d.x, w.ray.d.y, w.ray.d.z, w.ray.tmax);
@@ -1190,14 +1220,6 @@ __global__ void __launch_bounds__(128, 7) scenePoolTrace(SceneDevice sc, PathSta
                 pool.h[slot].x = sp;
             }
             if (level_dirty) pool.s[slot] = sv;
-            uint32_t ready = 0;
-            if (0 == retired) {
-                if (kEnd != sv.z) {
-                    ready = 8u;
-                } else {
-                    ready = (node_group.y > 0x00FFFFFFu ? 1u : 0u) | (0 != tri_group.y ? (in_mesh ? 2u : 4u) : 0u);
-                }
-            }
             pool.ready[slot] = ready;
         }
         occupied -= __popc(__ballot_sync(kFull, 0 != retired));
@@ -1288,6 +1310,8 @@ const SceneTraceConfig& sceneTraceConfig() {
         c.mesh_min_blocks = envInt("ZYGPU_MESH_MIN_BLOCKS", 0);
         c.pool            = envInt("ZYGPU_SCENE_POOL", -1);  // the ray-pool variant of the fused kernel: 1 on, 0 off, -1 by prop-tree size
         c.pool_fetch_free = envInt("ZYGPU_POOL_FETCH_FREE", 16);
+        c.step.repeat       = uint32_t(std::max(1, envInt("ZYGPU_POOL_REPEAT", 4)));
+        c.step.repeat_lanes = uint32_t(envInt("ZYGPU_POOL_REPEAT_LANES", 16));
         c.sort            = envInt("ZYGPU_RAY_SORT", 0);       // bit 0: closest-hit rays, bit 1: shadow rays
         c.sort_from       = envInt("ZYGPU_RAY_SORT_FROM", 1);  // first bounce that sorts
         c.sort_mode       = envInt("ZYGPU_RAY_SORT_MODE", 1);  // 1: (cell, octant), 2: (octant, cell)
