@@ -5,11 +5,11 @@
  * success, -1 failure / not initialised, -3 bad material id, -4 material update failed). One
  * process-global engine, single caller thread (capi.zig:55).
  *
- * Scope: static scenes, perspective camera (pinhole / thin lens), PTMIS, the built-in shapes Rectangle / Cube /
+ * Scope: static scenes, perspective camera (pinhole / thin lens), PTMIS, the built-in shapes Rectangle / Cube / Disk /
  * Sphere / Canopy / Distant and triangle meshes (props, prop instances, instancers), materials Substitute / Glass / Light with
  * uniform parameters, image maps for colour / roughness / metallic / normal and emission (su_image_create: Float32 or UInt8 x 1, 2, 3),
  * the nine AOV classes next to the beauty. A scene that
- * uses a Disk or Dome prop, thin or dispersive Glass is refused by the render calls (-1 and a log message) rather than rendered
+ * uses a Dome prop, a Disk as a light, thin or dispersive Glass is refused by the render calls (-1 and a log message) rather than rendered
  * wrongly; unsupported material parameters are ignored with a warning through the log callback.
  * Entry points outside that scope exist and return -1 (animation frames other than 0).
  */

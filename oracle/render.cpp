@@ -388,6 +388,51 @@ float pdf(Vec4f p, const Fragment& frag, uint32_t num_samples) {
 
 }  // namespace rectangle
 
+namespace disk {
+
+bool intersect(const Ray& ray, const Trafo& trafo, Intersection& isec) {  // disk.zig:28-58
+    const Vec4f normal = trafo.r[2];
+    const float d      = dot3(normal, trafo.position);
+    const float denom  = -dot3(normal, ray.direction);
+    const float numer  = dot3(normal, ray.origin) - d;
+    const float hit_t  = numer / denom;
+
+    if (hit_t >= ray.min_t && ray.max_t >= hit_t) {
+        const Vec4f p      = ray.point(hit_t);
+        const Vec4f k      = p - trafo.position;
+        const float l      = dot3(k, k);
+        const float radius = 0.5f * trafo.scaleX();
+        if (l <= radius * radius) {
+            const Vec4f sk = k / splat(radius);
+            isec.u         = -dot3(trafo.r[0], sk);
+            isec.v         = -dot3(trafo.r[1], sk);
+            isec.t         = hit_t;
+            isec.primitive = 0;
+            isec.trafo     = trafo;
+            return true;
+        }
+    }
+    return false;
+}
+
+bool intersectP(const Ray& ray, const Trafo& trafo) {  // :115-134
+    Intersection unused;
+    return intersect(ray, trafo, unused);
+}
+
+void fragment(const Ray& ray, Fragment& frag) {  // :98-113
+    const float u = frag.isec.u, v = frag.isec.v;
+    frag.p     = ray.point(frag.isec.t);
+    frag.t     = -frag.isec.trafo.r[0];
+    frag.b     = -frag.isec.trafo.r[1];
+    frag.n     = frag.isec.trafo.r[2];
+    frag.geo_n = frag.isec.trafo.r[2];
+    frag.uvw   = {{0.5f * (u + 1.f), 0.5f * (v + 1.f), 0.f, 0.f}};
+    frag.part  = 0;
+}
+
+}  // namespace disk
+
 namespace cube {
 
 const AABB kUnit = {{{{-0.5f, -0.5f, -0.5f, -0.5f}}, {{0.5f, 0.5f, 0.5f, 0.5f}}}};
@@ -1129,6 +1174,7 @@ struct Scene {
     float shapeArea(uint32_t shape, Vec4f scale) const {  // shape.zig:143-156
         switch (shape) {
             case ZYG_SHAPE_RECTANGLE: return scale[0] * scale[1];
+            case ZYG_SHAPE_DISK: return kPi * ((0.5f * scale[0]) * (0.5f * scale[0]));
             case ZYG_SHAPE_SPHERE: return (4.f * kPi) * pow2(0.5f * scale[0]);
             case ZYG_SHAPE_DISTANT: return distant::solidAngle(scale[0]);  // "the solid angle, not the area", shape.zig:146-148
             case ZYG_SHAPE_CANOPY: return 2.f * kPi;
@@ -1152,6 +1198,7 @@ struct Scene {
             }
             case ZYG_SHAPE_CUBE: return cube::intersect(ray, trafo, isec);
             case ZYG_SHAPE_RECTANGLE: return rectangle::intersect(ray, trafo, isec);
+            case ZYG_SHAPE_DISK: return disk::intersect(ray, trafo, isec);
             case ZYG_SHAPE_SPHERE: return sphere::intersect(ray, trafo, isec);
             case ZYG_SHAPE_DISTANT: return distant::intersect(ray, trafo, isec);
             case ZYG_SHAPE_CANOPY: return canopy::intersect(ray, trafo, isec);
@@ -1163,6 +1210,7 @@ struct Scene {
             case ZYG_SHAPE_TRIANGLE_MESH: return treeOf(mesh_id).intersectP(trafo.worldToObjectRay(ray));  // triangle_mesh.zig:337-340
             case ZYG_SHAPE_CUBE: return cube::intersectP(ray, trafo);
             case ZYG_SHAPE_RECTANGLE: return rectangle::intersectP(ray, trafo);
+            case ZYG_SHAPE_DISK: return disk::intersectP(ray, trafo);
             case ZYG_SHAPE_SPHERE: return sphere::intersectP(ray, trafo);
             default: return false;
         }
@@ -1172,6 +1220,7 @@ struct Scene {
             case ZYG_SHAPE_TRIANGLE_MESH: mesh::fragment(meshes[mesh_id], frag); break;
             case ZYG_SHAPE_CUBE: cube::fragment(ray, frag); break;
             case ZYG_SHAPE_RECTANGLE: rectangle::fragment(ray, frag); break;
+            case ZYG_SHAPE_DISK: disk::fragment(ray, frag); break;
             case ZYG_SHAPE_SPHERE: sphere::fragment(ray, frag); break;
             case ZYG_SHAPE_DISTANT: distant::fragment(ray, frag); break;
             case ZYG_SHAPE_CANOPY: canopy::fragment(ray, frag); break;

@@ -861,3 +861,21 @@ def test_export_frame_writes_the_aov_layers(engine, tmp_path, monkeypatch):
     su.exporters_create({"Image": {"format": "PNG"}})
     su.export_frame()
     assert read_png("image_00_000003_depth.png").shape == (h, w, 1) and read_png("image_00_000003_mat.png").shape == (h, w, 3)
+
+
+@pytest.mark.parametrize("filter_name", [None, "Mitchell"])
+def test_disk_props_match_oracle(engine, filter_name):
+    """Disk.intersect / intersectP / fragment (disk.zig:28-134) as closest-hit and shadow geometry: a glossy, a metallic and an emissive
+    disk that is met by the paths (no next-event estimation towards it)."""
+    w, spp = 128, 16
+    scenes.disk_scene(w, w, spp=spp, filter_name=filter_name)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp)
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    if filter_name is None:
+        assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6
+    assert (rel > 1e-2).mean() < 5e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4

@@ -12,6 +12,7 @@ __device__ __forceinline__ void shapeFragment(const SceneDevice& sc, uint32_t pr
     switch (sc.props[prop].shape) {
         case ZYG_SHAPE_CUBE: cubeFragment(ray, isec, frag); break;
         case ZYG_SHAPE_RECTANGLE: rectangleFragment(ray, isec, frag); break;
+        case ZYG_SHAPE_DISK: diskFragment(ray, isec, frag); break;
         case ZYG_SHAPE_SPHERE: sphereFragment(ray, isec, frag); break;
         // Distant and Canopy are infinite props: only met on escape, where shade_a calls their fragment functions itself
         case ZYG_SHAPE_TRIANGLE_MESH: meshFragment(sc.mesh_shading[sc.props[prop].mesh], isec, frag); break;

@@ -203,6 +203,7 @@ __device__ __forceinline__ void clipToMedium(const SceneDevice& sc, const PathSt
 __device__ __forceinline__ float shapeArea(uint32_t shape, V3 scale) {  // shape.zig:143-156
     switch (shape) {
         case ZYG_SHAPE_RECTANGLE: return scale.x * scale.y;
+        case ZYG_SHAPE_DISK: return kPi * ((0.5f * scale.x) * (0.5f * scale.x));
         case ZYG_SHAPE_SPHERE: return (4.f * kPi) * ((0.5f * scale.x) * (0.5f * scale.x));
         case ZYG_SHAPE_DISTANT: return distantSolidAngle(scale.x);
         case ZYG_SHAPE_CANOPY: return 2.f * kPi;
@@ -219,6 +220,7 @@ __device__ __forceinline__ bool propIntersect(const SceneDevice& sc, uint32_t en
     switch (prop.shape) {
         case ZYG_SHAPE_CUBE: return cubeIntersect(ray, trafo, isec);
         case ZYG_SHAPE_RECTANGLE: return rectangleIntersect(ray, trafo, isec);
+        case ZYG_SHAPE_DISK: return diskIntersect(ray, trafo, isec);
         case ZYG_SHAPE_SPHERE: return sphereIntersect(ray, trafo, isec);
         case ZYG_SHAPE_TRIANGLE_MESH: {
             // TriangleTree.intersect, triangle_tree.zig:46-109: the ray goes to object space un-normalised, so t is shared
@@ -248,6 +250,10 @@ __device__ __forceinline__ bool propVisibility(const SceneDevice& sc, uint32_t e
         case ZYG_SHAPE_RECTANGLE: {
             HitD unused;
             return !rectangleIntersect(ray, trafo, unused);
+        }
+        case ZYG_SHAPE_DISK: {
+            HitD unused;
+            return !diskIntersect(ray, trafo, unused);
         }
         case ZYG_SHAPE_SPHERE: {
             HitD unused;

@@ -695,6 +695,7 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                             switch (prop.shape) {
                                 case ZYG_SHAPE_CUBE: hit = cubeIntersectP(w.ray, trafo); break;
                                 case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, unused); break;
+                                case ZYG_SHAPE_DISK: hit = diskIntersect(w.ray, trafo, unused); break;
                                 case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, unused); break;
                                 default: break;
                             }
@@ -710,6 +711,7 @@ __global__ void __launch_bounds__(128, MinBlocks) sceneTracePersistent(SceneDevi
                             switch (prop.shape) {
                                 case ZYG_SHAPE_CUBE: hit = cubeIntersect(w.ray, trafo, h); break;
                                 case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, h); break;
+                                case ZYG_SHAPE_DISK: hit = diskIntersect(w.ray, trafo, h); break;
                                 case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, h); break;
                                 default: break;
                             }
@@ -1080,6 +1082,7 @@ __global__ void __launch_bounds__(128, 7) scenePoolTrace(SceneDevice sc, PathSta
                         switch (prop.shape) {
                             case ZYG_SHAPE_CUBE: hit = cubeIntersectP(w.ray, trafo); break;
                             case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, unused); break;
+                                case ZYG_SHAPE_DISK: hit = diskIntersect(w.ray, trafo, unused); break;
                             case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, unused); break;
                             default: break;
                         }
@@ -1096,6 +1099,7 @@ __global__ void __launch_bounds__(128, 7) scenePoolTrace(SceneDevice sc, PathSta
                         switch (prop.shape) {
                             case ZYG_SHAPE_CUBE: hit = cubeIntersect(w.ray, trafo, hd); break;
                             case ZYG_SHAPE_RECTANGLE: hit = rectangleIntersect(w.ray, trafo, hd); break;
+                            case ZYG_SHAPE_DISK: hit = diskIntersect(w.ray, trafo, hd); break;
                             case ZYG_SHAPE_SPHERE: hit = sphereIntersect(w.ray, trafo, hd); break;
                             default: break;
                         }

@@ -226,6 +226,43 @@ __device__ __forceinline__ void rectangleFragment(const RayT& ray, const HitD& i
     frag.part = 0;
 }
 
+// Disk.intersect / intersectP, disk.zig:28-58, 115-134
+__device__ __forceinline__ bool diskIntersect(const RayT& ray, const TrafoD& trafo, HitD& isec) {
+    const V3    normal = trafo.r2;
+    const float d      = dot3(normal, trafo.position);
+    const float denom  = -dot3(normal, ray.d);
+    const float numer  = dot3(normal, ray.o) - d;
+    const float hit_t  = __fdiv_rn(numer, denom);
+
+    if (hit_t >= ray.tmin && ray.tmax >= hit_t) {
+        const V3    p      = rayPoint(ray, hit_t);
+        const V3    k      = sub3(p, trafo.position);
+        const float l      = dot3(k, k);
+        const float radius = 0.5f * trafo.scale.x;
+        if (l <= radius * radius) {
+            const V3 sk    = divs3(k, radius);
+            isec.u         = -dot3(trafo.r0, sk);
+            isec.v         = -dot3(trafo.r1, sk);
+            isec.t         = hit_t;
+            isec.primitive = 0;
+            return true;
+        }
+    }
+    return false;
+}
+
+// Disk.fragment, disk.zig:98-113
+__device__ __forceinline__ void diskFragment(const RayT& ray, const HitD& isec, FragD& frag) {
+    frag.p     = rayPoint(ray, isec.t);
+    frag.t     = neg3(frag.trafo.r0);
+    frag.b     = neg3(frag.trafo.r1);
+    frag.n     = frag.trafo.r2;
+    frag.geo_n = frag.trafo.r2;
+    frag.u     = 0.5f * (isec.u + 1.f);
+    frag.v     = 0.5f * (isec.v + 1.f);
+    frag.part  = 0;
+}
+
 // AABB.intersectP on the unit cube, aabb.zig:62-84
 __device__ __forceinline__ float unitCubeIntersectP(const RayT& ray) {
     const float lx = (-0.5f - ray.o.x) * ray.inv_d.x, ly = (-0.5f - ray.o.y) * ray.inv_d.y, lz = (-0.5f - ray.o.z) * ray.inv_d.z;

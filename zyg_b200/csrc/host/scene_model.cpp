@@ -989,8 +989,9 @@ bool SceneModel::compile(std::string& error) {
     const std::vector<float>& luts = ggxLuts(error);
     if (luts.empty()) return false;
 
-    // The device intersects Rectangle, Cube, Sphere, triangle meshes, Distant and Canopy. A Disk or Dome prop would be silently
-    // invisible (and black as a light): refuse the scene instead, like thin or dispersive Glass at upload.
+    // The device intersects Rectangle, Cube, Disk, Sphere, triangle meshes, Distant and Canopy. A Dome prop would be silently invisible,
+    // a Disk registered as a light (Disk.sampleTo: equi-angular sampling, disk.zig:252-360) or as an un-occluding emitter black: refuse
+    // the scene instead, like thin or dispersive Glass at upload.
     for (const PropRec& p : props_) {
         if (ZYGPU_NULL != p.shape && p.shape >= 7 && !meshes_[p.shape - 7].mesh) {
             error = "shape " + std::to_string(p.shape) + " has no triangle tree (its build failed)";
@@ -999,16 +1000,22 @@ bool SceneModel::compile(std::string& error) {
     }
     for (const std::vector<uint32_t>* list : {&finite_props_, &unoccluding_props_, &infinite_props_}) {
         for (uint32_t id : *list) {
-            if (ZYG_SHAPE_DISK == props_[id].shape || ZYG_SHAPE_DOME == props_[id].shape) {
-                error = "prop " + std::to_string(id) + ": the shapes Disk and Dome are not supported by the device path";
+            if (ZYG_SHAPE_DOME == props_[id].shape || (ZYG_SHAPE_DISK == props_[id].shape && list == &unoccluding_props_)) {
+                error = "prop " + std::to_string(id) + ": the shape Dome and un-occluding Disk emitters are not supported by the device path";
                 return false;
             }
         }
     }
+    for (const ZygpuLight& l : lights_) {
+        if (l.prop < props_.size() && ZYG_SHAPE_DISK == props_[l.prop].shape) {
+            error = "prop " + std::to_string(l.prop) + ": a Disk as a light is not supported by the device path (a Disk prop is)";
+            return false;
+        }
+    }
     for (const InstancerRec& ir : instancers_) {
         for (uint32_t proto : ir.prototypes) {
-            if (ZYG_SHAPE_DISK == props_[proto].shape || ZYG_SHAPE_DOME == props_[proto].shape) {
-                error = "prop " + std::to_string(proto) + ": the shapes Disk and Dome are not supported by the device path";
+            if (ZYG_SHAPE_DOME == props_[proto].shape) {
+                error = "prop " + std::to_string(proto) + ": the shape Dome is not supported by the device path";
                 return false;
             }
         }

@@ -526,6 +526,44 @@ def coated_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None, q
     return 1
 
 
+def disk_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None):
+    """Disk props (disk.zig:28-134): a glossy disk table top on a diffuse floor, a tilted metal disk that casts a round shadow, and an
+    emissive disk that is not registered as a light (its emission is met by the paths, without next-event estimation), under a
+    Rectangle lamp. Disk lights (Disk.sampleTo) are outside the scope."""
+    from . import su
+
+    su.init()
+    camera = su.perspective_camera_create(width, height)
+    su.camera_set_fov(float(np.radians(55.0)))
+    su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.6, -4.2), rotation_deg=(-14.0, 0.0, 0.0)))
+    su.sampler_create(spp)
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth}}}})
+    su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
+
+    floor = su.material_create({"rendering": {"Substitute": {"color": [0.55, 0.55, 0.5], "roughness": 1.0}}})
+    g = su.prop_create(su.RECTANGLE, [floor])
+    su.prop_set_transformation(g, su.transformation((0.0, 0.0, 0.0), (12.0, 12.0, 1.0), (90.0, 0.0, 0.0)))
+
+    top = su.material_create({"rendering": {"Substitute": {"color": [0.2, 0.35, 0.6], "roughness": 0.25, "two_sided": True}}})
+    table = su.prop_create(su.DISK, [top])
+    su.prop_set_transformation(table, su.transformation((-0.9, 0.6, 0.3), (2.0, 2.0, 1.0), (90.0, 0.0, 0.0)))
+
+    metal = su.material_create({"rendering": {"Substitute": {"color": [0.95, 0.8, 0.5], "roughness": 0.3, "metallic": 1.0, "two_sided": True}}})
+    mirror = su.prop_create(su.DISK, [metal])
+    su.prop_set_transformation(mirror, su.transformation((1.3, 1.1, 0.8), (1.6, 1.6, 1.0), (20.0, -35.0, 0.0)))
+
+    glow = su.material_create({"rendering": {"Substitute": {"color": [0.0, 0.0, 0.0], "roughness": 1.0, "two_sided": True,
+                                                             "emittance": {"value": 3.0}}}})
+    lamp_disk = su.prop_create(su.DISK, [glow])
+    su.prop_set_transformation(lamp_disk, su.transformation((0.4, 0.35, -0.9), (0.7, 0.7, 1.0), (0.0, 0.0, 0.0)))
+
+    light = su.material_create({"rendering": {"Light": {"emittance": {"value": 25.0}}}})
+    lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=True)
+    su.prop_set_transformation(lamp, su.transformation((0.0, 4.0, -0.5), (2.0, 2.0, 1.0), (-90.0, 0.0, 0.0)))
+    su.light_create(lamp)
+    return 0
+
+
 def image_light_scene(width=128, height=128, spp=16, max_depth=5, filter_name=None, split_threshold=0.5, num_samples=1,
                       image=None, value=6.0, two_sided=False, unoccluding=True):
     """A closed room lit by a Rectangle whose Light material carries an emission image (a PropImage light on a finite shape:
