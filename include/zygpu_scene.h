@@ -301,6 +301,22 @@ enum { /* aov.Value.Class, aov_value.zig:10-20 */
     ZYG_AOV_NUM_CLASSES      = 9
 };
 
+/* Records that are the reference's own, byte for byte: their sizes are pinned to the numbers the reference checks for itself
+ * (src/core/size_test.zig:36-47: ComposedTransformation 64, BvhNode 32, LightNode 32, Pack4f 16). */
+#if defined(__cplusplus)
+static_assert(sizeof(ZygpuTrafo) == 64, "ComposedTransformation");
+static_assert(sizeof(ZygpuBvhNode) == 32, "bvh.Node");
+static_assert(sizeof(ZygpuLightNode) == 32, "light_tree.Node");
+static_assert(sizeof(ZygpuAabb) == 32, "math.AABB = 2 x Vec4f");
+static_assert(sizeof(ZygpuMaterial) == 144, "ZygpuMaterial");
+#else
+_Static_assert(sizeof(ZygpuTrafo) == 64, "ComposedTransformation");
+_Static_assert(sizeof(ZygpuBvhNode) == 32, "bvh.Node");
+_Static_assert(sizeof(ZygpuLightNode) == 32, "light_tree.Node");
+_Static_assert(sizeof(ZygpuAabb) == 32, "math.AABB = 2 x Vec4f");
+_Static_assert(sizeof(ZygpuMaterial) == 144, "ZygpuMaterial");
+#endif
+
 #ifdef __cplusplus
 }
 #endif

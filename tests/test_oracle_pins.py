@@ -160,3 +160,19 @@ def test_bilinear_lookup_reproduces_reference_E_m_avg_table():
         got[a] = oracle.ggx_micro_average_albedo(luts, float(alpha))
         alpha = np.float32(alpha + step)
     assert np.abs(got - e_m_avg).max() < 2e-7, np.abs(got - e_m_avg).max()
+
+
+def test_reference_record_sizes_are_pinned_in_the_abi_header(tmp_path):
+    """The records the device ABI shares with the reference byte for byte carry the sizes the reference checks for itself
+    (src/core/size_test.zig:36-47: ComposedTransformation 64, BvhNode 32, LightNode 32): static assertions in include/zygpu_scene.h,
+    compiled here as C and as C++."""
+    import shutil
+    import subprocess
+
+    include = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    for compiler, name in (("gcc", "t.c"), ("g++", "t.cpp")):
+        if not shutil.which(compiler):
+            pytest.skip("no host compiler")
+        src = tmp_path / name
+        src.write_text('#include "zygpu_scene.h"\n#include "zygpu.h"\n#include "zyg_su.h"\nint main(void) { return 0; }\n')
+        subprocess.run([compiler, "-I", include, "-fsyntax-only", str(src)], check=True)
