@@ -5,6 +5,7 @@ The reference ships no tests; PCG32 is a published generator who
 """
 
 import numpy as np
+import pytest
 
 import oracle_lib as oracle
 from zyg_b200 import scenes
