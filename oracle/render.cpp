@@ -431,6 +431,126 @@ void fragment(const Ray& ray, Fragment& frag) {  // :98-113
     frag.part  = 0;
 }
 
+// DiskSamplerData + EquiAngularSampling, disk.zig:181-250
+struct DiskSamplerData {
+    Vec4f xd, yd;
+    static DiskSamplerData init(Vec4f p) {
+        const Vec4f td = {{p[1], -p[0], 0.f, 0.f}};
+        const Vec4f xd = (0.f == td[0] && 0.f == td[1] && 0.f == td[2]) ? Vec4f{{1.f, 0.f, 0.f, 0.f}} : normalize3(td);
+        return {xd, {{-xd[1], xd[0], 0.f, 0.f}}};
+    }
+};
+
+struct EquiAngularSampling {
+    float offset, min_t, max_t, scale, scale_sqr, angle_min, angle_extent;
+
+    static EquiAngularSampling init(Vec4f source, Vec4f origin, Vec4f direction, float min_t, float max_t) {
+        const float offset    = dot3(direction, source - origin) / squaredLength3(direction);
+        const float scale_sqr = squaredLength3((origin + splat(offset) * direction) - source);
+        const float scale     = std::sqrt(scale_sqr);
+        const float inv_scale = 0.f == scale ? 0.f : 1.f / scale;
+        const float angle_min = std::atan((min_t - offset) * inv_scale);
+        const float angle_max = std::atan((max_t - offset) * inv_scale);
+        return {offset, min_t, max_t, scale, scale_sqr, angle_min, angle_max - angle_min};
+    }
+    float sample(float u, float& t) const {
+        const float lt = scale * std::tan(angle_min + u * angle_extent);
+        const float p  = scale / (angle_extent * (scale_sqr + lt * lt));
+        t              = clamp(lt + offset, min_t, max_t);
+        return p;
+    }
+    float pdf(float t) const {
+        if (min_t <= t && t < max_t) {
+            const float lt = t - offset;
+            return scale / (angle_extent * (scale_sqr + lt * lt));
+        }
+        return 0.f;
+    }
+    float pdfAndSample(float t, float& u) const {
+        const float lt = t - offset;
+        u              = saturate((std::atan(lt / scale) - angle_min) / angle_extent);
+        return scale / (angle_extent * (scale_sqr + lt * lt));
+    }
+};
+
+// Disk.sampleTo, disk.zig:252-332 (UseEquiAngularSampling = true)
+uint32_t sampleTo(Vec4f p, Vec4f n, const Trafo& trafo, bool two_sided, bool total_sphere, uint32_t num_samples, Sampler& sampler,
+                  SampleTo* buffer) {
+    const float nsf    = float(num_samples);
+    const float radius = 0.5f * trafo.scaleX();
+
+    const Vec4f               lp   = trafo.worldToFramePoint(p);
+    const DiskSamplerData     dsd  = DiskSamplerData::init(lp);
+    const EquiAngularSampling eas0 = EquiAngularSampling::init(lp, splat(0.f), dsd.yd, -radius, radius);
+    if (0.f == eas0.angle_extent) return 0;
+
+    uint32_t current_sample = 0;
+    for (uint32_t i = 0; i < num_samples; ++i) {
+        const Vec2f r2 = sampler.sample2D();
+        float       xy[2];
+        diskConcentric(r2.v, xy);
+
+        float u    = xy[0];
+        float pdf_ = std::sqrt(1.f - u * u) / (0.25f * kPi);
+        u          = (u + 1.f) * 0.5f;
+
+        float y_coord;
+        pdf_ *= eas0.sample(u, y_coord);
+
+        const float x_chord = std::sqrt(radius * radius - y_coord * y_coord);
+        if (0.f == x_chord) continue;
+
+        const EquiAngularSampling eas1 = EquiAngularSampling::init(lp, splat(y_coord) * dsd.yd, dsd.xd, -x_chord, x_chord);
+        if (0.f == eas1.angle_extent) continue;
+
+        float x_coord;
+        pdf_ *= eas1.sample(sampler.sample1D(), x_coord);
+
+        const Vec4f l_direction = splat(x_coord) * dsd.xd + splat(y_coord) * dsd.yd - lp;
+        const Vec4f axis        = trafo.objectToWorldNormal(l_direction);
+        const Vec4f ws          = p + axis;
+
+        Vec4f wn = trafo.r[2];
+        if (two_sided && dot3(wn, ws - p) > 0.f) wn = -wn;
+
+        const float sl  = squaredLength3(axis);
+        const Vec4f dir = axis / splat(std::sqrt(sl));
+        const float c   = -dot3(wn, dir);
+        if (c < safe::DotMin || (dot3(dir, n) <= 0.f && !total_sphere)) continue;
+
+        const float v            = (xy[1] + 1.f) * 0.5f;
+        buffer[current_sample++] = {{{ws[0], ws[1], ws[2], (nsf * pdf_ * sl) / c}}, wn, dir, {{u, v, 0.f, 0.f}}};
+    }
+    return current_sample;
+}
+
+// Disk.pdf, disk.zig:492-533
+float pdf(Vec4f dir, Vec4f p, const Fragment& frag, uint32_t num_samples) {
+    const float c      = std::fabs(dot3(frag.isec.trafo.r[2], dir));
+    const float nsf    = float(num_samples);
+    const float radius = 0.5f * frag.isec.trafo.scaleX();
+    const float sl     = squaredDistance3(p, frag.p);
+
+    const Vec4f               lp      = frag.isec.trafo.worldToFramePoint(p);
+    const DiskSamplerData     dsd     = DiskSamplerData::init(lp);
+    const EquiAngularSampling eas0    = EquiAngularSampling::init(lp, splat(0.f), dsd.yd, -radius, radius);
+    const Vec4f               l_point = frag.isec.trafo.worldToFramePoint(frag.p);
+    const float               y_coord = dot3(l_point, dsd.yd);
+
+    float       u;
+    const float eas_pdf = eas0.pdfAndSample(y_coord, u);
+    u                   = u * 2.f - 1.f;
+    float pdf_          = std::sqrt(1.f - u * u) / (0.25f * kPi);
+    pdf_ *= eas_pdf;
+
+    const float               x_chord = std::sqrt(radius * radius - y_coord * y_coord);
+    const EquiAngularSampling eas1    = EquiAngularSampling::init(lp, splat(y_coord) * dsd.yd, dsd.xd, -x_chord, x_chord);
+    const float               x_coord = dot3(l_point, dsd.xd);
+    pdf_ *= eas1.pdf(x_coord);
+
+    return (nsf * pdf_ * sl) / c;
+}
+
 }  // namespace disk
 
 namespace cube {
@@ -1816,6 +1936,7 @@ struct Scene {
                 return rectangle::sampleTo(p, n, trafo, 0 != l.two_sided, total_sphere, num_samples, sampler, buffer);
             case ZYG_SHAPE_DISTANT: return distant::sampleTo(n, trafo, total_sphere, sampler, buffer);
             case ZYG_SHAPE_SPHERE: return sphere::sampleTo(p, n, trafo, total_sphere, num_samples, sampler, buffer);
+            case ZYG_SHAPE_DISK: return disk::sampleTo(p, n, trafo, 0 != l.two_sided, total_sphere, num_samples, sampler, buffer);
             case ZYG_SHAPE_CANOPY:  // Light.propSampleMaterialTo -> Shape.sampleMaterialTo, light.zig:191-215, shape.zig:348-371
                 if (ZYG_LIGHT_PROP_IMAGE != l.light_class) return 0;  // Canopy.sampleTo (uniform sky) is not in scope
                 return canopy::sampleMaterialTo(n, trafo, total_sphere, image_samplers[l.sampler], sampler, buffer);
@@ -2032,6 +2153,9 @@ struct Worker {
                                                           scene.lightNumSamples(l, vertex.light_split_threshold), scene.image_samplers[l.sampler])
                                  : rectangle::pdf(vertex.origin, frag, scene.lightNumSamples(l, vertex.light_split_threshold));
                 break;
+            case ZYG_SHAPE_DISK:
+                sample_pdf = disk::pdf(vertex.ray.direction, vertex.origin, frag, scene.lightNumSamples(l, vertex.light_split_threshold));
+                break;
             case ZYG_SHAPE_DISTANT: sample_pdf = 1.f / distant::solidAngle(frag.isec.trafo.scaleX()); break;  // distant.zig:139-141
             case ZYG_SHAPE_SPHERE:
                 sample_pdf = sphere::pdf(vertex.origin, frag.isec.trafo, scene.lightNumSamples(l, vertex.light_split_threshold));
@@ -2116,6 +2240,10 @@ struct Worker {
             case ZYG_SHAPE_RECTANGLE:
                 if (!rectangle::intersect(vertex.ray, frag.isec.trafo, frag.isec)) return splat(0.f);
                 rectangle::fragment(vertex.ray, frag);
+                return evaluateRadiance(vertex, frag, sampler);
+            case ZYG_SHAPE_DISK:  // Disk.emission, disk.zig:171-179
+                if (!disk::intersect(vertex.ray, frag.isec.trafo, frag.isec)) return splat(0.f);
+                disk::fragment(vertex.ray, frag);
                 return evaluateRadiance(vertex, frag, sampler);
             case ZYG_SHAPE_TRIANGLE_MESH: {  // Mesh.emission -> Tree.emission, triangle_mesh.zig:379-388, triangle_tree.zig:405-477
                 const Ray    local_ray = frag.isec.trafo.worldToObjectRay(vertex.ray);

@@ -879,3 +879,21 @@ def test_disk_props_match_oracle(engine, filter_name):
     assert np.median(rel) < 5e-6
     assert (rel > 1e-2).mean() < 5e-3
     assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4
+
+
+@pytest.mark.parametrize("deferred, split_threshold, num_samples", [(False, 0.5, 1), (False, 0.0, 4), (True, 0.5, 3)])
+def test_disk_lights_match_oracle(engine, monkeypatch, deferred, split_threshold, num_samples):
+    """Disk.sampleTo (equi-angular sampling of the chord through the shading point's foot, disk.zig:181-332), Disk.pdf (:492-533) for
+    paths that meet the lit disk and Disk.emission (:171-179) for the un-occluding lamp; in the shade kernel and in the light kernels."""
+    monkeypatch.setenv("ZYGPU_DEFERRED_LIGHTS", "1" if deferred else "0")
+    w, spp = 128, 16
+    scenes.disk_scene(w, w, spp=spp, disk_lights=True, split_threshold=split_threshold, num_samples=num_samples)
+    scene, view = su.compile_scene()
+    ref = oracle.render(scene, view, w, w, 0, spp, wavefront_light_order=True)  # two lights: several picks per vertex
+    su.render_frame(0)
+    gpu = download_film(w, w)
+    assert np.array_equal(gpu[..., 3], ref[..., 3])
+    rel = rel_error(gpu, ref)
+    assert np.median(rel) < 5e-6
+    assert (rel > 1e-2).mean() < 5e-3
+    assert abs(gpu[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 2e-4

@@ -302,6 +302,8 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
     r.has_image_area_lights = false;
     for (uint32_t l = 0; l < scene->num_lights; ++l) {
         const ZygpuLight& light = scene->lights[l];
+        // Disk.sampleTo lives in the shade kernel instances that carry the rarer features (device/render.cu shadeAKernel<.., Textured>)
+        if (light.prop < scene->num_props && ZYG_SHAPE_DISK == scene->props[light.prop].shape) r.has_textures = true;
         if (ZYG_LIGHT_PROP_IMAGE != light.light_class) continue;
         const uint32_t shape = scene->props[light.prop].shape;
         if (ZYG_SHAPE_CANOPY != shape && ZYG_SHAPE_RECTANGLE != shape) {

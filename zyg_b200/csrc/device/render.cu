@@ -670,6 +670,10 @@ __device__ __forceinline__ float sceneLightPdf(const SceneDevice& sc, const Vert
         sample_pdf = __fdiv_rn(1.f, distantSolidAngle(frag.trafo.scale.x));
     } else if (ZYG_SHAPE_SPHERE == sc.props[l.prop].shape) {  // Sphere.pdf, sphere.zig:472-487
         sample_pdf = float(lightNumSamples(l, vertex.light_split_threshold)) * sphereLightPdf(frag.trafo, vertex.origin);
+    } else if (ZYG_SHAPE_DISK == sc.props[l.prop].shape) {  // Disk.pdf, disk.zig:492-533
+        sample_pdf = diskLightPdfLocal(frag.trafo.worldToFramePoint(vertex.origin), frag.trafo.worldToFramePoint(frag.p), 0.5f * frag.trafo.scale.x,
+                                       fabsf(dot3(frag.trafo.r2, vertex.ray.d)), squaredLength3(sub3(vertex.origin, frag.p)),
+                                       float(lightNumSamples(l, vertex.light_split_threshold)));
     } else if (ZYG_SHAPE_CANOPY == sc.props[l.prop].shape) {  // Light.propMaterialPdf -> Shape.materialPdf, shape.zig:519
         if (ZYG_LIGHT_PROP_IMAGE == l.light_class) sample_pdf = __fdiv_rn(imagePdf(sc.image_samplers[l.sampler], frag.u, frag.v), 2.f * kPi);
     } else if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == sc.props[l.prop].shape && ZYGPU_NULL != l.sampler) {
@@ -767,7 +771,7 @@ __device__ __forceinline__ V3 propEmission(const SceneDevice& sc, uint32_t entit
     if (!propVisible(prop.flags, vertex.probe_depth)) return splat3(0.f);
     if (!aabbIntersect(sc.aabbs, entity, vertex.ray)) return splat3(0.f);
     if (MeshLights && ZYG_SHAPE_TRIANGLE_MESH == prop.shape) return meshEmission<MeshLights>(sc, entity, prop, vertex, sampler);
-    if (ZYG_SHAPE_RECTANGLE != prop.shape && ZYG_SHAPE_SPHERE != prop.shape) return splat3(0.f);
+    if (ZYG_SHAPE_RECTANGLE != prop.shape && ZYG_SHAPE_SPHERE != prop.shape && ZYG_SHAPE_DISK != prop.shape) return splat3(0.f);
 
     FragD frag;
     frag.prop  = entity;
@@ -776,6 +780,9 @@ __device__ __forceinline__ V3 propEmission(const SceneDevice& sc, uint32_t entit
     if (ZYG_SHAPE_SPHERE == prop.shape) {  // Sphere.emission, sphere.zig:271-279
         if (!sphereIntersect(vertex.ray, frag.trafo, isec)) return splat3(0.f);
         sphereFragment(vertex.ray, isec, frag);
+    } else if (ZYG_SHAPE_DISK == prop.shape) {  // Disk.emission, disk.zig:171-179
+        if (!diskIntersect(vertex.ray, frag.trafo, isec)) return splat3(0.f);
+        diskFragment(vertex.ray, isec, frag);
     } else {
         if (!rectangleIntersect(vertex.ray, frag.trafo, isec)) return splat3(0.f);
         rectangleFragment(vertex.ray, isec, frag);
@@ -1337,6 +1344,29 @@ __global__ void __launch_bounds__(kBlock, ZYGPU_SHADE_BLOCKS) shadeAKernel(Scene
                             }
                             continue;
                         }
+                        if (Textured && ZYG_SHAPE_DISK == shape) {  // Disk.sampleTo, disk.zig:252-332
+                            DiskLightD dl;
+                            dl.init(trafo, p);
+                            if (!dl.valid) continue;
+                            const uint32_t ns = lightNumSamples(light, vertex.light_split_threshold);
+                            for (uint32_t k = 0; k < ns; ++k) {
+                                V3    lp, wn, dir;
+                                float pdf;
+                                if (!dl.sample(trafo, p, n, 0 != light.two_sided, translucent, float(ns), sampler, lp, wn, dir, pdf)) continue;
+                                if (num_records < st.shadow_stride) {
+                                    const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+                                    const V3     origin    = frag.offsetP(dir);
+                                    const V3     light_pos = offsetRay(lp, wn);
+                                    st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, pdf * pick.pdf);
+                                    st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+                                    st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                                    num_records += 1;
+                                } else {
+                                    st.counters[3] = 1;
+                                }
+                            }
+                            continue;
+                        }
                         if (ZYG_SHAPE_RECTANGLE == shape && ZYG_LIGHT_PROP_IMAGE == light.light_class) {  // Rectangle.sampleMaterialTo
                             const uint32_t            ns   = lightNumSamples(light, vertex.light_split_threshold);
                             const ImageSamplerDevice& is   = sc.image_samplers[light.sampler];
@@ -1707,6 +1737,26 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                         const V3     origin    = offsetPoint(p, geo_n, dir);
                         const V3     light_pos = offsetRay(lp, wn);
                         st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, (float(ns) * pdf) * pick.pdf);
+                        st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+                        st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+                        num_records += 1;
+                    } else {
+                        st.counters[3] = 1;
+                    }
+                }
+            } else if (kFinitePicks && ZYG_SHAPE_DISK == shape) {  // Disk.sampleTo, disk.zig:252-332
+                DiskLightD dl;
+                dl.init(trafo, p);
+                const uint32_t ns = dl.valid ? lightNumSamples(light, threshold) : 0;
+                for (uint32_t k = 0; k < ns; ++k) {
+                    V3    lp, wn, dir;
+                    float pdf;
+                    if (!dl.sample(trafo, p, n, 0 != light.two_sided, translucent, float(ns), sampler, lp, wn, dir, pdf)) continue;
+                    if (num_records < st.shadow_stride) {
+                        const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+                        const V3     origin    = offsetPoint(p, geo_n, dir);
+                        const V3     light_pos = offsetRay(lp, wn);
+                        st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, pdf * pick.pdf);
                         st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
                         st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
                         num_records += 1;

@@ -263,6 +263,117 @@ __device__ __forceinline__ void diskFragment(const RayT& ray, const HitD& isec, 
     frag.part  = 0;
 }
 
+// Disk as a light: DiskSamplerData + EquiAngularSampling + Disk.sampleTo / pdf, disk.zig:181-332, 492-533 (UseEquiAngularSampling)
+struct EquiAngularD {
+    float offset, min_t, max_t, scale, scale_sqr, angle_min, angle_extent;
+
+    __device__ __forceinline__ void init(V3 source, V3 origin, V3 direction, float mi, float ma) {
+        offset                = __fdiv_rn(dot3(direction, sub3(source, origin)), squaredLength3(direction));
+        const V3 foot         = sub3(add3(origin, scale3(offset, direction)), source);
+        scale_sqr             = squaredLength3(foot);
+        scale                 = __fsqrt_rn(scale_sqr);
+        const float inv_scale = 0.f == scale ? 0.f : __fdiv_rn(1.f, scale);
+        angle_min             = atanf((mi - offset) * inv_scale);
+        const float angle_max = atanf((ma - offset) * inv_scale);
+        angle_extent          = angle_max - angle_min;
+        min_t                 = mi;
+        max_t                 = ma;
+    }
+    __device__ __forceinline__ float sample(float u, float& t) const {
+        const float lt = scale * tanf(angle_min + u * angle_extent);
+        const float p  = __fdiv_rn(scale, angle_extent * (scale_sqr + lt * lt));
+        t              = zclamp(lt + offset, min_t, max_t);
+        return p;
+    }
+    __device__ __forceinline__ float pdf(float t) const {
+        if (min_t <= t && t < max_t) {
+            const float lt = t - offset;
+            return __fdiv_rn(scale, angle_extent * (scale_sqr + lt * lt));
+        }
+        return 0.f;
+    }
+    __device__ __forceinline__ float pdfAndSample(float t, float& u) const {
+        const float lt = t - offset;
+        u              = saturate(__fdiv_rn(atanf(__fdiv_rn(lt, scale)) - angle_min, angle_extent));
+        return __fdiv_rn(scale, angle_extent * (scale_sqr + lt * lt));
+    }
+};
+
+struct DiskLightD {
+    V3           lp, xd, yd;
+    float        radius;
+    EquiAngularD eas0;
+    bool         valid;
+
+    __device__ __forceinline__ void init(const TrafoD& trafo, V3 p) { initLocal(trafo.worldToFramePoint(p), 0.5f * trafo.scale.x); }
+    __device__ __forceinline__ void initLocal(V3 local_p, float r) {
+        radius      = r;
+        lp          = local_p;
+        const V3 td = {lp.y, -lp.x, 0.f};
+        xd          = (0.f == td.x && 0.f == td.y) ? V3{1.f, 0.f, 0.f} : normalize3(td);
+        yd          = {-xd.y, xd.x, 0.f};
+        eas0.init(lp, splat3(0.f), yd, -radius, radius);
+        valid = 0.f != eas0.angle_extent;
+    }
+    // one sample of Disk.sampleTo's loop; false = the reference's `continue`
+    template <typename Sampler>
+    __device__ __forceinline__ bool sample(const TrafoD& trafo, V3 p, V3 n, bool two_sided, bool total_sphere, float nsf, Sampler& sampler, V3& ws,
+                                           V3& wn, V3& dir, float& pdf) const {
+        float u0, u1;
+        sampler.sample2D(u0, u1);
+        float x, y;
+        diskConcentric(u0, u1, x, y);
+        float u    = x;
+        float pdf_ = __fdiv_rn(__fsqrt_rn(1.f - u * u), 0.25f * kPi);
+        u          = (u + 1.f) * 0.5f;
+
+        float y_coord;
+        pdf_ *= eas0.sample(u, y_coord);
+
+        const float x_chord = __fsqrt_rn(radius * radius - y_coord * y_coord);
+        if (0.f == x_chord) return false;
+
+        EquiAngularD eas1;
+        eas1.init(lp, scale3(y_coord, yd), xd, -x_chord, x_chord);
+        if (0.f == eas1.angle_extent) return false;
+
+        float x_coord;
+        pdf_ *= eas1.sample(sampler.sample1D(), x_coord);
+
+        const V3 l_direction = sub3(add3(scale3(x_coord, xd), scale3(y_coord, yd)), lp);
+        const V3 axis        = trafo.objectToWorldNormal(l_direction);
+        ws                   = add3(p, axis);
+        wn                   = trafo.r2;
+        if (two_sided && dot3(wn, sub3(ws, p)) > 0.f) wn = neg3(wn);
+
+        const float sl = squaredLength3(axis);
+        dir            = divs3(axis, __fsqrt_rn(sl));
+        const float c  = -dot3(wn, dir);
+        if (c < kDotMin || (dot3(dir, n) <= 0.f && !total_sphere)) return false;
+        pdf = __fdiv_rn((nsf * pdf_) * sl, c);
+        return true;
+    }
+};
+
+// Disk.pdf, disk.zig:492-533, in the disk's frame: lp = where the ray started, l_point = where it met the disk, c = |n . dir|, sl = the
+// squared distance between the two. Out of line and on plain values: it sits on the emission path of every shade kernel instance, and
+// inlined its atanf chains raise the spills of the instances that never see a Disk light.
+static __device__ __noinline__ float diskLightPdfLocal(V3 lp, V3 l_point, float radius, float c, float sl, float nsf) {
+    DiskLightD dl;
+    dl.initLocal(lp, radius);
+    const float y_coord = dot3(l_point, dl.yd);
+    float       u;
+    const float eas_pdf = dl.eas0.pdfAndSample(y_coord, u);
+    u                   = u * 2.f - 1.f;
+    float pdf_          = __fdiv_rn(__fsqrt_rn(1.f - u * u), 0.25f * kPi);
+    pdf_ *= eas_pdf;
+    const float  x_chord = __fsqrt_rn(dl.radius * dl.radius - y_coord * y_coord);
+    EquiAngularD eas1;
+    eas1.init(dl.lp, scale3(y_coord, dl.yd), dl.xd, -x_chord, x_chord);
+    pdf_ *= eas1.pdf(dot3(l_point, dl.xd));
+    return __fdiv_rn((nsf * pdf_) * sl, c);
+}
+
 // AABB.intersectP on the unit cube, aabb.zig:62-84
 __device__ __forceinline__ float unitCubeIntersectP(const RayT& ray) {
     const float lx = (-0.5f - ray.o.x) * ray.inv_d.x, ly = (-0.5f - ray.o.y) * ray.inv_d.y, lz = (-0.5f - ray.o.z) * ray.inv_d.z;

@@ -989,9 +989,9 @@ bool SceneModel::compile(std::string& error) {
     const std::vector<float>& luts = ggxLuts(error);
     if (luts.empty()) return false;
 
-    // The device intersects Rectangle, Cube, Disk, Sphere, triangle meshes, Distant and Canopy. A Dome prop would be silently invisible,
-    // a Disk registered as a light (Disk.sampleTo: equi-angular sampling, disk.zig:252-360) or as an un-occluding emitter black: refuse
-    // the scene instead, like thin or dispersive Glass at upload.
+    // The device intersects Rectangle, Cube, Disk, Sphere, triangle meshes, Distant and Canopy. A Dome prop would be silently invisible and
+    // a Disk light with an emission map (Disk.sampleMaterialTo, disk.zig:334-412) would be sampled uniformly: refuse the scene instead,
+    // like thin or dispersive Glass at upload.
     for (const PropRec& p : props_) {
         if (ZYGPU_NULL != p.shape && p.shape >= 7 && !meshes_[p.shape - 7].mesh) {
             error = "shape " + std::to_string(p.shape) + " has no triangle tree (its build failed)";
@@ -1000,16 +1000,10 @@ bool SceneModel::compile(std::string& error) {
     }
     for (const std::vector<uint32_t>* list : {&finite_props_, &unoccluding_props_, &infinite_props_}) {
         for (uint32_t id : *list) {
-            if (ZYG_SHAPE_DOME == props_[id].shape || (ZYG_SHAPE_DISK == props_[id].shape && list == &unoccluding_props_)) {
-                error = "prop " + std::to_string(id) + ": the shape Dome and un-occluding Disk emitters are not supported by the device path";
+            if (ZYG_SHAPE_DOME == props_[id].shape) {
+                error = "prop " + std::to_string(id) + ": the shape Dome is not supported by the device path";
                 return false;
             }
-        }
-    }
-    for (const ZygpuLight& l : lights_) {
-        if (l.prop < props_.size() && ZYG_SHAPE_DISK == props_[l.prop].shape) {
-            error = "prop " + std::to_string(l.prop) + ": a Disk as a light is not supported by the device path (a Disk prop is)";
-            return false;
         }
     }
     for (const InstancerRec& ir : instancers_) {
@@ -1150,6 +1144,10 @@ bool SceneModel::compile(std::string& error) {
         const uint32_t        light_material = material_ids_[p.parts_start + light.part];
         const ImageSamplerRec* image_sampler = nullptr;
         light.light_class                    = ZYG_LIGHT_PROP;
+        if (ZYG_SHAPE_DISK == p.shape && ZYGPU_NULL != emission_maps_[light_material].image) {
+            error = "prop " + std::to_string(light.prop) + ": a Disk light with an emission map is not supported by the device path";
+            return false;
+        }
         if (p.shape < 7 && ZYGPU_NULL != emission_maps_[light_material].image) {
             light.light_class = ZYG_LIGHT_PROP_IMAGE;
             light.sampler     = imageSampler(light_material, p.shape);

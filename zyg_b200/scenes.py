@@ -526,10 +526,11 @@ def coated_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None, q
     return 1
 
 
-def disk_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None):
+def disk_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None, disk_lights=False, split_threshold=0.5, num_samples=1):
     """Disk props (disk.zig:28-134): a glossy disk table top on a diffuse floor, a tilted metal disk that casts a round shadow, and an
     emissive disk that is not registered as a light (its emission is met by the paths, without next-event estimation), under a
-    Rectangle lamp. Disk lights (Disk.sampleTo) are outside the scope."""
+    Rectangle lamp. With `disk_lights` the lamp is an un-occluding Disk (Disk.emission, disk.zig:171-179) and the small emissive disk is
+    registered as a light too (Disk.sampleTo with equi-angular sampling and Disk.pdf, disk.zig:181-332, 492-533)."""
     from . import su
 
     su.init()
@@ -537,7 +538,8 @@ def disk_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None):
     su.camera_set_fov(float(np.radians(55.0)))
     su.prop_set_transformation(camera, su.transformation(position=(0.0, 1.6, -4.2), rotation_deg=(-14.0, 0.0, 0.0)))
     su.sampler_create(spp)
-    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth}}}})
+    su.integrators_create({"surface": {"PTMIS": {"depth": {"surface": max_depth},
+                                                 "light_sampling": {"split_threshold": split_threshold}}}})
     su.sensor_create({"filter": {filter_name: {}}} if filter_name else {})
 
     floor = su.material_create({"rendering": {"Substitute": {"color": [0.55, 0.55, 0.5], "roughness": 1.0}}})
@@ -556,9 +558,11 @@ def disk_scene(width=128, height=128, spp=16, max_depth=6, filter_name=None):
                                                              "emittance": {"value": 3.0}}}})
     lamp_disk = su.prop_create(su.DISK, [glow])
     su.prop_set_transformation(lamp_disk, su.transformation((0.4, 0.35, -0.9), (0.7, 0.7, 1.0), (0.0, 0.0, 0.0)))
+    if disk_lights:
+        su.light_create(lamp_disk)
 
-    light = su.material_create({"rendering": {"Light": {"emittance": {"value": 25.0}}}})
-    lamp = su.prop_create(su.RECTANGLE, [light], unoccluding=True)
+    light = su.material_create({"rendering": {"Light": {"emittance": {"value": 25.0, "num_samples": num_samples}}}})
+    lamp = su.prop_create(su.DISK if disk_lights else su.RECTANGLE, [light], unoccluding=True)
     su.prop_set_transformation(lamp, su.transformation((0.0, 4.0, -0.5), (2.0, 2.0, 1.0), (-90.0, 0.0, 0.0)))
     su.light_create(lamp)
     return 0
