@@ -245,6 +245,10 @@ __device__ __forceinline__ LightNodeD loadLightNode(const TreeD& sc, uint32_t i)
     return n;
 }
 
+__device__ __forceinline__ bool lightNodeIsLeaf(const TreeD& tr, uint32_t i) {  // the `has_children` bit of Node.meta
+    return 0 == (__ldg(reinterpret_cast<const uint32_t*>(tr.nodes + i) + 6) & 1u);
+}
+
 __device__ __forceinline__ float lightNodeWeight(const LightNodeD& node, V3 p, V3 n, bool total_sphere) {  // light_tree.zig:57-63
     return lightImportance(p, n, node.center, node.cone_axis, node.cone_cos, node.radius, node.power, 0 != (node.meta & 2u), total_sphere);
 }
@@ -284,29 +288,43 @@ __device__ __forceinline__ LightPickD lightNodeRandomLight(const SceneDevice& sc
     uint32_t front = light;
     uint32_t back  = light + num_lights - 1;
 
-    float w_front = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + front));
-    float w_back  = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + back));
-
-    float w_sum_front = w_front;
-    float w_sum_back  = w_back;
-    float w_sum       = 0.f;
-
-    while (front != back) {
-        w_sum = w_sum_front + w_sum_back;
-        if (w_sum_front <= random * w_sum) {
-            front += 1;
-            if (front != back) {
-                w_front = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + front));
-                w_sum_front += w_front;
-            } else {
-                w_front = w_back;
-            }
+    // The reference weighs the first and the last light, then the next one from whichever end the running sums point at. Here every
+    // weight comes from one call site (stage 0 and 1 are the two initial ones): the lanes of a warp stay on one copy of the code
+    // whichever end they advance, and the kernels hold one copy of Light properties + importance instead of four.
+    float w_front = 0.f, w_back = 0.f;
+    float w_sum_front = 0.f, w_sum_back = 0.f;
+    float w_sum = 0.f;
+    for (uint32_t stage = 0;; stage = stage < 2 ? stage + 1 : 2) {
+        bool     advance_front;
+        uint32_t index;
+        if (0 == stage) {
+            advance_front = true;
+            index         = front;
+        } else if (1 == stage) {
+            advance_front = false;
+            index         = back;
         } else {
-            back -= 1;
-            if (front != back) {
-                w_back = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + back));
-                w_sum_back += w_back;
+            if (front == back) break;
+            w_sum         = w_sum_front + w_sum_back;
+            advance_front = w_sum_front <= random * w_sum;
+            if (advance_front) {
+                front += 1;
+            } else {
+                back -= 1;
             }
+            if (front == back) {
+                if (advance_front) w_front = w_back;
+                break;
+            }
+            index = advance_front ? front : back;
+        }
+        const float w = lightWeight(sc, tr, p, n, total_sphere, __ldg(tr.mapping + index));
+        if (advance_front) {
+            w_front = w;
+            w_sum_front += w;  // the first one: 0 + w
+        } else {
+            w_back = w;
+            w_sum_back += w;
         }
     }
     if (0.f == w_sum) return {0, 0.f};
@@ -405,25 +423,28 @@ __device__ __forceinline__ void lightTreeRandomLight(const SceneDevice& sc, V3 p
     }
 }
 
-// PrimitiveTree.randomLight, light_tree.zig:577-650. `emit` receives (part triangle, pdf) in the reference's order.
-template <typename Emit>
-__device__ __forceinline__ void primitiveTreeRandomLight(const SceneDevice& sc, const MeshSamplerDevice& m, V3 p, V3 n, bool total_sphere, float random,
-                                         float split_threshold, Emit&& emit) {
-    constexpr uint32_t kMaxSplitDepth = 6;
-    const TreeD        tr             = primitiveTree(m);
-    const bool         split          = split_threshold > 0.f;
-
+// PrimitiveTree.randomLight, light_tree.zig:577-650, as a walk that can be left and resumed between two iterations of the reference's
+// loop: the light kernel gives every lane one iteration per step of its own loop, so a lane whose pick splits into 64 triangles does not
+// hold 31 others that found one. `emit` receives (part triangle, pdf) in the reference's order.
+struct PrimitiveWalkD {
+    static constexpr uint32_t kMaxSplitDepth = 6;
     struct Value {
         float    pdf, random;
         uint32_t node, depth;
     };
     Value    stack[kMaxSplitDepth + 1];
-    uint32_t end = 0;
+    Value    t;
+    uint32_t end;
 
-    Value t{1.f, random, 0, split ? 0 : kMaxSplitDepth};
-    stack[end++] = t;
+    __device__ __forceinline__ void start(float random, float split_threshold) {
+        t        = {1.f, random, 0, split_threshold > 0.f ? 0 : kMaxSplitDepth};
+        stack[0] = t;
+        end      = 1;
+    }
 
-    while (end > 0) {
+    // one iteration; false once the stack is empty
+    template <typename Emit>
+    __device__ __forceinline__ bool step(const SceneDevice& sc, const TreeD& tr, V3 p, V3 n, bool total_sphere, float split_threshold, Emit&& emit) {
         const LightNodeD node = loadLightNode(tr, t.node);
         if (0 != (node.meta & 1u)) {
             const bool     do_split = t.depth < kMaxSplitDepth && lightNodeSplit(node, p, split_threshold);
@@ -442,7 +463,7 @@ __device__ __forceinline__ void primitiveTreeRandomLight(const SceneDevice& sc, 
                 const float pt = p0 + p1;
                 if (0.f == pt) {
                     t = stack[--end];
-                    continue;
+                    return end > 0;
                 }
                 p0 = __fdiv_rn(p0, pt);
                 p1 = __fdiv_rn(p1, pt);
@@ -461,6 +482,17 @@ __device__ __forceinline__ void primitiveTreeRandomLight(const SceneDevice& sc, 
             if (pick.pdf > 0.f) emit(LightPickD{pick.offset, pick.pdf * t.pdf});
             t = stack[--end];
         }
+        return end > 0;
+    }
+};
+
+template <typename Emit>
+__device__ __forceinline__ void primitiveTreeRandomLight(const SceneDevice& sc, const MeshSamplerDevice& m, V3 p, V3 n, bool total_sphere, float random,
+                                         float split_threshold, Emit&& emit) {
+    const TreeD    tr = primitiveTree(m);
+    PrimitiveWalkD walk;
+    walk.start(random, split_threshold);
+    while (walk.step(sc, tr, p, n, total_sphere, split_threshold, emit)) {
     }
 }
 
@@ -575,70 +607,79 @@ __device__ __forceinline__ float meshLightPdf(const SceneDevice& sc, const MeshS
     return __fdiv_rn(tri_pdf * sl, n_dot_dir * tri_area);
 }
 
+// One triangle of Mesh.sampleTo, triangle_mesh.zig:492-608: `sp` = (triangle of the part, its pdf) as PrimitiveTree.randomLight emits it
+__device__ __forceinline__ uint32_t meshLightTriangleSample(const SceneDevice& sc, const PathState& st, uint32_t slot, const ZygpuLight& light,
+                                                         LightPickD pick, const TrafoD& trafo, const FragD& frag, V3 n, V3 op, V3 on,
+                                                         bool translucent, LightPickD sp, SamplerD& sampler, uint32_t num_records) {
+    const MeshSamplerDevice& m = sc.mesh_samplers[light.sampler];
+    const V3                 p = frag.p;
+    const V3     scale_squared = mul3(trafo.scale, trafo.scale);
+    V3 a, b, c;
+    meshTriangle(sc.meshes[m.mesh], __ldg(m.triangle_mapping + sp.offset), a, b, c);
+
+    const V3    ca  = mul3(scale_squared, cross3(sub3(b, a), sub3(c, a)));
+    const float lca = length3(ca);
+    V3          wn  = trafo.objectToWorldNormal(divs3(ca, lca));
+
+    const float tri_area = 0.5f * lca;
+    const V3    center   = divs3(add3(add3(a, b), c), 3.f);
+
+    float u0, u1;
+    sampler.sample2D(u0, u1);
+
+    V3    dir, v;
+    float sample_pdf, n_dot_dir;
+    if (__fdiv_rn(tri_area, length3(sub3(center, op))) > kAreaDistanceRatio) {
+        V3    sdir;
+        float bu, bv, spdf;
+        if (!sampleSpherical(op, a, b, c, u0, u1, sdir, bu, bv, spdf)) return num_records;
+        if (dot3(sdir, on) <= 0.f && !translucent) return num_records;
+        dir        = trafo.objectToWorldNormal(sdir);
+        v          = trafo.objectToWorldPoint(interpolate3(a, b, c, bu, bv));
+        sample_pdf = sp.pdf * spdf;
+        if (0 != light.two_sided && dot3(wn, dir) > 0.f) wn = neg3(wn);
+        n_dot_dir = -dot3(wn, dir);
+    } else {
+        float bu, bv;
+        triangleUniform(u0, u1, bu, bv);
+        v = trafo.objectToWorldPoint(interpolate3(a, b, c, bu, bv));
+
+        const V3    axis = sub3(v, p);
+        const float sl   = squaredLength3(axis);
+        const float d    = __fsqrt_rn(sl);
+        dir              = divs3(axis, d);
+        if (dot3(dir, n) <= 0.f && !translucent) return num_records;
+        if (0 != light.two_sided && dot3(wn, dir) > 0.f) wn = neg3(wn);
+        n_dot_dir  = -dot3(wn, dir);
+        sample_pdf = __fdiv_rn(sp.pdf * sl, n_dot_dir * tri_area);
+    }
+    if (n_dot_dir < kDotMin) return num_records;
+
+    if (num_records < st.shadow_stride) {
+        const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
+        const V3     origin    = frag.offsetP(dir);
+        const V3     light_pos = offsetRay(v, wn);
+        st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, sample_pdf * pick.pdf);
+        st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
+        st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
+        num_records += 1;
+    } else {
+        st.counters[3] = 1;
+    }
+    return num_records;
+}
+
 // Mesh.sampleTo, triangle_mesh.zig:492-608: appends the shadow records of one picked mesh light, returns the new record count.
 // Inlined for the same reason.
 __device__ __forceinline__ uint32_t meshLightSampleTo(const SceneDevice& sc, const PathState& st, uint32_t slot, const ZygpuLight& light,
                                                    LightPickD pick, const TrafoD& trafo, const FragD& frag, V3 n, bool translucent,
                                                    float split_threshold, SamplerD& sampler, uint32_t num_records) {
     const MeshSamplerDevice& m  = sc.mesh_samplers[light.sampler];
-    const V3                 p  = frag.p;
-    const V3                 op = trafo.worldToObjectPoint(p);
+    const V3                 op = trafo.worldToObjectPoint(frag.p);
     const V3                 on = trafo.worldToObjectNormal(n);
-    const V3    scale_squared   = mul3(trafo.scale, trafo.scale);
-    const float r1              = sampler.sample1D();
+    const float              r1 = sampler.sample1D();
     primitiveTreeRandomLight(sc, m, op, on, translucent, r1, split_threshold, [&](LightPickD sp) {
-        V3 a, b, c;
-        meshTriangle(sc.meshes[m.mesh], __ldg(m.triangle_mapping + sp.offset), a, b, c);
-
-        const V3    ca  = mul3(scale_squared, cross3(sub3(b, a), sub3(c, a)));
-        const float lca = length3(ca);
-        V3          wn  = trafo.objectToWorldNormal(divs3(ca, lca));
-
-        const float tri_area = 0.5f * lca;
-        const V3    center   = divs3(add3(add3(a, b), c), 3.f);
-
-        float u0, u1;
-        sampler.sample2D(u0, u1);
-
-        V3    dir, v;
-        float sample_pdf, n_dot_dir;
-        if (__fdiv_rn(tri_area, length3(sub3(center, op))) > kAreaDistanceRatio) {
-            V3    sdir;
-            float bu, bv, spdf;
-            if (!sampleSpherical(op, a, b, c, u0, u1, sdir, bu, bv, spdf)) return;
-            if (dot3(sdir, on) <= 0.f && !translucent) return;
-            dir        = trafo.objectToWorldNormal(sdir);
-            v          = trafo.objectToWorldPoint(interpolate3(a, b, c, bu, bv));
-            sample_pdf = sp.pdf * spdf;
-            if (0 != light.two_sided && dot3(wn, dir) > 0.f) wn = neg3(wn);
-            n_dot_dir = -dot3(wn, dir);
-        } else {
-            float bu, bv;
-            triangleUniform(u0, u1, bu, bv);
-            v = trafo.objectToWorldPoint(interpolate3(a, b, c, bu, bv));
-
-            const V3    axis = sub3(v, p);
-            const float sl   = squaredLength3(axis);
-            const float d    = __fsqrt_rn(sl);
-            dir              = divs3(axis, d);
-            if (dot3(dir, n) <= 0.f && !translucent) return;
-            if (0 != light.two_sided && dot3(wn, dir) > 0.f) wn = neg3(wn);
-            n_dot_dir  = -dot3(wn, dir);
-            sample_pdf = __fdiv_rn(sp.pdf * sl, n_dot_dir * tri_area);
-        }
-        if (n_dot_dir < kDotMin) return;
-
-        if (num_records < st.shadow_stride) {
-            const size_t rec       = size_t(slot) * st.shadow_stride + num_records;
-            const V3     origin    = frag.offsetP(dir);
-            const V3     light_pos = offsetRay(v, wn);
-            st.sh_o[rec]  = make_float4(origin.x, origin.y, origin.z, sample_pdf * pick.pdf);
-            st.sh_p[rec]  = make_float4(light_pos.x, light_pos.y, light_pos.z, __uint_as_float(pick.offset));
-            st.sh_wi[rec] = make_float4(dir.x, dir.y, dir.z, 0.f);
-            num_records += 1;
-        } else {
-            st.counters[3] = 1;
-        }
+        num_records = meshLightTriangleSample(sc, st, slot, light, pick, trafo, frag, n, op, on, translucent, sp, sampler, num_records);
     });
     return num_records;
 }
@@ -1602,6 +1643,12 @@ __global__ void __launch_bounds__(128) lightSelectPersistent(SceneDevice sc, Zyg
 #ifndef ZYGPU_LIGHT_BLOCKS
 #define ZYGPU_LIGHT_BLOCKS 8
 #endif
+#ifndef ZYGPU_WALK_REFILL
+#define ZYGPU_WALK_REFILL 8
+#endif
+#ifndef ZYGPU_WALK_LEAF_RATIO
+#define ZYGPU_WALK_LEAF_RATIO 3u  // leaf iterations are taken when this many times more walks wait at a leaf than at an inner node
+#endif
 // Scenes with infinite lights run it twice: their picks come first in a vertex's list (Tree.randomLight, light_tree.zig:353-371), so
 // phase 1 takes the Distant / Canopy picks of every vertex and phase 2 the finite ones, each on the sampler state the other left.
 // A warp then works on one class of light at a time (and each instance holds half the code): lanes that fetch a new vertex no longer
@@ -1626,6 +1673,13 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
     uint32_t pool_word   = 0;
     SamplerD sampler;
     sampler.sobol.tables = sobol_tables;
+
+    // a triangle-mesh pick in progress: PrimitiveTree.randomLight advances by one iteration per step of this loop
+    constexpr bool kWalks   = kFinitePicks && MeshLights;
+    bool           walking = false, walk_leaf = false;
+    PrimitiveWalkD walk;
+    LightPickD     walk_pick{0, 0.f};
+    V3             walk_op = {0.f, 0.f, 0.f}, walk_on = {0.f, 0.f, 0.f};
 
     for (;;) {
         const uint32_t idle = __ballot_sync(kFull, !active);
@@ -1660,7 +1714,7 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
             if (exhausted) break;
             continue;
         }
-        if (active && pick_i < pick_count) {  // Light.sampleTo for one pick, pathtracer_mis.zig:214-250
+        if (active && !(kWalks && walking) && pick_i < pick_count) {  // Light.sampleTo for one pick, pathtracer_mis.zig:214-250
             const uint2      pk = st.picks[size_t(slot) * kMaxLightPicks + pick_i];
             const LightPickD pick{pk.x, __uint_as_float(pk.y)};
             pick_i += 1;
@@ -1718,10 +1772,13 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                     }
                 }
             } else if (kFinitePicks && MeshLights && ZYG_SHAPE_TRIANGLE_MESH == shape && ZYGPU_NULL != light.sampler) {
-                FragD frag;  // meshLightSampleTo reads the shading point and offsets from it
-                frag.p      = p;
-                frag.geo_n  = geo_n;
-                num_records = meshLightSampleTo(sc, st, slot, light, pick, trafo, frag, n, translucent, threshold, sampler, num_records);
+                // Mesh.sampleTo, triangle_mesh.zig:492-608: the draw that picks the triangles, then the walk below
+                walk_pick = pick;
+                walk_op   = trafo.worldToObjectPoint(p);
+                walk_on   = trafo.worldToObjectNormal(n);
+                walk.start(sampler.sample1D(), threshold);
+                walking   = true;
+                walk_leaf = lightNodeIsLeaf(primitiveTree(sc.mesh_samplers[light.sampler]), 0);
             } else if (kFinitePicks && ZYG_SHAPE_SPHERE == shape) {  // Sphere.sampleTo, sphere.zig:323-393
                 SphereLightD sl;
                 sl.init(trafo, p);
@@ -1829,7 +1886,34 @@ __global__ void __launch_bounds__(128, ZYGPU_LIGHT_BLOCKS) lightSamplePersistent
                 }
             }
         }
-        if (active && pick_i >= pick_count) {
+        if (kWalks) {
+            // The walks stay in this short loop until ZYGPU_WALK_REFILL lanes have finished theirs: every trip through the code around
+            // it (fetching vertices and picks, the other shapes, the write-back) is paid in instruction fetches by the whole warp.
+            // A leaf iteration (Node.randomLight over up to four triangles + the triangle sample) costs several inner ones, so the
+            // lanes that reached a leaf wait for the others to arrive and the warp takes the leaves together.
+            uint32_t       walkers = __ballot_sync(kFull, walking);
+            const uint32_t n0      = uint32_t(__popc(walkers));
+            const uint32_t leave   = n0 > ZYGPU_WALK_REFILL ? n0 - ZYGPU_WALK_REFILL : 0u;
+            while (0 != walkers) {
+                const uint32_t leaves  = __ballot_sync(kFull, walking && walk_leaf);
+                const bool     do_leaf = uint32_t(__popc(leaves)) >= ZYGPU_WALK_LEAF_RATIO * uint32_t(__popc(walkers & ~leaves));
+                if (walking && walk_leaf == do_leaf) {
+                    const ZygpuLight light = sc.lights[walk_pick.offset];
+                    const TreeD      tr    = primitiveTree(sc.mesh_samplers[light.sampler]);
+                    walking = walk.step(sc, tr, walk_op, walk_on, translucent, threshold, [&](LightPickD sp) {
+                        FragD frag;  // the shading point and what offsets from it
+                        frag.p      = p;
+                        frag.geo_n  = geo_n;
+                        num_records = meshLightTriangleSample(sc, st, slot, light, walk_pick, loadTrafo(sc.trafos, light.prop), frag, n, walk_op,
+                                                              walk_on, translucent, sp, sampler, num_records);
+                    });
+                    if (walking) walk_leaf = lightNodeIsLeaf(tr, walk.t.node);
+                }
+                walkers = __ballot_sync(kFull, walking);
+                if (uint32_t(__popc(walkers)) <= leave) break;
+            }
+        }
+        if (active && !(kWalks && walking) && pick_i >= pick_count) {
             if (1 == Phase) st.pick_n[slot] = pick_count | (pick_count << 16);  // no finite pick: phase 2 only queues the records
             st.sh_n[slot] = num_records;
             storeSampler(st, slot, sampler, pool_word);
