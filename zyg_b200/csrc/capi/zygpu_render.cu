@@ -31,7 +31,7 @@ int uploadArray(RenderState& r, const T* host, size_t count, const T** device) {
         r.scene_buffer_bytes[slot] = capacity;
     }
     void* d = r.scene_buffers[slot];
-    if (count > 0) CUDA_OK(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    if (count > 0 && host) CUDA_OK(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));  // no host array: the caller fills it
     *device = static_cast<const T*>(d);
     return 0;
 }
@@ -293,6 +293,9 @@ int zygpu_upload_scene(zygpu_device* dev, const ZygpuScene* scene) {
             0 != uploadArray(r, ms.primitive_mapping, tree_triangles, &sd.primitive_mapping)) {
             return -1;
         }
+        // centre, radius and normal of every light triangle, derived once on the device (device/render.cu meshLightPropsKernel)
+        if (0 != uploadArray<float4>(r, nullptr, size_t(ms.num_triangles) * 2, &sd.triangle_props)) return -1;
+        CUDA_OK(zygpu::launchMeshLightProps(mesh_views[ms.mesh], sd, const_cast<float4*>(sd.triangle_props), r.stream));
     }
     if (0 != uploadArray(r, samplers.data(), samplers.size(), &d.mesh_samplers)) return -1;
     d.num_mesh_samplers = scene->num_mesh_samplers;

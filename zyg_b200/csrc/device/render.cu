@@ -198,17 +198,27 @@ __device__ __forceinline__ void meshTriangle(const MeshDevice& mesh, uint32_t t,
     c = meshPosition(mesh, __ldg(mesh.triangles + 3 * size_t(t) + 2));
 }
 
-// MeshImpl.lightProperties, shape_sampler.zig:198-226
-__device__ __forceinline__ LightPropsD meshLightProperties(const SceneDevice& sc, const MeshSamplerDevice& m, uint32_t light) {
+// MeshImpl.lightProperties, shape_sampler.zig:198-226. The reference derives centre, bounding radius and normal of the triangle every
+// time a leaf of the primitive tree weighs it; here one kernel does that at upload with the same arithmetic and the walks read 32 bytes.
+__global__ void meshLightPropsKernel(MeshDevice mesh, MeshSamplerDevice m, float4* __restrict__ props) {
+    const uint32_t light = blockIdx.x * blockDim.x + threadIdx.x;
+    if (light >= m.num_triangles) return;
     V3 a, b, c;
-    meshTriangle(sc.meshes[m.mesh], __ldg(m.triangle_mapping + light), a, b, c);
+    meshTriangle(mesh, __ldg(m.triangle_mapping + light), a, b, c);
     const V3    center = divs3(add3(add3(a, b), c), 3.f);
     const float sra    = squaredLength3(sub3(a, center));
     const float srb    = squaredLength3(sub3(b, center));
     const float src    = squaredLength3(sub3(c, center));
     const float radius = __fsqrt_rn(zmax(sra, zmax(srb, src)));
     const V3    nn     = normalize3(cross3(sub3(b, a), sub3(c, a)));
-    return {center, radius, nn, 1.f, __ldg(m.triangle_pdfs + light), 0 != m.two_sided};
+    props[2 * size_t(light)]     = make_float4(center.x, center.y, center.z, radius);
+    props[2 * size_t(light) + 1] = make_float4(nn.x, nn.y, nn.z, __ldg(m.triangle_pdfs + light));
+}
+
+__device__ __forceinline__ LightPropsD meshLightProperties(const SceneDevice&, const MeshSamplerDevice& m, uint32_t light) {
+    const float4 a = __ldg(m.triangle_props + 2 * size_t(light));
+    const float4 b = __ldg(m.triangle_props + 2 * size_t(light) + 1);
+    return {{a.x, a.y, a.z}, a.w, {b.x, b.y, b.z}, 1.f, b.w, 0 != m.two_sided};
 }
 
 __device__ __forceinline__ float lightWeight(const SceneDevice& sc, const TreeD& tr, V3 p, V3 n, bool total_sphere, uint32_t light) {  // light_tree.zig:227-233
@@ -1639,9 +1649,11 @@ __global__ void __launch_bounds__(128) lightSelectPersistent(SceneDevice sc, Zyg
 
 // The kernel is long and branchy and its warps mostly wait for instruction fetch (ncu: no_instruction is the top stall, issue
 // slots 13 % busy at 122 registers / 4 blocks per SM): more resident warps hide that better than registers help, so it is
-// compiled for 8 blocks per SM (64 registers; measured 310 -> 265 ms per 4-spp pass of config 4, 12 and 16 blocks are slower).
+// compiled for more blocks per SM than its registers ask for (8 blocks = 64 registers: 310 -> 265 ms per 4-spp pass of config 4, 12 and
+// 16 blocks are slower). Since the mesh-light walks run in their own short loop the spills of 64 registers cost more than the two
+// blocks give: 6 blocks = 80 registers (288.5 -> 280.8 ms per 8-spp frame).
 #ifndef ZYGPU_LIGHT_BLOCKS
-#define ZYGPU_LIGHT_BLOCKS 8
+#define ZYGPU_LIGHT_BLOCKS 6
 #endif
 #ifndef ZYGPU_WALK_REFILL
 #define ZYGPU_WALK_REFILL 8
@@ -2520,6 +2532,12 @@ cudaError_t launchFilm(const ZygpuView& view, const PathState& st, const PassPar
     filmKernel<<<gridFor(uint32_t(view.resolution[0] * view.resolution[1]), 16), kBlock, 0, stream>>>(view, st, pass, film, film_alpha);
     return cudaGetLastError();
 }
+cudaError_t launchMeshLightProps(const MeshDevice& mesh, const MeshSamplerDevice& sampler, float4* props, cudaStream_t stream) {
+    if (0 == sampler.num_triangles) return cudaSuccess;
+    meshLightPropsKernel<<<(sampler.num_triangles + 127u) / 128u, 128, 0, stream>>>(mesh, sampler, props);
+    return cudaGetLastError();
+}
+
 cudaError_t launchAovClear(const AovFilm& aov, uint32_t num_pixels, cudaStream_t stream) {
     aovClearKernel<<<gridFor(num_pixels, 16), kBlock, 0, stream>>>(aov, num_pixels);
     return cudaGetLastError();

@@ -43,6 +43,7 @@ struct MeshSamplerDevice {  // ZygpuMeshSampler with device pointers
     const uint32_t*       triangle_mapping;
     const float*          triangle_pdfs;
     const uint32_t*       primitive_mapping;
+    const float4*         triangle_props;  // per light triangle {centre, radius}, {normal, pdf}: MeshImpl.lightProperties, filled at upload
 };
 
 // ZygpuImageSampler on the device: the emission image and the cdf rows of its Distribution2D.
@@ -221,6 +222,8 @@ struct AovFilm {
     float4* layers[9];  // by aov.Value.Class; null = inactive
 };
 cudaError_t launchAovClear(const AovFilm& aov, uint32_t num_pixels, cudaStream_t stream);  // aov.Buffer.clear
+// MeshImpl.lightProperties (shape_sampler.zig:198-226) of every light triangle of `sampler` into props[2 * num_triangles]
+cudaError_t launchMeshLightProps(const MeshDevice& mesh, const MeshSamplerDevice& sampler, float4* props, cudaStream_t stream);
 cudaError_t launchAovFilm(const ZygpuView& view, const PathState& st, const PassParams& pass, const AovFilm& aov, cudaStream_t stream);
 cudaError_t launchResolveAov(uint32_t aov_class, const float4* layer, float4* rgba, uint32_t num_pixels, cudaStream_t stream);
 // The `it` tool's denoise operator (src/it/denoise.zig:137-246, 375-451) as a post kernel over the film and the ShadingNormal / Albedo
