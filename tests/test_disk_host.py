@@ -91,3 +91,18 @@ def test_disk_scene_renders_with_round_shadows(engine, disk_lights):
     film = oracle.render(scene, view, w, w, 0, spp)
     img = film[..., :3] / film[..., 3:]
     assert np.isfinite(img).all() and img.min() >= 0 and 0.02 < img.mean() < 2.0
+
+
+def test_disk_lights_draw_orders_are_statistically_equivalent(engine):
+    """Disk.sampleTo takes a 1D draw per sample; the device takes the draws of all picks before the draws of Light.evaluateTo
+    (zyg_oracle.h: zo_set_wavefront_light_order). Both orders estimate the same image."""
+    w, spp = 48, 128
+    scenes.disk_scene(w, w, spp=spp, disk_lights=True)
+    scene, view = su.compile_scene()
+    a = oracle.render(scene, view, w, w, 0, spp)
+    b = oracle.render(scene, view, w, w, 0, spp, wavefront_light_order=True)
+    ia, ib = a[..., :3] / a[..., 3:4], b[..., :3] / b[..., 3:4]
+    assert not np.array_equal(ia, ib)
+    assert abs(ia.mean() - ib.mean()) / ia.mean() < 1e-2
+    blocks = lambda img: img.reshape(6, 8, 6, 8, 3).mean((1, 3))
+    assert np.abs(blocks(ia) - blocks(ib)).max() / blocks(ia).mean() < 0.15
