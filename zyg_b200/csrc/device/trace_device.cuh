@@ -134,6 +134,31 @@ __device__ __forceinline__ F8 ldg256(const float4* p) {  // p must be 32-byte al
     return r;
 }
 
+// The same load with an L2 eviction priority (LDG.E.ELL2 / .EFL2): Hint 1 = evict last (the node arrays, reused by every ray), 2 = evict
+// first (triangle records of scenes that do not fit the 126 MB L2). ZYGPU_NODE_L2 / ZYGPU_TRI_L2 choose; measured in profiles/r02_sweeps.md.
+#ifndef ZYGPU_NODE_L2
+#define ZYGPU_NODE_L2 0
+#endif
+#ifndef ZYGPU_TRI_L2
+#define ZYGPU_TRI_L2 0
+#endif
+template <int Hint>
+__device__ __forceinline__ F8 ldg256Hint(const float4* p) {
+    F8 r;
+    if (1 == Hint) {
+        asm("ld.global.nc.L1::evict_normal.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+            : "l"(p));
+    } else if (2 == Hint) {
+        asm("ld.global.nc.L1::evict_normal.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+            : "l"(p));
+    } else {
+        r = ldg256(p);
+    }
+    return r;
+}
+
 constexpr uint32_t kWideNodeWords = 6;  // float4 per node: 80 bytes of node + 16 bytes of padding = three 32-byte loads
 
 struct WideNodeRegs {
@@ -141,7 +166,7 @@ struct WideNodeRegs {
 };
 __device__ __forceinline__ WideNodeRegs loadWideNode(const float4* nodes, uint32_t index) {
     const float4* np = nodes + kWideNodeWords * size_t(index);
-    const F8      a = ldg256(np), b = ldg256(np + 2);
+    const F8      a = ldg256Hint<ZYGPU_NODE_L2>(np), b = ldg256Hint<ZYGPU_NODE_L2>(np + 2);
     const float4  c = __ldg(np + 4);
     return {a.lo, a.hi, b.lo, b.hi, c};
 }
@@ -257,7 +282,7 @@ __device__ __forceinline__ bool gateBox(const float4 bmin, const float4 bmax, co
 __device__ __forceinline__ bool testWideTriangle(const MeshDevice& mesh, const RayT& ray, float gate_tmax, uint32_t index, float& t,
                                                  float& u, float& v, uint32_t& primitive) {
     const float4* tp = mesh.wide_tris + 4 * size_t(index);
-    const F8      ta = ldg256(tp), tb = ldg256(tp + 2);
+    const F8      ta = ldg256Hint<ZYGPU_TRI_L2>(tp), tb = ldg256Hint<ZYGPU_TRI_L2>(tp + 2);
     const float4  t0 = ta.lo, t1 = ta.hi, t2 = tb.lo, t3 = tb.hi;
 
     // Gate with the reference's own (non-watertight) slab test on the reference leaf box: the
