@@ -50,10 +50,12 @@ int allocPath(RenderState& r, T** out, size_t count) {
     return 0;
 }
 
-// Path slots per pass: enough to fill the machine several times over, small enough to stay a modest share of HBM.
+// Path slots per pass: the late bounces of a pass run on what is left of it, so a pass should fill the machine many times over
+// (measured, profiles/r02_sweeps.md: 4 Mi instead of 16 Mi slots costs 6 - 28 % of a frame; the 66 M paths of a 4K x 8 spp frame in
+// passes of 32 Mi instead of 16 Mi: 1300 -> 1256 ms) while the path state stays a modest share of the 180 GB.
 uint32_t targetPathsPerPass() {
     const char* v = getenv("ZYGPU_PATHS_PER_PASS");
-    return v ? uint32_t(std::max(1, atoi(v))) : (16u << 20);
+    return v ? uint32_t(std::max(1, atoi(v))) : (32u << 20);
 }
 
 // `lanes` vertex records per slot (1, or 4 when a material of the scene can split a path); trace items are vertex ids for
